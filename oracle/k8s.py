@@ -1,0 +1,497 @@
+"""ORACLE (test infrastructure, NOT product code) -- CPU restatement of the in-tree Go parts of the
+Review hot path: the `spec.match` pre-filter, wildcard globbing, the process excluder, enforcement-point
+filtering, review construction and the `Client.Review` loop that ties them to the Rego evaluation.
+
+Every function cites the reference file:line it restates (paths relative to /root/reference).
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.
+"""
+from __future__ import annotations
+
+import re
+
+from . import rego
+
+TARGET_NAME = "admission.k8s.gatekeeper.sh"  # pkg/target/target.go:25
+
+# enforcement points / actions -- pkg/util/enforcement_action.go:16-39
+WEBHOOK_EP = "validation.gatekeeper.sh"
+AUDIT_EP = "audit.gatekeeper.sh"
+GATOR_EP = "gator.gatekeeper.sh"
+VAP_EP = "vap.k8s.io"
+ALL_EPS = "*"
+
+
+class MatchError(Exception):
+    """A matcher returned an error (tri-state: match / no match / error)."""
+
+
+# ---------------------------------------------------------------------------------------------------
+# pkg/wildcard/wildcard.go:17-41
+
+
+def wildcard_matches(w: str, candidate: str) -> bool:
+    """wildcard.Wildcard.Matches -- pkg/wildcard/wildcard.go:17-29"""
+    if w.startswith("*") and w.endswith("*"):
+        # strings.TrimSuffix(strings.TrimPrefix(w, "*"), "*"): for w == "*" the prefix trim leaves ""
+        inner = w[1:]
+        if inner.endswith("*"):
+            inner = inner[:-1]
+        return inner in candidate
+    if w.startswith("*"):
+        return candidate.endswith(w[1:])
+    if w.endswith("*"):
+        return candidate.startswith(w[:-1])
+    return w == candidate
+
+
+def wildcard_matches_generate_name(w: str, candidate: str) -> bool:
+    """wildcard.Wildcard.MatchesGenerateName -- pkg/wildcard/wildcard.go:31-41"""
+    if w.startswith("*") and w.endswith("*"):
+        inner = w[1:]
+        if inner.endswith("*"):
+            inner = inner[:-1]
+        return inner in candidate
+    if w.endswith("*"):
+        return candidate.startswith(w[:-1])
+    return False
+
+
+# ---------------------------------------------------------------------------------------------------
+# k8s.io/apimachinery v0.35.4 (go.mod:43, NOT vendored) metav1.LabelSelectorAsSelector + labels.Selector,
+# restated from its published behaviour; call sites pkg/mutation/match/match.go:87,110.
+
+_NAME_RE = re.compile(r"^[A-Za-z0-9]([-A-Za-z0-9_.]*[A-Za-z0-9])?$")
+_DNS1123_SUB = re.compile(r"^[a-z0-9]([-a-z0-9]*[a-z0-9])?(\.[a-z0-9]([-a-z0-9]*[a-z0-9])?)*$")
+
+
+def _valid_label_key(k: str) -> bool:
+    parts = k.split("/")
+    if len(parts) == 1:
+        name = parts[0]
+    elif len(parts) == 2:
+        prefix, name = parts
+        if not prefix or len(prefix) > 253 or not _DNS1123_SUB.match(prefix):
+            return False
+    else:
+        return False
+    return bool(name) and len(name) <= 63 and bool(_NAME_RE.match(name))
+
+
+def _valid_label_value(v: str) -> bool:
+    return len(v) <= 63 and (v == "" or bool(_NAME_RE.match(v)))
+
+
+def label_selector_requirements(sel):
+    """LabelSelectorAsSelector: returns a list of (key, op, values) or raises MatchError."""
+    reqs = []
+    if sel is None:
+        return None
+    for k, v in sorted((sel.get("matchLabels") or {}).items()):
+        reqs.append((k, "In", [v]))
+    for e in sel.get("matchExpressions") or []:
+        op = e.get("operator", "")
+        vals = list(e.get("values") or [])
+        if op not in ("In", "NotIn", "Exists", "DoesNotExist"):
+            raise MatchError(f'"{op}" is not a valid label selector operator')
+        reqs.append((e.get("key", ""), op, vals))
+    for k, op, vals in reqs:
+        if op in ("In", "NotIn") and not vals:
+            raise MatchError("for 'in', 'notin' operators, values set can't be empty")
+        if op in ("Exists", "DoesNotExist") and vals:
+            raise MatchError("values set must be empty for exists and does not exist")
+        if not _valid_label_key(k):
+            raise MatchError(f"key: Invalid value: {k!r}")
+        for v in vals:
+            if not _valid_label_value(v):
+                raise MatchError(f"values: Invalid value: {v!r}")
+    return reqs
+
+
+def selector_matches(reqs, labels) -> bool:
+    """labels.Selector.Matches: all requirements ANDed; NotIn is true when the key is absent."""
+    labels = labels or {}
+    for k, op, vals in reqs:
+        has = k in labels
+        if op == "In":
+            if not (has and labels[k] in vals):
+                return False
+        elif op == "NotIn":
+            if has and labels[k] in vals:
+                return False
+        elif op == "Exists":
+            if not has:
+                return False
+        elif op == "DoesNotExist":
+            if has:
+                return False
+    return True
+
+
+# ---------------------------------------------------------------------------------------------------
+# object accessors (unstructured.Unstructured getters)
+
+
+def _gvk(obj):
+    api = obj.get("apiVersion", "") or ""
+    if not isinstance(api, str):
+        api = ""
+    if "/" in api:
+        g, v = api.split("/", 1)
+    else:
+        g, v = "", api
+    kind = obj.get("kind", "")
+    return g, v, kind if isinstance(kind, str) else ""
+
+
+def _meta(obj, field):
+    md = obj.get("metadata")
+    if not isinstance(md, dict):
+        return ""
+    v = md.get(field, "")
+    return v if isinstance(v, str) else ""
+
+
+def _labels(obj):
+    md = obj.get("metadata")
+    if not isinstance(md, dict):
+        return {}
+    ls = md.get("labels")
+    if not isinstance(ls, dict):
+        return {}
+    # unstructured.GetLabels -> NestedStringMap: any non-string value makes the whole map unreadable
+    if any(not isinstance(v, str) for v in ls.values()):
+        return {}
+    return ls
+
+
+def is_namespace(obj) -> bool:
+    """match.IsNamespace -- pkg/mutation/match/match.go:255-258"""
+    g, _, k = _gvk(obj)
+    return k == "Namespace" and g == ""
+
+
+# ---------------------------------------------------------------------------------------------------
+# pkg/mutation/match/match.go:32-268
+
+
+def _ns_name_for(match_list_empty, obj, ns):
+    """Shared name selection of namespacesMatch/excludedNamespacesMatch -- match.go:118-179.
+    Returns (decided, value): decided=True means `value` is the final answer's "no name" case."""
+    if is_namespace(obj):
+        return _meta(obj, "name")
+    if ns is not None:
+        return _meta(ns, "name")
+    if _meta(obj, "namespace") != "":
+        return _meta(obj, "namespace")
+    return None
+
+
+def matches(match, obj, ns, source) -> bool:
+    """match.Matches -- pkg/mutation/match/match.go:32-65: AND of 8 matchers in fixed order with early
+    exit; raises MatchError where the Go code returns an error."""
+    if obj is None:
+        raise MatchError("failed to run Match criteria: obj must be non-nil")  # :33-38
+    try:
+        for fn in (_kinds, _scope, _namespaces, _excluded_namespaces, _label_selector, _namespace_selector,
+                   _names, _source):
+            if not fn(match, obj, ns, source):
+                return False
+    except MatchError as e:
+        raise MatchError(f"failed to run Match criteria: {e}")  # :52-54
+    return True
+
+
+def _kinds(m, obj, ns, src):  # match.go:181-201
+    kinds = m.get("kinds") or []
+    if not kinds:
+        return True
+    g, _, k = _gvk(obj)
+    for kk in kinds:
+        ks = kk.get("kinds") or []
+        gs = kk.get("apiGroups") or []
+        if not (len(ks) == 0 or "*" in ks or k in ks):
+            continue
+        if len(gs) == 0 or "*" in gs or g in gs:
+            return True
+    return False
+
+
+def _scope(m, obj, ns, src):  # match.go:214-227
+    has_ns = _meta(obj, "namespace") != "" or ns is not None
+    is_ns = is_namespace(obj)
+    scope = m.get("scope", "")
+    if scope == "Cluster":
+        return is_ns or not has_ns
+    if scope == "Namespaced":
+        return (not is_ns) and has_ns
+    return True
+
+
+def _namespaces(m, obj, ns, src):  # match.go:150-179
+    pats = m.get("namespaces") or []
+    if not pats:
+        return True
+    name = _ns_name_for(False, obj, ns)
+    if name is None:
+        return True
+    return any(wildcard_matches(p, name) for p in pats)
+
+
+def _excluded_namespaces(m, obj, ns, src):  # match.go:118-148
+    pats = m.get("excludedNamespaces") or []
+    if not pats:
+        return True
+    name = _ns_name_for(False, obj, ns)
+    if name is None:
+        return True
+    return not any(wildcard_matches(p, name) for p in pats)
+
+
+def _label_selector(m, obj, ns, src):  # match.go:103-116
+    sel = m.get("labelSelector")
+    if sel is None:
+        return True
+    reqs = label_selector_requirements(sel)
+    return selector_matches(reqs, _labels(obj))
+
+
+def _namespace_selector(m, obj, ns, src):  # match.go:73-101
+    sel = m.get("namespaceSelector")
+    if sel is None:
+        return True
+    is_ns = is_namespace(obj)
+    if not is_ns and ns is None and _meta(obj, "namespace") == "":
+        return True
+    reqs = label_selector_requirements(sel)
+    if is_ns:
+        return selector_matches(reqs, _labels(obj))
+    if ns is None:
+        raise MatchError("namespace selector for namespace-scoped object but missing Namespace")
+    return selector_matches(reqs, _labels(ns))
+
+
+def _names(m, obj, ns, src):  # match.go:203-212
+    name = m.get("name", "") or ""
+    if name == "":
+        return True
+    return wildcard_matches(name, _meta(obj, "name")) or wildcard_matches_generate_name(
+        name, _meta(obj, "generateName"))
+
+
+_VALID_SOURCES = ("All", "Generated", "Original")  # pkg/mutation/types/mutator.go:14-27
+
+
+def _source(m, obj, ns, src):  # match.go:229-253
+    msrc = m.get("source", "") or ""
+    if msrc == "":
+        msrc = "All"
+    elif msrc not in _VALID_SOURCES:
+        raise MatchError(f'invalid source field "{msrc}"')
+    if (src or "") == "" and msrc != "All":
+        raise MatchError(f"source field not specified for resource {_meta(obj, 'name')}")
+    if msrc == "All":
+        return True
+    if src not in _VALID_SOURCES:
+        raise MatchError(f'invalid source field "{src}"')
+    return msrc == src
+
+
+# ---------------------------------------------------------------------------------------------------
+# pkg/target/matcher.go:21-93  (Matcher.Match / matchAny)
+
+
+class Review:
+    """gkReview (pkg/target/review.go:16-29) after HandleReview normalisation."""
+
+    __slots__ = ("obj", "old", "ns", "source", "kind", "name", "namespace", "operation", "user_info",
+                 "is_admission")
+
+    def __init__(self, obj=None, old=None, ns=None, source="", operation="", user_info=None, kind=None,
+                 name=None, namespace=None, is_admission=False):
+        self.obj, self.old, self.ns, self.source = obj, old, ns, source
+        self.operation, self.user_info, self.is_admission = operation, user_info or {}, is_admission
+        ref = obj if obj is not None else old
+        if kind is None and ref is not None:
+            g, v, k = _gvk(ref)
+            kind = {"group": g, "version": v, "kind": k}
+        self.kind = kind or {"group": "", "version": "", "kind": ""}
+        self.name = name if name is not None else (_meta(ref, "name") if ref else "")
+        self.namespace = namespace if namespace is not None else (_meta(ref, "namespace") if ref else "")
+
+
+def handle_review(review: Review) -> Review:
+    """K8sValidationTarget.handleReview tail -- setObjectOnDelete, pkg/target/target.go:262-280."""
+    if review.operation == "DELETE":
+        if review.old is None:
+            raise ValueError("oldObject cannot be nil for DELETE operations")
+        review.obj = review.old
+    return review
+
+
+def matcher_match(match, review: Review, ns_cache=None) -> bool:
+    """Matcher.Match + matchAny -- pkg/target/matcher.go:21-71."""
+    if match is None:
+        return True  # :22-25 no-op if Match unspecified
+    ns = review.ns
+    if ns is None and review.namespace != "" and ns_cache is not None:
+        ns = ns_cache.get(review.namespace)  # :37-39
+    nil = 0
+    for o in (review.obj, review.old):
+        if o is None:
+            nil += 1
+            continue
+        try:
+            if matches(match, o, ns, review.source):
+                return True
+        except MatchError as e:
+            # fmt.Errorf("%w: %v :%w", ErrMatching, obj.GetName(), err) -- matcher.go:58-60
+            raise MatchError(f"error matching the requested object: {_meta(o, 'name')} :{e}")
+    if nil == 2:
+        raise MatchError("invalid request object: neither object nor old object are defined")
+    return False
+
+
+# ---------------------------------------------------------------------------------------------------
+# pkg/controller/config/process/excluder.go:95-127
+
+
+def is_namespace_excluded(excluded_patterns, obj) -> bool:
+    name = _meta(obj, "name") if is_namespace(obj) else _meta(obj, "namespace")
+    return any(wildcard_matches(p, name) for p in excluded_patterns)
+
+
+# ---------------------------------------------------------------------------------------------------
+# enforcement actions -- pkg/util/enforcement_action.go:132-174
+
+
+def get_enforcement_action(constraint) -> str:
+    ea = (constraint.get("spec") or {}).get("enforcementAction", "") or ""
+    if ea == "":
+        return "deny"
+    return ea if ea in ("deny", "dryrun", "warn", "scoped") else "unrecognized"
+
+
+def scoped_actions_for_ep(ep: str, constraint):
+    out = []
+    for sea in (constraint.get("spec") or {}).get("scopedEnforcementActions") or []:
+        for p in sea.get("enforcementPoints") or []:
+            if p.get("name") == ep or p.get("name") == ALL_EPS:
+                out.append(sea.get("action", ""))
+                break
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# input.review document -- shape of gkReview as JSON (k8s.io/api admission/v1
+# AdmissionRequest JSON tags, module not vendored).  `namespaceObject` is injected from
+# reviews.Namespace(nsMap) (pkg/util/namespace.go:15-25, website/docs/input.md:6-16).
+
+
+def review_document(review: Review):
+    doc = {
+        "uid": "",
+        "kind": dict(review.kind),
+        "resource": {"group": "", "version": "", "resource": ""},
+        "operation": review.operation or "",
+        "userInfo": dict(review.user_info or {}),
+        "object": review.obj,
+        "oldObject": review.old if review.operation != "DELETE" or review.old is not review.obj else review.old,
+        "options": None,
+    }
+    if review.name:
+        doc["name"] = review.name
+    if review.namespace:
+        doc["namespace"] = review.namespace
+    if review.ns is not None:
+        doc["namespaceObject"] = review.ns
+    return doc
+
+
+# ---------------------------------------------------------------------------------------------------
+# Client (frameworks/constraint pkg/client, NOT vendored): AddTemplate / AddConstraint / Review restated
+# from its call sites and the reference tests that pin its behaviour.
+
+
+class Template:
+    def __init__(self, kind, rego_src):
+        self.kind = kind
+        self.module = rego.Module(rego_src)
+
+
+def template_from_yaml_obj(ct):
+    """ConstraintTemplate dict -> (kind, rego source).  Legacy `targets[].rego` is surfaced as engine
+    "Rego" (pkg/fakes/fixtures.go:32-44)."""
+    kind = ct["spec"]["crd"]["spec"]["names"]["kind"]
+    tgt = ct["spec"]["targets"][0]
+    src = tgt.get("rego")
+    if not src:
+        for c in tgt.get("code") or []:
+            if c.get("engine") == "Rego":
+                src = c["source"]["rego"]
+    if not src:
+        raise rego.RegoError("no Rego source for template (ErrNoDriver)")
+    return kind, src
+
+
+class Client:
+    """Sequential, one-object-at-a-time evaluation -- exactly the shape of the reference's audit loop
+    (pkg/audit/manager.go:686-720) around Client.Review."""
+
+    def __init__(self):
+        self.templates = {}     # kind -> Template
+        self.constraints = {}   # (kind, name) -> constraint dict ; insertion-ordered
+        self.ns_cache = {}      # name -> namespace object   (pkg/target/ns_cache.go:15-85)
+
+    def add_template(self, kind, rego_src):
+        self.templates[kind] = Template(kind, rego_src)
+
+    def add_constraint(self, constraint):
+        kind = constraint["kind"]
+        if kind not in self.templates:
+            raise KeyError(f"no template for constraint kind {kind}")
+        m = (constraint.get("spec") or {}).get("match")
+        if m is not None:
+            # ValidateConstraint (pkg/target/target.go:178-214) rejects bad selectors at load time
+            for f in ("labelSelector", "namespaceSelector"):
+                if m.get(f) is not None:
+                    try:
+                        label_selector_requirements(m[f])
+                    except MatchError:
+                        pass  # invalid operators are only caught at match time (match_test.go:388-405)
+        self.constraints[(kind, constraint["metadata"]["name"])] = constraint
+
+    def remove_constraint(self, kind, name):
+        self.constraints.pop((kind, name), None)
+
+    def add_namespace(self, ns_obj):
+        self.ns_cache[_meta(ns_obj, "name")] = ns_obj
+
+    def review(self, review: Review, enforcement_point: str = AUDIT_EP):
+        """Returns a list of result dicts {constraint:(kind,name), msg, details, enforcementAction,
+        scopedEnforcementActions}.  Matcher errors become results carrying the error text (pinned by
+        pkg/gator/verify/runner_test.go:986-989: `Violations: yes, Message: "missing Namespace"`)."""
+        review = handle_review(review)
+        doc = rego.from_json(review_document(review))
+        results = []
+        for (kind, name), c in self.constraints.items():
+            action = get_enforcement_action(c)
+            scoped = None
+            if action == "scoped":
+                scoped = scoped_actions_for_ep(enforcement_point, c)
+                if not scoped:
+                    continue  # constraint not enforced at this enforcement point
+            spec = c.get("spec") or {}
+            try:
+                if not matcher_match(spec.get("match"), review, self.ns_cache):
+                    continue
+            except MatchError as e:
+                results.append({"constraint": (kind, name), "msg": str(e), "details": {},
+                                "enforcementAction": action, "scopedEnforcementActions": scoped or [],
+                                "autoreject": True})
+                continue
+            inp = rego.RObj({"review": doc, "parameters": rego.from_json(spec.get("parameters") or {})})
+            for v in rego.eval_violations(self.templates[kind].module, inp):
+                results.append({"constraint": (kind, name), "msg": v["msg"],
+                                "details": rego.to_json(v["details"]) if "details" in v else None,
+                                "enforcementAction": action, "scopedEnforcementActions": scoped or []})
+        return results
