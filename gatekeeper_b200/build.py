@@ -1,0 +1,89 @@
+"""In-tree build of the native libraries (no JIT cache: the .so files travel with the repo snapshot).
+
+  gatekeeper_b200/libgk_engine.so   -- the product: C++ host engine + CUDA kernels for sm_100a (nvcc)
+  tests/_hostemu/libgk_hostemu.so   -- TEST-ONLY: same host engine linked against the CPU emulation backend
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "gatekeeper_b200", "csrc")
+OBJ = os.path.join(ROOT, "build", "obj")
+LIB = os.path.join(ROOT, "gatekeeper_b200", "libgk_engine.so")
+EMU = os.path.join(ROOT, "tests", "_hostemu", "libgk_hostemu.so")
+
+HOST_SRCS = ["val.cpp", "rego_parse.cpp", "rego_eval.cpp", "lower.cpp", "engine.cpp", "capi.cpp", "synth.cpp"]
+CXXFLAGS = ["-std=c++17", "-O2", "-g1", "-fPIC", "-Wall", "-Wextra", "-pthread"]
+NVCCFLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC"]
+
+
+def _nvcc():
+    for c in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if c and os.path.exists(c):
+            return c
+    raise RuntimeError("nvcc not found")
+
+
+def _deps_mtime():
+    m = 0.0
+    for d in (CSRC, os.path.join(ROOT, "include")):
+        for f in os.listdir(d):
+            if f.endswith((".h", ".hpp")):
+                m = max(m, os.path.getmtime(os.path.join(d, f)))
+    return m
+
+
+def _stale(out, srcs, hdr_m):
+    if not os.path.exists(out):
+        return True
+    t = os.path.getmtime(out)
+    return any(os.path.getmtime(s) > t for s in srcs) or hdr_m > t
+
+
+def _run(cmd):
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("build failed: " + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+    return r.stdout + r.stderr
+
+
+def build(verbose=False, hostemu=True, force=False):
+    os.makedirs(OBJ, exist_ok=True)
+    hdr_m = _deps_mtime()
+    jobs = []
+    objs = []
+    for s in HOST_SRCS:
+        src = os.path.join(CSRC, s)
+        if not os.path.exists(src):
+            continue
+        o = os.path.join(OBJ, s + ".o")
+        objs.append(o)
+        if force or _stale(o, [src], hdr_m):
+            jobs.append(["g++", *CXXFLAGS, "-c", src, "-o", o])
+    ko = os.path.join(OBJ, "kernels.cu.o")
+    ksrc = os.path.join(CSRC, "kernels.cu")
+    if force or _stale(ko, [ksrc], hdr_m):
+        jobs.append([_nvcc(), *NVCCFLAGS, "-c", ksrc, "-o", ko])
+    eo = os.path.join(OBJ, "hostemu.cpp.o")
+    esrc = os.path.join(ROOT, "tests", "_hostemu", "hostemu.cpp")
+    if hostemu and (force or _stale(eo, [esrc], hdr_m)):
+        jobs.append(["g++", *CXXFLAGS, "-c", esrc, "-o", eo])
+    with ThreadPoolExecutor(max_workers=8) as ex:
+        for out in ex.map(_run, jobs):
+            if verbose and out.strip():
+                print(out)
+    if force or _stale(LIB, objs + [ko], 0):
+        _run([_nvcc(), "-shared", "-o", LIB, *objs, ko, "-Xcompiler", "-pthread", "-cudart", "static"])
+    if hostemu and (force or _stale(EMU, objs + [eo], 0)):
+        _run(["g++", "-shared", "-o", EMU, *objs, eo, "-pthread"])
+    return LIB
+
+
+if __name__ == "__main__":
+    build(verbose=True, force="--force" in sys.argv)
+    print("built", LIB)

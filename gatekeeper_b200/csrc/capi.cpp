@@ -1,0 +1,351 @@
+// C ABI (include/gk_engine.h) over Engine + Backend.  No exceptions cross this file's extern "C" surface.
+#include <chrono>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <unordered_map>
+
+#include "../../include/gk_engine.h"
+#include "backend.hpp"
+#include "engine.hpp"
+
+using namespace gk;
+
+struct gk_engine {
+  std::unique_ptr<Engine> eng;
+  std::unique_ptr<Backend> be;
+  std::vector<std::string> keys;   // constraint keys of the last compiled program
+  uint64_t keys_version = 0;
+};
+
+struct gk_batch {
+  void* dev = nullptr;
+  std::shared_ptr<const Compiled> compiled;
+  std::shared_ptr<HostBatch> host;     // kept for object_errors / alg_bytes (column data is released after upload)
+  std::vector<gk_obj> objs;            // shallow copy: the caller keeps the JSON alive while the batch lives
+  uint32_t n = 0;
+  uint64_t alg_bytes = 0;
+};
+
+namespace {
+
+struct ResultPriv {
+  EvalOut ev;
+  std::vector<Violation> vio;
+  std::vector<gk_violation> cvio;
+  std::vector<std::string> obj_errors;
+  std::vector<const char*> obj_error_ptrs;
+};
+
+char* dup_str(const std::string& s) {
+  char* p = (char*)malloc(s.size() + 1);
+  if (p) memcpy(p, s.c_str(), s.size() + 1);
+  return p;
+}
+
+template <class F>
+int guard(char** err, F&& f) {
+  try {
+    f();
+    return GK_OK;
+  } catch (RegoError& e) {
+    if (err) *err = dup_str(e.msg);
+    return GK_ERR_REGO;
+  } catch (BackendError& e) {
+    if (err) *err = dup_str(e.msg);
+    return GK_ERR_BACKEND;
+  } catch (JsonError& e) {
+    if (err) *err = dup_str(e.msg);
+    return GK_ERR_INVALID;
+  } catch (std::exception& e) {
+    if (err) *err = dup_str(std::string("internal: ") + e.what());
+    return GK_ERR_INTERNAL;
+  } catch (...) {
+    if (err) *err = dup_str("internal: unknown exception");
+    return GK_ERR_INTERNAL;
+  }
+}
+
+double now_ms() {
+  using namespace std::chrono;
+  return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+ObjIn to_in(const gk_obj& o) {
+  ObjIn in;
+  in.json = o.json;
+  in.len = o.len;
+  in.old_json = o.old_json;
+  in.old_len = o.old_len;
+  in.ns_json = o.ns_json;
+  in.ns_len = o.ns_len;
+  in.ns_name = o.ns_name;
+  in.operation = o.operation;
+  in.userinfo_json = o.userinfo_json;
+  in.userinfo_len = o.userinfo_len;
+  in.source = o.source;
+  return in;
+}
+
+void fill_result(gk_result* out, ResultPriv* rp, bool have_bits) {
+  out->n_objects = rp->ev.n;
+  out->n_constraints = rp->ev.nconstraints;
+  out->words = rp->ev.words;
+  out->viol_bits = have_bits && !rp->ev.viol.empty() ? rp->ev.viol.data() : nullptr;
+  out->err_bits = have_bits && !rp->ev.err.empty() ? rp->ev.err.data() : nullptr;
+  out->totals = rp->ev.totals.data();
+  out->err_totals = rp->ev.err_totals.data();
+  rp->cvio.clear();
+  for (auto& v : rp->vio) {
+    gk_violation g;
+    g.object = v.object;
+    g.constraint = v.constraint;
+    g.msg = v.msg.c_str();
+    g.details_json = v.details_json.c_str();
+    g.enforcement_action = v.action.c_str();
+    g.scoped_actions_json = v.scoped_json.c_str();
+    g.autoreject = v.autoreject ? 1 : 0;
+    rp->cvio.push_back(g);
+  }
+  out->violations = rp->cvio.data();
+  out->n_violations = rp->cvio.size();
+  rp->obj_error_ptrs.clear();
+  for (auto& s : rp->obj_errors) rp->obj_error_ptrs.push_back(s.empty() ? nullptr : s.c_str());
+  out->object_errors = rp->obj_error_ptrs.data();
+  out->kernel_ms = rp->ev.kernel_ms;
+  out->gpu_launches = rp->ev.launches;
+  out->priv = rp;
+}
+
+// evaluate a resident batch; optionally render messages for flagged pairs
+void eval_batch(gk_engine* e, gk_batch* b, const char* ep_c, uint32_t flags, gk_result* out) {
+  std::string ep = ep_c ? ep_c : "";
+  const Compiled& c = *b->compiled;
+  auto rp = std::make_unique<ResultPriv>();
+  std::vector<uint32_t> active;
+  e->eng->active_mask(c, ep, active);
+  bool copy_back = !(flags & GK_F_NO_COPY_BACK) || (flags & GK_F_MATERIALIZE);
+  double t0 = now_ms();
+  e->be->eval(b->dev, active, rp->ev, copy_back);
+  double t1 = now_ms();
+  rp->obj_errors = b->host->obj_errors;
+  out->d2h_bytes = copy_back ? (uint64_t)rp->ev.viol.size() * 8 : 0;
+  out->d2h_ms = (t1 - t0) - rp->ev.kernel_ms;
+  if (out->d2h_ms < 0) out->d2h_ms = 0;
+  out->alg_bytes = b->alg_bytes + (uint64_t)b->n * rp->ev.words * 8;
+  out->materialize_ms = 0;
+  if (flags & GK_F_MATERIALIZE) {
+    double m0 = now_ms();
+    const uint32_t W = rp->ev.words, C = rp->ev.nconstraints;
+    // matcher errors first (autoreject results), then rendered violations, both in (object, constraint) order
+    std::vector<std::vector<std::pair<uint32_t, uint32_t>>> err_of;   // sparse
+    std::unordered_map<uint64_t, uint32_t> err_code;
+    for (size_t i = 0; i + 2 < rp->ev.errlist.size(); i += 3)
+      err_code[((uint64_t)rp->ev.errlist[i] << 32) | rp->ev.errlist[i + 1]] = rp->ev.errlist[i + 2];
+    for (uint32_t o = 0; o < b->n; ++o) {
+      for (uint32_t w = 0; w < W; ++w) {
+        uint32_t vb = rp->ev.viol[(size_t)o * W + w], eb = rp->ev.err[(size_t)o * W + w];
+        if (!(vb | eb)) continue;
+        for (uint32_t k = 0; k < 32 && w * 32 + k < C; ++k) {
+          uint32_t cix = w * 32 + k;
+          ObjIn in = to_in(b->objs[o]);
+          if (eb >> k & 1u) {
+            auto it = err_code.find(((uint64_t)o << 32) | cix);
+            e->eng->autoreject(c, in, o, cix, it == err_code.end() ? 0u : it->second, ep, rp->vio);
+          } else if (vb >> k & 1u) {
+            e->eng->materialize(c, in, o, cix, ep, rp->vio);
+          }
+        }
+      }
+    }
+    out->materialize_ms = now_ms() - m0;
+  }
+  bool give_bits = !(flags & GK_F_NO_COPY_BACK);
+  fill_result(out, rp.release(), give_bits);
+}
+
+void upload_batch(gk_engine* e, const gk_obj* objs, size_t n, gk_batch** outb, gk_result* stats) {
+  auto c = e->eng->compiled();
+  e->be->set_program(*c);
+  std::vector<ObjIn> ins(n);
+  for (size_t i = 0; i < n; ++i) ins[i] = to_in(objs[i]);
+  double t0 = now_ms();
+  auto hb = e->eng->flatten(ins.data(), n, *c);
+  double t1 = now_ms();
+  e->be->sync_strings(e->eng->strings());
+  auto b = std::make_unique<gk_batch>();
+  double h2d_ms = 0;
+  uint64_t h2d_bytes = 0;
+  b->dev = e->be->upload(*hb, *c, &h2d_ms, &h2d_bytes);
+  b->compiled = c;
+  b->n = hb->n;
+  b->alg_bytes = hb->alg_bytes;
+  b->objs.assign(objs, objs + n);
+  // drop the host column data; keep the small per-object error list
+  auto slim = std::make_shared<HostBatch>();
+  slim->n = hb->n;
+  slim->obj_errors = std::move(hb->obj_errors);
+  slim->alg_bytes = hb->alg_bytes;
+  b->host = slim;
+  if (stats) {
+    stats->flatten_ms = t1 - t0;
+    stats->h2d_ms = h2d_ms;
+    stats->h2d_bytes = h2d_bytes;
+    stats->alg_bytes = hb->alg_bytes;
+    stats->n_objects = hb->n;
+    stats->n_constraints = (uint32_t)c->match.size();
+  }
+  *outb = b.release();
+}
+
+}  // namespace
+
+extern "C" {
+
+gk_engine_t* gk_engine_create(const gk_cfg* cfg, char** err) {
+  gk_engine* e = nullptr;
+  int rc = guard(err, [&]() {
+    auto x = std::make_unique<gk_engine>();
+    x->eng.reset(new Engine(cfg ? cfg->threads : 0));
+    x->be.reset(make_backend(cfg ? cfg->device : 0));
+    e = x.release();
+  });
+  return rc == GK_OK ? e : nullptr;
+}
+
+void gk_engine_destroy(gk_engine_t* e) { delete e; }
+const char* gk_backend_name(gk_engine_t* e) { return e && e->be ? e->be->name() : ""; }
+
+int gk_add_template(gk_engine_t* e, const char* kind, const char* rego_src, size_t len, char** err) {
+  if (!e || !kind || !rego_src) return GK_ERR_INVALID;
+  return guard(err, [&]() { e->eng->add_template(kind, std::string(rego_src, len)); });
+}
+int gk_remove_template(gk_engine_t* e, const char* kind) {
+  if (!e || !kind) return GK_ERR_INVALID;
+  return guard(nullptr, [&]() { e->eng->remove_template(kind); });
+}
+int gk_add_constraint(gk_engine_t* e, const char* json, size_t len, char** err) {
+  if (!e || !json) return GK_ERR_INVALID;
+  return guard(err, [&]() { e->eng->add_constraint(std::string(json, len)); });
+}
+int gk_remove_constraint(gk_engine_t* e, const char* kind, const char* name) {
+  if (!e || !kind || !name) return GK_ERR_INVALID;
+  return guard(nullptr, [&]() { e->eng->remove_constraint(kind, name); });
+}
+int gk_put_namespace(gk_engine_t* e, const char* name, const char* ns_json, size_t len, char** err) {
+  if (!e || !name || !ns_json) return GK_ERR_INVALID;
+  return guard(err, [&]() { e->eng->put_namespace(name, std::string(ns_json, len)); });
+}
+int gk_remove_namespace(gk_engine_t* e, const char* name) {
+  if (!e || !name) return GK_ERR_INVALID;
+  return guard(nullptr, [&]() { e->eng->remove_namespace(name); });
+}
+
+uint32_t gk_constraint_count(gk_engine_t* e) {
+  if (!e) return 0;
+  uint32_t n = 0;
+  guard(nullptr, [&]() {
+    auto c = e->eng->compiled();
+    if (e->keys_version != c->version) {
+      e->keys.clear();
+      for (auto* k : c->order) e->keys.push_back(k->kind + "/" + k->name);
+      e->keys_version = c->version;
+    }
+    n = (uint32_t)e->keys.size();
+  });
+  return n;
+}
+const char* gk_constraint_key(gk_engine_t* e, uint32_t index) {
+  uint32_t n = gk_constraint_count(e);
+  return index < n ? e->keys[index].c_str() : nullptr;
+}
+
+int gk_review_batch(gk_engine_t* e, const gk_obj* objs, size_t n, const char* ep, uint32_t flags, gk_result* out, char** err) {
+  if (!e || !out || (!objs && n)) return GK_ERR_INVALID;
+  memset(out, 0, sizeof *out);
+  return guard(err, [&]() {
+    gk_batch* b = nullptr;
+    gk_result stats;
+    memset(&stats, 0, sizeof stats);
+    upload_batch(e, objs, n, &b, &stats);
+    std::unique_ptr<gk_batch, std::function<void(gk_batch*)>> hold(b, [&](gk_batch* x) {
+      e->be->release(x->dev);
+      delete x;
+    });
+    eval_batch(e, b, ep, flags, out);
+    out->flatten_ms = stats.flatten_ms;
+    out->h2d_ms = stats.h2d_ms;
+    out->h2d_bytes = stats.h2d_bytes;
+  });
+}
+
+int gk_batch_upload(gk_engine_t* e, const gk_obj* objs, size_t n, gk_batch_t** outb, gk_result* stats, char** err) {
+  if (!e || !outb || (!objs && n)) return GK_ERR_INVALID;
+  if (stats) memset(stats, 0, sizeof *stats);
+  return guard(err, [&]() { upload_batch(e, objs, n, outb, stats); });
+}
+
+int gk_batch_eval(gk_engine_t* e, gk_batch_t* b, const char* ep, uint32_t flags, gk_result* out, char** err) {
+  if (!e || !b || !out) return GK_ERR_INVALID;
+  memset(out, 0, sizeof *out);
+  return guard(err, [&]() {
+    auto c = e->eng->compiled();
+    if (c->version != b->compiled->version) throw RegoError{"batch was flattened against an older constraint set; upload it again"};
+    e->be->set_program(*c);
+    eval_batch(e, b, ep, flags, out);
+  });
+}
+
+int gk_batch_eval_device(gk_engine_t* e, gk_batch_t* b, const char* ep, void* d_viol, void* d_err, void* d_totals, void* d_err_totals,
+                         void* stream, char** err) {
+  if (!e || !b || !d_viol || !d_err || !d_totals || !d_err_totals) return GK_ERR_INVALID;
+  return guard(err, [&]() {
+    auto c = e->eng->compiled();
+    if (c->version != b->compiled->version) throw RegoError{"batch was flattened against an older constraint set; upload it again"};
+    e->be->set_program(*c);
+    std::vector<uint32_t> active;
+    e->eng->active_mask(*c, ep ? ep : "", active);
+    DevOutPtrs d;
+    d.viol = d_viol;
+    d.err = d_err;
+    d.totals = d_totals;
+    d.err_totals = d_err_totals;
+    d.stream = stream;
+    e->be->eval_into(b->dev, active, d);
+  });
+}
+
+uint32_t gk_batch_size(gk_batch_t* b) { return b ? b->n : 0; }
+uint64_t gk_batch_alg_bytes(gk_batch_t* b) { return b ? b->alg_bytes : 0; }
+void gk_batch_free(gk_engine_t* e, gk_batch_t* b) {
+  if (!e || !b) return;
+  guard(nullptr, [&]() { e->be->release(b->dev); });
+  delete b;
+}
+
+void gk_free_result(gk_result* r) {
+  if (!r || !r->priv) return;
+  delete static_cast<ResultPriv*>(r->priv);
+  memset(r, 0, sizeof *r);
+}
+void gk_free_str(char* s) { free(s); }
+
+char* gk_dump(gk_engine_t* e) {
+  if (!e) return nullptr;
+  std::string s;
+  guard(nullptr, [&]() { s = e->eng->dump(); });
+  return dup_str(s);
+}
+
+const char* gk_stat_description(const char* n) {
+  // the StatsEntry names this driver emits (cf. runTimeNS in pkg/drivers/k8scel/driver.go:256-263)
+  if (!n) return nullptr;
+  if (!strcmp(n, "kernelTimeNS")) return "the number of nanoseconds the GPU kernel took to evaluate every constraint against the batch";
+  if (!strcmp(n, "flattenTimeNS")) return "the number of nanoseconds spent flattening the batch of objects into columns on the host";
+  if (!strcmp(n, "batchSize")) return "the number of objects evaluated together";
+  if (!strcmp(n, "bytesRead")) return "the algorithmic bytes of column data the kernel read for the batch";
+  return nullptr;
+}
+
+}  // extern "C"

@@ -1,0 +1,977 @@
+#include "engine.hpp"
+
+#include <algorithm>
+#include <cstring>
+#include <thread>
+
+namespace gk {
+
+// ============================================================================================ strings
+StringTable::StringTable() {
+  off_.push_back(0);
+  // sid 0 = GK_SID_UNDEF: reserved, empty bytes
+  off_.push_back(0);
+  map_.reserve(1 << 16);
+}
+uint32_t StringTable::intern(const std::string& key) {
+  {
+    std::shared_lock<std::shared_mutex> l(mu_);
+    auto it = map_.find(key);
+    if (it != map_.end()) return it->second;
+  }
+  std::unique_lock<std::shared_mutex> l(mu_);
+  auto it = map_.find(key);
+  if (it != map_.end()) return it->second;
+  uint32_t id = (uint32_t)off_.size() - 1;
+  bytes_.insert(bytes_.end(), key.begin(), key.end());
+  off_.push_back((uint32_t)bytes_.size());
+  map_.emplace(key, id);
+  return id;
+}
+uint32_t StringTable::lookup(const std::string& key) const {
+  std::shared_lock<std::shared_mutex> l(mu_);
+  auto it = map_.find(key);
+  return it == map_.end() ? GK_SID_UNDEF : it->second;
+}
+void StringTable::snapshot(std::vector<uint32_t>& off, std::vector<uint8_t>& bytes) const {
+  std::shared_lock<std::shared_mutex> l(mu_);
+  off = off_;
+  bytes = bytes_;
+}
+uint32_t StringTable::size() const {
+  std::shared_lock<std::shared_mutex> l(mu_);
+  return (uint32_t)off_.size() - 1;
+}
+std::string StringTable::get(uint32_t sid) const {
+  std::shared_lock<std::shared_mutex> l(mu_);
+  if (sid + 1 >= off_.size()) return "";
+  return std::string(bytes_.begin() + off_[sid], bytes_.begin() + off_[sid + 1]);
+}
+
+// ====================================================================================== small helpers
+static std::string str_field(const VP& o, const char* k) {
+  VP v = obj_get(o, k);
+  return v && v->t == VT::Str ? v->s : std::string();
+}
+static void split_gv(const VP& obj, std::string& group, std::string& version, std::string& kind) {
+  std::string api = str_field(obj, "apiVersion");
+  size_t p = api.find('/');
+  if (p == std::string::npos) {
+    group.clear();
+    version = api;
+  } else {
+    group = api.substr(0, p);
+    version = api.substr(p + 1);
+  }
+  kind = str_field(obj, "kind");
+}
+static std::string meta_str(const VP& obj, const char* f) {
+  VP md = obj_get(obj, "metadata");
+  if (!md || md->t != VT::Obj) return "";
+  return str_field(md, f);
+}
+// unstructured.GetLabels -> NestedStringMap: any non-string value makes the whole map unreadable
+static const Node* labels_of(const VP& obj) {
+  VP md = obj_get(obj, "metadata");
+  if (!md || md->t != VT::Obj) return nullptr;
+  VP ls = obj_get(md, "labels");
+  if (!ls || ls->t != VT::Obj) return nullptr;
+  for (auto& e : ls->kv)
+    if (e.second->t != VT::Str) return nullptr;
+  return ls.get();
+}
+
+static void parse_wildcard(const std::string& w, uint32_t& mode, std::string& lit) {
+  // pkg/wildcard/wildcard.go:17-29
+  bool pre = !w.empty() && w.front() == '*', suf = !w.empty() && w.back() == '*';
+  if (pre && suf) {
+    lit = w.substr(1);
+    if (!lit.empty() && lit.back() == '*') lit.pop_back();
+    mode = GK_W_CONTAINS;
+  } else if (pre) {
+    lit = w.substr(1);
+    mode = GK_W_SUFFIX;
+  } else if (suf) {
+    lit = w.substr(0, w.size() - 1);
+    mode = GK_W_PREFIX;
+  } else {
+    lit = w;
+    mode = GK_W_EXACT;
+  }
+}
+
+// k8s.io/apimachinery validation of label keys / values (restated; module not vendored)
+static bool name_part_ok(const std::string& s) {
+  if (s.empty() || s.size() > 63) return false;
+  auto alnum = [](char c) { return (c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z') || (c >= '0' && c <= '9'); };
+  if (!alnum(s.front()) || !alnum(s.back())) return false;
+  for (char c : s)
+    if (!alnum(c) && c != '-' && c != '_' && c != '.') return false;
+  return true;
+}
+static bool dns_subdomain_ok(const std::string& s) {
+  if (s.empty() || s.size() > 253) return false;
+  size_t i = 0;
+  while (i <= s.size()) {
+    size_t j = s.find('.', i);
+    if (j == std::string::npos) j = s.size();
+    if (j == i) return false;
+    for (size_t q = i; q < j; ++q) {
+      char c = s[q];
+      bool an = (c >= 'a' && c <= 'z') || (c >= '0' && c <= '9');
+      if (!an && !(c == '-' && q != i && q + 1 != j)) return false;
+    }
+    i = j + 1;
+  }
+  return true;
+}
+static bool label_key_ok(const std::string& k) {
+  size_t p = k.find('/');
+  if (p == std::string::npos) return name_part_ok(k);
+  if (k.find('/', p + 1) != std::string::npos) return false;
+  return dns_subdomain_ok(k.substr(0, p)) && name_part_ok(k.substr(p + 1));
+}
+static bool label_value_ok(const std::string& v) { return v.empty() || name_part_ok(v); }
+
+struct SelReq {
+  std::string key;
+  uint32_t op;
+  std::vector<std::string> vals;
+};
+// metav1.LabelSelectorAsSelector: returns "" or the error text
+static std::string parse_selector(const VP& sel, std::vector<SelReq>& out) {
+  if (!sel || sel->t != VT::Obj) return "";
+  VP ml = obj_get(sel, "matchLabels");
+  if (ml && ml->t == VT::Obj)
+    for (auto& e : ml->kv) {
+      SelReq r;
+      r.key = e.first->s;
+      r.op = GK_SEL_IN;
+      r.vals.push_back(e.second->t == VT::Str ? e.second->s : fmt_value(e.second, true));
+      out.push_back(r);
+    }
+  VP me = obj_get(sel, "matchExpressions");
+  std::string err;
+  if (me && me->t == VT::Arr)
+    for (auto& x : me->items) {
+      SelReq r;
+      r.key = str_field(x, "key");
+      std::string op = str_field(x, "operator");
+      VP vals = obj_get(x, "values");
+      if (vals && vals->t == VT::Arr)
+        for (auto& v : vals->items) r.vals.push_back(v->t == VT::Str ? v->s : fmt_value(v, true));
+      if (op == "In") r.op = GK_SEL_IN;
+      else if (op == "NotIn") r.op = GK_SEL_NOTIN;
+      else if (op == "Exists") r.op = GK_SEL_EXISTS;
+      else if (op == "DoesNotExist") r.op = GK_SEL_NOTEXISTS;
+      else {
+        if (err.empty()) err = "\"" + op + "\" is not a valid label selector operator";
+        continue;
+      }
+      out.push_back(r);
+    }
+  if (!err.empty()) return err;
+  for (auto& r : out) {
+    if ((r.op == GK_SEL_IN || r.op == GK_SEL_NOTIN) && r.vals.empty()) return "values: Invalid value: []: for 'in', 'notin' operators, values set can't be empty";
+    if ((r.op == GK_SEL_EXISTS || r.op == GK_SEL_NOTEXISTS) && !r.vals.empty()) return "values: Invalid value: values set must be empty for exists and does not exist";
+    if (!label_key_ok(r.key)) return "key: Invalid value: \"" + r.key + "\"";
+    for (auto& v : r.vals)
+      if (!label_value_ok(v)) return "values: Invalid value: \"" + v + "\"";
+  }
+  return "";
+}
+
+// ============================================================================================== engine
+Engine::Engine(int threads) : threads_(threads > 0 ? threads : (int)std::max(1u, std::thread::hardware_concurrency())) {}
+
+void Engine::add_template(const std::string& kind, const std::string& rego) {
+  auto mod = rego_parse(rego);   // throws RegoError on syntax / unsafe-var errors
+  if (!mod->is_rule("violation")) throw RegoError{"rego_compile_error: template " + kind + " has no `violation` rule"};
+  // lowering is parameter-specific, but unsupported constructs that do not depend on parameters surface
+  // here: lower once against empty parameters and discard (errors that need parameters surface at AddConstraint)
+  {
+    Schema tmp;
+    try {
+      (void)lower_violation(mod, v_obj({}), tmp);
+    } catch (RegoError& e) {
+      if (e.msg.rfind("rego_unsupported", 0) == 0 || e.msg.rfind("rego_type_error", 0) == 0 || e.msg.rfind("rego_unsafe", 0) == 0) throw;
+    }
+  }
+  std::unique_lock<std::shared_mutex> l(mu_);
+  TemplateEntry t;
+  t.kind = kind;
+  t.src = rego;
+  t.mod = mod;
+  templates_[kind] = std::move(t);
+  dirty_ = true;
+}
+
+bool Engine::remove_template(const std::string& kind) {
+  std::unique_lock<std::shared_mutex> l(mu_);
+  bool had = templates_.erase(kind) != 0;
+  // constraints of that kind go with it (the reference's client drops them with the template)
+  constraints_.erase(std::remove_if(constraints_.begin(), constraints_.end(), [&](auto& c) { return c->kind == kind; }), constraints_.end());
+  dirty_ = true;
+  return had;
+}
+
+static std::string enforcement_action_of(const VP& obj) {
+  // util.GetEnforcementAction -- pkg/util/enforcement_action.go:132-151
+  VP spec = obj_get(obj, "spec");
+  std::string ea = spec ? str_field(spec, "enforcementAction") : "";
+  if (ea.empty()) return "deny";
+  if (ea == "deny" || ea == "dryrun" || ea == "warn" || ea == "scoped") return ea;
+  return "unrecognized";
+}
+
+void Engine::add_constraint(const std::string& json) {
+  VP obj;
+  try {
+    obj = json_parse(json.data(), json.size());
+  } catch (JsonError& e) {
+    throw RegoError{"invalid constraint: " + e.msg};
+  }
+  if (obj->t != VT::Obj) throw RegoError{"invalid constraint: not an object"};
+  auto c = std::make_unique<Constraint>();
+  c->kind = str_field(obj, "kind");
+  c->name = meta_str(obj, "name");
+  if (c->kind.empty() || c->name.empty()) throw RegoError{"invalid constraint: kind and metadata.name are required"};
+  c->obj = obj;
+  VP spec = obj_get(obj, "spec");
+  VP params = spec ? obj_get(spec, "parameters") : nullptr;
+  c->params = params && params->t != VT::Null ? params : v_obj({});
+  c->action = enforcement_action_of(obj);
+  if (spec) {
+    VP sea = obj_get(spec, "scopedEnforcementActions");
+    if (sea && sea->t == VT::Arr)
+      for (auto& x : sea->items) {
+        ScopedAction a;
+        a.action = str_field(x, "action");
+        VP eps = obj_get(x, "enforcementPoints");
+        if (eps && eps->t == VT::Arr)
+          for (auto& p : eps->items) a.points.push_back(str_field(p, "name"));
+        c->scoped.push_back(a);
+      }
+    VP m = obj_get(spec, "match");
+    if (m && m->t == VT::Obj) {
+      c->match.has = true;
+      c->match.raw = m;
+    }
+  }
+  std::unique_lock<std::shared_mutex> l(mu_);
+  auto tit = templates_.find(c->kind);
+  if (tit == templates_.end()) throw RegoError{"no template registered for constraint kind " + c->kind};
+  // lower now so that unsupported constructs are an AddConstraint error (like a Rego compile error)
+  {
+    Schema tmp;
+    (void)lower_violation(tit->second.mod, c->params, tmp);
+  }
+  for (auto& e : constraints_)
+    if (e->kind == c->kind && e->name == c->name) {
+      e = std::move(c);
+      dirty_ = true;
+      return;
+    }
+  constraints_.push_back(std::move(c));
+  dirty_ = true;
+}
+
+bool Engine::remove_constraint(const std::string& kind, const std::string& name) {
+  std::unique_lock<std::shared_mutex> l(mu_);
+  size_t before = constraints_.size();
+  constraints_.erase(std::remove_if(constraints_.begin(), constraints_.end(), [&](auto& c) { return c->kind == kind && c->name == name; }),
+                     constraints_.end());
+  dirty_ = true;
+  return constraints_.size() != before;
+}
+
+void Engine::put_namespace(const std::string& name, const std::string& json) {
+  VP v;
+  try {
+    v = json_parse(json.data(), json.size());
+  } catch (JsonError& e) {
+    throw RegoError{"invalid namespace object: " + e.msg};
+  }
+  std::unique_lock<std::shared_mutex> l(mu_);
+  namespaces_[name] = v;
+}
+bool Engine::remove_namespace(const std::string& name) {
+  std::unique_lock<std::shared_mutex> l(mu_);
+  return namespaces_.erase(name) != 0;
+}
+
+std::vector<std::string> scoped_actions_for(const Constraint& c, const std::string& ep) {
+  std::vector<std::string> out;
+  for (auto& a : c.scoped)
+    for (auto& p : a.points)
+      if (p == ep || p == "*") {
+        out.push_back(a.action);
+        break;
+      }
+  return out;
+}
+
+void Engine::active_mask(const Compiled& c, const std::string& ep, std::vector<uint32_t>& active) const {
+  active.assign(c.order.size(), 1);
+  for (size_t i = 0; i < c.order.size(); ++i)
+    if (c.order[i]->action == "scoped" && scoped_actions_for(*c.order[i], ep).empty()) active[i] = 0;
+}
+
+// ---------------------------------------------------------------------------------------------- compile
+std::shared_ptr<const Compiled> Engine::compiled() {
+  {
+    std::shared_lock<std::shared_mutex> l(mu_);
+    if (!dirty_ && compiled_) return compiled_;
+  }
+  std::unique_lock<std::shared_mutex> l(mu_);
+  if (dirty_ || !compiled_) compile_locked();
+  return compiled_;
+}
+
+void Engine::compile_locked() {
+  auto out = std::make_shared<Compiled>();
+  out->version = ++version_;
+  ProgramBuilder pb;
+  pb.interner = &strings_;
+  pb.schema = &out->schema;
+  // pass 1: lower every constraint (fills the shared schema)
+  for (auto& cp : constraints_) {
+    Constraint& c = *cp;
+    auto tit = templates_.find(c.kind);
+    if (tit == templates_.end()) continue;
+    c.formula = lower_violation(tit->second.mod, c.params, out->schema);
+    out->order.push_back(&c);
+  }
+  // pass 2: emit code + match blocks
+  for (auto* cc : out->order) {
+    Constraint& c = *const_cast<Constraint*>(cc);
+    c.pc = pb.emit(c.formula);
+    GkMatch m{};
+    m.prog_pc = c.pc;
+    m.active = 1;
+    MatchSpec& ms = c.match;
+    ms.lsel_err.clear();
+    ms.nssel_err.clear();
+    ms.src_err.clear();
+    if (ms.has) {
+      m.flags |= GK_M_HAS_MATCH;
+      const VP& r = ms.raw;
+      VP kinds = obj_get(r, "kinds");
+      if (kinds && kinds->t == VT::Arr && !kinds->items.empty()) {
+        m.kinds_off = (uint32_t)pb.pool.size();
+        for (auto& e : kinds->items) {
+          std::vector<uint32_t> ks, gs;
+          uint32_t wild = 0;
+          VP kk = obj_get(e, "kinds"), gg = obj_get(e, "apiGroups");
+          if (kk && kk->t == VT::Arr)
+            for (auto& x : kk->items) {
+              std::string s = x->t == VT::Str ? x->s : "";
+              if (s == "*") wild |= 1;
+              ks.push_back(strings_.intern("s" + s));
+            }
+          if (gg && gg->t == VT::Arr)
+            for (auto& x : gg->items) {
+              std::string s = x->t == VT::Str ? x->s : "";
+              if (s == "*") wild |= 2;
+              gs.push_back(strings_.intern("s" + s));
+            }
+          pb.pool.push_back((uint32_t)ks.size());
+          pb.pool.push_back((uint32_t)gs.size());
+          pb.pool.push_back(wild);
+          pb.pool.insert(pb.pool.end(), ks.begin(), ks.end());
+          pb.pool.insert(pb.pool.end(), gs.begin(), gs.end());
+          ++m.kinds_n;
+        }
+      }
+      std::string scope = str_field(r, "scope");
+      if (scope == "Cluster") m.flags |= GK_M_SCOPE_CLUSTER;
+      else if (scope == "Namespaced") m.flags |= GK_M_SCOPE_NAMESPACED;
+      auto wild_list = [&](const char* field, uint32_t& off, uint32_t& n) {
+        VP l = obj_get(r, field);
+        if (!l || l->t != VT::Arr) return;
+        off = (uint32_t)pb.pool.size();
+        for (auto& x : l->items) {
+          uint32_t mode;
+          std::string lit;
+          parse_wildcard(x->t == VT::Str ? x->s : "", mode, lit);
+          pb.pool.push_back(mode);
+          pb.pool.push_back(pb.add_bytes(lit));
+          pb.pool.push_back((uint32_t)lit.size());
+          ++n;
+        }
+      };
+      wild_list("namespaces", m.ns_off, m.ns_n);
+      wild_list("excludedNamespaces", m.exns_off, m.exns_n);
+      auto selector = [&](const char* field, uint32_t has_flag, uint32_t bad_flag, uint32_t& off, uint32_t& n, std::string& err) {
+        VP s = obj_get(r, field);
+        if (!s || s->t == VT::Null) return;
+        m.flags |= has_flag;
+        std::vector<SelReq> reqs;
+        err = parse_selector(s, reqs);
+        if (!err.empty()) {
+          m.flags |= bad_flag;
+          return;
+        }
+        off = (uint32_t)pb.pool.size();
+        for (auto& q : reqs) {
+          pb.pool.push_back(strings_.intern("s" + q.key));
+          pb.pool.push_back(q.op);
+          pb.pool.push_back((uint32_t)q.vals.size());
+          for (auto& v : q.vals) pb.pool.push_back(strings_.intern("s" + v));
+          ++n;
+        }
+      };
+      selector("labelSelector", GK_M_HAS_LSEL, GK_M_LSEL_INVALID, m.lsel_off, m.lsel_n, ms.lsel_err);
+      selector("namespaceSelector", GK_M_HAS_NSSEL, GK_M_NSSEL_INVALID, m.nssel_off, m.nssel_n, ms.nssel_err);
+      std::string name = str_field(r, "name");
+      if (!name.empty()) {
+        m.flags |= GK_M_HAS_NAME;
+        std::string lit;
+        parse_wildcard(name, m.name_mode, lit);
+        m.name_boff = pb.add_bytes(lit);
+        m.name_len = (uint32_t)lit.size();
+      }
+      std::string src = str_field(r, "source");
+      uint32_t code = GK_SRC_ALL;
+      if (src.empty() || src == "All") code = GK_SRC_ALL;
+      else if (src == "Original") code = GK_SRC_ORIGINAL;
+      else if (src == "Generated") code = GK_SRC_GENERATED;
+      else {
+        m.flags |= GK_M_SRC_INVALID;
+        ms.src_err = "invalid source field \"" + src + "\"";
+      }
+      m.flags |= code << GK_M_SRC_SHIFT;
+    }
+    ms.dev = m;
+    out->match.push_back(m);
+  }
+  out->instr = std::move(pb.instr);
+  out->pool = std::move(pb.pool);
+  out->cbytes = std::move(pb.cbytes);
+  if (out->pool.empty()) out->pool.push_back(0);
+  if (out->cbytes.empty()) out->cbytes.push_back(0);
+  if (out->instr.empty()) out->instr.push_back(GkInstr{GK_OP_JMP, 0, GK_PC_REJECT | (GK_PC_REJECT << 16), 0});
+  compiled_ = out;
+  dirty_ = false;
+}
+
+std::string Engine::dump() {
+  auto c = compiled();
+  std::string o = "schema: " + std::to_string(c->schema.scopes.size() - 1) + " scopes, " + std::to_string(c->schema.cols.size()) +
+                  " columns, " + std::to_string(c->instr.size()) + " instructions\n";
+  for (size_t i = 1; i < c->schema.scopes.size(); ++i)
+    o += "  scope " + std::to_string(i) + " parent " + std::to_string(c->schema.scopes[i].parent) + ": " + c->schema.scopes[i].gen->key + "\n";
+  for (size_t i = 0; i < c->schema.cols.size(); ++i)
+    o += "  col " + std::to_string(i) + " scope " + std::to_string(c->schema.cols[i].scope) + " enc " + std::to_string(c->schema.cols[i].enc) + ": " +
+         c->schema.cols[i].expr->key + "\n";
+  for (size_t i = 0; i < c->order.size(); ++i)
+    o += "constraint " + std::to_string(i) + " " + c->order[i]->kind + "/" + c->order[i]->name + " pc=" + std::to_string(c->order[i]->pc) + ": " +
+         formula_str(c->order[i]->formula, c->schema) + "\n";
+  return o;
+}
+
+// ------------------------------------------------------------------------------------------- review doc
+VP Engine::review_doc(const ObjIn& in, VP* obj_out, VP* old_out, VP* ns_out, std::string* err) {
+  VP obj, old, ns;
+  auto parse = [&](const char* p, size_t n, const char* what, VP& dst) -> bool {
+    if (!p) return true;
+    try {
+      dst = json_parse(p, n);
+    } catch (JsonError& e) {
+      *err = std::string("invalid request object: failed to unmarshal gkReview ") + what + ": " + e.msg;
+      return false;
+    }
+    if (dst->t == VT::Null) {
+      dst = nullptr;
+      return true;
+    }
+    if (dst->t != VT::Obj) {
+      *err = std::string("invalid request object: ") + what + " is not a JSON object";
+      return false;
+    }
+    if (str_field(dst, "kind").empty()) {
+      *err = std::string("invalid request object: failed to unmarshal gkReview ") + what + ": Object 'Kind' is missing";
+      return false;
+    }
+    return true;
+  };
+  if (!parse(in.json, in.len, "object", obj) || !parse(in.old_json, in.old_len, "oldObject", old)) return nullptr;
+  if (in.ns_json) {
+    try {
+      ns = json_parse(in.ns_json, in.ns_len);
+      if (ns->t != VT::Obj) ns = nullptr;
+    } catch (JsonError& e) {
+      *err = "invalid namespace object: " + e.msg;
+      return nullptr;
+    }
+  }
+  std::string op = in.operation ? in.operation : "";
+  if (op == "DELETE") {   // setObjectOnDelete -- pkg/target/target.go:262-280
+    if (!old) {
+      *err = "oldObject cannot be nil for DELETE operations";
+      return nullptr;
+    }
+    obj = old;
+  }
+  VP ref = obj ? obj : old;
+  std::string g, v, k, name, nsname;
+  if (ref) {
+    split_gv(ref, g, v, k);
+    name = meta_str(ref, "name");
+    nsname = meta_str(ref, "namespace");
+  }
+  if (in.ns_name) nsname = in.ns_name;
+  VP user = v_obj({});
+  if (in.userinfo_json) {
+    try {
+      user = json_parse(in.userinfo_json, in.userinfo_len);
+    } catch (JsonError&) {
+    }
+  }
+  std::vector<std::pair<VP, VP>> kv;
+  kv.emplace_back(v_str("uid"), v_str(""));
+  kv.emplace_back(v_str("kind"), v_obj({{v_str("group"), v_str(g)}, {v_str("version"), v_str(v)}, {v_str("kind"), v_str(k)}}));
+  kv.emplace_back(v_str("resource"), v_obj({{v_str("group"), v_str("")}, {v_str("version"), v_str("")}, {v_str("resource"), v_str("")}}));
+  kv.emplace_back(v_str("operation"), v_str(op));
+  kv.emplace_back(v_str("userInfo"), user);
+  kv.emplace_back(v_str("object"), obj ? obj : v_null());
+  kv.emplace_back(v_str("oldObject"), old ? old : v_null());
+  kv.emplace_back(v_str("options"), v_null());
+  if (!name.empty()) kv.emplace_back(v_str("name"), v_str(name));
+  if (!nsname.empty()) kv.emplace_back(v_str("namespace"), v_str(nsname));
+  if (ns) kv.emplace_back(v_str("namespaceObject"), ns);
+  if (obj_out) *obj_out = obj;
+  if (old_out) *old_out = old;
+  if (ns_out) {
+    // Matcher.Match: review's namespace object, else the cache entry for review.Namespace (matcher.go:37-39)
+    if (!ns && !nsname.empty()) {
+      std::shared_lock<std::shared_mutex> l(mu_);
+      auto it = namespaces_.find(nsname);
+      if (it != namespaces_.end()) ns = it->second;
+    }
+    *ns_out = ns;
+  }
+  return v_obj(std::move(kv));
+}
+
+// =========================================================================================== flatten
+struct Flattener {
+  Engine& eng;
+  const Compiled& c;
+  HostBatch hb;                                        // this worker's chunk
+  std::unordered_map<std::string, uint32_t> sid_cache;
+  std::unordered_map<const Module*, std::unique_ptr<Eval>> evals;
+  std::vector<VP> ns_objs;                             // namespace table rows of this chunk
+  std::unordered_map<const Node*, uint32_t> ns_row_of;
+
+  struct Row {
+    VP elem, key;
+    uint32_t parent;
+  };
+  std::vector<std::vector<Row>> rows;                  // per scope, for the current object
+
+  Flattener(Engine& e, const Compiled& cc) : eng(e), c(cc) {
+    size_t ns = c.schema.scopes.size();
+    hb.scope_off.resize(ns);
+    for (size_t s = 1; s < ns; ++s) hb.scope_off[s].push_back(0);
+    hb.scope_rows.assign(ns, 0);
+    hb.cols.resize(c.schema.cols.size());
+    for (size_t i = 0; i < hb.cols.size(); ++i)
+      if (c.schema.cols[i].enc & GK_ENC_BYTES) hb.cols[i].boff.push_back(0);
+    hb.name_off.push_back(0);
+    hb.gen_off.push_back(0);
+    hb.lbl_off.push_back(0);
+    hb.nsl_off.push_back(0);
+    rows.resize(ns);
+  }
+
+  uint32_t sid(const std::string& key) {
+    auto it = sid_cache.find(key);
+    if (it != sid_cache.end()) return it->second;
+    uint32_t id = eng.strings().intern(key);
+    sid_cache.emplace(key, id);
+    return id;
+  }
+
+  Eval& eval_for(const Closure& cl, const VP& input) {
+    auto& slot = evals[cl.mod.get()];
+    if (!slot) slot.reset(new Eval(*cl.mod, input));
+    return *slot;
+  }
+
+  // value of closure `cl` for the row `r` of scope cl.scope (chain resolved through parents)
+  VP eval_closure(const Closure& cl, int scope, uint32_t r, const VP& input) {
+    // move up to the closure's own scope
+    while (scope != cl.scope && scope != 0) {
+      r = rows[scope][r].parent;
+      scope = c.schema.scopes[scope].parent;
+    }
+    if (cl.leaf == Closure::Elem) return rows[scope][r].elem;
+    if (cl.leaf == Closure::Key) return rows[scope][r].key;
+    Env env;
+    for (auto& cap : cl.caps) {
+      if (cap.second.k == CapArg::Conc) env.bind(cap.first, cap.second.v);
+      else {
+        VP v = eval_closure(*cap.second.col, scope, r, input);
+        if (!v) return nullptr;
+        env.bind(cap.first, v);
+      }
+    }
+    Eval& ev = eval_for(cl, input);
+    // fast path: constant path off a bound variable
+    const Term& t = *cl.term;
+    if (t.k == TK::Ref && t.head->k == TK::Var) {
+      bool simple = true;
+      for (auto& a : t.args) simple = simple && a->k == TK::Scalar;
+      if (simple) {
+        VP cur;
+        if (const VP* b = env.find(t.head->vid)) cur = *b;
+        else if (t.head->vid == cl.mod->vid_input) cur = input;
+        if (cur) {
+          for (auto& a : t.args) {
+            if (cur->t == VT::Obj) cur = obj_get(cur, a->val);
+            else if (cur->t == VT::Arr) {
+              int64_t ix;
+              if (a->val->t == VT::Num && num_fits_i64(a->val->n, &ix) && ix >= 0 && (size_t)ix < cur->items.size()) cur = cur->items[ix];
+              else cur = nullptr;
+            } else if (cur->t == VT::Set) cur = set_find(cur, a->val);
+            else cur = nullptr;
+            if (!cur) break;
+          }
+          return cur;
+        }
+      }
+    }
+    return ev.eval_first(cl.term, env);
+  }
+
+  void header_row(const VP& o, const VP& ns, uint8_t source, bool present) {
+    uint32_t fl = 0;
+    uint32_t kind = GK_SID_UNDEF, group = GK_SID_UNDEF, nsname = GK_NONE;
+    if (present && o) {
+      fl |= GK_F_HAS_OBJ;
+      std::string g, v, k;
+      split_gv(o, g, v, k);
+      kind = sid("s" + k);
+      group = sid("s" + g);
+      bool is_ns = k == "Namespace" && g.empty();
+      if (is_ns) fl |= GK_F_IS_NS;
+      std::string objns = meta_str(o, "namespace");
+      if (!objns.empty()) fl |= GK_F_HAS_NS;
+      if (ns) fl |= GK_F_NS_OBJ;
+      std::string name = meta_str(o, "name"), gen = meta_str(o, "generateName");
+      hb.name_bytes.insert(hb.name_bytes.end(), name.begin(), name.end());
+      hb.gen_bytes.insert(hb.gen_bytes.end(), gen.begin(), gen.end());
+      // name used by namespaces / excludedNamespaces -- match.go:118-179
+      if (is_ns) nsname = sid("s" + name);
+      else if (ns) nsname = sid("s" + meta_str(ns, "name"));
+      else if (!objns.empty()) nsname = sid("s" + objns);
+      if (const Node* ls = labels_of(o))
+        for (auto& e : ls->kv) {
+          hb.lbl_kv.push_back(sid("s" + e.first->s));
+          hb.lbl_kv.push_back(sid("s" + e.second->s));
+        }
+    }
+    fl |= ((uint32_t)source << GK_F_SRC_SHIFT) & GK_F_SRC_MASK;
+    hb.flags.push_back(fl);
+    hb.kind_sid.push_back(kind);
+    hb.group_sid.push_back(group);
+    hb.nsname_sid.push_back(nsname);
+    hb.name_off.push_back((uint32_t)hb.name_bytes.size());
+    hb.gen_off.push_back((uint32_t)hb.gen_bytes.size());
+    hb.lbl_off.push_back((uint32_t)hb.lbl_kv.size() / 2);
+  }
+
+  // old-object header rows are kept in a second set of vectors and appended after the merge
+  std::vector<uint32_t> o_flags, o_kind, o_group, o_nsname, o_name_off{0}, o_gen_off{0}, o_lbl_off{0}, o_lbl_kv;
+  std::vector<uint8_t> o_name_bytes, o_gen_bytes;
+  bool any_old = false;
+
+  void encode(size_t ci, const VP& v) {
+    const uint32_t enc = c.schema.cols[ci].enc;
+    HostColumn& hc = hb.cols[ci];
+    uint8_t vt = v ? (uint8_t)v->t : (uint8_t)GK_VT_UNDEF;
+    int64_t num = 0;
+    if (v && v->t == VT::Num && (enc & GK_ENC_NUM) && !num_fits_i64(v->n, &num)) vt = GK_VT_NUM_INEXACT;
+    if (enc & GK_ENC_VT) hc.vt.push_back(vt);
+    if (enc & GK_ENC_SID) hc.sid.push_back(v ? sid(intern_key(v)) : GK_SID_UNDEF);
+    if (enc & GK_ENC_NUM) hc.num.push_back(num);
+    if (enc & GK_ENC_BYTES) {
+      if (v && v->t == VT::Str) hc.bytes.insert(hc.bytes.end(), v->s.begin(), v->s.end());
+      hc.boff.push_back((uint32_t)hc.bytes.size());
+    }
+  }
+
+  void add(const ObjIn& in) {
+    std::string err;
+    VP obj, old, ns;
+    VP doc = eng.review_doc(in, &obj, &old, &ns, &err);
+    hb.obj_errors.push_back(err);
+    const size_t nscopes = c.schema.scopes.size();
+    if (!doc) {
+      // placeholder rows: skipped by the kernel
+      size_t before = hb.flags.size();
+      header_row(nullptr, nullptr, 0, false);
+      hb.flags[before] |= GK_F_SKIP;
+      std::swap(hb.flags, o_flags), std::swap(hb.kind_sid, o_kind), std::swap(hb.group_sid, o_group), std::swap(hb.nsname_sid, o_nsname);
+      std::swap(hb.name_off, o_name_off), std::swap(hb.gen_off, o_gen_off), std::swap(hb.lbl_off, o_lbl_off), std::swap(hb.lbl_kv, o_lbl_kv);
+      std::swap(hb.name_bytes, o_name_bytes), std::swap(hb.gen_bytes, o_gen_bytes);
+      header_row(nullptr, nullptr, 0, false);
+      std::swap(hb.flags, o_flags), std::swap(hb.kind_sid, o_kind), std::swap(hb.group_sid, o_group), std::swap(hb.nsname_sid, o_nsname);
+      std::swap(hb.name_off, o_name_off), std::swap(hb.gen_off, o_gen_off), std::swap(hb.lbl_off, o_lbl_off), std::swap(hb.lbl_kv, o_lbl_kv);
+      std::swap(hb.name_bytes, o_name_bytes), std::swap(hb.gen_bytes, o_gen_bytes);
+      hb.nsrow.push_back(GK_NONE);
+      for (size_t s = 1; s < nscopes; ++s) {
+        // every parent row of this object gets an empty range; the root contributes exactly one row
+        if (c.schema.scopes[s].parent == 0) hb.scope_off[s].push_back(hb.scope_off[s].back());
+      }
+      for (size_t ci = 0; ci < hb.cols.size(); ++ci)
+        if (c.schema.cols[ci].scope == 0) encode(ci, nullptr);
+      ++hb.n;
+      return;
+    }
+    // ---- header (object row, then old-object row into the side vectors)
+    header_row(obj, ns, in.source, (bool)obj);
+    std::swap(hb.flags, o_flags), std::swap(hb.kind_sid, o_kind), std::swap(hb.group_sid, o_group), std::swap(hb.nsname_sid, o_nsname);
+    std::swap(hb.name_off, o_name_off), std::swap(hb.gen_off, o_gen_off), std::swap(hb.lbl_off, o_lbl_off), std::swap(hb.lbl_kv, o_lbl_kv);
+    std::swap(hb.name_bytes, o_name_bytes), std::swap(hb.gen_bytes, o_gen_bytes);
+    bool old_distinct = old && old.get() != obj.get();
+    header_row(old, ns, in.source, old_distinct);
+    std::swap(hb.flags, o_flags), std::swap(hb.kind_sid, o_kind), std::swap(hb.group_sid, o_group), std::swap(hb.nsname_sid, o_nsname);
+    std::swap(hb.name_off, o_name_off), std::swap(hb.gen_off, o_gen_off), std::swap(hb.lbl_off, o_lbl_off), std::swap(hb.lbl_kv, o_lbl_kv);
+    std::swap(hb.name_bytes, o_name_bytes), std::swap(hb.gen_bytes, o_gen_bytes);
+    any_old = any_old || old_distinct;
+    // ---- namespace table row
+    if (ns) {
+      auto it = ns_row_of.find(ns.get());
+      uint32_t row;
+      if (it == ns_row_of.end()) {
+        row = (uint32_t)ns_objs.size();
+        ns_objs.push_back(ns);
+        ns_row_of.emplace(ns.get(), row);
+        if (const Node* ls = labels_of(ns))
+          for (auto& e : ls->kv) {
+            hb.nsl_kv.push_back(sid("s" + e.first->s));
+            hb.nsl_kv.push_back(sid("s" + e.second->s));
+          }
+        hb.nsl_off.push_back((uint32_t)hb.nsl_kv.size() / 2);
+      } else {
+        row = it->second;
+      }
+      hb.nsrow.push_back(row);
+    } else {
+      hb.nsrow.push_back(GK_NONE);
+    }
+    // ---- scopes + columns
+    if (nscopes > 1 || !hb.cols.empty()) {
+      VP input = v_obj({{v_str("review"), doc}});
+      for (auto& e : evals) e.second->reset_input(input);
+      for (auto& r : rows) r.clear();
+      rows[0].push_back(Row{nullptr, nullptr, 0});
+      for (size_t s = 1; s < nscopes; ++s) {
+        const ScopeDef& sd = c.schema.scopes[s];
+        auto& prow = rows[sd.parent];
+        for (uint32_t pr = 0; pr < prow.size(); ++pr) {
+          VP coll = eval_closure(*sd.gen, sd.parent, pr, input);
+          if (coll) {
+            if (coll->t == VT::Arr)
+              for (size_t j = 0; j < coll->items.size(); ++j) rows[s].push_back(Row{coll->items[j], v_int((long long)j), pr});
+            else if (coll->t == VT::Set)
+              for (auto& x : coll->items) rows[s].push_back(Row{x, x, pr});
+            else if (coll->t == VT::Obj)
+              for (auto& e : coll->kv) rows[s].push_back(Row{e.second, e.first, pr});
+          }
+          hb.scope_off[s].push_back(hb.scope_rows[s] + (uint32_t)rows[s].size());
+        }
+      }
+      for (size_t ci = 0; ci < hb.cols.size(); ++ci) {
+        const ColDef& cd = c.schema.cols[ci];
+        for (uint32_t r = 0; r < rows[cd.scope].size(); ++r) encode(ci, eval_closure(*cd.expr, cd.scope, r, input));
+      }
+      for (size_t s = 1; s < nscopes; ++s) hb.scope_rows[s] += (uint32_t)rows[s].size();
+    }
+    ++hb.n;
+  }
+};
+
+template <class T>
+static void append(std::vector<T>& dst, const std::vector<T>& src) { dst.insert(dst.end(), src.begin(), src.end()); }
+static void append_off(std::vector<uint32_t>& dst, const std::vector<uint32_t>& src, size_t skip_first) {
+  uint32_t base = dst.empty() ? 0 : dst.back();
+  for (size_t i = skip_first; i < src.size(); ++i) dst.push_back(base + src[i]);
+}
+
+std::shared_ptr<HostBatch> Engine::flatten(const ObjIn* objs, size_t n, const Compiled& c) {
+  size_t T = std::min<size_t>((size_t)threads_, std::max<size_t>(1, n / 256));
+  std::vector<std::unique_ptr<Flattener>> parts(T);
+  std::vector<std::string> errs(T);
+  auto work = [&](size_t t) {
+    try {
+      parts[t].reset(new Flattener(*this, c));
+      size_t lo = n * t / T, hi = n * (t + 1) / T;
+      for (size_t i = lo; i < hi; ++i) parts[t]->add(objs[i]);
+    } catch (RegoError& e) {
+      errs[t] = e.msg;
+    } catch (std::exception& e) {
+      errs[t] = e.what();
+    }
+  };
+  if (T == 1) work(0);
+  else {
+    std::vector<std::thread> th;
+    for (size_t t = 0; t < T; ++t) th.emplace_back(work, t);
+    for (auto& x : th) x.join();
+  }
+  for (auto& e : errs)
+    if (!e.empty()) throw RegoError{"flatten: " + e};
+  // ---- merge
+  auto out = std::make_shared<HostBatch>();
+  HostBatch& hb = *out;
+  hb.schema_version = c.version;
+  const size_t nscopes = c.schema.scopes.size(), ncols = c.schema.cols.size();
+  hb.scope_off.resize(nscopes);
+  hb.scope_rows.assign(nscopes, 0);
+  hb.cols.resize(ncols);
+  hb.name_off.push_back(0);
+  hb.gen_off.push_back(0);
+  hb.lbl_off.push_back(0);
+  hb.nsl_off.push_back(0);
+  for (size_t s = 1; s < nscopes; ++s) hb.scope_off[s].push_back(0);
+  for (size_t i = 0; i < ncols; ++i)
+    if (c.schema.cols[i].enc & GK_ENC_BYTES) hb.cols[i].boff.push_back(0);
+  bool any_old = false;
+  for (auto& p : parts) any_old = any_old || p->any_old;
+  hb.has_old = any_old;
+  for (auto& p : parts) {
+    HostBatch& q = p->hb;
+    uint32_t nsbase = (uint32_t)hb.nsl_off.size() - 1;
+    hb.n += q.n;
+    append(hb.flags, q.flags);
+    append(hb.kind_sid, q.kind_sid);
+    append(hb.group_sid, q.group_sid);
+    append(hb.nsname_sid, q.nsname_sid);
+    append_off(hb.name_off, q.name_off, 1);
+    append_off(hb.gen_off, q.gen_off, 1);
+    append_off(hb.lbl_off, q.lbl_off, 1);
+    append(hb.name_bytes, q.name_bytes);
+    append(hb.gen_bytes, q.gen_bytes);
+    append(hb.lbl_kv, q.lbl_kv);
+    for (uint32_t r : q.nsrow) hb.nsrow.push_back(r == GK_NONE ? GK_NONE : r + nsbase);
+    append_off(hb.nsl_off, q.nsl_off, 1);
+    append(hb.nsl_kv, q.nsl_kv);
+    append(hb.obj_errors, q.obj_errors);
+    for (size_t s = 1; s < nscopes; ++s) {
+      append_off(hb.scope_off[s], q.scope_off[s], 1);
+      hb.scope_rows[s] += q.scope_rows[s];
+    }
+    for (size_t i = 0; i < ncols; ++i) {
+      append(hb.cols[i].vt, q.cols[i].vt);
+      append(hb.cols[i].sid, q.cols[i].sid);
+      append(hb.cols[i].num, q.cols[i].num);
+      if (c.schema.cols[i].enc & GK_ENC_BYTES) append_off(hb.cols[i].boff, q.cols[i].boff, 1);
+      append(hb.cols[i].bytes, q.cols[i].bytes);
+    }
+  }
+  if (any_old) {
+    // rows [n, 2n): old objects
+    for (auto& p : parts) {
+      append(hb.flags, p->o_flags);
+      append(hb.kind_sid, p->o_kind);
+      append(hb.group_sid, p->o_group);
+      append(hb.nsname_sid, p->o_nsname);
+      append_off(hb.name_off, p->o_name_off, 1);
+      append_off(hb.gen_off, p->o_gen_off, 1);
+      append_off(hb.lbl_off, p->o_lbl_off, 1);
+      append(hb.name_bytes, p->o_name_bytes);
+      append(hb.gen_bytes, p->o_gen_bytes);
+      append(hb.lbl_kv, p->o_lbl_kv);
+    }
+  }
+  // ---- algorithmic bytes: every array the kernel may read, counted once
+  uint64_t b = 0;
+  auto sz = [&](auto& v) { b += (uint64_t)v.size() * sizeof(v[0]); };
+  sz(hb.flags), sz(hb.kind_sid), sz(hb.group_sid), sz(hb.nsname_sid), sz(hb.name_off), sz(hb.gen_off), sz(hb.lbl_off), sz(hb.lbl_kv);
+  sz(hb.name_bytes), sz(hb.gen_bytes), sz(hb.nsrow), sz(hb.nsl_off), sz(hb.nsl_kv);
+  for (size_t s = 1; s < nscopes; ++s) sz(hb.scope_off[s]);
+  for (auto& col : hb.cols) sz(col.vt), sz(col.sid), sz(col.num), sz(col.boff), sz(col.bytes);
+  hb.alg_bytes = b;
+  return out;
+}
+
+// ====================================================================================== materialisation
+static std::string scoped_json(const std::vector<std::string>& v) {
+  std::string o = "[";
+  for (size_t i = 0; i < v.size(); ++i) {
+    if (i) o += ",";
+    json_quote(v[i], o);
+  }
+  return o + "]";
+}
+
+void Engine::materialize(const Compiled& c, const ObjIn& in, uint32_t obj_ix, uint32_t cix, const std::string& ep, std::vector<Violation>& out) {
+  const Constraint& con = *c.order[cix];
+  std::string err;
+  VP doc = review_doc(in, nullptr, nullptr, nullptr, &err);
+  if (!doc) throw RegoError{"materialize: " + err};
+  std::shared_ptr<Module> mod;
+  {
+    std::shared_lock<std::shared_mutex> l(mu_);
+    auto it = templates_.find(con.kind);
+    if (it == templates_.end()) throw RegoError{"materialize: template gone"};
+    mod = it->second.mod;
+  }
+  Eval ev(*mod, v_obj({{v_str("review"), doc}, {v_str("parameters"), con.params}}));
+  VP vs = ev.rule_value("violation");
+  size_t before = out.size();
+  std::vector<std::string> sc = con.action == "scoped" ? scoped_actions_for(con, ep) : std::vector<std::string>();
+  if (vs)
+    for (auto& v : vs->items) {
+      VP msg = obj_get(v, "msg");
+      if (v->t != VT::Obj || !msg || msg->t != VT::Str) throw RegoError{"rego_type_error: violation element must be {\"msg\": string, ...}"};
+      Violation x;
+      x.object = obj_ix;
+      x.constraint = cix;
+      x.msg = msg->s;
+      VP d = obj_get(v, "details");
+      x.details_json = d ? json_str(d) : "";
+      x.action = con.action;
+      x.scoped_json = scoped_json(sc);
+      out.push_back(std::move(x));
+    }
+  if (out.size() == before)
+    throw RegoError{"internal: GPU flagged (" + con.kind + "/" + con.name + ", object " + std::to_string(obj_ix) +
+                    ") but the message renderer finds no violation -- lowering bug"};
+}
+
+void Engine::autoreject(const Compiled& c, const ObjIn& in, uint32_t obj_ix, uint32_t cix, uint32_t code, const std::string& ep,
+                        std::vector<Violation>& out) {
+  const Constraint& con = *c.order[cix];
+  std::string err;
+  VP obj, old;
+  (void)review_doc(in, &obj, &old, nullptr, &err);
+  VP ref = obj ? obj : old;
+  std::string name = ref ? meta_str(ref, "name") : "";
+  std::string detail;
+  switch (code) {
+    case GK_E_LSEL_INVALID: detail = con.match.lsel_err; break;
+    case GK_E_NSSEL_INVALID: detail = con.match.nssel_err; break;
+    case GK_E_NS_MISSING: detail = "namespace selector for namespace-scoped object but missing Namespace"; break;
+    case GK_E_SRC_INVALID_MATCH: detail = con.match.src_err; break;
+    case GK_E_SRC_UNSPECIFIED: detail = "source field not specified for resource " + name; break;
+    case GK_E_SRC_INVALID_OBJ: detail = "invalid source field"; break;
+    case GK_E_NUM_RANGE: detail = "number outside the exact int64 range in an ordered comparison"; break;
+    default: break;
+  }
+  Violation x;
+  x.object = obj_ix;
+  x.constraint = cix;
+  x.autoreject = true;
+  if (code == GK_E_NO_OBJECT) x.msg = "invalid request object: neither object nor old object are defined";
+  else x.msg = "error matching the requested object: " + name + " :failed to run Match criteria: " + detail;   // matcher.go:58-60, match.go:52-54
+  x.details_json = "{}";
+  x.action = con.action;
+  x.scoped_json = scoped_json(con.action == "scoped" ? scoped_actions_for(con, ep) : std::vector<std::string>());
+  out.push_back(std::move(x));
+}
+
+}  // namespace gk

@@ -1,0 +1,161 @@
+// Engine: templates + constraints + namespace cache -> compiled (schema, program); object batches ->
+// flattened columnar batches -> GPU evaluation -> violation bitmaps (+ lazily rendered messages).
+#pragma once
+#include <atomic>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <shared_mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "lower.hpp"
+#include "program.h"
+#include "rego.hpp"
+
+namespace gk {
+
+// ---- review inputs (one per object) -- mirrors target.AugmentedUnstructured / AugmentedReview
+struct ObjIn {
+  const char* json = nullptr;
+  size_t len = 0;
+  const char* old_json = nullptr;
+  size_t old_len = 0;
+  const char* ns_json = nullptr;   // explicit Namespace object (review.namespace), optional
+  size_t ns_len = 0;
+  const char* ns_name = nullptr;   // AdmissionRequest.Namespace; null => object's metadata.namespace
+  const char* operation = nullptr; // "", CREATE, UPDATE, DELETE
+  const char* userinfo_json = nullptr;
+  size_t userinfo_len = 0;
+  uint8_t source = 0;              // GK_SRC_*
+};
+
+struct HostColumn {
+  std::vector<uint8_t> vt;
+  std::vector<uint32_t> sid;
+  std::vector<int64_t> num;
+  std::vector<uint32_t> boff;   // rows + 1
+  std::vector<uint8_t> bytes;
+};
+
+struct HostBatch {
+  uint32_t n = 0;
+  bool has_old = false;
+  // header rows: [0,n) objects, [n,2n) old objects when has_old
+  std::vector<uint32_t> flags, kind_sid, group_sid, nsname_sid, name_off, gen_off, lbl_off, lbl_kv;
+  std::vector<uint8_t> name_bytes, gen_bytes;
+  std::vector<uint32_t> nsrow;                 // [n]
+  std::vector<uint32_t> nsl_off, nsl_kv;       // per-batch namespace label table
+  std::vector<std::vector<uint32_t>> scope_off;   // [scope][parent_rows+1]; [0] unused
+  std::vector<uint32_t> scope_rows;
+  std::vector<HostColumn> cols;
+  std::vector<std::string> obj_errors;         // per object: "" or a review-level error (bad JSON, missing kind, ...)
+  uint64_t alg_bytes = 0;                      // bytes of every array the kernel may read (each counted once)
+  uint64_t schema_version = 0;
+};
+
+struct MatchSpec {
+  bool has = false;
+  VP raw;                                      // spec.match
+  GkMatch dev{};                               // pool offsets filled by the compiler
+  std::string lsel_err, nssel_err, src_err;    // error texts when the corresponding *_INVALID flag is set
+};
+
+struct ScopedAction {
+  std::string action;
+  std::vector<std::string> points;
+};
+
+struct Constraint {
+  std::string kind, name;
+  VP obj, params;
+  MatchSpec match;
+  std::string action;                          // deny / dryrun / warn / scoped / unrecognized
+  std::vector<ScopedAction> scoped;
+  FP formula;
+  uint32_t pc = GK_PC_REJECT;
+};
+
+struct TemplateEntry {
+  std::string kind;
+  std::string src;
+  std::shared_ptr<Module> mod;
+};
+
+struct Compiled {
+  uint64_t version = 0;
+  Schema schema;
+  std::vector<GkInstr> instr;
+  std::vector<uint32_t> pool;
+  std::vector<uint8_t> cbytes;
+  std::vector<GkMatch> match;                  // per constraint
+  std::vector<const Constraint*> order;        // constraint index -> constraint
+};
+
+class StringTable : public Interner {
+ public:
+  StringTable();
+  uint32_t intern(const std::string& key) override;
+  uint32_t lookup(const std::string& key) const;   // GK_SID_UNDEF if absent
+  // snapshot for upload: offsets [n+1] and bytes
+  void snapshot(std::vector<uint32_t>& off, std::vector<uint8_t>& bytes) const;
+  uint32_t size() const;
+  std::string get(uint32_t sid) const;
+
+ private:
+  mutable std::shared_mutex mu_;
+  std::unordered_map<std::string, uint32_t> map_;
+  std::vector<uint32_t> off_;
+  std::vector<uint8_t> bytes_;
+};
+
+struct Violation {
+  uint32_t object, constraint;
+  std::string msg, details_json, action, scoped_json;
+  bool autoreject = false;
+};
+
+class Engine {
+ public:
+  explicit Engine(int threads);
+  // mutators (exclusive) -- mirror drivers.Driver AddTemplate/RemoveTemplate/AddConstraint/RemoveConstraint/AddData
+  void add_template(const std::string& kind, const std::string& rego);
+  bool remove_template(const std::string& kind);
+  void add_constraint(const std::string& json);
+  bool remove_constraint(const std::string& kind, const std::string& name);
+  void put_namespace(const std::string& name, const std::string& json);
+  bool remove_namespace(const std::string& name);
+
+  std::shared_ptr<const Compiled> compiled();                 // compiles lazily after mutations
+  std::shared_ptr<HostBatch> flatten(const ObjIn* objs, size_t n, const Compiled& c);
+  // which constraints apply at an enforcement point + their effective actions
+  void active_mask(const Compiled& c, const std::string& ep, std::vector<uint32_t>& active) const;
+  // render messages for one flagged pair (never decides a violation; throws if the GPU bit is unjustified)
+  void materialize(const Compiled& c, const ObjIn& obj, uint32_t obj_ix, uint32_t cix, const std::string& ep,
+                   std::vector<Violation>& out);
+  void autoreject(const Compiled& c, const ObjIn& obj, uint32_t obj_ix, uint32_t cix, uint32_t code, const std::string& ep,
+                  std::vector<Violation>& out);
+  std::string dump();
+  StringTable& strings() { return strings_; }
+  int threads() const { return threads_; }
+  VP review_doc(const ObjIn& in, VP* obj_out, VP* old_out, VP* ns_out, std::string* err);
+
+ private:
+  friend struct Flattener;
+  void compile_locked();
+  std::shared_mutex mu_;
+  std::map<std::string, TemplateEntry> templates_;
+  std::vector<std::unique_ptr<Constraint>> constraints_;
+  std::map<std::string, VP> namespaces_;
+  std::shared_ptr<Compiled> compiled_;
+  bool dirty_ = true;
+  uint64_t version_ = 0;
+  StringTable strings_;
+  int threads_;
+};
+
+// scoped/unscoped action resolution -- pkg/util/enforcement_action.go:132-174
+std::vector<std::string> scoped_actions_for(const Constraint& c, const std::string& ep);
+
+}  // namespace gk

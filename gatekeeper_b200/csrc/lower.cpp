@@ -1,0 +1,1586 @@
+// Partial evaluation of a template's `violation` rule against concrete parameters -> formula tree, and
+// formula tree -> jump-threaded instructions.  See lower.hpp for the scheme.
+#include "lower.hpp"
+
+#include <algorithm>
+#include <functional>
+#include <set>
+
+namespace gk {
+
+// ====================================================================================== formulas
+static FP mk(Formula::K k) {
+  auto f = std::make_shared<Formula>();
+  f->k = k;
+  return f;
+}
+FP f_true() {
+  static FP t = mk(Formula::True);
+  return t;
+}
+FP f_false() {
+  static FP f = mk(Formula::False);
+  return f;
+}
+FP f_and(FP a, FP b) {
+  if (a->k == Formula::False || b->k == Formula::False) return f_false();
+  if (a->k == Formula::True) return b;
+  if (b->k == Formula::True) return a;
+  auto f = std::make_shared<Formula>();
+  f->k = Formula::And;
+  if (a->k == Formula::And) f->kids = a->kids;
+  else f->kids.push_back(a);
+  if (b->k == Formula::And) f->kids.insert(f->kids.end(), b->kids.begin(), b->kids.end());
+  else f->kids.push_back(b);
+  return f;
+}
+FP f_or(FP a, FP b) {
+  if (a->k == Formula::True || b->k == Formula::True) return f_true();
+  if (a->k == Formula::False) return b;
+  if (b->k == Formula::False) return a;
+  auto f = std::make_shared<Formula>();
+  f->k = Formula::Or;
+  if (a->k == Formula::Or) f->kids = a->kids;
+  else f->kids.push_back(a);
+  if (b->k == Formula::Or) f->kids.insert(f->kids.end(), b->kids.begin(), b->kids.end());
+  else f->kids.push_back(b);
+  return f;
+}
+FP f_not(FP a) {
+  if (a->k == Formula::True) return f_false();
+  if (a->k == Formula::False) return f_true();
+  if (a->k == Formula::Not) return a->kids[0];
+  auto f = std::make_shared<Formula>();
+  f->k = Formula::Not;
+  f->kids.push_back(a);
+  return f;
+}
+FP f_exists(int scope, FP body) {
+  if (body->k == Formula::False) return f_false();
+  auto f = std::make_shared<Formula>();
+  f->k = Formula::Exists;
+  f->scope = scope;
+  f->kids.push_back(body);
+  return f;
+}
+static FP f_atom(int op, int col, VP cval = nullptr, uint32_t imm = 0) {
+  auto f = std::make_shared<Formula>();
+  f->k = Formula::Atom;
+  f->op = op;
+  f->col = col;
+  f->cval = std::move(cval);
+  f->imm = imm;
+  return f;
+}
+size_t formula_size(const FP& f) {
+  size_t n = 1;
+  for (auto& k : f->kids) n += formula_size(k);
+  return n;
+}
+std::string formula_str(const FP& f, const Schema& s) {
+  switch (f->k) {
+    case Formula::True: return "T";
+    case Formula::False: return "F";
+    case Formula::Not: return "!" + formula_str(f->kids[0], s);
+    case Formula::And:
+    case Formula::Or: {
+      std::string o = "(";
+      for (size_t i = 0; i < f->kids.size(); ++i) {
+        if (i) o += f->k == Formula::And ? " & " : " | ";
+        o += formula_str(f->kids[i], s);
+      }
+      return o + ")";
+    }
+    case Formula::Exists: return "E[s" + std::to_string(f->scope) + ":" + s.scopes[f->scope].gen->key + "]{" + formula_str(f->kids[0], s) + "}";
+    case Formula::Atom: {
+      static const char* names[] = {"?", "truthy", "defined", "vtmask", "sid_eq", "sid_in", "num_cmp", "prefix", "suffix",
+                                    "contains", "anyprefix", "anysuffix"};
+      std::string o = std::string(names[f->op]) + "(" + s.cols[f->col].expr->key;
+      if (f->cval) o += ", " + fmt_value(f->cval, false);
+      if (f->op == GK_OP_NUM_CMP || f->op == GK_OP_VTMASK) o += ", #" + std::to_string(f->imm);
+      return o + ")";
+    }
+  }
+  return "?";
+}
+
+// ====================================================================================== schema
+int Schema::scope_for(const CP& gen) {
+  auto it = scope_ix.find(gen->key);
+  if (it != scope_ix.end()) return it->second;
+  ScopeDef d;
+  d.parent = gen->scope;
+  d.gen = gen;
+  d.depth = scopes[gen->scope].depth + 1;
+  if (d.depth > GK_MAX_LOOP_DEPTH) throw RegoError{"rego_unsupported: iteration nesting deeper than " + std::to_string(GK_MAX_LOOP_DEPTH)};
+  scopes.push_back(d);
+  int id = (int)scopes.size() - 1;
+  scope_ix[gen->key] = id;
+  return id;
+}
+int Schema::col_for(const CP& expr, uint32_t enc) {
+  auto it = col_ix.find(expr->key);
+  if (it != col_ix.end()) {
+    cols[it->second].enc |= enc;
+    return it->second;
+  }
+  ColDef d;
+  d.expr = expr;
+  d.scope = expr->scope;
+  d.enc = enc;
+  cols.push_back(d);
+  int id = (int)cols.size() - 1;
+  if (id >= 65535) throw RegoError{"rego_unsupported: too many feature columns"};
+  col_ix[expr->key] = id;
+  return id;
+}
+
+// ====================================================================================== lowering
+namespace {
+
+struct SymVal {
+  enum K : uint8_t { Conc, Col, Bool, Arr, ObjLit, Opaque, DiffCS, DiffSC, Count, SetOf } k = Conc;
+  VP v;                                                   // Conc; DiffCS/DiffSC: the concrete set
+  CP col;                                                 // Col
+  std::shared_ptr<SymVal> sym;                            // DiffCS/DiffSC: the symbolic collection (Col or SetOf)
+  // SetOf: `f` is a formula with holes (Atom op == -1, imm == j); items[j].second is the head produced at hole j.
+  // The set is { head_j | path condition of hole j }.
+  FP f;                                                   // Bool: value; Opaque: definedness
+  std::vector<std::pair<FP, SymVal>> items;               // Arr: (guard, element); Count: [0] = counted value
+  std::vector<std::pair<VP, SymVal>> fields;              // ObjLit
+  bool tainted = false;                                   // Conc: derived from input.parameters
+  static SymVal conc(VP v, bool tainted = false) { SymVal s; s.k = Conc; s.v = std::move(v); s.tainted = tainted; return s; }
+  static SymVal column(CP c) { SymVal s; s.k = Col; s.col = std::move(c); return s; }
+  static SymVal boolean(FP f) { SymVal s; s.k = Bool; s.f = std::move(f); return s; }
+  static SymVal opaque(FP def) { SymVal s; s.k = Opaque; s.f = std::move(def); return s; }
+};
+
+struct LEnv {
+  std::vector<std::pair<int, SymVal>> b;
+  const SymVal* find(int vid) const {
+    for (size_t i = b.size(); i-- > 0;)
+      if (b[i].first == vid) return &b[i].second;
+    return nullptr;
+  }
+  size_t mark() const { return b.size(); }
+  void undo(size_t m) { b.resize(m); }
+  void bind(int vid, SymVal v) { b.emplace_back(vid, std::move(v)); }
+};
+
+struct Deps {
+  bool obj = false, param = false, iter = false, mixed = false;
+  void operator|=(const Deps& o) {
+    obj |= o.obj;
+    param |= o.param;
+    iter |= o.iter;
+    mixed |= o.mixed;
+  }
+};
+
+[[noreturn]] void unsupported(const std::string& what, int line) {
+  throw RegoError{"rego_unsupported: " + what + " (line " + std::to_string(line) + ") cannot be lowered to the GPU predicate table"};
+}
+
+using BodyK = std::function<FP(LEnv&)>;
+using SymK = std::function<FP(const SymVal&)>;
+
+class Lowerer {
+ public:
+  Lowerer(std::shared_ptr<const Module> mod, VP params, Schema& schema)
+      : mod_(std::move(mod)), m_(*mod_), schema_(schema),
+        ev_(m_, v_obj({{v_str("parameters"), params}})) {
+    vid_cur_ = const_cast<Module&>(m_).intern("$cur");
+    vid_key_ = const_cast<Module&>(m_).intern("$key");
+  }
+
+  FP run() {
+    auto it = m_.rules.find("violation");
+    if (it == m_.rules.end()) throw RegoError{"rego_compile_error: template has no `violation` rule"};
+    FP out = f_false();
+    for (auto& r : it->second) {
+      if (r.kind != Rule::PSet) throw RegoError{"rego_type_error: `violation` must be a partial set rule"};
+      LEnv env;
+      FP f = lower_body(r.body, 0, env, [&](LEnv& e) { return sym_term(r.key, e, [&](const SymVal& kv) { return defined_cond(kv); }); });
+      out = f_or(out, f);
+      check_size(out, r.line);
+    }
+    return out;
+  }
+
+ private:
+  std::shared_ptr<const Module> mod_;
+  const Module& m_;
+  Schema& schema_;
+  Eval ev_;
+  int vid_cur_, vid_key_;
+  int depth_ = 0;
+  std::map<std::string, Deps> rule_deps_;
+  std::set<std::string> rule_deps_busy_;
+  std::vector<std::shared_ptr<Term>> synth_;   // keeps synthesized terms alive
+
+  void check_size(const FP& f, int line) {
+    if (formula_size(f) > 20000) unsupported("predicate too large after partial evaluation", line);
+  }
+
+  // ------------------------------------------------------------------ dependency classification
+  bool unbound(const Term& t, const LEnv& env) const {
+    return t.k == TK::Var && !env.find(t.vid) && t.vid != m_.vid_input && t.vid != m_.vid_data && !m_.is_rule(t.name);
+  }
+
+  Deps rule_deps(const std::string& name) {
+    auto it = rule_deps_.find(name);
+    if (it != rule_deps_.end()) return it->second;
+    if (rule_deps_busy_.count(name)) return Deps();
+    rule_deps_busy_.insert(name);
+    Deps d;
+    LEnv empty;
+    for (auto& r : m_.rules.at(name)) {
+      if (r.key) d |= deps(r.key, empty, true);
+      if (r.value) d |= deps(r.value, empty, true);
+      d |= body_deps(r.body, empty);
+      for (auto& el : r.els) {
+        if (el.first) d |= deps(el.first, empty, true);
+        d |= body_deps(el.second, empty);
+      }
+    }
+    d.iter = false;
+    rule_deps_busy_.erase(name);
+    rule_deps_[name] = d;
+    return d;
+  }
+
+  Deps body_deps(const std::vector<Stmt>& body, const LEnv& env) {
+    Deps d;
+    for (auto& s : body) {
+      if (s.a) d |= deps(s.a, env, true);
+      if (s.b) d |= deps(s.b, env, true);
+      if (s.c) d |= deps(s.c, env, true);
+    }
+    return d;
+  }
+
+  // `local`: unbound variables are comprehension/function locals, not iteration at this level
+  Deps deps(const TP& t, const LEnv& env, bool local) {
+    Deps d;
+    switch (t->k) {
+      case TK::Scalar: break;
+      case TK::Var: {
+        if (const SymVal* s = env.find(t->vid)) {
+          if (s->k == SymVal::Col) d.obj = true;
+          else if (s->k != SymVal::Conc) d.mixed = d.obj = d.param = true;
+          else if (s->tainted) d.param = true;
+        } else if (t->vid == m_.vid_input) {
+          d.obj = d.param = true;
+        } else if (t->vid == m_.vid_data) {
+          unsupported("reference to `data` (referential constraints / data.inventory, SURVEY.md f-4)", t->line);
+        } else if (m_.is_rule(t->name)) {
+          d |= rule_deps(t->name);
+        } else if (!local) {
+          d.iter = true;
+        }
+        break;
+      }
+      case TK::Ref: {
+        size_t start = 0;
+        if (t->head->k == TK::Var && t->head->vid == m_.vid_input && !env.find(t->head->vid) && !t->args.empty() &&
+            t->args[0]->k == TK::Scalar && t->args[0]->val->t == VT::Str) {
+          const std::string& f = t->args[0]->val->s;
+          if (f == "parameters") d.param = true;
+          else if (f == "review") d.obj = true;
+          else d.obj = d.param = true;
+          start = 1;
+        } else {
+          d |= deps(t->head, env, local);
+        }
+        for (size_t i = start; i < t->args.size(); ++i) d |= deps(t->args[i], env, local);
+        break;
+      }
+      case TK::Call: {
+        auto it = m_.rules.find(t->name);
+        if (it != m_.rules.end()) d |= rule_deps(t->name);
+        else if (!is_builtin(t->name)) throw RegoError{"rego_type_error: undefined function " + t->name + " (line " + std::to_string(t->line) + ")"};
+        for (auto& a : t->args) d |= deps(a, env, local);
+        break;
+      }
+      case TK::Array:
+      case TK::Set:
+        for (auto& a : t->args) d |= deps(a, env, local);
+        break;
+      case TK::Object:
+        for (auto& kv : t->kvs) {
+          d |= deps(kv.first, env, local);
+          d |= deps(kv.second, env, local);
+        }
+        break;
+      case TK::ArrCompr:
+      case TK::SetCompr:
+      case TK::ObjCompr: {
+        Deps x;
+        if (t->key) x |= deps(t->key, env, true);
+        x |= deps(t->value, env, true);
+        x |= body_deps(t->body, env);
+        x.iter = false;
+        d |= x;
+        break;
+      }
+    }
+    return d;
+  }
+
+  static bool pure_conc(const Deps& d) { return !d.obj && !d.mixed; }
+  static bool pure_obj(const Deps& d) { return d.obj && !d.param && !d.mixed && !d.iter; }
+
+  // ------------------------------------------------------------------ closures
+  void free_vars(const TP& t, std::vector<int>& out) const {
+    if (!t) return;
+    if (t->k == TK::Var) out.push_back(t->vid);
+    if (t->head) free_vars(t->head, out);
+    for (auto& a : t->args) free_vars(a, out);
+    for (auto& kv : t->kvs) {
+      free_vars(kv.first, out);
+      free_vars(kv.second, out);
+    }
+    free_vars(t->key, out);
+    free_vars(t->value, out);
+    for (auto& s : t->body) {
+      free_vars(s.a, out);
+      free_vars(s.b, out);
+      free_vars(s.c, out);
+    }
+  }
+
+  bool refs_module(const TP& t) const {
+    if (!t) return false;
+    if (t->k == TK::Var && m_.is_rule(t->name)) return true;
+    if (t->k == TK::Call && m_.is_rule(t->name)) return true;
+    if (t->head && refs_module(t->head)) return true;
+    for (auto& a : t->args)
+      if (refs_module(a)) return true;
+    for (auto& kv : t->kvs)
+      if (refs_module(kv.first) || refs_module(kv.second)) return true;
+    if (refs_module(t->key) || refs_module(t->value)) return true;
+    for (auto& s : t->body)
+      if (refs_module(s.a) || refs_module(s.b) || refs_module(s.c)) return true;
+    return false;
+  }
+
+  static void subst_print(const Term& t, const std::map<int, std::string>& sub, std::string& out);
+
+  CP make_closure(const TP& term, const LEnv& env) {
+    auto c = std::make_shared<Closure>();
+    c->mod = mod_;
+    c->term = term;
+    std::vector<int> fv;
+    free_vars(term, fv);
+    std::sort(fv.begin(), fv.end());
+    fv.erase(std::unique(fv.begin(), fv.end()), fv.end());
+    std::map<int, std::string> sub;
+    int scope = 0;
+    for (int v : fv) {
+      const SymVal* s = env.find(v);
+      if (!s) continue;
+      CapArg a;
+      if (s->k == SymVal::Conc) {
+        a.k = CapArg::Conc;
+        a.v = s->v;
+        sub[v] = "<" + intern_key(s->v) + ">";
+      } else if (s->k == SymVal::Col) {
+        a.k = CapArg::Col;
+        a.col = s->col;
+        sub[v] = "<" + s->col->key + ">";
+        int sc = s->col->scope;
+        if (sc != scope) {
+          // scopes must lie on one ancestor chain; keep the deeper one
+          int deep = schema_.scopes[sc].depth >= schema_.scopes[scope].depth ? sc : scope;
+          int shallow = deep == sc ? scope : sc;
+          int p = deep;
+          while (p != 0 && p != shallow) p = schema_.scopes[p].parent;
+          if (p != shallow) unsupported("expression over two unrelated iteration scopes", term->line);
+          scope = deep;
+        }
+      } else {
+        unsupported("internal: closure over a mixed value", term->line);
+      }
+      c->caps.emplace_back(v, a);
+    }
+    c->scope = scope;
+    std::string body;
+    subst_print(*term, sub, body);
+    c->key = (refs_module(term) ? "m" + std::to_string(m_.uid) + ":" : std::string()) + body;
+    return c;
+  }
+
+  CP leaf(int scope, bool is_key) {
+    auto c = std::make_shared<Closure>();
+    c->leaf = is_key ? Closure::Key : Closure::Elem;
+    c->scope = scope;
+    c->key = (is_key ? "$K" : "$E") + std::to_string(scope) + "{" + schema_.scopes[scope].gen->key + "}";
+    return c;
+  }
+
+  TP synth_ref(const TP& head, std::vector<TP> path, int line) {
+    auto t = std::make_shared<Term>();
+    t->k = TK::Ref;
+    t->head = head;
+    t->args = std::move(path);
+    t->line = line;
+    synth_.push_back(t);
+    return t;
+  }
+  TP synth_var(int vid, const std::string& name) {
+    auto t = std::make_shared<Term>();
+    t->k = TK::Var;
+    t->vid = vid;
+    t->name = name;
+    synth_.push_back(t);
+    return t;
+  }
+  TP synth_scalar(const VP& v) {
+    auto t = std::make_shared<Term>();
+    t->k = TK::Scalar;
+    t->val = v;
+    synth_.push_back(t);
+    return t;
+  }
+  TP synth_call(const std::string& name, std::vector<TP> args, int line) {
+    auto t = std::make_shared<Term>();
+    t->k = TK::Call;
+    t->name = name;
+    t->args = std::move(args);
+    t->line = line;
+    synth_.push_back(t);
+    return t;
+  }
+
+  // closure for  <col>[key]  /  f(<col>...)
+  CP make_dot(const CP& base, const VP& key) {
+    LEnv e;
+    e.bind(vid_cur_, SymVal::column(base));
+    return make_closure(synth_ref(synth_var(vid_cur_, "$cur"), {synth_scalar(key)}, 0), e);
+  }
+  CP make_call1(const std::string& fn, const CP& a) {
+    LEnv e;
+    e.bind(vid_cur_, SymVal::column(a));
+    return make_closure(synth_call(fn, {synth_var(vid_cur_, "$cur")}, 0), e);
+  }
+  CP make_call2(const std::string& fn, const CP& a, const CP& b) {
+    LEnv e;
+    e.bind(vid_cur_, SymVal::column(a));
+    e.bind(vid_key_, SymVal::column(b));
+    return make_closure(synth_call(fn, {synth_var(vid_cur_, "$cur"), synth_var(vid_key_, "$key")}, 0), e);
+  }
+
+  // ------------------------------------------------------------------ atoms
+  FP a_truthy(const CP& c) { return f_atom(GK_OP_TRUTHY, schema_.col_for(c, GK_ENC_VT)); }
+  FP a_defined(const CP& c) { return f_atom(GK_OP_DEFINED, schema_.col_for(c, GK_ENC_VT)); }
+  FP a_eq(const CP& c, const VP& v) { return f_atom(GK_OP_SID_EQ, schema_.col_for(c, GK_ENC_VT | GK_ENC_SID), v); }
+  FP a_in(const CP& c, const VP& set) {
+    if (set->items.empty()) return f_false();
+    return f_atom(GK_OP_SID_IN, schema_.col_for(c, GK_ENC_VT | GK_ENC_SID), set);
+  }
+  // const c is a member of the collection-valued column S
+  // existential over the elements of a symbolic collection (a collection-valued column or a SetOf)
+  FP for_each_elem(const SymVal& S, int line, const std::function<FP(const SymVal& key, const SymVal& elem)>& body) {
+    if (S.k == SymVal::Col) {
+      int s = schema_.scope_for(S.col);
+      return f_exists(s, body(SymVal::column(leaf(s, true)), SymVal::column(leaf(s, false))));
+    }
+    if (S.k == SymVal::SetOf)
+      return fill_tree(S.f, [&](uint32_t j) {
+        const SymVal& h = S.items[j].second;
+        FP d = defined_cond(h);
+        if (d->k == Formula::False) return d;
+        return f_and(d, body(h, h));
+      });
+    unsupported("iteration over this symbolic value", line);
+  }
+  FP fill_tree(const FP& f, const std::function<FP(uint32_t)>& fn) {
+    switch (f->k) {
+      case Formula::Atom: return f->op == -1 ? fn(f->imm) : f;
+      case Formula::And: {
+        FP o = f_true();
+        for (auto& c : f->kids) o = f_and(o, fill_tree(c, fn));
+        return o;
+      }
+      case Formula::Or: {
+        FP o = f_false();
+        for (auto& c : f->kids) o = f_or(o, fill_tree(c, fn));
+        return o;
+      }
+      case Formula::Not: return f_not(fill_tree(f->kids[0], fn));
+      case Formula::Exists: return f_exists(f->scope, fill_tree(f->kids[0], fn));
+      default: return f;
+    }
+  }
+  FP member_cond(const VP& c, const SymVal& S, int line) {
+    return for_each_elem(S, line, [&](const SymVal&, const SymVal& e) { return eq_cond(e, SymVal::conc(c), line); });
+  }
+  FP in_const_cond(const SymVal& e, const VP& set, int line) {
+    if (e.k == SymVal::Conc) return set_find(set, e.v) ? f_true() : f_false();
+    if (e.k == SymVal::Col) return a_in(e.col, set);
+    unsupported("membership of a composite symbolic value", line);
+  }
+  FP a_numcmp(const CP& c, uint32_t cmp, const VP& k, int line) {
+    if (k->t != VT::Num) {
+      // cross-type ordering against a non-number constant: only the rank matters unless the column is the same type
+      unsupported("ordered comparison against a non-numeric parameter", line);
+    }
+    int64_t dummy;
+    if (!num_fits_i64(k->n, &dummy)) unsupported("ordered comparison against a parameter outside int64", line);
+    return f_atom(GK_OP_NUM_CMP, schema_.col_for(c, GK_ENC_VT | GK_ENC_NUM), k, cmp);
+  }
+  FP a_strop(int op, const CP& c, const VP& k) { return f_atom(op, schema_.col_for(c, GK_ENC_VT | GK_ENC_BYTES), k); }
+
+  FP defined_cond(const SymVal& v) {
+    switch (v.k) {
+      case SymVal::Conc: return f_true();
+      case SymVal::Col: return v.col->leaf != Closure::None ? f_true() : a_defined(v.col);
+      case SymVal::Bool: return f_true();
+      case SymVal::Opaque: return v.f ? v.f : f_true();
+      case SymVal::Arr: {
+        FP f = f_true();
+        for (auto& it : v.items) f = f_and(f, f_or(f_not(it.first), defined_cond(it.second)));
+        return f;
+      }
+      case SymVal::ObjLit: {
+        FP f = f_true();
+        for (auto& it : v.fields) f = f_and(f, defined_cond(it.second));
+        return f;
+      }
+      default: return f_true();
+    }
+  }
+
+  FP truthy_cond(const SymVal& v) {
+    switch (v.k) {
+      case SymVal::Conc: return v.v->t == VT::False ? f_false() : f_true();
+      case SymVal::Col: return a_truthy(v.col);
+      case SymVal::Bool: return v.f;
+      case SymVal::Opaque: return v.f ? v.f : f_true();
+      default: return defined_cond(v);
+    }
+  }
+
+  // ------------------------------------------------------------------ concrete evaluation of param-only terms
+  struct Alt {
+    VP val;
+    std::vector<std::pair<int, VP>> binds;
+  };
+  std::vector<Alt> concrete_solve(const TP& term, const LEnv& env) {
+    Env ce;
+    for (auto& b : env.b)
+      if (b.second.k == SymVal::Conc) ce.bind(b.first, b.second.v);
+    size_t base = ce.mark();
+    std::vector<Alt> out;
+    ev_.eval_term(term, ce, [&](const VP& v) {
+      Alt a;
+      a.val = v;
+      for (size_t i = base; i < ce.b.size(); ++i) a.binds.push_back(ce.b[i]);
+      out.push_back(std::move(a));
+      if (out.size() > 4096) throw RegoError{"rego_unsupported: parameter iteration too large"};
+      return false;
+    });
+    return out;
+  }
+
+  // ------------------------------------------------------------------ bodies
+  FP lower_body(const std::vector<Stmt>& body, size_t i, LEnv& env, const BodyK& k) {
+    if (i == body.size()) return k(env);
+    const Stmt& st = body[i];
+    auto rest = [&](LEnv& e) { return lower_body(body, i + 1, e, k); };
+    switch (st.k) {
+      case Stmt::Some: return rest(env);
+      case Stmt::Not: {
+        size_t mk = env.mark();
+        FP inner = lower_expr(st.a, env, [](LEnv&) { return f_true(); });
+        env.undo(mk);
+        FP n = f_not(inner);
+        if (n->k == Formula::False) return n;
+        return f_and(n, rest(env));
+      }
+      case Stmt::Expr: return lower_expr(st.a, env, rest);
+      case Stmt::Assign:
+      case Stmt::Unify: return lower_unify(st.a, st.b, env, rest, st.line);
+      case Stmt::SomeIn:
+        return sym_term(st.c, env, [&](const SymVal& coll) { return iterate(coll, st.a, st.b, env, rest, st.line); });
+    }
+    return f_false();
+  }
+
+  FP lower_expr(const TP& t, LEnv& env, const BodyK& k) {
+    Deps d = deps(t, env, false);
+    if (pure_conc(d)) {
+      FP out = f_false();
+      for (auto& alt : concrete_solve(t, env)) {
+        if (alt.val->t == VT::False) continue;
+        size_t mk = env.mark();
+        for (auto& b : alt.binds) env.bind(b.first, SymVal::conc(b.second, d.param));
+        out = f_or(out, k(env));
+        env.undo(mk);
+      }
+      return out;
+    }
+    return sym_term(t, env, [&](const SymVal& v) {
+      FP c = truthy_cond(v);
+      if (c->k == Formula::False) return c;
+      return f_and(c, k(env));
+    });
+  }
+
+  bool has_unbound(const TP& t, const LEnv& env) const {
+    switch (t->k) {
+      case TK::Var: return unbound(*t, env);
+      case TK::Array:
+      case TK::Set:
+        for (auto& a : t->args)
+          if (has_unbound(a, env)) return true;
+        return false;
+      case TK::Object:
+        for (auto& kv : t->kvs)
+          if (has_unbound(kv.first, env) || has_unbound(kv.second, env)) return true;
+        return false;
+      default: return false;
+    }
+  }
+
+  FP lower_unify(const TP& a, const TP& b, LEnv& env, const BodyK& k, int line) {
+    bool ua = has_unbound(a, env), ub = has_unbound(b, env);
+    if (ua && !ub) return sym_term(b, env, [&](const SymVal& v) { return unify_pattern(a, v, env, k, line); });
+    if (ub && !ua) return sym_term(a, env, [&](const SymVal& v) { return unify_pattern(b, v, env, k, line); });
+    if (ua && ub) unsupported("unification of two non-ground terms", line);
+    return lower_expr(synth_call("equal", {a, b}, line), env, k);
+  }
+
+  FP eq_cond(const SymVal& a, const SymVal& b, int line) {
+    if (a.k == SymVal::Conc && b.k == SymVal::Conc) return v_eq(a.v, b.v) ? f_true() : f_false();
+    if (a.k == SymVal::Col && b.k == SymVal::Conc) return a_eq(a.col, b.v);
+    if (a.k == SymVal::Conc && b.k == SymVal::Col) return a_eq(b.col, a.v);
+    if (a.k == SymVal::Col && b.k == SymVal::Col) return a_truthy(make_call2("equal", a.col, b.col));
+    if (a.k == SymVal::Bool && b.k == SymVal::Conc) {
+      if (b.v->t == VT::True) return a.f;
+      unsupported("comparison of a symbolic boolean with a non-true constant", line);
+    }
+    if (b.k == SymVal::Bool && a.k == SymVal::Conc) return eq_cond(b, a, line);
+    if (a.k == SymVal::Count || b.k == SymVal::Count) return count_cmp(GK_CMP_EQ, a, b, line);
+    unsupported("equality between composite symbolic values", line);
+  }
+
+  FP unify_pattern(const TP& pat, const SymVal& v, LEnv& env, const BodyK& k, int line) {
+    if (pat->k == TK::Var && unbound(*pat, env)) {
+      FP c = defined_cond(v);
+      if (c->k == Formula::False) return c;
+      size_t mk = env.mark();
+      env.bind(pat->vid, v);
+      FP r = f_and(c, k(env));
+      env.undo(mk);
+      return r;
+    }
+    if (!has_unbound(pat, env)) {
+      return sym_term(pat, env, [&](const SymVal& pv) {
+        FP c = eq_cond(pv, v, line);
+        if (c->k == Formula::False) return c;
+        return f_and(c, k(env));
+      });
+    }
+    if (v.k == SymVal::Conc) {
+      // concrete unification of a composite pattern
+      Env ce;
+      for (auto& b : env.b)
+        if (b.second.k == SymVal::Conc) ce.bind(b.first, b.second.v);
+      size_t base = ce.mark();
+      std::vector<std::vector<std::pair<int, VP>>> alts;
+      ev_.unify_val(pat, v.v, ce, [&]() {
+        alts.emplace_back(ce.b.begin() + base, ce.b.end());
+        return false;
+      });
+      FP out = f_false();
+      for (auto& al : alts) {
+        size_t mk = env.mark();
+        for (auto& b : al) env.bind(b.first, SymVal::conc(b.second, v.tainted));
+        out = f_or(out, k(env));
+        env.undo(mk);
+      }
+      return out;
+    }
+    if (pat->k == TK::Object && (v.k == SymVal::ObjLit || v.k == SymVal::Col)) {
+      std::function<FP(size_t)> rec = [&](size_t i) -> FP {
+        if (i == pat->kvs.size()) return k(env);
+        const TP& kt = pat->kvs[i].first;
+        if (kt->k != TK::Scalar) unsupported("non-constant key in object pattern", line);
+        SymVal field;
+        if (v.k == SymVal::ObjLit) {
+          bool found = false;
+          for (auto& f : v.fields)
+            if (v_eq(f.first, kt->val)) {
+              field = f.second;
+              found = true;
+            }
+          if (!found) return f_false();
+        } else {
+          field = SymVal::column(make_dot(v.col, kt->val));
+        }
+        return unify_pattern(pat->kvs[i].second, field, env, [&](LEnv&) { return rec(i + 1); }, line);
+      };
+      if (v.k == SymVal::ObjLit && v.fields.size() != pat->kvs.size()) return f_false();
+      return rec(0);
+    }
+    unsupported("pattern unification against a symbolic value", line);
+  }
+
+  // iterate `coll`, binding key pattern kp (may be null) and value pattern vp
+  FP iterate(const SymVal& coll, const TP& kp, const TP& vp, LEnv& env, const BodyK& k, int line) {
+    auto each = [&](const SymVal& key, const SymVal& val) -> FP {
+      if (kp) return unify_pattern(kp, key, env, [&](LEnv&) { return unify_pattern(vp, val, env, k, line); }, line);
+      return unify_pattern(vp, val, env, k, line);
+    };
+    switch (coll.k) {
+      case SymVal::Conc: {
+        FP out = f_false();
+        const VP& c = coll.v;
+        if (c->t == VT::Arr)
+          for (size_t j = 0; j < c->items.size(); ++j) out = f_or(out, each(SymVal::conc(v_int((long long)j), coll.tainted), SymVal::conc(c->items[j], coll.tainted)));
+        else if (c->t == VT::Set)
+          for (auto& x : c->items) out = f_or(out, each(SymVal::conc(x, coll.tainted), SymVal::conc(x, coll.tainted)));
+        else if (c->t == VT::Obj)
+          for (auto& e : c->kv) out = f_or(out, each(SymVal::conc(e.first, coll.tainted), SymVal::conc(e.second, coll.tainted)));
+        return out;
+      }
+      case SymVal::Col: {
+        int s = schema_.scope_for(coll.col);
+        return f_exists(s, each(SymVal::column(leaf(s, true)), SymVal::column(leaf(s, false))));
+      }
+      case SymVal::Arr: {
+        FP out = f_false();
+        for (size_t j = 0; j < coll.items.size(); ++j)
+          out = f_or(out, f_and(coll.items[j].first, each(SymVal::conc(v_int((long long)j)), coll.items[j].second)));
+        return out;
+      }
+      case SymVal::DiffCS: {
+        FP out = f_false();
+        for (auto& x : coll.v->items) out = f_or(out, f_and(f_not(member_cond(x, *coll.sym, line)), each(SymVal::conc(x, true), SymVal::conc(x, true))));
+        return out;
+      }
+      case SymVal::DiffSC:
+        return for_each_elem(*coll.sym, line, [&](const SymVal&, const SymVal& e) { return f_and(f_not(in_const_cond(e, coll.v, line)), each(e, e)); });
+      case SymVal::SetOf:
+        return for_each_elem(coll, line, [&](const SymVal& kk, const SymVal& e) { return each(kk, e); });
+      default: unsupported("iteration over this symbolic value", line);
+    }
+  }
+
+  // ------------------------------------------------------------------ terms
+  FP sym_term(const TP& t, LEnv& env, const SymK& k) {
+    Deps d = deps(t, env, false);
+    if (pure_conc(d)) {
+      FP out = f_false();
+      for (auto& alt : concrete_solve(t, env)) {
+        size_t mk = env.mark();
+        for (auto& b : alt.binds) env.bind(b.first, SymVal::conc(b.second, d.param));
+        out = f_or(out, k(SymVal::conc(alt.val, d.param)));
+        env.undo(mk);
+      }
+      return out;
+    }
+    if (pure_obj(d) && !(t->k == TK::Call && t->name == "sprintf") && t->k != TK::Array && t->k != TK::Object && t->k != TK::Set) {
+      if (t->k == TK::Var) {
+        if (const SymVal* s = env.find(t->vid)) {
+          SymVal copy = *s;
+          return k(copy);
+        }
+      }
+      return k(SymVal::column(make_closure(t, env)));
+    }
+    switch (t->k) {
+      case TK::Var: {
+        if (const SymVal* s = env.find(t->vid)) {
+          SymVal copy = *s;
+          return k(copy);
+        }
+        if (m_.is_rule(t->name)) return inline_rule_value(t, env, k);
+        if (t->vid == m_.vid_input) unsupported("use of the whole `input` document", t->line);
+        unsupported("unbound variable " + t->name, t->line);
+      }
+      case TK::Ref: return sym_ref(t, env, k);
+      case TK::Call: return sym_call(t, env, k);
+      case TK::Array:
+      case TK::Set: {
+        SymVal arr;
+        arr.k = SymVal::Arr;
+        std::function<FP(size_t)> rec = [&](size_t i) -> FP {
+          if (i == t->args.size()) return k(arr);
+          return sym_term(t->args[i], env, [&](const SymVal& v) {
+            arr.items.emplace_back(f_true(), v);
+            FP r = rec(i + 1);
+            arr.items.pop_back();
+            return r;
+          });
+        };
+        return rec(0);
+      }
+      case TK::Object: {
+        SymVal obj;
+        obj.k = SymVal::ObjLit;
+        std::function<FP(size_t)> rec = [&](size_t i) -> FP {
+          if (i == t->kvs.size()) return k(obj);
+          return sym_term(t->kvs[i].first, env, [&](const SymVal& kv) {
+            if (kv.k != SymVal::Conc) unsupported("symbolic object key", t->line);
+            return sym_term(t->kvs[i].second, env, [&](const SymVal& vv) {
+              obj.fields.emplace_back(kv.v, vv);
+              FP r = rec(i + 1);
+              obj.fields.pop_back();
+              return r;
+            });
+          });
+        };
+        return rec(0);
+      }
+      case TK::ArrCompr: return sym_arr_compr(t, env, k);
+      case TK::SetCompr: return sym_set_compr(t, env, k);
+      default: unsupported("set/object comprehension mixing parameters and object fields", t->line);
+    }
+  }
+
+  // [head | body] whose body mixes parameters and object fields: concrete-length result, symbolic elements
+  FP sym_arr_compr(const TP& t, LEnv& env, const SymK& k) {
+    std::vector<SymVal> vals;
+    size_t mk = env.mark();
+    FP tree = lower_body(t->body, 0, env, [&](LEnv& e) {
+      return sym_term(t->value, e, [&](const SymVal& v) {
+        vals.push_back(v);
+        auto h = std::make_shared<Formula>();
+        h->k = Formula::Atom;
+        h->op = -1;                       // hole marker
+        h->imm = (uint32_t)vals.size() - 1;
+        return FP(h);
+      });
+    });
+    env.undo(mk);
+    SymVal arr;
+    arr.k = SymVal::Arr;
+    for (size_t j = 0; j < vals.size(); ++j) {
+      FP guard = fill_holes(tree, (uint32_t)j, t->line);
+      arr.items.emplace_back(guard, vals[j]);
+    }
+    return k(arr);
+  }
+  // {head | body} whose body mixes parameters and object fields: kept as a formula with one hole per way of
+  // producing an element; membership / emptiness tests substitute the hole (see for_each_elem)
+  FP sym_set_compr(const TP& t, LEnv& env, const SymK& k) {
+    SymVal set;
+    set.k = SymVal::SetOf;
+    size_t mk = env.mark();
+    set.f = lower_body(t->body, 0, env, [&](LEnv& e) {
+      return sym_term(t->value, e, [&](const SymVal& v) {
+        if (v.k != SymVal::Col && v.k != SymVal::Conc) unsupported("set comprehension over composite symbolic values", t->line);
+        set.items.emplace_back(f_true(), v);
+        auto h = std::make_shared<Formula>();
+        h->k = Formula::Atom;
+        h->op = -1;
+        h->imm = (uint32_t)set.items.size() - 1;
+        return FP(h);
+      });
+    });
+    env.undo(mk);
+    return k(set);
+  }
+  FP fill_holes(const FP& f, uint32_t which, int line) {
+    switch (f->k) {
+      case Formula::Atom:
+        if (f->op == -1) return f->imm == which ? f_true() : f_false();
+        return f;
+      case Formula::And: {
+        FP o = f_true();
+        for (auto& c : f->kids) o = f_and(o, fill_holes(c, which, line));
+        return o;
+      }
+      case Formula::Or: {
+        FP o = f_false();
+        for (auto& c : f->kids) o = f_or(o, fill_holes(c, which, line));
+        return o;
+      }
+      case Formula::Not: return f_not(fill_holes(f->kids[0], which, line));
+      case Formula::Exists: unsupported("comprehension over an object collection mixed with parameters", line);
+      default: return f;
+    }
+  }
+
+  // complete rule referenced by name whose definition mixes parameters and object fields
+  FP inline_rule_value(const TP& t, LEnv& env, const SymK& k) {
+    auto& defs = m_.rules.at(t->name);
+    if (defs[0].kind != Rule::Complete) unsupported("partial rule `" + t->name + "` used as a value while mixing parameters and object fields", t->line);
+    if (++depth_ > 24) unsupported("rule nesting too deep", t->line);
+    FP out = f_false();
+    for (auto& r : defs) {
+      if (r.is_default || !r.els.empty()) unsupported("default/else rule mixing parameters and object fields", r.line);
+      LEnv fe;
+      out = f_or(out, lower_body(r.body, 0, fe, [&](LEnv& e) { return sym_term(r.value, e, k); }));
+    }
+    --depth_;
+    return out;
+  }
+
+  FP sym_ref(const TP& t, LEnv& env, const SymK& k) {
+    // partial set/object rule that mixes parameters and object fields: inline its definitions
+    if (t->head->k == TK::Var && !env.find(t->head->vid) && m_.is_rule(t->head->name)) {
+      auto& defs = m_.rules.at(t->head->name);
+      Deps rd = rule_deps(t->head->name);
+      if ((defs[0].kind == Rule::PSet || defs[0].kind == Rule::PObj) && !(pure_obj(rd) || pure_conc(rd))) return inline_partial(t, env, k);
+    }
+    // longest prefix that is purely parameters or purely object
+    for (size_t j = t->args.size(); j-- > 0;) {
+      TP prefix = j == 0 ? t->head : synth_ref(t->head, std::vector<TP>(t->args.begin(), t->args.begin() + j), t->line);
+      Deps d = deps(prefix, env, false);
+      if (d.iter) continue;
+      if (pure_conc(d) || pure_obj(d) || j == 0) {
+        return sym_term(prefix, env, [&](const SymVal& base) { return walk_sym(base, t->args, j, env, k, t->line); });
+      }
+    }
+    unsupported("reference", t->line);
+  }
+
+  FP inline_partial(const TP& t, LEnv& env, const SymK& k) {
+    auto& defs = m_.rules.at(t->head->name);
+    if (t->args.empty()) unsupported("partial rule used as a whole value", t->line);
+    if (++depth_ > 24) unsupported("rule nesting too deep", t->line);
+    const TP& p0 = t->args[0];
+    FP out = f_false();
+    for (auto& r : defs) {
+      LEnv fe;
+      // pre-bind head variables from constant parts of the call-site pattern (a filter on the head var)
+      if (p0->k == TK::Object && r.key->k == TK::Object) {
+        for (auto& pk : p0->kvs)
+          for (auto& rk : r.key->kvs)
+            if (pk.first->k == TK::Scalar && rk.first->k == TK::Scalar && v_eq(pk.first->val, rk.first->val) &&
+                pk.second->k == TK::Scalar && rk.second->k == TK::Var && unbound(*rk.second, fe))
+              fe.bind(rk.second->vid, SymVal::conc(pk.second->val));
+      }
+      FP f = lower_body(r.body, 0, fe, [&](LEnv& e) {
+        return sym_term(r.key, e, [&](const SymVal& kv) {
+          auto cont = [&](LEnv&) {
+            if (defs[0].kind == Rule::PObj) return sym_term(r.value, e, [&](const SymVal& vv) { return walk_sym(vv, t->args, 1, env, k, t->line); });
+            return walk_sym(kv, t->args, 1, env, k, t->line);
+          };
+          return unify_pattern(p0, kv, env, cont, t->line);
+        });
+      });
+      out = f_or(out, f);
+    }
+    --depth_;
+    return out;
+  }
+
+  FP walk_sym(const SymVal& cur, const std::vector<TP>& path, size_t i, LEnv& env, const SymK& k, int line) {
+    if (i == path.size()) return k(cur);
+    const TP& p = path[i];
+    auto next = [&](const SymVal& v) { return walk_sym(v, path, i + 1, env, k, line); };
+    if (has_unbound(p, env)) {
+      // iteration (plain variable / wildcard) or pattern key
+      TP keypat = p;
+      return iterate_keyed(cur, keypat, env, next, line);
+    }
+    return sym_term(p, env, [&](const SymVal& kv) -> FP {
+      switch (cur.k) {
+        case SymVal::Conc: {
+          if (kv.k == SymVal::Conc) {
+            VP got;
+            const VP& c = cur.v;
+            if (c->t == VT::Obj) got = obj_get(c, kv.v);
+            else if (c->t == VT::Arr) {
+              int64_t ix;
+              if (kv.v->t == VT::Num && num_fits_i64(kv.v->n, &ix) && ix >= 0 && (size_t)ix < c->items.size()) got = c->items[ix];
+            } else if (c->t == VT::Set) got = set_find(c, kv.v);
+            if (!got) return f_false();
+            return next(SymVal::conc(got, cur.tainted || kv.tainted));
+          }
+          if (kv.k == SymVal::Col && cur.v->t == VT::Set) {
+            FP c = a_in(kv.col, cur.v);
+            if (c->k == Formula::False) return c;
+            return f_and(c, next(kv));
+          }
+          if (kv.k == SymVal::Col && cur.v->t == VT::Obj) {
+            // obj[col]: value depends on which key matched -> one alternative per key
+            FP out = f_false();
+            for (auto& e : cur.v->kv) out = f_or(out, f_and(a_eq(kv.col, e.first), next(SymVal::conc(e.second, cur.tainted))));
+            return out;
+          }
+          unsupported("index of a constant by a symbolic value", line);
+        }
+        case SymVal::Col: {
+          if (kv.k == SymVal::Conc) return next(SymVal::column(make_dot(cur.col, kv.v)));
+          if (kv.k == SymVal::Col) {
+            LEnv e;
+            e.bind(vid_cur_, cur);
+            e.bind(vid_key_, kv);
+            return next(SymVal::column(make_closure(synth_ref(synth_var(vid_cur_, "$cur"), {synth_var(vid_key_, "$key")}, line), e)));
+          }
+          unsupported("index of an object field by a mixed value", line);
+        }
+        case SymVal::ObjLit: {
+          if (kv.k != SymVal::Conc) unsupported("symbolic key into object literal", line);
+          for (auto& f : cur.fields)
+            if (v_eq(f.first, kv.v)) return next(f.second);
+          return f_false();
+        }
+        case SymVal::Arr: {
+          int64_t ix;
+          if (kv.k != SymVal::Conc || kv.v->t != VT::Num || !num_fits_i64(kv.v->n, &ix)) unsupported("symbolic index", line);
+          if (ix < 0 || (size_t)ix >= cur.items.size()) return f_false();
+          // positions shift when guards are false: only exact when every earlier guard is constant true
+          for (int64_t j = 0; j <= ix; ++j)
+            if (cur.items[j].first->k != Formula::True) unsupported("index into a conditionally-built array", line);
+          return next(cur.items[ix].second);
+        }
+        case SymVal::DiffCS: {
+          if (kv.k != SymVal::Conc) unsupported("symbolic membership in a set difference", line);
+          if (!set_find(cur.v, kv.v)) return f_false();
+          return f_and(f_not(member_cond(kv.v, *cur.sym, line)), next(kv));
+        }
+        default: unsupported("reference into this symbolic value", line);
+      }
+    });
+  }
+
+  // x[p] where p contains unbound variables: iterate x and unify p with each key (sets: the element)
+  FP iterate_keyed(const SymVal& cur, const TP& keypat, LEnv& env, const SymK& next, int line) {
+    auto each = [&](const SymVal& key, const SymVal& val) -> FP {
+      return unify_pattern(keypat, key, env, [&](LEnv&) { return next(val); }, line);
+    };
+    switch (cur.k) {
+      case SymVal::Conc: {
+        FP out = f_false();
+        const VP& c = cur.v;
+        if (c->t == VT::Arr)
+          for (size_t j = 0; j < c->items.size(); ++j) out = f_or(out, each(SymVal::conc(v_int((long long)j), cur.tainted), SymVal::conc(c->items[j], cur.tainted)));
+        else if (c->t == VT::Set)
+          for (auto& x : c->items) out = f_or(out, each(SymVal::conc(x, cur.tainted), SymVal::conc(x, cur.tainted)));
+        else if (c->t == VT::Obj)
+          for (auto& e : c->kv) out = f_or(out, each(SymVal::conc(e.first, cur.tainted), SymVal::conc(e.second, cur.tainted)));
+        return out;
+      }
+      case SymVal::Col: {
+        int s = schema_.scope_for(cur.col);
+        return f_exists(s, each(SymVal::column(leaf(s, true)), SymVal::column(leaf(s, false))));
+      }
+      case SymVal::Arr: {
+        FP out = f_false();
+        for (size_t j = 0; j < cur.items.size(); ++j) {
+          if (cur.items[j].first->k != Formula::True && keypat->k == TK::Var && keypat->name[0] != '$')
+            unsupported("index variable over a conditionally-built array", line);
+          out = f_or(out, f_and(cur.items[j].first, each(SymVal::conc(v_int((long long)j)), cur.items[j].second)));
+        }
+        return out;
+      }
+      case SymVal::DiffCS: {
+        FP out = f_false();
+        for (auto& x : cur.v->items) out = f_or(out, f_and(f_not(member_cond(x, *cur.sym, line)), each(SymVal::conc(x, true), SymVal::conc(x, true))));
+        return out;
+      }
+      case SymVal::DiffSC:
+        return for_each_elem(*cur.sym, line, [&](const SymVal&, const SymVal& e) { return f_and(f_not(in_const_cond(e, cur.v, line)), each(e, e)); });
+      case SymVal::SetOf:
+        return for_each_elem(cur, line, [&](const SymVal& kk, const SymVal& e) { return each(kk, e); });
+      default: unsupported("iteration over this symbolic value", line);
+    }
+  }
+
+  // ------------------------------------------------------------------ calls
+  FP sym_call(const TP& t, LEnv& env, const SymK& k) {
+    auto rit = m_.rules.find(t->name);
+    bool user = rit != m_.rules.end();
+    if (user && rit->second[0].kind != Rule::Func) throw RegoError{"rego_type_error: " + t->name + " is not a function"};
+    size_t nformal = user ? rit->second[0].args.size() : t->args.size();
+    if (user && t->args.size() != nformal) unsupported("function call with output argument", t->line);
+    std::vector<SymVal> args;
+    std::function<FP(size_t)> rec = [&](size_t i) -> FP {
+      if (i == t->args.size()) return user ? inline_function(t, args, k) : builtin_sym(t, args, k);
+      return sym_term(t->args[i], env, [&](const SymVal& v) {
+        args.push_back(v);
+        FP r = rec(i + 1);
+        args.pop_back();
+        return r;
+      });
+    };
+    return rec(0);
+  }
+
+  FP inline_function(const TP& t, const std::vector<SymVal>& args, const SymK& k) {
+    if (++depth_ > 24) unsupported("function nesting too deep (recursion?)", t->line);
+    FP out = f_false();
+    for (auto& r : m_.rules.at(t->name)) {
+      if (r.args.size() != args.size()) continue;
+      if (!r.els.empty()) unsupported("`else` in a function that mixes parameters and object fields", r.line);
+      LEnv fe;
+      std::function<FP(size_t)> bind = [&](size_t i) -> FP {
+        if (i == args.size()) return lower_body(r.body, 0, fe, [&](LEnv& e) { return sym_term(r.value, e, k); });
+        return unify_pattern(r.args[i], args[i], fe, [&](LEnv&) { return bind(i + 1); }, r.line);
+      };
+      out = f_or(out, bind(0));
+      check_size(out, t->line);
+    }
+    --depth_;
+    return out;
+  }
+
+  static uint32_t flip_cmp(uint32_t c) {
+    switch (c) {
+      case GK_CMP_LT: return GK_CMP_GT;
+      case GK_CMP_LE: return GK_CMP_GE;
+      case GK_CMP_GT: return GK_CMP_LT;
+      case GK_CMP_GE: return GK_CMP_LE;
+      default: return c;
+    }
+  }
+
+  // count(X) <cmp> n  (X symbolic collection, n constant) or flipped
+  FP count_cmp(uint32_t cmp, const SymVal& a, const SymVal& b, int line) {
+    if (a.k != SymVal::Count) {
+      if (b.k != SymVal::Count) unsupported("count comparison", line);
+      return count_cmp(flip_cmp(cmp), b, a, line);
+    }
+    if (b.k != SymVal::Conc || b.v->t != VT::Num) unsupported("count compared with a non-constant", line);
+    int64_t n;
+    if (!num_fits_i64(b.v->n, &n)) unsupported("count compared with a huge constant", line);
+    const SymVal& x = a.items[0].second;
+    // normalise to: at-least(k) / at-most(k) / exactly(k)
+    std::vector<FP> bools;
+    bool scoped = false;
+    FP any_scoped;
+    if (x.k == SymVal::DiffCS) {
+      for (auto& c : x.v->items) bools.push_back(f_not(member_cond(c, *x.sym, line)));
+    } else if (x.k == SymVal::Arr) {
+      for (auto& it : x.items) bools.push_back(it.first);
+    } else if (x.k == SymVal::DiffSC) {
+      scoped = true;
+      any_scoped = for_each_elem(*x.sym, line, [&](const SymVal&, const SymVal& e) { return f_not(in_const_cond(e, x.v, line)); });
+    } else if (x.k == SymVal::SetOf) {
+      scoped = true;
+      any_scoped = for_each_elem(x, line, [&](const SymVal&, const SymVal&) { return f_true(); });
+    } else if (x.k == SymVal::Col) {
+      return a_numcmp(make_call1("count", x.col), cmp, b.v, line);
+    } else {
+      unsupported("count of this symbolic value", line);
+    }
+    auto any = [&]() -> FP {
+      if (scoped) return any_scoped;
+      FP o = f_false();
+      for (auto& f : bools) o = f_or(o, f);
+      return o;
+    };
+    auto all = [&]() -> FP {
+      FP o = f_true();
+      for (auto& f : bools) o = f_and(o, f);
+      return o;
+    };
+    int64_t total = scoped ? -1 : (int64_t)bools.size();
+    // count in [0, total]
+    switch (cmp) {
+      case GK_CMP_GT:
+        if (n < 0) return f_true();
+        if (n == 0) return any();
+        if (!scoped && n >= total) return f_false();
+        if (!scoped && n == total - 1) return all();
+        break;
+      case GK_CMP_GE:
+        if (n <= 0) return f_true();
+        if (n == 1) return any();
+        if (!scoped && n > total) return f_false();
+        if (!scoped && n == total) return all();
+        break;
+      case GK_CMP_LT:
+        if (n <= 0) return f_false();
+        if (n == 1) return f_not(any());
+        if (!scoped && n > total) return f_true();
+        if (!scoped && n == total) return f_not(all());
+        break;
+      case GK_CMP_LE:
+        if (n < 0) return f_false();
+        if (n == 0) return f_not(any());
+        if (!scoped && n >= total) return f_true();
+        if (!scoped && n == total - 1) return f_not(all());
+        break;
+      case GK_CMP_EQ:
+        if (n < 0) return f_false();
+        if (n == 0) return f_not(any());
+        if (!scoped && n > total) return f_false();
+        if (!scoped && n == total) return all();
+        break;
+      case GK_CMP_NE:
+        if (n < 0) return f_true();
+        if (n == 0) return any();
+        if (!scoped && n > total) return f_true();
+        if (!scoped && n == total) return f_not(all());
+        break;
+    }
+    unsupported("count compared with a constant other than 0 / the full size", line);
+  }
+
+  FP builtin_sym(const TP& t, const std::vector<SymVal>& a, const SymK& k) {
+    const std::string& n = t->name;
+    const int line = t->line;
+    auto is_conc = [](const SymVal& s) { return s.k == SymVal::Conc; };
+    auto is_col = [](const SymVal& s) { return s.k == SymVal::Col; };
+    auto ret_bool = [&](FP f) { return k(SymVal::boolean(std::move(f))); };
+
+    if (n == "print" || n == "trace") return k(SymVal::conc(v_bool(true)));
+    if (n == "sprintf") {
+      FP def = f_true();
+      for (auto& x : a) def = f_and(def, defined_cond(x));
+      if (def->k == Formula::False) return def;
+      return k(SymVal::opaque(def));
+    }
+    if (n == "equal" && a.size() == 2) return ret_bool(eq_cond(a[0], a[1], line));
+    if (n == "neq" && a.size() == 2) {
+      if (a[0].k == SymVal::Count || a[1].k == SymVal::Count) return ret_bool(count_cmp(GK_CMP_NE, a[0], a[1], line));
+      FP eq = eq_cond(a[0], a[1], line);
+      // `x != y` is undefined (not true) when an operand is undefined
+      return ret_bool(f_and(f_and(defined_cond(a[0]), defined_cond(a[1])), f_not(eq)));
+    }
+    if ((n == "lt" || n == "lte" || n == "gt" || n == "gte") && a.size() == 2) {
+      uint32_t cmp = n == "lt" ? GK_CMP_LT : n == "lte" ? GK_CMP_LE : n == "gt" ? GK_CMP_GT : GK_CMP_GE;
+      if (a[0].k == SymVal::Count || a[1].k == SymVal::Count) return ret_bool(count_cmp(cmp, a[0], a[1], line));
+      if (is_col(a[0]) && is_conc(a[1])) return ret_bool(a_numcmp(a[0].col, cmp, a[1].v, line));
+      if (is_conc(a[0]) && is_col(a[1])) return ret_bool(a_numcmp(a[1].col, flip_cmp(cmp), a[0].v, line));
+      if (is_col(a[0]) && is_col(a[1])) return ret_bool(a_truthy(make_call2(n, a[0].col, a[1].col)));
+      unsupported("ordered comparison of composite symbolic values", line);
+    }
+    if (n == "count" && a.size() == 1) {
+      SymVal c;
+      c.k = SymVal::Count;
+      c.items.emplace_back(f_true(), a[0]);
+      if (a[0].k == SymVal::Opaque || a[0].k == SymVal::Bool || a[0].k == SymVal::ObjLit) unsupported("count of this value", line);
+      return k(c);
+    }
+    if (n == "minus" && a.size() == 2) {
+      auto is_symset = [](const SymVal& s) { return s.k == SymVal::Col || s.k == SymVal::SetOf; };
+      if (is_conc(a[0]) && a[0].v->t == VT::Set && is_symset(a[1])) {
+        SymVal d;
+        d.k = SymVal::DiffCS;
+        d.v = a[0].v;
+        d.sym = std::make_shared<SymVal>(a[1]);
+        return k(d);
+      }
+      if (is_symset(a[0]) && is_conc(a[1]) && a[1].v->t == VT::Set) {
+        SymVal d;
+        d.k = SymVal::DiffSC;
+        d.v = a[1].v;
+        d.sym = std::make_shared<SymVal>(a[0]);
+        return k(d);
+      }
+      unsupported("arithmetic mixing parameters and object fields", line);
+    }
+    if ((n == "startswith" || n == "endswith" || n == "contains") && a.size() == 2) {
+      int op = n == "startswith" ? GK_OP_PREFIX : n == "endswith" ? GK_OP_SUFFIX : GK_OP_CONTAINS;
+      if (is_col(a[0]) && is_conc(a[1])) {
+        if (a[1].v->t != VT::Str) return k(SymVal::boolean(f_false()));   // type error => undefined
+        return ret_bool(a_strop(op, a[0].col, a[1].v));
+      }
+      unsupported(n + " with a symbolic second operand", line);
+    }
+    if ((n == "strings.any_prefix_match" || n == "strings.any_suffix_match") && a.size() == 2) {
+      if (is_col(a[0]) && is_conc(a[1])) {
+        std::vector<VP> pats;
+        const VP& b = a[1].v;
+        if (b->t == VT::Str) pats.push_back(b);
+        else if (b->t == VT::Arr || b->t == VT::Set) {
+          for (auto& x : b->items) {
+            if (x->t != VT::Str) return k(SymVal::boolean(f_false()));
+            pats.push_back(x);
+          }
+        } else {
+          return k(SymVal::boolean(f_false()));
+        }
+        if (pats.empty()) return ret_bool(f_false());
+        return ret_bool(a_strop(n == "strings.any_prefix_match" ? GK_OP_ANYPREFIX : GK_OP_ANYSUFFIX, a[0].col, v_arr(pats)));
+      }
+      unsupported(n + " with a symbolic pattern list", line);
+    }
+    if (n == "any" && a.size() == 1) {
+      if (a[0].k != SymVal::Arr) unsupported("any() of this value", line);
+      FP o = f_false();
+      for (auto& it : a[0].items) {
+        FP e;
+        if (it.second.k == SymVal::Bool) e = it.second.f;
+        else if (it.second.k == SymVal::Conc) e = it.second.v->t == VT::True ? f_true() : f_false();
+        else if (it.second.k == SymVal::Col) e = f_atom(GK_OP_VTMASK, schema_.col_for(it.second.col, GK_ENC_VT), nullptr, 1u << GK_VT_TRUE);
+        else unsupported("any() over non-boolean symbolic elements", line);
+        o = f_or(o, f_and(it.first, e));
+      }
+      return ret_bool(o);
+    }
+    if (n == "internal.member_2" && a.size() == 2) {
+      if (is_col(a[0]) && is_conc(a[1])) {
+        std::vector<VP> vals;
+        if (a[1].v->t == VT::Obj)
+          for (auto& e : a[1].v->kv) vals.push_back(e.second);
+        else if (a[1].v->t == VT::Arr || a[1].v->t == VT::Set) vals = a[1].v->items;
+        return ret_bool(f_and(a_defined(a[0].col), a_in(a[0].col, v_set(vals))));
+      }
+      if (is_conc(a[0]) && (is_col(a[1]) || a[1].k == SymVal::SetOf)) return ret_bool(member_cond(a[0].v, a[1], line));
+      unsupported("`in` over this symbolic value", line);
+    }
+    if (n == "re_match" || n == "regex.match") unsupported("regular expression over an object field with a parameter-dependent pattern", line);
+    unsupported("builtin " + n + " mixing parameters and object fields", line);
+  }
+};
+
+void Lowerer::subst_print(const Term& t, const std::map<int, std::string>& sub, std::string& out) {
+  // term_str with captured variables replaced by their canonical keys
+  if (t.k == TK::Var) {
+    auto it = sub.find(t.vid);
+    out += it != sub.end() ? it->second : t.name;
+    return;
+  }
+  if (sub.empty()) {
+    out += term_str(t);
+    return;
+  }
+  // structural print (mirrors term_str) so nested vars are substituted
+  switch (t.k) {
+    case TK::Scalar: out += fmt_value(t.val, false); break;
+    case TK::Ref:
+      subst_print(*t.head, sub, out);
+      for (auto& a : t.args) {
+        out.push_back('[');
+        subst_print(*a, sub, out);
+        out.push_back(']');
+      }
+      break;
+    case TK::Call:
+      out += t.name + "(";
+      for (size_t i = 0; i < t.args.size(); ++i) {
+        if (i) out += ", ";
+        subst_print(*t.args[i], sub, out);
+      }
+      out += ")";
+      break;
+    case TK::Array:
+    case TK::Set:
+      out += t.k == TK::Array ? "[" : "{";
+      for (size_t i = 0; i < t.args.size(); ++i) {
+        if (i) out += ", ";
+        subst_print(*t.args[i], sub, out);
+      }
+      out += t.k == TK::Array ? "]" : "}";
+      break;
+    case TK::Object:
+      out += "{";
+      for (size_t i = 0; i < t.kvs.size(); ++i) {
+        if (i) out += ", ";
+        subst_print(*t.kvs[i].first, sub, out);
+        out += ": ";
+        subst_print(*t.kvs[i].second, sub, out);
+      }
+      out += "}";
+      break;
+    default: {
+      // comprehensions: print head/body with substitution
+      out += t.k == TK::ArrCompr ? "[" : "{";
+      if (t.key) {
+        subst_print(*t.key, sub, out);
+        out += ": ";
+      }
+      subst_print(*t.value, sub, out);
+      out += " | ";
+      for (size_t i = 0; i < t.body.size(); ++i) {
+        const Stmt& s = t.body[i];
+        if (i) out += "; ";
+        if (s.k == Stmt::Not) out += "not ";
+        if (s.k == Stmt::Some) out += "some";
+        if (s.a) subst_print(*s.a, sub, out);
+        if (s.k == Stmt::Assign) out += " := ";
+        if (s.k == Stmt::Unify) out += " = ";
+        if (s.k == Stmt::SomeIn) out += " <- ";
+        if (s.b) subst_print(*s.b, sub, out);
+        if (s.c) {
+          out += " in ";
+          subst_print(*s.c, sub, out);
+        }
+      }
+      out += t.k == TK::ArrCompr ? "]" : "}";
+    }
+  }
+}
+
+}  // namespace
+
+FP lower_violation(const std::shared_ptr<const Module>& mod, const VP& parameters, Schema& schema) {
+  Lowerer lw(mod, parameters, schema);
+  return lw.run();
+}
+
+// ====================================================================================== code generation
+uint32_t ProgramBuilder::add_bytes(const std::string& s) {
+  uint32_t off = (uint32_t)cbytes.size();
+  cbytes.insert(cbytes.end(), s.begin(), s.end());
+  return off;
+}
+
+namespace {
+struct Gen {
+  ProgramBuilder& pb;
+  std::vector<int> label_pc;                // label -> pc (or -1)
+  std::vector<int> open;                    // open scopes (slot = index + 1)
+  size_t base;
+  static constexpr uint32_t LBL = 0x8000u;  // label ids are encoded as LBL | id until patched
+
+  int new_label() {
+    label_pc.push_back(-1);
+    return (int)label_pc.size() - 1;
+  }
+  void bind(int l) { label_pc[l] = (int)pb.instr.size(); }
+  uint32_t enc(int target) { return target < 0 ? (target == -1 ? GK_PC_ACCEPT : GK_PC_REJECT) : (LBL | (uint32_t)target); }
+  // targets: >=0 label id; -1 accept; -2 reject
+  void emit(uint32_t op, uint32_t slot, uint32_t col, uint32_t w1, int lt, int lf, uint32_t w3) {
+    GkInstr in;
+    in.w0 = op | (slot << 8) | (col << 16);
+    in.w1 = w1;
+    in.w2 = enc(lt) | (enc(lf) << 16);
+    in.w3 = w3;
+    pb.instr.push_back(in);
+  }
+  uint32_t slot_of(int scope) {
+    if (scope == 0) return 0;
+    for (size_t i = 0; i < open.size(); ++i)
+      if (open[i] == scope) return (uint32_t)i + 1;
+    throw RegoError{"internal: column scope is not open in the generated loop nest"};
+  }
+  void gen(const FP& f, int lt, int lf) {
+    switch (f->k) {
+      case Formula::True: emit(GK_OP_JMP, 0, 0, 0, lt, lt, 0); break;
+      case Formula::False: emit(GK_OP_JMP, 0, 0, 0, lf, lf, 0); break;
+      case Formula::Not: gen(f->kids[0], lf, lt); break;
+      case Formula::And:
+        for (size_t i = 0; i < f->kids.size(); ++i) {
+          if (i + 1 == f->kids.size()) gen(f->kids[i], lt, lf);
+          else {
+            int mid = new_label();
+            gen(f->kids[i], mid, lf);
+            bind(mid);
+          }
+        }
+        break;
+      case Formula::Or:
+        for (size_t i = 0; i < f->kids.size(); ++i) {
+          if (i + 1 == f->kids.size()) gen(f->kids[i], lt, lf);
+          else {
+            int mid = new_label();
+            gen(f->kids[i], lt, mid);
+            bind(mid);
+          }
+        }
+        break;
+      case Formula::Exists: {
+        const ScopeDef& sd = pb.schema->scopes[f->scope];
+        uint32_t pslot = slot_of(sd.parent);
+        uint32_t slot = (uint32_t)open.size() + 1;
+        if (slot > GK_MAX_LOOP_DEPTH) throw RegoError{"rego_unsupported: loop nest deeper than " + std::to_string(GK_MAX_LOOP_DEPTH)};
+        int ltest = new_label(), lbody = new_label(), lnext = new_label();
+        emit(GK_OP_LOOP_BEGIN, slot, pslot, (uint32_t)f->scope, ltest, ltest, 0);
+        bind(ltest);
+        emit(GK_OP_LOOP_TEST, slot, 0, 0, lbody, lf, 0);
+        bind(lbody);
+        open.push_back(f->scope);
+        gen(f->kids[0], lt, lnext);
+        open.pop_back();
+        bind(lnext);
+        emit(GK_OP_LOOP_NEXT, slot, 0, 0, ltest, ltest, 0);
+        break;
+      }
+      case Formula::Atom: {
+        const ColDef& cd = pb.schema->cols[f->col];
+        uint32_t slot = slot_of(cd.scope);
+        uint32_t w1 = 0, w3 = 0;
+        switch (f->op) {
+          case GK_OP_TRUTHY:
+          case GK_OP_DEFINED: break;
+          case GK_OP_VTMASK: w1 = f->imm; break;
+          case GK_OP_SID_EQ: w1 = pb.interner->intern(intern_key(f->cval)); break;
+          case GK_OP_SID_IN: {
+            std::vector<uint32_t> ids;
+            for (auto& x : f->cval->items) ids.push_back(pb.interner->intern(intern_key(x)));
+            std::sort(ids.begin(), ids.end());
+            ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
+            w1 = (uint32_t)pb.pool.size();
+            w3 = (uint32_t)ids.size();
+            pb.pool.insert(pb.pool.end(), ids.begin(), ids.end());
+            break;
+          }
+          case GK_OP_NUM_CMP: {
+            int64_t k = 0;
+            num_fits_i64(f->cval->n, &k);
+            w1 = (uint32_t)pb.pool.size();
+            pb.pool.push_back((uint32_t)((uint64_t)k & 0xffffffffu));
+            pb.pool.push_back((uint32_t)((uint64_t)k >> 32));
+            w3 = f->imm;
+            break;
+          }
+          case GK_OP_PREFIX:
+          case GK_OP_SUFFIX:
+          case GK_OP_CONTAINS:
+            w1 = pb.add_bytes(f->cval->s);
+            w3 = (uint32_t)f->cval->s.size();
+            break;
+          case GK_OP_ANYPREFIX:
+          case GK_OP_ANYSUFFIX: {
+            std::vector<uint32_t> ent;
+            for (auto& x : f->cval->items) {
+              ent.push_back(pb.add_bytes(x->s));
+              ent.push_back((uint32_t)x->s.size());
+            }
+            w1 = (uint32_t)pb.pool.size();
+            w3 = (uint32_t)f->cval->items.size();
+            pb.pool.insert(pb.pool.end(), ent.begin(), ent.end());
+            break;
+          }
+          default: throw RegoError{"internal: unknown atom"};
+        }
+        emit((uint32_t)f->op, slot, (uint32_t)f->col, w1, lt, lf, w3);
+        break;
+      }
+    }
+  }
+  void patch() {
+    auto fix = [&](uint32_t t) -> uint32_t {
+      if (t == GK_PC_ACCEPT || t == GK_PC_REJECT) return t;
+      int pc = label_pc[t & ~LBL];
+      if (pc < 0) throw RegoError{"internal: unbound label"};
+      return (uint32_t)pc;
+    };
+    for (size_t i = base; i < pb.instr.size(); ++i) {
+      uint32_t w2 = pb.instr[i].w2;
+      pb.instr[i].w2 = fix(w2 & 0xffffu) | (fix(w2 >> 16) << 16);
+    }
+  }
+};
+}  // namespace
+
+uint32_t ProgramBuilder::emit(const FP& f) {
+  if (f->k == Formula::True) return GK_PC_ACCEPT;
+  if (f->k == Formula::False) return GK_PC_REJECT;
+  Gen g{*this, {}, {}, instr.size()};
+  uint32_t entry = (uint32_t)instr.size();
+  g.gen(f, -1, -2);
+  g.patch();
+  if (instr.size() >= 0x7ff0u) throw RegoError{"rego_unsupported: predicate table exceeds 32k instructions"};
+  // peephole: thread jumps through unconditional JMPs
+  for (size_t i = entry; i < instr.size(); ++i) {
+    auto thread = [&](uint32_t t) {
+      int guard = 0;
+      while (t < GK_PC_REJECT && (instr[t].w0 & 0xffu) == GK_OP_JMP && ++guard < 64) t = instr[t].w2 & 0xffffu;
+      return t;
+    };
+    uint32_t w2 = instr[i].w2;
+    instr[i].w2 = thread(w2 & 0xffffu) | (thread(w2 >> 16) << 16);
+  }
+  while (entry < instr.size() && (instr[entry].w0 & 0xffu) == GK_OP_JMP) {
+    uint32_t t = instr[entry].w2 & 0xffffu;
+    if (t >= GK_PC_REJECT) return t;
+    entry = t;
+  }
+  return entry;
+}
+
+void ProgramBuilder::gen(const FP&, uint32_t, uint32_t, std::vector<int>&) {}
+uint32_t ProgramBuilder::gen_to(const FP&, uint32_t, uint32_t, std::vector<int>&) { return 0; }
+
+}  // namespace gk

@@ -1,0 +1,111 @@
+// Ahead-of-time lowering: (template Rego, constraint parameters) -> flat predicate program + column schema.
+//
+// At AddConstraint time `input.parameters` is a constant, so the template's `violation` rule is partially
+// evaluated with parameters concrete and `input.review` symbolic:
+//   * sub-terms that depend only on parameters are folded by the concrete evaluator;
+//   * sub-terms that depend only on the object become *closures*: parameter-independent feature columns
+//     that the flattener extracts once per object (or per iterated element) and lays out column-wise;
+//   * iteration over object collections (`spec.containers[_]`) becomes an EXISTS over a CSR scope;
+//   * every comparison / membership / prefix test that mixes a column with a parameter constant becomes a
+//     device atom; boolean structure (rule bodies = AND, multiple definitions = OR, `not`) becomes the
+//     formula tree that is compiled to jump-threaded instructions (program.h).
+// Anything outside this scheme is rejected with a rego_unsupported error -- there is no fallback path.
+#pragma once
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "program.h"
+#include "rego.hpp"
+
+namespace gk {
+
+struct Closure;
+using CP = std::shared_ptr<const Closure>;
+
+struct CapArg {
+  enum K : uint8_t { Conc, Col } k = Conc;
+  VP v;
+  CP col;
+};
+
+struct Closure {
+  enum Leaf : uint8_t { None, Elem, Key } leaf = None;   // Elem/Key: the element / key of scope `scope`
+  std::shared_ptr<const Module> mod;
+  TP term;
+  std::vector<std::pair<int, CapArg>> caps;             // captured variables (vid -> value)
+  int scope = 0;                                         // innermost scope the value depends on (0 = root)
+  std::string key;                                       // canonical text: dedupes columns across constraints
+};
+
+struct ScopeDef {
+  int parent = 0;
+  CP gen;          // closure producing the iterated collection (evaluated per parent row); null for root
+  int depth = 0;
+};
+
+struct ColDef {
+  CP expr;
+  int scope = 0;
+  uint32_t enc = 0;
+};
+
+// The column/scope schema shared by every constraint of an engine (rebuilt on each compile).
+struct Schema {
+  std::vector<ScopeDef> scopes;   // [0] = root
+  std::vector<ColDef> cols;
+  std::map<std::string, int> scope_ix, col_ix;
+  Schema() { scopes.emplace_back(); }
+  int scope_for(const CP& gen);
+  int col_for(const CP& expr, uint32_t enc);
+};
+
+// ---- formula tree
+struct Formula;
+using FP = std::shared_ptr<const Formula>;
+struct Formula {
+  enum K : uint8_t { True, False, And, Or, Not, Exists, Atom } k = True;
+  std::vector<FP> kids;
+  int scope = 0;          // Exists
+  // Atom:
+  int op = 0;             // GK_OP_*
+  int col = -1;           // schema column
+  VP cval;                // constant operand (string / number / set / list)
+  uint32_t imm = 0;       // VTMASK mask / compare op
+};
+FP f_true();
+FP f_false();
+FP f_and(FP a, FP b);
+FP f_or(FP a, FP b);
+FP f_not(FP a);
+FP f_exists(int scope, FP body);
+std::string formula_str(const FP& f, const Schema& s);
+size_t formula_size(const FP& f);
+
+// Interns strings/values for SID columns and constants (engine-global, append-only).
+struct Interner {
+  virtual ~Interner() {}
+  virtual uint32_t intern(const std::string& key) = 0;
+};
+
+// Lower one constraint's violation predicate.  Throws RegoError on unsupported constructs.
+FP lower_violation(const std::shared_ptr<const Module>& mod, const VP& parameters, Schema& schema);
+
+// Program assembly: constant pools + instruction emission shared by all constraints.
+struct ProgramBuilder {
+  std::vector<GkInstr> instr;
+  std::vector<uint32_t> pool;
+  std::vector<uint8_t> cbytes;
+  Interner* interner = nullptr;
+  const Schema* schema = nullptr;
+  uint32_t add_bytes(const std::string& s);
+  // returns entry pc (or GK_PC_ACCEPT / GK_PC_REJECT for constant formulas)
+  uint32_t emit(const FP& f);
+
+ private:
+  void gen(const FP& f, uint32_t pt, uint32_t pf, std::vector<int>& open_scopes);
+  uint32_t gen_to(const FP& f, uint32_t pt, uint32_t pf, std::vector<int>& open_scopes);
+};
+
+}  // namespace gk

@@ -1,0 +1,130 @@
+// Rego front-end: AST, parser and the concrete (host) evaluator.
+//
+// The engine never interprets Rego per (constraint, object) pair to DECIDE a violation -- that is the job
+// of the lowered predicate program on the GPU (lower.hpp / kernels.cu).  The concrete evaluator is used
+//   (1) at AddConstraint time to fold everything that depends only on `input.parameters`,
+//   (2) at flatten time to extract parameter-independent feature columns from each object, and
+//   (3) after the kernel, to render `msg`/`details` for pairs the GPU already flagged.
+// Language subset: what every in-tree ConstraintTemplate uses; anything else is
+// rejected at AddTemplate with a rego_* error, like a compile error from the reference's Rego driver.
+#pragma once
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "val.hpp"
+
+namespace gk {
+
+struct RegoError {
+  std::string msg;
+};
+
+enum class TK : uint8_t { Scalar, Var, Ref, Call, Array, Object, Set, ArrCompr, SetCompr, ObjCompr };
+
+struct Term;
+using TP = std::shared_ptr<const Term>;
+
+struct Stmt {
+  enum K : uint8_t { Expr, Not, Assign, Unify, Some, SomeIn } k = Expr;
+  TP a, b, c;   // Expr/Not: a ; Assign/Unify: a,b ; SomeIn: a=key(or null), b=value, c=collection
+  int line = 0;
+};
+
+struct Term {
+  TK k = TK::Scalar;
+  VP val;                               // Scalar
+  int vid = -1;                         // Var: symbol id (module-wide); wildcards get fresh ids
+  std::string name;                     // Var / Call name
+  TP head;                              // Ref
+  std::vector<TP> args;                 // Ref path / Call args / Array+Set items
+  std::vector<std::pair<TP, TP>> kvs;   // Object
+  TP key, value;                        // comprehension head (ObjCompr: key+value; others: value)
+  std::vector<Stmt> body;               // comprehension body
+  int line = 0;
+};
+
+struct Rule {
+  enum Kind : uint8_t { Complete, Func, PSet, PObj } kind = Complete;
+  std::string name;
+  std::vector<TP> args;
+  TP key, value;
+  std::vector<Stmt> body;
+  bool is_default = false;
+  bool has_body = false;
+  std::vector<std::pair<TP, std::vector<Stmt>>> els;
+  int line = 0;
+};
+
+struct Module {
+  std::string package;
+  std::map<std::string, std::vector<Rule>> rules;
+  std::unordered_map<std::string, int> symtab;   // var name -> vid
+  int next_vid = 0;
+  int vid_input = -1, vid_data = -1;
+  uint64_t uid = 0;                               // unique per parsed module (column-key namespace)
+  int intern(const std::string& n);
+  bool is_rule(const std::string& n) const { return rules.count(n) != 0; }
+};
+
+std::shared_ptr<Module> rego_parse(const std::string& src);   // throws RegoError
+std::string term_str(const Term& t);                          // debug / canonical printing
+
+// ---- concrete evaluator ---------------------------------------------------------------------------
+struct Env {
+  std::vector<std::pair<int, VP>> b;
+  const VP* find(int vid) const {
+    for (size_t i = b.size(); i-- > 0;)
+      if (b[i].first == vid) return &b[i].second;
+    return nullptr;
+  }
+  size_t mark() const { return b.size(); }
+  void undo(size_t m) { b.resize(m); }
+  void bind(int vid, VP v) { b.emplace_back(vid, std::move(v)); }
+};
+
+// Continuations return true to STOP the search (first-solution / negation probes).
+using ValK = std::function<bool(const VP&)>;
+using EnvK = std::function<bool()>;
+
+class Eval {
+ public:
+  Eval(const Module& m, VP input, VP data = nullptr) : m_(m), input_(std::move(input)), data_(std::move(data)) {}
+  void reset_input(VP input) {
+    input_ = std::move(input);
+    cache_.clear();
+    cache_has_.clear();
+  }
+  bool eval_body(const std::vector<Stmt>& body, size_t i, Env& env, const EnvK& k);
+  bool eval_term(const TP& t, Env& env, const ValK& k);
+  VP eval_first(const TP& t, Env& env);                 // first solution or nullptr (undefined)
+  VP rule_value(const std::string& name);               // nullptr if undefined
+  VP call_function(const std::string& name, const std::vector<VP>& args);   // nullptr if undefined
+  bool unify_val(const TP& pat, const VP& val, Env& env, const EnvK& k);
+  bool is_ground(const TP& t, const Env& env) const;
+  const Module& module() const { return m_; }
+
+ private:
+  bool eval_stmt(const Stmt& st, Env& env, const EnvK& k);
+  bool unify(const TP& a, const TP& b, Env& env, const EnvK& k);
+  bool walk(const VP& cur, const std::vector<TP>& path, size_t i, Env& env, const ValK& k);
+  bool eval_call(const Term& t, Env& env, const ValK& k);
+  bool eval_seq(const std::vector<TP>& items, size_t i, std::vector<VP>& acc, Env& env, const EnvK& k);
+  VP rule_chain(const Rule& r, Env& env);
+  bool var_unbound(const Term& t, const Env& env) const;
+  const Module& m_;
+  VP input_, data_;
+  std::unordered_map<std::string, VP> cache_;   // rule extents; nullptr entries = undefined
+  std::unordered_map<std::string, bool> cache_has_;
+  int depth_ = 0;
+};
+
+// builtins: returns nullptr for undefined (type errors are undefined, as in OPA's non-strict mode).
+// `known` is set to false when the name is not a builtin at all.
+VP call_builtin(const std::string& name, const std::vector<VP>& args, bool* known);
+bool is_builtin(const std::string& name);
+
+}  // namespace gk

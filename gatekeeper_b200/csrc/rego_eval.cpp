@@ -1,0 +1,880 @@
+// Concrete top-down evaluation of the Rego subset + builtins.  See rego.hpp for where this is (and is
+// not) used.  Semantics restate OPA v1.13.2's documented behaviour: undefined propagation, negation as
+// failure, partial-set extents, multi-definition functions as OR, type errors => undefined.
+#include <algorithm>
+#include <cmath>
+#include <regex>
+
+#include "rego.hpp"
+
+namespace gk {
+
+// ------------------------------------------------------------------------------------------ builtins
+namespace {
+
+inline bool is_num(const VP& v) { return v->t == VT::Num; }
+inline bool is_str(const VP& v) { return v->t == VT::Str; }
+inline bool is_coll(const VP& v) { return v->t == VT::Arr || v->t == VT::Set; }
+
+VP arith(const std::string& op, const VP& a, const VP& b) {
+  if (a->t == VT::Set && b->t == VT::Set && (op == "minus" || op == "and" || op == "or")) {
+    std::vector<VP> out;
+    if (op == "minus") {
+      for (auto& x : a->items)
+        if (!set_find(b, x)) out.push_back(x);
+    } else if (op == "and") {
+      for (auto& x : a->items)
+        if (set_find(b, x)) out.push_back(x);
+    } else {
+      out = a->items;
+      out.insert(out.end(), b->items.begin(), b->items.end());
+    }
+    return v_set(std::move(out));
+  }
+  if (!is_num(a) || !is_num(b)) return nullptr;
+  const Num &x = a->n, &y = b->n;
+  if (x.is_int && y.is_int) {
+    __int128 r;
+    if (op == "plus") {
+      if (__builtin_add_overflow(x.i, y.i, &r)) return v_num(Num::of_double(x.d + y.d));
+      return v_num(Num::of_int(r));
+    }
+    if (op == "minus") {
+      if (__builtin_sub_overflow(x.i, y.i, &r)) return v_num(Num::of_double(x.d - y.d));
+      return v_num(Num::of_int(r));
+    }
+    if (op == "mul") {
+      if (__builtin_mul_overflow(x.i, y.i, &r)) return v_num(Num::of_double(x.d * y.d));
+      return v_num(Num::of_int(r));
+    }
+    if (op == "div") {
+      if (y.i == 0) return nullptr;
+      if (x.i % y.i == 0) return v_num(Num::of_int(x.i / y.i));
+      return v_num(Num::of_double((double)x.i / (double)y.i));
+    }
+    if (op == "rem") {
+      if (y.i == 0) return nullptr;
+      return v_num(Num::of_int(x.i % y.i));   // C++ % truncates toward zero like Go's big.Int.Rem
+    }
+    return nullptr;
+  }
+  double p = x.as_double(), q = y.as_double();
+  if (op == "plus") return v_num(Num::of_double(p + q));
+  if (op == "minus") return v_num(Num::of_double(p - q));
+  if (op == "mul") return v_num(Num::of_double(p * q));
+  if (op == "div") return q == 0 ? nullptr : v_num(Num::of_double(p / q));
+  return nullptr;
+}
+
+size_t utf8_len(const std::string& s) {
+  size_t n = 0;
+  for (unsigned char c : s)
+    if ((c & 0xC0) != 0x80) ++n;
+  return n;
+}
+// byte offset of the cp-th code point
+size_t utf8_off(const std::string& s, size_t cp) {
+  size_t i = 0, n = 0;
+  while (i < s.size() && n < cp) {
+    ++i;
+    while (i < s.size() && ((unsigned char)s[i] & 0xC0) == 0x80) ++i;
+    ++n;
+  }
+  return i;
+}
+
+VP to_number(const VP& x) {
+  switch (x->t) {
+    case VT::Null: return v_int(0);
+    case VT::False: return v_int(0);
+    case VT::True: return v_int(1);
+    case VT::Num: return x;
+    case VT::Str: {
+      const std::string& s = x->s;
+      if (s.empty()) return nullptr;
+      size_t i = 0;
+      if (s[i] == '+' || s[i] == '-') ++i;
+      bool digits = false, dot = false, exp = false, ok = true;
+      for (; i < s.size(); ++i) {
+        char c = s[i];
+        if (c >= '0' && c <= '9') digits = true;
+        else if (c == '.' && !dot && !exp) dot = true;
+        else if ((c == 'e' || c == 'E') && digits && !exp) {
+          exp = true;
+          if (i + 1 < s.size() && (s[i + 1] == '+' || s[i + 1] == '-')) ++i;
+          if (i + 1 >= s.size()) ok = false;
+        } else {
+          ok = false;
+          break;
+        }
+      }
+      if (!ok || !digits) return nullptr;
+      if (!dot && !exp) {
+        std::string t = s[0] == '+' ? s.substr(1) : s;
+        try {
+          return json_parse(t.data(), t.size());
+        } catch (JsonError&) {
+          // leading zeros etc.: fall through to strtod
+        }
+      }
+      return v_num(Num::of_double(strtod(s.c_str(), nullptr)));
+    }
+    default: return nullptr;
+  }
+}
+
+std::string trim_cutset(const std::string& s, const std::string& cut, bool left, bool right) {
+  size_t b = 0, e = s.size();
+  if (left)
+    while (b < e && cut.find(s[b]) != std::string::npos) ++b;
+  if (right)
+    while (e > b && cut.find(s[e - 1]) != std::string::npos) --e;
+  return s.substr(b, e - b);
+}
+
+std::string replace_all(const std::string& s, const std::string& from, const std::string& to) {
+  if (from.empty()) {
+    // Go strings.ReplaceAll with empty `old` inserts `new` between every rune and at both ends
+    std::string out = to;
+    size_t i = 0;
+    while (i < s.size()) {
+      size_t j = i + 1;
+      while (j < s.size() && ((unsigned char)s[j] & 0xC0) == 0x80) ++j;
+      out.append(s, i, j - i);
+      out += to;
+      i = j;
+    }
+    return out;
+  }
+  std::string out;
+  size_t i = 0;
+  while (true) {
+    size_t j = s.find(from, i);
+    if (j == std::string::npos) break;
+    out.append(s, i, j - i);
+    out += to;
+    i = j + from.size();
+  }
+  out.append(s, i, std::string::npos);
+  return out;
+}
+
+VP split(const std::string& s, const std::string& d) {
+  std::vector<VP> out;
+  if (d.empty()) {
+    size_t i = 0;
+    while (i < s.size()) {
+      size_t j = i + 1;
+      while (j < s.size() && ((unsigned char)s[j] & 0xC0) == 0x80) ++j;
+      out.push_back(v_str(s.substr(i, j - i)));
+      i = j;
+    }
+    return v_arr(std::move(out));
+  }
+  size_t i = 0;
+  while (true) {
+    size_t j = s.find(d, i);
+    if (j == std::string::npos) break;
+    out.push_back(v_str(s.substr(i, j - i)));
+    i = j + d.size();
+  }
+  out.push_back(v_str(s.substr(i)));
+  return v_arr(std::move(out));
+}
+
+// OPA sprintf == Go fmt.Sprintf over ast.Values: only the verbs the in-tree templates use.
+VP sprintf_(const VP& f, const VP& args) {
+  if (!is_str(f) || args->t != VT::Arr) return nullptr;
+  const std::string& fmt = f->s;
+  std::string out;
+  size_t ai = 0;
+  auto go_type = [](const VP& a) { return a->t == VT::Str ? "string" : "ast.Value"; };
+  for (size_t i = 0; i < fmt.size(); ++i) {
+    char c = fmt[i];
+    if (c != '%') {
+      out.push_back(c);
+      continue;
+    }
+    if (++i >= fmt.size()) {
+      out += "%!(NOVERB)";
+      break;
+    }
+    char v = fmt[i];
+    if (v == '%') {
+      out.push_back('%');
+      continue;
+    }
+    if (ai >= args->items.size()) {
+      out += "%!";
+      out.push_back(v);
+      out += "(MISSING)";
+      continue;
+    }
+    const VP& a = args->items[ai++];
+    if (v == 'v' || v == 's') out += fmt_value(a, true);
+    else if (v == 'd') {
+      if (a->t == VT::Num && a->n.is_int) out += num_str(a->n);
+      else out += std::string("%!d(") + go_type(a) + "=" + fmt_value(a, true) + ")";
+    } else if (v == 'q' && a->t == VT::Str) json_quote(a->s, out);
+    else throw RegoError{std::string("rego_unsupported: sprintf verb %") + v};
+  }
+  if (ai < args->items.size()) {
+    out += "%!(EXTRA ";
+    for (size_t j = ai; j < args->items.size(); ++j) {
+      if (j > ai) out += ", ";
+      out += std::string(go_type(args->items[j])) + "=" + fmt_value(args->items[j], true);
+    }
+    out += ")";
+  }
+  return v_str(out);
+}
+
+bool str_list(const VP& v, std::vector<const std::string*>& out) {
+  if (is_str(v)) {
+    out.push_back(&v->s);
+    return true;
+  }
+  if (!is_coll(v)) return false;
+  for (auto& x : v->items) {
+    if (!is_str(x)) return false;
+    out.push_back(&x->s);
+  }
+  return true;
+}
+
+bool starts_with(const std::string& s, const std::string& p) { return s.size() >= p.size() && !s.compare(0, p.size(), p); }
+bool ends_with(const std::string& s, const std::string& p) {
+  return s.size() >= p.size() && !s.compare(s.size() - p.size(), p.size(), p);
+}
+
+VP re_match(const VP& pat, const VP& s) {
+  if (!is_str(pat) || !is_str(s)) return nullptr;
+  try {
+    // RE2 syntax is close to ECMAScript for the anchors/classes/quantifiers the fixtures use
+    std::regex re(pat->s, std::regex::ECMAScript);
+    return v_bool(std::regex_search(s->s, re));
+  } catch (std::regex_error&) {
+    return nullptr;
+  }
+}
+
+VP object_get(const VP& o, const VP& k, const VP& d) {
+  if (o->t != VT::Obj) return nullptr;
+  if (k->t == VT::Arr) {
+    VP cur = o;
+    for (auto& p : k->items) {
+      VP nx;
+      if (cur->t == VT::Obj) nx = obj_get(cur, p);
+      else if (cur->t == VT::Arr && p->t == VT::Num) {
+        int64_t ix;
+        if (num_fits_i64(p->n, &ix) && ix >= 0 && (size_t)ix < cur->items.size()) nx = cur->items[ix];
+      }
+      if (!nx) return d;
+      cur = nx;
+    }
+    return cur;
+  }
+  VP r = obj_get(o, k);
+  return r ? r : d;
+}
+
+}  // namespace
+
+bool is_builtin(const std::string& name) {
+  bool known = true;
+  (void)call_builtin(name, {}, &known);
+  return known;
+}
+
+VP call_builtin(const std::string& n, const std::vector<VP>& a, bool* known) {
+  *known = true;
+  auto need = [&](size_t k) { return a.size() == k; };
+#define B(name, arity) if (n == name) { if (!need(arity)) return nullptr;
+#define E }
+  B("equal", 2) return v_bool(v_eq(a[0], a[1])); E
+  B("neq", 2) return v_bool(!v_eq(a[0], a[1])); E
+  B("lt", 2) return v_bool(v_cmp(a[0], a[1]) < 0); E
+  B("lte", 2) return v_bool(v_cmp(a[0], a[1]) <= 0); E
+  B("gt", 2) return v_bool(v_cmp(a[0], a[1]) > 0); E
+  B("gte", 2) return v_bool(v_cmp(a[0], a[1]) >= 0); E
+  if (n == "plus" || n == "minus" || n == "mul" || n == "div" || n == "rem" || n == "and" || n == "or") {
+    if (!need(2)) return nullptr;
+    return arith(n, a[0], a[1]);
+  }
+  B("count", 1)
+    switch (a[0]->t) {
+      case VT::Str: return v_int((long long)utf8_len(a[0]->s));
+      case VT::Arr:
+      case VT::Set: return v_int((long long)a[0]->items.size());
+      case VT::Obj: return v_int((long long)a[0]->kv.size());
+      default: return nullptr;
+    }
+  E
+  B("sprintf", 2) return sprintf_(a[0], a[1]); E
+  B("startswith", 2) if (!is_str(a[0]) || !is_str(a[1])) return nullptr; return v_bool(starts_with(a[0]->s, a[1]->s)); E
+  B("endswith", 2) if (!is_str(a[0]) || !is_str(a[1])) return nullptr; return v_bool(ends_with(a[0]->s, a[1]->s)); E
+  B("contains", 2) if (!is_str(a[0]) || !is_str(a[1])) return nullptr; return v_bool(a[0]->s.find(a[1]->s) != std::string::npos); E
+  if (n == "strings.any_prefix_match" || n == "strings.any_suffix_match") {
+    if (!need(2)) return nullptr;
+    std::vector<const std::string*> ss, bb;
+    if (!str_list(a[0], ss) || !str_list(a[1], bb)) return nullptr;
+    bool pre = n == "strings.any_prefix_match";
+    for (auto s : ss)
+      for (auto b : bb)
+        if (pre ? starts_with(*s, *b) : ends_with(*s, *b)) return v_bool(true);
+    return v_bool(false);
+  }
+  B("split", 2) if (!is_str(a[0]) || !is_str(a[1])) return nullptr; return split(a[0]->s, a[1]->s); E
+  B("trim", 2) if (!is_str(a[0]) || !is_str(a[1])) return nullptr; return v_str(trim_cutset(a[0]->s, a[1]->s, true, true)); E
+  B("trim_left", 2) if (!is_str(a[0]) || !is_str(a[1])) return nullptr; return v_str(trim_cutset(a[0]->s, a[1]->s, true, false)); E
+  B("trim_right", 2) if (!is_str(a[0]) || !is_str(a[1])) return nullptr; return v_str(trim_cutset(a[0]->s, a[1]->s, false, true)); E
+  B("trim_space", 1) if (!is_str(a[0])) return nullptr; return v_str(trim_cutset(a[0]->s, " \t\n\r\v\f", true, true)); E
+  B("trim_prefix", 2)
+    if (!is_str(a[0]) || !is_str(a[1])) return nullptr;
+    return starts_with(a[0]->s, a[1]->s) ? v_str(a[0]->s.substr(a[1]->s.size())) : a[0];
+  E
+  B("trim_suffix", 2)
+    if (!is_str(a[0]) || !is_str(a[1])) return nullptr;
+    return ends_with(a[0]->s, a[1]->s) ? v_str(a[0]->s.substr(0, a[0]->s.size() - a[1]->s.size())) : a[0];
+  E
+  B("replace", 3)
+    if (!is_str(a[0]) || !is_str(a[1]) || !is_str(a[2])) return nullptr;
+    return v_str(replace_all(a[0]->s, a[1]->s, a[2]->s));
+  E
+  B("substring", 3)
+    if (!is_str(a[0]) || !is_num(a[1]) || !is_num(a[2])) return nullptr;
+    {
+      int64_t off, len;
+      if (!num_fits_i64(a[1]->n, &off) || !num_fits_i64(a[2]->n, &len) || off < 0) return nullptr;
+      size_t total = utf8_len(a[0]->s);
+      if ((size_t)off >= total) return v_str("");
+      size_t b = utf8_off(a[0]->s, (size_t)off);
+      if (len < 0) return v_str(a[0]->s.substr(b));
+      size_t e = utf8_off(a[0]->s, std::min(total, (size_t)off + (size_t)len));
+      return v_str(a[0]->s.substr(b, e - b));
+    }
+  E
+  B("lower", 1)
+    if (!is_str(a[0])) return nullptr;
+    { std::string s = a[0]->s; for (auto& c : s) if (c >= 'A' && c <= 'Z') c = char(c + 32); return v_str(s); }
+  E
+  B("upper", 1)
+    if (!is_str(a[0])) return nullptr;
+    { std::string s = a[0]->s; for (auto& c : s) if (c >= 'a' && c <= 'z') c = char(c - 32); return v_str(s); }
+  E
+  B("concat", 2)
+    if (!is_str(a[0]) || !is_coll(a[1])) return nullptr;
+    {
+      std::string out;
+      for (size_t i = 0; i < a[1]->items.size(); ++i) {
+        if (!is_str(a[1]->items[i])) return nullptr;
+        if (i) out += a[0]->s;
+        out += a[1]->items[i]->s;
+      }
+      return v_str(out);
+    }
+  E
+  B("indexof", 2)
+    if (!is_str(a[0]) || !is_str(a[1])) return nullptr;
+    {
+      size_t p = a[0]->s.find(a[1]->s);
+      if (p == std::string::npos) return v_int(-1);
+      return v_int((long long)utf8_len(a[0]->s.substr(0, p)));
+    }
+  E
+  if (n == "re_match" || n == "regex.match") {
+    if (!need(2)) return nullptr;
+    return re_match(a[0], a[1]);
+  }
+  B("to_number", 1) return to_number(a[0]); E
+  B("is_number", 1) return v_bool(a[0]->t == VT::Num); E
+  B("is_string", 1) return v_bool(a[0]->t == VT::Str); E
+  B("is_boolean", 1) return v_bool(a[0]->t == VT::True || a[0]->t == VT::False); E
+  B("is_array", 1) return v_bool(a[0]->t == VT::Arr); E
+  B("is_object", 1) return v_bool(a[0]->t == VT::Obj); E
+  B("is_set", 1) return v_bool(a[0]->t == VT::Set); E
+  B("is_null", 1) return v_bool(a[0]->t == VT::Null); E
+  B("any", 1)
+    if (!is_coll(a[0])) return nullptr;
+    for (auto& x : a[0]->items) if (x->t == VT::True) return v_bool(true);
+    return v_bool(false);
+  E
+  B("all", 1)
+    if (!is_coll(a[0])) return nullptr;
+    for (auto& x : a[0]->items) if (x->t != VT::True) return v_bool(false);
+    return v_bool(true);
+  E
+  B("object.get", 3) return object_get(a[0], a[1], a[2]); E
+  B("array.concat", 2)
+    if (a[0]->t != VT::Arr || a[1]->t != VT::Arr) return nullptr;
+    { auto v = a[0]->items; v.insert(v.end(), a[1]->items.begin(), a[1]->items.end()); return v_arr(std::move(v)); }
+  E
+  B("abs", 1)
+    if (!is_num(a[0])) return nullptr;
+    return a[0]->n.is_int ? v_num(Num::of_int(a[0]->n.i < 0 ? -a[0]->n.i : a[0]->n.i)) : v_num(Num::of_double(std::fabs(a[0]->n.d)));
+  E
+  if (n == "max" || n == "min") {
+    if (!need(1) || !is_coll(a[0]) || a[0]->items.empty()) return nullptr;
+    VP best = a[0]->items[0];
+    for (auto& x : a[0]->items)
+      if ((n == "max") ? v_cmp(x, best) > 0 : v_cmp(x, best) < 0) best = x;
+    return best;
+  }
+  B("sum", 1)
+    if (!is_coll(a[0])) return nullptr;
+    { VP acc = v_int(0); for (auto& x : a[0]->items) { acc = arith("plus", acc, x); if (!acc) return nullptr; } return acc; }
+  E
+  B("internal.member_2", 2)
+    if (a[1]->t == VT::Obj) { for (auto& e : a[1]->kv) if (v_eq(e.second, a[0])) return v_bool(true); return v_bool(false); }
+    if (is_coll(a[1])) { for (auto& x : a[1]->items) if (v_eq(x, a[0])) return v_bool(true); return v_bool(false); }
+    return v_bool(false);
+  E
+  if (n == "print" || n == "trace") return v_bool(true);
+#undef B
+#undef E
+  *known = false;
+  return nullptr;
+}
+
+// ----------------------------------------------------------------------------------------- evaluator
+bool Eval::var_unbound(const Term& t, const Env& env) const {
+  return t.k == TK::Var && !env.find(t.vid) && t.vid != m_.vid_input && t.vid != m_.vid_data && !m_.is_rule(t.name);
+}
+
+bool Eval::is_ground(const TP& t, const Env& env) const {
+  switch (t->k) {
+    case TK::Scalar: return true;
+    case TK::Var: return !var_unbound(*t, env);
+    case TK::Array:
+    case TK::Set:
+      for (auto& x : t->args)
+        if (!is_ground(x, env)) return false;
+      return true;
+    case TK::Object:
+      for (auto& kv : t->kvs)
+        if (!is_ground(kv.first, env) || !is_ground(kv.second, env)) return false;
+      return true;
+    default: return true;   // refs / calls / comprehensions evaluate (refs may bind inner vars)
+  }
+}
+
+VP Eval::eval_first(const TP& t, Env& env) {
+  VP out;
+  size_t mk = env.mark();
+  eval_term(t, env, [&](const VP& v) {
+    out = v;
+    return true;
+  });
+  env.undo(mk);
+  return out;
+}
+
+VP Eval::rule_chain(const Rule& r, Env& env) {
+  VP out;
+  size_t mk = env.mark();
+  eval_body(r.body, 0, env, [&]() {
+    out = eval_first(r.value, env);
+    return (bool)out;
+  });
+  env.undo(mk);
+  if (out) return out;
+  for (auto& el : r.els) {
+    eval_body(el.second, 0, env, [&]() {
+      out = el.first ? eval_first(el.first, env) : v_bool(true);
+      return (bool)out;
+    });
+    env.undo(mk);
+    if (out) return out;
+  }
+  return nullptr;
+}
+
+VP Eval::rule_value(const std::string& name) {
+  auto it = cache_has_.find(name);
+  if (it != cache_has_.end()) return cache_[name];
+  auto rit = m_.rules.find(name);
+  if (rit == m_.rules.end()) throw RegoError{"rego_type_error: unknown rule " + name};
+  const auto& rules = rit->second;
+  if (++depth_ > 64) {
+    --depth_;
+    throw RegoError{"rego_recursion_error: rule " + name};
+  }
+  VP val;
+  Rule::Kind kind = rules[0].kind;
+  if (kind == Rule::PSet) {
+    std::vector<VP> out;
+    for (auto& r : rules) {
+      Env env;
+      eval_body(r.body, 0, env, [&]() {
+        eval_term(r.key, env, [&](const VP& v) {
+          out.push_back(v);
+          return false;
+        });
+        return false;
+      });
+    }
+    val = v_set(std::move(out));
+  } else if (kind == Rule::PObj) {
+    std::vector<std::pair<VP, VP>> out;
+    for (auto& r : rules) {
+      Env env;
+      eval_body(r.body, 0, env, [&]() {
+        eval_term(r.key, env, [&](const VP& k) {
+          VP v = eval_first(r.value, env);
+          if (v) out.emplace_back(k, v);
+          return false;
+        });
+        return false;
+      });
+    }
+    val = v_obj(std::move(out));
+  } else if (kind == Rule::Complete) {
+    VP dflt;
+    for (auto& r : rules) {
+      Env env;
+      if (r.is_default) {
+        dflt = eval_first(r.value, env);
+        continue;
+      }
+      val = rule_chain(r, env);
+      if (val) break;
+    }
+    if (!val) val = dflt;
+  } else {
+    --depth_;
+    throw RegoError{"rego_type_error: " + name + " is a function"};
+  }
+  --depth_;
+  cache_has_[name] = true;
+  cache_[name] = val;
+  return val;
+}
+
+VP Eval::call_function(const std::string& name, const std::vector<VP>& args) {
+  auto rit = m_.rules.find(name);
+  if (rit == m_.rules.end()) return nullptr;
+  if (++depth_ > 64) {
+    --depth_;
+    throw RegoError{"rego_recursion_error: function " + name};
+  }
+  VP out;
+  for (auto& r : rit->second) {
+    if (r.kind != Rule::Func || r.args.size() != args.size()) continue;
+    Env env;
+    // unify formals with actuals
+    std::function<bool(size_t)> bind = [&](size_t i) -> bool {
+      if (i == args.size()) {
+        out = rule_chain(r, env);
+        return (bool)out;
+      }
+      return unify_val(r.args[i], args[i], env, [&]() { return bind(i + 1); });
+    };
+    bind(0);
+    if (out) break;
+  }
+  --depth_;
+  return out;
+}
+
+bool Eval::eval_body(const std::vector<Stmt>& body, size_t i, Env& env, const EnvK& k) {
+  if (i == body.size()) return k();
+  const Stmt& st = body[i];
+  if (st.k == Stmt::Some) return eval_body(body, i + 1, env, k);
+  if (st.k == Stmt::Not) {
+    bool found = false;
+    size_t mk = env.mark();
+    Stmt inner;
+    inner.k = Stmt::Expr;
+    inner.a = st.a;
+    eval_stmt(inner, env, [&]() {
+      found = true;
+      return true;
+    });
+    env.undo(mk);
+    if (found) return false;
+    return eval_body(body, i + 1, env, k);
+  }
+  return eval_stmt(st, env, [&]() { return eval_body(body, i + 1, env, k); });
+}
+
+bool Eval::eval_stmt(const Stmt& st, Env& env, const EnvK& k) {
+  switch (st.k) {
+    case Stmt::Expr: {
+      size_t mk = env.mark();
+      bool stop = eval_term(st.a, env, [&](const VP& v) {
+        if (v->t == VT::False) return false;
+        return k();
+      });
+      env.undo(mk);
+      return stop;
+    }
+    case Stmt::Assign:
+    case Stmt::Unify: {
+      size_t mk = env.mark();
+      bool stop = unify(st.a, st.b, env, k);
+      env.undo(mk);
+      return stop;
+    }
+    case Stmt::SomeIn: {
+      size_t mk = env.mark();
+      bool stop = eval_term(st.c, env, [&](const VP& coll) {
+        auto each = [&](const VP& kk, const VP& vv) -> bool {
+          size_t m2 = env.mark();
+          bool s;
+          if (st.a) s = unify_val(st.a, kk, env, [&]() { return unify_val(st.b, vv, env, k); });
+          else s = unify_val(st.b, vv, env, k);
+          env.undo(m2);
+          return s;
+        };
+        if (coll->t == VT::Arr) {
+          for (size_t j = 0; j < coll->items.size(); ++j)
+            if (each(v_int((long long)j), coll->items[j])) return true;
+        } else if (coll->t == VT::Set) {
+          for (auto& x : coll->items)
+            if (each(x, x)) return true;
+        } else if (coll->t == VT::Obj) {
+          for (auto& e : coll->kv)
+            if (each(e.first, e.second)) return true;
+        }
+        return false;
+      });
+      env.undo(mk);
+      return stop;
+    }
+    default: throw RegoError{"rego_unsupported: statement kind"};
+  }
+}
+
+bool Eval::unify(const TP& a, const TP& b, Env& env, const EnvK& k) {
+  bool ga = is_ground(a, env), gb = is_ground(b, env);
+  if (ga && gb) {
+    return eval_term(a, env, [&](const VP& va) {
+      return eval_term(b, env, [&](const VP& vb) { return v_eq(va, vb) ? k() : false; });
+    });
+  }
+  if (gb) return eval_term(b, env, [&](const VP& vb) { return unify_val(a, vb, env, k); });
+  if (ga) return eval_term(a, env, [&](const VP& va) { return unify_val(b, va, env, k); });
+  if (a->k == TK::Array && b->k == TK::Array && a->args.size() == b->args.size()) {
+    std::function<bool(size_t)> rec = [&](size_t i) -> bool {
+      if (i == a->args.size()) return k();
+      return unify(a->args[i], b->args[i], env, [&]() { return rec(i + 1); });
+    };
+    return rec(0);
+  }
+  throw RegoError{"rego_unsafe_var_error: cannot unify two non-ground terms (line " + std::to_string(a->line) + ")"};
+}
+
+bool Eval::unify_val(const TP& pat, const VP& val, Env& env, const EnvK& k) {
+  switch (pat->k) {
+    case TK::Var: {
+      if (const VP* b = env.find(pat->vid)) return v_eq(*b, val) ? k() : false;
+      if (!var_unbound(*pat, env)) return eval_term(pat, env, [&](const VP& v) { return v_eq(v, val) ? k() : false; });
+      size_t mk = env.mark();
+      env.bind(pat->vid, val);
+      bool s = k();
+      env.undo(mk);
+      return s;
+    }
+    case TK::Array: {
+      if (val->t != VT::Arr || val->items.size() != pat->args.size()) return false;
+      std::function<bool(size_t)> rec = [&](size_t i) -> bool {
+        if (i == pat->args.size()) return k();
+        return unify_val(pat->args[i], val->items[i], env, [&]() { return rec(i + 1); });
+      };
+      return rec(0);
+    }
+    case TK::Object: {
+      if (val->t != VT::Obj || val->kv.size() != pat->kvs.size()) return false;
+      std::function<bool(size_t)> rec = [&](size_t i) -> bool {
+        if (i == pat->kvs.size()) return k();
+        return eval_term(pat->kvs[i].first, env, [&](const VP& kv) {
+          VP got = obj_get(val, kv);
+          if (!got) return false;
+          return unify_val(pat->kvs[i].second, got, env, [&]() { return rec(i + 1); });
+        });
+      };
+      return rec(0);
+    }
+    default: return eval_term(pat, env, [&](const VP& v) { return v_eq(v, val) ? k() : false; });
+  }
+}
+
+bool Eval::eval_seq(const std::vector<TP>& items, size_t i, std::vector<VP>& acc, Env& env, const EnvK& k) {
+  if (i == items.size()) return k();
+  return eval_term(items[i], env, [&](const VP& v) {
+    acc.push_back(v);
+    bool s = eval_seq(items, i + 1, acc, env, k);
+    acc.pop_back();
+    return s;
+  });
+}
+
+bool Eval::eval_term(const TP& t, Env& env, const ValK& k) {
+  switch (t->k) {
+    case TK::Scalar: return k(t->val);
+    case TK::Var: {
+      if (const VP* b = env.find(t->vid)) {
+        VP v = *b;   // copy: the continuation may grow env and invalidate b
+        return k(v);
+      }
+      if (t->vid == m_.vid_input) return input_ ? k(input_) : false;
+      if (t->vid == m_.vid_data) return data_ ? k(data_) : false;
+      if (m_.is_rule(t->name)) {
+        VP v = rule_value(t->name);
+        return v ? k(v) : false;
+      }
+      throw RegoError{"rego_unsafe_var_error: var " + t->name + " is unsafe (line " + std::to_string(t->line) + ")"};
+    }
+    case TK::Ref:
+      return eval_term(t->head, env, [&](const VP& base) { return walk(base, t->args, 0, env, k); });
+    case TK::Call: return eval_call(*t, env, k);
+    case TK::Array: {
+      std::vector<VP> acc;
+      return eval_seq(t->args, 0, acc, env, [&]() { return k(v_arr(acc)); });
+    }
+    case TK::Set: {
+      std::vector<VP> acc;
+      return eval_seq(t->args, 0, acc, env, [&]() { return k(v_set(acc)); });
+    }
+    case TK::Object: {
+      std::vector<std::pair<VP, VP>> acc;
+      std::function<bool(size_t)> rec = [&](size_t i) -> bool {
+        if (i == t->kvs.size()) return k(v_obj(acc));
+        return eval_term(t->kvs[i].first, env, [&](const VP& kk) {
+          return eval_term(t->kvs[i].second, env, [&](const VP& vv) {
+            acc.emplace_back(kk, vv);
+            bool s = rec(i + 1);
+            acc.pop_back();
+            return s;
+          });
+        });
+      };
+      return rec(0);
+    }
+    case TK::ArrCompr:
+    case TK::SetCompr: {
+      std::vector<VP> out;
+      size_t mk = env.mark();
+      eval_body(t->body, 0, env, [&]() {
+        eval_term(t->value, env, [&](const VP& v) {
+          out.push_back(v);
+          return false;
+        });
+        return false;
+      });
+      env.undo(mk);
+      return k(t->k == TK::ArrCompr ? v_arr(std::move(out)) : v_set(std::move(out)));
+    }
+    case TK::ObjCompr: {
+      std::vector<std::pair<VP, VP>> out;
+      size_t mk = env.mark();
+      eval_body(t->body, 0, env, [&]() {
+        eval_term(t->key, env, [&](const VP& kk) {
+          VP vv = eval_first(t->value, env);
+          if (vv) out.emplace_back(kk, vv);
+          return false;
+        });
+        return false;
+      });
+      env.undo(mk);
+      return k(v_obj(std::move(out)));
+    }
+  }
+  return false;
+}
+
+bool Eval::walk(const VP& cur, const std::vector<TP>& path, size_t i, Env& env, const ValK& k) {
+  if (i == path.size()) return k(cur);
+  const TP& p = path[i];
+  if (var_unbound(*p, env)) {
+    auto step = [&](const VP& kk, const VP& vv) -> bool {
+      size_t mk = env.mark();
+      env.bind(p->vid, kk);
+      bool s = walk(vv, path, i + 1, env, k);
+      env.undo(mk);
+      return s;
+    };
+    if (cur->t == VT::Arr) {
+      for (size_t j = 0; j < cur->items.size(); ++j)
+        if (step(v_int((long long)j), cur->items[j])) return true;
+    } else if (cur->t == VT::Obj) {
+      for (auto& e : cur->kv)
+        if (step(e.first, e.second)) return true;
+    } else if (cur->t == VT::Set) {
+      for (auto& x : cur->items)
+        if (step(x, x)) return true;
+    }
+    return false;
+  }
+  if (!is_ground(p, env)) {
+    // pattern key, e.g. general_violation[{"msg": msg, "field": "containers"}]
+    if (cur->t == VT::Set) {
+      for (auto& x : cur->items) {
+        size_t mk = env.mark();
+        bool s = unify_val(p, x, env, [&]() { return walk(x, path, i + 1, env, k); });
+        env.undo(mk);
+        if (s) return true;
+      }
+    } else if (cur->t == VT::Obj) {
+      for (auto& e : cur->kv) {
+        size_t mk = env.mark();
+        bool s = unify_val(p, e.first, env, [&]() { return walk(e.second, path, i + 1, env, k); });
+        env.undo(mk);
+        if (s) return true;
+      }
+    }
+    return false;
+  }
+  return eval_term(p, env, [&](const VP& kv) {
+    if (cur->t == VT::Obj) {
+      VP got = obj_get(cur, kv);
+      return got ? walk(got, path, i + 1, env, k) : false;
+    }
+    if (cur->t == VT::Arr) {
+      int64_t ix;
+      if (kv->t == VT::Num && num_fits_i64(kv->n, &ix) && ix >= 0 && (size_t)ix < cur->items.size())
+        return walk(cur->items[ix], path, i + 1, env, k);
+      return false;
+    }
+    if (cur->t == VT::Set) {
+      VP got = set_find(cur, kv);
+      return got ? walk(got, path, i + 1, env, k) : false;
+    }
+    return false;
+  });
+}
+
+bool Eval::eval_call(const Term& t, Env& env, const ValK& k) {
+  auto rit = m_.rules.find(t.name);
+  bool user = rit != m_.rules.end() && rit->second[0].kind == Rule::Func;
+  size_t nargs = t.args.size();
+  TP out_pat;
+  if (user && nargs == rit->second[0].args.size() + 1) {
+    out_pat = t.args.back();
+    --nargs;
+  }
+  std::vector<VP> acc;
+  std::function<bool(size_t)> rec = [&](size_t i) -> bool {
+    if (i == nargs) {
+      VP v;
+      if (user) v = call_function(t.name, acc);
+      else {
+        bool known = true;
+        v = call_builtin(t.name, acc, &known);
+        if (!known) throw RegoError{"rego_type_error: undefined function " + t.name + " (line " + std::to_string(t.line) + ")"};
+      }
+      if (!v) return false;
+      if (out_pat) return unify_val(out_pat, v, env, [&]() { return k(v_bool(true)); });
+      return k(v);
+    }
+    return eval_term(t.args[i], env, [&](const VP& v) {
+      acc.push_back(v);
+      bool s = rec(i + 1);
+      acc.pop_back();
+      return s;
+    });
+  };
+  return rec(0);
+}
+
+}  // namespace gk

@@ -1,0 +1,696 @@
+// Rego subset parser (v0 and v1 rule syntax).  See rego.hpp for scope.
+#include <atomic>
+#include <cstring>
+
+#include "rego.hpp"
+
+namespace gk {
+
+namespace {
+
+enum class TT : uint8_t { Num, Str, Id, Op, Eof };
+struct Tok {
+  TT k;
+  std::string s;
+  VP v;
+  int line;
+  size_t pos, end;
+};
+
+[[noreturn]] void perr(const std::string& m, int line) {
+  throw RegoError{"rego_parse_error: " + m + " (line " + std::to_string(line) + ")"};
+}
+
+std::vector<Tok> lex(const std::string& src) {
+  std::vector<Tok> out;
+  size_t i = 0, n = src.size();
+  int line = 1;
+  auto prev_is_operand = [&]() {
+    if (out.empty() || out.back().line != line) return false;
+    const Tok& t = out.back();
+    if (t.k == TT::Num || t.k == TT::Str || t.k == TT::Id) return true;
+    return t.k == TT::Op && (t.s == ")" || t.s == "]" || t.s == "}");
+  };
+  while (i < n) {
+    char c = src[i];
+    if (c == '\n') {
+      ++line;
+      ++i;
+      continue;
+    }
+    if (c == ' ' || c == '\t' || c == '\r') {
+      ++i;
+      continue;
+    }
+    if (c == '#') {
+      while (i < n && src[i] != '\n') ++i;
+      continue;
+    }
+    size_t st = i;
+    if ((c >= '0' && c <= '9') || (c == '-' && i + 1 < n && src[i + 1] >= '0' && src[i + 1] <= '9' && !prev_is_operand())) {
+      if (c == '-') ++i;
+      bool isint = true;
+      while (i < n && src[i] >= '0' && src[i] <= '9') ++i;
+      if (i + 1 < n && src[i] == '.' && src[i + 1] >= '0' && src[i + 1] <= '9') {
+        isint = false;
+        ++i;
+        while (i < n && src[i] >= '0' && src[i] <= '9') ++i;
+      }
+      if (i < n && (src[i] == 'e' || src[i] == 'E')) {
+        size_t j = i + 1;
+        if (j < n && (src[j] == '+' || src[j] == '-')) ++j;
+        if (j < n && src[j] >= '0' && src[j] <= '9') {
+          isint = false;
+          i = j;
+          while (i < n && src[i] >= '0' && src[i] <= '9') ++i;
+        }
+      }
+      std::string txt = src.substr(st, i - st);
+      VP v;
+      try {
+        v = json_parse(txt.data(), txt.size());
+      } catch (JsonError&) {
+        perr("bad number " + txt, line);
+      }
+      (void)isint;
+      out.push_back({TT::Num, txt, v, line, st, i});
+      continue;
+    }
+    if (c == '"') {
+      size_t j = i + 1;
+      while (j < n && src[j] != '"') {
+        if (src[j] == '\\') ++j;
+        if (j < n && src[j] == '\n') perr("newline in string", line);
+        ++j;
+      }
+      if (j >= n) perr("unterminated string", line);
+      std::string txt = src.substr(i, j + 1 - i);
+      VP v;
+      try {
+        v = json_parse(txt.data(), txt.size());
+      } catch (JsonError&) {
+        perr("bad string literal", line);
+      }
+      out.push_back({TT::Str, v->s, v, line, st, j + 1});
+      i = j + 1;
+      continue;
+    }
+    if (c == '`') {
+      size_t j = src.find('`', i + 1);
+      if (j == std::string::npos) perr("unterminated raw string", line);
+      std::string body = src.substr(i + 1, j - i - 1);
+      out.push_back({TT::Str, body, v_str(body), line, st, j + 1});
+      for (char ch : body)
+        if (ch == '\n') ++line;
+      i = j + 1;
+      continue;
+    }
+    if ((c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z') || c == '_') {
+      while (i < n && ((src[i] >= 'a' && src[i] <= 'z') || (src[i] >= 'A' && src[i] <= 'Z') || (src[i] >= '0' && src[i] <= '9') || src[i] == '_')) ++i;
+      out.push_back({TT::Id, src.substr(st, i - st), nullptr, line, st, i});
+      continue;
+    }
+    static const char* two[] = {":=", "==", "!=", "<=", ">="};
+    bool got = false;
+    for (const char* t : two) {
+      if (i + 1 < n && src[i] == t[0] && src[i + 1] == t[1]) {
+        out.push_back({TT::Op, t, nullptr, line, st, i + 2});
+        i += 2;
+        got = true;
+        break;
+      }
+    }
+    if (got) continue;
+    if (strchr("=<>+-*/%&|[]{}().,;:", c)) {
+      out.push_back({TT::Op, std::string(1, c), nullptr, line, st, i + 1});
+      ++i;
+      continue;
+    }
+    perr(std::string("illegal character '") + c + "'", line);
+  }
+  out.push_back({TT::Eof, "", nullptr, line, n, n});
+  return out;
+}
+
+int prec_of(const std::string& op) {
+  if (op == "==" || op == "!=" || op == "<" || op == "<=" || op == ">" || op == ">=" || op == "in") return 1;
+  if (op == "|") return 2;
+  if (op == "&") return 3;
+  if (op == "+" || op == "-") return 4;
+  if (op == "*" || op == "/" || op == "%") return 5;
+  return 0;
+}
+
+const char* infix_name(const std::string& op) {
+  if (op == "==") return "equal";
+  if (op == "!=") return "neq";
+  if (op == "<") return "lt";
+  if (op == "<=") return "lte";
+  if (op == ">") return "gt";
+  if (op == ">=") return "gte";
+  if (op == "+") return "plus";
+  if (op == "-") return "minus";
+  if (op == "*") return "mul";
+  if (op == "/") return "div";
+  if (op == "%") return "rem";
+  if (op == "&") return "and";
+  if (op == "|") return "or";
+  return "";
+}
+
+bool is_keyword(const std::string& s) {
+  static const char* kw[] = {"not", "some", "default", "package", "import", "else", "with", "as"};
+  for (auto k : kw)
+    if (s == k) return true;
+  return false;
+}
+
+struct Parser {
+  std::vector<Tok> t;
+  size_t i = 0;
+  Module& m;
+  int wild = 0;
+  explicit Parser(const std::string& src, Module& mod) : t(lex(src)), m(mod) {}
+
+  const Tok& peek(size_t k = 0) const { return t[std::min(i + k, t.size() - 1)]; }
+  const Tok& next() { return t[i < t.size() - 1 ? i++ : i]; }
+  bool at(const char* v) const {
+    const Tok& x = peek();
+    return (x.k == TT::Op || x.k == TT::Id) && x.s == v;
+  }
+  bool accept(const char* v) {
+    if (at(v)) {
+      ++i;
+      return true;
+    }
+    return false;
+  }
+  void expect(const char* v) {
+    if (!accept(v)) perr(std::string("expected '") + v + "' got '" + peek().s + "'", peek().line);
+  }
+  bool same_line() const { return i > 0 && peek().line == t[i - 1].line; }
+  bool adjacent() const { return i > 0 && peek().pos == t[i - 1].end; }
+
+  std::shared_ptr<Term> mk(TK k, int line) {
+    auto x = std::make_shared<Term>();
+    x->k = k;
+    x->line = line;
+    return x;
+  }
+  TP scalar(VP v, int line) {
+    auto x = mk(TK::Scalar, line);
+    x->val = std::move(v);
+    return x;
+  }
+  TP var(const std::string& n, int line) {
+    auto x = mk(TK::Var, line);
+    x->name = n;
+    x->vid = m.intern(n);
+    return x;
+  }
+  TP call(const std::string& n, std::vector<TP> args, int line) {
+    auto x = mk(TK::Call, line);
+    x->name = n;
+    x->args = std::move(args);
+    return x;
+  }
+  TP ref_append(const TP& base, TP idx) {
+    if (base->k == TK::Ref) {
+      auto x = std::make_shared<Term>(*base);
+      x->args.push_back(std::move(idx));
+      return x;
+    }
+    auto x = mk(TK::Ref, base->line);
+    x->head = base;
+    x->args.push_back(std::move(idx));
+    return x;
+  }
+  static std::string dotted(const TP& b, int line) {
+    if (b->k == TK::Var) return b->name;
+    std::string s = b->head->name;
+    for (auto& a : b->args) {
+      if (a->k != TK::Scalar || a->val->t != VT::Str) perr("bad function name", line);
+      s += "." + a->val->s;
+    }
+    return s;
+  }
+
+  void parse_module() {
+    bool have_pkg = false;
+    while (peek().k != TT::Eof) {
+      if (at("package")) {
+        next();
+        std::string p = next().s;
+        while (accept(".")) p += "." + next().s;
+        m.package = p;
+        have_pkg = true;
+      } else if (at("import")) {
+        int line = next().line;
+        std::string p = next().s;
+        std::string first = p;
+        while (same_line() && accept(".")) p += "." + next().s;
+        if (first != "future" && first != "rego")
+          throw RegoError{"rego_unsupported: import " + p + " (line " + std::to_string(line) + ")"};
+        if (same_line() && accept("as")) next();
+      } else {
+        Rule r = parse_rule();
+        m.rules[r.name].push_back(std::move(r));
+      }
+    }
+    if (!have_pkg) throw RegoError{"rego_parse_error: package expected"};
+  }
+
+  Rule parse_rule() {
+    Rule r;
+    r.is_default = accept("default");
+    const Tok& nt = next();
+    if (nt.k != TT::Id || is_keyword(nt.s)) perr("unexpected '" + nt.s + "'", nt.line);
+    r.name = nt.s;
+    r.line = nt.line;
+    if (same_line() && at("(") && adjacent()) {
+      next();
+      while (!at(")")) {
+        r.args.push_back(parse_term());
+        if (!accept(",")) break;
+      }
+      expect(")");
+      r.kind = Rule::Func;
+    } else if (same_line() && at("[") && adjacent()) {
+      next();
+      r.key = parse_term();
+      expect("]");
+      r.kind = Rule::PSet;
+    }
+    if (at("contains")) {
+      next();
+      r.key = parse_term();
+      r.kind = Rule::PSet;
+    }
+    if (at("=") || at(":=")) {
+      next();
+      r.value = parse_term();
+      if (r.kind == Rule::PSet) r.kind = Rule::PObj;
+    }
+    bool has_if = accept("if");
+    if (at("{")) {
+      next();
+      r.body = parse_body("}");
+      expect("}");
+      r.has_body = true;
+    } else if (has_if) {
+      r.body.push_back(parse_stmt());
+      r.has_body = true;
+    }
+    while (at("else")) {
+      next();
+      TP ev;
+      if (at("=") || at(":=")) {
+        next();
+        ev = parse_term();
+      }
+      accept("if");
+      std::vector<Stmt> eb;
+      if (at("{")) {
+        next();
+        eb = parse_body("}");
+        expect("}");
+      }
+      r.els.emplace_back(ev, std::move(eb));
+    }
+    if (!r.value && (r.kind == Rule::Complete || r.kind == Rule::Func)) r.value = scalar(v_bool(true), r.line);
+    return r;
+  }
+
+  std::vector<Stmt> parse_body(const char* closer) {
+    std::vector<Stmt> out;
+    while (!at(closer)) {
+      if (peek().k == TT::Eof) perr("unexpected eof in body", peek().line);
+      out.push_back(parse_stmt());
+      if (accept(";")) continue;
+      if (!at(closer) && same_line()) perr("unexpected '" + peek().s + "'", peek().line);
+    }
+    return out;
+  }
+
+  Stmt parse_stmt() {
+    Stmt s;
+    s.line = peek().line;
+    if (at("some")) {
+      next();
+      std::vector<TP> names;
+      names.push_back(parse_term(0, true));
+      while (accept(",")) names.push_back(parse_term(0, true));
+      if (accept("in")) {
+        s.k = Stmt::SomeIn;
+        s.c = parse_term();
+        if (names.size() == 1) s.b = names[0];
+        else {
+          s.a = names[0];
+          s.b = names[1];
+        }
+        return s;
+      }
+      s.k = Stmt::Some;
+      return s;
+    }
+    if (at("not")) {
+      next();
+      Stmt inner = parse_expr();
+      if (inner.k != Stmt::Expr) {
+        // `not a = b` : negated unification, treat as not (a == b) when ground
+        s.k = Stmt::Not;
+        s.a = call("equal", {inner.a, inner.b}, s.line);
+        return s;
+      }
+      s.k = Stmt::Not;
+      s.a = inner.a;
+      return s;
+    }
+    s = parse_expr();
+    if (same_line() && at("with")) throw RegoError{"rego_unsupported: `with` modifier (line " + std::to_string(s.line) + ")"};
+    return s;
+  }
+
+  Stmt parse_expr() {
+    Stmt s;
+    s.line = peek().line;
+    TP lhs = parse_term();
+    if (same_line() && (at(":=") || at("="))) {
+      bool assign = next().s == ":=";
+      s.k = assign ? Stmt::Assign : Stmt::Unify;
+      s.a = lhs;
+      s.b = parse_term();
+      return s;
+    }
+    s.k = Stmt::Expr;
+    s.a = lhs;
+    return s;
+  }
+
+  TP parse_term(int prec = 0, bool no_in = false, bool no_bar = false) {
+    TP lhs = parse_unary();
+    while (same_line()) {
+      const Tok& x = peek();
+      std::string op;
+      if (x.k == TT::Op && prec_of(x.s) && !(no_bar && x.s == "|")) op = x.s;
+      else if (x.k == TT::Id && x.s == "in" && !no_in) op = "in";
+      else break;
+      int p = prec_of(op);
+      if (p <= prec) break;
+      int line = next().line;
+      TP rhs = parse_term(p, no_in, no_bar);
+      if (op == "in") lhs = call("internal.member_2", {lhs, rhs}, line);
+      else lhs = call(infix_name(op), {lhs, rhs}, line);
+    }
+    return lhs;
+  }
+
+  TP parse_unary() {
+    if (peek().k == TT::Op && peek().s == "-") {
+      int line = next().line;
+      TP x = parse_unary();
+      return call("minus", {scalar(v_int(0), line), x}, line);
+    }
+    return parse_postfix(parse_primary());
+  }
+
+  TP parse_postfix(TP base) {
+    while (same_line()) {
+      if (at(".") ) {
+        next();
+        const Tok& f = next();
+        if (f.k != TT::Id) perr("bad ref", f.line);
+        base = ref_append(base, scalar(v_str(f.s), f.line));
+      } else if (at("[") && adjacent()) {
+        next();
+        TP idx = parse_term();
+        expect("]");
+        base = ref_append(base, idx);
+      } else if (at("(") && adjacent() && (base->k == TK::Var || base->k == TK::Ref)) {
+        int line = next().line;
+        std::vector<TP> args;
+        while (!at(")")) {
+          args.push_back(parse_term());
+          if (!accept(",")) break;
+        }
+        expect(")");
+        base = call(dotted(base, line), std::move(args), line);
+      } else {
+        break;
+      }
+    }
+    return base;
+  }
+
+  TP parse_primary() {
+    const Tok& x = next();
+    int line = x.line;
+    if (x.k == TT::Num || x.k == TT::Str) return scalar(x.v, line);
+    if (x.k == TT::Id) {
+      if (x.s == "true") return scalar(v_bool(true), line);
+      if (x.s == "false") return scalar(v_bool(false), line);
+      if (x.s == "null") return scalar(v_null(), line);
+      if (x.s == "_") return var("$w" + std::to_string(++wild), line);
+      if (x.s == "set" && at("(") && peek(1).s == ")") {
+        next();
+        next();
+        return mk(TK::Set, line);
+      }
+      if (is_keyword(x.s)) perr("unexpected keyword '" + x.s + "'", line);
+      return var(x.s, line);
+    }
+    if (x.k == TT::Op) {
+      if (x.s == "(") {
+        TP e = parse_term();
+        expect(")");
+        return e;
+      }
+      if (x.s == "[") {
+        if (accept("]")) return mk(TK::Array, line);
+        TP first = parse_term(0, false, true);
+        if (accept("|")) {
+          auto c = mk(TK::ArrCompr, line);
+          c->value = first;
+          c->body = parse_body("]");
+          expect("]");
+          return c;
+        }
+        auto a = mk(TK::Array, line);
+        a->args.push_back(first);
+        while (accept(",")) {
+          if (at("]")) break;
+          a->args.push_back(parse_term());
+        }
+        expect("]");
+        return a;
+      }
+      if (x.s == "{") {
+        if (accept("}")) return mk(TK::Object, line);
+        TP first = parse_term(0, false, true);
+        if (accept(":")) {
+          TP val = parse_term(0, false, true);
+          if (accept("|")) {
+            auto c = mk(TK::ObjCompr, line);
+            c->key = first;
+            c->value = val;
+            c->body = parse_body("}");
+            expect("}");
+            return c;
+          }
+          auto o = mk(TK::Object, line);
+          o->kvs.emplace_back(first, val);
+          while (accept(",")) {
+            if (at("}")) break;
+            TP k = parse_term();
+            expect(":");
+            o->kvs.emplace_back(k, parse_term());
+          }
+          expect("}");
+          return o;
+        }
+        if (accept("|")) {
+          auto c = mk(TK::SetCompr, line);
+          c->value = first;
+          c->body = parse_body("}");
+          expect("}");
+          return c;
+        }
+        auto s = mk(TK::Set, line);
+        s->args.push_back(first);
+        while (accept(",")) {
+          if (at("}")) break;
+          s->args.push_back(parse_term());
+        }
+        expect("}");
+        return s;
+      }
+    }
+    perr("unexpected token '" + x.s + "'", line);
+  }
+};
+
+void collect_vars(const TP& t, std::vector<int>& out);
+void collect_vars_body(const std::vector<Stmt>& b, std::vector<int>& out) {
+  for (auto& s : b) {
+    if (s.a) collect_vars(s.a, out);
+    if (s.b) collect_vars(s.b, out);
+    if (s.c) collect_vars(s.c, out);
+  }
+}
+void collect_vars(const TP& t, std::vector<int>& out) {
+  if (!t) return;
+  if (t->k == TK::Var) out.push_back(t->vid);
+  if (t->head) collect_vars(t->head, out);
+  for (auto& a : t->args) collect_vars(a, out);
+  for (auto& kv : t->kvs) {
+    collect_vars(kv.first, out);
+    collect_vars(kv.second, out);
+  }
+  collect_vars(t->key, out);
+  collect_vars(t->value, out);
+  collect_vars_body(t->body, out);
+}
+
+// The one compile-time check the reference's tests pin (pkg/gator/fixtures/fixtures.go TemplateCompileError,
+// a body that is just the undeclared identifier `f`): a bare variable statement must be bound earlier.
+void check_unsafe(const Module& m) {
+  for (auto& kv : m.rules)
+    for (auto& r : kv.second) {
+      std::vector<int> bound;
+      for (auto& a : r.args) collect_vars(a, bound);
+      for (auto& s : r.body) {
+        if (s.k == Stmt::Expr && s.a->k == TK::Var) {
+          const std::string& n = s.a->name;
+          bool ok = n == "input" || n == "data" || m.is_rule(n) || n[0] == '$';
+          for (int v : bound) ok = ok || v == s.a->vid;
+          if (!ok) throw RegoError{"rego_unsafe_var_error: var " + n + " is unsafe (line " + std::to_string(s.line) + ")"};
+        }
+        if (s.a) collect_vars(s.a, bound);
+        if (s.b) collect_vars(s.b, bound);
+        if (s.c) collect_vars(s.c, bound);
+      }
+    }
+}
+
+}  // namespace
+
+int Module::intern(const std::string& n) {
+  auto it = symtab.find(n);
+  if (it != symtab.end()) return it->second;
+  int id = next_vid++;
+  symtab.emplace(n, id);
+  return id;
+}
+
+std::shared_ptr<Module> rego_parse(const std::string& src) {
+  static std::atomic<uint64_t> uid{1};
+  auto m = std::make_shared<Module>();
+  m->uid = uid++;
+  m->vid_input = m->intern("input");
+  m->vid_data = m->intern("data");
+  Parser p(src, *m);
+  p.parse_module();
+  for (auto& kv : m->rules) {
+    Rule::Kind k0 = kv.second[0].kind;
+    for (auto& r : kv.second)
+      if ((r.kind == Rule::Func) != (k0 == Rule::Func))
+        throw RegoError{"rego_type_error: conflicting rules named " + kv.first};
+  }
+  check_unsafe(*m);
+  return m;
+}
+
+// ------------------------------------------------------------------------------------- printing
+static void stmt_str(const Stmt& s, std::string& out);
+static void term_rec(const Term& t, std::string& out) {
+  switch (t.k) {
+    case TK::Scalar: out += fmt_value(t.val, false); break;
+    case TK::Var: out += t.name; break;
+    case TK::Ref:
+      term_rec(*t.head, out);
+      for (auto& a : t.args) {
+        out.push_back('[');
+        term_rec(*a, out);
+        out.push_back(']');
+      }
+      break;
+    case TK::Call:
+      out += t.name;
+      out.push_back('(');
+      for (size_t i = 0; i < t.args.size(); ++i) {
+        if (i) out += ", ";
+        term_rec(*t.args[i], out);
+      }
+      out.push_back(')');
+      break;
+    case TK::Array:
+    case TK::Set:
+      out += t.k == TK::Array ? "[" : "{";
+      for (size_t i = 0; i < t.args.size(); ++i) {
+        if (i) out += ", ";
+        term_rec(*t.args[i], out);
+      }
+      if (t.k == TK::Set && t.args.empty()) out += "set()";
+      out += t.k == TK::Array ? "]" : "}";
+      break;
+    case TK::Object:
+      out.push_back('{');
+      for (size_t i = 0; i < t.kvs.size(); ++i) {
+        if (i) out += ", ";
+        term_rec(*t.kvs[i].first, out);
+        out += ": ";
+        term_rec(*t.kvs[i].second, out);
+      }
+      out.push_back('}');
+      break;
+    case TK::ArrCompr:
+    case TK::SetCompr:
+    case TK::ObjCompr:
+      out += t.k == TK::ArrCompr ? "[" : "{";
+      if (t.k == TK::ObjCompr) {
+        term_rec(*t.key, out);
+        out += ": ";
+      }
+      term_rec(*t.value, out);
+      out += " | ";
+      for (size_t i = 0; i < t.body.size(); ++i) {
+        if (i) out += "; ";
+        stmt_str(t.body[i], out);
+      }
+      out += t.k == TK::ArrCompr ? "]" : "}";
+      break;
+  }
+}
+static void stmt_str(const Stmt& s, std::string& out) {
+  switch (s.k) {
+    case Stmt::Expr: term_rec(*s.a, out); break;
+    case Stmt::Not:
+      out += "not ";
+      term_rec(*s.a, out);
+      break;
+    case Stmt::Assign:
+    case Stmt::Unify:
+      term_rec(*s.a, out);
+      out += s.k == Stmt::Assign ? " := " : " = ";
+      term_rec(*s.b, out);
+      break;
+    case Stmt::Some: out += "some"; break;
+    case Stmt::SomeIn:
+      out += "some ";
+      if (s.a) {
+        term_rec(*s.a, out);
+        out += ", ";
+      }
+      term_rec(*s.b, out);
+      out += " in ";
+      term_rec(*s.c, out);
+      break;
+  }
+}
+std::string term_str(const Term& t) {
+  std::string out;
+  term_rec(t, out);
+  return out;
+}
+
+}  // namespace gk

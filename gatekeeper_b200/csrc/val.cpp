@@ -1,0 +1,533 @@
+#include "val.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+namespace gk {
+
+// ------------------------------------------------------------------------------------------- numbers
+Num Num::of_double(double v) {
+  Num n;
+  if (std::isfinite(v) && v == std::floor(v) && std::fabs(v) < 1e37) {
+    n.is_int = true;
+    n.i = (__int128)v;
+    n.d = v;
+  } else {
+    n.is_int = false;
+    n.d = v;
+  }
+  return n;
+}
+
+int num_cmp(const Num& a, const Num& b) {
+  if (a.is_int && b.is_int) return a.i < b.i ? -1 : (a.i > b.i ? 1 : 0);
+  double x = a.as_double(), y = b.as_double();
+  return x < y ? -1 : (x > y ? 1 : 0);
+}
+
+static std::string i128_str(__int128 v) {
+  if (v == 0) return "0";
+  bool neg = v < 0;
+  unsigned __int128 u = neg ? (unsigned __int128)(-(v + 1)) + 1 : (unsigned __int128)v;
+  char buf[48];
+  int p = 47;
+  buf[p] = 0;
+  while (u) {
+    buf[--p] = char('0' + (int)(u % 10));
+    u /= 10;
+  }
+  if (neg) buf[--p] = '-';
+  return std::string(buf + p);
+}
+
+std::string num_str(const Num& n) {
+  if (n.is_int) return i128_str(n.i);
+  char buf[64];
+  // shortest round-trip repr
+  for (int prec = 1; prec <= 17; ++prec) {
+    snprintf(buf, sizeof buf, "%.*g", prec, n.d);
+    if (strtod(buf, nullptr) == n.d) break;
+  }
+  return buf;
+}
+
+bool num_fits_i64(const Num& n, int64_t* out) {
+  if (!n.is_int) return false;
+  if (n.i < (__int128)INT64_MIN || n.i > (__int128)INT64_MAX) return false;
+  *out = (int64_t)n.i;
+  return true;
+}
+
+// -------------------------------------------------------------------------------------- constructors
+VP v_null() {
+  static VP v = [] { auto n = std::make_shared<Node>(); n->t = VT::Null; return VP(n); }();
+  return v;
+}
+VP v_bool(bool b) {
+  static VP t = [] { auto n = std::make_shared<Node>(); n->t = VT::True; return VP(n); }();
+  static VP f = [] { auto n = std::make_shared<Node>(); n->t = VT::False; return VP(n); }();
+  return b ? t : f;
+}
+VP v_num(const Num& x) {
+  auto n = std::make_shared<Node>();
+  n->t = VT::Num;
+  n->n = x;
+  return n;
+}
+VP v_int(long long i) { return v_num(Num::of_int(i)); }
+VP v_str(std::string s) {
+  auto n = std::make_shared<Node>();
+  n->t = VT::Str;
+  n->s = std::move(s);
+  return n;
+}
+VP v_arr(std::vector<VP> items) {
+  auto n = std::make_shared<Node>();
+  n->t = VT::Arr;
+  n->items = std::move(items);
+  return n;
+}
+VP v_set(std::vector<VP> items) {
+  std::stable_sort(items.begin(), items.end(), [](const VP& a, const VP& b) { return v_cmp(a, b) < 0; });
+  items.erase(std::unique(items.begin(), items.end(), [](const VP& a, const VP& b) { return v_eq(a, b); }),
+              items.end());
+  auto n = std::make_shared<Node>();
+  n->t = VT::Set;
+  n->items = std::move(items);
+  return n;
+}
+VP v_obj(std::vector<std::pair<VP, VP>> kv) {
+  std::stable_sort(kv.begin(), kv.end(), [](const auto& a, const auto& b) { return v_cmp(a.first, b.first) < 0; });
+  // later duplicates win (json.Unmarshal into map semantics)
+  std::vector<std::pair<VP, VP>> out;
+  for (auto& e : kv) {
+    if (!out.empty() && v_eq(out.back().first, e.first)) out.back().second = e.second;
+    else out.push_back(std::move(e));
+  }
+  auto n = std::make_shared<Node>();
+  n->t = VT::Obj;
+  n->kv = std::move(out);
+  return n;
+}
+
+// ------------------------------------------------------------------------------------------ ordering
+int type_rank(VT t) {
+  switch (t) {
+    case VT::Null: return 0;
+    case VT::False:
+    case VT::True: return 1;
+    case VT::Num: return 2;
+    case VT::Str: return 3;
+    case VT::Arr: return 4;
+    case VT::Obj: return 5;
+    case VT::Set: return 6;
+    default: return -1;
+  }
+}
+
+int v_cmp(const VP& a, const VP& b) {
+  if (a.get() == b.get()) return 0;
+  int ra = type_rank(a->t), rb = type_rank(b->t);
+  if (ra != rb) return ra < rb ? -1 : 1;
+  switch (a->t) {
+    case VT::Null: return 0;
+    case VT::False:
+    case VT::True: return (int)a->t - (int)b->t;
+    case VT::Num: return num_cmp(a->n, b->n);
+    case VT::Str: {
+      int c = a->s.compare(b->s);
+      return c < 0 ? -1 : (c > 0 ? 1 : 0);
+    }
+    case VT::Arr:
+    case VT::Set: {
+      size_t n = std::min(a->items.size(), b->items.size());
+      for (size_t i = 0; i < n; ++i) {
+        int c = v_cmp(a->items[i], b->items[i]);
+        if (c) return c;
+      }
+      return a->items.size() < b->items.size() ? -1 : (a->items.size() > b->items.size() ? 1 : 0);
+    }
+    case VT::Obj: {
+      size_t n = std::min(a->kv.size(), b->kv.size());
+      for (size_t i = 0; i < n; ++i) {
+        int c = v_cmp(a->kv[i].first, b->kv[i].first);
+        if (c) return c;
+        c = v_cmp(a->kv[i].second, b->kv[i].second);
+        if (c) return c;
+      }
+      return a->kv.size() < b->kv.size() ? -1 : (a->kv.size() > b->kv.size() ? 1 : 0);
+    }
+    default: return 0;
+  }
+}
+
+VP obj_get(const VP& o, const VP& key) {
+  if (!o || o->t != VT::Obj) return nullptr;
+  size_t lo = 0, hi = o->kv.size();
+  while (lo < hi) {
+    size_t mid = (lo + hi) / 2;
+    int c = v_cmp(o->kv[mid].first, key);
+    if (c == 0) return o->kv[mid].second;
+    if (c < 0) lo = mid + 1;
+    else hi = mid;
+  }
+  return nullptr;
+}
+
+VP obj_get(const VP& o, const char* key) {
+  if (!o || o->t != VT::Obj) return nullptr;
+  size_t lo = 0, hi = o->kv.size();
+  while (lo < hi) {
+    size_t mid = (lo + hi) / 2;
+    const VP& k = o->kv[mid].first;
+    int c;
+    if (k->t != VT::Str) c = type_rank(k->t) < 3 ? -1 : 1;
+    else {
+      c = k->s.compare(key);
+    }
+    if (c == 0) return o->kv[mid].second;
+    if (c < 0) lo = mid + 1;
+    else hi = mid;
+  }
+  return nullptr;
+}
+
+VP set_find(const VP& s, const VP& x) {
+  if (!s || s->t != VT::Set) return nullptr;
+  size_t lo = 0, hi = s->items.size();
+  while (lo < hi) {
+    size_t mid = (lo + hi) / 2;
+    int c = v_cmp(s->items[mid], x);
+    if (c == 0) return s->items[mid];
+    if (c < 0) lo = mid + 1;
+    else hi = mid;
+  }
+  return nullptr;
+}
+
+// ---------------------------------------------------------------------------------------------- JSON
+namespace {
+struct JP {
+  const char* p;
+  const char* e;
+  int depth = 0;
+  [[noreturn]] void fail(const char* m) { throw JsonError{std::string("invalid JSON: ") + m}; }
+  void ws() {
+    while (p < e && (*p == ' ' || *p == '\n' || *p == '\t' || *p == '\r')) ++p;
+  }
+  static void utf8(std::string& out, unsigned cp) {
+    if (cp < 0x80) out.push_back((char)cp);
+    else if (cp < 0x800) {
+      out.push_back((char)(0xC0 | (cp >> 6)));
+      out.push_back((char)(0x80 | (cp & 0x3F)));
+    } else if (cp < 0x10000) {
+      out.push_back((char)(0xE0 | (cp >> 12)));
+      out.push_back((char)(0x80 | ((cp >> 6) & 0x3F)));
+      out.push_back((char)(0x80 | (cp & 0x3F)));
+    } else {
+      out.push_back((char)(0xF0 | (cp >> 18)));
+      out.push_back((char)(0x80 | ((cp >> 12) & 0x3F)));
+      out.push_back((char)(0x80 | ((cp >> 6) & 0x3F)));
+      out.push_back((char)(0x80 | (cp & 0x3F)));
+    }
+  }
+  unsigned hex4() {
+    if (e - p < 4) fail("bad \\u escape");
+    unsigned v = 0;
+    for (int i = 0; i < 4; ++i) {
+      char c = *p++;
+      v <<= 4;
+      if (c >= '0' && c <= '9') v |= c - '0';
+      else if (c >= 'a' && c <= 'f') v |= c - 'a' + 10;
+      else if (c >= 'A' && c <= 'F') v |= c - 'A' + 10;
+      else fail("bad \\u escape");
+    }
+    return v;
+  }
+  std::string str() {
+    // *p == '"'
+    ++p;
+    std::string out;
+    const char* s = p;
+    while (p < e && *p != '"' && *p != '\\') ++p;
+    out.assign(s, p - s);
+    while (p < e && *p != '"') {
+      if (*p == '\\') {
+        ++p;
+        if (p >= e) fail("bad escape");
+        char c = *p++;
+        switch (c) {
+          case 'n': out.push_back('\n'); break;
+          case 't': out.push_back('\t'); break;
+          case 'r': out.push_back('\r'); break;
+          case 'b': out.push_back('\b'); break;
+          case 'f': out.push_back('\f'); break;
+          case '/': out.push_back('/'); break;
+          case '\\': out.push_back('\\'); break;
+          case '"': out.push_back('"'); break;
+          case 'u': {
+            unsigned cp = hex4();
+            if (cp >= 0xD800 && cp < 0xDC00 && e - p >= 6 && p[0] == '\\' && p[1] == 'u') {
+              p += 2;
+              unsigned lo = hex4();
+              if (lo >= 0xDC00 && lo < 0xE000) cp = 0x10000 + ((cp - 0xD800) << 10) + (lo - 0xDC00);
+              else cp = 0xFFFD;
+            }
+            utf8(out, cp);
+            break;
+          }
+          default: fail("bad escape");
+        }
+      } else {
+        out.push_back(*p++);
+      }
+    }
+    if (p >= e) fail("unterminated string");
+    ++p;
+    return out;
+  }
+  VP value() {
+    ws();
+    if (p >= e) fail("unexpected end");
+    if (++depth > 512) fail("too deep");
+    VP r;
+    char c = *p;
+    if (c == '{') {
+      ++p;
+      std::vector<std::pair<VP, VP>> kv;
+      ws();
+      if (p < e && *p == '}') {
+        ++p;
+      } else {
+        while (true) {
+          ws();
+          if (p >= e || *p != '"') fail("object key expected");
+          VP k = v_str(str());
+          ws();
+          if (p >= e || *p != ':') fail("':' expected");
+          ++p;
+          VP v = value();
+          kv.emplace_back(std::move(k), std::move(v));
+          ws();
+          if (p < e && *p == ',') {
+            ++p;
+            continue;
+          }
+          if (p < e && *p == '}') {
+            ++p;
+            break;
+          }
+          fail("',' or '}' expected");
+        }
+      }
+      r = v_obj(std::move(kv));
+    } else if (c == '[') {
+      ++p;
+      std::vector<VP> items;
+      ws();
+      if (p < e && *p == ']') {
+        ++p;
+      } else {
+        while (true) {
+          items.push_back(value());
+          ws();
+          if (p < e && *p == ',') {
+            ++p;
+            continue;
+          }
+          if (p < e && *p == ']') {
+            ++p;
+            break;
+          }
+          fail("',' or ']' expected");
+        }
+      }
+      r = v_arr(std::move(items));
+    } else if (c == '"') {
+      r = v_str(str());
+    } else if (c == 't' && e - p >= 4 && !memcmp(p, "true", 4)) {
+      p += 4;
+      r = v_bool(true);
+    } else if (c == 'f' && e - p >= 5 && !memcmp(p, "false", 5)) {
+      p += 5;
+      r = v_bool(false);
+    } else if (c == 'n' && e - p >= 4 && !memcmp(p, "null", 4)) {
+      p += 4;
+      r = v_null();
+    } else if (c == '-' || (c >= '0' && c <= '9')) {
+      const char* s = p;
+      bool isint = true;
+      if (*p == '-') ++p;
+      while (p < e && *p >= '0' && *p <= '9') ++p;
+      if (p < e && (*p == '.' || *p == 'e' || *p == 'E')) {
+        isint = false;
+        while (p < e && ((*p >= '0' && *p <= '9') || *p == '.' || *p == 'e' || *p == 'E' || *p == '+' || *p == '-')) ++p;
+      }
+      size_t len = p - s;
+      if (isint && len <= 37) {
+        __int128 v = 0;
+        const char* q = s;
+        bool neg = *q == '-';
+        if (neg) ++q;
+        if (q == p) fail("bad number");
+        for (; q < p; ++q) v = v * 10 + (*q - '0');
+        r = v_num(Num::of_int(neg ? -v : v));
+      } else {
+        std::string tmp(s, len);
+        char* endp = nullptr;
+        double d = strtod(tmp.c_str(), &endp);
+        if (endp != tmp.c_str() + len) fail("bad number");
+        r = v_num(Num::of_double(d));
+      }
+    } else {
+      fail("unexpected character");
+    }
+    --depth;
+    return r;
+  }
+};
+}  // namespace
+
+VP json_parse(const char* p, size_t n) {
+  JP jp{p, p + n};
+  VP v = jp.value();
+  jp.ws();
+  if (jp.p != jp.e) jp.fail("trailing characters");
+  return v;
+}
+
+void json_quote(const std::string& s, std::string& out) {
+  out.push_back('"');
+  for (unsigned char c : s) {
+    switch (c) {
+      case '"': out += "\\\""; break;
+      case '\\': out += "\\\\"; break;
+      case '\n': out += "\\n"; break;
+      case '\r': out += "\\r"; break;
+      case '\t': out += "\\t"; break;
+      default:
+        if (c < 0x20) {
+          char b[8];
+          snprintf(b, sizeof b, "\\u%04x", c);
+          out += b;
+        } else {
+          out.push_back((char)c);
+        }
+    }
+  }
+  out.push_back('"');
+}
+
+static void json_rec(const VP& v, std::string& out) {
+  switch (v->t) {
+    case VT::Null: out += "null"; break;
+    case VT::True: out += "true"; break;
+    case VT::False: out += "false"; break;
+    case VT::Num: out += num_str(v->n); break;
+    case VT::Str: json_quote(v->s, out); break;
+    case VT::Arr:
+    case VT::Set: {
+      out.push_back('[');
+      bool first = true;
+      for (auto& x : v->items) {
+        if (!first) out.push_back(',');
+        first = false;
+        json_rec(x, out);
+      }
+      out.push_back(']');
+      break;
+    }
+    case VT::Obj: {
+      out.push_back('{');
+      bool first = true;
+      for (auto& e : v->kv) {
+        if (!first) out.push_back(',');
+        first = false;
+        if (e.first->t == VT::Str) json_quote(e.first->s, out);
+        else json_quote(fmt_value(e.first, false), out);
+        out.push_back(':');
+        json_rec(e.second, out);
+      }
+      out.push_back('}');
+      break;
+    }
+    default: out += "null";
+  }
+}
+
+std::string json_str(const VP& v) {
+  std::string out;
+  if (!v) return "null";
+  json_rec(v, out);
+  return out;
+}
+
+// ------------------------------------------------------------------------------------------ `%v`
+static void fmt_rec(const VP& v, bool top, std::string& out) {
+  switch (v->t) {
+    case VT::Null: out += "null"; break;
+    case VT::True: out += "true"; break;
+    case VT::False: out += "false"; break;
+    case VT::Num: out += num_str(v->n); break;
+    case VT::Str:
+      if (top) out += v->s;
+      else json_quote(v->s, out);
+      break;
+    case VT::Arr: {
+      out.push_back('[');
+      for (size_t i = 0; i < v->items.size(); ++i) {
+        if (i) out += ", ";
+        fmt_rec(v->items[i], false, out);
+      }
+      out.push_back(']');
+      break;
+    }
+    case VT::Set: {
+      if (v->items.empty()) {
+        out += "set()";
+        break;
+      }
+      out.push_back('{');
+      for (size_t i = 0; i < v->items.size(); ++i) {
+        if (i) out += ", ";
+        fmt_rec(v->items[i], false, out);
+      }
+      out.push_back('}');
+      break;
+    }
+    case VT::Obj: {
+      out.push_back('{');
+      for (size_t i = 0; i < v->kv.size(); ++i) {
+        if (i) out += ", ";
+        fmt_rec(v->kv[i].first, false, out);
+        out += ": ";
+        fmt_rec(v->kv[i].second, false, out);
+      }
+      out.push_back('}');
+      break;
+    }
+    default: break;
+  }
+}
+
+std::string fmt_value(const VP& v, bool top) {
+  std::string out;
+  if (v) fmt_rec(v, top, out);
+  return out;
+}
+
+std::string intern_key(const VP& v) {
+  switch (v->t) {
+    case VT::Null: return "z";
+    case VT::True: return "t";
+    case VT::False: return "f";
+    case VT::Num: return "n" + num_str(v->n);
+    case VT::Str: return "s" + v->s;
+    default: return "j" + fmt_value(v, false);
+  }
+}
+
+}  // namespace gk

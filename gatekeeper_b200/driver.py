@@ -1,0 +1,391 @@
+"""Host-side mirror of the constraint-framework `drivers.Driver` interface over the C ABI.
+
+The reference is Go and its host side would bind include/gk_engine.h with cgo (go/gpudriver/driver.go,
+INTEGRATION.md).  There is no Go toolchain in this image, so this module is the same thin shim in Python
+(ctypes): identical method names, argument meaning and error behaviour as the Driver implementation in
+the reference tree (pkg/drivers/k8scel/driver.go:70-263), plus the additive batch entry point the audit
+sweep uses.  Everything that decides a violation happens below the C ABI on the GPU; this file only
+marshals arguments.  It fails loudly when the native library or a CUDA device is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+from dataclasses import dataclass, field
+from typing import Any, Iterable, Optional, Sequence
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgk_engine.so")
+
+WEBHOOK_EP = "validation.gatekeeper.sh"   # pkg/util/enforcement_action.go:24-39
+AUDIT_EP = "audit.gatekeeper.sh"
+GATOR_EP = "gator.gatekeeper.sh"
+
+SOURCE = {"": 0, None: 0, "Original": 1, "Generated": 2, "All": 3}
+
+F_BITMAP_ONLY, F_MATERIALIZE, F_NO_COPY_BACK = 0, 1, 2
+
+
+class GkError(RuntimeError):
+    """Error returned across the C ABI (AddTemplate compile errors, CUDA failures, ...)."""
+
+    def __init__(self, code: int, msg: str):
+        super().__init__(msg)
+        self.code = code
+
+
+class gk_cfg(C.Structure):
+    _fields_ = [("device", C.c_int32), ("threads", C.c_int32)]
+
+
+class gk_obj(C.Structure):
+    _fields_ = [("json", C.c_char_p), ("len", C.c_size_t), ("old_json", C.c_char_p), ("old_len", C.c_size_t),
+                ("ns_json", C.c_char_p), ("ns_len", C.c_size_t), ("ns_name", C.c_char_p), ("operation", C.c_char_p),
+                ("userinfo_json", C.c_char_p), ("userinfo_len", C.c_size_t), ("source", C.c_uint8)]
+
+
+class gk_violation(C.Structure):
+    _fields_ = [("object", C.c_uint32), ("constraint", C.c_uint32), ("msg", C.c_char_p), ("details_json", C.c_char_p),
+                ("enforcement_action", C.c_char_p), ("scoped_actions_json", C.c_char_p), ("autoreject", C.c_uint8)]
+
+
+class gk_result(C.Structure):
+    _fields_ = [("n_objects", C.c_uint32), ("n_constraints", C.c_uint32), ("words", C.c_uint32),
+                ("viol_bits", C.POINTER(C.c_uint32)), ("err_bits", C.POINTER(C.c_uint32)),
+                ("totals", C.POINTER(C.c_uint64)), ("err_totals", C.POINTER(C.c_uint64)),
+                ("violations", C.POINTER(gk_violation)), ("n_violations", C.c_size_t),
+                ("object_errors", C.POINTER(C.c_char_p)),
+                ("flatten_ms", C.c_double), ("h2d_ms", C.c_double), ("kernel_ms", C.c_double), ("d2h_ms", C.c_double),
+                ("materialize_ms", C.c_double), ("alg_bytes", C.c_uint64), ("h2d_bytes", C.c_uint64),
+                ("d2h_bytes", C.c_uint64), ("gpu_launches", C.c_uint64), ("priv", C.c_void_p)]
+
+
+EXPORTS = [
+    "gk_engine_create", "gk_engine_destroy", "gk_backend_name", "gk_add_template", "gk_remove_template",
+    "gk_add_constraint", "gk_remove_constraint", "gk_put_namespace", "gk_remove_namespace", "gk_constraint_count",
+    "gk_constraint_key", "gk_review_batch", "gk_batch_upload", "gk_batch_eval", "gk_batch_eval_device",
+    "gk_batch_size", "gk_batch_alg_bytes", "gk_batch_free", "gk_free_result", "gk_free_str", "gk_dump",
+    "gk_stat_description",
+]
+
+
+def load_library(path: Optional[str] = None) -> C.CDLL:
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise GkError(-3, f"native library {path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    lib = C.CDLL(path)
+    P, S, U32, U64 = C.c_void_p, C.c_char_p, C.c_uint32, C.c_uint64
+    PP = C.POINTER(C.c_char_p)
+    lib.gk_engine_create.restype = P
+    lib.gk_engine_create.argtypes = [C.POINTER(gk_cfg), PP]
+    lib.gk_engine_destroy.argtypes = [P]
+    lib.gk_backend_name.restype = S
+    lib.gk_backend_name.argtypes = [P]
+    lib.gk_add_template.argtypes = [P, S, S, C.c_size_t, PP]
+    lib.gk_remove_template.argtypes = [P, S]
+    lib.gk_add_constraint.argtypes = [P, S, C.c_size_t, PP]
+    lib.gk_remove_constraint.argtypes = [P, S, S]
+    lib.gk_put_namespace.argtypes = [P, S, S, C.c_size_t, PP]
+    lib.gk_remove_namespace.argtypes = [P, S]
+    lib.gk_constraint_count.restype = U32
+    lib.gk_constraint_count.argtypes = [P]
+    lib.gk_constraint_key.restype = S
+    lib.gk_constraint_key.argtypes = [P, U32]
+    lib.gk_review_batch.argtypes = [P, C.POINTER(gk_obj), C.c_size_t, S, U32, C.POINTER(gk_result), PP]
+    lib.gk_batch_upload.argtypes = [P, C.POINTER(gk_obj), C.c_size_t, C.POINTER(P), C.POINTER(gk_result), PP]
+    lib.gk_batch_eval.argtypes = [P, P, S, U32, C.POINTER(gk_result), PP]
+    lib.gk_batch_eval_device.argtypes = [P, P, S, P, P, P, P, P, PP]
+    lib.gk_batch_size.restype = U32
+    lib.gk_batch_size.argtypes = [P]
+    lib.gk_batch_alg_bytes.restype = U64
+    lib.gk_batch_alg_bytes.argtypes = [P]
+    lib.gk_batch_free.argtypes = [P, P]
+    lib.gk_free_result.argtypes = [C.POINTER(gk_result)]
+    lib.gk_free_str.argtypes = [C.c_void_p]
+    lib.gk_dump.restype = C.c_void_p
+    lib.gk_dump.argtypes = [P]
+    lib.gk_stat_description.restype = S
+    lib.gk_stat_description.argtypes = [S]
+    return lib
+
+
+@dataclass
+class Review:
+    """What target.HandleReview accepts: an object (+ optional oldObject / Namespace / source / operation)
+    -- pkg/target/target.go:86-138, pkg/target/data.go:24-28."""
+    object: Any = None                 # dict, JSON str/bytes, or None
+    old_object: Any = None
+    namespace: Any = None              # explicit Namespace object
+    namespace_name: Optional[str] = None
+    source: str = ""
+    operation: str = ""
+    user_info: Any = None
+
+
+@dataclass
+class Result:
+    """types.Result -- fields as used at pkg/audit/manager.go:895-923."""
+    object: int
+    constraint: str                    # "Kind/name"
+    msg: str
+    details: Any
+    enforcement_action: str
+    scoped_enforcement_actions: list
+    autoreject: bool = False
+
+
+@dataclass
+class BatchResponse:
+    n_objects: int
+    constraints: list                  # index -> "Kind/name"
+    viol_bits: Any                     # numpy uint32 [n, words] or None
+    err_bits: Any
+    totals: list
+    err_totals: list
+    results: list = field(default_factory=list)
+    object_errors: list = field(default_factory=list)
+    stats: dict = field(default_factory=dict)
+
+    def pairs(self):
+        """Set of (object index, constraint key) with the violation bit set."""
+        out = set()
+        if self.viol_bits is None:
+            return out
+        n, w = self.viol_bits.shape
+        for o in range(n):
+            for k in range(w):
+                bits = int(self.viol_bits[o, k])
+                while bits:
+                    b = bits & -bits
+                    out.add((o, self.constraints[k * 32 + b.bit_length() - 1]))
+                    bits ^= b
+        return out
+
+
+def _to_bytes(x) -> Optional[bytes]:
+    if x is None:
+        return None
+    if isinstance(x, bytes):
+        return x
+    if isinstance(x, str):
+        return x.encode()
+    return json.dumps(x, separators=(",", ":")).encode()
+
+
+class Driver:
+    """Mirror of `drivers.Driver` (method set at pkg/drivers/k8scel/driver.go:70-263).  `Name()` is "Rego":
+    templates carrying `targets[].rego` / `code[engine: Rego]` route to this driver."""
+
+    def __init__(self, device: int = 0, threads: int = 0, lib_path: Optional[str] = None):
+        self._lib = load_library(lib_path)
+        err = C.c_char_p()
+        cfg = gk_cfg(device, threads)
+        self._e = self._lib.gk_engine_create(C.byref(cfg), C.byref(err))
+        if not self._e:
+            raise GkError(-3, self._take(err) or "gk_engine_create failed")
+
+    # ---- plumbing
+    def _take(self, err) -> str:
+        if not err or not err.value:
+            return ""
+        s = err.value.decode(errors="replace")
+        self._lib.gk_free_str(C.cast(err, C.c_void_p))
+        return s
+
+    def _check(self, rc: int, err):
+        if rc != 0:
+            raise GkError(rc, self._take(err) or f"error {rc}")
+
+    def close(self):
+        if getattr(self, "_e", None):
+            self._lib.gk_engine_destroy(self._e)
+            self._e = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- drivers.Driver
+    def Name(self) -> str:
+        return "Rego"
+
+    def backend(self) -> str:
+        return self._lib.gk_backend_name(self._e).decode()
+
+    def AddTemplate(self, template: dict) -> None:
+        kind = template["spec"]["crd"]["spec"]["names"]["kind"]
+        tgt = template["spec"]["targets"][0]
+        src = tgt.get("rego")
+        if not src:
+            for c in tgt.get("code") or []:
+                if c.get("engine") == "Rego":
+                    src = c["source"]["rego"]
+        if not src:
+            raise GkError(-2, "no Rego source for this driver in the template (ErrNoDriver)")
+        self.add_template(kind, src)
+
+    def add_template(self, kind: str, rego: str) -> None:
+        err = C.c_char_p()
+        b = rego.encode()
+        self._check(self._lib.gk_add_template(self._e, kind.encode(), b, len(b), C.byref(err)), err)
+
+    def RemoveTemplate(self, template_or_kind) -> None:
+        kind = template_or_kind if isinstance(template_or_kind, str) else template_or_kind["spec"]["crd"]["spec"]["names"]["kind"]
+        self._lib.gk_remove_template(self._e, kind.encode())
+
+    def AddConstraint(self, constraint: dict) -> None:
+        err = C.c_char_p()
+        b = _to_bytes(constraint)
+        self._check(self._lib.gk_add_constraint(self._e, b, len(b), C.byref(err)), err)
+
+    def RemoveConstraint(self, constraint: dict) -> None:
+        self._lib.gk_remove_constraint(self._e, constraint["kind"].encode(), constraint["metadata"]["name"].encode())
+
+    def AddData(self, target: str, path: Sequence[str], data: Any) -> None:
+        """Only Namespace objects matter to this driver (they feed the namespaceSelector table);
+        path shapes per pkg/target/target.go:60-66."""
+        if len(path) >= 4 and path[0] == "cluster" and path[2] == "Namespace":
+            err = C.c_char_p()
+            b = _to_bytes(data)
+            self._check(self._lib.gk_put_namespace(self._e, path[3].encode(), b, len(b), C.byref(err)), err)
+
+    def RemoveData(self, target: str, path: Sequence[str]) -> None:
+        if len(path) >= 4 and path[0] == "cluster" and path[2] == "Namespace":
+            self._lib.gk_remove_namespace(self._e, path[3].encode())
+
+    def Dump(self) -> str:
+        p = self._lib.gk_dump(self._e)
+        s = C.string_at(p).decode() if p else ""
+        if p:
+            self._lib.gk_free_str(p)
+        return s
+
+    def GetDescriptionForStat(self, name: str) -> str:
+        d = self._lib.gk_stat_description(name.encode())
+        if d is None:
+            raise GkError(-1, f"unknown stat name for Rego (GPU): {name}")
+        return d.decode()
+
+    def constraints(self) -> list:
+        n = self._lib.gk_constraint_count(self._e)
+        return [self._lib.gk_constraint_key(self._e, i).decode() for i in range(n)]
+
+    # ---- reviews
+    def _marshal(self, reviews: Iterable):
+        keep = []
+        arr_t = []
+        for r in reviews:
+            if not isinstance(r, Review):
+                r = Review(object=r)
+            o = gk_obj()
+            j, oj, nj, uj = _to_bytes(r.object), _to_bytes(r.old_object), _to_bytes(r.namespace), _to_bytes(r.user_info)
+            nn = r.namespace_name.encode() if r.namespace_name is not None else None
+            op = r.operation.encode() if r.operation else None
+            keep.append((j, oj, nj, uj, nn, op))
+            o.json, o.len = j, len(j) if j else 0
+            o.old_json, o.old_len = oj, len(oj) if oj else 0
+            o.ns_json, o.ns_len = nj, len(nj) if nj else 0
+            o.ns_name = nn
+            o.operation = op
+            o.userinfo_json, o.userinfo_len = uj, len(uj) if uj else 0
+            o.source = SOURCE.get(r.source, 4)
+            arr_t.append(o)
+        arr = (gk_obj * max(1, len(arr_t)))(*arr_t)
+        return arr, len(arr_t), keep
+
+    def _unpack(self, res: gk_result, keys: list) -> BatchResponse:
+        import numpy as np
+        n, w, c = res.n_objects, res.words, res.n_constraints
+        vb = eb = None
+        if res.viol_bits:
+            vb = np.ctypeslib.as_array(res.viol_bits, shape=(n * w,)).copy().reshape(n, w) if n else np.zeros((0, w), np.uint32)
+        if res.err_bits:
+            eb = np.ctypeslib.as_array(res.err_bits, shape=(n * w,)).copy().reshape(n, w) if n else np.zeros((0, w), np.uint32)
+        out = BatchResponse(
+            n_objects=n, constraints=keys, viol_bits=vb, err_bits=eb,
+            totals=[int(res.totals[i]) for i in range(c)], err_totals=[int(res.err_totals[i]) for i in range(c)],
+            stats={k: getattr(res, k) for k in ("flatten_ms", "h2d_ms", "kernel_ms", "d2h_ms", "materialize_ms", "alg_bytes",
+                                                "h2d_bytes", "d2h_bytes", "gpu_launches")})
+        for i in range(res.n_violations):
+            v = res.violations[i]
+            dj = v.details_json.decode() if v.details_json else ""
+            out.results.append(Result(v.object, keys[v.constraint], v.msg.decode(errors="replace"), json.loads(dj) if dj else None,
+                                      v.enforcement_action.decode(), json.loads(v.scoped_actions_json.decode()), bool(v.autoreject)))
+        if res.object_errors:
+            out.object_errors = [(res.object_errors[i].decode() if res.object_errors[i] else None) for i in range(n)]
+        return out
+
+    def ReviewBatch(self, reviews: Iterable, enforcement_point: str = AUDIT_EP, materialize: bool = True) -> BatchResponse:
+        """The additive batch entry point (SURVEY.md 8(b) `BatchReviewer`): Client.Review semantics -- match
+        pre-filter, enforcement-point filter, evaluation, EnforcementAction stamping -- for many reviews at once."""
+        arr, n, keep = self._marshal(reviews)
+        res = gk_result()
+        err = C.c_char_p()
+        keys = self.constraints()
+        rc = self._lib.gk_review_batch(self._e, arr, n, enforcement_point.encode(), F_MATERIALIZE if materialize else 0,
+                                       C.byref(res), C.byref(err))
+        self._check(rc, err)
+        try:
+            return self._unpack(res, keys)
+        finally:
+            self._lib.gk_free_result(C.byref(res))
+
+    def Query(self, target: str, constraints: Sequence[dict], review, enforcement_point: str = AUDIT_EP) -> list:
+        """drivers.Driver.Query shape (pkg/drivers/k8scel/driver.go:161-250): one review, the (already
+        matched) constraints; returns the Results for those constraints."""
+        want = {f"{c['kind']}/{c['metadata']['name']}" for c in constraints}
+        resp = self.ReviewBatch([review], enforcement_point)
+        if resp.object_errors and resp.object_errors[0]:
+            raise GkError(-1, resp.object_errors[0])
+        return [r for r in resp.results if r.constraint in want]
+
+    # ---- resident batches (audit sweep / bench)
+    def upload(self, reviews: Iterable):
+        arr, n, keep = self._marshal(reviews)
+        h = C.c_void_p()
+        stats = gk_result()
+        err = C.c_char_p()
+        self._check(self._lib.gk_batch_upload(self._e, arr, n, C.byref(h), C.byref(stats), C.byref(err)), err)
+        return ResidentBatch(self, h, (arr, keep), {"flatten_ms": stats.flatten_ms, "h2d_ms": stats.h2d_ms,
+                                                    "h2d_bytes": stats.h2d_bytes, "alg_bytes": stats.alg_bytes})
+
+
+class ResidentBatch:
+    def __init__(self, drv: Driver, handle, keep, stats):
+        self.drv, self.h, self._keep, self.stats = drv, handle, keep, stats
+
+    def __len__(self):
+        return self.drv._lib.gk_batch_size(self.h)
+
+    @property
+    def alg_bytes(self) -> int:
+        return self.drv._lib.gk_batch_alg_bytes(self.h)
+
+    def eval(self, enforcement_point: str = AUDIT_EP, flags: int = 0) -> BatchResponse:
+        res = gk_result()
+        err = C.c_char_p()
+        keys = self.drv.constraints()
+        self.drv._check(self.drv._lib.gk_batch_eval(self.drv._e, self.h, enforcement_point.encode(), flags, C.byref(res), C.byref(err)), err)
+        try:
+            return self.drv._unpack(res, keys)
+        finally:
+            self.drv._lib.gk_free_result(C.byref(res))
+
+    def eval_device(self, enforcement_point, d_viol: int, d_err: int, d_totals: int, d_err_totals: int, stream: int = 0):
+        err = C.c_char_p()
+        self.drv._check(self.drv._lib.gk_batch_eval_device(self.drv._e, self.h, enforcement_point.encode(), d_viol, d_err, d_totals,
+                                                           d_err_totals, stream, C.byref(err)), err)
+
+    def free(self):
+        if self.h:
+            self.drv._lib.gk_batch_free(self.drv._e, self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

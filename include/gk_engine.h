@@ -1,0 +1,134 @@
+/* gk_engine.h -- C ABI of the B200 constraint-evaluation engine.
+ *
+ * This is the boundary a Go `drivers.Driver` shim binds with cgo (see INTEGRATION.md and go/gpudriver/).
+ * Each entry point names the reference interface it stands behind (paths relative to the gatekeeper repo):
+ *
+ *   gk_engine_create/destroy  <- rego.New(args...) / driver lifetime          main.go:457-462, pkg/gator/opa.go:32-37
+ *   gk_add_template           <- Driver.AddTemplate(ctx, *ConstraintTemplate)  pkg/drivers/k8scel/driver.go:74-136
+ *   gk_remove_template        <- Driver.RemoveTemplate                          pkg/drivers/k8scel/driver.go:138-147
+ *   gk_add_constraint         <- Driver.AddConstraint + TargetHandler.ToMatcher pkg/drivers/k8scel/driver.go:149-151, pkg/target/target.go:239-254
+ *   gk_remove_constraint      <- Driver.RemoveConstraint                        pkg/drivers/k8scel/driver.go:153-155
+ *   gk_put_namespace / remove <- Driver.AddData/RemoveData for Namespace paths + nsCache   pkg/target/ns_cache.go:15-85, pkg/target/target.go:60-66
+ *   gk_review_batch           <- Client.Review -> Matcher.Match -> Driver.Query, for a BATCH of reviews
+ *                                pkg/audit/manager.go:622,720 ; pkg/webhook/policy.go:661 ; pkg/target/matcher.go:21-71 ;
+ *                                pkg/drivers/k8scel/driver.go:161-250
+ *   gk_batch_upload/eval/free <- the same, split so an audit sweep can keep flattened batches resident in HBM
+ *   gk_dump                   <- Driver.Dump                                    pkg/drivers/k8scel/driver.go:252-254
+ *   gk_stat_description       <- Driver.GetDescriptionForStat                   pkg/drivers/k8scel/driver.go:256-263
+ *
+ * Conventions: plain pointers and sizes; 0 = success, negative = error with *err set to an engine-allocated
+ * message (free with gk_free_str); the caller owns inputs for the duration of a call; the engine owns
+ * gk_result buffers until gk_free_result.  Mutators take an exclusive lock, reviews a shared one
+ * (mirrors k8scel.Driver's sync.RWMutex, pkg/drivers/k8scel/driver.go:61,130,167).  No exceptions or
+ * panics cross this boundary.  There is no CPU fallback: without a CUDA device gk_engine_create fails.
+ */
+#ifndef GK_ENGINE_H
+#define GK_ENGINE_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gk_engine gk_engine_t;
+typedef struct gk_batch gk_batch_t;
+
+enum { GK_OK = 0, GK_ERR_INVALID = -1, GK_ERR_REGO = -2, GK_ERR_BACKEND = -3, GK_ERR_INTERNAL = -4 };
+
+/* review source -- pkg/mutation/types/mutator.go:14-27 */
+enum { GK_SOURCE_UNSET = 0, GK_SOURCE_ORIGINAL = 1, GK_SOURCE_GENERATED = 2, GK_SOURCE_ALL = 3, GK_SOURCE_INVALID = 4 };
+
+/* gk_review_batch / gk_batch_eval flags */
+enum {
+  GK_F_BITMAP_ONLY = 0,      /* violation / error bitmaps + per-constraint totals */
+  GK_F_MATERIALIZE = 1,      /* also render {msg, details} for every flagged pair (types.Result list) */
+  GK_F_NO_COPY_BACK = 2      /* leave bitmaps on the device (throughput measurement); totals still returned */
+};
+
+typedef struct {
+  int32_t device;            /* CUDA device ordinal */
+  int32_t threads;           /* host flatten threads; 0 = hardware concurrency */
+} gk_cfg;
+
+/* One review: target.AugmentedUnstructured / AugmentedReview (pkg/target/data.go:24-28, review.go:9-14). */
+typedef struct {
+  const char* json;          /* Object.Raw (may be NULL when only old_json is set) */
+  size_t len;
+  const char* old_json;      /* OldObject.Raw or NULL */
+  size_t old_len;
+  const char* ns_json;       /* the review's Namespace object, or NULL (then the namespace cache is consulted) */
+  size_t ns_len;
+  const char* ns_name;       /* AdmissionRequest.Namespace; NULL = object's metadata.namespace */
+  const char* operation;     /* "", "CREATE", "UPDATE", "DELETE"; NULL = "" */
+  const char* userinfo_json; /* AdmissionRequest.UserInfo or NULL */
+  size_t userinfo_len;
+  uint8_t source;            /* GK_SOURCE_* */
+} gk_obj;
+
+/* One types.Result (pkg/drivers/k8scel/driver.go:223-227 for the field set). */
+typedef struct {
+  uint32_t object;                 /* index into the batch */
+  uint32_t constraint;             /* index, see gk_constraint_key */
+  const char* msg;
+  const char* details_json;        /* Metadata["details"] as JSON, "" when absent */
+  const char* enforcement_action;  /* deny | dryrun | warn | scoped | unrecognized */
+  const char* scoped_actions_json; /* JSON array of actions for the enforcement point ("[]" unless scoped) */
+  uint8_t autoreject;              /* 1: the matcher returned an error; msg carries its text */
+} gk_violation;
+
+typedef struct {
+  uint32_t n_objects, n_constraints, words;   /* words = ceil(n_constraints / 32) */
+  const uint32_t* viol_bits;       /* [n_objects * words] or NULL with GK_F_NO_COPY_BACK */
+  const uint32_t* err_bits;        /* [n_objects * words] matcher-error plane */
+  const uint64_t* totals;          /* [n_constraints] violating (constraint, object) pairs */
+  const uint64_t* err_totals;      /* [n_constraints] */
+  const gk_violation* violations;  /* with GK_F_MATERIALIZE */
+  size_t n_violations;
+  const char* const* object_errors;/* [n_objects] NULL or review-level error (bad JSON, DELETE without oldObject) */
+  /* instrumentation (StatsEntry material, pkg/instrumentation/types.go:28-59) */
+  double flatten_ms, h2d_ms, kernel_ms, d2h_ms, materialize_ms;
+  uint64_t alg_bytes;              /* algorithmic bytes the kernel had to read + bitmap bytes written */
+  uint64_t h2d_bytes, d2h_bytes;
+  uint64_t gpu_launches;
+  void* priv;
+} gk_result;
+
+gk_engine_t* gk_engine_create(const gk_cfg* cfg, char** err);
+void gk_engine_destroy(gk_engine_t* e);
+const char* gk_backend_name(gk_engine_t* e);
+
+int gk_add_template(gk_engine_t* e, const char* kind, const char* rego_src, size_t len, char** err);
+int gk_remove_template(gk_engine_t* e, const char* kind);
+int gk_add_constraint(gk_engine_t* e, const char* constraint_json, size_t len, char** err);
+int gk_remove_constraint(gk_engine_t* e, const char* kind, const char* name);
+int gk_put_namespace(gk_engine_t* e, const char* name, const char* ns_json, size_t len, char** err);
+int gk_remove_namespace(gk_engine_t* e, const char* name);
+
+/* constraint index <-> identity ("Kind/name"); the returned string is engine-owned until the next mutation */
+uint32_t gk_constraint_count(gk_engine_t* e);
+const char* gk_constraint_key(gk_engine_t* e, uint32_t index);
+
+int gk_review_batch(gk_engine_t* e, const gk_obj* objs, size_t n, const char* enforcement_point, uint32_t flags,
+                    gk_result* out, char** err);
+
+/* resident batches: flatten + upload once, evaluate many times (audit sweep / benchmarking) */
+int gk_batch_upload(gk_engine_t* e, const gk_obj* objs, size_t n, gk_batch_t** out, gk_result* stats, char** err);
+int gk_batch_eval(gk_engine_t* e, gk_batch_t* b, const char* enforcement_point, uint32_t flags, gk_result* out, char** err);
+/* writes into caller-owned DEVICE buffers on a caller stream and returns without synchronising:
+ * viol/err u32[n*words], totals/err_totals u64[n_constraints] (multi-GPU gather path) */
+int gk_batch_eval_device(gk_engine_t* e, gk_batch_t* b, const char* enforcement_point, void* d_viol, void* d_err,
+                         void* d_totals, void* d_err_totals, void* cuda_stream, char** err);
+uint32_t gk_batch_size(gk_batch_t* b);
+uint64_t gk_batch_alg_bytes(gk_batch_t* b);
+void gk_batch_free(gk_engine_t* e, gk_batch_t* b);
+
+void gk_free_result(gk_result* r);
+void gk_free_str(char* s);
+char* gk_dump(gk_engine_t* e);
+const char* gk_stat_description(const char* stat_name);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
