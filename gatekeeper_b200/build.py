@@ -2,6 +2,7 @@
 
   gatekeeper_b200/libgk_engine.so   -- the product: C++ host engine + CUDA kernels for sm_100a (nvcc)
   tests/_hostemu/libgk_hostemu.so   -- TEST-ONLY: same host engine linked against the CPU emulation backend
+  gatekeeper_b200/libgk_synth.so    -- deterministic synthetic workload generator (bench / tests), not part of the engine
 """
 from __future__ import annotations
 
@@ -17,7 +18,8 @@ OBJ = os.path.join(ROOT, "build", "obj")
 LIB = os.path.join(ROOT, "gatekeeper_b200", "libgk_engine.so")
 EMU = os.path.join(ROOT, "tests", "_hostemu", "libgk_hostemu.so")
 
-HOST_SRCS = ["val.cpp", "rego_parse.cpp", "rego_eval.cpp", "lower.cpp", "engine.cpp", "capi.cpp", "synth.cpp"]
+HOST_SRCS = ["val.cpp", "rego_parse.cpp", "rego_eval.cpp", "lower.cpp", "engine.cpp", "capi.cpp"]
+SYNTH = os.path.join(ROOT, "gatekeeper_b200", "libgk_synth.so")
 CXXFLAGS = ["-std=c++17", "-O2", "-g1", "-fPIC", "-Wall", "-Wextra", "-pthread"]
 NVCCFLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC"]
 
@@ -81,6 +83,9 @@ def build(verbose=False, hostemu=True, force=False):
         _run([_nvcc(), "-shared", "-o", LIB, *objs, ko, "-Xcompiler", "-pthread", "-cudart", "static"])
     if hostemu and (force or _stale(EMU, objs + [eo], 0)):
         _run(["g++", "-shared", "-o", EMU, *objs, eo, "-pthread"])
+    ssrc = os.path.join(CSRC, "synth.cpp")
+    if force or _stale(SYNTH, [ssrc], 0):
+        _run(["g++", *CXXFLAGS, "-shared", "-o", SYNTH, ssrc])
     return LIB
 
 

@@ -316,6 +316,34 @@ int gk_batch_eval_device(gk_engine_t* e, gk_batch_t* b, const char* ep, void* d_
   });
 }
 
+static std::vector<gk_obj> blob_objs(const char* buf, const uint64_t* off, size_t n, uint8_t source) {
+  std::vector<gk_obj> v(n);
+  for (size_t i = 0; i < n; ++i) {
+    memset(&v[i], 0, sizeof(gk_obj));
+    v[i].json = buf + off[i];
+    v[i].len = (size_t)(off[i + 1] - off[i]);
+    v[i].source = source;
+  }
+  return v;
+}
+
+int gk_batch_upload_blob(gk_engine_t* e, const char* buf, const uint64_t* offsets, size_t n, uint8_t source, gk_batch_t** outb,
+                         gk_result* stats, char** err) {
+  if (!e || !outb || ((!buf || !offsets) && n)) return GK_ERR_INVALID;
+  if (stats) memset(stats, 0, sizeof *stats);
+  return guard(err, [&]() {
+    auto v = blob_objs(buf, offsets, n, source);
+    upload_batch(e, v.data(), n, outb, stats);
+  });
+}
+
+int gk_review_blob(gk_engine_t* e, const char* buf, const uint64_t* offsets, size_t n, uint8_t source, const char* ep, uint32_t flags,
+                   gk_result* out, char** err) {
+  if (!e || !out || ((!buf || !offsets) && n)) return GK_ERR_INVALID;
+  auto v = blob_objs(buf, offsets, n, source);
+  return gk_review_batch(e, v.data(), n, ep, flags, out, err);
+}
+
 uint32_t gk_batch_size(gk_batch_t* b) { return b ? b->n : 0; }
 uint64_t gk_batch_alg_bytes(gk_batch_t* b) { return b ? b->alg_bytes : 0; }
 void gk_batch_free(gk_engine_t* e, gk_batch_t* b) {

@@ -65,7 +65,7 @@ EXPORTS = [
     "gk_engine_create", "gk_engine_destroy", "gk_backend_name", "gk_add_template", "gk_remove_template",
     "gk_add_constraint", "gk_remove_constraint", "gk_put_namespace", "gk_remove_namespace", "gk_constraint_count",
     "gk_constraint_key", "gk_review_batch", "gk_batch_upload", "gk_batch_eval", "gk_batch_eval_device",
-    "gk_batch_size", "gk_batch_alg_bytes", "gk_batch_free", "gk_free_result", "gk_free_str", "gk_dump",
+    "gk_batch_upload_blob", "gk_review_blob", "gk_batch_size", "gk_batch_alg_bytes", "gk_batch_free", "gk_free_result", "gk_free_str", "gk_dump",
     "gk_stat_description",
 ]
 
@@ -96,6 +96,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.gk_batch_upload.argtypes = [P, C.POINTER(gk_obj), C.c_size_t, C.POINTER(P), C.POINTER(gk_result), PP]
     lib.gk_batch_eval.argtypes = [P, P, S, U32, C.POINTER(gk_result), PP]
     lib.gk_batch_eval_device.argtypes = [P, P, S, P, P, P, P, P, PP]
+    lib.gk_batch_upload_blob.argtypes = [P, P, C.POINTER(C.c_uint64), C.c_size_t, C.c_uint8, C.POINTER(P), C.POINTER(gk_result), PP]
+    lib.gk_review_blob.argtypes = [P, P, C.POINTER(C.c_uint64), C.c_size_t, C.c_uint8, S, U32, C.POINTER(gk_result), PP]
     lib.gk_batch_size.restype = U32
     lib.gk_batch_size.argtypes = [P]
     lib.gk_batch_alg_bytes.restype = U64
@@ -351,6 +353,29 @@ class Driver:
         self._check(self._lib.gk_batch_upload(self._e, arr, n, C.byref(h), C.byref(stats), C.byref(err)), err)
         return ResidentBatch(self, h, (arr, keep), {"flatten_ms": stats.flatten_ms, "h2d_ms": stats.h2d_ms,
                                                     "h2d_bytes": stats.h2d_bytes, "alg_bytes": stats.alg_bytes})
+
+
+    def upload_blob(self, blob, source: str = "Original"):
+        """Flatten + upload a page of objects held in one contiguous buffer (workloads.ObjectBlob)."""
+        h = C.c_void_p()
+        stats = gk_result()
+        err = C.c_char_p()
+        self._check(self._lib.gk_batch_upload_blob(self._e, blob.buf, blob.offsets, len(blob), SOURCE.get(source, 4), C.byref(h),
+                                                   C.byref(stats), C.byref(err)), err)
+        return ResidentBatch(self, h, blob, {"flatten_ms": stats.flatten_ms, "h2d_ms": stats.h2d_ms, "h2d_bytes": stats.h2d_bytes,
+                                             "alg_bytes": stats.alg_bytes})
+
+    def ReviewBlob(self, blob, enforcement_point: str = AUDIT_EP, flags: int = 0, source: str = "Original") -> BatchResponse:
+        """End-to-end audit page: host JSON -> flatten -> H2D -> kernel -> D2H (+ optional message rendering)."""
+        res = gk_result()
+        err = C.c_char_p()
+        keys = self.constraints()
+        self._check(self._lib.gk_review_blob(self._e, blob.buf, blob.offsets, len(blob), SOURCE.get(source, 4), enforcement_point.encode(),
+                                             flags, C.byref(res), C.byref(err)), err)
+        try:
+            return self._unpack(res, keys)
+        finally:
+            self._lib.gk_free_result(C.byref(res))
 
 
 class ResidentBatch:

@@ -119,6 +119,13 @@ int gk_batch_eval(gk_engine_t* e, gk_batch_t* b, const char* enforcement_point, 
  * viol/err u32[n*words], totals/err_totals u64[n_constraints] (multi-GPU gather path) */
 int gk_batch_eval_device(gk_engine_t* e, gk_batch_t* b, const char* enforcement_point, void* d_viol, void* d_err,
                          void* d_totals, void* d_err_totals, void* cuda_stream, char** err);
+/* the same two calls for a page of objects held in ONE contiguous buffer (a LIST page / spill directory as the
+ * audit loop reads it, pkg/audit/manager.go:502-561,686-695): document i is buf[offsets[i], offsets[i+1]).
+ * Every object is reviewed as an AugmentedUnstructured with the given source and no oldObject. */
+int gk_batch_upload_blob(gk_engine_t* e, const char* buf, const uint64_t* offsets, size_t n, uint8_t source, gk_batch_t** out,
+                         gk_result* stats, char** err);
+int gk_review_blob(gk_engine_t* e, const char* buf, const uint64_t* offsets, size_t n, uint8_t source, const char* enforcement_point,
+                   uint32_t flags, gk_result* out, char** err);
 uint32_t gk_batch_size(gk_batch_t* b);
 uint64_t gk_batch_alg_bytes(gk_batch_t* b);
 void gk_batch_free(gk_engine_t* e, gk_batch_t* b);

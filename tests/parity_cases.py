@@ -1,0 +1,210 @@
+"""Parity cases shared by the CPU (host-emulation backend) and GPU (product library) test modules.
+Every case loads the SAME templates / constraints / objects into the oracle and into the engine and
+compares the full result set: (object, constraint, msg, details, enforcement action(s), autoreject)."""
+import json
+
+from conftest import assert_same, engine_results, golden, make_pair, oracle_results
+from gatekeeper_b200 import driver as D
+from gatekeeper_b200 import workloads as W
+from oracle import k8s
+
+
+def _split_docs(docs):
+    tm, cons, nss = [], [], []
+    for d in docs:
+        if d.get("kind") == "ConstraintTemplate":
+            tm.append(k8s.template_from_yaml_obj(d))
+        elif str(d.get("apiVersion", "")).startswith("constraints.gatekeeper.sh"):
+            cons.append(d)
+        elif d.get("kind") == "Namespace":
+            nss.append(d)
+    return tm, cons, nss
+
+
+def case_gator(lib, case):
+    tm, cons, nss = _split_docs(case["docs"])
+    orc, drv, skipped = make_pair(tm, cons, nss, lib_path=lib, skip_unsupported=True)
+    revs = [D.Review(object=d) for d in case["docs"]]
+    resp = drv.ReviewBatch(revs, k8s.GATOR_EP)
+    assert_same(oracle_results(orc, revs, k8s.GATOR_EP), engine_results(resp))
+    if case["must_contain"] and not skipped:
+        msgs = {r.msg for r in resp.results}
+        for m in case["must_contain"]:
+            assert m in msgs
+    return resp
+
+
+def case_psp(lib):
+    psp = golden("psp_suite.json")
+    orc, drv, _ = make_pair([(t["kind"], t["rego"]) for t in psp["templates"]], psp["constraints"], lib_path=lib)
+    revs = [D.Review(object=p) for p in psp["pods"]]
+    for ep in (k8s.WEBHOOK_EP, k8s.AUDIT_EP):
+        resp = drv.ReviewBatch(revs, ep)
+        want = oracle_results(orc, revs, ep)
+        assert len(want) >= 5
+        assert_same(want, engine_results(resp))
+    return resp
+
+
+def case_config2(lib, n, start=0, with_namespaces=True, ep=k8s.AUDIT_EP):
+    tm, cons = W.config2()
+    nss = W.synth_namespaces() if with_namespaces else []
+    orc, drv, _ = make_pair(tm, cons, nss, lib_path=lib)
+    blob = W.synth_objects(start, n)
+    revs = [D.Review(object=json.loads(blob.get(i)), source="Original") for i in range(n)]
+    resp = drv.ReviewBatch(revs, ep)
+    want = oracle_results(orc, revs, ep)
+    assert_same(want, engine_results(resp))
+    # bitmap == set of violating (object, constraint) pairs; totals == column popcounts
+    pairs = {(o, c) for (o, c, *_rest) in want if not _rest[-1]}
+    assert resp.pairs() == pairs
+    for ci, key in enumerate(resp.constraints):
+        assert resp.totals[ci] == sum(1 for (_, c) in pairs if c == key)
+    return resp, want
+
+
+def case_mixed_kinds(lib, n):
+    """config 4 shape: PSP suite over mixed GVKs (only Pods match `kinds`)."""
+    tm, cons = W.config4()
+    orc, drv, _ = make_pair(tm, cons, lib_path=lib)
+    blob = W.synth_objects(0, n, mode=1)
+    revs = [D.Review(object=json.loads(blob.get(i))) for i in range(n)]
+    resp = drv.ReviewBatch(revs, k8s.AUDIT_EP)
+    assert_same(oracle_results(orc, revs, k8s.AUDIT_EP), engine_results(resp))
+    return resp
+
+
+def case_config5(lib, n):
+    tm, cons = W.config5()
+    orc, drv, _ = make_pair(tm, cons, lib_path=lib)
+    blob = W.synth_objects(1000, n)
+    revs = [D.Review(object=json.loads(blob.get(i))) for i in range(n)]
+    resp = drv.ReviewBatch(revs, k8s.AUDIT_EP)
+    assert_same(oracle_results(orc, revs, k8s.AUDIT_EP), engine_results(resp))
+    return resp
+
+
+def case_allowedrepos_comprehension_variant(lib, n):
+    """demo/agilebank variant: `satisfied := [good | repo = ...; good = startswith(...)]; not any(satisfied)`."""
+    t = W.templates()["allowedrepos"]
+    cons = [W._constraint(t["kind"], "repos", match=dict(W.POD), params={"repos": ["openpolicyagent/", "gcr.io/proj-0"]}),
+            W._constraint(t["kind"], "none", params={"repos": []})]
+    orc, drv, _ = make_pair([(t["kind"], t["rego"])], cons, lib_path=lib)
+    blob = W.synth_objects(50, n)
+    revs = [D.Review(object=json.loads(blob.get(i))) for i in range(n)]
+    resp = drv.ReviewBatch(revs, k8s.AUDIT_EP)
+    assert_same(oracle_results(orc, revs, k8s.AUDIT_EP), engine_results(resp))
+
+
+def case_match_vectors(lib):
+    """Every reference Matcher vector through the engine's in-kernel pre-filter (deny-all template): the
+    object is flagged iff the reference says it matches; errors become autoreject results."""
+    t = golden("templates.json")["fixtures_TemplateNeverValidate"]
+    vectors = [v for v in golden("match_vectors.json") if v["object"] is not None]
+    checked = 0
+    for v in vectors:
+        con = {"kind": t["kind"], "metadata": {"name": "c"}, "spec": {"match": v["match"]}}
+        drv = D.Driver(lib_path=lib)
+        drv.add_template(t["kind"], t["rego"])
+        drv.AddConstraint(con)
+        r = D.Review(object=v["object"], namespace=v["namespace"], source=v["source"])
+        resp = drv.ReviewBatch([r], k8s.AUDIT_EP)
+        flagged = bool(resp.viol_bits[0, 0] & 1)
+        errored = bool(resp.err_bits[0, 0] & 1)
+        assert (flagged, errored) == (v["wantMatch"], v["wantErr"]), v["name"]
+        if errored:
+            assert resp.results and resp.results[0].autoreject
+        checked += 1
+    assert checked >= 50
+
+
+def case_admission_shapes(lib):
+    """UPDATE with object+oldObject (either may match), DELETE (object := oldObject), explicit / cached /
+    missing Namespace for namespaceSelector, user info -- pkg/target/target.go:86-138,262-280."""
+    t = golden("templates.json")
+    tm = [(t[n]["kind"], t[n]["rego"]) for n in ("fixtures_TemplateNeverValidate", "fixtures_TemplateValidateUserInfo", "namespacelabelcheck")]
+    cons = [
+        {"kind": "NeverValidate", "metadata": {"name": "only-a"}, "spec": {"match": {"namespaces": ["a"]}}},
+        {"kind": "NeverValidate", "metadata": {"name": "nssel"}, "spec": {"match": {"namespaceSelector": {"matchLabels": {"bar": "qux"}}}}},
+        {"kind": "NeverValidate", "metadata": {"name": "generated-only"}, "spec": {"match": {"source": "Generated"}}},
+        {"kind": "NeverValidate", "metadata": {"name": "by-name"}, "spec": {"match": {"name": "web-*"}}},
+        {"kind": "ValidateUserInfo", "metadata": {"name": "users"}, "spec": {"enforcementAction": "warn"}},
+        {"kind": "K8sNamespaceLabelCheckRego", "metadata": {"name": "nslabel"}, "spec": {"parameters": {"requiredLabel": "bar"}}},
+    ]
+    ns_qux = {"apiVersion": "v1", "kind": "Namespace", "metadata": {"name": "cached", "labels": {"bar": "qux"}}}
+    orc, drv, _ = make_pair(tm, cons, [ns_qux], lib_path=lib)
+    pod = lambda ns, name="p", gen=None: {"apiVersion": "v1", "kind": "Pod",
+                                          "metadata": dict({"name": name, "namespace": ns}, **({"generateName": gen} if gen else {}))}
+    revs = [
+        D.Review(object=pod("a"), old_object=pod("b"), operation="UPDATE", source="Original"),
+        D.Review(object=pod("b"), old_object=pod("a"), operation="UPDATE", source="Original"),
+        D.Review(object=None, old_object=pod("a"), operation="DELETE", source="Original"),
+        D.Review(object=pod("cached"), source="Generated"),
+        D.Review(object=pod("uncached"), source="Original"),
+        D.Review(object=pod("x"), namespace={"apiVersion": "v1", "kind": "Namespace", "metadata": {"name": "x", "labels": {"bar": "qux"}}}, source="Original"),
+        D.Review(object=pod("b", name="web-1"), source="Original", user_info={"username": "alice"}),
+        D.Review(object=pod("b", name="", gen="web-"), source="Original", user_info={"username": "system:serviceaccount:x"}),
+        D.Review(object={"apiVersion": "v1", "kind": "Namespace", "metadata": {"name": "nsobj", "labels": {"bar": "qux"}}}, source="Original"),
+        D.Review(object=pod("b"), source=""),   # source unset vs matcher Generated => error (match.go:244-246)
+    ]
+    for ep in (k8s.WEBHOOK_EP, k8s.AUDIT_EP):
+        resp = drv.ReviewBatch(revs, ep)
+        assert_same(oracle_results(orc, revs, ep), engine_results(resp))
+    return resp
+
+
+def case_review_errors(lib):
+    """Bad JSON / missing kind / DELETE without oldObject are per-object review errors, not violations
+    (pkg/target/matcher.go:73-93, pkg/target/target.go:262-270); the rest of the batch is unaffected."""
+    t = golden("templates.json")["fixtures_TemplateNeverValidate"]
+    drv = D.Driver(lib_path=lib)
+    drv.add_template(t["kind"], t["rego"])
+    drv.AddConstraint({"kind": t["kind"], "metadata": {"name": "c"}, "spec": {}})
+    ok = {"apiVersion": "v1", "kind": "Pod", "metadata": {"name": "p"}}
+    revs = [D.Review(object=ok), D.Review(object=b"{not json"), D.Review(object={"apiVersion": "v1", "metadata": {}}),
+            D.Review(object=None, old_object=None, operation="DELETE"), D.Review(object=ok)]
+    resp = drv.ReviewBatch(revs, k8s.AUDIT_EP)
+    assert [bool(e) for e in resp.object_errors] == [False, True, True, True, False]
+    assert sorted(r.object for r in resp.results) == [0, 4]
+
+
+def case_edge_batches(lib):
+    """Empty batch, single object, no constraints, >32 constraints (two bitmap words), constant predicates."""
+    t = golden("templates.json")
+    drv = D.Driver(lib_path=lib)
+    ok = {"apiVersion": "v1", "kind": "Pod", "metadata": {"name": "p"}}
+    resp = drv.ReviewBatch([D.Review(object=ok)], k8s.AUDIT_EP)      # no templates at all
+    assert resp.results == [] and resp.totals == []
+    drv.add_template(t["fixtures_TemplateNeverValidate"]["kind"], t["fixtures_TemplateNeverValidate"]["rego"])
+    drv.add_template(t["fixtures_TemplateAlwaysValidate"]["kind"], t["fixtures_TemplateAlwaysValidate"]["rego"])
+    for i in range(40):
+        kind = "NeverValidate" if i % 3 else "AlwaysValidate"
+        drv.AddConstraint({"kind": kind, "metadata": {"name": f"c{i}"}, "spec": {}})
+    resp = drv.ReviewBatch([], k8s.AUDIT_EP)
+    assert resp.n_objects == 0 and resp.results == []
+    resp = drv.ReviewBatch([D.Review(object=ok)] * 3, k8s.AUDIT_EP)
+    assert resp.viol_bits.shape == (3, 2)
+    want = {k for i, k in enumerate(resp.constraints) if k.startswith("NeverValidate/")}
+    assert {c for (o, c) in resp.pairs() if o == 1} == want and len(want) == 26
+    # removal keeps indices consistent
+    drv.RemoveConstraint({"kind": "NeverValidate", "metadata": {"name": "c1"}})
+    resp = drv.ReviewBatch([D.Review(object=ok)], k8s.AUDIT_EP)
+    assert len(resp.results) == 25
+
+
+def case_unsupported_is_an_error_not_a_fallback(lib):
+    """Constructs outside the lowered subset fail AddTemplate/AddConstraint loudly (no CPU fallback)."""
+    import pytest
+    t = golden("templates.json")
+    drv = D.Driver(lib_path=lib)
+    with pytest.raises(D.GkError, match="unsafe"):
+        drv.add_template("CompileError", t["fixtures_TemplateCompileError"]["rego"])
+    with pytest.raises(D.GkError, match="data"):
+        drv.add_template("K8sUniqueLabel", 'package u\nviolation[{"msg": msg}] {\n  other := data.inventory.cluster[_][_][_]\n'
+                         '  other.metadata.labels.x == input.review.object.metadata.labels.x\n  msg := "dup"\n}\n')
+    drv.add_template("K8sRequiredLabels", t["requiredlabels_agilebank"]["rego"])
+    with pytest.raises(D.GkError, match="rego_unsupported: regular expression"):
+        drv.AddConstraint({"kind": "K8sRequiredLabels", "metadata": {"name": "x"},
+                           "spec": {"parameters": {"labels": [{"key": "owner", "allowedRegex": "^[a-z]+$"}]}}})
+    assert drv.Name() == "Rego"
+    assert "kernel" in drv.GetDescriptionForStat("kernelTimeNS")

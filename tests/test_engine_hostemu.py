@@ -1,0 +1,99 @@
+"""CPU-only tests of the host logic (Rego lowering, flattening, C-ABI plumbing, result materialisation)
+through tests/_hostemu/libgk_hostemu.so -- the engine linked against a TEST-ONLY backend that runs the very
+same per-object core (csrc/vm_core.h) in a CPU loop.  The GPU path is covered by test_gpu.py (`-m gpu`)."""
+import ctypes
+import os
+
+import pytest
+
+import parity_cases as P
+from conftest import HOSTEMU, ROOT, golden, has_cuda
+from gatekeeper_b200 import driver as D
+
+
+@pytest.mark.parametrize("case", golden("gator_cases.json"), ids=lambda c: c["name"])
+def test_gator_cases(case):
+    P.case_gator(HOSTEMU, case)
+
+
+def test_psp_suite():
+    P.case_psp(HOSTEMU)
+
+
+def test_config2_small():
+    resp, want = P.case_config2(HOSTEMU, 150)
+    assert len(want) > 500
+
+
+def test_config2_without_namespace_cache_errors_are_autorejects():
+    """namespaceSelector constraints with no cached Namespace: the error plane + autoreject results."""
+    resp, want = P.case_config2(HOSTEMU, 40, start=5000, with_namespaces=False)
+    assert any(w[-1] for w in want)
+    assert sum(resp.err_totals) == sum(1 for w in want if w[-1])
+
+
+def test_mixed_kinds():
+    P.case_mixed_kinds(HOSTEMU, 150)
+
+
+def test_config5_wildcards():
+    P.case_config5(HOSTEMU, 150)
+
+
+def test_allowedrepos_comprehension_variant():
+    P.case_allowedrepos_comprehension_variant(HOSTEMU, 100)
+
+
+def test_match_vectors_through_kernel_core():
+    P.case_match_vectors(HOSTEMU)
+
+
+def test_admission_shapes():
+    P.case_admission_shapes(HOSTEMU)
+
+
+def test_review_errors():
+    P.case_review_errors(HOSTEMU)
+
+
+def test_edge_batches():
+    P.case_edge_batches(HOSTEMU)
+
+
+def test_unsupported_is_an_error():
+    P.case_unsupported_is_an_error_not_a_fallback(HOSTEMU)
+
+
+def test_resident_batch_and_stale_program():
+    from gatekeeper_b200 import workloads as W
+    tm, cons = W.config1()
+    drv = D.Driver(lib_path=HOSTEMU)
+    for k, r in tm:
+        drv.add_template(k, r)
+    drv.AddConstraint(cons[0])
+    blob = W.synth_objects(0, 100)
+    rb = drv.upload([D.Review(object=blob.get(i)) for i in range(100)])
+    a = rb.eval()
+    b = rb.eval()
+    assert (a.viol_bits == b.viol_bits).all() and a.totals == b.totals and len(rb) == 100 and rb.alg_bytes > 0
+    drv.AddConstraint(dict(cons[0], metadata={"name": "second"}))
+    with pytest.raises(D.GkError, match="older constraint set"):
+        rb.eval()
+    rb.free()
+
+
+# ---- the product library: loads, exports the whole C ABI, and refuses to run without a GPU ---------------
+def test_product_library_exports_every_declared_symbol():
+    import re
+    hdr = open(os.path.join(ROOT, "include", "gk_engine.h")).read()
+    declared = set(re.findall(r"\b(gk_[a-z_]+)\s*\(", hdr)) - {"gk_cfg"}
+    lib = ctypes.CDLL(D.LIB_PATH)
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, missing
+    assert set(D.EXPORTS) <= declared
+
+
+@pytest.mark.skipif(has_cuda(), reason="only meaningful on a box without a GPU")
+def test_product_library_has_no_cpu_fallback():
+    with pytest.raises(D.GkError, match="no CPU fallback|CUDA"):
+        D.Driver()

@@ -1,0 +1,156 @@
+"""GPU parity tests: the product library (CUDA kernels, through the C ABI) against the oracle on the same
+seeded inputs, the committed golden fixtures, and size-independent properties at larger sizes.
+Run on the B200 box:  python -m pytest tests -m gpu -x -q"""
+import json
+
+import numpy as np
+import pytest
+
+import parity_cases as P
+from conftest import golden, has_cuda
+from gatekeeper_b200 import driver as D
+from gatekeeper_b200 import workloads as W
+from oracle import k8s
+
+pytestmark = pytest.mark.gpu
+LIB = None   # the product library, gatekeeper_b200/libgk_engine.so
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _needs_gpu():
+    if not has_cuda():
+        pytest.fail("GPU tests selected but no CUDA device is visible")
+    d = D.Driver()
+    assert d.backend() == "cuda-sm100a"
+    d.close()
+
+
+@pytest.mark.parametrize("case", golden("gator_cases.json"), ids=lambda c: c["name"])
+def test_gator_cases(case):
+    resp = P.case_gator(LIB, case)
+    assert resp.stats["gpu_launches"] >= 1 or resp.n_objects == 0
+
+
+def test_psp_suite():
+    P.case_psp(LIB)
+
+
+def test_config2_parity_2000_objects():
+    resp, want = P.case_config2(LIB, 2000)
+    assert len(want) > 5000 and resp.stats["gpu_launches"] >= 1 and resp.stats["kernel_ms"] > 0
+
+
+def test_config2_other_range_and_admission_ep():
+    P.case_config2(LIB, 700, start=123456, ep=k8s.WEBHOOK_EP)
+
+
+def test_config2_missing_namespace_cache():
+    resp, want = P.case_config2(LIB, 300, start=9000, with_namespaces=False)
+    assert sum(resp.err_totals) == sum(1 for w in want if w[-1]) > 0
+
+
+def test_mixed_kinds():
+    P.case_mixed_kinds(LIB, 1500)
+
+
+def test_config5_wildcards():
+    P.case_config5(LIB, 1500)
+
+
+def test_allowedrepos_comprehension_variant():
+    P.case_allowedrepos_comprehension_variant(LIB, 500)
+
+
+def test_match_vectors():
+    P.case_match_vectors(LIB)
+
+
+def test_admission_shapes():
+    P.case_admission_shapes(LIB)
+
+
+def test_review_errors():
+    P.case_review_errors(LIB)
+
+
+def test_edge_batches():
+    P.case_edge_batches(LIB)
+
+
+def test_unsupported_is_an_error():
+    P.case_unsupported_is_an_error_not_a_fallback(LIB)
+
+
+def test_config3_admission_microbatches():
+    """200 PSP constraints (7 bitmap words) x 64-request micro-batches, UPDATE with object + oldObject."""
+    tm, cons, pods = W.config3(200)
+    from conftest import assert_same, engine_results, make_pair, oracle_results
+    orc, drv, _ = make_pair(tm, cons, lib_path=LIB)
+    revs = [D.Review(object=pods[i % 5], old_object=pods[(i + 1) % 5], operation="UPDATE", user_info={"username": "u"}) for i in range(64)]
+    resp = drv.ReviewBatch(revs, k8s.WEBHOOK_EP)
+    assert resp.viol_bits.shape == (64, 7)
+    assert_same(oracle_results(orc, revs, k8s.WEBHOOK_EP), engine_results(resp))
+
+
+# ---- size-independent properties at larger sizes -----------------------------------------------------------
+@pytest.fixture(scope="module")
+def big():
+    tm, cons = W.config2()
+    drv = D.Driver()
+    for k, r in tm:
+        drv.add_template(k, r)
+    for c in cons:
+        drv.AddConstraint(c)
+    for ns in W.synth_namespaces():
+        drv.AddData("admission.k8s.gatekeeper.sh", ["cluster", "v1", "Namespace", ns["metadata"]["name"]], ns)
+    n = 200_000
+    blob = W.synth_objects(0, n)
+    revs = [D.Review(object=blob.get(i), source="Original") for i in range(n)]
+    return drv, blob, revs, n
+
+
+def test_large_batch_properties(big):
+    drv, blob, revs, n = big
+    rb = drv.upload(revs)
+    a = rb.eval()
+    b = rb.eval()
+    # determinism
+    assert (a.viol_bits == b.viol_bits).all() and a.totals == b.totals
+    # totals are the column popcounts of the bitmap (a checksum of checksums)
+    bits = a.viol_bits
+    for ci in range(len(a.constraints)):
+        col = (bits[:, ci // 32] >> np.uint32(ci % 32)) & np.uint32(1)
+        assert int(col.sum()) == a.totals[ci]
+    # sharding invariance: evaluating halves separately and concatenating equals the whole
+    h = n // 2
+    r1 = drv.upload(revs[:h]).eval()
+    r2 = drv.upload(revs[h:]).eval()
+    assert (np.concatenate([r1.viol_bits, r2.viol_bits]) == bits).all()
+    assert [x + y for x, y in zip(r1.totals, r2.totals)] == a.totals
+    # spot-check 300 random objects of the big batch against the oracle
+    rng = np.random.default_rng(1)
+    idx = sorted(rng.choice(n, 300, replace=False).tolist())
+    tm, cons = W.config2()
+    orc = k8s.Client()
+    for k, r in tm:
+        orc.add_template(k, r)
+    for c in cons:
+        orc.add_constraint(c)
+    for ns in W.synth_namespaces():
+        orc.add_namespace(ns)
+    keys = a.constraints
+    for i in idx:
+        want = {"%s/%s" % r["constraint"] for r in orc.review(k8s.Review(obj=json.loads(blob.get(i)), source="Original"), k8s.AUDIT_EP)
+                if not r.get("autoreject")}
+        got = {keys[c] for c in range(len(keys)) if (int(bits[i, c // 32]) >> (c % 32)) & 1}
+        assert got == want, i
+    rb.free()
+
+
+def test_enforcement_point_mask_only_hides_scoped_constraints(big):
+    drv, blob, revs, n = big
+    rb = drv.upload(revs[:5000])
+    audit = rb.eval(k8s.AUDIT_EP)
+    vap = rb.eval("vap.k8s.io")   # scoped constraints list audit + "*": still active ("*")
+    assert audit.totals == vap.totals
+    rb.free()
