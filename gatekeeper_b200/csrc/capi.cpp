@@ -194,7 +194,7 @@ void upload_batch(gk_engine* e, const gk_obj* objs, size_t n, gk_batch** outb, g
     stats->h2d_bytes = h2d_bytes;
     stats->alg_bytes = hb->alg_bytes;
     stats->n_objects = hb->n;
-    stats->n_constraints = (uint32_t)c->match.size();
+    stats->n_constraints = (uint32_t)c->cons.size();
   }
   *outb = b.release();
 }

@@ -334,21 +334,42 @@ void Engine::compile_locked() {
   ProgramBuilder pb;
   pb.interner = &strings_;
   pb.schema = &out->schema;
-  // pass 1: lower every constraint (fills the shared schema)
+  // pass 1: lower every constraint (fills the shared schema); group constraints that share a match block so the
+  // kernel evaluates each distinct spec.match once per object
+  std::vector<Constraint*> live;
+  std::map<std::string, uint32_t> match_ix;
+  std::vector<uint32_t> mid_of;
   for (auto& cp : constraints_) {
     Constraint& c = *cp;
     auto tit = templates_.find(c.kind);
     if (tit == templates_.end()) continue;
     c.formula = lower_violation(tit->second.mod, c.params, out->schema);
-    out->order.push_back(&c);
+    std::string key = c.match.has ? json_str(c.match.raw) : std::string();
+    auto it = match_ix.find(key);
+    uint32_t mid = it == match_ix.end() ? (uint32_t)match_ix.size() : it->second;
+    if (it == match_ix.end()) match_ix.emplace(key, mid);
+    live.push_back(&c);
+    mid_of.push_back(mid);
   }
+  std::vector<size_t> perm(live.size());
+  for (size_t i = 0; i < perm.size(); ++i) perm[i] = i;
+  std::stable_sort(perm.begin(), perm.end(), [&](size_t a, size_t b) { return mid_of[a] < mid_of[b]; });
+  std::vector<FP> all;
+  for (size_t i : perm) {
+    out->order.push_back(live[i]);
+    all.push_back(live[i]->formula);
+  }
+  pb.plan(all);
+  out->n_shared = pb.n_shared();
+  out->match.resize(match_ix.size());
+  std::vector<bool> built(match_ix.size(), false);
   // pass 2: emit code + match blocks
-  for (auto* cc : out->order) {
-    Constraint& c = *const_cast<Constraint*>(cc);
+  for (size_t oi = 0; oi < perm.size(); ++oi) {
+    Constraint& c = *live[perm[oi]];
+    const uint32_t mid = mid_of[perm[oi]];
     c.pc = pb.emit(c.formula);
+    out->cons.push_back(GkCons{mid, c.pc});
     GkMatch m{};
-    m.prog_pc = c.pc;
-    m.active = 1;
     MatchSpec& ms = c.match;
     ms.lsel_err.clear();
     ms.nssel_err.clear();
@@ -356,8 +377,9 @@ void Engine::compile_locked() {
     if (ms.has) {
       m.flags |= GK_M_HAS_MATCH;
       const VP& r = ms.raw;
+      const bool emit_pool = !built[mid];   // pool entries are written once per distinct block
       VP kinds = obj_get(r, "kinds");
-      if (kinds && kinds->t == VT::Arr && !kinds->items.empty()) {
+      if (emit_pool && kinds && kinds->t == VT::Arr && !kinds->items.empty()) {
         m.kinds_off = (uint32_t)pb.pool.size();
         for (auto& e : kinds->items) {
           std::vector<uint32_t> ks, gs;
@@ -388,7 +410,7 @@ void Engine::compile_locked() {
       else if (scope == "Namespaced") m.flags |= GK_M_SCOPE_NAMESPACED;
       auto wild_list = [&](const char* field, uint32_t& off, uint32_t& n) {
         VP l = obj_get(r, field);
-        if (!l || l->t != VT::Arr) return;
+        if (!emit_pool || !l || l->t != VT::Arr) return;
         off = (uint32_t)pb.pool.size();
         for (auto& x : l->items) {
           uint32_t mode;
@@ -412,6 +434,7 @@ void Engine::compile_locked() {
           m.flags |= bad_flag;
           return;
         }
+        if (!emit_pool) return;
         off = (uint32_t)pb.pool.size();
         for (auto& q : reqs) {
           pb.pool.push_back(strings_.intern("s" + q.key));
@@ -428,7 +451,7 @@ void Engine::compile_locked() {
         m.flags |= GK_M_HAS_NAME;
         std::string lit;
         parse_wildcard(name, m.name_mode, lit);
-        m.name_boff = pb.add_bytes(lit);
+        if (emit_pool) m.name_boff = pb.add_bytes(lit);
         m.name_len = (uint32_t)lit.size();
       }
       std::string src = str_field(r, "source");
@@ -442,15 +465,19 @@ void Engine::compile_locked() {
       }
       m.flags |= code << GK_M_SRC_SHIFT;
     }
-    ms.dev = m;
-    out->match.push_back(m);
+    if (!built[mid]) {
+      out->match[mid] = m;
+      built[mid] = true;
+    }
+    ms.dev = out->match[mid];
   }
   out->instr = std::move(pb.instr);
   out->pool = std::move(pb.pool);
   out->cbytes = std::move(pb.cbytes);
   if (out->pool.empty()) out->pool.push_back(0);
   if (out->cbytes.empty()) out->cbytes.push_back(0);
-  if (out->instr.empty()) out->instr.push_back(GkInstr{GK_OP_JMP, 0, GK_PC_REJECT | (GK_PC_REJECT << 16), 0});
+  if (out->instr.empty()) out->instr.push_back(GkInstr{GK_OP_END, 0, 0, 0});
+  if (out->match.empty()) out->match.push_back(GkMatch{});
   compiled_ = out;
   dirty_ = false;
 }
@@ -458,7 +485,8 @@ void Engine::compile_locked() {
 std::string Engine::dump() {
   auto c = compiled();
   std::string o = "schema: " + std::to_string(c->schema.scopes.size() - 1) + " scopes, " + std::to_string(c->schema.cols.size()) +
-                  " columns, " + std::to_string(c->instr.size()) + " instructions\n";
+                  " columns, " + std::to_string(c->instr.size()) + " instructions, " + std::to_string(c->match.size()) +
+                  " distinct match blocks, " + std::to_string(c->n_shared) + " shared sub-formulas\n";
   for (size_t i = 1; i < c->schema.scopes.size(); ++i)
     o += "  scope " + std::to_string(i) + " parent " + std::to_string(c->schema.scopes[i].parent) + ": " + c->schema.scopes[i].gen->key + "\n";
   for (size_t i = 0; i < c->schema.cols.size(); ++i)

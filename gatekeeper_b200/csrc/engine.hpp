@@ -89,8 +89,10 @@ struct Compiled {
   std::vector<GkInstr> instr;
   std::vector<uint32_t> pool;
   std::vector<uint8_t> cbytes;
-  std::vector<GkMatch> match;                  // per constraint
-  std::vector<const Constraint*> order;        // constraint index -> constraint
+  std::vector<GkMatch> match;                  // DISTINCT match blocks
+  std::vector<GkCons> cons;                    // per constraint: match block id + entry pc
+  std::vector<const Constraint*> order;        // constraint index -> constraint (grouped by match block)
+  size_t n_shared = 0;                         // sub-formulas shared across constraints (CSE bits)
 };
 
 class StringTable : public Interner {

@@ -47,65 +47,76 @@ __global__ void __launch_bounds__(kThreads) gk_eval_kernel(const KParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   const uint32_t C = p.prog.nconstraints;
   const uint32_t W = p.out.words;
-  // ---- shared-memory layout: [totals C u32][err totals C u32][match][instr][pool][cbytes]
+  // ---- shared-memory layout: [totals C u32][err totals C u32][active C u32] then (when they fit) the tables:
+  //      [cons][match][columns][scopes][instr][pool][cbytes]
   uint32_t* s_tot = reinterpret_cast<uint32_t*>(smem);
   uint32_t* s_err = s_tot + C;
-  size_t off = ((size_t)2 * C * 4 + 15) / 16 * 16;
+  uint32_t* s_act = s_err + C;
+  size_t off = ((size_t)3 * C * 4 + 15) / 16 * 16;
+  const GkCons* cons = p.prog.cons;
   const GkMatch* match = p.prog.match;
   const GkInstr* instr = p.prog.instr;
   const uint32_t* pool = p.prog.pool;
   const uint8_t* cbytes = p.prog.cbytes;
+  const GkColumn* cols = p.batch.cols;
+  const GkScope* scopes = p.batch.scopes;
   for (uint32_t i = threadIdx.x; i < 2 * C; i += blockDim.x) s_tot[i] = 0;
+  for (uint32_t i = threadIdx.x; i < C; i += blockDim.x) s_act[i] = p.active[i];
   if (p.smem_tables) {
-    GkMatch* sm = reinterpret_cast<GkMatch*>(smem + off);
-    stage(sm, p.prog.match, (size_t)C * sizeof(GkMatch));
-    off += ((size_t)C * sizeof(GkMatch) + 15) / 16 * 16;
-    GkInstr* si = reinterpret_cast<GkInstr*>(smem + off);
-    stage(si, p.prog.instr, (size_t)p.prog.ninstr * sizeof(GkInstr));
-    off += (size_t)p.prog.ninstr * sizeof(GkInstr);
-    uint32_t* sp = reinterpret_cast<uint32_t*>(smem + off);
-    stage(sp, p.prog.pool, ((size_t)p.prog.npool * 4 + 15) / 16 * 16);
-    off += ((size_t)p.prog.npool * 4 + 15) / 16 * 16;
-    uint8_t* sb = smem + off;
-    stage(sb, p.prog.cbytes, ((size_t)p.prog.ncbytes + 15) / 16 * 16);
-    match = sm;
-    instr = si;
-    pool = sp;
-    cbytes = sb;
+    auto place = [&](const void* src, size_t bytes) {
+      void* dst = smem + off;
+      stage(dst, src, (bytes + 15) / 16 * 16);
+      off += (bytes + 15) / 16 * 16;
+      return dst;
+    };
+    cons = static_cast<const GkCons*>(place(p.prog.cons, (size_t)C * sizeof(GkCons)));
+    match = static_cast<const GkMatch*>(place(p.prog.match, (size_t)p.prog.nmatch * sizeof(GkMatch)));
+    cols = static_cast<const GkColumn*>(place(p.batch.cols, (size_t)p.batch.ncols * sizeof(GkColumn)));
+    scopes = static_cast<const GkScope*>(place(p.batch.scopes, (size_t)p.batch.nscopes * sizeof(GkScope)));
+    instr = static_cast<const GkInstr*>(place(p.prog.instr, (size_t)p.prog.ninstr * sizeof(GkInstr)));
+    pool = static_cast<const uint32_t*>(place(p.prog.pool, (size_t)p.prog.npool * 4));
+    cbytes = static_cast<const uint8_t*>(place(p.prog.cbytes, (size_t)p.prog.ncbytes));
   }
   __syncthreads();
 
   const uint32_t n = p.batch.n;
   const uint32_t lane = threadIdx.x & 31u;
+  // one object per thread, 32 consecutive objects per warp; every lane of a warp walks the same constraint and the
+  // same instruction, so table reads broadcast and there is no divergent dispatch
   for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
-    const uint32_t obj = base + threadIdx.x;
-    const bool live = obj < n && !(p.batch.flags[obj < n ? obj : 0] & GK_F_SKIP);
+    const uint32_t obj_raw = base + threadIdx.x;
+    const uint32_t obj = obj_raw < n ? obj_raw : n - 1;
+    const bool live = obj_raw < n && !(p.batch.flags[obj] & GK_F_SKIP);
+    unsigned long long cse = 0, cse_valid = 0;
+    uint32_t cur_mid = GK_NONE;
+    int mres = 0;
     for (uint32_t w = 0; w < W; ++w) {
       uint32_t vbits = 0, ebits = 0;
       const uint32_t cend = min(C, (w + 1) * 32u);
       for (uint32_t c = w * 32u; c < cend; ++c) {
-        if (!p.active[c]) continue;   // warp-uniform
-        bool v = false, e = false;
-        if (live) {
-          const int r = gk_match(p.batch, pool, cbytes, match[c], obj);
-          int code = r < 0 ? -r : 0;
-          if (r > 0) {
-            const uint32_t pc = match[c].prog_pc;
-            int flag = 0;
-            v = pc == GK_PC_ACCEPT ? true : pc == GK_PC_REJECT ? false : gk_run(p.batch, instr, pool, cbytes, pc, obj, &flag);
-            if (flag) {
-              v = false;
-              code = flag;
-            }
-          }
-          if (code) {
-            e = true;
-            const uint32_t slot = atomicAdd(p.out.errcount, 1u);
-            if (slot < p.out.errcap) {
-              p.out.errlist[3 * slot] = obj;
-              p.out.errlist[3 * slot + 1] = c;
-              p.out.errlist[3 * slot + 2] = (uint32_t)code;
-            }
+        if (!s_act[c]) continue;   // enforcement-point filter: warp-uniform
+        const GkCons cc = cons[c];
+        if (cc.match_id != cur_mid) {   // warp-uniform: constraints are grouped by match block
+          cur_mid = cc.match_id;
+          mres = live ? gk_match(p.batch, pool, cbytes, match[cur_mid], obj) : 0;
+        }
+        int flag = 0;
+        bool v = cc.pc == GK_PC_ACCEPT ? true
+                 : cc.pc == GK_PC_REJECT ? false
+                                         : gk_eval_prog(cols, scopes, instr, pool, cbytes, cc.pc, obj, live, cse, cse_valid, &flag);
+        v = v && mres > 0;
+        int code = mres < 0 ? -mres : 0;
+        if (mres > 0 && flag) {
+          v = false;
+          code = flag;
+        }
+        const bool e = code != 0;
+        if (e) {
+          const uint32_t slot = atomicAdd(p.out.errcount, 1u);
+          if (slot < p.out.errcap) {
+            p.out.errlist[3 * slot] = obj;
+            p.out.errlist[3 * slot + 1] = c;
+            p.out.errlist[3 * slot + 2] = (uint32_t)code;
           }
         }
         vbits |= (uint32_t)v << (c & 31u);
@@ -117,7 +128,7 @@ __global__ void __launch_bounds__(kThreads) gk_eval_kernel(const KParams p) {
           if (be) atomicAdd(&s_err[c], __popc(be));
         }
       }
-      if (obj < n) {
+      if (obj_raw < n) {
         p.out.viol[(size_t)obj * W + w] = vbits;
         p.out.err[(size_t)obj * W + w] = ebits;
       }
@@ -183,7 +194,8 @@ class CudaBackend : public Backend {
     CK(cudaSetDevice(device_));
     free_tables();
     prog_ = GkProgram{};
-    prog_.nconstraints = (uint32_t)c.match.size();
+    prog_.nconstraints = (uint32_t)c.cons.size();
+    prog_.nmatch = (uint32_t)c.match.size();
     prog_.ninstr = (uint32_t)c.instr.size();
     prog_.npool = (uint32_t)c.pool.size();
     prog_.ncbytes = (uint32_t)c.cbytes.size();
@@ -193,10 +205,12 @@ class CudaBackend : public Backend {
       CK(cudaMemset(*dst, 0, padded));
       if (bytes) CK(cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
     };
+    up(c.cons.data(), c.cons.size() * sizeof(GkCons), (void**)&d_cons_);
     up(c.match.data(), c.match.size() * sizeof(GkMatch), (void**)&d_match_);
     up(c.instr.data(), c.instr.size() * sizeof(GkInstr), (void**)&d_instr_);
     up(c.pool.data(), c.pool.size() * 4, (void**)&d_pool_);
     up(c.cbytes.data(), c.cbytes.size(), (void**)&d_cbytes_);
+    prog_.cons = d_cons_;
     prog_.match = d_match_;
     prog_.instr = d_instr_;
     prog_.pool = d_pool_;
@@ -207,8 +221,11 @@ class CudaBackend : public Backend {
     if (d_active_) cudaFree(d_active_);
     CK(cudaMalloc(&d_active_, (size_t)std::max(C, 1u) * 4));
     if (!d_errlist_) CK(cudaMalloc(&d_errlist_, (size_t)kErrCap * 3 * 4));
-    smem_need_ = ((size_t)2 * C * 4 + 15) / 16 * 16 + ((size_t)C * sizeof(GkMatch) + 15) / 16 * 16 + (size_t)prog_.ninstr * sizeof(GkInstr) +
-                 ((size_t)prog_.npool * 4 + 15) / 16 * 16 + ((size_t)prog_.ncbytes + 15) / 16 * 16;
+    auto r16 = [](size_t x) { return (x + 15) / 16 * 16; };
+    smem_base_ = r16((size_t)3 * C * 4);
+    smem_need_ = smem_base_ + r16((size_t)C * sizeof(GkCons)) + r16((size_t)prog_.nmatch * sizeof(GkMatch)) +
+                 r16(c.schema.cols.size() * sizeof(GkColumn)) + r16(c.schema.scopes.size() * sizeof(GkScope)) +
+                 r16((size_t)prog_.ninstr * sizeof(GkInstr)) + r16((size_t)prog_.npool * 4) + r16((size_t)prog_.ncbytes);
     version_ = c.version;
   }
 
@@ -261,7 +278,7 @@ class CudaBackend : public Backend {
     cudaEventDestroy(b);
     if (h2d_ms) *h2d_ms = ms;
     if (h2d_bytes) *h2d_bytes = pb.arena.size();
-    db->words = (uint32_t)((c.match.size() + 31) / 32);
+    db->words = (uint32_t)((c.cons.size() + 31) / 32);
     if (db->words == 0) db->words = 1;
     CK(cudaMalloc(&db->viol, (size_t)std::max(db->n, 1u) * db->words * 4));
     CK(cudaMalloc(&db->err, (size_t)std::max(db->n, 1u) * db->words * 4));
@@ -304,7 +321,7 @@ class CudaBackend : public Backend {
     CK(cudaMemsetAsync(d_scalars_, 0, 64, st));
     size_t smem = smem_need_ + 64;
     p.smem_tables = smem <= max_smem_ ? 1u : 0u;
-    if (!p.smem_tables) smem = ((size_t)2 * C * 4 + 15) / 16 * 16 + 64;
+    if (!p.smem_tables) smem = smem_base_ + 64;
     if (smem > max_smem_) throw BackendError{"too many constraints for one launch (per-constraint counters exceed shared memory)"};
     *smem_out = smem;
     return p;
@@ -383,6 +400,8 @@ class CudaBackend : public Backend {
  private:
   static constexpr uint32_t kErrCap = 1u << 20;
   void free_tables() {
+    if (d_cons_) cudaFree(d_cons_);
+    d_cons_ = nullptr;
     if (d_match_) cudaFree(d_match_);
     if (d_instr_) cudaFree(d_instr_);
     if (d_pool_) cudaFree(d_pool_);
@@ -394,12 +413,13 @@ class CudaBackend : public Backend {
   }
   int device_;
   int sms_ = 148;
-  size_t max_smem_ = 0, smem_need_ = 0;
+  size_t max_smem_ = 0, smem_need_ = 0, smem_base_ = 0;
   cudaStream_t stream_ = nullptr;
   cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
   std::mutex mu_;
   uint64_t version_ = 0, launches_ = 0;
   GkProgram prog_{};
+  GkCons* d_cons_ = nullptr;
   GkMatch* d_match_ = nullptr;
   GkInstr* d_instr_ = nullptr;
   uint32_t* d_pool_ = nullptr;

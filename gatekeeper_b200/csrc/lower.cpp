@@ -1415,172 +1415,216 @@ uint32_t ProgramBuilder::add_bytes(const std::string& s) {
   return off;
 }
 
-namespace {
-struct Gen {
-  ProgramBuilder& pb;
-  std::vector<int> label_pc;                // label -> pc (or -1)
-  std::vector<int> open;                    // open scopes (slot = index + 1)
-  size_t base;
-  static constexpr uint32_t LBL = 0x8000u;  // label ids are encoded as LBL | id until patched
+const ProgramBuilder::Info& ProgramBuilder::info(const FP& f) {
+  auto it = info_.find(f.get());
+  if (it != info_.end()) return it->second;
+  Info x;
+  auto merge = [&](const std::vector<int>& o) {
+    for (int s : o)
+      if (std::find(x.free.begin(), x.free.end(), s) == x.free.end()) x.free.push_back(s);
+  };
+  switch (f->k) {
+    case Formula::True: x.key = "T"; x.size = 1; break;
+    case Formula::False: x.key = "F"; x.size = 1; break;
+    case Formula::Atom: {
+      x.key = "a" + std::to_string(f->op) + ":" + std::to_string(f->col) + ":" + std::to_string(f->imm) + ":" + (f->cval ? intern_key(f->cval) : std::string());
+      x.size = f->op >= GK_OP_PREFIX ? 4 : 2;
+      // the column's scope and all its ancestors must be open
+      for (int s = schema->cols[f->col].scope; s != 0; s = schema->scopes[s].parent) x.free.push_back(s);
+      break;
+    }
+    case Formula::Not: {
+      const Info& k = info(f->kids[0]);
+      x.key = "!(" + k.key + ")";
+      x.size = k.size + 1;
+      x.free = k.free;
+      break;
+    }
+    case Formula::And:
+    case Formula::Or: {
+      x.key = f->k == Formula::And ? "&(" : "|(";
+      for (auto& c : f->kids) {
+        const Info& k = info(c);
+        x.key += k.key + ",";
+        x.size += k.size + 1;
+        merge(k.free);
+      }
+      x.key += ")";
+      break;
+    }
+    case Formula::Exists: {
+      const Info& k = info(f->kids[0]);
+      x.key = "E" + std::to_string(f->scope) + "(" + k.key + ")";
+      x.size = k.size * 2 + 6;   // a loop: body runs ~1.7 times on average
+      for (int s : k.free)
+        if (s != f->scope) x.free.push_back(s);
+      for (int s = schema->scopes[f->scope].parent; s != 0; s = schema->scopes[s].parent)
+        if (std::find(x.free.begin(), x.free.end(), s) == x.free.end()) x.free.push_back(s);
+      break;
+    }
+  }
+  std::sort(x.free.begin(), x.free.end());
+  return info_.emplace(f.get(), std::move(x)).first->second;
+}
 
-  int new_label() {
-    label_pc.push_back(-1);
-    return (int)label_pc.size() - 1;
+void ProgramBuilder::plan(const std::vector<FP>& all) {
+  // occurrences of every closed (loop-independent) sub-formula over the whole constraint set
+  struct Cand {
+    uint32_t count = 0, size = 0;
+  };
+  std::map<std::string, Cand> cands;
+  std::function<void(const FP&)> walk = [&](const FP& f) {
+    const Info& x = info(f);
+    if (x.free.empty() && f->k != Formula::True && f->k != Formula::False) {
+      Cand& c = cands[x.key];
+      c.count++;
+      c.size = x.size;
+    }
+    for (auto& k : f->kids) walk(k);
+  };
+  for (auto& f : all) walk(f);
+  std::vector<std::pair<uint64_t, std::string>> ranked;
+  for (auto& c : cands)
+    if (c.second.count >= 2) ranked.emplace_back((uint64_t)(c.second.count - 1) * c.second.size, c.first);
+  std::sort(ranked.begin(), ranked.end(), [](auto& a, auto& b) { return a.first != b.first ? a.first > b.first : a.second < b.second; });
+  cse_bit_.clear();
+  for (auto& r : ranked) {
+    if (cse_bit_.size() >= GK_MAX_CSE) break;
+    int bit = (int)cse_bit_.size();
+    cse_bit_[r.second] = bit;
   }
-  void bind(int l) { label_pc[l] = (int)pb.instr.size(); }
-  uint32_t enc(int target) { return target < 0 ? (target == -1 ? GK_PC_ACCEPT : GK_PC_REJECT) : (LBL | (uint32_t)target); }
-  // targets: >=0 label id; -1 accept; -2 reject
-  void emit(uint32_t op, uint32_t slot, uint32_t col, uint32_t w1, int lt, int lf, uint32_t w3) {
-    GkInstr in;
-    in.w0 = op | (slot << 8) | (col << 16);
-    in.w1 = w1;
-    in.w2 = enc(lt) | (enc(lf) << 16);
-    in.w3 = w3;
-    pb.instr.push_back(in);
+}
+
+uint32_t ProgramBuilder::slot_of(int scope, const std::vector<int>& open) const {
+  if (scope == 0) return 0;
+  for (size_t i = 0; i < open.size(); ++i)
+    if (open[i] == scope) return (uint32_t)i + 1;
+  throw RegoError{"internal: column scope is not open in the generated loop nest"};
+}
+
+void ProgramBuilder::emit_node(const FP& f, std::vector<int>& open, int& depth, int& maxdepth) {
+  const Info& x = info(f);
+  auto it = x.free.empty() ? cse_bit_.find(x.key) : cse_bit_.end();
+  if (it == cse_bit_.end()) {
+    emit_plain(f, open, depth, maxdepth);
+    return;
   }
-  uint32_t slot_of(int scope) {
-    if (scope == 0) return 0;
-    for (size_t i = 0; i < open.size(); ++i)
-      if (open[i] == scope) return (uint32_t)i + 1;
-    throw RegoError{"internal: column scope is not open in the generated loop nest"};
-  }
-  void gen(const FP& f, int lt, int lf) {
-    switch (f->k) {
-      case Formula::True: emit(GK_OP_JMP, 0, 0, 0, lt, lt, 0); break;
-      case Formula::False: emit(GK_OP_JMP, 0, 0, 0, lf, lf, 0); break;
-      case Formula::Not: gen(f->kids[0], lf, lt); break;
-      case Formula::And:
-        for (size_t i = 0; i < f->kids.size(); ++i) {
-          if (i + 1 == f->kids.size()) gen(f->kids[i], lt, lf);
-          else {
-            int mid = new_label();
-            gen(f->kids[i], mid, lf);
-            bind(mid);
-          }
+  size_t at = instr.size();
+  instr.push_back(GkInstr{GK_OP_CSE_TRY, (uint32_t)it->second, 0, 0});
+  int d0 = depth;
+  emit_plain(f, open, depth, maxdepth);
+  instr.push_back(GkInstr{GK_OP_CSE_STORE, (uint32_t)it->second, 0, 0});
+  instr[at].w2 = (uint32_t)instr.size();
+  depth = d0 + 1;
+}
+
+void ProgramBuilder::emit_plain(const FP& f, std::vector<int>& open, int& depth, int& maxdepth) {
+  auto push = [&]() {
+    if (++depth > maxdepth) maxdepth = depth;
+  };
+  switch (f->k) {
+    case Formula::True:
+    case Formula::False:
+      instr.push_back(GkInstr{GK_OP_PUSH, f->k == Formula::True ? 1u : 0u, 0, 0});
+      push();
+      break;
+    case Formula::Not:
+      emit_node(f->kids[0], open, depth, maxdepth);
+      instr.push_back(GkInstr{GK_OP_NOT, 0, 0, 0});
+      break;
+    case Formula::And:
+    case Formula::Or:
+      for (size_t i = 0; i < f->kids.size(); ++i) {
+        emit_node(f->kids[i], open, depth, maxdepth);
+        if (i) {
+          instr.push_back(GkInstr{f->k == Formula::And ? (uint32_t)GK_OP_AND : (uint32_t)GK_OP_OR, 0, 0, 0});
+          --depth;
         }
-        break;
-      case Formula::Or:
-        for (size_t i = 0; i < f->kids.size(); ++i) {
-          if (i + 1 == f->kids.size()) gen(f->kids[i], lt, lf);
-          else {
-            int mid = new_label();
-            gen(f->kids[i], lt, mid);
-            bind(mid);
-          }
-        }
-        break;
-      case Formula::Exists: {
-        const ScopeDef& sd = pb.schema->scopes[f->scope];
-        uint32_t pslot = slot_of(sd.parent);
-        uint32_t slot = (uint32_t)open.size() + 1;
-        if (slot > GK_MAX_LOOP_DEPTH) throw RegoError{"rego_unsupported: loop nest deeper than " + std::to_string(GK_MAX_LOOP_DEPTH)};
-        int ltest = new_label(), lbody = new_label(), lnext = new_label();
-        emit(GK_OP_LOOP_BEGIN, slot, pslot, (uint32_t)f->scope, ltest, ltest, 0);
-        bind(ltest);
-        emit(GK_OP_LOOP_TEST, slot, 0, 0, lbody, lf, 0);
-        bind(lbody);
-        open.push_back(f->scope);
-        gen(f->kids[0], lt, lnext);
-        open.pop_back();
-        bind(lnext);
-        emit(GK_OP_LOOP_NEXT, slot, 0, 0, ltest, ltest, 0);
-        break;
       }
-      case Formula::Atom: {
-        const ColDef& cd = pb.schema->cols[f->col];
-        uint32_t slot = slot_of(cd.scope);
-        uint32_t w1 = 0, w3 = 0;
-        switch (f->op) {
-          case GK_OP_TRUTHY:
-          case GK_OP_DEFINED: break;
-          case GK_OP_VTMASK: w1 = f->imm; break;
-          case GK_OP_SID_EQ: w1 = pb.interner->intern(intern_key(f->cval)); break;
-          case GK_OP_SID_IN: {
-            std::vector<uint32_t> ids;
-            for (auto& x : f->cval->items) ids.push_back(pb.interner->intern(intern_key(x)));
-            std::sort(ids.begin(), ids.end());
-            ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
-            w1 = (uint32_t)pb.pool.size();
-            w3 = (uint32_t)ids.size();
-            pb.pool.insert(pb.pool.end(), ids.begin(), ids.end());
-            break;
-          }
-          case GK_OP_NUM_CMP: {
-            int64_t k = 0;
-            num_fits_i64(f->cval->n, &k);
-            w1 = (uint32_t)pb.pool.size();
-            pb.pool.push_back((uint32_t)((uint64_t)k & 0xffffffffu));
-            pb.pool.push_back((uint32_t)((uint64_t)k >> 32));
-            w3 = f->imm;
-            break;
-          }
-          case GK_OP_PREFIX:
-          case GK_OP_SUFFIX:
-          case GK_OP_CONTAINS:
-            w1 = pb.add_bytes(f->cval->s);
-            w3 = (uint32_t)f->cval->s.size();
-            break;
-          case GK_OP_ANYPREFIX:
-          case GK_OP_ANYSUFFIX: {
-            std::vector<uint32_t> ent;
-            for (auto& x : f->cval->items) {
-              ent.push_back(pb.add_bytes(x->s));
-              ent.push_back((uint32_t)x->s.size());
-            }
-            w1 = (uint32_t)pb.pool.size();
-            w3 = (uint32_t)f->cval->items.size();
-            pb.pool.insert(pb.pool.end(), ent.begin(), ent.end());
-            break;
-          }
-          default: throw RegoError{"internal: unknown atom"};
+      break;
+    case Formula::Exists: {
+      const ScopeDef& sd = schema->scopes[f->scope];
+      uint32_t pslot = slot_of(sd.parent, open);
+      uint32_t slot = (uint32_t)open.size() + 1;
+      if (slot > GK_MAX_LOOP_DEPTH) throw RegoError{"rego_unsupported: loop nest deeper than " + std::to_string(GK_MAX_LOOP_DEPTH)};
+      size_t begin = instr.size();
+      instr.push_back(GkInstr{GK_OP_LOOP_BEGIN | (slot << 8) | (pslot << 16), (uint32_t)f->scope, 0, 0});
+      push();   // accumulator
+      uint32_t body = (uint32_t)instr.size();
+      open.push_back(f->scope);
+      emit_node(f->kids[0], open, depth, maxdepth);
+      open.pop_back();
+      instr.push_back(GkInstr{GK_OP_LOOP_END | (slot << 8), 0, body, 0});
+      --depth;   // body result folded into the accumulator
+      instr[begin].w2 = (uint32_t)instr.size();
+      break;
+    }
+    case Formula::Atom: {
+      const ColDef& cd = schema->cols[f->col];
+      uint32_t slot = slot_of(cd.scope, open);
+      uint32_t w1 = 0, w3 = 0;
+      switch (f->op) {
+        case GK_OP_TRUTHY:
+        case GK_OP_DEFINED: break;
+        case GK_OP_VTMASK: w1 = f->imm; break;
+        case GK_OP_SID_EQ: w1 = interner->intern(intern_key(f->cval)); break;
+        case GK_OP_SID_IN: {
+          std::vector<uint32_t> ids;
+          for (auto& v : f->cval->items) ids.push_back(interner->intern(intern_key(v)));
+          std::sort(ids.begin(), ids.end());
+          ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
+          w1 = (uint32_t)pool.size();
+          w3 = (uint32_t)ids.size();
+          pool.insert(pool.end(), ids.begin(), ids.end());
+          break;
         }
-        emit((uint32_t)f->op, slot, (uint32_t)f->col, w1, lt, lf, w3);
-        break;
+        case GK_OP_NUM_CMP: {
+          int64_t k = 0;
+          num_fits_i64(f->cval->n, &k);
+          w1 = (uint32_t)pool.size();
+          pool.push_back((uint32_t)((uint64_t)k & 0xffffffffu));
+          pool.push_back((uint32_t)((uint64_t)k >> 32));
+          w3 = f->imm;
+          break;
+        }
+        case GK_OP_PREFIX:
+        case GK_OP_SUFFIX:
+        case GK_OP_CONTAINS:
+          w1 = add_bytes(f->cval->s);
+          w3 = (uint32_t)f->cval->s.size();
+          break;
+        case GK_OP_ANYPREFIX:
+        case GK_OP_ANYSUFFIX: {
+          std::vector<uint32_t> ent;
+          for (auto& v : f->cval->items) {
+            ent.push_back(add_bytes(v->s));
+            ent.push_back((uint32_t)v->s.size());
+          }
+          w1 = (uint32_t)pool.size();
+          w3 = (uint32_t)f->cval->items.size();
+          pool.insert(pool.end(), ent.begin(), ent.end());
+          break;
+        }
+        default: throw RegoError{"internal: unknown atom"};
       }
+      instr.push_back(GkInstr{(uint32_t)f->op | (slot << 8) | ((uint32_t)f->col << 16), w1, 0, w3});
+      push();
+      break;
     }
   }
-  void patch() {
-    auto fix = [&](uint32_t t) -> uint32_t {
-      if (t == GK_PC_ACCEPT || t == GK_PC_REJECT) return t;
-      int pc = label_pc[t & ~LBL];
-      if (pc < 0) throw RegoError{"internal: unbound label"};
-      return (uint32_t)pc;
-    };
-    for (size_t i = base; i < pb.instr.size(); ++i) {
-      uint32_t w2 = pb.instr[i].w2;
-      pb.instr[i].w2 = fix(w2 & 0xffffu) | (fix(w2 >> 16) << 16);
-    }
-  }
-};
-}  // namespace
+}
 
 uint32_t ProgramBuilder::emit(const FP& f) {
   if (f->k == Formula::True) return GK_PC_ACCEPT;
   if (f->k == Formula::False) return GK_PC_REJECT;
-  Gen g{*this, {}, {}, instr.size()};
   uint32_t entry = (uint32_t)instr.size();
-  g.gen(f, -1, -2);
-  g.patch();
-  if (instr.size() >= 0x7ff0u) throw RegoError{"rego_unsupported: predicate table exceeds 32k instructions"};
-  // peephole: thread jumps through unconditional JMPs
-  for (size_t i = entry; i < instr.size(); ++i) {
-    auto thread = [&](uint32_t t) {
-      int guard = 0;
-      while (t < GK_PC_REJECT && (instr[t].w0 & 0xffu) == GK_OP_JMP && ++guard < 64) t = instr[t].w2 & 0xffffu;
-      return t;
-    };
-    uint32_t w2 = instr[i].w2;
-    instr[i].w2 = thread(w2 & 0xffffu) | (thread(w2 >> 16) << 16);
-  }
-  while (entry < instr.size() && (instr[entry].w0 & 0xffu) == GK_OP_JMP) {
-    uint32_t t = instr[entry].w2 & 0xffffu;
-    if (t >= GK_PC_REJECT) return t;
-    entry = t;
-  }
+  std::vector<int> open;
+  int depth = 0, maxdepth = 0;
+  emit_node(f, open, depth, maxdepth);
+  instr.push_back(GkInstr{GK_OP_END, 0, 0, 0});
+  if (maxdepth > GK_MAX_STACK) throw RegoError{"rego_unsupported: predicate nesting exceeds the " + std::to_string(GK_MAX_STACK) + "-entry boolean stack"};
+  if (instr.size() > (1u << 22)) throw RegoError{"rego_unsupported: predicate table too large"};
   return entry;
 }
-
-void ProgramBuilder::gen(const FP&, uint32_t, uint32_t, std::vector<int>&) {}
-uint32_t ProgramBuilder::gen_to(const FP&, uint32_t, uint32_t, std::vector<int>&) { return 0; }
 
 }  // namespace gk

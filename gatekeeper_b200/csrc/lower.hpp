@@ -92,7 +92,7 @@ struct Interner {
 // Lower one constraint's violation predicate.  Throws RegoError on unsupported constructs.
 FP lower_violation(const std::shared_ptr<const Module>& mod, const VP& parameters, Schema& schema);
 
-// Program assembly: constant pools + instruction emission shared by all constraints.
+// Program assembly: constant pools + postfix instruction emission shared by all constraints.
 struct ProgramBuilder {
   std::vector<GkInstr> instr;
   std::vector<uint32_t> pool;
@@ -100,12 +100,24 @@ struct ProgramBuilder {
   Interner* interner = nullptr;
   const Schema* schema = nullptr;
   uint32_t add_bytes(const std::string& s);
-  // returns entry pc (or GK_PC_ACCEPT / GK_PC_REJECT for constant formulas)
+  // pass 1: look at every constraint's formula and pick the sub-formulas worth sharing across constraints
+  void plan(const std::vector<FP>& all);
+  // pass 2: returns the entry pc (or GK_PC_ACCEPT / GK_PC_REJECT for constant formulas)
   uint32_t emit(const FP& f);
+  size_t n_shared() const { return cse_bit_.size(); }
 
  private:
-  void gen(const FP& f, uint32_t pt, uint32_t pf, std::vector<int>& open_scopes);
-  uint32_t gen_to(const FP& f, uint32_t pt, uint32_t pf, std::vector<int>& open_scopes);
+  struct Info {
+    std::string key;
+    std::vector<int> free;   // scopes that must already be open (sorted)
+    uint32_t size = 0;
+  };
+  const Info& info(const FP& f);
+  void emit_node(const FP& f, std::vector<int>& open, int& depth, int& maxdepth);
+  void emit_plain(const FP& f, std::vector<int>& open, int& depth, int& maxdepth);
+  uint32_t slot_of(int scope, const std::vector<int>& open) const;
+  std::map<const Formula*, Info> info_;
+  std::map<std::string, int> cse_bit_;
 };
 
 }  // namespace gk

@@ -3,8 +3,9 @@
 //
 //   batch  : column-wise (SoA) -- header columns one row per object, CSR label table, CSR "scopes" (one
 //            row per iterated element, e.g. spec.containers[_]) with fixed-width feature columns.
-//   program: per constraint a match block (the spec.match pre-filter, pkg/mutation/match/match.go:32-65)
-//            and an entry pc into one shared instruction array (the lowered violation predicate).
+//   program: DISTINCT match blocks (the spec.match pre-filter, pkg/mutation/match/match.go:32-65), a
+//            constraint table (match block id + entry pc) ordered so that constraints sharing a match block
+//            are adjacent, and one shared instruction array of warp-uniform postfix predicate code.
 #pragma once
 #include <stdint.h>
 
@@ -24,8 +25,10 @@ enum { GK_ENC_VT = 1, GK_ENC_SID = 2, GK_ENC_NUM = 4, GK_ENC_BYTES = 8 };
 #define GK_SID_UNDEF 0u          /* intern id 0 is reserved: "no value" */
 #define GK_NONE 0xFFFFFFFFu
 #define GK_MAX_LOOP_DEPTH 4
-#define GK_PC_ACCEPT 0xFFFFu
-#define GK_PC_REJECT 0xFFFEu
+#define GK_MAX_STACK 60          /* boolean stack lives in one 64-bit register per thread */
+#define GK_MAX_CSE 64            /* shared sub-formula results live in one 64-bit register per thread */
+#define GK_PC_ACCEPT 0xFFFFFFFFu
+#define GK_PC_REJECT 0xFFFFFFFEu
 
 typedef struct {
   int32_t scope;           // 0 = root (one row per object)
@@ -93,31 +96,44 @@ typedef struct {
   uint32_t lsel_off, lsel_n;      // pool: per requirement [key sid, op, nvals, vals...]
   uint32_t nssel_off, nssel_n;
   uint32_t name_mode, name_boff, name_len;
-  uint32_t prog_pc;               // GK_PC_ACCEPT / GK_PC_REJECT allowed (constant predicates)
-  uint32_t active;                // 0: skip (enforcement-point filter)
+  uint32_t pad0, pad1;
 } GkMatch;
 
-// ---- predicate instructions: 4 x u32
+typedef struct {
+  uint32_t match_id;              // index into the distinct match blocks
+  uint32_t pc;                    // entry pc, or GK_PC_ACCEPT / GK_PC_REJECT for constant predicates
+} GkCons;
+
+// ---- predicate instructions: 4 x u32, executed by ALL lanes of a warp in lock step (the pc is warp-uniform).
+// Every lane owns a boolean stack held in one 64-bit register (bit 0 = top) and a 64-bit register of shared
+// sub-formula results.  There are no data-dependent jumps: loops run for the warp-wide maximum trip count with
+// finished lanes masked off, so the only divergence left is inside byte-string comparisons.
 //   w0 = op | slot<<8 | col<<16      (slot: which open loop supplies the row; 0 = the object itself)
-//   w1 = operand A (immediate / pool offset / scope id)
-//   w2 = (pc_true) | (pc_false << 16)
+//   w1 = operand A (immediate / pool offset / scope id / cse bit)
+//   w2 = jump target (loops)
 //   w3 = operand B (count / length / compare op)
 enum {
-  GK_OP_TRUTHY = 1,     // vt != undef && vt != false
-  GK_OP_DEFINED = 2,    // vt != undef
-  GK_OP_VTMASK = 3,     // (1 << vt) & w1
-  GK_OP_SID_EQ = 4,     // sid == w1
-  GK_OP_SID_IN = 5,     // sid in pool[w1 .. w1+w3) (sorted)
+  GK_OP_END = 0,        // result = top of stack
+  GK_OP_TRUTHY = 1,     // push vt != undef && vt != false
+  GK_OP_DEFINED = 2,    // push vt != undef
+  GK_OP_VTMASK = 3,     // push (1 << vt) & w1
+  GK_OP_SID_EQ = 4,     // push sid == w1
+  GK_OP_SID_IN = 5,     // push sid in pool[w1 .. w1+w3) (sorted)
   GK_OP_NUM_CMP = 6,    // w3 = GK_CMP_*; i64 constant at pool[w1], pool[w1+1] (lo, hi); OPA cross-type ordering
-  GK_OP_PREFIX = 7,     // vt == str && bytes startswith cbytes[w1 .. w1+w3)
+  GK_OP_PREFIX = 7,     // push vt == str && bytes startswith cbytes[w1 .. w1+w3)
   GK_OP_SUFFIX = 8,
   GK_OP_CONTAINS = 9,
   GK_OP_ANYPREFIX = 10, // pool[w1 ..]: w3 entries of [byte_off, len]
   GK_OP_ANYSUFFIX = 11,
-  GK_OP_LOOP_BEGIN = 12, // w1 = scope id; slot = new loop slot; col field = parent slot; falls through to pc+1
-  GK_OP_LOOP_TEST = 13,  // slot; iter < end ? pc_true : pc_false
-  GK_OP_LOOP_NEXT = 14,  // slot; ++iter; goto pc_true
-  GK_OP_JMP = 15,
+  GK_OP_LOOP_BEGIN = 12, // w1 = scope id; slot = new loop slot; col field = parent slot; pushes acc = false;
+                         // trip = warp max of the lane ranges; if trip == 0 jump to w2 (just past LOOP_END)
+  GK_OP_LOOP_END = 13,   // acc |= top & lane-still-in-range; pop; ++iter; if --trip jump to w2 (loop body)
+  GK_OP_AND = 14,
+  GK_OP_OR = 15,
+  GK_OP_NOT = 16,
+  GK_OP_PUSH = 17,       // push (w1 & 1)
+  GK_OP_CSE_TRY = 18,    // if shared result w1 is already valid for this warp: push it and jump to w2
+  GK_OP_CSE_STORE = 19,  // shared result w1 = top (stays on the stack); mark valid
 };
 enum { GK_CMP_LT = 0, GK_CMP_LE = 1, GK_CMP_GT = 2, GK_CMP_GE = 3, GK_CMP_EQ = 4, GK_CMP_NE = 5 };
 
@@ -125,10 +141,12 @@ typedef struct { uint32_t w0, w1, w2, w3; } GkInstr;
 
 typedef struct {
   uint32_t nconstraints;
+  uint32_t nmatch;
   uint32_t ninstr;
   uint32_t npool;
   uint32_t ncbytes;
-  const GkMatch* match;      // [nconstraints]
+  const GkCons* cons;        // [nconstraints]
+  const GkMatch* match;      // [nmatch]
   const GkInstr* instr;      // [ninstr]
   const uint32_t* pool;      // u32 constant pool
   const uint8_t* cbytes;     // constant byte strings (wildcard literals, prefixes)

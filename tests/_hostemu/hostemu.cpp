@@ -26,7 +26,7 @@ class HostEmuBackend : public Backend {
     pack_batch(hb, c, b->pb);
     b->hdr = rebase_batch(b->pb, b->pb.arena.data(), b->pb.arena.data());
     b->n = hb.n;
-    b->words = std::max<uint32_t>(1, (uint32_t)((c.match.size() + 31) / 32));
+    b->words = std::max<uint32_t>(1, (uint32_t)((c.cons.size() + 31) / 32));
     if (ms) *ms = 0;
     if (bytes) *bytes = b->pb.arena.size();
     return b;
@@ -35,7 +35,7 @@ class HostEmuBackend : public Backend {
   void eval(void* bb, const std::vector<uint32_t>& active, EvalOut& out, bool) override {
     auto* b = static_cast<EmuBatch*>(bb);
     const Compiled& c = *prog_;
-    const uint32_t C = (uint32_t)c.match.size(), W = b->words;
+    const uint32_t C = (uint32_t)c.cons.size(), W = b->words;
     GkBatch h = b->hdr;
     h.dict_off = dict_off_.data();
     h.dict_bytes = dict_bytes_.data();
@@ -49,23 +49,29 @@ class HostEmuBackend : public Backend {
     out.err_totals.assign(C, 0);
     out.errlist.clear();
     auto t0 = std::chrono::steady_clock::now();
+    const GkColumn* cols = h.cols;
+    const GkScope* scopes = h.scopes;
     for (uint32_t obj = 0; obj < b->n; ++obj) {
       if (h.flags[obj] & GK_F_SKIP) continue;
+      unsigned long long cse = 0, cse_valid = 0;
+      uint32_t cur_mid = GK_NONE;
+      int mres = 0;
       for (uint32_t cix = 0; cix < C; ++cix) {
         if (!active[cix]) continue;
-        const GkMatch& m = c.match[cix];
-        int r = gk_match(h, c.pool.data(), c.cbytes.data(), m, obj);
-        int code = r < 0 ? -r : 0;
-        bool v = false;
-        if (r > 0) {
-          int flag = 0;
-          v = m.prog_pc == GK_PC_ACCEPT ? true
-              : m.prog_pc == GK_PC_REJECT ? false
-                                          : gk_run(h, c.instr.data(), c.pool.data(), c.cbytes.data(), m.prog_pc, obj, &flag);
-          if (flag) {
-            v = false;
-            code = flag;
-          }
+        const GkCons& cc = c.cons[cix];
+        if (cc.match_id != cur_mid) {
+          cur_mid = cc.match_id;
+          mres = gk_match(h, c.pool.data(), c.cbytes.data(), c.match[cur_mid], obj);
+        }
+        int code = mres < 0 ? -mres : 0;
+        int flag = 0;
+        bool v = cc.pc == GK_PC_ACCEPT ? true
+                 : cc.pc == GK_PC_REJECT ? false
+                                         : gk_eval_prog(cols, scopes, c.instr.data(), c.pool.data(), c.cbytes.data(), cc.pc, obj, true, cse, cse_valid, &flag);
+        v = v && mres > 0;
+        if (mres > 0 && flag) {
+          v = false;
+          code = flag;
         }
         if (code) {
           out.err[(size_t)obj * W + cix / 32] |= 1u << (cix & 31);
