@@ -151,7 +151,7 @@ void eval_batch(gk_engine* e, gk_batch* b, const char* ep_c, uint32_t flags, gk_
           uint32_t cix = w * 32 + k;
           ObjIn in = to_in(b->objs[o]);
           if (eb >> k & 1u) {
-            auto it = err_code.find(((uint64_t)o << 32) | cix);
+            auto it = err_code.find(((uint64_t)o << 32) | c.cons_match[cix]);   // error list is keyed by match block
             e->eng->autoreject(c, in, o, cix, it == err_code.end() ? 0u : it->second, ep, rp->vio);
           } else if (vb >> k & 1u) {
             e->eng->materialize(c, in, o, cix, ep, rp->vio);
@@ -194,7 +194,7 @@ void upload_batch(gk_engine* e, const gk_obj* objs, size_t n, gk_batch** outb, g
     stats->h2d_bytes = h2d_bytes;
     stats->alg_bytes = hb->alg_bytes;
     stats->n_objects = hb->n;
-    stats->n_constraints = (uint32_t)c->cons.size();
+    stats->n_constraints = (uint32_t)c->cons_match.size();
   }
   *outb = b.release();
 }

@@ -331,7 +331,7 @@ std::shared_ptr<const Compiled> Engine::compiled() {
 void Engine::compile_locked() {
   auto out = std::make_shared<Compiled>();
   out->version = ++version_;
-  ProgramBuilder pb;
+  NetBuilder pb;
   pb.interner = &strings_;
   pb.schema = &out->schema;
   // pass 1: lower every constraint (fills the shared schema); group constraints that share a match block so the
@@ -358,17 +358,14 @@ void Engine::compile_locked() {
   for (size_t i : perm) {
     out->order.push_back(live[i]);
     all.push_back(live[i]->formula);
+    out->cons_match.push_back(mid_of[i]);
   }
-  pb.plan(all);
-  out->n_shared = pb.n_shared();
   out->match.resize(match_ix.size());
   std::vector<bool> built(match_ix.size(), false);
   // pass 2: emit code + match blocks
   for (size_t oi = 0; oi < perm.size(); ++oi) {
     Constraint& c = *live[perm[oi]];
     const uint32_t mid = mid_of[perm[oi]];
-    c.pc = pb.emit(c.formula);
-    out->cons.push_back(GkCons{mid, c.pc});
     GkMatch m{};
     MatchSpec& ms = c.match;
     ms.lsel_err.clear();
@@ -471,13 +468,19 @@ void Engine::compile_locked() {
     }
     ms.dev = out->match[mid];
   }
-  out->instr = std::move(pb.instr);
+  if (out->match.empty()) out->match.push_back(GkMatch{});
+  pb.build(all, out->cons_match, (uint32_t)match_ix.size());
+  out->ops = std::move(pb.ops);
+  out->slot_level = std::move(pb.slot_level);
   out->pool = std::move(pb.pool);
   out->cbytes = std::move(pb.cbytes);
   if (out->pool.empty()) out->pool.push_back(0);
   if (out->cbytes.empty()) out->cbytes.push_back(0);
-  if (out->instr.empty()) out->instr.push_back(GkInstr{GK_OP_END, 0, 0, 0});
-  if (out->match.empty()) out->match.push_back(GkMatch{});
+  if (out->slot_level.empty()) out->slot_level.push_back(0);
+  out->n_nodes = pb.n_nodes;
+  out->n_atoms = pb.n_atoms;
+  out->n_gates = pb.n_gates;
+  out->n_phases = pb.n_phases;
   compiled_ = out;
   dirty_ = false;
 }
@@ -485,15 +488,16 @@ void Engine::compile_locked() {
 std::string Engine::dump() {
   auto c = compiled();
   std::string o = "schema: " + std::to_string(c->schema.scopes.size() - 1) + " scopes, " + std::to_string(c->schema.cols.size()) +
-                  " columns, " + std::to_string(c->instr.size()) + " instructions, " + std::to_string(c->match.size()) +
-                  " distinct match blocks, " + std::to_string(c->n_shared) + " shared sub-formulas\n";
+                  " columns; netlist: " + std::to_string(c->n_nodes) + " nodes (" + std::to_string(c->n_atoms) + " atoms, " +
+                  std::to_string(c->n_gates) + " gates) in " + std::to_string(c->n_phases) + " phases, " + std::to_string(c->slot_level.size()) +
+                  " live slots, " + std::to_string(c->match.size()) + " distinct match blocks\n";
   for (size_t i = 1; i < c->schema.scopes.size(); ++i)
     o += "  scope " + std::to_string(i) + " parent " + std::to_string(c->schema.scopes[i].parent) + ": " + c->schema.scopes[i].gen->key + "\n";
   for (size_t i = 0; i < c->schema.cols.size(); ++i)
     o += "  col " + std::to_string(i) + " scope " + std::to_string(c->schema.cols[i].scope) + " enc " + std::to_string(c->schema.cols[i].enc) + ": " +
          c->schema.cols[i].expr->key + "\n";
   for (size_t i = 0; i < c->order.size(); ++i)
-    o += "constraint " + std::to_string(i) + " " + c->order[i]->kind + "/" + c->order[i]->name + " pc=" + std::to_string(c->order[i]->pc) + ": " +
+    o += "constraint " + std::to_string(i) + " " + c->order[i]->kind + "/" + c->order[i]->name + ": " +
          formula_str(c->order[i]->formula, c->schema) + "\n";
   return o;
 }
@@ -720,7 +724,12 @@ struct Flattener {
     HostColumn& hc = hb.cols[ci];
     uint8_t vt = v ? (uint8_t)v->t : (uint8_t)GK_VT_UNDEF;
     int64_t num = 0;
-    if (v && v->t == VT::Num && (enc & GK_ENC_NUM) && !num_fits_i64(v->n, &num)) vt = GK_VT_NUM_INEXACT;
+    if (v && v->t == VT::Num && (enc & GK_ENC_NUM) && !num_fits_i64(v->n, &num)) {
+      // the device compares numbers as exact int64: refuse the object loudly instead of comparing approximately
+      vt = GK_VT_NUM_INEXACT;
+      num_range_error = "number " + num_str(v->n) + " in " + c.schema.cols[ci].expr->key +
+                        " is outside the exact int64 range of the GPU predicate table";
+    }
     if (enc & GK_ENC_VT) hc.vt.push_back(vt);
     if (enc & GK_ENC_SID) hc.sid.push_back(v ? sid(intern_key(v)) : GK_SID_UNDEF);
     if (enc & GK_ENC_NUM) hc.num.push_back(num);
@@ -818,8 +827,14 @@ struct Flattener {
       }
       for (size_t s = 1; s < nscopes; ++s) hb.scope_rows[s] += (uint32_t)rows[s].size();
     }
+    if (!num_range_error.empty()) {
+      hb.obj_errors.back() = num_range_error;
+      hb.flags[hb.n] |= GK_F_SKIP;
+      num_range_error.clear();
+    }
     ++hb.n;
   }
+  std::string num_range_error;
 };
 
 template <class T>

@@ -74,7 +74,6 @@ struct Constraint {
   std::string action;                          // deny / dryrun / warn / scoped / unrecognized
   std::vector<ScopedAction> scoped;
   FP formula;
-  uint32_t pc = GK_PC_REJECT;
 };
 
 struct TemplateEntry {
@@ -86,13 +85,14 @@ struct TemplateEntry {
 struct Compiled {
   uint64_t version = 0;
   Schema schema;
-  std::vector<GkInstr> instr;
+  std::vector<GkOp> ops;                       // the joint netlist (program.h)
+  std::vector<uint8_t> slot_level;             // scope of each shared-memory slot
   std::vector<uint32_t> pool;
   std::vector<uint8_t> cbytes;
   std::vector<GkMatch> match;                  // DISTINCT match blocks
-  std::vector<GkCons> cons;                    // per constraint: match block id + entry pc
+  std::vector<uint32_t> cons_match;            // per constraint: match block id
   std::vector<const Constraint*> order;        // constraint index -> constraint (grouped by match block)
-  size_t n_shared = 0;                         // sub-formulas shared across constraints (CSE bits)
+  size_t n_nodes = 0, n_atoms = 0, n_gates = 0, n_phases = 0;
 };
 
 class StringTable : public Interner {

@@ -30,11 +30,17 @@ struct KParams {
   GkBatch batch;
   GkProgram prog;
   GkOut out;
-  const uint32_t* active;   // [nconstraints]
-  uint32_t smem_tables;     // 1: tables staged in shared memory
+  const uint32_t* active;     // [nconstraints] enforcement-point filter
+  const uint32_t* slot_off;   // [nslots] word offset of each slot inside the slot area (depends on the batch's tile capacities)
+  const uint32_t* tile_lo;    // [(ntiles + 1) * nscopes] first row of every scope for every tile (row ranges are contiguous)
+  uint32_t ntiles;
+  uint32_t tile;              // objects per tile (multiple of 32)
+  uint32_t slot_words;        // words in the slot area
 };
 
-constexpr int kThreads = 128;
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr uint32_t kTile = 512;
 
 __device__ __forceinline__ void stage(void* dst, const void* src, size_t bytes) {
   // 16-byte vector copies; sizes/offsets are padded to 16 on the host
@@ -43,98 +49,212 @@ __device__ __forceinline__ void stage(void* dst, const void* src, size_t bytes) 
   for (size_t i = threadIdx.x; i < bytes / 16; i += blockDim.x) d[i] = s[i];
 }
 
+__device__ __forceinline__ uint32_t range_mask(uint32_t w, uint32_t a, uint32_t b) {
+  // bits of word w that lie in the row range [a, b)
+  const uint32_t lo = w * 32u, hi = lo + 32u;
+  const uint32_t x = a > lo ? a : lo, y = b < hi ? b : hi;
+  if (x >= y) return 0u;
+  const uint32_t nb = y - x;
+  return (nb == 32u ? 0xffffffffu : ((1u << nb) - 1u)) << (x - lo);
+}
+
+// One CTA = one tile of consecutive objects at a time; all intermediate bit columns live in shared memory.
 __global__ void __launch_bounds__(kThreads) gk_eval_kernel(const KParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
-  const uint32_t C = p.prog.nconstraints;
-  const uint32_t W = p.out.words;
-  // ---- shared-memory layout: [totals C u32][err totals C u32][active C u32] then (when they fit) the tables:
-  //      [cons][match][columns][scopes][instr][pool][cbytes]
-  uint32_t* s_tot = reinterpret_cast<uint32_t*>(smem);
-  uint32_t* s_err = s_tot + C;
-  uint32_t* s_act = s_err + C;
-  size_t off = ((size_t)3 * C * 4 + 15) / 16 * 16;
-  const GkCons* cons = p.prog.cons;
-  const GkMatch* match = p.prog.match;
-  const GkInstr* instr = p.prog.instr;
-  const uint32_t* pool = p.prog.pool;
-  const uint8_t* cbytes = p.prog.cbytes;
-  const GkColumn* cols = p.batch.cols;
-  const GkScope* scopes = p.batch.scopes;
-  for (uint32_t i = threadIdx.x; i < 2 * C; i += blockDim.x) s_tot[i] = 0;
-  for (uint32_t i = threadIdx.x; i < C; i += blockDim.x) s_act[i] = p.active[i];
-  if (p.smem_tables) {
-    auto place = [&](const void* src, size_t bytes) {
-      void* dst = smem + off;
-      stage(dst, src, (bytes + 15) / 16 * 16);
-      off += (bytes + 15) / 16 * 16;
-      return dst;
-    };
-    cons = static_cast<const GkCons*>(place(p.prog.cons, (size_t)C * sizeof(GkCons)));
-    match = static_cast<const GkMatch*>(place(p.prog.match, (size_t)p.prog.nmatch * sizeof(GkMatch)));
-    cols = static_cast<const GkColumn*>(place(p.batch.cols, (size_t)p.batch.ncols * sizeof(GkColumn)));
-    scopes = static_cast<const GkScope*>(place(p.batch.scopes, (size_t)p.batch.nscopes * sizeof(GkScope)));
-    instr = static_cast<const GkInstr*>(place(p.prog.instr, (size_t)p.prog.ninstr * sizeof(GkInstr)));
-    pool = static_cast<const uint32_t*>(place(p.prog.pool, (size_t)p.prog.npool * 4));
-    cbytes = static_cast<const uint8_t*>(place(p.prog.cbytes, (size_t)p.prog.ncbytes));
+  const uint32_t C = p.prog.nconstraints, W = p.out.words, NS = p.batch.nscopes;
+  const uint32_t TW = p.tile / 32u;
+  // ---- shared-memory layout
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    void* q = smem + off;
+    off += (bytes + 15) / 16 * 16;
+    return q;
+  };
+  uint32_t* s_tot = static_cast<uint32_t*>(take((size_t)C * 4));
+  uint32_t* s_err = static_cast<uint32_t*>(take((size_t)C * 4));
+  uint32_t* s_act = static_cast<uint32_t*>(take((size_t)C * 4));
+  uint32_t* s_lo = static_cast<uint32_t*>(take((size_t)NS * 4));
+  uint32_t* s_cnt = static_cast<uint32_t*>(take((size_t)NS * 4));
+  uint32_t* s_soff = static_cast<uint32_t*>(take((size_t)p.prog.nslots * 4));
+  uint32_t* res_v = static_cast<uint32_t*>(take((size_t)p.tile * W * 4));
+  uint32_t* res_e = static_cast<uint32_t*>(take((size_t)p.tile * W * 4));
+  uint32_t* slots = static_cast<uint32_t*>(take((size_t)p.slot_words * 4));
+  GkOp* ops = static_cast<GkOp*>(take((size_t)p.prog.nops * sizeof(GkOp)));
+  GkMatch* match = static_cast<GkMatch*>(take((size_t)p.prog.nmatch * sizeof(GkMatch)));
+  GkColumn* cols = static_cast<GkColumn*>(take((size_t)p.batch.ncols * sizeof(GkColumn)));
+  GkScope* scopes = static_cast<GkScope*>(take((size_t)NS * sizeof(GkScope)));
+  uint32_t* pool = static_cast<uint32_t*>(take((size_t)p.prog.npool * 4));
+  uint8_t* cbytes = static_cast<uint8_t*>(take((size_t)p.prog.ncbytes));
+
+  for (uint32_t i = threadIdx.x; i < C; i += blockDim.x) {
+    s_tot[i] = 0;
+    s_err[i] = 0;
+    s_act[i] = p.active[i];
   }
+  for (uint32_t i = threadIdx.x; i < p.prog.nslots; i += blockDim.x) s_soff[i] = p.slot_off[i];
+  stage(ops, p.prog.ops, ((size_t)p.prog.nops * sizeof(GkOp) + 15) / 16 * 16);
+  stage(match, p.prog.match, ((size_t)p.prog.nmatch * sizeof(GkMatch) + 15) / 16 * 16);
+  stage(cols, p.batch.cols, ((size_t)p.batch.ncols * sizeof(GkColumn) + 15) / 16 * 16);
+  stage(scopes, p.batch.scopes, ((size_t)NS * sizeof(GkScope) + 15) / 16 * 16);
+  stage(pool, p.prog.pool, ((size_t)p.prog.npool * 4 + 15) / 16 * 16);
+  stage(cbytes, p.prog.cbytes, ((size_t)p.prog.ncbytes + 15) / 16 * 16);
   __syncthreads();
 
-  const uint32_t n = p.batch.n;
-  const uint32_t lane = threadIdx.x & 31u;
-  // one object per thread, 32 consecutive objects per warp; every lane of a warp walks the same constraint and the
-  // same instruction, so table reads broadcast and there is no divergent dispatch
-  for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
-    const uint32_t obj_raw = base + threadIdx.x;
-    const uint32_t obj = obj_raw < n ? obj_raw : n - 1;
-    const bool live = obj_raw < n && !(p.batch.flags[obj] & GK_F_SKIP);
-    unsigned long long cse = 0, cse_valid = 0;
-    uint32_t cur_mid = GK_NONE;
-    int mres = 0;
-    for (uint32_t w = 0; w < W; ++w) {
-      uint32_t vbits = 0, ebits = 0;
-      const uint32_t cend = min(C, (w + 1) * 32u);
-      for (uint32_t c = w * 32u; c < cend; ++c) {
-        if (!s_act[c]) continue;   // enforcement-point filter: warp-uniform
-        const GkCons cc = cons[c];
-        if (cc.match_id != cur_mid) {   // warp-uniform: constraints are grouped by match block
-          cur_mid = cc.match_id;
-          mres = live ? gk_match(p.batch, pool, cbytes, match[cur_mid], obj) : 0;
-        }
-        int flag = 0;
-        bool v = cc.pc == GK_PC_ACCEPT ? true
-                 : cc.pc == GK_PC_REJECT ? false
-                                         : gk_eval_prog(cols, scopes, instr, pool, cbytes, cc.pc, obj, live, cse, cse_valid, &flag);
-        v = v && mres > 0;
-        int code = mres < 0 ? -mres : 0;
-        if (mres > 0 && flag) {
-          v = false;
-          code = flag;
-        }
-        const bool e = code != 0;
-        if (e) {
-          const uint32_t slot = atomicAdd(p.out.errcount, 1u);
-          if (slot < p.out.errcap) {
-            p.out.errlist[3 * slot] = obj;
-            p.out.errlist[3 * slot + 1] = c;
-            p.out.errlist[3 * slot + 2] = (uint32_t)code;
-          }
-        }
-        vbits |= (uint32_t)v << (c & 31u);
-        ebits |= (uint32_t)e << (c & 31u);
-        const uint32_t bv = __ballot_sync(0xffffffffu, v);
-        const uint32_t be = __ballot_sync(0xffffffffu, e);
-        if (lane == 0) {
-          if (bv) atomicAdd(&s_tot[c], __popc(bv));
-          if (be) atomicAdd(&s_err[c], __popc(be));
-        }
-      }
-      if (obj_raw < n) {
-        p.out.viol[(size_t)obj * W + w] = vbits;
-        p.out.err[(size_t)obj * W + w] = ebits;
-      }
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t FULL = 0xffffffffu;
+
+  for (uint32_t t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+    // ---- tile row ranges (precomputed on the host: rows of a tile are contiguous at every scope)
+    for (uint32_t s = threadIdx.x; s < NS; s += blockDim.x) {
+      const uint32_t a = p.tile_lo[(size_t)t * NS + s], b = p.tile_lo[(size_t)(t + 1) * NS + s];
+      s_lo[s] = a;
+      s_cnt[s] = b - a;
     }
+    for (uint32_t i = threadIdx.x; i < p.tile * W; i += blockDim.x) {
+      res_v[i] = 0;
+      res_e[i] = 0;
+    }
+    __syncthreads();
+    const uint32_t nobj = s_cnt[0], obj0 = s_lo[0];
+
+    uint32_t pc = 0;
+    for (;;) {   // phases
+      uint32_t k = 0;
+      bool end = false;
+      for (;; ++pc, ++k) {
+        const GkOp op = ops[pc];
+        const uint32_t kind = op.w0 & 0xffu;
+        if (kind == GK_N_PHASE) {
+          ++pc;
+          break;
+        }
+        if (kind == GK_N_END) {
+          end = true;
+          break;
+        }
+        if (k % kWarps != warp) continue;   // ops of a phase are independent: one warp per op, round-robin
+        const uint32_t level = (op.w0 >> 8) & 0xffu;
+        uint32_t* out = slots + s_soff[op.w0 >> 16];
+        switch (kind) {
+          case GK_N_ATOM: {
+            const GkColumn& c = cols[op.w1 >> 8];
+            const uint32_t aop = op.w1 & 0xffu, lo = s_lo[level], cnt = s_cnt[level];
+            for (uint32_t r = lane; r < ((cnt + 31u) & ~31u); r += 32u) {
+              const bool v = r < cnt && gk_atom(c, lo + r, aop, op.w2, op.w3, pool, cbytes);
+              const uint32_t w = __ballot_sync(FULL, v);
+              if (lane == 0) out[r >> 5] = w;
+            }
+            break;
+          }
+          case GK_N_GATE: {
+            const uint32_t* a = slots + s_soff[op.w1 & 0xffffu];
+            const uint32_t* b = slots + s_soff[op.w1 >> 16];
+            const uint32_t f = op.w2, words = (s_cnt[level] + 31u) >> 5;
+            const uint32_t na = (f & GK_G_NEG_A) ? FULL : 0u, nb = (f & GK_G_NEG_B) ? FULL : 0u, no = (f & GK_G_NEG_OUT) ? FULL : 0u;
+            for (uint32_t i = lane; i < words; i += 32u) {
+              const uint32_t x = a[i] ^ na, y = b[i] ^ nb;
+              out[i] = ((f & GK_G_OR) ? (x | y) : (x & y)) ^ no;
+            }
+            break;
+          }
+          case GK_N_CONST: {
+            const uint32_t v = (op.w1 & 1u) ? FULL : 0u, words = (s_cnt[level] + 31u) >> 5;
+            for (uint32_t i = lane; i < words; i += 32u) out[i] = v;
+            break;
+          }
+          case GK_N_BCAST: {   // parent-level column -> rows of the child scope `level`
+            const uint32_t* in = slots + s_soff[op.w1 & 0xffffu];
+            const uint32_t par = (uint32_t)scopes[level].parent;
+            const uint32_t* coff = scopes[level].off + s_lo[par];
+            const uint32_t clo = s_lo[level], pcnt = s_cnt[par], words = (s_cnt[level] + 31u) >> 5;
+            for (uint32_t i = lane; i < words; i += 32u) out[i] = 0u;
+            __syncwarp();
+            for (uint32_t r = lane; r < pcnt; r += 32u) {
+              if ((in[r >> 5] >> (r & 31u)) & 1u) {
+                const uint32_t a = coff[r] - clo, b = coff[r + 1] - clo;
+                if (b > a)
+                  for (uint32_t w = a >> 5; w <= (b - 1u) >> 5; ++w) atomicOr(&out[w], range_mask(w, a, b));
+              }
+            }
+            break;
+          }
+          case GK_N_ACC: {     // EXISTS: OR over each parent's child range of the scope `level`
+            const uint32_t* in = slots + s_soff[op.w1 & 0xffffu];
+            const uint32_t par = (uint32_t)scopes[level].parent;
+            const uint32_t* coff = scopes[level].off + s_lo[par];
+            const uint32_t clo = s_lo[level], pcnt = s_cnt[par];
+            for (uint32_t r = lane; r < ((pcnt + 31u) & ~31u); r += 32u) {
+              bool any = false;
+              if (r < pcnt) {
+                const uint32_t a = coff[r] - clo, b = coff[r + 1] - clo;
+                if (b > a)
+                  for (uint32_t w = a >> 5; w <= (b - 1u) >> 5 && !any; ++w) any = (in[w] & range_mask(w, a, b)) != 0u;
+              }
+              const uint32_t w = __ballot_sync(FULL, any);
+              if (lane == 0) out[r >> 5] = w;
+            }
+            break;
+          }
+          case GK_N_MATCH: {
+            uint32_t* err = slots + s_soff[op.w1 & 0xffffu];
+            const GkMatch& m = match[op.w2];
+            for (uint32_t r = lane; r < ((nobj + 31u) & ~31u); r += 32u) {
+              int res = 0;
+              if (r < nobj && !(p.batch.flags[obj0 + r] & GK_F_SKIP)) res = gk_match(p.batch, pool, cbytes, m, obj0 + r);
+              if (res < 0) {
+                const uint32_t slot = atomicAdd(p.out.errcount, 1u);
+                if (slot < p.out.errcap) {
+                  p.out.errlist[3 * slot] = obj0 + r;
+                  p.out.errlist[3 * slot + 1] = op.w2;
+                  p.out.errlist[3 * slot + 2] = (uint32_t)(-res);
+                }
+              }
+              const uint32_t wm = __ballot_sync(FULL, res > 0), we = __ballot_sync(FULL, res < 0);
+              if (lane == 0) {
+                out[r >> 5] = wm;
+                err[r >> 5] = we;
+              }
+            }
+            break;
+          }
+          case GK_N_OUT: {
+            const uint32_t c = op.w2, flags = op.w3 >> 16;
+            if (!s_act[c]) break;
+            const uint32_t* prog = slots + s_soff[op.w1 & 0xffffu];
+            const uint32_t* mt = slots + s_soff[op.w1 >> 16];
+            const uint32_t* er = slots + s_soff[op.w3 & 0xffffu];
+            const uint32_t bit = 1u << (c & 31u), wi = c >> 5;
+            uint32_t nv = 0, ne = 0;
+            for (uint32_t i = 0; i < ((nobj + 31u) >> 5); ++i) {
+              const uint32_t valid = range_mask(i, 0u, nobj);
+              const uint32_t pv = (flags & 1u) ? FULL : (flags & 2u) ? 0u : prog[i];
+              const uint32_t v = pv & mt[i] & valid, e = er[i] & valid;
+              const uint32_t o = i * 32u + lane;
+              if ((v >> lane) & 1u) atomicOr(&res_v[o * W + wi], bit);
+              if ((e >> lane) & 1u) atomicOr(&res_e[o * W + wi], bit);
+              nv += __popc(v);
+              ne += __popc(e);
+            }
+            if (lane == 0) {
+              if (nv) atomicAdd(&s_tot[c], nv);
+              if (ne) atomicAdd(&s_err[c], ne);
+            }
+            break;
+          }
+          default: break;
+        }
+      }
+      __syncthreads();
+      if (end) break;
+    }
+    // ---- the tile's bitmap rows are contiguous in the object-major output: coalesced copy out
+    const size_t base = (size_t)obj0 * W;
+    for (uint32_t i = threadIdx.x; i < nobj * W; i += blockDim.x) {
+      p.out.viol[base + i] = res_v[i];
+      p.out.err[base + i] = res_e[i];
+    }
+    __syncthreads();
   }
-  __syncthreads();
   for (uint32_t c = threadIdx.x; c < C; c += blockDim.x) {
     if (s_tot[c]) atomicAdd(p.out.totals + c, (unsigned long long)s_tot[c]);
     if (s_err[c]) atomicAdd(p.out.err_totals + c, (unsigned long long)s_err[c]);
@@ -151,6 +271,11 @@ struct DevBatch {
   uint32_t* viol = nullptr;
   uint32_t* err = nullptr;
   uint32_t words = 0;
+  // tiling (depends on the batch's row distribution and on the program's slot table)
+  uint32_t* d_tile_lo = nullptr;
+  uint32_t* d_slot_off = nullptr;
+  uint32_t ntiles = 0, slot_words = 0;
+  uint64_t prog_version = 0;
 };
 
 class CudaBackend : public Backend {
@@ -166,6 +291,7 @@ class CudaBackend : public Backend {
     CK(cudaGetDeviceProperties(&prop, device_));
     sms_ = prop.multiProcessorCount;
     max_smem_ = (size_t)prop.sharedMemPerBlockOptin;
+    sm_smem_ = (size_t)prop.sharedMemPerMultiprocessor;
     CK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     CK(cudaEventCreate(&ev0_));
     CK(cudaEventCreate(&ev1_));
@@ -194,9 +320,10 @@ class CudaBackend : public Backend {
     CK(cudaSetDevice(device_));
     free_tables();
     prog_ = GkProgram{};
-    prog_.nconstraints = (uint32_t)c.cons.size();
+    prog_.nconstraints = (uint32_t)c.cons_match.size();
     prog_.nmatch = (uint32_t)c.match.size();
-    prog_.ninstr = (uint32_t)c.instr.size();
+    prog_.nops = (uint32_t)c.ops.size();
+    prog_.nslots = (uint32_t)c.slot_level.size();
     prog_.npool = (uint32_t)c.pool.size();
     prog_.ncbytes = (uint32_t)c.cbytes.size();
     auto up = [&](const void* src, size_t bytes, void** dst) {
@@ -205,27 +332,25 @@ class CudaBackend : public Backend {
       CK(cudaMemset(*dst, 0, padded));
       if (bytes) CK(cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
     };
-    up(c.cons.data(), c.cons.size() * sizeof(GkCons), (void**)&d_cons_);
+    up(c.ops.data(), c.ops.size() * sizeof(GkOp), (void**)&d_ops_);
     up(c.match.data(), c.match.size() * sizeof(GkMatch), (void**)&d_match_);
-    up(c.instr.data(), c.instr.size() * sizeof(GkInstr), (void**)&d_instr_);
     up(c.pool.data(), c.pool.size() * 4, (void**)&d_pool_);
     up(c.cbytes.data(), c.cbytes.size(), (void**)&d_cbytes_);
-    prog_.cons = d_cons_;
+    prog_.ops = d_ops_;
     prog_.match = d_match_;
-    prog_.instr = d_instr_;
     prog_.pool = d_pool_;
     prog_.cbytes = d_cbytes_;
+    slot_level_ = c.slot_level;
+    scope_parent_.clear();
+    for (auto& sd : c.schema.scopes) scope_parent_.push_back(sd.parent);
+    ncols_ = (uint32_t)c.schema.cols.size();
     const uint32_t C = prog_.nconstraints;
     if (d_totals_) cudaFree(d_totals_);
     CK(cudaMalloc(&d_totals_, (size_t)(2 * std::max(C, 1u)) * sizeof(unsigned long long)));
     if (d_active_) cudaFree(d_active_);
     CK(cudaMalloc(&d_active_, (size_t)std::max(C, 1u) * 4));
     if (!d_errlist_) CK(cudaMalloc(&d_errlist_, (size_t)kErrCap * 3 * 4));
-    auto r16 = [](size_t x) { return (x + 15) / 16 * 16; };
-    smem_base_ = r16((size_t)3 * C * 4);
-    smem_need_ = smem_base_ + r16((size_t)C * sizeof(GkCons)) + r16((size_t)prog_.nmatch * sizeof(GkMatch)) +
-                 r16(c.schema.cols.size() * sizeof(GkColumn)) + r16(c.schema.scopes.size() * sizeof(GkScope)) +
-                 r16((size_t)prog_.ninstr * sizeof(GkInstr)) + r16((size_t)prog_.npool * 4) + r16((size_t)prog_.ncbytes);
+    last_active_.clear();
     version_ = c.version;
   }
 
@@ -250,10 +375,33 @@ class CudaBackend : public Backend {
     CK(cudaSetDevice(device_));
     PackedBatch pb;
     pack_batch(hb, c, pb);
+    // ---- tiling: first row of every scope for every tile, slot offsets from the per-scope tile capacities
+    const uint32_t NS = (uint32_t)c.schema.scopes.size();
+    const uint32_t ntiles = (hb.n + kTile - 1) / kTile;
+    std::vector<uint32_t> tile_lo((size_t)(ntiles + 1) * NS), cap(NS, 0);
+    for (uint32_t t = 0; t <= ntiles; ++t) {
+      uint32_t* lo = &tile_lo[(size_t)t * NS];
+      lo[0] = std::min<uint32_t>(t * kTile, hb.n);
+      for (uint32_t s = 1; s < NS; ++s) lo[s] = hb.scope_off[s][lo[c.schema.scopes[s].parent]];
+      if (t)
+        for (uint32_t s = 0; s < NS; ++s) cap[s] = std::max(cap[s], lo[s] - tile_lo[(size_t)(t - 1) * NS + s]);
+    }
+    cap[0] = kTile;
+    std::vector<uint32_t> slot_off(c.slot_level.size());
+    uint32_t slot_words = 0;
+    for (size_t i = 0; i < slot_off.size(); ++i) {
+      slot_off[i] = slot_words;
+      slot_words += (cap[c.slot_level[i]] + 31) / 32 + 1;
+    }
     auto* db = new DevBatch();
     db->bytes = gk_align(pb.arena.size());
     db->n = hb.n;
+    db->ntiles = ntiles;
+    db->slot_words = slot_words;
+    db->prog_version = c.version;
     CK(cudaMalloc(&db->arena, db->bytes));
+    CK(cudaMalloc(&db->d_tile_lo, tile_lo.size() * 4 + 64));
+    CK(cudaMalloc(&db->d_slot_off, slot_off.size() * 4 + 64));
     db->hdr = rebase_batch(pb, pb.arena.data(), db->arena);
     cudaEvent_t a, b;
     CK(cudaEventCreate(&a));
@@ -269,6 +417,8 @@ class CudaBackend : public Backend {
       memcpy(pinned_, pb.arena.data(), pb.arena.size());
       CK(cudaEventRecord(a, stream_));
       CK(cudaMemcpyAsync(db->arena, pinned_, pb.arena.size(), cudaMemcpyHostToDevice, stream_));
+      CK(cudaMemcpyAsync(db->d_tile_lo, tile_lo.data(), tile_lo.size() * 4, cudaMemcpyHostToDevice, stream_));
+      CK(cudaMemcpyAsync(db->d_slot_off, slot_off.data(), slot_off.size() * 4, cudaMemcpyHostToDevice, stream_));
       CK(cudaEventRecord(b, stream_));
       CK(cudaStreamSynchronize(stream_));
     }
@@ -277,9 +427,8 @@ class CudaBackend : public Backend {
     cudaEventDestroy(a);
     cudaEventDestroy(b);
     if (h2d_ms) *h2d_ms = ms;
-    if (h2d_bytes) *h2d_bytes = pb.arena.size();
-    db->words = (uint32_t)((c.cons.size() + 31) / 32);
-    if (db->words == 0) db->words = 1;
+    if (h2d_bytes) *h2d_bytes = pb.arena.size() + tile_lo.size() * 4 + slot_off.size() * 4;
+    db->words = std::max<uint32_t>(1, (uint32_t)((c.cons_match.size() + 31) / 32));
     CK(cudaMalloc(&db->viol, (size_t)std::max(db->n, 1u) * db->words * 4));
     CK(cudaMalloc(&db->err, (size_t)std::max(db->n, 1u) * db->words * 4));
     return db;
@@ -292,6 +441,8 @@ class CudaBackend : public Backend {
     cudaFree(db->arena);
     cudaFree(db->viol);
     cudaFree(db->err);
+    cudaFree(db->d_tile_lo);
+    cudaFree(db->d_slot_off);
     delete db;
   }
 
@@ -299,6 +450,7 @@ class CudaBackend : public Backend {
   KParams prepare(DevBatch* db, const std::vector<uint32_t>& active, uint32_t* viol, uint32_t* err, unsigned long long* totals,
                   unsigned long long* err_totals, cudaStream_t st, size_t* smem_out) {
     const uint32_t C = prog_.nconstraints;
+    if (db->prog_version != version_) throw BackendError{"batch was uploaded for another constraint set"};
     KParams p;
     p.batch = db->hdr;
     p.batch.dict_off = d_dict_off_;
@@ -314,27 +466,37 @@ class CudaBackend : public Backend {
     p.out.errcap = kErrCap;
     p.out.words = db->words;
     p.active = d_active_;
+    p.slot_off = db->d_slot_off;
+    p.tile_lo = db->d_tile_lo;
+    p.ntiles = db->ntiles;
+    p.tile = kTile;
+    p.slot_words = db->slot_words;
     if (active.size() != C) throw BackendError{"active mask size mismatch"};
-    if (C) CK(cudaMemcpyAsync(d_active_, active.data(), (size_t)C * 4, cudaMemcpyHostToDevice, st));
+    if (C && active != last_active_) {
+      CK(cudaMemcpyAsync(d_active_, active.data(), (size_t)C * 4, cudaMemcpyHostToDevice, st));
+      CK(cudaStreamSynchronize(st));   // `active` is a caller temporary
+      last_active_ = active;
+    }
     if (C) CK(cudaMemsetAsync(totals, 0, (size_t)C * sizeof(unsigned long long), st));
     if (C) CK(cudaMemsetAsync(err_totals, 0, (size_t)C * sizeof(unsigned long long), st));
     CK(cudaMemsetAsync(d_scalars_, 0, 64, st));
-    size_t smem = smem_need_ + 64;
-    p.smem_tables = smem <= max_smem_ ? 1u : 0u;
-    if (!p.smem_tables) smem = smem_base_ + 64;
-    if (smem > max_smem_) throw BackendError{"too many constraints for one launch (per-constraint counters exceed shared memory)"};
+    auto r16 = [](size_t x) { return (x + 15) / 16 * 16; };
+    const size_t NS = scope_parent_.size();
+    size_t smem = 3 * r16((size_t)C * 4) + 2 * r16(NS * 4) + r16((size_t)prog_.nslots * 4) + 2 * r16((size_t)kTile * db->words * 4) +
+                  r16((size_t)db->slot_words * 4) + r16((size_t)prog_.nops * sizeof(GkOp)) + r16((size_t)prog_.nmatch * sizeof(GkMatch)) +
+                  r16((size_t)ncols_ * sizeof(GkColumn)) + r16(NS * sizeof(GkScope)) + r16((size_t)prog_.npool * 4) + r16((size_t)prog_.ncbytes) + 64;
+    if (smem > max_smem_)
+      throw BackendError{"constraint set needs " + std::to_string(smem) + " bytes of shared memory per CTA (limit " + std::to_string(max_smem_) +
+                         "): too many live netlist columns for one launch"};
     *smem_out = smem;
     return p;
   }
 
-  void fire(const KParams& p, uint32_t n, size_t smem, cudaStream_t st) {
-    if (n == 0) return;
-    // persistent-style grid: a multiple of the SM count, grid-stride over objects
-    int per_sm = 8;
-    if (smem > 24 * 1024) per_sm = (int)std::max<size_t>(1, (max_smem_ + 1024) / (smem + 1024));
-    per_sm = std::min(per_sm, 16);
-    uint32_t blocks_needed = (n + kThreads - 1) / kThreads;
-    uint32_t grid = std::max(1u, std::min<uint32_t>(blocks_needed, (uint32_t)(sms_ * per_sm)));
+  void fire(const KParams& p, size_t smem, cudaStream_t st) {
+    if (p.ntiles == 0) return;
+    // persistent CTAs: as many as fit per SM (shared-memory bound), each walks tiles with a grid stride
+    int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2048 / kThreads, (sm_smem_ - 1024) / (smem + 1024)));
+    uint32_t grid = std::max(1u, std::min<uint32_t>(p.ntiles, (uint32_t)(sms_ * per_sm)));
     gk_eval_kernel<<<grid, kThreads, smem, st>>>(p);
     CK(cudaGetLastError());
     ++launches_;
@@ -350,13 +512,12 @@ class CudaBackend : public Backend {
     out.words = db->words;
     unsigned long long* totals = d_totals_;
     unsigned long long* err_totals = d_totals_ + std::max(C, 1u);
-    // outputs other than the kernel itself are reset outside the timed region
     size_t smem = 0;
     KParams p = prepare(db, active, db->viol, db->err, totals, err_totals, stream_, &smem);
     CK(cudaStreamSynchronize(stream_));
     // the event pair brackets exactly the evaluation kernel
     CK(cudaEventRecord(ev0_, stream_));
-    fire(p, db->n, smem, stream_);
+    fire(p, smem, stream_);
     CK(cudaEventRecord(ev1_, stream_));
     CK(cudaStreamSynchronize(stream_));
     CK(cudaEventElapsedTime(&out.kernel_ms, ev0_, ev1_));
@@ -394,34 +555,35 @@ class CudaBackend : public Backend {
     cudaStream_t st = static_cast<cudaStream_t>(dst.stream);
     KParams p = prepare(db, active, static_cast<uint32_t*>(dst.viol), static_cast<uint32_t*>(dst.err), static_cast<unsigned long long*>(dst.totals),
                         static_cast<unsigned long long*>(dst.err_totals), st, &smem);
-    fire(p, db->n, smem, st);
+    fire(p, smem, st);
   }
 
  private:
   static constexpr uint32_t kErrCap = 1u << 20;
   void free_tables() {
-    if (d_cons_) cudaFree(d_cons_);
-    d_cons_ = nullptr;
+    if (d_ops_) cudaFree(d_ops_);
     if (d_match_) cudaFree(d_match_);
-    if (d_instr_) cudaFree(d_instr_);
     if (d_pool_) cudaFree(d_pool_);
     if (d_cbytes_) cudaFree(d_cbytes_);
+    d_ops_ = nullptr;
     d_match_ = nullptr;
-    d_instr_ = nullptr;
     d_pool_ = nullptr;
     d_cbytes_ = nullptr;
   }
   int device_;
   int sms_ = 148;
-  size_t max_smem_ = 0, smem_need_ = 0, smem_base_ = 0;
+  size_t max_smem_ = 0, sm_smem_ = 0;
   cudaStream_t stream_ = nullptr;
   cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
   std::mutex mu_;
   uint64_t version_ = 0, launches_ = 0;
   GkProgram prog_{};
-  GkCons* d_cons_ = nullptr;
+  std::vector<uint8_t> slot_level_;
+  std::vector<int> scope_parent_;
+  std::vector<uint32_t> last_active_;
+  uint32_t ncols_ = 0;
+  GkOp* d_ops_ = nullptr;
   GkMatch* d_match_ = nullptr;
-  GkInstr* d_instr_ = nullptr;
   uint32_t* d_pool_ = nullptr;
   uint8_t* d_cbytes_ = nullptr;
   uint32_t* d_dict_off_ = nullptr;

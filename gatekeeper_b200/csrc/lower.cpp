@@ -1408,223 +1408,365 @@ FP lower_violation(const std::shared_ptr<const Module>& mod, const VP& parameter
   return lw.run();
 }
 
-// ====================================================================================== code generation
-uint32_t ProgramBuilder::add_bytes(const std::string& s) {
+// ====================================================================================== netlist construction
+uint32_t NetBuilder::add_bytes(const std::string& s) {
   uint32_t off = (uint32_t)cbytes.size();
   cbytes.insert(cbytes.end(), s.begin(), s.end());
   return off;
 }
 
-const ProgramBuilder::Info& ProgramBuilder::info(const FP& f) {
-  auto it = info_.find(f.get());
-  if (it != info_.end()) return it->second;
-  Info x;
-  auto merge = [&](const std::vector<int>& o) {
-    for (int s : o)
-      if (std::find(x.free.begin(), x.free.end(), s) == x.free.end()) x.free.push_back(s);
-  };
-  switch (f->k) {
-    case Formula::True: x.key = "T"; x.size = 1; break;
-    case Formula::False: x.key = "F"; x.size = 1; break;
-    case Formula::Atom: {
-      x.key = "a" + std::to_string(f->op) + ":" + std::to_string(f->col) + ":" + std::to_string(f->imm) + ":" + (f->cval ? intern_key(f->cval) : std::string());
-      x.size = f->op >= GK_OP_PREFIX ? 4 : 2;
-      // the column's scope and all its ancestors must be open
-      for (int s = schema->cols[f->col].scope; s != 0; s = schema->scopes[s].parent) x.free.push_back(s);
-      break;
+namespace {
+
+struct NNode {
+  uint8_t kind = 0;        // GK_N_*
+  int level = 0;           // scope of the rows this node has one bit for
+  int a = -1, b = -1;      // inputs (node ids)
+  uint32_t flags = 0;      // gate flags / const value
+  int scope = 0;           // BCAST / ACC: the child scope
+  // atom
+  int op = 0, col = -1;
+  VP cval;
+  uint32_t imm = 0;
+  uint32_t match_id = 0;
+  int err_of = -1;         // MATCH: id of the paired error node (a pseudo node that only owns a slot)
+  int phase = 0, last_use = 0, slot = -1;
+};
+
+struct Ref {
+  int node;
+  bool neg;
+};
+
+struct Net {
+  const Schema& schema;
+  std::vector<NNode> nodes;
+  std::map<std::string, int> memo;
+  explicit Net(const Schema& s) : schema(s) {}
+
+  int depth(int scope) const { return schema.scopes[scope].depth; }
+
+  int intern_node(const std::string& key, NNode n) {
+    auto it = memo.find(key);
+    if (it != memo.end()) return it->second;
+    n.phase = 0;
+    if (n.a >= 0) n.phase = std::max(n.phase, nodes[n.a].phase + 1);
+    if (n.b >= 0) n.phase = std::max(n.phase, nodes[n.b].phase + 1);
+    nodes.push_back(std::move(n));
+    int id = (int)nodes.size() - 1;
+    memo.emplace(key, id);
+    return id;
+  }
+
+  Ref constant(bool v) {
+    NNode n;
+    n.kind = GK_N_CONST;
+    n.flags = 0;
+    return Ref{intern_node("const0", n), v};
+  }
+  bool is_const(const Ref& r) const { return nodes[r.node].kind == GK_N_CONST; }
+  bool const_val(const Ref& r) const { return r.neg; }   // the only CONST node holds 0
+
+  int bcast(int node, int child_scope) {
+    NNode n;
+    n.kind = GK_N_BCAST;
+    n.level = child_scope;
+    n.scope = child_scope;
+    n.a = node;
+    return intern_node("bc" + std::to_string(node) + ">" + std::to_string(child_scope), n);
+  }
+  // bring a node up to a deeper level (target must be a descendant of the node's level)
+  int raise(int node, int target) {
+    int lvl = nodes[node].level;
+    if (lvl == target) return node;
+    std::vector<int> chain;
+    for (int s = target; s != lvl; s = schema.scopes[s].parent) {
+      if (s == 0) throw RegoError{"internal: netlist levels are not on one scope chain"};
+      chain.push_back(s);
     }
-    case Formula::Not: {
-      const Info& k = info(f->kids[0]);
-      x.key = "!(" + k.key + ")";
-      x.size = k.size + 1;
-      x.free = k.free;
-      break;
+    for (size_t i = chain.size(); i-- > 0;) node = bcast(node, chain[i]);
+    return node;
+  }
+
+  Ref gate(bool is_or, Ref x, Ref y) {
+    // constant folding
+    if (is_const(x) || is_const(y)) {
+      if (is_const(y)) std::swap(x, y);
+      bool cv = const_val(x);
+      if (is_or) return cv ? constant(true) : y;
+      return cv ? y : constant(false);
     }
-    case Formula::And:
-    case Formula::Or: {
-      x.key = f->k == Formula::And ? "&(" : "|(";
-      for (auto& c : f->kids) {
-        const Info& k = info(c);
-        x.key += k.key + ",";
-        x.size += k.size + 1;
-        merge(k.free);
+    if (x.node == y.node) {
+      if (x.neg == y.neg) return x;
+      return constant(is_or);   // a | !a = 1 ; a & !a = 0
+    }
+    int lx = nodes[x.node].level, ly = nodes[y.node].level;
+    int target = depth(lx) >= depth(ly) ? lx : ly;
+    x.node = raise(x.node, target);
+    y.node = raise(y.node, target);
+    if (x.node > y.node) std::swap(x, y);
+    NNode n;
+    n.kind = GK_N_GATE;
+    n.level = target;
+    n.a = x.node;
+    n.b = y.node;
+    n.flags = (is_or ? GK_G_OR : 0) | (x.neg ? GK_G_NEG_A : 0) | (y.neg ? GK_G_NEG_B : 0);
+    int id = intern_node("g" + std::to_string(n.flags) + ":" + std::to_string(n.a) + "," + std::to_string(n.b), n);
+    return Ref{id, false};
+  }
+
+  // materialise a possibly negated reference as a plain node (needed where negation cannot be folded)
+  int plain(Ref r) {
+    if (!r.neg) return r.node;
+    NNode n;
+    n.kind = GK_N_GATE;
+    n.level = nodes[r.node].level;
+    n.a = n.b = r.node;
+    n.flags = GK_G_NEG_A | GK_G_NEG_B;
+    return intern_node("not" + std::to_string(r.node), n);
+  }
+
+  Ref build(const FP& f) {
+    switch (f->k) {
+      case Formula::True: return constant(true);
+      case Formula::False: return constant(false);
+      case Formula::Not: {
+        Ref r = build(f->kids[0]);
+        r.neg = !r.neg;
+        return r;
       }
-      x.key += ")";
-      break;
-    }
-    case Formula::Exists: {
-      const Info& k = info(f->kids[0]);
-      x.key = "E" + std::to_string(f->scope) + "(" + k.key + ")";
-      x.size = k.size * 2 + 6;   // a loop: body runs ~1.7 times on average
-      for (int s : k.free)
-        if (s != f->scope) x.free.push_back(s);
-      for (int s = schema->scopes[f->scope].parent; s != 0; s = schema->scopes[s].parent)
-        if (std::find(x.free.begin(), x.free.end(), s) == x.free.end()) x.free.push_back(s);
-      break;
-    }
-  }
-  std::sort(x.free.begin(), x.free.end());
-  return info_.emplace(f.get(), std::move(x)).first->second;
-}
-
-void ProgramBuilder::plan(const std::vector<FP>& all) {
-  // occurrences of every closed (loop-independent) sub-formula over the whole constraint set
-  struct Cand {
-    uint32_t count = 0, size = 0;
-  };
-  std::map<std::string, Cand> cands;
-  std::function<void(const FP&)> walk = [&](const FP& f) {
-    const Info& x = info(f);
-    if (x.free.empty() && f->k != Formula::True && f->k != Formula::False) {
-      Cand& c = cands[x.key];
-      c.count++;
-      c.size = x.size;
-    }
-    for (auto& k : f->kids) walk(k);
-  };
-  for (auto& f : all) walk(f);
-  std::vector<std::pair<uint64_t, std::string>> ranked;
-  for (auto& c : cands)
-    if (c.second.count >= 2) ranked.emplace_back((uint64_t)(c.second.count - 1) * c.second.size, c.first);
-  std::sort(ranked.begin(), ranked.end(), [](auto& a, auto& b) { return a.first != b.first ? a.first > b.first : a.second < b.second; });
-  cse_bit_.clear();
-  for (auto& r : ranked) {
-    if (cse_bit_.size() >= GK_MAX_CSE) break;
-    int bit = (int)cse_bit_.size();
-    cse_bit_[r.second] = bit;
-  }
-}
-
-uint32_t ProgramBuilder::slot_of(int scope, const std::vector<int>& open) const {
-  if (scope == 0) return 0;
-  for (size_t i = 0; i < open.size(); ++i)
-    if (open[i] == scope) return (uint32_t)i + 1;
-  throw RegoError{"internal: column scope is not open in the generated loop nest"};
-}
-
-void ProgramBuilder::emit_node(const FP& f, std::vector<int>& open, int& depth, int& maxdepth) {
-  const Info& x = info(f);
-  auto it = x.free.empty() ? cse_bit_.find(x.key) : cse_bit_.end();
-  if (it == cse_bit_.end()) {
-    emit_plain(f, open, depth, maxdepth);
-    return;
-  }
-  size_t at = instr.size();
-  instr.push_back(GkInstr{GK_OP_CSE_TRY, (uint32_t)it->second, 0, 0});
-  int d0 = depth;
-  emit_plain(f, open, depth, maxdepth);
-  instr.push_back(GkInstr{GK_OP_CSE_STORE, (uint32_t)it->second, 0, 0});
-  instr[at].w2 = (uint32_t)instr.size();
-  depth = d0 + 1;
-}
-
-void ProgramBuilder::emit_plain(const FP& f, std::vector<int>& open, int& depth, int& maxdepth) {
-  auto push = [&]() {
-    if (++depth > maxdepth) maxdepth = depth;
-  };
-  switch (f->k) {
-    case Formula::True:
-    case Formula::False:
-      instr.push_back(GkInstr{GK_OP_PUSH, f->k == Formula::True ? 1u : 0u, 0, 0});
-      push();
-      break;
-    case Formula::Not:
-      emit_node(f->kids[0], open, depth, maxdepth);
-      instr.push_back(GkInstr{GK_OP_NOT, 0, 0, 0});
-      break;
-    case Formula::And:
-    case Formula::Or:
-      for (size_t i = 0; i < f->kids.size(); ++i) {
-        emit_node(f->kids[i], open, depth, maxdepth);
-        if (i) {
-          instr.push_back(GkInstr{f->k == Formula::And ? (uint32_t)GK_OP_AND : (uint32_t)GK_OP_OR, 0, 0, 0});
-          --depth;
-        }
+      case Formula::Atom: {
+        NNode n;
+        n.kind = GK_N_ATOM;
+        n.level = schema.cols[f->col].scope;
+        n.op = f->op;
+        n.col = f->col;
+        n.cval = f->cval;
+        n.imm = f->imm;
+        std::string key = "a" + std::to_string(f->op) + ":" + std::to_string(f->col) + ":" + std::to_string(f->imm) + ":" +
+                          (f->cval ? intern_key(f->cval) : std::string());
+        return Ref{intern_node(key, n), false};
       }
-      break;
-    case Formula::Exists: {
-      const ScopeDef& sd = schema->scopes[f->scope];
-      uint32_t pslot = slot_of(sd.parent, open);
-      uint32_t slot = (uint32_t)open.size() + 1;
-      if (slot > GK_MAX_LOOP_DEPTH) throw RegoError{"rego_unsupported: loop nest deeper than " + std::to_string(GK_MAX_LOOP_DEPTH)};
-      size_t begin = instr.size();
-      instr.push_back(GkInstr{GK_OP_LOOP_BEGIN | (slot << 8) | (pslot << 16), (uint32_t)f->scope, 0, 0});
-      push();   // accumulator
-      uint32_t body = (uint32_t)instr.size();
-      open.push_back(f->scope);
-      emit_node(f->kids[0], open, depth, maxdepth);
-      open.pop_back();
-      instr.push_back(GkInstr{GK_OP_LOOP_END | (slot << 8), 0, body, 0});
-      --depth;   // body result folded into the accumulator
-      instr[begin].w2 = (uint32_t)instr.size();
-      break;
+      case Formula::And:
+      case Formula::Or: {
+        std::vector<Ref> refs;
+        for (auto& k : f->kids) refs.push_back(build(k));
+        // combine shallow levels first so that a loop-invariant group is broadcast into the loop once
+        std::stable_sort(refs.begin(), refs.end(), [&](const Ref& p, const Ref& q) { return depth(nodes[p.node].level) < depth(nodes[q.node].level); });
+        Ref acc = refs[0];
+        for (size_t i = 1; i < refs.size(); ++i) acc = gate(f->k == Formula::Or, acc, refs[i]);
+        return acc;
+      }
+      case Formula::Exists: {
+        Ref r = build(f->kids[0]);
+        if (is_const(r)) {
+          if (!const_val(r)) return constant(false);
+          // EXISTS row: true  == the collection is non-empty: broadcast a constant 1 into the scope and OR-reduce it
+        }
+        int body = raise(plain(r), f->scope);
+        if (nodes[body].level != f->scope) throw RegoError{"internal: EXISTS body is deeper than its scope"};
+        NNode n;
+        n.kind = GK_N_ACC;
+        n.level = schema.scopes[f->scope].parent;
+        n.scope = f->scope;
+        n.a = body;
+        return Ref{intern_node("acc" + std::to_string(body) + "@" + std::to_string(f->scope), n), false};
+      }
     }
-    case Formula::Atom: {
-      const ColDef& cd = schema->cols[f->col];
-      uint32_t slot = slot_of(cd.scope, open);
-      uint32_t w1 = 0, w3 = 0;
-      switch (f->op) {
-        case GK_OP_TRUTHY:
-        case GK_OP_DEFINED: break;
-        case GK_OP_VTMASK: w1 = f->imm; break;
-        case GK_OP_SID_EQ: w1 = interner->intern(intern_key(f->cval)); break;
-        case GK_OP_SID_IN: {
-          std::vector<uint32_t> ids;
-          for (auto& v : f->cval->items) ids.push_back(interner->intern(intern_key(v)));
-          std::sort(ids.begin(), ids.end());
-          ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
-          w1 = (uint32_t)pool.size();
-          w3 = (uint32_t)ids.size();
-          pool.insert(pool.end(), ids.begin(), ids.end());
+    throw RegoError{"internal: unknown formula node"};
+  }
+};
+
+}  // namespace
+
+void NetBuilder::build(const std::vector<FP>& formulas, const std::vector<uint32_t>& match_id, uint32_t nmatch) {
+  Net net(*schema);
+  if (schema->scopes.size() > GK_MAX_SCOPES) throw RegoError{"rego_unsupported: too many iteration scopes"};
+  // match nodes (+ a pseudo node that owns the error column's slot)
+  std::vector<int> match_node(nmatch), err_node(nmatch);
+  for (uint32_t m = 0; m < nmatch; ++m) {
+    NNode e;
+    e.kind = GK_N_CONST;   // placeholder kind; never emitted (flags = 2 marks it)
+    e.flags = 2;
+    err_node[m] = net.intern_node("err" + std::to_string(m), e);
+    NNode n;
+    n.kind = GK_N_MATCH;
+    n.match_id = m;
+    n.err_of = err_node[m];
+    match_node[m] = net.intern_node("match" + std::to_string(m), n);
+  }
+  struct Out {
+    int prog;
+    uint32_t flags;
+  };
+  std::vector<Out> outs;
+  for (auto& f : formulas) {
+    Ref r = net.build(f);
+    Out o{-1, 0};
+    if (net.is_const(r)) o.flags = net.const_val(r) ? 1u : 2u;
+    else {
+      o.prog = net.plain(r);
+      if (net.nodes[o.prog].level != 0) throw RegoError{"internal: constraint result is not at the object level"};
+    }
+    outs.push_back(o);
+  }
+  auto& N = net.nodes;
+  // ---- phases and liveness
+  int maxphase = 0;
+  for (auto& n : N) maxphase = std::max(maxphase, n.phase);
+  const int out_phase = maxphase + 1;
+  for (auto& n : N) n.last_use = n.phase;
+  for (auto& n : N) {
+    if (n.a >= 0) N[n.a].last_use = std::max(N[n.a].last_use, n.phase);
+    if (n.b >= 0) N[n.b].last_use = std::max(N[n.b].last_use, n.phase);
+  }
+  for (size_t c = 0; c < outs.size(); ++c) {
+    if (outs[c].prog >= 0) N[outs[c].prog].last_use = out_phase;
+    N[match_node[match_id[c]]].last_use = out_phase;
+    N[err_node[match_id[c]]].last_use = out_phase;
+  }
+  // drop nodes nobody uses (e.g. the CONST node when every constant folded away)
+  std::vector<bool> used(N.size(), false);
+  for (size_t c = 0; c < outs.size(); ++c) {
+    if (outs[c].prog >= 0) used[outs[c].prog] = true;
+    used[match_node[match_id[c]]] = true;
+    used[err_node[match_id[c]]] = true;
+  }
+  for (size_t i = N.size(); i-- > 0;) {
+    if (!used[i]) continue;
+    if (N[i].a >= 0) used[N[i].a] = true;
+    if (N[i].b >= 0) used[N[i].b] = true;
+  }
+  // ---- slot allocation: per level free lists, a slot is reusable in the phase after its last use
+  std::vector<std::vector<int>> by_phase(out_phase + 1);
+  for (size_t i = 0; i < N.size(); ++i)
+    if (used[i]) by_phase[N[i].phase].push_back((int)i);
+  std::map<int, std::vector<int>> free_slots;           // level -> slots
+  std::vector<std::vector<int>> release_at(out_phase + 2);
+  slot_level.clear();
+  auto alloc = [&](int level) {
+    auto& fl = free_slots[level];
+    if (!fl.empty()) {
+      int s = fl.back();
+      fl.pop_back();
+      return s;
+    }
+    if (slot_level.size() >= GK_MAX_SLOTS) throw RegoError{"rego_unsupported: netlist needs too many live columns"};
+    slot_level.push_back((uint8_t)level);
+    return (int)slot_level.size() - 1;
+  };
+  ops.clear();
+  n_nodes = n_atoms = n_gates = 0;
+  for (int ph = 0; ph <= maxphase; ++ph) {
+    for (int s : release_at[ph]) free_slots[slot_level[s]].push_back(s);
+    auto& ids = by_phase[ph];
+    std::stable_sort(ids.begin(), ids.end(), [&](int x, int y) { return N[x].level < N[y].level; });
+    for (int id : ids) {
+      NNode& n = N[id];
+      n.slot = alloc(n.level);
+      release_at[std::min(n.last_use + 1, out_phase + 1)].push_back(n.slot);
+    }
+    for (int id : ids) {
+      NNode& n = N[id];
+      ++n_nodes;
+      GkOp op{};
+      const uint32_t out = (uint32_t)n.slot;
+      switch (n.kind) {
+        case GK_N_CONST:
+          if (n.flags == 2) continue;   // error-column placeholder: written by its MATCH op
+          op.w0 = GK_N_CONST | (0u << 8) | (out << 16);
+          op.w1 = 0;
           break;
-        }
-        case GK_OP_NUM_CMP: {
-          int64_t k = 0;
-          num_fits_i64(f->cval->n, &k);
-          w1 = (uint32_t)pool.size();
-          pool.push_back((uint32_t)((uint64_t)k & 0xffffffffu));
-          pool.push_back((uint32_t)((uint64_t)k >> 32));
-          w3 = f->imm;
+        case GK_N_MATCH:
+          op.w0 = GK_N_MATCH | (0u << 8) | (out << 16);
+          op.w1 = (uint32_t)N[n.err_of].slot;
+          op.w2 = n.match_id;
           break;
-        }
-        case GK_OP_PREFIX:
-        case GK_OP_SUFFIX:
-        case GK_OP_CONTAINS:
-          w1 = add_bytes(f->cval->s);
-          w3 = (uint32_t)f->cval->s.size();
+        case GK_N_GATE:
+          ++n_gates;
+          op.w0 = GK_N_GATE | ((uint32_t)n.level << 8) | (out << 16);
+          op.w1 = (uint32_t)N[n.a].slot | ((uint32_t)N[n.b].slot << 16);
+          op.w2 = n.flags;
           break;
-        case GK_OP_ANYPREFIX:
-        case GK_OP_ANYSUFFIX: {
-          std::vector<uint32_t> ent;
-          for (auto& v : f->cval->items) {
-            ent.push_back(add_bytes(v->s));
-            ent.push_back((uint32_t)v->s.size());
+        case GK_N_BCAST:
+          op.w0 = GK_N_BCAST | ((uint32_t)n.scope << 8) | (out << 16);
+          op.w1 = (uint32_t)N[n.a].slot;
+          break;
+        case GK_N_ACC:
+          op.w0 = GK_N_ACC | ((uint32_t)n.scope << 8) | (out << 16);
+          op.w1 = (uint32_t)N[n.a].slot;
+          break;
+        case GK_N_ATOM: {
+          ++n_atoms;
+          uint32_t w2 = 0, w3 = 0;
+          switch (n.op) {
+            case GK_OP_TRUTHY:
+            case GK_OP_DEFINED: break;
+            case GK_OP_VTMASK: w2 = n.imm; break;
+            case GK_OP_SID_EQ: w2 = interner->intern(intern_key(n.cval)); break;
+            case GK_OP_SID_IN: {
+              std::vector<uint32_t> ids2;
+              for (auto& v : n.cval->items) ids2.push_back(interner->intern(intern_key(v)));
+              std::sort(ids2.begin(), ids2.end());
+              ids2.erase(std::unique(ids2.begin(), ids2.end()), ids2.end());
+              w2 = (uint32_t)pool.size();
+              w3 = (uint32_t)ids2.size();
+              pool.insert(pool.end(), ids2.begin(), ids2.end());
+              break;
+            }
+            case GK_OP_NUM_CMP: {
+              int64_t k = 0;
+              num_fits_i64(n.cval->n, &k);
+              w2 = (uint32_t)pool.size();
+              pool.push_back((uint32_t)((uint64_t)k & 0xffffffffu));
+              pool.push_back((uint32_t)((uint64_t)k >> 32));
+              w3 = n.imm;
+              break;
+            }
+            case GK_OP_PREFIX:
+            case GK_OP_SUFFIX:
+            case GK_OP_CONTAINS:
+              w2 = add_bytes(n.cval->s);
+              w3 = (uint32_t)n.cval->s.size();
+              break;
+            case GK_OP_ANYPREFIX:
+            case GK_OP_ANYSUFFIX: {
+              std::vector<uint32_t> ent;
+              for (auto& v : n.cval->items) {
+                ent.push_back(add_bytes(v->s));
+                ent.push_back((uint32_t)v->s.size());
+              }
+              w2 = (uint32_t)pool.size();
+              w3 = (uint32_t)n.cval->items.size();
+              pool.insert(pool.end(), ent.begin(), ent.end());
+              break;
+            }
+            default: throw RegoError{"internal: unknown atom"};
           }
-          w1 = (uint32_t)pool.size();
-          w3 = (uint32_t)f->cval->items.size();
-          pool.insert(pool.end(), ent.begin(), ent.end());
+          op.w0 = GK_N_ATOM | ((uint32_t)n.level << 8) | (out << 16);
+          op.w1 = (uint32_t)n.op | ((uint32_t)n.col << 8);
+          op.w2 = w2;
+          op.w3 = w3;
           break;
         }
-        default: throw RegoError{"internal: unknown atom"};
+        default: throw RegoError{"internal: unknown netlist node"};
       }
-      instr.push_back(GkInstr{(uint32_t)f->op | (slot << 8) | ((uint32_t)f->col << 16), w1, 0, w3});
-      push();
-      break;
+      ops.push_back(op);
     }
+    ops.push_back(GkOp{GK_N_PHASE, 0, 0, 0});
   }
-}
-
-uint32_t ProgramBuilder::emit(const FP& f) {
-  if (f->k == Formula::True) return GK_PC_ACCEPT;
-  if (f->k == Formula::False) return GK_PC_REJECT;
-  uint32_t entry = (uint32_t)instr.size();
-  std::vector<int> open;
-  int depth = 0, maxdepth = 0;
-  emit_node(f, open, depth, maxdepth);
-  instr.push_back(GkInstr{GK_OP_END, 0, 0, 0});
-  if (maxdepth > GK_MAX_STACK) throw RegoError{"rego_unsupported: predicate nesting exceeds the " + std::to_string(GK_MAX_STACK) + "-entry boolean stack"};
-  if (instr.size() > (1u << 22)) throw RegoError{"rego_unsupported: predicate table too large"};
-  return entry;
+  // the error placeholder slots must exist even if their phase-0 allocation happened above (it did)
+  for (size_t c = 0; c < outs.size(); ++c) {
+    GkOp op{};
+    op.w0 = GK_N_OUT;
+    uint32_t prog = outs[c].prog >= 0 ? (uint32_t)N[outs[c].prog].slot : 0u;
+    op.w1 = prog | ((uint32_t)N[match_node[match_id[c]]].slot << 16);
+    op.w2 = (uint32_t)c;
+    op.w3 = (uint32_t)N[err_node[match_id[c]]].slot | (outs[c].flags << 16);
+    ops.push_back(op);
+  }
+  ops.push_back(GkOp{GK_N_PHASE, 0, 0, 0});
+  ops.push_back(GkOp{GK_N_END, 0, 0, 0});
+  n_phases = (size_t)out_phase + 1;
 }
 
 }  // namespace gk

@@ -92,32 +92,18 @@ struct Interner {
 // Lower one constraint's violation predicate.  Throws RegoError on unsupported constructs.
 FP lower_violation(const std::shared_ptr<const Module>& mod, const VP& parameters, Schema& schema);
 
-// Program assembly: constant pools + postfix instruction emission shared by all constraints.
-struct ProgramBuilder {
-  std::vector<GkInstr> instr;
+// Netlist assembly: every constraint's formula is merged into one DAG of bit-column ops (program.h GkOp).
+struct NetBuilder {
+  std::vector<GkOp> ops;
+  std::vector<uint8_t> slot_level;       // scope id of each shared-memory slot
   std::vector<uint32_t> pool;
   std::vector<uint8_t> cbytes;
   Interner* interner = nullptr;
   const Schema* schema = nullptr;
+  size_t n_nodes = 0, n_atoms = 0, n_gates = 0, n_phases = 0;
   uint32_t add_bytes(const std::string& s);
-  // pass 1: look at every constraint's formula and pick the sub-formulas worth sharing across constraints
-  void plan(const std::vector<FP>& all);
-  // pass 2: returns the entry pc (or GK_PC_ACCEPT / GK_PC_REJECT for constant formulas)
-  uint32_t emit(const FP& f);
-  size_t n_shared() const { return cse_bit_.size(); }
-
- private:
-  struct Info {
-    std::string key;
-    std::vector<int> free;   // scopes that must already be open (sorted)
-    uint32_t size = 0;
-  };
-  const Info& info(const FP& f);
-  void emit_node(const FP& f, std::vector<int>& open, int& depth, int& maxdepth);
-  void emit_plain(const FP& f, std::vector<int>& open, int& depth, int& maxdepth);
-  uint32_t slot_of(int scope, const std::vector<int>& open) const;
-  std::map<const Formula*, Info> info_;
-  std::map<std::string, int> cse_bit_;
+  // formulas[c] / match_id[c] per constraint (in final constraint order); nmatch distinct match blocks
+  void build(const std::vector<FP>& formulas, const std::vector<uint32_t>& match_id, uint32_t nmatch);
 };
 
 }  // namespace gk

@@ -3,9 +3,8 @@
 //
 //   batch  : column-wise (SoA) -- header columns one row per object, CSR label table, CSR "scopes" (one
 //            row per iterated element, e.g. spec.containers[_]) with fixed-width feature columns.
-//   program: DISTINCT match blocks (the spec.match pre-filter, pkg/mutation/match/match.go:32-65), a
-//            constraint table (match block id + entry pc) ordered so that constraints sharing a match block
-//            are adjacent, and one shared instruction array of warp-uniform postfix predicate code.
+//   program: DISTINCT match blocks (the spec.match pre-filter, pkg/mutation/match/match.go:32-65) and one
+//            netlist of bit-column ops shared by all constraints (see GkOp).
 #pragma once
 #include <stdint.h>
 
@@ -25,10 +24,8 @@ enum { GK_ENC_VT = 1, GK_ENC_SID = 2, GK_ENC_NUM = 4, GK_ENC_BYTES = 8 };
 #define GK_SID_UNDEF 0u          /* intern id 0 is reserved: "no value" */
 #define GK_NONE 0xFFFFFFFFu
 #define GK_MAX_LOOP_DEPTH 4
-#define GK_MAX_STACK 60          /* boolean stack lives in one 64-bit register per thread */
-#define GK_MAX_CSE 64            /* shared sub-formula results live in one 64-bit register per thread */
-#define GK_PC_ACCEPT 0xFFFFFFFFu
-#define GK_PC_REJECT 0xFFFFFFFEu
+#define GK_MAX_SCOPES 250        /* scope ids fit one byte */
+#define GK_MAX_SLOTS 65535
 
 typedef struct {
   int32_t scope;           // 0 = root (one row per object)
@@ -99,55 +96,66 @@ typedef struct {
   uint32_t pad0, pad1;
 } GkMatch;
 
+// ---- the constraint netlist.
+// ALL constraints are compiled jointly into one DAG whose nodes are BIT COLUMNS: one bit per object (root
+// level) or per iterated element (scope level).  A CTA owns a tile of consecutive objects; every node of the
+// tile lives in shared memory as packed 32-bit words (32 rows per word):
+//   ATOM   column value <op> constant          one bit per row, assembled with warp ballots (coalesced loads)
+//   GATE   AND/OR of two columns (negations folded into flags)   bitwise on words: 32 rows per instruction
+//   BCAST  parent-level column -> child-level rows   (loop-invariant sub-formulas hoisted out of an EXISTS)
+//   ACC    EXISTS: child-level column -> parent level by OR over each parent's CSR child range
+//   MATCH  the spec.match pre-filter of one DISTINCT match block -> match column + error column
+//   OUT    constraint result = program column AND match column -> result area, per-constraint totals
+// Ops are sorted into dependency phases; inside a phase the warps of the CTA take ops round-robin, a
+// __syncthreads separates phases.  Identical sub-formulas of different constraints are one node.
 typedef struct {
-  uint32_t match_id;              // index into the distinct match blocks
-  uint32_t pc;                    // entry pc, or GK_PC_ACCEPT / GK_PC_REJECT for constant predicates
-} GkCons;
+  uint32_t w0;   // kind | level<<8 | out_slot<<16     (level = scope id of the rows the op iterates)
+  uint32_t w1;
+  uint32_t w2;
+  uint32_t w3;
+} GkOp;
 
-// ---- predicate instructions: 4 x u32, executed by ALL lanes of a warp in lock step (the pc is warp-uniform).
-// Every lane owns a boolean stack held in one 64-bit register (bit 0 = top) and a 64-bit register of shared
-// sub-formula results.  There are no data-dependent jumps: loops run for the warp-wide maximum trip count with
-// finished lanes masked off, so the only divergence left is inside byte-string comparisons.
-//   w0 = op | slot<<8 | col<<16      (slot: which open loop supplies the row; 0 = the object itself)
-//   w1 = operand A (immediate / pool offset / scope id / cse bit)
-//   w2 = jump target (loops)
-//   w3 = operand B (count / length / compare op)
 enum {
-  GK_OP_END = 0,        // result = top of stack
-  GK_OP_TRUTHY = 1,     // push vt != undef && vt != false
-  GK_OP_DEFINED = 2,    // push vt != undef
-  GK_OP_VTMASK = 3,     // push (1 << vt) & w1
-  GK_OP_SID_EQ = 4,     // push sid == w1
-  GK_OP_SID_IN = 5,     // push sid in pool[w1 .. w1+w3) (sorted)
-  GK_OP_NUM_CMP = 6,    // w3 = GK_CMP_*; i64 constant at pool[w1], pool[w1+1] (lo, hi); OPA cross-type ordering
-  GK_OP_PREFIX = 7,     // push vt == str && bytes startswith cbytes[w1 .. w1+w3)
+  GK_N_END = 0,
+  GK_N_PHASE = 1,   // barrier between dependency phases
+  GK_N_ATOM = 2,    // w1 = atom op | col<<8 ; w2, w3 = operands (see GK_OP_*)
+  GK_N_GATE = 3,    // w1 = a | b<<16 ; w2 = flags: 1 OR (else AND), 2 negate a, 4 negate b, 8 negate out
+  GK_N_CONST = 4,   // w1 = 0 / 1
+  GK_N_BCAST = 5,   // level = child scope (rows written); w1 = input slot at the parent level
+  GK_N_ACC = 6,     // level = child scope (rows read); out at the parent level; w1 = input slot
+  GK_N_MATCH = 7,   // w1 = error-column slot ; w2 = match block id
+  GK_N_OUT = 8,     // w1 = program slot | match slot<<16 ; w2 = constraint index ; w3 = error slot | flags<<16
+                    //   flags: 1 = program is constant TRUE, 2 = constant FALSE (program slot ignored)
+};
+
+// atom ops (w1 low byte of an ATOM)
+enum {
+  GK_OP_TRUTHY = 1,     // vt != undef && vt != false
+  GK_OP_DEFINED = 2,    // vt != undef
+  GK_OP_VTMASK = 3,     // (1 << vt) & w2
+  GK_OP_SID_EQ = 4,     // sid == w2
+  GK_OP_SID_IN = 5,     // sid in pool[w2 .. w2+w3) (sorted)
+  GK_OP_NUM_CMP = 6,    // w3 = GK_CMP_*; i64 constant at pool[w2], pool[w2+1] (lo, hi); OPA cross-type ordering
+  GK_OP_PREFIX = 7,     // vt == str && bytes startswith cbytes[w2 .. w2+w3)
   GK_OP_SUFFIX = 8,
   GK_OP_CONTAINS = 9,
-  GK_OP_ANYPREFIX = 10, // pool[w1 ..]: w3 entries of [byte_off, len]
+  GK_OP_ANYPREFIX = 10, // pool[w2 ..]: w3 entries of [byte_off, len]
   GK_OP_ANYSUFFIX = 11,
-  GK_OP_LOOP_BEGIN = 12, // w1 = scope id; slot = new loop slot; col field = parent slot; pushes acc = false;
-                         // trip = warp max of the lane ranges; if trip == 0 jump to w2 (just past LOOP_END)
-  GK_OP_LOOP_END = 13,   // acc |= top & lane-still-in-range; pop; ++iter; if --trip jump to w2 (loop body)
-  GK_OP_AND = 14,
-  GK_OP_OR = 15,
-  GK_OP_NOT = 16,
-  GK_OP_PUSH = 17,       // push (w1 & 1)
-  GK_OP_CSE_TRY = 18,    // if shared result w1 is already valid for this warp: push it and jump to w2
-  GK_OP_CSE_STORE = 19,  // shared result w1 = top (stays on the stack); mark valid
 };
 enum { GK_CMP_LT = 0, GK_CMP_LE = 1, GK_CMP_GT = 2, GK_CMP_GE = 3, GK_CMP_EQ = 4, GK_CMP_NE = 5 };
-
-typedef struct { uint32_t w0, w1, w2, w3; } GkInstr;
+enum { GK_G_OR = 1, GK_G_NEG_A = 2, GK_G_NEG_B = 4, GK_G_NEG_OUT = 8 };
 
 typedef struct {
   uint32_t nconstraints;
   uint32_t nmatch;
-  uint32_t ninstr;
+  uint32_t nops;
+  uint32_t nslots;
   uint32_t npool;
   uint32_t ncbytes;
-  const GkCons* cons;        // [nconstraints]
+  const GkOp* ops;           // [nops]
+  const uint8_t* slot_level; // [nslots] scope id of each slot
+  const uint32_t* cons_match;// [nconstraints] match block id
   const GkMatch* match;      // [nmatch]
-  const GkInstr* instr;      // [ninstr]
   const uint32_t* pool;      // u32 constant pool
   const uint8_t* cbytes;     // constant byte strings (wildcard literals, prefixes)
 } GkProgram;
@@ -157,7 +165,7 @@ typedef struct {
   uint32_t* err;             // [n * words]   matcher error ("autoreject") plane
   unsigned long long* totals;     // [nconstraints] violating pairs
   unsigned long long* err_totals; // [nconstraints]
-  uint32_t* errlist;         // [errcap * 3]  (object, constraint, code)
+  uint32_t* errlist;         // [errcap * 3]  (object, match block, code)
   uint32_t* errcount;        // [1]
   uint32_t errcap;
   uint32_t words;            // ceil(nconstraints / 32)

@@ -195,159 +195,52 @@ GK_HD bool gk_cmp_apply(uint32_t op, int c) {
   }
 }
 
-// ---- warp-uniform helpers: on the GPU every lane of a warp executes the same instruction stream; the host
-// emulation is a "warp" of one lane.
-#ifdef __CUDA_ARCH__
-#define GK_WARP_MAX(x) __reduce_max_sync(0xffffffffu, (x))
-#else
-#define GK_WARP_MAX(x) (x)
-#endif
-
-struct GkLoop {
-  uint32_t it, end;
-};
-
-// Evaluates the postfix predicate starting at `pc` for object `obj`.  MUST be called by all lanes of the warp
-// with the same pc (lanes without a live object pass live = false and evaluate to false).  `cse` carries the
-// shared sub-formula bits of this object across the constraints of the batch; *flag is set to GK_E_NUM_RANGE
-// when an ordered compare met a number the flattener could not represent exactly as int64.
-GK_HD bool gk_eval_prog(const GkColumn* cols, const GkScope* scopes, const GkInstr* instr, const uint32_t* pool, const uint8_t* cbytes,
-                        uint32_t pc, uint32_t obj, bool live, unsigned long long& cse, unsigned long long& cse_valid, int* flag) {
-  unsigned long long st = 0;
-  uint32_t it1 = 0, it2 = 0, it3 = 0, it4 = 0, en1 = 0, en2 = 0, en3 = 0, en4 = 0;
-  uint32_t tr1 = 0, tr2 = 0, tr3 = 0, tr4 = 0;   // warp-uniform remaining trip counts
-  for (;;) {
-    const GkInstr in = instr[pc];
-    const uint32_t op = in.w0 & 0xffu, slot = (in.w0 >> 8) & 0xffu, col = in.w0 >> 16;
-    switch (op) {
-      case GK_OP_END: return (st & 1ull) != 0;
-      case GK_OP_AND: {
-        const unsigned long long t = st & 1ull;
-        st >>= 1;
-        st &= (t | ~1ull);
-        break;
+// One atom on one row.  Shared by the CUDA tile executor and the test-only host emulation.
+GK_HD bool gk_atom(const GkColumn& c, uint32_t row, uint32_t op, uint32_t w2, uint32_t w3, const uint32_t* pool, const uint8_t* cbytes) {
+  switch (op) {
+    case GK_OP_TRUTHY: { const uint32_t vt = c.vt[row]; return vt != GK_VT_UNDEF && vt != GK_VT_FALSE; }
+    case GK_OP_DEFINED: return c.vt[row] != GK_VT_UNDEF;
+    case GK_OP_VTMASK: return ((1u << c.vt[row]) & w2) != 0;
+    case GK_OP_SID_EQ: return c.sid[row] == w2;
+    case GK_OP_SID_IN: {
+      const uint32_t v = c.sid[row];
+      uint32_t lo = w2, hi = w2 + w3;
+      while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1, x = pool[mid];
+        if (x == v) return true;
+        if (x < v) lo = mid + 1; else hi = mid;
       }
-      case GK_OP_OR: {
-        const unsigned long long t = st & 1ull;
-        st >>= 1;
-        st |= t;
-        break;
-      }
-      case GK_OP_NOT: st ^= 1ull; break;
-      case GK_OP_PUSH: st = (st << 1) | (in.w1 & 1u); break;
-      case GK_OP_CSE_TRY:
-        if ((cse_valid >> in.w1) & 1ull) {   // warp-uniform
-          st = (st << 1) | ((cse >> in.w1) & 1ull);
-          pc = in.w2;
-          continue;
-        }
-        break;
-      case GK_OP_CSE_STORE:
-        cse = (cse & ~(1ull << in.w1)) | ((st & 1ull) << in.w1);
-        cse_valid |= 1ull << in.w1;
-        break;
-      case GK_OP_LOOP_BEGIN: {
-        // parent row (col field = parent slot) and whether this lane is still inside the parent loop
-        const uint32_t prow = col == 0 ? obj : col == 1 ? it1 : col == 2 ? it2 : it3;
-        const bool pvalid = col == 0 ? live : col == 1 ? it1 < en1 : col == 2 ? it2 < en2 : it3 < en3;
-        uint32_t lo = 0, hi = 0;
-        if (pvalid) {
-          const uint32_t* off = scopes[in.w1].off;
-          lo = off[prow];
-          hi = off[prow + 1];
-        }
-        const uint32_t trip = GK_WARP_MAX(hi - lo);
-        if (slot == 1) { it1 = lo; en1 = hi; tr1 = trip; }
-        else if (slot == 2) { it2 = lo; en2 = hi; tr2 = trip; }
-        else if (slot == 3) { it3 = lo; en3 = hi; tr3 = trip; }
-        else { it4 = lo; en4 = hi; tr4 = trip; }
-        st <<= 1;   // accumulator = false
-        if (trip == 0) {
-          pc = in.w2;
-          continue;
-        }
-        break;
-      }
-      case GK_OP_LOOP_END: {
-        bool valid;
-        uint32_t left;
-        if (slot == 1) { valid = it1 < en1; ++it1; left = --tr1; }
-        else if (slot == 2) { valid = it2 < en2; ++it2; left = --tr2; }
-        else if (slot == 3) { valid = it3 < en3; ++it3; left = --tr3; }
-        else { valid = it4 < en4; ++it4; left = --tr4; }
-        const unsigned long long t = (st & 1ull) & (valid ? 1ull : 0ull);
-        st >>= 1;
-        st |= t;
-        if (left) {
-          pc = in.w2;
-          continue;
-        }
-        break;
-      }
-      default: {
-        // ---- atoms: push one bit
-        const uint32_t row = slot == 0 ? obj : slot == 1 ? it1 : slot == 2 ? it2 : slot == 3 ? it3 : it4;
-        const bool valid = slot == 0 ? live : slot == 1 ? it1 < en1 : slot == 2 ? it2 < en2 : slot == 3 ? it3 < en3 : it4 < en4;
-        bool r = false;
-        if (valid) {
-          const GkColumn& c = cols[col];
-          switch (op) {
-            case GK_OP_TRUTHY: { const uint32_t vt = c.vt[row]; r = vt != GK_VT_UNDEF && vt != GK_VT_FALSE; break; }
-            case GK_OP_DEFINED: r = c.vt[row] != GK_VT_UNDEF; break;
-            case GK_OP_VTMASK: r = ((1u << c.vt[row]) & in.w1) != 0; break;
-            case GK_OP_SID_EQ: r = c.sid[row] == in.w1; break;
-            case GK_OP_SID_IN: {
-              const uint32_t v = c.sid[row];
-              uint32_t lo = in.w1, hi = in.w1 + in.w3;
-              while (lo < hi) {
-                const uint32_t mid = (lo + hi) >> 1, x = pool[mid];
-                if (x == v) { r = true; break; }
-                if (x < v) lo = mid + 1; else hi = mid;
-              }
-              break;
-            }
-            case GK_OP_NUM_CMP: {
-              const uint32_t vt = c.vt[row];
-              if (vt == GK_VT_UNDEF) break;
-              if (vt == GK_VT_NUM) {
-                const int64_t v = c.num[row];
-                const int64_t k = (int64_t)(((uint64_t)pool[in.w1 + 1] << 32) | pool[in.w1]);
-                r = gk_cmp_apply(in.w3, v < k ? -1 : (v > k ? 1 : 0));
-              } else if (vt == GK_VT_NUM_INEXACT) {
-                *flag = GK_E_NUM_RANGE;
-              } else {
-                r = gk_cmp_apply(in.w3, gk_vt_rank(vt) < 2 ? -1 : 1);
-              }
-              break;
-            }
-            case GK_OP_PREFIX:
-            case GK_OP_SUFFIX:
-            case GK_OP_CONTAINS: {
-              if (c.vt[row] != GK_VT_STR) break;
-              const uint32_t a = c.boff[row], sl = c.boff[row + 1] - a;
-              const uint8_t* s = c.bytes + a;
-              r = op == GK_OP_PREFIX   ? gk_prefix(s, sl, cbytes + in.w1, in.w3)
-                  : op == GK_OP_SUFFIX ? gk_suffix(s, sl, cbytes + in.w1, in.w3)
-                                       : gk_contains(s, sl, cbytes + in.w1, in.w3);
-              break;
-            }
-            case GK_OP_ANYPREFIX:
-            case GK_OP_ANYSUFFIX: {
-              if (c.vt[row] != GK_VT_STR) break;
-              const uint32_t a = c.boff[row], sl = c.boff[row + 1] - a;
-              const uint8_t* s = c.bytes + a;
-              for (uint32_t j = 0; j < in.w3 && !r; ++j) {
-                const uint32_t po = pool[in.w1 + 2 * j], pl = pool[in.w1 + 2 * j + 1];
-                r = op == GK_OP_ANYPREFIX ? gk_prefix(s, sl, cbytes + po, pl) : gk_suffix(s, sl, cbytes + po, pl);
-              }
-              break;
-            }
-            default: break;
-          }
-        }
-        st = (st << 1) | (r ? 1ull : 0ull);
-      }
+      return false;
     }
-    ++pc;
+    case GK_OP_NUM_CMP: {
+      const uint32_t vt = c.vt[row];
+      if (vt == GK_VT_UNDEF || vt == GK_VT_NUM_INEXACT) return false;   // inexact numbers never reach the device: the flattener rejects the object
+      if (vt == GK_VT_NUM) {
+        const int64_t v = c.num[row];
+        const int64_t k = (int64_t)(((uint64_t)pool[w2 + 1] << 32) | pool[w2]);
+        return gk_cmp_apply(w3, v < k ? -1 : (v > k ? 1 : 0));
+      }
+      return gk_cmp_apply(w3, gk_vt_rank(vt) < 2 ? -1 : 1);
+    }
+    case GK_OP_PREFIX:
+    case GK_OP_SUFFIX:
+    case GK_OP_CONTAINS: {
+      if (c.vt[row] != GK_VT_STR) return false;
+      const uint32_t a = c.boff[row], sl = c.boff[row + 1] - a;
+      const uint8_t* s = c.bytes + a;
+      return op == GK_OP_PREFIX ? gk_prefix(s, sl, cbytes + w2, w3) : op == GK_OP_SUFFIX ? gk_suffix(s, sl, cbytes + w2, w3) : gk_contains(s, sl, cbytes + w2, w3);
+    }
+    case GK_OP_ANYPREFIX:
+    case GK_OP_ANYSUFFIX: {
+      if (c.vt[row] != GK_VT_STR) return false;
+      const uint32_t a = c.boff[row], sl = c.boff[row + 1] - a;
+      const uint8_t* s = c.bytes + a;
+      for (uint32_t j = 0; j < w3; ++j) {
+        const uint32_t po = pool[w2 + 2 * j], pl = pool[w2 + 2 * j + 1];
+        if (op == GK_OP_ANYPREFIX ? gk_prefix(s, sl, cbytes + po, pl) : gk_suffix(s, sl, cbytes + po, pl)) return true;
+      }
+      return false;
+    }
+    default: return false;
   }
 }

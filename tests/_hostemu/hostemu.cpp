@@ -1,5 +1,6 @@
-// TEST-ONLY backend: runs the per-object core (gatekeeper_b200/csrc/vm_core.h) in a plain CPU loop so the
-// lowering + flattening logic can be unit-tested in the authoring container, which has no GPU.
+// TEST-ONLY backend: executes the constraint netlist (gatekeeper_b200/csrc/program.h GkOp) on the CPU with the
+// whole batch as one tile, using the same per-row core (csrc/vm_core.h: gk_atom, gk_match) as the CUDA tile
+// executor, so the lowering + flattening logic can be unit-tested in the authoring container (no GPU).
 // It is linked ONLY into tests/_hostemu/libgk_hostemu.so.  The product library
 // (gatekeeper_b200/libgk_engine.so) links kernels.cu instead and has no CPU path at all.
 #include <algorithm>
@@ -14,6 +15,8 @@ struct EmuBatch {
   PackedBatch pb;
   GkBatch hdr{};
   uint32_t n = 0, words = 1;
+  std::vector<uint32_t> scope_rows;
+  std::vector<std::vector<uint32_t>> scope_off;   // host copies for range lookups
 };
 
 class HostEmuBackend : public Backend {
@@ -26,64 +29,108 @@ class HostEmuBackend : public Backend {
     pack_batch(hb, c, b->pb);
     b->hdr = rebase_batch(b->pb, b->pb.arena.data(), b->pb.arena.data());
     b->n = hb.n;
-    b->words = std::max<uint32_t>(1, (uint32_t)((c.cons.size() + 31) / 32));
+    b->words = std::max<uint32_t>(1, (uint32_t)((c.cons_match.size() + 31) / 32));
+    b->scope_rows = hb.scope_rows;
+    b->scope_off = hb.scope_off;
     if (ms) *ms = 0;
     if (bytes) *bytes = b->pb.arena.size();
     return b;
   }
   void release(void* b) override { delete static_cast<EmuBatch*>(b); }
+
   void eval(void* bb, const std::vector<uint32_t>& active, EvalOut& out, bool) override {
     auto* b = static_cast<EmuBatch*>(bb);
     const Compiled& c = *prog_;
-    const uint32_t C = (uint32_t)c.cons.size(), W = b->words;
+    const uint32_t C = (uint32_t)c.cons_match.size(), W = b->words, n = b->n;
     GkBatch h = b->hdr;
     h.dict_off = dict_off_.data();
     h.dict_bytes = dict_bytes_.data();
     h.dict_n = (uint32_t)dict_off_.size() - 1;
-    out.n = b->n;
+    out.n = n;
     out.nconstraints = C;
     out.words = W;
-    out.viol.assign((size_t)b->n * W, 0);
-    out.err.assign((size_t)b->n * W, 0);
+    out.viol.assign((size_t)n * W, 0);
+    out.err.assign((size_t)n * W, 0);
     out.totals.assign(C, 0);
     out.err_totals.assign(C, 0);
     out.errlist.clear();
     auto t0 = std::chrono::steady_clock::now();
-    const GkColumn* cols = h.cols;
-    const GkScope* scopes = h.scopes;
-    for (uint32_t obj = 0; obj < b->n; ++obj) {
-      if (h.flags[obj] & GK_F_SKIP) continue;
-      unsigned long long cse = 0, cse_valid = 0;
-      uint32_t cur_mid = GK_NONE;
-      int mres = 0;
-      for (uint32_t cix = 0; cix < C; ++cix) {
-        if (!active[cix]) continue;
-        const GkCons& cc = c.cons[cix];
-        if (cc.match_id != cur_mid) {
-          cur_mid = cc.match_id;
-          mres = gk_match(h, c.pool.data(), c.cbytes.data(), c.match[cur_mid], obj);
+    auto rows_of = [&](uint32_t level) -> uint32_t { return level == 0 ? n : b->scope_rows[level]; };
+    std::vector<std::vector<uint8_t>> slot(c.slot_level.size());
+    for (size_t s = 0; s < slot.size(); ++s) slot[s].assign(rows_of(c.slot_level[s]), 0);
+    for (const GkOp& op : c.ops) {
+      const uint32_t kind = op.w0 & 0xffu, level = (op.w0 >> 8) & 0xffu, o = op.w0 >> 16;
+      if (kind == GK_N_END) break;
+      if (kind == GK_N_PHASE) continue;
+      switch (kind) {
+        case GK_N_CONST:
+          std::fill(slot[o].begin(), slot[o].end(), (uint8_t)(op.w1 & 1));
+          break;
+        case GK_N_ATOM: {
+          const GkColumn& col = h.cols[op.w1 >> 8];
+          const uint32_t aop = op.w1 & 0xffu, R = rows_of(level);
+          for (uint32_t r = 0; r < R; ++r) slot[o][r] = gk_atom(col, r, aop, op.w2, op.w3, c.pool.data(), c.cbytes.data());
+          break;
         }
-        int code = mres < 0 ? -mres : 0;
-        int flag = 0;
-        bool v = cc.pc == GK_PC_ACCEPT ? true
-                 : cc.pc == GK_PC_REJECT ? false
-                                         : gk_eval_prog(cols, scopes, c.instr.data(), c.pool.data(), c.cbytes.data(), cc.pc, obj, true, cse, cse_valid, &flag);
-        v = v && mres > 0;
-        if (mres > 0 && flag) {
-          v = false;
-          code = flag;
+        case GK_N_GATE: {
+          const auto &a = slot[op.w1 & 0xffffu], &bb2 = slot[op.w1 >> 16];
+          const uint32_t f = op.w2, R = rows_of(level);
+          for (uint32_t r = 0; r < R; ++r) {
+            bool x = a[r] ^ ((f & GK_G_NEG_A) != 0), y = bb2[r] ^ ((f & GK_G_NEG_B) != 0);
+            bool v = (f & GK_G_OR) ? (x || y) : (x && y);
+            slot[o][r] = v ^ ((f & GK_G_NEG_OUT) != 0);
+          }
+          break;
         }
-        if (code) {
-          out.err[(size_t)obj * W + cix / 32] |= 1u << (cix & 31);
-          out.err_totals[cix]++;
-          out.errlist.push_back(obj);
-          out.errlist.push_back(cix);
-          out.errlist.push_back((uint32_t)code);
+        case GK_N_BCAST: {
+          const auto& in = slot[op.w1 & 0xffffu];
+          const auto& off = b->scope_off[level];
+          for (size_t p = 0; p + 1 < off.size(); ++p)
+            for (uint32_t r = off[p]; r < off[p + 1]; ++r) slot[o][r] = in[p];
+          break;
         }
-        if (v) {
-          out.viol[(size_t)obj * W + cix / 32] |= 1u << (cix & 31);
-          out.totals[cix]++;
+        case GK_N_ACC: {
+          const auto& in = slot[op.w1 & 0xffffu];
+          const auto& off = b->scope_off[level];
+          for (size_t p = 0; p + 1 < off.size(); ++p) {
+            bool any = false;
+            for (uint32_t r = off[p]; r < off[p + 1]; ++r) any = any || in[r];
+            slot[o][p] = any;
+          }
+          break;
         }
+        case GK_N_MATCH: {
+          auto& err = slot[op.w1 & 0xffffu];
+          for (uint32_t obj = 0; obj < n; ++obj) {
+            int m = (h.flags[obj] & GK_F_SKIP) ? 0 : gk_match(h, c.pool.data(), c.cbytes.data(), c.match[op.w2], obj);
+            slot[o][obj] = m > 0;
+            err[obj] = m < 0;
+            if (m < 0) {
+              out.errlist.push_back(obj);
+              out.errlist.push_back(op.w2);
+              out.errlist.push_back((uint32_t)-m);
+            }
+          }
+          break;
+        }
+        case GK_N_OUT: {
+          const uint32_t cix = op.w2, flags = op.w3 >> 16;
+          if (!active[cix]) break;
+          const auto &prog = slot[op.w1 & 0xffffu], &mt = slot[op.w1 >> 16], &er = slot[op.w3 & 0xffffu];
+          for (uint32_t obj = 0; obj < n; ++obj) {
+            bool pv = (flags & 1) ? true : (flags & 2) ? false : prog[obj] != 0;
+            if (pv && mt[obj]) {
+              out.viol[(size_t)obj * W + cix / 32] |= 1u << (cix & 31);
+              out.totals[cix]++;
+            }
+            if (er[obj]) {
+              out.err[(size_t)obj * W + cix / 32] |= 1u << (cix & 31);
+              out.err_totals[cix]++;
+            }
+          }
+          break;
+        }
+        default: throw BackendError{"hostemu: unknown netlist op"};
       }
     }
     out.kernel_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
