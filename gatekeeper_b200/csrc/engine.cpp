@@ -471,6 +471,8 @@ void Engine::compile_locked() {
   if (out->match.empty()) out->match.push_back(GkMatch{});
   pb.build(all, out->cons_match, (uint32_t)match_ix.size());
   out->ops = std::move(pb.ops);
+  out->items = std::move(pb.items);
+  out->phase_off = std::move(pb.phase_off);
   out->slot_level = std::move(pb.slot_level);
   out->pool = std::move(pb.pool);
   out->cbytes = std::move(pb.cbytes);

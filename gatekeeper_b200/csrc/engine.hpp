@@ -86,6 +86,7 @@ struct Compiled {
   uint64_t version = 0;
   Schema schema;
   std::vector<GkOp> ops;                       // the joint netlist (program.h)
+  std::vector<uint32_t> items, phase_off;      // work items per dependency phase
   std::vector<uint8_t> slot_level;             // scope of each shared-memory slot
   std::vector<uint32_t> pool;
   std::vector<uint8_t> cbytes;

@@ -1,13 +1,7 @@
-// CUDA backend for sm_100a: one thread per object evaluates every constraint (match pre-filter + lowered
-// predicate) against the column-wise batch resident in HBM.
-//
-//   * the constraint table (match blocks, instructions, constant pools) is staged into shared memory once
-//     per CTA; every lane of a warp walks the same constraint at the same time, so table reads broadcast;
-//   * header columns are read with unit stride across the warp (coalesced 128 B lines); scope/label CSR
-//     rows of neighbouring objects are adjacent in memory, so the ragged reads stay within a few lines;
-//   * per-constraint totals use warp ballot + popc into shared counters, one global atomic per CTA;
-//   * each thread assembles its own 32-constraint bitmap words in registers and stores them once.
-// This is integer / byte work bounded by HBM traffic -- there is nothing to put on tensor cores.
+// CUDA backend for sm_100a: device memory management, uploads and launches around the tile kernel
+// (tile_kernel.cuh).  Host <-> device transfers are staged through pinned memory on a private stream; the
+// kernel itself can also be launched on a caller-provided stream into caller-owned device buffers (multi-GPU
+// gather path, where torch.distributed owns the buffers).
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -16,7 +10,7 @@
 #include <mutex>
 
 #include "backend.hpp"
-#include "vm_core.h"
+#include "tile_kernel.cuh"
 
 namespace gk {
 
@@ -26,242 +20,6 @@ namespace gk {
     if (e_ != cudaSuccess) throw BackendError{std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #x}; \
   } while (0)
 
-struct KParams {
-  GkBatch batch;
-  GkProgram prog;
-  GkOut out;
-  const uint32_t* active;     // [nconstraints] enforcement-point filter
-  const uint32_t* slot_off;   // [nslots] word offset of each slot inside the slot area (depends on the batch's tile capacities)
-  const uint32_t* tile_lo;    // [(ntiles + 1) * nscopes] first row of every scope for every tile (row ranges are contiguous)
-  uint32_t ntiles;
-  uint32_t tile;              // objects per tile (multiple of 32)
-  uint32_t slot_words;        // words in the slot area
-};
-
-constexpr int kThreads = 256;
-constexpr int kWarps = kThreads / 32;
-constexpr uint32_t kTile = 512;
-
-__device__ __forceinline__ void stage(void* dst, const void* src, size_t bytes) {
-  // 16-byte vector copies; sizes/offsets are padded to 16 on the host
-  const uint4* s = reinterpret_cast<const uint4*>(src);
-  uint4* d = reinterpret_cast<uint4*>(dst);
-  for (size_t i = threadIdx.x; i < bytes / 16; i += blockDim.x) d[i] = s[i];
-}
-
-__device__ __forceinline__ uint32_t range_mask(uint32_t w, uint32_t a, uint32_t b) {
-  // bits of word w that lie in the row range [a, b)
-  const uint32_t lo = w * 32u, hi = lo + 32u;
-  const uint32_t x = a > lo ? a : lo, y = b < hi ? b : hi;
-  if (x >= y) return 0u;
-  const uint32_t nb = y - x;
-  return (nb == 32u ? 0xffffffffu : ((1u << nb) - 1u)) << (x - lo);
-}
-
-// One CTA = one tile of consecutive objects at a time; all intermediate bit columns live in shared memory.
-__global__ void __launch_bounds__(kThreads) gk_eval_kernel(const KParams p) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  const uint32_t C = p.prog.nconstraints, W = p.out.words, NS = p.batch.nscopes;
-  const uint32_t TW = p.tile / 32u;
-  // ---- shared-memory layout
-  size_t off = 0;
-  auto take = [&](size_t bytes) {
-    void* q = smem + off;
-    off += (bytes + 15) / 16 * 16;
-    return q;
-  };
-  uint32_t* s_tot = static_cast<uint32_t*>(take((size_t)C * 4));
-  uint32_t* s_err = static_cast<uint32_t*>(take((size_t)C * 4));
-  uint32_t* s_act = static_cast<uint32_t*>(take((size_t)C * 4));
-  uint32_t* s_lo = static_cast<uint32_t*>(take((size_t)NS * 4));
-  uint32_t* s_cnt = static_cast<uint32_t*>(take((size_t)NS * 4));
-  uint32_t* s_soff = static_cast<uint32_t*>(take((size_t)p.prog.nslots * 4));
-  uint32_t* res_v = static_cast<uint32_t*>(take((size_t)p.tile * W * 4));
-  uint32_t* res_e = static_cast<uint32_t*>(take((size_t)p.tile * W * 4));
-  uint32_t* slots = static_cast<uint32_t*>(take((size_t)p.slot_words * 4));
-  GkOp* ops = static_cast<GkOp*>(take((size_t)p.prog.nops * sizeof(GkOp)));
-  GkMatch* match = static_cast<GkMatch*>(take((size_t)p.prog.nmatch * sizeof(GkMatch)));
-  GkColumn* cols = static_cast<GkColumn*>(take((size_t)p.batch.ncols * sizeof(GkColumn)));
-  GkScope* scopes = static_cast<GkScope*>(take((size_t)NS * sizeof(GkScope)));
-  uint32_t* pool = static_cast<uint32_t*>(take((size_t)p.prog.npool * 4));
-  uint8_t* cbytes = static_cast<uint8_t*>(take((size_t)p.prog.ncbytes));
-
-  for (uint32_t i = threadIdx.x; i < C; i += blockDim.x) {
-    s_tot[i] = 0;
-    s_err[i] = 0;
-    s_act[i] = p.active[i];
-  }
-  for (uint32_t i = threadIdx.x; i < p.prog.nslots; i += blockDim.x) s_soff[i] = p.slot_off[i];
-  stage(ops, p.prog.ops, ((size_t)p.prog.nops * sizeof(GkOp) + 15) / 16 * 16);
-  stage(match, p.prog.match, ((size_t)p.prog.nmatch * sizeof(GkMatch) + 15) / 16 * 16);
-  stage(cols, p.batch.cols, ((size_t)p.batch.ncols * sizeof(GkColumn) + 15) / 16 * 16);
-  stage(scopes, p.batch.scopes, ((size_t)NS * sizeof(GkScope) + 15) / 16 * 16);
-  stage(pool, p.prog.pool, ((size_t)p.prog.npool * 4 + 15) / 16 * 16);
-  stage(cbytes, p.prog.cbytes, ((size_t)p.prog.ncbytes + 15) / 16 * 16);
-  __syncthreads();
-
-  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  const uint32_t FULL = 0xffffffffu;
-
-  for (uint32_t t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
-    // ---- tile row ranges (precomputed on the host: rows of a tile are contiguous at every scope)
-    for (uint32_t s = threadIdx.x; s < NS; s += blockDim.x) {
-      const uint32_t a = p.tile_lo[(size_t)t * NS + s], b = p.tile_lo[(size_t)(t + 1) * NS + s];
-      s_lo[s] = a;
-      s_cnt[s] = b - a;
-    }
-    for (uint32_t i = threadIdx.x; i < p.tile * W; i += blockDim.x) {
-      res_v[i] = 0;
-      res_e[i] = 0;
-    }
-    __syncthreads();
-    const uint32_t nobj = s_cnt[0], obj0 = s_lo[0];
-
-    uint32_t pc = 0;
-    for (;;) {   // phases
-      uint32_t k = 0;
-      bool end = false;
-      for (;; ++pc, ++k) {
-        const GkOp op = ops[pc];
-        const uint32_t kind = op.w0 & 0xffu;
-        if (kind == GK_N_PHASE) {
-          ++pc;
-          break;
-        }
-        if (kind == GK_N_END) {
-          end = true;
-          break;
-        }
-        if (k % kWarps != warp) continue;   // ops of a phase are independent: one warp per op, round-robin
-        const uint32_t level = (op.w0 >> 8) & 0xffu;
-        uint32_t* out = slots + s_soff[op.w0 >> 16];
-        switch (kind) {
-          case GK_N_ATOM: {
-            const GkColumn& c = cols[op.w1 >> 8];
-            const uint32_t aop = op.w1 & 0xffu, lo = s_lo[level], cnt = s_cnt[level];
-            for (uint32_t r = lane; r < ((cnt + 31u) & ~31u); r += 32u) {
-              const bool v = r < cnt && gk_atom(c, lo + r, aop, op.w2, op.w3, pool, cbytes);
-              const uint32_t w = __ballot_sync(FULL, v);
-              if (lane == 0) out[r >> 5] = w;
-            }
-            break;
-          }
-          case GK_N_GATE: {
-            const uint32_t* a = slots + s_soff[op.w1 & 0xffffu];
-            const uint32_t* b = slots + s_soff[op.w1 >> 16];
-            const uint32_t f = op.w2, words = (s_cnt[level] + 31u) >> 5;
-            const uint32_t na = (f & GK_G_NEG_A) ? FULL : 0u, nb = (f & GK_G_NEG_B) ? FULL : 0u, no = (f & GK_G_NEG_OUT) ? FULL : 0u;
-            for (uint32_t i = lane; i < words; i += 32u) {
-              const uint32_t x = a[i] ^ na, y = b[i] ^ nb;
-              out[i] = ((f & GK_G_OR) ? (x | y) : (x & y)) ^ no;
-            }
-            break;
-          }
-          case GK_N_CONST: {
-            const uint32_t v = (op.w1 & 1u) ? FULL : 0u, words = (s_cnt[level] + 31u) >> 5;
-            for (uint32_t i = lane; i < words; i += 32u) out[i] = v;
-            break;
-          }
-          case GK_N_BCAST: {   // parent-level column -> rows of the child scope `level`
-            const uint32_t* in = slots + s_soff[op.w1 & 0xffffu];
-            const uint32_t par = (uint32_t)scopes[level].parent;
-            const uint32_t* coff = scopes[level].off + s_lo[par];
-            const uint32_t clo = s_lo[level], pcnt = s_cnt[par], words = (s_cnt[level] + 31u) >> 5;
-            for (uint32_t i = lane; i < words; i += 32u) out[i] = 0u;
-            __syncwarp();
-            for (uint32_t r = lane; r < pcnt; r += 32u) {
-              if ((in[r >> 5] >> (r & 31u)) & 1u) {
-                const uint32_t a = coff[r] - clo, b = coff[r + 1] - clo;
-                if (b > a)
-                  for (uint32_t w = a >> 5; w <= (b - 1u) >> 5; ++w) atomicOr(&out[w], range_mask(w, a, b));
-              }
-            }
-            break;
-          }
-          case GK_N_ACC: {     // EXISTS: OR over each parent's child range of the scope `level`
-            const uint32_t* in = slots + s_soff[op.w1 & 0xffffu];
-            const uint32_t par = (uint32_t)scopes[level].parent;
-            const uint32_t* coff = scopes[level].off + s_lo[par];
-            const uint32_t clo = s_lo[level], pcnt = s_cnt[par];
-            for (uint32_t r = lane; r < ((pcnt + 31u) & ~31u); r += 32u) {
-              bool any = false;
-              if (r < pcnt) {
-                const uint32_t a = coff[r] - clo, b = coff[r + 1] - clo;
-                if (b > a)
-                  for (uint32_t w = a >> 5; w <= (b - 1u) >> 5 && !any; ++w) any = (in[w] & range_mask(w, a, b)) != 0u;
-              }
-              const uint32_t w = __ballot_sync(FULL, any);
-              if (lane == 0) out[r >> 5] = w;
-            }
-            break;
-          }
-          case GK_N_MATCH: {
-            uint32_t* err = slots + s_soff[op.w1 & 0xffffu];
-            const GkMatch& m = match[op.w2];
-            for (uint32_t r = lane; r < ((nobj + 31u) & ~31u); r += 32u) {
-              int res = 0;
-              if (r < nobj && !(p.batch.flags[obj0 + r] & GK_F_SKIP)) res = gk_match(p.batch, pool, cbytes, m, obj0 + r);
-              if (res < 0) {
-                const uint32_t slot = atomicAdd(p.out.errcount, 1u);
-                if (slot < p.out.errcap) {
-                  p.out.errlist[3 * slot] = obj0 + r;
-                  p.out.errlist[3 * slot + 1] = op.w2;
-                  p.out.errlist[3 * slot + 2] = (uint32_t)(-res);
-                }
-              }
-              const uint32_t wm = __ballot_sync(FULL, res > 0), we = __ballot_sync(FULL, res < 0);
-              if (lane == 0) {
-                out[r >> 5] = wm;
-                err[r >> 5] = we;
-              }
-            }
-            break;
-          }
-          case GK_N_OUT: {
-            const uint32_t c = op.w2, flags = op.w3 >> 16;
-            if (!s_act[c]) break;
-            const uint32_t* prog = slots + s_soff[op.w1 & 0xffffu];
-            const uint32_t* mt = slots + s_soff[op.w1 >> 16];
-            const uint32_t* er = slots + s_soff[op.w3 & 0xffffu];
-            const uint32_t bit = 1u << (c & 31u), wi = c >> 5;
-            uint32_t nv = 0, ne = 0;
-            for (uint32_t i = 0; i < ((nobj + 31u) >> 5); ++i) {
-              const uint32_t valid = range_mask(i, 0u, nobj);
-              const uint32_t pv = (flags & 1u) ? FULL : (flags & 2u) ? 0u : prog[i];
-              const uint32_t v = pv & mt[i] & valid, e = er[i] & valid;
-              const uint32_t o = i * 32u + lane;
-              if ((v >> lane) & 1u) atomicOr(&res_v[o * W + wi], bit);
-              if ((e >> lane) & 1u) atomicOr(&res_e[o * W + wi], bit);
-              nv += __popc(v);
-              ne += __popc(e);
-            }
-            if (lane == 0) {
-              if (nv) atomicAdd(&s_tot[c], nv);
-              if (ne) atomicAdd(&s_err[c], ne);
-            }
-            break;
-          }
-          default: break;
-        }
-      }
-      __syncthreads();
-      if (end) break;
-    }
-    // ---- the tile's bitmap rows are contiguous in the object-major output: coalesced copy out
-    const size_t base = (size_t)obj0 * W;
-    for (uint32_t i = threadIdx.x; i < nobj * W; i += blockDim.x) {
-      p.out.viol[base + i] = res_v[i];
-      p.out.err[base + i] = res_e[i];
-    }
-    __syncthreads();
-  }
-  for (uint32_t c = threadIdx.x; c < C; c += blockDim.x) {
-    if (s_tot[c]) atomicAdd(p.out.totals + c, (unsigned long long)s_tot[c]);
-    if (s_err[c]) atomicAdd(p.out.err_totals + c, (unsigned long long)s_err[c]);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------ backend
 struct DevBatch {
   uint8_t* arena = nullptr;
   size_t bytes = 0;
@@ -326,6 +84,9 @@ class CudaBackend : public Backend {
     prog_.nslots = (uint32_t)c.slot_level.size();
     prog_.npool = (uint32_t)c.pool.size();
     prog_.ncbytes = (uint32_t)c.cbytes.size();
+    prog_.nphases = (uint32_t)c.phase_off.size() - 1;
+    prog_.nitems = (uint32_t)c.items.size();
+    if (prog_.nphases > kMaxPhases) throw BackendError{"netlist has more dependency phases than the kernel supports"};
     auto up = [&](const void* src, size_t bytes, void** dst) {
       size_t padded = (bytes + 63) / 64 * 64 + 64;
       CK(cudaMalloc(dst, padded));
@@ -333,16 +94,18 @@ class CudaBackend : public Backend {
       if (bytes) CK(cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
     };
     up(c.ops.data(), c.ops.size() * sizeof(GkOp), (void**)&d_ops_);
+    up(c.items.data(), c.items.size() * 4, (void**)&d_items_);
+    up(c.phase_off.data(), c.phase_off.size() * 4, (void**)&d_phase_off_);
     up(c.match.data(), c.match.size() * sizeof(GkMatch), (void**)&d_match_);
     up(c.pool.data(), c.pool.size() * 4, (void**)&d_pool_);
     up(c.cbytes.data(), c.cbytes.size(), (void**)&d_cbytes_);
     prog_.ops = d_ops_;
+    prog_.items = d_items_;
+    prog_.phase_off = d_phase_off_;
     prog_.match = d_match_;
     prog_.pool = d_pool_;
     prog_.cbytes = d_cbytes_;
-    slot_level_ = c.slot_level;
-    scope_parent_.clear();
-    for (auto& sd : c.schema.scopes) scope_parent_.push_back(sd.parent);
+    nscopes_ = (uint32_t)c.schema.scopes.size();
     ncols_ = (uint32_t)c.schema.cols.size();
     const uint32_t C = prog_.nconstraints;
     if (d_totals_) cudaFree(d_totals_);
@@ -481,9 +244,10 @@ class CudaBackend : public Backend {
     if (C) CK(cudaMemsetAsync(err_totals, 0, (size_t)C * sizeof(unsigned long long), st));
     CK(cudaMemsetAsync(d_scalars_, 0, 64, st));
     auto r16 = [](size_t x) { return (x + 15) / 16 * 16; };
-    const size_t NS = scope_parent_.size();
-    size_t smem = 3 * r16((size_t)C * 4) + 2 * r16(NS * 4) + r16((size_t)prog_.nslots * 4) + 2 * r16((size_t)kTile * db->words * 4) +
-                  r16((size_t)db->slot_words * 4) + r16((size_t)prog_.nops * sizeof(GkOp)) + r16((size_t)prog_.nmatch * sizeof(GkMatch)) +
+    const size_t NS = nscopes_;
+    size_t smem = 3 * r16((size_t)C * 4) + 2 * r16(NS * 4) + r16((size_t)kMaxPhases * 4) + r16((size_t)(prog_.nphases + 1) * 4) +
+                  r16((size_t)prog_.nslots * 4) + 2 * r16((size_t)kTile * db->words * 4) + r16((size_t)db->slot_words * 4) +
+                  r16((size_t)prog_.nops * sizeof(GkOp)) + r16((size_t)prog_.nitems * 4) + r16((size_t)prog_.nmatch * sizeof(GkMatch)) +
                   r16((size_t)ncols_ * sizeof(GkColumn)) + r16(NS * sizeof(GkScope)) + r16((size_t)prog_.npool * 4) + r16((size_t)prog_.ncbytes) + 64;
     if (smem > max_smem_)
       throw BackendError{"constraint set needs " + std::to_string(smem) + " bytes of shared memory per CTA (limit " + std::to_string(max_smem_) +
@@ -561,14 +325,11 @@ class CudaBackend : public Backend {
  private:
   static constexpr uint32_t kErrCap = 1u << 20;
   void free_tables() {
-    if (d_ops_) cudaFree(d_ops_);
-    if (d_match_) cudaFree(d_match_);
-    if (d_pool_) cudaFree(d_pool_);
-    if (d_cbytes_) cudaFree(d_cbytes_);
-    d_ops_ = nullptr;
-    d_match_ = nullptr;
-    d_pool_ = nullptr;
-    d_cbytes_ = nullptr;
+    void** ptrs[] = {(void**)&d_ops_, (void**)&d_items_, (void**)&d_phase_off_, (void**)&d_match_, (void**)&d_pool_, (void**)&d_cbytes_};
+    for (auto pp : ptrs) {
+      if (*pp) cudaFree(*pp);
+      *pp = nullptr;
+    }
   }
   int device_;
   int sms_ = 148;
@@ -578,11 +339,11 @@ class CudaBackend : public Backend {
   std::mutex mu_;
   uint64_t version_ = 0, launches_ = 0;
   GkProgram prog_{};
-  std::vector<uint8_t> slot_level_;
-  std::vector<int> scope_parent_;
   std::vector<uint32_t> last_active_;
-  uint32_t ncols_ = 0;
+  uint32_t ncols_ = 0, nscopes_ = 0;
   GkOp* d_ops_ = nullptr;
+  uint32_t* d_items_ = nullptr;
+  uint32_t* d_phase_off_ = nullptr;
   GkMatch* d_match_ = nullptr;
   uint32_t* d_pool_ = nullptr;
   uint8_t* d_cbytes_ = nullptr;

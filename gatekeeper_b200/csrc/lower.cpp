@@ -1420,7 +1420,8 @@ namespace {
 struct NNode {
   uint8_t kind = 0;        // GK_N_*
   int level = 0;           // scope of the rows this node has one bit for
-  int a = -1, b = -1;      // inputs (node ids)
+  int a = -1, b = -1;      // input (BCAST / ACC)
+  std::vector<std::pair<int, bool>> ins;   // GATE inputs: (node, negated)
   uint32_t flags = 0;      // gate flags / const value
   int scope = 0;           // BCAST / ACC: the child scope
   // atom
@@ -1451,6 +1452,7 @@ struct Net {
     n.phase = 0;
     if (n.a >= 0) n.phase = std::max(n.phase, nodes[n.a].phase + 1);
     if (n.b >= 0) n.phase = std::max(n.phase, nodes[n.b].phase + 1);
+    for (auto& in : n.ins) n.phase = std::max(n.phase, nodes[in.first].phase + 1);
     nodes.push_back(std::move(n));
     int id = (int)nodes.size() - 1;
     memo.emplace(key, id);
@@ -1487,31 +1489,36 @@ struct Net {
     return node;
   }
 
-  Ref gate(bool is_or, Ref x, Ref y) {
-    // constant folding
-    if (is_const(x) || is_const(y)) {
-      if (is_const(y)) std::swap(x, y);
-      bool cv = const_val(x);
-      if (is_or) return cv ? constant(true) : y;
-      return cv ? y : constant(false);
+  // n-ary AND / OR over references of ONE level (after raising); folds constants, duplicates and x op !x
+  Ref gate_n(bool is_or, std::vector<Ref> refs, int level) {
+    std::vector<Ref> in;
+    for (auto& r : refs) {
+      if (is_const(r)) {
+        bool cv = const_val(r);
+        if (is_or == cv) return constant(is_or);   // x | 1 = 1 ; x & 0 = 0
+        continue;                                  // x | 0 = x ; x & 1 = x
+      }
+      bool dup = false;
+      for (auto& q : in)
+        if (q.node == r.node) {
+          if (q.neg != r.neg) return constant(is_or);
+          dup = true;
+        }
+      if (!dup) in.push_back(r);
     }
-    if (x.node == y.node) {
-      if (x.neg == y.neg) return x;
-      return constant(is_or);   // a | !a = 1 ; a & !a = 0
-    }
-    int lx = nodes[x.node].level, ly = nodes[y.node].level;
-    int target = depth(lx) >= depth(ly) ? lx : ly;
-    x.node = raise(x.node, target);
-    y.node = raise(y.node, target);
-    if (x.node > y.node) std::swap(x, y);
+    if (in.empty()) return constant(!is_or);
+    if (in.size() == 1) return in[0];
+    std::sort(in.begin(), in.end(), [](const Ref& p, const Ref& q) { return p.node != q.node ? p.node < q.node : p.neg < q.neg; });
     NNode n;
     n.kind = GK_N_GATE;
-    n.level = target;
-    n.a = x.node;
-    n.b = y.node;
-    n.flags = (is_or ? GK_G_OR : 0) | (x.neg ? GK_G_NEG_A : 0) | (y.neg ? GK_G_NEG_B : 0);
-    int id = intern_node("g" + std::to_string(n.flags) + ":" + std::to_string(n.a) + "," + std::to_string(n.b), n);
-    return Ref{id, false};
+    n.level = level;
+    n.flags = is_or ? GK_G_OR : 0;
+    std::string key = is_or ? "or" : "and";
+    for (auto& r : in) {
+      n.ins.emplace_back(r.node, r.neg);
+      key += (r.neg ? ",!" : ",") + std::to_string(r.node);
+    }
+    return Ref{intern_node(key, n), false};
   }
 
   // materialise a possibly negated reference as a plain node (needed where negation cannot be folded)
@@ -1520,8 +1527,7 @@ struct Net {
     NNode n;
     n.kind = GK_N_GATE;
     n.level = nodes[r.node].level;
-    n.a = n.b = r.node;
-    n.flags = GK_G_NEG_A | GK_G_NEG_B;
+    n.ins.emplace_back(r.node, true);
     return intern_node("not" + std::to_string(r.node), n);
   }
 
@@ -1550,10 +1556,32 @@ struct Net {
       case Formula::Or: {
         std::vector<Ref> refs;
         for (auto& k : f->kids) refs.push_back(build(k));
-        // combine shallow levels first so that a loop-invariant group is broadcast into the loop once
+        // one n-ary gate per level, shallow levels first: a loop-invariant group is broadcast into the loop once
         std::stable_sort(refs.begin(), refs.end(), [&](const Ref& p, const Ref& q) { return depth(nodes[p.node].level) < depth(nodes[q.node].level); });
+        const bool is_or = f->k == Formula::Or;
         Ref acc = refs[0];
-        for (size_t i = 1; i < refs.size(); ++i) acc = gate(f->k == Formula::Or, acc, refs[i]);
+        size_t i = 1;
+        while (true) {
+          int lvl = nodes[acc.node].level;
+          std::vector<Ref> group{acc};
+          while (i < refs.size() && nodes[refs[i].node].level == lvl) group.push_back(refs[i++]);
+          acc = gate_n(is_or, group, lvl);
+          if (i >= refs.size()) break;
+          // next group is deeper: raise the accumulated value into it
+          int next = nodes[refs[i].node].level;
+          if (!is_const(acc)) {
+            if (depth(next) < depth(nodes[acc.node].level)) {   // constants sort first; keep the deeper level
+              next = nodes[acc.node].level;
+            }
+            acc.node = raise(acc.node, next);
+          }
+          std::vector<Ref> g2{acc};
+          while (i < refs.size() && nodes[refs[i].node].level == next) g2.push_back(refs[i++]);
+          for (auto& r : g2)
+            if (!is_const(r)) r.node = raise(r.node, next);
+          acc = gate_n(is_or, g2, next);
+          if (i >= refs.size()) break;
+        }
         return acc;
       }
       case Formula::Exists: {
@@ -1618,6 +1646,7 @@ void NetBuilder::build(const std::vector<FP>& formulas, const std::vector<uint32
   for (auto& n : N) {
     if (n.a >= 0) N[n.a].last_use = std::max(N[n.a].last_use, n.phase);
     if (n.b >= 0) N[n.b].last_use = std::max(N[n.b].last_use, n.phase);
+    for (auto& in : n.ins) N[in.first].last_use = std::max(N[in.first].last_use, n.phase);
   }
   for (size_t c = 0; c < outs.size(); ++c) {
     if (outs[c].prog >= 0) N[outs[c].prog].last_use = out_phase;
@@ -1635,6 +1664,7 @@ void NetBuilder::build(const std::vector<FP>& formulas, const std::vector<uint32
     if (!used[i]) continue;
     if (N[i].a >= 0) used[N[i].a] = true;
     if (N[i].b >= 0) used[N[i].b] = true;
+    for (auto& in : N[i].ins) used[in.first] = true;
   }
   // ---- slot allocation: per level free lists, a slot is reusable in the phase after its last use
   std::vector<std::vector<int>> by_phase(out_phase + 1);
@@ -1655,7 +1685,22 @@ void NetBuilder::build(const std::vector<FP>& formulas, const std::vector<uint32
     return (int)slot_level.size() - 1;
   };
   ops.clear();
+  items.clear();
+  phase_off.clear();
   n_nodes = n_atoms = n_gates = 0;
+  // (cost, item) per phase: heavy work first so the dynamic scheduler packs the phase tightly
+  auto flush_phase = [&](std::vector<std::pair<uint32_t, uint32_t>>& ph) {
+    std::stable_sort(ph.begin(), ph.end(), [](auto& x, auto& y) { return x.first > y.first; });
+    phase_off.push_back((uint32_t)items.size());
+    for (auto& it : ph) items.push_back(it.second);
+    ph.clear();
+  };
+  std::vector<std::pair<uint32_t, uint32_t>> cur_phase;
+  auto add_item = [&](uint32_t cost, uint32_t nparts) {
+    uint32_t ix = (uint32_t)ops.size();   // index of the op about to be pushed
+    if (ix >= (1u << 20)) throw RegoError{"rego_unsupported: netlist too large"};
+    for (uint32_t p2 = 0; p2 < nparts; ++p2) cur_phase.emplace_back(cost / nparts, ix | (p2 << 20) | (nparts << 26));
+  };
   for (int ph = 0; ph <= maxphase; ++ph) {
     for (int s : release_at[ph]) free_slots[slot_level[s]].push_back(s);
     auto& ids = by_phase[ph];
@@ -1684,8 +1729,10 @@ void NetBuilder::build(const std::vector<FP>& formulas, const std::vector<uint32
         case GK_N_GATE:
           ++n_gates;
           op.w0 = GK_N_GATE | ((uint32_t)n.level << 8) | (out << 16);
-          op.w1 = (uint32_t)N[n.a].slot | ((uint32_t)N[n.b].slot << 16);
+          op.w1 = (uint32_t)pool.size();
           op.w2 = n.flags;
+          op.w3 = (uint32_t)n.ins.size();
+          for (auto& in : n.ins) pool.push_back((uint32_t)N[in.first].slot | (in.second ? 0x80000000u : 0u));
           break;
         case GK_N_BCAST:
           op.w0 = GK_N_BCAST | ((uint32_t)n.scope << 8) | (out << 16);
@@ -1750,9 +1797,26 @@ void NetBuilder::build(const std::vector<FP>& formulas, const std::vector<uint32
         }
         default: throw RegoError{"internal: unknown netlist node"};
       }
+      {
+        const bool deep = n.level != 0;
+        uint32_t cost = 10, parts = 1;
+        switch (n.kind) {
+          case GK_N_MATCH: cost = 4000; parts = 4; break;
+          case GK_N_ATOM:
+            if (n.op >= GK_OP_PREFIX) { cost = deep ? 1200 : 600; parts = deep ? 4 : 2; }
+            else if (n.op == GK_OP_SID_IN) cost = deep ? 300 : 150;
+            else cost = deep ? 120 : 60;
+            break;
+          case GK_N_GATE: cost = (uint32_t)(8 + 4 * n.ins.size()) * (deep ? 2 : 1); break;
+          case GK_N_BCAST:
+          case GK_N_ACC: cost = 200; break;
+          default: break;
+        }
+        add_item(cost, parts);
+      }
       ops.push_back(op);
     }
-    ops.push_back(GkOp{GK_N_PHASE, 0, 0, 0});
+    flush_phase(cur_phase);
   }
   // the error placeholder slots must exist even if their phase-0 allocation happened above (it did)
   for (size_t c = 0; c < outs.size(); ++c) {
@@ -1762,11 +1826,13 @@ void NetBuilder::build(const std::vector<FP>& formulas, const std::vector<uint32
     op.w1 = prog | ((uint32_t)N[match_node[match_id[c]]].slot << 16);
     op.w2 = (uint32_t)c;
     op.w3 = (uint32_t)N[err_node[match_id[c]]].slot | (outs[c].flags << 16);
+    add_item(100, 1);
     ops.push_back(op);
   }
-  ops.push_back(GkOp{GK_N_PHASE, 0, 0, 0});
+  flush_phase(cur_phase);
+  phase_off.push_back((uint32_t)items.size());
   ops.push_back(GkOp{GK_N_END, 0, 0, 0});
-  n_phases = (size_t)out_phase + 1;
+  n_phases = phase_off.size() - 1;
 }
 
 }  // namespace gk

@@ -95,6 +95,8 @@ FP lower_violation(const std::shared_ptr<const Module>& mod, const VP& parameter
 // Netlist assembly: every constraint's formula is merged into one DAG of bit-column ops (program.h GkOp).
 struct NetBuilder {
   std::vector<GkOp> ops;
+  std::vector<uint32_t> items;           // work items (op | part<<20 | nparts<<26), grouped by phase
+  std::vector<uint32_t> phase_off;       // [nphases + 1]
   std::vector<uint8_t> slot_level;       // scope id of each shared-memory slot
   std::vector<uint32_t> pool;
   std::vector<uint8_t> cbytes;

@@ -106,8 +106,9 @@ typedef struct {
 //   ACC    EXISTS: child-level column -> parent level by OR over each parent's CSR child range
 //   MATCH  the spec.match pre-filter of one DISTINCT match block -> match column + error column
 //   OUT    constraint result = program column AND match column -> result area, per-constraint totals
-// Ops are sorted into dependency phases; inside a phase the warps of the CTA take ops round-robin, a
-// __syncthreads separates phases.  Identical sub-formulas of different constraints are one node.
+// Ops are sorted into dependency phases; inside a phase the warps of the CTA pull work items (an op, or a row
+// slice of a heavy op) from a shared counter; a __syncthreads separates phases.  Identical sub-formulas of
+// different constraints are one node.
 typedef struct {
   uint32_t w0;   // kind | level<<8 | out_slot<<16     (level = scope id of the rows the op iterates)
   uint32_t w1;
@@ -117,9 +118,9 @@ typedef struct {
 
 enum {
   GK_N_END = 0,
-  GK_N_PHASE = 1,   // barrier between dependency phases
+  GK_N_PHASE = 1,   // (unused marker)
   GK_N_ATOM = 2,    // w1 = atom op | col<<8 ; w2, w3 = operands (see GK_OP_*)
-  GK_N_GATE = 3,    // w1 = a | b<<16 ; w2 = flags: 1 OR (else AND), 2 negate a, 4 negate b, 8 negate out
+  GK_N_GATE = 3,    // n-ary: pool[w1 .. w1+w3) = input slots (bit 31: negate that input); w2 = flags: 1 OR (else AND), 8 negate out
   GK_N_CONST = 4,   // w1 = 0 / 1
   GK_N_BCAST = 5,   // level = child scope (rows written); w1 = input slot at the parent level
   GK_N_ACC = 6,     // level = child scope (rows read); out at the parent level; w1 = input slot
@@ -152,7 +153,11 @@ typedef struct {
   uint32_t nslots;
   uint32_t npool;
   uint32_t ncbytes;
+  uint32_t nphases;
+  uint32_t nitems;
   const GkOp* ops;           // [nops]
+  const uint32_t* items;     // [nitems] work items: op index | part<<20 | nparts<<26, heaviest first inside a phase
+  const uint32_t* phase_off; // [nphases + 1] item ranges of the phases
   const uint8_t* slot_level; // [nslots] scope id of each slot
   const uint32_t* cons_match;// [nconstraints] match block id
   const GkMatch* match;      // [nmatch]

@@ -1,0 +1,299 @@
+// The evaluation kernel for sm_100a: a tile-at-a-time columnar bitmap engine.
+//
+//   * ALL constraints are one netlist of bit-column ops (program.h GkOp).  A CTA owns a tile of kTile consecutive
+//     objects; every node of the netlist is a packed bit column of the tile held in shared memory (32 rows/word).
+//   * ATOM  : one warp streams the tile's slice of one feature column -- unit-stride, coalesced loads of 32 rows per
+//             instruction -- compares against the constant and packs the 32 verdicts with one __ballot_sync.
+//   * GATE  : n-ary AND/OR on whole words: 32 rows per instruction, operands broadcast from shared memory.
+//   * ACC / BCAST : EXISTS and loop-invariant hoisting as segmented OR / range fill over the CSR child ranges.
+//   * MATCH : the spec.match pre-filter, once per DISTINCT match block per object, ballot-packed like an atom.
+//   * OUT   : result = program & match, scattered into the tile's object-major bitmap rows in shared memory, which
+//             are then copied to HBM as one contiguous, coalesced block; per-constraint totals via popc.
+//   * ops of one dependency phase are independent; warps pull work items (an op, or a row slice of a heavy op,
+//     heaviest first) from a shared-memory counter, and one __syncthreads separates phases.
+// This is integer / byte work bounded by HBM traffic and instruction issue -- nothing here belongs on tensor cores.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "program.h"
+#include "vm_core.h"
+
+namespace gk {
+
+struct KParams {
+  GkBatch batch;
+  GkProgram prog;
+  GkOut out;
+  const uint32_t* active;     // [nconstraints] enforcement-point filter
+  const uint32_t* slot_off;   // [nslots] word offset of each slot inside the slot area (depends on the batch's tile capacities)
+  const uint32_t* tile_lo;    // [(ntiles + 1) * nscopes] first row of every scope for every tile (row ranges are contiguous)
+  uint32_t ntiles;
+  uint32_t tile;              // objects per tile (multiple of 32)
+  uint32_t slot_words;        // words in the slot area
+};
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr uint32_t kTile = 512;
+constexpr uint32_t kMaxPhases = 64;
+
+__device__ __forceinline__ void stage(void* dst, const void* src, size_t bytes) {
+  // 16-byte vector copies; sizes/offsets are padded to 16 on the host
+  const uint4* s = reinterpret_cast<const uint4*>(src);
+  uint4* d = reinterpret_cast<uint4*>(dst);
+  for (size_t i = threadIdx.x; i < bytes / 16; i += blockDim.x) d[i] = s[i];
+}
+
+__device__ __forceinline__ uint32_t range_mask(uint32_t w, uint32_t a, uint32_t b) {
+  // bits of word w that lie in the row range [a, b)
+  const uint32_t lo = w * 32u, hi = lo + 32u;
+  const uint32_t x = a > lo ? a : lo, y = b < hi ? b : hi;
+  if (x >= y) return 0u;
+  const uint32_t nb = y - x;
+  return (nb == 32u ? 0xffffffffu : ((1u << nb) - 1u)) << (x - lo);
+}
+
+// rows [w0*32, min(cnt, w1*32)) of one column, one ballot-packed word per 32 rows.  The op switch is OUTSIDE the row
+// loop: every loop body is a straight load-compare-ballot sequence.
+#define GK_ATOM_LOOP(EXPR)                                              \
+  for (uint32_t r = w0 * 32u + lane; r < w1 * 32u; r += 32u) {          \
+    const uint32_t row = lo + r;                                        \
+    const bool v = r < cnt && (EXPR);                                   \
+    const uint32_t wd = __ballot_sync(0xffffffffu, v);                  \
+    if (lane == 0) out[r >> 5] = wd;                                    \
+  }
+
+__device__ __forceinline__ void atom_rows(const GkColumn& c, uint32_t aop, uint32_t a, uint32_t b, const uint32_t* pool, const uint8_t* cbytes,
+                                          uint32_t lo, uint32_t cnt, uint32_t w0, uint32_t w1, uint32_t lane, uint32_t* out) {
+  switch (aop) {
+    case GK_OP_TRUTHY: {
+      const uint8_t* vt = c.vt;
+      GK_ATOM_LOOP(vt[row] != GK_VT_UNDEF && vt[row] != GK_VT_FALSE)
+      break;
+    }
+    case GK_OP_DEFINED: {
+      const uint8_t* vt = c.vt;
+      GK_ATOM_LOOP(vt[row] != GK_VT_UNDEF)
+      break;
+    }
+    case GK_OP_VTMASK: {
+      const uint8_t* vt = c.vt;
+      GK_ATOM_LOOP(((1u << vt[row]) & a) != 0u)
+      break;
+    }
+    case GK_OP_SID_EQ: {
+      const uint32_t* sid = c.sid;
+      GK_ATOM_LOOP(sid[row] == a)
+      break;
+    }
+    default: {
+      GK_ATOM_LOOP(gk_atom(c, row, aop, a, b, pool, cbytes))
+      break;
+    }
+  }
+}
+
+// One CTA = one tile of consecutive objects at a time; all intermediate bit columns live in shared memory.
+__global__ void __launch_bounds__(kThreads) gk_eval_kernel(const KParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const uint32_t C = p.prog.nconstraints, W = p.out.words, NS = p.batch.nscopes, NP = p.prog.nphases;
+  // ---- shared-memory layout
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    void* q = smem + off;
+    off += (bytes + 15) / 16 * 16;
+    return q;
+  };
+  uint32_t* s_tot = static_cast<uint32_t*>(take((size_t)C * 4));
+  uint32_t* s_err = static_cast<uint32_t*>(take((size_t)C * 4));
+  uint32_t* s_act = static_cast<uint32_t*>(take((size_t)C * 4));
+  uint32_t* s_lo = static_cast<uint32_t*>(take((size_t)NS * 4));
+  uint32_t* s_cnt = static_cast<uint32_t*>(take((size_t)NS * 4));
+  uint32_t* s_ctr = static_cast<uint32_t*>(take((size_t)kMaxPhases * 4));
+  uint32_t* s_poff = static_cast<uint32_t*>(take((size_t)(NP + 1) * 4));
+  uint32_t* s_soff = static_cast<uint32_t*>(take((size_t)p.prog.nslots * 4));
+  uint32_t* res_v = static_cast<uint32_t*>(take((size_t)p.tile * W * 4));
+  uint32_t* res_e = static_cast<uint32_t*>(take((size_t)p.tile * W * 4));
+  uint32_t* slots = static_cast<uint32_t*>(take((size_t)p.slot_words * 4));
+  GkOp* ops = static_cast<GkOp*>(take((size_t)p.prog.nops * sizeof(GkOp)));
+  uint32_t* items = static_cast<uint32_t*>(take((size_t)p.prog.nitems * 4));
+  GkMatch* match = static_cast<GkMatch*>(take((size_t)p.prog.nmatch * sizeof(GkMatch)));
+  GkColumn* cols = static_cast<GkColumn*>(take((size_t)p.batch.ncols * sizeof(GkColumn)));
+  GkScope* scopes = static_cast<GkScope*>(take((size_t)NS * sizeof(GkScope)));
+  uint32_t* pool = static_cast<uint32_t*>(take((size_t)p.prog.npool * 4));
+  uint8_t* cbytes = static_cast<uint8_t*>(take((size_t)p.prog.ncbytes));
+
+  for (uint32_t i = threadIdx.x; i < C; i += blockDim.x) {
+    s_tot[i] = 0;
+    s_err[i] = 0;
+    s_act[i] = p.active[i];
+  }
+  for (uint32_t i = threadIdx.x; i < p.prog.nslots; i += blockDim.x) s_soff[i] = p.slot_off[i];
+  for (uint32_t i = threadIdx.x; i <= NP; i += blockDim.x) s_poff[i] = p.prog.phase_off[i];
+  stage(ops, p.prog.ops, ((size_t)p.prog.nops * sizeof(GkOp) + 15) / 16 * 16);
+  stage(items, p.prog.items, ((size_t)p.prog.nitems * 4 + 15) / 16 * 16);
+  stage(match, p.prog.match, ((size_t)p.prog.nmatch * sizeof(GkMatch) + 15) / 16 * 16);
+  stage(cols, p.batch.cols, ((size_t)p.batch.ncols * sizeof(GkColumn) + 15) / 16 * 16);
+  stage(scopes, p.batch.scopes, ((size_t)NS * sizeof(GkScope) + 15) / 16 * 16);
+  stage(pool, p.prog.pool, ((size_t)p.prog.npool * 4 + 15) / 16 * 16);
+  stage(cbytes, p.prog.cbytes, ((size_t)p.prog.ncbytes + 15) / 16 * 16);
+  __syncthreads();
+
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t FULL = 0xffffffffu;
+
+  for (uint32_t t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+    // ---- tile row ranges (precomputed on the host: rows of a tile are contiguous at every scope)
+    for (uint32_t s = threadIdx.x; s < NS; s += blockDim.x) {
+      const uint32_t a = p.tile_lo[(size_t)t * NS + s], b = p.tile_lo[(size_t)(t + 1) * NS + s];
+      s_lo[s] = a;
+      s_cnt[s] = b - a;
+    }
+    for (uint32_t i = threadIdx.x; i < NP; i += blockDim.x) s_ctr[i] = 0;
+    for (uint32_t i = threadIdx.x; i < p.tile * W; i += blockDim.x) {
+      res_v[i] = 0;
+      res_e[i] = 0;
+    }
+    __syncthreads();
+    const uint32_t nobj = s_cnt[0], obj0 = s_lo[0];
+
+    for (uint32_t ph = 0; ph < NP; ++ph) {
+      const uint32_t ibase = s_poff[ph], icnt = s_poff[ph + 1] - ibase;
+      for (;;) {
+        uint32_t k = 0;
+        if (lane == 0) k = atomicAdd(&s_ctr[ph], 1u);
+        k = __shfl_sync(FULL, k, 0);
+        if (k >= icnt) break;
+        const uint32_t item = items[ibase + k];
+        const GkOp op = ops[item & 0xfffffu];
+        const uint32_t part = (item >> 20) & 0x3fu, nparts = item >> 26;
+        const uint32_t kind = op.w0 & 0xffu, level = (op.w0 >> 8) & 0xffu;
+        uint32_t* out = slots + s_soff[op.w0 >> 16];
+        switch (kind) {
+          case GK_N_ATOM: {
+            const uint32_t cnt = s_cnt[level], words = (cnt + 31u) >> 5;
+            atom_rows(cols[op.w1 >> 8], op.w1 & 0xffu, op.w2, op.w3, pool, cbytes, s_lo[level], cnt, words * part / nparts,
+                      words * (part + 1u) / nparts, lane, out);
+            break;
+          }
+          case GK_N_GATE: {
+            const uint32_t f = op.w2, words = (s_cnt[level] + 31u) >> 5, nin = op.w3;
+            const uint32_t* in = pool + op.w1;
+            const uint32_t no = (f & GK_G_NEG_OUT) ? FULL : 0u;
+            const bool is_or = (f & GK_G_OR) != 0u;
+            for (uint32_t i = lane; i < words; i += 32u) {
+              uint32_t acc = is_or ? 0u : FULL;
+              for (uint32_t j = 0; j < nin; ++j) {
+                const uint32_t e = in[j];
+                const uint32_t x = slots[s_soff[e & 0xffffu] + i] ^ (uint32_t)((int32_t)e >> 31);
+                acc = is_or ? (acc | x) : (acc & x);
+              }
+              out[i] = acc ^ no;
+            }
+            break;
+          }
+          case GK_N_CONST: {
+            const uint32_t v = (op.w1 & 1u) ? FULL : 0u, words = (s_cnt[level] + 31u) >> 5;
+            for (uint32_t i = lane; i < words; i += 32u) out[i] = v;
+            break;
+          }
+          case GK_N_BCAST: {   // parent-level column -> rows of the child scope `level`
+            const uint32_t* in = slots + s_soff[op.w1 & 0xffffu];
+            const uint32_t par = (uint32_t)scopes[level].parent;
+            const uint32_t* coff = scopes[level].off + s_lo[par];
+            const uint32_t clo = s_lo[level], pcnt = s_cnt[par], words = (s_cnt[level] + 31u) >> 5;
+            for (uint32_t i = lane; i < words; i += 32u) out[i] = 0u;
+            __syncwarp();
+            for (uint32_t r = lane; r < pcnt; r += 32u) {
+              if ((in[r >> 5] >> (r & 31u)) & 1u) {
+                const uint32_t a = coff[r] - clo, b = coff[r + 1] - clo;
+                if (b > a)
+                  for (uint32_t w = a >> 5; w <= (b - 1u) >> 5; ++w) atomicOr(&out[w], range_mask(w, a, b));
+              }
+            }
+            break;
+          }
+          case GK_N_ACC: {     // EXISTS: OR over each parent's child range of the scope `level`
+            const uint32_t* in = slots + s_soff[op.w1 & 0xffffu];
+            const uint32_t par = (uint32_t)scopes[level].parent;
+            const uint32_t* coff = scopes[level].off + s_lo[par];
+            const uint32_t clo = s_lo[level], pcnt = s_cnt[par];
+            for (uint32_t r = lane; r < ((pcnt + 31u) & ~31u); r += 32u) {
+              bool any = false;
+              if (r < pcnt) {
+                const uint32_t a = coff[r] - clo, b = coff[r + 1] - clo;
+                if (b > a)
+                  for (uint32_t w = a >> 5; w <= (b - 1u) >> 5 && !any; ++w) any = (in[w] & range_mask(w, a, b)) != 0u;
+              }
+              const uint32_t w = __ballot_sync(FULL, any);
+              if (lane == 0) out[r >> 5] = w;
+            }
+            break;
+          }
+          case GK_N_MATCH: {
+            uint32_t* err = slots + s_soff[op.w1 & 0xffffu];
+            const GkMatch& m = match[op.w2];
+            const uint32_t words = (nobj + 31u) >> 5;
+            for (uint32_t r = (words * part / nparts) * 32u + lane; r < (words * (part + 1u) / nparts) * 32u; r += 32u) {
+              int res = 0;
+              if (r < nobj && !(p.batch.flags[obj0 + r] & GK_F_SKIP)) res = gk_match(p.batch, pool, cbytes, m, obj0 + r);
+              if (res < 0) {
+                const uint32_t slot = atomicAdd(p.out.errcount, 1u);
+                if (slot < p.out.errcap) {
+                  p.out.errlist[3 * slot] = obj0 + r;
+                  p.out.errlist[3 * slot + 1] = op.w2;
+                  p.out.errlist[3 * slot + 2] = (uint32_t)(-res);
+                }
+              }
+              const uint32_t wm = __ballot_sync(FULL, res > 0), we = __ballot_sync(FULL, res < 0);
+              if (lane == 0) {
+                out[r >> 5] = wm;
+                err[r >> 5] = we;
+              }
+            }
+            break;
+          }
+          case GK_N_OUT: {
+            const uint32_t c = op.w2, flags = op.w3 >> 16;
+            if (!s_act[c]) break;
+            const uint32_t* prog = slots + s_soff[op.w1 & 0xffffu];
+            const uint32_t* mt = slots + s_soff[op.w1 >> 16];
+            const uint32_t* er = slots + s_soff[op.w3 & 0xffffu];
+            const uint32_t bit = 1u << (c & 31u), wi = c >> 5;
+            uint32_t nv = 0, ne = 0;
+            for (uint32_t i = 0; i < ((nobj + 31u) >> 5); ++i) {
+              const uint32_t valid = range_mask(i, 0u, nobj);
+              const uint32_t pv = (flags & 1u) ? FULL : (flags & 2u) ? 0u : prog[i];
+              const uint32_t v = pv & mt[i] & valid, e = er[i] & valid;
+              const uint32_t o = i * 32u + lane;
+              if ((v >> lane) & 1u) atomicOr(&res_v[o * W + wi], bit);
+              if ((e >> lane) & 1u) atomicOr(&res_e[o * W + wi], bit);
+              nv += __popc(v);
+              ne += __popc(e);
+            }
+            if (lane == 0) {
+              if (nv) atomicAdd(&s_tot[c], nv);
+              if (ne) atomicAdd(&s_err[c], ne);
+            }
+            break;
+          }
+          default: break;
+        }
+      }
+      __syncthreads();
+    }
+    // ---- the tile's bitmap rows are contiguous in the object-major output: coalesced copy out
+    const size_t base = (size_t)obj0 * W;
+    for (uint32_t i = threadIdx.x; i < nobj * W; i += blockDim.x) {
+      p.out.viol[base + i] = res_v[i];
+      p.out.err[base + i] = res_e[i];
+    }
+    __syncthreads();
+  }
+  for (uint32_t c = threadIdx.x; c < C; c += blockDim.x) {
+    if (s_tot[c]) atomicAdd(p.out.totals + c, (unsigned long long)s_tot[c]);
+    if (s_err[c]) atomicAdd(p.out.err_totals + c, (unsigned long long)s_err[c]);
+  }
+}
+
+}  // namespace gk

@@ -73,11 +73,14 @@ class HostEmuBackend : public Backend {
           break;
         }
         case GK_N_GATE: {
-          const auto &a = slot[op.w1 & 0xffffu], &bb2 = slot[op.w1 >> 16];
           const uint32_t f = op.w2, R = rows_of(level);
           for (uint32_t r = 0; r < R; ++r) {
-            bool x = a[r] ^ ((f & GK_G_NEG_A) != 0), y = bb2[r] ^ ((f & GK_G_NEG_B) != 0);
-            bool v = (f & GK_G_OR) ? (x || y) : (x && y);
+            bool v = !(f & GK_G_OR);
+            for (uint32_t j = 0; j < op.w3; ++j) {
+              const uint32_t e = c.pool[op.w1 + j];
+              bool x = slot[e & 0xffffu][r] ^ ((e >> 31) != 0);
+              v = (f & GK_G_OR) ? (v || x) : (v && x);
+            }
             slot[o][r] = v ^ ((f & GK_G_NEG_OUT) != 0);
           }
           break;
