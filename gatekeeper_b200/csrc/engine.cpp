@@ -493,6 +493,15 @@ std::string Engine::dump() {
                   " columns; netlist: " + std::to_string(c->n_nodes) + " nodes (" + std::to_string(c->n_atoms) + " atoms, " +
                   std::to_string(c->n_gates) + " gates) in " + std::to_string(c->n_phases) + " phases, " + std::to_string(c->slot_level.size()) +
                   " live slots, " + std::to_string(c->match.size()) + " distinct match blocks\n";
+  {
+    std::vector<int> per(c->schema.scopes.size(), 0);
+    for (uint8_t l : c->slot_level) per[l]++;
+    o += "  slots per scope:";
+    for (size_t i = 0; i < per.size(); ++i) o += " s" + std::to_string(i) + "=" + std::to_string(per[i]);
+    o += "; items per phase:";
+    for (size_t i = 0; i + 1 < c->phase_off.size(); ++i) o += " " + std::to_string(c->phase_off[i + 1] - c->phase_off[i]);
+    o += "\n";
+  }
   for (size_t i = 1; i < c->schema.scopes.size(); ++i)
     o += "  scope " + std::to_string(i) + " parent " + std::to_string(c->schema.scopes[i].parent) + ": " + c->schema.scopes[i].gen->key + "\n";
   for (size_t i = 0; i < c->schema.cols.size(); ++i)

@@ -366,6 +366,58 @@ class Lowerer {
 
   static void subst_print(const Term& t, const std::map<int, std::string>& sub, std::string& out);
 
+  void collect_rule_refs(const TP& t, std::set<std::string>& out) const {
+    if (!t) return;
+    if ((t->k == TK::Var || t->k == TK::Call) && m_.is_rule(t->name) && out.insert(t->name).second) {
+      for (auto& r : m_.rules.at(t->name)) {
+        for (auto& a : r.args) collect_rule_refs(a, out);
+        collect_rule_refs(r.key, out);
+        collect_rule_refs(r.value, out);
+        for (auto& s : r.body) {
+          collect_rule_refs(s.a, out);
+          collect_rule_refs(s.b, out);
+          collect_rule_refs(s.c, out);
+        }
+        for (auto& e : r.els) {
+          collect_rule_refs(e.first, out);
+          for (auto& s : e.second) {
+            collect_rule_refs(s.a, out);
+            collect_rule_refs(s.b, out);
+            collect_rule_refs(s.c, out);
+          }
+        }
+      }
+    }
+    if (t->head) collect_rule_refs(t->head, out);
+    for (auto& a : t->args) collect_rule_refs(a, out);
+    for (auto& kv : t->kvs) {
+      collect_rule_refs(kv.first, out);
+      collect_rule_refs(kv.second, out);
+    }
+    collect_rule_refs(t->key, out);
+    collect_rule_refs(t->value, out);
+    for (auto& s : t->body) {
+      collect_rule_refs(s.a, out);
+      collect_rule_refs(s.b, out);
+      collect_rule_refs(s.c, out);
+    }
+  }
+  std::string rules_signature(const TP& t) const {
+    std::set<std::string> names;
+    collect_rule_refs(t, names);
+    std::string text;
+    for (auto& n : names) text += rule_str(m_, n);
+    // FNV-1a 64
+    uint64_t h = 1469598103934665603ull;
+    for (unsigned char ch : text) {
+      h ^= ch;
+      h *= 1099511628211ull;
+    }
+    char buf[24];
+    snprintf(buf, sizeof buf, "%016llx", (unsigned long long)h);
+    return buf;
+  }
+
   CP make_closure(const TP& term, const LEnv& env) {
     auto c = std::make_shared<Closure>();
     c->mod = mod_;
@@ -383,7 +435,10 @@ class Lowerer {
       if (s->k == SymVal::Conc) {
         a.k = CapArg::Conc;
         a.v = s->v;
-        sub[v] = "<" + intern_key(s->v) + ">";
+        // scalars print as literals so that `spec[field]` with field = "containers" and `spec.containers` are one column
+        sub[v] = (s->v->t == VT::Str || s->v->t == VT::Num || s->v->t == VT::True || s->v->t == VT::False || s->v->t == VT::Null)
+                     ? fmt_value(s->v, false)
+                     : "<" + intern_key(s->v) + ">";
       } else if (s->k == SymVal::Col) {
         a.k = CapArg::Col;
         a.col = s->col;
@@ -406,7 +461,9 @@ class Lowerer {
     c->scope = scope;
     std::string body;
     subst_print(*term, sub, body);
-    c->key = (refs_module(term) ? "m" + std::to_string(m_.uid) + ":" : std::string()) + body;
+    // helper rules are identified by their TEXT (transitively), not by the template they live in: the same
+    // `input_containers` partial set in two templates is one scope / one set of columns
+    c->key = (refs_module(term) ? "r" + rules_signature(term) + ":" : std::string()) + body;
     return c;
   }
 
@@ -1327,7 +1384,8 @@ void Lowerer::subst_print(const Term& t, const std::map<int, std::string>& sub, 
   // term_str with captured variables replaced by their canonical keys
   if (t.k == TK::Var) {
     auto it = sub.find(t.vid);
-    out += it != sub.end() ? it->second : t.name;
+    if (it != sub.end()) out += it->second;
+    else out += (t.name.size() > 1 && t.name[0] == '$' && t.name[1] == 'w') ? std::string("_") : t.name;
     return;
   }
   if (sub.empty()) {

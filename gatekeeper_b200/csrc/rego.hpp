@@ -72,6 +72,7 @@ struct Module {
 
 std::shared_ptr<Module> rego_parse(const std::string& src);   // throws RegoError
 std::string term_str(const Term& t);                          // debug / canonical printing
+std::string rule_str(const Module& m, const std::string& name); // canonical text of all definitions of a rule
 
 // ---- concrete evaluator ---------------------------------------------------------------------------
 struct Env {

@@ -605,7 +605,7 @@ static void stmt_str(const Stmt& s, std::string& out);
 static void term_rec(const Term& t, std::string& out) {
   switch (t.k) {
     case TK::Scalar: out += fmt_value(t.val, false); break;
-    case TK::Var: out += t.name; break;
+    case TK::Var: out += (t.name.size() > 1 && t.name[0] == '$' && t.name[1] == 'w') ? std::string("_") : t.name; break;   // every wildcard is a fresh variable
     case TK::Ref:
       term_rec(*t.head, out);
       for (auto& a : t.args) {
@@ -693,4 +693,39 @@ std::string term_str(const Term& t) {
   return out;
 }
 
+}  // namespace gk
+
+namespace gk {
+// Canonical text of every definition of a rule (used to recognise identical helper rules of different templates).
+std::string rule_str(const Module& m, const std::string& name) {
+  std::string out;
+  auto it = m.rules.find(name);
+  if (it == m.rules.end()) return out;
+  for (auto& r : it->second) {
+    out += name;
+    out += r.kind == Rule::Func ? "(" : r.kind == Rule::PSet ? "[" : r.kind == Rule::PObj ? "{" : "=";
+    for (auto& a : r.args) out += term_str(*a) + ",";
+    if (r.key) out += term_str(*r.key);
+    out += "=";
+    if (r.value) out += term_str(*r.value);
+    out += r.is_default ? " default{" : " {";
+    for (auto& s : r.body) {
+      stmt_str(s, out);
+      out += ";";
+    }
+    out += "}";
+    for (auto& e : r.els) {
+      out += "else=";
+      if (e.first) out += term_str(*e.first);
+      out += "{";
+      for (auto& s : e.second) {
+        stmt_str(s, out);
+        out += ";";
+      }
+      out += "}";
+    }
+    out += "\n";
+  }
+  return out;
+}
 }  // namespace gk

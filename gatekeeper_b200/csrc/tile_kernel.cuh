@@ -55,12 +55,23 @@ __device__ __forceinline__ uint32_t range_mask(uint32_t w, uint32_t a, uint32_t 
 
 // rows [w0*32, min(cnt, w1*32)) of one column, one ballot-packed word per 32 rows.  The op switch is OUTSIDE the row
 // loop: every loop body is a straight load-compare-ballot sequence.
-#define GK_ATOM_LOOP(EXPR)                                              \
-  for (uint32_t r = w0 * 32u + lane; r < w1 * 32u; r += 32u) {          \
-    const uint32_t row = lo + r;                                        \
-    const bool v = r < cnt && (EXPR);                                   \
-    const uint32_t wd = __ballot_sync(0xffffffffu, v);                  \
-    if (lane == 0) out[r >> 5] = wd;                                    \
+// Four 32-row groups per trip: the four loads are independent, so four memory requests per lane are in flight
+// before the first compare (the loop is latency-bound otherwise: one warp owns the whole op).
+#define GK_ATOM_LOOP(EXPR)                                                        \
+  for (uint32_t r0 = w0 * 32u + lane; r0 < w1 * 32u; r0 += 128u) {                \
+    bool v4[4];                                                                   \
+    _Pragma("unroll") for (int u = 0; u < 4; ++u) {                               \
+      const uint32_t r = r0 + 32u * u;                                            \
+      const uint32_t row = lo + r;                                                \
+      v4[u] = r < cnt && r < w1 * 32u && (EXPR);                                  \
+    }                                                                             \
+    _Pragma("unroll") for (int u = 0; u < 4; ++u) {                               \
+      const uint32_t r = r0 + 32u * u;                                            \
+      if (r - lane < w1 * 32u) { /* warp-uniform */                               \
+        const uint32_t wd = __ballot_sync(0xffffffffu, v4[u]);                    \
+        if (lane == 0) out[r >> 5] = wd;                                          \
+      }                                                                           \
+    }                                                                             \
   }
 
 __device__ __forceinline__ void atom_rows(const GkColumn& c, uint32_t aop, uint32_t a, uint32_t b, const uint32_t* pool, const uint8_t* cbytes,
