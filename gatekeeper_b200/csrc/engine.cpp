@@ -514,7 +514,7 @@ std::string Engine::dump() {
 }
 
 // ------------------------------------------------------------------------------------------- review doc
-VP Engine::review_doc(const ObjIn& in, VP* obj_out, VP* old_out, VP* ns_out, std::string* err) {
+VP Engine::review_doc(const ObjIn& in, VP* obj_out, VP* old_out, VP* ns_out, std::string* err, const std::map<std::string, VP>* ns_snapshot) {
   VP obj, old, ns;
   auto parse = [&](const char* p, size_t n, const char* what, VP& dst) -> bool {
     if (!p) return true;
@@ -588,9 +588,14 @@ VP Engine::review_doc(const ObjIn& in, VP* obj_out, VP* old_out, VP* ns_out, std
   if (ns_out) {
     // Matcher.Match: review's namespace object, else the cache entry for review.Namespace (matcher.go:37-39)
     if (!ns && !nsname.empty()) {
-      std::shared_lock<std::shared_mutex> l(mu_);
-      auto it = namespaces_.find(nsname);
-      if (it != namespaces_.end()) ns = it->second;
+      if (ns_snapshot) {   // flatten workers use a private copy: no lock traffic per object
+        auto it = ns_snapshot->find(nsname);
+        if (it != ns_snapshot->end()) ns = it->second;
+      } else {
+        std::shared_lock<std::shared_mutex> l(mu_);
+        auto it = namespaces_.find(nsname);
+        if (it != namespaces_.end()) ns = it->second;
+      }
     }
     *ns_out = ns;
   }
@@ -613,7 +618,40 @@ struct Flattener {
   };
   std::vector<std::vector<Row>> rows;                  // per scope, for the current object
 
-  Flattener(Engine& e, const Compiled& cc) : eng(e), c(cc) {
+  std::map<std::string, VP> ns_private;                 // deep copy of the namespace cache
+  std::unordered_map<const Node*, VP> const_private;    // deep copies of constants captured by closures
+
+  static VP deep_copy(const VP& v) {
+    if (!v) return v;
+    switch (v->t) {
+      case VT::Null: return v_null();
+      case VT::True: return v_bool(true);
+      case VT::False: return v_bool(false);
+      case VT::Num: return v_num(v->n);
+      case VT::Str: return v_str(v->s);
+      case VT::Arr:
+      case VT::Set: {
+        auto n = std::make_shared<Node>();
+        n->t = v->t;
+        for (auto& x : v->items) n->items.push_back(deep_copy(x));
+        return n;
+      }
+      default: {
+        auto n = std::make_shared<Node>();
+        n->t = VT::Obj;
+        for (auto& e : v->kv) n->kv.emplace_back(deep_copy(e.first), deep_copy(e.second));
+        return n;
+      }
+    }
+  }
+  const VP& private_const(const VP& v) {
+    auto it = const_private.find(v.get());
+    if (it != const_private.end()) return it->second;
+    return const_private.emplace(v.get(), deep_copy(v)).first->second;
+  }
+
+  Flattener(Engine& e, const Compiled& cc, const std::map<std::string, VP>& ns_shared) : eng(e), c(cc) {
+    for (auto& kv : ns_shared) ns_private.emplace(kv.first, deep_copy(kv.second));
     size_t ns = c.schema.scopes.size();
     hb.scope_off.resize(ns);
     for (size_t s = 1; s < ns; ++s) hb.scope_off[s].push_back(0);
@@ -653,7 +691,7 @@ struct Flattener {
     if (cl.leaf == Closure::Key) return rows[scope][r].key;
     Env env;
     for (auto& cap : cl.caps) {
-      if (cap.second.k == CapArg::Conc) env.bind(cap.first, cap.second.v);
+      if (cap.second.k == CapArg::Conc) env.bind(cap.first, private_const(cap.second.v));
       else {
         VP v = eval_closure(*cap.second.col, scope, r, input);
         if (!v) return nullptr;
@@ -753,7 +791,7 @@ struct Flattener {
   void add(const ObjIn& in) {
     std::string err;
     VP obj, old, ns;
-    VP doc = eng.review_doc(in, &obj, &old, &ns, &err);
+    VP doc = eng.review_doc(in, &obj, &old, &ns, &err, &ns_private);
     hb.obj_errors.push_back(err);
     const size_t nscopes = c.schema.scopes.size();
     if (!doc) {
@@ -857,11 +895,16 @@ static void append_off(std::vector<uint32_t>& dst, const std::vector<uint32_t>& 
 
 std::shared_ptr<HostBatch> Engine::flatten(const ObjIn* objs, size_t n, const Compiled& c) {
   size_t T = std::min<size_t>((size_t)threads_, std::max<size_t>(1, n / 256));
+  std::map<std::string, VP> ns_copy;
+  {
+    std::shared_lock<std::shared_mutex> l(mu_);
+    ns_copy = namespaces_;
+  }
   std::vector<std::unique_ptr<Flattener>> parts(T);
   std::vector<std::string> errs(T);
   auto work = [&](size_t t) {
     try {
-      parts[t].reset(new Flattener(*this, c));
+      parts[t].reset(new Flattener(*this, c, ns_copy));
       size_t lo = n * t / T, hi = n * (t + 1) / T;
       for (size_t i = lo; i < hi; ++i) parts[t]->add(objs[i]);
     } catch (RegoError& e) {

@@ -142,7 +142,7 @@ class Engine {
   std::string dump();
   StringTable& strings() { return strings_; }
   int threads() const { return threads_; }
-  VP review_doc(const ObjIn& in, VP* obj_out, VP* old_out, VP* ns_out, std::string* err);
+  VP review_doc(const ObjIn& in, VP* obj_out, VP* old_out, VP* ns_out, std::string* err, const std::map<std::string, VP>* ns_snapshot = nullptr);
 
  private:
   friend struct Flattener;

@@ -32,9 +32,15 @@ struct KParams {
   uint32_t slot_words;        // words in the slot area
 };
 
-constexpr int kThreads = 256;
+#ifndef GK_THREADS
+#define GK_THREADS 256
+#endif
+#ifndef GK_TILE
+#define GK_TILE 512
+#endif
+constexpr int kThreads = GK_THREADS;
 constexpr int kWarps = kThreads / 32;
-constexpr uint32_t kTile = 512;
+constexpr uint32_t kTile = GK_TILE;
 constexpr uint32_t kMaxPhases = 64;
 
 __device__ __forceinline__ void stage(void* dst, const void* src, size_t bytes) {

@@ -63,12 +63,12 @@ bool num_fits_i64(const Num& n, int64_t* out) {
 
 // -------------------------------------------------------------------------------------- constructors
 VP v_null() {
-  static VP v = [] { auto n = std::make_shared<Node>(); n->t = VT::Null; return VP(n); }();
+  static thread_local VP v = [] { auto n = std::make_shared<Node>(); n->t = VT::Null; return VP(n); }();
   return v;
 }
 VP v_bool(bool b) {
-  static VP t = [] { auto n = std::make_shared<Node>(); n->t = VT::True; return VP(n); }();
-  static VP f = [] { auto n = std::make_shared<Node>(); n->t = VT::False; return VP(n); }();
+  static thread_local VP t = [] { auto n = std::make_shared<Node>(); n->t = VT::True; return VP(n); }();
+  static thread_local VP f = [] { auto n = std::make_shared<Node>(); n->t = VT::False; return VP(n); }();
   return b ? t : f;
 }
 VP v_num(const Num& x) {

@@ -16,7 +16,7 @@ from dataclasses import dataclass, field
 from typing import Any, Iterable, Optional, Sequence
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgk_engine.so")
+LIB_PATH = os.environ.get("GK_ENGINE_LIB") or os.path.join(_HERE, "libgk_engine.so")   # override only for kernel-variant experiments
 
 WEBHOOK_EP = "validation.gatekeeper.sh"   # pkg/util/enforcement_action.go:24-39
 AUDIT_EP = "audit.gatekeeper.sh"
