@@ -72,7 +72,7 @@ inline void pack_batch(const HostBatch& hb, const Compiled& c, PackedBatch& pb) 
   total += (hb.flags.size() * 4 + 256) * 4 + hb.name_off.size() * 4 + hb.gen_off.size() * 4 + hb.lbl_off.size() * 4 + hb.lbl_kv.size() * 4 +
            hb.name_bytes.size() + hb.gen_bytes.size() + hb.nsrow.size() * 4 + hb.nsl_off.size() * 4 + hb.nsl_kv.size() * 4 + 4096;
   for (auto& s : hb.scope_off) total += s.size() * 4 + 512;
-  for (auto& col : hb.cols) total += col.vt.size() + col.sid.size() * 4 + col.num.size() * 8 + col.boff.size() * 4 + col.bytes.size() + 2048;
+  for (auto& col : hb.cols) total += col.vt.size() + col.sid.size() * 4 + col.num.size() * 8 + col.boff.size() * 4 + col.bytes.size() + col.head.size() * 4 + 2560;
   total += hb.cols.size() * sizeof(GkColumn) + hb.scope_off.size() * sizeof(GkScope) + 1024;
   a.reserve(total);
   GkBatch& h = pb.hdr;
@@ -105,6 +105,7 @@ inline void pack_batch(const HostBatch& hb, const Compiled& c, PackedBatch& pb) 
     g.num = reinterpret_cast<const int64_t*>(pack_put(a, hb.cols[i].num));
     g.boff = reinterpret_cast<const uint32_t*>(pack_put(a, hb.cols[i].boff));
     g.bytes = reinterpret_cast<const uint8_t*>(pack_put(a, hb.cols[i].bytes));
+    g.head = reinterpret_cast<const uint32_t*>(pack_put(a, hb.cols[i].head));
   }
   std::vector<GkScope> scopes(hb.scope_off.size());
   for (size_t s = 0; s < scopes.size(); ++s) {
@@ -136,6 +137,7 @@ inline GkBatch rebase_batch(PackedBatch& pb, uint8_t* host_image, const uint8_t*
     g.num = reinterpret_cast<const int64_t*>(base + reinterpret_cast<size_t>(g.num));
     g.boff = reinterpret_cast<const uint32_t*>(base + reinterpret_cast<size_t>(g.boff));
     g.bytes = base + reinterpret_cast<size_t>(g.bytes);
+    g.head = reinterpret_cast<const uint32_t*>(base + reinterpret_cast<size_t>(g.head));
   }
   GkScope* scopes = reinterpret_cast<GkScope*>(host_image + pb.scopes_off);
   for (uint32_t s = 0; s < h.nscopes; ++s) scopes[s].off = reinterpret_cast<const uint32_t*>(base + reinterpret_cast<size_t>(scopes[s].off));

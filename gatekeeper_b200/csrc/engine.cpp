@@ -473,6 +473,7 @@ void Engine::compile_locked() {
   out->ops = std::move(pb.ops);
   out->items = std::move(pb.items);
   out->phase_off = std::move(pb.phase_off);
+  out->outs = std::move(pb.outs);
   out->slot_level = std::move(pb.slot_level);
   out->pool = std::move(pb.pool);
   out->cbytes = std::move(pb.cbytes);
@@ -786,6 +787,15 @@ struct Flattener {
       if (v && v->t == VT::Str) hc.bytes.insert(hc.bytes.end(), v->s.begin(), v->s.end());
       hc.boff.push_back((uint32_t)hc.bytes.size());
     }
+    if (enc & GK_ENC_HEAD) {
+      uint32_t h[GK_HEAD_WORDS] = {0, 0, 0, 0, 0, 0, 0, 0};
+      if (v && v->t == VT::Str) {
+        size_t n = std::min<size_t>(v->s.size(), GK_HEAD_BYTES);
+        memcpy(h, v->s.data(), n);
+        reinterpret_cast<uint8_t*>(h)[GK_HEAD_WORDS * 4 - 1] = (uint8_t)std::min<size_t>(v->s.size(), 255);
+      }
+      hc.head.insert(hc.head.end(), h, h + GK_HEAD_WORDS);
+    }
   }
 
   void add(const ObjIn& in) {
@@ -967,6 +977,7 @@ std::shared_ptr<HostBatch> Engine::flatten(const ObjIn* objs, size_t n, const Co
       append(hb.cols[i].num, q.cols[i].num);
       if (c.schema.cols[i].enc & GK_ENC_BYTES) append_off(hb.cols[i].boff, q.cols[i].boff, 1);
       append(hb.cols[i].bytes, q.cols[i].bytes);
+      append(hb.cols[i].head, q.cols[i].head);
     }
   }
   if (any_old) {
@@ -990,7 +1001,7 @@ std::shared_ptr<HostBatch> Engine::flatten(const ObjIn* objs, size_t n, const Co
   sz(hb.flags), sz(hb.kind_sid), sz(hb.group_sid), sz(hb.nsname_sid), sz(hb.name_off), sz(hb.gen_off), sz(hb.lbl_off), sz(hb.lbl_kv);
   sz(hb.name_bytes), sz(hb.gen_bytes), sz(hb.nsrow), sz(hb.nsl_off), sz(hb.nsl_kv);
   for (size_t s = 1; s < nscopes; ++s) sz(hb.scope_off[s]);
-  for (auto& col : hb.cols) sz(col.vt), sz(col.sid), sz(col.num), sz(col.boff), sz(col.bytes);
+  for (auto& col : hb.cols) sz(col.vt), sz(col.sid), sz(col.num), sz(col.boff), sz(col.bytes), sz(col.head);
   hb.alg_bytes = b;
   return out;
 }

@@ -37,6 +37,7 @@ struct HostColumn {
   std::vector<int64_t> num;
   std::vector<uint32_t> boff;   // rows + 1
   std::vector<uint8_t> bytes;
+  std::vector<uint32_t> head;   // rows * GK_HEAD_WORDS (GK_ENC_HEAD)
 };
 
 struct HostBatch {
@@ -87,6 +88,7 @@ struct Compiled {
   Schema schema;
   std::vector<GkOp> ops;                       // the joint netlist (program.h)
   std::vector<uint32_t> items, phase_off;      // work items per dependency phase
+  std::vector<GkOutEnt> outs;                  // per constraint: result / match / error slots
   std::vector<uint8_t> slot_level;             // scope of each shared-memory slot
   std::vector<uint32_t> pool;
   std::vector<uint8_t> cbytes;

@@ -95,12 +95,14 @@ class CudaBackend : public Backend {
     };
     up(c.ops.data(), c.ops.size() * sizeof(GkOp), (void**)&d_ops_);
     up(c.items.data(), c.items.size() * 4, (void**)&d_items_);
+    up(c.outs.data(), c.outs.size() * sizeof(GkOutEnt), (void**)&d_outs_);
     up(c.phase_off.data(), c.phase_off.size() * 4, (void**)&d_phase_off_);
     up(c.match.data(), c.match.size() * sizeof(GkMatch), (void**)&d_match_);
     up(c.pool.data(), c.pool.size() * 4, (void**)&d_pool_);
     up(c.cbytes.data(), c.cbytes.size(), (void**)&d_cbytes_);
     prog_.ops = d_ops_;
     prog_.items = d_items_;
+    prog_.outs = d_outs_;
     prog_.phase_off = d_phase_off_;
     prog_.match = d_match_;
     prog_.pool = d_pool_;
@@ -246,7 +248,7 @@ class CudaBackend : public Backend {
     auto r16 = [](size_t x) { return (x + 15) / 16 * 16; };
     const size_t NS = nscopes_;
     size_t smem = 3 * r16((size_t)C * 4) + 2 * r16(NS * 4) + r16((size_t)kMaxPhases * 4) + r16((size_t)(prog_.nphases + 1) * 4) +
-                  r16((size_t)prog_.nslots * 4) + 2 * r16((size_t)kTile * db->words * 4) + r16((size_t)db->slot_words * 4) +
+                  r16((size_t)prog_.nslots * 4) + r16((size_t)C * sizeof(GkOutEnt)) + r16((size_t)db->slot_words * 4) +
                   r16((size_t)prog_.nops * sizeof(GkOp)) + r16((size_t)prog_.nitems * 4) + r16((size_t)prog_.nmatch * sizeof(GkMatch)) +
                   r16((size_t)ncols_ * sizeof(GkColumn)) + r16(NS * sizeof(GkScope)) + r16((size_t)prog_.npool * 4) + r16((size_t)prog_.ncbytes) + 64;
     if (smem > max_smem_)
@@ -325,7 +327,7 @@ class CudaBackend : public Backend {
  private:
   static constexpr uint32_t kErrCap = 1u << 20;
   void free_tables() {
-    void** ptrs[] = {(void**)&d_ops_, (void**)&d_items_, (void**)&d_phase_off_, (void**)&d_match_, (void**)&d_pool_, (void**)&d_cbytes_};
+    void** ptrs[] = {(void**)&d_outs_, (void**)&d_ops_, (void**)&d_items_, (void**)&d_phase_off_, (void**)&d_match_, (void**)&d_pool_, (void**)&d_cbytes_};
     for (auto pp : ptrs) {
       if (*pp) cudaFree(*pp);
       *pp = nullptr;
@@ -343,6 +345,7 @@ class CudaBackend : public Backend {
   uint32_t ncols_ = 0, nscopes_ = 0;
   GkOp* d_ops_ = nullptr;
   uint32_t* d_items_ = nullptr;
+  GkOutEnt* d_outs_ = nullptr;
   uint32_t* d_phase_off_ = nullptr;
   GkMatch* d_match_ = nullptr;
   uint32_t* d_pool_ = nullptr;

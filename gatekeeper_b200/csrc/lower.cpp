@@ -3,6 +3,7 @@
 #include "lower.hpp"
 
 #include <algorithm>
+#include <cstring>
 #include <functional>
 #include <set>
 
@@ -586,7 +587,12 @@ class Lowerer {
     if (!num_fits_i64(k->n, &dummy)) unsupported("ordered comparison against a parameter outside int64", line);
     return f_atom(GK_OP_NUM_CMP, schema_.col_for(c, GK_ENC_VT | GK_ENC_NUM), k, cmp);
   }
-  FP a_strop(int op, const CP& c, const VP& k) { return f_atom(op, schema_.col_for(c, GK_ENC_VT | GK_ENC_BYTES), k); }
+  FP a_strop(int op, const CP& c, const VP& k) {
+    // prefix tests run on the fixed-width HEAD record (plus the byte pool for prefixes longer than 31 bytes)
+    if (op == GK_OP_PREFIX) return f_atom(GK_OP_ANYPREFIX, schema_.col_for(c, GK_ENC_VT | GK_ENC_BYTES | GK_ENC_HEAD), v_arr({k}));
+    if (op == GK_OP_ANYPREFIX) return f_atom(op, schema_.col_for(c, GK_ENC_VT | GK_ENC_BYTES | GK_ENC_HEAD), k);
+    return f_atom(op, schema_.col_for(c, GK_ENC_VT | GK_ENC_BYTES), k);
+  }
 
   FP defined_cond(const SymVal& v) {
     switch (v.k) {
@@ -1827,13 +1833,25 @@ void NetBuilder::build(const std::vector<FP>& formulas, const std::vector<uint32
               w3 = n.imm;
               break;
             }
-            case GK_OP_PREFIX:
             case GK_OP_SUFFIX:
             case GK_OP_CONTAINS:
               w2 = add_bytes(n.cval->s);
               w3 = (uint32_t)n.cval->s.size();
               break;
-            case GK_OP_ANYPREFIX:
+            case GK_OP_ANYPREFIX: {
+              std::vector<uint32_t> ent;
+              for (auto& v : n.cval->items) {
+                uint32_t h[GK_HEAD_WORDS] = {0, 0, 0, 0, 0, 0, 0, 0};
+                memcpy(h, v->s.data(), std::min<size_t>(v->s.size(), GK_HEAD_BYTES));
+                ent.push_back((uint32_t)v->s.size());
+                ent.push_back(add_bytes(v->s));
+                ent.insert(ent.end(), h, h + GK_HEAD_WORDS);
+              }
+              w2 = (uint32_t)pool.size();
+              w3 = (uint32_t)n.cval->items.size();
+              pool.insert(pool.end(), ent.begin(), ent.end());
+              break;
+            }
             case GK_OP_ANYSUFFIX: {
               std::vector<uint32_t> ent;
               for (auto& v : n.cval->items) {
@@ -1877,17 +1895,15 @@ void NetBuilder::build(const std::vector<FP>& formulas, const std::vector<uint32
     flush_phase(cur_phase);
   }
   // the error placeholder slots must exist even if their phase-0 allocation happened above (it did)
+  this->outs.clear();
   for (size_t c = 0; c < outs.size(); ++c) {
-    GkOp op{};
-    op.w0 = GK_N_OUT;
-    uint32_t prog = outs[c].prog >= 0 ? (uint32_t)N[outs[c].prog].slot : 0u;
-    op.w1 = prog | ((uint32_t)N[match_node[match_id[c]]].slot << 16);
-    op.w2 = (uint32_t)c;
-    op.w3 = (uint32_t)N[err_node[match_id[c]]].slot | (outs[c].flags << 16);
-    add_item(100, 1);
-    ops.push_back(op);
+    GkOutEnt e{};
+    e.prog_slot = outs[c].prog >= 0 ? (uint16_t)N[outs[c].prog].slot : (uint16_t)0;
+    e.match_slot = (uint16_t)N[match_node[match_id[c]]].slot;
+    e.err_slot = (uint16_t)N[err_node[match_id[c]]].slot;
+    e.flags = (uint16_t)outs[c].flags;
+    this->outs.push_back(e);
   }
-  flush_phase(cur_phase);
   phase_off.push_back((uint32_t)items.size());
   ops.push_back(GkOp{GK_N_END, 0, 0, 0});
   n_phases = phase_off.size() - 1;

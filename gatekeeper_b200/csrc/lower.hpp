@@ -97,6 +97,7 @@ struct NetBuilder {
   std::vector<GkOp> ops;
   std::vector<uint32_t> items;           // work items (op | part<<20 | nparts<<26), grouped by phase
   std::vector<uint32_t> phase_off;       // [nphases + 1]
+  std::vector<GkOutEnt> outs;            // per constraint
   std::vector<uint8_t> slot_level;       // scope id of each shared-memory slot
   std::vector<uint32_t> pool;
   std::vector<uint8_t> cbytes;

@@ -19,7 +19,10 @@ enum { GK_VT_UNDEF = 0, GK_VT_NULL = 1, GK_VT_FALSE = 2, GK_VT_TRUE = 3, GK_VT_N
        GK_VT_ARR = 6, GK_VT_OBJ = 7, GK_VT_SET = 8, GK_VT_NUM_INEXACT = 9 /* number not representable as i64 */ };
 
 // ---- column encodings (bitmask)
-enum { GK_ENC_VT = 1, GK_ENC_SID = 2, GK_ENC_NUM = 4, GK_ENC_BYTES = 8 };
+enum { GK_ENC_VT = 1, GK_ENC_SID = 2, GK_ENC_NUM = 4, GK_ENC_BYTES = 8,
+       GK_ENC_HEAD = 16 /* fixed 32-byte record per row: the first 31 bytes of the string (zero padded) + min(len, 255) */ };
+#define GK_HEAD_WORDS 8
+#define GK_HEAD_BYTES 31
 
 #define GK_SID_UNDEF 0u          /* intern id 0 is reserved: "no value" */
 #define GK_NONE 0xFFFFFFFFu
@@ -35,6 +38,8 @@ typedef struct {
   const int64_t* num;      // [rows]
   const uint32_t* boff;    // [rows+1]
   const uint8_t* bytes;
+  const uint32_t* head;    // [rows * GK_HEAD_WORDS]
+  const void* pad_;        // keeps the struct a multiple of 16 bytes (it is staged with 16-byte copies)
 } GkColumn;
 
 typedef struct {
@@ -125,9 +130,14 @@ enum {
   GK_N_BCAST = 5,   // level = child scope (rows written); w1 = input slot at the parent level
   GK_N_ACC = 6,     // level = child scope (rows read); out at the parent level; w1 = input slot
   GK_N_MATCH = 7,   // w1 = error-column slot ; w2 = match block id
-  GK_N_OUT = 8,     // w1 = program slot | match slot<<16 ; w2 = constraint index ; w3 = error slot | flags<<16
-                    //   flags: 1 = program is constant TRUE, 2 = constant FALSE (program slot ignored)
 };
+
+// per constraint: where its result comes from.  After the last phase one pass over the tile's objects gathers bit c of
+// every constraint into the object-major bitmap words and writes them straight to HBM (coalesced).
+typedef struct {
+  uint16_t prog_slot, match_slot, err_slot;
+  uint16_t flags;            // 1 = program is constant TRUE, 2 = constant FALSE (prog_slot ignored)
+} GkOutEnt;
 
 // atom ops (w1 low byte of an ATOM)
 enum {
@@ -137,11 +147,11 @@ enum {
   GK_OP_SID_EQ = 4,     // sid == w2
   GK_OP_SID_IN = 5,     // sid in pool[w2 .. w2+w3) (sorted)
   GK_OP_NUM_CMP = 6,    // w3 = GK_CMP_*; i64 constant at pool[w2], pool[w2+1] (lo, hi); OPA cross-type ordering
-  GK_OP_PREFIX = 7,     // vt == str && bytes startswith cbytes[w2 .. w2+w3)
+  GK_OP_PREFIX = 7,     // (lowered as ANYPREFIX with one entry)
   GK_OP_SUFFIX = 8,
   GK_OP_CONTAINS = 9,
-  GK_OP_ANYPREFIX = 10, // pool[w2 ..]: w3 entries of [byte_off, len]
-  GK_OP_ANYSUFFIX = 11,
+  GK_OP_ANYPREFIX = 10, // pool[w2 ..]: w3 entries of [len, byte_off, 8 words = first 32 bytes zero padded]; uses the HEAD record
+  GK_OP_ANYSUFFIX = 11, // pool[w2 ..]: w3 entries of [byte_off, len]
 };
 enum { GK_CMP_LT = 0, GK_CMP_LE = 1, GK_CMP_GT = 2, GK_CMP_GE = 3, GK_CMP_EQ = 4, GK_CMP_NE = 5 };
 enum { GK_G_OR = 1, GK_G_NEG_A = 2, GK_G_NEG_B = 4, GK_G_NEG_OUT = 8 };
@@ -158,6 +168,7 @@ typedef struct {
   const GkOp* ops;           // [nops]
   const uint32_t* items;     // [nitems] work items: op index | part<<20 | nparts<<26, heaviest first inside a phase
   const uint32_t* phase_off; // [nphases + 1] item ranges of the phases
+  const GkOutEnt* outs;      // [nconstraints]
   const uint8_t* slot_level; // [nslots] scope id of each slot
   const uint32_t* cons_match;// [nconstraints] match block id
   const GkMatch* match;      // [nmatch]

@@ -103,6 +103,44 @@ __device__ __forceinline__ void atom_rows(const GkColumn& c, uint32_t aop, uint3
       GK_ATOM_LOOP(sid[row] == a)
       break;
     }
+    case GK_OP_ANYPREFIX: {
+      // two 128-bit loads fetch the row's 32-byte HEAD record (coalesced: 1 KB per warp); every prefix of the list is
+      // then tested with masked word compares against constants broadcast from shared memory
+      const uint8_t* vt = c.vt;
+      const uint4* head = reinterpret_cast<const uint4*>(c.head);
+      const uint32_t* ent = pool + a;
+      bool all_short = true;
+      for (uint32_t j = 0; j < b; ++j) all_short = all_short && ent[j * (2 + GK_HEAD_WORDS)] <= GK_HEAD_BYTES;
+      if (!all_short) {
+        GK_ATOM_LOOP(gk_atom(c, row, aop, a, b, pool, cbytes))
+        break;
+      }
+      for (uint32_t r = w0 * 32u + lane; r < w1 * 32u; r += 32u) {
+        bool v = false;
+        if (r < cnt && vt[lo + r] == GK_VT_STR) {
+          const uint4 h0 = head[2 * (size_t)(lo + r)], h1 = head[2 * (size_t)(lo + r) + 1];
+          const uint32_t h[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+          const uint32_t lenb = h1.w >> 24;
+          for (uint32_t j = 0; j < b && !v; ++j) {
+            const uint32_t* e = ent + j * (2 + GK_HEAD_WORDS);
+            const uint32_t L = e[0];
+            bool ok = lenb >= L;
+#pragma unroll
+            for (uint32_t w = 0; w < GK_HEAD_WORDS; ++w) {
+              if (w * 4u < L) {
+                const uint32_t nb = L - w * 4u;
+                const uint32_t mask = nb >= 4u ? 0xffffffffu : ((1u << (8u * nb)) - 1u);
+                ok = ok && (((h[w] ^ e[2 + w]) & mask) == 0u);
+              }
+            }
+            v = ok;
+          }
+        }
+        const uint32_t wd = __ballot_sync(0xffffffffu, v);
+        if (lane == 0) out[r >> 5] = wd;
+      }
+      break;
+    }
     default: {
       GK_ATOM_LOOP(gk_atom(c, row, aop, a, b, pool, cbytes))
       break;
@@ -129,8 +167,7 @@ __global__ void __launch_bounds__(kThreads) gk_eval_kernel(const KParams p) {
   uint32_t* s_ctr = static_cast<uint32_t*>(take((size_t)kMaxPhases * 4));
   uint32_t* s_poff = static_cast<uint32_t*>(take((size_t)(NP + 1) * 4));
   uint32_t* s_soff = static_cast<uint32_t*>(take((size_t)p.prog.nslots * 4));
-  uint32_t* res_v = static_cast<uint32_t*>(take((size_t)p.tile * W * 4));
-  uint32_t* res_e = static_cast<uint32_t*>(take((size_t)p.tile * W * 4));
+  GkOutEnt* outs = static_cast<GkOutEnt*>(take((size_t)C * sizeof(GkOutEnt)));
   uint32_t* slots = static_cast<uint32_t*>(take((size_t)p.slot_words * 4));
   GkOp* ops = static_cast<GkOp*>(take((size_t)p.prog.nops * sizeof(GkOp)));
   uint32_t* items = static_cast<uint32_t*>(take((size_t)p.prog.nitems * 4));
@@ -147,6 +184,7 @@ __global__ void __launch_bounds__(kThreads) gk_eval_kernel(const KParams p) {
   }
   for (uint32_t i = threadIdx.x; i < p.prog.nslots; i += blockDim.x) s_soff[i] = p.slot_off[i];
   for (uint32_t i = threadIdx.x; i <= NP; i += blockDim.x) s_poff[i] = p.prog.phase_off[i];
+  stage(outs, p.prog.outs, ((size_t)C * sizeof(GkOutEnt) + 15) / 16 * 16);
   stage(ops, p.prog.ops, ((size_t)p.prog.nops * sizeof(GkOp) + 15) / 16 * 16);
   stage(items, p.prog.items, ((size_t)p.prog.nitems * 4 + 15) / 16 * 16);
   stage(match, p.prog.match, ((size_t)p.prog.nmatch * sizeof(GkMatch) + 15) / 16 * 16);
@@ -167,10 +205,6 @@ __global__ void __launch_bounds__(kThreads) gk_eval_kernel(const KParams p) {
       s_cnt[s] = b - a;
     }
     for (uint32_t i = threadIdx.x; i < NP; i += blockDim.x) s_ctr[i] = 0;
-    for (uint32_t i = threadIdx.x; i < p.tile * W; i += blockDim.x) {
-      res_v[i] = 0;
-      res_e[i] = 0;
-    }
     __syncthreads();
     const uint32_t nobj = s_cnt[0], obj0 = s_lo[0];
 
@@ -239,8 +273,14 @@ __global__ void __launch_bounds__(kThreads) gk_eval_kernel(const KParams p) {
               bool any = false;
               if (r < pcnt) {
                 const uint32_t a = coff[r] - clo, b = coff[r + 1] - clo;
-                if (b > a)
-                  for (uint32_t w = a >> 5; w <= (b - 1u) >> 5 && !any; ++w) any = (in[w] & range_mask(w, a, b)) != 0u;
+                if (b > a) {
+                  if ((a >> 5) == ((b - 1u) >> 5)) {   // the usual case: a handful of children inside one word
+                    const uint32_t nb = b - a;
+                    any = (in[a >> 5] & ((nb == 32u ? 0xffffffffu : ((1u << nb) - 1u)) << (a & 31u))) != 0u;
+                  } else {
+                    for (uint32_t w = a >> 5; w <= (b - 1u) >> 5 && !any; ++w) any = (in[w] & range_mask(w, a, b)) != 0u;
+                  }
+                }
               }
               const uint32_t w = __ballot_sync(FULL, any);
               if (lane == 0) out[r >> 5] = w;
@@ -270,40 +310,52 @@ __global__ void __launch_bounds__(kThreads) gk_eval_kernel(const KParams p) {
             }
             break;
           }
-          case GK_N_OUT: {
-            const uint32_t c = op.w2, flags = op.w3 >> 16;
-            if (!s_act[c]) break;
-            const uint32_t* prog = slots + s_soff[op.w1 & 0xffffu];
-            const uint32_t* mt = slots + s_soff[op.w1 >> 16];
-            const uint32_t* er = slots + s_soff[op.w3 & 0xffffu];
-            const uint32_t bit = 1u << (c & 31u), wi = c >> 5;
-            uint32_t nv = 0, ne = 0;
-            for (uint32_t i = 0; i < ((nobj + 31u) >> 5); ++i) {
-              const uint32_t valid = range_mask(i, 0u, nobj);
-              const uint32_t pv = (flags & 1u) ? FULL : (flags & 2u) ? 0u : prog[i];
-              const uint32_t v = pv & mt[i] & valid, e = er[i] & valid;
-              const uint32_t o = i * 32u + lane;
-              if ((v >> lane) & 1u) atomicOr(&res_v[o * W + wi], bit);
-              if ((e >> lane) & 1u) atomicOr(&res_e[o * W + wi], bit);
-              nv += __popc(v);
-              ne += __popc(e);
-            }
-            if (lane == 0) {
-              if (nv) atomicAdd(&s_tot[c], nv);
-              if (ne) atomicAdd(&s_err[c], ne);
-            }
-            break;
-          }
           default: break;
         }
       }
       __syncthreads();
     }
-    // ---- the tile's bitmap rows are contiguous in the object-major output: coalesced copy out
-    const size_t base = (size_t)obj0 * W;
-    for (uint32_t i = threadIdx.x; i < nobj * W; i += blockDim.x) {
-      p.out.viol[base + i] = res_v[i];
-      p.out.err[base + i] = res_e[i];
+    // ---- gather: one thread per object collects bit c of every constraint (the column words are broadcast reads) and
+    // writes its object-major bitmap words; a warp covers 32 consecutive objects = one contiguous run of the output
+    for (uint32_t o = threadIdx.x; o < ((nobj + 31u) & ~31u); o += blockDim.x) {
+      const uint32_t wdx = o >> 5, sh = o & 31u;
+      for (uint32_t w = 0; w < W; ++w) {
+        uint32_t vb = 0, eb = 0;
+        const uint32_t cend = min(C, (w + 1u) * 32u);
+        for (uint32_t c = w * 32u; c < cend; ++c) {
+          if (!s_act[c]) continue;
+          const GkOutEnt oe = outs[c];
+          const uint32_t pv = (oe.flags & 1u) ? FULL : (oe.flags & 2u) ? 0u : slots[s_soff[oe.prog_slot] + wdx];
+          const uint32_t v = pv & slots[s_soff[oe.match_slot] + wdx];
+          const uint32_t e = slots[s_soff[oe.err_slot] + wdx];
+          vb |= ((v >> sh) & 1u) << (c & 31u);
+          eb |= ((e >> sh) & 1u) << (c & 31u);
+        }
+        if (o < nobj) {
+          p.out.viol[(size_t)(obj0 + o) * W + w] = vb;
+          p.out.err[(size_t)(obj0 + o) * W + w] = eb;
+        }
+      }
+    }
+    // per-constraint totals: popcount of the result columns (a warp per constraint, a lane per word)
+    for (uint32_t c = threadIdx.x >> 5; c < C; c += kWarps) {
+      if (!s_act[c]) continue;
+      const GkOutEnt oe = outs[c];
+      uint32_t nv = 0, ne = 0;
+      for (uint32_t i = lane; i < ((nobj + 31u) >> 5); i += 32u) {
+        const uint32_t valid = range_mask(i, 0u, nobj);
+        const uint32_t pv = (oe.flags & 1u) ? FULL : (oe.flags & 2u) ? 0u : slots[s_soff[oe.prog_slot] + i];
+        nv += __popc(pv & slots[s_soff[oe.match_slot] + i] & valid);
+        ne += __popc(slots[s_soff[oe.err_slot] + i] & valid);
+      }
+      for (int d = 16; d; d >>= 1) {
+        nv += __shfl_xor_sync(FULL, nv, d);
+        ne += __shfl_xor_sync(FULL, ne, d);
+      }
+      if (lane == 0) {
+        if (nv) atomicAdd(&s_tot[c], nv);
+        if (ne) atomicAdd(&s_err[c], ne);
+      }
     }
     __syncthreads();
   }

@@ -222,22 +222,48 @@ GK_HD bool gk_atom(const GkColumn& c, uint32_t row, uint32_t op, uint32_t w2, ui
       }
       return gk_cmp_apply(w3, gk_vt_rank(vt) < 2 ? -1 : 1);
     }
-    case GK_OP_PREFIX:
     case GK_OP_SUFFIX:
     case GK_OP_CONTAINS: {
       if (c.vt[row] != GK_VT_STR) return false;
       const uint32_t a = c.boff[row], sl = c.boff[row + 1] - a;
       const uint8_t* s = c.bytes + a;
-      return op == GK_OP_PREFIX ? gk_prefix(s, sl, cbytes + w2, w3) : op == GK_OP_SUFFIX ? gk_suffix(s, sl, cbytes + w2, w3) : gk_contains(s, sl, cbytes + w2, w3);
+      return op == GK_OP_SUFFIX ? gk_suffix(s, sl, cbytes + w2, w3) : gk_contains(s, sl, cbytes + w2, w3);
     }
-    case GK_OP_ANYPREFIX:
+    case GK_OP_ANYPREFIX: {
+      // prefix tests run on the fixed-width HEAD record: one aligned 32-byte load per row, word compares under a
+      // length mask; only prefixes longer than 31 bytes continue in the byte pool
+      if (c.vt[row] != GK_VT_STR) return false;
+      uint32_t h[GK_HEAD_WORDS];
+      const uint32_t* hp = c.head + (size_t)row * GK_HEAD_WORDS;
+      for (int i = 0; i < GK_HEAD_WORDS; ++i) h[i] = hp[i];
+      const uint32_t lenb = h[GK_HEAD_WORDS - 1] >> 24;   // min(len, 255)
+      for (uint32_t j = 0; j < w3; ++j) {
+        const uint32_t* e = pool + w2 + (size_t)j * (2 + GK_HEAD_WORDS);
+        const uint32_t L = e[0];
+        const uint32_t Lh = L < GK_HEAD_BYTES ? L : GK_HEAD_BYTES;
+        if (lenb < Lh) continue;
+        bool ok = true;
+        for (uint32_t w = 0; w < GK_HEAD_WORDS && ok; ++w) {
+          if (w * 4u >= Lh) break;
+          const uint32_t nb = Lh - w * 4u;
+          const uint32_t mask = nb >= 4u ? 0xffffffffu : ((1u << (8u * nb)) - 1u);
+          ok = ((h[w] ^ e[2 + w]) & mask) == 0u;
+        }
+        if (ok && L > GK_HEAD_BYTES) {
+          const uint32_t a = c.boff[row], sl = c.boff[row + 1] - a;
+          ok = gk_prefix(c.bytes + a, sl, cbytes + e[1], L);
+        }
+        if (ok) return true;
+      }
+      return false;
+    }
     case GK_OP_ANYSUFFIX: {
       if (c.vt[row] != GK_VT_STR) return false;
       const uint32_t a = c.boff[row], sl = c.boff[row + 1] - a;
       const uint8_t* s = c.bytes + a;
       for (uint32_t j = 0; j < w3; ++j) {
         const uint32_t po = pool[w2 + 2 * j], pl = pool[w2 + 2 * j + 1];
-        if (op == GK_OP_ANYPREFIX ? gk_prefix(s, sl, cbytes + po, pl) : gk_suffix(s, sl, cbytes + po, pl)) return true;
+        if (gk_suffix(s, sl, cbytes + po, pl)) return true;
       }
       return false;
     }

@@ -116,24 +116,23 @@ class HostEmuBackend : public Backend {
           }
           break;
         }
-        case GK_N_OUT: {
-          const uint32_t cix = op.w2, flags = op.w3 >> 16;
-          if (!active[cix]) break;
-          const auto &prog = slot[op.w1 & 0xffffu], &mt = slot[op.w1 >> 16], &er = slot[op.w3 & 0xffffu];
-          for (uint32_t obj = 0; obj < n; ++obj) {
-            bool pv = (flags & 1) ? true : (flags & 2) ? false : prog[obj] != 0;
-            if (pv && mt[obj]) {
-              out.viol[(size_t)obj * W + cix / 32] |= 1u << (cix & 31);
-              out.totals[cix]++;
-            }
-            if (er[obj]) {
-              out.err[(size_t)obj * W + cix / 32] |= 1u << (cix & 31);
-              out.err_totals[cix]++;
-            }
-          }
-          break;
-        }
         default: throw BackendError{"hostemu: unknown netlist op"};
+      }
+    }
+    for (uint32_t cix = 0; cix < C; ++cix) {
+      if (!active[cix]) continue;
+      const GkOutEnt& oe = c.outs[cix];
+      const auto &prog = slot[oe.prog_slot], &mt = slot[oe.match_slot], &er = slot[oe.err_slot];
+      for (uint32_t obj = 0; obj < n; ++obj) {
+        bool pv = (oe.flags & 1) ? true : (oe.flags & 2) ? false : prog[obj] != 0;
+        if (pv && mt[obj]) {
+          out.viol[(size_t)obj * W + cix / 32] |= 1u << (cix & 31);
+          out.totals[cix]++;
+        }
+        if (er[obj]) {
+          out.err[(size_t)obj * W + cix / 32] |= 1u << (cix & 31);
+          out.err_totals[cix]++;
+        }
       }
     }
     out.kernel_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
