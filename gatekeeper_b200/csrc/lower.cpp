@@ -1670,6 +1670,33 @@ struct Net {
 
 }  // namespace
 
+// E[s](A) | E[s](B) == E[s](A | B)   and   !E[s](A) & !E[s](B) == !E[s](A | B): fewer segmented reductions, and the
+// OR happens on packed child-level words
+static FP merge_exists(const FP& f) {
+  if (f->kids.empty()) return f;
+  std::vector<FP> kids;
+  for (auto& k : f->kids) kids.push_back(merge_exists(k));
+  if (f->k == Formula::Not) return f_not(kids[0]);
+  if (f->k == Formula::Exists) return f_exists(f->scope, kids[0]);
+  const bool is_or = f->k == Formula::Or;
+  std::map<int, std::vector<FP>> groups;
+  std::vector<FP> rest;
+  for (auto& k : kids) {
+    if (is_or && k->k == Formula::Exists) groups[k->scope].push_back(k->kids[0]);
+    else if (!is_or && k->k == Formula::Not && k->kids[0]->k == Formula::Exists) groups[k->kids[0]->scope].push_back(k->kids[0]->kids[0]);
+    else rest.push_back(k);
+  }
+  FP out = is_or ? f_false() : f_true();
+  for (auto& k : rest) out = is_or ? f_or(out, k) : f_and(out, k);
+  for (auto& g : groups) {
+    FP body = f_false();
+    for (auto& b : g.second) body = f_or(body, b);
+    FP e = f_exists(g.first, body);
+    out = is_or ? f_or(out, e) : f_and(out, f_not(e));
+  }
+  return out;
+}
+
 void NetBuilder::build(const std::vector<FP>& formulas, const std::vector<uint32_t>& match_id, uint32_t nmatch) {
   Net net(*schema);
   if (schema->scopes.size() > GK_MAX_SCOPES) throw RegoError{"rego_unsupported: too many iteration scopes"};
@@ -1692,7 +1719,7 @@ void NetBuilder::build(const std::vector<FP>& formulas, const std::vector<uint32
   };
   std::vector<Out> outs;
   for (auto& f : formulas) {
-    Ref r = net.build(f);
+    Ref r = net.build(merge_exists(f));
     Out o{-1, 0};
     if (net.is_const(r)) o.flags = net.const_val(r) ? 1u : 2u;
     else {
@@ -1774,9 +1801,14 @@ void NetBuilder::build(const std::vector<FP>& formulas, const std::vector<uint32
       n.slot = alloc(n.level);
       release_at[std::min(n.last_use + 1, out_phase + 1)].push_back(n.slot);
     }
+    std::map<int, std::vector<uint32_t>> acc_groups, bcast_groups;   // scope -> (in slot | out slot << 16)
     for (int id : ids) {
       NNode& n = N[id];
       ++n_nodes;
+      if (n.kind == GK_N_ACC || n.kind == GK_N_BCAST) {
+        (n.kind == GK_N_ACC ? acc_groups : bcast_groups)[n.scope].push_back((uint32_t)N[n.a].slot | ((uint32_t)n.slot << 16));
+        continue;
+      }
       GkOp op{};
       const uint32_t out = (uint32_t)n.slot;
       switch (n.kind) {
@@ -1797,14 +1829,6 @@ void NetBuilder::build(const std::vector<FP>& formulas, const std::vector<uint32
           op.w2 = n.flags;
           op.w3 = (uint32_t)n.ins.size();
           for (auto& in : n.ins) pool.push_back((uint32_t)N[in.first].slot | (in.second ? 0x80000000u : 0u));
-          break;
-        case GK_N_BCAST:
-          op.w0 = GK_N_BCAST | ((uint32_t)n.scope << 8) | (out << 16);
-          op.w1 = (uint32_t)N[n.a].slot;
-          break;
-        case GK_N_ACC:
-          op.w0 = GK_N_ACC | ((uint32_t)n.scope << 8) | (out << 16);
-          op.w1 = (uint32_t)N[n.a].slot;
           break;
         case GK_N_ATOM: {
           ++n_atoms;
@@ -1841,11 +1865,14 @@ void NetBuilder::build(const std::vector<FP>& formulas, const std::vector<uint32
             case GK_OP_ANYPREFIX: {
               std::vector<uint32_t> ent;
               for (auto& v : n.cval->items) {
-                uint32_t h[GK_HEAD_WORDS] = {0, 0, 0, 0, 0, 0, 0, 0};
-                memcpy(h, v->s.data(), std::min<size_t>(v->s.size(), GK_HEAD_BYTES));
+                uint32_t h[GK_HEAD_WORDS] = {0, 0, 0, 0, 0, 0, 0, 0}, m[GK_HEAD_WORDS] = {0, 0, 0, 0, 0, 0, 0, 0};
+                const size_t nb = std::min<size_t>(v->s.size(), GK_HEAD_BYTES);
+                memcpy(h, v->s.data(), nb);
+                memset(m, 0xff, nb);
                 ent.push_back((uint32_t)v->s.size());
                 ent.push_back(add_bytes(v->s));
                 ent.insert(ent.end(), h, h + GK_HEAD_WORDS);
+                ent.insert(ent.end(), m, m + GK_HEAD_WORDS);   // byte masks of the compared prefix
               }
               w2 = (uint32_t)pool.size();
               w3 = (uint32_t)n.cval->items.size();
@@ -1892,6 +1919,19 @@ void NetBuilder::build(const std::vector<FP>& formulas, const std::vector<uint32
       }
       ops.push_back(op);
     }
+    // every EXISTS (and every hoisted broadcast) over the same scope in this phase is ONE op: the child ranges and
+    // their masks are computed once per parent row and applied to all (input, output) column pairs
+    for (int pass = 0; pass < 2; ++pass)
+      for (auto& g : pass == 0 ? acc_groups : bcast_groups) {
+        GkOp op{};
+        op.w0 = (pass == 0 ? GK_N_ACC : GK_N_BCAST) | ((uint32_t)g.first << 8);
+        op.w1 = (uint32_t)pool.size();
+        op.w3 = (uint32_t)g.second.size();
+        pool.insert(pool.end(), g.second.begin(), g.second.end());
+        const uint32_t parts = (pass == 0 && g.second.size() > 8) ? 2 : 1;   // a broadcast zeroes its outputs first: never split
+        add_item(150 + 30 * (uint32_t)g.second.size(), parts);
+        ops.push_back(op);
+      }
     flush_phase(cur_phase);
   }
   // the error placeholder slots must exist even if their phase-0 allocation happened above (it did)

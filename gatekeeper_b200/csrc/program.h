@@ -23,6 +23,7 @@ enum { GK_ENC_VT = 1, GK_ENC_SID = 2, GK_ENC_NUM = 4, GK_ENC_BYTES = 8,
        GK_ENC_HEAD = 16 /* fixed 32-byte record per row: the first 31 bytes of the string (zero padded) + min(len, 255) */ };
 #define GK_HEAD_WORDS 8
 #define GK_HEAD_BYTES 31
+#define GK_PREFIX_ENT (2 + 2 * GK_HEAD_WORDS)
 
 #define GK_SID_UNDEF 0u          /* intern id 0 is reserved: "no value" */
 #define GK_NONE 0xFFFFFFFFu
@@ -127,8 +128,8 @@ enum {
   GK_N_ATOM = 2,    // w1 = atom op | col<<8 ; w2, w3 = operands (see GK_OP_*)
   GK_N_GATE = 3,    // n-ary: pool[w1 .. w1+w3) = input slots (bit 31: negate that input); w2 = flags: 1 OR (else AND), 8 negate out
   GK_N_CONST = 4,   // w1 = 0 / 1
-  GK_N_BCAST = 5,   // level = child scope (rows written); w1 = input slot at the parent level
-  GK_N_ACC = 6,     // level = child scope (rows read); out at the parent level; w1 = input slot
+  GK_N_BCAST = 5,   // level = child scope; pool[w1 .. w1+w3) = (input slot at the parent level | output slot << 16)
+  GK_N_ACC = 6,     // level = child scope; pool[w1 .. w1+w3) = (input slot at the child level | output slot at the parent level << 16)
   GK_N_MATCH = 7,   // w1 = error-column slot ; w2 = match block id
 };
 
@@ -150,7 +151,7 @@ enum {
   GK_OP_PREFIX = 7,     // (lowered as ANYPREFIX with one entry)
   GK_OP_SUFFIX = 8,
   GK_OP_CONTAINS = 9,
-  GK_OP_ANYPREFIX = 10, // pool[w2 ..]: w3 entries of [len, byte_off, 8 words = first 32 bytes zero padded]; uses the HEAD record
+  GK_OP_ANYPREFIX = 10, // pool[w2 ..]: w3 entries of GK_PREFIX_ENT words [len, byte_off, 8 words = first 32 bytes, 8 byte-mask words]
   GK_OP_ANYSUFFIX = 11, // pool[w2 ..]: w3 entries of [byte_off, len]
 };
 enum { GK_CMP_LT = 0, GK_CMP_LE = 1, GK_CMP_GT = 2, GK_CMP_GE = 3, GK_CMP_EQ = 4, GK_CMP_NE = 5 };

@@ -4,14 +4,16 @@
 //     objects; every node of the netlist is a packed bit column of the tile held in shared memory (32 rows/word).
 //   * ATOM  : one warp streams the tile's slice of one feature column -- unit-stride, coalesced loads of 32 rows per
 //             instruction -- compares against the constant and packs the 32 verdicts with one __ballot_sync.
+//             Prefix tests read a fixed 32-byte HEAD record per row with two 128-bit loads and do masked word compares.
 //   * GATE  : n-ary AND/OR on whole words: 32 rows per instruction, operands broadcast from shared memory.
-//   * ACC / BCAST : EXISTS and loop-invariant hoisting as segmented OR / range fill over the CSR child ranges.
+//   * ACC / BCAST : EXISTS and loop-invariant hoisting as segmented OR / range fill over the CSR child ranges; all
+//             reductions over the same scope in a phase share one pass over the ranges.
 //   * MATCH : the spec.match pre-filter, once per DISTINCT match block per object, ballot-packed like an atom.
-//   * OUT   : result = program & match, scattered into the tile's object-major bitmap rows in shared memory, which
-//             are then copied to HBM as one contiguous, coalesced block; per-constraint totals via popc.
+//   * gather: after the last phase a 32x32 bit transpose per warp (32 ballots) turns the per-constraint result columns
+//             into the object-major bitmap rows, which are contiguous in HBM: coalesced stores; totals via popc.
 //   * ops of one dependency phase are independent; warps pull work items (an op, or a row slice of a heavy op,
 //     heaviest first) from a shared-memory counter, and one __syncthreads separates phases.
-// This is integer / byte work bounded by HBM traffic and instruction issue -- nothing here belongs on tensor cores.
+// This is integer / byte work bounded by instruction issue and HBM traffic -- nothing here belongs on tensor cores.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -62,7 +64,7 @@ __device__ __forceinline__ uint32_t range_mask(uint32_t w, uint32_t a, uint32_t 
 // rows [w0*32, min(cnt, w1*32)) of one column, one ballot-packed word per 32 rows.  The op switch is OUTSIDE the row
 // loop: every loop body is a straight load-compare-ballot sequence.
 // Four 32-row groups per trip: the four loads are independent, so four memory requests per lane are in flight
-// before the first compare (the loop is latency-bound otherwise: one warp owns the whole op).
+// before the first compare.
 #define GK_ATOM_LOOP(EXPR)                                                        \
   for (uint32_t r0 = w0 * 32u + lane; r0 < w1 * 32u; r0 += 128u) {                \
     bool v4[4];                                                                   \
@@ -79,6 +81,22 @@ __device__ __forceinline__ uint32_t range_mask(uint32_t w, uint32_t a, uint32_t 
       }                                                                           \
     }                                                                             \
   }
+
+__device__ __forceinline__ bool sid_in_small(const uint32_t* pool, uint32_t a, uint32_t b, uint32_t v) {
+  bool hit = false;
+  for (uint32_t j = 0; j < b; ++j) hit = hit || pool[a + j] == v;
+  return hit;
+}
+
+__device__ __forceinline__ bool num_cmp_row(const uint8_t* vt, const int64_t* num, uint32_t row, int64_t k, uint32_t cmp) {
+  const uint32_t t = vt[row];
+  if (t == GK_VT_NUM) {
+    const int64_t v = num[row];
+    return gk_cmp_apply(cmp, v < k ? -1 : (v > k ? 1 : 0));
+  }
+  if (t == GK_VT_UNDEF || t == GK_VT_NUM_INEXACT) return false;
+  return gk_cmp_apply(cmp, gk_vt_rank(t) < 2 ? -1 : 1);
+}
 
 __device__ __forceinline__ void atom_rows(const GkColumn& c, uint32_t aop, uint32_t a, uint32_t b, const uint32_t* pool, const uint8_t* cbytes,
                                           uint32_t lo, uint32_t cnt, uint32_t w0, uint32_t w1, uint32_t lane, uint32_t* out) {
@@ -103,6 +121,22 @@ __device__ __forceinline__ void atom_rows(const GkColumn& c, uint32_t aop, uint3
       GK_ATOM_LOOP(sid[row] == a)
       break;
     }
+    case GK_OP_SID_IN: {
+      const uint32_t* sid = c.sid;
+      if (b <= 8u) {   // small sets: a broadcast linear scan beats the binary search
+        GK_ATOM_LOOP(sid_in_small(pool, a, b, sid[row]))
+      } else {
+        GK_ATOM_LOOP(gk_atom(c, row, aop, a, b, pool, cbytes))
+      }
+      break;
+    }
+    case GK_OP_NUM_CMP: {
+      const uint8_t* vt = c.vt;
+      const int64_t* num = c.num;
+      const int64_t k = (int64_t)(((uint64_t)pool[a + 1] << 32) | pool[a]);
+      GK_ATOM_LOOP(num_cmp_row(vt, num, row, k, b))
+      break;
+    }
     case GK_OP_ANYPREFIX: {
       // two 128-bit loads fetch the row's 32-byte HEAD record (coalesced: 1 KB per warp); every prefix of the list is
       // then tested with masked word compares against constants broadcast from shared memory
@@ -110,7 +144,7 @@ __device__ __forceinline__ void atom_rows(const GkColumn& c, uint32_t aop, uint3
       const uint4* head = reinterpret_cast<const uint4*>(c.head);
       const uint32_t* ent = pool + a;
       bool all_short = true;
-      for (uint32_t j = 0; j < b; ++j) all_short = all_short && ent[j * (2 + GK_HEAD_WORDS)] <= GK_HEAD_BYTES;
+      for (uint32_t j = 0; j < b; ++j) all_short = all_short && ent[j * GK_PREFIX_ENT] <= GK_HEAD_BYTES;
       if (!all_short) {
         GK_ATOM_LOOP(gk_atom(c, row, aop, a, b, pool, cbytes))
         break;
@@ -119,21 +153,13 @@ __device__ __forceinline__ void atom_rows(const GkColumn& c, uint32_t aop, uint3
         bool v = false;
         if (r < cnt && vt[lo + r] == GK_VT_STR) {
           const uint4 h0 = head[2 * (size_t)(lo + r)], h1 = head[2 * (size_t)(lo + r) + 1];
-          const uint32_t h[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
           const uint32_t lenb = h1.w >> 24;
           for (uint32_t j = 0; j < b && !v; ++j) {
-            const uint32_t* e = ent + j * (2 + GK_HEAD_WORDS);
-            const uint32_t L = e[0];
-            bool ok = lenb >= L;
-#pragma unroll
-            for (uint32_t w = 0; w < GK_HEAD_WORDS; ++w) {
-              if (w * 4u < L) {
-                const uint32_t nb = L - w * 4u;
-                const uint32_t mask = nb >= 4u ? 0xffffffffu : ((1u << (8u * nb)) - 1u);
-                ok = ok && (((h[w] ^ e[2 + w]) & mask) == 0u);
-              }
-            }
-            v = ok;
+            const uint32_t* e = ent + j * GK_PREFIX_ENT;
+            const uint32_t* m = e + 2 + GK_HEAD_WORDS;
+            const uint32_t diff = ((h0.x ^ e[2]) & m[0]) | ((h0.y ^ e[3]) & m[1]) | ((h0.z ^ e[4]) & m[2]) | ((h0.w ^ e[5]) & m[3]) |
+                                  ((h1.x ^ e[6]) & m[4]) | ((h1.y ^ e[7]) & m[5]) | ((h1.z ^ e[8]) & m[6]) | ((h1.w ^ e[9]) & m[7]);
+            v = diff == 0u && lenb >= e[0];
           }
         }
         const uint32_t wd = __ballot_sync(0xffffffffu, v);
@@ -194,7 +220,7 @@ __global__ void __launch_bounds__(kThreads) gk_eval_kernel(const KParams p) {
   stage(cbytes, p.prog.cbytes, ((size_t)p.prog.ncbytes + 15) / 16 * 16);
   __syncthreads();
 
-  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const uint32_t FULL = 0xffffffffu;
 
   for (uint32_t t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
@@ -248,42 +274,55 @@ __global__ void __launch_bounds__(kThreads) gk_eval_kernel(const KParams p) {
             for (uint32_t i = lane; i < words; i += 32u) out[i] = v;
             break;
           }
-          case GK_N_BCAST: {   // parent-level column -> rows of the child scope `level`
-            const uint32_t* in = slots + s_soff[op.w1 & 0xffffu];
-            const uint32_t par = (uint32_t)scopes[level].parent;
+          case GK_N_BCAST: {   // parent-level columns -> rows of the child scope `level`, for every (in, out) pair of the group
+            const uint32_t par = (uint32_t)scopes[level].parent, npair = op.w3;
+            const uint32_t* pairs = pool + op.w1;
             const uint32_t* coff = scopes[level].off + s_lo[par];
             const uint32_t clo = s_lo[level], pcnt = s_cnt[par], words = (s_cnt[level] + 31u) >> 5;
-            for (uint32_t i = lane; i < words; i += 32u) out[i] = 0u;
+            for (uint32_t j = 0; j < npair; ++j) {
+              uint32_t* dst = slots + s_soff[pairs[j] >> 16];
+              for (uint32_t i = lane; i < words; i += 32u) dst[i] = 0u;
+            }
             __syncwarp();
             for (uint32_t r = lane; r < pcnt; r += 32u) {
-              if ((in[r >> 5] >> (r & 31u)) & 1u) {
-                const uint32_t a = coff[r] - clo, b = coff[r + 1] - clo;
-                if (b > a)
-                  for (uint32_t w = a >> 5; w <= (b - 1u) >> 5; ++w) atomicOr(&out[w], range_mask(w, a, b));
+              const uint32_t a = coff[r] - clo, b = coff[r + 1] - clo;
+              if (b <= a) continue;
+              for (uint32_t j = 0; j < npair; ++j) {
+                const uint32_t e = pairs[j];
+                if ((slots[s_soff[e & 0xffffu] + (r >> 5)] >> (r & 31u)) & 1u) {
+                  uint32_t* dst = slots + s_soff[e >> 16];
+                  for (uint32_t w = a >> 5; w <= (b - 1u) >> 5; ++w) atomicOr(&dst[w], range_mask(w, a, b));
+                }
               }
             }
             break;
           }
-          case GK_N_ACC: {     // EXISTS: OR over each parent's child range of the scope `level`
-            const uint32_t* in = slots + s_soff[op.w1 & 0xffffu];
-            const uint32_t par = (uint32_t)scopes[level].parent;
+          case GK_N_ACC: {     // EXISTS: OR over each parent's child range; ranges + masks computed once for the whole group
+            const uint32_t par = (uint32_t)scopes[level].parent, npair = op.w3;
+            const uint32_t* pairs = pool + op.w1;
             const uint32_t* coff = scopes[level].off + s_lo[par];
             const uint32_t clo = s_lo[level], pcnt = s_cnt[par];
-            for (uint32_t r = lane; r < ((pcnt + 31u) & ~31u); r += 32u) {
-              bool any = false;
+            const uint32_t pw = (pcnt + 31u) >> 5;
+            for (uint32_t r = (pw * part / nparts) * 32u + lane; r < (pw * (part + 1u) / nparts) * 32u; r += 32u) {
+              uint32_t a = 0, b = 0;
               if (r < pcnt) {
-                const uint32_t a = coff[r] - clo, b = coff[r + 1] - clo;
-                if (b > a) {
-                  if ((a >> 5) == ((b - 1u) >> 5)) {   // the usual case: a handful of children inside one word
-                    const uint32_t nb = b - a;
-                    any = (in[a >> 5] & ((nb == 32u ? 0xffffffffu : ((1u << nb) - 1u)) << (a & 31u))) != 0u;
-                  } else {
-                    for (uint32_t w = a >> 5; w <= (b - 1u) >> 5 && !any; ++w) any = (in[w] & range_mask(w, a, b)) != 0u;
-                  }
-                }
+                a = coff[r] - clo;
+                b = coff[r + 1] - clo;
               }
-              const uint32_t w = __ballot_sync(FULL, any);
-              if (lane == 0) out[r >> 5] = w;
+              const bool one = b > a && (a >> 5) == ((b - 1u) >> 5);     // the usual case: children inside one word
+              const uint32_t wi = a >> 5;
+              const uint32_t nb = b - a;
+              const uint32_t m = one ? ((nb == 32u ? FULL : ((1u << nb) - 1u)) << (a & 31u)) : 0u;
+              for (uint32_t j = 0; j < npair; ++j) {
+                const uint32_t e = pairs[j];
+                const uint32_t* in = slots + s_soff[e & 0xffffu];
+                bool any = false;
+                if (one) any = (in[wi] & m) != 0u;
+                else if (b > a)
+                  for (uint32_t w = wi; w <= (b - 1u) >> 5 && !any; ++w) any = (in[w] & range_mask(w, a, b)) != 0u;
+                const uint32_t wd = __ballot_sync(FULL, any);
+                if (lane == 0) slots[s_soff[e >> 16] + (r >> 5)] = wd;
+              }
             }
             break;
           }
@@ -315,44 +354,38 @@ __global__ void __launch_bounds__(kThreads) gk_eval_kernel(const KParams p) {
       }
       __syncthreads();
     }
-    // ---- gather: one thread per object collects bit c of every constraint (the column words are broadcast reads) and
-    // writes its object-major bitmap words; a warp covers 32 consecutive objects = one contiguous run of the output
-    for (uint32_t o = threadIdx.x; o < ((nobj + 31u) & ~31u); o += blockDim.x) {
-      const uint32_t wdx = o >> 5, sh = o & 31u;
-      for (uint32_t w = 0; w < W; ++w) {
-        uint32_t vb = 0, eb = 0;
-        const uint32_t cend = min(C, (w + 1u) * 32u);
-        for (uint32_t c = w * 32u; c < cend; ++c) {
-          if (!s_act[c]) continue;
-          const GkOutEnt oe = outs[c];
-          const uint32_t pv = (oe.flags & 1u) ? FULL : (oe.flags & 2u) ? 0u : slots[s_soff[oe.prog_slot] + wdx];
-          const uint32_t v = pv & slots[s_soff[oe.match_slot] + wdx];
-          const uint32_t e = slots[s_soff[oe.err_slot] + wdx];
-          vb |= ((v >> sh) & 1u) << (c & 31u);
-          eb |= ((e >> sh) & 1u) << (c & 31u);
+    // ---- gather: lane l of a warp holds the result word of constraint (32 w + l) for one group of 32 objects; 32 ballots
+    // transpose that 32x32 bit block so that lane o ends up with the bitmap word of object o.  The 32 objects of a group
+    // are consecutive rows of the object-major output: the stores are contiguous.
+    const uint32_t owords = (nobj + 31u) >> 5;
+    for (uint32_t g = warp; g < owords * W; g += kWarps) {
+      const uint32_t wi = g % W, ow = g / W;          // constraint word, object word
+      const uint32_t c = wi * 32u + lane;
+      uint32_t xv = 0, xe = 0;
+      if (c < C && s_act[c]) {
+        const GkOutEnt oe = outs[c];
+        const uint32_t pv = (oe.flags & 1u) ? FULL : (oe.flags & 2u) ? 0u : slots[s_soff[oe.prog_slot] + ow];
+        xv = pv & slots[s_soff[oe.match_slot] + ow];
+        xe = slots[s_soff[oe.err_slot] + ow];
+      }
+      uint32_t yv = 0, ye = 0;
+#pragma unroll
+      for (uint32_t o = 0; o < 32u; ++o) {
+        const uint32_t bv = __ballot_sync(FULL, (xv >> o) & 1u), be = __ballot_sync(FULL, (xe >> o) & 1u);
+        if (lane == o) {
+          yv = bv;
+          ye = be;
         }
-        if (o < nobj) {
-          p.out.viol[(size_t)(obj0 + o) * W + w] = vb;
-          p.out.err[(size_t)(obj0 + o) * W + w] = eb;
-        }
       }
-    }
-    // per-constraint totals: popcount of the result columns (a warp per constraint, a lane per word)
-    for (uint32_t c = threadIdx.x >> 5; c < C; c += kWarps) {
-      if (!s_act[c]) continue;
-      const GkOutEnt oe = outs[c];
-      uint32_t nv = 0, ne = 0;
-      for (uint32_t i = lane; i < ((nobj + 31u) >> 5); i += 32u) {
-        const uint32_t valid = range_mask(i, 0u, nobj);
-        const uint32_t pv = (oe.flags & 1u) ? FULL : (oe.flags & 2u) ? 0u : slots[s_soff[oe.prog_slot] + i];
-        nv += __popc(pv & slots[s_soff[oe.match_slot] + i] & valid);
-        ne += __popc(slots[s_soff[oe.err_slot] + i] & valid);
+      const uint32_t obj = ow * 32u + lane;
+      if (obj < nobj) {
+        p.out.viol[(size_t)(obj0 + obj) * W + wi] = yv;
+        p.out.err[(size_t)(obj0 + obj) * W + wi] = ye;
       }
-      for (int d = 16; d; d >>= 1) {
-        nv += __shfl_xor_sync(FULL, nv, d);
-        ne += __shfl_xor_sync(FULL, ne, d);
-      }
-      if (lane == 0) {
+      // totals: every lane's column word covers 32 objects of ITS constraint
+      const uint32_t valid = range_mask(ow, 0u, nobj);
+      const uint32_t nv = __popc(xv & valid), ne = __popc(xe & valid);
+      if (c < C) {
         if (nv) atomicAdd(&s_tot[c], nv);
         if (ne) atomicAdd(&s_err[c], ne);
       }

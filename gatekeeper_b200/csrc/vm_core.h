@@ -238,17 +238,12 @@ GK_HD bool gk_atom(const GkColumn& c, uint32_t row, uint32_t op, uint32_t w2, ui
       for (int i = 0; i < GK_HEAD_WORDS; ++i) h[i] = hp[i];
       const uint32_t lenb = h[GK_HEAD_WORDS - 1] >> 24;   // min(len, 255)
       for (uint32_t j = 0; j < w3; ++j) {
-        const uint32_t* e = pool + w2 + (size_t)j * (2 + GK_HEAD_WORDS);
+        const uint32_t* e = pool + w2 + (size_t)j * GK_PREFIX_ENT;
         const uint32_t L = e[0];
         const uint32_t Lh = L < GK_HEAD_BYTES ? L : GK_HEAD_BYTES;
         if (lenb < Lh) continue;
         bool ok = true;
-        for (uint32_t w = 0; w < GK_HEAD_WORDS && ok; ++w) {
-          if (w * 4u >= Lh) break;
-          const uint32_t nb = Lh - w * 4u;
-          const uint32_t mask = nb >= 4u ? 0xffffffffu : ((1u << (8u * nb)) - 1u);
-          ok = ((h[w] ^ e[2 + w]) & mask) == 0u;
-        }
+        for (uint32_t w = 0; w < GK_HEAD_WORDS; ++w) ok = ok && (((h[w] ^ e[2 + w]) & e[2 + GK_HEAD_WORDS + w]) == 0u);
         if (ok && L > GK_HEAD_BYTES) {
           const uint32_t a = c.boff[row], sl = c.boff[row + 1] - a;
           ok = gk_prefix(c.bytes + a, sl, cbytes + e[1], L);

@@ -86,19 +86,27 @@ class HostEmuBackend : public Backend {
           break;
         }
         case GK_N_BCAST: {
-          const auto& in = slot[op.w1 & 0xffffu];
           const auto& off = b->scope_off[level];
-          for (size_t p = 0; p + 1 < off.size(); ++p)
-            for (uint32_t r = off[p]; r < off[p + 1]; ++r) slot[o][r] = in[p];
+          for (uint32_t j = 0; j < op.w3; ++j) {
+            const uint32_t e = c.pool[op.w1 + j];
+            const auto& in = slot[e & 0xffffu];
+            auto& dst = slot[e >> 16];
+            for (size_t p = 0; p + 1 < off.size(); ++p)
+              for (uint32_t r = off[p]; r < off[p + 1]; ++r) dst[r] = in[p];
+          }
           break;
         }
         case GK_N_ACC: {
-          const auto& in = slot[op.w1 & 0xffffu];
           const auto& off = b->scope_off[level];
-          for (size_t p = 0; p + 1 < off.size(); ++p) {
-            bool any = false;
-            for (uint32_t r = off[p]; r < off[p + 1]; ++r) any = any || in[r];
-            slot[o][p] = any;
+          for (uint32_t j = 0; j < op.w3; ++j) {
+            const uint32_t e = c.pool[op.w1 + j];
+            const auto& in = slot[e & 0xffffu];
+            auto& dst = slot[e >> 16];
+            for (size_t p = 0; p + 1 < off.size(); ++p) {
+              bool any = false;
+              for (uint32_t r = off[p]; r < off[p + 1]; ++r) any = any || in[r];
+              dst[p] = any;
+            }
           }
           break;
         }
