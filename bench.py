@@ -205,10 +205,8 @@ def run_ours(args):
     alg_in = rb.alg_bytes
     alg_bytes = alg_in + n * words * 4 * 2           # + violation and error planes written
 
-    viol = torch.zeros((n, words), dtype=torch.int32, device=dev)
-    err = torch.zeros((n, words), dtype=torch.int32, device=dev)
-    tot = torch.zeros((2, C), dtype=torch.int64, device=dev)
-    gathered = torch.zeros((world * n, words), dtype=torch.int32, device=dev) if world > 1 else None
+    from gatekeeper_b200.sweep import ShardedSweep
+    sweep = ShardedSweep(drv, rb, n, C, dev, world)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev) if alg_in < 2 * L2_BYTES else None
     ep = D.AUDIT_EP
     stream = torch.cuda.current_stream()
@@ -218,12 +216,10 @@ def run_ours(args):
             flush.fill_(1)                            # evict L2 between iterations when the batch could fit in it
         if e0 is not None:
             e0.record(stream)
-        rb.eval_device(ep, viol.data_ptr(), err.data_ptr(), tot[0].data_ptr(), tot[1].data_ptr(), stream.cuda_stream)
+        sweep.evaluate(ep, stream)                    # the fused match + predicate kernel over the resident shard
         if e1 is not None:
             e1.record(stream)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, viol)
-            dist.all_reduce(tot)
+        sweep.exchange()                              # N > 1: bitmap all-gather + totals all-reduce (NCCL)
 
     for _ in range(max(3, args.warmup)):
         step()
@@ -256,7 +252,7 @@ def run_ours(args):
     ms_per_step = total_ms / K
     value = world * n * C / (ms_per_step / 1e3)
     launches = rb.eval(ep, D.F_NO_COPY_BACK).stats["gpu_launches"] - launches0 - 1   # minus this probe's own launch
-    totals_host = tot[0].tolist()
+    totals_host = sweep.tot[0].tolist()
 
     # ---- e2e: public API, host JSON buffers in, bitmaps + totals out, every step
     e2e_steps = max(1, min(K, args.e2e_steps))

@@ -1,0 +1,76 @@
+"""The N > 1 path on CPU: two `gloo` ranks each sweep their shard (test-only CPU backend), all-gather the bitmaps and
+all-reduce the totals; the result must equal the single-process sweep of the whole range."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import HOSTEMU, ROOT
+
+N_TOTAL = 600
+
+
+def _setup_driver():
+    from gatekeeper_b200 import driver as D
+    from gatekeeper_b200 import workloads as W
+    tm, cons = W.config2()
+    drv = D.Driver(lib_path=HOSTEMU, threads=2)
+    for k, r in tm:
+        drv.add_template(k, r)
+    for c in cons:
+        drv.AddConstraint(c)
+    for ns in W.synth_namespaces():
+        drv.AddData("admission.k8s.gatekeeper.sh", ["cluster", "v1", "Namespace", ns["metadata"]["name"]], ns)
+    return drv
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from gatekeeper_b200 import driver as D
+    from gatekeeper_b200 import workloads as W
+    from gatekeeper_b200.sweep import ShardedSweep, shard_range
+    drv = _setup_driver()
+    lo, hi = shard_range(N_TOTAL, rank, world)
+    blob = W.synth_objects(lo, hi - lo)
+    rb = drv.upload_blob(blob)
+    sw = ShardedSweep(drv, rb, hi - lo, len(drv.constraints()), torch.device("cpu"), world)
+    gathered, tot = sw.step(D.AUDIT_EP)
+    if rank == 0:
+        np.save(os.path.join(out_dir, "gathered.npy"), gathered.numpy())
+        np.save(os.path.join(out_dir, "totals.npy"), tot.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_sweep_equals_single_process(tmp_path):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    gathered = np.load(tmp_path / "gathered.npy")
+    totals = np.load(tmp_path / "totals.npy")
+    from gatekeeper_b200 import driver as D
+    from gatekeeper_b200 import workloads as W
+    drv = _setup_driver()
+    whole = drv.upload_blob(W.synth_objects(0, N_TOTAL)).eval(D.AUDIT_EP)
+    assert (gathered.view("uint32") == whole.viol_bits).all()
+    assert totals[0, :len(whole.totals)].tolist() == whole.totals
+    assert totals[1, :len(whole.totals)].tolist() == whole.err_totals
+
+
+def test_shard_ranges_partition_the_batch():
+    from gatekeeper_b200.sweep import shard_range
+    for n in (0, 1, 7, 1000, 10**6 + 3):
+        for g in (1, 2, 4, 8):
+            rs = [shard_range(n, r, g) for r in range(g)]
+            assert rs[0][0] == 0 and rs[-1][1] == n
+            assert all(rs[i][1] == rs[i + 1][0] for i in range(g - 1))
