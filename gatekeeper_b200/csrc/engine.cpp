@@ -9,7 +9,8 @@ namespace gk {
 // ============================================================================================ strings
 StringTable::StringTable() {
   off_.push_back(0);
-  // sid 0 = GK_SID_UNDEF: reserved, empty bytes
+  // sid 0 = GK_SID_UNDEF, sid 1 = GK_SID_OTHER: reserved, empty bytes
+  off_.push_back(0);
   off_.push_back(0);
   map_.reserve(1 << 16);
 }
@@ -667,11 +668,23 @@ struct Flattener {
     rows.resize(ns);
   }
 
+  // Object data is only ever compared with constants the compiler interned, so values are LOOKED UP, never added:
+  // an unknown string gets GK_SID_OTHER (equal to no constant).  The dictionary stays small and read-mostly.
   uint32_t sid(const std::string& key) {
     auto it = sid_cache.find(key);
     if (it != sid_cache.end()) return it->second;
-    uint32_t id = eng.strings().intern(key);
+    uint32_t id = eng.strings().lookup(key);
+    if (id == GK_SID_UNDEF) id = GK_SID_OTHER;
+    if (sid_cache.size() > (1u << 18)) sid_cache.clear();
     sid_cache.emplace(key, id);
+    return id;
+  }
+  // namespace names are matched by wildcard on the device, which needs their bytes: those (few) are interned
+  uint32_t sid_interned(const std::string& key) {
+    auto it = sid_cache.find(key);
+    if (it != sid_cache.end() && it->second != GK_SID_OTHER) return it->second;
+    uint32_t id = eng.strings().intern(key);
+    sid_cache[key] = id;
     return id;
   }
 
@@ -745,9 +758,9 @@ struct Flattener {
       hb.name_bytes.insert(hb.name_bytes.end(), name.begin(), name.end());
       hb.gen_bytes.insert(hb.gen_bytes.end(), gen.begin(), gen.end());
       // name used by namespaces / excludedNamespaces -- match.go:118-179
-      if (is_ns) nsname = sid("s" + name);
-      else if (ns) nsname = sid("s" + meta_str(ns, "name"));
-      else if (!objns.empty()) nsname = sid("s" + objns);
+      if (is_ns) nsname = sid_interned("s" + name);
+      else if (ns) nsname = sid_interned("s" + meta_str(ns, "name"));
+      else if (!objns.empty()) nsname = sid_interned("s" + objns);
       if (const Node* ls = labels_of(o))
         for (auto& e : ls->kv) {
           hb.lbl_kv.push_back(sid("s" + e.first->s));

@@ -26,6 +26,7 @@ enum { GK_ENC_VT = 1, GK_ENC_SID = 2, GK_ENC_NUM = 4, GK_ENC_BYTES = 8,
 #define GK_PREFIX_ENT (2 + 2 * GK_HEAD_WORDS)
 
 #define GK_SID_UNDEF 0u          /* intern id 0 is reserved: "no value" */
+#define GK_SID_OTHER 1u          /* a defined value that equals none of the constants the program mentions */
 #define GK_NONE 0xFFFFFFFFu
 #define GK_MAX_LOOP_DEPTH 4
 #define GK_MAX_SCOPES 250        /* scope ids fit one byte */

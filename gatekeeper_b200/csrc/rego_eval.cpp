@@ -725,7 +725,20 @@ bool Eval::eval_seq(const std::vector<TP>& items, size_t i, std::vector<VP>& acc
 
 bool Eval::eval_term(const TP& t, Env& env, const ValK& k) {
   switch (t->k) {
-    case TK::Scalar: return k(t->val);
+    case TK::Scalar: {
+      // literals are shared by every thread that evaluates this module: hand out a thread-private copy so that
+      // reference counting never bounces a cache line between flatten workers
+      // (the entry pins the original node, so its address cannot be recycled while it is a key)
+      static thread_local std::unordered_map<const Node*, std::pair<VP, VP>> priv;
+      auto it = priv.find(t->val.get());
+      if (it == priv.end()) {
+        if (priv.size() > 65536) priv.clear();
+        const Node& n = *t->val;
+        VP c = n.t == VT::Str ? v_str(n.s) : n.t == VT::Num ? v_num(n.n) : n.t == VT::Null ? v_null() : v_bool(n.t == VT::True);
+        it = priv.emplace(t->val.get(), std::make_pair(t->val, std::move(c))).first;
+      }
+      return k(it->second.second);
+    }
     case TK::Var: {
       if (const VP* b = env.find(t->vid)) {
         VP v = *b;   // copy: the continuation may grow env and invalidate b
