@@ -1,0 +1,50 @@
+// Host-side aggregation around the batch review: audit status lists and admission messages (see audit.cpp).
+#pragma once
+#include <map>
+#include <string>
+#include <vector>
+
+#include "engine.hpp"
+
+namespace gk {
+
+// StatusViolation -- pkg/audit/manager.go:99-109
+struct StatusViolation {
+  std::string group, version, kind, ns, name, message, action;
+  std::string scoped_json;   // EnforcementActions as a JSON array ("[]" / "" when none)
+};
+
+std::string truncate_string(const std::string& s, size_t size);
+bool sv_less(const StatusViolation& a, const StatusViolation& b);
+
+// LimitQueue -- pkg/audit/manager.go:161-202: keeps the `limit` smallest violations (max-heap, largest on top)
+struct LimitQueue {
+  size_t limit = 20;
+  std::vector<StatusViolation> heap;
+  void push(StatusViolation v);
+  std::vector<StatusViolation> drain_descending();
+};
+
+struct AuditRun {
+  size_t limit = 20;      // --constraint-violations-limit (manager.go:64)
+  size_t msg_size = 256;  // msgSize (manager.go:48)
+  struct PerConstraint {
+    uint64_t total = 0;
+    LimitQueue queue;
+  };
+  std::map<std::string, PerConstraint> per_constraint;   // key: "Kind/name"
+  std::map<std::string, uint64_t> by_action;
+  uint64_t objects = 0, results = 0;
+
+  void fold(const std::string& key, StatusViolation sv);
+  void merge(AuditRun& other);
+  // fold every result of a reviewed batch: viol/err are the kernel's bitmaps [n * words]
+  void add_batch(Engine& eng, const Compiled& c, const std::vector<ObjIn>& objs, const uint32_t* viol, const uint32_t* err,
+                 uint32_t words, const std::vector<uint32_t>& errlist, const std::string& ep);
+  std::string report();
+};
+
+void validation_messages(const Compiled& c, const std::vector<Violation>& vio, uint32_t object, std::vector<std::string>& deny,
+                         std::vector<std::string>& warn);
+
+}  // namespace gk

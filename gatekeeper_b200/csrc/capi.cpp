@@ -8,6 +8,7 @@
 
 #include "../../include/gk_engine.h"
 #include "backend.hpp"
+#include "audit.hpp"
 #include "engine.hpp"
 
 using namespace gk;
@@ -165,13 +166,15 @@ void eval_batch(gk_engine* e, gk_batch* b, const char* ep_c, uint32_t flags, gk_
   fill_result(out, rp.release(), give_bits);
 }
 
-void upload_batch(gk_engine* e, const gk_obj* objs, size_t n, gk_batch** outb, gk_result* stats) {
+const char* process_of(uint32_t flags) { return flags & GK_F_PROCESS_AUDIT ? "audit" : flags & GK_F_PROCESS_WEBHOOK ? "webhook" : ""; }
+
+void upload_batch(gk_engine* e, const gk_obj* objs, size_t n, uint32_t flags, gk_batch** outb, gk_result* stats) {
   auto c = e->eng->compiled();
   e->be->set_program(*c);
   std::vector<ObjIn> ins(n);
   for (size_t i = 0; i < n; ++i) ins[i] = to_in(objs[i]);
   double t0 = now_ms();
-  auto hb = e->eng->flatten(ins.data(), n, *c);
+  auto hb = e->eng->flatten(ins.data(), n, *c, process_of(flags));
   double t1 = now_ms();
   e->be->sync_strings(e->eng->strings());
   auto b = std::make_unique<gk_batch>();
@@ -268,7 +271,7 @@ int gk_review_batch(gk_engine_t* e, const gk_obj* objs, size_t n, const char* ep
     gk_batch* b = nullptr;
     gk_result stats;
     memset(&stats, 0, sizeof stats);
-    upload_batch(e, objs, n, &b, &stats);
+    upload_batch(e, objs, n, flags, &b, &stats);
     std::unique_ptr<gk_batch, std::function<void(gk_batch*)>> hold(b, [&](gk_batch* x) {
       e->be->release(x->dev);
       delete x;
@@ -280,10 +283,10 @@ int gk_review_batch(gk_engine_t* e, const gk_obj* objs, size_t n, const char* ep
   });
 }
 
-int gk_batch_upload(gk_engine_t* e, const gk_obj* objs, size_t n, gk_batch_t** outb, gk_result* stats, char** err) {
+int gk_batch_upload(gk_engine_t* e, const gk_obj* objs, size_t n, uint32_t flags, gk_batch_t** outb, gk_result* stats, char** err) {
   if (!e || !outb || (!objs && n)) return GK_ERR_INVALID;
   if (stats) memset(stats, 0, sizeof *stats);
-  return guard(err, [&]() { upload_batch(e, objs, n, outb, stats); });
+  return guard(err, [&]() { upload_batch(e, objs, n, flags, outb, stats); });
 }
 
 int gk_batch_eval(gk_engine_t* e, gk_batch_t* b, const char* ep, uint32_t flags, gk_result* out, char** err) {
@@ -327,13 +330,13 @@ static std::vector<gk_obj> blob_objs(const char* buf, const uint64_t* off, size_
   return v;
 }
 
-int gk_batch_upload_blob(gk_engine_t* e, const char* buf, const uint64_t* offsets, size_t n, uint8_t source, gk_batch_t** outb,
+int gk_batch_upload_blob(gk_engine_t* e, const char* buf, const uint64_t* offsets, size_t n, uint8_t source, uint32_t flags, gk_batch_t** outb,
                          gk_result* stats, char** err) {
   if (!e || !outb || ((!buf || !offsets) && n)) return GK_ERR_INVALID;
   if (stats) memset(stats, 0, sizeof *stats);
   return guard(err, [&]() {
     auto v = blob_objs(buf, offsets, n, source);
-    upload_batch(e, v.data(), n, outb, stats);
+    upload_batch(e, v.data(), n, flags, outb, stats);
   });
 }
 
@@ -350,6 +353,82 @@ void gk_batch_free(gk_engine_t* e, gk_batch_t* b) {
   if (!e || !b) return;
   guard(nullptr, [&]() { e->be->release(b->dev); });
   delete b;
+}
+
+int gk_set_excluded_namespaces(gk_engine_t* e, const char* process, const char* const* patterns, size_t n, char** err) {
+  if (!e || !process || (!patterns && n)) return GK_ERR_INVALID;
+  return guard(err, [&]() {
+    std::vector<std::string> v;
+    for (size_t i = 0; i < n; ++i) v.push_back(patterns[i] ? patterns[i] : "");
+    e->eng->set_excluded_namespaces(process, v);
+  });
+}
+
+struct gk_audit {
+  gk_engine* e;
+  AuditRun run;
+};
+
+gk_audit_t* gk_audit_begin(gk_engine_t* e, uint32_t violations_limit, uint32_t msg_size, char** err) {
+  if (!e) return nullptr;
+  gk_audit* a = nullptr;
+  guard(err, [&]() {
+    a = new gk_audit{e, {}};
+    a->run.limit = violations_limit ? violations_limit : 20;
+    a->run.msg_size = msg_size ? msg_size : 256;
+  });
+  return a;
+}
+
+int gk_audit_add_batch(gk_audit_t* a, gk_batch_t* b, const char* ep_c, char** err) {
+  if (!a || !b) return GK_ERR_INVALID;
+  return guard(err, [&]() {
+    gk_engine* e = a->e;
+    auto c = e->eng->compiled();
+    if (c->version != b->compiled->version) throw RegoError{"batch was flattened against an older constraint set; upload it again"};
+    e->be->set_program(*c);
+    std::string ep = ep_c ? ep_c : "";
+    std::vector<uint32_t> active;
+    e->eng->active_mask(*c, ep, active);
+    EvalOut ev;
+    e->be->eval(b->dev, active, ev, true);
+    std::vector<ObjIn> ins(b->objs.size());
+    for (size_t i = 0; i < ins.size(); ++i) ins[i] = to_in(b->objs[i]);
+    a->run.add_batch(*e->eng, *c, ins, ev.viol.data(), ev.err.empty() ? nullptr : ev.err.data(), ev.words, ev.errlist, ep);
+  });
+}
+
+char* gk_audit_report(gk_audit_t* a, char** err) {
+  if (!a) return nullptr;
+  char* out = nullptr;
+  guard(err, [&]() { out = dup_str(a->run.report()); });
+  return out;
+}
+
+void gk_audit_end(gk_audit_t* a) { delete a; }
+
+char* gk_validation_messages(gk_engine_t* e, const gk_result* r, uint32_t object, char** err) {
+  if (!e || !r || !r->priv) return nullptr;
+  char* out = nullptr;
+  guard(err, [&]() {
+    auto* rp = static_cast<ResultPriv*>(r->priv);
+    auto c = e->eng->compiled();
+    std::vector<std::string> deny, warn;
+    validation_messages(*c, rp->vio, object, deny, warn);
+    std::string o = "{\"deny\":[";
+    for (size_t i = 0; i < deny.size(); ++i) {
+      if (i) o += ",";
+      json_quote(deny[i], o);
+    }
+    o += "],\"warn\":[";
+    for (size_t i = 0; i < warn.size(); ++i) {
+      if (i) o += ",";
+      json_quote(warn[i], o);
+    }
+    o += "]}";
+    out = dup_str(o);
+  });
+  return out;
 }
 
 void gk_free_result(gk_result* r) {

@@ -54,7 +54,7 @@ static std::string str_field(const VP& o, const char* k) {
   VP v = obj_get(o, k);
   return v && v->t == VT::Str ? v->s : std::string();
 }
-static void split_gv(const VP& obj, std::string& group, std::string& version, std::string& kind) {
+void split_gv(const VP& obj, std::string& group, std::string& version, std::string& kind) {
   std::string api = str_field(obj, "apiVersion");
   size_t p = api.find('/');
   if (p == std::string::npos) {
@@ -66,7 +66,7 @@ static void split_gv(const VP& obj, std::string& group, std::string& version, st
   }
   kind = str_field(obj, "kind");
 }
-static std::string meta_str(const VP& obj, const char* f) {
+std::string meta_str(const VP& obj, const char* f) {
   VP md = obj_get(obj, "metadata");
   if (!md || md->t != VT::Obj) return "";
   return str_field(md, f);
@@ -605,6 +605,16 @@ VP Engine::review_doc(const ObjIn& in, VP* obj_out, VP* old_out, VP* ns_out, std
 }
 
 // =========================================================================================== flatten
+// Wildcard.Matches -- pkg/wildcard/wildcard.go:17-30 (host copy for the excluder stage; the matcher's runs on the device)
+static bool wildcard_match(const std::string& pat, const std::string& s) {
+  bool pre = !pat.empty() && pat.front() == '*', suf = pat.size() > (pre ? 1u : 0u) && pat.back() == '*';
+  if (pat == "*") return true;
+  std::string core = pat.substr(pre ? 1 : 0, pat.size() - (pre ? 1 : 0) - (suf ? 1 : 0));
+  if (pre && suf) return s.find(core) != std::string::npos;
+  if (pre) return s.size() >= core.size() && s.compare(s.size() - core.size(), core.size(), core) == 0;
+  if (suf) return s.compare(0, core.size(), core) == 0;
+  return s == pat;
+}
 struct Flattener {
   Engine& eng;
   const Compiled& c;
@@ -621,6 +631,7 @@ struct Flattener {
   std::vector<std::vector<Row>> rows;                  // per scope, for the current object
 
   std::map<std::string, VP> ns_private;                 // deep copy of the namespace cache
+  const std::vector<std::string>* excluded = nullptr;   // excluder patterns of the calling process (may be empty)
   std::unordered_map<const Node*, VP> const_private;    // deep copies of constants captured by closures
 
   static VP deep_copy(const VP& v) {
@@ -811,34 +822,48 @@ struct Flattener {
     }
   }
 
+  // placeholder rows for an object that is not evaluated (review error or excluded namespace): skipped by the kernel
+  void placeholder() {
+    const size_t nscopes = c.schema.scopes.size();
+    size_t before = hb.flags.size();
+    header_row(nullptr, nullptr, 0, false);
+    hb.flags[before] |= GK_F_SKIP;
+    std::swap(hb.flags, o_flags), std::swap(hb.kind_sid, o_kind), std::swap(hb.group_sid, o_group), std::swap(hb.nsname_sid, o_nsname);
+    std::swap(hb.name_off, o_name_off), std::swap(hb.gen_off, o_gen_off), std::swap(hb.lbl_off, o_lbl_off), std::swap(hb.lbl_kv, o_lbl_kv);
+    std::swap(hb.name_bytes, o_name_bytes), std::swap(hb.gen_bytes, o_gen_bytes);
+    header_row(nullptr, nullptr, 0, false);
+    std::swap(hb.flags, o_flags), std::swap(hb.kind_sid, o_kind), std::swap(hb.group_sid, o_group), std::swap(hb.nsname_sid, o_nsname);
+    std::swap(hb.name_off, o_name_off), std::swap(hb.gen_off, o_gen_off), std::swap(hb.lbl_off, o_lbl_off), std::swap(hb.lbl_kv, o_lbl_kv);
+    std::swap(hb.name_bytes, o_name_bytes), std::swap(hb.gen_bytes, o_gen_bytes);
+    hb.nsrow.push_back(GK_NONE);
+    for (size_t s = 1; s < nscopes; ++s) {
+      // every parent row of this object gets an empty range; the root contributes exactly one row
+      if (c.schema.scopes[s].parent == 0) hb.scope_off[s].push_back(hb.scope_off[s].back());
+    }
+    for (size_t ci = 0; ci < hb.cols.size(); ++ci)
+      if (c.schema.cols[ci].scope == 0) encode(ci, nullptr);
+    ++hb.n;
+  }
+
   void add(const ObjIn& in) {
     std::string err;
     VP obj, old, ns;
     VP doc = eng.review_doc(in, &obj, &old, &ns, &err, &ns_private);
     hb.obj_errors.push_back(err);
     const size_t nscopes = c.schema.scopes.size();
-    if (!doc) {
-      // placeholder rows: skipped by the kernel
-      size_t before = hb.flags.size();
-      header_row(nullptr, nullptr, 0, false);
-      hb.flags[before] |= GK_F_SKIP;
-      std::swap(hb.flags, o_flags), std::swap(hb.kind_sid, o_kind), std::swap(hb.group_sid, o_group), std::swap(hb.nsname_sid, o_nsname);
-      std::swap(hb.name_off, o_name_off), std::swap(hb.gen_off, o_gen_off), std::swap(hb.lbl_off, o_lbl_off), std::swap(hb.lbl_kv, o_lbl_kv);
-      std::swap(hb.name_bytes, o_name_bytes), std::swap(hb.gen_bytes, o_gen_bytes);
-      header_row(nullptr, nullptr, 0, false);
-      std::swap(hb.flags, o_flags), std::swap(hb.kind_sid, o_kind), std::swap(hb.group_sid, o_group), std::swap(hb.nsname_sid, o_nsname);
-      std::swap(hb.name_off, o_name_off), std::swap(hb.gen_off, o_gen_off), std::swap(hb.lbl_off, o_lbl_off), std::swap(hb.lbl_kv, o_lbl_kv);
-      std::swap(hb.name_bytes, o_name_bytes), std::swap(hb.gen_bytes, o_gen_bytes);
-      hb.nsrow.push_back(GK_NONE);
-      for (size_t s = 1; s < nscopes; ++s) {
-        // every parent row of this object gets an empty range; the root contributes exactly one row
-        if (c.schema.scopes[s].parent == 0) hb.scope_off[s].push_back(hb.scope_off[s].back());
-      }
-      for (size_t ci = 0; ci < hb.cols.size(); ++ci)
-        if (c.schema.cols[ci].scope == 0) encode(ci, nullptr);
-      ++hb.n;
-      return;
+    if (!doc) return placeholder();
+    // ---- stage 0: Excluder.IsNamespaceExcluded (excluder.go:95-127): a Namespace is tested by its own name, anything
+    // else by its namespace (the webhook sets it from the request: pkg/webhook/common.go:181)
+    if (excluded && !excluded->empty()) {
+      const VP& ref = obj ? obj : old;
+      std::string g, v, k;
+      split_gv(ref, g, v, k);
+      std::string subject = (k == "Namespace" && g.empty()) ? meta_str(ref, "name") : (in.ns_name ? std::string(in.ns_name) : meta_str(ref, "namespace"));
+      bool skip = false;
+      for (auto& p : *excluded) skip = skip || wildcard_match(p, subject);
+      if (skip) doc = nullptr;   // falls into the placeholder path below: the kernel skips the row, no error text
     }
+    if (!doc) return placeholder();
     // ---- header (object row, then old-object row into the side vectors)
     header_row(obj, ns, in.source, (bool)obj);
     std::swap(hb.flags, o_flags), std::swap(hb.kind_sid, o_kind), std::swap(hb.group_sid, o_group), std::swap(hb.nsname_sid, o_nsname);
@@ -916,18 +941,37 @@ static void append_off(std::vector<uint32_t>& dst, const std::vector<uint32_t>& 
   for (size_t i = skip_first; i < src.size(); ++i) dst.push_back(base + src[i]);
 }
 
-std::shared_ptr<HostBatch> Engine::flatten(const ObjIn* objs, size_t n, const Compiled& c) {
+void Engine::set_excluded_namespaces(const std::string& process, const std::vector<std::string>& patterns) {
+  static const char* all[] = {"audit", "webhook", "mutation-webhook", "sync"};   // excluder.go:31-36 allProcesses
+  std::unique_lock<std::shared_mutex> l(mu_);
+  if (process == "*") {
+    for (auto* p : all) excluded_[p] = patterns;
+  } else {
+    excluded_[process] = patterns;
+  }
+}
+std::vector<std::string> Engine::excluded_namespaces(const std::string& process) {
+  std::shared_lock<std::shared_mutex> l(mu_);
+  auto it = excluded_.find(process);
+  return it == excluded_.end() ? std::vector<std::string>() : it->second;
+}
+
+std::shared_ptr<HostBatch> Engine::flatten(const ObjIn* objs, size_t n, const Compiled& c, const std::string& process) {
   size_t T = std::min<size_t>((size_t)threads_, std::max<size_t>(1, n / 256));
   std::map<std::string, VP> ns_copy;
+  std::vector<std::string> excluded;
   {
     std::shared_lock<std::shared_mutex> l(mu_);
     ns_copy = namespaces_;
+    auto it = excluded_.find(process);
+    if (!process.empty() && it != excluded_.end()) excluded = it->second;
   }
   std::vector<std::unique_ptr<Flattener>> parts(T);
   std::vector<std::string> errs(T);
   auto work = [&](size_t t) {
     try {
       parts[t].reset(new Flattener(*this, c, ns_copy));
+      parts[t]->excluded = &excluded;
       size_t lo = n * t / T, hi = n * (t + 1) / T;
       for (size_t i = lo; i < hi; ++i) parts[t]->add(objs[i]);
     } catch (RegoError& e) {
@@ -1030,38 +1074,52 @@ static std::string scoped_json(const std::vector<std::string>& v) {
 }
 
 void Engine::materialize(const Compiled& c, const ObjIn& in, uint32_t obj_ix, uint32_t cix, const std::string& ep, std::vector<Violation>& out) {
-  const Constraint& con = *c.order[cix];
+  materialize_object(c, in, obj_ix, {Flagged{cix, false, 0}}, ep, out, nullptr);
+}
+
+void Engine::materialize_object(const Compiled& c, const ObjIn& in, uint32_t obj_ix, const std::vector<Flagged>& flagged,
+                                const std::string& ep, std::vector<Violation>& out, VP* obj_out) {
   std::string err;
-  VP doc = review_doc(in, nullptr, nullptr, nullptr, &err);
-  if (!doc) throw RegoError{"materialize: " + err};
-  std::shared_ptr<Module> mod;
-  {
-    std::shared_lock<std::shared_mutex> l(mu_);
-    auto it = templates_.find(con.kind);
-    if (it == templates_.end()) throw RegoError{"materialize: template gone"};
-    mod = it->second.mod;
-  }
-  Eval ev(*mod, v_obj({{v_str("review"), doc}, {v_str("parameters"), con.params}}));
-  VP vs = ev.rule_value("violation");
-  size_t before = out.size();
-  std::vector<std::string> sc = con.action == "scoped" ? scoped_actions_for(con, ep) : std::vector<std::string>();
-  if (vs)
-    for (auto& v : vs->items) {
-      VP msg = obj_get(v, "msg");
-      if (v->t != VT::Obj || !msg || msg->t != VT::Str) throw RegoError{"rego_type_error: violation element must be {\"msg\": string, ...}"};
-      Violation x;
-      x.object = obj_ix;
-      x.constraint = cix;
-      x.msg = msg->s;
-      VP d = obj_get(v, "details");
-      x.details_json = d ? json_str(d) : "";
-      x.action = con.action;
-      x.scoped_json = scoped_json(sc);
-      out.push_back(std::move(x));
+  VP obj, old;
+  VP doc = review_doc(in, &obj, &old, nullptr, &err);
+  if (obj_out) *obj_out = obj ? obj : old;
+  VP input_review;
+  for (auto& f : flagged) {
+    if (f.is_err) {
+      autoreject(c, in, obj_ix, f.cix, f.err_code, ep, out);
+      continue;
     }
-  if (out.size() == before)
-    throw RegoError{"internal: GPU flagged (" + con.kind + "/" + con.name + ", object " + std::to_string(obj_ix) +
-                    ") but the message renderer finds no violation -- lowering bug"};
+    const Constraint& con = *c.order[f.cix];
+    if (!doc) throw RegoError{"materialize: " + err};
+    std::shared_ptr<Module> mod;
+    {
+      std::shared_lock<std::shared_mutex> l(mu_);
+      auto it = templates_.find(con.kind);
+      if (it == templates_.end()) throw RegoError{"materialize: template gone"};
+      mod = it->second.mod;
+    }
+    Eval ev(*mod, v_obj({{v_str("review"), doc}, {v_str("parameters"), con.params}}));
+    VP vs = ev.rule_value("violation");
+    size_t before = out.size();
+    std::vector<std::string> sc = con.action == "scoped" ? scoped_actions_for(con, ep) : std::vector<std::string>();
+    if (vs)
+      for (auto& v : vs->items) {
+        VP msg = obj_get(v, "msg");
+        if (v->t != VT::Obj || !msg || msg->t != VT::Str) throw RegoError{"rego_type_error: violation element must be {\"msg\": string, ...}"};
+        Violation x;
+        x.object = obj_ix;
+        x.constraint = f.cix;
+        x.msg = msg->s;
+        VP d = obj_get(v, "details");
+        x.details_json = d ? json_str(d) : "";
+        x.action = con.action;
+        x.scoped_json = scoped_json(sc);
+        out.push_back(std::move(x));
+      }
+    if (out.size() == before)
+      throw RegoError{"internal: GPU flagged (" + con.kind + "/" + con.name + ", object " + std::to_string(obj_ix) +
+                      ") but the message renderer finds no violation -- lowering bug"};
+  }
 }
 
 void Engine::autoreject(const Compiled& c, const ObjIn& in, uint32_t obj_ix, uint32_t cix, uint32_t code, const std::string& ep,

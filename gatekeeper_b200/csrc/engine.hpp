@@ -133,7 +133,20 @@ class Engine {
   bool remove_namespace(const std::string& name);
 
   std::shared_ptr<const Compiled> compiled();                 // compiles lazily after mutations
-  std::shared_ptr<HostBatch> flatten(const ObjIn* objs, size_t n, const Compiled& c);
+  // process: "" (no excluder stage), "audit", "webhook" -- objects in a namespace excluded for that process are
+  // skipped as the callers do before Review (pkg/audit/manager.go:531-538,600; pkg/webhook/policy.go:170-178)
+  std::shared_ptr<HostBatch> flatten(const ObjIn* objs, size_t n, const Compiled& c, const std::string& process = "");
+  // Config.spec.match[].excludedNamespaces per process -- pkg/controller/config/process/excluder.go:53-77
+  void set_excluded_namespaces(const std::string& process, const std::vector<std::string>& patterns);
+  std::vector<std::string> excluded_namespaces(const std::string& process);
+  // all results of one object for the flagged constraints (one DOM parse); `obj_out` receives the reviewed object
+  struct Flagged {
+    uint32_t cix;
+    bool is_err;
+    uint32_t err_code;
+  };
+  void materialize_object(const Compiled& c, const ObjIn& obj, uint32_t obj_ix, const std::vector<Flagged>& flagged,
+                          const std::string& ep, std::vector<Violation>& out, VP* obj_out = nullptr);
   // which constraints apply at an enforcement point + their effective actions
   void active_mask(const Compiled& c, const std::string& ep, std::vector<uint32_t>& active) const;
   // render messages for one flagged pair (never decides a violation; throws if the GPU bit is unjustified)
@@ -153,12 +166,16 @@ class Engine {
   std::map<std::string, TemplateEntry> templates_;
   std::vector<std::unique_ptr<Constraint>> constraints_;
   std::map<std::string, VP> namespaces_;
+  std::map<std::string, std::vector<std::string>> excluded_;
   std::shared_ptr<Compiled> compiled_;
   bool dirty_ = true;
   uint64_t version_ = 0;
   StringTable strings_;
   int threads_;
 };
+
+void split_gv(const VP& obj, std::string& group, std::string& version, std::string& kind);   // apiVersion -> (group, version), kind
+std::string meta_str(const VP& obj, const char* field);                                       // metadata.<field> or ""
 
 // scoped/unscoped action resolution -- pkg/util/enforcement_action.go:132-174
 std::vector<std::string> scoped_actions_for(const Constraint& c, const std::string& ep);

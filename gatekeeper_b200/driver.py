@@ -25,6 +25,8 @@ GATOR_EP = "gator.gatekeeper.sh"
 SOURCE = {"": 0, None: 0, "Original": 1, "Generated": 2, "All": 3}
 
 F_BITMAP_ONLY, F_MATERIALIZE, F_NO_COPY_BACK = 0, 1, 2
+F_PROCESS_AUDIT, F_PROCESS_WEBHOOK = 16, 32
+PROCESS_FLAG = {"": 0, None: 0, "audit": F_PROCESS_AUDIT, "webhook": F_PROCESS_WEBHOOK}
 
 
 class GkError(RuntimeError):
@@ -65,7 +67,8 @@ EXPORTS = [
     "gk_engine_create", "gk_engine_destroy", "gk_backend_name", "gk_add_template", "gk_remove_template",
     "gk_add_constraint", "gk_remove_constraint", "gk_put_namespace", "gk_remove_namespace", "gk_constraint_count",
     "gk_constraint_key", "gk_review_batch", "gk_batch_upload", "gk_batch_eval", "gk_batch_eval_device",
-    "gk_batch_upload_blob", "gk_review_blob", "gk_batch_size", "gk_batch_alg_bytes", "gk_batch_free", "gk_free_result", "gk_free_str", "gk_dump",
+    "gk_batch_upload_blob", "gk_review_blob", "gk_set_excluded_namespaces", "gk_audit_begin", "gk_audit_add_batch", "gk_audit_report",
+    "gk_audit_end", "gk_validation_messages", "gk_batch_size", "gk_batch_alg_bytes", "gk_batch_free", "gk_free_result", "gk_free_str", "gk_dump",
     "gk_stat_description",
 ]
 
@@ -93,12 +96,22 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.gk_constraint_key.restype = S
     lib.gk_constraint_key.argtypes = [P, U32]
     lib.gk_review_batch.argtypes = [P, C.POINTER(gk_obj), C.c_size_t, S, U32, C.POINTER(gk_result), PP]
-    lib.gk_batch_upload.argtypes = [P, C.POINTER(gk_obj), C.c_size_t, C.POINTER(P), C.POINTER(gk_result), PP]
+    lib.gk_batch_upload.argtypes = [P, C.POINTER(gk_obj), C.c_size_t, U32, C.POINTER(P), C.POINTER(gk_result), PP]
     lib.gk_batch_eval.argtypes = [P, P, S, U32, C.POINTER(gk_result), PP]
     lib.gk_batch_eval_device.argtypes = [P, P, S, P, P, P, P, P, PP]
-    lib.gk_batch_upload_blob.argtypes = [P, P, C.POINTER(C.c_uint64), C.c_size_t, C.c_uint8, C.POINTER(P), C.POINTER(gk_result), PP]
+    lib.gk_batch_upload_blob.argtypes = [P, P, C.POINTER(C.c_uint64), C.c_size_t, C.c_uint8, U32, C.POINTER(P), C.POINTER(gk_result), PP]
     lib.gk_review_blob.argtypes = [P, P, C.POINTER(C.c_uint64), C.c_size_t, C.c_uint8, S, U32, C.POINTER(gk_result), PP]
     lib.gk_batch_size.restype = U32
+    lib.gk_set_excluded_namespaces.argtypes = [P, S, C.POINTER(C.c_char_p), C.c_size_t, PP]
+    lib.gk_audit_begin.argtypes = [P, U32, U32, PP]
+    lib.gk_audit_begin.restype = P
+    lib.gk_audit_add_batch.argtypes = [P, P, S, PP]
+    lib.gk_audit_report.argtypes = [P, PP]
+    lib.gk_audit_report.restype = C.c_void_p
+    lib.gk_audit_end.argtypes = [P]
+    lib.gk_audit_end.restype = None
+    lib.gk_validation_messages.argtypes = [P, C.POINTER(gk_result), U32, PP]
+    lib.gk_validation_messages.restype = C.c_void_p
     lib.gk_batch_size.argtypes = [P]
     lib.gk_batch_alg_bytes.restype = U64
     lib.gk_batch_alg_bytes.argtypes = [P]
@@ -320,15 +333,15 @@ class Driver:
             out.object_errors = [(res.object_errors[i].decode() if res.object_errors[i] else None) for i in range(n)]
         return out
 
-    def ReviewBatch(self, reviews: Iterable, enforcement_point: str = AUDIT_EP, materialize: bool = True) -> BatchResponse:
+    def ReviewBatch(self, reviews: Iterable, enforcement_point: str = AUDIT_EP, materialize: bool = True, process: str = "") -> BatchResponse:
         """The additive batch entry point (SURVEY.md 8(b) `BatchReviewer`): Client.Review semantics -- match
         pre-filter, enforcement-point filter, evaluation, EnforcementAction stamping -- for many reviews at once."""
         arr, n, keep = self._marshal(reviews)
         res = gk_result()
         err = C.c_char_p()
         keys = self.constraints()
-        rc = self._lib.gk_review_batch(self._e, arr, n, enforcement_point.encode(), F_MATERIALIZE if materialize else 0,
-                                       C.byref(res), C.byref(err))
+        rc = self._lib.gk_review_batch(self._e, arr, n, enforcement_point.encode(),
+                                       (F_MATERIALIZE if materialize else 0) | PROCESS_FLAG.get(process, 0), C.byref(res), C.byref(err))
         self._check(rc, err)
         try:
             return self._unpack(res, keys)
@@ -344,23 +357,50 @@ class Driver:
             raise GkError(-1, resp.object_errors[0])
         return [r for r in resp.results if r.constraint in want]
 
+    def SetExcludedNamespaces(self, process: str, patterns: Sequence[str]):
+        """process.Excluder.Add for one process (pkg/controller/config/process/excluder.go:53-77)."""
+        arr = (C.c_char_p * max(1, len(patterns)))(*[p.encode() for p in patterns])
+        err = C.c_char_p()
+        self._check(self._lib.gk_set_excluded_namespaces(self._e, process.encode(), arr, len(patterns), C.byref(err)), err)
+
+    def ValidationMessages(self, reviews: Iterable, process: str = "webhook"):
+        """validationHandler.review + getValidationMessages (pkg/webhook/policy.go:238-355,661) for a micro-batch of
+        admission reviews: per request (denyMsgs, warnMsgs)."""
+        arr, n, keep = self._marshal(reviews)
+        res = gk_result()
+        err = C.c_char_p()
+        self._check(self._lib.gk_review_batch(self._e, arr, n, WEBHOOK_EP.encode(), F_MATERIALIZE | PROCESS_FLAG.get(process, 0),
+                                              C.byref(res), C.byref(err)), err)
+        out = []
+        try:
+            for i in range(n):
+                p = self._lib.gk_validation_messages(self._e, C.byref(res), i, C.byref(err))
+                if not p:
+                    self._check(-1, err)
+                d = json.loads(C.string_at(p).decode(errors="surrogateescape"))
+                self._lib.gk_free_str(p)
+                out.append((d["deny"], d["warn"]))
+        finally:
+            self._lib.gk_free_result(C.byref(res))
+        return out
+
     # ---- resident batches (audit sweep / bench)
-    def upload(self, reviews: Iterable):
+    def upload(self, reviews: Iterable, process: str = ""):
         arr, n, keep = self._marshal(reviews)
         h = C.c_void_p()
         stats = gk_result()
         err = C.c_char_p()
-        self._check(self._lib.gk_batch_upload(self._e, arr, n, C.byref(h), C.byref(stats), C.byref(err)), err)
+        self._check(self._lib.gk_batch_upload(self._e, arr, n, PROCESS_FLAG.get(process, 0), C.byref(h), C.byref(stats), C.byref(err)), err)
         return ResidentBatch(self, h, (arr, keep), {"flatten_ms": stats.flatten_ms, "h2d_ms": stats.h2d_ms,
                                                     "h2d_bytes": stats.h2d_bytes, "alg_bytes": stats.alg_bytes})
 
 
-    def upload_blob(self, blob, source: str = "Original"):
+    def upload_blob(self, blob, source: str = "Original", process: str = ""):
         """Flatten + upload a page of objects held in one contiguous buffer (workloads.ObjectBlob)."""
         h = C.c_void_p()
         stats = gk_result()
         err = C.c_char_p()
-        self._check(self._lib.gk_batch_upload_blob(self._e, blob.buf, blob.offsets, len(blob), SOURCE.get(source, 4), C.byref(h),
+        self._check(self._lib.gk_batch_upload_blob(self._e, blob.buf, blob.offsets, len(blob), SOURCE.get(source, 4), PROCESS_FLAG.get(process, 0), C.byref(h),
                                                    C.byref(stats), C.byref(err)), err)
         return ResidentBatch(self, h, blob, {"flatten_ms": stats.flatten_ms, "h2d_ms": stats.h2d_ms, "h2d_bytes": stats.h2d_bytes,
                                              "alg_bytes": stats.alg_bytes})
@@ -376,6 +416,43 @@ class Driver:
             return self._unpack(res, keys)
         finally:
             self._lib.gk_free_result(C.byref(res))
+
+
+class AuditRun:
+    """One audit sweep's aggregation (pkg/audit/manager.go:886-945,984-1041): fold reviewed batches, then report
+    totalViolations and the per-constraint status lists."""
+
+    def __init__(self, drv: "Driver", violations_limit: int = 0, msg_size: int = 0):
+        self.drv = drv
+        err = C.c_char_p()
+        self._a = drv._lib.gk_audit_begin(drv._e, violations_limit, msg_size, C.byref(err))
+        if not self._a:
+            drv._check(-1, err)
+
+    def add_batch(self, rb: "ResidentBatch", enforcement_point: str = AUDIT_EP):
+        err = C.c_char_p()
+        self.drv._check(self.drv._lib.gk_audit_add_batch(self._a, rb.h, enforcement_point.encode(), C.byref(err)), err)
+
+    def report(self) -> dict:
+        err = C.c_char_p()
+        p = self.drv._lib.gk_audit_report(self._a, C.byref(err))
+        if not p:
+            self.drv._check(-1, err)
+        try:
+            return json.loads(C.string_at(p).decode(errors="surrogateescape"))
+        finally:
+            self.drv._lib.gk_free_str(p)
+
+    def close(self):
+        if self._a:
+            self.drv._lib.gk_audit_end(self._a)
+            self._a = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class ResidentBatch:

@@ -43,7 +43,10 @@ enum { GK_SOURCE_UNSET = 0, GK_SOURCE_ORIGINAL = 1, GK_SOURCE_GENERATED = 2, GK_
 enum {
   GK_F_BITMAP_ONLY = 0,      /* violation / error bitmaps + per-constraint totals */
   GK_F_MATERIALIZE = 1,      /* also render {msg, details} for every flagged pair (types.Result list) */
-  GK_F_NO_COPY_BACK = 2      /* leave bitmaps on the device (throughput measurement); totals still returned */
+  GK_F_NO_COPY_BACK = 2,     /* leave bitmaps on the device (throughput measurement); totals still returned */
+  /* which caller's excluder applies at flatten time (gk_set_excluded_namespaces); neither bit = no excluder stage (gator) */
+  GK_F_PROCESS_AUDIT = 16,   /* process.Audit   -- pkg/audit/manager.go:531-538,600 */
+  GK_F_PROCESS_WEBHOOK = 32  /* process.Webhook -- pkg/webhook/policy.go:170-178 */
 };
 
 typedef struct {
@@ -113,7 +116,7 @@ int gk_review_batch(gk_engine_t* e, const gk_obj* objs, size_t n, const char* en
                     gk_result* out, char** err);
 
 /* resident batches: flatten + upload once, evaluate many times (audit sweep / benchmarking) */
-int gk_batch_upload(gk_engine_t* e, const gk_obj* objs, size_t n, gk_batch_t** out, gk_result* stats, char** err);
+int gk_batch_upload(gk_engine_t* e, const gk_obj* objs, size_t n, uint32_t flags, gk_batch_t** out, gk_result* stats, char** err);
 int gk_batch_eval(gk_engine_t* e, gk_batch_t* b, const char* enforcement_point, uint32_t flags, gk_result* out, char** err);
 /* writes into caller-owned DEVICE buffers on a caller stream and returns without synchronising:
  * viol/err u32[n*words], totals/err_totals u64[n_constraints] (multi-GPU gather path) */
@@ -122,13 +125,38 @@ int gk_batch_eval_device(gk_engine_t* e, gk_batch_t* b, const char* enforcement_
 /* the same two calls for a page of objects held in ONE contiguous buffer (a LIST page / spill directory as the
  * audit loop reads it, pkg/audit/manager.go:502-561,686-695): document i is buf[offsets[i], offsets[i+1]).
  * Every object is reviewed as an AugmentedUnstructured with the given source and no oldObject. */
-int gk_batch_upload_blob(gk_engine_t* e, const char* buf, const uint64_t* offsets, size_t n, uint8_t source, gk_batch_t** out,
+int gk_batch_upload_blob(gk_engine_t* e, const char* buf, const uint64_t* offsets, size_t n, uint8_t source, uint32_t flags, gk_batch_t** out,
                          gk_result* stats, char** err);
 int gk_review_blob(gk_engine_t* e, const char* buf, const uint64_t* offsets, size_t n, uint8_t source, const char* enforcement_point,
                    uint32_t flags, gk_result* out, char** err);
 uint32_t gk_batch_size(gk_batch_t* b);
 uint64_t gk_batch_alg_bytes(gk_batch_t* b);
 void gk_batch_free(gk_engine_t* e, gk_batch_t* b);
+
+/* ---- stage-0 excluder: Config.spec.match[].excludedNamespaces of one process ("audit", "webhook", "sync",
+ * "mutation-webhook", or "*" = all four), pkg/controller/config/process/excluder.go:53-127.  Replaces the process' set.
+ * Objects whose namespace (own name for a Namespace) matches a pattern are skipped by batches flattened with the
+ * matching GK_F_PROCESS_* flag: no results, no error. */
+int gk_set_excluded_namespaces(gk_engine_t* e, const char* process, const char* const* patterns, size_t n, char** err);
+
+/* ---- audit aggregation: what addAuditResponsesToUpdateLists / updateConstraintStatus do with the results of a sweep
+ * (pkg/audit/manager.go:886-945,984-1041): totalViolations per constraint and per enforcement action, and per
+ * constraint the `violations_limit` smallest StatusViolations under SVQueue.Less (manager.go:117-137), messages
+ * truncated to `msg_size` bytes (manager.go:1043-1052).  0 selects the reference defaults (20, 256). */
+typedef struct gk_audit gk_audit_t;
+gk_audit_t* gk_audit_begin(gk_engine_t* e, uint32_t violations_limit, uint32_t msg_size, char** err);
+/* evaluate a resident batch at the enforcement point and fold every result into the run (messages are rendered for the
+ * flagged pairs on all host cores) */
+int gk_audit_add_batch(gk_audit_t* a, gk_batch_t* b, const char* enforcement_point, char** err);
+/* JSON: {"objects", "results", "totalViolations": {"Kind/name": n}, "totalViolationsPerEnforcementAction": {action: n},
+ * "violations": {"Kind/name": [StatusViolation...]}} -- lists in the order updateConstraintStatus emits them (descending).
+ * Caller frees with gk_free_str. */
+char* gk_audit_report(gk_audit_t* a, char** err);
+void gk_audit_end(gk_audit_t* a);
+
+/* ---- admission: getValidationMessages (pkg/webhook/policy.go:238-355) for object `object` of a materialised result:
+ * JSON {"deny": ["[<constraint name>] <msg>", ...], "warn": [...]}.  Caller frees with gk_free_str. */
+char* gk_validation_messages(gk_engine_t* e, const gk_result* r, uint32_t object, char** err);
 
 void gk_free_result(gk_result* r);
 void gk_free_str(char* s);

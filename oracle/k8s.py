@@ -495,3 +495,32 @@ class Client:
                                 "details": rego.to_json(v["details"]) if "details" in v else None,
                                 "enforcementAction": action, "scopedEnforcementActions": scoped or []})
         return results
+
+
+# ---------------------------------------------------------------------------------------------------
+# admission messages -- pkg/webhook/policy.go:238-355 (getValidationMessages)
+
+SUPPORTED_ACTIONS = ("deny", "dryrun", "warn")     # pkg/util/enforcement_action.go:60-70
+
+
+def validation_messages(results):
+    """results: the Client.Review results of ONE admission request at the webhook enforcement point.
+    Returns (denyMsgs, warnMsgs): scoped results use their actions for the enforcement point (unsupported ones
+    skipped; none left => the result is dropped), others their own action (unsupported => dropped)."""
+    deny, warn = [], []
+    for r in results:
+        if r["enforcementAction"] == "scoped":
+            actions = [a for a in r["scopedEnforcementActions"] if a in SUPPORTED_ACTIONS]
+            if not actions:
+                continue
+        else:
+            if r["enforcementAction"] not in SUPPORTED_ACTIONS:
+                continue
+            actions = [r["enforcementAction"]]
+        name = r["constraint"][1] if isinstance(r["constraint"], tuple) else r["constraint"].split("/", 1)[1]
+        for a in actions:
+            if a == "deny":
+                deny.append("[%s] %s" % (name, r["msg"]))
+            if a == "warn":
+                warn.append("[%s] %s" % (name, r["msg"]))
+    return deny, warn

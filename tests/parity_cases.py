@@ -208,3 +208,80 @@ def case_unsupported_is_an_error_not_a_fallback(lib):
                            "spec": {"parameters": {"labels": [{"key": "owner", "allowedRegex": "^[a-z]+$"}]}}})
     assert drv.Name() == "Rego"
     assert "kernel" in drv.GetDescriptionForStat("kernelTimeNS")
+
+
+# ------------------------------------------------------------------------------------------ audit aggregation
+def case_audit(lib, n=1500, limit=20, excluded=("kube-*", "ns-000*")):
+    """The audit sweep's aggregation: excluder stage, totalViolations per constraint and per
+    enforcement action, K-smallest status violations in the order updateConstraintStatus emits them, truncation."""
+    from oracle import audit as OA
+    tm, cons = W.config2()
+    # one constraint with a message far beyond 256 bytes exercises truncateString on real results
+    long_labels = ["label-%02d-%s" % (i, "x" * 12) for i in range(24)]
+    cons = cons + [W._constraint("K8sRequiredLabels", "many-required-labels", params={"labels": long_labels}, action="warn")]
+    nss = W.synth_namespaces()
+    orc, drv, _ = make_pair(tm, cons, nss, lib_path=lib)
+    blob = W.synth_objects(0, n)
+    objs = [json.loads(blob.get(i)) for i in range(n)]
+    want = OA.audit(orc, objs, namespaces={x["metadata"]["name"]: x for x in nss}, excluded_namespaces=excluded, limit=limit)
+    drv.SetExcludedNamespaces("audit", list(excluded))
+    run = D.AuditRun(drv, violations_limit=limit)
+    half = n // 2
+    # two pages, as the audit loop feeds LIST pages (pkg/audit/manager.go:502-561)
+    keep = []
+    for lo, hi in ((0, half), (half, n)):
+        rb = drv.upload([D.Review(object=o, source="Original") for o in objs[lo:hi]], process="audit")
+        keep.append(rb)
+        run.add_batch(rb, k8s.AUDIT_EP)
+    got = run.report()
+    want_totals = {"%s/%s" % k: v for k, v in want["totals"].items()}
+    assert got["totalViolations"] == want_totals
+    assert got["totalViolationsPerEnforcementAction"] == want["by_action"]
+    assert sum(want_totals.values()) == got["results"] > 0
+    assert any(len(v["message"]) == 256 and v["message"].endswith("...") for v in got["violations"]["K8sRequiredLabels/many-required-labels"])
+    for key, lst in want["violations"].items():
+        g = got["violations"]["%s/%s" % key]
+        w = [{k: v for k, v in sv.items() if not (k in ("namespace", "enforcementActions") and not v)} for sv in lst]
+        assert g == w, (key, g[:2], w[:2])
+        assert len(g) <= limit
+    # without the process flag nothing is excluded
+    rb = drv.upload([D.Review(object=o, source="Original") for o in objs[:200]])
+    run2 = D.AuditRun(drv, violations_limit=3)
+    run2.add_batch(rb, k8s.AUDIT_EP)
+    want2 = OA.audit(orc, objs[:200], namespaces={x["metadata"]["name"]: x for x in nss}, limit=3)
+    assert run2.report()["totalViolations"] == {"%s/%s" % k: v for k, v in want2["totals"].items()}
+    return got
+
+
+def case_validation_messages(lib):
+    """getValidationMessages (a-14): "[<constraint name>] <msg>" lists per admission request, scoped actions resolved for
+    the webhook enforcement point, excluder stage of the webhook process."""
+    psp = golden("psp_suite.json")
+    cons = [json.loads(json.dumps(c)) for c in psp["constraints"]]
+    cons[0].setdefault("spec", {})["enforcementAction"] = "warn"
+    cons[1]["spec"]["enforcementAction"] = "dryrun"
+    cons[2]["spec"]["enforcementAction"] = "scoped"
+    cons[2]["spec"]["scopedEnforcementActions"] = [
+        {"action": "warn", "enforcementPoints": [{"name": k8s.WEBHOOK_EP}]},
+        {"action": "deny", "enforcementPoints": [{"name": "*"}]},
+        {"action": "dryrun", "enforcementPoints": [{"name": k8s.AUDIT_EP}]}]
+    cons[3]["spec"]["enforcementAction"] = "scoped"
+    cons[3]["spec"]["scopedEnforcementActions"] = [{"action": "deny", "enforcementPoints": [{"name": k8s.AUDIT_EP}]}]
+    orc, drv, _ = make_pair([(t["kind"], t["rego"]) for t in psp["templates"]], cons, lib_path=lib)
+    pods = [json.loads(json.dumps(p)) for p in psp["pods"]]
+    pods[-1]["metadata"]["namespace"] = "kube-system"
+    revs = [D.Review(object=p, old_object=p, operation="UPDATE", namespace_name=p["metadata"].get("namespace")) for p in pods]
+    drv.SetExcludedNamespaces("webhook", ["kube-*"])
+    got = drv.ValidationMessages(revs, process="webhook")
+    any_deny = any_warn = False
+    for i, r in enumerate(revs):
+        if k8s.is_namespace_excluded(["kube-*"], pods[i]):
+            assert got[i] == ([], [])
+            continue
+        rv = k8s.Review(obj=r.object, old=r.old_object, operation="UPDATE", namespace=r.namespace_name)
+        res = sorted(orc.review(rv, k8s.WEBHOOK_EP), key=lambda x: (x["constraint"], x["msg"]))
+        deny, warn = k8s.validation_messages(res)
+        assert (sorted(got[i][0]), sorted(got[i][1])) == (sorted(deny), sorted(warn))
+        any_deny, any_warn = any_deny or bool(deny), any_warn or bool(warn)
+    assert any_deny and any_warn
+    return got

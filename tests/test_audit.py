@@ -1,0 +1,51 @@
+"""SURVEY 8 rows a-3 (audit aggregation), a-4 (excluder), a-14 (admission messages), a-17 (bench metric definitions):
+the engine's host code against the oracle, on the test-only CPU backend.  The same cases run on the GPU in test_gpu.py."""
+import parity_cases as P
+from conftest import HOSTEMU
+from gatekeeper_b200 import metrics as M
+from oracle import audit as OA
+
+MS = 1_000_000
+
+
+def test_audit_aggregation_matches_oracle():
+    P.case_audit(HOSTEMU, n=1200)
+
+
+def test_audit_small_limit():
+    P.case_audit(HOSTEMU, n=400, limit=2, excluded=())
+
+
+def test_validation_messages():
+    P.case_validation_messages(HOSTEMU)
+
+
+def test_truncate_string_reference_behaviour():
+    # pkg/audit/manager.go:1043-1052: > size => first size-3 bytes + "..."; size <= 3 keeps `size` bytes + "..."
+    assert OA.truncate_string("a" * 256) == "a" * 256
+    assert OA.truncate_string("a" * 257) == "a" * 253 + "..."
+    assert OA.truncate_string("abcdef", 3) == "abc..."
+
+
+def test_percentile_vectors_of_the_reference():
+    # pkg/gator/bench/metrics_test.go:75-147 (tolerance there: 1 ms)
+    five = [10 * MS, 20 * MS, 30 * MS, 40 * MS, 50 * MS]
+    assert M.percentile([], 50) == 0
+    assert M.percentile([100 * MS], 50) == 100 * MS
+    assert M.percentile(five, 50) == 30 * MS
+    assert abs(M.percentile(five, 99) - 49600 * 1000) <= MS
+    assert M.percentile([10 * MS, 20 * MS, 30 * MS], 100) == 30 * MS
+    assert M.percentile([10 * MS, 20 * MS], 0) == 10 * MS
+
+
+def test_latencies_and_throughput_vectors_of_the_reference():
+    # pkg/gator/bench/metrics_test.go:8-73,151-176
+    assert M.calculate_latencies([]) == {"min": 0, "max": 0, "mean": 0, "p50": 0, "p95": 0, "p99": 0}
+    one = M.calculate_latencies([100 * MS])
+    assert (one["min"], one["max"], one["mean"]) == (100 * MS,) * 3
+    for ds in ([10, 20, 30, 40, 50], [50, 10, 30, 20, 40]):
+        l = M.calculate_latencies([d * MS for d in ds])
+        assert (l["min"], l["max"], l["mean"]) == (10 * MS, 50 * MS, 30 * MS)
+    assert M.calculate_throughput(100, 0) == 0
+    assert M.calculate_throughput(100, 1000 * MS) == 100
+    assert M.calculate_throughput(50, 500 * MS) == 100

@@ -81,6 +81,14 @@ def test_unsupported_is_an_error():
     P.case_unsupported_is_an_error_not_a_fallback(LIB)
 
 
+def test_audit_aggregation_matches_oracle():
+    P.case_audit(LIB, n=1500)
+
+
+def test_validation_messages():
+    P.case_validation_messages(LIB)
+
+
 def test_config3_admission_microbatches():
     """200 PSP constraints (7 bitmap words) x 64-request micro-batches, UPDATE with object + oldObject."""
     tm, cons, pods = W.config3(200)
