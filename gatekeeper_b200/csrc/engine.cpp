@@ -1,5 +1,7 @@
 #include "engine.hpp"
 
+#include <chrono>
+
 #include <algorithm>
 #include <cstring>
 #include <thread>
@@ -566,25 +568,36 @@ VP Engine::review_doc(const ObjIn& in, VP* obj_out, VP* old_out, VP* ns_out, std
     nsname = meta_str(ref, "namespace");
   }
   if (in.ns_name) nsname = in.ns_name;
-  VP user = v_obj({});
+  VP user;
   if (in.userinfo_json) {
     try {
       user = json_parse(in.userinfo_json, in.userinfo_len);
     } catch (JsonError&) {
     }
   }
+  // keys and constant members are per-thread singletons: the document is rebuilt for every object
+  struct Keys {
+    VP uid = v_str("uid"), kind = v_str("kind"), resource = v_str("resource"), operation = v_str("operation"), userInfo = v_str("userInfo"),
+       object = v_str("object"), oldObject = v_str("oldObject"), options = v_str("options"), name = v_str("name"), ns = v_str("namespace"),
+       nsobj = v_str("namespaceObject"), group = v_str("group"), version = v_str("version"), empty = v_str(""),
+       no_resource = v_obj({{v_str("group"), v_str("")}, {v_str("version"), v_str("")}, {v_str("resource"), v_str("")}}), no_user = v_obj({});
+  };
+  static thread_local Keys K;
+  if (!user) user = K.no_user;
   std::vector<std::pair<VP, VP>> kv;
-  kv.emplace_back(v_str("uid"), v_str(""));
-  kv.emplace_back(v_str("kind"), v_obj({{v_str("group"), v_str(g)}, {v_str("version"), v_str(v)}, {v_str("kind"), v_str(k)}}));
-  kv.emplace_back(v_str("resource"), v_obj({{v_str("group"), v_str("")}, {v_str("version"), v_str("")}, {v_str("resource"), v_str("")}}));
-  kv.emplace_back(v_str("operation"), v_str(op));
-  kv.emplace_back(v_str("userInfo"), user);
-  kv.emplace_back(v_str("object"), obj ? obj : v_null());
-  kv.emplace_back(v_str("oldObject"), old ? old : v_null());
-  kv.emplace_back(v_str("options"), v_null());
-  if (!name.empty()) kv.emplace_back(v_str("name"), v_str(name));
-  if (!nsname.empty()) kv.emplace_back(v_str("namespace"), v_str(nsname));
-  if (ns) kv.emplace_back(v_str("namespaceObject"), ns);
+  kv.reserve(11);
+  // (already in key order: v_obj's sort has nothing to move)
+  kv.emplace_back(K.kind, v_obj({{K.group, v_str(g)}, {K.kind, v_str(k)}, {K.version, v_str(v)}}));
+  if (!name.empty()) kv.emplace_back(K.name, v_str(name));
+  if (!nsname.empty()) kv.emplace_back(K.ns, v_str(nsname));
+  if (ns) kv.emplace_back(K.nsobj, ns);
+  kv.emplace_back(K.object, obj ? obj : v_null());
+  kv.emplace_back(K.oldObject, old ? old : v_null());
+  kv.emplace_back(K.operation, op.empty() ? K.empty : v_str(op));
+  kv.emplace_back(K.options, v_null());
+  kv.emplace_back(K.resource, K.no_resource);
+  kv.emplace_back(K.uid, K.empty);
+  kv.emplace_back(K.userInfo, user);
   if (obj_out) *obj_out = obj;
   if (old_out) *old_out = old;
   if (ns_out) {
@@ -848,7 +861,9 @@ struct Flattener {
   void add(const ObjIn& in) {
     std::string err;
     VP obj, old, ns;
+    uint64_t tc0 = trace ? __builtin_ia32_rdtsc() : 0;
     VP doc = eng.review_doc(in, &obj, &old, &ns, &err, &ns_private);
+    if (trace) doc_cycles += __builtin_ia32_rdtsc() - tc0;
     hb.obj_errors.push_back(err);
     const size_t nscopes = c.schema.scopes.size();
     if (!doc) return placeholder();
@@ -865,6 +880,7 @@ struct Flattener {
     }
     if (!doc) return placeholder();
     // ---- header (object row, then old-object row into the side vectors)
+    uint64_t th0 = trace ? __builtin_ia32_rdtsc() : 0;
     header_row(obj, ns, in.source, (bool)obj);
     std::swap(hb.flags, o_flags), std::swap(hb.kind_sid, o_kind), std::swap(hb.group_sid, o_group), std::swap(hb.nsname_sid, o_nsname);
     std::swap(hb.name_off, o_name_off), std::swap(hb.gen_off, o_gen_off), std::swap(hb.lbl_off, o_lbl_off), std::swap(hb.lbl_kv, o_lbl_kv);
@@ -875,6 +891,7 @@ struct Flattener {
     std::swap(hb.name_off, o_name_off), std::swap(hb.gen_off, o_gen_off), std::swap(hb.lbl_off, o_lbl_off), std::swap(hb.lbl_kv, o_lbl_kv);
     std::swap(hb.name_bytes, o_name_bytes), std::swap(hb.gen_bytes, o_gen_bytes);
     any_old = any_old || old_distinct;
+    if (trace) hdr_cycles += __builtin_ia32_rdtsc() - th0;
     // ---- namespace table row
     if (ns) {
       auto it = ns_row_of.find(ns.get());
@@ -906,7 +923,9 @@ struct Flattener {
         const ScopeDef& sd = c.schema.scopes[s];
         auto& prow = rows[sd.parent];
         for (uint32_t pr = 0; pr < prow.size(); ++pr) {
+          uint64_t t0 = trace ? __builtin_ia32_rdtsc() : 0;
           VP coll = eval_closure(*sd.gen, sd.parent, pr, input);
+          if (trace) scope_cycles[s] += __builtin_ia32_rdtsc() - t0;
           if (coll) {
             if (coll->t == VT::Arr)
               for (size_t j = 0; j < coll->items.size(); ++j) rows[s].push_back(Row{coll->items[j], v_int((long long)j), pr});
@@ -920,7 +939,9 @@ struct Flattener {
       }
       for (size_t ci = 0; ci < hb.cols.size(); ++ci) {
         const ColDef& cd = c.schema.cols[ci];
+        uint64_t t0 = trace ? __builtin_ia32_rdtsc() : 0;
         for (uint32_t r = 0; r < rows[cd.scope].size(); ++r) encode(ci, eval_closure(*cd.expr, cd.scope, r, input));
+        if (trace) col_cycles[ci] += __builtin_ia32_rdtsc() - t0;
       }
       for (size_t s = 1; s < nscopes; ++s) hb.scope_rows[s] += (uint32_t)rows[s].size();
     }
@@ -932,6 +953,24 @@ struct Flattener {
     ++hb.n;
   }
   std::string num_range_error;
+  bool trace = getenv("GK_FLATTEN_TRACE") != nullptr;
+  std::vector<uint64_t> col_cycles = std::vector<uint64_t>(4096, 0), scope_cycles = std::vector<uint64_t>(256, 0);
+  uint64_t doc_cycles = 0, hdr_cycles = 0;
+  ~Flattener() {
+    if (!trace || hb.n == 0) return;
+    static std::mutex m;
+    std::lock_guard<std::mutex> l(m);
+    std::vector<std::pair<uint64_t, std::string>> v;
+    for (size_t i = 0; i < c.schema.cols.size(); ++i) v.push_back({col_cycles[i], "col " + std::to_string(i) + " " + c.schema.cols[i].expr->key});
+    for (size_t i = 1; i < c.schema.scopes.size(); ++i) v.push_back({scope_cycles[i], "scope " + std::to_string(i) + " " + c.schema.scopes[i].gen->key});
+    v.push_back({doc_cycles, "review_doc (JSON parse)"});
+    v.push_back({hdr_cycles, "header rows"});
+    std::sort(v.rbegin(), v.rend());
+    uint64_t tot = 0;
+    for (auto& x : v) tot += x.first;
+    fprintf(stderr, "[flatten worker] %u objects, %.0f cycles/object accounted\n", hb.n, (double)tot / hb.n);
+    for (size_t i = 0; i < v.size() && i < 25; ++i) fprintf(stderr, "  %7.0f cyc/obj  %.100s\n", (double)v[i].first / hb.n, v[i].second.c_str());
+  }
 };
 
 template <class T>
@@ -980,12 +1019,23 @@ std::shared_ptr<HostBatch> Engine::flatten(const ObjIn* objs, size_t n, const Co
       errs[t] = e.what();
     }
   };
+  auto tp0 = std::chrono::steady_clock::now();
   if (T == 1) work(0);
   else {
     std::vector<std::thread> th;
     for (size_t t = 0; t < T; ++t) th.emplace_back(work, t);
     for (auto& x : th) x.join();
   }
+  auto tp1 = std::chrono::steady_clock::now();
+  struct MergeTrace {
+    std::chrono::steady_clock::time_point a, b;
+    size_t T;
+    ~MergeTrace() {
+      if (getenv("GK_FLATTEN_TRACE"))
+        fprintf(stderr, "[flatten] threads=%zu parallel part %.1f ms, merge %.1f ms\n", T, std::chrono::duration<double, std::milli>(b - a).count(),
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - b).count());
+    }
+  } trace{tp0, tp1, T};
   for (auto& e : errs)
     if (!e.empty()) throw RegoError{"flatten: " + e};
   // ---- merge

@@ -45,6 +45,9 @@ struct Term {
   TP key, value;                        // comprehension head (ObjCompr: key+value; others: value)
   std::vector<Stmt> body;               // comprehension body
   int line = 0;
+  // resolved lazily by the evaluator (same value from every thread): is `name` a rule of the module / a builtin id
+  mutable signed char is_rule_ = -1;
+  mutable const void* rules_ = nullptr;
 };
 
 struct Rule {
@@ -66,6 +69,9 @@ struct Module {
   int next_vid = 0;
   int vid_input = -1, vid_data = -1;
   uint64_t uid = 0;                               // unique per parsed module (column-key namespace)
+  // functions whose value depends on their arguments only (no `input` / `data`, transitively): their results
+  // can be memoised across objects
+  std::unordered_map<std::string, bool> pure_fn;
   int intern(const std::string& n);
   bool is_rule(const std::string& n) const { return rules.count(n) != 0; }
 };
@@ -87,9 +93,26 @@ struct Env {
   void bind(int vid, VP v) { b.emplace_back(vid, std::move(v)); }
 };
 
+// Non-owning callable reference: continuations are only ever passed DOWN the evaluator's recursion and never stored,
+// so they need neither a copy nor a heap allocation (std::function allocates for every capture list > 16 bytes).
+template <class Sig>
+class FnRef;
+template <class R, class... A>
+class FnRef<R(A...)> {
+  void* obj_;
+  R (*call_)(void*, A...);
+
+ public:
+  template <class F, class = typename std::enable_if<!std::is_same<typename std::decay<F>::type, FnRef>::value>::type>
+  FnRef(F&& f)
+      : obj_((void*)std::addressof(f)),
+        call_([](void* o, A... a) -> R { return (*static_cast<typename std::remove_reference<F>::type*>(o))(std::forward<A>(a)...); }) {}
+  R operator()(A... a) const { return call_(obj_, std::forward<A>(a)...); }
+};
+
 // Continuations return true to STOP the search (first-solution / negation probes).
-using ValK = std::function<bool(const VP&)>;
-using EnvK = std::function<bool()>;
+using ValK = FnRef<bool(const VP&)>;
+using EnvK = FnRef<bool()>;
 
 class Eval {
  public:
@@ -120,6 +143,7 @@ class Eval {
   VP input_, data_;
   std::unordered_map<std::string, VP> cache_;   // rule extents; nullptr entries = undefined
   std::unordered_map<std::string, bool> cache_has_;
+  std::unordered_map<std::string, VP> fn_memo_;  // pure functions on scalar arguments (survives reset_input)
   int depth_ = 0;
 };
 

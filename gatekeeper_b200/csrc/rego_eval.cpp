@@ -300,10 +300,18 @@ bool is_builtin(const std::string& name) {
   return known;
 }
 
+static constexpr uint64_t name_hash(const char* s) {
+  uint64_t h = 1469598103934665603ull;
+  for (; *s; ++s) h = (h ^ (unsigned char)*s) * 1099511628211ull;
+  return h;
+}
 VP call_builtin(const std::string& n, const std::vector<VP>& a, bool* known) {
   *known = true;
   auto need = [&](size_t k) { return a.size() == k; };
-#define B(name, arity) if (n == name) { if (!need(arity)) return nullptr;
+  // names are dispatched on a 64-bit hash (compile-time constants on the right-hand side), confirmed by one compare
+  const uint64_t nh = name_hash(n.c_str());
+#define IS(name) (nh == std::integral_constant<uint64_t, name_hash(name)>::value && n == name)
+#define B(name, arity) if (IS(name)) { if (!need(arity)) return nullptr;
 #define E }
   B("equal", 2) return v_bool(v_eq(a[0], a[1])); E
   B("neq", 2) return v_bool(!v_eq(a[0], a[1])); E
@@ -311,7 +319,7 @@ VP call_builtin(const std::string& n, const std::vector<VP>& a, bool* known) {
   B("lte", 2) return v_bool(v_cmp(a[0], a[1]) <= 0); E
   B("gt", 2) return v_bool(v_cmp(a[0], a[1]) > 0); E
   B("gte", 2) return v_bool(v_cmp(a[0], a[1]) >= 0); E
-  if (n == "plus" || n == "minus" || n == "mul" || n == "div" || n == "rem" || n == "and" || n == "or") {
+  if (IS("plus") || IS("minus") || IS("mul") || IS("div") || IS("rem") || IS("and") || IS("or")) {
     if (!need(2)) return nullptr;
     return arith(n, a[0], a[1]);
   }
@@ -328,7 +336,7 @@ VP call_builtin(const std::string& n, const std::vector<VP>& a, bool* known) {
   B("startswith", 2) if (!is_str(a[0]) || !is_str(a[1])) return nullptr; return v_bool(starts_with(a[0]->s, a[1]->s)); E
   B("endswith", 2) if (!is_str(a[0]) || !is_str(a[1])) return nullptr; return v_bool(ends_with(a[0]->s, a[1]->s)); E
   B("contains", 2) if (!is_str(a[0]) || !is_str(a[1])) return nullptr; return v_bool(a[0]->s.find(a[1]->s) != std::string::npos); E
-  if (n == "strings.any_prefix_match" || n == "strings.any_suffix_match") {
+  if (IS("strings.any_prefix_match") || IS("strings.any_suffix_match")) {
     if (!need(2)) return nullptr;
     std::vector<const std::string*> ss, bb;
     if (!str_list(a[0], ss) || !str_list(a[1], bb)) return nullptr;
@@ -396,7 +404,7 @@ VP call_builtin(const std::string& n, const std::vector<VP>& a, bool* known) {
       return v_int((long long)utf8_len(a[0]->s.substr(0, p)));
     }
   E
-  if (n == "re_match" || n == "regex.match") {
+  if (IS("re_match") || IS("regex.match")) {
     if (!need(2)) return nullptr;
     return re_match(a[0], a[1]);
   }
@@ -427,7 +435,7 @@ VP call_builtin(const std::string& n, const std::vector<VP>& a, bool* known) {
     if (!is_num(a[0])) return nullptr;
     return a[0]->n.is_int ? v_num(Num::of_int(a[0]->n.i < 0 ? -a[0]->n.i : a[0]->n.i)) : v_num(Num::of_double(std::fabs(a[0]->n.d)));
   E
-  if (n == "max" || n == "min") {
+  if (IS("max") || IS("min")) {
     if (!need(1) || !is_coll(a[0]) || a[0]->items.empty()) return nullptr;
     VP best = a[0]->items[0];
     for (auto& x : a[0]->items)
@@ -443,16 +451,19 @@ VP call_builtin(const std::string& n, const std::vector<VP>& a, bool* known) {
     if (is_coll(a[1])) { for (auto& x : a[1]->items) if (v_eq(x, a[0])) return v_bool(true); return v_bool(false); }
     return v_bool(false);
   E
-  if (n == "print" || n == "trace") return v_bool(true);
+  if (IS("print") || IS("trace")) return v_bool(true);
 #undef B
 #undef E
+#undef IS
   *known = false;
   return nullptr;
 }
 
 // ----------------------------------------------------------------------------------------- evaluator
 bool Eval::var_unbound(const Term& t, const Env& env) const {
-  return t.k == TK::Var && !env.find(t.vid) && t.vid != m_.vid_input && t.vid != m_.vid_data && !m_.is_rule(t.name);
+  if (t.k != TK::Var || env.find(t.vid) || t.vid == m_.vid_input || t.vid == m_.vid_data) return false;
+  if (t.is_rule_ < 0) t.is_rule_ = m_.is_rule(t.name) ? 1 : 0;
+  return !t.is_rule_;
 }
 
 bool Eval::is_ground(const TP& t, const Env& env) const {
@@ -567,6 +578,24 @@ VP Eval::rule_value(const std::string& name) {
 VP Eval::call_function(const std::string& name, const std::vector<VP>& args) {
   auto rit = m_.rules.find(name);
   if (rit == m_.rules.end()) return nullptr;
+  // pure function of scalar arguments: one evaluation per distinct argument tuple
+  std::string memo_key;
+  {
+    auto pit = m_.pure_fn.find(name);
+    bool memo = pit != m_.pure_fn.end() && pit->second;
+    for (auto& a : args) memo = memo && a && (uint8_t)a->t <= (uint8_t)VT::Str;
+    if (memo) {
+      memo_key = name;
+      for (auto& a : args) {
+        memo_key.push_back('\x01');
+        memo_key.push_back((char)('0' + (int)a->t));
+        if (a->t == VT::Str) memo_key += a->s;
+        else if (a->t == VT::Num) memo_key += num_str(a->n);
+      }
+      auto it = fn_memo_.find(memo_key);
+      if (it != fn_memo_.end()) return it->second;
+    }
+  }
   if (++depth_ > 64) {
     --depth_;
     throw RegoError{"rego_recursion_error: function " + name};
@@ -576,17 +605,21 @@ VP Eval::call_function(const std::string& name, const std::vector<VP>& args) {
     if (r.kind != Rule::Func || r.args.size() != args.size()) continue;
     Env env;
     // unify formals with actuals
-    std::function<bool(size_t)> bind = [&](size_t i) -> bool {
+    auto bind = [&](auto&& self, size_t i) -> bool {
       if (i == args.size()) {
         out = rule_chain(r, env);
         return (bool)out;
       }
-      return unify_val(r.args[i], args[i], env, [&]() { return bind(i + 1); });
+      return unify_val(r.args[i], args[i], env, [&]() { return self(self, i + 1); });
     };
-    bind(0);
+    bind(bind, 0);
     if (out) break;
   }
   --depth_;
+  if (!memo_key.empty()) {
+    if (fn_memo_.size() > (1u << 16)) fn_memo_.clear();
+    fn_memo_.emplace(std::move(memo_key), out);
+  }
   return out;
 }
 
@@ -872,16 +905,22 @@ bool Eval::walk(const VP& cur, const std::vector<TP>& path, size_t i, Env& env, 
 }
 
 bool Eval::eval_call(const Term& t, Env& env, const ValK& k) {
-  auto rit = m_.rules.find(t.name);
-  bool user = rit != m_.rules.end() && rit->second[0].kind == Rule::Func;
+  if (__atomic_load_n(&t.is_rule_, __ATOMIC_ACQUIRE) < 0) {
+    auto rit = m_.rules.find(t.name);
+    t.rules_ = rit != m_.rules.end() && rit->second[0].kind == Rule::Func ? &rit->second : nullptr;
+    __atomic_store_n(&t.is_rule_, (signed char)(t.rules_ ? 1 : 0), __ATOMIC_RELEASE);
+  }
+  const auto* frules = static_cast<const std::vector<Rule>*>(t.rules_);
+  bool user = frules != nullptr;
   size_t nargs = t.args.size();
   TP out_pat;
-  if (user && nargs == rit->second[0].args.size() + 1) {
+  if (user && nargs == (*frules)[0].args.size() + 1) {
     out_pat = t.args.back();
     --nargs;
   }
   std::vector<VP> acc;
-  std::function<bool(size_t)> rec = [&](size_t i) -> bool {
+  acc.reserve(nargs);
+  auto rec = [&](auto&& self, size_t i) -> bool {
     if (i == nargs) {
       VP v;
       if (user) v = call_function(t.name, acc);
@@ -896,12 +935,12 @@ bool Eval::eval_call(const Term& t, Env& env, const ValK& k) {
     }
     return eval_term(t.args[i], env, [&](const VP& v) {
       acc.push_back(v);
-      bool s = rec(i + 1);
+      bool s = self(self, i + 1);
       acc.pop_back();
       return s;
     });
   };
-  return rec(0);
+  return rec(rec, 0);
 }
 
 }  // namespace gk

@@ -582,6 +582,59 @@ int Module::intern(const std::string& n) {
   return id;
 }
 
+// ---- purity: which rules never look at `input` / `data`
+static void term_deps(const Module& m, const Term& t, bool& touches_doc, std::vector<std::string>& refs);
+static void stmts_deps(const Module& m, const std::vector<Stmt>& b, bool& touches_doc, std::vector<std::string>& refs) {
+  for (auto& st : b)
+    for (const TP* x : {&st.a, &st.b, &st.c})
+      if (*x) term_deps(m, **x, touches_doc, refs);
+}
+static void term_deps(const Module& m, const Term& t, bool& touches_doc, std::vector<std::string>& refs) {
+  if (t.k == TK::Var) {
+    if (t.vid == m.vid_input || t.vid == m.vid_data) touches_doc = true;
+    if (m.is_rule(t.name)) refs.push_back(t.name);
+  }
+  if (t.k == TK::Call && m.is_rule(t.name)) refs.push_back(t.name);
+  if (t.head) term_deps(m, *t.head, touches_doc, refs);
+  for (auto& a : t.args) term_deps(m, *a, touches_doc, refs);
+  for (auto& kv : t.kvs) term_deps(m, *kv.first, touches_doc, refs), term_deps(m, *kv.second, touches_doc, refs);
+  if (t.key) term_deps(m, *t.key, touches_doc, refs);
+  if (t.value) term_deps(m, *t.value, touches_doc, refs);
+  stmts_deps(m, t.body, touches_doc, refs);
+}
+static void compute_purity(Module& m) {
+  std::map<std::string, std::vector<std::string>> refs;
+  std::map<std::string, bool> impure;
+  for (auto& kv : m.rules) {
+    bool doc = false;
+    auto& rf = refs[kv.first];
+    for (auto& r : kv.second) {
+      for (auto& a : r.args) term_deps(m, *a, doc, rf);
+      if (r.key) term_deps(m, *r.key, doc, rf);
+      if (r.value) term_deps(m, *r.value, doc, rf);
+      stmts_deps(m, r.body, doc, rf);
+      for (auto& e : r.els) {
+        if (e.first) term_deps(m, *e.first, doc, rf);
+        stmts_deps(m, e.second, doc, rf);
+      }
+    }
+    impure[kv.first] = doc;
+  }
+  for (bool changed = true; changed;) {
+    changed = false;
+    for (auto& kv : refs)
+      if (!impure[kv.first])
+        for (auto& r : kv.second)
+          if (impure[r]) {
+            impure[kv.first] = true;
+            changed = true;
+            break;
+          }
+  }
+  for (auto& kv : m.rules)
+    if (kv.second[0].kind == Rule::Func) m.pure_fn[kv.first] = !impure[kv.first];
+}
+
 std::shared_ptr<Module> rego_parse(const std::string& src) {
   static std::atomic<uint64_t> uid{1};
   auto m = std::make_shared<Module>();
@@ -597,6 +650,7 @@ std::shared_ptr<Module> rego_parse(const std::string& src) {
         throw RegoError{"rego_type_error: conflicting rules named " + kv.first};
   }
   check_unsafe(*m);
+  compute_purity(*m);
   return m;
 }
 

@@ -100,6 +100,14 @@ VP v_set(std::vector<VP> items) {
   return n;
 }
 VP v_obj(std::vector<std::pair<VP, VP>> kv) {
+  bool sorted = true;
+  for (size_t i = 1; i < kv.size() && sorted; ++i) sorted = v_cmp(kv[i - 1].first, kv[i].first) < 0;
+  if (sorted) {   // strictly ascending: nothing to sort, nothing to merge
+    auto n = std::make_shared<Node>();
+    n->t = VT::Obj;
+    n->kv = std::move(kv);
+    return n;
+  }
   std::stable_sort(kv.begin(), kv.end(), [](const auto& a, const auto& b) { return v_cmp(a.first, b.first) < 0; });
   // later duplicates win (json.Unmarshal into map semantics)
   std::vector<std::pair<VP, VP>> out;
@@ -210,11 +218,76 @@ VP set_find(const VP& s, const VP& x) {
 
 // ---------------------------------------------------------------------------------------------- JSON
 namespace {
+// Per-thread recycling of the nodes a Kubernetes document repeats endlessly (object keys, short enum-like strings,
+// small integers): direct-mapped, so a hit costs one hash + one compare and no allocation.
+struct StrCache {
+  static const size_t N = 2048;
+  VP slot[N];
+  const VP& get(const char* s, size_t n) {
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < n; ++i) h = (h ^ (unsigned char)s[i]) * 1099511628211ull;
+    VP& v = slot[(h ^ (h >> 29)) & (N - 1)];
+    if (!v || v->s.size() != n || memcmp(v->s.data(), s, n) != 0) v = v_str(std::string(s, n));
+    return v;
+  }
+};
 struct JP {
   const char* p;
   const char* e;
   int depth = 0;
+  std::vector<std::pair<VP, VP>>& kvs;   // scratch stacks: children are collected here, then moved into an exact-size vector
+  std::vector<VP>& its;
+  StrCache& keys;
+  StrCache& shorts;
   [[noreturn]] void fail(const char* m) { throw JsonError{std::string("invalid JSON: ") + m}; }
+  // a string without escapes is viewed in place
+  bool plain_str(const char*& s, size_t& n) {
+    const char* q = p + 1;
+    while (q < e && *q != '"' && *q != '\\') ++q;
+    if (q >= e || *q != '"') return false;
+    s = p + 1;
+    n = q - s;
+    p = q + 1;
+    return true;
+  }
+  VP str_node(StrCache& cache, size_t max_cached) {
+    const char* s;
+    size_t n;
+    if (plain_str(s, n)) return n <= max_cached ? cache.get(s, n) : v_str(std::string(s, n));
+    return v_str(str());
+  }
+  VP make_obj(size_t base) {
+    size_t n = kvs.size() - base;
+    auto* a = kvs.data() + base;
+    bool sorted = true;
+    for (size_t i = 1; i < n && sorted; ++i) sorted = a[i - 1].first->s < a[i].first->s;   // strictly ascending: no duplicates
+    if (!sorted) {
+      // stable insertion sort on the (small) child list, then later duplicates win (json.Unmarshal into a map)
+      for (size_t i = 1; i < n; ++i) {
+        auto x = std::move(a[i]);
+        size_t j = i;
+        while (j > 0 && x.first->s < a[j - 1].first->s) {
+          a[j] = std::move(a[j - 1]);
+          --j;
+        }
+        a[j] = std::move(x);
+      }
+      size_t w = 0;
+      for (size_t i = 0; i < n; ++i) {
+        if (w > 0 && a[w - 1].first->s == a[i].first->s) a[w - 1].second = std::move(a[i].second);
+        else {
+          if (w != i) a[w] = std::move(a[i]);
+          ++w;
+        }
+      }
+      n = w;
+    }
+    auto node = std::make_shared<Node>();
+    node->t = VT::Obj;
+    node->kv.assign(std::make_move_iterator(a), std::make_move_iterator(a + n));
+    kvs.resize(base);
+    return node;
+  }
   void ws() {
     while (p < e && (*p == ' ' || *p == '\n' || *p == '\t' || *p == '\r')) ++p;
   }
@@ -297,7 +370,7 @@ struct JP {
     char c = *p;
     if (c == '{') {
       ++p;
-      std::vector<std::pair<VP, VP>> kv;
+      const size_t base = kvs.size();
       ws();
       if (p < e && *p == '}') {
         ++p;
@@ -305,12 +378,12 @@ struct JP {
         while (true) {
           ws();
           if (p >= e || *p != '"') fail("object key expected");
-          VP k = v_str(str());
+          VP k = str_node(keys, 48);
           ws();
           if (p >= e || *p != ':') fail("':' expected");
           ++p;
           VP v = value();
-          kv.emplace_back(std::move(k), std::move(v));
+          kvs.emplace_back(std::move(k), std::move(v));
           ws();
           if (p < e && *p == ',') {
             ++p;
@@ -323,16 +396,17 @@ struct JP {
           fail("',' or '}' expected");
         }
       }
-      r = v_obj(std::move(kv));
+      r = make_obj(base);
     } else if (c == '[') {
       ++p;
-      std::vector<VP> items;
+      const size_t base = its.size();
       ws();
       if (p < e && *p == ']') {
         ++p;
       } else {
         while (true) {
-          items.push_back(value());
+          VP x = value();
+          its.push_back(std::move(x));
           ws();
           if (p < e && *p == ',') {
             ++p;
@@ -345,9 +419,15 @@ struct JP {
           fail("',' or ']' expected");
         }
       }
-      r = v_arr(std::move(items));
+      {
+        auto node = std::make_shared<Node>();
+        node->t = VT::Arr;
+        node->items.assign(std::make_move_iterator(its.begin() + base), std::make_move_iterator(its.end()));
+        its.resize(base);
+        r = std::move(node);
+      }
     } else if (c == '"') {
-      r = v_str(str());
+      r = str_node(shorts, 12);
     } else if (c == 't' && e - p >= 4 && !memcmp(p, "true", 4)) {
       p += 4;
       r = v_bool(true);
@@ -392,7 +472,12 @@ struct JP {
 }  // namespace
 
 VP json_parse(const char* p, size_t n) {
-  JP jp{p, p + n};
+  static thread_local std::vector<std::pair<VP, VP>> kvs;
+  static thread_local std::vector<VP> its;
+  static thread_local StrCache keys, shorts;
+  kvs.clear();   // (a failed parse leaves its partial children behind)
+  its.clear();
+  JP jp{p, p + n, 0, kvs, its, keys, shorts};
   VP v = jp.value();
   jp.ws();
   if (jp.p != jp.e) jp.fail("trailing characters");
