@@ -141,8 +141,8 @@ def run_reference(args):
     if rank != 0:
         return 0
     import multiprocessing as mp
-    cores = os.cpu_count() or 1
-    procs = max(1, min(cores, 64))
+    from gatekeeper_b200.hostinfo import host_cpus
+    procs = max(1, host_cpus())                      # every CPU the cgroup lets this process use
     per = args.ref_objects_per_core
     C = 50
     ctx = mp.get_context("fork")
@@ -160,7 +160,7 @@ def run_reference(args):
             total_t += dt
             total_n += n
     value = total_n * C / total_t
-    sample = (f"oracle/ port of the reference CPU path over {procs} processes; each step reviews {procs * per} synthetic Pods x {C} constraints "
+    sample = (f"oracle/ port of the reference CPU path over {procs} processes (= usable CPUs: affinity + cgroup quota of a {os.cpu_count()}-thread host); each step reviews {procs * per} synthetic Pods x {C} constraints "
               f"(a bounded sample of the 1M-Pod workload; objects are independent so throughput is size-independent)")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * total_t / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int",
@@ -188,7 +188,9 @@ def run_ours(args):
     dev = torch.device("cuda", local)
 
     tm, cons = W.config2()
-    drv = D.Driver(device=local, threads=max(1, (os.cpu_count() or 8) // max(1, world)))
+    from gatekeeper_b200.hostinfo import host_cpus
+    host_threads = max(1, host_cpus() // max(1, world))
+    drv = D.Driver(device=local, threads=host_threads)
     for k, r in tm:
         drv.add_template(k, r)
     for c in cons:
@@ -199,7 +201,7 @@ def run_ours(args):
     words = (C + 31) // 32
     n = args.objects
     t0 = time.perf_counter()
-    blob = W.synth_objects(rank * n, n, threads=max(1, (os.cpu_count() or 8) // max(1, world)))
+    blob = W.synth_objects(rank * n, n, threads=host_threads)
     gen_s = time.perf_counter() - t0
     rb = drv.upload_blob(blob)                       # flatten + H2D once: inputs resident for the `value` leg
     alg_in = rb.alg_bytes
@@ -272,7 +274,8 @@ def run_ours(args):
     assert resp.totals == totals_host, "e2e path and resident path disagree"
     e2e = {"value": world * n * C / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(resp.stats["h2d_bytes"]) * world,
            "d2h_bytes_per_step": int(resp.stats["d2h_bytes"] + 16 * C) * world, "steps": e2e_steps,
-           "breakdown_ms": {k: round(resp.stats[k], 3) for k in ("flatten_ms", "h2d_ms", "kernel_ms", "d2h_ms")}}
+           "breakdown_ms": {k: round(resp.stats[k], 3) for k in ("flatten_ms", "h2d_ms", "kernel_ms", "d2h_ms")},
+           "host_threads_per_gpu": host_threads}
 
     if rank != 0:
         if world > 1:

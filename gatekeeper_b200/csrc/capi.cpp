@@ -431,6 +431,8 @@ char* gk_validation_messages(gk_engine_t* e, const gk_result* r, uint32_t object
   return out;
 }
 
+int gk_host_cpus(void) { return effective_cpus(); }
+
 void gk_free_result(gk_result* r) {
   if (!r || !r->priv) return;
   delete static_cast<ResultPriv*>(r->priv);

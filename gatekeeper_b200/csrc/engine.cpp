@@ -1,5 +1,7 @@
 #include "engine.hpp"
 
+#include <sched.h>
+
 #include <chrono>
 
 #include <algorithm>
@@ -185,7 +187,35 @@ static std::string parse_selector(const VP& sel, std::vector<SelReq>& out) {
 }
 
 // ============================================================================================== engine
-Engine::Engine(int threads) : threads_(threads > 0 ? threads : (int)std::max(1u, std::thread::hardware_concurrency())) {}
+// CPUs this process may actually use: the smaller of the affinity mask and the cgroup CPU quota (a container on a
+// 128-thread host is often capped at a fraction of it; more runnable threads than quota only buys throttling).
+int effective_cpus() {
+  int n = (int)std::max(1u, std::thread::hardware_concurrency());
+  cpu_set_t set;
+  if (sched_getaffinity(0, sizeof set, &set) == 0) n = std::min(n, std::max(1, CPU_COUNT(&set)));
+  auto quota = [&](const char* path_quota, const char* path_period) {
+    FILE* f = fopen(path_quota, "r");
+    if (!f) return;
+    char a[64] = {0}, b[64] = {0};
+    int got = fscanf(f, "%63s %63s", a, b);
+    fclose(f);
+    if (got < 1 || !strcmp(a, "max")) return;
+    double q = atof(a), p = got >= 2 ? atof(b) : 0;
+    if (path_period) {
+      FILE* g = fopen(path_period, "r");
+      if (g) {
+        if (fscanf(g, "%63s", b) == 1) p = atof(b);
+        fclose(g);
+      }
+    }
+    if (q > 0 && p > 0) n = std::min(n, std::max(1, (int)(q / p + 0.5)));
+  };
+  quota("/sys/fs/cgroup/cpu.max", nullptr);                                                        // cgroup v2
+  quota("/sys/fs/cgroup/cpu/cpu.cfs_quota_us", "/sys/fs/cgroup/cpu/cpu.cfs_period_us");          // cgroup v1
+  return n;
+}
+
+Engine::Engine(int threads) : threads_(threads > 0 ? threads : effective_cpus()) {}
 
 void Engine::add_template(const std::string& kind, const std::string& rego) {
   auto mod = rego_parse(rego);   // throws RegoError on syntax / unsafe-var errors
@@ -761,8 +791,16 @@ struct Flattener {
         }
       }
     }
-    return ev.eval_first(cl.term, env);
+    // slow path through the evaluator: remember the value for this object -- the same closure feeds several columns
+    // (a scope generator that is also a column, split(image, ":") under both its count and its last element, ...)
+    const uint64_t mkey = (uint64_t)(uintptr_t)&cl * 0x9E3779B97F4A7C15ull + r;
+    auto mit = memo.find(mkey);
+    if (mit != memo.end()) return mit->second;
+    VP out = ev.eval_first(cl.term, env);
+    memo.emplace(mkey, out);
+    return out;
   }
+  std::unordered_map<uint64_t, VP> memo;   // per object: (closure, row) -> value
 
   void header_row(const VP& o, const VP& ns, uint8_t source, bool present) {
     uint32_t fl = 0;
@@ -917,6 +955,7 @@ struct Flattener {
     if (nscopes > 1 || !hb.cols.empty()) {
       VP input = v_obj({{v_str("review"), doc}});
       for (auto& e : evals) e.second->reset_input(input);
+      memo.clear();
       for (auto& r : rows) r.clear();
       rows[0].push_back(Row{nullptr, nullptr, 0});
       for (size_t s = 1; s < nscopes; ++s) {

@@ -174,6 +174,7 @@ class Engine {
   int threads_;
 };
 
+int effective_cpus();   // affinity mask and cgroup quota respected
 void split_gv(const VP& obj, std::string& group, std::string& version, std::string& kind);   // apiVersion -> (group, version), kind
 std::string meta_str(const VP& obj, const char* field);                                       // metadata.<field> or ""
 

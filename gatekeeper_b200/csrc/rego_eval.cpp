@@ -630,10 +630,9 @@ bool Eval::eval_body(const std::vector<Stmt>& body, size_t i, Env& env, const En
   if (st.k == Stmt::Not) {
     bool found = false;
     size_t mk = env.mark();
-    Stmt inner;
-    inner.k = Stmt::Expr;
-    inner.a = st.a;
-    eval_stmt(inner, env, [&]() {
+    // (no copy of the statement: a TP copy would bounce the term's reference count between all flatten threads)
+    eval_term(st.a, env, [&](const VP& v) {
+      if (v->t == VT::False) return false;
       found = true;
       return true;
     });
@@ -913,9 +912,9 @@ bool Eval::eval_call(const Term& t, Env& env, const ValK& k) {
   const auto* frules = static_cast<const std::vector<Rule>*>(t.rules_);
   bool user = frules != nullptr;
   size_t nargs = t.args.size();
-  TP out_pat;
+  const TP* out_pat = nullptr;
   if (user && nargs == (*frules)[0].args.size() + 1) {
-    out_pat = t.args.back();
+    out_pat = &t.args.back();
     --nargs;
   }
   std::vector<VP> acc;
@@ -930,7 +929,7 @@ bool Eval::eval_call(const Term& t, Env& env, const ValK& k) {
         if (!known) throw RegoError{"rego_type_error: undefined function " + t.name + " (line " + std::to_string(t.line) + ")"};
       }
       if (!v) return false;
-      if (out_pat) return unify_val(out_pat, v, env, [&]() { return k(v_bool(true)); });
+      if (out_pat) return unify_val(*out_pat, v, env, [&]() { return k(v_bool(true)); });
       return k(v);
     }
     return eval_term(t.args[i], env, [&](const VP& v) {

@@ -68,7 +68,7 @@ EXPORTS = [
     "gk_add_constraint", "gk_remove_constraint", "gk_put_namespace", "gk_remove_namespace", "gk_constraint_count",
     "gk_constraint_key", "gk_review_batch", "gk_batch_upload", "gk_batch_eval", "gk_batch_eval_device",
     "gk_batch_upload_blob", "gk_review_blob", "gk_set_excluded_namespaces", "gk_audit_begin", "gk_audit_add_batch", "gk_audit_report",
-    "gk_audit_end", "gk_validation_messages", "gk_batch_size", "gk_batch_alg_bytes", "gk_batch_free", "gk_free_result", "gk_free_str", "gk_dump",
+    "gk_audit_end", "gk_validation_messages", "gk_host_cpus", "gk_batch_size", "gk_batch_alg_bytes", "gk_batch_free", "gk_free_result", "gk_free_str", "gk_dump",
     "gk_stat_description",
 ]
 
@@ -112,6 +112,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.gk_audit_end.restype = None
     lib.gk_validation_messages.argtypes = [P, C.POINTER(gk_result), U32, PP]
     lib.gk_validation_messages.restype = C.c_void_p
+    lib.gk_host_cpus.argtypes = []
+    lib.gk_host_cpus.restype = C.c_int
     lib.gk_batch_size.argtypes = [P]
     lib.gk_batch_alg_bytes.restype = U64
     lib.gk_batch_alg_bytes.argtypes = [P]

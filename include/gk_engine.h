@@ -158,6 +158,9 @@ void gk_audit_end(gk_audit_t* a);
  * JSON {"deny": ["[<constraint name>] <msg>", ...], "warn": [...]}.  Caller frees with gk_free_str. */
 char* gk_validation_messages(gk_engine_t* e, const gk_result* r, uint32_t object, char** err);
 
+/* CPUs the flattener will use by default (gk_cfg.threads = 0): affinity mask and cgroup CPU quota respected */
+int gk_host_cpus(void);
+
 void gk_free_result(gk_result* r);
 void gk_free_str(char* s);
 char* gk_dump(gk_engine_t* e);
