@@ -536,6 +536,25 @@ std::string Engine::dump() {
     for (size_t i = 0; i + 1 < c->phase_off.size(); ++i) o += " " + std::to_string(c->phase_off[i + 1] - c->phase_off[i]);
     o += "\n";
   }
+  {
+    // op mix: per kind and level, the number of ops and of (input, output) pairs / gate inputs / atoms per column
+    std::map<std::string, std::pair<int, int>> mix;
+    std::map<uint32_t, int> atoms_per_col;
+    for (auto& op : c->ops) {
+      uint32_t kind = op.w0 & 0xff, level = (op.w0 >> 8) & 0xff;
+      const char* nm = kind == GK_N_ATOM ? "atom" : kind == GK_N_GATE ? "gate" : kind == GK_N_BCAST ? "bcast" : kind == GK_N_ACC ? "acc"
+                       : kind == GK_N_MATCH ? "match" : kind == GK_N_CONST ? "const" : "?";
+      auto& m = mix[std::string(nm) + "@s" + std::to_string(level)];
+      m.first++;
+      m.second += (kind == GK_N_GATE || kind == GK_N_BCAST || kind == GK_N_ACC) ? (int)op.w3 : 1;
+      if (kind == GK_N_ATOM) atoms_per_col[op.w1 >> 8]++;
+    }
+    o += "  op mix (ops/operands):";
+    for (auto& kv : mix) o += " " + kv.first + "=" + std::to_string(kv.second.first) + "/" + std::to_string(kv.second.second);
+    o += "\n  atoms per column:";
+    for (auto& kv : atoms_per_col) o += " c" + std::to_string(kv.first) + "=" + std::to_string(kv.second);
+    o += "\n";
+  }
   for (size_t i = 1; i < c->schema.scopes.size(); ++i)
     o += "  scope " + std::to_string(i) + " parent " + std::to_string(c->schema.scopes[i].parent) + ": " + c->schema.scopes[i].gen->key + "\n";
   for (size_t i = 0; i < c->schema.cols.size(); ++i)
@@ -857,6 +876,9 @@ struct Flattener {
     }
     if (enc & GK_ENC_VT) hc.vt.push_back(vt);
     if (enc & GK_ENC_SID) hc.sid.push_back(v ? sid(intern_key(v)) : GK_SID_UNDEF);
+    // non-numbers carry the extreme that OPA's cross-type order gives them relative to every number (null, booleans
+    // below; strings, composites above): the device's ordered compares then need no type dispatch
+    if (v && v->t != VT::Num && (enc & GK_ENC_NUM)) num = type_rank(v->t) < type_rank(VT::Num) ? INT64_MIN : INT64_MAX;
     if (enc & GK_ENC_NUM) hc.num.push_back(num);
     if (enc & GK_ENC_BYTES) {
       if (v && v->t == VT::Str) hc.bytes.insert(hc.bytes.end(), v->s.begin(), v->s.end());

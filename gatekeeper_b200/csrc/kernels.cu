@@ -156,7 +156,7 @@ class CudaBackend : public Backend {
     uint32_t slot_words = 0;
     for (size_t i = 0; i < slot_off.size(); ++i) {
       slot_off[i] = slot_words;
-      slot_words += (cap[c.slot_level[i]] + 31) / 32 + 1;
+      slot_words += ((cap[c.slot_level[i]] + 31) / 32 + 1 + 3) & ~3u;   // 16-byte aligned, padded: atoms store 4 words at a time
     }
     auto* db = new DevBatch();
     db->bytes = gk_align(pb.arena.size());

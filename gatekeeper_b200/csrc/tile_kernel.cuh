@@ -61,25 +61,25 @@ __device__ __forceinline__ uint32_t range_mask(uint32_t w, uint32_t a, uint32_t 
   return (nb == 32u ? 0xffffffffu : ((1u << nb) - 1u)) << (x - lo);
 }
 
-// rows [w0*32, min(cnt, w1*32)) of one column, one ballot-packed word per 32 rows.  The op switch is OUTSIDE the row
-// loop: every loop body is a straight load-compare-ballot sequence.
-// Four 32-row groups per trip: the four loads are independent, so four memory requests per lane are in flight
-// before the first compare.
+// words [w0, w1) of one column's tile slice, one ballot-packed word per 32 rows.  The op switch is OUTSIDE the row loop:
+// every loop body is a straight load-compare-ballot sequence over FOUR 32-row groups -- four independent loads per lane
+// in flight, no per-group bounds branch (rows past the tile's count evaluate to 0; slots are padded to 4 words), and
+// lane 0 stores the four result words with one 128-bit shared-memory store.  w0 is a multiple of 4.
 #define GK_ATOM_LOOP(EXPR)                                                        \
-  for (uint32_t r0 = w0 * 32u + lane; r0 < w1 * 32u; r0 += 128u) {                \
+  for (uint32_t w = w0; w < w1; w += 4u) {                                        \
+    const uint32_t r0 = w * 32u + lane;                                           \
+    const size_t row0 = (size_t)lo + r0;                                          \
     bool v4[4];                                                                   \
     _Pragma("unroll") for (int u = 0; u < 4; ++u) {                               \
-      const uint32_t r = r0 + 32u * u;                                            \
-      const uint32_t row = lo + r;                                                \
-      v4[u] = r < cnt && r < w1 * 32u && (EXPR);                                  \
+      const size_t row = row0 + 32u * u;                                          \
+      v4[u] = (r0 + 32u * u < cnt) && (EXPR);                                     \
     }                                                                             \
-    _Pragma("unroll") for (int u = 0; u < 4; ++u) {                               \
-      const uint32_t r = r0 + 32u * u;                                            \
-      if (r - lane < w1 * 32u) { /* warp-uniform */                               \
-        const uint32_t wd = __ballot_sync(0xffffffffu, v4[u]);                    \
-        if (lane == 0) out[r >> 5] = wd;                                          \
-      }                                                                           \
-    }                                                                             \
+    uint4 wd;                                                                     \
+    wd.x = __ballot_sync(0xffffffffu, v4[0]);                                     \
+    wd.y = __ballot_sync(0xffffffffu, v4[1]);                                     \
+    wd.z = __ballot_sync(0xffffffffu, v4[2]);                                     \
+    wd.w = __ballot_sync(0xffffffffu, v4[3]);                                     \
+    if (lane == 0) *reinterpret_cast<uint4*>(out + w) = wd;                       \
   }
 
 __device__ __forceinline__ bool sid_in_small(const uint32_t* pool, uint32_t a, uint32_t b, uint32_t v) {
@@ -88,7 +88,7 @@ __device__ __forceinline__ bool sid_in_small(const uint32_t* pool, uint32_t a, u
   return hit;
 }
 
-__device__ __forceinline__ bool num_cmp_row(const uint8_t* vt, const int64_t* num, uint32_t row, int64_t k, uint32_t cmp) {
+__device__ __forceinline__ bool num_cmp_row(const uint8_t* vt, const int64_t* num, size_t row, int64_t k, uint32_t cmp) {
   const uint32_t t = vt[row];
   if (t == GK_VT_NUM) {
     const int64_t v = num[row];
@@ -134,7 +134,19 @@ __device__ __forceinline__ void atom_rows(const GkColumn& c, uint32_t aop, uint3
       const uint8_t* vt = c.vt;
       const int64_t* num = c.num;
       const int64_t k = (int64_t)(((uint64_t)pool[a + 1] << 32) | pool[a]);
-      GK_ATOM_LOOP(num_cmp_row(vt, num, row, k, b))
+      if (k == INT64_MIN || k == INT64_MAX) {   // the sentinels of non-numbers (see Flattener::encode): generic path
+        GK_ATOM_LOOP(num_cmp_row(vt, num, row, k, b))
+        break;
+      }
+      // a defined non-number holds INT64_MIN / INT64_MAX according to its type rank, so one signed compare is OPA's order
+      switch (b) {
+        case GK_CMP_LT: GK_ATOM_LOOP(vt[row] != GK_VT_UNDEF && num[row] < k) break;
+        case GK_CMP_LE: GK_ATOM_LOOP(vt[row] != GK_VT_UNDEF && num[row] <= k) break;
+        case GK_CMP_GT: GK_ATOM_LOOP(vt[row] != GK_VT_UNDEF && num[row] > k) break;
+        case GK_CMP_GE: GK_ATOM_LOOP(vt[row] != GK_VT_UNDEF && num[row] >= k) break;
+        case GK_CMP_EQ: GK_ATOM_LOOP(vt[row] != GK_VT_UNDEF && num[row] == k) break;
+        default: GK_ATOM_LOOP(vt[row] != GK_VT_UNDEF && num[row] != k) break;
+      }
       break;
     }
     case GK_OP_ANYPREFIX: {
@@ -149,7 +161,8 @@ __device__ __forceinline__ void atom_rows(const GkColumn& c, uint32_t aop, uint3
         GK_ATOM_LOOP(gk_atom(c, row, aop, a, b, pool, cbytes))
         break;
       }
-      for (uint32_t r = w0 * 32u + lane; r < w1 * 32u; r += 32u) {
+      const uint32_t wend = min(w1, (cnt + 31u) >> 5);
+      for (uint32_t r = w0 * 32u + lane; r < wend * 32u; r += 32u) {
         bool v = false;
         if (r < cnt && vt[lo + r] == GK_VT_STR) {
           const uint4 h0 = head[2 * (size_t)(lo + r)], h1 = head[2 * (size_t)(lo + r) + 1];
@@ -249,8 +262,8 @@ __global__ void __launch_bounds__(kThreads) gk_eval_kernel(const KParams p) {
         switch (kind) {
           case GK_N_ATOM: {
             const uint32_t cnt = s_cnt[level], words = (cnt + 31u) >> 5;
-            atom_rows(cols[op.w1 >> 8], op.w1 & 0xffu, op.w2, op.w3, pool, cbytes, s_lo[level], cnt, words * part / nparts,
-                      words * (part + 1u) / nparts, lane, out);
+            const uint32_t pw0 = (words * part / nparts) & ~3u, pw1 = part + 1u == nparts ? words : ((words * (part + 1u) / nparts) & ~3u);
+            atom_rows(cols[op.w1 >> 8], op.w1 & 0xffu, op.w2, op.w3, pool, cbytes, s_lo[level], cnt, pw0, pw1, lane, out);
             break;
           }
           case GK_N_GATE: {
@@ -302,24 +315,26 @@ __global__ void __launch_bounds__(kThreads) gk_eval_kernel(const KParams p) {
             const uint32_t* pairs = pool + op.w1;
             const uint32_t* coff = scopes[level].off + s_lo[par];
             const uint32_t clo = s_lo[level], pcnt = s_cnt[par];
-            const uint32_t pw = (pcnt + 31u) >> 5;
+            const uint32_t pw = (pcnt + 31u) >> 5, cw = (s_cnt[level] + 31u) >> 5;
             for (uint32_t r = (pw * part / nparts) * 32u + lane; r < (pw * (part + 1u) / nparts) * 32u; r += 32u) {
               uint32_t a = 0, b = 0;
               if (r < pcnt) {
                 a = coff[r] - clo;
                 b = coff[r + 1] - clo;
               }
-              const bool one = b > a && (a >> 5) == ((b - 1u) >> 5);     // the usual case: children inside one word
-              const uint32_t wi = a >> 5;
-              const uint32_t nb = b - a;
-              const uint32_t m = one ? ((nb == 32u ? FULL : ((1u << nb) - 1u)) << (a & 31u)) : 0u;
+              // A range of up to 32 children is a 32-bit window of the child bit column starting at bit a: one funnel
+              // shift over two adjacent words, branch-free for every lane.  Longer ranges (rare) add a tail loop.
+              const uint32_t nb = b - a, sh = a & 31u;
+              const uint32_t m = nb >= 32u ? FULL : ((1u << nb) - 1u);
+              const uint32_t wl = cw ? min(a >> 5, cw - 1u) : 0u, wh = cw ? min((a >> 5) + 1u, cw - 1u) : 0u;
+              const bool wide = nb > 32u;
+              const bool any_wide = __any_sync(FULL, wide);
               for (uint32_t j = 0; j < npair; ++j) {
                 const uint32_t e = pairs[j];
                 const uint32_t* in = slots + s_soff[e & 0xffffu];
-                bool any = false;
-                if (one) any = (in[wi] & m) != 0u;
-                else if (b > a)
-                  for (uint32_t w = wi; w <= (b - 1u) >> 5 && !any; ++w) any = (in[w] & range_mask(w, a, b)) != 0u;
+                bool any = cw != 0u && (__funnelshift_r(in[wl], in[wh], sh) & m) != 0u;
+                if (any_wide && wide && !any)
+                  for (uint32_t w = (a + 32u) >> 5; w <= (b - 1u) >> 5 && !any; ++w) any = (in[w] & range_mask(w, a + 32u, b)) != 0u;
                 const uint32_t wd = __ballot_sync(FULL, any);
                 if (lane == 0) slots[s_soff[e >> 16] + (r >> 5)] = wd;
               }
