@@ -35,7 +35,7 @@ def _deps_mtime():
     m = 0.0
     for d in (CSRC, os.path.join(ROOT, "include")):
         for f in os.listdir(d):
-            if f.endswith((".h", ".hpp")):
+            if f.endswith((".h", ".hpp", ".cuh")):
                 m = max(m, os.path.getmtime(os.path.join(d, f)))
     return m
 
@@ -52,6 +52,18 @@ def _run(cmd):
     if r.returncode != 0:
         raise RuntimeError("build failed: " + " ".join(cmd) + "\n" + r.stdout + r.stderr)
     return r.stdout + r.stderr
+
+
+def build_variant(suffix, defines):
+    """Kernel experiment: libgk_engine<suffix>.so with extra -D flags on the CUDA translation unit
+    (select it with GK_ENGINE_LIB=...).  The host objects of the regular build are reused."""
+    build()
+    ko = os.path.join(OBJ, "kernels%s.cu.o" % suffix)
+    _run([_nvcc(), *NVCCFLAGS, *["-D" + d for d in defines], "-c", os.path.join(CSRC, "kernels.cu"), "-o", ko])
+    objs = [os.path.join(OBJ, s + ".o") for s in HOST_SRCS]
+    out = os.path.join(ROOT, "gatekeeper_b200", "libgk_engine%s.so" % suffix)
+    _run([_nvcc(), "-shared", "-o", out, *objs, ko, "-Xcompiler", "-pthread", "-cudart", "static"])
+    return out
 
 
 def build(verbose=False, hostemu=True, force=False):
@@ -90,5 +102,8 @@ def build(verbose=False, hostemu=True, force=False):
 
 
 if __name__ == "__main__":
-    build(verbose=True, force="--force" in sys.argv)
-    print("built", LIB)
+    if len(sys.argv) > 2 and sys.argv[1] == "--variant":      # python build.py --variant _timing GK_PHASE_TIMING=1 ...
+        print("built", build_variant(sys.argv[2], sys.argv[3:]))
+    else:
+        build(verbose=True, force="--force" in sys.argv)
+        print("built", LIB)

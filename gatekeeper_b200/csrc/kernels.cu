@@ -31,7 +31,10 @@ struct DevBatch {
   uint32_t words = 0;
   // tiling (depends on the batch's row distribution and on the program's slot table)
   uint32_t* d_tile_lo = nullptr;
-  uint32_t* d_slot_off = nullptr;
+  // the netlist with every slot id replaced by the slot's word offset in this batch's shared-memory slot area
+  GkOp* d_ops = nullptr;
+  uint32_t* d_pool = nullptr;
+  GkOutEnt* d_outs = nullptr;
   uint32_t ntiles = 0, slot_words = 0;
   uint64_t prog_version = 0;
 };
@@ -166,7 +169,49 @@ class CudaBackend : public Backend {
     db->prog_version = c.version;
     CK(cudaMalloc(&db->arena, db->bytes));
     CK(cudaMalloc(&db->d_tile_lo, tile_lo.size() * 4 + 64));
-    CK(cudaMalloc(&db->d_slot_off, slot_off.size() * 4 + 64));
+    // resolve slot ids -> word offsets once per batch: the kernel then addresses slots without a table lookup
+    std::vector<GkOp> ops_r = c.ops;
+    std::vector<uint32_t> pool_r = c.pool;
+    std::vector<GkOutEnt> outs_r = c.outs;
+    {
+      if (slot_words > 0xffffu) throw BackendError{"slot area exceeds 16-bit word offsets"};
+      std::vector<uint8_t> done(pool_r.size(), 0);
+      auto so = [&](uint32_t slot) { return slot < slot_off.size() ? slot_off[slot] : 0u; };
+      for (auto& op : ops_r) {
+        const uint32_t kind = op.w0 & 0xffu;
+        op.w0 = (op.w0 & 0xffffu) | (so(op.w0 >> 16) << 16);
+        if (kind == GK_N_GATE) {
+          for (uint32_t j = 0; j < op.w3; ++j) {
+            uint32_t& e = pool_r[op.w1 + j];
+            if (done[op.w1 + j]++) continue;
+            e = (e & 0x80000000u) | so(e & 0xffffu);
+          }
+        } else if (kind == GK_N_BCAST || kind == GK_N_ACC) {
+          for (uint32_t j = 0; j < op.w3; ++j) {
+            uint32_t& e = pool_r[op.w1 + j];
+            if (done[op.w1 + j]++) continue;
+            e = so(e & 0xffffu) | (so(e >> 16) << 16);
+          }
+        } else if (kind == GK_N_MATCH) {
+          op.w1 = so(op.w1 & 0xffffu);
+        }
+      }
+      for (auto& oe : outs_r) {
+        oe.prog_slot = (uint16_t)so(oe.prog_slot);
+        oe.match_slot = (uint16_t)so(oe.match_slot);
+        oe.err_slot = (uint16_t)so(oe.err_slot);
+      }
+    }
+    auto r64 = [](size_t b) { return (b + 63) / 64 * 64 + 64; };
+    CK(cudaMalloc(&db->d_ops, r64(ops_r.size() * sizeof(GkOp))));
+    CK(cudaMalloc(&db->d_pool, r64(pool_r.size() * 4)));
+    CK(cudaMalloc(&db->d_outs, r64(outs_r.size() * sizeof(GkOutEnt))));
+    CK(cudaMemset(db->d_ops, 0, r64(ops_r.size() * sizeof(GkOp))));
+    CK(cudaMemset(db->d_pool, 0, r64(pool_r.size() * 4)));
+    CK(cudaMemset(db->d_outs, 0, r64(outs_r.size() * sizeof(GkOutEnt))));
+    if (!ops_r.empty()) CK(cudaMemcpy(db->d_ops, ops_r.data(), ops_r.size() * sizeof(GkOp), cudaMemcpyHostToDevice));
+    if (!pool_r.empty()) CK(cudaMemcpy(db->d_pool, pool_r.data(), pool_r.size() * 4, cudaMemcpyHostToDevice));
+    if (!outs_r.empty()) CK(cudaMemcpy(db->d_outs, outs_r.data(), outs_r.size() * sizeof(GkOutEnt), cudaMemcpyHostToDevice));
     db->hdr = rebase_batch(pb, pb.arena.data(), db->arena);
     cudaEvent_t a, b;
     CK(cudaEventCreate(&a));
@@ -183,7 +228,6 @@ class CudaBackend : public Backend {
       CK(cudaEventRecord(a, stream_));
       CK(cudaMemcpyAsync(db->arena, pinned_, pb.arena.size(), cudaMemcpyHostToDevice, stream_));
       CK(cudaMemcpyAsync(db->d_tile_lo, tile_lo.data(), tile_lo.size() * 4, cudaMemcpyHostToDevice, stream_));
-      CK(cudaMemcpyAsync(db->d_slot_off, slot_off.data(), slot_off.size() * 4, cudaMemcpyHostToDevice, stream_));
       CK(cudaEventRecord(b, stream_));
       CK(cudaStreamSynchronize(stream_));
     }
@@ -192,7 +236,7 @@ class CudaBackend : public Backend {
     cudaEventDestroy(a);
     cudaEventDestroy(b);
     if (h2d_ms) *h2d_ms = ms;
-    if (h2d_bytes) *h2d_bytes = pb.arena.size() + tile_lo.size() * 4 + slot_off.size() * 4;
+    if (h2d_bytes) *h2d_bytes = pb.arena.size() + tile_lo.size() * 4 + ops_r.size() * sizeof(GkOp) + pool_r.size() * 4 + outs_r.size() * sizeof(GkOutEnt);
     db->words = std::max<uint32_t>(1, (uint32_t)((c.cons_match.size() + 31) / 32));
     CK(cudaMalloc(&db->viol, (size_t)std::max(db->n, 1u) * db->words * 4));
     CK(cudaMalloc(&db->err, (size_t)std::max(db->n, 1u) * db->words * 4));
@@ -207,7 +251,9 @@ class CudaBackend : public Backend {
     cudaFree(db->viol);
     cudaFree(db->err);
     cudaFree(db->d_tile_lo);
-    cudaFree(db->d_slot_off);
+    cudaFree(db->d_ops);
+    cudaFree(db->d_pool);
+    cudaFree(db->d_outs);
     delete db;
   }
 
@@ -231,11 +277,19 @@ class CudaBackend : public Backend {
     p.out.errcap = kErrCap;
     p.out.words = db->words;
     p.active = d_active_;
-    p.slot_off = db->d_slot_off;
+    p.prog.ops = db->d_ops;      // slot ids resolved for this batch
+    p.prog.pool = db->d_pool;
+    p.prog.outs = db->d_outs;
     p.tile_lo = db->d_tile_lo;
     p.ntiles = db->ntiles;
     p.tile = kTile;
     p.slot_words = db->slot_words;
+    p.timing = nullptr;
+#ifdef GK_PHASE_TIMING
+    if (!d_timing_) CK(cudaMalloc(&d_timing_, (kMaxPhases + 2 + 16) * 16));
+    CK(cudaMemsetAsync(d_timing_, 0, (kMaxPhases + 2 + 16) * 16, st));
+    p.timing = d_timing_;
+#endif
     if (active.size() != C) throw BackendError{"active mask size mismatch"};
     if (C && active != last_active_) {
       CK(cudaMemcpyAsync(d_active_, active.data(), (size_t)C * 4, cudaMemcpyHostToDevice, st));
@@ -247,10 +301,12 @@ class CudaBackend : public Backend {
     CK(cudaMemsetAsync(d_scalars_, 0, 64, st));
     auto r16 = [](size_t x) { return (x + 15) / 16 * 16; };
     const size_t NS = nscopes_;
-    size_t smem = 3 * r16((size_t)C * 4) + 2 * r16(NS * 4) + r16((size_t)kMaxPhases * 4) + r16((size_t)(prog_.nphases + 1) * 4) +
-                  r16((size_t)prog_.nslots * 4) + r16((size_t)C * sizeof(GkOutEnt)) + r16((size_t)db->slot_words * 4) +
-                  r16((size_t)prog_.nops * sizeof(GkOp)) + r16((size_t)prog_.nitems * 4) + r16((size_t)prog_.nmatch * sizeof(GkMatch)) +
-                  r16((size_t)ncols_ * sizeof(GkColumn)) + r16(NS * sizeof(GkScope)) + r16((size_t)prog_.npool * 4) + r16((size_t)prog_.ncbytes) + 64;
+    size_t smem = 3 * r16((size_t)C * 4) + 2 * r16(NS * 4) + r16((size_t)(prog_.nphases + 1) * 4) + r16((size_t)db->slot_words * 4) + 64;
+#if GK_TABLES_IN_SMEM
+    smem += r16((size_t)C * sizeof(GkOutEnt)) + r16((size_t)prog_.nops * sizeof(GkOp)) + r16((size_t)prog_.nitems * 4) +
+            r16((size_t)prog_.nmatch * sizeof(GkMatch)) + r16((size_t)ncols_ * sizeof(GkColumn)) + r16(NS * sizeof(GkScope)) +
+            r16((size_t)prog_.npool * 4) + r16((size_t)prog_.ncbytes);
+#endif
     if (smem > max_smem_)
       throw BackendError{"constraint set needs " + std::to_string(smem) + " bytes of shared memory per CTA (limit " + std::to_string(max_smem_) +
                          "): too many live netlist columns for one launch"};
@@ -261,7 +317,10 @@ class CudaBackend : public Backend {
   void fire(const KParams& p, size_t smem, cudaStream_t st) {
     if (p.ntiles == 0) return;
     // persistent CTAs: as many as fit per SM (shared-memory bound), each walks tiles with a grid stride
-    int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2048 / kThreads, (sm_smem_ - 1024) / (smem + 1024)));
+    int per_sm = 1;   // resident CTAs per SM for this launch configuration (registers and shared memory)
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gk_eval_kernel, kThreads, smem));
+    per_sm = std::max(1, per_sm);
+    if (getenv("GK_TRACE_LAUNCH")) fprintf(stderr, "[launch] %d CTAs/SM x %d threads, %zu B smem/CTA, %u tiles of %u objects\n", per_sm, kThreads, smem, p.ntiles, kTile);
     uint32_t grid = std::max(1u, std::min<uint32_t>(p.ntiles, (uint32_t)(sms_ * per_sm)));
     gk_eval_kernel<<<grid, kThreads, smem, st>>>(p);
     CK(cudaGetLastError());
@@ -287,6 +346,25 @@ class CudaBackend : public Backend {
     CK(cudaEventRecord(ev1_, stream_));
     CK(cudaStreamSynchronize(stream_));
     CK(cudaEventElapsedTime(&out.kernel_ms, ev0_, ev1_));
+#ifdef GK_PHASE_TIMING
+    {
+      std::vector<unsigned long long> t((kMaxPhases + 2 + 16) * 2);
+      CK(cudaMemcpy(t.data(), d_timing_, t.size() * 8, cudaMemcpyDeviceToHost));
+      unsigned long long tot = 0;
+      for (uint32_t ph = 0; ph <= prog_.nphases; ++ph) tot += t[2 * ph];
+      fprintf(stderr, "[phase timing] kernel %.3f ms, %u tiles\n", out.kernel_ms, db->ntiles);
+      for (uint32_t ph = 0; ph <= prog_.nphases; ++ph)
+        fprintf(stderr, "  %s %2u: %5.1f%% of CTA time, %7.0f cycles/tile, warp utilisation %4.1f%%\n", ph == prog_.nphases ? "gather" : "phase ", ph,
+                100.0 * t[2 * ph] / std::max(1ull, tot), (double)t[2 * ph] / std::max(1u, db->ntiles),
+                100.0 * t[2 * ph + 1] / std::max(1.0, (double)t[2 * ph] * kWarps));
+      const char* kn[] = {"", "", "atom", "gate", "const", "bcast", "acc", "match"};
+      for (uint32_t k = 2; k < 8; ++k) {
+        const unsigned long long cyc = t[2 * (kMaxPhases + 2) + 2 * k], cnt = t[2 * (kMaxPhases + 2) + 2 * k + 1];
+        if (cnt) fprintf(stderr, "  items %-5s: %6.1f per tile, %7.0f cycles each, %8.0f warp-cycles per tile\n", kn[k], (double)cnt / db->ntiles,
+                         (double)cyc / cnt, (double)cyc / db->ntiles);
+      }
+    }
+#endif
     out.launches = launches_;
     out.totals.assign(C, 0);
     out.err_totals.assign(C, 0);
@@ -357,6 +435,7 @@ class CudaBackend : public Backend {
   unsigned long long* d_totals_ = nullptr;
   uint32_t* d_errlist_ = nullptr;
   uint32_t* d_active_ = nullptr;
+  unsigned long long* d_timing_ = nullptr;
   void* pinned_ = nullptr;
   size_t pinned_bytes_ = 0;
 };

@@ -27,15 +27,18 @@ struct KParams {
   GkProgram prog;
   GkOut out;
   const uint32_t* active;     // [nconstraints] enforcement-point filter
-  const uint32_t* slot_off;   // [nslots] word offset of each slot inside the slot area (depends on the batch's tile capacities)
   const uint32_t* tile_lo;    // [(ntiles + 1) * nscopes] first row of every scope for every tile (row ranges are contiguous)
   uint32_t ntiles;
   uint32_t tile;              // objects per tile (multiple of 32)
   uint32_t slot_words;        // words in the slot area
+  unsigned long long* timing; // GK_PHASE_TIMING builds: [kMaxPhases + 2][2] = (CTA cycles between barriers, summed warp busy cycles)
 };
 
 #ifndef GK_THREADS
 #define GK_THREADS 256
+#endif
+#ifndef GK_TABLES_IN_SMEM
+#define GK_TABLES_IN_SMEM 1   /* measured: 0.825 ms (tables staged in shared memory) vs 0.858 ms (read through L1) per 1M objects */
 #endif
 #ifndef GK_TILE
 #define GK_TILE 512
@@ -65,21 +68,26 @@ __device__ __forceinline__ uint32_t range_mask(uint32_t w, uint32_t a, uint32_t 
 // every loop body is a straight load-compare-ballot sequence over FOUR 32-row groups -- four independent loads per lane
 // in flight, no per-group bounds branch (rows past the tile's count evaluate to 0; slots are padded to 4 words), and
 // lane 0 stores the four result words with one 128-bit shared-memory store.  w0 is a multiple of 4.
+#ifndef GK_ATOM_UNROLL
+#define GK_ATOM_UNROLL 4      /* measured: 8 or 16 groups per trip cost registers (resident CTAs) and buy nothing */
+#endif
 #define GK_ATOM_LOOP(EXPR)                                                        \
-  for (uint32_t w = w0; w < w1; w += 4u) {                                        \
+  for (uint32_t w = w0; w < w1; w += GK_ATOM_UNROLL) {                            \
     const uint32_t r0 = w * 32u + lane;                                           \
     const size_t row0 = (size_t)lo + r0;                                          \
-    bool v4[4];                                                                   \
-    _Pragma("unroll") for (int u = 0; u < 4; ++u) {                               \
+    bool v4[GK_ATOM_UNROLL];                                                      \
+    _Pragma("unroll") for (int u = 0; u < GK_ATOM_UNROLL; ++u) {                  \
       const size_t row = row0 + 32u * u;                                          \
       v4[u] = (r0 + 32u * u < cnt) && (EXPR);                                     \
     }                                                                             \
-    uint4 wd;                                                                     \
-    wd.x = __ballot_sync(0xffffffffu, v4[0]);                                     \
-    wd.y = __ballot_sync(0xffffffffu, v4[1]);                                     \
-    wd.z = __ballot_sync(0xffffffffu, v4[2]);                                     \
-    wd.w = __ballot_sync(0xffffffffu, v4[3]);                                     \
-    if (lane == 0) *reinterpret_cast<uint4*>(out + w) = wd;                       \
+    _Pragma("unroll") for (int u = 0; u < GK_ATOM_UNROLL; u += 4) {               \
+      uint4 wd;                                                                   \
+      wd.x = __ballot_sync(0xffffffffu, v4[u]);                                   \
+      wd.y = __ballot_sync(0xffffffffu, v4[u + 1]);                               \
+      wd.z = __ballot_sync(0xffffffffu, v4[u + 2]);                               \
+      wd.w = __ballot_sync(0xffffffffu, v4[u + 3]);                               \
+      if (lane == 0 && w + u < wcap) *reinterpret_cast<uint4*>(out + w + u) = wd; \
+    }                                                                             \
   }
 
 __device__ __forceinline__ bool sid_in_small(const uint32_t* pool, uint32_t a, uint32_t b, uint32_t v) {
@@ -100,6 +108,7 @@ __device__ __forceinline__ bool num_cmp_row(const uint8_t* vt, const int64_t* nu
 
 __device__ __forceinline__ void atom_rows(const GkColumn& c, uint32_t aop, uint32_t a, uint32_t b, const uint32_t* pool, const uint8_t* cbytes,
                                           uint32_t lo, uint32_t cnt, uint32_t w0, uint32_t w1, uint32_t lane, uint32_t* out) {
+  const uint32_t wcap = (((cnt + 31u) >> 5) + 3u) & ~3u;   // words of the slot that may be written (slots are padded to 4 words)
   switch (aop) {
     case GK_OP_TRUTHY: {
       const uint8_t* vt = c.vt;
@@ -187,8 +196,59 @@ __device__ __forceinline__ void atom_rows(const GkColumn& c, uint32_t aop, uint3
   }
 }
 
+#ifdef GK_L2_PREFETCH
+// ---- L2 prefetch of a tile's input slices.
+// The netlist walks ~100 arrays per tile with short dependent loops, so a warp rarely has more than a few loads in flight:
+// without help every one of them pays DRAM latency.  While a CTA is busy with the (load-free) gate / EXISTS phases of tile
+// t, one warp asks the L2 for every array slice tile t + gridDim.x will read -- one bulk-prefetch instruction per array
+// slice, no registers or shared memory tied up.
+__device__ __forceinline__ void l2_prefetch(const void* base, size_t lo_bytes, size_t hi_bytes) {
+  if (!base || hi_bytes <= lo_bytes) return;
+  const uintptr_t a = (reinterpret_cast<uintptr_t>(base) + lo_bytes) & ~(uintptr_t)15;
+  const uintptr_t b = (reinterpret_cast<uintptr_t>(base) + hi_bytes + 15) & ~(uintptr_t)15;
+  const uint32_t n = (uint32_t)(b - a);
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(n) : "memory");
+}
+
+__device__ __noinline__ void prefetch_tile(const KParams& p, const GkColumn* cols, const GkScope* scopes, uint32_t t, uint32_t lane) {
+  const uint32_t NS = p.batch.nscopes;
+  const uint32_t* tl = p.tile_lo + (size_t)t * NS;
+  // header arrays (scope 0 rows) and the CSR offsets of every scope (rows of the parent, +1)
+  if (lane == 0) {
+    const size_t a = tl[0], b = tl[NS];
+    const GkBatch& h = p.batch;
+    l2_prefetch(h.flags, a * 4, b * 4);
+    l2_prefetch(h.kind_sid, a * 4, b * 4);
+    l2_prefetch(h.group_sid, a * 4, b * 4);
+    l2_prefetch(h.nsname_sid, a * 4, b * 4);
+    l2_prefetch(h.nsrow, a * 4, b * 4);
+    l2_prefetch(h.name_off, a * 4, (b + 1) * 4);
+    l2_prefetch(h.gen_off, a * 4, (b + 1) * 4);
+    l2_prefetch(h.lbl_off, a * 4, (b + 1) * 4);
+    if (h.lbl_off && b > a) l2_prefetch(h.lbl_kv, (size_t)h.lbl_off[a] * 8, (size_t)h.lbl_off[b] * 8);
+  }
+  for (uint32_t s = 1 + lane; s < NS; s += 32u) {
+    const uint32_t par = (uint32_t)scopes[s].parent;
+    l2_prefetch(scopes[s].off, (size_t)tl[par] * 4, ((size_t)tl[NS + par] + 1) * 4);
+  }
+  for (uint32_t c = lane; c < p.batch.ncols; c += 32u) {
+    const GkColumn& col = cols[c];
+    const size_t a = tl[col.scope], b = tl[NS + col.scope];
+    if (col.enc & GK_ENC_VT) l2_prefetch(col.vt, a, b);
+    if (col.enc & GK_ENC_SID) l2_prefetch(col.sid, a * 4, b * 4);
+    if (col.enc & GK_ENC_NUM) l2_prefetch(col.num, a * 8, b * 8);
+    if (col.enc & GK_ENC_HEAD) l2_prefetch(col.head, a * 32, b * 32);
+    if (col.enc & GK_ENC_BYTES) l2_prefetch(col.boff, a * 4, (b + 1) * 4);
+  }
+}
+
+#endif
+
 // One CTA = one tile of consecutive objects at a time; all intermediate bit columns live in shared memory.
-__global__ void __launch_bounds__(kThreads) gk_eval_kernel(const KParams p) {
+#ifndef GK_MIN_CTAS
+#define GK_MIN_CTAS 5         /* 5 resident CTAs per SM: the register cap this implies (<= 48) costs no spills */
+#endif
+__global__ void __launch_bounds__(kThreads, GK_MIN_CTAS) gk_eval_kernel(const KParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   const uint32_t C = p.prog.nconstraints, W = p.out.words, NS = p.batch.nscopes, NP = p.prog.nphases;
   // ---- shared-memory layout
@@ -203,11 +263,10 @@ __global__ void __launch_bounds__(kThreads) gk_eval_kernel(const KParams p) {
   uint32_t* s_act = static_cast<uint32_t*>(take((size_t)C * 4));
   uint32_t* s_lo = static_cast<uint32_t*>(take((size_t)NS * 4));
   uint32_t* s_cnt = static_cast<uint32_t*>(take((size_t)NS * 4));
-  uint32_t* s_ctr = static_cast<uint32_t*>(take((size_t)kMaxPhases * 4));
   uint32_t* s_poff = static_cast<uint32_t*>(take((size_t)(NP + 1) * 4));
-  uint32_t* s_soff = static_cast<uint32_t*>(take((size_t)p.prog.nslots * 4));
-  GkOutEnt* outs = static_cast<GkOutEnt*>(take((size_t)C * sizeof(GkOutEnt)));
   uint32_t* slots = static_cast<uint32_t*>(take((size_t)p.slot_words * 4));
+#if GK_TABLES_IN_SMEM
+  GkOutEnt* outs = static_cast<GkOutEnt*>(take((size_t)C * sizeof(GkOutEnt)));
   GkOp* ops = static_cast<GkOp*>(take((size_t)p.prog.nops * sizeof(GkOp)));
   uint32_t* items = static_cast<uint32_t*>(take((size_t)p.prog.nitems * 4));
   GkMatch* match = static_cast<GkMatch*>(take((size_t)p.prog.nmatch * sizeof(GkMatch)));
@@ -215,14 +274,26 @@ __global__ void __launch_bounds__(kThreads) gk_eval_kernel(const KParams p) {
   GkScope* scopes = static_cast<GkScope*>(take((size_t)NS * sizeof(GkScope)));
   uint32_t* pool = static_cast<uint32_t*>(take((size_t)p.prog.npool * 4));
   uint8_t* cbytes = static_cast<uint8_t*>(take((size_t)p.prog.ncbytes));
+#else
+  // the program / schema tables stay in global memory: every access is warp-uniform and read-only, so they live in L1
+  // after the first tile, and the shared memory they would occupy buys resident CTAs instead
+  const GkOutEnt* __restrict__ outs = p.prog.outs;
+  const GkOp* __restrict__ ops = p.prog.ops;
+  const uint32_t* __restrict__ items = p.prog.items;
+  const GkMatch* __restrict__ match = p.prog.match;
+  const GkColumn* __restrict__ cols = p.batch.cols;
+  const GkScope* __restrict__ scopes = p.batch.scopes;
+  const uint32_t* __restrict__ pool = p.prog.pool;
+  const uint8_t* __restrict__ cbytes = p.prog.cbytes;
+#endif
 
   for (uint32_t i = threadIdx.x; i < C; i += blockDim.x) {
     s_tot[i] = 0;
     s_err[i] = 0;
     s_act[i] = p.active[i];
   }
-  for (uint32_t i = threadIdx.x; i < p.prog.nslots; i += blockDim.x) s_soff[i] = p.slot_off[i];
   for (uint32_t i = threadIdx.x; i <= NP; i += blockDim.x) s_poff[i] = p.prog.phase_off[i];
+#if GK_TABLES_IN_SMEM
   stage(outs, p.prog.outs, ((size_t)C * sizeof(GkOutEnt) + 15) / 16 * 16);
   stage(ops, p.prog.ops, ((size_t)p.prog.nops * sizeof(GkOp) + 15) / 16 * 16);
   stage(items, p.prog.items, ((size_t)p.prog.nitems * 4 + 15) / 16 * 16);
@@ -231,10 +302,14 @@ __global__ void __launch_bounds__(kThreads) gk_eval_kernel(const KParams p) {
   stage(scopes, p.batch.scopes, ((size_t)NS * sizeof(GkScope) + 15) / 16 * 16);
   stage(pool, p.prog.pool, ((size_t)p.prog.npool * 4 + 15) / 16 * 16);
   stage(cbytes, p.prog.cbytes, ((size_t)p.prog.ncbytes + 15) / 16 * 16);
+#endif
   __syncthreads();
 
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const uint32_t FULL = 0xffffffffu;
+#ifdef GK_L2_PREFETCH   /* measured on B200: 0.78 ms -> 1.04 ms per 1M objects -- the bulk prefetches serialise on the issuing warp; off */
+  if (warp == kWarps - 1 && blockIdx.x < p.ntiles) prefetch_tile(p, cols, scopes, blockIdx.x, lane);
+#endif
 
   for (uint32_t t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
     // ---- tile row ranges (precomputed on the host: rows of a tile are contiguous at every scope)
@@ -243,26 +318,32 @@ __global__ void __launch_bounds__(kThreads) gk_eval_kernel(const KParams p) {
       s_lo[s] = a;
       s_cnt[s] = b - a;
     }
-    for (uint32_t i = threadIdx.x; i < NP; i += blockDim.x) s_ctr[i] = 0;
     __syncthreads();
     const uint32_t nobj = s_cnt[0], obj0 = s_lo[0];
 
     for (uint32_t ph = 0; ph < NP; ++ph) {
       const uint32_t ibase = s_poff[ph], icnt = s_poff[ph + 1] - ibase;
-      for (;;) {
-        uint32_t k = 0;
-        if (lane == 0) k = atomicAdd(&s_ctr[ph], 1u);
-        k = __shfl_sync(FULL, k, 0);
-        if (k >= icnt) break;
+#ifdef GK_PHASE_TIMING
+      const long long tp0 = clock64();
+#endif
+#ifdef GK_L2_PREFETCH   /* measured on B200: 0.78 ms -> 1.04 ms per 1M objects -- the bulk prefetches serialise on the issuing warp; off */
+      if (ph + 2 == NP && warp == kWarps - 1 && t + gridDim.x < p.ntiles) prefetch_tile(p, cols, scopes, t + gridDim.x, lane);
+#endif
+      // items are sorted heaviest first: dealing them round-robin to the warps is a longest-processing-time schedule
+      for (uint32_t k = warp; k < icnt; k += kWarps) {
         const uint32_t item = items[ibase + k];
         const GkOp op = ops[item & 0xfffffu];
         const uint32_t part = (item >> 20) & 0x3fu, nparts = item >> 26;
         const uint32_t kind = op.w0 & 0xffu, level = (op.w0 >> 8) & 0xffu;
-        uint32_t* out = slots + s_soff[op.w0 >> 16];
+        uint32_t* out = slots + (op.w0 >> 16);
+#ifdef GK_PHASE_TIMING
+        const long long ti0 = clock64();
+#endif
         switch (kind) {
           case GK_N_ATOM: {
             const uint32_t cnt = s_cnt[level], words = (cnt + 31u) >> 5;
-            const uint32_t pw0 = (words * part / nparts) & ~3u, pw1 = part + 1u == nparts ? words : ((words * (part + 1u) / nparts) & ~3u);
+            const uint32_t amask = ~(uint32_t)(GK_ATOM_UNROLL - 1);
+            const uint32_t pw0 = (words * part / nparts) & amask, pw1 = part + 1u == nparts ? words : ((words * (part + 1u) / nparts) & amask);
             atom_rows(cols[op.w1 >> 8], op.w1 & 0xffu, op.w2, op.w3, pool, cbytes, s_lo[level], cnt, pw0, pw1, lane, out);
             break;
           }
@@ -275,7 +356,7 @@ __global__ void __launch_bounds__(kThreads) gk_eval_kernel(const KParams p) {
               uint32_t acc = is_or ? 0u : FULL;
               for (uint32_t j = 0; j < nin; ++j) {
                 const uint32_t e = in[j];
-                const uint32_t x = slots[s_soff[e & 0xffffu] + i] ^ (uint32_t)((int32_t)e >> 31);
+                const uint32_t x = slots[(e & 0xffffu) + i] ^ (uint32_t)((int32_t)e >> 31);
                 acc = is_or ? (acc | x) : (acc & x);
               }
               out[i] = acc ^ no;
@@ -293,7 +374,7 @@ __global__ void __launch_bounds__(kThreads) gk_eval_kernel(const KParams p) {
             const uint32_t* coff = scopes[level].off + s_lo[par];
             const uint32_t clo = s_lo[level], pcnt = s_cnt[par], words = (s_cnt[level] + 31u) >> 5;
             for (uint32_t j = 0; j < npair; ++j) {
-              uint32_t* dst = slots + s_soff[pairs[j] >> 16];
+              uint32_t* dst = slots + (pairs[j] >> 16);
               for (uint32_t i = lane; i < words; i += 32u) dst[i] = 0u;
             }
             __syncwarp();
@@ -302,8 +383,8 @@ __global__ void __launch_bounds__(kThreads) gk_eval_kernel(const KParams p) {
               if (b <= a) continue;
               for (uint32_t j = 0; j < npair; ++j) {
                 const uint32_t e = pairs[j];
-                if ((slots[s_soff[e & 0xffffu] + (r >> 5)] >> (r & 31u)) & 1u) {
-                  uint32_t* dst = slots + s_soff[e >> 16];
+                if ((slots[(e & 0xffffu) + (r >> 5)] >> (r & 31u)) & 1u) {
+                  uint32_t* dst = slots + (e >> 16);
                   for (uint32_t w = a >> 5; w <= (b - 1u) >> 5; ++w) atomicOr(&dst[w], range_mask(w, a, b));
                 }
               }
@@ -331,18 +412,19 @@ __global__ void __launch_bounds__(kThreads) gk_eval_kernel(const KParams p) {
               const bool any_wide = __any_sync(FULL, wide);
               for (uint32_t j = 0; j < npair; ++j) {
                 const uint32_t e = pairs[j];
-                const uint32_t* in = slots + s_soff[e & 0xffffu];
-                bool any = cw != 0u && (__funnelshift_r(in[wl], in[wh], sh) & m) != 0u;
-                if (any_wide && wide && !any)
-                  for (uint32_t w = (a + 32u) >> 5; w <= (b - 1u) >> 5 && !any; ++w) any = (in[w] & range_mask(w, a + 32u, b)) != 0u;
+                const uint32_t* in = slots + (e & 0xffffu);
+                bool any = (__funnelshift_r(in[wl], in[wh], sh) & m) != 0u;   // (m == 0 for a parent without children)
+                if (any_wide)
+                  if (wide && !any)
+                    for (uint32_t w = (a + 32u) >> 5; w <= (b - 1u) >> 5 && !any; ++w) any = (in[w] & range_mask(w, a + 32u, b)) != 0u;
                 const uint32_t wd = __ballot_sync(FULL, any);
-                if (lane == 0) slots[s_soff[e >> 16] + (r >> 5)] = wd;
+                if (lane == 0) slots[(e >> 16) + (r >> 5)] = wd;
               }
             }
             break;
           }
           case GK_N_MATCH: {
-            uint32_t* err = slots + s_soff[op.w1 & 0xffffu];
+            uint32_t* err = slots + (op.w1 & 0xffffu);
             const GkMatch& m = match[op.w2];
             const uint32_t words = (nobj + 31u) >> 5;
             for (uint32_t r = (words * part / nparts) * 32u + lane; r < (words * (part + 1u) / nparts) * 32u; r += 32u) {
@@ -366,9 +448,24 @@ __global__ void __launch_bounds__(kThreads) gk_eval_kernel(const KParams p) {
           }
           default: break;
         }
+#ifdef GK_PHASE_TIMING
+        if (lane == 0) {
+          atomicAdd(p.timing + 2 * (kMaxPhases + 2) + 2 * kind, (unsigned long long)(clock64() - ti0));
+          atomicAdd(p.timing + 2 * (kMaxPhases + 2) + 2 * kind + 1, 1ull);
+        }
+#endif
       }
+#ifdef GK_PHASE_TIMING
+      if (lane == 0) atomicAdd(p.timing + 2 * ph + 1, (unsigned long long)(clock64() - tp0));
       __syncthreads();
+      if (threadIdx.x == 0) atomicAdd(p.timing + 2 * ph, (unsigned long long)(clock64() - tp0));
+#else
+      __syncthreads();
+#endif
     }
+#ifdef GK_PHASE_TIMING
+    const long long tg0 = clock64();
+#endif
     // ---- gather: lane l of a warp holds the result word of constraint (32 w + l) for one group of 32 objects; 32 ballots
     // transpose that 32x32 bit block so that lane o ends up with the bitmap word of object o.  The 32 objects of a group
     // are consecutive rows of the object-major output: the stores are contiguous.
@@ -379,9 +476,9 @@ __global__ void __launch_bounds__(kThreads) gk_eval_kernel(const KParams p) {
       uint32_t xv = 0, xe = 0;
       if (c < C && s_act[c]) {
         const GkOutEnt oe = outs[c];
-        const uint32_t pv = (oe.flags & 1u) ? FULL : (oe.flags & 2u) ? 0u : slots[s_soff[oe.prog_slot] + ow];
-        xv = pv & slots[s_soff[oe.match_slot] + ow];
-        xe = slots[s_soff[oe.err_slot] + ow];
+        const uint32_t pv = (oe.flags & 1u) ? FULL : (oe.flags & 2u) ? 0u : slots[(oe.prog_slot) + ow];
+        xv = pv & slots[(oe.match_slot) + ow];
+        xe = slots[(oe.err_slot) + ow];
       }
       uint32_t yv = 0, ye = 0;
 #pragma unroll
@@ -405,7 +502,13 @@ __global__ void __launch_bounds__(kThreads) gk_eval_kernel(const KParams p) {
         if (ne) atomicAdd(&s_err[c], ne);
       }
     }
+#ifdef GK_PHASE_TIMING
+    if (lane == 0) atomicAdd(p.timing + 2 * NP + 1, (unsigned long long)(clock64() - tg0));
     __syncthreads();
+    if (threadIdx.x == 0) atomicAdd(p.timing + 2 * NP, (unsigned long long)(clock64() - tg0));
+#else
+    __syncthreads();
+#endif
   }
   for (uint32_t c = threadIdx.x; c < C; c += blockDim.x) {
     if (s_tot[c]) atomicAdd(p.out.totals + c, (unsigned long long)s_tot[c]);
