@@ -254,7 +254,10 @@ def run_ours(args):
     ms_per_step = total_ms / K
     value = world * n * C / (ms_per_step / 1e3)
     launches = rb.eval(ep, D.F_NO_COPY_BACK).stats["gpu_launches"] - launches0 - 1   # minus this probe's own launch
-    totals_host = sweep.tot[0].tolist()
+    totals_host = sweep.tot[0].tolist()              # after the exchange: summed over ranks
+    sweep.evaluate(ep, stream)                       # this rank's own totals again (untimed), to check the e2e path against
+    torch.cuda.synchronize()
+    totals_local = sweep.tot[0].tolist()
 
     # ---- e2e: public API, host JSON buffers in, bitmaps + totals out, every step
     e2e_steps = max(1, min(K, args.e2e_steps))
@@ -271,7 +274,7 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s = float(te[0])
-    assert resp.totals == totals_host, "e2e path and resident path disagree"
+    assert resp.totals == totals_local[:len(resp.totals)], "e2e path and resident path disagree"
     e2e = {"value": world * n * C / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(resp.stats["h2d_bytes"]) * world,
            "d2h_bytes_per_step": int(resp.stats["d2h_bytes"] + 16 * C) * world, "steps": e2e_steps,
            "breakdown_ms": {k: round(resp.stats[k], 3) for k in ("flatten_ms", "h2d_ms", "kernel_ms", "d2h_ms")},

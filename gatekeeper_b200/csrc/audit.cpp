@@ -220,8 +220,10 @@ std::string AuditRun::report() {
 void validation_messages(const Compiled& c, const std::vector<Violation>& vio, uint32_t object, std::vector<std::string>& deny,
                          std::vector<std::string>& warn) {
   auto supported = [](const std::string& a) { return a == "deny" || a == "dryrun" || a == "warn"; };
-  for (auto& x : vio) {
-    if (x.object != object) continue;
+  // results are in object order: binary-search the object's range
+  auto lo = std::lower_bound(vio.begin(), vio.end(), object, [](const Violation& v, uint32_t o) { return v.object < o; });
+  for (auto it = lo; it != vio.end() && it->object == object; ++it) {
+    const Violation& x = *it;
     const Constraint& con = *c.order[x.constraint];
     std::vector<std::string> actions;
     if (x.action == "scoped") {

@@ -4,6 +4,7 @@
 #include <cstring>
 #include <functional>
 #include <memory>
+#include <thread>
 #include <unordered_map>
 
 #include "../../include/gk_engine.h"
@@ -140,26 +141,53 @@ void eval_batch(gk_engine* e, gk_batch* b, const char* ep_c, uint32_t flags, gk_
     double m0 = now_ms();
     const uint32_t W = rp->ev.words, C = rp->ev.nconstraints;
     // matcher errors first (autoreject results), then rendered violations, both in (object, constraint) order
-    std::vector<std::vector<std::pair<uint32_t, uint32_t>>> err_of;   // sparse
     std::unordered_map<uint64_t, uint32_t> err_code;
     for (size_t i = 0; i + 2 < rp->ev.errlist.size(); i += 3)
       err_code[((uint64_t)rp->ev.errlist[i] << 32) | rp->ev.errlist[i + 1]] = rp->ev.errlist[i + 2];
-    for (uint32_t o = 0; o < b->n; ++o) {
-      for (uint32_t w = 0; w < W; ++w) {
-        uint32_t vb = rp->ev.viol[(size_t)o * W + w], eb = rp->ev.err[(size_t)o * W + w];
-        if (!(vb | eb)) continue;
-        for (uint32_t k = 0; k < 32 && w * 32 + k < C; ++k) {
-          uint32_t cix = w * 32 + k;
-          ObjIn in = to_in(b->objs[o]);
-          if (eb >> k & 1u) {
-            auto it = err_code.find(((uint64_t)o << 32) | c.cons_match[cix]);   // error list is keyed by match block
-            e->eng->autoreject(c, in, o, cix, it == err_code.end() ? 0u : it->second, ep, rp->vio);
-          } else if (vb >> k & 1u) {
-            e->eng->materialize(c, in, o, cix, ep, rp->vio);
+    // one DOM parse per object, all of its flagged constraints rendered from it; objects are spread over the host threads
+    const uint32_t n = b->n;
+    const size_t T = std::min<size_t>((size_t)std::max(1, e->eng->threads()), std::max<size_t>(1, n / 16));
+    std::vector<std::vector<Violation>> part(T);
+    std::vector<std::string> errs(T);
+    auto work = [&](size_t t) {
+      std::vector<Engine::Flagged> flagged;
+      try {
+        for (uint32_t o = (uint32_t)(n * t / T); o < (uint32_t)(n * (t + 1) / T); ++o) {
+          flagged.clear();
+          for (uint32_t w = 0; w < W; ++w) {
+            const uint32_t vb = rp->ev.viol[(size_t)o * W + w], eb = rp->ev.err[(size_t)o * W + w];
+            uint32_t any = vb | eb;
+            while (any) {
+              const uint32_t k = (uint32_t)__builtin_ctz(any);
+              any &= any - 1;
+              const uint32_t cix = w * 32 + k;
+              if (cix >= C) continue;
+              const bool is_err = eb >> k & 1u;
+              uint32_t code = 0;
+              if (is_err) {
+                auto it = err_code.find(((uint64_t)o << 32) | c.cons_match[cix]);   // error list is keyed by match block
+                if (it != err_code.end()) code = it->second;
+              }
+              flagged.push_back({cix, is_err, code});
+            }
           }
+          if (!flagged.empty()) e->eng->materialize_object(c, to_in(b->objs[o]), o, flagged, ep, part[t]);
         }
+      } catch (RegoError& x) {
+        errs[t] = x.msg;
+      } catch (std::exception& x) {
+        errs[t] = x.what();
       }
+    };
+    if (T == 1) work(0);
+    else {
+      std::vector<std::thread> th;
+      for (size_t t = 0; t < T; ++t) th.emplace_back(work, t);
+      for (auto& x : th) x.join();
     }
+    for (auto& x : errs)
+      if (!x.empty()) throw RegoError{x};
+    for (auto& v : part) rp->vio.insert(rp->vio.end(), std::make_move_iterator(v.begin()), std::make_move_iterator(v.end()));
     out->materialize_ms = now_ms() - m0;
   }
   bool give_bits = !(flags & GK_F_NO_COPY_BACK);

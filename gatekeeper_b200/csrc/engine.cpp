@@ -273,6 +273,7 @@ void Engine::add_constraint(const std::string& json) {
   VP spec = obj_get(obj, "spec");
   VP params = spec ? obj_get(spec, "parameters") : nullptr;
   c->params = params && params->t != VT::Null ? params : v_obj({});
+  c->params_key = json_str(c->params);
   c->action = enforcement_action_of(obj);
   if (spec) {
     VP sea = obj_get(spec, "scopedEnforcementActions");
@@ -543,11 +544,12 @@ std::string Engine::dump() {
     for (auto& op : c->ops) {
       uint32_t kind = op.w0 & 0xff, level = (op.w0 >> 8) & 0xff;
       const char* nm = kind == GK_N_ATOM ? "atom" : kind == GK_N_GATE ? "gate" : kind == GK_N_BCAST ? "bcast" : kind == GK_N_ACC ? "acc"
-                       : kind == GK_N_MATCH ? "match" : kind == GK_N_CONST ? "const" : "?";
+                       : kind == GK_N_MATCH ? "match" : kind == GK_N_CONST ? "const" : kind == GK_N_ATOMS ? "atoms" : kind == GK_N_END ? "end" : "?";
       auto& m = mix[std::string(nm) + "@s" + std::to_string(level)];
       m.first++;
-      m.second += (kind == GK_N_GATE || kind == GK_N_BCAST || kind == GK_N_ACC) ? (int)op.w3 : 1;
+      m.second += (kind == GK_N_GATE || kind == GK_N_BCAST || kind == GK_N_ACC || kind == GK_N_ATOMS) ? (int)op.w3 : 1;
       if (kind == GK_N_ATOM) atoms_per_col[op.w1 >> 8]++;
+      if (kind == GK_N_ATOMS) atoms_per_col[op.w1 >> 8] += (int)op.w3;
     }
     o += "  op mix (ops/operands):";
     for (auto& kv : mix) o += " " + kv.first + "=" + std::to_string(kv.second.first) + "/" + std::to_string(kv.second.second);
@@ -1194,7 +1196,11 @@ void Engine::materialize_object(const Compiled& c, const ObjIn& in, uint32_t obj
   VP obj, old;
   VP doc = review_doc(in, &obj, &old, nullptr, &err);
   if (obj_out) *obj_out = obj ? obj : old;
-  VP input_review;
+  struct Rendered {
+    bool done = false;
+    std::vector<std::pair<std::string, std::string>> items;   // (msg, details JSON)
+  };
+  std::map<std::string, Rendered> memo;
   for (auto& f : flagged) {
     if (f.is_err) {
       autoreject(c, in, obj_ix, f.cix, f.err_code, ep, out);
@@ -1209,24 +1215,34 @@ void Engine::materialize_object(const Compiled& c, const ObjIn& in, uint32_t obj
       if (it == templates_.end()) throw RegoError{"materialize: template gone"};
       mod = it->second.mod;
     }
-    Eval ev(*mod, v_obj({{v_str("review"), doc}, {v_str("parameters"), con.params}}));
-    VP vs = ev.rule_value("violation");
     size_t before = out.size();
     std::vector<std::string> sc = con.action == "scoped" ? scoped_actions_for(con, ep) : std::vector<std::string>();
-    if (vs)
-      for (auto& v : vs->items) {
-        VP msg = obj_get(v, "msg");
-        if (v->t != VT::Obj || !msg || msg->t != VT::Str) throw RegoError{"rego_type_error: violation element must be {\"msg\": string, ...}"};
-        Violation x;
-        x.object = obj_ix;
-        x.constraint = f.cix;
-        x.msg = msg->s;
-        VP d = obj_get(v, "details");
-        x.details_json = d ? json_str(d) : "";
-        x.action = con.action;
-        x.scoped_json = scoped_json(sc);
-        out.push_back(std::move(x));
-      }
+    const std::string sc_json = scoped_json(sc);
+    // constraints of one kind with equal parameters (e.g. the same policy scoped to different namespaces) render the
+    // same messages for this object: evaluate once
+    auto& rendered = memo[con.kind + '\x01' + con.params_key];
+    if (!rendered.done) {
+      rendered.done = true;
+      Eval ev(*mod, v_obj({{v_str("review"), doc}, {v_str("parameters"), con.params}}));
+      VP vs = ev.rule_value("violation");
+      if (vs)
+        for (auto& v : vs->items) {
+          VP msg = obj_get(v, "msg");
+          if (v->t != VT::Obj || !msg || msg->t != VT::Str) throw RegoError{"rego_type_error: violation element must be {\"msg\": string, ...}"};
+          VP d = obj_get(v, "details");
+          rendered.items.emplace_back(msg->s, d ? json_str(d) : "");
+        }
+    }
+    for (auto& it : rendered.items) {
+      Violation x;
+      x.object = obj_ix;
+      x.constraint = f.cix;
+      x.msg = it.first;
+      x.details_json = it.second;
+      x.action = con.action;
+      x.scoped_json = sc_json;
+      out.push_back(std::move(x));
+    }
     if (out.size() == before)
       throw RegoError{"internal: GPU flagged (" + con.kind + "/" + con.name + ", object " + std::to_string(obj_ix) +
                       ") but the message renderer finds no violation -- lowering bug"};

@@ -71,6 +71,7 @@ struct ScopedAction {
 struct Constraint {
   std::string kind, name;
   VP obj, params;
+  std::string params_key;                      // canonical JSON of spec.parameters: constraints of a kind with equal parameters render equal messages
   MatchSpec match;
   std::string action;                          // deny / dryrun / warn / scoped / unrecognized
   std::vector<ScopedAction> scoped;

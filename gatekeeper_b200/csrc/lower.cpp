@@ -1802,6 +1802,12 @@ void NetBuilder::build(const std::vector<FP>& formulas, const std::vector<uint32
       release_at[std::min(n.last_use + 1, out_phase + 1)].push_back(n.slot);
     }
     std::map<int, std::vector<uint32_t>> acc_groups, bcast_groups;   // scope -> (in slot | out slot << 16)
+    struct ColAtoms {
+      std::vector<GkOp> ops;
+      uint32_t cost = 0;
+      bool deep = false, heavy = false;
+    };
+    std::map<std::pair<int, int>, ColAtoms> col_atoms;               // (level, column) -> its atoms in this phase
     for (int id : ids) {
       NNode& n = N[id];
       ++n_nodes;
@@ -1915,8 +1921,56 @@ void NetBuilder::build(const std::vector<FP>& formulas, const std::vector<uint32
           case GK_N_ACC: cost = 200; break;
           default: break;
         }
+        if (n.kind == GK_N_ATOM) {   // deferred: all atoms of a column become one op below
+          ColAtoms& ca = col_atoms[{n.level, n.col}];
+          ca.ops.push_back(op);
+          ca.cost += cost;
+          ca.deep = deep;
+          ca.heavy = ca.heavy || n.op >= GK_OP_PREFIX;
+          continue;
+        }
         add_item(cost, parts);
       }
+      ops.push_back(op);
+    }
+    for (auto& kv : col_atoms) {
+      ColAtoms& ca = kv.second;
+      const uint32_t parts = ca.deep ? (ca.heavy ? 6u : 4u) : (ca.heavy ? 2u : 1u);
+      // Fusing every atom of a column into one GK_N_ATOMS op (one load of the row for all of them) is implemented but OFF:
+      // measured on B200 it is slower than one op per atom (1.5 ms vs 0.8 ms per 1M objects) -- the fused loop keeps the
+      // row's encodings live across the whole atom list, and at 48 registers per thread (5 resident CTAs) that spills.
+#ifdef GK_FUSED_ATOMS
+      const bool fuse = true;
+#else
+      const bool fuse = false;
+#endif
+      if (!fuse) {
+        for (auto& a : ca.ops) {
+          const bool heavy1 = (a.w1 & 0xffu) >= GK_OP_PREFIX;
+          const uint32_t cost1 = heavy1 ? (ca.deep ? 1200u : 600u) : (a.w1 & 0xffu) == GK_OP_SID_IN ? (ca.deep ? 300u : 150u) : (ca.deep ? 120u : 60u);
+          add_item(cost1, heavy1 ? (ca.deep ? 4u : 2u) : 1u);
+          ops.push_back(a);
+        }
+        continue;
+      }
+      if (ca.ops.size() == 1) {
+        add_item(ca.cost, ca.heavy ? parts : 1u);
+        ops.push_back(ca.ops[0]);
+        continue;
+      }
+      while (pool.size() % 4) pool.push_back(0);   // entries are read with 128-bit loads
+      GkOp op{};
+      op.w0 = GK_N_ATOMS | ((uint32_t)kv.first.first << 8);
+      op.w1 = (uint32_t)kv.first.second << 8;
+      op.w2 = (uint32_t)pool.size();
+      op.w3 = (uint32_t)ca.ops.size();
+      for (auto& a : ca.ops) {
+        pool.push_back((a.w1 & 0xffu) | (a.w0 & 0xffff0000u));   // atom op | out slot << 16
+        pool.push_back(a.w2);
+        pool.push_back(a.w3);
+        pool.push_back(0);
+      }
+      add_item(ca.cost, parts);
       ops.push_back(op);
     }
     // every EXISTS (and every hoisted broadcast) over the same scope in this phase is ONE op: the child ranges and
@@ -1928,7 +1982,9 @@ void NetBuilder::build(const std::vector<FP>& formulas, const std::vector<uint32
         op.w1 = (uint32_t)pool.size();
         op.w3 = (uint32_t)g.second.size();
         pool.insert(pool.end(), g.second.begin(), g.second.end());
-        const uint32_t parts = (pass == 0 && g.second.size() > 8) ? 2 : 1;   // a broadcast zeroes its outputs first: never split
+        // a large EXISTS group is split by parent rows (finer splits measured slower); a broadcast zeroes its outputs
+        // first: never split
+        const uint32_t parts = (pass == 0 && g.second.size() > 8) ? 2u : 1u;
         add_item(150 + 30 * (uint32_t)g.second.size(), parts);
         ops.push_back(op);
       }

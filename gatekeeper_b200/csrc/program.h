@@ -132,7 +132,10 @@ enum {
   GK_N_BCAST = 5,   // level = child scope; pool[w1 .. w1+w3) = (input slot at the parent level | output slot << 16)
   GK_N_ACC = 6,     // level = child scope; pool[w1 .. w1+w3) = (input slot at the child level | output slot at the parent level << 16)
   GK_N_MATCH = 7,   // w1 = error-column slot ; w2 = match block id
+  GK_N_ATOMS = 8,   // every atom of ONE column (same phase): w1 = col<<8 ; pool[w2 ..]: w3 entries of GK_ATOMS_ENT words
+                    //   [atom op | out_slot<<16, operand a, operand b, 0] -- the column is loaded once per row for all of them
 };
+#define GK_ATOMS_ENT 4
 
 // per constraint: where its result comes from.  After the last phase one pass over the tile's objects gathers bit c of
 // every constraint into the object-major bitmap words and writes them straight to HBM (coalesced).

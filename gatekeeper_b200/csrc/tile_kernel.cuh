@@ -196,6 +196,120 @@ __device__ __forceinline__ void atom_rows(const GkColumn& c, uint32_t aop, uint3
   }
 }
 
+#ifdef GK_FUSED_ATOMS   /* experiment, off: see NetBuilder::build */
+// ---- every atom of one column in one pass (GK_N_ATOMS): the row's encodings are loaded once into registers -- four
+// 32-row groups at a time, all loads in flight together -- and each atom is then a compare + ballot on registers.
+// Columns with a HEAD record (prefix tests) go one group at a time: the 32-byte record is 8 registers per row.
+__device__ __forceinline__ bool atom_on_regs(uint32_t aop, uint32_t a, uint32_t b, uint32_t vt, uint32_t sid, long long num, const uint32_t* pool) {
+  switch (aop) {
+    case GK_OP_TRUTHY: return vt != GK_VT_UNDEF && vt != GK_VT_FALSE;
+    case GK_OP_DEFINED: return vt != GK_VT_UNDEF;
+    case GK_OP_VTMASK: return ((1u << vt) & a) != 0u;
+    case GK_OP_SID_EQ: return sid == a;
+    case GK_OP_SID_IN: {
+      bool hit = false;
+      for (uint32_t j = 0; j < b; ++j) hit = hit || pool[a + j] == sid;
+      return hit;
+    }
+    default: {   // GK_OP_NUM_CMP (the only other op the register path is used for)
+      const long long k = (long long)(((uint64_t)pool[a + 1] << 32) | pool[a]);
+      if (vt == GK_VT_UNDEF) return false;
+      if (k == INT64_MIN || k == INT64_MAX) {   // sentinel constants: spell the cross-type order out
+        if (vt == GK_VT_NUM) return gk_cmp_apply(b, num < k ? -1 : (num > k ? 1 : 0));
+        return gk_cmp_apply(b, gk_vt_rank(vt) < 2 ? -1 : 1);
+      }
+      return gk_cmp_apply(b, num < k ? -1 : (num > k ? 1 : 0));
+    }
+  }
+}
+
+__device__ __forceinline__ bool reg_op(uint32_t aop) { return aop <= GK_OP_NUM_CMP; }
+
+__device__ __noinline__ void atoms_rows(const GkColumn& c, const uint32_t* ent, uint32_t nent, const uint32_t* pool, const uint8_t* cbytes, uint32_t lo,
+                                        uint32_t cnt, uint32_t w0, uint32_t w1, uint32_t lane, uint32_t* slots) {
+  const uint32_t FULL = 0xffffffffu;
+  const uint32_t wcap = (((cnt + 31u) >> 5) + 3u) & ~3u;
+  const bool has_vt = (c.enc & GK_ENC_VT) != 0u, has_sid = (c.enc & GK_ENC_SID) != 0u, has_num = (c.enc & GK_ENC_NUM) != 0u;
+  if (!(c.enc & GK_ENC_HEAD)) {
+    for (uint32_t w = w0; w < w1; w += 4u) {
+      const uint32_t r0 = w * 32u + lane;
+      const size_t row0 = (size_t)lo + r0;
+      uint32_t vt[4], sid[4];
+      long long num[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const bool ok = r0 + 32u * u < cnt;
+        vt[u] = (ok && has_vt) ? c.vt[row0 + 32u * u] : (uint32_t)GK_VT_UNDEF;
+        sid[u] = (ok && has_sid) ? c.sid[row0 + 32u * u] : GK_SID_UNDEF;
+        num[u] = (ok && has_num) ? c.num[row0 + 32u * u] : 0ll;
+      }
+      for (uint32_t j = 0; j < nent; ++j) {
+        const uint4 e = *reinterpret_cast<const uint4*>(ent + j * GK_ATOMS_ENT);
+        const uint32_t aop = e.x & 0xffu;
+        bool v[4];
+        if (reg_op(aop)) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) v[u] = (r0 + 32u * u < cnt) && atom_on_regs(aop, e.y, e.z, vt[u], sid[u], num[u], pool);
+        } else {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) v[u] = (r0 + 32u * u < cnt) && gk_atom(c, (uint32_t)(row0 + 32u * u), aop, e.y, e.z, pool, cbytes);
+        }
+        uint4 wd;
+        wd.x = __ballot_sync(FULL, v[0]);
+        wd.y = __ballot_sync(FULL, v[1]);
+        wd.z = __ballot_sync(FULL, v[2]);
+        wd.w = __ballot_sync(FULL, v[3]);
+        if (lane == 0 && w < wcap) *reinterpret_cast<uint4*>(slots + (e.x >> 16) + w) = wd;
+      }
+    }
+    return;
+  }
+  const uint4* head = reinterpret_cast<const uint4*>(c.head);
+  const uint32_t wend = min(w1, (cnt + 31u) >> 5);
+  for (uint32_t w = w0; w < wend; ++w) {
+    const uint32_t r = w * 32u + lane;
+    const bool ok = r < cnt;
+    const size_t row = (size_t)lo + r;
+    const uint32_t vt = (ok && has_vt) ? c.vt[row] : (uint32_t)GK_VT_UNDEF;
+    const uint32_t sid = (ok && has_sid) ? c.sid[row] : GK_SID_UNDEF;
+    uint4 h0 = make_uint4(0, 0, 0, 0), h1 = make_uint4(0, 0, 0, 0);
+    if (ok) {
+      h0 = head[2 * row];
+      h1 = head[2 * row + 1];
+    }
+    const uint32_t lenb = h1.w >> 24;
+    for (uint32_t j = 0; j < nent; ++j) {
+      const uint4 e = *reinterpret_cast<const uint4*>(ent + j * GK_ATOMS_ENT);
+      const uint32_t aop = e.x & 0xffu;
+      bool v = false;
+      if (aop == GK_OP_ANYPREFIX) {
+        bool all_short = true;
+        for (uint32_t q = 0; q < e.z; ++q) all_short = all_short && pool[e.y + q * GK_PREFIX_ENT] <= GK_HEAD_BYTES;
+        if (all_short) {
+          if (ok && vt == GK_VT_STR)
+            for (uint32_t q = 0; q < e.z && !v; ++q) {
+              const uint32_t* pe = pool + e.y + q * GK_PREFIX_ENT;
+              const uint32_t* m = pe + 2 + GK_HEAD_WORDS;
+              const uint32_t diff = ((h0.x ^ pe[2]) & m[0]) | ((h0.y ^ pe[3]) & m[1]) | ((h0.z ^ pe[4]) & m[2]) | ((h0.w ^ pe[5]) & m[3]) |
+                                    ((h1.x ^ pe[6]) & m[4]) | ((h1.y ^ pe[7]) & m[5]) | ((h1.z ^ pe[8]) & m[6]) | ((h1.w ^ pe[9]) & m[7]);
+              v = diff == 0u && lenb >= pe[0];
+            }
+        } else {
+          v = ok && gk_atom(c, (uint32_t)row, aop, e.y, e.z, pool, cbytes);
+        }
+      } else if (reg_op(aop) && aop != GK_OP_NUM_CMP) {
+        v = ok && atom_on_regs(aop, e.y, e.z, vt, sid, 0ll, pool);
+      } else {
+        v = ok && gk_atom(c, (uint32_t)row, aop, e.y, e.z, pool, cbytes);
+      }
+      const uint32_t wd = __ballot_sync(FULL, v);
+      if (lane == 0) slots[(e.x >> 16) + w] = wd;
+    }
+  }
+}
+
+#endif
+
 #ifdef GK_L2_PREFETCH
 // ---- L2 prefetch of a tile's input slices.
 // The netlist walks ~100 arrays per tile with short dependent loops, so a warp rarely has more than a few loads in flight:
@@ -347,6 +461,14 @@ __global__ void __launch_bounds__(kThreads, GK_MIN_CTAS) gk_eval_kernel(const KP
             atom_rows(cols[op.w1 >> 8], op.w1 & 0xffu, op.w2, op.w3, pool, cbytes, s_lo[level], cnt, pw0, pw1, lane, out);
             break;
           }
+#ifdef GK_FUSED_ATOMS
+          case GK_N_ATOMS: {
+            const uint32_t cnt = s_cnt[level], words = (cnt + 31u) >> 5;
+            const uint32_t pw0 = (words * part / nparts) & ~3u, pw1 = part + 1u == nparts ? words : ((words * (part + 1u) / nparts) & ~3u);
+            atoms_rows(cols[op.w1 >> 8], pool + op.w2, op.w3, pool, cbytes, s_lo[level], cnt, pw0, pw1, lane, slots);
+            break;
+          }
+#endif
           case GK_N_GATE: {
             const uint32_t f = op.w2, words = (s_cnt[level] + 31u) >> 5, nin = op.w3;
             const uint32_t* in = pool + op.w1;
@@ -378,14 +500,29 @@ __global__ void __launch_bounds__(kThreads, GK_MIN_CTAS) gk_eval_kernel(const KP
               for (uint32_t i = lane; i < words; i += 32u) dst[i] = 0u;
             }
             __syncwarp();
-            for (uint32_t r = lane; r < pcnt; r += 32u) {
-              const uint32_t a = coff[r] - clo, b = coff[r + 1] - clo;
-              if (b <= a) continue;
-              for (uint32_t j = 0; j < npair; ++j) {
-                const uint32_t e = pairs[j];
-                if ((slots[(e & 0xffffu) + (r >> 5)] >> (r & 31u)) & 1u) {
-                  uint32_t* dst = slots + (e >> 16);
-                  for (uint32_t w = a >> 5; w <= (b - 1u) >> 5; ++w) atomicOr(&dst[w], range_mask(w, a, b));
+            // the CSR offsets are the only global loads here: fetch them for four 32-row groups before touching any, so the
+            // op pays one memory latency per 128 parent rows instead of one per 32
+            for (uint32_t r0 = lane; r0 < pcnt; r0 += 128u) {
+              uint32_t ra[4], rb[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const uint32_t r = r0 + 32u * u;
+                ra[u] = rb[u] = 0u;
+                if (r < pcnt) {
+                  ra[u] = coff[r] - clo;
+                  rb[u] = coff[r + 1] - clo;
+                }
+              }
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const uint32_t r = r0 + 32u * u, a = ra[u], b = rb[u];
+                if (b <= a) continue;
+                for (uint32_t j = 0; j < npair; ++j) {
+                  const uint32_t e = pairs[j];
+                  if ((slots[(e & 0xffffu) + (r >> 5)] >> (r & 31u)) & 1u) {
+                    uint32_t* dst = slots + (e >> 16);
+                    for (uint32_t w = a >> 5; w <= (b - 1u) >> 5; ++w) atomicOr(&dst[w], range_mask(w, a, b));
+                  }
                 }
               }
             }
@@ -397,28 +534,40 @@ __global__ void __launch_bounds__(kThreads, GK_MIN_CTAS) gk_eval_kernel(const KP
             const uint32_t* coff = scopes[level].off + s_lo[par];
             const uint32_t clo = s_lo[level], pcnt = s_cnt[par];
             const uint32_t pw = (pcnt + 31u) >> 5, cw = (s_cnt[level] + 31u) >> 5;
-            for (uint32_t r = (pw * part / nparts) * 32u + lane; r < (pw * (part + 1u) / nparts) * 32u; r += 32u) {
-              uint32_t a = 0, b = 0;
-              if (r < pcnt) {
-                a = coff[r] - clo;
-                b = coff[r + 1] - clo;
+            const uint32_t g0 = pw * part / nparts, g1 = pw * (part + 1u) / nparts;   // parent-row groups of this part
+            for (uint32_t g = g0; g < g1; g += 4u) {
+              // CSR offsets of four groups first (the only global loads of the op): one memory latency per 128 parent rows
+              uint32_t ra[4], rb[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const uint32_t r = (g + u) * 32u + lane;
+                ra[u] = rb[u] = 0u;
+                if (g + u < g1 && r < pcnt) {
+                  ra[u] = coff[r] - clo;
+                  rb[u] = coff[r + 1] - clo;
+                }
               }
-              // A range of up to 32 children is a 32-bit window of the child bit column starting at bit a: one funnel
-              // shift over two adjacent words, branch-free for every lane.  Longer ranges (rare) add a tail loop.
-              const uint32_t nb = b - a, sh = a & 31u;
-              const uint32_t m = nb >= 32u ? FULL : ((1u << nb) - 1u);
-              const uint32_t wl = cw ? min(a >> 5, cw - 1u) : 0u, wh = cw ? min((a >> 5) + 1u, cw - 1u) : 0u;
-              const bool wide = nb > 32u;
-              const bool any_wide = __any_sync(FULL, wide);
-              for (uint32_t j = 0; j < npair; ++j) {
-                const uint32_t e = pairs[j];
-                const uint32_t* in = slots + (e & 0xffffu);
-                bool any = (__funnelshift_r(in[wl], in[wh], sh) & m) != 0u;   // (m == 0 for a parent without children)
-                if (any_wide)
-                  if (wide && !any)
-                    for (uint32_t w = (a + 32u) >> 5; w <= (b - 1u) >> 5 && !any; ++w) any = (in[w] & range_mask(w, a + 32u, b)) != 0u;
-                const uint32_t wd = __ballot_sync(FULL, any);
-                if (lane == 0) slots[(e >> 16) + (r >> 5)] = wd;
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                if (g + u >= g1) break;   // warp-uniform
+                const uint32_t a = ra[u], b = rb[u];
+                // A range of up to 32 children is a 32-bit window of the child bit column starting at bit a: one funnel
+                // shift over two adjacent words, branch-free for every lane.  Longer ranges (rare) add a tail loop.
+                const uint32_t nb = b - a, sh = a & 31u;
+                const uint32_t m = nb >= 32u ? FULL : ((1u << nb) - 1u);
+                const uint32_t wl = cw ? min(a >> 5, cw - 1u) : 0u, wh = cw ? min((a >> 5) + 1u, cw - 1u) : 0u;
+                const bool wide = nb > 32u;
+                const bool any_wide = __any_sync(FULL, wide);
+                for (uint32_t j = 0; j < npair; ++j) {
+                  const uint32_t e = pairs[j];
+                  const uint32_t* in = slots + (e & 0xffffu);
+                  bool any = (__funnelshift_r(in[wl], in[wh], sh) & m) != 0u;   // (m == 0 for a parent without children)
+                  if (any_wide)
+                    if (wide && !any)
+                      for (uint32_t w = (a + 32u) >> 5; w <= (b - 1u) >> 5 && !any; ++w) any = (in[w] & range_mask(w, a + 32u, b)) != 0u;
+                  const uint32_t wd = __ballot_sync(FULL, any);
+                  if (lane == 0) slots[(e >> 16) + g + u] = wd;
+                }
               }
             }
             break;
@@ -450,8 +599,9 @@ __global__ void __launch_bounds__(kThreads, GK_MIN_CTAS) gk_eval_kernel(const KP
         }
 #ifdef GK_PHASE_TIMING
         if (lane == 0) {
-          atomicAdd(p.timing + 2 * (kMaxPhases + 2) + 2 * kind, (unsigned long long)(clock64() - ti0));
-          atomicAdd(p.timing + 2 * (kMaxPhases + 2) + 2 * kind + 1, 1ull);
+          const uint32_t tk = kind;
+          atomicAdd(p.timing + 2 * (kMaxPhases + 2) + 2 * tk, (unsigned long long)(clock64() - ti0));
+          atomicAdd(p.timing + 2 * (kMaxPhases + 2) + 2 * tk + 1, 1ull);
         }
 #endif
       }

@@ -72,6 +72,16 @@ class HostEmuBackend : public Backend {
           for (uint32_t r = 0; r < R; ++r) slot[o][r] = gk_atom(col, r, aop, op.w2, op.w3, c.pool.data(), c.cbytes.data());
           break;
         }
+        case GK_N_ATOMS: {
+          const GkColumn& col = h.cols[op.w1 >> 8];
+          const uint32_t R = rows_of(level);
+          for (uint32_t j = 0; j < op.w3; ++j) {
+            const uint32_t* e = &c.pool[op.w2 + j * GK_ATOMS_ENT];
+            auto& dst = slot[e[0] >> 16];
+            for (uint32_t r = 0; r < R; ++r) dst[r] = gk_atom(col, r, e[0] & 0xffu, e[1], e[2], c.pool.data(), c.cbytes.data());
+          }
+          break;
+        }
         case GK_N_GATE: {
           const uint32_t f = op.w2, R = rows_of(level);
           for (uint32_t r = 0; r < R; ++r) {
