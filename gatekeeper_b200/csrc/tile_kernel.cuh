@@ -90,6 +90,58 @@ __device__ __forceinline__ uint32_t range_mask(uint32_t w, uint32_t a, uint32_t 
     }                                                                             \
   }
 
+// The same loop with the row's loads separated from the test: LOAD fills A[u] (32-bit) / B[u] (64-bit) for the four groups
+// unconditionally -- a test written `vt[row] != UNDEF && num[row] < k` makes the second load wait for the first -- and
+// TEST then runs on registers (a, b).
+#ifdef GK_EXP_NOLOAD   /* latency experiment: atoms test a function of the row index instead of loaded data */
+#define GK_EXP_LOAD(L) A[u] = (uint32_t)row & 7u; B[u] = (long long)row
+#else
+#define GK_EXP_LOAD(L) L
+#endif
+#define GK_ATOM_LOOP2(LOAD, TEST)                                                 \
+  for (uint32_t w = w0; w < w1; w += GK_ATOM_UNROLL) {                            \
+    const uint32_t r0 = w * 32u + lane;                                           \
+    const size_t row0 = (size_t)lo + r0;                                          \
+    uint32_t A[GK_ATOM_UNROLL];                                                   \
+    long long B[GK_ATOM_UNROLL];                                                  \
+    bool v4[GK_ATOM_UNROLL];                                                      \
+    if ((w + GK_ATOM_UNROLL) * 32u <= cnt) { /* interior trip (warp-uniform): no bounds predicates at all */ \
+      _Pragma("unroll") for (int u = 0; u < GK_ATOM_UNROLL; ++u) {                \
+        const size_t row = row0 + 32u * u;                                        \
+        A[u] = 0u;                                                                \
+        B[u] = 0ll;                                                               \
+        GK_EXP_LOAD(LOAD);                                                        \
+      }                                                                           \
+      _Pragma("unroll") for (int u = 0; u < GK_ATOM_UNROLL; ++u) {                \
+        const uint32_t a = A[u];                                                  \
+        const long long b = B[u];                                                 \
+        (void)a; (void)b;                                                         \
+        v4[u] = (TEST);                                                           \
+      }                                                                           \
+    } else {                                                                      \
+      _Pragma("unroll") for (int u = 0; u < GK_ATOM_UNROLL; ++u) {                \
+        const size_t row = row0 + 32u * u;                                        \
+        A[u] = 0u;                                                                \
+        B[u] = 0ll;                                                               \
+        if (r0 + 32u * u < cnt) { GK_EXP_LOAD(LOAD); }                            \
+      }                                                                           \
+      _Pragma("unroll") for (int u = 0; u < GK_ATOM_UNROLL; ++u) {                \
+        const uint32_t a = A[u];                                                  \
+        const long long b = B[u];                                                 \
+        (void)a; (void)b;                                                         \
+        v4[u] = (r0 + 32u * u < cnt) && (TEST);                                   \
+      }                                                                           \
+    }                                                                             \
+    _Pragma("unroll") for (int u = 0; u < GK_ATOM_UNROLL; u += 4) {               \
+      uint4 wd;                                                                   \
+      wd.x = __ballot_sync(0xffffffffu, v4[u]);                                   \
+      wd.y = __ballot_sync(0xffffffffu, v4[u + 1]);                               \
+      wd.z = __ballot_sync(0xffffffffu, v4[u + 2]);                               \
+      wd.w = __ballot_sync(0xffffffffu, v4[u + 3]);                               \
+      if (lane == 0 && w + u < wcap) *reinterpret_cast<uint4*>(out + w + u) = wd; \
+    }                                                                             \
+  }
+
 __device__ __forceinline__ bool sid_in_small(const uint32_t* pool, uint32_t a, uint32_t b, uint32_t v) {
   bool hit = false;
   for (uint32_t j = 0; j < b; ++j) hit = hit || pool[a + j] == v;
@@ -112,28 +164,31 @@ __device__ __forceinline__ void atom_rows(const GkColumn& c, uint32_t aop, uint3
   switch (aop) {
     case GK_OP_TRUTHY: {
       const uint8_t* vt = c.vt;
-      GK_ATOM_LOOP(vt[row] != GK_VT_UNDEF && vt[row] != GK_VT_FALSE)
+      GK_ATOM_LOOP2(A[u] = vt[row], a != GK_VT_UNDEF && a != GK_VT_FALSE)
       break;
     }
     case GK_OP_DEFINED: {
       const uint8_t* vt = c.vt;
-      GK_ATOM_LOOP(vt[row] != GK_VT_UNDEF)
+      GK_ATOM_LOOP2(A[u] = vt[row], a != GK_VT_UNDEF)
       break;
     }
     case GK_OP_VTMASK: {
       const uint8_t* vt = c.vt;
-      GK_ATOM_LOOP(((1u << vt[row]) & a) != 0u)
+      const uint32_t mask = a;
+      GK_ATOM_LOOP2(A[u] = vt[row], ((1u << a) & mask) != 0u)
       break;
     }
     case GK_OP_SID_EQ: {
       const uint32_t* sid = c.sid;
-      GK_ATOM_LOOP(sid[row] == a)
+      const uint32_t want = a;
+      GK_ATOM_LOOP2(A[u] = sid[row], a == want)
       break;
     }
     case GK_OP_SID_IN: {
       const uint32_t* sid = c.sid;
       if (b <= 8u) {   // small sets: a broadcast linear scan beats the binary search
-        GK_ATOM_LOOP(sid_in_small(pool, a, b, sid[row]))
+        const uint32_t pa = a, pn = b;
+        GK_ATOM_LOOP2(A[u] = sid[row], sid_in_small(pool, pa, pn, a))
       } else {
         GK_ATOM_LOOP(gk_atom(c, row, aop, a, b, pool, cbytes))
       }
@@ -149,12 +204,12 @@ __device__ __forceinline__ void atom_rows(const GkColumn& c, uint32_t aop, uint3
       }
       // a defined non-number holds INT64_MIN / INT64_MAX according to its type rank, so one signed compare is OPA's order
       switch (b) {
-        case GK_CMP_LT: GK_ATOM_LOOP(vt[row] != GK_VT_UNDEF && num[row] < k) break;
-        case GK_CMP_LE: GK_ATOM_LOOP(vt[row] != GK_VT_UNDEF && num[row] <= k) break;
-        case GK_CMP_GT: GK_ATOM_LOOP(vt[row] != GK_VT_UNDEF && num[row] > k) break;
-        case GK_CMP_GE: GK_ATOM_LOOP(vt[row] != GK_VT_UNDEF && num[row] >= k) break;
-        case GK_CMP_EQ: GK_ATOM_LOOP(vt[row] != GK_VT_UNDEF && num[row] == k) break;
-        default: GK_ATOM_LOOP(vt[row] != GK_VT_UNDEF && num[row] != k) break;
+        case GK_CMP_LT: GK_ATOM_LOOP2(A[u] = vt[row]; B[u] = num[row], a != GK_VT_UNDEF && b < k) break;
+        case GK_CMP_LE: GK_ATOM_LOOP2(A[u] = vt[row]; B[u] = num[row], a != GK_VT_UNDEF && b <= k) break;
+        case GK_CMP_GT: GK_ATOM_LOOP2(A[u] = vt[row]; B[u] = num[row], a != GK_VT_UNDEF && b > k) break;
+        case GK_CMP_GE: GK_ATOM_LOOP2(A[u] = vt[row]; B[u] = num[row], a != GK_VT_UNDEF && b >= k) break;
+        case GK_CMP_EQ: GK_ATOM_LOOP2(A[u] = vt[row]; B[u] = num[row], a != GK_VT_UNDEF && b == k) break;
+        default: GK_ATOM_LOOP2(A[u] = vt[row]; B[u] = num[row], a != GK_VT_UNDEF && b != k) break;
       }
       break;
     }
@@ -173,8 +228,15 @@ __device__ __forceinline__ void atom_rows(const GkColumn& c, uint32_t aop, uint3
       const uint32_t wend = min(w1, (cnt + 31u) >> 5);
       for (uint32_t r = w0 * 32u + lane; r < wend * 32u; r += 32u) {
         bool v = false;
-        if (r < cnt && vt[lo + r] == GK_VT_STR) {
-          const uint4 h0 = head[2 * (size_t)(lo + r)], h1 = head[2 * (size_t)(lo + r) + 1];
+        // the type byte and the 32-byte record are fetched together (independent loads), then tested
+        uint32_t t = GK_VT_UNDEF;
+        uint4 h0 = make_uint4(0, 0, 0, 0), h1 = make_uint4(0, 0, 0, 0);
+        if (r < cnt) {
+          t = vt[lo + r];
+          h0 = head[2 * (size_t)(lo + r)];
+          h1 = head[2 * (size_t)(lo + r) + 1];
+        }
+        if (t == GK_VT_STR) {
           const uint32_t lenb = h1.w >> 24;
           for (uint32_t j = 0; j < b && !v; ++j) {
             const uint32_t* e = ent + j * GK_PREFIX_ENT;
