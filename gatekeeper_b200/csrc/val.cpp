@@ -11,7 +11,9 @@ namespace gk {
 // ------------------------------------------------------------------------------------------- numbers
 Num Num::of_double(double v) {
   Num n;
-  if (std::isfinite(v) && v == std::floor(v) && std::fabs(v) < 1e37) {
+  // Integral doubles below 1e21 are integers to Rego: Go's JSON encoder writes them without an exponent, and OPA keeps
+  // the literal.  From 1e21 on the literal has an exponent and the value prints as a float (`1e+30`).
+  if (std::isfinite(v) && v == std::floor(v) && std::fabs(v) < 1e21) {
     n.is_int = true;
     n.i = (__int128)v;
     n.d = v;

@@ -285,3 +285,85 @@ def case_validation_messages(lib):
         any_deny, any_warn = any_deny or bool(deny), any_warn or bool(warn)
     assert any_deny and any_warn
     return got
+
+
+# ------------------------------------------------------------------------------------------ mutation fuzz
+_WEIRD = [None, True, False, 0, -1, 1, 65535, 65536, 2 ** 31, 2 ** 53 + 1, 0.5, 1e30, "", "0", "1", "true", "latest", "500m", "0.5", "1Gi", "1e3", "é", "x" * 31,
+          "x" * 32, "x" * 300, "a:b:c", ":", "/", "//foo/", "registry.k8s.io/", "gcr.io/proj-01/img@sha256:" + "0" * 64, [], [None], ["a"], {}, {"a": 1},
+          [[1]], {"privileged": "true"}, 9223372036854775807, -9223372036854775808, 9223372036854775808]
+
+
+def _mutate(rnd, doc, n_mut):
+    """Random structural damage: delete / retype / replace / duplicate members anywhere in the object."""
+    def nodes(x, path, out):
+        if isinstance(x, dict):
+            for k, v in x.items():
+                out.append((x, k))
+                nodes(v, path + [k], out)
+        elif isinstance(x, list):
+            for i, v in enumerate(x):
+                out.append((x, i))
+                nodes(v, path + [i], out)
+    for _ in range(n_mut):
+        sites = []
+        nodes(doc, [], sites)
+        # never damage what makes the document reviewable at all (kind / apiVersion): those are request-level errors,
+        # covered by case_review_errors
+        sites = [(c, k) for c, k in sites if not (c is doc and k in ("kind", "apiVersion"))]
+        if not sites:
+            break
+        cont, key = rnd.choice(sites)
+        op = rnd.random()
+        if op < 0.25:
+            if isinstance(cont, dict):
+                del cont[key]
+            else:
+                cont.pop(key)
+        elif op < 0.75:
+            cont[key] = json.loads(json.dumps(rnd.choice(_WEIRD)))
+        elif op < 0.85 and isinstance(cont, list):
+            cont.append(json.loads(json.dumps(cont[key])))
+        elif isinstance(cont, dict):
+            cont[rnd.choice(["name", "image", "hostPort", "privileged", "cpu", "memory", "team", "path", "readOnly", "extra"])] = json.loads(
+                json.dumps(rnd.choice(_WEIRD)))
+    return doc
+
+
+def case_fuzz(lib, n=800, seed=1234, start=5000):
+    """config-2 constraints against synthetic Pods with random structural damage: wrong types, nulls, missing members,
+    out-of-range numbers, strings on the 31/32/255-byte boundaries of the column encodings.  Objects whose numbers the
+    device cannot compare exactly are per-object review errors in the engine and are excluded from the comparison."""
+    import random
+    rnd = random.Random(seed)
+    tm, cons = W.config2()
+    nss = W.synth_namespaces()
+    orc, drv, _ = make_pair(tm, cons, nss, lib_path=lib)
+    blob = W.synth_objects(start, n)
+    objs = []
+    for i in range(n):
+        o = json.loads(blob.get(i))
+        objs.append(_mutate(rnd, o, rnd.choice([0, 1, 1, 2, 3, 5])))
+    revs = [D.Review(object=o, source="Original") for o in objs]
+    resp = drv.ReviewBatch(revs, k8s.AUDIT_EP)
+    errs = resp.object_errors or [None] * n
+    bad = {i for i, e in enumerate(errs) if e}
+    assert len(bad) < n // 4, "too many objects refused: %r" % [errs[i] for i in sorted(bad)[:5]]
+    for i in bad:
+        assert "int64" in errs[i] or "invalid request object" in errs[i], errs[i]
+    want = set()
+    for x in oracle_results_safe(orc, revs, k8s.AUDIT_EP, skip=bad):
+        want.add(x)
+    got = {x for x in engine_results(resp) if x[0] not in bad}
+    assert_same(want, got)
+    return len(want), len(bad)
+
+
+def oracle_results_safe(orc, reviews, ep, skip=()):
+    """oracle_results for the objects not in `skip` (keeps the original object indices)."""
+    out = set()
+    for i, r in enumerate(reviews):
+        if i in skip:
+            continue
+        for x in oracle_results(orc, [r], ep):
+            out.add((i,) + x[1:])
+    return out

@@ -97,3 +97,9 @@ def test_product_library_exports_every_declared_symbol():
 def test_product_library_has_no_cpu_fallback():
     with pytest.raises(D.GkError, match="no CPU fallback|CUDA"):
         D.Driver()
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_mutation_fuzz(seed):
+    nres, nbad = P.case_fuzz(HOSTEMU, n=500, seed=seed, start=7000 + 1000 * seed)
+    assert nres > 500

@@ -89,6 +89,13 @@ def test_validation_messages():
     P.case_validation_messages(LIB)
 
 
+@pytest.mark.parametrize("seed", [101, 202])
+def test_mutation_fuzz(seed):
+    """Synthetic Pods with random structural damage (wrong types, nulls, missing members, boundary-length strings)."""
+    nres, nbad = P.case_fuzz(LIB, n=1500, seed=seed, start=100000 + seed)
+    assert nres > 1500
+
+
 def test_config3_admission_microbatches():
     """200 PSP constraints (7 bitmap words) x 64-request micro-batches, UPDATE with object + oldObject."""
     tm, cons, pods = W.config3(200)
