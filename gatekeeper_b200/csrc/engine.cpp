@@ -106,16 +106,16 @@ static void parse_wildcard(const std::string& w, uint32_t& mode, std::string& li
 }
 
 // k8s.io/apimachinery validation of label keys / values (restated; module not vendored)
-static bool name_part_ok(const std::string& s) {
-  if (s.empty() || s.size() > 63) return false;
+static bool name_part_chars_ok(const std::string& s) {   // ([A-Za-z0-9][-A-Za-z0-9_.]*)?[A-Za-z0-9]
+  if (s.empty()) return false;
   auto alnum = [](char c) { return (c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z') || (c >= '0' && c <= '9'); };
   if (!alnum(s.front()) || !alnum(s.back())) return false;
   for (char c : s)
     if (!alnum(c) && c != '-' && c != '_' && c != '.') return false;
   return true;
 }
-static bool dns_subdomain_ok(const std::string& s) {
-  if (s.empty() || s.size() > 253) return false;
+static bool dns_subdomain_ok(const std::string& s) {      // the regex only; the length has its own message
+  if (s.empty()) return false;
   size_t i = 0;
   while (i <= s.size()) {
     size_t j = s.find('.', i);
@@ -130,20 +130,97 @@ static bool dns_subdomain_ok(const std::string& s) {
   }
   return true;
 }
-static bool label_key_ok(const std::string& k) {
+// ---- label key / value validation with apimachinery's messages (util/validation IsQualifiedName, IsValidLabelValue)
+static const char* kQNameMsg =
+    "must consist of alphanumeric characters, '-', '_' or '.', and must start and end with an alphanumeric character "
+    "(e.g. 'MyName',  or 'my.name',  or '123-abc', regex used for validation is '([A-Za-z0-9][-A-Za-z0-9_.]*)?[A-Za-z0-9]')";
+static const char* kSubdomainMsg =
+    "a lowercase RFC 1123 subdomain must consist of lower case alphanumeric characters, '-' or '.', and must start and end with "
+    "an alphanumeric character (e.g. 'example.com', regex used for validation is "
+    "'[a-z0-9]([-a-z0-9]*[a-z0-9])?(\\.[a-z0-9]([-a-z0-9]*[a-z0-9])?)*')";
+static const char* kLabelValueMsg =
+    "a valid label must be an empty string or consist of alphanumeric characters, '-', '_' or '.', and must start and end with "
+    "an alphanumeric character (e.g. 'MyValue',  or 'my_value',  or '12345', regex used for validation is "
+    "'(([A-Za-z0-9][-A-Za-z0-9_.]*)?[A-Za-z0-9])?')";
+
+static std::vector<std::string> qualified_name_errors(const std::string& k) {
+  std::vector<std::string> errs;
   size_t p = k.find('/');
-  if (p == std::string::npos) return name_part_ok(k);
-  if (k.find('/', p + 1) != std::string::npos) return false;
-  return dns_subdomain_ok(k.substr(0, p)) && name_part_ok(k.substr(p + 1));
+  std::string name = k;
+  if (p != std::string::npos) {
+    if (k.find('/', p + 1) != std::string::npos)
+      return {std::string("a qualified name ") + kQNameMsg + " with an optional DNS subdomain prefix and '/' (e.g. 'example.com/MyName')"};
+    std::string prefix = k.substr(0, p);
+    name = k.substr(p + 1);
+    if (prefix.empty()) errs.push_back("prefix part must be non-empty");
+    else {
+      if (prefix.size() > 253) errs.push_back("prefix part must be no more than 253 characters");
+      if (!dns_subdomain_ok(prefix)) errs.push_back(std::string("prefix part ") + kSubdomainMsg);
+    }
+  }
+  if (name.empty()) errs.push_back("name part must be non-empty");
+  else if (name.size() > 63) errs.push_back("name part must be no more than 63 characters");
+  if (!name_part_chars_ok(name)) errs.push_back(std::string("name part ") + kQNameMsg);
+  return errs;
 }
-static bool label_value_ok(const std::string& v) { return v.empty() || name_part_ok(v); }
+static std::vector<std::string> label_value_errors(const std::string& v) {
+  std::vector<std::string> errs;
+  if (v.size() > 63) errs.push_back("must be no more than 63 characters");
+  if (!v.empty() && !name_part_chars_ok(v)) errs.push_back(kLabelValueMsg);
+  return errs;
+}
+static std::string join(const std::vector<std::string>& v, const char* sep) {
+  std::string o;
+  for (size_t i = 0; i < v.size(); ++i) {
+    if (i) o += sep;
+    o += v[i];
+  }
+  return o;
+}
+static std::string go_strings(const std::vector<std::string>& vals) {   // fmt %#v of a []string
+  if (vals.empty()) return "[]string(nil)";
+  std::string o = "[]string{";
+  for (size_t i = 0; i < vals.size(); ++i) {
+    if (i) o += ", ";
+    json_quote(vals[i], o);
+  }
+  return o + "}";
+}
 
 struct SelReq {
   std::string key;
   uint32_t op;
   std::vector<std::string> vals;
 };
-// metav1.LabelSelectorAsSelector: returns "" or the error text
+// labels.NewRequirement: every problem of one requirement, aggregated as field.ErrorList.ToAggregate prints them
+static std::string requirement_error(const SelReq& r) {
+  std::vector<std::string> errs;
+  auto ke = qualified_name_errors(r.key);
+  std::string q;
+  if (!ke.empty()) {
+    q.clear();
+    json_quote(r.key, q);
+    errs.push_back("key: Invalid value: " + q + ": " + join(ke, "; "));
+  }
+  if ((r.op == GK_SEL_IN || r.op == GK_SEL_NOTIN) && r.vals.empty())
+    errs.push_back("values: Invalid value: " + go_strings(r.vals) + ": for 'in', 'notin' operators, values set can't be empty");
+  if ((r.op == GK_SEL_EXISTS || r.op == GK_SEL_NOTEXISTS) && !r.vals.empty())
+    errs.push_back("values: Invalid value: " + go_strings(r.vals) + ": values set must be empty for exists and does not exist");
+  for (size_t i = 0; i < r.vals.size(); ++i) {
+    auto ve = label_value_errors(r.vals[i]);
+    if (ve.empty()) continue;
+    q.clear();
+    json_quote(r.vals[i], q);
+    errs.push_back("values[" + std::to_string(i) + "][" + r.key + "]: Invalid value: " + q + ": " + join(ve, "; "));
+  }
+  std::vector<std::string> uniq;
+  for (auto& e : errs)
+    if (std::find(uniq.begin(), uniq.end(), e) == uniq.end()) uniq.push_back(e);
+  if (uniq.empty()) return "";
+  return uniq.size() == 1 ? uniq[0] : "[" + join(uniq, ", ") + "]";
+}
+// metav1.LabelSelectorAsSelector: returns "" or the error text.  Requirements are built in order (matchLabels -- sorted
+// here, a Go map there -- then matchExpressions); the first failing one is the error.
 static std::string parse_selector(const VP& sel, std::vector<SelReq>& out) {
   if (!sel || sel->t != VT::Obj) return "";
   VP ml = obj_get(sel, "matchLabels");
@@ -153,10 +230,11 @@ static std::string parse_selector(const VP& sel, std::vector<SelReq>& out) {
       r.key = e.first->s;
       r.op = GK_SEL_IN;
       r.vals.push_back(e.second->t == VT::Str ? e.second->s : fmt_value(e.second, true));
+      std::string err = requirement_error(r);
+      if (!err.empty()) return err;
       out.push_back(r);
     }
   VP me = obj_get(sel, "matchExpressions");
-  std::string err;
   if (me && me->t == VT::Arr)
     for (auto& x : me->items) {
       SelReq r;
@@ -169,20 +247,11 @@ static std::string parse_selector(const VP& sel, std::vector<SelReq>& out) {
       else if (op == "NotIn") r.op = GK_SEL_NOTIN;
       else if (op == "Exists") r.op = GK_SEL_EXISTS;
       else if (op == "DoesNotExist") r.op = GK_SEL_NOTEXISTS;
-      else {
-        if (err.empty()) err = "\"" + op + "\" is not a valid label selector operator";
-        continue;
-      }
+      else return "\"" + op + "\" is not a valid label selector operator";
+      std::string err = requirement_error(r);
+      if (!err.empty()) return err;
       out.push_back(r);
     }
-  if (!err.empty()) return err;
-  for (auto& r : out) {
-    if ((r.op == GK_SEL_IN || r.op == GK_SEL_NOTIN) && r.vals.empty()) return "values: Invalid value: []: for 'in', 'notin' operators, values set can't be empty";
-    if ((r.op == GK_SEL_EXISTS || r.op == GK_SEL_NOTEXISTS) && !r.vals.empty()) return "values: Invalid value: values set must be empty for exists and does not exist";
-    if (!label_key_ok(r.key)) return "key: Invalid value: \"" + r.key + "\"";
-    for (auto& v : r.vals)
-      if (!label_value_ok(v)) return "values: Invalid value: \"" + v + "\"";
-  }
   return "";
 }
 
@@ -1255,7 +1324,9 @@ void Engine::autoreject(const Compiled& c, const ObjIn& in, uint32_t obj_ix, uin
   std::string err;
   VP obj, old;
   (void)review_doc(in, &obj, &old, nullptr, &err);
-  VP ref = obj ? obj : old;
+  // matcher.go:58-60: the text names the object on which Matches failed -- Object first, OldObject if Object did not match
+  VP ref = (code & GK_E_FROM_OLD) ? old : (obj ? obj : old);
+  code &= GK_E_FROM_OLD - 1;
   std::string name = ref ? meta_str(ref, "name") : "";
   std::string detail;
   switch (code) {

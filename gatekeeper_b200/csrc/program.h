@@ -90,7 +90,8 @@ enum { GK_SEL_IN = 0, GK_SEL_NOTIN = 1, GK_SEL_EXISTS = 2, GK_SEL_NOTEXISTS = 3 
 
 // error codes written to the error list (host renders the reference's error text from them)
 enum { GK_E_NONE = 0, GK_E_LSEL_INVALID = 1, GK_E_NSSEL_INVALID = 2, GK_E_NS_MISSING = 3, GK_E_SRC_INVALID_MATCH = 4,
-       GK_E_SRC_UNSPECIFIED = 5, GK_E_SRC_INVALID_OBJ = 6, GK_E_NO_OBJECT = 7, GK_E_NUM_RANGE = 8 };
+       GK_E_SRC_UNSPECIFIED = 5, GK_E_SRC_INVALID_OBJ = 6, GK_E_NO_OBJECT = 7, GK_E_NUM_RANGE = 8,
+       GK_E_FROM_OLD = 256 /* added to the code when the failing object was OldObject */ };
 
 typedef struct {
   uint32_t flags;

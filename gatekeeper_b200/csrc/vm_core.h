@@ -171,6 +171,7 @@ GK_HD int gk_match(const GkBatch& b, const uint32_t* pool, const uint8_t* cbytes
   }
   if (b.has_old && (b.flags[b.n + obj] & GK_F_HAS_OBJ)) {
     int r = gk_match_row(b, pool, cbytes, m, b.n + obj, obj);
+    if (r < 0) return r - GK_E_FROM_OLD;   // the error text names the object that failed (matcher.go:58-60): here the old one
     if (r) return r;
   } else {
     ++nil;

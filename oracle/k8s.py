@@ -7,6 +7,7 @@ Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl refere
 """
 from __future__ import annotations
 
+import json
 import re
 
 from . import rego
@@ -64,46 +65,102 @@ _NAME_RE = re.compile(r"^[A-Za-z0-9]([-A-Za-z0-9_.]*[A-Za-z0-9])?$")
 _DNS1123_SUB = re.compile(r"^[a-z0-9]([-a-z0-9]*[a-z0-9])?(\.[a-z0-9]([-a-z0-9]*[a-z0-9])?)*$")
 
 
-def _valid_label_key(k: str) -> bool:
+_QNAME_MSG = ("must consist of alphanumeric characters, '-', '_' or '.', and must start and end with an alphanumeric character "
+              "(e.g. 'MyName',  or 'my.name',  or '123-abc', regex used for validation is '([A-Za-z0-9][-A-Za-z0-9_.]*)?[A-Za-z0-9]')")
+_SUBDOMAIN_MSG = ("a lowercase RFC 1123 subdomain must consist of lower case alphanumeric characters, '-' or '.', and must start and end with "
+                  "an alphanumeric character (e.g. 'example.com', regex used for validation is "
+                  "'[a-z0-9]([-a-z0-9]*[a-z0-9])?(\\.[a-z0-9]([-a-z0-9]*[a-z0-9])?)*')")
+_LABEL_VALUE_MSG = ("a valid label must be an empty string or consist of alphanumeric characters, '-', '_' or '.', and must start and end with "
+                    "an alphanumeric character (e.g. 'MyValue',  or 'my_value',  or '12345', regex used for validation is "
+                    "'(([A-Za-z0-9][-A-Za-z0-9_.]*)?[A-Za-z0-9])?')")
+
+
+def _qualified_name_errors(k: str):
+    """validation.IsQualifiedName (apimachinery util/validation): the messages, in order."""
+    errs = []
     parts = k.split("/")
     if len(parts) == 1:
         name = parts[0]
     elif len(parts) == 2:
         prefix, name = parts
-        if not prefix or len(prefix) > 253 or not _DNS1123_SUB.match(prefix):
-            return False
+        if not prefix:
+            errs.append("prefix part must be non-empty")
+        else:
+            if len(prefix) > 253:
+                errs.append("prefix part must be no more than 253 characters")
+            if not _DNS1123_SUB.match(prefix):
+                errs.append("prefix part " + _SUBDOMAIN_MSG)
     else:
-        return False
-    return bool(name) and len(name) <= 63 and bool(_NAME_RE.match(name))
+        return ["a qualified name " + _QNAME_MSG + " with an optional DNS subdomain prefix and '/' (e.g. 'example.com/MyName')"]
+    if not name:
+        errs.append("name part must be non-empty")
+    elif len(name) > 63:
+        errs.append("name part must be no more than 63 characters")
+    if not _NAME_RE.match(name):
+        errs.append("name part " + _QNAME_MSG)
+    return errs
 
 
-def _valid_label_value(v: str) -> bool:
-    return len(v) <= 63 and (v == "" or bool(_NAME_RE.match(v)))
+def _label_value_errors(v: str):
+    """validation.IsValidLabelValue."""
+    errs = []
+    if len(v) > 63:
+        errs.append("must be no more than 63 characters")
+    if v != "" and not _NAME_RE.match(v):
+        errs.append(_LABEL_VALUE_MSG)
+    return errs
+
+
+def _go_quote(x: str) -> str:
+    return json.dumps(x, ensure_ascii=False)
+
+
+def _go_strings(vals) -> str:
+    """fmt %#v of a []string."""
+    return "[]string(nil)" if not vals else "[]string{" + ", ".join(_go_quote(v) for v in vals) + "}"
+
+
+def _requirement_error(key, op, vals):
+    """labels.NewRequirement: every problem of one requirement as field errors, aggregated the way
+    field.ErrorList.ToAggregate prints them (one: the message; several: [m1, m2])."""
+    errs = []
+    ke = _qualified_name_errors(key)
+    if ke:
+        errs.append("key: Invalid value: %s: %s" % (_go_quote(key), "; ".join(ke)))
+    if op in ("In", "NotIn") and not vals:
+        errs.append("values: Invalid value: %s: for 'in', 'notin' operators, values set can't be empty" % _go_strings(vals))
+    if op in ("Exists", "DoesNotExist") and vals:
+        errs.append("values: Invalid value: %s: values set must be empty for exists and does not exist" % _go_strings(vals))
+    for i, v in enumerate(vals):
+        ve = _label_value_errors(v)
+        if ve:
+            errs.append("values[%d][%s]: Invalid value: %s: %s" % (i, key, _go_quote(v), "; ".join(ve)))
+    if not errs:
+        return None
+    uniq = list(dict.fromkeys(errs))
+    return uniq[0] if len(uniq) == 1 else "[" + ", ".join(uniq) + "]"
 
 
 def label_selector_requirements(sel):
-    """LabelSelectorAsSelector: returns a list of (key, op, values) or raises MatchError."""
+    """LabelSelectorAsSelector: returns a list of (key, op, values) or raises MatchError.  Requirements are built in
+    order (matchLabels -- sorted here, a Go map there -- then matchExpressions) and the first failing one is the error."""
     reqs = []
     if sel is None:
         return None
     for k, v in sorted((sel.get("matchLabels") or {}).items()):
+        e = _requirement_error(k, "In", [v])
+        if e:
+            raise MatchError(e)
         reqs.append((k, "In", [v]))
-    for e in sel.get("matchExpressions") or []:
-        op = e.get("operator", "")
-        vals = list(e.get("values") or [])
+    for x in sel.get("matchExpressions") or []:
+        op = x.get("operator", "")
+        vals = list(x.get("values") or [])
         if op not in ("In", "NotIn", "Exists", "DoesNotExist"):
             raise MatchError(f'"{op}" is not a valid label selector operator')
-        reqs.append((e.get("key", ""), op, vals))
-    for k, op, vals in reqs:
-        if op in ("In", "NotIn") and not vals:
-            raise MatchError("for 'in', 'notin' operators, values set can't be empty")
-        if op in ("Exists", "DoesNotExist") and vals:
-            raise MatchError("values set must be empty for exists and does not exist")
-        if not _valid_label_key(k):
-            raise MatchError(f"key: Invalid value: {k!r}")
-        for v in vals:
-            if not _valid_label_value(v):
-                raise MatchError(f"values: Invalid value: {v!r}")
+        e = _requirement_error(x.get("key", ""), op, vals)
+        if e:
+            raise MatchError(e)
+        reqs.append((x.get("key", ""), op, vals))
     return reqs
 
 

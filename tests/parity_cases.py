@@ -367,3 +367,84 @@ def oracle_results_safe(orc, reviews, ep, skip=()):
         for x in oracle_results(orc, [r], ep):
             out.add((i,) + x[1:])
     return out
+
+
+# ------------------------------------------------------------------------------------------ match fuzz
+def case_match_fuzz(lib, n_constraints=60, n_objects=400, seed=5):
+    """Random `spec.match` blocks x random review shapes through the in-kernel pre-filter, against the oracle's
+    restatement of match.Matches / Matcher.Match (which the reference's own vectors pin).  The template always
+    violates, so the result set is exactly the match relation (plus autoreject results for matcher errors)."""
+    import random
+    rnd = random.Random(seed)
+    t = golden("templates.json")["fixtures_TemplateNeverValidate"]
+    names = ["a", "ab", "abc", "kube-system", "kube-public", "prod-1", "prod-22", "dev", "x-system", ""]
+    wild = lambda: rnd.choice(names[:-1] + ["*", "a*", "*a", "*b*", "kube-*", "*-system", "prod-*", "*-1", "**"])
+    keys, vals = ["app", "team", "tier", "env", "example.com/role", "bad key!", "", "a/b/c", "-x"], ["a", "b", "c", "", "not ok", "x" * 64]
+    def selector():
+        s = {}
+        if rnd.random() < 0.6:
+            s["matchLabels"] = {rnd.choice(keys): rnd.choice(vals) for _ in range(rnd.randint(0, 2))}
+        if rnd.random() < 0.6:
+            s["matchExpressions"] = []
+            for _ in range(rnd.randint(0, 2)):
+                op = rnd.choice(["In", "NotIn", "Exists", "DoesNotExist"])
+                e = {"key": rnd.choice(keys), "operator": op}
+                if op in ("In", "NotIn"):
+                    e["values"] = [rnd.choice(vals[:3]) for _ in range(rnd.randint(1, 3))]
+                elif rnd.random() < 0.1:
+                    e["values"] = ["a"]                      # invalid: Exists with values
+                s["matchExpressions"].append(e)
+        return s
+    cons = []
+    for i in range(n_constraints):
+        m = {}
+        if rnd.random() < 0.5:
+            m["kinds"] = [{"apiGroups": rnd.choice([[""], ["*"], ["apps"], ["", "apps"], []]),
+                           "kinds": rnd.choice([["Pod"], ["*"], ["Deployment", "Pod"], ["Namespace"], []])} for _ in range(rnd.randint(1, 2))]
+        if rnd.random() < 0.3:
+            m["scope"] = rnd.choice(["Cluster", "Namespaced", "*", "Bogus"])
+        if rnd.random() < 0.4:
+            m["namespaces"] = [wild() for _ in range(rnd.randint(1, 3))]
+        if rnd.random() < 0.4:
+            m["excludedNamespaces"] = [wild() for _ in range(rnd.randint(1, 3))]
+        if rnd.random() < 0.4:
+            m["labelSelector"] = selector()
+        if rnd.random() < 0.4:
+            m["namespaceSelector"] = selector()
+        if rnd.random() < 0.3:
+            m["name"] = wild()
+        if rnd.random() < 0.3:
+            m["source"] = rnd.choice(["All", "Original", "Generated", "", "Bogus"])
+        cons.append({"kind": t["kind"], "metadata": {"name": "m%03d" % i}, "spec": ({"match": m} if (m or rnd.random() < 0.5) else {})})
+    cached = [{"apiVersion": "v1", "kind": "Namespace", "metadata": {"name": n, "labels": {rnd.choice(keys): rnd.choice(vals) for _ in range(rnd.randint(0, 3))}}}
+              for n in names[:6]]
+    orc, drv, _ = make_pair([(t["kind"], t["rego"])], cons, cached, lib_path=lib)
+    def obj():
+        kind, group = rnd.choice([("Pod", ""), ("Pod", ""), ("Deployment", "apps"), ("Namespace", ""), ("ClusterRole", "rbac.authorization.k8s.io")])
+        meta = {}
+        if rnd.random() < 0.85:
+            meta["name"] = rnd.choice(names)
+        if rnd.random() < 0.2:
+            meta["generateName"] = rnd.choice(names)
+        if kind in ("Pod", "Deployment") and rnd.random() < 0.9:
+            meta["namespace"] = rnd.choice(names)
+        if rnd.random() < 0.7:
+            meta["labels"] = {rnd.choice(keys): rnd.choice(vals) for _ in range(rnd.randint(0, 3))}
+        return {"apiVersion": (group + "/v1") if group else "v1", "kind": kind, "metadata": meta}
+    revs = []
+    for _ in range(n_objects):
+        o = obj()
+        kw = {"object": o, "source": rnd.choice(["Original", "Generated", "", "All"])}
+        r = rnd.random()
+        if r < 0.15:
+            kw.update(old_object=obj(), operation="UPDATE")
+        elif r < 0.25:
+            kw = {"object": None, "old_object": o, "operation": "DELETE", "source": kw["source"]}
+        if rnd.random() < 0.25:
+            kw["namespace"] = {"apiVersion": "v1", "kind": "Namespace",
+                               "metadata": {"name": o["metadata"].get("namespace", "zz"), "labels": {rnd.choice(keys): rnd.choice(vals)}}}
+        revs.append(D.Review(**kw))
+    for ep in (k8s.AUDIT_EP, k8s.WEBHOOK_EP):
+        resp = drv.ReviewBatch(revs, ep)
+        assert_same(oracle_results(orc, revs, ep), engine_results(resp))
+    return len(resp.results)

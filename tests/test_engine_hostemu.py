@@ -103,3 +103,8 @@ def test_product_library_has_no_cpu_fallback():
 def test_mutation_fuzz(seed):
     nres, nbad = P.case_fuzz(HOSTEMU, n=500, seed=seed, start=7000 + 1000 * seed)
     assert nres > 500
+
+
+@pytest.mark.parametrize("seed", [5, 6, 7])
+def test_match_fuzz(seed):
+    assert P.case_match_fuzz(HOSTEMU, seed=seed) > 1000

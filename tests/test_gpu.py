@@ -96,6 +96,12 @@ def test_mutation_fuzz(seed):
     assert nres > 1500
 
 
+@pytest.mark.parametrize("seed", [11, 12])
+def test_match_fuzz(seed):
+    """Random spec.match blocks x random review shapes through the in-kernel pre-filter."""
+    assert P.case_match_fuzz(LIB, n_constraints=96, n_objects=700, seed=seed) > 1000
+
+
 def test_config3_admission_microbatches():
     """200 PSP constraints (7 bitmap words) x 64-request micro-batches, UPDATE with object + oldObject."""
     tm, cons, pods = W.config3(200)
