@@ -188,7 +188,7 @@ using SymK = std::function<FP(const SymVal&)>;
 class Lowerer {
  public:
   Lowerer(std::shared_ptr<const Module> mod, VP params, Schema& schema)
-      : mod_(std::move(mod)), m_(*mod_), schema_(schema),
+      : mod_(std::move(mod)), m_(*mod_), schema_(schema), params_(params),
         ev_(m_, v_obj({{v_str("parameters"), params}})) {
     vid_cur_ = const_cast<Module&>(m_).intern("$cur");
     vid_key_ = const_cast<Module&>(m_).intern("$key");
@@ -212,6 +212,7 @@ class Lowerer {
   std::shared_ptr<const Module> mod_;
   const Module& m_;
   Schema& schema_;
+  VP params_;
   Eval ev_;
   int vid_cur_, vid_key_;
   int depth_ = 0;
@@ -860,7 +861,16 @@ class Lowerer {
           return k(copy);
         }
         if (m_.is_rule(t->name)) return inline_rule_value(t, env, k);
-        if (t->vid == m_.vid_input) unsupported("use of the whole `input` document", t->line);
+        if (t->vid == m_.vid_input) {
+          // the whole input document: {"parameters": <constant>, "review": <the object side>} -- e.g. the argument of
+          // object.get(input, "parameters", {}) (test/gator/verify/template.yaml:23)
+          SymVal doc;
+          doc.k = SymVal::ObjLit;
+          doc.fields.emplace_back(v_str("parameters"), SymVal::conc(params_, true));
+          LEnv none;
+          doc.fields.emplace_back(v_str("review"), SymVal::column(make_closure(synth_ref(synth_var(m_.vid_input, "input"), {synth_scalar(v_str("review"))}, t->line), none)));
+          return k(doc);
+        }
         unsupported("unbound variable " + t->name, t->line);
       }
       case TK::Ref: return sym_ref(t, env, k);
@@ -1291,6 +1301,11 @@ class Lowerer {
       if (def->k == Formula::False) return def;
       return k(SymVal::opaque(def));
     }
+    if (n == "object.get" && a.size() == 3 && a[0].k == SymVal::ObjLit && is_conc(a[1])) {
+      for (auto& f : a[0].fields)
+        if (v_eq(f.first, a[1].v)) return k(f.second);
+      return k(a[2]);
+    }
     if (n == "equal" && a.size() == 2) return ret_bool(eq_cond(a[0], a[1], line));
     if (n == "neq" && a.size() == 2) {
       if (a[0].k == SymVal::Count || a[1].k == SymVal::Count) return ret_bool(count_cmp(GK_CMP_NE, a[0], a[1], line));
@@ -1381,7 +1396,17 @@ class Lowerer {
       if (is_conc(a[0]) && (is_col(a[1]) || a[1].k == SymVal::SetOf)) return ret_bool(member_cond(a[0].v, a[1], line));
       unsupported("`in` over this symbolic value", line);
     }
-    if (n == "re_match" || n == "regex.match") unsupported("regular expression over an object field with a parameter-dependent pattern", line);
+    if ((n == "re_match" || n == "regex.match") && a.size() == 2 && is_conc(a[0]) && is_col(a[1])) {
+      // Regular expressions are not evaluated on the device: `re_match(<pattern from the parameters>, <object string>)`
+      // becomes a boolean FEATURE COLUMN of its own -- the flattener runs the (cached, compiled) pattern once per row --
+      // keyed by the pattern text, so constraints that share a pattern share the column.
+      if (a[0].v->t != VT::Str) return ret_bool(f_false());   // non-string pattern: undefined
+      LEnv e;
+      e.bind(vid_cur_, a[1]);
+      CP c = make_closure(synth_call(n, {synth_scalar(a[0].v), synth_var(vid_cur_, "$cur")}, line), e);
+      return ret_bool(f_atom(GK_OP_VTMASK, schema_.col_for(c, GK_ENC_VT), nullptr, 1u << GK_VT_TRUE));
+    }
+    if (n == "re_match" || n == "regex.match") unsupported("regular expression with a pattern taken from the object", line);
     unsupported("builtin " + n + " mixing parameters and object fields", line);
   }
 };

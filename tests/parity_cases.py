@@ -202,10 +202,11 @@ def case_unsupported_is_an_error_not_a_fallback(lib):
     with pytest.raises(D.GkError, match="data"):
         drv.add_template("K8sUniqueLabel", 'package u\nviolation[{"msg": msg}] {\n  other := data.inventory.cluster[_][_][_]\n'
                          '  other.metadata.labels.x == input.review.object.metadata.labels.x\n  msg := "dup"\n}\n')
-    drv.add_template("K8sRequiredLabels", t["requiredlabels_agilebank"]["rego"])
+    # a pattern taken from the OBJECT (not from the parameters) cannot become a feature column: rejected at AddConstraint
+    drv.add_template("PatternFromObject", 'package p\nviolation[{"msg": "m"}] {\n  re_match(input.review.object.metadata.annotations.pat, '
+                     'input.parameters.v)\n}\n')
     with pytest.raises(D.GkError, match="rego_unsupported: regular expression"):
-        drv.AddConstraint({"kind": "K8sRequiredLabels", "metadata": {"name": "x"},
-                           "spec": {"parameters": {"labels": [{"key": "owner", "allowedRegex": "^[a-z]+$"}]}}})
+        drv.AddConstraint({"kind": "PatternFromObject", "metadata": {"name": "x"}, "spec": {"parameters": {"v": "abc"}}})
     assert drv.Name() == "Rego"
     assert "kernel" in drv.GetDescriptionForStat("kernelTimeNS")
 
@@ -448,3 +449,62 @@ def case_match_fuzz(lib, n_constraints=60, n_objects=400, seed=5):
         resp = drv.ReviewBatch(revs, ep)
         assert_same(oracle_results(orc, revs, ep), engine_results(resp))
     return len(resp.results)
+
+
+def case_fuzz_other_templates(lib, n=400, seed=77):
+    """The in-tree templates outside config 2 (regex labels, object.get defaults, namespaceObject, user info, custom
+    fields, the comprehension form of allowed repos, `violation contains ... if`), with varied parameters, against
+    mutated objects of several kinds."""
+    import random
+    rnd = random.Random(seed)
+    t = golden("templates.json")
+    pick = {"requiredlabels_agilebank": [{"labels": [{"key": "owner", "allowedRegex": "^[a-z]+[.]agilebank[.]demo$"}, {"key": "team"}]},
+                                         {"message": "custom message", "labels": [{"key": "team", "allowedRegex": "^(a|b|team-[0-9]+)$"}]},
+                                         {"labels": [{"key": "app", "allowedRegex": ""}]}],
+            "requiredlabels_regov1": [{"labels": ["team", "owner"]}, {"labels": []}],
+            "fooischeck": [{"foo": "bar"}, {"foo": ""}, {}, {"foo": 7}],
+            "namespacelabelcheck": [{"requiredLabel": "team"}, {"requiredLabel": "bar"}],
+            "allowedrepos": [{"repos": ["gcr.io/", "quay.io/"]}, {"repos": []}, {"repos": ["openpolicyagent/opa:", "docker.io/library/nginx"]}],
+            "fixtures_TemplateValidateUserInfo": [None],
+            "fixtures_TemplateRestrictCustomField": [{"expectedCustomField": "x"}, {"expectedCustomField": 7}, {"expectedCustomField": {"a": [1, 2]}},
+                                                     {"expectedCustomField": None}]}
+    tm, cons = [], []
+    for name, plist in pick.items():
+        tm.append((t[name]["kind"], t[name]["rego"]))
+        for i, params in enumerate(plist):
+            cons.append(W._constraint(t[name]["kind"], "%s-%d" % (name.replace("_", "-").lower(), i), params=params,
+                                      action=rnd.choice([None, "warn", "dryrun"])))
+    nss = W.synth_namespaces()
+    orc, drv, skipped = make_pair(tm, cons, nss, lib_path=lib, skip_unsupported=True)
+    assert not skipped, skipped
+    blob = W.synth_objects(31000 + seed, n)
+    revs = []
+    for i in range(n):
+        o = json.loads(blob.get(i))
+        if rnd.random() < 0.3:
+            o.setdefault("metadata", {}).setdefault("labels", {})[rnd.choice(["owner", "team", "app"])] = rnd.choice(
+                ["alice.agilebank.demo", "bob", "team-7", "a", "", "Team-1", "x.agilebank.demo.evil"])
+        if rnd.random() < 0.3:
+            o["foo"] = rnd.choice(["bar", "", "baz", 7, None, ["bar"]])
+        if rnd.random() < 0.3:
+            o.setdefault("spec", {})["customField"] = rnd.choice(["x", "y", 7, 7.0, {"a": [1, 2]}, {"a": [2, 1]}, None, [1]])
+        o = _mutate(rnd, o, rnd.choice([0, 0, 1, 2]))
+        kw = {"object": o, "source": "Original"}
+        if rnd.random() < 0.5:
+            kw["user_info"] = {"username": rnd.choice(["system:serviceaccount:kube-system:x", "alice", "", "system:", "System:admin"])}
+        if rnd.random() < 0.3:
+            kw["namespace"] = {"apiVersion": "v1", "kind": "Namespace",
+                               "metadata": dict({"name": rnd.choice(["explicit-ns", "ns-0001"])},
+                                                **({"labels": {rnd.choice(["team", "bar", "other"]): "v"}} if rnd.random() < 0.7 else {}))}
+        revs.append(D.Review(**kw))
+    n_results = 0
+    for ep in (k8s.AUDIT_EP, k8s.WEBHOOK_EP):
+        resp = drv.ReviewBatch(revs, ep)
+        errs = resp.object_errors or [None] * n
+        bad = {i for i, e in enumerate(errs) if e}
+        assert len(bad) < n // 4
+        want = oracle_results_safe(orc, revs, ep, skip=bad)
+        got = {x for x in engine_results(resp) if x[0] not in bad}
+        assert_same(want, got)
+        n_results += len(want)
+    return n_results

@@ -108,3 +108,8 @@ def test_mutation_fuzz(seed):
 @pytest.mark.parametrize("seed", [5, 6, 7])
 def test_match_fuzz(seed):
     assert P.case_match_fuzz(HOSTEMU, seed=seed) > 1000
+
+
+@pytest.mark.parametrize("seed", [77, 78])
+def test_fuzz_other_templates(seed):
+    assert P.case_fuzz_other_templates(HOSTEMU, seed=seed) > 500

@@ -102,6 +102,11 @@ def test_match_fuzz(seed):
     assert P.case_match_fuzz(LIB, n_constraints=96, n_objects=700, seed=seed) > 1000
 
 
+def test_fuzz_other_templates():
+    """The in-tree templates outside config 2 (regex labels, object.get(input, ...), namespaceObject, user info ...)."""
+    assert P.case_fuzz_other_templates(LIB, n=600, seed=314) > 800
+
+
 def test_config3_admission_microbatches():
     """200 PSP constraints (7 bitmap words) x 64-request micro-batches, UPDATE with object + oldObject."""
     tm, cons, pods = W.config3(200)
