@@ -5,9 +5,9 @@
  *
  *   gk_engine_create/destroy  <- rego.New(args...) / driver lifetime          main.go:457-462, pkg/gator/opa.go:32-37
  *   gk_add_template           <- Driver.AddTemplate(ctx, *ConstraintTemplate)  pkg/drivers/k8scel/driver.go:74-136
- *   gk_remove_template        <- Driver.RemoveTemplate                          pkg/drivers/k8scel/driver.go:138-147
- *   gk_add_constraint         <- Driver.AddConstraint + TargetHandler.ToMatcher pkg/drivers/k8scel/driver.go:149-151, pkg/target/target.go:239-254
- *   gk_remove_constraint      <- Driver.RemoveConstraint                        pkg/drivers/k8scel/driver.go:153-155
+ *   gk_remove_template        <- Driver.RemoveTemplate                          pkg/drivers/k8scel/driver.go:138-143
+ *   gk_add_constraint         <- Driver.AddConstraint + TargetHandler.ToMatcher pkg/drivers/k8scel/driver.go:145-147, pkg/target/target.go:239-254
+ *   gk_remove_constraint      <- Driver.RemoveConstraint                        pkg/drivers/k8scel/driver.go:149-151
  *   gk_put_namespace / remove <- Driver.AddData/RemoveData for Namespace paths + nsCache   pkg/target/ns_cache.go:15-85, pkg/target/target.go:60-66
  *   gk_review_batch           <- Client.Review -> Matcher.Match -> Driver.Query, for a BATCH of reviews
  *                                pkg/audit/manager.go:622,720 ; pkg/webhook/policy.go:661 ; pkg/target/matcher.go:21-71 ;
