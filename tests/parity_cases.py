@@ -508,3 +508,66 @@ def case_fuzz_other_templates(lib, n=400, seed=77):
         assert_same(want, got)
         n_results += len(want)
     return n_results
+
+
+# ------------------------------------------------------------------------------------------ pkg/target vectors
+DENY_ALL = 'package denyall\nviolation[{"msg": msg}] {\n  msg := "denyall constraint installed"\n}\n'   # target_integration_test.go:37-43
+
+
+def _target_shapes(v):
+    """The three request shapes TestConstraintEnforcement reviews (target_integration_test.go:446-520)."""
+    ns = v["namespace"]
+    nsn = ns["metadata"]["name"] if ns else ""
+    yield "object", dict(object=v["object"], namespace=ns, namespace_name=nsn)
+    yield "oldObject", dict(object=None, old_object=v["object"], namespace=ns, namespace_name=nsn)
+    yield "unstructured", dict(object=v["object"], namespace=ns)
+
+
+def case_target_enforcement(lib):
+    """26 scenarios the reference runs through its real client + Rego driver: allowed <=> no results."""
+    n = 0
+    for v in golden("target_vectors.json")["constraint_enforcement"]:
+        orc, drv, _ = make_pair([("DenyAll", DENY_ALL)], [v["constraint"]], lib_path=lib)
+        for shape, kw in _target_shapes(v):
+            rev = D.Review(**kw)
+            resp = drv.ReviewBatch([rev], k8s.AUDIT_EP)
+            assert (len(resp.results) == 0) == v["allowed"], (v["name"], shape, [r.msg for r in resp.results])
+            assert_same(oracle_results(orc, [rev], k8s.AUDIT_EP), engine_results(resp))
+            n += 1
+    assert n == 78
+
+
+def _matcher_review(req):
+    kw = dict(object=req.get("object"), old_object=req.get("oldObject"), namespace=req.get("namespace"))
+    if req["shape"] in ("AugmentedReview", "AdmissionRequest"):
+        kw["namespace_name"] = req.get("namespaceName", "")     # AdmissionRequest.Namespace is explicit (matcher.go:37-39)
+    return kw
+
+
+def case_target_matcher(lib):
+    """TestMatcher_Match: object OR old object, review namespace vs cached namespace, the two error classes."""
+    t = golden("templates.json")["fixtures_TemplateNeverValidate"]
+    n = 0
+    for v in golden("target_vectors.json")["matcher_match"]:
+        if v["request"] is None or v["match"] is None:
+            continue                                               # "nil": HandleReview does not handle a nil request
+        con = {"kind": t["kind"], "metadata": {"name": "c"}, "spec": {"match": v["match"]}}
+        nss = [v["cachedNamespace"]] if v["cachedNamespace"] else []
+        orc, drv, _ = make_pair([(t["kind"], t["rego"])], [con], nss, lib_path=lib)
+        rev = D.Review(**_matcher_review(v["request"]))
+        resp = drv.ReviewBatch([rev], k8s.AUDIT_EP)
+        obj_err = (resp.object_errors or [None])[0]
+        flagged = bool(resp.viol_bits[0, 0] & 1) and not obj_err
+        errored = bool(resp.err_bits[0, 0] & 1)
+        if v["wantErr"] == "ErrRequestObject":
+            assert obj_err or (resp.results and resp.results[0].autoreject and "invalid request object" in resp.results[0].msg), v["name"]
+            assert not flagged
+        elif v["wantErr"] == "ErrMatching":
+            assert errored and resp.results[0].autoreject and resp.results[0].msg.startswith("error matching the requested object"), v["name"]
+        else:
+            assert not errored and not obj_err, (v["name"], obj_err)
+            assert flagged == v["want"], v["name"]
+        if not obj_err:
+            assert_same(oracle_results(orc, [rev], k8s.AUDIT_EP), engine_results(resp))
+        n += 1
+    assert n >= 15

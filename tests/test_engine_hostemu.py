@@ -113,3 +113,11 @@ def test_match_fuzz(seed):
 @pytest.mark.parametrize("seed", [77, 78])
 def test_fuzz_other_templates(seed):
     assert P.case_fuzz_other_templates(HOSTEMU, seed=seed) > 500
+
+
+def test_target_enforcement_vectors():
+    P.case_target_enforcement(HOSTEMU)
+
+
+def test_target_matcher_vectors():
+    P.case_target_matcher(HOSTEMU)

@@ -107,6 +107,15 @@ def test_fuzz_other_templates():
     assert P.case_fuzz_other_templates(LIB, n=600, seed=314) > 800
 
 
+def test_target_enforcement_vectors():
+    """pkg/target/target_integration_test.go: 26 scenarios x 3 request shapes, allowed <=> no results."""
+    P.case_target_enforcement(LIB)
+
+
+def test_target_matcher_vectors():
+    P.case_target_matcher(LIB)
+
+
 def test_config3_admission_microbatches():
     """200 PSP constraints (7 bitmap words) x 64-request micro-batches, UPDATE with object + oldObject."""
     tm, cons, pods = W.config3(200)

@@ -195,3 +195,48 @@ violation[{"msg": msg}] { msg := sprintf("%v %v %v", [f("b"), 10 * 100, {"k": [1
     inp = rego.from_json({"review": {"object": {"zero": 0, "f": False, "list": [1, 1, 1.0]}}, "parameters": {}})
     msgs = sorted(v["msg"] for v in rego.eval_violations(m, inp))
     assert msgs == ['2 1000 {"k": [1, "s"]}', "dup 1", "undefined is not-able", "zero is truthy"]
+
+
+# ---- pkg/target: the reference's own Review-boundary scenarios and Matcher.Match vectors (tests/golden/make_target_vectors.py)
+def test_target_constraint_enforcement_scenarios():
+    """pkg/target/target_integration_test.go:164-520 -- 26 scenarios x 3 request shapes through the real client + Rego
+    driver in the reference: `allowed` <=> Review returns no results."""
+    from parity_cases import DENY_ALL, _target_shapes
+    n = 0
+    for v in golden("target_vectors.json")["constraint_enforcement"]:
+        c = k8s.Client()
+        c.add_template("DenyAll", DENY_ALL)
+        c.add_constraint(v["constraint"])
+        for shape, kw in _target_shapes(v):
+            rv = k8s.Review(obj=kw.get("object"), old=kw.get("old_object"), ns=kw.get("namespace"), namespace=kw.get("namespace_name"))
+            res = c.review(rv, k8s.AUDIT_EP)
+            assert (len(res) == 0) == v["allowed"], (v["name"], shape, res)
+            n += 1
+    assert n == 78
+
+
+def test_target_matcher_match_vectors():
+    """pkg/target/target_test.go:657-914 TestMatcher_Match."""
+    n = 0
+    for v in golden("target_vectors.json")["matcher_match"]:
+        req = v["request"]
+        if req is None or v["match"] is None:
+            continue
+        cache = {v["cachedNamespace"]["metadata"]["name"]: v["cachedNamespace"]} if v["cachedNamespace"] else {}
+        obj = req.get("object")
+        if v["wantErr"] == "ErrRequestObject" and obj is not None and "kind" not in obj:
+            continue    # "Raw object doesn't unmarshal": rejected while decoding the request, before Matcher.Match
+        nsn = req.get("namespaceName", "") if req["shape"] in ("AugmentedReview", "AdmissionRequest") else None
+        rv = k8s.Review(obj=obj, old=req.get("oldObject"), ns=req.get("namespace"), namespace=nsn)
+        try:
+            got, err = k8s.matcher_match(v["match"], rv, cache), None
+        except k8s.MatchError as e:
+            got, err = False, str(e)
+        if v["wantErr"] == "ErrMatching":
+            assert err and err.startswith("error matching the requested object"), v["name"]
+        elif v["wantErr"] == "ErrRequestObject":
+            assert err and err.startswith("invalid request object"), v["name"]
+        else:
+            assert err is None and got == v["want"], (v["name"], got, err)
+        n += 1
+    assert n >= 14
