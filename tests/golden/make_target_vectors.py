@@ -5,6 +5,7 @@ the small helper calls they use (data only -- no reference code is copied):
   pkg/target/target_integration_test.go:164-413  TestConstraintEnforcement -- 26 scenarios through the REAL client + Rego driver
        with a deny-all template: `allowed` == no results, for three request shapes (Object, OldObject only,
        AugmentedUnstructured), :433-520
+  pkg/controller/config/process/excluder_test.go:11-66  TestExactOrWildcardMatch -- the excluder's namespace patterns
   pkg/target/target_test.go:657-914              TestMatcher_Match -- Matcher.Match: object OR old object, review namespace
        vs cached namespace, error cases
 
@@ -217,6 +218,13 @@ def main():
             "source_test": "pkg/target/target_test.go:TestMatcher_Match", "name": val(f["name"]), "match": match_of(f["match"]),
             "cachedNamespace": namespace(f.get("cachedNs")), "request": request(f["req"]), "wantHandled": val(f["wantHandled"]),
             "wantErr": None if err is None or (err[0] == "ident" and err[1] == "nil") else err[1], "want": val(f["want"]) if "want" in f else False})
+    src = open(f"{REF}/pkg/controller/config/process/excluder_test.go").read()
+    rows, _ = table(src, "TestExactOrWildcardMatch", "tcs := []struct")
+    out["excluder"] = []
+    for _, row in rows:
+        f = {a[1]: b for a, b in row[2]}
+        out["excluder"].append({"source_test": "pkg/controller/config/process/excluder_test.go:TestExactOrWildcardMatch", "name": val(f["name"]),
+                                "patterns": sorted(val(f["nsMap"]).keys()), "namespace": val(f["ns"]), "excluded": val(f["excluded"])})
     with open(os.path.join(HERE, "target_vectors.json"), "w") as fo:
         json.dump(out, fo, indent=1, sort_keys=True)
     print(len(out["constraint_enforcement"]), "enforcement scenarios,", len(out["matcher_match"]), "Matcher.Match vectors")

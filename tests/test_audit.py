@@ -49,3 +49,23 @@ def test_latencies_and_throughput_vectors_of_the_reference():
     assert M.calculate_throughput(100, 0) == 0
     assert M.calculate_throughput(100, 1000 * MS) == 100
     assert M.calculate_throughput(50, 500 * MS) == 100
+
+
+def test_excluder_vectors_of_the_reference():
+    """pkg/controller/config/process/excluder_test.go:11-66 through the oracle and through the engine's excluder stage."""
+    from conftest import golden, make_pair
+    from gatekeeper_b200 import driver as D
+    from oracle import k8s
+    t = golden("templates.json")["fixtures_TemplateNeverValidate"]
+    for v in golden("target_vectors.json")["excluder"]:
+        pod = {"apiVersion": "v1", "kind": "Pod", "metadata": {"name": "p", "namespace": v["namespace"]}}
+        nsobj = {"apiVersion": "v1", "kind": "Namespace", "metadata": {"name": v["namespace"]}}
+        assert k8s.is_namespace_excluded(v["patterns"], pod) == v["excluded"], v["name"]
+        assert k8s.is_namespace_excluded(v["patterns"], nsobj) == v["excluded"], v["name"]      # a Namespace is tested by its own name
+        orc, drv, _ = make_pair([(t["kind"], t["rego"])], [{"kind": t["kind"], "metadata": {"name": "c"}}], lib_path=HOSTEMU)
+        drv.SetExcludedNamespaces("audit", v["patterns"])
+        for o in (pod, nsobj):
+            resp = drv.ReviewBatch([D.Review(object=o, source="Original")], k8s.AUDIT_EP, process="audit")
+            assert (len(resp.results) == 0) == v["excluded"], (v["name"], o["kind"])
+            resp = drv.ReviewBatch([D.Review(object=o, source="Original")], k8s.AUDIT_EP, process="webhook")   # other process: not excluded
+            assert len(resp.results) == 1
