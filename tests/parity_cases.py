@@ -571,3 +571,39 @@ def case_target_matcher(lib):
             assert_same(oracle_results(orc, [rev], k8s.AUDIT_EP), engine_results(resp))
         n += 1
     assert n >= 15
+
+
+# ------------------------------------------------------------------------------------------ gator TestTest table
+def case_gator_test_table(lib):
+    """pkg/gator/test/test_test.go:85-268: every input document is reviewed at the gator enforcement point; the exact
+    list of (message, constraint, action, scoped actions) is what the reference asserts.  Referential rows
+    (data.inventory) must be REJECTED by the engine at AddTemplate -- they are out of the independent-object model."""
+    import pytest
+    n = 0
+    for row in golden("gator_test_table.json"):
+        tm, cons, nss = _split_docs(row["docs"])
+        referential = any("Referential" in i for i in row["inputs"] if i.startswith("Template"))
+        if referential:
+            drv = D.Driver(lib_path=lib)
+            with pytest.raises(D.GkError):
+                for kind, rego in tm:
+                    drv.add_template(kind, rego)
+            continue
+        if row["wantErr"]:
+            drv = D.Driver(lib_path=lib)
+            with pytest.raises(D.GkError, match="no template|template"):
+                for c in cons:
+                    drv.AddConstraint(c)
+            continue
+        orc, drv, _ = make_pair(tm, cons, nss, lib_path=lib)
+        revs = [D.Review(object=d) for d in row["docs"]]
+        resp = drv.ReviewBatch(revs, k8s.GATOR_EP)
+        assert_same(oracle_results(orc, revs, k8s.GATOR_EP), engine_results(resp))
+        got = sorted((r.msg, r.constraint) + ((r.enforcement_action, tuple(r.scoped_enforcement_actions)) if any("enforcementAction" in w for w in row["want"]) else ())
+                     for r in resp.results)
+        want = sorted((w["msg"], "%s/%s" % (w["constraintKind"], w["constraint"])) +
+                      ((w["enforcementAction"], tuple(w.get("scopedEnforcementActions", []))) if "enforcementAction" in w else ())
+                      for w in row["want"])
+        assert got == want, (row["name"], got, want)
+        n += 1
+    assert n >= 6

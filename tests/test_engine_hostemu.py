@@ -121,3 +121,7 @@ def test_target_enforcement_vectors():
 
 def test_target_matcher_vectors():
     P.case_target_matcher(HOSTEMU)
+
+
+def test_gator_test_table():
+    P.case_gator_test_table(HOSTEMU)

@@ -116,6 +116,11 @@ def test_target_matcher_vectors():
     P.case_target_matcher(LIB)
 
 
+def test_gator_test_table():
+    """pkg/gator/test/test_test.go:85-268: exact (message, constraint, action, scoped actions) lists."""
+    P.case_gator_test_table(LIB)
+
+
 def test_config3_admission_microbatches():
     """200 PSP constraints (7 bitmap words) x 64-request micro-batches, UPDATE with object + oldObject."""
     tm, cons, pods = W.config3(200)
