@@ -69,3 +69,52 @@ def test_excluder_vectors_of_the_reference():
             assert (len(resp.results) == 0) == v["excluded"], (v["name"], o["kind"])
             resp = drv.ReviewBatch([D.Review(object=o, source="Original")], k8s.AUDIT_EP, process="webhook")   # other process: not excluded
             assert len(resp.results) == 1
+
+
+def test_audit_from_cache_scenarios_of_the_reference():
+    """pkg/audit/manager_test.go:103-171 Test_auditFromCache (transcribed; fakes from pkg/fakes/fixtures.go:14-90): one Pod in
+    test-namespace-1, the deny-all template; violations: excluded namespace 0, not excluded 1, constraint scoped to the
+    webhook point only 0, scoped to the audit point 1.  Through the oracle and through the engine's audit aggregation."""
+    from conftest import make_pair
+    from gatekeeper_b200 import driver as D
+    from oracle import audit as OA
+    from oracle import k8s
+    rego = 'package goodrego\n\nviolation[{"msg": msg}] {\n   msg := "denyall"\n}'
+    pod = {"apiVersion": "v1", "kind": "Pod", "metadata": {"name": "test-pod", "namespace": "test-namespace-1"}}
+    def scoped(ep):
+        return {"apiVersion": "constraints.gatekeeper.sh/v1beta1", "kind": "denyall", "metadata": {"name": "constraint"},
+                "spec": {"enforcementAction": "scoped", "scopedEnforcementActions": [
+                    {"enforcementPoints": [{"name": ep}], "action": "deny"}, {"enforcementPoints": [{"name": ep}], "action": "warn"}]}}
+    denyall = {"apiVersion": "constraints.gatekeeper.sh/v1beta1", "kind": "denyall", "metadata": {"name": "constraint"}}
+    for name, excluded, con, want in (("obj excluded from audit", ["test-namespace-1"], denyall, 0), ("obj not excluded from audit", [], denyall, 1),
+                                      ("audit excluded from constraint", [], scoped(k8s.WEBHOOK_EP), 0),
+                                      ("audit included in constraints", [], scoped(k8s.AUDIT_EP), 1)):
+        orc, drv, _ = make_pair([("denyall", rego)], [con], lib_path=HOSTEMU)
+        assert len(OA.audit(orc, [pod], excluded_namespaces=excluded)["results"]) == want, name
+        drv.SetExcludedNamespaces("audit", excluded)
+        run = D.AuditRun(drv)
+        run.add_batch(drv.upload([D.Review(object=pod, source="Original")], process="audit"), k8s.AUDIT_EP)
+        rep = run.report()
+        assert rep["results"] == want, (name, rep)
+        if want and con is not denyall:
+            v = rep["violations"]["denyall/constraint"][0]
+            assert v["enforcementAction"] == "scoped" and v["enforcementActions"] == ["deny", "warn"]
+
+
+def test_limit_queue_vectors_of_the_reference_through_the_engine():
+    """pkg/audit/manager_test.go:40-103 (Test_newSVQueue / Test_LimitQueue): three violations on objects of the three GVKs the
+    reference uses; limit 3 pops sv3, sv1, sv2 -- limit 2 keeps and pops sv1, sv2.  Here as the order of the status list."""
+    from conftest import make_pair
+    from gatekeeper_b200 import driver as D
+    from oracle import k8s
+    rego = 'package p\nviolation[{"msg": "m"}] { true }'
+    objs = [{"apiVersion": "rbac.authorization.k8s.io/v1", "kind": "ClusterRoleBinding", "metadata": {"name": "x"}},
+            {"apiVersion": "authorization.k8s.io/v1", "kind": "SubjectAccessReview", "metadata": {"name": "x"}},
+            {"apiVersion": "rbac.authorization.k8s.io/v1", "kind": "RoleBinding", "metadata": {"name": "x"}}]
+    orc, drv, _ = make_pair([("P", rego)], [{"kind": "P", "metadata": {"name": "c"}}], lib_path=HOSTEMU)
+    for limit, want in ((3, ["RoleBinding", "ClusterRoleBinding", "SubjectAccessReview"]), (2, ["ClusterRoleBinding", "SubjectAccessReview"])):
+        run = D.AuditRun(drv, violations_limit=limit)
+        run.add_batch(drv.upload([D.Review(object=o, source="Original") for o in objs]), k8s.AUDIT_EP)
+        rep = run.report()
+        assert [v["kind"] for v in rep["violations"]["P/c"]] == want
+        assert rep["totalViolations"] == {"P/c": 3}
