@@ -118,3 +118,31 @@ def test_limit_queue_vectors_of_the_reference_through_the_engine():
         rep = run.report()
         assert [v["kind"] for v in rep["violations"]["P/c"]] == want
         assert rep["totalViolations"] == {"P/c": 3}
+
+
+GVM_VECTORS = [   # pkg/webhook/policy_test.go:840-948 TestGetValidationMessages: (name, result actions, deny count, warn count)
+    ("Only One Dry Run", ["dryrun"], 0, 0), ("Only One Deny", ["deny"], 1, 0), ("Only One Warn", ["warn"], 0, 1),
+    ("One Dry Run and One Deny", ["dryrun", "deny"], 1, 0), ("One Dry Run, One Deny, One Warn", ["dryrun", "deny", "warn"], 1, 1),
+    ("Two Deny", ["deny", "deny"], 2, 0), ("Two Warn", ["warn", "warn"], 0, 2), ("Two Dry Run", ["dryrun", "dryrun"], 0, 0),
+    ("Random EnforcementAction", ["random"], 0, 0)]
+
+
+def test_get_validation_messages_vectors_of_the_reference():
+    """The nine action mixes the reference pins (message counts), through the oracle's restatement on bare results and
+    through the engine: one deny-all constraint per listed action, the reference's nameless Namespace request."""
+    from conftest import make_pair
+    from gatekeeper_b200 import driver as D
+    from oracle import k8s
+    rego = 'package foo\nviolation[{"msg": "test"}] { true }'
+    ns = {"apiVersion": "v1", "kind": "Namespace"}
+    for name, actions, n_deny, n_warn in GVM_VECTORS:
+        bare = [{"msg": "test", "constraint": ("Foo", "ph"), "enforcementAction": a if a != "random" else "unrecognized", "scopedEnforcementActions": []}
+                for a in actions]
+        d, w = k8s.validation_messages(bare)
+        assert (len(d), len(w)) == (n_deny, n_warn), name
+        assert all(m == "[ph] test" for m in d + w)
+        cons = [{"kind": "Foo", "metadata": {"name": "ph-%d" % i}, "spec": {"enforcementAction": a}} for i, a in enumerate(actions)]
+        orc, drv, _ = make_pair([("Foo", rego)], cons, lib_path=HOSTEMU)
+        (deny, warn), = drv.ValidationMessages([D.Review(object=ns, namespace_name="")])
+        assert (len(deny), len(warn)) == (n_deny, n_warn), (name, deny, warn)
+        assert all(m.startswith("[ph-") and m.endswith("] test") for m in deny + warn)
