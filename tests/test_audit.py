@@ -146,3 +146,35 @@ def test_get_validation_messages_vectors_of_the_reference():
         (deny, warn), = drv.ValidationMessages([D.Review(object=ns, namespace_name="")])
         assert (len(deny), len(warn)) == (n_deny, n_warn), (name, deny, warn)
         assert all(m.startswith("[ph-") and m.endswith("] test") for m in deny + warn)
+
+
+def test_webhook_excluded_namespaces_vectors_of_the_reference():
+    """pkg/webhook/policy_test.go:422-523 TestExcludedNamespaces (transcribed): Config excludes "kube-*" for every process; the
+    deny-everything template K8sGoodRego (:157-200); the request's Namespace decides (the object's own is empty,
+    pkg/webhook/common.go:181); DELETE is judged on OldObject and is an error without one."""
+    from conftest import make_pair
+    from gatekeeper_b200 import driver as D
+    from oracle import k8s
+    rego = 'package goodrego\n\nviolation[{"msg": msg}] {\n   msg := "Maybe this will work?"\n}'
+    raw = {"apiVersion": "v1", "kind": "Pod", "metadata": {"name": "acbd", "namespace": ""}}
+    orc, drv, _ = make_pair([("K8sGoodRego", rego)], [{"kind": "K8sGoodRego", "metadata": {"name": "constraint"}}], lib_path=HOSTEMU)
+    drv.SetExcludedNamespaces("*", ["kube-*"])
+    for name, ns, op, obj, old, allowed in (("ExcludedNamespace invalid create", "notkube-test", "CREATE", raw, None, False),
+                                            ("ExcludedNamespace valid create", "kube-test", "CREATE", raw, None, True),
+                                            ("ExcludedNamespace invalid delete", "kube-test", "DELETE", None, None, False),
+                                            ("ExcludedNamespace valid delete", "kube-test", "DELETE", None, raw, True)):
+        rev = D.Review(object=obj, old_object=old, operation=op, namespace_name=ns)
+        resp = drv.ReviewBatch([rev], k8s.WEBHOOK_EP, process="webhook")
+        err = (resp.object_errors or [None])[0]
+        denied = bool(err) or any(r.enforcement_action == "deny" for r in resp.results)
+        assert (not denied) == allowed, (name, err, [r.msg for r in resp.results])
+        if name.endswith("invalid delete"):
+            assert err and "oldObject" in err          # errOldObjectIsNil
+        # the oracle: the excluder stage, then Client.Review
+        target_obj = old if op == "DELETE" else obj
+        if target_obj is None:
+            continue
+        probe = dict(target_obj, metadata=dict(target_obj["metadata"], namespace=ns))
+        o_allowed = k8s.is_namespace_excluded(["kube-*"], probe) or not orc.review(
+            k8s.Review(obj=obj, old=old, operation=op, namespace=ns), k8s.WEBHOOK_EP)
+        assert o_allowed == allowed, name
