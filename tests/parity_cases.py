@@ -607,3 +607,22 @@ def case_gator_test_table(lib):
         assert got == want, (row["name"], got, want)
         n += 1
     assert n >= 6
+
+
+def case_verify_suite(lib):
+    """test/gator/verify/suite.yaml:1-37 through the engine (K8sFooIs: object.get(input, "parameters", {})): the
+    allow / deny expectation of every non-expansion case, and parity with the oracle."""
+    vs = golden("verify_suite.json")
+    files = vs["files"]
+    tmpl = k8s.template_from_yaml_obj(vs["template"])
+    expect = [("constraint.yaml", "allow_foo.yaml", False), ("constraint.yaml", "deny_foo.yaml", True),
+              ("constraint_with_scopedEA.yaml", "allow_foo.yaml", False), ("constraint_with_scopedEA.yaml", "deny_foo.yaml", True),
+              ("constraint_with_scopedEA_without_gator_ep.yaml", "allow_foo.yaml", False),
+              ("constraint_with_scopedEA_without_gator_ep.yaml", "deny_foo.yaml", False)]
+    for cfile, ofile, violations in expect:
+        orc, drv, skipped = make_pair([tmpl], [files[cfile][0]], lib_path=lib)
+        assert not skipped
+        revs = [D.Review(object=files[ofile][0])]
+        resp = drv.ReviewBatch(revs, k8s.GATOR_EP)
+        assert bool(resp.results) == violations, (cfile, ofile, [r.msg for r in resp.results])
+        assert_same(oracle_results(orc, revs, k8s.GATOR_EP), engine_results(resp))

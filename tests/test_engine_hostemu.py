@@ -125,3 +125,7 @@ def test_target_matcher_vectors():
 
 def test_gator_test_table():
     P.case_gator_test_table(HOSTEMU)
+
+
+def test_verify_suite():
+    P.case_verify_suite(HOSTEMU)

@@ -121,6 +121,11 @@ def test_gator_test_table():
     P.case_gator_test_table(LIB)
 
 
+def test_verify_suite():
+    """test/gator/verify/suite.yaml:1-37 (K8sFooIs) through the engine."""
+    P.case_verify_suite(LIB)
+
+
 def test_config3_admission_microbatches():
     """200 PSP constraints (7 bitmap words) x 64-request micro-batches, UPDATE with object + oldObject."""
     tm, cons, pods = W.config3(200)
