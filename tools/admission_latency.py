@@ -5,7 +5,8 @@ createAdmissionRequests (:210-249), reviewed in micro-batches of 64 through the 
 messages out).  Latency of a request = latency of its micro-batch; percentiles as `gator bench` defines them
 (pkg/gator/bench/metrics.go:9-59).
 
-  python tools/admission_latency.py [batches] [batch_size] [--cpu N]   # --cpu: time the oracle on N requests instead
+  python tools/admission_latency.py [batches] [batch_size]
+(the CPU restatement of the same replay is timed by tests/admission_cpu_baseline.py -- the oracle is test infrastructure)
 """
 import json
 import os
@@ -28,24 +29,6 @@ def main():
     batches = int(args[0]) if args else 200
     bs = int(args[1]) if len(args) > 1 else 64
     tm, cons, pods = W.config3(200)
-    if "--cpu" in sys.argv:
-        sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
-        from oracle import k8s
-        n = int(sys.argv[sys.argv.index("--cpu") + 1])
-        c = k8s.Client()
-        for k, r in tm:
-            c.add_template(k, r)
-        for x in cons:
-            c.add_constraint(x)
-        lat = []
-        for i in range(n):
-            t0 = time.perf_counter_ns()
-            c.review(k8s.Review(obj=pods[i % 5], old=pods[(i + 1) % 5], operation="UPDATE"), k8s.WEBHOOK_EP)
-            lat.append(time.perf_counter_ns() - t0)
-        out = {"impl": "oracle (CPU restatement, 1 core)", "requests": n, "constraints": len(cons), "latency_ns": M.calculate_latencies(lat),
-               "requests_per_s": M.calculate_throughput(n, sum(lat))}
-        print(json.dumps(out))
-        return
     drv = D.Driver()
     for k, r in tm:
         drv.add_template(k, r)
