@@ -3,6 +3,8 @@
 // lowering/flattening logic can be unit-tested in a container without a GPU; it is never part of the
 // product library and the product has no CPU fallback.
 #pragma once
+#include <atomic>
+#include <thread>
 #include <cstdint>
 #include <cstring>
 #include <string>
@@ -57,29 +59,35 @@ struct PackedBatch {
 
 inline size_t gk_align(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
+// Packing is two steps so that the bytes are copied exactly once, by all host threads, straight into the buffer the
+// device copy reads from (pinned memory for the CUDA backend):
+//   pack_layout : assigns every array its 256-byte aligned offset in the arena image and records one copy job per array
+//   pack_copy   : runs the copy jobs (memcpy, parallel over arrays and over slices of big arrays) into `dst`
+struct PackJob {
+  const void* src;
+  size_t bytes, off;
+};
+struct PackPlan {
+  std::vector<PackJob> jobs;
+  std::vector<GkColumn> cols;      // tables that live in the arena themselves (offsets, rebased later)
+  std::vector<GkScope> scopes;
+  size_t total = 0;
+};
+
 template <class T>
-inline size_t pack_put(std::vector<uint8_t>& arena, const std::vector<T>& v) {
-  size_t off = gk_align(arena.size());
-  arena.resize(off + std::max<size_t>(v.size() * sizeof(T), 16));
-  if (!v.empty()) memcpy(arena.data() + off, v.data(), v.size() * sizeof(T));
+inline size_t plan_put(PackPlan& pl, const std::vector<T>& v) {
+  size_t off = gk_align(pl.total);
+  pl.total = off + std::max<size_t>(v.size() * sizeof(T), 16);
+  if (!v.empty()) pl.jobs.push_back({v.data(), v.size() * sizeof(T), off});
   return off;
 }
 
-inline void pack_batch(const HostBatch& hb, const Compiled& c, PackedBatch& pb) {
-  auto& a = pb.arena;
-  a.clear();
-  size_t total = 4096;
-  total += (hb.flags.size() * 4 + 256) * 4 + hb.name_off.size() * 4 + hb.gen_off.size() * 4 + hb.lbl_off.size() * 4 + hb.lbl_kv.size() * 4 +
-           hb.name_bytes.size() + hb.gen_bytes.size() + hb.nsrow.size() * 4 + hb.nsl_off.size() * 4 + hb.nsl_kv.size() * 4 + 4096;
-  for (auto& s : hb.scope_off) total += s.size() * 4 + 512;
-  for (auto& col : hb.cols) total += col.vt.size() + col.sid.size() * 4 + col.num.size() * 8 + col.boff.size() * 4 + col.bytes.size() + col.head.size() * 4 + 2560;
-  total += hb.cols.size() * sizeof(GkColumn) + hb.scope_off.size() * sizeof(GkScope) + 1024;
-  a.reserve(total);
+inline void pack_layout(const HostBatch& hb, const Compiled& c, PackedBatch& pb, PackPlan& pl) {
   GkBatch& h = pb.hdr;
   memset(&h, 0, sizeof h);
   h.n = hb.n;
   h.has_old = hb.has_old ? 1 : 0;
-#define PUT(field, vec) h.field = reinterpret_cast<decltype(h.field)>(pack_put(a, vec))
+#define PUT(field, vec) h.field = reinterpret_cast<decltype(h.field)>(plan_put(pl, vec))
   PUT(flags, hb.flags);
   PUT(kind_sid, hb.kind_sid);
   PUT(group_sid, hb.group_sid);
@@ -94,32 +102,71 @@ inline void pack_batch(const HostBatch& hb, const Compiled& c, PackedBatch& pb) 
   PUT(nsl_off, hb.nsl_off);
   PUT(nsl_kv, hb.nsl_kv);
 #undef PUT
-  std::vector<GkColumn> cols(hb.cols.size());
+  pl.cols.resize(hb.cols.size());
   for (size_t i = 0; i < hb.cols.size(); ++i) {
-    GkColumn& g = cols[i];
+    GkColumn& g = pl.cols[i];
     memset(&g, 0, sizeof g);
     g.scope = c.schema.cols[i].scope;
     g.enc = c.schema.cols[i].enc;
-    g.vt = reinterpret_cast<const uint8_t*>(pack_put(a, hb.cols[i].vt));
-    g.sid = reinterpret_cast<const uint32_t*>(pack_put(a, hb.cols[i].sid));
-    g.num = reinterpret_cast<const int64_t*>(pack_put(a, hb.cols[i].num));
-    g.boff = reinterpret_cast<const uint32_t*>(pack_put(a, hb.cols[i].boff));
-    g.bytes = reinterpret_cast<const uint8_t*>(pack_put(a, hb.cols[i].bytes));
-    g.head = reinterpret_cast<const uint32_t*>(pack_put(a, hb.cols[i].head));
+    g.vt = reinterpret_cast<const uint8_t*>(plan_put(pl, hb.cols[i].vt));
+    g.sid = reinterpret_cast<const uint32_t*>(plan_put(pl, hb.cols[i].sid));
+    g.num = reinterpret_cast<const int64_t*>(plan_put(pl, hb.cols[i].num));
+    g.boff = reinterpret_cast<const uint32_t*>(plan_put(pl, hb.cols[i].boff));
+    g.bytes = reinterpret_cast<const uint8_t*>(plan_put(pl, hb.cols[i].bytes));
+    g.head = reinterpret_cast<const uint32_t*>(plan_put(pl, hb.cols[i].head));
   }
-  std::vector<GkScope> scopes(hb.scope_off.size());
-  for (size_t s = 0; s < scopes.size(); ++s) {
-    memset(&scopes[s], 0, sizeof(GkScope));
-    scopes[s].parent = c.schema.scopes[s].parent;
-    scopes[s].rows = hb.scope_rows[s];
-    scopes[s].off = reinterpret_cast<const uint32_t*>(pack_put(a, hb.scope_off[s]));
+  pl.scopes.resize(hb.scope_off.size());
+  for (size_t s = 0; s < pl.scopes.size(); ++s) {
+    memset(&pl.scopes[s], 0, sizeof(GkScope));
+    pl.scopes[s].parent = c.schema.scopes[s].parent;
+    pl.scopes[s].rows = hb.scope_rows[s];
+    pl.scopes[s].off = reinterpret_cast<const uint32_t*>(plan_put(pl, hb.scope_off[s]));
   }
-  pb.cols_off = pack_put(a, cols);
-  pb.scopes_off = pack_put(a, scopes);
+  pb.cols_off = plan_put(pl, pl.cols);
+  pb.scopes_off = plan_put(pl, pl.scopes);
   h.cols = reinterpret_cast<const GkColumn*>(pb.cols_off);
   h.scopes = reinterpret_cast<const GkScope*>(pb.scopes_off);
-  h.ncols = (uint32_t)cols.size();
-  h.nscopes = (uint32_t)scopes.size();
+  h.ncols = (uint32_t)pl.cols.size();
+  h.nscopes = (uint32_t)pl.scopes.size();
+  pl.total = gk_align(pl.total);
+}
+
+inline void pack_copy(const PackPlan& pl, uint8_t* dst, int threads) {
+  // slice big arrays so that the work spreads evenly
+  struct Piece {
+    const uint8_t* src;
+    uint8_t* dst;
+    size_t bytes;
+  };
+  std::vector<Piece> pieces;
+  const size_t kSlice = 4u << 20;
+  for (auto& j : pl.jobs)
+    for (size_t o = 0; o < j.bytes; o += kSlice)
+      pieces.push_back({static_cast<const uint8_t*>(j.src) + o, dst + j.off + o, std::min(kSlice, j.bytes - o)});
+  const size_t T = std::max<size_t>(1, std::min<size_t>((size_t)std::max(1, threads), pieces.size() / 4 + 1));
+  if (T == 1) {
+    for (auto& p : pieces) memcpy(p.dst, p.src, p.bytes);
+    return;
+  }
+  std::atomic<size_t> next{0};
+  std::vector<std::thread> th;
+  for (size_t t = 0; t < T; ++t)
+    th.emplace_back([&]() {
+      for (;;) {
+        size_t i = next.fetch_add(1);
+        if (i >= pieces.size()) break;
+        memcpy(pieces[i].dst, pieces[i].src, pieces[i].bytes);
+      }
+    });
+  for (auto& x : th) x.join();
+}
+
+// one-shot form (host image in pb.arena): used by the test backend
+inline void pack_batch(const HostBatch& hb, const Compiled& c, PackedBatch& pb) {
+  PackPlan pl;
+  pack_layout(hb, c, pb, pl);
+  pb.arena.assign(pl.total, 0);
+  pack_copy(pl, pb.arena.data(), 1);
 }
 
 // turn the arena-relative offsets into pointers valid at `base` (device or host); patches the in-arena tables

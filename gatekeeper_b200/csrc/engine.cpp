@@ -2,6 +2,8 @@
 
 #include <sched.h>
 
+#include <functional>
+
 #include <chrono>
 
 #include <algorithm>
@@ -748,10 +750,18 @@ static bool wildcard_match(const std::string& pat, const std::string& s) {
   if (suf) return s.compare(0, core.size(), core) == 0;
   return s == pat;
 }
-struct Flattener {
+// What one chunk of objects flattens to; chunks are merged in object order afterwards.
+struct ChunkOut {
+  HostBatch hb;
+  // old-object header rows are kept in a second set of vectors and appended after the merge
+  std::vector<uint32_t> o_flags, o_kind, o_group, o_nsname, o_name_off{0}, o_gen_off{0}, o_lbl_off{0}, o_lbl_kv;
+  std::vector<uint8_t> o_name_bytes, o_gen_bytes;
+  bool any_old = false;
+};
+
+struct Flattener : ChunkOut {
   Engine& eng;
   const Compiled& c;
-  HostBatch hb;                                        // this worker's chunk
   std::unordered_map<std::string, uint32_t> sid_cache;
   std::unordered_map<const Module*, std::unique_ptr<Eval>> evals;
   std::vector<VP> ns_objs;                             // namespace table rows of this chunk
@@ -798,6 +808,14 @@ struct Flattener {
 
   Flattener(Engine& e, const Compiled& cc, const std::map<std::string, VP>& ns_shared) : eng(e), c(cc) {
     for (auto& kv : ns_shared) ns_private.emplace(kv.first, deep_copy(kv.second));
+    rows.resize(c.schema.scopes.size());
+    begin_chunk();
+  }
+  // the worker keeps its caches (evaluators, string ids, private namespace copies) across chunks; only the output resets
+  void begin_chunk() {
+    static_cast<ChunkOut&>(*this) = ChunkOut();
+    ns_objs.clear();
+    ns_row_of.clear();
     size_t ns = c.schema.scopes.size();
     hb.scope_off.resize(ns);
     for (size_t s = 1; s < ns; ++s) hb.scope_off[s].push_back(0);
@@ -809,8 +827,8 @@ struct Flattener {
     hb.gen_off.push_back(0);
     hb.lbl_off.push_back(0);
     hb.nsl_off.push_back(0);
-    rows.resize(ns);
   }
+  std::unique_ptr<ChunkOut> take() { return std::unique_ptr<ChunkOut>(new ChunkOut(std::move(static_cast<ChunkOut&>(*this)))); }
 
   // Object data is only ever compared with constants the compiler interned, so values are LOOKED UP, never added:
   // an unknown string gets GK_SID_OTHER (equal to no constant).  The dictionary stays small and read-mostly.
@@ -928,11 +946,6 @@ struct Flattener {
     hb.gen_off.push_back((uint32_t)hb.gen_bytes.size());
     hb.lbl_off.push_back((uint32_t)hb.lbl_kv.size() / 2);
   }
-
-  // old-object header rows are kept in a second set of vectors and appended after the merge
-  std::vector<uint32_t> o_flags, o_kind, o_group, o_nsname, o_name_off{0}, o_gen_off{0}, o_lbl_off{0}, o_lbl_kv;
-  std::vector<uint8_t> o_name_bytes, o_gen_bytes;
-  bool any_old = false;
 
   void encode(size_t ci, const VP& v) {
     const uint32_t enc = c.schema.cols[ci].enc;
@@ -1087,9 +1100,10 @@ struct Flattener {
   std::string num_range_error;
   bool trace = getenv("GK_FLATTEN_TRACE") != nullptr;
   std::vector<uint64_t> col_cycles = std::vector<uint64_t>(4096, 0), scope_cycles = std::vector<uint64_t>(256, 0);
-  uint64_t doc_cycles = 0, hdr_cycles = 0;
+  uint64_t doc_cycles = 0, hdr_cycles = 0, traced_objects = 0;
   ~Flattener() {
-    if (!trace || hb.n == 0) return;
+    if (!trace || traced_objects == 0) return;
+    const uint64_t nobj = traced_objects;
     static std::mutex m;
     std::lock_guard<std::mutex> l(m);
     std::vector<std::pair<uint64_t, std::string>> v;
@@ -1100,8 +1114,8 @@ struct Flattener {
     std::sort(v.rbegin(), v.rend());
     uint64_t tot = 0;
     for (auto& x : v) tot += x.first;
-    fprintf(stderr, "[flatten worker] %u objects, %.0f cycles/object accounted\n", hb.n, (double)tot / hb.n);
-    for (size_t i = 0; i < v.size() && i < 25; ++i) fprintf(stderr, "  %7.0f cyc/obj  %.100s\n", (double)v[i].first / hb.n, v[i].second.c_str());
+    fprintf(stderr, "[flatten worker] %llu objects, %.0f cycles/object accounted\n", (unsigned long long)nobj, (double)tot / nobj);
+    for (size_t i = 0; i < v.size() && i < 25; ++i) fprintf(stderr, "  %7.0f cyc/obj  %.100s\n", (double)v[i].first / nobj, v[i].second.c_str());
   }
 };
 
@@ -1137,14 +1151,26 @@ std::shared_ptr<HostBatch> Engine::flatten(const ObjIn* objs, size_t n, const Co
     auto it = excluded_.find(process);
     if (!process.empty() && it != excluded_.end()) excluded = it->second;
   }
-  std::vector<std::unique_ptr<Flattener>> parts(T);
+  // objects are handed out in chunks from a shared counter (threads on a throttled / shared host finish unevenly);
+  // every chunk becomes one part, merged in object order below
+  const size_t kChunk = T == 1 ? std::max<size_t>(n, 1) : 4096;
+  const size_t nchunks = (n + kChunk - 1) / kChunk;
+  std::vector<std::unique_ptr<ChunkOut>> parts(std::max<size_t>(nchunks, 1));
   std::vector<std::string> errs(T);
+  std::atomic<size_t> next_chunk{0};
   auto work = [&](size_t t) {
     try {
-      parts[t].reset(new Flattener(*this, c, ns_copy));
-      parts[t]->excluded = &excluded;
-      size_t lo = n * t / T, hi = n * (t + 1) / T;
-      for (size_t i = lo; i < hi; ++i) parts[t]->add(objs[i]);
+      Flattener fl(*this, c, ns_copy);
+      fl.excluded = &excluded;
+      for (;;) {
+        const size_t k = next_chunk.fetch_add(1);
+        if (k >= parts.size()) break;
+        if (k) fl.begin_chunk();
+        const size_t lo = k * kChunk, hi = std::min(n, lo + kChunk);
+        for (size_t i = lo; i < hi; ++i) fl.add(objs[i]);
+        fl.traced_objects += fl.hb.n;
+        parts[k] = fl.take();
+      }
     } catch (RegoError& e) {
       errs[t] = e.msg;
     } catch (std::exception& e) {
@@ -1188,50 +1214,103 @@ std::shared_ptr<HostBatch> Engine::flatten(const ObjIn* objs, size_t n, const Co
   bool any_old = false;
   for (auto& p : parts) any_old = any_old || p->any_old;
   hb.has_old = any_old;
-  for (auto& p : parts) {
-    HostBatch& q = p->hb;
-    uint32_t nsbase = (uint32_t)hb.nsl_off.size() - 1;
-    hb.n += q.n;
-    append(hb.flags, q.flags);
-    append(hb.kind_sid, q.kind_sid);
-    append(hb.group_sid, q.group_sid);
-    append(hb.nsname_sid, q.nsname_sid);
-    append_off(hb.name_off, q.name_off, 1);
-    append_off(hb.gen_off, q.gen_off, 1);
-    append_off(hb.lbl_off, q.lbl_off, 1);
-    append(hb.name_bytes, q.name_bytes);
-    append(hb.gen_bytes, q.gen_bytes);
-    append(hb.lbl_kv, q.lbl_kv);
-    for (uint32_t r : q.nsrow) hb.nsrow.push_back(r == GK_NONE ? GK_NONE : r + nsbase);
-    append_off(hb.nsl_off, q.nsl_off, 1);
-    append(hb.nsl_kv, q.nsl_kv);
-    append(hb.obj_errors, q.obj_errors);
-    for (size_t s = 1; s < nscopes; ++s) {
-      append_off(hb.scope_off[s], q.scope_off[s], 1);
-      hb.scope_rows[s] += q.scope_rows[s];
-    }
-    for (size_t i = 0; i < ncols; ++i) {
-      append(hb.cols[i].vt, q.cols[i].vt);
-      append(hb.cols[i].sid, q.cols[i].sid);
-      append(hb.cols[i].num, q.cols[i].num);
-      if (c.schema.cols[i].enc & GK_ENC_BYTES) append_off(hb.cols[i].boff, q.cols[i].boff, 1);
-      append(hb.cols[i].bytes, q.cols[i].bytes);
-      append(hb.cols[i].head, q.cols[i].head);
-    }
+  // every destination array is one task (its parts are appended in order, into exactly-reserved storage); the tasks
+  // run on all host threads -- the merge moves as many bytes as the H2D copy and must not be a serial tail
+  std::vector<uint32_t> nsbase(parts.size(), 0);
+  for (size_t pi = 0; pi < parts.size(); ++pi) {
+    hb.n += parts[pi]->hb.n;
+    if (pi + 1 < parts.size()) nsbase[pi + 1] = nsbase[pi] + (uint32_t)parts[pi]->hb.nsl_off.size() - 1;
+    for (size_t s2 = 1; s2 < nscopes; ++s2) hb.scope_rows[s2] += parts[pi]->hb.scope_rows[s2];
   }
-  if (any_old) {
-    // rows [n, 2n): old objects
-    for (auto& p : parts) {
-      append(hb.flags, p->o_flags);
-      append(hb.kind_sid, p->o_kind);
-      append(hb.group_sid, p->o_group);
-      append(hb.nsname_sid, p->o_nsname);
-      append_off(hb.name_off, p->o_name_off, 1);
-      append_off(hb.gen_off, p->o_gen_off, 1);
-      append_off(hb.lbl_off, p->o_lbl_off, 1);
-      append(hb.name_bytes, p->o_name_bytes);
-      append(hb.gen_bytes, p->o_gen_bytes);
-      append(hb.lbl_kv, p->o_lbl_kv);
+  std::vector<std::function<void()>> tasks;
+  // plain concatenation of one member over all parts (then, with OldObject rows present, of its old-object twin)
+#define GK_CAT(dst, member, oldmember)                                                   \
+  tasks.push_back([&]() {                                                                \
+    size_t tot = dst.size();                                                             \
+    for (auto& p : parts) tot += p->hb.member.size() + (any_old ? p->oldmember.size() : 0); \
+    dst.reserve(tot);                                                                    \
+    for (auto& p : parts) append(dst, p->hb.member);                                     \
+    if (any_old)                                                                         \
+      for (auto& p : parts) append(dst, p->oldmember);                                   \
+  })
+#define GK_CAT_OFF(dst, member, oldmember)                                               \
+  tasks.push_back([&]() {                                                                \
+    size_t tot = dst.size();                                                             \
+    for (auto& p : parts) tot += p->hb.member.size() + (any_old ? p->oldmember.size() : 0); \
+    dst.reserve(tot);                                                                    \
+    for (auto& p : parts) append_off(dst, p->hb.member, 1);                              \
+    if (any_old)                                                                         \
+      for (auto& p : parts) append_off(dst, p->oldmember, 1);                            \
+  })
+  GK_CAT(hb.flags, flags, o_flags);
+  GK_CAT(hb.kind_sid, kind_sid, o_kind);
+  GK_CAT(hb.group_sid, group_sid, o_group);
+  GK_CAT(hb.nsname_sid, nsname_sid, o_nsname);
+  GK_CAT_OFF(hb.name_off, name_off, o_name_off);
+  GK_CAT_OFF(hb.gen_off, gen_off, o_gen_off);
+  GK_CAT_OFF(hb.lbl_off, lbl_off, o_lbl_off);
+  GK_CAT(hb.name_bytes, name_bytes, o_name_bytes);
+  GK_CAT(hb.gen_bytes, gen_bytes, o_gen_bytes);
+  GK_CAT(hb.lbl_kv, lbl_kv, o_lbl_kv);
+#undef GK_CAT
+#undef GK_CAT_OFF
+  tasks.push_back([&]() {
+    hb.nsrow.reserve(hb.n);
+    for (size_t pi = 0; pi < parts.size(); ++pi)
+      for (uint32_t r : parts[pi]->hb.nsrow) hb.nsrow.push_back(r == GK_NONE ? GK_NONE : r + nsbase[pi]);
+  });
+  tasks.push_back([&]() {
+    for (auto& p : parts) append_off(hb.nsl_off, p->hb.nsl_off, 1);
+  });
+  tasks.push_back([&]() {
+    for (auto& p : parts) append(hb.nsl_kv, p->hb.nsl_kv);
+  });
+  tasks.push_back([&]() {
+    hb.obj_errors.reserve(hb.n);
+    for (auto& p : parts) append(hb.obj_errors, p->hb.obj_errors);
+  });
+  for (size_t s2 = 1; s2 < nscopes; ++s2)
+    tasks.push_back([&, s2]() {
+      size_t tot = 1;
+      for (auto& p : parts) tot += p->hb.scope_off[s2].size();
+      hb.scope_off[s2].reserve(tot);
+      for (auto& p : parts) append_off(hb.scope_off[s2], p->hb.scope_off[s2], 1);
+    });
+  for (size_t i = 0; i < ncols; ++i) {
+#define GK_COL(member)                                                  \
+  tasks.push_back([&, i]() {                                            \
+    size_t tot = 0;                                                     \
+    for (auto& p : parts) tot += p->hb.cols[i].member.size();           \
+    hb.cols[i].member.reserve(tot);                                     \
+    for (auto& p : parts) append(hb.cols[i].member, p->hb.cols[i].member); \
+  })
+    GK_COL(vt);
+    GK_COL(sid);
+    GK_COL(num);
+    GK_COL(bytes);
+    GK_COL(head);
+#undef GK_COL
+    if (c.schema.cols[i].enc & GK_ENC_BYTES)
+      tasks.push_back([&, i]() {
+        for (auto& p : parts) append_off(hb.cols[i].boff, p->hb.cols[i].boff, 1);
+      });
+  }
+  {
+    const size_t MT = std::min<size_t>(std::max<size_t>(1, T), tasks.size());
+    if (MT <= 1) {
+      for (auto& t : tasks) t();
+    } else {
+      std::atomic<size_t> next{0};
+      std::vector<std::thread> th;
+      for (size_t t = 0; t < MT; ++t)
+        th.emplace_back([&]() {
+          for (;;) {
+            size_t k = next.fetch_add(1);
+            if (k >= tasks.size()) break;
+            tasks[k]();
+          }
+        });
+      for (auto& x : th) x.join();
     }
   }
   // ---- algorithmic bytes: every array the kernel may read, counted once

@@ -142,7 +142,8 @@ class CudaBackend : public Backend {
   void* upload(const HostBatch& hb, const Compiled& c, double* h2d_ms, uint64_t* h2d_bytes) override {
     CK(cudaSetDevice(device_));
     PackedBatch pb;
-    pack_batch(hb, c, pb);
+    PackPlan plan;
+    pack_layout(hb, c, pb, plan);   // offsets only: the bytes are copied once, below, straight into pinned memory
     // ---- tiling: first row of every scope for every tile, slot offsets from the per-scope tile capacities
     const uint32_t NS = (uint32_t)c.schema.scopes.size();
     // Tile size: kTile objects.  (Shrinking tiles so that the tile count fills whole waves of resident CTAs -- 480 instead
@@ -166,7 +167,7 @@ class CudaBackend : public Backend {
       slot_words += ((cap[c.slot_level[i]] + 31) / 32 + 1 + 3) & ~3u;   // 16-byte aligned, padded: atoms store 4 words at a time
     }
     auto* db = new DevBatch();
-    db->bytes = gk_align(pb.arena.size());
+    db->bytes = gk_align(plan.total);
     db->n = hb.n;
     db->ntiles = ntiles;
     db->tile = tile;
@@ -223,21 +224,23 @@ class CudaBackend : public Backend {
     if (!ops_r.empty()) CK(cudaMemcpy(db->d_ops, ops_r.data(), ops_r.size() * sizeof(GkOp), cudaMemcpyHostToDevice));
     if (!pool_r.empty()) CK(cudaMemcpy(db->d_pool, pool_r.data(), pool_r.size() * 4, cudaMemcpyHostToDevice));
     if (!outs_r.empty()) CK(cudaMemcpy(db->d_outs, outs_r.data(), outs_r.size() * sizeof(GkOutEnt), cudaMemcpyHostToDevice));
-    db->hdr = rebase_batch(pb, pb.arena.data(), db->arena);
     cudaEvent_t a, b;
     CK(cudaEventCreate(&a));
     CK(cudaEventCreate(&b));
     {
       std::lock_guard<std::mutex> l(mu_);
-      // stage through pinned memory so the copy runs at full PCIe rate
-      if (pinned_bytes_ < pb.arena.size()) {
+      // the arena image is assembled by all host threads directly in pinned memory (one copy of every byte), its
+      // in-arena pointer tables are rebased to the device address, and one DMA moves it
+      if (pinned_bytes_ < plan.total) {
         if (pinned_) cudaFreeHost(pinned_);
-        pinned_bytes_ = pb.arena.size() + (pb.arena.size() >> 2);
+        pinned_bytes_ = plan.total + (plan.total >> 2);
         CK(cudaMallocHost(&pinned_, pinned_bytes_));
       }
-      memcpy(pinned_, pb.arena.data(), pb.arena.size());
+      uint8_t* image = static_cast<uint8_t*>(pinned_);
+      pack_copy(plan, image, host_threads_);
+      db->hdr = rebase_batch(pb, image, db->arena);
       CK(cudaEventRecord(a, stream_));
-      CK(cudaMemcpyAsync(db->arena, pinned_, pb.arena.size(), cudaMemcpyHostToDevice, stream_));
+      CK(cudaMemcpyAsync(db->arena, image, plan.total, cudaMemcpyHostToDevice, stream_));
       CK(cudaMemcpyAsync(db->d_tile_lo, tile_lo.data(), tile_lo.size() * 4, cudaMemcpyHostToDevice, stream_));
       CK(cudaEventRecord(b, stream_));
       CK(cudaStreamSynchronize(stream_));
@@ -247,7 +250,7 @@ class CudaBackend : public Backend {
     cudaEventDestroy(a);
     cudaEventDestroy(b);
     if (h2d_ms) *h2d_ms = ms;
-    if (h2d_bytes) *h2d_bytes = pb.arena.size() + tile_lo.size() * 4 + ops_r.size() * sizeof(GkOp) + pool_r.size() * 4 + outs_r.size() * sizeof(GkOutEnt);
+    if (h2d_bytes) *h2d_bytes = plan.total + tile_lo.size() * 4 + ops_r.size() * sizeof(GkOp) + pool_r.size() * 4 + outs_r.size() * sizeof(GkOutEnt);
     db->words = std::max<uint32_t>(1, (uint32_t)((c.cons_match.size() + 31) / 32));
     CK(cudaMalloc(&db->viol, (size_t)std::max(db->n, 1u) * db->words * 4));
     CK(cudaMalloc(&db->err, (size_t)std::max(db->n, 1u) * db->words * 4));
@@ -447,6 +450,7 @@ class CudaBackend : public Backend {
   uint32_t* d_errlist_ = nullptr;
   uint32_t* d_active_ = nullptr;
   unsigned long long* d_timing_ = nullptr;
+  int host_threads_ = effective_cpus();
   void* pinned_ = nullptr;
   size_t pinned_bytes_ = 0;
 };
