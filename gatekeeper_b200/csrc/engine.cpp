@@ -2,6 +2,7 @@
 
 #include <sched.h>
 
+#include <deque>
 #include <functional>
 
 #include <chrono>
@@ -856,6 +857,63 @@ struct Flattener : ChunkOut {
     return *slot;
   }
 
+  // Direct evaluation of a deterministic term.  `ok` is cleared when the term needs the general evaluator; a null result
+  // with ok set means "undefined".
+  VP eval_direct(const Term& t, const Env& env, const VP& input, Eval& ev, const Module& mod, bool& ok) {
+    switch (t.k) {
+      case TK::Scalar: return t.val;
+      case TK::Var: {
+        if (const VP* b = env.find(t.vid)) return *b;
+        if (t.vid == mod.vid_input) return input;
+        ok = false;
+        return nullptr;
+      }
+      case TK::Ref: {
+        VP cur = eval_direct(*t.head, env, input, ev, mod, ok);
+        if (!ok || !cur) return nullptr;
+        for (auto& a : t.args) {
+          VP key = a->k == TK::Scalar ? a->val : eval_direct(*a, env, input, ev, mod, ok);
+          if (!ok) return nullptr;
+          if (!key) return nullptr;
+          if (cur->t == VT::Obj) cur = obj_get(cur, key);
+          else if (cur->t == VT::Arr) {
+            int64_t ix;
+            if (key->t == VT::Num && num_fits_i64(key->n, &ix) && ix >= 0 && (size_t)ix < cur->items.size()) cur = cur->items[ix];
+            else cur = nullptr;
+          } else if (cur->t == VT::Set) cur = set_find(cur, key);
+          else cur = nullptr;
+          if (!cur) return nullptr;
+        }
+        return cur;
+      }
+      case TK::Call: {
+        const bool user = mod.is_rule(t.name);
+        if (user && mod.rules.at(t.name)[0].kind != Rule::Func) {
+          ok = false;
+          return nullptr;
+        }
+        if (user && t.args.size() != mod.rules.at(t.name)[0].args.size()) {   // call with an output argument
+          ok = false;
+          return nullptr;
+        }
+        std::vector<VP> args;
+        args.reserve(t.args.size());
+        for (auto& a : t.args) {
+          VP v = a->k == TK::Scalar ? a->val : eval_direct(*a, env, input, ev, mod, ok);
+          if (!ok) return nullptr;
+          if (!v) return nullptr;   // an undefined argument makes the call undefined
+          args.push_back(std::move(v));
+        }
+        if (user) return ev.call_function(t.name, args);
+        bool known = true;
+        VP v = call_builtin(t.name, args, &known);
+        if (!known) ok = false;
+        return v;
+      }
+      default: ok = false; return nullptr;
+    }
+  }
+
   // value of closure `cl` for the row `r` of scope cl.scope (chain resolved through parents)
   VP eval_closure(const Closure& cl, int scope, uint32_t r, const VP& input) {
     // move up to the closure's own scope
@@ -865,7 +923,28 @@ struct Flattener : ChunkOut {
     }
     if (cl.leaf == Closure::Elem) return rows[scope][r].elem;
     if (cl.leaf == Closure::Key) return rows[scope][r].key;
-    Env env;
+    // values of function calls and computed references are remembered for this object: the same closure feeds several
+    // columns (a scope generator that is also a column; split(image, ":") under its count and under its last element)
+    const Term& t = *cl.term;
+    const bool memoise = t.k != TK::Ref || t.head->k != TK::Var || [&]() {
+      for (auto& a : t.args)
+        if (a->k != TK::Scalar) return true;
+      return false;
+    }();
+    const uint64_t mkey = (uint64_t)(uintptr_t)&cl * 0x9E3779B97F4A7C15ull + r;
+    if (memoise) {
+      auto mit = memo.find(mkey);
+      if (mit != memo.end()) return mit->second;
+    }
+    // environments are recycled per recursion depth (their storage is the only allocation a closure evaluation needs)
+    if (env_depth >= env_pool.size()) env_pool.emplace_back();
+    Env& env = env_pool[env_depth];
+    env.b.clear();
+    struct Depth {
+      size_t& d;
+      explicit Depth(size_t& x) : d(x) { ++d; }
+      ~Depth() { --d; }
+    } depth_guard(env_depth);
     for (auto& cap : cl.caps) {
       if (cap.second.k == CapArg::Conc) env.bind(cap.first, private_const(cap.second.v));
       else {
@@ -875,39 +954,23 @@ struct Flattener : ChunkOut {
       }
     }
     Eval& ev = eval_for(cl, input);
-    // fast path: constant path off a bound variable
-    const Term& t = *cl.term;
-    if (t.k == TK::Ref && t.head->k == TK::Var) {
-      bool simple = true;
-      for (auto& a : t.args) simple = simple && a->k == TK::Scalar;
-      if (simple) {
-        VP cur;
-        if (const VP* b = env.find(t.head->vid)) cur = *b;
-        else if (t.head->vid == cl.mod->vid_input) cur = input;
-        if (cur) {
-          for (auto& a : t.args) {
-            if (cur->t == VT::Obj) cur = obj_get(cur, a->val);
-            else if (cur->t == VT::Arr) {
-              int64_t ix;
-              if (a->val->t == VT::Num && num_fits_i64(a->val->n, &ix) && ix >= 0 && (size_t)ix < cur->items.size()) cur = cur->items[ix];
-              else cur = nullptr;
-            } else if (cur->t == VT::Set) cur = set_find(cur, a->val);
-            else cur = nullptr;
-            if (!cur) break;
-          }
-          return cur;
-        }
+    // fast path: single-valued terms built from bound variables, constant paths and function calls are evaluated by a
+    // direct recursion (no continuations, no environment growth); anything else -- iteration, comprehensions, rule
+    // references -- goes through the general evaluator below
+    {
+      bool ok = true;
+      VP v = eval_direct(t, env, input, ev, *cl.mod, ok);
+      if (ok) {
+        if (memoise) memo.emplace(mkey, v);
+        return v;
       }
     }
-    // slow path through the evaluator: remember the value for this object -- the same closure feeds several columns
-    // (a scope generator that is also a column, split(image, ":") under both its count and its last element, ...)
-    const uint64_t mkey = (uint64_t)(uintptr_t)&cl * 0x9E3779B97F4A7C15ull + r;
-    auto mit = memo.find(mkey);
-    if (mit != memo.end()) return mit->second;
     VP out = ev.eval_first(cl.term, env);
-    memo.emplace(mkey, out);
+    if (memoise) memo.emplace(mkey, out);
     return out;
   }
+  std::deque<Env> env_pool;   // (deque: a nested evaluation may grow it while outer references are live)
+  size_t env_depth = 0;
   std::unordered_map<uint64_t, VP> memo;   // per object: (closure, row) -> value
 
   void header_row(const VP& o, const VP& ns, uint8_t source, bool present) {
