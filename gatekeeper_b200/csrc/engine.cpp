@@ -34,7 +34,13 @@ uint32_t StringTable::intern(const std::string& key) {
   bytes_.insert(bytes_.end(), key.begin(), key.end());
   off_.push_back((uint32_t)bytes_.size());
   map_.emplace(key, id);
+  n_.store((uint32_t)map_.size(), std::memory_order_relaxed);
   return id;
+}
+std::shared_ptr<const StringTable::Frozen> StringTable::freeze() {
+  std::unique_lock<std::shared_mutex> l(mu_);
+  if (!frozen_ || frozen_->size() != map_.size()) frozen_ = std::make_shared<const Frozen>(map_);
+  return frozen_;
 }
 uint32_t StringTable::lookup(const std::string& key) const {
   std::shared_lock<std::shared_mutex> l(mu_);
@@ -774,6 +780,7 @@ struct Flattener : ChunkOut {
   };
   std::vector<std::vector<Row>> rows;                  // per scope, for the current object
 
+  std::shared_ptr<const StringTable::Frozen> frozen;    // string ids as of the start of this flatten (lock-free lookups)
   std::map<std::string, VP> ns_private;                 // deep copy of the namespace cache
   const std::vector<std::string>* excluded = nullptr;   // excluder patterns of the calling process (may be empty)
   std::unordered_map<const Node*, VP> const_private;    // deep copies of constants captured by closures
@@ -788,13 +795,13 @@ struct Flattener : ChunkOut {
       case VT::Str: return v_str(v->s);
       case VT::Arr:
       case VT::Set: {
-        auto n = std::make_shared<Node>();
+        auto n = new_node();
         n->t = v->t;
         for (auto& x : v->items) n->items.push_back(deep_copy(x));
         return n;
       }
       default: {
-        auto n = std::make_shared<Node>();
+        auto n = new_node();
         n->t = VT::Obj;
         for (auto& e : v->kv) n->kv.emplace_back(deep_copy(e.first), deep_copy(e.second));
         return n;
@@ -836,7 +843,12 @@ struct Flattener : ChunkOut {
   uint32_t sid(const std::string& key) {
     auto it = sid_cache.find(key);
     if (it != sid_cache.end()) return it->second;
-    uint32_t id = eng.strings().lookup(key);
+    // the frozen copy answers without touching the table's lock (a reader lock is still an atomic update of one shared
+    // cache line, 16 threads deep); only strings interned after the freeze need the locked path
+    uint32_t id = GK_SID_UNDEF;
+    auto fit = frozen->find(key);
+    if (fit != frozen->end()) id = fit->second;
+    else if (eng.strings().size_relaxed() != (uint32_t)frozen->size()) id = eng.strings().lookup(key);
     if (id == GK_SID_UNDEF) id = GK_SID_OTHER;
     if (sid_cache.size() > (1u << 18)) sid_cache.clear();
     sid_cache.emplace(key, id);
@@ -1214,6 +1226,10 @@ std::shared_ptr<HostBatch> Engine::flatten(const ObjIn* objs, size_t n, const Co
     auto it = excluded_.find(process);
     if (!process.empty() && it != excluded_.end()) excluded = it->second;
   }
+  // namespace names are matched by wildcard on the device and so must be in the table: intern the known ones before the
+  // freeze, so that the workers' lookups stay on the lock-free path
+  for (auto& kv : ns_copy) strings_.intern("s" + kv.first);
+  auto frozen = strings_.freeze();
   // objects are handed out in chunks from a shared counter (threads on a throttled / shared host finish unevenly);
   // every chunk becomes one part, merged in object order below
   const size_t kChunk = T == 1 ? std::max<size_t>(n, 1) : 4096;
@@ -1225,6 +1241,7 @@ std::shared_ptr<HostBatch> Engine::flatten(const ObjIn* objs, size_t n, const Co
     try {
       Flattener fl(*this, c, ns_copy);
       fl.excluded = &excluded;
+      fl.frozen = frozen;
       for (;;) {
         const size_t k = next_chunk.fetch_add(1);
         if (k >= parts.size()) break;

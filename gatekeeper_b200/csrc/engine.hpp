@@ -104,6 +104,11 @@ class StringTable : public Interner {
   StringTable();
   uint32_t intern(const std::string& key) override;
   uint32_t lookup(const std::string& key) const;   // GK_SID_UNDEF if absent
+  // Lock-free lookups for the flatten workers: an immutable copy of the table as of the last freeze() plus the table's
+  // size then.  A miss in the frozen copy is final unless the table has grown since (size_relaxed() != frozen size).
+  using Frozen = std::unordered_map<std::string, uint32_t>;
+  std::shared_ptr<const Frozen> freeze();
+  uint32_t size_relaxed() const { return n_.load(std::memory_order_relaxed); }
   // snapshot for upload: offsets [n+1] and bytes
   void snapshot(std::vector<uint32_t>& off, std::vector<uint8_t>& bytes) const;
   uint32_t size() const;
@@ -114,6 +119,8 @@ class StringTable : public Interner {
   std::unordered_map<std::string, uint32_t> map_;
   std::vector<uint32_t> off_;
   std::vector<uint8_t> bytes_;
+  std::shared_ptr<const Frozen> frozen_;
+  std::atomic<uint32_t> n_{0};
 };
 
 struct Violation {

@@ -1,5 +1,7 @@
 #include "val.hpp"
 
+#include <mutex>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -63,31 +65,94 @@ bool num_fits_i64(const Num& n, int64_t* out) {
   return true;
 }
 
+// ------------------------------------------------------------------------------------------ node pool
+namespace {
+struct BlockPool {
+  static std::mutex& mu() { static std::mutex m; return m; }
+  static std::vector<void*>& global() { static std::vector<void*> g; return g; }
+  std::vector<void*> free_;
+  size_t block = 0;
+  ~BlockPool() {
+    std::lock_guard<std::mutex> l(mu());
+    auto& g = global();
+    g.insert(g.end(), free_.begin(), free_.end());
+  }
+  void* get(size_t bytes) {
+    if (!block) block = (bytes + 15) / 16 * 16;
+    if (bytes > block) return ::operator new(bytes);      // (never: one block type per pool)
+    if (free_.empty()) {
+      {
+        std::lock_guard<std::mutex> l(mu());
+        auto& g = global();
+        size_t take = std::min<size_t>(g.size(), 1024);
+        free_.assign(g.end() - take, g.end());
+        g.resize(g.size() - take);
+      }
+      if (free_.empty()) {
+        const size_t n = 512;
+        char* slab = static_cast<char*>(::operator new(n * block));
+        for (size_t i = 0; i < n; ++i) free_.push_back(slab + i * block);
+      }
+    }
+    void* p = free_.back();
+    free_.pop_back();
+    return p;
+  }
+  void put(void* p) { free_.push_back(p); }
+};
+thread_local BlockPool t_pool;
+
+template <class T>
+struct PoolAlloc {
+  using value_type = T;
+  PoolAlloc() = default;
+  template <class U>
+  PoolAlloc(const PoolAlloc<U>&) {}
+  T* allocate(size_t n) { return n == 1 ? static_cast<T*>(t_pool.get(sizeof(T))) : static_cast<T*>(::operator new(n * sizeof(T))); }
+  void deallocate(T* p, size_t n) {
+    if (n == 1) t_pool.put(p);
+    else ::operator delete(p);
+  }
+  template <class U>
+  bool operator==(const PoolAlloc<U>&) const { return true; }
+  template <class U>
+  bool operator!=(const PoolAlloc<U>&) const { return false; }
+};
+}  // namespace
+
+std::shared_ptr<Node> new_node() {
+  static const bool pooled = [] {
+    const char* e = getenv("GK_NODE_POOL");
+    return !(e && e[0] == '0');
+  }();
+  return pooled ? std::allocate_shared<Node>(PoolAlloc<Node>()) : std::make_shared<Node>();
+}
+
 // -------------------------------------------------------------------------------------- constructors
 VP v_null() {
-  static thread_local VP v = [] { auto n = std::make_shared<Node>(); n->t = VT::Null; return VP(n); }();
+  static thread_local VP v = [] { auto n = new_node(); n->t = VT::Null; return VP(n); }();
   return v;
 }
 VP v_bool(bool b) {
-  static thread_local VP t = [] { auto n = std::make_shared<Node>(); n->t = VT::True; return VP(n); }();
-  static thread_local VP f = [] { auto n = std::make_shared<Node>(); n->t = VT::False; return VP(n); }();
+  static thread_local VP t = [] { auto n = new_node(); n->t = VT::True; return VP(n); }();
+  static thread_local VP f = [] { auto n = new_node(); n->t = VT::False; return VP(n); }();
   return b ? t : f;
 }
 VP v_num(const Num& x) {
-  auto n = std::make_shared<Node>();
+  auto n = new_node();
   n->t = VT::Num;
   n->n = x;
   return n;
 }
 VP v_int(long long i) { return v_num(Num::of_int(i)); }
 VP v_str(std::string s) {
-  auto n = std::make_shared<Node>();
+  auto n = new_node();
   n->t = VT::Str;
   n->s = std::move(s);
   return n;
 }
 VP v_arr(std::vector<VP> items) {
-  auto n = std::make_shared<Node>();
+  auto n = new_node();
   n->t = VT::Arr;
   n->items = std::move(items);
   return n;
@@ -96,7 +161,7 @@ VP v_set(std::vector<VP> items) {
   std::stable_sort(items.begin(), items.end(), [](const VP& a, const VP& b) { return v_cmp(a, b) < 0; });
   items.erase(std::unique(items.begin(), items.end(), [](const VP& a, const VP& b) { return v_eq(a, b); }),
               items.end());
-  auto n = std::make_shared<Node>();
+  auto n = new_node();
   n->t = VT::Set;
   n->items = std::move(items);
   return n;
@@ -105,7 +170,7 @@ VP v_obj(std::vector<std::pair<VP, VP>> kv) {
   bool sorted = true;
   for (size_t i = 1; i < kv.size() && sorted; ++i) sorted = v_cmp(kv[i - 1].first, kv[i].first) < 0;
   if (sorted) {   // strictly ascending: nothing to sort, nothing to merge
-    auto n = std::make_shared<Node>();
+    auto n = new_node();
     n->t = VT::Obj;
     n->kv = std::move(kv);
     return n;
@@ -117,7 +182,7 @@ VP v_obj(std::vector<std::pair<VP, VP>> kv) {
     if (!out.empty() && v_eq(out.back().first, e.first)) out.back().second = e.second;
     else out.push_back(std::move(e));
   }
-  auto n = std::make_shared<Node>();
+  auto n = new_node();
   n->t = VT::Obj;
   n->kv = std::move(out);
   return n;
@@ -284,7 +349,7 @@ struct JP {
       }
       n = w;
     }
-    auto node = std::make_shared<Node>();
+    auto node = new_node();
     node->t = VT::Obj;
     node->kv.assign(std::make_move_iterator(a), std::make_move_iterator(a + n));
     kvs.resize(base);
@@ -422,7 +487,7 @@ struct JP {
         }
       }
       {
-        auto node = std::make_shared<Node>();
+        auto node = new_node();
         node->t = VT::Arr;
         node->items.assign(std::make_move_iterator(its.begin() + base), std::make_move_iterator(its.end()));
         its.resize(base);

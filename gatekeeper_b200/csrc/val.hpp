@@ -38,6 +38,11 @@ struct Node {
   std::vector<std::pair<VP, VP>> kv;        // Obj (sorted by key, unique)
 };
 
+// Nodes come from a per-thread free list of fixed-size blocks (a document is a few hundred short-lived nodes; the general
+// allocator's lock-free fast path is still several times the cost of a list pop).  Blocks freed on another thread simply
+// join that thread's list; a thread's list is handed to a global pool when the thread ends.
+std::shared_ptr<Node> new_node();
+
 VP v_null();
 VP v_bool(bool b);
 VP v_num(const Num& n);

@@ -1,10 +1,10 @@
 import os, sys, time
 sys.path.insert(0, os.getcwd())
 from gatekeeper_b200 import driver as D, workloads as W
-n=400000
+n=int(os.environ.get("N", "400000"))
 blob = W.synth_objects(0, n)
 tm, cons = W.config2()
-for th in (8, 12, 14, 15, 16, 18, 24, 32):
+for th in (1, 16):
     drv = D.Driver(threads=th)
     for k, r in tm: drv.add_template(k, r)
     for c in cons: drv.AddConstraint(c)
