@@ -279,7 +279,19 @@ def run_ours(args):
            "d2h_bytes_per_step": int(resp.stats["d2h_bytes"] + 16 * C) * world, "steps": e2e_steps,
            "breakdown_ms": {k: round(resp.stats[k], 3) for k in ("flatten_ms", "h2d_ms", "kernel_ms", "d2h_ms")},
            "host_threads_per_gpu": host_threads}
+    # (filled in below on rank 0) e2e["with_messages"]: the same path with every violation message rendered
 
+    # the same call asked to also render every violation's {msg, details} (what Client.Review returns in the reference):
+    # measured on a bounded sample, reported beside the decision-only figure
+    msg_n = min(n, args.msg_sample)
+    e2e_msgs = None
+    if msg_n > 0 and rank == 0:
+        sub = W.synth_objects(rank * n, msg_n, threads=host_threads)
+        r2 = drv.ReviewBlob(sub, ep, flags=D.F_MATERIALIZE, with_results=False)   # results stay in the engine's buffers: not converted to Python
+        dt = sum(r2.stats[k] for k in ("flatten_ms", "h2d_ms", "kernel_ms", "d2h_ms", "materialize_ms")) / 1e3
+        e2e_msgs = {"value": msg_n * C / dt, "unit": UNIT, "objects": msg_n, "results_rendered": r2.stats["n_violations"],
+                    "materialize_ms": round(r2.stats["materialize_ms"], 1), "flatten_ms": round(r2.stats["flatten_ms"], 1)}
+        del r2
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -310,7 +322,7 @@ def run_ours(args):
                    "flatten_ms_once": round(rb.stats["flatten_ms"], 1)},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "kernel": "gk_eval_kernel", "kernel_ms": kern_ms, "alg_bytes_per_launch": alg_bytes, "peak_source": peak_src},
-        "e2e": e2e, "gpu_launches": int(launches) if launches > 0 else K, "clocks": clocks,
+        "e2e": dict(e2e, with_messages=e2e_msgs), "gpu_launches": int(launches) if launches > 0 else K, "clocks": clocks,
     }
     if world == 1:
         line["cpu_baseline"] = cpu_baseline_single(args.cpu_sample)
@@ -329,6 +341,7 @@ def main():
     ap.add_argument("--objects", type=int, default=1_000_000, help="objects per GPU (weak scaling)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-sample", type=int, default=300)
+    ap.add_argument("--msg-sample", type=int, default=50_000, help="objects of the sample whose messages are all rendered (e2e.with_messages)")
     ap.add_argument("--ref-objects-per-core", type=int, default=48)
     args = ap.parse_args()
     sys.exit(run_reference(args) if args.impl == "reference" else run_ours(args))

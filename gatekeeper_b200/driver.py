@@ -313,7 +313,7 @@ class Driver:
         arr = (gk_obj * max(1, len(arr_t)))(*arr_t)
         return arr, len(arr_t), keep
 
-    def _unpack(self, res: gk_result, keys: list) -> BatchResponse:
+    def _unpack(self, res: gk_result, keys: list, with_results: bool = True) -> BatchResponse:
         import numpy as np
         n, w, c = res.n_objects, res.words, res.n_constraints
         vb = eb = None
@@ -326,7 +326,8 @@ class Driver:
             totals=[int(res.totals[i]) for i in range(c)], err_totals=[int(res.err_totals[i]) for i in range(c)],
             stats={k: getattr(res, k) for k in ("flatten_ms", "h2d_ms", "kernel_ms", "d2h_ms", "materialize_ms", "alg_bytes",
                                                 "h2d_bytes", "d2h_bytes", "gpu_launches")})
-        for i in range(res.n_violations):
+        out.stats["n_violations"] = int(res.n_violations)
+        for i in range(res.n_violations if with_results else 0):
             v = res.violations[i]
             dj = v.details_json.decode() if v.details_json else ""
             out.results.append(Result(v.object, keys[v.constraint], v.msg.decode(errors="replace"), json.loads(dj) if dj else None,
@@ -407,7 +408,7 @@ class Driver:
         return ResidentBatch(self, h, blob, {"flatten_ms": stats.flatten_ms, "h2d_ms": stats.h2d_ms, "h2d_bytes": stats.h2d_bytes,
                                              "alg_bytes": stats.alg_bytes})
 
-    def ReviewBlob(self, blob, enforcement_point: str = AUDIT_EP, flags: int = 0, source: str = "Original") -> BatchResponse:
+    def ReviewBlob(self, blob, enforcement_point: str = AUDIT_EP, flags: int = 0, source: str = "Original", with_results: bool = True) -> BatchResponse:
         """End-to-end audit page: host JSON -> flatten -> H2D -> kernel -> D2H (+ optional message rendering)."""
         res = gk_result()
         err = C.c_char_p()
@@ -415,7 +416,7 @@ class Driver:
         self._check(self._lib.gk_review_blob(self._e, blob.buf, blob.offsets, len(blob), SOURCE.get(source, 4), enforcement_point.encode(),
                                              flags, C.byref(res), C.byref(err)), err)
         try:
-            return self._unpack(res, keys)
+            return self._unpack(res, keys, with_results)
         finally:
             self._lib.gk_free_result(C.byref(res))
 
