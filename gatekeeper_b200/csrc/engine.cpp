@@ -854,6 +854,17 @@ struct Flattener : ChunkOut {
     sid_cache.emplace(key, id);
     return id;
   }
+  // string values are by far the commonest: their cache is keyed by the raw string (no "s"-prefixed key is built on a hit)
+  std::unordered_map<std::string, uint32_t> str_sid_cache;
+  uint32_t sid_str(const std::string& raw) {
+    auto it = str_sid_cache.find(raw);
+    if (it != str_sid_cache.end()) return it->second;
+    uint32_t id = sid("s" + raw);
+    if (str_sid_cache.size() > (1u << 18)) str_sid_cache.clear();
+    str_sid_cache.emplace(raw, id);
+    return id;
+  }
+  uint32_t sid_value(const VP& v) { return v->t == VT::Str ? sid_str(v->s) : sid(intern_key(v)); }
   // namespace names are matched by wildcard on the device, which needs their bytes: those (few) are interned
   uint32_t sid_interned(const std::string& key) {
     auto it = sid_cache.find(key);
@@ -992,8 +1003,8 @@ struct Flattener : ChunkOut {
       fl |= GK_F_HAS_OBJ;
       std::string g, v, k;
       split_gv(o, g, v, k);
-      kind = sid("s" + k);
-      group = sid("s" + g);
+      kind = sid_str(k);
+      group = sid_str(g);
       bool is_ns = k == "Namespace" && g.empty();
       if (is_ns) fl |= GK_F_IS_NS;
       std::string objns = meta_str(o, "namespace");
@@ -1008,8 +1019,8 @@ struct Flattener : ChunkOut {
       else if (!objns.empty()) nsname = sid_interned("s" + objns);
       if (const Node* ls = labels_of(o))
         for (auto& e : ls->kv) {
-          hb.lbl_kv.push_back(sid("s" + e.first->s));
-          hb.lbl_kv.push_back(sid("s" + e.second->s));
+          hb.lbl_kv.push_back(sid_str(e.first->s));
+          hb.lbl_kv.push_back(sid_value(e.second));
         }
     }
     fl |= ((uint32_t)source << GK_F_SRC_SHIFT) & GK_F_SRC_MASK;
@@ -1034,7 +1045,7 @@ struct Flattener : ChunkOut {
                         " is outside the exact int64 range of the GPU predicate table";
     }
     if (enc & GK_ENC_VT) hc.vt.push_back(vt);
-    if (enc & GK_ENC_SID) hc.sid.push_back(v ? sid(intern_key(v)) : GK_SID_UNDEF);
+    if (enc & GK_ENC_SID) hc.sid.push_back(v ? sid_value(v) : GK_SID_UNDEF);
     // non-numbers carry the extreme that OPA's cross-type order gives them relative to every number (null, booleans
     // below; strings, composites above): the device's ordered compares then need no type dispatch
     if (v && v->t != VT::Num && (enc & GK_ENC_NUM)) num = type_rank(v->t) < type_rank(VT::Num) ? INT64_MIN : INT64_MAX;
@@ -1121,8 +1132,8 @@ struct Flattener : ChunkOut {
         ns_row_of.emplace(ns.get(), row);
         if (const Node* ls = labels_of(ns))
           for (auto& e : ls->kv) {
-            hb.nsl_kv.push_back(sid("s" + e.first->s));
-            hb.nsl_kv.push_back(sid("s" + e.second->s));
+            hb.nsl_kv.push_back(sid_str(e.first->s));
+            hb.nsl_kv.push_back(sid_value(e.second));
           }
         hb.nsl_off.push_back((uint32_t)hb.nsl_kv.size() / 2);
       } else {
