@@ -1,0 +1,125 @@
+// Package gpudriver -- bindings for the batch-side host work the engine does around Review: the namespace excluder,
+// the audit sweep's aggregation, and the webhook's deny / warn message lists.  (Source only: this image has no Go
+// toolchain; see INTEGRATION.md.)
+package gpudriver
+
+/*
+#cgo CFLAGS: -I${SRCDIR}/../../include
+#cgo LDFLAGS: -L${SRCDIR}/../../gatekeeper_b200 -lgk_engine
+#include <stdlib.h>
+#include "gk_engine.h"
+*/
+import "C"
+
+import (
+	"encoding/json"
+	"unsafe"
+)
+
+// SetExcludedNamespaces mirrors process.Excluder.Add for one process ("audit", "webhook", "sync", "mutation-webhook" or "*"):
+// pkg/controller/config/process/excluder.go:53-77.  The config controller calls it whenever Config.spec.match changes.
+func (d *Driver) SetExcludedNamespaces(process string, patterns []string) error {
+	d.mux.Lock()
+	defer d.mux.Unlock()
+	cp := C.CString(process)
+	defer C.free(unsafe.Pointer(cp))
+	arr := make([]*C.char, len(patterns)+1)
+	for i, p := range patterns {
+		arr[i] = C.CString(p)
+		defer C.free(unsafe.Pointer(arr[i]))
+	}
+	var cerr *C.char
+	if rc := C.gk_set_excluded_namespaces(d.e, cp, (**C.char)(unsafe.Pointer(&arr[0])), C.size_t(len(patterns)), &cerr); rc != 0 {
+		return takeErr(cerr)
+	}
+	return nil
+}
+
+// StatusViolation is pkg/audit/manager.go:99-109.
+type StatusViolation struct {
+	Group              string   `json:"group"`
+	Version            string   `json:"version"`
+	Kind               string   `json:"kind"`
+	Name               string   `json:"name"`
+	Namespace          string   `json:"namespace,omitempty"`
+	Message            string   `json:"message"`
+	EnforcementAction  string   `json:"enforcementAction"`
+	EnforcementActions []string `json:"enforcementActions,omitempty"`
+}
+
+// AuditReport is what addAuditResponsesToUpdateLists accumulates and updateConstraintStatus writes
+// (pkg/audit/manager.go:886-945,984-1041): keys are "Kind/name".
+type AuditReport struct {
+	Objects                             uint64                       `json:"objects"`
+	Results                             uint64                       `json:"results"`
+	TotalViolations                     map[string]int64             `json:"totalViolations"`
+	TotalViolationsPerEnforcementAction map[string]int64             `json:"totalViolationsPerEnforcementAction"`
+	Violations                          map[string][]StatusViolation `json:"violations"`
+}
+
+// AuditRun folds reviewed pages (resident batches) into one sweep's status lists.
+type AuditRun struct {
+	d *Driver
+	a *C.gk_audit_t
+}
+
+// NewAuditRun: limit = --constraint-violations-limit (manager.go:64), msgSize = 256 (manager.go:48); 0 selects the defaults.
+func (d *Driver) NewAuditRun(limit, msgSize uint32) (*AuditRun, error) {
+	var cerr *C.char
+	a := C.gk_audit_begin(d.e, C.uint32_t(limit), C.uint32_t(msgSize), &cerr)
+	if a == nil {
+		return nil, takeErr(cerr)
+	}
+	return &AuditRun{d: d, a: a}, nil
+}
+
+// AddPage evaluates a resident batch at the audit enforcement point and folds every result into the run.
+func (r *AuditRun) AddPage(b *C.gk_batch_t, enforcementPoint string) error {
+	cep := C.CString(enforcementPoint)
+	defer C.free(unsafe.Pointer(cep))
+	var cerr *C.char
+	if rc := C.gk_audit_add_batch(r.a, b, cep, &cerr); rc != 0 {
+		return takeErr(cerr)
+	}
+	return nil
+}
+
+func (r *AuditRun) Report() (*AuditReport, error) {
+	var cerr *C.char
+	js := C.gk_audit_report(r.a, &cerr)
+	if js == nil {
+		return nil, takeErr(cerr)
+	}
+	defer C.gk_free_str(js)
+	out := &AuditReport{}
+	if err := json.Unmarshal([]byte(C.GoString(js)), out); err != nil {
+		return nil, err
+	}
+	return out, nil
+}
+
+func (r *AuditRun) Close() {
+	if r.a != nil {
+		C.gk_audit_end(r.a)
+		r.a = nil
+	}
+}
+
+// validationMessages is validationHandler.getValidationMessages (pkg/webhook/policy.go:238-355) for request i of a
+// materialised micro-batch result.
+func (d *Driver) validationMessages(res *C.gk_result, i int) (deny, warn []string, err error) {
+	var cerr *C.char
+	js := C.gk_validation_messages(d.e, res, C.uint32_t(i), &cerr)
+	if js == nil {
+		return nil, nil, takeErr(cerr)
+	}
+	defer C.gk_free_str(js)
+	var m struct {
+		Deny []string `json:"deny"`
+		Warn []string `json:"warn"`
+	}
+	if err := json.Unmarshal([]byte(C.GoString(js)), &m); err != nil {
+		return nil, nil, err
+	}
+	return m.Deny, m.Warn, nil
+}
