@@ -16,7 +16,10 @@ def shard_range(n_total: int, rank: int, world: int) -> Tuple[int, int]:
 
 
 class ShardedSweep:
-    """Holds a resident batch (this rank's shard) and the torch buffers for the exchange."""
+    """Holds a resident batch (this rank's shard) and the torch buffers for the exchange.
+
+    The per-constraint totals ride at the tail of the bitmap shard, so the step's exchange is ONE collective (an
+    all-gather); the totals of all ranks are then summed locally."""
 
     def __init__(self, drv, resident_batch, n_local: int, n_constraints: int, device, world: int = 1):
         import torch
@@ -26,33 +29,44 @@ class ShardedSweep:
         self.world = world
         self.device = device
         self.on_gpu = device.type == "cuda"
-        self.viol = torch.zeros((n_local, self.words), dtype=torch.int32, device=device)
+        cmax = max(1, n_constraints)
+        bitmap_i32 = n_local * self.words
+        pad = bitmap_i32 % 2                                   # the int64 totals that follow must be 8-byte aligned
+        self._tot_off = bitmap_i32 + pad
+        self._send = torch.zeros(self._tot_off + 4 * cmax, dtype=torch.int32, device=device)
+        self.viol = self._send[:bitmap_i32].view(n_local, self.words)
+        self.tot_local = self._send[self._tot_off:].view(torch.int64).view(2, cmax)     # [violations, matcher errors] x constraint
+        self.tot = self.tot_local if world == 1 else torch.zeros((2, cmax), dtype=torch.int64, device=device)
         self.err = torch.zeros((n_local, self.words), dtype=torch.int32, device=device)
-        self.tot = torch.zeros((2, max(1, n_constraints)), dtype=torch.int64, device=device)
-        self.gathered = torch.zeros((world * n_local, self.words), dtype=torch.int32, device=device) if world > 1 else None
+        self._recv = torch.zeros(world * self._send.numel(), dtype=torch.int32, device=device) if world > 1 else None
+        self.gathered = None
 
     def evaluate(self, enforcement_point: str, stream=None):
         """One pass of the hot path over the shard: kernel -> (viol, err, totals) in this rank's buffers."""
         torch = self.torch
         if self.on_gpu:
             st = stream if stream is not None else torch.cuda.current_stream()
-            self.rb.eval_device(enforcement_point, self.viol.data_ptr(), self.err.data_ptr(), self.tot[0].data_ptr(), self.tot[1].data_ptr(),
-                                st.cuda_stream)
+            self.rb.eval_device(enforcement_point, self.viol.data_ptr(), self.err.data_ptr(), self.tot_local[0].data_ptr(),
+                                self.tot_local[1].data_ptr(), st.cuda_stream)
         else:
             r = self.rb.eval(enforcement_point)
             self.viol.copy_(torch.from_numpy(r.viol_bits.view("int32")))
             self.err.copy_(torch.from_numpy(r.err_bits.view("int32")))
-            self.tot[0, :self.C] = torch.tensor(r.totals, dtype=torch.int64)
-            self.tot[1, :self.C] = torch.tensor(r.err_totals, dtype=torch.int64)
+            self.tot_local.zero_()
+            self.tot_local[0, :self.C] = torch.tensor(r.totals, dtype=torch.int64)
+            self.tot_local[1, :self.C] = torch.tensor(r.err_totals, dtype=torch.int64)
 
     def exchange(self):
-        """The one collective of the path: all-gather of the bitmap shards + all-reduce of the totals."""
+        """The one collective of the path: all-gather of (bitmap shard | totals); totals are summed over ranks locally."""
         if self.world == 1:
             return self.viol, self.tot
         import torch.distributed as dist
-        dist.all_gather_into_tensor(self.gathered, self.viol)
-        dist.all_reduce(self.tot)
-        return self.gathered, self.tot
+        dist.all_gather_into_tensor(self._recv, self._send)
+        recv = self._recv.view(self.world, -1)
+        bitmap_i32 = self.n * self.words
+        self.gathered = recv[:, :bitmap_i32]                                         # [world, n_local * words] (a view)
+        self.tot.copy_(recv[:, self._tot_off:].contiguous().view(self.torch.int64).view(self.world, 2, -1).sum(0))
+        return self.gathered, self.tot       # row g = rank g's bitmap shard, n_local * words int32 (no copy is made)
 
     def step(self, enforcement_point: str):
         self.evaluate(enforcement_point)

@@ -44,7 +44,7 @@ def _worker(rank, world, port, out_dir):
     sw = ShardedSweep(drv, rb, hi - lo, len(drv.constraints()), torch.device("cpu"), world)
     gathered, tot = sw.step(D.AUDIT_EP)
     if rank == 0:
-        np.save(os.path.join(out_dir, "gathered.npy"), gathered.numpy())
+        np.save(os.path.join(out_dir, "gathered.npy"), gathered.contiguous().numpy().reshape(world * (hi - lo), -1))
         np.save(os.path.join(out_dir, "totals.npy"), tot.numpy())
     dist.barrier()
     dist.destroy_process_group()
