@@ -257,7 +257,7 @@ def run_ours(args):
     totals_host = sweep.tot[0].tolist()              # after the exchange: summed over ranks
     sweep.evaluate(ep, stream)                       # this rank's own totals again (untimed), to check the e2e path against
     torch.cuda.synchronize()
-    totals_local = sweep.tot[0].tolist()
+    totals_local = sweep.tot_local[0].tolist()
 
     # ---- e2e: public API, host JSON buffers in, bitmaps + totals out, every step
     e2e_steps = max(1, min(K, args.e2e_steps))
