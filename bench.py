@@ -258,6 +258,15 @@ def run_ours(args):
     sweep.evaluate(ep, stream)                       # this rank's own totals again (untimed), to check the e2e path against
     torch.cuda.synchronize()
     totals_local = sweep.tot_local[0].tolist()
+    if world > 1:
+        # the exchange (fused peer stores or NCCL all-gather) must agree with an independent all-reduce of the local totals,
+        # and the gathered bitmap with the totals it came with
+        ref = sweep.tot_local.clone()
+        dist.all_reduce(ref)
+        assert torch.equal(ref, sweep.tot), "exchanged totals differ from the all-reduced local totals"
+        g = sweep.gathered.contiguous().view(world * n, words)
+        bit0 = int(((g[:, 0] & 1) != 0).sum())
+        assert bit0 == int(sweep.tot[0, 0]), "gathered bitmap and exchanged totals disagree"
 
     # ---- e2e: public API, host JSON buffers in, bitmaps + totals out, every step
     e2e_steps = max(1, min(K, args.e2e_steps))
@@ -317,7 +326,9 @@ def run_ours(args):
         "config": {"workload": "audit sweep: 10 gatekeeper in-tree templates, 50 constraints, 1M synthetic Pods per GPU (BASELINE.json configs[1])",
                    "objects_per_gpu": n, "constraints": C, "evals_per_step": world * n * C,
                    "l2": ("inputs larger than L2: %.0f MB of columns per GPU" % (alg_in / 1e6)) if flush is None else "explicit 256 MB L2 flush between steps",
-                   "parallelism": f"objects sharded over {world} GPU(s); bitmap all-gather + totals all-reduce per step" if world > 1 else "single GPU",
+                   "parallelism": (f"objects sharded over {world} GPU(s); exchange per step: " +
+                                   ("fused into the kernel -- bitmap words and totals stored straight into every peer's buffer over NVLink, one device-side barrier"
+                                    if sweep.p2p is not None else "one NCCL all-gather (bitmap shard + totals)")) if world > 1 else "single GPU",
                    "violating_pairs_per_step": int(sum(totals_host)) * 1, "synth_s": round(gen_s, 2),
                    "flatten_ms_once": round(rb.stats["flatten_ms"], 1)},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,

@@ -34,6 +34,10 @@ struct DevOutPtrs {          // caller-owned device buffers (e.g. torch tensors)
   void* totals = nullptr;    // u64 [nconstraints]
   void* err_totals = nullptr;
   void* stream = nullptr;    // cudaStream_t
+  // fused exchange: device addresses, on every peer GPU, of the place THIS rank's bitmap shard / totals go
+  uint64_t peer_viol[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  uint64_t peer_tot[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  uint32_t npeers = 0, tot_stride = 0;
 };
 
 class Backend {

@@ -347,6 +347,32 @@ int gk_batch_eval_device(gk_engine_t* e, gk_batch_t* b, const char* ep, void* d_
   });
 }
 
+int gk_batch_eval_device_peers(gk_engine_t* e, gk_batch_t* b, const char* ep, const uint64_t* peer_bases, uint32_t npeers, uint32_t rank,
+                               uint64_t slot_i32, uint64_t tot_off_i32, uint32_t tot_stride, void* d_err, void* d_totals, void* d_err_totals,
+                               void* stream, char** err) {
+  if (!e || !b || !peer_bases || !npeers || npeers > 8 || rank >= npeers || !d_err || !d_totals || !d_err_totals) return GK_ERR_INVALID;
+  return guard(err, [&]() {
+    auto c = e->eng->compiled();
+    if (c->version != b->compiled->version) throw RegoError{"batch was flattened against an older constraint set; upload it again"};
+    e->be->set_program(*c);
+    std::vector<uint32_t> active;
+    e->eng->active_mask(*c, ep ? ep : "", active);
+    DevOutPtrs d;
+    d.viol = nullptr;
+    d.err = d_err;
+    d.totals = d_totals;
+    d.err_totals = d_err_totals;
+    d.stream = stream;
+    d.npeers = npeers;
+    d.tot_stride = tot_stride;
+    for (uint32_t q = 0; q < npeers; ++q) {
+      d.peer_viol[q] = peer_bases[q] + (uint64_t)rank * slot_i32 * 4;
+      d.peer_tot[q] = peer_bases[q] + ((uint64_t)rank * slot_i32 + tot_off_i32) * 4;
+    }
+    e->be->eval_into(b->dev, active, d);
+  });
+}
+
 static std::vector<gk_obj> blob_objs(const char* buf, const uint64_t* off, size_t n, uint8_t source) {
   std::vector<gk_obj> v(n);
   for (size_t i = 0; i < n; ++i) {

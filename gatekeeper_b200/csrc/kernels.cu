@@ -298,6 +298,13 @@ class CudaBackend : public Backend {
     p.ntiles = db->ntiles;
     p.tile = db->tile;
     p.slot_words = db->slot_words;
+    p.npeers = 0;
+    p.tot_stride = 0;
+    p.done_ctr = reinterpret_cast<uint32_t*>(d_scalars_) + 4;   // zeroed with the error counter before every launch
+    for (int q = 0; q < GK_MAX_PEERS; ++q) {
+      p.peer_viol[q] = nullptr;
+      p.peer_tot[q] = nullptr;
+    }
     p.timing = nullptr;
 #ifdef GK_PHASE_TIMING
     if (!d_timing_) CK(cudaMalloc(&d_timing_, (kMaxPhases + 2 + 16) * 16));
@@ -413,6 +420,13 @@ class CudaBackend : public Backend {
     cudaStream_t st = static_cast<cudaStream_t>(dst.stream);
     KParams p = prepare(db, active, static_cast<uint32_t*>(dst.viol), static_cast<uint32_t*>(dst.err), static_cast<unsigned long long*>(dst.totals),
                         static_cast<unsigned long long*>(dst.err_totals), st, &smem);
+    if (dst.npeers > GK_MAX_PEERS) throw BackendError{"too many peers for the fused exchange"};
+    p.npeers = dst.npeers;
+    p.tot_stride = dst.tot_stride;
+    for (uint32_t q = 0; q < dst.npeers; ++q) {
+      p.peer_viol[q] = reinterpret_cast<uint32_t*>(dst.peer_viol[q]);
+      p.peer_tot[q] = reinterpret_cast<unsigned long long*>(dst.peer_tot[q]);
+    }
     fire(p, smem, st);
   }
 

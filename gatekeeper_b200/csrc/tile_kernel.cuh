@@ -22,6 +22,8 @@
 
 namespace gk {
 
+#define GK_MAX_PEERS 8
+
 struct KParams {
   GkBatch batch;
   GkProgram prog;
@@ -31,6 +33,15 @@ struct KParams {
   uint32_t ntiles;
   uint32_t tile;              // objects per tile (multiple of 32)
   uint32_t slot_words;        // words in the slot area
+  // Fused exchange (multi-GPU sweep): with npeers > 0 the gather epilogue stores every bitmap word straight into each
+  // peer's receive buffer over NVLink (peer_viol[q] already points at THIS rank's shard inside peer q's buffer), and the
+  // last CTA to finish publishes the per-constraint totals the same way.  A device-side barrier on the caller's stream
+  // then replaces the all-gather collective.
+  uint32_t* peer_viol[GK_MAX_PEERS];
+  unsigned long long* peer_tot[GK_MAX_PEERS];   // [2 * tot_stride]: violations, then matcher errors
+  uint32_t npeers;
+  uint32_t tot_stride;
+  uint32_t* done_ctr;
   unsigned long long* timing; // GK_PHASE_TIMING builds: [kMaxPhases + 2][2] = (CTA cycles between barriers, summed warp busy cycles)
 };
 
@@ -703,8 +714,13 @@ __global__ void __launch_bounds__(kThreads, GK_MIN_CTAS) gk_eval_kernel(const KP
       }
       const uint32_t obj = ow * 32u + lane;
       if (obj < nobj) {
-        p.out.viol[(size_t)(obj0 + obj) * W + wi] = yv;
-        p.out.err[(size_t)(obj0 + obj) * W + wi] = ye;
+        const size_t at = (size_t)(obj0 + obj) * W + wi;
+        if (p.npeers) {
+          for (uint32_t q = 0; q < p.npeers; ++q) p.peer_viol[q][at] = yv;   // this rank is one of the peers
+        } else {
+          p.out.viol[at] = yv;
+        }
+        p.out.err[at] = ye;
       }
       // totals: every lane's column word covers 32 objects of ITS constraint
       const uint32_t valid = range_mask(ow, 0u, nobj);
@@ -725,6 +741,25 @@ __global__ void __launch_bounds__(kThreads, GK_MIN_CTAS) gk_eval_kernel(const KP
   for (uint32_t c = threadIdx.x; c < C; c += blockDim.x) {
     if (s_tot[c]) atomicAdd(p.out.totals + c, (unsigned long long)s_tot[c]);
     if (s_err[c]) atomicAdd(p.out.err_totals + c, (unsigned long long)s_err[c]);
+  }
+  if (p.npeers) {
+    // the last CTA to arrive sees every CTA's contribution and publishes the totals to all peers
+    __shared__ uint32_t s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(p.done_ctr, 1u) == gridDim.x - 1u ? 1u : 0u;
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      for (uint32_t c = threadIdx.x; c < C; c += blockDim.x) {
+        const unsigned long long tv = atomicAdd(p.out.totals + c, 0ull), te = atomicAdd(p.out.err_totals + c, 0ull);
+        for (uint32_t q = 0; q < p.npeers; ++q) {
+          p.peer_tot[q][c] = tv;
+          p.peer_tot[q][p.tot_stride + c] = te;
+        }
+      }
+      __threadfence_system();
+    }
   }
 }
 

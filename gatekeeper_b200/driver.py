@@ -67,7 +67,7 @@ EXPORTS = [
     "gk_engine_create", "gk_engine_destroy", "gk_backend_name", "gk_add_template", "gk_remove_template",
     "gk_add_constraint", "gk_remove_constraint", "gk_put_namespace", "gk_remove_namespace", "gk_constraint_count",
     "gk_constraint_key", "gk_review_batch", "gk_batch_upload", "gk_batch_eval", "gk_batch_eval_device",
-    "gk_batch_upload_blob", "gk_review_blob", "gk_set_excluded_namespaces", "gk_audit_begin", "gk_audit_add_batch", "gk_audit_report",
+    "gk_batch_eval_device_peers", "gk_batch_upload_blob", "gk_review_blob", "gk_set_excluded_namespaces", "gk_audit_begin", "gk_audit_add_batch", "gk_audit_report",
     "gk_audit_end", "gk_validation_messages", "gk_host_cpus", "gk_batch_size", "gk_batch_alg_bytes", "gk_batch_free", "gk_free_result", "gk_free_str", "gk_dump",
     "gk_stat_description",
 ]
@@ -99,6 +99,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.gk_batch_upload.argtypes = [P, C.POINTER(gk_obj), C.c_size_t, U32, C.POINTER(P), C.POINTER(gk_result), PP]
     lib.gk_batch_eval.argtypes = [P, P, S, U32, C.POINTER(gk_result), PP]
     lib.gk_batch_eval_device.argtypes = [P, P, S, P, P, P, P, P, PP]
+    lib.gk_batch_eval_device_peers.argtypes = [P, P, S, C.POINTER(C.c_uint64), U32, U32, C.c_uint64, C.c_uint64, U32, P, P, P, P, PP]
     lib.gk_batch_upload_blob.argtypes = [P, P, C.POINTER(C.c_uint64), C.c_size_t, C.c_uint8, U32, C.POINTER(P), C.POINTER(gk_result), PP]
     lib.gk_review_blob.argtypes = [P, P, C.POINTER(C.c_uint64), C.c_size_t, C.c_uint8, S, U32, C.POINTER(gk_result), PP]
     lib.gk_batch_size.restype = U32
@@ -483,6 +484,15 @@ class ResidentBatch:
         err = C.c_char_p()
         self.drv._check(self.drv._lib.gk_batch_eval_device(self.drv._e, self.h, enforcement_point.encode(), d_viol, d_err, d_totals,
                                                            d_err_totals, stream, C.byref(err)), err)
+
+    def eval_device_peers(self, enforcement_point, peer_bases, rank: int, slot_i32: int, tot_off_i32: int, tot_stride: int,
+                          d_err: int, d_totals: int, d_err_totals: int, stream: int = 0):
+        """Kernel with the fused exchange: bitmap words and totals go straight into every peer's receive buffer."""
+        err = C.c_char_p()
+        arr = (C.c_uint64 * len(peer_bases))(*peer_bases)
+        self.drv._check(self.drv._lib.gk_batch_eval_device_peers(self.drv._e, self.h, enforcement_point.encode(), arr, len(peer_bases), rank,
+                                                                 slot_i32, tot_off_i32, tot_stride, d_err, d_totals, d_err_totals, stream,
+                                                                 C.byref(err)), err)
 
     def free(self):
         if self.h:

@@ -7,7 +7,28 @@ same function runs under `gloo` with host tensors (tests use the CPU test backen
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Tuple
+
+
+class _PeerExchange:
+    """Symmetric (peer-mapped) receive buffers: buffers[k] is this rank's k-th buffer, bases[k][q] the device address of
+    rank q's k-th buffer as mapped into this process."""
+
+    def __init__(self, torch, world, slot_i32, device):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self.rank = dist.get_rank()
+        self.buffers, self.handles, self.bases = [], [], []
+        for _ in range(2):
+            buf = symm.empty(world * slot_i32, dtype=torch.int32, device=device)
+            buf.zero_()
+            hdl = symm.rendezvous(buf, dist.group.WORLD)
+            self.buffers.append(buf)
+            self.handles.append(hdl)
+            self.bases.append([int(p) for p in hdl.buffer_ptrs])
+        torch.cuda.synchronize()
+        dist.barrier()
 
 
 def shard_range(n_total: int, rank: int, world: int) -> Tuple[int, int]:
@@ -40,11 +61,26 @@ class ShardedSweep:
         self.err = torch.zeros((n_local, self.words), dtype=torch.int32, device=device)
         self._recv = torch.zeros(world * self._send.numel(), dtype=torch.int32, device=device) if world > 1 else None
         self.gathered = None
+        # Fused exchange over NVLink peer memory (GPUs only): two symmetric receive buffers used alternately, so that a
+        # fast rank's next kernel never overwrites what a slow rank is still reading; one device-side barrier per step.
+        self.p2p = None
+        if world > 1 and self.on_gpu and os.environ.get("GK_P2P", "1") != "0":
+            try:
+                self.p2p = _PeerExchange(torch, world, self._send.numel(), device)
+            except Exception as e:                      # no peer access / symmetric memory: the NCCL all-gather remains
+                self.p2p_error = repr(e)
+                self.p2p = None
+        self._step = 0
 
     def evaluate(self, enforcement_point: str, stream=None):
         """One pass of the hot path over the shard: kernel -> (viol, err, totals) in this rank's buffers."""
         torch = self.torch
-        if self.on_gpu:
+        if self.on_gpu and self.p2p is not None:
+            st = stream if stream is not None else torch.cuda.current_stream()
+            px = self.p2p
+            self.rb.eval_device_peers(enforcement_point, px.bases[self._step & 1], px.rank, self._send.numel(), self._tot_off, self.tot_local.shape[1],
+                                      self.err.data_ptr(), self.tot_local[0].data_ptr(), self.tot_local[1].data_ptr(), st.cuda_stream)
+        elif self.on_gpu:
             st = stream if stream is not None else torch.cuda.current_stream()
             self.rb.eval_device(enforcement_point, self.viol.data_ptr(), self.err.data_ptr(), self.tot_local[0].data_ptr(),
                                 self.tot_local[1].data_ptr(), st.cuda_stream)
@@ -60,9 +96,15 @@ class ShardedSweep:
         """The one collective of the path: all-gather of (bitmap shard | totals); totals are summed over ranks locally."""
         if self.world == 1:
             return self.viol, self.tot
-        import torch.distributed as dist
-        dist.all_gather_into_tensor(self._recv, self._send)
-        recv = self._recv.view(self.world, -1)
+        if self.p2p is not None:
+            # every rank's kernel has written its shard (and totals) into everybody's buffer: wait for all of them
+            self.p2p.handles[self._step & 1].barrier(channel=0)
+            recv = self.p2p.buffers[self._step & 1].view(self.world, -1)
+            self._step += 1
+        else:
+            import torch.distributed as dist
+            dist.all_gather_into_tensor(self._recv, self._send)
+            recv = self._recv.view(self.world, -1)
         bitmap_i32 = self.n * self.words
         self.gathered = recv[:, :bitmap_i32]                                         # [world, n_local * words] (a view)
         self.tot.copy_(recv[:, self._tot_off:].contiguous().view(self.torch.int64).view(self.world, 2, -1).sum(0))

@@ -122,6 +122,15 @@ int gk_batch_eval(gk_engine_t* e, gk_batch_t* b, const char* enforcement_point, 
  * viol/err u32[n*words], totals/err_totals u64[n_constraints] (multi-GPU gather path) */
 int gk_batch_eval_device(gk_engine_t* e, gk_batch_t* b, const char* enforcement_point, void* d_viol, void* d_err,
                          void* d_totals, void* d_err_totals, void* cuda_stream, char** err);
+/* Multi-GPU sweep with the exchange FUSED into the kernel (replaces kernel + NCCL all-gather): every rank's kernel stores its
+ * bitmap words, and its per-constraint totals, straight into the receive buffer of each peer GPU over NVLink.
+ * peer_bases[q] is the device address of rank q's receive buffer (this rank included) in this process' address space
+ * (CUDA IPC / symmetric memory); a rank's slot in it starts at `rank * slot_i32` int32 words: bitmap [n * words], then at
+ * `tot_off_i32` the totals as u64 [2 * tot_stride] (violations, matcher errors).  d_viol may be NULL.  The call returns
+ * without synchronising; the caller orders a device-side barrier across ranks after it on `cuda_stream`. */
+int gk_batch_eval_device_peers(gk_engine_t* e, gk_batch_t* b, const char* enforcement_point, const uint64_t* peer_bases, uint32_t npeers,
+                               uint32_t rank, uint64_t slot_i32, uint64_t tot_off_i32, uint32_t tot_stride, void* d_err, void* d_totals,
+                               void* d_err_totals, void* cuda_stream, char** err);
 /* the same two calls for a page of objects held in ONE contiguous buffer (a LIST page / spill directory as the
  * audit loop reads it, pkg/audit/manager.go:502-561,686-695): document i is buf[offsets[i], offsets[i+1]).
  * Every object is reviewed as an AugmentedUnstructured with the given source and no oldObject. */
