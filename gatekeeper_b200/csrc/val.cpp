@@ -67,12 +67,16 @@ bool num_fits_i64(const Num& n, int64_t* out) {
 
 // ------------------------------------------------------------------------------------------ node pool
 namespace {
+// Nodes outlive thread-local storage at process exit (engines are torn down after the main thread's thread_locals): once
+// the pool is gone, blocks are simply not recycled.  (A trivially destructible flag stays readable after destruction.)
+thread_local bool t_pool_alive = true;
 struct BlockPool {
   static std::mutex& mu() { static std::mutex m; return m; }
   static std::vector<void*>& global() { static std::vector<void*> g; return g; }
   std::vector<void*> free_;
   size_t block = 0;
   ~BlockPool() {
+    t_pool_alive = false;
     std::lock_guard<std::mutex> l(mu());
     auto& g = global();
     g.insert(g.end(), free_.begin(), free_.end());
@@ -108,10 +112,15 @@ struct PoolAlloc {
   PoolAlloc() = default;
   template <class U>
   PoolAlloc(const PoolAlloc<U>&) {}
-  T* allocate(size_t n) { return n == 1 ? static_cast<T*>(t_pool.get(sizeof(T))) : static_cast<T*>(::operator new(n * sizeof(T))); }
+  T* allocate(size_t n) {
+    if (n != 1) return static_cast<T*>(::operator new(n * sizeof(T)));
+    if (!t_pool_alive) return static_cast<T*>(::operator new((sizeof(T) + 15) / 16 * 16));
+    return static_cast<T*>(t_pool.get(sizeof(T)));
+  }
   void deallocate(T* p, size_t n) {
-    if (n == 1) t_pool.put(p);
-    else ::operator delete(p);
+    if (n != 1) ::operator delete(p);
+    else if (t_pool_alive) t_pool.put(p);
+    // else: the pool of this thread is gone (process exit); the block is part of a slab and is left alone
   }
   template <class U>
   bool operator==(const PoolAlloc<U>&) const { return true; }
