@@ -156,8 +156,27 @@ class HostEmuBackend : public Backend {
     out.kernel_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
     out.launches = 0;
   }
-  void eval_into(void*, const std::vector<uint32_t>&, const DevOutPtrs&) override {
-    throw BackendError{"hostemu has no device buffers"};
+  // "device" buffers are host memory here: the same address arithmetic as the CUDA backend (bitmap shard and totals of this
+  // rank stored into every peer's receive buffer), so the C ABI's peer addressing can be tested without GPUs
+  void eval_into(void* b, const std::vector<uint32_t>& active, const DevOutPtrs& dst) override {
+    EvalOut out;
+    eval(b, active, out, true);
+    const size_t nw = out.viol.size();
+    if (dst.err && nw) memcpy(dst.err, out.err.data(), nw * 4);
+    if (dst.totals) memcpy(dst.totals, out.totals.data(), out.totals.size() * 8);
+    if (dst.err_totals) memcpy(dst.err_totals, out.err_totals.data(), out.err_totals.size() * 8);
+    if (dst.npeers == 0) {
+      if (dst.viol && nw) memcpy(dst.viol, out.viol.data(), nw * 4);
+      return;
+    }
+    for (uint32_t q = 0; q < dst.npeers; ++q) {
+      if (nw) memcpy(reinterpret_cast<void*>(dst.peer_viol[q]), out.viol.data(), nw * 4);
+      auto* t = reinterpret_cast<unsigned long long*>(dst.peer_tot[q]);
+      for (size_t c = 0; c < out.totals.size(); ++c) {
+        t[c] = out.totals[c];
+        t[dst.tot_stride + c] = out.err_totals[c];
+      }
+    }
   }
 
  private:

@@ -74,3 +74,36 @@ def test_shard_ranges_partition_the_batch():
             rs = [shard_range(n, r, g) for r in range(g)]
             assert rs[0][0] == 0 and rs[-1][1] == n
             assert all(rs[i][1] == rs[i + 1][0] for i in range(g - 1))
+
+
+def test_peer_addressing_of_the_fused_exchange():
+    """gk_batch_eval_device_peers on the test backend: two "ranks" in one process write their bitmap shard and totals
+    into each other's receive buffers (host arrays standing in for peer-mapped device memory); every buffer must end up
+    holding both shards in rank order and totals that sum to the single-process sweep."""
+    from gatekeeper_b200 import driver as D
+    from gatekeeper_b200 import workloads as W
+    from gatekeeper_b200.sweep import shard_range
+    world, n_total = 2, 500
+    drv = _setup_driver()
+    C = len(drv.constraints())
+    words = (C + 31) // 32
+    whole = drv.upload_blob(W.synth_objects(0, n_total)).eval(D.AUDIT_EP)
+    n_local = n_total // world
+    tot_off = n_local * words + (n_local * words) % 2
+    slot = tot_off + 4 * C
+    recv = [np.zeros(world * slot, dtype=np.int32) for _ in range(world)]
+    bases = [int(r.ctypes.data) for r in recv]
+    keep = []
+    for rank in range(world):
+        lo, hi = shard_range(n_total, rank, world)
+        rb = drv.upload_blob(W.synth_objects(lo, hi - lo))
+        keep.append(rb)
+        err = np.zeros(n_local * words, dtype=np.int32)
+        tot = np.zeros((2, C), dtype=np.int64)
+        rb.eval_device_peers(D.AUDIT_EP, bases, rank, slot, tot_off, C, int(err.ctypes.data), int(tot[0].ctypes.data), int(tot[1].ctypes.data), 0)
+    for r in recv:
+        g = r.reshape(world, slot)
+        bitmap = g[:, :n_local * words].reshape(world * n_local, words).view(np.uint32)
+        assert (bitmap == whole.viol_bits).all()
+        totals = g[:, tot_off:].copy().view(np.int64).reshape(world, 2, C).sum(0)
+        assert totals[0].tolist() == whole.totals and totals[1].tolist() == whole.err_totals
