@@ -1440,6 +1440,7 @@ void Engine::materialize_object(const Compiled& c, const ObjIn& in, uint32_t obj
     std::vector<std::pair<std::string, std::string>> items;   // (msg, details JSON)
   };
   std::map<std::string, Rendered> memo;
+  std::map<const Module*, std::pair<std::shared_ptr<Module>, std::unique_ptr<Eval>>> evals;   // (the module is pinned while its evaluator lives)
   for (auto& f : flagged) {
     if (f.is_err) {
       autoreject(c, in, obj_ix, f.cix, f.err_code, ep, out);
@@ -1462,7 +1463,17 @@ void Engine::materialize_object(const Compiled& c, const ObjIn& in, uint32_t obj
     auto& rendered = memo[con.kind + '\x01' + con.params_key];
     if (!rendered.done) {
       rendered.done = true;
-      Eval ev(*mod, v_obj({{v_str("review"), doc}, {v_str("parameters"), con.params}}));
+      // one evaluator per template for this object: switching constraints keeps the extents of parameter-free helper
+      // rules (input_containers, ...)
+      VP inp = v_obj({{v_str("review"), doc}, {v_str("parameters"), con.params}});
+      auto& slot = evals[mod.get()];
+      if (!slot.second) {
+        slot.first = mod;
+        slot.second.reset(new Eval(*mod, inp));
+      } else {
+        slot.second->reset_parameters(inp);
+      }
+      Eval& ev = *slot.second;
       VP vs = ev.rule_value("violation");
       if (vs)
         for (auto& v : vs->items) {

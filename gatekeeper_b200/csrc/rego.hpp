@@ -72,6 +72,9 @@ struct Module {
   // functions whose value depends on their arguments only (no `input` / `data`, transitively): their results
   // can be memoised across objects
   std::unordered_map<std::string, bool> pure_fn;
+  // rules whose value does not depend on `input.parameters` (nor on `data`), transitively: for one object their extents
+  // are the same under every constraint of the template
+  std::unordered_map<std::string, bool> param_free;
   int intern(const std::string& n);
   bool is_rule(const std::string& n) const { return rules.count(n) != 0; }
 };
@@ -121,6 +124,19 @@ class Eval {
     input_ = std::move(input);
     cache_.clear();
     cache_has_.clear();
+  }
+  // same review, other parameters: extents of parameter-free rules stay valid
+  void reset_parameters(VP input) {
+    input_ = std::move(input);
+    for (auto it = cache_has_.begin(); it != cache_has_.end();) {
+      auto pf = m_.param_free.find(it->first);
+      if (pf != m_.param_free.end() && pf->second) {
+        ++it;
+      } else {
+        cache_.erase(it->first);
+        it = cache_has_.erase(it);
+      }
+    }
   }
   bool eval_body(const std::vector<Stmt>& body, size_t i, Env& env, const EnvK& k);
   bool eval_term(const TP& t, Env& env, const ValK& k);

@@ -589,10 +589,21 @@ static void stmts_deps(const Module& m, const std::vector<Stmt>& b, bool& touche
     for (const TP* x : {&st.a, &st.b, &st.c})
       if (*x) term_deps(m, **x, touches_doc, refs);
 }
+static thread_local bool* g_touches_params = nullptr;   // optional second flag: input.parameters / bare input / data
 static void term_deps(const Module& m, const Term& t, bool& touches_doc, std::vector<std::string>& refs) {
   if (t.k == TK::Var) {
-    if (t.vid == m.vid_input || t.vid == m.vid_data) touches_doc = true;
+    if (t.vid == m.vid_input || t.vid == m.vid_data) {
+      touches_doc = true;
+      if (g_touches_params) *g_touches_params = true;    // a bare `input` / `data` (reference heads are handled below)
+    }
     if (m.is_rule(t.name)) refs.push_back(t.name);
+  }
+  if (t.k == TK::Ref && t.head && t.head->k == TK::Var && t.head->vid == m.vid_input && !t.args.empty() && t.args[0]->k == TK::Scalar &&
+      t.args[0]->val->t == VT::Str && t.args[0]->val->s != "parameters") {
+    // input.review... : touches the document but not the parameters
+    touches_doc = true;
+    for (auto& a : t.args) term_deps(m, *a, touches_doc, refs);
+    return;
   }
   if (t.k == TK::Call && m.is_rule(t.name)) refs.push_back(t.name);
   if (t.head) term_deps(m, *t.head, touches_doc, refs);
@@ -604,9 +615,10 @@ static void term_deps(const Module& m, const Term& t, bool& touches_doc, std::ve
 }
 static void compute_purity(Module& m) {
   std::map<std::string, std::vector<std::string>> refs;
-  std::map<std::string, bool> impure;
+  std::map<std::string, bool> impure, uses_params;
   for (auto& kv : m.rules) {
-    bool doc = false;
+    bool doc = false, par = false;
+    g_touches_params = &par;
     auto& rf = refs[kv.first];
     for (auto& r : kv.second) {
       for (auto& a : r.args) term_deps(m, *a, doc, rf);
@@ -619,6 +631,8 @@ static void compute_purity(Module& m) {
       }
     }
     impure[kv.first] = doc;
+    uses_params[kv.first] = par;
+    g_touches_params = nullptr;
   }
   for (bool changed = true; changed;) {
     changed = false;
@@ -631,8 +645,21 @@ static void compute_purity(Module& m) {
             break;
           }
   }
-  for (auto& kv : m.rules)
+  for (bool changed = true; changed;) {
+    changed = false;
+    for (auto& kv : refs)
+      if (!uses_params[kv.first])
+        for (auto& r : kv.second)
+          if (uses_params[r]) {
+            uses_params[kv.first] = true;
+            changed = true;
+            break;
+          }
+  }
+  for (auto& kv : m.rules) {
     if (kv.second[0].kind == Rule::Func) m.pure_fn[kv.first] = !impure[kv.first];
+    m.param_free[kv.first] = !uses_params[kv.first];
+  }
 }
 
 std::shared_ptr<Module> rego_parse(const std::string& src) {
