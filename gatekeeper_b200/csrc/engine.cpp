@@ -864,6 +864,14 @@ struct Flattener : ChunkOut {
     str_sid_cache.emplace(raw, id);
     return id;
   }
+  std::unordered_map<std::string, uint32_t> ns_sid_cache;   // namespace names (interned: the device needs their bytes), raw-keyed
+  uint32_t sid_ns(const std::string& raw) {
+    auto it = ns_sid_cache.find(raw);
+    if (it != ns_sid_cache.end()) return it->second;
+    uint32_t id = sid_interned("s" + raw);
+    ns_sid_cache.emplace(raw, id);
+    return id;
+  }
   uint32_t sid_value(const VP& v) { return v->t == VT::Str ? sid_str(v->s) : sid(intern_key(v)); }
   // namespace names are matched by wildcard on the device, which needs their bytes: those (few) are interned
   uint32_t sid_interned(const std::string& key) {
@@ -1014,9 +1022,9 @@ struct Flattener : ChunkOut {
       hb.name_bytes.insert(hb.name_bytes.end(), name.begin(), name.end());
       hb.gen_bytes.insert(hb.gen_bytes.end(), gen.begin(), gen.end());
       // name used by namespaces / excludedNamespaces -- match.go:118-179
-      if (is_ns) nsname = sid_interned("s" + name);
-      else if (ns) nsname = sid_interned("s" + meta_str(ns, "name"));
-      else if (!objns.empty()) nsname = sid_interned("s" + objns);
+      if (is_ns) nsname = sid_ns(name);
+      else if (ns) nsname = sid_ns(meta_str(ns, "name"));
+      else if (!objns.empty()) nsname = sid_ns(objns);
       if (const Node* ls = labels_of(o))
         for (auto& e : ls->kv) {
           hb.lbl_kv.push_back(sid_str(e.first->s));
