@@ -56,6 +56,9 @@ class CudaBackend : public Backend {
     CK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     CK(cudaEventCreate(&ev0_));
     CK(cudaEventCreate(&ev1_));
+    cudaFuncAttributes fa;
+    CK(cudaFuncGetAttributes(&fa, gk_eval_kernel));
+    max_smem_ -= fa.sharedSizeBytes;   // the kernel's few static shared bytes come out of the same per-CTA budget
     CK(cudaFuncSetAttribute(gk_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem_));
     CK(cudaMalloc(&d_scalars_, 4096));
   }
