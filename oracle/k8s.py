@@ -2,7 +2,11 @@
 Review hot path: the `spec.match` pre-filter, wildcard globbing, the process excluder, enforcement-point
 filtering, review construction and the `Client.Review` loop that ties them to the Rego evaluation.
 
-Every function cites the reference file:line it restates (paths relative to /root/reference).
+Every function cites the reference file:line it restates (paths relative to /root/reference).  Pinned by the reference's
+own vectors (tests/golden/match_vectors.json, wildcard_vectors.json, target_vectors.json -- extracted from
+pkg/mutation/match/match_test.go, pkg/wildcard/wildcard_test.go, pkg/target/target_test.go, pkg/target/target_integration_test.go,
+pkg/controller/config/process/excluder_test.go); the text of label-selector validation errors (apimachinery, un-vendored)
+is parity unpinned.
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.
 """
 from __future__ import annotations

@@ -7,9 +7,12 @@ The evaluator itself is NOT in /root/reference: it lives in the un-vendored Go m
 so this file restates OPA's *published* Rego semantics (topdown evaluation of partial-set rules,
 undefined propagation, negation-as-failure, comprehensions, set algebra, `sprintf("%v")` rendering) for
 the language subset used by every in-tree ConstraintTemplate.  Parity is pinned
-on the reference's own golden messages (tests/golden/*.json, transcribed from
-test/gator/test/test.bats:73-249, pkg/gator/test/test_test.go:85-452, website/docs/audit.md:52); templates
-with no such pin are flagged "oracle-by-restatement" in tests.
+on the reference's own golden results (tests/golden/*.json: test/gator/test/test.bats:73-249, the TestTest table of
+pkg/gator/test/test_test.go:85-268, test/gator/verify/suite.yaml, the psp-all-violations suite,
+pkg/target/target_integration_test.go:164-520, website/docs/audit.md:52).
+PARITY UNPINNED for what the reference holds no expectation for: the exact violation sets / messages of K8sAllowedRepos,
+K8sContainerLimits, K8sBannedImageTags, agilebank K8sRequiredLabels and the K8sPSP* templates beyond the all-violating suite,
+and `sprintf("%v")` of composite values -- there this file is an "oracle-by-restatement" (SURVEY.md section 8(c)).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.
 
