@@ -344,7 +344,15 @@ def case_fuzz(lib, n=800, seed=1234, start=5000):
     for i in range(n):
         o = json.loads(blob.get(i))
         objs.append(_mutate(rnd, o, rnd.choice([0, 1, 1, 2, 3, 5])))
-    revs = [D.Review(object=o, source="Original") for o in objs]
+    revs = []
+    for i, o in enumerate(objs):
+        r = rnd.random()
+        if r < 0.15 and i:       # UPDATE carrying another (damaged) Pod as oldObject: either may match (matcher.go:44-71)
+            revs.append(D.Review(object=o, old_object=objs[i - 1], operation="UPDATE", source="Original"))
+        elif r < 0.20:           # DELETE: the object under review IS the old object (target.go:262-280)
+            revs.append(D.Review(object=None, old_object=o, operation="DELETE", source="Original"))
+        else:
+            revs.append(D.Review(object=o, source="Original"))
     resp = drv.ReviewBatch(revs, k8s.AUDIT_EP)
     errs = resp.object_errors or [None] * n
     bad = {i for i, e in enumerate(errs) if e}
