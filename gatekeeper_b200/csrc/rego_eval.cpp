@@ -462,8 +462,12 @@ VP call_builtin(const std::string& n, const std::vector<VP>& a, bool* known) {
 // ----------------------------------------------------------------------------------------- evaluator
 bool Eval::var_unbound(const Term& t, const Env& env) const {
   if (t.k != TK::Var || env.find(t.vid) || t.vid == m_.vid_input || t.vid == m_.vid_data) return false;
-  if (t.is_rule_ < 0) t.is_rule_ = m_.is_rule(t.name) ? 1 : 0;
-  return !t.is_rule_;
+  signed char r = __atomic_load_n(&t.is_rule_, __ATOMIC_RELAXED);   // every thread computes the same value
+  if (r < 0) {
+    r = m_.is_rule(t.name) ? 1 : 0;
+    __atomic_store_n(&t.is_rule_, r, __ATOMIC_RELAXED);
+  }
+  return !r;
 }
 
 bool Eval::is_ground(const TP& t, const Env& env) const {
@@ -906,10 +910,11 @@ bool Eval::walk(const VP& cur, const std::vector<TP>& path, size_t i, Env& env, 
 bool Eval::eval_call(const Term& t, Env& env, const ValK& k) {
   if (__atomic_load_n(&t.is_rule_, __ATOMIC_ACQUIRE) < 0) {
     auto rit = m_.rules.find(t.name);
-    t.rules_ = rit != m_.rules.end() && rit->second[0].kind == Rule::Func ? &rit->second : nullptr;
-    __atomic_store_n(&t.is_rule_, (signed char)(t.rules_ ? 1 : 0), __ATOMIC_RELEASE);
+    const void* fr = rit != m_.rules.end() && rit->second[0].kind == Rule::Func ? &rit->second : nullptr;
+    __atomic_store_n(&t.rules_, fr, __ATOMIC_RELAXED);   // every thread stores the same pointer
+    __atomic_store_n(&t.is_rule_, (signed char)(fr ? 1 : 0), __ATOMIC_RELEASE);
   }
-  const auto* frules = static_cast<const std::vector<Rule>*>(t.rules_);
+  const auto* frules = static_cast<const std::vector<Rule>*>(__atomic_load_n(&t.rules_, __ATOMIC_RELAXED));
   bool user = frules != nullptr;
   size_t nargs = t.args.size();
   const TP* out_pat = nullptr;
