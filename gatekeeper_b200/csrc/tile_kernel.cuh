@@ -744,12 +744,13 @@ __global__ void __launch_bounds__(kThreads, GK_MIN_CTAS) gk_eval_kernel(const KP
   }
   if (p.npeers) {
     // the last CTA to arrive sees every CTA's contribution and publishes the totals to all peers
-    __shared__ uint32_t s_last;
+    // (the flag lives in the dynamic shared-memory area -- s_lo is free by now -- so the kernel keeps zero static shared bytes)
+    volatile uint32_t* s_last = s_lo;
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) s_last = atomicAdd(p.done_ctr, 1u) == gridDim.x - 1u ? 1u : 0u;
+    if (threadIdx.x == 0) *s_last = atomicAdd(p.done_ctr, 1u) == gridDim.x - 1u ? 1u : 0u;
     __syncthreads();
-    if (s_last) {
+    if (*s_last) {
       __threadfence();
       for (uint32_t c = threadIdx.x; c < C; c += blockDim.x) {
         const unsigned long long tv = atomicAdd(p.out.totals + c, 0ull), te = atomicAdd(p.out.err_totals + c, 0ull);
