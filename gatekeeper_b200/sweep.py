@@ -64,7 +64,7 @@ class ShardedSweep:
         # Fused exchange over NVLink peer memory (GPUs only): two symmetric receive buffers used alternately, so that a
         # fast rank's next kernel never overwrites what a slow rank is still reading; one device-side barrier per step.
         self.p2p = None
-        if world > 1 and self.on_gpu and os.environ.get("GK_P2P", "0") == "1":
+        if world > 1 and self.on_gpu and os.environ.get("GK_P2P", "1") != "0":
             try:
                 self.p2p = _PeerExchange(torch, world, self._send.numel(), device)
             except Exception as e:                      # no peer access / symmetric memory: the NCCL all-gather remains
