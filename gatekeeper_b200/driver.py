@@ -68,7 +68,8 @@ EXPORTS = [
     "gk_add_constraint", "gk_remove_constraint", "gk_put_namespace", "gk_remove_namespace", "gk_constraint_count",
     "gk_constraint_key", "gk_review_batch", "gk_batch_upload", "gk_batch_eval", "gk_batch_eval_device",
     "gk_batch_eval_device_peers", "gk_batch_upload_blob", "gk_review_blob", "gk_set_excluded_namespaces", "gk_audit_begin", "gk_audit_add_batch", "gk_audit_report",
-    "gk_audit_end", "gk_validation_messages", "gk_host_cpus", "gk_batch_size", "gk_batch_alg_bytes", "gk_batch_free", "gk_free_result", "gk_free_str", "gk_dump",
+    "gk_audit_end", "gk_validation_messages", "gk_host_cpus", "gk_coalescer_create", "gk_coalescer_review", "gk_coalescer_stats",
+    "gk_coalescer_destroy", "gk_batch_size", "gk_batch_alg_bytes", "gk_batch_free", "gk_free_result", "gk_free_str", "gk_dump",
     "gk_stat_description",
 ]
 
@@ -113,6 +114,13 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.gk_audit_end.restype = None
     lib.gk_validation_messages.argtypes = [P, C.POINTER(gk_result), U32, PP]
     lib.gk_validation_messages.restype = C.c_void_p
+    lib.gk_coalescer_create.argtypes = [P, U32, U32, S, U32, PP]
+    lib.gk_coalescer_create.restype = P
+    lib.gk_coalescer_review.argtypes = [P, C.POINTER(gk_obj), C.POINTER(C.c_void_p), PP]
+    lib.gk_coalescer_stats.argtypes = [P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    lib.gk_coalescer_stats.restype = None
+    lib.gk_coalescer_destroy.argtypes = [P]
+    lib.gk_coalescer_destroy.restype = None
     lib.gk_host_cpus.argtypes = []
     lib.gk_host_cpus.restype = C.c_int
     lib.gk_batch_size.argtypes = [P]
@@ -420,6 +428,38 @@ class Driver:
             return self._unpack(res, keys, with_results)
         finally:
             self._lib.gk_free_result(C.byref(res))
+
+
+class Coalescer:
+    """Admission micro-batching (gk_coalescer_*): `review()` may be called from many threads; each call blocks until the
+    micro-batch it joined has been evaluated and returns that request's outcome."""
+
+    def __init__(self, drv: "Driver", max_batch: int = 64, max_wait_us: int = 200, enforcement_point: str = WEBHOOK_EP, process: str = "webhook"):
+        self.drv = drv
+        err = C.c_char_p()
+        self._c = drv._lib.gk_coalescer_create(drv._e, max_batch, max_wait_us, enforcement_point.encode(), PROCESS_FLAG.get(process, 0), C.byref(err))
+        if not self._c:
+            drv._check(-1, err)
+
+    def review(self, review: "Review") -> dict:
+        arr, n, keep = self.drv._marshal([review])
+        out = C.c_void_p()
+        err = C.c_char_p()
+        self.drv._check(self.drv._lib.gk_coalescer_review(self._c, arr, C.byref(out), C.byref(err)), err)   # (ctypes releases the GIL)
+        try:
+            return json.loads(C.string_at(out).decode(errors="surrogateescape"))
+        finally:
+            self.drv._lib.gk_free_str(out)
+
+    def stats(self):
+        b, r = C.c_uint64(), C.c_uint64()
+        self.drv._lib.gk_coalescer_stats(self._c, C.byref(b), C.byref(r))
+        return {"batches": b.value, "reviews": r.value}
+
+    def close(self):
+        if self._c:
+            self.drv._lib.gk_coalescer_destroy(self._c)
+            self._c = None
 
 
 class AuditRun:

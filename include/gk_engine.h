@@ -167,6 +167,20 @@ void gk_audit_end(gk_audit_t* a);
  * JSON {"deny": ["[<constraint name>] <msg>", ...], "warn": [...]}.  Caller frees with gk_free_str. */
 char* gk_validation_messages(gk_engine_t* e, const gk_result* r, uint32_t object, char** err);
 
+/* ---- admission coalescer ("Webhook: internal coalescer inside Query"): concurrent single-review callers
+ * -- the webhook's request goroutines around Client.Review, pkg/webhook/policy.go:580-675 -- are gathered into micro-batches
+ * (flushed at `max_batch` reviews or after `max_wait_us`) and evaluated with one gk_review_batch.  gk_coalescer_review
+ * blocks until the caller's batch is done and returns its own request's outcome as JSON:
+ *   {"batch_size": n, "error": null | "review-level error", "messages": {"deny": [...], "warn": [...]}, "results": [{"constraint",
+ *    "msg", "details", "enforcementAction", "scopedEnforcementActions", "autoreject"}]}     (free with gk_free_str)
+ * `flags`: GK_F_PROCESS_WEBHOOK applies the webhook's namespace excluder.  Thread-safe; no background thread. */
+typedef struct gk_coalescer gk_coalescer_t;
+gk_coalescer_t* gk_coalescer_create(gk_engine_t* e, uint32_t max_batch, uint32_t max_wait_us, const char* enforcement_point, uint32_t flags,
+                                    char** err);
+int gk_coalescer_review(gk_coalescer_t* c, const gk_obj* obj, char** out_json, char** err);
+void gk_coalescer_stats(gk_coalescer_t* c, uint64_t* batches, uint64_t* reviews);
+void gk_coalescer_destroy(gk_coalescer_t* c);
+
 /* CPUs the flattener will use by default (gk_cfg.threads = 0): affinity mask and cgroup CPU quota respected */
 int gk_host_cpus(void);
 

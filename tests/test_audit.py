@@ -1,5 +1,7 @@
 """SURVEY 8 rows a-3 (audit aggregation), a-4 (excluder), a-14 (admission messages), a-17 (bench metric definitions):
 the engine's host code against the oracle, on the test-only CPU backend.  The same cases run on the GPU in test_gpu.py."""
+import json
+
 import parity_cases as P
 from conftest import HOSTEMU
 from gatekeeper_b200 import metrics as M
@@ -178,3 +180,41 @@ def test_webhook_excluded_namespaces_vectors_of_the_reference():
         o_allowed = k8s.is_namespace_excluded(["kube-*"], probe) or not orc.review(
             k8s.Review(obj=obj, old=old, operation=op, namespace=ns), k8s.WEBHOOK_EP)
         assert o_allowed == allowed, name
+
+
+def test_admission_coalescer_batches_concurrent_reviews():
+    """gk_coalescer_*: 48 threads each send one admission review; every caller must get exactly its own request's outcome
+    (compared with a direct ReviewBatch of the same request), and the requests must have been gathered into micro-batches."""
+    import threading
+    from conftest import golden, make_pair
+    from gatekeeper_b200 import driver as D
+    from oracle import k8s
+    psp = golden("psp_suite.json")
+    cons = [json.loads(json.dumps(c)) for c in psp["constraints"]]
+    cons[0].setdefault("spec", {})["enforcementAction"] = "warn"
+    orc, drv, _ = make_pair([(t["kind"], t["rego"]) for t in psp["templates"]], cons, lib_path=HOSTEMU)
+    pods = psp["pods"]
+    ok_pod = {"apiVersion": "v1", "kind": "Pod", "metadata": {"name": "fine", "namespace": "default"}, "spec": {"containers": [{"name": "c", "image": "x"}]}}
+    reqs = [D.Review(object=(ok_pod if i % 7 == 0 else pods[i % len(pods)]), operation="CREATE", namespace_name="default") for i in range(48)]
+    co = D.Coalescer(drv, max_batch=16, max_wait_us=20000)
+    out = [None] * len(reqs)
+    def worker(i):
+        out[i] = co.review(reqs[i])
+    th = [threading.Thread(target=worker, args=(i,)) for i in range(len(reqs))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    st = co.stats()
+    assert st["reviews"] == len(reqs) and st["batches"] < len(reqs), st          # some coalescing happened
+    assert max(o["batch_size"] for o in out) > 1 and max(o["batch_size"] for o in out) <= 16
+    for i, r in enumerate(reqs):
+        direct = drv.ReviewBatch([r], k8s.WEBHOOK_EP, process="webhook")
+        want = sorted((x.constraint, x.msg, x.enforcement_action) for x in direct.results)
+        got = sorted((x["constraint"], x["msg"], x["enforcementAction"]) for x in out[i]["results"])
+        assert got == want, i
+        (deny, warn), = drv.ValidationMessages([r])
+        assert sorted(out[i]["messages"]["deny"]) == sorted(deny) and sorted(out[i]["messages"]["warn"]) == sorted(warn)
+        assert out[i]["error"] is None
+    assert any(o["messages"]["deny"] for o in out) and any(not o["results"] for o in out)
+    co.close()
