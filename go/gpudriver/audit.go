@@ -123,3 +123,70 @@ func (d *Driver) validationMessages(res *C.gk_result, i int) (deny, warn []strin
 	}
 	return m.Deny, m.Warn, nil
 }
+
+// Coalescer gathers the webhook's concurrent Query calls (one goroutine per admission request, policy.go:580-675) into
+// micro-batches: each Review call blocks until the batch it joined has been evaluated on the GPU.
+type Coalescer struct {
+	c *C.gk_coalescer_t
+}
+
+// AdmissionOutcome is one request's share of a micro-batch.
+type AdmissionOutcome struct {
+	BatchSize int     `json:"batch_size"`
+	Error     *string `json:"error"`
+	Messages  struct {
+		Deny []string `json:"deny"`
+		Warn []string `json:"warn"`
+	} `json:"messages"`
+	Results []struct {
+		Constraint               string      `json:"constraint"`
+		Msg                      string      `json:"msg"`
+		Details                  interface{} `json:"details"`
+		EnforcementAction        string      `json:"enforcementAction"`
+		ScopedEnforcementActions []string    `json:"scopedEnforcementActions"`
+		Autoreject               bool        `json:"autoreject"`
+	} `json:"results"`
+}
+
+func (d *Driver) NewCoalescer(maxBatch, maxWaitMicros uint32, enforcementPoint string) (*Coalescer, error) {
+	cep := C.CString(enforcementPoint)
+	defer C.free(unsafe.Pointer(cep))
+	var cerr *C.char
+	c := C.gk_coalescer_create(d.e, C.uint32_t(maxBatch), C.uint32_t(maxWaitMicros), cep, C.GK_F_PROCESS_WEBHOOK, &cerr)
+	if c == nil {
+		return nil, takeErr(cerr)
+	}
+	return &Coalescer{c: c}, nil
+}
+
+// Review blocks until the request's micro-batch is done.  raw / oldRaw are AdmissionRequest.Object.Raw / OldObject.Raw.
+func (c *Coalescer) Review(raw, oldRaw []byte, namespace, operation string) (*AdmissionOutcome, error) {
+	var o C.gk_obj
+	if len(raw) > 0 {
+		o.json, o.len = (*C.char)(unsafe.Pointer(&raw[0])), C.size_t(len(raw))
+	}
+	if len(oldRaw) > 0 {
+		o.old_json, o.old_len = (*C.char)(unsafe.Pointer(&oldRaw[0])), C.size_t(len(oldRaw))
+	}
+	cns, cop := C.CString(namespace), C.CString(operation)
+	defer C.free(unsafe.Pointer(cns))
+	defer C.free(unsafe.Pointer(cop))
+	o.ns_name, o.operation = cns, cop
+	var out, cerr *C.char
+	if rc := C.gk_coalescer_review(c.c, &o, &out, &cerr); rc != 0 {
+		return nil, takeErr(cerr)
+	}
+	defer C.gk_free_str(out)
+	res := &AdmissionOutcome{}
+	if err := json.Unmarshal([]byte(C.GoString(out)), res); err != nil {
+		return nil, err
+	}
+	return res, nil
+}
+
+func (c *Coalescer) Close() {
+	if c.c != nil {
+		C.gk_coalescer_destroy(c.c)
+		c.c = nil
+	}
+}
