@@ -252,6 +252,15 @@ int gk_add_template(gk_engine_t* e, const char* kind, const char* rego_src, size
   if (!e || !kind || !rego_src) return GK_ERR_INVALID;
   return guard(err, [&]() { e->eng->add_template(kind, std::string(rego_src, len)); });
 }
+int gk_add_template_libs(gk_engine_t* e, const char* kind, const char* rego_src, size_t len, const char* const* libs, const size_t* lib_lens,
+                         size_t n_libs, char** err) {
+  if (!e || !kind || !rego_src || (n_libs && (!libs || !lib_lens))) return GK_ERR_INVALID;
+  return guard(err, [&]() {
+    std::vector<std::string> ls;
+    for (size_t i = 0; i < n_libs; ++i) ls.emplace_back(libs[i] ? libs[i] : "", libs[i] ? lib_lens[i] : 0);
+    e->eng->add_template(kind, std::string(rego_src, len), ls);
+  });
+}
 int gk_remove_template(gk_engine_t* e, const char* kind) {
   if (!e || !kind) return GK_ERR_INVALID;
   return guard(nullptr, [&]() { e->eng->remove_template(kind); });

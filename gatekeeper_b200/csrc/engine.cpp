@@ -295,8 +295,8 @@ int effective_cpus() {
 
 Engine::Engine(int threads) : threads_(threads > 0 ? threads : effective_cpus()) {}
 
-void Engine::add_template(const std::string& kind, const std::string& rego) {
-  auto mod = rego_parse(rego);   // throws RegoError on syntax / unsafe-var errors
+void Engine::add_template(const std::string& kind, const std::string& rego, const std::vector<std::string>& libs) {
+  auto mod = rego_parse(rego, libs);   // throws RegoError on syntax / unsafe-var errors
   if (!mod->is_rule("violation")) throw RegoError{"rego_compile_error: template " + kind + " has no `violation` rule"};
   // lowering is parameter-specific, but unsupported constructs that do not depend on parameters surface
   // here: lower once against empty parameters and discard (errors that need parameters surface at AddConstraint)

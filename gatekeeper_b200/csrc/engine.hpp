@@ -133,7 +133,7 @@ class Engine {
  public:
   explicit Engine(int threads);
   // mutators (exclusive) -- mirror drivers.Driver AddTemplate/RemoveTemplate/AddConstraint/RemoveConstraint/AddData
-  void add_template(const std::string& kind, const std::string& rego);
+  void add_template(const std::string& kind, const std::string& rego, const std::vector<std::string>& libs = {});
   bool remove_template(const std::string& kind);
   void add_constraint(const std::string& json);
   bool remove_constraint(const std::string& kind, const std::string& name);

@@ -79,7 +79,8 @@ struct Module {
   bool is_rule(const std::string& n) const { return rules.count(n) != 0; }
 };
 
-std::shared_ptr<Module> rego_parse(const std::string& src);   // throws RegoError
+// `libs`: the template's `spec.targets[].libs` modules (package lib.<...>), importable as data.lib.<...>
+std::shared_ptr<Module> rego_parse(const std::string& src, const std::vector<std::string>& libs = {});   // throws RegoError
 std::string term_str(const Term& t);                          // debug / canonical printing
 std::string rule_str(const Module& m, const std::string& name); // canonical text of all definitions of a rule
 

@@ -1,6 +1,7 @@
 // Rego subset parser (v0 and v1 rule syntax).  See rego.hpp for scope.
 #include <atomic>
 #include <cstring>
+#include <set>
 
 #include "rego.hpp"
 
@@ -170,7 +171,24 @@ struct Parser {
   size_t i = 0;
   Module& m;
   int wild = 0;
+  // template libs (`spec.targets[].libs`): every lib is parsed into the SAME module, its rules renamed to
+  // "data.<package>.<rule>"; an `import data.lib.x [as y]` makes `y.rule` / `y.fn(...)` mean "data.lib.x.rule".
+  std::string prefix;                              // "data.lib.helpers." while a lib is parsed, "" for the entry point
+  const std::set<std::string>* own_rules = nullptr;   // the lib's own rule names (unqualified)
+  const std::set<std::string>* lib_pkgs = nullptr;    // "data.lib.helpers", ... : every lib package of the template
+  std::map<std::string, std::string> aliases;      // import alias -> "data.lib.helpers."
+  bool lenient_imports = false;                    // pre-scan: take any data.lib import
   explicit Parser(const std::string& src, Module& mod) : t(lex(src)), m(mod) {}
+
+  std::string resolve(const std::string& n) const {
+    if (!prefix.empty() && own_rules && own_rules->count(n)) return prefix + n;
+    size_t dot = n.find('.');
+    if (dot != std::string::npos) {
+      auto it = aliases.find(n.substr(0, dot));
+      if (it != aliases.end()) return it->second + n.substr(dot + 1);
+    }
+    return n;
+  }
 
   const Tok& peek(size_t k = 0) const { return t[std::min(i + k, t.size() - 1)]; }
   const Tok& next() { return t[i < t.size() - 1 ? i++ : i]; }
@@ -202,19 +220,40 @@ struct Parser {
     x->val = std::move(v);
     return x;
   }
-  TP var(const std::string& n, int line) {
+  TP var(const std::string& n0, int line) {
+    const std::string n = resolve(n0);
     auto x = mk(TK::Var, line);
     x->name = n;
     x->vid = m.intern(n);
     return x;
   }
-  TP call(const std::string& n, std::vector<TP> args, int line) {
+  TP call(const std::string& n0, std::vector<TP> args, int line) {
+    const std::string n = resolve(n0);
     auto x = mk(TK::Call, line);
     x->name = n;
     x->args = std::move(args);
     return x;
   }
   TP ref_append(const TP& base, TP idx) {
+    if (idx->k == TK::Scalar && idx->val->t == VT::Str) {
+      // <alias>.<rule> and data.lib.<pkg>.<rule> name a lib rule
+      if (base->k == TK::Var) {
+        auto it = aliases.find(base->name);
+        if (it != aliases.end()) return var(it->second + idx->val->s, base->line);
+      }
+      if (lib_pkgs && base->k == TK::Ref && base->head->k == TK::Var && base->head->vid == m.vid_data) {
+        std::string pkg = "data";
+        bool plain = true;
+        for (auto& a : base->args) {
+          if (a->k != TK::Scalar || a->val->t != VT::Str) {
+            plain = false;
+            break;
+          }
+          pkg += "." + a->val->s;
+        }
+        if (plain && lib_pkgs->count(pkg)) return var(pkg + "." + idx->val->s, base->line);
+      }
+    }
     if (base->k == TK::Ref) {
       auto x = std::make_shared<Term>(*base);
       x->args.push_back(std::move(idx));
@@ -249,9 +288,16 @@ struct Parser {
         std::string p = next().s;
         std::string first = p;
         while (same_line() && accept(".")) p += "." + next().s;
-        if (first != "future" && first != "rego")
+        std::string alias = p.substr(p.rfind('.') + 1);
+        if (same_line() && accept("as")) alias = next().s;
+        if (first == "future" || first == "rego") {
+        } else if (p.rfind("data.lib.", 0) == 0 && (lenient_imports || (lib_pkgs && lib_pkgs->count(p)))) {
+          aliases[alias] = p + ".";
+        } else if (p.rfind("data.lib.", 0) == 0 || p == "data.lib") {
+          throw RegoError{"rego_compile_error: import " + p + ": the template has no lib with that package (line " + std::to_string(line) + ")"};
+        } else {
           throw RegoError{"rego_unsupported: import " + p + " (line " + std::to_string(line) + ")"};
-        if (same_line() && accept("as")) next();
+        }
       } else {
         Rule r = parse_rule();
         m.rules[r.name].push_back(std::move(r));
@@ -265,7 +311,7 @@ struct Parser {
     r.is_default = accept("default");
     const Tok& nt = next();
     if (nt.k != TT::Id || is_keyword(nt.s)) perr("unexpected '" + nt.s + "'", nt.line);
-    r.name = nt.s;
+    r.name = prefix + nt.s;
     r.line = nt.line;
     if (same_line() && at("(") && adjacent()) {
       next();
@@ -662,13 +708,39 @@ static void compute_purity(Module& m) {
   }
 }
 
-std::shared_ptr<Module> rego_parse(const std::string& src) {
+std::shared_ptr<Module> rego_parse(const std::string& src, const std::vector<std::string>& libs) {
   static std::atomic<uint64_t> uid{1};
   auto m = std::make_shared<Module>();
   m->uid = uid++;
   m->vid_input = m->intern("input");
   m->vid_data = m->intern("data");
+  // libs first (pre-scan each for its package and rule names, then parse it into `m` under its package prefix)
+  std::set<std::string> lib_pkgs;
+  std::vector<std::set<std::string>> lib_rules(libs.size());
+  std::vector<std::string> lib_pkg(libs.size());
+  for (size_t i = 0; i < libs.size(); ++i) {
+    Module scratch;
+    scratch.vid_input = scratch.intern("input");
+    scratch.vid_data = scratch.intern("data");
+    Parser p0(libs[i], scratch);
+    p0.lenient_imports = true;
+    p0.parse_module();
+    // frameworks' regorewriter: a lib lives under data.lib (constraint/pkg/regorewriter, libs must be `package lib.<...>`)
+    if (scratch.package != "lib" && scratch.package.rfind("lib.", 0) != 0)
+      throw RegoError{"rego_compile_error: lib package `" + scratch.package + "` must begin with `lib`"};
+    lib_pkg[i] = "data." + scratch.package;
+    lib_pkgs.insert(lib_pkg[i]);
+    for (auto& kv : scratch.rules) lib_rules[i].insert(kv.first);
+  }
+  for (size_t i = 0; i < libs.size(); ++i) {
+    Parser pl(libs[i], *m);
+    pl.prefix = lib_pkg[i] + ".";
+    pl.own_rules = &lib_rules[i];
+    pl.lib_pkgs = &lib_pkgs;
+    pl.parse_module();
+  }
   Parser p(src, *m);
+  p.lib_pkgs = &lib_pkgs;
   p.parse_module();
   for (auto& kv : m->rules) {
     Rule::Kind k0 = kv.second[0].kind;

@@ -64,7 +64,7 @@ class gk_result(C.Structure):
 
 
 EXPORTS = [
-    "gk_engine_create", "gk_engine_destroy", "gk_backend_name", "gk_add_template", "gk_remove_template",
+    "gk_engine_create", "gk_engine_destroy", "gk_backend_name", "gk_add_template", "gk_add_template_libs", "gk_remove_template",
     "gk_add_constraint", "gk_remove_constraint", "gk_put_namespace", "gk_remove_namespace", "gk_constraint_count",
     "gk_constraint_key", "gk_review_batch", "gk_batch_upload", "gk_batch_eval", "gk_batch_eval_device",
     "gk_batch_eval_device_peers", "gk_batch_upload_blob", "gk_review_blob", "gk_set_excluded_namespaces", "gk_audit_begin", "gk_audit_add_batch", "gk_audit_report",
@@ -87,6 +87,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.gk_backend_name.restype = S
     lib.gk_backend_name.argtypes = [P]
     lib.gk_add_template.argtypes = [P, S, S, C.c_size_t, PP]
+    lib.gk_add_template_libs.argtypes = [P, S, S, C.c_size_t, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), C.c_size_t, PP]
     lib.gk_remove_template.argtypes = [P, S]
     lib.gk_add_constraint.argtypes = [P, S, C.c_size_t, PP]
     lib.gk_remove_constraint.argtypes = [P, S, S]
@@ -244,18 +245,26 @@ class Driver:
     def AddTemplate(self, template: dict) -> None:
         kind = template["spec"]["crd"]["spec"]["names"]["kind"]
         tgt = template["spec"]["targets"][0]
-        src = tgt.get("rego")
+        src, libs = None, None
+        for c in tgt.get("code") or []:      # `code` wins over the legacy fields, as in the framework's rego driver
+            if c.get("engine") == "Rego":
+                src = (c.get("source") or {}).get("rego")
+                libs = (c.get("source") or {}).get("libs")
         if not src:
-            for c in tgt.get("code") or []:
-                if c.get("engine") == "Rego":
-                    src = c["source"]["rego"]
+            src, libs = tgt.get("rego"), tgt.get("libs")
         if not src:
             raise GkError(-2, "no Rego source for this driver in the template (ErrNoDriver)")
-        self.add_template(kind, src)
+        self.add_template(kind, src, libs or ())
 
-    def add_template(self, kind: str, rego: str) -> None:
+    def add_template(self, kind: str, rego: str, libs: Sequence[str] = ()) -> None:
         err = C.c_char_p()
         b = rego.encode()
+        if libs:
+            lb = [x.encode() for x in libs]
+            arr = (C.c_char_p * len(lb))(*lb)
+            lens = (C.c_size_t * len(lb))(*[len(x) for x in lb])
+            self._check(self._lib.gk_add_template_libs(self._e, kind.encode(), b, len(b), arr, lens, len(lb), C.byref(err)), err)
+            return
         self._check(self._lib.gk_add_template(self._e, kind.encode(), b, len(b), C.byref(err)), err)
 
     def RemoveTemplate(self, template_or_kind) -> None:

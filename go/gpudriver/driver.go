@@ -86,7 +86,7 @@ func (d *Driver) Name() string { return Name }
 // AddTemplate lowers the template's Rego ahead of time; unsupported constructs are an error here, exactly where a
 // Rego compile error surfaces in the reference (pkg/controller/constrainttemplate/constrainttemplate_controller.go:476-479).
 func (d *Driver) AddTemplate(_ context.Context, ct *templates.ConstraintTemplate) error {
-	src, err := regoSource(ct)
+	src, libs, err := regoSource(ct)
 	if err != nil {
 		return err
 	}
@@ -97,7 +97,24 @@ func (d *Driver) AddTemplate(_ context.Context, ct *templates.ConstraintTemplate
 	csrc := C.CString(src)
 	defer C.free(unsafe.Pointer(csrc))
 	var cerr *C.char
-	if rc := C.gk_add_template(d.e, kind, csrc, C.size_t(len(src)), &cerr); rc != 0 {
+	if len(libs) == 0 {
+		if rc := C.gk_add_template(d.e, kind, csrc, C.size_t(len(src)), &cerr); rc != 0 {
+			return takeErr(cerr)
+		}
+		return nil
+	}
+	// the pointer array lives in C memory (cgo forbids Go memory that holds C pointers... and vice versa)
+	n := len(libs)
+	arr := (*[1 << 20]*C.char)(C.malloc(C.size_t(n) * C.size_t(unsafe.Sizeof(uintptr(0)))))
+	lens := (*[1 << 20]C.size_t)(C.malloc(C.size_t(n) * C.size_t(unsafe.Sizeof(C.size_t(0)))))
+	defer C.free(unsafe.Pointer(arr))
+	defer C.free(unsafe.Pointer(lens))
+	for i, l := range libs {
+		arr[i] = C.CString(l)
+		lens[i] = C.size_t(len(l))
+		defer C.free(unsafe.Pointer(arr[i]))
+	}
+	if rc := C.gk_add_template_libs(d.e, kind, csrc, C.size_t(len(src)), (**C.char)(unsafe.Pointer(arr)), (*C.size_t)(unsafe.Pointer(lens)), C.size_t(n), &cerr); rc != 0 {
 		return takeErr(cerr)
 	}
 	return nil
@@ -300,22 +317,32 @@ func (d *Driver) GetDescriptionForStat(statName string) (string, error) {
 	return "", fmt.Errorf("unknown stat name for Rego (GPU): %s", statName)
 }
 
-func regoSource(ct *templates.ConstraintTemplate) (string, error) {
+// regoSource returns the entry-point module and the template's libs (`package lib.<...>` modules the entry point imports as
+// data.lib.<...>): `code[engine=Rego].source.{rego,libs}` first, the legacy `rego` / `libs` target fields otherwise.
+func regoSource(ct *templates.ConstraintTemplate) (string, []string, error) {
 	if len(ct.Spec.Targets) != 1 {
-		return "", errors.New("expected exactly one target")
+		return "", nil, errors.New("expected exactly one target")
 	}
 	t := ct.Spec.Targets[0]
 	for _, code := range t.Code {
 		if code.Engine == Name {
 			if m, ok := code.Source.Value.(map[string]interface{}); ok {
 				if s, ok := m["rego"].(string); ok {
-					return s, nil
+					var libs []string
+					if ls, ok := m["libs"].([]interface{}); ok {
+						for _, l := range ls {
+							if str, ok := l.(string); ok {
+								libs = append(libs, str)
+							}
+						}
+					}
+					return s, libs, nil
 				}
 			}
 		}
 	}
 	if t.Rego != "" {
-		return t.Rego, nil
+		return t.Rego, t.Libs, nil
 	}
-	return "", errors.New("no Rego source in template (ErrNoDriver)")
+	return "", nil, errors.New("no Rego source in template (ErrNoDriver)")
 }

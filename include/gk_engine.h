@@ -102,6 +102,10 @@ void gk_engine_destroy(gk_engine_t* e);
 const char* gk_backend_name(gk_engine_t* e);
 
 int gk_add_template(gk_engine_t* e, const char* kind, const char* rego_src, size_t len, char** err);
+/* The same with the template's `spec.targets[].libs` (or `code[].source.libs`): Rego modules under `package lib.<...>` that the
+ * entry point imports as `data.lib.<...>` (constraint framework: templates.Target.Libs / schema.Source.Libs). */
+int gk_add_template_libs(gk_engine_t* e, const char* kind, const char* rego_src, size_t len, const char* const* libs, const size_t* lib_lens,
+                         size_t n_libs, char** err);
 int gk_remove_template(gk_engine_t* e, const char* kind);
 int gk_add_constraint(gk_engine_t* e, const char* constraint_json, size_t len, char** err);
 int gk_remove_constraint(gk_engine_t* e, const char* kind, const char* name);

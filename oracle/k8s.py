@@ -474,24 +474,27 @@ def review_document(review: Review):
 
 
 class Template:
-    def __init__(self, kind, rego_src):
+    def __init__(self, kind, rego_src, libs=()):
         self.kind = kind
-        self.module = rego.Module(rego_src)
+        self.module = rego.Module(rego_src, libs)
 
 
 def template_from_yaml_obj(ct):
-    """ConstraintTemplate dict -> (kind, rego source).  Legacy `targets[].rego` is surfaced as engine
-    "Rego" (pkg/fakes/fixtures.go:32-44)."""
+    """ConstraintTemplate dict -> (kind, rego source) or, for a template with libs, (kind, rego source, libs).  Legacy
+    `targets[].rego` / `targets[].libs` are surfaced as engine "Rego" (pkg/fakes/fixtures.go:32-44); a `code` entry for the
+    Rego engine wins over them."""
     kind = ct["spec"]["crd"]["spec"]["names"]["kind"]
     tgt = ct["spec"]["targets"][0]
-    src = tgt.get("rego")
+    src = libs = None
+    for c in tgt.get("code") or []:
+        if c.get("engine") == "Rego":
+            src = (c.get("source") or {}).get("rego")
+            libs = (c.get("source") or {}).get("libs")
     if not src:
-        for c in tgt.get("code") or []:
-            if c.get("engine") == "Rego":
-                src = c["source"]["rego"]
+        src, libs = tgt.get("rego"), tgt.get("libs")
     if not src:
         raise rego.RegoError("no Rego source for template (ErrNoDriver)")
-    return kind, src
+    return (kind, src, tuple(libs)) if libs else (kind, src)
 
 
 class Client:
@@ -503,8 +506,8 @@ class Client:
         self.constraints = {}   # (kind, name) -> constraint dict ; insertion-ordered
         self.ns_cache = {}      # name -> namespace object   (pkg/target/ns_cache.go:15-85)
 
-    def add_template(self, kind, rego_src):
-        self.templates[kind] = Template(kind, rego_src)
+    def add_template(self, kind, rego_src, libs=()):
+        self.templates[kind] = Template(kind, rego_src, libs)
 
     def add_constraint(self, constraint):
         kind = constraint["kind"]

@@ -359,6 +359,7 @@ class Parser:
     def parse_module(self):
         pkg = None
         rules = []
+        self.imports = {}     # alias -> "lib.<...>" (template libs; frameworks: templates.Target.Libs)
         while self.peek().kind != "eof":
             if self.at("package"):
                 self.next()
@@ -371,10 +372,15 @@ class Parser:
                 parts = [self.next().val]
                 while self.same_line() and self.accept("."):
                     parts.append(self.next().val)
-                if parts[0] not in ("future", "rego"):
-                    raise RegoError(f"rego_unsupported: import {'.'.join(parts)} (data/lib imports are not lowered)")
+                alias = parts[-1]
                 if self.same_line() and self.accept("as"):
-                    self.next()
+                    alias = self.next().val
+                if parts[0] in ("future", "rego"):
+                    pass
+                elif parts[:2] == ["data", "lib"] and len(parts) > 2:
+                    self.imports[alias] = ".".join(parts[1:])
+                else:
+                    raise RegoError(f"rego_unsupported: import {'.'.join(parts)}")
             else:
                 rules.append(self.parse_rule())
         if pkg is None:
@@ -926,13 +932,40 @@ def _raise_undef():
 
 
 class Module:
-    def __init__(self, src):
+    def __init__(self, src, libs=(), _registry=None):
         p = Parser(src)
         self.package, rules = p.parse_module()
+        self.imports = p.imports
         self.rules = {}
         for r in rules:
             self.rules.setdefault(r.name, []).append(r)
+        # template libs: each is its own module under `package lib.<...>`; the entry point (and other libs) reach their
+        # rules through `import data.lib.<...>` or the full data.lib path.  One registry per template.
+        self.libs = _registry if _registry is not None else {}
+        if _registry is None:
+            for lsrc in libs:
+                lm = Module(lsrc, _registry=self.libs)
+                if lm.package != "lib" and not lm.package.startswith("lib."):
+                    raise RegoError(f"rego_compile_error: lib package `{lm.package}` must begin with `lib`")
+                self.libs[lm.package] = lm
+            for mod in [self] + list(self.libs.values()):
+                for alias, pkg in mod.imports.items():
+                    if pkg not in self.libs:
+                        raise RegoError(f"rego_compile_error: import data.{pkg}: the template has no lib with that package")
         self._check()
+
+    def lib_of_call(self, name):
+        """`alias.fn` / `data.lib.<pkg>.fn` -> (lib module, fn) or None."""
+        if "." not in name:
+            return None
+        first, rest = name.split(".", 1)
+        if first in self.imports:
+            return self.libs[self.imports[first]], rest
+        if name.startswith("data.lib."):
+            pkg, _, fn = name[5:].rpartition(".")
+            if pkg in self.libs:
+                return self.libs[pkg], fn
+        return None
 
     def _check(self):
         # the compile-time checks the reference surfaces from AddTemplate as rego_* errors
@@ -986,6 +1019,13 @@ class Evaluator:
         self.data = data if data is not None else RObj()
         self.cache = {}
         self.depth = 0
+        self.subs = {}
+
+    def sub(self, lib_module):
+        ev = self.subs.get(id(lib_module))
+        if ev is None:
+            ev = self.subs[id(lib_module)] = Evaluator(lib_module, self.input, self.data)
+        return ev
 
     # -- public ---------------------------------------------------------------------------------
     def rule_value(self, name):
@@ -1256,6 +1296,33 @@ class Evaluator:
 
     def eval_ref(self, t, env):
         head, path = t[1], t[2]
+        # <import alias>.<rule>...  and  data.lib.<pkg>.<rule>... : a rule of one of the template's libs
+        if head[0] == "var" and head[1] not in env and path and path[0][0] == "scalar":
+            lib = rest = None
+            if head[1] in self.m.imports:
+                lib, rest = self.m.libs[self.m.imports[head[1]]], path
+            elif head[1] == "data" and path[0][1] == "lib":
+                names = []
+                for p in path:
+                    if p[0] != "scalar" or not isinstance(p[1], str):
+                        break
+                    names.append(p[1])
+                for n in range(len(names) - 1, 0, -1):
+                    if ".".join(names[:n]) in self.m.libs:
+                        lib, rest = self.m.libs[".".join(names[:n])], path[n:]
+                        break
+            if lib is not None:
+                rn = rest[0][1]
+                if rn not in lib.rules:
+                    return
+                if lib.rules[rn][0].kind == "func":
+                    raise RegoError("rego_type_error: function used as ref")
+                try:
+                    base = self.sub(lib).rule_value(rn)
+                except Undefined:
+                    return
+                yield from self._walk(base, rest[1:], 0, env)
+                return
         # data.<...> refs: data.inventory... is the synced cache; data.lib unsupported
         if head[0] == "var" and head[1] not in env and head[1] in self.m.rules and self.m.rules[head[1]][0].kind == "func":
             raise RegoError("rego_type_error: function used as ref")
@@ -1317,8 +1384,12 @@ class Evaluator:
             for v, e1 in self.eval_term(args[i], e):
                 yield from rec(i + 1, e1, acc + [v])
 
-        user = name in self.m.rules and self.m.rules[name][0].kind == "func"
-        nargs = len(self.m.rules[name][0].args) if user else None
+        target = self
+        lib = self.m.lib_of_call(name)
+        if lib is not None and lib[1] in lib[0].rules:
+            target, name = self.sub(lib[0]), lib[1]
+        user = name in target.m.rules and target.m.rules[name][0].kind == "func"
+        nargs = len(target.m.rules[name][0].args) if user else None
         out_pat = None
         if user and len(args) == nargs + 1:
             out_pat, args = args[-1], args[:-1]
@@ -1329,7 +1400,7 @@ class Evaluator:
                     if self.depth > 200:
                         raise RegoError("rego_recursion_error")
                     try:
-                        v = self.call_function(name, argvals)
+                        v = target.call_function(name, argvals)
                     finally:
                         self.depth -= 1
                 else:

@@ -45,16 +45,17 @@ def make_pair(tmpls, constraints, namespaces=(), lib_path=None, skip_unsupported
     drv = D.Driver(lib_path=lib_path)
     skipped = []
     dropped_kinds = set()
-    for kind, rego in tmpls:
+    for kind, rego, *rest in tmpls:      # (kind, rego) or (kind, rego, libs)
+        libs = tuple(rest[0]) if rest and rest[0] else ()
         try:
-            drv.add_template(kind, rego)
+            drv.add_template(kind, rego, libs)
         except D.GkError as e:
             if skip_unsupported and "rego_unsupported" in str(e):
                 skipped.append((kind, None, str(e)))
                 dropped_kinds.add(kind)
                 continue
             raise
-        orc.add_template(kind, rego)
+        orc.add_template(kind, rego, libs)
     for c in constraints:
         if c["kind"] in dropped_kinds:
             continue

@@ -518,6 +518,88 @@ def case_fuzz_other_templates(lib, n=400, seed=77):
     return n_results
 
 
+def case_template_libs(lib, n=300, seed=99):
+    """A template with `spec.targets[].libs` (test/bats/tests/templates/k8scontainterlimits_template.yaml: the entry point
+    imports data.lib.helpers): the bats expectation (test/bats/test.bats:268-279 -- opa_no_limits.yaml denied, opa.yaml
+    admitted), then fuzzed limits / parameters against the oracle."""
+    import random
+    g = golden("libs_template.json")
+    tmpl = k8s.template_from_yaml_obj(g["template"])
+    assert len(tmpl) == 3 and len(tmpl[2]) == 1
+    orc, drv, skipped = make_pair([tmpl], [g["constraint"]], lib_path=lib)
+    assert not skipped
+    revs = [D.Review(object=g["denied"]), D.Review(object=g["admitted"])]
+    resp = drv.ReviewBatch(revs, k8s.WEBHOOK_EP)
+    assert_same(oracle_results(orc, revs, k8s.WEBHOOK_EP), engine_results(resp))
+    by_obj = {}
+    for r in resp.results:
+        by_obj.setdefault(r.object, []).append(r.msg)
+    assert by_obj.get(0) == ["container <opa> has no resource limits"] and 1 not in by_obj
+
+    rnd = random.Random(seed)
+    kind = tmpl[0]
+    cons = [W._constraint(kind, "limits-%d" % i, params=p, action=rnd.choice([None, "warn"]))
+            for i, p in enumerate([{"cpu": "200m", "memory": "1Gi"}, {"cpu": "2", "memory": "512Mi"}, {"cpu": 1, "memory": 1073741824},
+                                   {"cpu": "500m", "memory": "2G"}, {"cpu": "bogus", "memory": "1Ti"}, {"memory": "100M"}, {}])]
+    orc, drv, skipped = make_pair([tmpl], cons, lib_path=lib)
+    assert not skipped
+    cpus = ["100m", "200m", "201m", "1", "2", "3", 1, 2, 0.5, "0.5", "abc", "", "1000m", "m", None]
+    mems = ["1Gi", "2Gi", "512Mi", "513Mi", "100M", "101M", "1G", "3G", 1073741824, 2000000000, "1Ki", "1000", "1Ei", "1.5Gi", "Gi", "", "xyz",
+            "128974848", "129e6", "1E", "1P", "1T", "100k", "100m", None]
+    revs = []
+    for i in range(n):
+        cs = []
+        for j in range(rnd.choice([0, 1, 1, 2, 3])):
+            c = {"name": "c%d" % j, "image": "img"}
+            mode = rnd.random()
+            if mode < 0.1:
+                pass
+            elif mode < 0.2:
+                c["resources"] = rnd.choice([{}, {"requests": {"cpu": "1"}}, None])
+            else:
+                lim = {}
+                cpu, mem = rnd.choice(cpus), rnd.choice(mems)
+                if rnd.random() < 0.9:
+                    lim["cpu"] = cpu
+                if rnd.random() < 0.9:
+                    lim["memory"] = mem
+                c["resources"] = {"limits": lim}
+            cs.append(c)
+        revs.append(D.Review(object={"apiVersion": "v1", "kind": "Pod", "metadata": {"name": "p%d" % i, "namespace": "default"},
+                                     "spec": {"containers": cs}}))
+    resp = drv.ReviewBatch(revs, k8s.AUDIT_EP)
+    # "1E" / "1Ei" canonify to 1e21 / 1.15e21 millibytes: beyond the exact int64 columns, reported per object (never guessed)
+    bad = {i for i, e in enumerate(resp.object_errors or []) if e}
+    assert all("int64" in resp.object_errors[i] for i in bad) and len(bad) < n // 5
+    want = oracle_results_safe(orc, revs, k8s.AUDIT_EP, skip=bad)
+    assert len(want) > n
+    assert_same(want, {x for x in engine_results(resp) if x[0] not in bad})
+
+    # a lib outside `package lib...` and an import of a lib the template does not have are compile errors in both
+    import pytest
+    from oracle import rego as orego
+    main = 'package x\nimport data.lib.nothere\nviolation[{"msg": "m"}] { nothere.f(1) }\n'
+    for libs, src in (([("package helpers\nf(x) = x { true }\n")], tmpl[1]), ([], main)):
+        with pytest.raises(orego.RegoError, match="rego_compile_error"):
+            k8s.Client().add_template("X", src, libs)
+        with pytest.raises(D.GkError, match="rego_compile_error"):
+            D.Driver(lib_path=lib).add_template("X", src, libs or ["package lib.other\ng(x) = x { true }\n"])
+    # libs that import each other, full data.lib paths, and a non-function lib rule
+    a = 'package lib.a\nimport data.lib.b\nbig(x) { b.limit < x }\nnames[n] { n := input.review.object.spec.containers[_].name }\n'
+    b = 'package lib.b\nlimit = 2 { true }\n'
+    main = ('package y\nimport data.lib.a as util\n'
+            'violation[{"msg": msg}] { util.big(count(input.review.object.spec.containers)); msg := sprintf("too many: %v", [data.lib.a.names]) }\n'
+            'violation[{"msg": msg}] { util.names["c0"]; data.lib.b.limit == 2; msg := "has c0" }\n')
+    orc, drv, skipped = make_pair([("Y", main, (a, b))], [W._constraint("Y", "y", params=None)], lib_path=lib)
+    assert not skipped
+    resp = drv.ReviewBatch(revs, k8s.AUDIT_EP)
+    assert not any(resp.object_errors or [])
+    want = oracle_results(orc, revs, k8s.AUDIT_EP)
+    assert len(want) > 10
+    assert_same(want, engine_results(resp))
+    return len(want)
+
+
 # ------------------------------------------------------------------------------------------ pkg/target vectors
 DENY_ALL = 'package denyall\nviolation[{"msg": msg}] {\n  msg := "denyall constraint installed"\n}\n'   # target_integration_test.go:37-43
 

@@ -115,6 +115,10 @@ def test_fuzz_other_templates(seed):
     assert P.case_fuzz_other_templates(HOSTEMU, seed=seed) > 500
 
 
+def test_template_libs():
+    assert P.case_template_libs(HOSTEMU) > 10
+
+
 def test_target_enforcement_vectors():
     P.case_target_enforcement(HOSTEMU)
 

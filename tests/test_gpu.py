@@ -107,6 +107,11 @@ def test_fuzz_other_templates():
     assert P.case_fuzz_other_templates(LIB, n=600, seed=314) > 800
 
 
+def test_template_libs():
+    """A template with `libs` (the bats container-limits template: package lib.helpers imported as data.lib.helpers)."""
+    assert P.case_template_libs(LIB, n=600) > 10
+
+
 def test_target_enforcement_vectors():
     """pkg/target/target_integration_test.go: 26 scenarios x 3 request shapes, allowed <=> no results."""
     P.case_target_enforcement(LIB)
