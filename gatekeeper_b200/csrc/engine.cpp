@@ -892,7 +892,7 @@ struct Flattener : ChunkOut {
   // with ok set means "undefined".
   VP eval_direct(const Term& t, const Env& env, const VP& input, Eval& ev, const Module& mod, bool& ok) {
     switch (t.k) {
-      case TK::Scalar: return t.val;
+      case TK::Scalar: return private_const(t.val);   // (never copy a literal of the shared AST: its reference count would bounce between workers)
       case TK::Var: {
         if (const VP* b = env.find(t.vid)) return *b;
         if (t.vid == mod.vid_input) return input;
@@ -903,7 +903,9 @@ struct Flattener : ChunkOut {
         VP cur = eval_direct(*t.head, env, input, ev, mod, ok);
         if (!ok || !cur) return nullptr;
         for (auto& a : t.args) {
-          VP key = a->k == TK::Scalar ? a->val : eval_direct(*a, env, input, ev, mod, ok);
+          VP computed;
+          if (a->k != TK::Scalar) computed = eval_direct(*a, env, input, ev, mod, ok);
+          const VP& key = a->k == TK::Scalar ? a->val : computed;   // a literal key is only read: no copy, no reference-count traffic
           if (!ok) return nullptr;
           if (!key) return nullptr;
           if (cur->t == VT::Obj) cur = obj_get(cur, key);
@@ -930,7 +932,7 @@ struct Flattener : ChunkOut {
         std::vector<VP> args;
         args.reserve(t.args.size());
         for (auto& a : t.args) {
-          VP v = a->k == TK::Scalar ? a->val : eval_direct(*a, env, input, ev, mod, ok);
+          VP v = a->k == TK::Scalar ? private_const(a->val) : eval_direct(*a, env, input, ev, mod, ok);
           if (!ok) return nullptr;
           if (!v) return nullptr;   // an undefined argument makes the call undefined
           args.push_back(std::move(v));
@@ -999,6 +1001,92 @@ struct Flattener : ChunkOut {
     VP out = ev.eval_first(cl.term, env);
     if (memoise) memo.emplace(mkey, out);
     return out;
+  }
+  // ---- path closures: `<base>["a"]["b"][0]` with literal keys over `input`, a scope element or another closure -- most
+  // columns.  They are walked in place: the result is a pointer to the value's slot inside its parent (no environment, no
+  // evaluator, no reference-count traffic).  eval_slot() gives every other closure the same interface by parking its value
+  // in `hold` until the object is done.
+  struct PathPlan {
+    bool is_path = false, from_input = false;
+    const Closure* base = nullptr;
+  };
+  std::unordered_map<const Closure*, PathPlan> plans;
+  const PathPlan& plan_of(const Closure& cl) {
+    auto it = plans.find(&cl);
+    if (it != plans.end()) return it->second;
+    PathPlan pl;
+    if (cl.leaf == Closure::None && cl.term->k == TK::Ref && cl.term->head->k == TK::Var) {
+      bool lit = true;
+      for (auto& a : cl.term->args) lit = lit && a->k == TK::Scalar;
+      const int hv = cl.term->head->vid;
+      const CapArg* cap = nullptr;
+      for (auto& c2 : cl.caps)
+        if (c2.first == hv) cap = &c2.second;
+      if (lit && cap && cap->k == CapArg::Col) {
+        pl.is_path = true;
+        pl.base = cap->col.get();
+      } else if (lit && !cap && hv == cl.mod->vid_input) {
+        pl.is_path = pl.from_input = true;
+      }
+    }
+    return plans.emplace(&cl, pl).first->second;
+  }
+  static const VP* child_slot(const Node& cur, const VP& key) {
+    if (cur.t == VT::Obj) {
+      size_t lo = 0, hi = cur.kv.size();
+      const bool skey = key->t == VT::Str;
+      while (lo < hi) {
+        const size_t mid = (lo + hi) / 2;
+        const VP& k = cur.kv[mid].first;
+        const int c = (skey && k->t == VT::Str) ? k->s.compare(key->s) : v_cmp(k, key);
+        if (c == 0) return &cur.kv[mid].second;
+        if (c < 0) lo = mid + 1;
+        else hi = mid;
+      }
+      return nullptr;
+    }
+    if (cur.t == VT::Arr) {
+      int64_t ix;
+      if (key->t == VT::Num && num_fits_i64(key->n, &ix) && ix >= 0 && (size_t)ix < cur.items.size()) return &cur.items[ix];
+      return nullptr;
+    }
+    if (cur.t == VT::Set) {
+      size_t lo = 0, hi = cur.items.size();
+      while (lo < hi) {
+        const size_t mid = (lo + hi) / 2;
+        const int c = v_cmp(cur.items[mid], key);
+        if (c == 0) return &cur.items[mid];
+        if (c < 0) lo = mid + 1;
+        else hi = mid;
+      }
+    }
+    return nullptr;
+  }
+  std::deque<VP> hold;   // per object: values of non-path closures handed out by eval_slot (a deque never moves its elements)
+  // slot of closure `cl`'s value for row `r` of `scope`, valid until the next object; nullptr = undefined
+  const VP* eval_slot(const Closure& cl, int scope, uint32_t r, const VP& input) {
+    if (cl.leaf != Closure::None) {
+      while (scope != cl.scope && scope != 0) {
+        r = rows[scope][r].parent;
+        scope = c.schema.scopes[scope].parent;
+      }
+      const VP& v = cl.leaf == Closure::Elem ? rows[scope][r].elem : rows[scope][r].key;
+      return v ? &v : nullptr;
+    }
+    const PathPlan& pl = plan_of(cl);
+    if (pl.is_path) {
+      const VP* cur = pl.from_input ? &input : eval_slot(*pl.base, scope, r, input);
+      if (!cur || !*cur) return nullptr;
+      for (auto& a : cl.term->args) {
+        cur = child_slot(**cur, a->val);
+        if (!cur) return nullptr;
+      }
+      return cur;
+    }
+    VP v = eval_closure(cl, scope, r, input);
+    if (!v) return nullptr;
+    hold.push_back(std::move(v));
+    return &hold.back();
   }
   std::deque<Env> env_pool;   // (deque: a nested evaluation may grow it while outer references are live)
   size_t env_depth = 0;
@@ -1156,6 +1244,7 @@ struct Flattener : ChunkOut {
       VP input = v_obj({{v_str("review"), doc}});
       for (auto& e : evals) e.second->reset_input(input);
       memo.clear();
+      hold.clear();
       for (auto& r : rows) r.clear();
       rows[0].push_back(Row{nullptr, nullptr, 0});
       for (size_t s = 1; s < nscopes; ++s) {
@@ -1163,9 +1252,10 @@ struct Flattener : ChunkOut {
         auto& prow = rows[sd.parent];
         for (uint32_t pr = 0; pr < prow.size(); ++pr) {
           uint64_t t0 = trace ? __builtin_ia32_rdtsc() : 0;
-          VP coll = eval_closure(*sd.gen, sd.parent, pr, input);
+          const VP* cslot = eval_slot(*sd.gen, sd.parent, pr, input);
           if (trace) scope_cycles[s] += __builtin_ia32_rdtsc() - t0;
-          if (coll) {
+          if (cslot) {
+            const VP& coll = *cslot;
             if (coll->t == VT::Arr)
               for (size_t j = 0; j < coll->items.size(); ++j) rows[s].push_back(Row{coll->items[j], v_int((long long)j), pr});
             else if (coll->t == VT::Set)
@@ -1179,7 +1269,11 @@ struct Flattener : ChunkOut {
       for (size_t ci = 0; ci < hb.cols.size(); ++ci) {
         const ColDef& cd = c.schema.cols[ci];
         uint64_t t0 = trace ? __builtin_ia32_rdtsc() : 0;
-        for (uint32_t r = 0; r < rows[cd.scope].size(); ++r) encode(ci, eval_closure(*cd.expr, cd.scope, r, input));
+        static const VP undefined;
+        for (uint32_t r = 0; r < rows[cd.scope].size(); ++r) {
+          const VP* v = eval_slot(*cd.expr, cd.scope, r, input);
+          encode(ci, v ? *v : undefined);
+        }
         if (trace) col_cycles[ci] += __builtin_ia32_rdtsc() - t0;
       }
       for (size_t s = 1; s < nscopes; ++s) hb.scope_rows[s] += (uint32_t)rows[s].size();
