@@ -920,12 +920,13 @@ struct Flattener : ChunkOut {
         return cur;
       }
       case TK::Call: {
-        const bool user = mod.is_rule(t.name);
-        if (user && mod.rules.at(t.name)[0].kind != Rule::Func) {
+        const std::vector<Rule>* frules = ev.function_rules(t);
+        const bool user = frules != nullptr;
+        if (!user && mod.is_rule(t.name)) {   // a non-function rule "called"
           ok = false;
           return nullptr;
         }
-        if (user && t.args.size() != mod.rules.at(t.name)[0].args.size()) {   // call with an output argument
+        if (user && t.args.size() != (*frules)[0].args.size()) {   // call with an output argument
           ok = false;
           return nullptr;
         }
@@ -937,7 +938,7 @@ struct Flattener : ChunkOut {
           if (!v) return nullptr;   // an undefined argument makes the call undefined
           args.push_back(std::move(v));
         }
-        if (user) return ev.call_function(t.name, args);
+        if (user) return ev.call_function(*frules, args);
         bool known = true;
         VP v = call_builtin(t.name, args, &known);
         if (!known) ok = false;
@@ -981,9 +982,9 @@ struct Flattener : ChunkOut {
     for (auto& cap : cl.caps) {
       if (cap.second.k == CapArg::Conc) env.bind(cap.first, private_const(cap.second.v));
       else {
-        VP v = eval_closure(*cap.second.col, scope, r, input);
+        const VP* v = eval_slot(*cap.second.col, scope, r, input);
         if (!v) return nullptr;
-        env.bind(cap.first, v);
+        env.bind(cap.first, *v);
       }
     }
     Eval& ev = eval_for(cl, input);

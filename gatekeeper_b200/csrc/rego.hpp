@@ -144,6 +144,9 @@ class Eval {
   VP eval_first(const TP& t, Env& env);                 // first solution or nullptr (undefined)
   VP rule_value(const std::string& name);               // nullptr if undefined
   VP call_function(const std::string& name, const std::vector<VP>& args);   // nullptr if undefined
+  VP call_function(const std::vector<Rule>& rules, const std::vector<VP>& args);
+  // the definitions of the function a Call term names (resolved once per term), or nullptr for a builtin / non-function
+  const std::vector<Rule>* function_rules(const Term& t) const;
   bool unify_val(const TP& pat, const VP& val, Env& env, const EnvK& k);
   bool is_ground(const TP& t, const Env& env) const;
   const Module& module() const { return m_; }
@@ -160,7 +163,9 @@ class Eval {
   VP input_, data_;
   std::unordered_map<std::string, VP> cache_;   // rule extents; nullptr entries = undefined
   std::unordered_map<std::string, bool> cache_has_;
-  std::unordered_map<std::string, VP> fn_memo_;  // pure functions on scalar arguments (survives reset_input)
+  // pure functions on scalar arguments (survives reset_input): per function, argument tuple -> value
+  std::unordered_map<const void*, std::unordered_map<std::string, VP>> fn_memo_;
+  std::unordered_map<const void*, bool> pure_of_;
   int depth_ = 0;
 };
 

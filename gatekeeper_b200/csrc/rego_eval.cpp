@@ -579,25 +579,53 @@ VP Eval::rule_value(const std::string& name) {
   return val;
 }
 
+const std::vector<Rule>* Eval::function_rules(const Term& t) const {
+  if (__atomic_load_n(&t.is_rule_, __ATOMIC_ACQUIRE) < 0) {
+    auto rit = m_.rules.find(t.name);
+    const void* fr = rit != m_.rules.end() && rit->second[0].kind == Rule::Func ? &rit->second : nullptr;
+    __atomic_store_n(&t.rules_, fr, __ATOMIC_RELAXED);   // every thread stores the same pointer
+    __atomic_store_n(&t.is_rule_, (signed char)(fr ? 1 : 0), __ATOMIC_RELEASE);
+  }
+  return static_cast<const std::vector<Rule>*>(__atomic_load_n(&t.rules_, __ATOMIC_RELAXED));
+}
+
 VP Eval::call_function(const std::string& name, const std::vector<VP>& args) {
   auto rit = m_.rules.find(name);
   if (rit == m_.rules.end()) return nullptr;
+  return call_function(rit->second, args);
+}
+
+VP Eval::call_function(const std::vector<Rule>& rules, const std::vector<VP>& args) {
+  const std::string& name = rules[0].name;
   // pure function of scalar arguments: one evaluation per distinct argument tuple
   std::string memo_key;
+  std::unordered_map<std::string, VP>* memo_map = nullptr;
   {
-    auto pit = m_.pure_fn.find(name);
-    bool memo = pit != m_.pure_fn.end() && pit->second;
+    auto pit = pure_of_.find(&rules);
+    if (pit == pure_of_.end()) {
+      auto pf = m_.pure_fn.find(name);
+      pit = pure_of_.emplace(&rules, pf != m_.pure_fn.end() && pf->second).first;
+    }
+    bool memo = pit->second;
     for (auto& a : args) memo = memo && a && (uint8_t)a->t <= (uint8_t)VT::Str;
     if (memo) {
-      memo_key = name;
-      for (auto& a : args) {
-        memo_key.push_back('\x01');
-        memo_key.push_back((char)('0' + (int)a->t));
-        if (a->t == VT::Str) memo_key += a->s;
-        else if (a->t == VT::Num) memo_key += num_str(a->n);
+      const bool one_str = args.size() == 1 && args[0]->t == VT::Str;
+      memo_map = &fn_memo_[reinterpret_cast<const char*>(&rules) + (one_str ? 1 : 0)];   // (two key spaces per function)
+      if (one_str) {
+        // by far the commonest shape (a quantity / image string): the argument itself is the key
+        auto it = memo_map->find(args[0]->s);
+        if (it != memo_map->end()) return it->second;
+        memo_key = args[0]->s;
+      } else {
+        for (auto& a : args) {
+          memo_key.push_back('\x01');
+          memo_key.push_back((char)('0' + (int)a->t));
+          if (a->t == VT::Str) memo_key += a->s;
+          else if (a->t == VT::Num) memo_key += num_str(a->n);
+        }
+        auto it = memo_map->find(memo_key);
+        if (it != memo_map->end()) return it->second;
       }
-      auto it = fn_memo_.find(memo_key);
-      if (it != fn_memo_.end()) return it->second;
     }
   }
   if (++depth_ > 64) {
@@ -605,7 +633,7 @@ VP Eval::call_function(const std::string& name, const std::vector<VP>& args) {
     throw RegoError{"rego_recursion_error: function " + name};
   }
   VP out;
-  for (auto& r : rit->second) {
+  for (auto& r : rules) {
     if (r.kind != Rule::Func || r.args.size() != args.size()) continue;
     Env env;
     // unify formals with actuals
@@ -620,9 +648,9 @@ VP Eval::call_function(const std::string& name, const std::vector<VP>& args) {
     if (out) break;
   }
   --depth_;
-  if (!memo_key.empty()) {
-    if (fn_memo_.size() > (1u << 16)) fn_memo_.clear();
-    fn_memo_.emplace(std::move(memo_key), out);
+  if (memo_map) {
+    if (memo_map->size() > (1u << 16)) memo_map->clear();
+    memo_map->emplace(std::move(memo_key), out);
   }
   return out;
 }
@@ -908,13 +936,7 @@ bool Eval::walk(const VP& cur, const std::vector<TP>& path, size_t i, Env& env, 
 }
 
 bool Eval::eval_call(const Term& t, Env& env, const ValK& k) {
-  if (__atomic_load_n(&t.is_rule_, __ATOMIC_ACQUIRE) < 0) {
-    auto rit = m_.rules.find(t.name);
-    const void* fr = rit != m_.rules.end() && rit->second[0].kind == Rule::Func ? &rit->second : nullptr;
-    __atomic_store_n(&t.rules_, fr, __ATOMIC_RELAXED);   // every thread stores the same pointer
-    __atomic_store_n(&t.is_rule_, (signed char)(fr ? 1 : 0), __ATOMIC_RELEASE);
-  }
-  const auto* frules = static_cast<const std::vector<Rule>*>(__atomic_load_n(&t.rules_, __ATOMIC_RELAXED));
+  const auto* frules = function_rules(t);
   bool user = frules != nullptr;
   size_t nargs = t.args.size();
   const TP* out_pat = nullptr;
@@ -927,7 +949,7 @@ bool Eval::eval_call(const Term& t, Env& env, const ValK& k) {
   auto rec = [&](auto&& self, size_t i) -> bool {
     if (i == nargs) {
       VP v;
-      if (user) v = call_function(t.name, acc);
+      if (user) v = call_function(*frules, acc);
       else {
         bool known = true;
         v = call_builtin(t.name, acc, &known);
