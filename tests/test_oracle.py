@@ -127,6 +127,38 @@ def test_verify_suite_fooisbar():
     assert run("constraint_with_scopedEA_without_gator_ep.yaml", "deny_foo.yaml") == []
 
 
+def test_template_libs_container_limits():
+    """test/bats/test.bats:268-279 with test/bats/tests/templates/k8scontainterlimits_template.yaml (`libs`: package
+    lib.helpers imported as data.lib.helpers): bad/opa_no_limits.yaml is denied, good/opa.yaml is admitted; plus the helper
+    functions' arithmetic on hand-checked quantities."""
+    g = golden("libs_template.json")
+    tmpl = k8s.template_from_yaml_obj(g["template"])
+    assert len(tmpl) == 3 and tmpl[2][0].lstrip().startswith("package lib.helpers")
+    c = k8s.Client()
+    c.add_template(*tmpl)
+    c.add_constraint(g["constraint"])      # cpu 200m, memory 1Gi
+    assert [r["msg"] for r in c.review(k8s.Review(obj=g["denied"]), k8s.WEBHOOK_EP)] == ["container <opa> has no resource limits"]
+    assert c.review(k8s.Review(obj=g["admitted"]), k8s.WEBHOOK_EP) == []
+
+    def msgs(cpu, mem):
+        pod = {"apiVersion": "v1", "kind": "Pod", "metadata": {"name": "p", "namespace": "gatekeeper-test-playground"},
+               "spec": {"containers": [{"name": "c", "resources": {"limits": {"cpu": cpu, "memory": mem}}}]}}
+        return sorted(r["msg"] for r in c.review(k8s.Review(obj=pod), k8s.WEBHOOK_EP))
+
+    assert msgs("200m", "1Gi") == []
+    assert msgs("201m", "1Gi") == ["container <c> cpu limit <201m> is higher than the maximum allowed of <200m>"]
+    assert msgs("0.1", "1Gi") == ["container <c> cpu limit <0.1> could not be parsed"]          # canonify_cpu: digits only, or <n>m
+    assert msgs(1, "1024Mi") == ["container <c> cpu limit <1> is higher than the maximum allowed of <200m>"]
+    assert msgs("100m", "1025Mi") == ["container <c> memory limit <1025Mi> is higher than the maximum allowed of <1Gi>"]
+    assert msgs("100m", "1G") == []                                                              # 10^12 < 2^30 * 1000
+    assert msgs("100m", "") == ["container <c> has no memory limit", "container <c> memory limit <> could not be parsed"]
+    # a lib must live under `package lib...`; an import must name a lib of the template
+    with pytest.raises(rego.RegoError, match="rego_compile_error"):
+        k8s.Client().add_template("X", tmpl[1], ["package helpers\nf(x) = x { true }\n"])
+    with pytest.raises(rego.RegoError, match="rego_compile_error"):
+        k8s.Client().add_template("X", tmpl[1], [])
+
+
 def test_fixture_templates():
     """pkg/gator/test/test_test.go:85-452: "never validate" x N, first/second message, compile error."""
     t = golden("templates.json")
