@@ -125,7 +125,7 @@ def _oracle_chunk(rng):
     return hi - lo, nv
 
 
-def cpu_baseline_single(sample=300):
+def cpu_baseline_single(sample=2000):
     _oracle_init()
     t0 = time.perf_counter()
     n, nv = _oracle_chunk((0, sample))
@@ -351,7 +351,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--objects", type=int, default=1_000_000, help="objects per GPU (weak scaling)")
     ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--cpu-sample", type=int, default=300)
+    ap.add_argument("--cpu-sample", type=int, default=2000, help="Pods reviewed by the single-core oracle leg (about 11 s of CPU)")
     ap.add_argument("--msg-sample", type=int, default=50_000, help="objects of the sample whose messages are all rendered (e2e.with_messages)")
     ap.add_argument("--ref-objects-per-core", type=int, default=48)
     args = ap.parse_args()

@@ -927,6 +927,166 @@ def _raise_undef():
     raise Undefined
 
 
+# ---- further OPA builtins the gatekeeper policy library leans on (collections, objects, rounding); semantics as documented
+# in OPA's policy reference (v1.x); type mismatches are undefined (non-strict builtin errors)
+def _int_arg(x):
+    x = _num(x)
+    if isinstance(x, float) or (isinstance(x, Fraction) and x.denominator != 1):
+        raise Undefined
+    return int(x)
+
+
+def _sort(xs):
+    return tuple(sorted_values(_bool_coll(xs)))
+
+
+def _obj(x):
+    if not isinstance(x, RObj):
+        raise Undefined
+    return x
+
+
+def _key_set(ks):
+    if isinstance(ks, RObj):
+        return list(ks.keys())
+    return list(_bool_coll(ks))
+
+
+def _has_key(keys, k):
+    return any(equal(k, x) for x in keys)
+
+
+def _object_union(a, b):
+    a, b = _obj(a), _obj(b)
+    out = dict(a)
+    for k, v in b.items():
+        if k in a and isinstance(a[k], RObj) and isinstance(v, RObj):
+            out[k] = _object_union(a[k], v)
+        else:
+            out[k] = v
+    return RObj(out)
+
+
+def _numbers_range(a, b):
+    a, b = _int_arg(a), _int_arg(b)
+    return tuple(range(a, b + 1)) if a <= b else tuple(range(a, b - 1, -1))
+
+
+def _array_slice(arr, lo, hi):
+    if not isinstance(arr, tuple):
+        raise Undefined
+    lo, hi = _int_arg(lo), _int_arg(hi)
+    lo = max(lo, 0)
+    hi = min(hi, len(arr))
+    return arr[lo:hi] if lo < hi else ()
+
+
+def _round(x):
+    x = _num(x)
+    if isinstance(x, int):
+        return x
+    f = Fraction(x)
+    import math
+    return math.floor(f + Fraction(1, 2)) if f >= 0 else -math.floor(-f + Fraction(1, 2))      # half away from zero (Go math.Round)
+
+
+def _floor(x):
+    import math
+    x = _num(x)
+    return x if isinstance(x, int) else math.floor(Fraction(x))
+
+
+def _ceil(x):
+    import math
+    x = _num(x)
+    return x if isinstance(x, int) else math.ceil(Fraction(x))
+
+
+def _format_int(x, base):
+    base = _int_arg(base)
+    if base not in (2, 8, 10, 16):
+        raise Undefined
+    n = _floor(x)
+    digits = "0123456789abcdef"
+    neg, n = n < 0, abs(n)
+    out = ""
+    while True:
+        out = digits[n % base] + out
+        n //= base
+        if n == 0:
+            break
+    return ("-" if neg else "") + out
+
+
+def _set_of_sets(xs):
+    if not isinstance(xs, frozenset) or not all(isinstance(x, frozenset) for x in xs):
+        raise Undefined
+    return xs
+
+
+def _union(xs):
+    out = frozenset()
+    for x in _set_of_sets(xs):
+        out |= x
+    return out
+
+
+def _intersection(xs):
+    xs = list(_set_of_sets(xs))
+    if not xs:
+        return frozenset()
+    out = xs[0]
+    for x in xs[1:]:
+        out &= x
+    return out
+
+
+def _product(xs):
+    acc = Fraction(1)
+    for x in _bool_coll(xs):
+        acc *= Fraction(_num(x))
+    return _norm(acc)
+
+
+def _type_name(x):
+    return ["null", "boolean", "number", "string", "array", "object", "set"][type_rank(x)]
+
+
+def _b64(x, enc):
+    import base64
+    import binascii
+    x = _str(x)
+    if enc:
+        return base64.b64encode(x.encode()).decode()
+    try:
+        return base64.b64decode(x.encode(), validate=True).decode()
+    except (binascii.Error, UnicodeDecodeError):
+        raise Undefined
+
+
+BUILTINS.update({
+    "sort": _sort,
+    "object.keys": lambda o: frozenset(_obj(o).keys()),
+    "object.union": _object_union,
+    "object.remove": lambda o, ks: (lambda keys: RObj({k: v for k, v in _obj(o).items() if not _has_key(keys, k)}))(_key_set(ks)),
+    "object.filter": lambda o, ks: (lambda keys: RObj({k: v for k, v in _obj(o).items() if _has_key(keys, k)}))(_key_set(ks)),
+    "numbers.range": _numbers_range,
+    "array.slice": _array_slice,
+    "array.reverse": lambda a: tuple(reversed(a)) if isinstance(a, tuple) else _raise_undef(),
+    "strings.reverse": lambda x: _str(x)[::-1],
+    "round": _round,
+    "floor": _floor,
+    "ceil": _ceil,
+    "format_int": _format_int,
+    "union": _union,
+    "intersection": _intersection,
+    "product": _product,
+    "type_name": _type_name,
+    "base64.encode": lambda x: _b64(x, True),
+    "base64.decode": lambda x: _b64(x, False),
+})
+
+
 # --------------------------------------------------------------------------------------------------
 # evaluator
 
