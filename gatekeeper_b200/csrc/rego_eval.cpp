@@ -3,6 +3,7 @@
 // failure, partial-set extents, multi-definition functions as OR, type errors => undefined.
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <regex>
 #include <unordered_map>
 
@@ -300,6 +301,123 @@ bool is_builtin(const std::string& name) {
   return known;
 }
 
+// ---- collection / object / rounding builtins of OPA's policy reference (v1.x) used by the gatekeeper policy library
+static bool int_arg(const VP& v, int64_t* out) { return v->t == VT::Num && num_fits_i64(v->n, out); }
+static VP object_union(const VP& a, const VP& b) {
+  std::vector<std::pair<VP, VP>> kv(a->kv.begin(), a->kv.end());
+  for (auto& e : b->kv) {
+    bool merged = false;
+    for (auto& x : kv)
+      if (v_eq(x.first, e.first)) {
+        x.second = (x.second->t == VT::Obj && e.second->t == VT::Obj) ? object_union(x.second, e.second) : e.second;
+        merged = true;
+        break;
+      }
+    if (!merged) kv.emplace_back(e.first, e.second);
+  }
+  return v_obj(std::move(kv));
+}
+static bool key_list(const VP& ks, std::vector<VP>& out) {
+  if (ks->t == VT::Obj) {
+    for (auto& e : ks->kv) out.push_back(e.first);
+    return true;
+  }
+  if (!is_coll(ks)) return false;
+  out = ks->items;
+  return true;
+}
+static VP object_pick(const VP& o, const VP& ks, bool keep) {
+  std::vector<VP> keys;
+  if (o->t != VT::Obj || !key_list(ks, keys)) return nullptr;
+  std::vector<std::pair<VP, VP>> kv;
+  for (auto& e : o->kv) {
+    bool has = false;
+    for (auto& k : keys) has = has || v_eq(k, e.first);
+    if (has == keep) kv.emplace_back(e.first, e.second);
+  }
+  return v_obj(std::move(kv));
+}
+static std::string utf8_reverse(const std::string& s) {
+  std::string out;
+  out.reserve(s.size());
+  size_t i = s.size();
+  while (i > 0) {
+    size_t j = i - 1;
+    while (j > 0 && ((unsigned char)s[j] & 0xC0) == 0x80) --j;
+    out.append(s, j, i - j);
+    i = j;
+  }
+  return out;
+}
+static VP round_like(const VP& x, int mode) {   // 0 round (half away from zero, Go math.Round), 1 floor, 2 ceil
+  if (!is_num(x)) return nullptr;
+  if (x->n.is_int) return x;
+  const double d = x->n.d;
+  return v_num(Num::of_double(mode == 0 ? std::round(d) : mode == 1 ? std::floor(d) : std::ceil(d)));
+}
+static VP format_int(const VP& x, const VP& base) {
+  int64_t b;
+  if (!is_num(x) || !int_arg(base, &b) || (b != 2 && b != 8 && b != 10 && b != 16)) return nullptr;
+  __int128 n;
+  if (x->n.is_int) n = x->n.i;
+  else {
+    const double f = std::floor(x->n.d);
+    if (!(std::fabs(f) < 1e30)) return nullptr;
+    n = (__int128)f;
+  }
+  const bool neg = n < 0;
+  unsigned __int128 u = neg ? (unsigned __int128)(-n) : (unsigned __int128)n;
+  std::string out;
+  do {
+    out.insert(out.begin(), "0123456789abcdef"[(int)(u % (unsigned)b)]);
+    u /= (unsigned)b;
+  } while (u != 0);
+  return v_str((neg ? "-" : "") + out);
+}
+static const char kB64[] = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789+/";
+static std::string b64_encode(const std::string& in) {
+  std::string out;
+  size_t i = 0;
+  for (; i + 2 < in.size(); i += 3) {
+    const uint32_t v = ((unsigned char)in[i] << 16) | ((unsigned char)in[i + 1] << 8) | (unsigned char)in[i + 2];
+    out += kB64[v >> 18], out += kB64[(v >> 12) & 63], out += kB64[(v >> 6) & 63], out += kB64[v & 63];
+  }
+  if (i + 1 == in.size()) {
+    const uint32_t v = (unsigned char)in[i] << 16;
+    out += kB64[v >> 18], out += kB64[(v >> 12) & 63], out += "==";
+  } else if (i + 2 == in.size()) {
+    const uint32_t v = ((unsigned char)in[i] << 16) | ((unsigned char)in[i + 1] << 8);
+    out += kB64[v >> 18], out += kB64[(v >> 12) & 63], out += kB64[(v >> 6) & 63], out += '=';
+  }
+  return out;
+}
+static bool b64_decode(const std::string& in, std::string& out) {   // StdEncoding: padded, strict alphabet
+  if (in.size() % 4) return false;
+  auto val = [](char c) -> int {
+    const char* p = c ? strchr(kB64, c) : nullptr;
+    return p ? (int)(p - kB64) : -1;
+  };
+  for (size_t i = 0; i < in.size(); i += 4) {
+    int v[4], pad = 0;
+    for (int k = 0; k < 4; ++k) {
+      if (in[i + k] == '=') {
+        if (i + 4 != in.size() || k < 2) return false;
+        v[k] = 0;
+        ++pad;
+      } else {
+        if (pad) return false;
+        v[k] = val(in[i + k]);
+        if (v[k] < 0) return false;
+      }
+    }
+    const uint32_t w = (v[0] << 18) | (v[1] << 12) | (v[2] << 6) | v[3];
+    out += (char)(w >> 16);
+    if (pad < 2) out += (char)((w >> 8) & 255);
+    if (pad < 1) out += (char)(w & 255);
+  }
+  return true;
+}
+
 static constexpr uint64_t name_hash(const char* s) {
   uint64_t h = 1469598103934665603ull;
   for (; *s; ++s) h = (h ^ (unsigned char)*s) * 1099511628211ull;
@@ -450,6 +568,67 @@ VP call_builtin(const std::string& n, const std::vector<VP>& a, bool* known) {
     if (a[1]->t == VT::Obj) { for (auto& e : a[1]->kv) if (v_eq(e.second, a[0])) return v_bool(true); return v_bool(false); }
     if (is_coll(a[1])) { for (auto& x : a[1]->items) if (v_eq(x, a[0])) return v_bool(true); return v_bool(false); }
     return v_bool(false);
+  E
+  B("sort", 1)
+    if (!is_coll(a[0])) return nullptr;
+    { auto v = a[0]->items; std::stable_sort(v.begin(), v.end(), [](const VP& x, const VP& y) { return v_cmp(x, y) < 0; }); return v_arr(std::move(v)); }
+  E
+  B("object.keys", 1)
+    if (a[0]->t != VT::Obj) return nullptr;
+    { std::vector<VP> ks; for (auto& e : a[0]->kv) ks.push_back(e.first); return v_set(std::move(ks)); }
+  E
+  B("object.union", 2) if (a[0]->t != VT::Obj || a[1]->t != VT::Obj) return nullptr; return object_union(a[0], a[1]); E
+  B("object.remove", 2) return object_pick(a[0], a[1], false); E
+  B("object.filter", 2) return object_pick(a[0], a[1], true); E
+  B("numbers.range", 2)
+    {
+      int64_t lo, hi;
+      if (!int_arg(a[0], &lo) || !int_arg(a[1], &hi)) return nullptr;
+      if ((lo < hi ? hi - lo : lo - hi) > 1000000) return nullptr;
+      std::vector<VP> v;
+      if (lo <= hi) for (int64_t i = lo; i <= hi; ++i) v.push_back(v_int(i));
+      else for (int64_t i = lo; i >= hi; --i) v.push_back(v_int(i));
+      return v_arr(std::move(v));
+    }
+  E
+  B("array.slice", 3)
+    {
+      int64_t lo, hi;
+      if (a[0]->t != VT::Arr || !int_arg(a[1], &lo) || !int_arg(a[2], &hi)) return nullptr;
+      lo = std::max<int64_t>(lo, 0);
+      hi = std::min<int64_t>(hi, (int64_t)a[0]->items.size());
+      if (lo >= hi) return v_arr({});
+      return v_arr(std::vector<VP>(a[0]->items.begin() + lo, a[0]->items.begin() + hi));
+    }
+  E
+  B("array.reverse", 1) if (a[0]->t != VT::Arr) return nullptr; return v_arr(std::vector<VP>(a[0]->items.rbegin(), a[0]->items.rend())); E
+  B("strings.reverse", 1) if (!is_str(a[0])) return nullptr; return v_str(utf8_reverse(a[0]->s)); E
+  B("round", 1) return round_like(a[0], 0); E
+  B("floor", 1) return round_like(a[0], 1); E
+  B("ceil", 1) return round_like(a[0], 2); E
+  B("format_int", 2) return format_int(a[0], a[1]); E
+  if (IS("union") || IS("intersection")) {
+    if (!need(1) || a[0]->t != VT::Set) return nullptr;
+    for (auto& x : a[0]->items) if (x->t != VT::Set) return nullptr;
+    if (a[0]->items.empty()) return v_set({});
+    VP acc = a[0]->items[0];
+    for (size_t i = 1; i < a[0]->items.size(); ++i) acc = arith(n == "union" ? "or" : "and", acc, a[0]->items[i]);
+    return acc;
+  }
+  B("product", 1)
+    if (!is_coll(a[0])) return nullptr;
+    { VP acc = v_int(1); for (auto& x : a[0]->items) { acc = arith("mul", acc, x); if (!acc) return nullptr; } return acc; }
+  E
+  B("type_name", 1)
+    {
+      static const char* names[] = {"", "null", "boolean", "boolean", "number", "string", "array", "object", "set"};
+      return v_str(names[(int)a[0]->t]);
+    }
+  E
+  B("base64.encode", 1) if (!is_str(a[0])) return nullptr; return v_str(b64_encode(a[0]->s)); E
+  B("base64.decode", 1)
+    if (!is_str(a[0])) return nullptr;
+    { std::string out; if (!b64_decode(a[0]->s, out)) return nullptr; return v_str(out); }
   E
   if (IS("print") || IS("trace")) return v_bool(true);
 #undef B

@@ -600,6 +600,55 @@ def case_template_libs(lib, n=300, seed=99):
     return len(want)
 
 
+def case_more_builtins(lib):
+    """Collection / object / rounding builtins (sort, object.keys|union|remove|filter, numbers.range, array.slice|reverse,
+    strings.reverse, round|floor|ceil, format_int, union, intersection, product, type_name, base64.*) on object values (host
+    feature columns), on parameters (folded at AddConstraint) and compared across the two (device atoms)."""
+    src = '''package bx
+violation[{"msg": msg}] {
+  o := input.review.object
+  ks := sort(object.keys(o.metadata.labels))
+  msg := sprintf("%v|%v|%v|%v|%v|%v|%v|%v|%v|%v|%v|%v|%v|%v", [ks, object.union(o.a, o.b), object.remove(o.a, ["x"]), object.filter(o.a, {"x"}),
+     numbers.range(o.lo, o.hi), array.slice(o.arr, 1, 3), array.reverse(o.arr), strings.reverse(o.s), round(o.f), floor(o.f), ceil(o.f),
+     format_int(o.f, 16), type_name(o.arr), base64.decode(base64.encode(o.s))])
+}
+violation[{"msg": msg}] {
+  o := input.review.object
+  u := union({{x | x := o.arr[_]}, {1, 99}})
+  i := intersection({{x | x := o.arr[_]}, {1, 3, 99}})
+  msg := sprintf("sets %v %v %v", [u, i, product(o.arr)])
+}
+violation[{"msg": msg}] {
+  allowed := sort(input.parameters.names)
+  first := allowed[0]
+  input.review.object.metadata.name == first
+  msg := sprintf("first of %v", [allowed])
+}
+violation[{"msg": msg}] {
+  floor(input.review.object.f) > count(numbers.range(1, input.parameters.n))
+  msg := sprintf("f above %v", [format_int(input.parameters.n, 2)])
+}
+'''
+    objs = [{"apiVersion": "v1", "kind": "X", "metadata": {"name": "o%d" % i, "labels": {"b": "1", "a": "2", "c": "3"}},
+             "a": {"x": 1, "y": {"p": 1, "q": 2}}, "b": {"y": {"q": 3, "r": 4}, "z": 5}, "lo": lo, "hi": hi, "arr": [3, 1, 2, 7], "s": s, "f": f}
+            for i, (lo, hi, s, f) in enumerate([(1, 4, "h\u00e9llo", 2.5), (4, 1, "", -2.5), (0, 0, "abc", 3.49), (2, 2, "x", -0.5),
+                                                (1, 3, "\u65e5\u672c\u8a9e", 1000.5), (1, 2, "q", 7)])]
+    cons = [W._constraint("BX", "bx-%d" % i, params=p) for i, p in enumerate([{"names": ["o3", "o1", "o2"], "n": 3}, {"names": ["zz", "o0"], "n": 2.0},
+                                                                                {"names": [], "n": 0}])]
+    orc, drv, skipped = make_pair([("BX", src)], cons, lib_path=lib)
+    assert not skipped
+    revs = [D.Review(object=o) for o in objs]
+    resp = drv.ReviewBatch(revs, k8s.AUDIT_EP)
+    assert not any(resp.object_errors or [])
+    want = oracle_results(orc, revs, k8s.AUDIT_EP)
+    assert len(want) >= 3 * 2 * len(objs)
+    msgs = {w[2] for w in want}
+    assert '["a", "b", "c"]|{"x": 1, "y": {"p": 1, "q": 3, "r": 4}, "z": 5}|{"y": {"p": 1, "q": 2}}|{"x": 1}|[1, 2, 3, 4]|[1, 2]|[7, 2, 1, 3]|oll\u00e9h|3|2|3|2|array|h\u00e9llo' in msgs
+    assert 'first of ["o1", "o2", "o3"]' in msgs and "f above 11" in msgs
+    assert_same(want, engine_results(resp))
+    return len(want)
+
+
 # ------------------------------------------------------------------------------------------ pkg/target vectors
 DENY_ALL = 'package denyall\nviolation[{"msg": msg}] {\n  msg := "denyall constraint installed"\n}\n'   # target_integration_test.go:37-43
 

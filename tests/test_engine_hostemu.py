@@ -119,6 +119,10 @@ def test_template_libs():
     assert P.case_template_libs(HOSTEMU) > 10
 
 
+def test_more_builtins():
+    assert P.case_more_builtins(HOSTEMU) > 30
+
+
 def test_target_enforcement_vectors():
     P.case_target_enforcement(HOSTEMU)
 

@@ -112,6 +112,11 @@ def test_template_libs():
     assert P.case_template_libs(LIB, n=600) > 10
 
 
+def test_more_builtins():
+    """sort / object.* / numbers.range / rounding / set builtins as feature columns, folded parameters and device atoms."""
+    assert P.case_more_builtins(LIB) > 30
+
+
 def test_target_enforcement_vectors():
     """pkg/target/target_integration_test.go: 26 scenarios x 3 request shapes, allowed <=> no results."""
     P.case_target_enforcement(LIB)
