@@ -92,6 +92,7 @@ void AuditRun::add_batch(Engine& eng, const Compiled& c, const std::vector<ObjIn
     part.msg_size = msg_size;
     std::vector<Engine::Flagged> flagged;
     std::vector<Violation> vio;
+    Engine::MaterializeCtx mctx;
     try {
       for (;;) {
         size_t lo = next.fetch_add(256), hi = std::min(n, lo + 256);
@@ -118,7 +119,7 @@ void AuditRun::add_batch(Engine& eng, const Compiled& c, const std::vector<ObjIn
           if (flagged.empty()) continue;
           vio.clear();
           VP obj;
-          eng.materialize_object(c, objs[o], (uint32_t)o, flagged, ep, vio, &obj);
+          eng.materialize_object(c, objs[o], (uint32_t)o, flagged, ep, vio, &obj, &mctx);
           std::string g, v, k, ns, name;
           if (obj) {
             split_gv(obj, g, v, k);

@@ -151,6 +151,7 @@ void eval_batch(gk_engine* e, gk_batch* b, const char* ep_c, uint32_t flags, gk_
     std::vector<std::string> errs(T);
     auto work = [&](size_t t) {
       std::vector<Engine::Flagged> flagged;
+      Engine::MaterializeCtx mctx;
       try {
         for (uint32_t o = (uint32_t)(n * t / T); o < (uint32_t)(n * (t + 1) / T); ++o) {
           flagged.clear();
@@ -171,7 +172,7 @@ void eval_batch(gk_engine* e, gk_batch* b, const char* ep_c, uint32_t flags, gk_
               flagged.push_back({cix, is_err, code});
             }
           }
-          if (!flagged.empty()) e->eng->materialize_object(c, to_in(b->objs[o]), o, flagged, ep, part[t]);
+          if (!flagged.empty()) e->eng->materialize_object(c, to_in(b->objs[o]), o, flagged, ep, part[t], nullptr, &mctx);
         }
       } catch (RegoError& x) {
         errs[t] = x.msg;

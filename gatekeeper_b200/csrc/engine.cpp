@@ -469,6 +469,7 @@ void Engine::compile_locked() {
   std::vector<FP> all;
   for (size_t i : perm) {
     out->order.push_back(live[i]);
+    out->mods.push_back(templates_.at(live[i]->kind).mod);
     all.push_back(live[i]->formula);
     out->cons_match.push_back(mid_of[i]);
   }
@@ -1533,17 +1534,20 @@ void Engine::materialize(const Compiled& c, const ObjIn& in, uint32_t obj_ix, ui
 }
 
 void Engine::materialize_object(const Compiled& c, const ObjIn& in, uint32_t obj_ix, const std::vector<Flagged>& flagged,
-                                const std::string& ep, std::vector<Violation>& out, VP* obj_out) {
+                                const std::string& ep, std::vector<Violation>& out, VP* obj_out, MaterializeCtx* ctx) {
+  MaterializeCtx local;
+  if (!ctx) ctx = &local;
+  ++ctx->epoch;
   std::string err;
   VP obj, old;
   VP doc = review_doc(in, &obj, &old, nullptr, &err);
   if (obj_out) *obj_out = obj ? obj : old;
   struct Rendered {
-    bool done = false;
     std::vector<std::pair<std::string, std::string>> items;   // (msg, details JSON)
   };
-  std::map<std::string, Rendered> memo;
-  std::map<const Module*, std::pair<std::shared_ptr<Module>, std::unique_ptr<Eval>>> evals;   // (the module is pinned while its evaluator lives)
+  // constraints of one kind with equal parameters (e.g. the same policy scoped to different namespaces) render the same
+  // messages for this object: evaluate once
+  std::vector<std::pair<const Constraint*, Rendered>> memo;
   for (auto& f : flagged) {
     if (f.is_err) {
       autoreject(c, in, obj_ix, f.cix, f.err_code, ep, out);
@@ -1551,42 +1555,38 @@ void Engine::materialize_object(const Compiled& c, const ObjIn& in, uint32_t obj
     }
     const Constraint& con = *c.order[f.cix];
     if (!doc) throw RegoError{"materialize: " + err};
-    std::shared_ptr<Module> mod;
-    {
-      std::shared_lock<std::shared_mutex> l(mu_);
-      auto it = templates_.find(con.kind);
-      if (it == templates_.end()) throw RegoError{"materialize: template gone"};
-      mod = it->second.mod;
-    }
+    const Module& mod = *c.mods[f.cix];   // (pinned by the snapshot: no engine lock, no shared reference count per pair)
     size_t before = out.size();
-    std::vector<std::string> sc = con.action == "scoped" ? scoped_actions_for(con, ep) : std::vector<std::string>();
-    const std::string sc_json = scoped_json(sc);
-    // constraints of one kind with equal parameters (e.g. the same policy scoped to different namespaces) render the
-    // same messages for this object: evaluate once
-    auto& rendered = memo[con.kind + '\x01' + con.params_key];
-    if (!rendered.done) {
-      rendered.done = true;
-      // one evaluator per template for this object: switching constraints keeps the extents of parameter-free helper
-      // rules (input_containers, ...)
-      VP inp = v_obj({{v_str("review"), doc}, {v_str("parameters"), con.params}});
-      auto& slot = evals[mod.get()];
-      if (!slot.second) {
-        slot.first = mod;
-        slot.second.reset(new Eval(*mod, inp));
-      } else {
-        slot.second->reset_parameters(inp);
-      }
-      Eval& ev = *slot.second;
+    const std::string sc_json = scoped_json(con.action == "scoped" ? scoped_actions_for(con, ep) : std::vector<std::string>());
+    const Rendered* rendered = nullptr;
+    for (auto& m : memo)
+      if (m.first->kind == con.kind && m.first->params_key == con.params_key) rendered = &m.second;
+    if (!rendered) {
+      memo.emplace_back(&con, Rendered());
+      Rendered& r = memo.back().second;
+      auto pit = ctx->params.find(&con);
+      if (pit == ctx->params.end()) pit = ctx->params.emplace(&con, v_deep_copy(con.params)).first;
+      VP inp = v_obj({{v_str("review"), doc}, {v_str("parameters"), pit->second}});
+      // one evaluator per template and worker; within one object, switching constraints keeps the extents of
+      // parameter-free helper rules (input_containers, ...)
+      auto& slot = ctx->evals[&mod];
+      uint64_t& seen = ctx->eval_epoch[&mod];
+      if (!slot) slot.reset(new Eval(mod, inp));
+      else if (seen == ctx->epoch) slot->reset_parameters(inp);
+      else slot->reset_input(inp);
+      seen = ctx->epoch;
+      Eval& ev = *slot;
       VP vs = ev.rule_value("violation");
       if (vs)
         for (auto& v : vs->items) {
           VP msg = obj_get(v, "msg");
           if (v->t != VT::Obj || !msg || msg->t != VT::Str) throw RegoError{"rego_type_error: violation element must be {\"msg\": string, ...}"};
           VP d = obj_get(v, "details");
-          rendered.items.emplace_back(msg->s, d ? json_str(d) : "");
+          r.items.emplace_back(msg->s, d ? json_str(d) : "");
         }
+      rendered = &r;
     }
-    for (auto& it : rendered.items) {
+    for (auto& it : rendered->items) {
       Violation x;
       x.object = obj_ix;
       x.constraint = f.cix;
@@ -1600,6 +1600,9 @@ void Engine::materialize_object(const Compiled& c, const ObjIn& in, uint32_t obj
       throw RegoError{"internal: GPU flagged (" + con.kind + "/" + con.name + ", object " + std::to_string(obj_ix) +
                       ") but the message renderer finds no violation -- lowering bug"};
   }
+  // the evaluators keep the last input alive until their next reset: drop the document now (it is per object)
+  for (auto& e : ctx->evals)
+    if (ctx->eval_epoch[e.first] == ctx->epoch) e.second->reset_input(nullptr);
 }
 
 void Engine::autoreject(const Compiled& c, const ObjIn& in, uint32_t obj_ix, uint32_t cix, uint32_t code, const std::string& ep,

@@ -96,6 +96,7 @@ struct Compiled {
   std::vector<GkMatch> match;                  // DISTINCT match blocks
   std::vector<uint32_t> cons_match;            // per constraint: match block id
   std::vector<const Constraint*> order;        // constraint index -> constraint (grouped by match block)
+  std::vector<std::shared_ptr<Module>> mods;   // constraint index -> its template's module (pinned by this snapshot)
   size_t n_nodes = 0, n_atoms = 0, n_gates = 0, n_phases = 0;
 };
 
@@ -153,8 +154,17 @@ class Engine {
     bool is_err;
     uint32_t err_code;
   };
+  // Per-worker state of message rendering over ONE Compiled snapshot: evaluators are kept across objects, and every
+  // constraint's parameters are a thread-private deep copy (walking a shared document copies node references, and
+  // reference counts shared by all workers bounce between their caches).
+  struct MaterializeCtx {
+    std::unordered_map<const Module*, std::unique_ptr<Eval>> evals;
+    std::unordered_map<const Module*, uint64_t> eval_epoch;
+    std::unordered_map<const Constraint*, VP> params;
+    uint64_t epoch = 0;   // one per object
+  };
   void materialize_object(const Compiled& c, const ObjIn& obj, uint32_t obj_ix, const std::vector<Flagged>& flagged,
-                          const std::string& ep, std::vector<Violation>& out, VP* obj_out = nullptr);
+                          const std::string& ep, std::vector<Violation>& out, VP* obj_out = nullptr, MaterializeCtx* ctx = nullptr);
   // which constraints apply at an enforcement point + their effective actions
   void active_mask(const Compiled& c, const std::string& ep, std::vector<uint32_t>& active) const;
   // render messages for one flagged pair (never decides a violation; throws if the GPU bit is unjustified)

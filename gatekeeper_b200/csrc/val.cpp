@@ -248,6 +248,30 @@ int v_cmp(const VP& a, const VP& b) {
   }
 }
 
+VP v_deep_copy(const VP& v) {
+  if (!v) return v;
+  switch (v->t) {
+    case VT::Null: return v_null();
+    case VT::True: return v_bool(true);
+    case VT::False: return v_bool(false);
+    case VT::Num: return v_num(v->n);
+    case VT::Str: return v_str(v->s);
+    case VT::Arr:
+    case VT::Set: {
+      auto n = new_node();
+      n->t = v->t;
+      for (auto& x : v->items) n->items.push_back(v_deep_copy(x));
+      return n;
+    }
+    default: {
+      auto n = new_node();
+      n->t = VT::Obj;
+      for (auto& e : v->kv) n->kv.emplace_back(v_deep_copy(e.first), v_deep_copy(e.second));
+      return n;
+    }
+  }
+}
+
 VP obj_get(const VP& o, const VP& key) {
   if (!o || o->t != VT::Obj) return nullptr;
   size_t lo = 0, hi = o->kv.size();

@@ -52,6 +52,7 @@ VP v_arr(std::vector<VP> items);
 VP v_set(std::vector<VP> items);             // sorts + dedups
 VP v_obj(std::vector<std::pair<VP, VP>> kv); // sorts; later duplicates win
 
+VP v_deep_copy(const VP& v);                 // a copy that shares no node with `v` (thread-private documents)
 int v_cmp(const VP& a, const VP& b);         // total order; both non-null
 inline bool v_eq(const VP& a, const VP& b) { return v_cmp(a, b) == 0; }
 int type_rank(VT t);
