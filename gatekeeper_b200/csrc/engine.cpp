@@ -376,7 +376,7 @@ void Engine::add_constraint(const std::string& json) {
   // lower now so that unsupported constructs are an AddConstraint error (like a Rego compile error)
   {
     Schema tmp;
-    (void)lower_violation(tit->second.mod, c->params, tmp);
+    check_netlist_shape(lower_violation(tit->second.mod, c->params, tmp), tmp);
   }
   for (auto& e : constraints_)
     if (e->kind == c->kind && e->name == c->name) {

@@ -1,5 +1,6 @@
 // Partial evaluation of a template's `violation` rule against concrete parameters -> formula tree, and
 // formula tree -> jump-threaded instructions.  See lower.hpp for the scheme.
+#include <cmath>
 #include "lower.hpp"
 
 #include <algorithm>
@@ -193,6 +194,8 @@ class Lowerer {
     vid_cur_ = const_cast<Module&>(m_).intern("$cur");
     vid_key_ = const_cast<Module&>(m_).intern("$key");
   }
+
+  bool product_mode = false;
 
   FP run() {
     auto it = m_.rules.find("violation");
@@ -469,6 +472,32 @@ class Lowerer {
     return c;
   }
 
+  // ---- product mode (second attempt of lower_violation): a collection iterated inside another, unrelated iteration becomes a
+  // scope NESTED under the enclosing one (its generator is evaluated once per enclosing row), so that the two loop variables
+  // lie on one scope chain and may be tested together -- `m := c.volumeMounts[_]; vol := spec.volumes[_]; vol.name == m.name`.
+  // Rows are the cross product, as in the reference's nested iteration.
+  struct IterGuard {
+    std::vector<int>& st;
+    IterGuard(std::vector<int>& s, int scope) : st(s) { st.push_back(scope); }
+    ~IterGuard() { st.pop_back(); }
+  };
+  std::vector<int> iter_stack_;   // scopes whose EXISTS body is being lowered, outermost first
+  int scope_of_collection(const CP& gen) {
+    if (product_mode && !iter_stack_.empty()) {
+      const int cur = iter_stack_.back();
+      bool nested_in_cur = false;
+      for (int p = gen->scope; p != 0; p = schema_.scopes[p].parent)
+        if (p == cur) nested_in_cur = true;
+      if (!nested_in_cur) {
+        auto c = std::make_shared<Closure>(*gen);
+        c->scope = cur;
+        c->key = "@" + std::to_string(cur) + ":" + gen->key;
+        return schema_.scope_for(c);
+      }
+    }
+    return schema_.scope_for(gen);
+  }
+
   CP leaf(int scope, bool is_key) {
     auto c = std::make_shared<Closure>();
     c->leaf = is_key ? Closure::Key : Closure::Elem;
@@ -541,7 +570,8 @@ class Lowerer {
   // existential over the elements of a symbolic collection (a collection-valued column or a SetOf)
   FP for_each_elem(const SymVal& S, int line, const std::function<FP(const SymVal& key, const SymVal& elem)>& body) {
     if (S.k == SymVal::Col) {
-      int s = schema_.scope_for(S.col);
+      int s = scope_of_collection(S.col);
+      IterGuard g(iter_stack_, s);
       return f_exists(s, body(SymVal::column(leaf(s, true)), SymVal::column(leaf(s, false))));
     }
     if (S.k == SymVal::SetOf)
@@ -585,7 +615,17 @@ class Lowerer {
       unsupported("ordered comparison against a non-numeric parameter", line);
     }
     int64_t dummy;
-    if (!num_fits_i64(k->n, &dummy)) unsupported("ordered comparison against a parameter outside int64", line);
+    if (!num_fits_i64(k->n, &dummy)) {
+      // a fractional threshold against the device's exact-integer columns (an object whose number is not an exact int64 is a
+      // per-object error, never compared):  x > 1.5 == x >= 1.5 == x > 1   and   x < 1.5 == x <= 1.5 == x <= 1
+      const bool ordered = cmp == GK_CMP_LT || cmp == GK_CMP_LE || cmp == GK_CMP_GT || cmp == GK_CMP_GE;
+      if (ordered && !k->n.is_int && std::isfinite(k->n.d) && std::fabs(k->n.d) < 9.0e18) {
+        const VP fl = v_int((long long)std::floor(k->n.d));
+        const uint32_t c2 = (cmp == GK_CMP_GT || cmp == GK_CMP_GE) ? (uint32_t)GK_CMP_GT : (uint32_t)GK_CMP_LE;
+        return f_atom(GK_OP_NUM_CMP, schema_.col_for(c, GK_ENC_VT | GK_ENC_NUM), fl, c2);
+      }
+      unsupported("ordered comparison against a parameter outside int64", line);
+    }
     return f_atom(GK_OP_NUM_CMP, schema_.col_for(c, GK_ENC_VT | GK_ENC_NUM), k, cmp);
   }
   FP a_strop(int op, const CP& c, const VP& k) {
@@ -810,7 +850,8 @@ class Lowerer {
         return out;
       }
       case SymVal::Col: {
-        int s = schema_.scope_for(coll.col);
+        int s = scope_of_collection(coll.col);
+        IterGuard g(iter_stack_, s);
         return f_exists(s, each(SymVal::column(leaf(s, true)), SymVal::column(leaf(s, false))));
       }
       case SymVal::Arr: {
@@ -1131,7 +1172,8 @@ class Lowerer {
         return out;
       }
       case SymVal::Col: {
-        int s = schema_.scope_for(cur.col);
+        int s = scope_of_collection(cur.col);
+        IterGuard g(iter_stack_, s);
         return f_exists(s, each(SymVal::column(leaf(s, true)), SymVal::column(leaf(s, false))));
       }
       case SymVal::Arr: {
@@ -1493,8 +1535,25 @@ void Lowerer::subst_print(const Term& t, const std::map<int, std::string>& sub, 
 }  // namespace
 
 FP lower_violation(const std::shared_ptr<const Module>& mod, const VP& parameters, Schema& schema) {
-  Lowerer lw(mod, parameters, schema);
-  return lw.run();
+  const Schema before = schema;   // (a failed attempt must not leave its scopes and columns behind)
+  try {
+    Lowerer lw(mod, parameters, schema);
+    return lw.run();
+  } catch (RegoError& e) {
+    if (e.msg.find("two unrelated iteration scopes") == std::string::npos) {
+      schema = before;
+      throw;
+    }
+  }
+  schema = before;
+  try {
+    Lowerer lw(mod, parameters, schema);
+    lw.product_mode = true;
+    return lw.run();
+  } catch (RegoError&) {
+    schema = before;
+    throw;
+  }
 }
 
 // ====================================================================================== netlist construction
@@ -1722,6 +1781,84 @@ static FP merge_exists(const FP& f) {
   return out;
 }
 
+// Nested independent iterations (`l := labels[k]; c := containers[_]; <test on c>; <test on l>`) lower to an EXISTS whose body
+// mixes rows of two scopes that are not nested in each other.  The netlist only relates a scope to its ancestors, but a conjunct
+// that does not depend on the inner loop can leave it:  E[s](A & B) == E[s](A) & B  when B has no row of s -- exact, also
+// for an empty s (both sides false).
+static bool on_chain(int level, int scope, const Schema& sc) {   // is `level` an ancestor-or-self of `scope`?
+  for (int s = scope;; s = sc.scopes[s].parent) {
+    if (s == level) return true;
+    if (s == 0) return level == 0;
+  }
+}
+// level at which the formula's value lives once built (deepest leaf after the reductions); -2: its leaves are not on one chain
+static int formula_level(const FP& f, const Schema& sc) {
+  switch (f->k) {
+    case Formula::True:
+    case Formula::False: return 0;
+    case Formula::Atom: return sc.cols[f->col].scope;
+    case Formula::Not: return formula_level(f->kids[0], sc);
+    case Formula::Exists: {
+      int b = formula_level(f->kids[0], sc);
+      if (b == -2 || !on_chain(b, f->scope, sc)) return -2;
+      return sc.scopes[f->scope].parent;
+    }
+    default: {
+      int deepest = 0;
+      for (auto& k : f->kids) {
+        int l = formula_level(k, sc);
+        if (l == -2) return -2;
+        if (on_chain(deepest, l, sc)) deepest = l;
+        else if (!on_chain(l, deepest, sc)) return -2;
+      }
+      return deepest;
+    }
+  }
+}
+static FP hoist_invariants(const FP& f, const Schema& sc) {
+  if (f->kids.empty()) return f;
+  std::vector<FP> kids;
+  for (auto& k : f->kids) kids.push_back(hoist_invariants(k, sc));
+  switch (f->k) {
+    case Formula::Not: return f_not(kids[0]);
+    case Formula::And: {
+      FP out = f_true();
+      for (auto& k : kids) out = f_and(out, k);
+      return out;
+    }
+    case Formula::Or: {
+      FP out = f_false();
+      for (auto& k : kids) out = f_or(out, k);
+      return out;
+    }
+    case Formula::Exists: {
+      const FP& body = kids[0];
+      std::vector<FP> conj = body->k == Formula::And ? body->kids : std::vector<FP>{body};
+      FP inner = f_true(), outer = f_true();
+      bool moved = false;
+      for (auto& k : conj) {
+        const int l = formula_level(k, sc);
+        if (l != -2 && !on_chain(l, f->scope, sc)) {
+          outer = f_and(outer, k);
+          moved = true;
+        } else {
+          inner = f_and(inner, k);
+        }
+      }
+      if (!moved) return f_exists(f->scope, body);
+      return f_and(f_exists(f->scope, inner), outer);
+    }
+    default: return f;
+  }
+}
+
+// does the formula fit the netlist's scope tree?  (add_constraint asks before the constraint is accepted)
+void check_netlist_shape(const FP& formula, const Schema& sc) {
+  if (formula_level(hoist_invariants(formula, sc), sc) == -2)
+    throw RegoError{"rego_unsupported: the rule iterates two unrelated collections in one body and tests them together in a way that cannot be "
+                    "separated (a cross product); the GPU predicate table only nests a collection inside its parents"};
+}
+
 void NetBuilder::build(const std::vector<FP>& formulas, const std::vector<uint32_t>& match_id, uint32_t nmatch) {
   Net net(*schema);
   if (schema->scopes.size() > GK_MAX_SCOPES) throw RegoError{"rego_unsupported: too many iteration scopes"};
@@ -1744,7 +1881,7 @@ void NetBuilder::build(const std::vector<FP>& formulas, const std::vector<uint32
   };
   std::vector<Out> outs;
   for (auto& f : formulas) {
-    Ref r = net.build(merge_exists(f));
+    Ref r = net.build(merge_exists(hoist_invariants(f, *schema)));
     Out o{-1, 0};
     if (net.is_const(r)) o.flags = net.const_val(r) ? 1u : 2u;
     else {

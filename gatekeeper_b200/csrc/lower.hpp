@@ -81,6 +81,7 @@ FP f_or(FP a, FP b);
 FP f_not(FP a);
 FP f_exists(int scope, FP body);
 std::string formula_str(const FP& f, const Schema& s);
+void check_netlist_shape(const FP& formula, const Schema& s);   // throws rego_unsupported for shapes the netlist cannot hold
 size_t formula_size(const FP& f);
 
 // Interns strings/values for SID columns and constants (engine-global, append-only).

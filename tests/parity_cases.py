@@ -649,6 +649,239 @@ violation[{"msg": msg}] {
     return len(want)
 
 
+# ------------------------------------------------------------------------------------------ random policies
+_RF_HELPERS = """
+input_containers[c] { c := input.review.object.spec.containers[_] }
+input_containers[c] { c := input.review.object.spec.initContainers[_] }
+has_probe(c) { c.readinessProbe }
+has_probe(c) { c.livenessProbe }
+tag_of(image) = t { parts := split(image, ":"); count(parts) > 1; t := parts[count(parts) - 1] }
+tag_of(image) = "latest" { not contains(image, ":") }
+level(c) = "high" { c.securityContext.privileged } else = "low" { true }
+"""
+
+_RF_CONDS = {
+    "container": [
+        'not startswith(c.image, input.parameters.prefix)',
+        'startswith(c.image, input.parameters.prefixes[_])',
+        'satisfied := [good | repo = input.parameters.prefixes[_]; good = startswith(c.image, repo)]\n  not any(satisfied)',
+        'not strings.any_prefix_match(c.image, input.parameters.prefixes)',
+        'c.securityContext.privileged',
+        'not c.securityContext.privileged',
+        'not c.resources.limits.cpu',
+        'c.resources.limits.cpu == input.parameters.cpu',
+        'c.resources.limits.memory != input.parameters.mem',
+        'to_number(c.resources.limits.cpu) > input.parameters.n',
+        'endswith(c.image, ":latest")',
+        'contains(c.image, input.parameters.sub)',
+        'count(c.ports) > input.parameters.n',
+        'count(c.volumeMounts) >= input.parameters.n',
+        'c.name != input.parameters.name',
+        're_match(input.parameters.pattern, c.image)',
+        'not re_match("^[a-z0-9./-]+:[a-z0-9.]+$", c.image)',
+        'tag_of(c.image) == input.parameters.tag',
+        'tag_of(c.image) != "latest"',
+        'not has_probe(c)',
+        'has_probe(c)',
+        'input.parameters.tags[_] == tag_of(c.image)',
+        'p := c.ports[_]\n  p.hostPort > input.parameters.n',
+        'p := c.ports[_]\n  not p.hostPort',
+        'm := c.volumeMounts[_]\n  not m.readOnly\n  startswith(m.mountPath, input.parameters.mount)',
+        'object.get(c, "imagePullPolicy", "Always") == input.parameters.policy',
+        'lower(c.name) == input.parameters.name',
+        # stranger shapes: joins across scopes, object-object compares, arithmetic, more builtins, `in`, `else`
+        'm := c.volumeMounts[_]\n  vol := input.review.object.spec.volumes[_]\n  vol.name == m.name\n  vol.hostPath',
+        'm := c.volumeMounts[_]\n  vol := input.review.object.spec.volumes[_]\n  vol.name == m.name\n  not m.readOnly\n  not vol.emptyDir',
+        'c.resources.limits.cpu == c.resources.requests.cpu',
+        'x := to_number(c.resources.limits.cpu) * 1000\n  x > input.parameters.n',
+        'replace(c.image, ":", "@") == input.parameters.sub',
+        'trim(c.name, "c") == "0"',
+        'upper(c.name) == "C0"',
+        'concat("/", [input.review.object.metadata.namespace, c.name]) == input.parameters.name',
+        'sprintf("%v", [c.name]) == input.parameters.name',
+        'count([p | p := c.ports[_]; p.hostPort]) > 0',
+        'ports := {p.containerPort | p := c.ports[_]}\n  ports[input.parameters.n]',
+        'c.securityContext.privileged == true',
+        'is_string(c.resources.limits.cpu)',
+        'is_number(c.resources.limits.cpu)',
+        'indexof(c.image, "/") > input.parameters.n',
+        'substring(c.image, 0, 3) == "gcr"',
+        'some p in c.ports\n  p.hostPort == input.parameters.n',
+        'tag_of(c.image) in input.parameters.tags',
+        'not tag_of(c.image) in input.parameters.tags',
+        'level(c) == input.parameters.tag',
+        'level(c) != "low"',
+    ],
+    "label": [
+        'k == input.parameters.key',
+        'v != input.parameters.val',
+        'startswith(k, "label-0")',
+        'input.parameters.labels[_] == k',
+        'not re_match(input.parameters.pattern, v)',
+        'count(v) > input.parameters.n',
+        'endswith(v, input.parameters.sub)',
+    ],
+    "volume": [
+        'vol.hostPath',
+        'not vol.emptyDir',
+        'startswith(vol.hostPath.path, input.parameters.prefix)',
+        'fields := {x | vol[x]; x != "name"}\n  count(fields - {y | y := input.parameters.volumes[_]}) > 0',
+        'vol.name == input.parameters.name',
+        'vol.persistentVolumeClaim.claimName != input.parameters.name',
+    ],
+    "none": [
+        'provided := {l | input.review.object.metadata.labels[l]}\n  required := {l | l := input.parameters.labels[_]}\n  missing := required - provided\n  count(missing) > 0',
+        'input.review.object.spec.hostNetwork',
+        'not input.review.object.metadata.labels[input.parameters.key]',
+        'count(input.review.object.spec.containers) > input.parameters.n',
+        'input.review.object.metadata.namespace == input.parameters.ns',
+        'object.get(input.review.object.spec, "hostPID", false) == input.parameters.flag',
+        'input.review.object.metadata.labels[input.parameters.key] == input.parameters.val',
+        'count({c | c := input_containers[_]; c.securityContext.privileged}) >= input.parameters.n',
+        'input.review.kind.kind == input.parameters.kind',
+        'not input.parameters.flag',
+        'input.parameters.n > 1',
+        'ns := input.review.object.metadata.namespace\n  not startswith(ns, input.parameters.prefix)',
+        'count(input.review.object.spec.containers) != count(input.review.object.spec.volumes)',
+        'names := [c.name | c := input.review.object.spec.containers[_]]\n  concat(",", names) == input.parameters.name',
+        'input.review.object.spec.containers[0].image == input.parameters.sub',
+        'input.review.object.metadata.labels.team',
+        'all([startswith(c.image, input.parameters.prefix) | c := input.review.object.spec.containers[_]])',
+        'any([c.securityContext.privileged | c := input_containers[_]])',
+        'x := input.parameters.n + 1\n  count(input.review.object.spec.containers) < x',
+        'input.review.object.metadata.name == input.review.object.spec.containers[_].name',
+        'input.review.object.spec.containers[_].name == input.review.object.spec.volumes[_].name',
+        'not input.review.object.spec.volumes',
+        'count({v | v := input.review.object.metadata.labels[_]}) < count(input.review.object.metadata.labels)',
+    ],
+}
+_RF_SRC = {"container": ["c := input.review.object.spec.containers[_]", "c := input_containers[_]", "some i\n  c := input.review.object.spec.containers[i]"],
+           "label": ["v := input.review.object.metadata.labels[k]"], "volume": ["vol := input.review.object.spec.volumes[_]"], "none": [""]}
+_RF_SUBJ = {"container": "c.name", "label": "k", "volume": "vol.name", "none": "input.review.object.metadata.name"}
+
+
+def _rf_params(rnd):
+    return {"prefix": rnd.choice(["gcr.io/", "openpolicyagent/", "/mnt", "ns-0", "", "registry.k8s.io/repo-1"]),
+            "prefixes": rnd.sample(["gcr.io/", "quay.io/", "docker.io/library/", "openpolicyagent/", "registry.k8s.io/", "evil.example.com/repo-001"], rnd.randint(0, 3)),
+            "cpu": rnd.choice(["100m", "2", "1", 4]), "mem": rnd.choice(["128Mi", "1Gi", "2G"]), "n": rnd.choice([0, 1, 2, 3, 8080, 1.5]),
+            "name": rnd.choice(["c0", "c1", "vol-0", "pvc-1", "C0"]), "sub": rnd.choice(["repo-0", "latest", "v1", ""]),
+            "tag": rnd.choice(["latest", "v1.0.18", "1.2.3"]), "tags": rnd.sample(["latest", "v1.0.18", "v2.1.0", "1.2.3"], rnd.randint(0, 3)),
+            "pattern": rnd.choice(["^gcr[.]io/", "^(openpolicyagent|quay[.]io)/.+$", ":latest$", "^v[0-9]+$", "^team-[0-9]+$"]),
+            "key": rnd.choice(["team", "label-06", "app", "label-15"]), "val": rnd.choice(["team-42", "v9", ""]),
+            "labels": rnd.sample(["team", "label-01", "label-06", "label-22", "owner"], rnd.randint(0, 3)), "ns": rnd.choice(["ns-0001", "kube-system", "production"]),
+            "flag": rnd.choice([True, False]), "volumes": rnd.sample(["emptyDir", "configMap", "secret", "hostPath", "persistentVolumeClaim", "projected"], rnd.randint(0, 4)),
+            "mount": rnd.choice(["/mnt", "/", "/mnt/1"]), "policy": rnd.choice(["Always", "IfNotPresent"]), "kind": rnd.choice(["Pod", "Deployment"])}
+
+
+def _rf_template(rnd, idx):
+    bodies = []
+    for b in range(rnd.choice([1, 1, 2, 3])):
+        src = rnd.choice(["container", "container", "container", "label", "volume", "none", "none"])
+        lines = [rnd.choice(_RF_SRC[src])] if _RF_SRC[src][0] else []
+        conds = rnd.sample(_RF_CONDS[src], rnd.randint(1, 3))
+        if src != "none" and rnd.random() < 0.3:
+            conds.append(rnd.choice(_RF_CONDS["none"]))
+        # two conditions of one body must not introduce the same local name twice
+        seen, keep = set(), []
+        for c in conds:
+            intro = {ln.split(":=")[0].strip() for ln in c.split("\n") if ":=" in ln}
+            if intro & seen:
+                continue
+            seen |= intro
+            keep.append(c)
+        rnd.shuffle(keep)
+        lines += keep
+        extra = rnd.choice(["input.parameters.n", "input.parameters.prefixes", "input.parameters.key", "input.review.object.metadata.name", "%d" % b])
+        lines.append('msg := sprintf("b%d <%%v> <%%v>", [%s, %s])' % (b, _RF_SUBJ[src], extra))
+        head = 'violation[{"msg": msg, "details": {"body": %d}}]' % b if rnd.random() < 0.3 else 'violation[{"msg": msg}]'
+        bodies.append(head + " {\n  " + "\n  ".join(lines) + "\n}\n")
+    return "package fz%d\nimport future.keywords.in\n" % idx + "".join(bodies) + _RF_HELPERS
+
+
+def case_rego_fuzz(lib, n_templates=40, n_objects=120, seed=1):
+    """Random policies: `violation` bodies assembled from a menu of ~50 statement shapes of the in-tree templates (iteration
+    over containers / labels / volumes, comprehensions, set difference, helper rules and multi-body functions, negation,
+    builtins on object fields against parameters), each with three random parameter sets, against damaged synthetic Pods.
+    Whatever the engine accepts must agree with the oracle result for result; rejected policies (rego_unsupported) are
+    counted, never compared."""
+    import random
+    rnd = random.Random(seed)
+    blob = W.synth_objects(52000 + seed, n_objects)
+    revs = []
+    for i in range(n_objects):
+        o = json.loads(blob.get(i))
+        o = _mutate(rnd, o, rnd.choice([0, 0, 0, 1, 2]))
+        revs.append(D.Review(object=o))
+    accepted = n_results = 0
+    rejected = []
+    for t in range(n_templates):
+        src = _rf_template(rnd, t)
+        kind = "Fz%d" % t
+        cons = [W._constraint(kind, "fz-%d-%d" % (t, i), params=_rf_params(rnd), action=rnd.choice([None, "warn"])) for i in range(3)]
+        try:
+            orc, drv, skipped = make_pair([(kind, src)], cons, lib_path=lib, skip_unsupported=True)
+        except Exception as e:
+            raise AssertionError("template %d of seed %d failed to load: %r\n%s" % (t, seed, e, src))
+        if skipped:
+            rejected.append((t, skipped[0][2]))
+            if len(skipped) == 3 or skipped[0][1] is None:
+                continue
+        accepted += 1
+        resp = drv.ReviewBatch(revs, k8s.AUDIT_EP)
+        bad = {i for i, e in enumerate(resp.object_errors or []) if e}
+        try:
+            want = oracle_results_safe(orc, revs, k8s.AUDIT_EP, skip=bad)
+            got = {x for x in engine_results(resp) if x[0] not in bad}
+            assert_same(want, got)
+        except AssertionError as e:
+            raise AssertionError("seed %d template %d:\n%s\nparams %s\n%s" % (seed, t, src, [c["spec"].get("parameters") for c in cons], str(e)[:1500]))
+        n_results += len(want)
+    assert accepted >= n_templates * 0.6, rejected
+    return accepted, n_results, rejected
+
+
+def case_cross_scope_join(lib, n=3000):
+    """Nested independent iterations tested together (containers x volumeMounts x volumes joined by name -- the shape of the
+    host-filesystem policies when written without helper rules): lowered with the inner collection nested under the outer
+    loop's rows; a conjunct that does not depend on the inner loop is hoisted out of it."""
+    src = '''package j
+violation[{"msg": msg}] {
+  c := input.review.object.spec.containers[_]
+  m := c.volumeMounts[_]
+  vol := input.review.object.spec.volumes[_]
+  vol.name == m.name
+  vol.hostPath
+  not m.readOnly
+  startswith(vol.hostPath.path, input.parameters.prefix)
+  msg := sprintf("container <%v> mounts hostPath volume <%v> read-write", [c.name, vol.name])
+}
+violation[{"msg": msg}] {
+  input.review.object.spec.containers[_].name == input.review.object.spec.volumes[_].name
+  msg := "a container is named like a volume"
+}
+violation[{"msg": msg}] {
+  v := input.review.object.metadata.labels[k]
+  input.review.object.spec.containers[_].securityContext.privileged
+  startswith(k, input.parameters.label)
+  msg := sprintf("privileged pod carries label <%v>=<%v>", [k, v])
+}
+'''
+    blob = W.synth_objects(99, n)
+    revs = [D.Review(object=json.loads(blob.get(i))) for i in range(n)]
+    revs.append(D.Review(object={"apiVersion": "v1", "kind": "Pod", "metadata": {"name": "same", "namespace": "default"},
+                                 "spec": {"containers": [{"name": "x", "image": "i"}], "volumes": [{"name": "x", "emptyDir": {}}]}}))
+    cons = [W._constraint("J", "j", params={"prefix": "/", "label": "label-0"}), W._constraint("J", "j2", params={"prefix": "/var", "label": "team"})]
+    orc, drv, skipped = make_pair([("J", src)], cons, lib_path=lib)
+    assert not skipped
+    resp = drv.ReviewBatch(revs, k8s.AUDIT_EP)
+    assert not any(resp.object_errors or [])
+    want = oracle_results(orc, revs, k8s.AUDIT_EP)
+    msgs = {w[2] for w in want}
+    assert "a container is named like a volume" in msgs and any(m.startswith("container <") for m in msgs) and any(m.startswith("privileged pod") for m in msgs)
+    assert_same(want, engine_results(resp))
+    return len(want)
+
+
 # ------------------------------------------------------------------------------------------ pkg/target vectors
 DENY_ALL = 'package denyall\nviolation[{"msg": msg}] {\n  msg := "denyall constraint installed"\n}\n'   # target_integration_test.go:37-43
 

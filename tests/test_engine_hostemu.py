@@ -123,6 +123,17 @@ def test_more_builtins():
     assert P.case_more_builtins(HOSTEMU) > 30
 
 
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_rego_fuzz(seed):
+    """Random policies assembled from ~80 statement shapes x random parameters x damaged Pods: whatever loads must agree."""
+    accepted, n_results, _ = P.case_rego_fuzz(HOSTEMU, n_templates=30, seed=seed)
+    assert accepted >= 20 and n_results > 500
+
+
+def test_cross_scope_join():
+    assert P.case_cross_scope_join(HOSTEMU) > 20
+
+
 def test_target_enforcement_vectors():
     P.case_target_enforcement(HOSTEMU)
 

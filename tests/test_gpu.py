@@ -117,6 +117,17 @@ def test_more_builtins():
     assert P.case_more_builtins(LIB) > 30
 
 
+@pytest.mark.parametrize("seed", [11, 12])
+def test_rego_fuzz(seed):
+    """Random policies assembled from ~80 statement shapes x random parameters x damaged Pods: whatever loads must agree."""
+    accepted, n_results, _ = P.case_rego_fuzz(LIB, n_templates=30, seed=seed)
+    assert accepted >= 20 and n_results > 500
+
+
+def test_cross_scope_join():
+    assert P.case_cross_scope_join(LIB) > 20
+
+
 def test_target_enforcement_vectors():
     """pkg/target/target_integration_test.go: 26 scenarios x 3 request shapes, allowed <=> no results."""
     P.case_target_enforcement(LIB)
