@@ -148,12 +148,16 @@ struct SymVal {
   // SetOf: `f` is a formula with holes (Atom op == -1, imm == j); items[j].second is the head produced at hole j.
   // The set is { head_j | path condition of hole j }.
   FP f;                                                   // Bool: value; Opaque: definedness
+  FP d;                                                   // Bool: definedness of the value (null: always defined).  `f` decides statements
+                                                          // (`x`, `not x`); `d` matters where an undefined value differs from a false one:
+                                                          // `y := x`, comprehension heads, count(), all(), `x == false`
+  bool compr = false;                                     // Arr: built by a comprehension (undefined heads are absent), not a literal
   std::vector<std::pair<FP, SymVal>> items;               // Arr: (guard, element); Count: [0] = counted value
   std::vector<std::pair<VP, SymVal>> fields;              // ObjLit
   bool tainted = false;                                   // Conc: derived from input.parameters
   static SymVal conc(VP v, bool tainted = false) { SymVal s; s.k = Conc; s.v = std::move(v); s.tainted = tainted; return s; }
   static SymVal column(CP c) { SymVal s; s.k = Col; s.col = std::move(c); return s; }
-  static SymVal boolean(FP f) { SymVal s; s.k = Bool; s.f = std::move(f); return s; }
+  static SymVal boolean(FP f, FP d = nullptr) { SymVal s; s.k = Bool; s.f = std::move(f); s.d = std::move(d); return s; }
   static SymVal opaque(FP def) { SymVal s; s.k = Opaque; s.f = std::move(def); return s; }
 };
 
@@ -639,9 +643,14 @@ class Lowerer {
     switch (v.k) {
       case SymVal::Conc: return f_true();
       case SymVal::Col: return v.col->leaf != Closure::None ? f_true() : a_defined(v.col);
-      case SymVal::Bool: return f_true();
+      case SymVal::Bool: return v.d ? v.d : f_true();
       case SymVal::Opaque: return v.f ? v.f : f_true();
+      case SymVal::Count: {
+        const SymVal& x = v.items[0].second;   // count() of a column is undefined unless it holds a collection or a string
+        return x.k == SymVal::Col ? a_defined(make_call1("count", x.col)) : f_true();
+      }
       case SymVal::Arr: {
+        if (v.compr) return f_true();
         FP f = f_true();
         for (auto& it : v.items) f = f_and(f, f_or(f_not(it.first), defined_cond(it.second)));
         return f;
@@ -654,6 +663,19 @@ class Lowerer {
       default: return f_true();
     }
   }
+
+  // is element `it` of array `arr` there?  (a comprehension drops heads that are undefined; a literal array is all or nothing)
+  FP present(const SymVal& arr, const std::pair<FP, SymVal>& it) {
+    if (!arr.compr || it.second.k != SymVal::Bool || !it.second.d) return it.first;
+    return f_and(it.first, it.second.d);
+  }
+  FP is_true_cond(const SymVal& v, int line) {
+    if (v.k == SymVal::Bool) return v.f;
+    if (v.k == SymVal::Conc) return v.v->t == VT::True ? f_true() : f_false();
+    if (v.k == SymVal::Col) return f_atom(GK_OP_VTMASK, schema_.col_for(v.col, GK_ENC_VT), nullptr, 1u << GK_VT_TRUE);
+    unsupported("any() / all() over non-boolean symbolic elements", line);
+  }
+  FP a_is_string(const CP& c) { return f_atom(GK_OP_VTMASK, schema_.col_for(c, GK_ENC_VT), nullptr, 1u << GK_VT_STR); }
 
   FP truthy_cond(const SymVal& v) {
     switch (v.k) {
@@ -762,7 +784,8 @@ class Lowerer {
     if (a.k == SymVal::Col && b.k == SymVal::Col) return a_truthy(make_call2("equal", a.col, b.col));
     if (a.k == SymVal::Bool && b.k == SymVal::Conc) {
       if (b.v->t == VT::True) return a.f;
-      unsupported("comparison of a symbolic boolean with a non-true constant", line);
+      if (b.v->t == VT::False) return f_and(defined_cond(a), f_not(a.f));
+      return f_false();   // a boolean never equals a non-boolean
     }
     if (b.k == SymVal::Bool && a.k == SymVal::Conc) return eq_cond(b, a, line);
     if (a.k == SymVal::Count || b.k == SymVal::Count) return count_cmp(GK_CMP_EQ, a, b, line);
@@ -857,7 +880,7 @@ class Lowerer {
       case SymVal::Arr: {
         FP out = f_false();
         for (size_t j = 0; j < coll.items.size(); ++j)
-          out = f_or(out, f_and(coll.items[j].first, each(SymVal::conc(v_int((long long)j)), coll.items[j].second)));
+          out = f_or(out, f_and(present(coll, coll.items[j]), each(SymVal::conc(v_int((long long)j)), coll.items[j].second)));
         return out;
       }
       case SymVal::DiffCS: {
@@ -971,6 +994,7 @@ class Lowerer {
     env.undo(mk);
     SymVal arr;
     arr.k = SymVal::Arr;
+    arr.compr = true;
     for (size_t j = 0; j < vals.size(); ++j) {
       FP guard = fill_holes(tree, (uint32_t)j, t->line);
       arr.items.emplace_back(guard, vals[j]);
@@ -1181,7 +1205,7 @@ class Lowerer {
         for (size_t j = 0; j < cur.items.size(); ++j) {
           if (cur.items[j].first->k != Formula::True && keypat->k == TK::Var && keypat->name[0] != '$')
             unsupported("index variable over a conditionally-built array", line);
-          out = f_or(out, f_and(cur.items[j].first, each(SymVal::conc(v_int((long long)j)), cur.items[j].second)));
+          out = f_or(out, f_and(present(cur, cur.items[j]), each(SymVal::conc(v_int((long long)j)), cur.items[j].second)));
         }
         return out;
       }
@@ -1263,7 +1287,7 @@ class Lowerer {
     if (x.k == SymVal::DiffCS) {
       for (auto& c : x.v->items) bools.push_back(f_not(member_cond(c, *x.sym, line)));
     } else if (x.k == SymVal::Arr) {
-      for (auto& it : x.items) bools.push_back(it.first);
+      for (auto& it : x.items) bools.push_back(present(x, it));
     } else if (x.k == SymVal::DiffSC) {
       scoped = true;
       any_scoped = for_each_elem(*x.sym, line, [&](const SymVal&, const SymVal& e) { return f_not(in_const_cond(e, x.v, line)); });
@@ -1334,7 +1358,13 @@ class Lowerer {
     const int line = t->line;
     auto is_conc = [](const SymVal& s) { return s.k == SymVal::Conc; };
     auto is_col = [](const SymVal& s) { return s.k == SymVal::Col; };
-    auto ret_bool = [&](FP f) { return k(SymVal::boolean(std::move(f))); };
+    // the value is defined only where every argument is (plus whatever type the builtin insists on: `extra`)
+    auto ret_bool = [&](FP f, FP extra = nullptr) {
+      FP d = extra ? extra : f_true();
+      for (auto& x : a) d = f_and(d, defined_cond(x));
+      return k(SymVal::boolean(std::move(f), d->k == Formula::True ? FP() : d));
+    };
+    auto undefined_bool = [&]() { return k(SymVal::boolean(f_false(), f_false())); };
 
     if (n == "print" || n == "trace") return k(SymVal::conc(v_bool(true)));
     if (n == "sprintf") {
@@ -1391,8 +1421,8 @@ class Lowerer {
     if ((n == "startswith" || n == "endswith" || n == "contains") && a.size() == 2) {
       int op = n == "startswith" ? GK_OP_PREFIX : n == "endswith" ? GK_OP_SUFFIX : GK_OP_CONTAINS;
       if (is_col(a[0]) && is_conc(a[1])) {
-        if (a[1].v->t != VT::Str) return k(SymVal::boolean(f_false()));   // type error => undefined
-        return ret_bool(a_strop(op, a[0].col, a[1].v));
+        if (a[1].v->t != VT::Str) return undefined_bool();   // type error => undefined
+        return ret_bool(a_strop(op, a[0].col, a[1].v), a_is_string(a[0].col));
       }
       unsupported(n + " with a symbolic second operand", line);
     }
@@ -1403,29 +1433,32 @@ class Lowerer {
         if (b->t == VT::Str) pats.push_back(b);
         else if (b->t == VT::Arr || b->t == VT::Set) {
           for (auto& x : b->items) {
-            if (x->t != VT::Str) return k(SymVal::boolean(f_false()));
+            if (x->t != VT::Str) return undefined_bool();
             pats.push_back(x);
           }
         } else {
-          return k(SymVal::boolean(f_false()));
+          return undefined_bool();
         }
-        if (pats.empty()) return ret_bool(f_false());
-        return ret_bool(a_strop(n == "strings.any_prefix_match" ? GK_OP_ANYPREFIX : GK_OP_ANYSUFFIX, a[0].col, v_arr(pats)));
+        if (pats.empty()) return ret_bool(f_false(), a_is_string(a[0].col));
+        return ret_bool(a_strop(n == "strings.any_prefix_match" ? GK_OP_ANYPREFIX : GK_OP_ANYSUFFIX, a[0].col, v_arr(pats)), a_is_string(a[0].col));
       }
       unsupported(n + " with a symbolic pattern list", line);
     }
     if (n == "any" && a.size() == 1) {
       if (a[0].k != SymVal::Arr) unsupported("any() of this value", line);
       FP o = f_false();
-      for (auto& it : a[0].items) {
-        FP e;
-        if (it.second.k == SymVal::Bool) e = it.second.f;
-        else if (it.second.k == SymVal::Conc) e = it.second.v->t == VT::True ? f_true() : f_false();
-        else if (it.second.k == SymVal::Col) e = f_atom(GK_OP_VTMASK, schema_.col_for(it.second.col, GK_ENC_VT), nullptr, 1u << GK_VT_TRUE);
-        else unsupported("any() over non-boolean symbolic elements", line);
-        o = f_or(o, f_and(it.first, e));
-      }
+      for (auto& it : a[0].items) o = f_or(o, f_and(it.first, is_true_cond(it.second, line)));   // (a true element is a defined one)
       return ret_bool(o);
+    }
+    if (n == "all" && a.size() == 1) {
+      if (a[0].k != SymVal::Arr) unsupported("all() of this value", line);
+      // false as soon as one element that is THERE is not `true`
+      FP bad = f_false();
+      for (auto& it : a[0].items) {
+        FP there = a[0].compr ? f_and(it.first, defined_cond(it.second)) : it.first;
+        bad = f_or(bad, f_and(there, f_not(is_true_cond(it.second, line))));
+      }
+      return ret_bool(f_not(bad));
     }
     if (n == "internal.member_2" && a.size() == 2) {
       if (is_col(a[0]) && is_conc(a[1])) {
@@ -1442,11 +1475,11 @@ class Lowerer {
       // Regular expressions are not evaluated on the device: `re_match(<pattern from the parameters>, <object string>)`
       // becomes a boolean FEATURE COLUMN of its own -- the flattener runs the (cached, compiled) pattern once per row --
       // keyed by the pattern text, so constraints that share a pattern share the column.
-      if (a[0].v->t != VT::Str) return ret_bool(f_false());   // non-string pattern: undefined
+      if (a[0].v->t != VT::Str) return undefined_bool();   // non-string pattern: undefined
       LEnv e;
       e.bind(vid_cur_, a[1]);
       CP c = make_closure(synth_call(n, {synth_scalar(a[0].v), synth_var(vid_cur_, "$cur")}, line), e);
-      return ret_bool(f_atom(GK_OP_VTMASK, schema_.col_for(c, GK_ENC_VT), nullptr, 1u << GK_VT_TRUE));
+      return ret_bool(f_atom(GK_OP_VTMASK, schema_.col_for(c, GK_ENC_VT), nullptr, 1u << GK_VT_TRUE), a_is_string(a[1].col));
     }
     if (n == "re_match" || n == "regex.match") unsupported("regular expression with a pattern taken from the object", line);
     unsupported("builtin " + n + " mixing parameters and object fields", line);

@@ -711,6 +711,19 @@ _RF_CONDS = {
         'not tag_of(c.image) in input.parameters.tags',
         'level(c) == input.parameters.tag',
         'level(c) != "low"',
+        # boolean VALUES (an undefined builtin result is not a false one)
+        'x := startswith(c.image, input.parameters.prefix)\n  not x',
+        'x := re_match(input.parameters.pattern, c.image)\n  not x',
+        'x := c.image == input.parameters.sub\n  not x',
+        'x := tag_of(c.image) in input.parameters.tags\n  not x',
+        'x := endswith(c.image, ":latest")\n  x == false',
+        'x := count(c.ports) > input.parameters.n\n  not x',
+        'goods := [g | p := input.parameters.prefixes[_]; g := startswith(c.image, p)]\n  count(goods) == 0',
+        'goods := [g | p := input.parameters.prefixes[_]; g := startswith(c.image, p)]\n  all(goods)',
+        'goods := [g | p := input.parameters.prefixes[_]; g := endswith(c.image, p)]\n  not all(goods)',
+        'goods := [g | p := input.parameters.prefixes[_]; g := contains(c.image, p)]\n  count(goods) > 0',
+        'flags := [startswith(c.image, input.parameters.prefix), c.name == input.parameters.name]\n  any(flags)',
+        'flags := [startswith(c.image, input.parameters.prefix), c.name != input.parameters.name]\n  all(flags)',
     ],
     "label": [
         'k == input.parameters.key',
@@ -812,6 +825,16 @@ def case_rego_fuzz(lib, n_templates=40, n_objects=120, seed=1):
         o = json.loads(blob.get(i))
         o = _mutate(rnd, o, rnd.choice([0, 0, 0, 1, 2]))
         revs.append(D.Review(object=o))
+    # single-container copies: a decision the device gets wrong for ONE container cannot hide behind another container's result
+    # (a flagged pair the renderer finds nothing for is an engine error)
+    for r in list(revs[:40]):
+        cs = ((r.object.get("spec") or {}).get("containers") if isinstance(r.object.get("spec"), dict) else None) or []
+        if isinstance(cs, list) and len(cs) > 1:
+            for c in cs:
+                o = json.loads(json.dumps(r.object))
+                o["spec"]["containers"] = [c]
+                revs.append(D.Review(object=o))
+    n_objects = len(revs)
     accepted = n_results = 0
     rejected = []
     for t in range(n_templates):
