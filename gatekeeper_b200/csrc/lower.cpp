@@ -141,11 +141,13 @@ int Schema::col_for(const CP& expr, uint32_t enc) {
 namespace {
 
 struct SymVal {
-  enum K : uint8_t { Conc, Col, Bool, Arr, ObjLit, Opaque, DiffCS, DiffSC, Count, SetOf } k = Conc;
+  enum K : uint8_t { Conc, Col, Bool, Arr, ObjLit, Opaque, DiffCS, DiffSC, Count, SetOf, ArrHoles } k = Conc;
   VP v;                                                   // Conc; DiffCS/DiffSC: the concrete set
   CP col;                                                 // Col
   std::shared_ptr<SymVal> sym;                            // DiffCS/DiffSC: the symbolic collection (Col or SetOf)
-  // SetOf: `f` is a formula with holes (Atom op == -1, imm == j); items[j].second is the head produced at hole j.
+  // SetOf / ArrHoles: `f` is a formula with holes (Atom op == -1, imm == j); items[j].second is the head produced at hole j.
+  // ArrHoles is an array comprehension that iterates an OBJECT collection while mixing in parameters: its length is not
+  // known at lowering time, so only the existential consumers take it -- any(), all(), count() against 0.
   // The set is { head_j | path condition of hole j }.
   FP f;                                                   // Bool: value; Opaque: definedness
   FP d;                                                   // Bool: definedness of the value (null: always defined).  `f` decides statements
@@ -995,9 +997,18 @@ class Lowerer {
     SymVal arr;
     arr.k = SymVal::Arr;
     arr.compr = true;
-    for (size_t j = 0; j < vals.size(); ++j) {
-      FP guard = fill_holes(tree, (uint32_t)j, t->line);
-      arr.items.emplace_back(guard, vals[j]);
+    try {
+      for (size_t j = 0; j < vals.size(); ++j) {
+        FP guard = fill_holes(tree, (uint32_t)j, t->line);
+        arr.items.emplace_back(guard, vals[j]);
+      }
+    } catch (RegoError& e) {
+      if (e.msg.find("comprehension over an object collection mixed with parameters") == std::string::npos) throw;
+      SymVal h;
+      h.k = SymVal::ArrHoles;
+      h.f = tree;
+      for (auto& v : vals) h.items.emplace_back(f_true(), v);
+      return k(h);
     }
     return k(arr);
   }
@@ -1294,6 +1305,9 @@ class Lowerer {
     } else if (x.k == SymVal::SetOf) {
       scoped = true;
       any_scoped = for_each_elem(x, line, [&](const SymVal&, const SymVal&) { return f_true(); });
+    } else if (x.k == SymVal::ArrHoles) {
+      scoped = true;
+      any_scoped = fill_tree(x.f, [&](uint32_t j) { return defined_cond(x.items[j].second); });
     } else if (x.k == SymVal::Col) {
       return a_numcmp(make_call1("count", x.col), cmp, b.v, line);
     } else {
@@ -1443,6 +1457,13 @@ class Lowerer {
         return ret_bool(a_strop(n == "strings.any_prefix_match" ? GK_OP_ANYPREFIX : GK_OP_ANYSUFFIX, a[0].col, v_arr(pats)), a_is_string(a[0].col));
       }
       unsupported(n + " with a symbolic pattern list", line);
+    }
+    if ((n == "any" || n == "all") && a.size() == 1 && a[0].k == SymVal::ArrHoles) {
+      const SymVal& h = a[0];
+      if (n == "any") return ret_bool(fill_tree(h.f, [&](uint32_t j) { return is_true_cond(h.items[j].second, line); }));
+      return ret_bool(f_not(fill_tree(h.f, [&](uint32_t j) {
+        return f_and(defined_cond(h.items[j].second), f_not(is_true_cond(h.items[j].second, line)));
+      })));
     }
     if (n == "any" && a.size() == 1) {
       if (a[0].k != SymVal::Arr) unsupported("any() of this value", line);

@@ -397,6 +397,11 @@ struct Parser {
         return s;
       }
       s.k = Stmt::Some;
+      {   // the declared names are kept (as an array term) for the scoping pass below; evaluation ignores the statement
+        auto arr = mk(TK::Array, s.line);
+        arr->args = names;
+        s.a = arr;
+      }
       return s;
     }
     if (at("not")) {
@@ -597,6 +602,91 @@ void collect_vars(const TP& t, std::vector<int>& out) {
   collect_vars_body(t->body, out);
 }
 
+// ---- scoping of comprehension locals.  A variable declared with `:=` / `some` inside a comprehension is local to it and
+// SHADOWS a variable of the same name in the enclosing body (`c := containers[i]; all([ok(c) | c := containers[_]])` tests every
+// container, not just the outer one).  The evaluators bind by name, so every such local gets a name of its own.
+struct ComprScoper {
+  Module& m;
+  int counter = 0;
+  using Ren = std::map<int, std::pair<int, std::string>>;
+
+  static void pattern_vars(const TP& t, std::vector<const Term*>& out) {
+    if (!t) return;
+    if (t->k == TK::Var) out.push_back(t.get());
+    else if (t->k == TK::Array || t->k == TK::Set)
+      for (auto& a : t->args) pattern_vars(a, out);
+    else if (t->k == TK::Object)
+      for (auto& kv : t->kvs) pattern_vars(kv.second, out);
+  }
+  TP rename(const TP& t, const Ren& ren) {
+    if (!t) return t;
+    auto x = std::make_shared<Term>(*t);
+    x->is_rule_ = -1;
+    x->rules_ = nullptr;
+    if (t->k == TK::Var) {
+      auto it = ren.find(t->vid);
+      if (it == ren.end()) return t;
+      x->vid = it->second.first;
+      x->name = it->second.second;
+      return x;
+    }
+    x->head = rename(t->head, ren);
+    for (auto& a : x->args) a = rename(a, ren);
+    for (auto& kv : x->kvs) kv = {rename(kv.first, ren), rename(kv.second, ren)};
+    x->key = rename(t->key, ren);
+    x->value = rename(t->value, ren);
+    for (auto& st : x->body) st = rename(st, ren);
+    return x;
+  }
+  Stmt rename(const Stmt& s, const Ren& ren) {
+    Stmt o = s;
+    o.a = rename(s.a, ren), o.b = rename(s.b, ren), o.c = rename(s.c, ren);
+    return o;
+  }
+  TP fix(const TP& t) {
+    if (!t) return t;
+    if (t->k == TK::Scalar || t->k == TK::Var) return t;
+    auto x = std::make_shared<Term>(*t);
+    x->head = fix(t->head);
+    for (auto& a : x->args) a = fix(a);
+    for (auto& kv : x->kvs) kv = {fix(kv.first), fix(kv.second)};
+    x->key = fix(t->key);
+    x->value = fix(t->value);
+    for (auto& st : x->body) st = fix(st);
+    if (t->k != TK::ArrCompr && t->k != TK::SetCompr && t->k != TK::ObjCompr) return x;
+    std::vector<const Term*> decl;
+    for (auto& st : x->body) {
+      if (st.k == Stmt::Assign || st.k == Stmt::Some) pattern_vars(st.a, decl);
+      if (st.k == Stmt::SomeIn) pattern_vars(st.a, decl), pattern_vars(st.b, decl);
+    }
+    Ren ren;
+    for (const Term* v : decl) {
+      if (v->name.empty() || v->name[0] == '$' || ren.count(v->vid)) continue;
+      std::string nn = v->name + "$" + std::to_string(++counter);
+      ren[v->vid] = {m.intern(nn), nn};
+    }
+    if (ren.empty()) return x;
+    return rename(TP(x), ren);
+  }
+  Stmt fix(const Stmt& s) {
+    Stmt o = s;
+    o.a = fix(s.a), o.b = fix(s.b), o.c = fix(s.c);
+    return o;
+  }
+  void run() {
+    for (auto& kv : m.rules)
+      for (auto& r : kv.second) {
+        for (auto& a : r.args) a = fix(a);
+        r.key = fix(r.key), r.value = fix(r.value);
+        for (auto& st : r.body) st = fix(st);
+        for (auto& e : r.els) {
+          e.first = fix(e.first);
+          for (auto& st : e.second) st = fix(st);
+        }
+      }
+  }
+};
+
 // The one compile-time check the reference's tests pin (pkg/gator/fixtures/fixtures.go TemplateCompileError,
 // a body that is just the undeclared identifier `f`): a bare variable statement must be bound earlier.
 void check_unsafe(const Module& m) {
@@ -748,6 +838,7 @@ std::shared_ptr<Module> rego_parse(const std::string& src, const std::vector<std
       if ((r.kind == Rule::Func) != (k0 == Rule::Func))
         throw RegoError{"rego_type_error: conflicting rules named " + kv.first};
   }
+  ComprScoper{*m}.run();
   check_unsafe(*m);
   compute_purity(*m);
   return m;

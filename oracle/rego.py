@@ -1091,10 +1091,74 @@ BUILTINS.update({
 # evaluator
 
 
+# ---- scoping of comprehension locals: a variable declared with `:=` / `some` inside a comprehension is local to it and shadows
+# an outer variable of the same name (OPA rewrites declared locals per closure).  The evaluator binds by name, so every
+# such local is given a name of its own.
+_scope_counter = [0]
+
+
+def _pattern_vars(t, out):
+    if not isinstance(t, tuple) or not t:
+        return
+    if t[0] == "var":
+        out.append(t[1])
+    elif t[0] in ("array", "set"):
+        for x in t[1]:
+            _pattern_vars(x, out)
+    elif t[0] == "object":
+        for _, v in t[1]:
+            _pattern_vars(v, out)
+
+
+def _rename(x, ren):
+    if isinstance(x, tuple):
+        if x and x[0] == "var" and len(x) == 2 and isinstance(x[1], str):
+            return ("var", ren.get(x[1], x[1]))
+        if x and x[0] == "some":
+            return ("some", [ren.get(n, n) for n in x[1]])
+        return tuple(_rename(y, ren) for y in x)
+    if isinstance(x, list):
+        return [_rename(y, ren) for y in x]
+    return x
+
+
+def _scope_fix(x):
+    if isinstance(x, list):
+        return [_scope_fix(y) for y in x]
+    if not isinstance(x, tuple) or not x:
+        return x
+    if x[0] in ("scalar", "var", "some"):
+        return x
+    x = tuple(_scope_fix(y) for y in x)
+    if x[0] in ("acompr", "scompr", "ocompr"):
+        body = x[-1]
+        decl = []
+        for st in body:
+            if st[0] == "assign":
+                _pattern_vars(st[1], decl)
+            elif st[0] == "some":
+                decl.extend(st[1])
+            elif st[0] == "somein":
+                _pattern_vars(st[1], decl)
+                _pattern_vars(st[2], decl)
+        ren = {}
+        for n in decl:
+            if n and not n.startswith("$") and n not in ren:
+                _scope_counter[0] += 1
+                ren[n] = "%s$%d" % (n, _scope_counter[0])
+        if ren:
+            x = _rename(x, ren)
+    return x
+
+
 class Module:
     def __init__(self, src, libs=(), _registry=None):
         p = Parser(src)
         self.package, rules = p.parse_module()
+        for r in rules:
+            r.args = _scope_fix(r.args) if r.args is not None else None
+            r.key, r.value, r.body = _scope_fix(r.key), _scope_fix(r.value), _scope_fix(r.body)
+            r.els = [(_scope_fix(ev), _scope_fix(eb)) for ev, eb in r.els]
         self.imports = p.imports
         self.rules = {}
         for r in rules:

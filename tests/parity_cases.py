@@ -724,6 +724,9 @@ _RF_CONDS = {
         'goods := [g | p := input.parameters.prefixes[_]; g := contains(c.image, p)]\n  count(goods) > 0',
         'flags := [startswith(c.image, input.parameters.prefix), c.name == input.parameters.name]\n  any(flags)',
         'flags := [startswith(c.image, input.parameters.prefix), c.name != input.parameters.name]\n  all(flags)',
+        'count([p | p := c.ports[_]; p.containerPort > input.parameters.n]) > 0',
+        'all([m.readOnly | m := c.volumeMounts[_]; startswith(m.mountPath, input.parameters.mount)])',
+        'not any([m.readOnly | m := c.volumeMounts[_]; startswith(m.mountPath, input.parameters.mount)])',
     ],
     "label": [
         'k == input.parameters.key',
@@ -765,6 +768,10 @@ _RF_CONDS = {
         'input.review.object.metadata.name == input.review.object.spec.containers[_].name',
         'input.review.object.spec.containers[_].name == input.review.object.spec.volumes[_].name',
         'not input.review.object.spec.volumes',
+        'not all([startswith(c.image, input.parameters.prefix) | c := input.review.object.spec.containers[_]])',
+        'any([endswith(c.image, input.parameters.sub) | c := input_containers[_]])',
+        'count([c | c := input.review.object.spec.containers[_]; startswith(c.image, input.parameters.prefix)]) == 0',
+        'count([p | c := input.review.object.spec.containers[_]; p := c.ports[_]; p.hostPort > input.parameters.n]) > 0',
         'count({v | v := input.review.object.metadata.labels[_]}) < count(input.review.object.metadata.labels)',
     ],
 }
@@ -850,7 +857,12 @@ def case_rego_fuzz(lib, n_templates=40, n_objects=120, seed=1):
             if len(skipped) == 3 or skipped[0][1] is None:
                 continue
         accepted += 1
-        resp = drv.ReviewBatch(revs, k8s.AUDIT_EP)
+        try:
+            resp = drv.ReviewBatch(revs, k8s.AUDIT_EP)
+        except D.GkError as e:
+            m = __import__("re").search(r"object (\d+)\)", str(e))
+            raise AssertionError("seed %d template %d: %s\n%s\nparams %s\nobject %s" % (
+                seed, t, e, src, [c["spec"].get("parameters") for c in cons], json.dumps(revs[int(m.group(1))].object) if m else "?"))
         bad = {i for i, e in enumerate(resp.object_errors or []) if e}
         try:
             want = oracle_results_safe(orc, revs, k8s.AUDIT_EP, skip=bad)
