@@ -29,9 +29,11 @@ struct Term;
 using TP = std::shared_ptr<const Term>;
 
 struct Stmt {
-  enum K : uint8_t { Expr, Not, Assign, Unify, Some, SomeIn } k = Expr;
+  enum K : uint8_t { Expr, Not, Assign, Unify, Some, SomeIn, Every } k = Expr;
   TP a, b, c;   // Expr/Not: a ; Assign/Unify: a,b ; SomeIn: a=key(or null), b=value, c=collection
   int line = 0;
+  // Every (`every k, v in c { body }`) exists only between the parser and its desugaring pass (rego_parse.cpp): no evaluator sees it
+  std::vector<Stmt> body;
 };
 
 struct Term {

@@ -1,4 +1,5 @@
 // Rego subset parser (v0 and v1 rule syntax).  See rego.hpp for scope.
+#include <algorithm>
 #include <atomic>
 #include <cstring>
 #include <set>
@@ -404,6 +405,20 @@ struct Parser {
       }
       return s;
     }
+    if (at("every") && peek(1).k == TT::Id && !is_keyword(peek(1).s)) {
+      next();
+      TP first = parse_term(0, true), second;
+      if (accept(",")) second = parse_term(0, true);
+      expect("in");
+      s.k = Stmt::Every;
+      s.c = parse_term();
+      if (second) s.a = first, s.b = second;
+      else s.b = first;
+      expect("{");
+      s.body = parse_body("}");
+      expect("}");
+      return s;
+    }
     if (at("not")) {
       next();
       Stmt inner = parse_expr();
@@ -601,6 +616,163 @@ void collect_vars(const TP& t, std::vector<int>& out) {
   collect_vars(t->value, out);
   collect_vars_body(t->body, out);
 }
+
+// ---- `every k, v in coll { body }` (OPA v1 keyword: the body holds for every element; an empty domain is true, an undefined
+// one undefined) is rewritten into constructs both evaluators already have:
+//       $evN := coll
+//       count([1 | some $ekN, $exN in $evN; not $everyN($ekN, $exN, <captured>)]) == 0
+//       $everyN(k, v, <captured>) { body }
+// where <captured> are the variables of the body that the enclosing bodies have bound before the statement.
+struct EveryDesugar {
+  Module& m;
+  int counter = 0;
+  std::vector<std::pair<std::string, Rule>> new_rules;
+
+  static void var_terms(const TP& t, std::vector<TP>& out) {
+    if (!t) return;
+    if (t->k == TK::Var) out.push_back(t);
+    var_terms(t->head, out);
+    for (auto& a : t->args) var_terms(a, out);
+    for (auto& kv : t->kvs) var_terms(kv.first, out), var_terms(kv.second, out);
+    var_terms(t->key, out);
+    var_terms(t->value, out);
+    for (auto& st : t->body) var_terms(st, out);
+  }
+  static void var_terms(const Stmt& st, std::vector<TP>& out) {
+    var_terms(st.a, out), var_terms(st.b, out), var_terms(st.c, out);
+    for (auto& b : st.body) var_terms(b, out);
+  }
+  std::shared_ptr<Term> mk(TK k, int line) {
+    auto x = std::make_shared<Term>();
+    x->k = k;
+    x->line = line;
+    return x;
+  }
+  TP var(const std::string& n, int line) {
+    auto x = mk(TK::Var, line);
+    x->name = n;
+    x->vid = m.intern(n);
+    return x;
+  }
+  TP call(const std::string& n, std::vector<TP> args, int line) {
+    auto x = mk(TK::Call, line);
+    x->name = n;
+    x->args = std::move(args);
+    return x;
+  }
+  TP num(long long v, int line) {
+    auto x = mk(TK::Scalar, line);
+    x->val = v_int(v);
+    return x;
+  }
+
+  TP fix_term(const TP& t, const std::vector<int>& bound) {
+    if (!t || t->k == TK::Scalar || t->k == TK::Var) return t;
+    auto x = std::make_shared<Term>(*t);
+    x->head = fix_term(t->head, bound);
+    for (auto& a : x->args) a = fix_term(a, bound);
+    for (auto& kv : x->kvs) kv = {fix_term(kv.first, bound), fix_term(kv.second, bound)};
+    x->key = fix_term(t->key, bound);
+    x->value = fix_term(t->value, bound);
+    if (!t->body.empty()) x->body = fix_body(t->body, bound);
+    return x;
+  }
+  std::vector<Stmt> fix_body(const std::vector<Stmt>& body, std::vector<int> bound) {
+    std::vector<Stmt> out;
+    for (auto& st0 : body) {
+      Stmt st = st0;
+      st.a = fix_term(st.a, bound), st.b = fix_term(st.b, bound), st.c = fix_term(st.c, bound);
+      if (st.k == Stmt::Every) {
+        const int id = ++counter, line = st.line;
+        for (const TP* p : {&st.a, &st.b})
+          if (*p && (*p)->k != TK::Var) throw RegoError{"rego_unsupported: `every` with a non-variable key / value pattern (line " + std::to_string(line) + ")"};
+        std::vector<int> inner = bound;
+        if (st.a) inner.push_back(st.a->vid);
+        inner.push_back(st.b->vid);
+        std::vector<Stmt> fbody = fix_body(st.body, inner);
+        // captured: variables of the body bound by the enclosing bodies (not the key / value, not documents, not rules)
+        std::vector<TP> used, caps;
+        for (auto& b : fbody) var_terms(b, used);
+        for (auto& u : used) {
+          if (u->vid == m.vid_input || u->vid == m.vid_data || m.is_rule(u->name)) continue;
+          if ((st.a && u->vid == st.a->vid) || u->vid == st.b->vid) continue;
+          if (std::find(bound.begin(), bound.end(), u->vid) == bound.end()) continue;
+          bool dup = false;
+          for (auto& c : caps) dup = dup || c->vid == u->vid;
+          if (!dup) caps.push_back(u);
+        }
+        const std::string sfx = std::to_string(id), fn = "$every" + sfx;
+        Rule r;
+        r.kind = Rule::Func;
+        r.name = fn;
+        r.line = line;
+        r.args.push_back(st.a ? st.a : var("$eku" + sfx, line));
+        r.args.push_back(st.b);
+        for (auto& c : caps) r.args.push_back(c);
+        r.body = fbody;
+        r.has_body = true;
+        auto tv = mk(TK::Scalar, line);
+        tv->val = v_bool(true);
+        r.value = tv;
+        new_rules.emplace_back(fn, std::move(r));
+        // $evN := coll
+        Stmt s1;
+        s1.k = Stmt::Assign;
+        s1.line = line;
+        s1.a = var("$ev" + sfx, line);
+        s1.b = st.c;
+        // count([1 | some $ekN, $exN in $evN; not $everyN($ekN, $exN, caps...)]) == 0
+        TP ek = var("$ek" + sfx, line), ex = var("$ex" + sfx, line);
+        Stmt it;
+        it.k = Stmt::SomeIn;
+        it.line = line;
+        it.a = ek, it.b = ex, it.c = s1.a;
+        std::vector<TP> cargs{ek, ex};
+        for (auto& c : caps) cargs.push_back(c);
+        Stmt neg;
+        neg.k = Stmt::Not;
+        neg.line = line;
+        neg.a = call(fn, cargs, line);
+        auto compr = mk(TK::ArrCompr, line);
+        compr->value = num(1, line);
+        compr->body = {it, neg};
+        Stmt s2;
+        s2.k = Stmt::Expr;
+        s2.line = line;
+        s2.a = call("equal", {call("count", {TP(compr)}, line), num(0, line)}, line);
+        out.push_back(s1);
+        out.push_back(s2);
+        bound.push_back(s1.a->vid);
+        continue;
+      }
+      out.push_back(st);
+      std::vector<TP> vs;
+      var_terms(st, vs);
+      for (auto& v : vs) bound.push_back(v->vid);
+    }
+    return out;
+  }
+  void run() {
+    for (auto& kv : m.rules)
+      for (auto& r : kv.second) {
+        std::vector<int> bound;
+        std::vector<TP> vs;
+        for (auto& a : r.args) var_terms(a, vs);
+        for (auto& v : vs) bound.push_back(v->vid);
+        r.body = fix_body(r.body, bound);
+        std::vector<TP> bv;
+        for (auto& st : r.body) var_terms(st, bv);
+        std::vector<int> after = bound;
+        for (auto& v : bv) after.push_back(v->vid);
+        r.key = fix_term(r.key, after), r.value = fix_term(r.value, after);
+        for (auto& e : r.els) {
+          e.second = fix_body(e.second, bound);
+          e.first = fix_term(e.first, after);
+        }
+      }
+    for (auto& nr : new_rules) m.rules[nr.first].push_back(std::move(nr.second));
+  }
+};
 
 // ---- scoping of comprehension locals.  A variable declared with `:=` / `some` inside a comprehension is local to it and
 // SHADOWS a variable of the same name in the enclosing body (`c := containers[i]; all([ok(c) | c := containers[_]])` tests every
@@ -838,6 +1010,7 @@ std::shared_ptr<Module> rego_parse(const std::string& src, const std::vector<std
       if ((r.kind == Rule::Func) != (k0 == Rule::Func))
         throw RegoError{"rego_type_error: conflicting rules named " + kv.first};
   }
+  EveryDesugar{*m}.run();
   ComprScoper{*m}.run();
   check_unsafe(*m);
   compute_purity(*m);

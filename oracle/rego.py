@@ -471,6 +471,17 @@ class Parser:
                     return ("somein", None, names[0], coll)
                 return ("somein", names[0], names[1], coll)
             return ("some", [n[1] for n in names])
+        if self.at("every") and self.toks[self.i + 1].kind == "id":
+            # every [k,] v in coll { body }  (OPA v1 keyword): the body holds for every element; an empty domain is true
+            self.next()
+            first = self.parse_term(no_in=True)
+            second = self.parse_term(no_in=True) if self.accept(",") else None
+            self.expect("in")
+            coll = self.parse_term()
+            self.expect("{")
+            body = self.parse_body("}")
+            self.expect("}")
+            return ("every", first if second is not None else None, second if second is not None else first, coll, body)
         if self.at("not"):
             self.next()
             return ("not", self.parse_expr())
@@ -1130,6 +1141,21 @@ def _scope_fix(x):
     if x[0] in ("scalar", "var", "some"):
         return x
     x = tuple(_scope_fix(y) for y in x)
+    if x[0] == "every":
+        decl = []
+        _pattern_vars(x[1], decl)
+        _pattern_vars(x[2], decl)
+        for st in x[4]:
+            if st[0] == "assign":
+                _pattern_vars(st[1], decl)
+            elif st[0] == "some":
+                decl.extend(st[1])
+        ren = {}
+        for n in decl:
+            if n and not n.startswith("$") and n not in ren:
+                _scope_counter[0] += 1
+                ren[n] = "%s$%d" % (n, _scope_counter[0])
+        return ("every", _rename(x[1], ren), _rename(x[2], ren), x[3], _rename(x[4], ren))
     if x[0] in ("acompr", "scompr", "ocompr"):
         body = x[-1]
         decl = []
@@ -1354,6 +1380,27 @@ class Evaluator:
                     yield env2
         elif k in ("assign", "unify"):
             yield from self.unify(st[1], st[2], env)
+        elif k == "every":
+            for coll, env2 in self.eval_term(st[3], env):
+                if isinstance(coll, tuple):
+                    items = list(enumerate(coll))
+                elif isinstance(coll, RObj):
+                    items = sort_items(coll)
+                elif isinstance(coll, frozenset):
+                    items = [(x, x) for x in sorted_values(coll)]
+                else:
+                    items = []        # a defined non-collection has no members (OPA generates them with `domain[k] = v`): vacuously true
+                ok = True
+                for kk, vv in items:
+                    envs = [env2]
+                    if st[1] is not None:
+                        envs = list(self.unify_val(st[1], kk, env2))
+                    envs = [e2 for e in envs for e2 in self.unify_val(st[2], vv, e)]
+                    if not any(True for e in envs for _ in self.eval_body(st[4], e)):
+                        ok = False
+                        break
+                if ok:
+                    yield env2
         elif k == "somein":
             for coll, env2 in self.eval_term(st[3], env):
                 if isinstance(coll, tuple):

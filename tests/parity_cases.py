@@ -649,6 +649,52 @@ violation[{"msg": msg}] {
     return len(want)
 
 
+def case_every(lib, n=800):
+    """`every` (OPA v1 keyword): the engine rewrites it into a counted comprehension over a generated helper function, the
+    oracle evaluates it natively -- over object collections, parameter lists, with key and value, with an empty and with an
+    undefined domain."""
+    src = '''package e
+violation[{"msg": msg}] {
+  every c in input.review.object.spec.containers { startswith(c.image, input.parameters.prefix) }
+  msg := "every image has the prefix"
+}
+violation[{"msg": msg}] {
+  c := input.review.object.spec.containers[_]
+  every p in input.parameters.prefixes { not startswith(c.image, p) }
+  msg := sprintf("container <%v> matches no prefix", [c.name])
+}
+violation[{"msg": msg}] {
+  c := input.review.object.spec.containers[_]
+  every i, m in c.volumeMounts { m.readOnly; i < 2 }
+  msg := sprintf("container <%v> mounts (at most two) read-only only", [c.name])
+}
+violation[{"msg": msg}] {
+  every k, v in input.review.object.metadata.labels { startswith(k, "label-"); count(v) > input.parameters.n }
+  msg := "all labels are label-*"
+}
+'''
+    blob = W.synth_objects(7, n)
+    revs = [D.Review(object=json.loads(blob.get(i))) for i in range(n)]
+    revs.append(D.Review(object={"apiVersion": "v1", "kind": "Pod", "metadata": {"name": "nolabels"}, "spec": {}}))
+    revs.append(D.Review(object={"apiVersion": "v1", "kind": "Pod", "metadata": {"name": "empty", "labels": {}}, "spec": {"containers": []}}))
+    cons = [W._constraint("E", "e1", params={"prefix": "gcr.io/", "prefixes": ["gcr.io/", "quay.io/"], "n": 1}),
+            W._constraint("E", "e2", params={"prefix": "", "prefixes": [], "n": 3})]
+    orc, drv, skipped = make_pair([("E", src)], cons, lib_path=lib)
+    assert not skipped
+    resp = drv.ReviewBatch(revs, k8s.AUDIT_EP)
+    want = oracle_results(orc, revs, k8s.AUDIT_EP)
+    by_obj = {}
+    for w in want:
+        by_obj.setdefault(w[0], set()).add((w[1], w[2]))
+    # undefined domain (no labels, no containers): no result; empty domains: vacuously true
+    assert n not in by_obj
+    assert by_obj[n + 1] == {("E/e1", "every image has the prefix"), ("E/e2", "every image has the prefix"),
+                             ("E/e1", "all labels are label-*"), ("E/e2", "all labels are label-*")}
+    assert len(want) > n
+    assert_same(want, engine_results(resp))
+    return len(want)
+
+
 # ------------------------------------------------------------------------------------------ random policies
 _RF_HELPERS = """
 input_containers[c] { c := input.review.object.spec.containers[_] }
@@ -658,6 +704,7 @@ has_probe(c) { c.livenessProbe }
 tag_of(image) = t { parts := split(image, ":"); count(parts) > 1; t := parts[count(parts) - 1] }
 tag_of(image) = "latest" { not contains(image, ":") }
 level(c) = "high" { c.securityContext.privileged } else = "low" { true }
+every_mount_under(c, prefix) { every m in c.volumeMounts { startswith(m.mountPath, prefix) } }
 """
 
 _RF_CONDS = {
@@ -725,6 +772,10 @@ _RF_CONDS = {
         'flags := [startswith(c.image, input.parameters.prefix), c.name == input.parameters.name]\n  any(flags)',
         'flags := [startswith(c.image, input.parameters.prefix), c.name != input.parameters.name]\n  all(flags)',
         'count([p | p := c.ports[_]; p.containerPort > input.parameters.n]) > 0',
+        'every m in c.volumeMounts { m.readOnly }',
+        'not every_mount_under(c, input.parameters.mount)',
+        'every p in input.parameters.prefixes { not startswith(c.image, p) }',
+        'every i, p in c.ports { p.containerPort > input.parameters.n; i < 2 }',
         'all([m.readOnly | m := c.volumeMounts[_]; startswith(m.mountPath, input.parameters.mount)])',
         'not any([m.readOnly | m := c.volumeMounts[_]; startswith(m.mountPath, input.parameters.mount)])',
     ],
@@ -768,6 +819,10 @@ _RF_CONDS = {
         'input.review.object.metadata.name == input.review.object.spec.containers[_].name',
         'input.review.object.spec.containers[_].name == input.review.object.spec.volumes[_].name',
         'not input.review.object.spec.volumes',
+        'every c in input.review.object.spec.containers { startswith(c.image, input.parameters.prefix) }',
+        'every c in input_containers { c.resources.limits.cpu; not c.securityContext.privileged }',
+        'every k, v in input.review.object.metadata.labels { startswith(k, "label-"); count(v) > input.parameters.n }',
+        'every vol in input.review.object.spec.volumes { some t in input.parameters.volumes; vol[t] }',
         'not all([startswith(c.image, input.parameters.prefix) | c := input.review.object.spec.containers[_]])',
         'any([endswith(c.image, input.parameters.sub) | c := input_containers[_]])',
         'count([c | c := input.review.object.spec.containers[_]; startswith(c.image, input.parameters.prefix)]) == 0',

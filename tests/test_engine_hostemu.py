@@ -130,6 +130,10 @@ def test_rego_fuzz(seed):
     assert accepted >= 20 and n_results > 500
 
 
+def test_every():
+    assert P.case_every(HOSTEMU) > 800
+
+
 def test_cross_scope_join():
     assert P.case_cross_scope_join(HOSTEMU) > 20
 
