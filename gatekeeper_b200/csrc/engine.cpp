@@ -921,9 +921,10 @@ struct Flattener : ChunkOut {
         return cur;
       }
       case TK::Call: {
-        const std::vector<Rule>* frules = ev.function_rules(t);
+        bool other_rule = false;
+        const std::vector<Rule>* frules = ev.function_rules(t, &other_rule);
         const bool user = frules != nullptr;
-        if (!user && mod.is_rule(t.name)) {   // a non-function rule "called"
+        if (other_rule) {   // a non-function rule "called"
           ok = false;
           return nullptr;
         }
@@ -931,8 +932,15 @@ struct Flattener : ChunkOut {
           ok = false;
           return nullptr;
         }
-        std::vector<VP> args;
-        args.reserve(t.args.size());
+        // argument vectors are recycled per nesting depth (a call inside a call's arguments uses the next one)
+        if (call_depth_ >= arg_pool_.size()) arg_pool_.emplace_back();
+        std::vector<VP>& args = arg_pool_[call_depth_];
+        struct Depth {
+          size_t& d;
+          std::vector<VP>& v;
+          Depth(size_t& x, std::vector<VP>& vv) : d(x), v(vv) { ++d; v.clear(); }
+          ~Depth() { --d; v.clear(); }
+        } guard(call_depth_, args);
         for (auto& a : t.args) {
           VP v = a->k == TK::Scalar ? private_const(a->val) : eval_direct(*a, env, input, ev, mod, ok);
           if (!ok) return nullptr;
@@ -1090,6 +1098,8 @@ struct Flattener : ChunkOut {
     hold.push_back(std::move(v));
     return &hold.back();
   }
+  std::deque<std::vector<VP>> arg_pool_;
+  size_t call_depth_ = 0;
   std::deque<Env> env_pool;   // (deque: a nested evaluation may grow it while outer references are live)
   size_t env_depth = 0;
   std::unordered_map<uint64_t, VP> memo;   // per object: (closure, row) -> value

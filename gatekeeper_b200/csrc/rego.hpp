@@ -148,7 +148,7 @@ class Eval {
   VP call_function(const std::string& name, const std::vector<VP>& args);   // nullptr if undefined
   VP call_function(const std::vector<Rule>& rules, const std::vector<VP>& args);
   // the definitions of the function a Call term names (resolved once per term), or nullptr for a builtin / non-function
-  const std::vector<Rule>* function_rules(const Term& t) const;
+  const std::vector<Rule>* function_rules(const Term& t, bool* names_other_rule = nullptr) const;
   bool unify_val(const TP& pat, const VP& val, Env& env, const EnvK& k);
   bool is_ground(const TP& t, const Env& env) const;
   const Module& module() const { return m_; }

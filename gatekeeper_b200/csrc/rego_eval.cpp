@@ -758,13 +758,18 @@ VP Eval::rule_value(const std::string& name) {
   return val;
 }
 
-const std::vector<Rule>* Eval::function_rules(const Term& t) const {
-  if (__atomic_load_n(&t.is_rule_, __ATOMIC_ACQUIRE) < 0) {
+const std::vector<Rule>* Eval::function_rules(const Term& t, bool* names_other_rule) const {
+  // is_rule_ of a Call term: -1 unresolved, 1 a function, 2 a rule that is not a function, 0 no rule (a builtin, or unknown)
+  signed char st = __atomic_load_n(&t.is_rule_, __ATOMIC_ACQUIRE);
+  if (st < 0) {
     auto rit = m_.rules.find(t.name);
-    const void* fr = rit != m_.rules.end() && rit->second[0].kind == Rule::Func ? &rit->second : nullptr;
+    const bool is_rule = rit != m_.rules.end();
+    const void* fr = is_rule && rit->second[0].kind == Rule::Func ? &rit->second : nullptr;
+    st = fr ? 1 : is_rule ? 2 : 0;
     __atomic_store_n(&t.rules_, fr, __ATOMIC_RELAXED);   // every thread stores the same pointer
-    __atomic_store_n(&t.is_rule_, (signed char)(fr ? 1 : 0), __ATOMIC_RELEASE);
+    __atomic_store_n(&t.is_rule_, st, __ATOMIC_RELEASE);
   }
+  if (names_other_rule) *names_other_rule = st == 2;
   return static_cast<const std::vector<Rule>*>(__atomic_load_n(&t.rules_, __ATOMIC_RELAXED));
 }
 

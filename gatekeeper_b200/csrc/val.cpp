@@ -324,8 +324,21 @@ struct StrCache {
   static const size_t N = 2048;
   VP slot[N];
   const VP& get(const char* s, size_t n) {
-    uint64_t h = 1469598103934665603ull;
-    for (size_t i = 0; i < n; ++i) h = (h ^ (unsigned char)s[i]) * 1099511628211ull;
+    // eight bytes per multiply (keys and short values are 2 - 20 bytes: a byte-at-a-time hash was ~10 % of the parse)
+    uint64_t h = (uint64_t)n * 0x9E3779B97F4A7C15ull;
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8) {
+      uint64_t w;
+      memcpy(&w, s + i, 8);
+      h = (h ^ w) * 0xff51afd7ed558ccdull;
+      h ^= h >> 32;
+    }
+    if (i < n) {
+      uint64_t w = 0;
+      memcpy(&w, s + i, n - i);
+      h = (h ^ w) * 0xff51afd7ed558ccdull;
+      h ^= h >> 32;
+    }
     VP& v = slot[(h ^ (h >> 29)) & (N - 1)];
     if (!v || v->s.size() != n || memcmp(v->s.data(), s, n) != 0) v = v_str(std::string(s, n));
     return v;
