@@ -819,6 +819,19 @@ _RF_CONDS = {
         'input.review.object.metadata.name == input.review.object.spec.containers[_].name',
         'input.review.object.spec.containers[_].name == input.review.object.spec.volumes[_].name',
         'not input.review.object.spec.volumes',
+        # the review document around the object
+        'input.review.operation == "UPDATE"',
+        'input.review.operation != "DELETE"',
+        'input.review.oldObject.metadata.labels[input.parameters.key] != input.review.object.metadata.labels[input.parameters.key]',
+        'not input.review.oldObject.metadata',
+        'count(input.review.oldObject.spec.containers) != count(input.review.object.spec.containers)',
+        'startswith(input.review.userInfo.username, "system:")',
+        'not input.review.userInfo.username',
+        'not input.review.namespaceObject.metadata.labels[input.parameters.key]',
+        'input.review.namespaceObject.metadata.labels[input.parameters.key] == input.parameters.val',
+        'input.review.kind.group == ""',
+        'input.review.name == input.review.object.metadata.name',
+        'input.review.namespace == input.parameters.ns',
         'every c in input.review.object.spec.containers { startswith(c.image, input.parameters.prefix) }',
         'every c in input_containers { c.resources.limits.cpu; not c.securityContext.privileged }',
         'every k, v in input.review.object.metadata.labels { startswith(k, "label-"); count(v) > input.parameters.n }',
@@ -896,6 +909,20 @@ def case_rego_fuzz(lib, n_templates=40, n_objects=120, seed=1):
                 o = json.loads(json.dumps(r.object))
                 o["spec"]["containers"] = [c]
                 revs.append(D.Review(object=o))
+    # review shapes: UPDATE with an old object, DELETE (the old object is the one reviewed), user info, an explicit namespace object
+    for i in range(len(revs)):
+        r = rnd.random()
+        o = revs[i].object
+        if r < 0.12 and i:
+            revs[i] = D.Review(object=o, old_object=revs[i - 1].object, operation="UPDATE", source="Original")
+        elif r < 0.18:
+            revs[i] = D.Review(object=None, old_object=o, operation="DELETE", source="Original")
+        elif r < 0.30:
+            revs[i] = D.Review(object=o, operation=rnd.choice(["CREATE", "UPDATE"]), source="Original",
+                               user_info={"username": rnd.choice(["system:serviceaccount:kube-system:x", "alice", ""])})
+        elif r < 0.40:
+            revs[i] = D.Review(object=o, source="Original", namespace={"apiVersion": "v1", "kind": "Namespace", "metadata": dict(
+                {"name": rnd.choice(["explicit-ns", "ns-0001"])}, **({"labels": {rnd.choice(["team", "label-06", "app"]): rnd.choice(["v9", "team-42"])}} if rnd.random() < 0.7 else {}))})
     n_objects = len(revs)
     accepted = n_results = 0
     rejected = []
