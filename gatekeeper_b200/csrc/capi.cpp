@@ -1,5 +1,7 @@
 // C ABI (include/gk_engine.h) over Engine + Backend.  No exceptions cross this file's extern "C" surface.
 #include <chrono>
+#include <condition_variable>
+#include <mutex>
 #include <cstdlib>
 #include <cstring>
 #include <functional>
@@ -17,9 +19,35 @@ using namespace gk;
 struct gk_engine {
   std::unique_ptr<Engine> eng;
   std::unique_ptr<Backend> be;
+  std::mutex keys_mu;
   std::vector<std::string> keys;   // constraint keys of the last compiled program
   uint64_t keys_version = 0;
+  // The backend holds ONE program (the tables of one compiled snapshot).  Reviews of the same snapshot run concurrently; a
+  // review that needs another snapshot (constraints changed meanwhile) waits until the ones in flight have finished.
+  std::mutex lease_mu;
+  std::condition_variable lease_cv;
+  uint64_t lease_version = 0;
+  int lease_active = 0;
 };
+
+namespace {
+struct ProgramLease {
+  gk_engine* e;
+  ProgramLease(gk_engine* eng, const Compiled& c) : e(eng) {
+    std::unique_lock<std::mutex> l(e->lease_mu);
+    e->lease_cv.wait(l, [&] { return e->lease_active == 0 || e->lease_version == c.version; });
+    e->be->set_program(c);   // (a no-op when the backend already holds this version)
+    e->lease_version = c.version;
+    ++e->lease_active;
+  }
+  ~ProgramLease() {
+    std::lock_guard<std::mutex> l(e->lease_mu);
+    if (--e->lease_active == 0) e->lease_cv.notify_all();
+  }
+  ProgramLease(const ProgramLease&) = delete;
+  ProgramLease& operator=(const ProgramLease&) = delete;
+};
+}  // namespace
 
 struct gk_batch {
   void* dev = nullptr;
@@ -33,6 +61,8 @@ struct gk_batch {
 namespace {
 
 struct ResultPriv {
+  std::shared_ptr<const Compiled> compiled;   // the snapshot the result was computed with (constraint indices refer to it)
+  std::vector<std::string> keys;              // "Kind/name" per constraint index
   EvalOut ev;
   std::vector<Violation> vio;
   std::vector<gk_violation> cvio;
@@ -125,6 +155,8 @@ void eval_batch(gk_engine* e, gk_batch* b, const char* ep_c, uint32_t flags, gk_
   std::string ep = ep_c ? ep_c : "";
   const Compiled& c = *b->compiled;
   auto rp = std::make_unique<ResultPriv>();
+  rp->compiled = b->compiled;
+  for (auto* k : c.order) rp->keys.push_back(k->kind + "/" + k->name);
   std::vector<uint32_t> active;
   e->eng->active_mask(c, ep, active);
   bool copy_back = !(flags & GK_F_NO_COPY_BACK) || (flags & GK_F_MATERIALIZE);
@@ -197,9 +229,8 @@ void eval_batch(gk_engine* e, gk_batch* b, const char* ep_c, uint32_t flags, gk_
 
 const char* process_of(uint32_t flags) { return flags & GK_F_PROCESS_AUDIT ? "audit" : flags & GK_F_PROCESS_WEBHOOK ? "webhook" : ""; }
 
-void upload_batch(gk_engine* e, const gk_obj* objs, size_t n, uint32_t flags, gk_batch** outb, gk_result* stats) {
-  auto c = e->eng->compiled();
-  e->be->set_program(*c);
+void upload_batch(gk_engine* e, const std::shared_ptr<const Compiled>& c, const gk_obj* objs, size_t n, uint32_t flags, gk_batch** outb,
+                  gk_result* stats) {
   std::vector<ObjIn> ins(n);
   for (size_t i = 0; i < n; ++i) ins[i] = to_in(objs[i]);
   double t0 = now_ms();
@@ -288,6 +319,7 @@ uint32_t gk_constraint_count(gk_engine_t* e) {
   uint32_t n = 0;
   guard(nullptr, [&]() {
     auto c = e->eng->compiled();
+    std::lock_guard<std::mutex> l(e->keys_mu);
     if (e->keys_version != c->version) {
       e->keys.clear();
       for (auto* k : c->order) e->keys.push_back(k->kind + "/" + k->name);
@@ -299,7 +331,14 @@ uint32_t gk_constraint_count(gk_engine_t* e) {
 }
 const char* gk_constraint_key(gk_engine_t* e, uint32_t index) {
   uint32_t n = gk_constraint_count(e);
-  return index < n ? e->keys[index].c_str() : nullptr;
+  if (!e) return nullptr;
+  std::lock_guard<std::mutex> l(e->keys_mu);
+  return index < n && index < e->keys.size() ? e->keys[index].c_str() : nullptr;
+}
+const char* gk_result_constraint_key(const gk_result* r, uint32_t index) {
+  if (!r || !r->priv) return nullptr;
+  auto* rp = static_cast<const ResultPriv*>(r->priv);
+  return index < rp->keys.size() ? rp->keys[index].c_str() : nullptr;
 }
 
 int gk_review_batch(gk_engine_t* e, const gk_obj* objs, size_t n, const char* ep, uint32_t flags, gk_result* out, char** err) {
@@ -309,7 +348,9 @@ int gk_review_batch(gk_engine_t* e, const gk_obj* objs, size_t n, const char* ep
     gk_batch* b = nullptr;
     gk_result stats;
     memset(&stats, 0, sizeof stats);
-    upload_batch(e, objs, n, flags, &b, &stats);
+    auto c = e->eng->compiled();
+    ProgramLease lease(e, *c);   // flatten + upload + kernel + rendering all against this one snapshot
+    upload_batch(e, c, objs, n, flags, &b, &stats);
     std::unique_ptr<gk_batch, std::function<void(gk_batch*)>> hold(b, [&](gk_batch* x) {
       e->be->release(x->dev);
       delete x;
@@ -324,7 +365,11 @@ int gk_review_batch(gk_engine_t* e, const gk_obj* objs, size_t n, const char* ep
 int gk_batch_upload(gk_engine_t* e, const gk_obj* objs, size_t n, uint32_t flags, gk_batch_t** outb, gk_result* stats, char** err) {
   if (!e || !outb || (!objs && n)) return GK_ERR_INVALID;
   if (stats) memset(stats, 0, sizeof *stats);
-  return guard(err, [&]() { upload_batch(e, objs, n, flags, outb, stats); });
+  return guard(err, [&]() {
+    auto c = e->eng->compiled();
+    ProgramLease lease(e, *c);
+    upload_batch(e, c, objs, n, flags, outb, stats);
+  });
 }
 
 int gk_batch_eval(gk_engine_t* e, gk_batch_t* b, const char* ep, uint32_t flags, gk_result* out, char** err) {
@@ -333,7 +378,7 @@ int gk_batch_eval(gk_engine_t* e, gk_batch_t* b, const char* ep, uint32_t flags,
   return guard(err, [&]() {
     auto c = e->eng->compiled();
     if (c->version != b->compiled->version) throw RegoError{"batch was flattened against an older constraint set; upload it again"};
-    e->be->set_program(*c);
+    ProgramLease lease(e, *c);
     eval_batch(e, b, ep, flags, out);
   });
 }
@@ -344,7 +389,7 @@ int gk_batch_eval_device(gk_engine_t* e, gk_batch_t* b, const char* ep, void* d_
   return guard(err, [&]() {
     auto c = e->eng->compiled();
     if (c->version != b->compiled->version) throw RegoError{"batch was flattened against an older constraint set; upload it again"};
-    e->be->set_program(*c);
+    ProgramLease lease(e, *c);
     std::vector<uint32_t> active;
     e->eng->active_mask(*c, ep ? ep : "", active);
     DevOutPtrs d;
@@ -364,7 +409,7 @@ int gk_batch_eval_device_peers(gk_engine_t* e, gk_batch_t* b, const char* ep, co
   return guard(err, [&]() {
     auto c = e->eng->compiled();
     if (c->version != b->compiled->version) throw RegoError{"batch was flattened against an older constraint set; upload it again"};
-    e->be->set_program(*c);
+    ProgramLease lease(e, *c);
     std::vector<uint32_t> active;
     e->eng->active_mask(*c, ep ? ep : "", active);
     DevOutPtrs d;
@@ -400,7 +445,9 @@ int gk_batch_upload_blob(gk_engine_t* e, const char* buf, const uint64_t* offset
   if (stats) memset(stats, 0, sizeof *stats);
   return guard(err, [&]() {
     auto v = blob_objs(buf, offsets, n, source);
-    upload_batch(e, v.data(), n, flags, outb, stats);
+    auto c = e->eng->compiled();
+    ProgramLease lease(e, *c);
+    upload_batch(e, c, v.data(), n, flags, outb, stats);
   });
 }
 
@@ -450,7 +497,7 @@ int gk_audit_add_batch(gk_audit_t* a, gk_batch_t* b, const char* ep_c, char** er
     gk_engine* e = a->e;
     auto c = e->eng->compiled();
     if (c->version != b->compiled->version) throw RegoError{"batch was flattened against an older constraint set; upload it again"};
-    e->be->set_program(*c);
+    ProgramLease lease(e, *c);
     std::string ep = ep_c ? ep_c : "";
     std::vector<uint32_t> active;
     e->eng->active_mask(*c, ep, active);
@@ -476,7 +523,7 @@ char* gk_validation_messages(gk_engine_t* e, const gk_result* r, uint32_t object
   char* out = nullptr;
   guard(err, [&]() {
     auto* rp = static_cast<ResultPriv*>(r->priv);
-    auto c = e->eng->compiled();
+    auto c = rp->compiled ? rp->compiled : e->eng->compiled();
     std::vector<std::string> deny, warn;
     validation_messages(*c, rp->vio, object, deny, warn);
     std::string o = "{\"deny\":[";

@@ -84,7 +84,10 @@ static void run_batch(gk_coalescer* c, Batch& b) {
       if (!first) o += ",";
       first = false;
       o += "{\"constraint\":";
-      gk::json_quote(gk_constraint_key(c->e, x.constraint), o);
+      {
+        const char* key = gk_result_constraint_key(&res, x.constraint);   // (the result's own snapshot: constraints may change meanwhile)
+        gk::json_quote(key ? key : "", o);
+      }
       o += ",\"msg\":";
       gk::json_quote(x.msg, o);
       o += ",\"details\":";

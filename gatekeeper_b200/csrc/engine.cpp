@@ -343,7 +343,7 @@ void Engine::add_constraint(const std::string& json) {
     throw RegoError{"invalid constraint: " + e.msg};
   }
   if (obj->t != VT::Obj) throw RegoError{"invalid constraint: not an object"};
-  auto c = std::make_unique<Constraint>();
+  auto c = std::make_shared<Constraint>();
   c->kind = str_field(obj, "kind");
   c->name = meta_str(obj, "name");
   if (c->kind.empty() || c->name.empty()) throw RegoError{"invalid constraint: kind and metadata.name are required"};
@@ -449,13 +449,15 @@ void Engine::compile_locked() {
   // pass 1: lower every constraint (fills the shared schema); group constraints that share a match block so the
   // kernel evaluates each distinct spec.match once per object
   std::vector<Constraint*> live;
+  std::vector<FP> live_formula;
   std::map<std::string, uint32_t> match_ix;
   std::vector<uint32_t> mid_of;
   for (auto& cp : constraints_) {
     Constraint& c = *cp;
+    out->pins.push_back(cp);
     auto tit = templates_.find(c.kind);
     if (tit == templates_.end()) continue;
-    c.formula = lower_violation(tit->second.mod, c.params, out->schema);
+    live_formula.push_back(lower_violation(tit->second.mod, c.params, out->schema));
     std::string key = c.match.has ? json_str(c.match.raw) : std::string();
     auto it = match_ix.find(key);
     uint32_t mid = it == match_ix.end() ? (uint32_t)match_ix.size() : it->second;
@@ -470,7 +472,8 @@ void Engine::compile_locked() {
   for (size_t i : perm) {
     out->order.push_back(live[i]);
     out->mods.push_back(templates_.at(live[i]->kind).mod);
-    all.push_back(live[i]->formula);
+    all.push_back(live_formula[i]);
+    out->formulas.push_back(live_formula[i]);
     out->cons_match.push_back(mid_of[i]);
   }
   out->match.resize(match_ix.size());
@@ -480,7 +483,7 @@ void Engine::compile_locked() {
     Constraint& c = *live[perm[oi]];
     const uint32_t mid = mid_of[perm[oi]];
     GkMatch m{};
-    MatchSpec& ms = c.match;
+    MatchSpec ms = c.match;   // (a copy: the error texts below go into the snapshot)
     ms.lsel_err.clear();
     ms.nssel_err.clear();
     ms.src_err.clear();
@@ -579,7 +582,7 @@ void Engine::compile_locked() {
       out->match[mid] = m;
       built[mid] = true;
     }
-    ms.dev = out->match[mid];
+    out->match_errs.push_back(Compiled::MatchErrs{ms.lsel_err, ms.nssel_err, ms.src_err});
   }
   if (out->match.empty()) out->match.push_back(GkMatch{});
   pb.build(all, out->cons_match, (uint32_t)match_ix.size());
@@ -643,7 +646,7 @@ std::string Engine::dump() {
          c->schema.cols[i].expr->key + "\n";
   for (size_t i = 0; i < c->order.size(); ++i)
     o += "constraint " + std::to_string(i) + " " + c->order[i]->kind + "/" + c->order[i]->name + ": " +
-         formula_str(c->order[i]->formula, c->schema) + "\n";
+         formula_str(c->formulas[i], c->schema) + "\n";
   return o;
 }
 
@@ -1627,10 +1630,10 @@ void Engine::autoreject(const Compiled& c, const ObjIn& in, uint32_t obj_ix, uin
   std::string name = ref ? meta_str(ref, "name") : "";
   std::string detail;
   switch (code) {
-    case GK_E_LSEL_INVALID: detail = con.match.lsel_err; break;
-    case GK_E_NSSEL_INVALID: detail = con.match.nssel_err; break;
+    case GK_E_LSEL_INVALID: detail = c.match_errs[cix].lsel; break;
+    case GK_E_NSSEL_INVALID: detail = c.match_errs[cix].nssel; break;
     case GK_E_NS_MISSING: detail = "namespace selector for namespace-scoped object but missing Namespace"; break;
-    case GK_E_SRC_INVALID_MATCH: detail = con.match.src_err; break;
+    case GK_E_SRC_INVALID_MATCH: detail = c.match_errs[cix].src; break;
     case GK_E_SRC_UNSPECIFIED: detail = "source field not specified for resource " + name; break;
     case GK_E_SRC_INVALID_OBJ: detail = "invalid source field"; break;
     case GK_E_NUM_RANGE: detail = "number outside the exact int64 range in an ordered comparison"; break;

@@ -75,7 +75,6 @@ struct Constraint {
   MatchSpec match;
   std::string action;                          // deny / dryrun / warn / scoped / unrecognized
   std::vector<ScopedAction> scoped;
-  FP formula;
 };
 
 struct TemplateEntry {
@@ -96,6 +95,12 @@ struct Compiled {
   std::vector<GkMatch> match;                  // DISTINCT match blocks
   std::vector<uint32_t> cons_match;            // per constraint: match block id
   std::vector<const Constraint*> order;        // constraint index -> constraint (grouped by match block)
+  // per constraint, owned by the snapshot (compiling never writes into a Constraint that an older snapshot may be reading):
+  std::vector<FP> formulas;                              // the lowered violation predicate
+  struct MatchErrs { std::string lsel, nssel, src; };
+  std::vector<MatchErrs> match_errs;                     // error texts behind the *_INVALID match flags
+  std::vector<std::shared_ptr<const Constraint>> pins;   // keeps `order` alive while a review still uses this snapshot
+                                                         // (RemoveConstraint / a replacing AddConstraint may run meanwhile)
   std::vector<std::shared_ptr<Module>> mods;   // constraint index -> its template's module (pinned by this snapshot)
   size_t n_nodes = 0, n_atoms = 0, n_gates = 0, n_phases = 0;
 };
@@ -182,7 +187,7 @@ class Engine {
   void compile_locked();
   std::shared_mutex mu_;
   std::map<std::string, TemplateEntry> templates_;
-  std::vector<std::unique_ptr<Constraint>> constraints_;
+  std::vector<std::shared_ptr<Constraint>> constraints_;   // (shared: a compiled snapshot pins the constraints it was built from)
   std::map<std::string, VP> namespaces_;
   std::map<std::string, std::vector<std::string>> excluded_;
   std::shared_ptr<Compiled> compiled_;

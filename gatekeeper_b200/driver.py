@@ -66,7 +66,7 @@ class gk_result(C.Structure):
 EXPORTS = [
     "gk_engine_create", "gk_engine_destroy", "gk_backend_name", "gk_add_template", "gk_add_template_libs", "gk_remove_template",
     "gk_add_constraint", "gk_remove_constraint", "gk_put_namespace", "gk_remove_namespace", "gk_constraint_count",
-    "gk_constraint_key", "gk_review_batch", "gk_batch_upload", "gk_batch_eval", "gk_batch_eval_device",
+    "gk_constraint_key", "gk_result_constraint_key", "gk_review_batch", "gk_batch_upload", "gk_batch_eval", "gk_batch_eval_device",
     "gk_batch_eval_device_peers", "gk_batch_upload_blob", "gk_review_blob", "gk_set_excluded_namespaces", "gk_audit_begin", "gk_audit_add_batch", "gk_audit_report",
     "gk_audit_end", "gk_validation_messages", "gk_host_cpus", "gk_coalescer_create", "gk_coalescer_review", "gk_coalescer_stats",
     "gk_coalescer_destroy", "gk_batch_size", "gk_batch_alg_bytes", "gk_batch_free", "gk_free_result", "gk_free_str", "gk_dump",
@@ -97,6 +97,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.gk_constraint_count.argtypes = [P]
     lib.gk_constraint_key.restype = S
     lib.gk_constraint_key.argtypes = [P, U32]
+    lib.gk_result_constraint_key.restype = S
+    lib.gk_result_constraint_key.argtypes = [C.POINTER(gk_result), U32]
     lib.gk_review_batch.argtypes = [P, C.POINTER(gk_obj), C.c_size_t, S, U32, C.POINTER(gk_result), PP]
     lib.gk_batch_upload.argtypes = [P, C.POINTER(gk_obj), C.c_size_t, U32, C.POINTER(P), C.POINTER(gk_result), PP]
     lib.gk_batch_eval.argtypes = [P, P, S, U32, C.POINTER(gk_result), PP]
@@ -306,7 +308,13 @@ class Driver:
 
     def constraints(self) -> list:
         n = self._lib.gk_constraint_count(self._e)
-        return [self._lib.gk_constraint_key(self._e, i).decode() for i in range(n)]
+        out = []
+        for i in range(n):
+            k = self._lib.gk_constraint_key(self._e, i)      # None: the constraint set shrank between the two calls
+            if k is None:
+                break
+            out.append(k.decode())
+        return out
 
     # ---- reviews
     def _marshal(self, reviews: Iterable):
@@ -334,6 +342,13 @@ class Driver:
     def _unpack(self, res: gk_result, keys: list, with_results: bool = True) -> BatchResponse:
         import numpy as np
         n, w, c = res.n_objects, res.words, res.n_constraints
+        if res.priv:
+            # the result names its own columns (the engine's constraint set may have changed since the review started)
+            own = [self._lib.gk_result_constraint_key(C.byref(res), i) for i in range(c)]
+            if all(k is not None for k in own):
+                keys = [k.decode() for k in own]
+        if keys is None:
+            keys = self.constraints()
         vb = eb = None
         if res.viol_bits:
             vb = np.ctypeslib.as_array(res.viol_bits, shape=(n * w,)).copy().reshape(n, w) if n else np.zeros((0, w), np.uint32)
@@ -360,7 +375,7 @@ class Driver:
         arr, n, keep = self._marshal(reviews)
         res = gk_result()
         err = C.c_char_p()
-        keys = self.constraints()
+        keys = None           # (the result names its own constraint columns)
         rc = self._lib.gk_review_batch(self._e, arr, n, enforcement_point.encode(),
                                        (F_MATERIALIZE if materialize else 0) | PROCESS_FLAG.get(process, 0), C.byref(res), C.byref(err))
         self._check(rc, err)
@@ -430,7 +445,7 @@ class Driver:
         """End-to-end audit page: host JSON -> flatten -> H2D -> kernel -> D2H (+ optional message rendering)."""
         res = gk_result()
         err = C.c_char_p()
-        keys = self.constraints()
+        keys = None
         self._check(self._lib.gk_review_blob(self._e, blob.buf, blob.offsets, len(blob), SOURCE.get(source, 4), enforcement_point.encode(),
                                              flags, C.byref(res), C.byref(err)), err)
         try:
@@ -522,7 +537,7 @@ class ResidentBatch:
     def eval(self, enforcement_point: str = AUDIT_EP, flags: int = 0) -> BatchResponse:
         res = gk_result()
         err = C.c_char_p()
-        keys = self.drv.constraints()
+        keys = None
         self.drv._check(self.drv._lib.gk_batch_eval(self.drv._e, self.h, enforcement_point.encode(), flags, C.byref(res), C.byref(err)), err)
         try:
             return self.drv._unpack(res, keys)

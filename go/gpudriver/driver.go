@@ -288,7 +288,7 @@ func (d *Driver) reviewBatch(_ context.Context, ars []*admissionv1.AdmissionRequ
 		if dj := C.GoString(v.details_json); dj != "" {
 			_ = json.Unmarshal([]byte(dj), &details)
 		}
-		out = append(out, rawResult{key: C.GoString(C.gk_constraint_key(d.e, v.constraint)), msg: C.GoString(v.msg), details: details})
+		out = append(out, rawResult{key: C.GoString(C.gk_result_constraint_key(&res, v.constraint)), msg: C.GoString(v.msg), details: details})
 	}
 	stats := []*instrumentation.StatsEntry{{Scope: "batch", StatsFor: fmt.Sprintf("%d reviews", n),
 		Stats: []*instrumentation.Stat{

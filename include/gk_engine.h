@@ -115,6 +115,9 @@ int gk_remove_namespace(gk_engine_t* e, const char* name);
 /* constraint index <-> identity ("Kind/name"); the returned string is engine-owned until the next mutation */
 uint32_t gk_constraint_count(gk_engine_t* e);
 const char* gk_constraint_key(gk_engine_t* e, uint32_t index);
+/* The same mapping as of the snapshot a result was computed with: stays valid (until gk_free_result) when constraints are
+ * added or removed concurrently -- use this one to interpret `gk_violation.constraint` and the bitmap columns of `r`. */
+const char* gk_result_constraint_key(const gk_result* r, uint32_t index);
 
 int gk_review_batch(gk_engine_t* e, const gk_obj* objs, size_t n, const char* enforcement_point, uint32_t flags,
                     gk_result* out, char** err);

@@ -5,6 +5,8 @@
 // (gatekeeper_b200/libgk_engine.so) links kernels.cu instead and has no CPU path at all.
 #include <algorithm>
 #include <chrono>
+#include <memory>
+#include <mutex>
 
 #include "../../gatekeeper_b200/csrc/backend.hpp"
 #include "../../gatekeeper_b200/csrc/vm_core.h"
@@ -22,8 +24,17 @@ struct EmuBatch {
 class HostEmuBackend : public Backend {
  public:
   const char* name() const override { return "hostemu-TEST-ONLY"; }
-  void set_program(const Compiled& c) override { prog_ = &c; }
-  void sync_strings(const StringTable& st) override { st.snapshot(dict_off_, dict_bytes_); }
+  void set_program(const Compiled& c) override {
+    std::lock_guard<std::mutex> l(mu_);
+    prog_ = &c;
+  }
+  // the dictionary is replaced, never edited in place: an evaluation keeps the copy it started with
+  void sync_strings(const StringTable& st) override {
+    auto d = std::make_shared<Dict>();
+    st.snapshot(d->off, d->bytes);
+    std::lock_guard<std::mutex> l(mu_);
+    dict_ = std::move(d);
+  }
   void* upload(const HostBatch& hb, const Compiled& c, double* ms, uint64_t* bytes) override {
     auto* b = new EmuBatch();
     pack_batch(hb, c, b->pb);
@@ -40,12 +51,19 @@ class HostEmuBackend : public Backend {
 
   void eval(void* bb, const std::vector<uint32_t>& active, EvalOut& out, bool) override {
     auto* b = static_cast<EmuBatch*>(bb);
-    const Compiled& c = *prog_;
+    std::shared_ptr<const Dict> dict;
+    const Compiled* progp;
+    {
+      std::lock_guard<std::mutex> l(mu_);
+      dict = dict_;
+      progp = prog_;
+    }
+    const Compiled& c = *progp;
     const uint32_t C = (uint32_t)c.cons_match.size(), W = b->words, n = b->n;
     GkBatch h = b->hdr;
-    h.dict_off = dict_off_.data();
-    h.dict_bytes = dict_bytes_.data();
-    h.dict_n = (uint32_t)dict_off_.size() - 1;
+    h.dict_off = dict->off.data();
+    h.dict_bytes = dict->bytes.data();
+    h.dict_n = (uint32_t)dict->off.size() - 1;
     out.n = n;
     out.nconstraints = C;
     out.words = W;
@@ -180,9 +198,13 @@ class HostEmuBackend : public Backend {
   }
 
  private:
+  struct Dict {
+    std::vector<uint32_t> off;
+    std::vector<uint8_t> bytes;
+  };
+  std::mutex mu_;
   const Compiled* prog_ = nullptr;
-  std::vector<uint32_t> dict_off_;
-  std::vector<uint8_t> dict_bytes_;
+  std::shared_ptr<const Dict> dict_;
 };
 
 Backend* make_backend(int) { return new HostEmuBackend(); }

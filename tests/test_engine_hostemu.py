@@ -152,3 +152,57 @@ def test_gator_test_table():
 
 def test_verify_suite():
     P.case_verify_suite(HOSTEMU)
+
+
+def test_reviews_concurrent_with_constraint_changes():
+    """Reviews and AddConstraint / RemoveConstraint from several threads at once (the webhook serves while controllers
+    reconcile): a review runs against ONE compiled snapshot from flatten to rendering, a review that needs another snapshot
+    waits for the ones in flight, results name their own constraint columns, snapshots pin their constraints."""
+    import json
+    import random
+    import threading
+    import time
+    from gatekeeper_b200 import workloads as W
+    from oracle import k8s
+    tm, cons = W.config2()
+    drv = D.Driver(lib_path=HOSTEMU, threads=2)
+    for k, r in tm:
+        drv.add_template(k, r)
+    for c in cons:
+        drv.AddConstraint(c)
+    blob = W.synth_objects(0, 200)
+    revs = [D.Review(object=json.loads(blob.get(i))) for i in range(200)]
+    names = {c["kind"] + "/" + c["metadata"]["name"] for c in cons}
+    stop = time.time() + 3.0
+    errs, counts = [], {"rev": 0, "mut": 0}
+
+    def reviewer():
+        try:
+            while time.time() < stop:
+                r = drv.ReviewBatch(revs, k8s.AUDIT_EP)
+                counts["rev"] += 1
+                assert set(r.constraints) <= names and len(r.totals) == len(r.constraints)
+                for x in r.results:
+                    assert x.constraint in names
+        except Exception as e:      # noqa: BLE001
+            errs.append(repr(e))
+
+    def mutator(seed):
+        rnd = random.Random(seed)
+        try:
+            while time.time() < stop:
+                c = rnd.choice(cons)
+                if rnd.random() < 0.5:
+                    drv.RemoveConstraint(c)
+                drv.AddConstraint(c)
+                counts["mut"] += 1
+        except Exception as e:      # noqa: BLE001
+            errs.append(repr(e))
+
+    ts = [threading.Thread(target=reviewer) for _ in range(3)] + [threading.Thread(target=mutator, args=(i,)) for i in range(2)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs, errs[:3]
+    assert counts["rev"] >= 3 and counts["mut"] >= 10
