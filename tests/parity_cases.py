@@ -819,6 +819,13 @@ _RF_CONDS = {
         'input.review.object.metadata.name == input.review.object.spec.containers[_].name',
         'input.review.object.spec.containers[_].name == input.review.object.spec.volumes[_].name',
         'not input.review.object.spec.volumes',
+        # structured parameters (lists of objects, as in K8sRequiredLabels' {key, allowedRegex})
+        'expected := input.parameters.pairs[_]\n  input.review.object.metadata.labels[expected.key] != expected.val',
+        'some pair in input.parameters.pairs\n  not input.review.object.metadata.labels[pair.key]',
+        'expected := input.parameters.pairs[_]\n  v := input.review.object.metadata.labels[expected.key]\n  not re_match(expected.pattern, v)',
+        'every pair in input.parameters.pairs { input.review.object.metadata.labels[pair.key] }',
+        'wanted := {p.key | p := input.parameters.pairs[_]}\n  have := {k | input.review.object.metadata.labels[k]}\n  count(wanted - have) > 0',
+        'count({p.key | p := input.parameters.pairs[_]; input.review.object.metadata.labels[p.key] == p.val}) == 0',
         # the review document around the object
         'input.review.operation == "UPDATE"',
         'input.review.operation != "DELETE"',
@@ -858,6 +865,8 @@ def _rf_params(rnd):
             "key": rnd.choice(["team", "label-06", "app", "label-15"]), "val": rnd.choice(["team-42", "v9", ""]),
             "labels": rnd.sample(["team", "label-01", "label-06", "label-22", "owner"], rnd.randint(0, 3)), "ns": rnd.choice(["ns-0001", "kube-system", "production"]),
             "flag": rnd.choice([True, False]), "volumes": rnd.sample(["emptyDir", "configMap", "secret", "hostPath", "persistentVolumeClaim", "projected"], rnd.randint(0, 4)),
+            "pairs": [{"key": rnd.choice(["team", "label-06", "app", "label-15", "label-22"]), "val": rnd.choice(["team-42", "v9", "v123"]),
+                       "pattern": rnd.choice(["^team-[0-9]+$", "^v[0-9]+$", "^x"])} for _ in range(rnd.randint(0, 3))],
             "mount": rnd.choice(["/mnt", "/", "/mnt/1"]), "policy": rnd.choice(["Always", "IfNotPresent"]), "kind": rnd.choice(["Pod", "Deployment"])}
 
 
