@@ -791,6 +791,8 @@ class Lowerer {
     }
     if (b.k == SymVal::Bool && a.k == SymVal::Conc) return eq_cond(b, a, line);
     if (a.k == SymVal::Count || b.k == SymVal::Count) return count_cmp(GK_CMP_EQ, a, b, line);
+    if (a.k == SymVal::Opaque && a.col && b.k == SymVal::Conc) return a_eq(a.col, b.v);   // a formatted string against a constant
+    if (b.k == SymVal::Opaque && b.col && a.k == SymVal::Conc) return a_eq(b.col, a.v);
     unsupported("equality between composite symbolic values", line);
   }
 
@@ -1241,8 +1243,23 @@ class Lowerer {
     size_t nformal = user ? rit->second[0].args.size() : t->args.size();
     if (user && t->args.size() != nformal) unsupported("function call with output argument", t->line);
     std::vector<SymVal> args;
+    // a sprintf over object fields only is normally just a message (never a column: it would be computed for every object);
+    // it carries its closure along so that a COMPARISON with a constant can still become a column atom
+    CP text_closure;
+    if (!user && t->name == "sprintf" && pure_obj(deps(t, env, false))) {
+      try {
+        text_closure = make_closure(t, env);
+      } catch (RegoError&) {
+      }
+    }
+    SymK k2 = [&](const SymVal& v) {
+      if (!text_closure || v.k != SymVal::Opaque) return k(v);
+      SymVal w = v;
+      w.col = text_closure;
+      return k(w);
+    };
     std::function<FP(size_t)> rec = [&](size_t i) -> FP {
-      if (i == t->args.size()) return user ? inline_function(t, args, k) : builtin_sym(t, args, k);
+      if (i == t->args.size()) return user ? inline_function(t, args, k) : builtin_sym(t, args, text_closure ? k2 : k);
       return sym_term(t->args[i], env, [&](const SymVal& v) {
         args.push_back(v);
         FP r = rec(i + 1);
