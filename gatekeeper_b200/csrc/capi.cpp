@@ -301,6 +301,14 @@ int gk_add_constraint(gk_engine_t* e, const char* json, size_t len, char** err) 
   if (!e || !json) return GK_ERR_INVALID;
   return guard(err, [&]() { e->eng->add_constraint(std::string(json, len)); });
 }
+int gk_validate_constraint(gk_engine_t* e, const char* json, size_t len, char** err) {
+  (void)e;
+  if (!json) return GK_ERR_INVALID;
+  return guard(err, [&]() {
+    std::string msg = validate_constraint_json(std::string(json, len));
+    if (!msg.empty()) throw RegoError{msg};
+  });
+}
 int gk_remove_constraint(gk_engine_t* e, const char* kind, const char* name) {
   if (!e || !kind || !name) return GK_ERR_INVALID;
   return guard(nullptr, [&]() { e->eng->remove_constraint(kind, name); });

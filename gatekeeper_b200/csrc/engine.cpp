@@ -264,6 +264,109 @@ static std::string parse_selector(const VP& sel, std::vector<SelReq>& out) {
   return "";
 }
 
+// K8sValidationTarget.ValidateConstraint (pkg/target/target.go:178-214): spec.match.labelSelector / namespaceSelector must be
+// maps, must convert to metav1.LabelSelector (types), and must pass apimachinery's ValidateLabelSelector.  Returns "" or the
+// error text.  (The frameworks client calls this before Driver.AddConstraint; pinned by TestValidateConstraint.)
+static const char* go_type_name(const VP& v) {
+  switch (v->t) {
+    case VT::Null: return "null";
+    case VT::True:
+    case VT::False: return "bool";
+    case VT::Num: return "number";
+    case VT::Str: return "string";
+    case VT::Arr: return "array";
+    default: return "object";
+  }
+}
+static std::string selector_field_errors(const VP& sel, std::vector<std::string>& errs) {
+  const std::string P = "spec.labelSelector";
+  auto cannot = [&](const VP& v, const std::string& where) {
+    return std::string("Could not convert JSON to LabelSelector: json: cannot unmarshal ") + go_type_name(v) + " into Go struct field " + where;
+  };
+  auto quote = [](const std::string& x) {
+    std::string q;
+    json_quote(x, q);
+    return q;
+  };
+  VP ml = obj_get(sel, "matchLabels");
+  if (ml && ml->t != VT::Null) {
+    if (ml->t != VT::Obj) return cannot(ml, "LabelSelector.matchLabels of type map[string]string");
+    for (auto& e : ml->kv)
+      if (e.second->t != VT::Str) return cannot(e.second, "LabelSelector.matchLabels of type string");
+  }
+  VP me = obj_get(sel, "matchExpressions");
+  if (me && me->t != VT::Null) {
+    if (me->t != VT::Arr) return cannot(me, "LabelSelector.matchExpressions of type []v1.LabelSelectorRequirement");
+    for (auto& x : me->items) {
+      if (x->t != VT::Obj) return cannot(x, "LabelSelector.matchExpressions of type v1.LabelSelectorRequirement");
+      for (const char* f : {"key", "operator"}) {
+        VP v = obj_get(x, f);
+        if (v && v->t != VT::Null && v->t != VT::Str) return cannot(v, std::string("LabelSelectorRequirement.matchExpressions.") + f + " of type string");
+      }
+      VP vals = obj_get(x, "values");
+      if (vals && vals->t != VT::Null) {
+        if (vals->t != VT::Arr) return cannot(vals, "LabelSelectorRequirement.matchExpressions.values of type []string");
+        for (auto& v : vals->items)
+          if (v->t != VT::Str) return cannot(v, "LabelSelectorRequirement.matchExpressions.values of type []string");
+      }
+    }
+  }
+  if (ml && ml->t == VT::Obj)
+    for (auto& e : ml->kv) {   // (sorted by key)
+      for (auto& m : qualified_name_errors(e.first->s)) errs.push_back(P + ".matchLabels: Invalid value: " + quote(e.first->s) + ": " + m);
+      for (auto& m : label_value_errors(e.second->s)) errs.push_back(P + ".matchLabels: Invalid value: " + quote(e.second->s) + ": " + m);
+    }
+  if (me && me->t == VT::Arr)
+    for (size_t i = 0; i < me->items.size(); ++i) {
+      const VP& x = me->items[i];
+      const std::string fp = P + ".matchExpressions[" + std::to_string(i) + "]";
+      const std::string op = str_field(x, "operator"), key = str_field(x, "key");
+      std::vector<std::string> vals;
+      VP vs = obj_get(x, "values");
+      if (vs && vs->t == VT::Arr)
+        for (auto& v : vs->items) vals.push_back(v->s);
+      if (op == "In" || op == "NotIn") {
+        if (vals.empty()) errs.push_back(fp + ".values: Required value: must be specified when `operator` is 'In' or 'NotIn'");
+      } else if (op == "Exists" || op == "DoesNotExist") {
+        if (!vals.empty()) errs.push_back(fp + ".values: Forbidden: may not be specified when `operator` is 'Exists' or 'DoesNotExist'");
+      } else {
+        errs.push_back(fp + ".operator: Invalid value: " + quote(op) + ": not a valid selector operator");
+      }
+      for (auto& m : qualified_name_errors(key)) errs.push_back(fp + ".key: Invalid value: " + quote(key) + ": " + m);
+      for (size_t j = 0; j < vals.size(); ++j)
+        for (auto& m : label_value_errors(vals[j])) errs.push_back(fp + ".values[" + std::to_string(j) + "]: Invalid value: " + quote(vals[j]) + ": " + m);
+    }
+  return "";
+}
+std::string validate_constraint_json(const std::string& json) {
+  VP cur;
+  try {
+    cur = json_parse(json.data(), json.size());
+  } catch (JsonError& e) {
+    return "invalid constraint: " + e.msg;
+  }
+  for (const char* part : {"spec", "match"}) {
+    if (!cur || cur->t != VT::Obj) return "";
+    cur = obj_get(cur, part);
+    if (!cur) return "";
+  }
+  if (cur->t != VT::Obj) return ".spec.match accessor error: " + json_str(cur) + " is of the type " + go_type_name(cur) + ", expected map[string]interface{}";
+  for (const char* f : {"labelSelector", "namespaceSelector"}) {
+    VP sel = obj_get(cur, f);
+    if (!sel || sel->t == VT::Null) continue;
+    if (sel->t != VT::Obj)
+      return std::string(".spec.match.") + f + " accessor error: " + json_str(sel) + " is of the type " + go_type_name(sel) + ", expected map[string]interface{}";
+    std::vector<std::string> errs;
+    std::string conv = selector_field_errors(sel, errs);
+    if (!conv.empty()) return conv;
+    std::vector<std::string> uniq;
+    for (auto& e : errs)
+      if (std::find(uniq.begin(), uniq.end(), e) == uniq.end()) uniq.push_back(e);
+    if (!uniq.empty()) return uniq.size() == 1 ? uniq[0] : "[" + join(uniq, ", ") + "]";
+  }
+  return "";
+}
+
 // ============================================================================================== engine
 // CPUs this process may actually use: the smaller of the affinity mask and the cgroup CPU quota (a container on a
 // 128-thread host is often capped at a fraction of it; more runnable threads than quota only buys throttling).

@@ -105,6 +105,9 @@ struct Compiled {
   size_t n_nodes = 0, n_atoms = 0, n_gates = 0, n_phases = 0;
 };
 
+// K8sValidationTarget.ValidateConstraint (pkg/target/target.go:178-214) on a constraint document: "" or the error text
+std::string validate_constraint_json(const std::string& json);
+
 class StringTable : public Interner {
  public:
   StringTable();

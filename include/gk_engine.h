@@ -108,6 +108,10 @@ int gk_add_template_libs(gk_engine_t* e, const char* kind, const char* rego_src,
                          size_t n_libs, char** err);
 int gk_remove_template(gk_engine_t* e, const char* kind);
 int gk_add_constraint(gk_engine_t* e, const char* constraint_json, size_t len, char** err);
+/* TargetHandler.ValidateConstraint (pkg/target/target.go:178-214: spec.match.labelSelector / namespaceSelector must be maps that
+ * convert to metav1.LabelSelector and pass ValidateLabelSelector).  The frameworks client calls the Go handler's method before
+ * Driver.AddConstraint; this is the same check for hosts that do not go through that client.  0 = valid, else *err has the text. */
+int gk_validate_constraint(gk_engine_t* e, const char* constraint_json, size_t len, char** err);
 int gk_remove_constraint(gk_engine_t* e, const char* kind, const char* name);
 int gk_put_namespace(gk_engine_t* e, const char* name, const char* ns_json, size_t len, char** err);
 int gk_remove_namespace(gk_engine_t* e, const char* name);

@@ -145,6 +145,91 @@ def _requirement_error(key, op, vals):
     return uniq[0] if len(uniq) == 1 else "[" + ", ".join(uniq) + "]"
 
 
+def _go_type_name(v):
+    return {bool: "bool", int: "number", float: "number", str: "string", list: "array", dict: "object", type(None): "null"}[type(v)]
+
+
+def _selector_field_errors(sel):
+    """convertToLabelSelector (a JSON round-trip into metav1.LabelSelector: type errors) followed by
+    validation.ValidateLabelSelector(sel, {}, field.NewPath("spec", "labelSelector")) -- pkg/target/target.go:185-193,215-224
+    and apimachinery's apis/meta/v1/validation.  Returns the list of messages; raises ValidateError for a type error."""
+    P = "spec.labelSelector"
+    ml = sel.get("matchLabels")
+    if ml is not None and not isinstance(ml, dict):
+        raise ValidateError("Could not convert JSON to LabelSelector: json: cannot unmarshal %s into Go struct field LabelSelector.matchLabels "
+                            "of type map[string]string" % _go_type_name(ml))
+    for k, v in (ml or {}).items():
+        if not isinstance(v, str):
+            raise ValidateError("Could not convert JSON to LabelSelector: json: cannot unmarshal %s into Go struct field LabelSelector.matchLabels "
+                                "of type string" % _go_type_name(v))
+    me = sel.get("matchExpressions")
+    if me is not None and not isinstance(me, list):
+        raise ValidateError("Could not convert JSON to LabelSelector: json: cannot unmarshal %s into Go struct field LabelSelector.matchExpressions "
+                            "of type []v1.LabelSelectorRequirement" % _go_type_name(me))
+    for x in me or []:
+        if not isinstance(x, dict):
+            raise ValidateError("Could not convert JSON to LabelSelector: json: cannot unmarshal %s into Go struct field LabelSelector.matchExpressions "
+                                "of type v1.LabelSelectorRequirement" % _go_type_name(x))
+        for f in ("key", "operator"):
+            if x.get(f) is not None and not isinstance(x[f], str):
+                raise ValidateError("Could not convert JSON to LabelSelector: json: cannot unmarshal %s into Go struct field LabelSelectorRequirement."
+                                    "matchExpressions.%s of type string" % (_go_type_name(x[f]), f))
+        vals = x.get("values")
+        if vals is not None and (not isinstance(vals, list) or any(not isinstance(v, str) for v in vals)):
+            raise ValidateError("Could not convert JSON to LabelSelector: json: cannot unmarshal %s into Go struct field LabelSelectorRequirement."
+                                "matchExpressions.values of type []string" % _go_type_name(vals if not isinstance(vals, list) else
+                                                                                             next(v for v in vals if not isinstance(v, str))))
+    errs = []
+    for k in sorted(ml or {}):
+        for m in _qualified_name_errors(k):
+            errs.append("%s.matchLabels: Invalid value: %s: %s" % (P, _go_quote(k), m))
+        for m in _label_value_errors(ml[k]):
+            errs.append("%s.matchLabels: Invalid value: %s: %s" % (P, _go_quote(ml[k]), m))
+    for i, x in enumerate(me or []):
+        fp = "%s.matchExpressions[%d]" % (P, i)
+        op, vals, key = x.get("operator") or "", x.get("values") or [], x.get("key") or ""
+        if op in ("In", "NotIn"):
+            if not vals:
+                errs.append(fp + ".values: Required value: must be specified when `operator` is 'In' or 'NotIn'")
+        elif op in ("Exists", "DoesNotExist"):
+            if vals:
+                errs.append(fp + ".values: Forbidden: may not be specified when `operator` is 'Exists' or 'DoesNotExist'")
+        else:
+            errs.append(fp + ".operator: Invalid value: %s: not a valid selector operator" % _go_quote(op))
+        for m in _qualified_name_errors(key):
+            errs.append(fp + ".key: Invalid value: %s: %s" % (_go_quote(key), m))
+        for j, v in enumerate(vals):
+            for m in _label_value_errors(v):
+                errs.append(fp + ".values[%d]: Invalid value: %s: %s" % (j, _go_quote(v), m))
+    return errs
+
+
+class ValidateError(Exception):
+    pass
+
+
+def validate_constraint(constraint):
+    """K8sValidationTarget.ValidateConstraint (pkg/target/target.go:178-214): the frameworks client calls it before
+    Driver.AddConstraint.  Raises ValidateError; pinned by TestValidateConstraint (pkg/target/target_test.go:42-399)."""
+    cur = constraint
+    for part in ("spec", "match"):
+        if not isinstance(cur, dict) or part not in cur:
+            return
+        cur = cur[part]
+    if not isinstance(cur, dict):
+        raise ValidateError(".spec.match accessor error: %s is of the type %s, expected map[string]interface{}" % (json.dumps(cur), _go_type_name(cur)))
+    for f in ("labelSelector", "namespaceSelector"):
+        if f not in cur or cur[f] is None:
+            continue
+        sel = cur[f]
+        if not isinstance(sel, dict):
+            raise ValidateError(".spec.match.%s accessor error: %s is of the type %s, expected map[string]interface{}" % (f, json.dumps(sel), _go_type_name(sel)))
+        errs = _selector_field_errors(sel)
+        if errs:
+            uniq = list(dict.fromkeys(errs))
+            raise ValidateError(uniq[0] if len(uniq) == 1 else "[" + ", ".join(uniq) + "]")
+
+
 def label_selector_requirements(sel):
     """LabelSelectorAsSelector: returns a list of (key, op, values) or raises MatchError.  Requirements are built in
     order (matchLabels -- sorted here, a Go map there -- then matchExpressions) and the first failing one is the error."""

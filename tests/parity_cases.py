@@ -695,6 +695,58 @@ violation[{"msg": msg}] {
     return len(want)
 
 
+def case_validate_constraint(lib):
+    """TestValidateConstraint (pkg/target/target_test.go:42-399, 11 cases): which constraints ValidateConstraint refuses -- oracle
+    and engine -- plus hand-made selectors whose error TEXT the two restatements must agree on."""
+    import pytest
+    g = golden("validate_constraint_vectors.json")
+    drv = D.Driver(lib_path=lib)
+    assert len(g["cases"]) == 11
+    for cse in g["cases"]:
+        oerr = eerr = None
+        try:
+            k8s.validate_constraint(cse["constraint"])
+        except k8s.ValidateError as e:
+            oerr = str(e)
+        try:
+            drv.ValidateConstraint(cse["constraint"])
+        except D.GkError as e:
+            eerr = str(e)
+        assert (oerr is not None) == cse["error_expected"], (cse["name"], oerr)
+        assert (eerr is not None) == cse["error_expected"], (cse["name"], eerr)
+        if oerr is not None:
+            assert oerr in eerr, (cse["name"], oerr, eerr)
+
+    def con(match):
+        return {"apiVersion": "constraints.gatekeeper.sh/v1beta1", "kind": "K", "metadata": {"name": "k"}, "spec": {"match": match}}
+    extra = [{"labelSelector": {"matchLabels": {"bad key!": "v", "ok": "bad value!"}}},
+             {"labelSelector": {"matchExpressions": [{"key": "a", "operator": "In", "values": []}, {"key": "b", "operator": "Exists", "values": ["x"]}]}},
+             {"namespaceSelector": {"matchExpressions": [{"key": "", "operator": "NotIn", "values": ["not ok", "x" * 64]}]}},
+             {"labelSelector": {"matchExpressions": [{"key": "a/b/c", "operator": "DoesNotExist"}]}},
+             {"labelSelector": {"matchExpressions": {"key": "a"}}}, {"labelSelector": {"matchExpressions": [{"key": 1, "operator": "In"}]}},
+             {"labelSelector": {"matchExpressions": [{"key": "a", "operator": "In", "values": [1]}]}}, {"labelSelector": None, "namespaceSelector": {}},
+             {"labelSelector": {"matchLabels": {"a": 1}}}, {"kinds": [{"kinds": ["Pod"]}]}]
+    n_err = 0
+    for m in extra:
+        oerr = eerr = None
+        try:
+            k8s.validate_constraint(con(m))
+        except k8s.ValidateError as e:
+            oerr = str(e)
+        try:
+            drv.ValidateConstraint(con(m))
+        except D.GkError as e:
+            eerr = str(e)
+        assert (oerr is None) == (eerr is None), (m, oerr, eerr)
+        if oerr is not None:
+            n_err += 1
+            assert oerr in eerr, (m, oerr, eerr)
+    assert n_err == 8
+    # AddConstraint itself is the DRIVER's method and does not validate (the reference's client validates first): the matcher
+    # vectors rely on invalid selectors reaching Matches()
+    return n_err
+
+
 # ------------------------------------------------------------------------------------------ random policies
 _RF_HELPERS = """
 input_containers[c] { c := input.review.object.spec.containers[_] }

@@ -130,6 +130,11 @@ def test_rego_fuzz(seed):
     assert accepted >= 20 and n_results > 500
 
 
+def test_validate_constraint_vectors():
+    """pkg/target/target_test.go TestValidateConstraint: 11 vectors + error-text agreement on hand-made selectors."""
+    assert P.case_validate_constraint(HOSTEMU) == 8
+
+
 def test_every():
     assert P.case_every(HOSTEMU) > 800
 

@@ -159,6 +159,18 @@ def test_template_libs_container_limits():
         k8s.Client().add_template("X", tmpl[1], [])
 
 
+def test_validate_constraint_vectors():
+    """pkg/target/target_test.go:42-399 (TestValidateConstraint): the 11 cases, error expected or not."""
+    g = golden("validate_constraint_vectors.json")
+    assert len(g["cases"]) == 11
+    for cse in g["cases"]:
+        if cse["error_expected"]:
+            with pytest.raises(k8s.ValidateError):
+                k8s.validate_constraint(cse["constraint"])
+        else:
+            k8s.validate_constraint(cse["constraint"])
+
+
 def test_fixture_templates():
     """pkg/gator/test/test_test.go:85-452: "never validate" x N, first/second message, compile error."""
     t = golden("templates.json")
