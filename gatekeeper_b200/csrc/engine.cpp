@@ -338,6 +338,59 @@ static std::string selector_field_errors(const VP& sel, std::vector<std::string>
     }
   return "";
 }
+// K8sValidationTarget.ToMatcher / convertToMatch (pkg/target/target.go:226-254): spec.match must be a map whose members have the
+// JSON types of match.Match (pkg/mutation/match/match_types.go:13-51).  "" or the ErrCreatingMatcher text.
+static std::string to_matcher_error(const VP& constraint) {
+  VP spec = constraint && constraint->t == VT::Obj ? obj_get(constraint, "spec") : nullptr;
+  VP m = spec && spec->t == VT::Obj ? obj_get(spec, "match") : nullptr;
+  if (!m || m->t == VT::Null) return "";
+  const std::string pre = "unable to create matcher: ";
+  if (m->t != VT::Obj) return pre + ".spec.match accessor error: " + json_str(m) + " is of the type " + go_type_name(m) + ", expected map[string]interface{}";
+  auto bad = [&](const VP& v, const std::string& field, const std::string& typ) {
+    return pre + "could not convert JSON to Match: json: cannot unmarshal " + go_type_name(v) + " into Go struct field Match." + field + " of type " + typ;
+  };
+  auto strlist = [&](const VP& v, const std::string& field, const std::string& typ) -> std::string {
+    if (!v || v->t == VT::Null) return "";
+    if (v->t != VT::Arr) return bad(v, field, typ);
+    for (auto& x : v->items)
+      if (x->t != VT::Str) return bad(x, field, "string");
+    return "";
+  };
+  for (const char* f : {"source", "scope", "name"}) {
+    VP v = obj_get(m, f);
+    if (v && v->t != VT::Null && v->t != VT::Str) return bad(v, f, "string");
+  }
+  VP kinds = obj_get(m, "kinds");
+  if (kinds && kinds->t != VT::Null) {
+    if (kinds->t != VT::Arr) return bad(kinds, "kinds", "[]match.Kinds");
+    for (auto& k : kinds->items) {
+      if (k->t != VT::Obj) return bad(k, "kinds", "match.Kinds");
+      for (const char* f : {"apiGroups", "kinds"}) {
+        std::string e = strlist(obj_get(k, f), std::string("kinds.") + f, "[]string");
+        if (!e.empty()) return e;
+      }
+    }
+  }
+  for (const char* f : {"namespaces", "excludedNamespaces"}) {
+    std::string e = strlist(obj_get(m, f), f, "[]wildcard.Wildcard");
+    if (!e.empty()) return e;
+  }
+  for (const char* f : {"labelSelector", "namespaceSelector"}) {
+    VP sel = obj_get(m, f);
+    if (!sel || sel->t == VT::Null) continue;
+    if (sel->t != VT::Obj) return bad(sel, f, "v1.LabelSelector");
+    std::vector<std::string> ignored;
+    std::string conv = selector_field_errors(sel, ignored);
+    if (!conv.empty()) {
+      const std::string from = "Could not convert JSON to LabelSelector";
+      size_t at = conv.find(from);
+      if (at != std::string::npos) conv.replace(at, from.size(), "could not convert JSON to Match");
+      return pre + conv;
+    }
+  }
+  return "";
+}
+
 std::string validate_constraint_json(const std::string& json) {
   VP cur;
   try {
@@ -451,6 +504,10 @@ void Engine::add_constraint(const std::string& json) {
   c->name = meta_str(obj, "name");
   if (c->kind.empty() || c->name.empty()) throw RegoError{"invalid constraint: kind and metadata.name are required"};
   c->obj = obj;
+  {
+    std::string terr = to_matcher_error(obj);
+    if (!terr.empty()) throw RegoError{terr};
+  }
   VP spec = obj_get(obj, "spec");
   VP params = spec ? obj_get(spec, "parameters") : nullptr;
   c->params = params && params->t != VT::Null ? params : v_obj({});

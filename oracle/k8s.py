@@ -145,6 +145,10 @@ def _requirement_error(key, op, vals):
     return uniq[0] if len(uniq) == 1 else "[" + ", ".join(uniq) + "]"
 
 
+def _json_brief(v):
+    return json.dumps(int(v)) if isinstance(v, float) and v == int(v) else json.dumps(v)
+
+
 def _go_type_name(v):
     return {bool: "bool", int: "number", float: "number", str: "string", list: "array", dict: "object", type(None): "null"}[type(v)]
 
@@ -208,6 +212,61 @@ class ValidateError(Exception):
     pass
 
 
+def to_matcher_error(constraint):
+    """K8sValidationTarget.ToMatcher / convertToMatch (pkg/target/target.go:226-254): spec.match must be a map whose members have
+    the JSON types of match.Match (pkg/mutation/match/match_types.go:13-51).  Returns the error text ("unable to create
+    matcher: ...", ErrCreatingMatcher) or None; pinned by TestToMatcher (pkg/target/target_test.go:544-626)."""
+    spec = constraint.get("spec") if isinstance(constraint, dict) else None
+    if not isinstance(spec, dict) or spec.get("match") is None:
+        return None
+    m = spec["match"]
+    pre = "unable to create matcher: "
+    if not isinstance(m, dict):
+        return pre + ".spec.match accessor error: %s is of the type %s, expected map[string]interface{}" % (_json_brief(m), _go_type_name(m))
+
+    def bad(v, field, typ):
+        return pre + "could not convert JSON to Match: json: cannot unmarshal %s into Go struct field Match.%s of type %s" % (_go_type_name(v), field, typ)
+
+    def strlist(v, field, typ):
+        if v is None:
+            return None
+        if not isinstance(v, list):
+            return bad(v, field, typ)
+        for x in v:
+            if not isinstance(x, str):
+                return bad(x, field, "string")
+        return None
+    for f in ("source", "scope", "name"):
+        if m.get(f) is not None and not isinstance(m[f], str):
+            return bad(m[f], f, "string")
+    kinds = m.get("kinds")
+    if kinds is not None:
+        if not isinstance(kinds, list):
+            return bad(kinds, "kinds", "[]match.Kinds")
+        for k in kinds:
+            if not isinstance(k, dict):
+                return bad(k, "kinds", "match.Kinds")
+            for f in ("apiGroups", "kinds"):
+                e = strlist(k.get(f), "kinds." + f, "[]string")
+                if e:
+                    return e
+    for f in ("namespaces", "excludedNamespaces"):
+        e = strlist(m.get(f), f, "[]wildcard.Wildcard")
+        if e:
+            return e
+    for f in ("labelSelector", "namespaceSelector"):
+        sel = m.get(f)
+        if sel is None:
+            continue
+        if not isinstance(sel, dict):
+            return bad(sel, f, "v1.LabelSelector")
+        try:
+            _selector_field_errors(sel)
+        except ValidateError as e:
+            return pre + str(e).replace("Could not convert JSON to LabelSelector", "could not convert JSON to Match")
+    return None
+
+
 def validate_constraint(constraint):
     """K8sValidationTarget.ValidateConstraint (pkg/target/target.go:178-214): the frameworks client calls it before
     Driver.AddConstraint.  Raises ValidateError; pinned by TestValidateConstraint (pkg/target/target_test.go:42-399)."""
@@ -217,13 +276,13 @@ def validate_constraint(constraint):
             return
         cur = cur[part]
     if not isinstance(cur, dict):
-        raise ValidateError(".spec.match accessor error: %s is of the type %s, expected map[string]interface{}" % (json.dumps(cur), _go_type_name(cur)))
+        raise ValidateError(".spec.match accessor error: %s is of the type %s, expected map[string]interface{}" % (_json_brief(cur), _go_type_name(cur)))
     for f in ("labelSelector", "namespaceSelector"):
         if f not in cur or cur[f] is None:
             continue
         sel = cur[f]
         if not isinstance(sel, dict):
-            raise ValidateError(".spec.match.%s accessor error: %s is of the type %s, expected map[string]interface{}" % (f, json.dumps(sel), _go_type_name(sel)))
+            raise ValidateError(".spec.match.%s accessor error: %s is of the type %s, expected map[string]interface{}" % (f, _json_brief(sel), _go_type_name(sel)))
         errs = _selector_field_errors(sel)
         if errs:
             uniq = list(dict.fromkeys(errs))
@@ -598,6 +657,9 @@ class Client:
         kind = constraint["kind"]
         if kind not in self.templates:
             raise KeyError(f"no template for constraint kind {kind}")
+        terr = to_matcher_error(constraint)
+        if terr:
+            raise MatchError(terr)
         m = (constraint.get("spec") or {}).get("match")
         if m is not None:
             # ValidateConstraint (pkg/target/target.go:178-214) rejects bad selectors at load time

@@ -742,7 +742,33 @@ def case_validate_constraint(lib):
             n_err += 1
             assert oerr in eerr, (m, oerr, eerr)
     assert n_err == 8
-    # AddConstraint itself is the DRIVER's method and does not validate (the reference's client validates first): the matcher
+    # ToMatcher (pkg/target/target.go:239-254) runs at AddConstraint: TestToMatcher's two invalid constraints (target_test.go:544-560:
+    # spec.match = 3.0, spec.match.kinds = 3.0 => ErrCreatingMatcher) and other members of the wrong JSON type
+    rego_src = 'package k\nviolation[{"msg": "m"}] { true }\n'
+    n_match_err = 0
+    for m in (3.0, {"kinds": 3.0}, {"namespaces": "x"}, {"labelSelector": {"matchLabels": 3}}, {"name": 7}, {"kinds": [{"apiGroups": [1]}]},
+              {"scope": []}, None, {"kinds": [{"apiGroups": [""], "kinds": ["Pod"]}], "namespaces": ["a*"], "name": "x*", "scope": "Namespaced"}):
+        c = con({}) if m is None else con(m)
+        if m is None:
+            del c["spec"]["match"]
+        o, d = k8s.Client(), D.Driver(lib_path=lib)
+        o.add_template("K", rego_src)
+        d.add_template("K", rego_src)
+        oerr = eerr = None
+        try:
+            o.add_constraint(c)
+        except k8s.MatchError as e:
+            oerr = str(e)
+        try:
+            d.AddConstraint(c)
+        except D.GkError as e:
+            eerr = str(e)
+        assert (oerr is None) == (eerr is None), (m, oerr, eerr)
+        if oerr is not None:
+            n_match_err += 1
+            assert oerr.startswith("unable to create matcher: ") and oerr in eerr, (m, oerr, eerr)
+    assert n_match_err == 7
+    # Beyond that, AddConstraint is the DRIVER's method and does not validate (the reference's client validates first): the matcher
     # vectors rely on invalid selectors reaching Matches()
     return n_err
 
