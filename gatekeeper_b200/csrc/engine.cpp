@@ -564,6 +564,28 @@ void Engine::put_namespace(const std::string& name, const std::string& json) {
   } catch (JsonError& e) {
     throw RegoError{"invalid namespace object: " + e.msg};
   }
+  // nsCache.Add (pkg/target/ns_cache.go:22-44): a non-map is an error, a map that is not a core Namespace is ignored, a Namespace
+  // that does not convert to corev1.Namespace (a member of the wrong JSON type) is an error
+  if (v->t != VT::Obj) throw RegoError{std::string("cannot cache non-namespace type: cannot cache type ") + go_type_name(v) + ", want map[string]interface {}"};
+  {
+    std::string g, ver, k;
+    split_gv(v, g, ver, k);
+    if (k != "Namespace" || !g.empty()) return;
+  }
+  auto is_obj_or_absent = [](const VP& x) { return !x || x->t == VT::Null || x->t == VT::Obj; };
+  VP md = obj_get(v, "metadata");
+  bool ok = is_obj_or_absent(md) && is_obj_or_absent(obj_get(v, "spec")) && is_obj_or_absent(obj_get(v, "status"));
+  if (ok && md && md->t == VT::Obj) {
+    for (const char* f : {"labels", "annotations"}) {
+      VP ls = obj_get(md, f);
+      ok = ok && is_obj_or_absent(ls);
+      if (ok && ls && ls->t == VT::Obj)
+        for (auto& e : ls->kv) ok = ok && e.second->t == VT::Str;
+    }
+    VP nm = obj_get(md, "name");
+    ok = ok && (!nm || nm->t == VT::Null || nm->t == VT::Str);
+  }
+  if (!ok) throw RegoError{"cannot cache non-namespace type: cannot cache Namespace: <nil>"};
   std::unique_lock<std::shared_mutex> l(mu_);
   namespaces_[name] = v;
 }

@@ -674,8 +674,24 @@ class Client:
     def remove_constraint(self, kind, name):
         self.constraints.pop((kind, name), None)
 
-    def add_namespace(self, ns_obj):
-        self.ns_cache[_meta(ns_obj, "name")] = ns_obj
+    def add_namespace(self, ns_obj, name=None):
+        """nsCache.Add (pkg/target/ns_cache.go:22-44; TestNamespaceCache, pkg/target/target_test.go:983-1153): a non-map is an
+        error, a map that is not a core Namespace is ignored, a Namespace that does not convert to corev1.Namespace is an error."""
+        if not isinstance(ns_obj, dict):
+            raise MatchError("cannot cache non-namespace type: cannot cache type %s, want map[string]interface {}" % _go_type_name(ns_obj))
+        g, _, k = _gvk(ns_obj)
+        if k != "Namespace" or g:
+            return
+        md = ns_obj.get("metadata")
+        ok = all(x is None or isinstance(x, dict) for x in (md, ns_obj.get("spec"), ns_obj.get("status")))
+        if ok and isinstance(md, dict):
+            for f in ("labels", "annotations"):
+                ls = md.get(f)
+                ok = ok and (ls is None or (isinstance(ls, dict) and all(isinstance(v, str) for v in ls.values())))
+            ok = ok and (md.get("name") is None or isinstance(md.get("name"), str))
+        if not ok:
+            raise MatchError("cannot cache non-namespace type: cannot cache Namespace: <nil>")
+        self.ns_cache[name if name is not None else _meta(ns_obj, "name")] = ns_obj
 
     def review(self, review: Review, enforcement_point: str = AUDIT_EP):
         """Returns a list of result dicts {constraint:(kind,name), msg, details, enforcementAction,

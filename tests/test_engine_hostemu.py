@@ -130,6 +130,44 @@ def test_rego_fuzz(seed):
     assert accepted >= 20 and n_results > 500
 
 
+def test_namespace_cache_add_semantics():
+    """nsCache.Add (pkg/target/ns_cache.go:22-44; TestNamespaceCache, pkg/target/target_test.go:983-1153): a Namespace is cached, a
+    Namespace that does not convert (spec: 3.0 -- the reference's own vector) and a non-map are ErrCachingType, another kind is
+    ignored; a removed namespace is gone.  Observed through a namespaceSelector constraint."""
+    from oracle import k8s
+    rego_src = 'package k\nviolation[{"msg": "m"}] { true }\n'
+    con = {"apiVersion": "constraints.gatekeeper.sh/v1beta1", "kind": "K", "metadata": {"name": "k"},
+           "spec": {"match": {"namespaceSelector": {"matchLabels": {"ns1": "label"}}}}}
+    pod = {"apiVersion": "v1", "kind": "Pod", "metadata": {"name": "p", "namespace": "my-ns1"}}
+    for make in (lambda: ("oracle", k8s.Client()), lambda: ("engine", D.Driver(lib_path=HOSTEMU))):
+        who, x = make()
+        add = (lambda o, n: x.add_namespace(o, n)) if who == "oracle" else (lambda o, n: x.AddData("t", ["cluster", "v1", "Namespace", n], o))
+        err = k8s.MatchError if who == "oracle" else D.GkError
+        x.add_template("K", rego_src)
+        (x.add_constraint if who == "oracle" else x.AddConstraint)(con)
+
+        def n_results():
+            if who == "oracle":
+                return len(x.review(k8s.Review(obj=pod), k8s.AUDIT_EP))
+            return len(x.ReviewBatch([D.Review(object=pod)], k8s.AUDIT_EP).results)
+        assert n_results() == 1                      # namespace unknown: the matcher errors ("missing Namespace") -> one autoreject result
+        add({"apiVersion": "v1", "kind": "Namespace", "metadata": {"name": "my-ns1", "labels": {"ns1": "label"}}}, "my-ns1")
+        assert n_results() == 1                      # cached and selected: the violation
+        add({"apiVersion": "v1", "kind": "Namespace", "metadata": {"name": "my-ns1", "labels": {"ns1": "other"}}}, "my-ns1")
+        assert n_results() == 0                      # replaced: no longer selected
+        with pytest.raises(err, match="cannot cache non-namespace type"):
+            add({"apiVersion": "v1", "kind": "Namespace", "spec": 3.0}, "my-ns1")
+        with pytest.raises(err, match="cannot cache non-namespace type"):
+            add(3, "my-ns1")
+        add({"apiVersion": "apps/v1", "kind": "Deployment", "metadata": {"name": "my-ns1", "labels": {"ns1": "label"}}}, "my-ns1")
+        assert n_results() == 0                      # ignored: the cache still holds the replaced namespace
+        if who == "oracle":
+            x.ns_cache.pop("my-ns1")
+        else:
+            x.RemoveData("t", ["cluster", "v1", "Namespace", "my-ns1"])
+        assert n_results() == 1                      # gone again: missing Namespace
+
+
 def test_validate_constraint_vectors():
     """pkg/target/target_test.go TestValidateConstraint: 11 vectors + error-text agreement on hand-made selectors."""
     assert P.case_validate_constraint(HOSTEMU) == 8
