@@ -130,6 +130,30 @@ def test_rego_fuzz(seed):
     assert accepted >= 20 and n_results > 500
 
 
+def test_enforcement_action_vectors_through_review():
+    """pkg/util/enforcement_action_test.go (TestGetEnforcementAction :113-165, TestScopedActionForEP :235-385): the action a
+    result is stamped with, and whether a scoped constraint is enforced at all at the caller's enforcement point."""
+    from test_oracle import EA_VECTORS, SCOPED_VECTORS
+    rego_src = 'package k\nviolation[{"msg": "m"}] { true }\n'
+    pod = {"apiVersion": "v1", "kind": "Pod", "metadata": {"name": "p", "namespace": "default"}}
+    for item, want in EA_VECTORS:
+        drv = D.Driver(lib_path=HOSTEMU)
+        drv.add_template("K", rego_src)
+        drv.AddConstraint(dict({"apiVersion": "constraints.gatekeeper.sh/v1beta1", "kind": "K", "metadata": {"name": "k"}}, **item))
+        res = drv.ReviewBatch([D.Review(object=pod)], "audit.gatekeeper.sh").results
+        assert [r.enforcement_action for r in res] == [want]
+    for name, ep, item, want in SCOPED_VECTORS:
+        drv = D.Driver(lib_path=HOSTEMU)
+        drv.add_template("K", rego_src)
+        spec = dict(item["spec"], enforcementAction="scoped")
+        drv.AddConstraint({"apiVersion": "constraints.gatekeeper.sh/v1beta1", "kind": "K", "metadata": {"name": "k"}, "spec": spec})
+        res = drv.ReviewBatch([D.Review(object=pod)], ep).results
+        if want:
+            assert len(res) == 1 and res[0].enforcement_action == "scoped" and list(res[0].scoped_enforcement_actions) == want, name
+        else:
+            assert res == [], name      # not enforced at this point: the constraint is not even evaluated
+
+
 def test_namespace_cache_add_semantics():
     """nsCache.Add (pkg/target/ns_cache.go:22-44; TestNamespaceCache, pkg/target/target_test.go:983-1153): a Namespace is cached, a
     Namespace that does not convert (spec: 3.0 -- the reference's own vector) and a non-map are ErrCachingType, another kind is

@@ -159,6 +159,31 @@ def test_template_libs_container_limits():
         k8s.Client().add_template("X", tmpl[1], [])
 
 
+# pkg/util/enforcement_action_test.go:113-165 (TestGetEnforcementAction) and :235-385 (TestScopedActionForEP), hand-translated
+EA_VECTORS = [({}, "deny"), ({"spec": {"enforcementAction": "notsupported"}}, "unrecognized"), ({"spec": {"enforcementAction": "dryrun"}}, "dryrun")]
+AUDIT, WEBHOOK, ALL = "audit.gatekeeper.sh", "validation.gatekeeper.sh", "*"
+
+
+def _sea(*pairs):
+    return {"spec": {"scopedEnforcementActions": [{"action": a, "enforcementPoints": [{"name": n} for n in eps]} for a, eps in pairs]}}
+
+
+SCOPED_VECTORS = [
+    ("valid enforcement point", AUDIT, _sea(("deny", [AUDIT]), ("warn", [WEBHOOK])), ["deny"]),
+    ("multiple enforcement points", WEBHOOK, _sea(("deny", [AUDIT, WEBHOOK]), ("warn", [WEBHOOK])), ["deny", "warn"]),
+    ("no matching enforcement point", AUDIT, _sea(("deny", [WEBHOOK]), ("warn", [WEBHOOK])), []),
+    ("wildcard enforcement point", AUDIT, _sea(("deny", [ALL]), ("warn", [WEBHOOK])), ["deny"]),
+    ("missing scopedEnforcementActions", AUDIT, {"spec": {}}, []),
+]
+
+
+def test_enforcement_action_vectors():
+    for item, want in EA_VECTORS:
+        assert k8s.get_enforcement_action(item) == want
+    for name, ep, item, want in SCOPED_VECTORS:
+        assert k8s.scoped_actions_for_ep(ep, item) == want, name
+
+
 def test_validate_constraint_vectors():
     """pkg/target/target_test.go:42-399 (TestValidateConstraint): the 11 cases, error expected or not."""
     g = golden("validate_constraint_vectors.json")
