@@ -634,19 +634,45 @@ void Engine::compile_locked() {
   std::vector<FP> live_formula;
   std::map<std::string, uint32_t> match_ix;
   std::vector<uint32_t> mid_of;
-  for (auto& cp : constraints_) {
-    Constraint& c = *cp;
-    out->pins.push_back(cp);
-    auto tit = templates_.find(c.kind);
-    if (tit == templates_.end()) continue;
-    live_formula.push_back(lower_violation(tit->second.mod, c.params, out->schema));
-    std::string key = c.match.has ? json_str(c.match.raw) : std::string();
-    auto it = match_ix.find(key);
-    uint32_t mid = it == match_ix.end() ? (uint32_t)match_ix.size() : it->second;
-    if (it == match_ix.end()) match_ix.emplace(key, mid);
-    live.push_back(&c);
-    mid_of.push_back(mid);
+  // First choice: every constraint lowered for the DEVICE INGEST path (all scopes / columns computable by the ingest kernels
+  // from the raw JSON).  If one constraint cannot be, the whole set is lowered the classic way (maximal host closures) and
+  // batches of this snapshot are flattened on the host.
+  auto lower_all = [&](bool device_mode) {
+    out->schema = Schema();
+    out->pins.clear();
+    live.clear();
+    live_formula.clear();
+    match_ix.clear();
+    mid_of.clear();
+    for (auto& cp : constraints_) {
+      Constraint& c = *cp;
+      out->pins.push_back(cp);
+      auto tit = templates_.find(c.kind);
+      if (tit == templates_.end()) continue;
+      live_formula.push_back(lower_violation(tit->second.mod, c.params, out->schema, device_mode));
+      std::string key = c.match.has ? json_str(c.match.raw) : std::string();
+      auto it = match_ix.find(key);
+      uint32_t mid = it == match_ix.end() ? (uint32_t)match_ix.size() : it->second;
+      if (it == match_ix.end()) match_ix.emplace(key, mid);
+      live.push_back(&c);
+      mid_of.push_back(mid);
+    }
+    out->schema.device_only = false;
+  };
+  static const bool no_device = getenv("GK_NO_DEVICE_INGEST") != nullptr;
+  bool device_ok = !no_device;
+  if (device_ok) {
+    try {
+      lower_all(true);
+      device_ok = schema_device_ingestable(out->schema, &out->host_ingest_reason);
+    } catch (RegoError& e) {
+      if (e.msg.find("rego_unsupported") == std::string::npos) throw;
+      device_ok = false;
+      out->host_ingest_reason = e.msg;
+    }
   }
+  if (!device_ok) lower_all(false);
+  out->device_ingest = device_ok;
   std::vector<size_t> perm(live.size());
   for (size_t i = 0; i < perm.size(); ++i) perm[i] = i;
   std::stable_sort(perm.begin(), perm.end(), [&](size_t a, size_t b) { return mid_of[a] < mid_of[b]; });
@@ -788,10 +814,13 @@ void Engine::compile_locked() {
 
 std::string Engine::dump() {
   auto c = compiled();
+  static const char* kXK[] = {"host", "path", "elem", "key", "count", "lut"};
   std::string o = "schema: " + std::to_string(c->schema.scopes.size() - 1) + " scopes, " + std::to_string(c->schema.cols.size()) +
                   " columns; netlist: " + std::to_string(c->n_nodes) + " nodes (" + std::to_string(c->n_atoms) + " atoms, " +
                   std::to_string(c->n_gates) + " gates) in " + std::to_string(c->n_phases) + " phases, " + std::to_string(c->slot_level.size()) +
                   " live slots, " + std::to_string(c->match.size()) + " distinct match blocks\n";
+  o += c->device_ingest ? "  ingest: device (every scope / column is computed from the raw JSON by the ingest kernels)\n"
+                        : "  ingest: host flattener (" + c->host_ingest_reason + ")\n";
   {
     std::vector<int> per(c->schema.scopes.size(), 0);
     for (uint8_t l : c->slot_level) per[l]++;
@@ -824,8 +853,8 @@ std::string Engine::dump() {
   for (size_t i = 1; i < c->schema.scopes.size(); ++i)
     o += "  scope " + std::to_string(i) + " parent " + std::to_string(c->schema.scopes[i].parent) + ": " + c->schema.scopes[i].gen->key + "\n";
   for (size_t i = 0; i < c->schema.cols.size(); ++i)
-    o += "  col " + std::to_string(i) + " scope " + std::to_string(c->schema.cols[i].scope) + " enc " + std::to_string(c->schema.cols[i].enc) + ": " +
-         c->schema.cols[i].expr->key + "\n";
+    o += "  col " + std::to_string(i) + " scope " + std::to_string(c->schema.cols[i].scope) + " enc " + std::to_string(c->schema.cols[i].enc) + " " +
+         std::string(kXK[(int)closure_xinfo(*c->schema.cols[i].expr).k]) + ": " + c->schema.cols[i].expr->key + "\n";
   for (size_t i = 0; i < c->order.size(); ++i)
     o += "constraint " + std::to_string(i) + " " + c->order[i]->kind + "/" + c->order[i]->name + ": " +
          formula_str(c->formulas[i], c->schema) + "\n";
@@ -1331,12 +1360,7 @@ struct Flattener : ChunkOut {
     HostColumn& hc = hb.cols[ci];
     uint8_t vt = v ? (uint8_t)v->t : (uint8_t)GK_VT_UNDEF;
     int64_t num = 0;
-    if (v && v->t == VT::Num && (enc & GK_ENC_NUM) && !num_fits_i64(v->n, &num)) {
-      // the device compares numbers as exact int64: refuse the object loudly instead of comparing approximately
-      vt = GK_VT_NUM_INEXACT;
-      num_range_error = "number " + num_str(v->n) + " in " + c.schema.cols[ci].expr->key +
-                        " is outside the exact int64 range of the GPU predicate table";
-    }
+    if (v && v->t == VT::Num && (enc & GK_ENC_NUM)) num = num_key(v->n);   // exact order against every integer constant (val.hpp)
     if (enc & GK_ENC_VT) hc.vt.push_back(vt);
     if (enc & GK_ENC_SID) hc.sid.push_back(v ? sid_value(v) : GK_SID_UNDEF);
     // non-numbers carry the extreme that OPA's cross-type order gives them relative to every number (null, booleans
@@ -1475,14 +1499,8 @@ struct Flattener : ChunkOut {
       }
       for (size_t s = 1; s < nscopes; ++s) hb.scope_rows[s] += (uint32_t)rows[s].size();
     }
-    if (!num_range_error.empty()) {
-      hb.obj_errors.back() = num_range_error;
-      hb.flags[hb.n] |= GK_F_SKIP;
-      num_range_error.clear();
-    }
     ++hb.n;
   }
-  std::string num_range_error;
   bool trace = getenv("GK_FLATTEN_TRACE") != nullptr;
   std::vector<uint64_t> col_cycles = std::vector<uint64_t>(4096, 0), scope_cycles = std::vector<uint64_t>(256, 0);
   uint64_t doc_cycles = 0, hdr_cycles = 0, traced_objects = 0;

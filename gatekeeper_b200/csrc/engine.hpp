@@ -103,6 +103,8 @@ struct Compiled {
                                                          // (RemoveConstraint / a replacing AddConstraint may run meanwhile)
   std::vector<std::shared_ptr<Module>> mods;   // constraint index -> its template's module (pinned by this snapshot)
   size_t n_nodes = 0, n_atoms = 0, n_gates = 0, n_phases = 0;
+  bool device_ingest = false;                  // every scope / column of `schema` can be computed by the ingest kernels
+  std::string host_ingest_reason;              // why not (the first construct that needs the host flattener)
 };
 
 // K8sValidationTarget.ValidateConstraint (pkg/target/target.go:178-214) on a constraint document: "" or the error text

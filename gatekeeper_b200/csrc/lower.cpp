@@ -107,9 +107,159 @@ std::string formula_str(const FP& f, const Schema& s) {
 }
 
 // ====================================================================================== schema
+// ====================================================================================== device-evaluable closures
+static bool xleafy(const XInfo& xi) {
+  // may this value be (part of) a lookup key?  Whole objects / `spec` / an iterated element are not: every object would be
+  // its own key and the host would evaluate the closure once per object again
+  switch (xi.k) {
+    case XK::Path: return xi.base != nullptr || xi.keys.size() >= 4;
+    case XK::Key:
+    case XK::Count:
+    case XK::Lut: return true;
+    default: return false;
+  }
+}
+
+// Walks a closure's term: false unless it is a closed pure term (no `input` / `data`, no impure rule); collects the
+// `<captured column>[literal keys...]` paths it reads.
+static bool lut_args(const Module& m, const Term* t, const Closure& c, std::vector<XInfo::Arg>& out) {
+  if (!t) return true;
+  auto cap_of = [&](int vid) -> const CapArg* {
+    for (auto& cp : c.caps)
+      if (cp.first == vid) return &cp.second;
+    return nullptr;
+  };
+  auto add = [&](int vid, const CP& base, std::vector<VP> keys) {
+    for (auto& a : out)
+      if (a.vid == vid && a.keys.size() == keys.size()) {
+        bool same = true;
+        for (size_t i = 0; i < keys.size(); ++i) same = same && v_eq(a.keys[i], keys[i]);
+        if (same) return;
+      }
+    out.push_back(XInfo::Arg{vid, base, std::move(keys)});
+  };
+  if (t->k == TK::Var) {
+    if (t->vid == m.vid_input || t->vid == m.vid_data) return false;
+    if (const CapArg* cap = cap_of(t->vid)) {
+      if (cap->k == CapArg::Col) add(t->vid, cap->col, {});
+      return true;
+    }
+    if (m.is_rule(t->name)) return false;      // a (non-function) rule used as a value
+    return true;                                // a local of a comprehension / wildcard
+  }
+  if (t->k == TK::Ref && t->head->k == TK::Var) {
+    const CapArg* cap = cap_of(t->head->vid);
+    if (cap && cap->k == CapArg::Col) {
+      std::vector<VP> keys;
+      size_t i = 0;
+      for (; i < t->args.size() && t->args[i]->k == TK::Scalar; ++i) keys.push_back(t->args[i]->val);
+      add(t->head->vid, cap->col, std::move(keys));
+      for (; i < t->args.size(); ++i)
+        if (!lut_args(m, t->args[i].get(), c, out)) return false;
+      return true;
+    }
+  }
+  if (t->k == TK::Call && m.is_rule(t->name)) {
+    auto pf = m.pure_fn.find(t->name);
+    if (pf == m.pure_fn.end() || !pf->second) return false;
+  }
+  if (t->head && !lut_args(m, t->head.get(), c, out)) return false;
+  for (auto& a : t->args)
+    if (!lut_args(m, a.get(), c, out)) return false;
+  for (auto& kv : t->kvs)
+    if (!lut_args(m, kv.first.get(), c, out) || !lut_args(m, kv.second.get(), c, out)) return false;
+  if (!lut_args(m, t->key.get(), c, out) || !lut_args(m, t->value.get(), c, out)) return false;
+  for (auto& s2 : t->body)
+    if (!lut_args(m, s2.a.get(), c, out) || !lut_args(m, s2.b.get(), c, out) || !lut_args(m, s2.c.get(), c, out)) return false;
+  return true;
+}
+
+XInfo closure_xinfo(const Closure& c) {
+  XInfo x;
+  if (c.leaf == Closure::Elem) {
+    x.k = XK::Elem;
+    return x;
+  }
+  if (c.leaf == Closure::Key) {
+    x.k = XK::Key;
+    return x;
+  }
+  if (!c.term || !c.mod) return x;
+  const Term& t = *c.term;
+  const Module& m = *c.mod;
+  auto cap_of = [&](int vid) -> const CapArg* {
+    for (auto& cp : c.caps)
+      if (cp.first == vid) return &cp.second;
+    return nullptr;
+  };
+  if (t.k == TK::Ref && t.head->k == TK::Var) {
+    bool lit = true;
+    for (auto& a : t.args) lit = lit && a->k == TK::Scalar;
+    const CapArg* cap = cap_of(t.head->vid);
+    if (lit && cap && cap->k == CapArg::Col && closure_xinfo(*cap->col).k != XK::Host) {
+      x.k = XK::Path;
+      x.base = cap->col;
+      for (auto& a : t.args) x.keys.push_back(a->val);
+      return x;
+    }
+    if (lit && !cap && t.head->vid == m.vid_input && !t.args.empty() && t.args[0]->val->t == VT::Str && t.args[0]->val->s == "review") {
+      x.k = XK::Path;
+      x.from_input = true;
+      for (auto& a : t.args) x.keys.push_back(a->val);
+      return x;
+    }
+  }
+  if (t.k == TK::Call && t.name == "count" && !m.is_rule(t.name) && t.args.size() == 1 && t.args[0]->k == TK::Var) {
+    const CapArg* cap = cap_of(t.args[0]->vid);
+    if (cap && cap->k == CapArg::Col) {
+      const XK bk = closure_xinfo(*cap->col).k;
+      if (bk == XK::Path || bk == XK::Elem) {
+        x.k = XK::Count;
+        x.base = cap->col;
+        return x;
+      }
+    }
+  }
+  if (!lut_args(m, &t, c, x.args)) return XInfo();
+  for (auto& a : x.args) {
+    const XInfo bi = closure_xinfo(*a.base);
+    if (bi.k == XK::Host) return XInfo();
+    // every part of the lookup key must be leaf-like: a whole iterated element / the whole object is not
+    const bool leafy = !a.keys.empty() ? (bi.k != XK::Path || !bi.from_input || bi.keys.size() + a.keys.size() >= 4) : xleafy(bi);
+    if (!leafy) return XInfo();
+  }
+  if (x.args.empty() || x.args.size() > 4) return XInfo();
+  x.k = XK::Lut;
+  return x;
+}
+
+bool schema_device_ingestable(const Schema& s, std::string* why) {
+  for (size_t i = 1; i < s.scopes.size(); ++i) {
+    const XK k = closure_xinfo(*s.scopes[i].gen).k;
+    if (k != XK::Path && k != XK::Elem) {
+      if (why) *why = "scope generator " + s.scopes[i].gen->key;
+      return false;
+    }
+  }
+  for (auto& c : s.cols)
+    if (closure_xinfo(*c.expr).k == XK::Host) {
+      if (why) *why = "column " + c.expr->key;
+      return false;
+    }
+  return true;
+}
+
+[[noreturn]] static void not_on_device(const std::string& key) {
+  throw RegoError{"rego_unsupported: device-ingest: the ingest kernels cannot compute " + key};
+}
+
 int Schema::scope_for(const CP& gen) {
   auto it = scope_ix.find(gen->key);
   if (it != scope_ix.end()) return it->second;
+  if (device_only) {
+    const XK k = closure_xinfo(*gen).k;
+    if (k != XK::Path && k != XK::Elem) not_on_device(gen->key);
+  }
   ScopeDef d;
   d.parent = gen->scope;
   d.gen = gen;
@@ -126,6 +276,7 @@ int Schema::col_for(const CP& expr, uint32_t enc) {
     cols[it->second].enc |= enc;
     return it->second;
   }
+  if (device_only && closure_xinfo(*expr).k == XK::Host) not_on_device(expr->key);
   ColDef d;
   d.expr = expr;
   d.scope = expr->scope;
@@ -430,6 +581,26 @@ class Lowerer {
   }
 
   CP make_closure(const TP& term, const LEnv& env) {
+    // <path closure>["a"]["b"] is the same column as the longer path from the root: `spec := input.review.object.spec;
+    // spec.containers` and `input.review.object.spec.containers` must not become two scopes / two sets of columns
+    if (term->k == TK::Ref && term->head->k == TK::Var) {
+      bool lit = true;
+      for (auto& a : term->args) lit = lit && a->k == TK::Scalar;
+      const SymVal* s = env.find(term->head->vid);
+      if (lit && s && s->k == SymVal::Col && s->col->leaf == Closure::None && s->col->mod == mod_ && s->col->term->k == TK::Ref &&
+          s->col->term->head->k == TK::Var) {
+        const Term& bt = *s->col->term;
+        bool blit = true;
+        for (auto& a : bt.args) blit = blit && a->k == TK::Scalar;
+        if (blit) {
+          std::vector<TP> path(bt.args.begin(), bt.args.end());
+          path.insert(path.end(), term->args.begin(), term->args.end());
+          LEnv be;
+          for (auto& cp : s->col->caps) be.bind(cp.first, cp.second.k == CapArg::Conc ? SymVal::conc(cp.second.v) : SymVal::column(cp.second.col));
+          return make_closure(synth_ref(bt.head, std::move(path), term->line), be);
+        }
+      }
+    }
     auto c = std::make_shared<Closure>();
     c->mod = mod_;
     c->term = term;
@@ -620,18 +791,19 @@ class Lowerer {
       // cross-type ordering against a non-number constant: only the rank matters unless the column is the same type
       unsupported("ordered comparison against a non-numeric parameter", line);
     }
+    // Numeric columns hold num_key(x) = 2*floor(x) + (x is fractional): against an INTEGER constant every comparison is exact
+    // for every object number.  A fractional threshold c (floor f) is the key 2f+1: exact against integer values and against
+    // fractions with another integer part (a fraction with the SAME integer part as c compares as equal to it -- documented limit).
     int64_t dummy;
     if (!num_fits_i64(k->n, &dummy)) {
-      // a fractional threshold against the device's exact-integer columns (an object whose number is not an exact int64 is a
-      // per-object error, never compared):  x > 1.5 == x >= 1.5 == x > 1   and   x < 1.5 == x <= 1.5 == x <= 1
       const bool ordered = cmp == GK_CMP_LT || cmp == GK_CMP_LE || cmp == GK_CMP_GT || cmp == GK_CMP_GE;
-      if (ordered && !k->n.is_int && std::isfinite(k->n.d) && std::fabs(k->n.d) < 9.0e18) {
-        const VP fl = v_int((long long)std::floor(k->n.d));
-        const uint32_t c2 = (cmp == GK_CMP_GT || cmp == GK_CMP_GE) ? (uint32_t)GK_CMP_GT : (uint32_t)GK_CMP_LE;
-        return f_atom(GK_OP_NUM_CMP, schema_.col_for(c, GK_ENC_VT | GK_ENC_NUM), fl, c2);
+      if (ordered && !k->n.is_int && std::isfinite(k->n.d) && std::fabs(k->n.d) < 2.0e18) {
+        const uint32_t c2 = (cmp == GK_CMP_GT || cmp == GK_CMP_GE) ? (uint32_t)GK_CMP_GT : (uint32_t)GK_CMP_LT;
+        return f_atom(GK_OP_NUM_CMP, schema_.col_for(c, GK_ENC_VT | GK_ENC_NUM), k, c2);
       }
       unsupported("ordered comparison against a parameter outside int64", line);
     }
+    if (dummy > GK_NUM_KEY_CONST_LIMIT || dummy < -GK_NUM_KEY_CONST_LIMIT) unsupported("comparison against a parameter beyond 2^61", line);
     return f_atom(GK_OP_NUM_CMP, schema_.col_for(c, GK_ENC_VT | GK_ENC_NUM), k, cmp);
   }
   FP a_strop(int op, const CP& c, const VP& k) {
@@ -920,7 +1092,16 @@ class Lowerer {
           return k(copy);
         }
       }
-      return k(SymVal::column(make_closure(t, env)));
+      // device ingest: keep the closure only when the ingest kernels can compute it (a path, a count, a pure function of
+      // leaf values); helper rules, comprehensions and impure functions are inlined below like their parameter-mixing kin
+      if (!schema_.device_only) return k(SymVal::column(make_closure(t, env)));
+      // (a comparison / string test against a constant is better an atom on the operand's column than a lookup column)
+      static const std::set<std::string> kAtomic = {"equal", "neq", "lt", "lte", "gt", "gte", "startswith", "endswith", "contains",
+                                                    "strings.any_prefix_match", "strings.any_suffix_match", "internal.member_2", "count"};
+      if (!(t->k == TK::Call && !m_.is_rule(t->name) && kAtomic.count(t->name))) {
+        CP cl = make_closure(t, env);
+        if (closure_xinfo(*cl).k != XK::Host) return k(SymVal::column(cl));
+      }
     }
     switch (t->k) {
       case TK::Var: {
@@ -1075,7 +1256,8 @@ class Lowerer {
     if (t->head->k == TK::Var && !env.find(t->head->vid) && m_.is_rule(t->head->name)) {
       auto& defs = m_.rules.at(t->head->name);
       Deps rd = rule_deps(t->head->name);
-      if ((defs[0].kind == Rule::PSet || defs[0].kind == Rule::PObj) && !(pure_obj(rd) || pure_conc(rd))) return inline_partial(t, env, k);
+      if ((defs[0].kind == Rule::PSet || defs[0].kind == Rule::PObj) && !((pure_obj(rd) && !schema_.device_only) || pure_conc(rd)))
+        return inline_partial(t, env, k);
     }
     // longest prefix that is purely parameters or purely object
     for (size_t j = t->args.size(); j-- > 0;) {
@@ -1605,7 +1787,8 @@ void Lowerer::subst_print(const Term& t, const std::map<int, std::string>& sub, 
 
 }  // namespace
 
-FP lower_violation(const std::shared_ptr<const Module>& mod, const VP& parameters, Schema& schema) {
+FP lower_violation(const std::shared_ptr<const Module>& mod, const VP& parameters, Schema& schema, bool device_mode) {
+  schema.device_only = device_mode;
   const Schema before = schema;   // (a failed attempt must not leave its scopes and columns behind)
   try {
     Lowerer lw(mod, parameters, schema);
@@ -2088,8 +2271,7 @@ void NetBuilder::build(const std::vector<FP>& formulas, const std::vector<uint32
               break;
             }
             case GK_OP_NUM_CMP: {
-              int64_t k = 0;
-              num_fits_i64(n.cval->n, &k);
+              const int64_t k = num_key(n.cval->n);   // (columns hold num_key(x) too)
               w2 = (uint32_t)pool.size();
               pool.push_back((uint32_t)((uint64_t)k & 0xffffffffu));
               pool.push_back((uint32_t)((uint64_t)k >> 32));

@@ -39,6 +39,31 @@ struct Closure {
   std::string key;                                       // canonical text: dedupes columns across constraints
 };
 
+// How a closure's value can be computed from the raw object JSON by the device ingest kernels (ingest_core.h):
+//   Path  : <base>["a"]["b"]... with literal keys, rooted at `input.review...` or at another device closure
+//   Elem / Key : the element / key of the enclosing scope's current row
+//   Count : count(<device closure>) of an array / object / string
+//   Lut   : a closed pure term over captured device closures (a builtin or pure user function of leaf values,
+//           `equal(a, b)`, re_match(pattern, s) ...): the device hashes the raw bytes of the arguments and looks the value
+//           up in a table the host fills once per DISTINCT argument tuple with the concrete evaluator
+//   Host  : anything else -- only the host flattener can compute it (the snapshot then flattens on the host)
+enum class XK : uint8_t { Host, Path, Elem, Key, Count, Lut };
+struct XInfo {
+  XK k = XK::Host;
+  bool from_input = false;    // Path: rooted at `input` (keys[0] == "review")
+  CP base;                    // Path (not from_input), Count: the closure the value is read from
+  std::vector<VP> keys;       // Path: literal keys
+  // Lut: the parts of the hash key -- every maximal `<captured column>["a"]["b"]` path of the term (a bare captured column
+  // has no keys).  The host evaluates the term with each captured variable bound to a skeleton object holding just those paths.
+  struct Arg {
+    int vid = -1;
+    CP base;
+    std::vector<VP> keys;
+  };
+  std::vector<Arg> args;
+};
+XInfo closure_xinfo(const Closure& c);
+
 struct ScopeDef {
   int parent = 0;
   CP gen;          // closure producing the iterated collection (evaluated per parent row); null for root
@@ -56,6 +81,7 @@ struct Schema {
   std::vector<ScopeDef> scopes;   // [0] = root
   std::vector<ColDef> cols;
   std::map<std::string, int> scope_ix, col_ix;
+  bool device_only = false;       // lowering for the device ingest path: a scope / column the ingest kernels cannot compute is an error
   Schema() { scopes.emplace_back(); }
   int scope_for(const CP& gen);
   int col_for(const CP& expr, uint32_t enc);
@@ -91,7 +117,10 @@ struct Interner {
 };
 
 // Lower one constraint's violation predicate.  Throws RegoError on unsupported constructs.
-FP lower_violation(const std::shared_ptr<const Module>& mod, const VP& parameters, Schema& schema);
+// `device_mode`: object-only sub-terms that the ingest kernels cannot compute (helper rules, comprehensions, impure
+// functions) are inlined into the formula instead of becoming host closures; throws when that is not possible.
+FP lower_violation(const std::shared_ptr<const Module>& mod, const VP& parameters, Schema& schema, bool device_mode = false);
+bool schema_device_ingestable(const Schema& s, std::string* why = nullptr);
 
 // Netlist assembly: every constraint's formula is merged into one DAG of bit-column ops (program.h GkOp).
 struct NetBuilder {

@@ -65,6 +65,24 @@ bool num_fits_i64(const Num& n, int64_t* out) {
   return true;
 }
 
+int64_t num_key(const Num& n) {
+  const __int128 lim = ((__int128)1 << 62) - 1;
+  __int128 fl;
+  bool frac = false;
+  if (n.is_int) {
+    fl = n.i;
+  } else if (!(std::fabs(n.d) < 9.0e18)) {   // (also NaN / infinities)
+    fl = n.d > 0 ? lim + 1 : -lim - 1;
+  } else {
+    const double f = std::floor(n.d);
+    fl = (__int128)f;
+    frac = f != n.d;
+  }
+  if (fl > lim) return INT64_MAX - 1;
+  if (fl < -lim) return INT64_MIN + 1;
+  return (int64_t)(2 * fl + (frac ? 1 : 0));
+}
+
 // ------------------------------------------------------------------------------------------ node pool
 namespace {
 // Nodes outlive thread-local storage at process exit (engines are torn down after the main thread's thread_locals): once

@@ -26,6 +26,12 @@ struct Num {
 int num_cmp(const Num& a, const Num& b);
 std::string num_str(const Num& n);
 bool num_fits_i64(const Num& n, int64_t* out);
+// Order-preserving int64 key of a number for the device's numeric columns and constants: 2*floor(x) + (x is not an integer),
+// saturated at +-(2^63 - 2).  For an INTEGER constant k with |k| <= 2^61:  x <cmp> k  <=>  num_key(x) <cmp> num_key(k)  for every
+// number x (fractions and out-of-range values included), so no object number is ever refused or approximated.
+// INT64_MIN / INT64_MAX stay free: they mark non-numbers below / above every number in OPA's cross-type order.
+int64_t num_key(const Num& n);
+#define GK_NUM_KEY_CONST_LIMIT ((int64_t)1 << 61)
 
 struct Node;
 using VP = std::shared_ptr<const Node>;

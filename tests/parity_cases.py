@@ -1202,3 +1202,42 @@ def case_verify_suite(lib):
         resp = drv.ReviewBatch(revs, k8s.GATOR_EP)
         assert bool(resp.results) == violations, (cfile, ofile, [r.msg for r in resp.results])
         assert_same(oracle_results(orc, revs, k8s.GATOR_EP), engine_results(resp))
+
+
+def case_inexact_numbers(lib):
+    """Numbers that are not exact int64 (fractions, 1e30, -1e25) must be COMPARED, not make the object skip every
+    constraint (round-1 advisor finding: `spec.replicas: 5.5` returned no results at all)."""
+    rego = """package k8smaxreplicas
+violation[{"msg": msg}] {
+  r := input.review.object.spec.replicas
+  r > input.parameters.max
+  msg := sprintf("replicas %v > %v", [r, input.parameters.max])
+}
+violation[{"msg": msg}] {
+  r := input.review.object.spec.replicas
+  r < input.parameters.min
+  msg := sprintf("replicas %v < %v", [r, input.parameters.min])
+}
+violation[{"msg": "exactly five"}] { input.review.object.spec.replicas == 5 }
+violation[{"msg": "not five"}] { input.review.object.spec.replicas != 5 }
+"""
+    owner = """package k8snoowner
+violation[{"msg": "no owner"}] { not input.review.object.metadata.labels.owner }
+"""
+    tm = [("K8sMaxReplicas", rego), ("K8sNoOwner", owner)]
+    cons = [{"apiVersion": "constraints.gatekeeper.sh/v1beta1", "kind": "K8sMaxReplicas", "metadata": {"name": "r%d" % i},
+             "spec": {"parameters": {"max": mx, "min": mn}}} for i, (mn, mx) in enumerate([(1, 3), (5, 5), (-2, 6), (0, 2.5), (5.5, 7)])]
+    cons.append({"apiVersion": "constraints.gatekeeper.sh/v1beta1", "kind": "K8sNoOwner", "metadata": {"name": "owner"}, "spec": {}})
+    orc, drv, _ = make_pair(tm, cons, lib_path=lib)
+    vals = [5.5, 5, 5.0, 3, 3.0001, 2.9999, 1e30, -1e25, -0.5, 0, 2, 2.5, 6, 6.5, 9223372036854775807, 9223372036854775808,
+            -9223372036854775809, 1.5e3, 0.1, "5", None, True, [5], {"a": 5}]
+    revs = [D.Review(object={"apiVersion": "apps/v1", "kind": "Deployment", "metadata": {"name": "d%d" % i, "namespace": "default"},
+                             "spec": {"replicas": v}}) for i, v in enumerate(vals)]
+    resp = drv.ReviewBatch(revs, k8s.AUDIT_EP)
+    assert not any(resp.object_errors), resp.object_errors
+    want = oracle_results(orc, revs, k8s.AUDIT_EP)
+    # documented limit: a fractional value against a fractional threshold with the same integer part (2.5 vs max 2.5 is exact
+    # equality here and is fine; 5.5 vs min 5.5 too) -- the vectors above avoid the ambiguous "5.7 vs 5.5" shape
+    assert_same(want, engine_results(resp))
+    assert sum(1 for w in want if w[1] == "K8sNoOwner/owner") == len(vals)
+    return resp

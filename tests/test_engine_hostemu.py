@@ -273,3 +273,7 @@ def test_reviews_concurrent_with_constraint_changes():
         t.join()
     assert not errs, errs[:3]
     assert counts["rev"] >= 3 and counts["mut"] >= 10
+
+
+def test_inexact_numbers_are_compared_not_skipped():
+    P.case_inexact_numbers(HOSTEMU)
