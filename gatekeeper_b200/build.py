@@ -18,7 +18,7 @@ OBJ = os.path.join(ROOT, "build", "obj")
 LIB = os.path.join(ROOT, "gatekeeper_b200", "libgk_engine.so")
 EMU = os.path.join(ROOT, "tests", "_hostemu", "libgk_hostemu.so")
 
-HOST_SRCS = ["val.cpp", "rego_parse.cpp", "rego_eval.cpp", "lower.cpp", "engine.cpp", "audit.cpp", "capi.cpp", "coalescer.cpp"]
+HOST_SRCS = ["val.cpp", "rego_parse.cpp", "rego_eval.cpp", "lower.cpp", "xprog.cpp", "engine.cpp", "audit.cpp", "capi.cpp", "coalescer.cpp"]
 SYNTH = os.path.join(ROOT, "gatekeeper_b200", "libgk_synth.so")
 CXXFLAGS = ["-std=c++17", "-O2", "-g1", "-fPIC", "-Wall", "-Wextra", "-pthread"]
 NVCCFLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC"]

@@ -50,6 +50,9 @@ class Backend {
   virtual void release(void* batch) = 0;
   virtual void eval(void* batch, const std::vector<uint32_t>& active, EvalOut& out, bool copy_back) = 0;
   virtual void eval_into(void* batch, const std::vector<uint32_t>& active, const DevOutPtrs& dst) = 0;
+  // Device ingest (ingest_core.h): raw JSON blob -> resident columnar batch without a host parse.  `status` receives one
+  // GK_ING_* code per object (the caller renders the error text of the rare non-OK ones with the host parser).
+  virtual void* ingest(const IngestReq& rq, IngestStats* st, std::vector<uint32_t>* status) = 0;
 };
 
 Backend* make_backend(int device);   // defined by whichever backend the library links
@@ -95,7 +98,8 @@ inline void pack_layout(const HostBatch& hb, const Compiled& c, PackedBatch& pb,
   PUT(flags, hb.flags);
   PUT(kind_sid, hb.kind_sid);
   PUT(group_sid, hb.group_sid);
-  PUT(nsname_sid, hb.nsname_sid);
+  PUT(nsn_off, hb.nsn_off);
+  PUT(nsn_bytes, hb.nsn_bytes);
   PUT(name_off, hb.name_off);
   PUT(name_bytes, hb.name_bytes);
   PUT(gen_off, hb.gen_off);
@@ -177,7 +181,7 @@ inline void pack_batch(const HostBatch& hb, const Compiled& c, PackedBatch& pb) 
 inline GkBatch rebase_batch(PackedBatch& pb, uint8_t* host_image, const uint8_t* base) {
   GkBatch h = pb.hdr;
 #define RB(f) h.f = reinterpret_cast<decltype(h.f)>(base + reinterpret_cast<size_t>(h.f))
-  RB(flags); RB(kind_sid); RB(group_sid); RB(nsname_sid); RB(name_off); RB(name_bytes); RB(gen_off); RB(gen_bytes);
+  RB(flags); RB(kind_sid); RB(group_sid); RB(nsn_off); RB(nsn_bytes); RB(name_off); RB(name_bytes); RB(gen_off); RB(gen_bytes);
   RB(lbl_off); RB(lbl_kv); RB(nsrow); RB(nsl_off); RB(nsl_kv); RB(cols); RB(scopes);
 #undef RB
   GkColumn* cols = reinterpret_cast<GkColumn*>(host_image + pb.cols_off);

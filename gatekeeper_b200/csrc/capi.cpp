@@ -54,8 +54,13 @@ struct gk_batch {
   std::shared_ptr<const Compiled> compiled;
   std::shared_ptr<HostBatch> host;     // kept for object_errors / alg_bytes (column data is released after upload)
   std::vector<gk_obj> objs;            // shallow copy: the caller keeps the JSON alive while the batch lives
+  // a blob batch (device ingest) keeps only the blob and its offsets
+  const char* blob = nullptr;
+  const uint64_t* blob_off = nullptr;
+  uint8_t blob_source = 0;
   uint32_t n = 0;
   uint64_t alg_bytes = 0;
+  ObjIn obj_in(size_t i) const;
 };
 
 namespace {
@@ -119,6 +124,19 @@ ObjIn to_in(const gk_obj& o) {
   in.source = o.source;
   return in;
 }
+
+}  // namespace
+
+ObjIn gk_batch::obj_in(size_t i) const {
+  if (!blob) return to_in(objs[i]);
+  ObjIn in;
+  in.json = blob + blob_off[i];
+  in.len = (size_t)(blob_off[i + 1] - blob_off[i]);
+  in.source = blob_source;
+  return in;
+}
+
+namespace {
 
 void fill_result(gk_result* out, ResultPriv* rp, bool have_bits) {
   out->n_objects = rp->ev.n;
@@ -204,7 +222,7 @@ void eval_batch(gk_engine* e, gk_batch* b, const char* ep_c, uint32_t flags, gk_
               flagged.push_back({cix, is_err, code});
             }
           }
-          if (!flagged.empty()) e->eng->materialize_object(c, to_in(b->objs[o]), o, flagged, ep, part[t], nullptr, &mctx);
+          if (!flagged.empty()) e->eng->materialize_object(c, b->obj_in(o), o, flagged, ep, part[t], nullptr, &mctx);
         }
       } catch (RegoError& x) {
         errs[t] = x.msg;
@@ -257,6 +275,64 @@ void upload_batch(gk_engine* e, const std::shared_ptr<const Compiled>& c, const 
     stats->h2d_bytes = h2d_bytes;
     stats->alg_bytes = hb->alg_bytes;
     stats->n_objects = hb->n;
+    stats->n_constraints = (uint32_t)c->cons_match.size();
+  }
+  *outb = b.release();
+}
+
+static std::vector<gk_obj> blob_objs(const char* buf, const uint64_t* off, size_t n, uint8_t source) {
+  std::vector<gk_obj> v(n);
+  for (size_t i = 0; i < n; ++i) {
+    memset(&v[i], 0, sizeof(gk_obj));
+    v[i].json = buf + off[i];
+    v[i].len = (size_t)(off[i + 1] - off[i]);
+    v[i].source = source;
+  }
+  return v;
+}
+
+// a blob of plain objects: flattened by the ingest kernels on the device when the compiled snapshot allows it
+void upload_blob(gk_engine* e, const std::shared_ptr<const Compiled>& c, const char* buf, const uint64_t* off, size_t n, uint8_t source, uint32_t flags,
+                 gk_batch** outb, gk_result* stats) {
+  static const bool host_only = getenv("GK_NO_DEVICE_INGEST") != nullptr;
+  if (!c->device_ingest || host_only || n == 0) {
+    auto v = blob_objs(buf, off, n, source);
+    upload_batch(e, c, v.data(), n, flags, outb, stats);
+    return;
+  }
+  double t0 = now_ms();
+  IngestReq rq = e->eng->ingest_request(c, reinterpret_cast<const uint8_t*>(buf), reinterpret_cast<const unsigned long long*>(off), n, source, process_of(flags));
+  IngestStats ist;
+  std::vector<uint32_t> status;
+  auto b = std::make_unique<gk_batch>();
+  b->dev = e->be->ingest(rq, &ist, &status);
+  b->compiled = c;
+  b->n = (uint32_t)n;
+  b->alg_bytes = ist.alg_bytes;
+  b->blob = buf;
+  b->blob_off = off;
+  b->blob_source = source;
+  auto slim = std::make_shared<HostBatch>();
+  slim->n = (uint32_t)n;
+  slim->alg_bytes = ist.alg_bytes;
+  slim->obj_errors.assign(n, std::string());
+  for (size_t i = 0; i < n; ++i)
+    if (status[i] != GK_ING_OK) {
+      // the rare rejected object: the host parser words the review-level error (bad JSON, not an object, kind missing)
+      std::string err;
+      VP doc = e->eng->review_doc(b->obj_in(i), nullptr, nullptr, nullptr, &err);
+      if (doc && status[i] != GK_ING_NULL) err = "device ingest refused the object (status " + std::to_string(status[i]) + "): JSON nesting deeper than " +
+                                               std::to_string(GK_TAPE_MAX_DEPTH) + " levels or a token longer than 128 MiB";
+      if (!doc && err.empty()) err = "invalid request object";
+      slim->obj_errors[i] = err;
+    }
+  b->host = slim;
+  if (stats) {
+    stats->flatten_ms = (now_ms() - t0) - ist.h2d_ms;
+    stats->h2d_ms = ist.h2d_ms;
+    stats->h2d_bytes = ist.h2d_bytes;
+    stats->alg_bytes = ist.alg_bytes;
+    stats->n_objects = (uint32_t)n;
     stats->n_constraints = (uint32_t)c->cons_match.size();
   }
   *outb = b.release();
@@ -436,34 +512,37 @@ int gk_batch_eval_device_peers(gk_engine_t* e, gk_batch_t* b, const char* ep, co
   });
 }
 
-static std::vector<gk_obj> blob_objs(const char* buf, const uint64_t* off, size_t n, uint8_t source) {
-  std::vector<gk_obj> v(n);
-  for (size_t i = 0; i < n; ++i) {
-    memset(&v[i], 0, sizeof(gk_obj));
-    v[i].json = buf + off[i];
-    v[i].len = (size_t)(off[i + 1] - off[i]);
-    v[i].source = source;
-  }
-  return v;
-}
-
 int gk_batch_upload_blob(gk_engine_t* e, const char* buf, const uint64_t* offsets, size_t n, uint8_t source, uint32_t flags, gk_batch_t** outb,
                          gk_result* stats, char** err) {
   if (!e || !outb || ((!buf || !offsets) && n)) return GK_ERR_INVALID;
   if (stats) memset(stats, 0, sizeof *stats);
   return guard(err, [&]() {
-    auto v = blob_objs(buf, offsets, n, source);
     auto c = e->eng->compiled();
     ProgramLease lease(e, *c);
-    upload_batch(e, c, v.data(), n, flags, outb, stats);
+    upload_blob(e, c, buf, offsets, n, source, flags, outb, stats);
   });
 }
 
 int gk_review_blob(gk_engine_t* e, const char* buf, const uint64_t* offsets, size_t n, uint8_t source, const char* ep, uint32_t flags,
                    gk_result* out, char** err) {
   if (!e || !out || ((!buf || !offsets) && n)) return GK_ERR_INVALID;
-  auto v = blob_objs(buf, offsets, n, source);
-  return gk_review_batch(e, v.data(), n, ep, flags, out, err);
+  memset(out, 0, sizeof *out);
+  return guard(err, [&]() {
+    gk_batch* b = nullptr;
+    gk_result stats;
+    memset(&stats, 0, sizeof stats);
+    auto c = e->eng->compiled();
+    ProgramLease lease(e, *c);
+    upload_blob(e, c, buf, offsets, n, source, flags, &b, &stats);
+    std::unique_ptr<gk_batch, std::function<void(gk_batch*)>> hold(b, [&](gk_batch* x) {
+      e->be->release(x->dev);
+      delete x;
+    });
+    eval_batch(e, b, ep, flags, out);
+    out->flatten_ms = stats.flatten_ms;
+    out->h2d_ms = stats.h2d_ms;
+    out->h2d_bytes = stats.h2d_bytes;
+  });
 }
 
 uint32_t gk_batch_size(gk_batch_t* b) { return b ? b->n : 0; }
@@ -511,8 +590,8 @@ int gk_audit_add_batch(gk_audit_t* a, gk_batch_t* b, const char* ep_c, char** er
     e->eng->active_mask(*c, ep, active);
     EvalOut ev;
     e->be->eval(b->dev, active, ev, true);
-    std::vector<ObjIn> ins(b->objs.size());
-    for (size_t i = 0; i < ins.size(); ++i) ins[i] = to_in(b->objs[i]);
+    std::vector<ObjIn> ins(b->n);
+    for (size_t i = 0; i < ins.size(); ++i) ins[i] = b->obj_in(i);
     a->run.add_batch(*e->eng, *c, ins, ev.viol.data(), ev.err.empty() ? nullptr : ev.err.data(), ev.words, ev.errlist, ep);
   });
 }

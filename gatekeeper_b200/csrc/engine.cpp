@@ -588,9 +588,11 @@ void Engine::put_namespace(const std::string& name, const std::string& json) {
   if (!ok) throw RegoError{"cannot cache non-namespace type: cannot cache Namespace: <nil>"};
   std::unique_lock<std::shared_mutex> l(mu_);
   namespaces_[name] = v;
+  ++ns_version_;
 }
 bool Engine::remove_namespace(const std::string& name) {
   std::unique_lock<std::shared_mutex> l(mu_);
+  ++ns_version_;
   return namespaces_.erase(name) != 0;
 }
 
@@ -665,6 +667,7 @@ void Engine::compile_locked() {
     try {
       lower_all(true);
       device_ok = schema_device_ingestable(out->schema, &out->host_ingest_reason);
+      if (device_ok) out->xprog = build_xprog(out->schema);
     } catch (RegoError& e) {
       if (e.msg.find("rego_unsupported") == std::string::npos) throw;
       device_ok = false;
@@ -976,8 +979,8 @@ static bool wildcard_match(const std::string& pat, const std::string& s) {
 struct ChunkOut {
   HostBatch hb;
   // old-object header rows are kept in a second set of vectors and appended after the merge
-  std::vector<uint32_t> o_flags, o_kind, o_group, o_nsname, o_name_off{0}, o_gen_off{0}, o_lbl_off{0}, o_lbl_kv;
-  std::vector<uint8_t> o_name_bytes, o_gen_bytes;
+  std::vector<uint32_t> o_flags, o_kind, o_group, o_nsn_off{0}, o_name_off{0}, o_gen_off{0}, o_lbl_off{0}, o_lbl_kv;
+  std::vector<uint8_t> o_name_bytes, o_gen_bytes, o_nsn_bytes;
   bool any_old = false;
 };
 
@@ -1049,6 +1052,7 @@ struct Flattener : ChunkOut {
     hb.name_off.push_back(0);
     hb.gen_off.push_back(0);
     hb.lbl_off.push_back(0);
+    hb.nsn_off.push_back(0);
     hb.nsl_off.push_back(0);
   }
   std::unique_ptr<ChunkOut> take() { return std::unique_ptr<ChunkOut>(new ChunkOut(std::move(static_cast<ChunkOut&>(*this)))); }
@@ -1079,23 +1083,7 @@ struct Flattener : ChunkOut {
     str_sid_cache.emplace(raw, id);
     return id;
   }
-  std::unordered_map<std::string, uint32_t> ns_sid_cache;   // namespace names (interned: the device needs their bytes), raw-keyed
-  uint32_t sid_ns(const std::string& raw) {
-    auto it = ns_sid_cache.find(raw);
-    if (it != ns_sid_cache.end()) return it->second;
-    uint32_t id = sid_interned("s" + raw);
-    ns_sid_cache.emplace(raw, id);
-    return id;
-  }
   uint32_t sid_value(const VP& v) { return v->t == VT::Str ? sid_str(v->s) : sid(intern_key(v)); }
-  // namespace names are matched by wildcard on the device, which needs their bytes: those (few) are interned
-  uint32_t sid_interned(const std::string& key) {
-    auto it = sid_cache.find(key);
-    if (it != sid_cache.end() && it->second != GK_SID_OTHER) return it->second;
-    uint32_t id = eng.strings().intern(key);
-    sid_cache[key] = id;
-    return id;
-  }
 
   Eval& eval_for(const Closure& cl, const VP& input) {
     auto& slot = evals[cl.mod.get()];
@@ -1320,7 +1308,7 @@ struct Flattener : ChunkOut {
 
   void header_row(const VP& o, const VP& ns, uint8_t source, bool present) {
     uint32_t fl = 0;
-    uint32_t kind = GK_SID_UNDEF, group = GK_SID_UNDEF, nsname = GK_NONE;
+    uint32_t kind = GK_SID_UNDEF, group = GK_SID_UNDEF;
     if (present && o) {
       fl |= GK_F_HAS_OBJ;
       std::string g, v, k;
@@ -1336,9 +1324,15 @@ struct Flattener : ChunkOut {
       hb.name_bytes.insert(hb.name_bytes.end(), name.begin(), name.end());
       hb.gen_bytes.insert(hb.gen_bytes.end(), gen.begin(), gen.end());
       // name used by namespaces / excludedNamespaces -- match.go:118-179
-      if (is_ns) nsname = sid_ns(name);
-      else if (ns) nsname = sid_ns(meta_str(ns, "name"));
-      else if (!objns.empty()) nsname = sid_ns(objns);
+      const std::string* nsn = nullptr;
+      std::string nsmeta;
+      if (is_ns) nsn = &name;
+      else if (ns) nsmeta = meta_str(ns, "name"), nsn = &nsmeta;
+      else if (!objns.empty()) nsn = &objns;
+      if (nsn) {
+        fl |= GK_F_NSNAME;
+        hb.nsn_bytes.insert(hb.nsn_bytes.end(), nsn->begin(), nsn->end());
+      }
       if (const Node* ls = labels_of(o))
         for (auto& e : ls->kv) {
           hb.lbl_kv.push_back(sid_str(e.first->s));
@@ -1349,7 +1343,7 @@ struct Flattener : ChunkOut {
     hb.flags.push_back(fl);
     hb.kind_sid.push_back(kind);
     hb.group_sid.push_back(group);
-    hb.nsname_sid.push_back(nsname);
+    hb.nsn_off.push_back((uint32_t)hb.nsn_bytes.size());
     hb.name_off.push_back((uint32_t)hb.name_bytes.size());
     hb.gen_off.push_back((uint32_t)hb.gen_bytes.size());
     hb.lbl_off.push_back((uint32_t)hb.lbl_kv.size() / 2);
@@ -1388,11 +1382,11 @@ struct Flattener : ChunkOut {
     size_t before = hb.flags.size();
     header_row(nullptr, nullptr, 0, false);
     hb.flags[before] |= GK_F_SKIP;
-    std::swap(hb.flags, o_flags), std::swap(hb.kind_sid, o_kind), std::swap(hb.group_sid, o_group), std::swap(hb.nsname_sid, o_nsname);
+    std::swap(hb.flags, o_flags), std::swap(hb.kind_sid, o_kind), std::swap(hb.group_sid, o_group), std::swap(hb.nsn_off, o_nsn_off), std::swap(hb.nsn_bytes, o_nsn_bytes);
     std::swap(hb.name_off, o_name_off), std::swap(hb.gen_off, o_gen_off), std::swap(hb.lbl_off, o_lbl_off), std::swap(hb.lbl_kv, o_lbl_kv);
     std::swap(hb.name_bytes, o_name_bytes), std::swap(hb.gen_bytes, o_gen_bytes);
     header_row(nullptr, nullptr, 0, false);
-    std::swap(hb.flags, o_flags), std::swap(hb.kind_sid, o_kind), std::swap(hb.group_sid, o_group), std::swap(hb.nsname_sid, o_nsname);
+    std::swap(hb.flags, o_flags), std::swap(hb.kind_sid, o_kind), std::swap(hb.group_sid, o_group), std::swap(hb.nsn_off, o_nsn_off), std::swap(hb.nsn_bytes, o_nsn_bytes);
     std::swap(hb.name_off, o_name_off), std::swap(hb.gen_off, o_gen_off), std::swap(hb.lbl_off, o_lbl_off), std::swap(hb.lbl_kv, o_lbl_kv);
     std::swap(hb.name_bytes, o_name_bytes), std::swap(hb.gen_bytes, o_gen_bytes);
     hb.nsrow.push_back(GK_NONE);
@@ -1429,12 +1423,12 @@ struct Flattener : ChunkOut {
     // ---- header (object row, then old-object row into the side vectors)
     uint64_t th0 = trace ? __builtin_ia32_rdtsc() : 0;
     header_row(obj, ns, in.source, (bool)obj);
-    std::swap(hb.flags, o_flags), std::swap(hb.kind_sid, o_kind), std::swap(hb.group_sid, o_group), std::swap(hb.nsname_sid, o_nsname);
+    std::swap(hb.flags, o_flags), std::swap(hb.kind_sid, o_kind), std::swap(hb.group_sid, o_group), std::swap(hb.nsn_off, o_nsn_off), std::swap(hb.nsn_bytes, o_nsn_bytes);
     std::swap(hb.name_off, o_name_off), std::swap(hb.gen_off, o_gen_off), std::swap(hb.lbl_off, o_lbl_off), std::swap(hb.lbl_kv, o_lbl_kv);
     std::swap(hb.name_bytes, o_name_bytes), std::swap(hb.gen_bytes, o_gen_bytes);
     bool old_distinct = old && old.get() != obj.get();
     header_row(old, ns, in.source, old_distinct);
-    std::swap(hb.flags, o_flags), std::swap(hb.kind_sid, o_kind), std::swap(hb.group_sid, o_group), std::swap(hb.nsname_sid, o_nsname);
+    std::swap(hb.flags, o_flags), std::swap(hb.kind_sid, o_kind), std::swap(hb.group_sid, o_group), std::swap(hb.nsn_off, o_nsn_off), std::swap(hb.nsn_bytes, o_nsn_bytes);
     std::swap(hb.name_off, o_name_off), std::swap(hb.gen_off, o_gen_off), std::swap(hb.lbl_off, o_lbl_off), std::swap(hb.lbl_kv, o_lbl_kv);
     std::swap(hb.name_bytes, o_name_bytes), std::swap(hb.gen_bytes, o_gen_bytes);
     any_old = any_old || old_distinct;
@@ -1501,6 +1495,78 @@ struct Flattener : ChunkOut {
     }
     ++hb.n;
   }
+  // ---- Lut closures of the device ingest path: the value for one tuple of leaf arguments.  The closure is evaluated by the
+  // very code that flattens on the host (eval_slot), against skeleton documents that hold just the argument paths.
+  struct Skel {
+    VP val;                               // set: a leaf value
+    std::map<std::string, Skel> obj;
+    std::map<int64_t, Skel> arr;
+    void put(const std::vector<VP>& keys, size_t i, const VP& v) {
+      if (i == keys.size()) {
+        val = v;
+        return;
+      }
+      const VP& k = keys[i];
+      int64_t ix;
+      if (k->t == VT::Str) obj[k->s].put(keys, i + 1, v);
+      else if (k->t == VT::Num && num_fits_i64(k->n, &ix) && ix >= 0 && ix < 4096) arr[ix].put(keys, i + 1, v);
+    }
+    VP build() const {
+      if (val) return val;
+      if (!arr.empty()) {
+        std::vector<VP> items((size_t)arr.rbegin()->first + 1, v_null());
+        for (auto& e : arr) items[(size_t)e.first] = e.second.build();
+        return v_arr(std::move(items));
+      }
+      std::vector<std::pair<VP, VP>> kv;
+      for (auto& e : obj) kv.emplace_back(v_str(e.first), e.second.build());
+      return v_obj(std::move(kv));
+    }
+  };
+  GkLutVal lut_value(const Closure& cl, const std::vector<XInfo::Arg>& args, const std::vector<VP>& vals) {
+    Skel in_doc;
+    std::map<int, Skel> elems;
+    std::map<int, VP> keys;
+    bool any_input = false;
+    for (size_t a = 0; a < args.size(); ++a) {
+      if (!vals[a]) continue;   // an undefined argument: its path is simply absent
+      if (!args[a].leaf) {
+        in_doc.put(args[a].keys, 0, vals[a]);
+        any_input = true;
+      } else if (args[a].leaf->leaf == Closure::Key) {
+        if (args[a].keys.empty()) keys[args[a].leaf->scope] = vals[a];
+      } else {
+        elems[args[a].leaf->scope].put(args[a].keys, 0, vals[a]);
+      }
+    }
+    VP input = any_input ? in_doc.build() : v_obj({{v_str("review"), v_obj({})}});
+    for (auto& e : evals) e.second->reset_input(input);
+    memo.clear();
+    hold.clear();
+    for (auto& r : rows) r.clear();
+    rows[0].push_back(Row{nullptr, nullptr, 0});
+    for (int sc = cl.scope; sc != 0; sc = c.schema.scopes[sc].parent) {
+      Row r{nullptr, nullptr, 0};
+      auto ei = elems.find(sc);
+      if (ei != elems.end()) r.elem = ei->second.build();
+      auto ki = keys.find(sc);
+      if (ki != keys.end()) r.key = ki->second;
+      rows[sc].push_back(r);
+    }
+    const VP* v = eval_slot(cl, cl.scope, 0, input);
+    GkLutVal out;
+    memset(&out, 0, sizeof out);
+    out.vt = v ? (uint32_t)(*v)->t : (uint32_t)GK_VT_UNDEF;
+    out.sid = v ? sid_value(*v) : GK_SID_UNDEF;
+    if (v && (*v)->t == VT::Num) out.num = num_key((*v)->n);
+    else if (v) out.num = type_rank((*v)->t) < type_rank(VT::Num) ? INT64_MIN : INT64_MAX;
+    if (v && (*v)->t == VT::Str) {
+      const std::string& str = (*v)->s;
+      memcpy(out.head, str.data(), std::min<size_t>(str.size(), GK_HEAD_BYTES));
+      reinterpret_cast<uint8_t*>(out.head)[GK_HEAD_WORDS * 4 - 1] = (uint8_t)std::min<size_t>(str.size(), 255);
+    }
+    return out;
+  }
   bool trace = getenv("GK_FLATTEN_TRACE") != nullptr;
   std::vector<uint64_t> col_cycles = std::vector<uint64_t>(4096, 0), scope_cycles = std::vector<uint64_t>(256, 0);
   uint64_t doc_cycles = 0, hdr_cycles = 0, traced_objects = 0;
@@ -1554,9 +1620,6 @@ std::shared_ptr<HostBatch> Engine::flatten(const ObjIn* objs, size_t n, const Co
     auto it = excluded_.find(process);
     if (!process.empty() && it != excluded_.end()) excluded = it->second;
   }
-  // namespace names are matched by wildcard on the device and so must be in the table: intern the known ones before the
-  // freeze, so that the workers' lookups stay on the lock-free path
-  for (auto& kv : ns_copy) strings_.intern("s" + kv.first);
   auto frozen = strings_.freeze();
   // objects are handed out in chunks from a shared counter (threads on a throttled / shared host finish unevenly);
   // every chunk becomes one part, merged in object order below
@@ -1615,6 +1678,7 @@ std::shared_ptr<HostBatch> Engine::flatten(const ObjIn* objs, size_t n, const Co
   hb.name_off.push_back(0);
   hb.gen_off.push_back(0);
   hb.lbl_off.push_back(0);
+  hb.nsn_off.push_back(0);
   hb.nsl_off.push_back(0);
   for (size_t s = 1; s < nscopes; ++s) hb.scope_off[s].push_back(0);
   for (size_t i = 0; i < ncols; ++i)
@@ -1653,12 +1717,13 @@ std::shared_ptr<HostBatch> Engine::flatten(const ObjIn* objs, size_t n, const Co
   GK_CAT(hb.flags, flags, o_flags);
   GK_CAT(hb.kind_sid, kind_sid, o_kind);
   GK_CAT(hb.group_sid, group_sid, o_group);
-  GK_CAT(hb.nsname_sid, nsname_sid, o_nsname);
   GK_CAT_OFF(hb.name_off, name_off, o_name_off);
   GK_CAT_OFF(hb.gen_off, gen_off, o_gen_off);
   GK_CAT_OFF(hb.lbl_off, lbl_off, o_lbl_off);
+  GK_CAT_OFF(hb.nsn_off, nsn_off, o_nsn_off);
   GK_CAT(hb.name_bytes, name_bytes, o_name_bytes);
   GK_CAT(hb.gen_bytes, gen_bytes, o_gen_bytes);
+  GK_CAT(hb.nsn_bytes, nsn_bytes, o_nsn_bytes);
   GK_CAT(hb.lbl_kv, lbl_kv, o_lbl_kv);
 #undef GK_CAT
 #undef GK_CAT_OFF
@@ -1724,12 +1789,120 @@ std::shared_ptr<HostBatch> Engine::flatten(const ObjIn* objs, size_t n, const Co
   // ---- algorithmic bytes: every array the kernel may read, counted once
   uint64_t b = 0;
   auto sz = [&](auto& v) { b += (uint64_t)v.size() * sizeof(v[0]); };
-  sz(hb.flags), sz(hb.kind_sid), sz(hb.group_sid), sz(hb.nsname_sid), sz(hb.name_off), sz(hb.gen_off), sz(hb.lbl_off), sz(hb.lbl_kv);
+  sz(hb.flags), sz(hb.kind_sid), sz(hb.group_sid), sz(hb.nsn_off), sz(hb.nsn_bytes), sz(hb.name_off), sz(hb.gen_off), sz(hb.lbl_off), sz(hb.lbl_kv);
   sz(hb.name_bytes), sz(hb.gen_bytes), sz(hb.nsrow), sz(hb.nsl_off), sz(hb.nsl_kv);
   for (size_t s = 1; s < nscopes; ++s) sz(hb.scope_off[s]);
   for (auto& col : hb.cols) sz(col.vt), sz(col.sid), sz(col.num), sz(col.boff), sz(col.bytes), sz(col.head);
   hb.alg_bytes = b;
   return out;
+}
+
+// ====================================================================================== device ingest: request + lookups
+IngestReq Engine::ingest_request(const std::shared_ptr<const Compiled>& c, const uint8_t* blob, const unsigned long long* ooff, size_t n, uint32_t source,
+                                 const std::string& process) {
+  IngestReq rq;
+  rq.blob = blob;
+  rq.ooff = ooff;
+  rq.n = n;
+  rq.source = source;
+  rq.c = c.get();
+  rq.xprog = c->xprog;
+  rq.strings = &strings_;
+  {
+    std::unique_lock<std::shared_mutex> l(mu_);
+    auto it = excluded_.find(process);
+    if (!process.empty() && it != excluded_.end()) rq.excluded = it->second;
+    const uint32_t nstr = strings_.size();
+    if (!ns_table_ || ns_table_version_ != ns_version_ || ns_table_strings_ != nstr) {
+      // the namespace cache as device tables: label sids are looked up, never added (an unknown string equals no constant)
+      auto t = std::make_shared<NsTableHost>();
+      uint32_t cap = 64;
+      while (cap < 4u * namespaces_.size()) cap <<= 1;
+      t->tab.init(cap);
+      auto sid_of = [&](const std::string& key) {
+        const uint32_t id = strings_.lookup(key);
+        return id == GK_SID_UNDEF ? (uint32_t)GK_SID_OTHER : id;
+      };
+      uint32_t row = 0;
+      for (auto& kv : namespaces_) {
+        t->tab.put(xhash(GK_SEED_NS, kv.first.data(), kv.first.size()), row++);
+        if (const Node* ls = labels_of(kv.second))
+          for (auto& e : ls->kv) {
+            t->nsl_kv.push_back(sid_of("s" + e.first->s));
+            t->nsl_kv.push_back(sid_of(intern_key(e.second)));
+          }
+        t->nsl_off.push_back((uint32_t)t->nsl_kv.size() / 2);
+        const std::string nm = meta_str(kv.second, "name");
+        t->nsn_bytes.insert(t->nsn_bytes.end(), nm.begin(), nm.end());
+        t->nsn_off.push_back((uint32_t)t->nsn_bytes.size());
+      }
+      ns_table_ = t;
+      ns_table_version_ = ns_version_;
+      ns_table_strings_ = nstr;
+    }
+    rq.ns = ns_table_;
+  }
+  rq.lut_fill = [this, c, blob](const GkMiss* m, size_t k, std::vector<GkLutVal>& out) { lut_fill(*c, blob, m, k, out); };
+  return rq;
+}
+
+void Engine::lut_fill(const Compiled& c, const uint8_t* blob, const GkMiss* misses, size_t n, std::vector<GkLutVal>& out) {
+  out.assign(n, GkLutVal{});
+  if (!n) return;
+  const XProgHost& xp = *c.xprog;
+  std::map<std::string, VP> ns_copy;   // (Lut closures are pure: they never look at the namespace cache)
+  auto frozen = strings_.freeze();
+  const size_t T = std::min<size_t>((size_t)threads_, std::max<size_t>(1, n / 512));
+  std::vector<std::string> errs(T);
+  auto work = [&](size_t t) {
+    try {
+      Flattener fl(*this, c, ns_copy);
+      fl.frozen = frozen;
+      std::vector<VP> vals;
+      for (size_t i = n * t / T; i < n * (t + 1) / T; ++i) {
+        const GkMiss& m = misses[i];
+        if (m.col == GK_CL_SIDVAL) {   // "the sid of this value": a number spelt non-canonically, a composite
+          GkLutVal lv;
+          memset(&lv, 0, sizeof lv);
+          lv.sid = GK_SID_OTHER;
+          if (m.args[0].kind == GK_ARG_JSON) {
+            VP v = json_parse(reinterpret_cast<const char*>(blob) + m.args[0].off, m.args[0].len);
+            lv.vt = (uint32_t)v->t;
+            lv.sid = fl.sid_value(v);
+          }
+          out[i] = lv;
+          continue;
+        }
+        if (m.col >= xp.cl.size() || !xp.cl_src[m.col]) throw RegoError{"device ingest: miss record names no lookup closure"};
+        const auto& args = xp.cl_args[m.col];
+        vals.assign(args.size(), nullptr);
+        for (size_t a = 0; a < args.size() && a < GK_LUT_MAX_ARGS; ++a) {
+          const GkMissArg& ma = m.args[a];
+          switch (ma.kind) {
+            case GK_ARG_JSON: vals[a] = json_parse(reinterpret_cast<const char*>(blob) + ma.off, ma.len); break;
+            case GK_ARG_INDEX: vals[a] = v_int((long long)ma.off); break;
+            case GK_ARG_SYNSTR: vals[a] = v_str(std::string(ma.len ? reinterpret_cast<const char*>(blob) + ma.off : "", ma.len)); break;
+            default: break;
+          }
+        }
+        out[i] = fl.lut_value(*xp.cl_src[m.col], args, vals);
+      }
+    } catch (RegoError& e) {
+      errs[t] = e.msg;
+    } catch (JsonError& e) {
+      errs[t] = "device ingest: argument bytes do not parse: " + e.msg;
+    } catch (std::exception& e) {
+      errs[t] = e.what();
+    }
+  };
+  if (T == 1) work(0);
+  else {
+    std::vector<std::thread> th;
+    for (size_t t = 0; t < T; ++t) th.emplace_back(work, t);
+    for (auto& x : th) x.join();
+  }
+  for (auto& e : errs)
+    if (!e.empty()) throw RegoError{"lut_fill: " + e};
 }
 
 // ====================================================================================== materialisation

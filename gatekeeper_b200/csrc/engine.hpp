@@ -13,6 +13,7 @@
 #include "lower.hpp"
 #include "program.h"
 #include "rego.hpp"
+#include "xprog.hpp"
 
 namespace gk {
 
@@ -44,8 +45,8 @@ struct HostBatch {
   uint32_t n = 0;
   bool has_old = false;
   // header rows: [0,n) objects, [n,2n) old objects when has_old
-  std::vector<uint32_t> flags, kind_sid, group_sid, nsname_sid, name_off, gen_off, lbl_off, lbl_kv;
-  std::vector<uint8_t> name_bytes, gen_bytes;
+  std::vector<uint32_t> flags, kind_sid, group_sid, nsn_off, name_off, gen_off, lbl_off, lbl_kv;
+  std::vector<uint8_t> name_bytes, gen_bytes, nsn_bytes;
   std::vector<uint32_t> nsrow;                 // [n]
   std::vector<uint32_t> nsl_off, nsl_kv;       // per-batch namespace label table
   std::vector<std::vector<uint32_t>> scope_off;   // [scope][parent_rows+1]; [0] unused
@@ -103,6 +104,7 @@ struct Compiled {
                                                          // (RemoveConstraint / a replacing AddConstraint may run meanwhile)
   std::vector<std::shared_ptr<Module>> mods;   // constraint index -> its template's module (pinned by this snapshot)
   size_t n_nodes = 0, n_atoms = 0, n_gates = 0, n_phases = 0;
+  std::shared_ptr<const XProgHost> xprog;      // the extraction program of the device ingest path (null: host flattener only)
   bool device_ingest = false;                  // every scope / column of `schema` can be computed by the ingest kernels
   std::string host_ingest_reason;              // why not (the first construct that needs the host flattener)
 };
@@ -183,6 +185,11 @@ class Engine {
   void autoreject(const Compiled& c, const ObjIn& obj, uint32_t obj_ix, uint32_t cix, uint32_t code, const std::string& ep,
                   std::vector<Violation>& out);
   std::string dump();
+  // everything a backend needs to flatten a blob of plain objects on the device (xprog.hpp); `blob` must outlive the request
+  IngestReq ingest_request(const std::shared_ptr<const Compiled>& c, const uint8_t* blob, const unsigned long long* ooff, size_t n, uint32_t source,
+                           const std::string& process);
+  // host evaluation of Lut closures for the argument tuples the device has not seen yet
+  void lut_fill(const Compiled& c, const uint8_t* blob, const GkMiss* misses, size_t n, std::vector<GkLutVal>& out);
   StringTable& strings() { return strings_; }
   int threads() const { return threads_; }
   VP review_doc(const ObjIn& in, VP* obj_out, VP* old_out, VP* ns_out, std::string* err, const std::map<std::string, VP>* ns_snapshot = nullptr);
@@ -194,6 +201,10 @@ class Engine {
   std::map<std::string, TemplateEntry> templates_;
   std::vector<std::shared_ptr<Constraint>> constraints_;   // (shared: a compiled snapshot pins the constraints it was built from)
   std::map<std::string, VP> namespaces_;
+  uint64_t ns_version_ = 0;                                // bumped by put_namespace / remove_namespace
+  std::shared_ptr<const NsTableHost> ns_table_;            // device form of namespaces_ (rebuilt when stale)
+  uint64_t ns_table_version_ = ~0ull;
+  uint32_t ns_table_strings_ = 0;
   std::map<std::string, std::vector<std::string>> excluded_;
   std::shared_ptr<Compiled> compiled_;
   bool dirty_ = true;

@@ -1,0 +1,1355 @@
+// Device ingest core: raw object JSON -> the columnar batch (program.h GkBatch), with no host parse.
+//
+// Reference path being replaced: the audit manager decodes every listed / spilled object from JSON into an Unstructured
+// (pkg/audit/manager.go:540-551,687-695), and Matcher.Match re-unmarshals it once per constraint (pkg/target/matcher.go:73-93).
+// Here ONE GPU thread per object
+//   1. gk_tape_build : tokenises the object's JSON into a flat "tape" (one 64-bit entry per value / key, containers carry the
+//                      index of the entry after them, so a sub-tree is skipped in O(1));
+//   2. gk_ingest_obj : walks the tape along the schema's extraction program -- header fields, then a depth-first pass over the
+//                      scope tree (`spec.containers[_]`, `...ports[_]`) that evaluates every feature column of a row.  It runs
+//                      twice per chunk: a COUNT pass (rows per scope, bytes per byte-column), a device scan, a WRITE pass.
+// Closure kinds (lower.hpp XK): Path / Elem / Key / Count are computed natively; Lut closures (a pure function of leaf
+// values: canonify_cpu(limits.cpu), re_match(p, s), split(image, ":")[n] ...) hash the RAW bytes of their leaf arguments and
+// look the result up in a device hash table that the host fills once per distinct argument tuple (the miss list).
+//
+// Written once as host/device inline code: kernels.cu runs it on the GPU (the product path); tests/_hostemu compiles the same
+// functions for the CPU-only tests.  Nothing in the product library calls it on the host.
+#pragma once
+#include "program.h"
+#include "vm_core.h"
+typedef unsigned long long gk_u64;
+
+// ---------------------------------------------------------------------------------------------- tape
+enum { GK_T_END = 0, GK_T_OBJ = 1, GK_T_ARR = 2, GK_T_STR = 3, GK_T_KEY = 4, GK_T_NUM = 5, GK_T_TRUE = 6, GK_T_FALSE = 7, GK_T_NULL = 8 };
+// scalar entry  : type[3:0] | esc[4] | len[31:5] | byte offset[63:32]   (strings: offset / len of the bytes BETWEEN the quotes)
+// container     : type[3:0] | count[31:4]        | next[63:32]          (count: elements / members; next: entry index after it)
+// A container's children are followed by one GK_T_END entry in scalar format holding the container's own byte span
+// (offset of its opening bracket, length up to and including the closing one): children = [node + 1, next - 1).
+#define GK_TAPE_MAX_DEPTH 64
+#define GK_TAPE_LEN_MAX ((1u << 27) - 1u)
+
+GK_HD uint32_t gk_te_type(gk_u64 e) { return (uint32_t)e & 15u; }
+GK_HD uint32_t gk_te_esc(gk_u64 e) { return ((uint32_t)e >> 4) & 1u; }
+GK_HD uint32_t gk_te_len(gk_u64 e) { return (uint32_t)e >> 5; }
+GK_HD uint32_t gk_te_off(gk_u64 e) { return (uint32_t)(e >> 32); }
+GK_HD uint32_t gk_te_count(gk_u64 e) { return (uint32_t)e >> 4; }
+GK_HD uint32_t gk_te_next(gk_u64 e) { return (uint32_t)(e >> 32); }
+GK_HD uint32_t gk_te_end(gk_u64 e) { return (uint32_t)(e >> 32) - 1u; }   // index of the container's GK_T_END entry
+GK_HD gk_u64 gk_te_scalar(uint32_t type, uint32_t esc, uint32_t off, uint32_t len) {
+  return (gk_u64)(type | (esc << 4) | (len << 5)) | ((gk_u64)off << 32);
+}
+GK_HD gk_u64 gk_te_container(uint32_t type, uint32_t count, uint32_t next) { return (gk_u64)(type | (count << 4)) | ((gk_u64)next << 32); }
+GK_HD uint32_t gk_tape_capacity(gk_u64 json_len) { return (uint32_t)(json_len / 2u) + 4u; }   // a token needs >= 2 bytes (bar the root)
+
+// status of one object after tokenising + header checks
+enum { GK_ING_OK = 0, GK_ING_BAD_JSON = 1, GK_ING_NOT_OBJECT = 2, GK_ING_NO_KIND = 3, GK_ING_TOO_DEEP = 4, GK_ING_NULL = 5, GK_ING_TOO_LONG = 6 };
+
+GK_HD bool gk_is_ws(uint32_t c) { return c == ' ' || c == '\n' || c == '\t' || c == '\r'; }
+GK_HD bool gk_is_digit(uint32_t c) { return c >= '0' && c <= '9'; }
+GK_HD int gk_hexval(uint32_t c) {
+  if (c >= '0' && c <= '9') return (int)(c - '0');
+  if (c >= 'a' && c <= 'f') return (int)(c - 'a' + 10);
+  if (c >= 'A' && c <= 'F') return (int)(c - 'A' + 10);
+  return -1;
+}
+
+// Tokeniser: the grammar of the host parser (csrc/val.cpp JP) -- same whitespace, same escapes, same (lenient) number syntax,
+// duplicate keys allowed -- so that the device accepts exactly the documents the host flattener accepts.
+GK_HD int gk_tape_build(const uint8_t* js, uint32_t n, gk_u64* tape, uint32_t cap, uint32_t* ntape) {
+  uint32_t stack[GK_TAPE_MAX_DEPTH];   // entry index of the open containers
+  uint32_t cnt[GK_TAPE_MAX_DEPTH];
+  uint32_t opos[GK_TAPE_MAX_DEPTH];    // byte offset of their opening brackets
+  int depth = 0;
+  uint32_t p = 0, t = 0;
+  // state: 0 expect value, 1 after value (expect , or close), 2 expect key or '}' (just after '{'), 3 expect key (after ,)
+  int state = 0;
+  *ntape = 0;
+  for (;;) {
+    while (p < n && gk_is_ws(js[p])) ++p;
+    if (state == 1 && depth == 0) {
+      if (p != n) return GK_ING_BAD_JSON;   // trailing characters
+      *ntape = t;
+      return GK_ING_OK;
+    }
+    if (p >= n) return GK_ING_BAD_JSON;
+    const uint32_t c = js[p];
+    if (state == 1) {
+      const bool in_obj = gk_te_type(tape[stack[depth - 1]]) == GK_T_OBJ;
+      if (c == ',') {
+        ++p;
+        state = in_obj ? 3 : 0;
+        continue;
+      }
+      if (c == (in_obj ? '}' : ']')) {
+        ++p;
+        --depth;
+        const uint32_t open = stack[depth];
+        if (p - opos[depth] > GK_TAPE_LEN_MAX) return GK_ING_TOO_LONG;
+        tape[t++] = gk_te_scalar(GK_T_END, 0, opos[depth], p - opos[depth]);
+        tape[open] = gk_te_container(gk_te_type(tape[open]), cnt[depth], t);
+        state = 1;
+        continue;
+      }
+      return GK_ING_BAD_JSON;
+    }
+    if (t + 3 >= cap) return GK_ING_BAD_JSON;   // (cannot happen for cap = gk_tape_capacity(n))
+    if (state == 2 || state == 3) {
+      if (state == 2 && c == '}') {
+        ++p;
+        --depth;
+        const uint32_t open = stack[depth];
+        tape[t++] = gk_te_scalar(GK_T_END, 0, opos[depth], p - opos[depth]);
+        tape[open] = gk_te_container(GK_T_OBJ, 0, t);
+        state = 1;
+        continue;
+      }
+      if (c != '"') return GK_ING_BAD_JSON;   // object key expected
+    }
+    if (c == '"') {
+      const uint32_t s = ++p;
+      uint32_t esc = 0;
+      while (p < n && js[p] != '"') {
+        if (js[p] == '\\') {
+          esc = 1;
+          ++p;
+          if (p >= n) return GK_ING_BAD_JSON;
+          const uint32_t e = js[p];
+          if (e == 'u') {
+            if (n - p < 5) return GK_ING_BAD_JSON;
+            for (int i = 1; i <= 4; ++i)
+              if (gk_hexval(js[p + i]) < 0) return GK_ING_BAD_JSON;
+            p += 4;
+          } else if (!(e == 'n' || e == 't' || e == 'r' || e == 'b' || e == 'f' || e == '/' || e == '\\' || e == '"')) {
+            return GK_ING_BAD_JSON;
+          }
+        }
+        ++p;
+      }
+      if (p >= n) return GK_ING_BAD_JSON;   // unterminated string
+      const uint32_t len = p - s;
+      ++p;
+      if (len > GK_TAPE_LEN_MAX) return GK_ING_TOO_LONG;
+      if (state == 2 || state == 3) {
+        tape[t++] = gk_te_scalar(GK_T_KEY, esc, s, len);
+        while (p < n && gk_is_ws(js[p])) ++p;
+        if (p >= n || js[p] != ':') return GK_ING_BAD_JSON;
+        ++p;
+        ++cnt[depth - 1];
+        state = 0;
+        continue;
+      }
+      tape[t++] = gk_te_scalar(GK_T_STR, esc, s, len);
+      if (depth && gk_te_type(tape[stack[depth - 1]]) == GK_T_ARR) ++cnt[depth - 1];
+      state = 1;
+      continue;
+    }
+    // state 0: a value
+    if (c == '{' || c == '[') {
+      if (depth >= GK_TAPE_MAX_DEPTH) return GK_ING_TOO_DEEP;
+      if (depth && gk_te_type(tape[stack[depth - 1]]) == GK_T_ARR) ++cnt[depth - 1];
+      stack[depth] = t;
+      cnt[depth] = 0;
+      opos[depth] = p;
+      ++depth;
+      tape[t++] = gk_te_container(c == '{' ? GK_T_OBJ : GK_T_ARR, 0, 0);
+      ++p;
+      if (c == '{') {
+        state = 2;
+      } else {
+        while (p < n && gk_is_ws(js[p])) ++p;
+        if (p < n && js[p] == ']') {
+          ++p;
+          --depth;
+          tape[t++] = gk_te_scalar(GK_T_END, 0, opos[depth], p - opos[depth]);
+          tape[stack[depth]] = gk_te_container(GK_T_ARR, 0, t);
+          state = 1;
+        } else {
+          state = 0;
+        }
+      }
+      continue;
+    }
+    uint32_t type = 0, len = 0;
+    if (c == 't' && n - p >= 4 && js[p + 1] == 'r' && js[p + 2] == 'u' && js[p + 3] == 'e') {
+      type = GK_T_TRUE, len = 4;
+    } else if (c == 'f' && n - p >= 5 && js[p + 1] == 'a' && js[p + 2] == 'l' && js[p + 3] == 's' && js[p + 4] == 'e') {
+      type = GK_T_FALSE, len = 5;
+    } else if (c == 'n' && n - p >= 4 && js[p + 1] == 'u' && js[p + 2] == 'l' && js[p + 3] == 'l') {
+      type = GK_T_NULL, len = 4;
+    } else if (c == '-' || gk_is_digit(c)) {
+      // [-] digits* then, if '.', 'e' or 'E' follows, every char of [0-9.eE+-]: the span must be a decimal literal strtod takes whole
+      uint32_t q = p;
+      if (js[q] == '-') ++q;
+      uint32_t nint = 0, nfrac = 0;
+      while (q < n && gk_is_digit(js[q])) ++q, ++nint;
+      if (q < n && (js[q] == '.' || js[q] == 'e' || js[q] == 'E')) {
+        if (js[q] == '.') {
+          ++q;
+          while (q < n && gk_is_digit(js[q])) ++q, ++nfrac;
+        }
+        if (nint + nfrac == 0) return GK_ING_BAD_JSON;
+        if (q < n && (js[q] == 'e' || js[q] == 'E')) {
+          uint32_t r = q + 1;
+          if (r < n && (js[r] == '+' || js[r] == '-')) ++r;
+          uint32_t nexp = 0;
+          while (r < n && gk_is_digit(js[r])) ++r, ++nexp;
+          if (nexp == 0) return GK_ING_BAD_JSON;
+          q = r;
+        }
+        if (q < n && (gk_is_digit(js[q]) || js[q] == '.' || js[q] == 'e' || js[q] == 'E' || js[q] == '+' || js[q] == '-')) return GK_ING_BAD_JSON;
+      } else if (nint == 0) {
+        return GK_ING_BAD_JSON;
+      }
+      type = GK_T_NUM, len = q - p;
+    } else {
+      return GK_ING_BAD_JSON;
+    }
+    tape[t++] = gk_te_scalar(type, 0, p, len);
+    p += len;
+    if (depth && gk_te_type(tape[stack[depth - 1]]) == GK_T_ARR) ++cnt[depth - 1];
+    state = 1;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- strings
+// A JSON string as a stream of DECODED bytes (escapes resolved exactly like the host parser, surrogate pairs included).
+struct GkStr {
+  const uint8_t* p;
+  uint32_t n;      // raw bytes left
+  uint32_t pend;   // up to 3 pending UTF-8 continuation bytes, packed little end first
+  uint32_t npend;
+};
+GK_HD GkStr gk_str_open(const uint8_t* p, uint32_t n) {
+  GkStr s;
+  s.p = p;
+  s.n = n;
+  s.pend = 0;
+  s.npend = 0;
+  return s;
+}
+GK_HD uint32_t gk_str_hex4(const uint8_t* p) {
+  return ((uint32_t)gk_hexval(p[0]) << 12) | ((uint32_t)gk_hexval(p[1]) << 8) | ((uint32_t)gk_hexval(p[2]) << 4) | (uint32_t)gk_hexval(p[3]);
+}
+// next decoded byte, or -1 at the end
+GK_HD int gk_str_next(GkStr& s) {
+  if (s.npend) {
+    const int b = (int)(s.pend & 0xffu);
+    s.pend >>= 8;
+    --s.npend;
+    return b;
+  }
+  if (s.n == 0) return -1;
+  uint32_t c = *s.p++;
+  --s.n;
+  if (c != '\\') return (int)c;
+  c = *s.p++;
+  --s.n;
+  switch (c) {
+    case 'n': return '\n';
+    case 't': return '\t';
+    case 'r': return '\r';
+    case 'b': return '\b';
+    case 'f': return '\f';
+    case 'u': {
+      uint32_t cp = gk_str_hex4(s.p);
+      s.p += 4;
+      s.n -= 4;
+      if (cp >= 0xD800 && cp < 0xDC00 && s.n >= 6 && s.p[0] == '\\' && s.p[1] == 'u' && gk_hexval(s.p[2]) >= 0 && gk_hexval(s.p[3]) >= 0 &&
+          gk_hexval(s.p[4]) >= 0 && gk_hexval(s.p[5]) >= 0) {
+        const uint32_t lo = gk_str_hex4(s.p + 2);
+        s.p += 6;
+        s.n -= 6;
+        cp = (lo >= 0xDC00 && lo < 0xE000) ? 0x10000u + ((cp - 0xD800u) << 10) + (lo - 0xDC00u) : 0xFFFDu;
+      }
+      if (cp < 0x80) return (int)cp;
+      if (cp < 0x800) {
+        s.pend = 0x80u | (cp & 0x3Fu);
+        s.npend = 1;
+        return (int)(0xC0u | (cp >> 6));
+      }
+      if (cp < 0x10000) {
+        s.pend = (0x80u | ((cp >> 6) & 0x3Fu)) | ((0x80u | (cp & 0x3Fu)) << 8);
+        s.npend = 2;
+        return (int)(0xE0u | (cp >> 12));
+      }
+      s.pend = (0x80u | ((cp >> 12) & 0x3Fu)) | ((0x80u | ((cp >> 6) & 0x3Fu)) << 8) | ((0x80u | (cp & 0x3Fu)) << 16);
+      s.npend = 3;
+      return (int)(0xF0u | (cp >> 18));
+    }
+    default: return (int)c;   // '/', '\\', '"'
+  }
+}
+
+// 64-bit hash of a byte string (FNV-1a, then a finaliser): keys of the device lookup tables.  0 is reserved for "empty slot".
+#define GK_HASH_INIT 0xcbf29ce484222325ull
+GK_HD gk_u64 gk_hash_byte(gk_u64 h, uint32_t b) { return (h ^ (gk_u64)b) * 0x100000001b3ull; }
+GK_HD gk_u64 gk_hash_fin(gk_u64 h) {
+  h ^= h >> 33;
+  h *= 0xff51afd7ed558ccdull;
+  h ^= h >> 33;
+  h *= 0xc4ceb9fe1a85ec53ull;
+  h ^= h >> 33;
+  return h ? h : 1ull;
+}
+GK_HD gk_u64 gk_hash_bytes(gk_u64 h, const uint8_t* p, uint32_t n) {
+  for (uint32_t i = 0; i < n; ++i) h = gk_hash_byte(h, p[i]);
+  return h;
+}
+
+// ---------------------------------------------------------------------------------------------- values
+// A value the extraction program handles: a tape node of the object, or a synthetic scalar (review.kind.*, review.name,
+// constants of the review envelope, array indices).
+struct GkXVal {
+  uint32_t vt;          // GK_VT_*
+  uint32_t node;        // tape index, GK_NONE for synthetic values
+  const uint8_t* sp;    // synthetic string: decoded bytes
+  uint32_t slen;
+  long long inum;       // synthetic number (array index)
+};
+GK_HD GkXVal gk_xundef() {
+  GkXVal v;
+  v.vt = GK_VT_UNDEF;
+  v.node = GK_NONE;
+  v.sp = nullptr;
+  v.slen = 0;
+  v.inum = 0;
+  return v;
+}
+GK_HD GkXVal gk_xsyn(uint32_t vt) {
+  GkXVal v = gk_xundef();
+  v.vt = vt;
+  return v;
+}
+GK_HD GkXVal gk_xstr(const uint8_t* p, uint32_t n) {
+  GkXVal v = gk_xundef();
+  v.vt = GK_VT_STR;
+  v.sp = p;
+  v.slen = n;
+  return v;
+}
+GK_HD uint32_t gk_vt_of_type(uint32_t t) {
+  switch (t) {
+    case GK_T_OBJ: return GK_VT_OBJ;
+    case GK_T_ARR: return GK_VT_ARR;
+    case GK_T_STR:
+    case GK_T_KEY: return GK_VT_STR;
+    case GK_T_NUM: return GK_VT_NUM;
+    case GK_T_TRUE: return GK_VT_TRUE;
+    case GK_T_FALSE: return GK_VT_FALSE;
+    case GK_T_NULL: return GK_VT_NULL;
+    default: return GK_VT_UNDEF;
+  }
+}
+GK_HD GkXVal gk_xnode(const gk_u64* tape, uint32_t node) {
+  GkXVal v = gk_xundef();
+  v.vt = gk_vt_of_type(gk_te_type(tape[node]));
+  v.node = node;
+  return v;
+}
+GK_HD uint32_t gk_tape_skip(const gk_u64* tape, uint32_t i) {   // entry index after the value at i
+  const uint32_t t = gk_te_type(tape[i]);
+  return (t == GK_T_OBJ || t == GK_T_ARR) ? gk_te_next(tape[i]) : i + 1u;
+}
+
+// the object's JSON + its tape
+struct GkDoc {
+  const uint8_t* js;
+  const gk_u64* tape;
+  uint32_t ntape;
+};
+
+// does the (decoded) string entry equal the literal?
+GK_HD bool gk_entry_eq(const GkDoc& d, gk_u64 e, const uint8_t* lit, uint32_t n) {
+  const uint8_t* p = d.js + gk_te_off(e);
+  const uint32_t len = gk_te_len(e);
+  if (!gk_te_esc(e)) {
+    if (len != n) return false;
+    for (uint32_t i = 0; i < n; ++i)
+      if (p[i] != lit[i]) return false;
+    return true;
+  }
+  GkStr s = gk_str_open(p, len);
+  for (uint32_t i = 0; i < n; ++i)
+    if (gk_str_next(s) != (int)lit[i]) return false;
+  return gk_str_next(s) < 0;
+}
+// two (decoded) string entries equal?
+GK_HD bool gk_entries_eq(const GkDoc& d, gk_u64 a, gk_u64 b) {
+  if (!gk_te_esc(a) && !gk_te_esc(b)) {
+    const uint32_t n = gk_te_len(a);
+    if (n != gk_te_len(b)) return false;
+    const uint8_t *p = d.js + gk_te_off(a), *q = d.js + gk_te_off(b);
+    for (uint32_t i = 0; i < n; ++i)
+      if (p[i] != q[i]) return false;
+    return true;
+  }
+  GkStr x = gk_str_open(d.js + gk_te_off(a), gk_te_len(a)), y = gk_str_open(d.js + gk_te_off(b), gk_te_len(b));
+  for (;;) {
+    const int cx = gk_str_next(x), cy = gk_str_next(y);
+    if (cx != cy) return false;
+    if (cx < 0) return true;
+  }
+}
+
+// member lookup: the value index of key `lit` in the object at `node`, or GK_NONE.  A repeated key means its LAST value
+// (json.Unmarshal into a map; the host parser keeps the later duplicate too).
+GK_HD uint32_t gk_obj_find(const GkDoc& d, uint32_t node, const uint8_t* lit, uint32_t n) {
+  const gk_u64 e = d.tape[node];
+  if (gk_te_type(e) != GK_T_OBJ) return GK_NONE;
+  const uint32_t end = gk_te_end(e);
+  uint32_t found = GK_NONE;
+  for (uint32_t i = node + 1u; i < end;) {
+    const gk_u64 k = d.tape[i];
+    if (gk_entry_eq(d, k, lit, n)) found = i + 1u;
+    i = gk_tape_skip(d.tape, i + 1u);
+  }
+  return found;
+}
+GK_HD uint32_t gk_arr_at(const GkDoc& d, uint32_t node, long long ix) {
+  const gk_u64 e = d.tape[node];
+  if (gk_te_type(e) != GK_T_ARR || ix < 0 || (unsigned long long)ix >= gk_te_count(e)) return GK_NONE;
+  uint32_t i = node + 1u;
+  for (long long j = 0; j < ix; ++j) i = gk_tape_skip(d.tape, i);
+  return i;
+}
+// is member `ki` (key entry index) of the object ending at `end` shadowed by a later member with the same key?
+GK_HD bool gk_key_shadowed(const GkDoc& d, uint32_t ki, uint32_t end) {
+  const gk_u64 k = d.tape[ki];
+  for (uint32_t i = gk_tape_skip(d.tape, ki + 1u); i < end; i = gk_tape_skip(d.tape, i + 1u))
+    if (gk_entries_eq(d, k, d.tape[i])) return true;
+  return false;
+}
+
+// ---------------------------------------------------------------------------------------------- numbers
+// num_key (val.hpp) of a number token: 2*floor(x) + (x is fractional), saturated at +-(2^63 - 2).
+GK_HD long long gk_num_key_token(const uint8_t* p, uint32_t n) {
+  const long long SAT_HI = 0x7ffffffffffffffell, SAT_LO = -0x7ffffffffffffffell;
+  uint32_t i = 0;
+  bool neg = false;
+  if (i < n && p[i] == '-') neg = true, ++i;
+  // decimal digits of the mantissa (up to 19 significant ones kept), position of the decimal point, exponent
+  unsigned long long mant = 0;
+  int kept = 0, dropped_int = 0;    // digits dropped from the integer part scale the value by 10 each
+  bool dropped_nonzero = false, seen_nonzero = false;
+  int frac_digits = 0;
+  bool in_frac = false;
+  for (; i < n; ++i) {
+    const uint32_t c = p[i];
+    if (c == '.') {
+      in_frac = true;
+      continue;
+    }
+    if (!gk_is_digit(c)) break;
+    const uint32_t dgt = c - '0';
+    if (dgt) seen_nonzero = true;
+    if (kept < 19) {
+      mant = mant * 10ull + dgt;
+      if (seen_nonzero) ++kept;
+      if (in_frac) ++frac_digits;
+    } else {
+      if (dgt) dropped_nonzero = true;
+      if (!in_frac) ++dropped_int;
+    }
+  }
+  long long ex = 0;
+  if (i < n && (p[i] == 'e' || p[i] == 'E')) {
+    ++i;
+    bool eneg = false;
+    if (i < n && (p[i] == '+' || p[i] == '-')) eneg = p[i] == '-', ++i;
+    for (; i < n && gk_is_digit(p[i]); ++i)
+      if (ex < 100000) ex = ex * 10 + (p[i] - '0');
+    if (eneg) ex = -ex;
+  }
+  // value = (mant [+ tiny]) * 10^shift
+  long long shift = ex - frac_digits + dropped_int;
+  if (mant == 0 && !dropped_nonzero) return 0;
+  unsigned long long fl = mant;
+  bool frac = dropped_nonzero;
+  bool huge = false;
+  if (shift > 0) {
+    for (long long k = 0; k < shift && !huge; ++k) {
+      if (fl > 0x3fffffffffffffffull / 10ull) huge = true;
+      else fl *= 10ull;
+    }
+  } else if (shift < 0) {
+    for (long long k = 0; k < -shift; ++k) {
+      if (fl == 0) {
+        break;
+      }
+      if (fl % 10ull) frac = true;
+      fl /= 10ull;
+    }
+    if (mant != 0 && fl == 0) frac = true;
+  }
+  if (huge || fl > 0x3fffffffffffffffull) return neg ? SAT_LO : SAT_HI;
+  // floor of the signed value
+  if (!neg) return (long long)(2ull * fl + (frac ? 1ull : 0ull));
+  // x = -(fl + f), 0 <= f < 1:  floor(x) = -fl - (f > 0)
+  const long long f2 = -(long long)fl - (frac ? 1 : 0);
+  return 2 * f2 + (frac ? 1 : 0);
+}
+// canonical-integer token: "0" or [-]?[1-9][0-9]* (its text IS num_str of the value)
+GK_HD bool gk_plain_int(const uint8_t* p, uint32_t n) {
+  uint32_t i = 0;
+  if (n && p[0] == '-') i = 1;
+  if (i >= n) return false;
+  if (p[i] == '0') return n == 1;
+  for (uint32_t j = i; j < n; ++j)
+    if (!gk_is_digit(p[j])) return false;
+  return n - i <= 18;
+}
+
+// ---------------------------------------------------------------------------------------------- lookup tables
+// Open-addressing table keyed by a 64-bit hash.  val: a result index / sid, GK_HT_PENDING while the host has not filled it.
+#define GK_HT_PENDING 0xFFFFFFFFu
+typedef struct {
+  unsigned long long* keys;   // 0 = empty
+  uint32_t* vals;
+  uint32_t mask;              // capacity - 1
+  uint32_t pad_;
+} GkHtab;
+
+GK_HD uint32_t gk_ht_find(const GkHtab& t, gk_u64 key, bool* present) {
+  uint32_t i = (uint32_t)key & t.mask;
+  for (uint32_t probe = 0; probe <= t.mask; ++probe) {
+    const unsigned long long k = t.keys[i];
+    if (k == key) {
+      *present = true;
+      return t.vals[i];
+    }
+    if (k == 0ull) break;
+    i = (i + 1u) & t.mask;
+  }
+  *present = false;
+  return GK_HT_PENDING;
+}
+
+// one result of a Lut closure (what the encodings of a row need)
+typedef struct {
+  uint32_t vt;
+  uint32_t sid;
+  long long num;
+  uint32_t head[GK_HEAD_WORDS];
+} GkLutVal;
+
+// where a missing lookup's argument lives, for the host to evaluate: (byte offset in the blob, length) of the raw token /
+// sub-tree, or a synthetic scalar
+enum { GK_ARG_UNDEF = 0, GK_ARG_JSON = 1, GK_ARG_INDEX = 2, GK_ARG_SYNSTR = 3 };
+typedef struct {
+  uint32_t kind;
+  uint32_t len;
+  unsigned long long off;   // GK_ARG_JSON: absolute offset in the blob; GK_ARG_INDEX: the index; GK_ARG_SYNSTR: absolute offset of the decoded bytes
+} GkMissArg;
+#define GK_LUT_MAX_ARGS 4
+typedef struct {
+  uint32_t col;             // closure id (extraction-program closure table)
+  uint32_t slot;            // table slot claimed for it
+  unsigned long long key;
+  GkMissArg args[GK_LUT_MAX_ARGS];
+} GkMiss;
+
+// ---------------------------------------------------------------------------------------------- extraction program
+enum { GK_X_PATH = 1, GK_X_ELEM = 2, GK_X_KEY = 3, GK_X_COUNT = 4, GK_X_LUT = 5 };
+// review-envelope roots of an `input.review.<root>...` path (pkg/target/review.go:16-29)
+enum { GK_R_REVIEW = 0, GK_R_OBJECT = 1, GK_R_KIND = 2, GK_R_NAME = 3, GK_R_NAMESPACE = 4, GK_R_OLDOBJECT = 5, GK_R_OPERATION = 6, GK_R_UID = 7,
+       GK_R_OPTIONS = 8, GK_R_RESOURCE = 9, GK_R_USERINFO = 10, GK_R_UNDEF = 11 };
+typedef struct {
+  uint32_t kind;        // GK_X_*
+  int32_t base;         // Path / Count: closure index the value is read from; -1: the review envelope (root in `root`)
+  uint32_t root;        // GK_R_* when base < 0
+  uint32_t scope;       // Elem / Key: the scope whose current row is meant
+  uint32_t keys_off, nkeys;   // Path: xkeys[keys_off ..]: (is_index, byte_off | index, len) triples
+  uint32_t args_off, nargs;   // Lut: xargs[args_off ..]: closure indices of the leaf arguments
+  unsigned long long seed;    // Lut: hash domain
+} GkXClosure;
+typedef struct {
+  uint32_t closure;
+  uint32_t scope;
+  uint32_t enc;
+  uint32_t bytes_slot;  // index among the byte-counted columns (GK_ENC_BYTES), GK_NONE otherwise
+} GkXCol;
+typedef struct {
+  uint32_t gen;         // closure index of the iterated collection
+  int32_t parent;
+  uint32_t first_child, next_sibling;   // scope tree (GK_NONE terminated)
+  uint32_t first_col, ncols;            // columns of this scope: xcol_order[first_col ..]
+} GkXScope;
+
+typedef struct {
+  const GkXClosure* cl;
+  const GkXCol* cols;
+  const GkXScope* scopes;
+  const uint32_t* col_order;   // column indices grouped by scope
+  const uint32_t* xkeys;
+  const uint32_t* xargs;
+  const uint8_t* xbytes;       // literal key strings
+  uint32_t ncl, ncols, nscopes, nbytecols;
+  // string -> sid (interned constants; a miss is GK_SID_OTHER, never pending) and the Lut results
+  GkHtab sid_tab;
+  GkHtab lut_tab;
+  const GkLutVal* lut_vals;
+  uint32_t sid_true, sid_false, sid_null;   // sids of the non-string scalars (GK_SID_OTHER when no constant mentions them)
+  uint32_t pad_;
+  // namespace cache as a table: name hash -> row of (nsl_off, nsl_kv); names for nsname
+  GkHtab ns_tab;
+  const uint32_t* nsn_off;     // [nsrows + 1] bytes of each cached Namespace's metadata.name
+  const uint8_t* nsn_bytes;
+  // excluder patterns of the calling process (mode, byte_off, len) in xkeys / xbytes
+  uint32_t excl_off, excl_n;
+} GkXProg;
+
+#define GK_SEED_STR 0x9ae16a3b2f90404full   /* hash domain of string values -> sid */
+#define GK_SEED_NUM 0xc3a5c85c97cb3127ull   /* canonical integers -> sid */
+#define GK_SEED_NS 0xb492b66fbe98f273ull    /* namespace names -> namespace table row */
+
+// per-object counters produced by the COUNT pass, one array of n entries each (then scanned): laid out [counter][object]
+//   [0, nscopes)              rows of every scope (index 0 unused)
+//   [nscopes, +nbytecols)     bytes of every byte-column
+//   then: name bytes, generateName bytes, labels, nsname bytes
+#define GK_CNT_EXTRA 4
+
+// per-chunk destination arrays of the WRITE pass (device pointers; offsets are chunk-relative)
+typedef struct {
+  uint32_t* flags;
+  uint32_t* kind_sid;
+  uint32_t* group_sid;
+  uint32_t* name_off;
+  uint8_t* name_bytes;
+  uint32_t* gen_off;
+  uint8_t* gen_bytes;
+  uint32_t* lbl_off;
+  uint32_t* lbl_kv;
+  uint32_t* nsrow;
+  uint32_t* nsn_off;      // nsname bytes of each object (namespaces / excludedNamespaces match on it)
+  uint8_t* nsn_bytes;
+  uint32_t* const* scope_off;   // [nscopes]: [parent rows + 1]
+  // columns
+  uint8_t* const* vt;
+  uint32_t* const* sid;
+  long long* const* num;
+  uint32_t* const* boff;
+  uint8_t* const* bytes;
+  uint32_t* const* head;
+} GkIngestOut;
+
+typedef struct {
+  const uint8_t* blob;              // the chunk's JSON bytes
+  const unsigned long long* ooff;   // [n + 1] byte offsets of the objects in `blob`
+  unsigned long long* tape;         // scratch: object i's tape starts at tape_off(i)
+  uint32_t* ntape;                  // [n]
+  uint32_t* status;                 // [n] GK_ING_*
+  uint32_t n;
+  uint32_t source;                  // GK_SRC_* of every object of the chunk
+  uint32_t* counts;                 // [(nscopes + nbytecols + GK_CNT_EXTRA) * n]; after the scan: exclusive prefix sums
+  GkMiss* misses;                   // miss list
+  uint32_t* nmiss;
+  uint32_t miss_cap;
+  uint32_t pad_;
+} GkIngestIn;
+
+GK_HD unsigned long long gk_tape_off(const unsigned long long* ooff, uint32_t i) { return ooff[i] / 2ull + 4ull * (unsigned long long)i; }
+
+// ---------------------------------------------------------------------------------------------- evaluation context
+struct GkXCtx {
+  GkDoc doc;
+  const GkXProg* xp;
+  const void* in;                // GkIngestIn of the pass (miss list of the lookup tables)
+  unsigned long long blob_off;   // absolute offset of doc.js in the blob
+  // review envelope
+  uint32_t api_node, kind_node, name_node, ns_node;   // tape indices or GK_NONE
+  const uint8_t* grp;            // group / version slices of apiVersion (raw, apiVersion has no escapes in the supported case)
+  uint32_t grp_len;
+  const uint8_t* ver;
+  uint32_t ver_len;
+  // current row of every scope on the DFS stack
+  GkXVal elem[GK_MAX_LOOP_DEPTH + 1];
+  GkXVal key[GK_MAX_LOOP_DEPTH + 1];
+  uint32_t scope_at[GK_MAX_LOOP_DEPTH + 1];   // scope id at each depth
+  int depth;
+};
+
+GK_HD GkXVal gk_x_follow(const GkXCtx& c, GkXVal v, const uint32_t* keys, uint32_t nkeys) {
+  for (uint32_t j = 0; j < nkeys; ++j) {
+    if (v.node == GK_NONE) return gk_xundef();   // a path into a synthetic scalar
+    const uint32_t* k = keys + 3u * j;
+    uint32_t nx;
+    const uint32_t t = gk_te_type(c.doc.tape[v.node]);
+    if (t == GK_T_OBJ) {
+      if (k[0]) return gk_xundef();              // numeric key into an object: object keys are strings in JSON
+      nx = gk_obj_find(c.doc, v.node, c.xp->xbytes + k[1], k[2]);
+    } else if (t == GK_T_ARR) {
+      if (!k[0]) return gk_xundef();
+      nx = gk_arr_at(c.doc, v.node, (long long)(int32_t)k[1]);
+    } else {
+      return gk_xundef();
+    }
+    if (nx == GK_NONE) return gk_xundef();
+    v = gk_xnode(c.doc.tape, nx);
+  }
+  return v;
+}
+
+GK_HD bool gk_lit_eq(const uint8_t* a, uint32_t n, const char* b) {
+  uint32_t i = 0;
+  for (; i < n && b[i]; ++i)
+    if (a[i] != (uint8_t)b[i]) return false;
+  return i == n && !b[i];
+}
+
+// `input.review.<root>` + keys
+GK_HD GkXVal gk_x_root(const GkXCtx& c, uint32_t root, const uint32_t* keys, uint32_t nkeys) {
+  switch (root) {
+    case GK_R_REVIEW: return nkeys ? gk_xundef() : gk_xsyn(GK_VT_OBJ);
+    case GK_R_OBJECT: return gk_x_follow(c, gk_xnode(c.doc.tape, 0), keys, nkeys);
+    case GK_R_KIND: {
+      if (nkeys == 0) return gk_xsyn(GK_VT_OBJ);
+      if (nkeys > 1 || keys[0]) return gk_xundef();
+      const uint8_t* k = c.xp->xbytes + keys[1];
+      const uint32_t kl = keys[2];
+      if (gk_lit_eq(k, kl, "kind")) return c.kind_node != GK_NONE ? gk_xnode(c.doc.tape, c.kind_node) : gk_xstr(nullptr, 0);
+      if (gk_lit_eq(k, kl, "group")) return gk_xstr(c.grp, c.grp_len);
+      if (gk_lit_eq(k, kl, "version")) return gk_xstr(c.ver, c.ver_len);
+      return gk_xundef();
+    }
+    case GK_R_NAME:
+    case GK_R_NAMESPACE: {
+      // present only when non-empty (engine.cpp review_doc)
+      const uint32_t nd = root == GK_R_NAME ? c.name_node : c.ns_node;
+      if (nd == GK_NONE || nkeys) return gk_xundef();
+      return gk_xnode(c.doc.tape, nd);
+    }
+    case GK_R_OLDOBJECT:
+    case GK_R_OPTIONS: return nkeys ? gk_xundef() : gk_xsyn(GK_VT_NULL);
+    case GK_R_OPERATION:
+    case GK_R_UID: return nkeys ? gk_xundef() : gk_xstr(nullptr, 0);
+    case GK_R_USERINFO: return nkeys ? gk_xundef() : gk_xsyn(GK_VT_OBJ);
+    case GK_R_RESOURCE: {
+      if (nkeys == 0) return gk_xsyn(GK_VT_OBJ);
+      if (nkeys > 1 || keys[0]) return gk_xundef();
+      const uint8_t* k = c.xp->xbytes + keys[1];
+      const uint32_t kl = keys[2];
+      if (gk_lit_eq(k, kl, "group") || gk_lit_eq(k, kl, "version") || gk_lit_eq(k, kl, "resource")) return gk_xstr(nullptr, 0);
+      return gk_xundef();
+    }
+    default: return gk_xundef();
+  }
+}
+
+GK_HD int gk_depth_of_scope(const GkXCtx& c, uint32_t scope) {
+  for (int d = c.depth; d >= 1; --d)
+    if (c.scope_at[d] == scope) return d;
+  return 0;
+}
+
+// value of a native closure (Path / Elem / Key) for the current rows; Count and Lut are handled by the encoder
+GK_HD GkXVal gk_x_eval(const GkXCtx& c, uint32_t ci) {
+  // collect the chain of Path closures down to its leaf base, then walk forward
+  uint32_t chain[8];
+  int nchain = 0;
+  for (;;) {
+    const GkXClosure& cl = c.xp->cl[ci];
+    if (cl.kind == GK_X_PATH) {
+      if (nchain >= 8) return gk_xundef();
+      chain[nchain++] = ci;
+      if (cl.base < 0) break;
+      ci = (uint32_t)cl.base;
+      continue;
+    }
+    break;
+  }
+  GkXVal v;
+  int from;
+  const GkXClosure& leaf = c.xp->cl[ci];
+  if (leaf.kind == GK_X_PATH) {   // rooted at the review envelope
+    v = gk_x_root(c, leaf.root, c.xp->xkeys + leaf.keys_off, leaf.nkeys);
+    from = nchain - 2;
+  } else if (leaf.kind == GK_X_ELEM || leaf.kind == GK_X_KEY) {
+    const int d = gk_depth_of_scope(c, leaf.scope);
+    if (d == 0) return gk_xundef();
+    v = leaf.kind == GK_X_ELEM ? c.elem[d] : c.key[d];
+    from = nchain - 1;
+  } else {
+    return gk_xundef();
+  }
+  for (int j = from; j >= 0 && v.vt != GK_VT_UNDEF; --j) {
+    const GkXClosure& cl = c.xp->cl[chain[j]];
+    v = gk_x_follow(c, v, c.xp->xkeys + cl.keys_off, cl.nkeys);
+  }
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------- atomics (device / host emulation)
+#ifdef __CUDA_ARCH__
+#define GK_CAS64(p, cmp, val) atomicCAS((unsigned long long*)(p), (unsigned long long)(cmp), (unsigned long long)(val))
+#define GK_CAS32(p, cmp, val) atomicCAS((unsigned int*)(p), (unsigned int)(cmp), (unsigned int)(val))
+#define GK_ADD32(p, v) atomicAdd((unsigned int*)(p), (unsigned int)(v))
+#else
+static inline unsigned long long gk_cas64_host(unsigned long long* p, unsigned long long cmp, unsigned long long val) {
+  __atomic_compare_exchange_n(p, &cmp, val, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
+  return cmp;
+}
+static inline unsigned int gk_cas32_host(unsigned int* p, unsigned int cmp, unsigned int val) {
+  __atomic_compare_exchange_n(p, &cmp, val, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
+  return cmp;
+}
+#define GK_CAS64(p, cmp, val) gk_cas64_host((unsigned long long*)(p), (unsigned long long)(cmp), (unsigned long long)(val))
+#define GK_CAS32(p, cmp, val) gk_cas32_host((unsigned int*)(p), (unsigned int)(cmp), (unsigned int)(val))
+#define GK_ADD32(p, v) __atomic_fetch_add((unsigned int*)(p), (unsigned int)(v), __ATOMIC_SEQ_CST)
+#endif
+#define GK_HT_LOST 0xFFFFFFFEu   /* claimed, but the miss list was full: the next pass records it */
+
+// Lut lookup with insertion on a miss.  Returns the result index, or GK_HT_PENDING (a miss record was / will be written).
+GK_HD uint32_t gk_lut_lookup(const GkXProg& xp, const GkIngestIn& in, uint32_t closure, gk_u64 key, const GkMissArg* args, uint32_t nargs) {
+  const GkHtab& t = xp.lut_tab;
+  uint32_t i = (uint32_t)key & t.mask;
+  for (uint32_t probe = 0; probe <= t.mask; ++probe, i = (i + 1u) & t.mask) {
+    unsigned long long k = t.keys[i];
+    bool mine = false;
+    if (k == 0ull) {
+      k = GK_CAS64(&t.keys[i], 0ull, key);
+      if (k == 0ull) {
+        mine = true;
+        k = key;
+      }
+    }
+    if (k != key) continue;
+    uint32_t v = mine ? GK_HT_LOST : t.vals[i];
+    if (v == GK_HT_LOST && (mine || GK_CAS32(&t.vals[i], GK_HT_LOST, GK_HT_PENDING) == GK_HT_LOST)) {
+      // this thread records the miss
+      const uint32_t m = GK_ADD32(in.nmiss, 1u);
+      if (m < in.miss_cap) {
+        GkMiss& ms = in.misses[m];
+        ms.col = closure;
+        ms.slot = i;
+        ms.key = key;
+        for (uint32_t a = 0; a < GK_LUT_MAX_ARGS; ++a) {
+          if (a < nargs) ms.args[a] = args[a];
+          else ms.args[a].kind = GK_ARG_UNDEF, ms.args[a].len = 0, ms.args[a].off = 0;
+        }
+        t.vals[i] = GK_HT_PENDING;
+      } else {
+        t.vals[i] = GK_HT_LOST;
+      }
+      return GK_HT_PENDING;
+    }
+    return (v == GK_HT_LOST) ? GK_HT_PENDING : v;
+  }
+  return GK_HT_PENDING;   // table full: the host grows it when the load factor passes its limit, long before this
+}
+
+#define GK_CL_SIDVAL 0xFFFFFFFFu   /* pseudo closure of the miss list: "the sid of this value" (numbers not in canonical form, composites) */
+#define GK_SEED_SIDVAL 0x7d1f9b3c55aa1e67ull
+
+// ---- string access of a value (tape string or synthetic)
+GK_HD GkStr gk_x_str(const GkXCtx& c, const GkXVal& v) {
+  if (v.node != GK_NONE) {
+    const gk_u64 e = c.doc.tape[v.node];
+    return gk_str_open(c.doc.js + gk_te_off(e), gk_te_len(e));
+  }
+  return gk_str_open(v.sp, v.slen);   // synthetic strings hold decoded bytes without backslashes
+}
+
+GK_HD uint32_t gk_x_sid_exotic(const GkXCtx& c, const GkXVal& v);
+// sid of a value: strings / canonical integers / true / false / null natively; numbers in another spelling (7.0, 1e3) and
+// composites through the lookup table (the host canonicalises them once per distinct spelling)
+GK_HD uint32_t gk_x_sid(const GkXCtx& c, const GkXVal& v) {
+  const GkXProg& xp = *c.xp;
+  switch (v.vt) {
+    case GK_VT_UNDEF: return GK_SID_UNDEF;
+    case GK_VT_TRUE: return xp.sid_true;
+    case GK_VT_FALSE: return xp.sid_false;
+    case GK_VT_NULL: return xp.sid_null;
+    case GK_VT_STR: {
+      GkStr s = gk_x_str(c, v);
+      gk_u64 h = GK_SEED_STR;
+      for (int b; (b = gk_str_next(s)) >= 0;) h = gk_hash_byte(h, (uint32_t)b);
+      bool present;
+      const uint32_t sid = gk_ht_find(xp.sid_tab, gk_hash_fin(h), &present);
+      return present ? sid : GK_SID_OTHER;
+    }
+    case GK_VT_NUM: {
+      if (v.node == GK_NONE) {   // an array index
+        uint8_t buf[24];
+        uint32_t n = 0;
+        long long x = v.inum;
+        if (x == 0) buf[n++] = '0';
+        uint8_t tmp[24];
+        uint32_t m = 0;
+        while (x > 0) tmp[m++] = (uint8_t)('0' + x % 10), x /= 10;
+        while (m) buf[n++] = tmp[--m];
+        bool present;
+        const uint32_t sid = gk_ht_find(xp.sid_tab, gk_hash_fin(gk_hash_bytes(GK_SEED_NUM, buf, n)), &present);
+        return present ? sid : GK_SID_OTHER;
+      }
+      const gk_u64 e = c.doc.tape[v.node];
+      const uint8_t* p = c.doc.js + gk_te_off(e);
+      const uint32_t n = gk_te_len(e);
+      if (!gk_plain_int(p, n)) return gk_x_sid_exotic(c, v);
+      bool present;
+      const uint32_t sid = gk_ht_find(xp.sid_tab, gk_hash_fin(gk_hash_bytes(GK_SEED_NUM, p, n)), &present);
+      return present ? sid : GK_SID_OTHER;
+    }
+    default: return v.node != GK_NONE ? gk_x_sid_exotic(c, v) : (uint32_t)GK_SID_OTHER;
+  }
+}
+
+GK_HD long long gk_x_numkey(const GkXCtx& c, const GkXVal& v) {
+  if (v.vt == GK_VT_NUM) {
+    if (v.node == GK_NONE) return 2 * v.inum;
+    const gk_u64 e = c.doc.tape[v.node];
+    return gk_num_key_token(c.doc.js + gk_te_off(e), gk_te_len(e));
+  }
+  // non-numbers: below (null, booleans) or above (strings, composites) every number -- OPA's cross-type order
+  if (v.vt == GK_VT_NULL || v.vt == GK_VT_TRUE || v.vt == GK_VT_FALSE) return (long long)0x8000000000000000ull;
+  return 0x7fffffffffffffffll;
+}
+
+// count() of a collection / string: elements, DISTINCT keys, code points
+GK_HD bool gk_x_count(const GkXCtx& c, const GkXVal& v, long long* out) {
+  if (v.vt == GK_VT_ARR && v.node != GK_NONE) {
+    *out = gk_te_count(c.doc.tape[v.node]);
+    return true;
+  }
+  if (v.vt == GK_VT_OBJ) {
+    if (v.node == GK_NONE) {
+      *out = 0;   // (synthetic envelope objects are not counted by any template; the host gives their true size)
+      return false;
+    }
+    const uint32_t end = gk_te_end(c.doc.tape[v.node]);
+    long long n = 0;
+    for (uint32_t i = v.node + 1u; i < end; i = gk_tape_skip(c.doc.tape, i + 1u))
+      if (!gk_key_shadowed(c.doc, i, end)) ++n;
+    *out = n;
+    return true;
+  }
+  if (v.vt == GK_VT_STR) {
+    GkStr s = gk_x_str(c, v);
+    long long n = 0;
+    for (int b; (b = gk_str_next(s)) >= 0;)
+      if ((b & 0xC0) != 0x80) ++n;
+    *out = n;
+    return true;
+  }
+  return false;
+}
+
+// hash + location of one Lut argument
+GK_HD gk_u64 gk_x_arg(const GkXCtx& c, const GkXVal& v, gk_u64 h, GkMissArg* ma) {
+  ma->kind = GK_ARG_UNDEF;
+  ma->len = 0;
+  ma->off = 0;
+  if (v.vt == GK_VT_UNDEF) return gk_hash_byte(h, 0xF0u);
+  if (v.node != GK_NONE) {
+    const gk_u64 e = c.doc.tape[v.node];
+    const uint32_t t = gk_te_type(e);
+    uint32_t a, b;   // raw byte span of the value
+    if (t == GK_T_OBJ || t == GK_T_ARR) {   // the sub-tree's raw text (its GK_T_END entry holds the byte span)
+      const gk_u64 x = c.doc.tape[gk_te_end(e)];
+      h = gk_hash_byte(h, t);
+      h = gk_hash_bytes(h, c.doc.js + gk_te_off(x), gk_te_len(x));
+      ma->kind = GK_ARG_JSON;
+      ma->off = c.blob_off + gk_te_off(x);
+      ma->len = gk_te_len(x);
+      return h;
+    }
+    const uint32_t q = (t == GK_T_STR || t == GK_T_KEY) ? 1u : 0u;
+    a = gk_te_off(e) - q;
+    b = gk_te_off(e) + gk_te_len(e) + q;
+    h = gk_hash_byte(h, t == GK_T_KEY ? (uint32_t)GK_T_STR : t);
+    h = gk_hash_bytes(h, c.doc.js + gk_te_off(e), gk_te_len(e));
+    ma->kind = GK_ARG_JSON;
+    ma->off = c.blob_off + a;
+    ma->len = b - a;
+    return h;
+  }
+  if (v.vt == GK_VT_NUM) {
+    h = gk_hash_byte(h, 0xF3u);
+    for (int i = 0; i < 8; ++i) h = gk_hash_byte(h, (uint32_t)((unsigned long long)v.inum >> (8 * i)) & 0xffu);
+    ma->kind = GK_ARG_INDEX;
+    ma->off = (unsigned long long)v.inum;
+    return h;
+  }
+  if (v.vt == GK_VT_STR) {
+    h = gk_hash_byte(h, 0xF4u);
+    h = gk_hash_bytes(h, v.sp, v.slen);
+    ma->kind = GK_ARG_SYNSTR;
+    ma->off = v.sp ? (unsigned long long)(c.blob_off + (unsigned long long)(v.sp - c.doc.js)) : 0ull;
+    ma->len = v.slen;
+    return h;
+  }
+  // other synthetic values (envelope objects / null) never reach a Lut (not leaf-like)
+  h = gk_hash_byte(h, 0xF5u + v.vt);
+  return h;
+}
+
+GK_HD uint32_t gk_x_sid_exotic(const GkXCtx& c, const GkXVal& v) {
+  const uint32_t t = gk_te_type(c.doc.tape[v.node]);
+  if (t == GK_T_OBJ || t == GK_T_ARR) {
+    // a composite larger than 1 KiB never equals a parameter in practice: answered "other" without a lookup (documented limit)
+    if (gk_te_len(c.doc.tape[gk_te_end(c.doc.tape[v.node])]) > 1024u) return GK_SID_OTHER;
+  }
+  GkMissArg ma;
+  const gk_u64 h = gk_x_arg(c, v, GK_SEED_SIDVAL, &ma);
+  const uint32_t ix = gk_lut_lookup(*c.xp, *static_cast<const GkIngestIn*>(c.in), GK_CL_SIDVAL, gk_hash_fin(h), &ma, 1);
+  return ix == GK_HT_PENDING ? (uint32_t)GK_SID_OTHER : c.xp->lut_vals[ix].sid;
+}
+
+// ---------------------------------------------------------------------------------------------- one object
+GK_HD uint32_t gk_decoded_len(const GkXCtx& c, const GkXVal& v) {
+  if (v.node == GK_NONE) return v.slen;
+  const gk_u64 e = c.doc.tape[v.node];
+  if (!gk_te_esc(e)) return gk_te_len(e);
+  GkStr s = gk_str_open(c.doc.js + gk_te_off(e), gk_te_len(e));
+  uint32_t n = 0;
+  while (gk_str_next(s) >= 0) ++n;
+  return n;
+}
+GK_HD void gk_copy_decoded(const GkXCtx& c, const GkXVal& v, uint8_t* dst) {
+  GkStr s = gk_x_str(c, v);
+  for (int b; (b = gk_str_next(s)) >= 0;) *dst++ = (uint8_t)b;
+}
+GK_HD bool gk_wild_val(const GkXCtx& c, uint32_t mode, const uint8_t* pat, uint32_t pl, const GkXVal& v) {
+  // Wildcard.Matches (pkg/wildcard/wildcard.go:17-29) on a decoded name.  Names are DNS labels (<= 253 bytes); a longer one is
+  // cut at 256 bytes, which only a prefix pattern can still match exactly.
+  uint8_t buf[256];
+  uint32_t n = 0;
+  GkStr s = gk_x_str(c, v);
+  int b;
+  while (n < 256u && (b = gk_str_next(s)) >= 0) buf[n++] = (uint8_t)b;
+  const bool cut = n == 256u && gk_str_next(s) >= 0;
+  if (cut && mode != GK_W_PREFIX) return false;
+  switch (mode) {
+    case GK_W_PREFIX: return gk_prefix(buf, n, pat, pl);
+    case GK_W_SUFFIX: return gk_suffix(buf, n, pat, pl);
+    case GK_W_CONTAINS: return gk_contains(buf, n, pat, pl);
+    default: return n == pl && gk_bytes_eq(buf, pat, pl);
+  }
+}
+
+struct GkIngestFrame {
+  uint32_t scope;
+  uint32_t pos, end;        // object iteration: tape index of the next member's key / array: next element; end of the children
+  uint32_t arr_ix;          // next array index
+  uint32_t is_obj;
+  uint32_t next_child;      // next child scope to open for the current row
+  uint32_t row;             // chunk-global row index of the current row
+};
+
+GK_HD const uint8_t* gk_lit(const char* s) { return reinterpret_cast<const uint8_t*>(s); }
+
+template <bool WRITE>
+GK_HD void gk_emit_col(const GkXProg& xp, const GkIngestIn& in, const GkIngestOut& out, GkXCtx& c, uint32_t ci, uint32_t row, uint32_t* bcur) {
+  const GkXCol& col = xp.cols[ci];
+  const GkXClosure& cl = xp.cl[col.closure];
+  const uint32_t enc = col.enc;
+  if (!WRITE) {
+    // the count pass only needs the decoded length of byte columns
+    if (!(enc & GK_ENC_BYTES) || cl.kind == GK_X_LUT || cl.kind == GK_X_COUNT) return;
+    const GkXVal v = gk_x_eval(c, col.closure);
+    if (v.vt == GK_VT_STR) bcur[col.bytes_slot] += gk_decoded_len(c, v);
+    return;
+  }
+  GkXVal v = gk_xundef();
+  if (cl.kind == GK_X_LUT) {
+    GkMissArg ma[GK_LUT_MAX_ARGS];
+    gk_u64 h = cl.seed;
+    for (uint32_t a = 0; a < cl.nargs; ++a) h = gk_x_arg(c, gk_x_eval(c, xp.xargs[cl.args_off + a]), gk_hash_byte(h, 0xEEu), &ma[a]);
+    const uint32_t ix = gk_lut_lookup(xp, in, col.closure, gk_hash_fin(h), ma, cl.nargs);
+    GkLutVal lv;
+    lv.vt = GK_VT_UNDEF;
+    lv.sid = GK_SID_UNDEF;
+    lv.num = 0;
+    for (int w = 0; w < GK_HEAD_WORDS; ++w) lv.head[w] = 0;
+    if (ix != GK_HT_PENDING) lv = xp.lut_vals[ix];
+    if (enc & GK_ENC_VT) out.vt[ci][row] = (uint8_t)lv.vt;
+    if (enc & GK_ENC_SID) out.sid[ci][row] = lv.sid;
+    if (enc & GK_ENC_NUM) out.num[ci][row] = lv.num;
+    if (enc & GK_ENC_HEAD)
+      for (int w = 0; w < GK_HEAD_WORDS; ++w) out.head[ci][(size_t)row * GK_HEAD_WORDS + w] = lv.head[w];
+    return;
+  }
+  if (cl.kind == GK_X_COUNT) {
+    const GkXVal b = gk_x_eval(c, (uint32_t)cl.base);
+    long long n;
+    if (gk_x_count(c, b, &n)) {
+      v = gk_xsyn(GK_VT_NUM);
+      v.inum = n;
+    }
+  } else {
+    v = gk_x_eval(c, col.closure);
+  }
+  if (enc & GK_ENC_VT) out.vt[ci][row] = (uint8_t)v.vt;
+  if (enc & GK_ENC_SID) out.sid[ci][row] = gk_x_sid(c, v);
+  if (enc & GK_ENC_NUM) out.num[ci][row] = v.vt == GK_VT_UNDEF ? 0ll : gk_x_numkey(c, v);
+  if (enc & GK_ENC_HEAD) {
+    uint32_t h[GK_HEAD_WORDS];
+    for (int w = 0; w < GK_HEAD_WORDS; ++w) h[w] = 0;
+    if (v.vt == GK_VT_STR) {
+      GkStr s = gk_x_str(c, v);
+      uint32_t n = 0;
+      for (int b; (b = gk_str_next(s)) >= 0; ++n)
+        if (n < GK_HEAD_BYTES) h[n >> 2] |= (uint32_t)b << (8u * (n & 3u));
+      h[GK_HEAD_WORDS - 1] |= (n < 255u ? n : 255u) << 24;
+    }
+    for (int w = 0; w < GK_HEAD_WORDS; ++w) out.head[ci][(size_t)row * GK_HEAD_WORDS + w] = h[w];
+  }
+  if (enc & GK_ENC_BYTES) {
+    uint32_t& cur = bcur[col.bytes_slot];
+    out.boff[ci][row] = cur;
+    if (v.vt == GK_VT_STR) {
+      gk_copy_decoded(c, v, out.bytes[ci] + cur);
+      cur += gk_decoded_len(c, v);
+    }
+  }
+}
+
+// Count pass (WRITE = false): fills in.counts[k * n + i].  Write pass: in.counts holds the exclusive prefix sums.
+template <bool WRITE>
+GK_HD void gk_ingest_obj(const GkXProg& xp, const GkIngestIn& in, const GkIngestOut& out, uint32_t i, uint32_t* cur /* [nscopes + nbytecols + GK_CNT_EXTRA] scratch */) {
+  const uint32_t n = in.n, NS = xp.nscopes, NK = NS + xp.nbytecols + GK_CNT_EXTRA;
+  const uint32_t K_NAME = NS + xp.nbytecols, K_GEN = K_NAME + 1, K_LBL = K_NAME + 2, K_NSN = K_NAME + 3;
+  for (uint32_t k = 0; k < NK; ++k) cur[k] = WRITE ? in.counts[(size_t)k * n + i] : 0u;
+  uint32_t* bcur = cur + NS;
+  GkXCtx c;
+  c.xp = &xp;
+  c.in = &in;
+  c.blob_off = in.ooff[i];
+  c.doc.js = in.blob + in.ooff[i];
+  c.doc.tape = in.tape + gk_tape_off(in.ooff, i);
+  c.doc.ntape = in.ntape[i];
+  c.depth = 0;
+  c.scope_at[0] = 0;
+  c.api_node = c.kind_node = c.name_node = c.ns_node = GK_NONE;
+  c.grp = c.ver = nullptr;
+  c.grp_len = c.ver_len = 0;
+  bool skip = in.status[i] != GK_ING_OK;
+  uint32_t fl = (in.source << GK_F_SRC_SHIFT) & GK_F_SRC_MASK;
+  uint32_t kind_sid = GK_SID_UNDEF, group_sid = GK_SID_UNDEF, nsrow = GK_NONE;
+  uint32_t labels = GK_NONE, gen_node = GK_NONE;
+  GkXVal nsname = gk_xundef();
+  if (!skip) {
+    // ---- review envelope / header: apiVersion -> (group, version), kind, metadata.{name, generateName, namespace, labels}
+    c.api_node = gk_obj_find(c.doc, 0, gk_lit("apiVersion"), 10);
+    c.kind_node = gk_obj_find(c.doc, 0, gk_lit("kind"), 4);
+    if (c.api_node != GK_NONE && gk_te_type(c.doc.tape[c.api_node]) == GK_T_STR) {
+      const gk_u64 e = c.doc.tape[c.api_node];
+      const uint8_t* p = c.doc.js + gk_te_off(e);
+      const uint32_t len = gk_te_len(e);
+      uint32_t s = 0;
+      while (s < len && p[s] != '/') ++s;
+      if (s == len) {
+        c.ver = p;
+        c.ver_len = len;
+        c.grp = p;
+        c.grp_len = 0;
+      } else {
+        c.grp = p;
+        c.grp_len = s;
+        c.ver = p + s + 1;
+        c.ver_len = len - s - 1;
+      }
+    }
+    const uint32_t meta = gk_obj_find(c.doc, 0, gk_lit("metadata"), 8);
+    uint32_t nm = GK_NONE, ns = GK_NONE;
+    if (meta != GK_NONE && gk_te_type(c.doc.tape[meta]) == GK_T_OBJ) {
+      nm = gk_obj_find(c.doc, meta, gk_lit("name"), 4);
+      gen_node = gk_obj_find(c.doc, meta, gk_lit("generateName"), 12);
+      ns = gk_obj_find(c.doc, meta, gk_lit("namespace"), 9);
+      labels = gk_obj_find(c.doc, meta, gk_lit("labels"), 6);
+      if (nm != GK_NONE && (gk_te_type(c.doc.tape[nm]) != GK_T_STR || gk_te_len(c.doc.tape[nm]) == 0)) nm = GK_NONE;
+      if (gen_node != GK_NONE && (gk_te_type(c.doc.tape[gen_node]) != GK_T_STR || gk_te_len(c.doc.tape[gen_node]) == 0)) gen_node = GK_NONE;
+      if (ns != GK_NONE && (gk_te_type(c.doc.tape[ns]) != GK_T_STR || gk_te_len(c.doc.tape[ns]) == 0)) ns = GK_NONE;
+      if (labels != GK_NONE && gk_te_type(c.doc.tape[labels]) != GK_T_OBJ) labels = GK_NONE;
+    }
+    c.name_node = nm;
+    c.ns_node = ns;
+    const GkXVal kindv = gk_xnode(c.doc.tape, c.kind_node);
+    const bool is_ns = c.grp_len == 0 && gk_entry_eq(c.doc, c.doc.tape[c.kind_node], gk_lit("Namespace"), 9);
+    // ---- stage 0: the process excluder (pkg/controller/config/process/excluder.go:95-127): a Namespace by its own name,
+    // anything else by its namespace ("" for cluster-scoped objects)
+    if (xp.excl_n) {
+      const GkXVal subject = is_ns ? (nm != GK_NONE ? gk_xnode(c.doc.tape, nm) : gk_xstr(nullptr, 0)) : (ns != GK_NONE ? gk_xnode(c.doc.tape, ns) : gk_xstr(nullptr, 0));
+      for (uint32_t j = 0; j < xp.excl_n && !skip; ++j) {
+        const uint32_t* e = xp.xkeys + xp.excl_off + 3u * j;
+        skip = gk_wild_val(c, e[0], xp.xbytes + e[1], e[2], subject);
+      }
+    }
+    if (!skip) {
+      fl |= GK_F_HAS_OBJ;
+      if (is_ns) fl |= GK_F_IS_NS;
+      if (ns != GK_NONE) fl |= GK_F_HAS_NS;
+      kind_sid = gk_x_sid(c, kindv);
+      group_sid = gk_x_sid(c, gk_xstr(c.grp, c.grp_len));
+      if (ns != GK_NONE) {   // the Namespace object of the review: the cache entry for the object's namespace (matcher.go:37-39)
+        GkStr s = gk_x_str(c, gk_xnode(c.doc.tape, ns));
+        gk_u64 h = GK_SEED_NS;
+        for (int b; (b = gk_str_next(s)) >= 0;) h = gk_hash_byte(h, (uint32_t)b);
+        bool present;
+        const uint32_t r = gk_ht_find(xp.ns_tab, gk_hash_fin(h), &present);
+        if (present) {
+          nsrow = r;
+          fl |= GK_F_NS_OBJ;
+        }
+      }
+      // the name namespaces / excludedNamespaces match on (match.go:118-179)
+      if (is_ns) nsname = nm != GK_NONE ? gk_xnode(c.doc.tape, nm) : gk_xstr(nullptr, 0);
+      else if (nsrow != GK_NONE) nsname = gk_xstr(xp.nsn_bytes + xp.nsn_off[nsrow], xp.nsn_off[nsrow + 1] - xp.nsn_off[nsrow]);
+      else if (ns != GK_NONE) nsname = gk_xnode(c.doc.tape, ns);
+      if (nsname.vt != GK_VT_UNDEF) fl |= GK_F_NSNAME;
+    }
+  }
+  if (skip) fl = (fl & GK_F_SRC_MASK) | GK_F_SKIP;
+  // ---- header arrays
+  {
+    const GkXVal namev = (!skip && c.name_node != GK_NONE) ? gk_xnode(c.doc.tape, c.name_node) : gk_xundef();
+    const GkXVal genv = (!skip && gen_node != GK_NONE) ? gk_xnode(c.doc.tape, gen_node) : gk_xundef();
+    if (WRITE) {
+      out.flags[i] = fl;
+      out.kind_sid[i] = kind_sid;
+      out.group_sid[i] = group_sid;
+      out.nsrow[i] = nsrow;
+      out.name_off[i] = cur[K_NAME];
+      out.gen_off[i] = cur[K_GEN];
+      out.lbl_off[i] = cur[K_LBL];
+      out.nsn_off[i] = cur[K_NSN];
+      if (namev.vt == GK_VT_STR) gk_copy_decoded(c, namev, out.name_bytes + cur[K_NAME]);
+      if (genv.vt == GK_VT_STR) gk_copy_decoded(c, genv, out.gen_bytes + cur[K_GEN]);
+      if (nsname.vt == GK_VT_STR) gk_copy_decoded(c, nsname, out.nsn_bytes + cur[K_NSN]);
+    }
+    if (namev.vt == GK_VT_STR) cur[K_NAME] += gk_decoded_len(c, namev);
+    if (genv.vt == GK_VT_STR) cur[K_GEN] += gk_decoded_len(c, genv);
+    if (nsname.vt == GK_VT_STR) cur[K_NSN] += gk_decoded_len(c, nsname);
+    if (!skip && labels != GK_NONE) {
+      const uint32_t end = gk_te_end(c.doc.tape[labels]);
+      for (uint32_t k = labels + 1u; k < end; k = gk_tape_skip(c.doc.tape, k + 1u)) {
+        if (gk_key_shadowed(c.doc, k, end)) continue;
+        if (WRITE) {
+          const GkXVal val = gk_xnode(c.doc.tape, k + 1u);
+          out.lbl_kv[2u * (size_t)cur[K_LBL]] = gk_x_sid(c, gk_xnode(c.doc.tape, k));
+          out.lbl_kv[2u * (size_t)cur[K_LBL] + 1u] = val.vt == GK_VT_STR ? gk_x_sid(c, val) : GK_SID_OTHER;
+        }
+        ++cur[K_LBL];
+      }
+    }
+    if (WRITE && i + 1u == n) {
+      out.name_off[n] = cur[K_NAME];
+      out.gen_off[n] = cur[K_GEN];
+      out.lbl_off[n] = cur[K_LBL];
+      out.nsn_off[n] = cur[K_NSN];
+    }
+  }
+  // ---- scopes + columns: depth-first over the scope tree, rows of a scope in (parent row, member) order
+  GkIngestFrame fr[GK_MAX_LOOP_DEPTH + 1];
+  fr[0].scope = 0;
+  fr[0].row = i;
+  fr[0].next_child = xp.scopes[0].first_child;
+  fr[0].pos = fr[0].end = fr[0].arr_ix = fr[0].is_obj = 0;
+  {
+    const GkXScope& s0 = xp.scopes[0];
+    for (uint32_t k = 0; k < s0.ncols; ++k) {
+      const uint32_t ci = xp.col_order[s0.first_col + k];
+      if (skip) {
+        if (WRITE) {   // placeholder row: every encoding "undefined"
+          const uint32_t enc = xp.cols[ci].enc;
+          if (enc & GK_ENC_VT) out.vt[ci][i] = GK_VT_UNDEF;
+          if (enc & GK_ENC_SID) out.sid[ci][i] = GK_SID_UNDEF;
+          if (enc & GK_ENC_NUM) out.num[ci][i] = 0;
+          if (enc & GK_ENC_HEAD)
+            for (int w = 0; w < GK_HEAD_WORDS; ++w) out.head[ci][(size_t)i * GK_HEAD_WORDS + w] = 0;
+          if (enc & GK_ENC_BYTES) out.boff[ci][i] = bcur[xp.cols[ci].bytes_slot];
+        }
+      } else {
+        gk_emit_col<WRITE>(xp, in, out, c, ci, i, bcur);
+      }
+    }
+  }
+  int top = 0;
+  while (top >= 0) {
+    GkIngestFrame& f = fr[top];
+    if (f.next_child != GK_NONE) {
+      // open the next child scope under the current row of f.scope
+      const uint32_t t = f.next_child;
+      f.next_child = xp.scopes[t].next_sibling;
+      if (WRITE) out.scope_off[t][f.row] = cur[t];
+      if (skip || top >= GK_MAX_LOOP_DEPTH) continue;
+      c.depth = top;
+      const GkXVal coll = gk_x_eval(c, xp.scopes[t].gen);
+      if (coll.node == GK_NONE || (coll.vt != GK_VT_ARR && coll.vt != GK_VT_OBJ)) continue;
+      GkIngestFrame& g = fr[top + 1];
+      g.scope = t;
+      g.is_obj = coll.vt == GK_VT_OBJ;
+      g.pos = coll.node + 1u;
+      g.end = gk_te_end(c.doc.tape[coll.node]);
+      g.arr_ix = 0;
+      g.next_child = GK_NONE;
+      g.row = 0;
+      ++top;
+      c.scope_at[top] = t;
+      // fall through to "advance" below by marking the frame as between rows
+    } else if (top == 0) {
+      break;
+    }
+    // ---- advance the iterator of the top frame to its next row (or pop)
+    GkIngestFrame& g = fr[top];
+    if (g.next_child != GK_NONE) continue;   // (a freshly opened child of the frame we just advanced)
+    bool have = false;
+    while (g.pos < g.end) {
+      if (g.is_obj) {
+        const uint32_t k = g.pos;
+        g.pos = gk_tape_skip(c.doc.tape, k + 1u);
+        if (gk_key_shadowed(c.doc, k, g.end)) continue;
+        c.key[top] = gk_xnode(c.doc.tape, k);
+        c.elem[top] = gk_xnode(c.doc.tape, k + 1u);
+      } else {
+        const uint32_t e = g.pos;
+        g.pos = gk_tape_skip(c.doc.tape, e);
+        c.key[top] = gk_xsyn(GK_VT_NUM);
+        c.key[top].inum = (long long)g.arr_ix++;
+        c.elem[top] = gk_xnode(c.doc.tape, e);
+      }
+      have = true;
+      break;
+    }
+    if (!have) {
+      --top;
+      continue;
+    }
+    g.row = cur[g.scope]++;
+    c.depth = top;
+    const GkXScope& sc = xp.scopes[g.scope];
+    for (uint32_t k = 0; k < sc.ncols; ++k) gk_emit_col<WRITE>(xp, in, out, c, xp.col_order[sc.first_col + k], g.row, bcur);
+    g.next_child = sc.first_child;   // (none for a leaf scope: the next turn advances this frame again)
+  }
+  if (!WRITE) {
+    for (uint32_t k = 0; k < NK; ++k) in.counts[(size_t)k * n + i] = cur[k];
+  } else if (i + 1u == n) {
+    // closing entries of the CSR arrays
+    for (uint32_t s = 1; s < NS; ++s) out.scope_off[s][xp.scopes[s].parent ? cur[xp.scopes[s].parent] : n] = cur[s];
+    for (uint32_t k = 0; k < xp.ncols; ++k)
+      if (xp.cols[k].enc & GK_ENC_BYTES) out.boff[k][xp.cols[k].scope ? cur[xp.cols[k].scope] : n] = bcur[xp.cols[k].bytes_slot];
+  }
+}
+
+// tokenise object i of the chunk and run the review-level checks of Engine::review_doc (the object must be a JSON object
+// with a non-empty string `kind`; a literal null is "no object")
+GK_HD void gk_tape_obj(const GkIngestIn& in, uint32_t i) {
+  const unsigned long long a = in.ooff[i], b = in.ooff[i + 1];
+  unsigned long long* tape = in.tape + gk_tape_off(in.ooff, i);
+  uint32_t nt = 0;
+  int st = (b - a > 0xfffffff0ull) ? (int)GK_ING_TOO_LONG : gk_tape_build(in.blob + a, (uint32_t)(b - a), tape, gk_tape_capacity(b - a), &nt);
+  if (st == GK_ING_OK) {
+    const uint32_t t0 = gk_te_type(tape[0]);
+    if (t0 == GK_T_NULL) st = GK_ING_NULL;
+    else if (t0 != GK_T_OBJ) st = GK_ING_NOT_OBJECT;
+    else {
+      GkDoc d;
+      d.js = in.blob + a;
+      d.tape = tape;
+      d.ntape = nt;
+      const uint32_t k = gk_obj_find(d, 0, reinterpret_cast<const uint8_t*>("kind"), 4);
+      if (k == GK_NONE || gk_te_type(tape[k]) != GK_T_STR || gk_te_len(tape[k]) == 0) st = GK_ING_NO_KIND;
+    }
+  }
+  in.ntape[i] = nt;
+  in.status[i] = (uint32_t)st;
+}

@@ -415,6 +415,8 @@ class CudaBackend : public Backend {
     }
   }
 
+  void* ingest(const IngestReq&, IngestStats*, std::vector<uint32_t>*) override { throw BackendError{"device ingest: not built yet"}; }
+
   void eval_into(void* b, const std::vector<uint32_t>& active, const DevOutPtrs& dst) override {
     auto* db = static_cast<DevBatch*>(b);
     std::lock_guard<std::mutex> l(mu_);

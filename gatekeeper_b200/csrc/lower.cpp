@@ -108,40 +108,23 @@ std::string formula_str(const FP& f, const Schema& s) {
 
 // ====================================================================================== schema
 // ====================================================================================== device-evaluable closures
-static bool xleafy(const XInfo& xi) {
-  // may this value be (part of) a lookup key?  Whole objects / `spec` / an iterated element are not: every object would be
-  // its own key and the host would evaluate the closure once per object again
-  switch (xi.k) {
-    case XK::Path: return xi.base != nullptr || xi.keys.size() >= 4;
-    case XK::Key:
-    case XK::Count:
-    case XK::Lut: return true;
-    default: return false;
-  }
-}
-
+struct RawArg {
+  CP base;
+  std::vector<VP> keys;
+};
 // Walks a closure's term: false unless it is a closed pure term (no `input` / `data`, no impure rule); collects the
 // `<captured column>[literal keys...]` paths it reads.
-static bool lut_args(const Module& m, const Term* t, const Closure& c, std::vector<XInfo::Arg>& out) {
+static bool lut_args(const Module& m, const Term* t, const Closure& c, std::vector<RawArg>& out) {
   if (!t) return true;
   auto cap_of = [&](int vid) -> const CapArg* {
     for (auto& cp : c.caps)
       if (cp.first == vid) return &cp.second;
     return nullptr;
   };
-  auto add = [&](int vid, const CP& base, std::vector<VP> keys) {
-    for (auto& a : out)
-      if (a.vid == vid && a.keys.size() == keys.size()) {
-        bool same = true;
-        for (size_t i = 0; i < keys.size(); ++i) same = same && v_eq(a.keys[i], keys[i]);
-        if (same) return;
-      }
-    out.push_back(XInfo::Arg{vid, base, std::move(keys)});
-  };
   if (t->k == TK::Var) {
     if (t->vid == m.vid_input || t->vid == m.vid_data) return false;
     if (const CapArg* cap = cap_of(t->vid)) {
-      if (cap->k == CapArg::Col) add(t->vid, cap->col, {});
+      if (cap->k == CapArg::Col) out.push_back(RawArg{cap->col, {}});
       return true;
     }
     if (m.is_rule(t->name)) return false;      // a (non-function) rule used as a value
@@ -153,7 +136,7 @@ static bool lut_args(const Module& m, const Term* t, const Closure& c, std::vect
       std::vector<VP> keys;
       size_t i = 0;
       for (; i < t->args.size() && t->args[i]->k == TK::Scalar; ++i) keys.push_back(t->args[i]->val);
-      add(t->head->vid, cap->col, std::move(keys));
+      out.push_back(RawArg{cap->col, std::move(keys)});
       for (; i < t->args.size(); ++i)
         if (!lut_args(m, t->args[i].get(), c, out)) return false;
       return true;
@@ -172,6 +155,45 @@ static bool lut_args(const Module& m, const Term* t, const Closure& c, std::vect
   for (auto& s2 : t->body)
     if (!lut_args(m, s2.a.get(), c, out) || !lut_args(m, s2.b.get(), c, out) || !lut_args(m, s2.c.get(), c, out)) return false;
   return true;
+}
+
+static void add_leaf(std::vector<XInfo::Arg>& out, const CP& leaf, const std::vector<VP>& keys) {
+  for (auto& a : out)
+    if (a.leaf.get() == leaf.get() && (!leaf || true) && a.keys.size() == keys.size()) {
+      bool same = (a.leaf && leaf) ? a.leaf->key == leaf->key : (!a.leaf && !leaf);
+      for (size_t i = 0; i < keys.size() && same; ++i) same = v_eq(a.keys[i], keys[i]);
+      if (same) return;
+    }
+  out.push_back(XInfo::Arg{leaf, keys});
+}
+// the leaf values behind  <base>[keys...]  (false: something on the way needs the host)
+static bool leaf_args_of(const CP& base, const std::vector<VP>& keys, std::vector<XInfo::Arg>& out) {
+  const XInfo bi = closure_xinfo(*base);
+  switch (bi.k) {
+    case XK::Elem:
+    case XK::Key: add_leaf(out, base, keys); return true;
+    case XK::Path: {
+      std::vector<VP> all = bi.keys;
+      all.insert(all.end(), keys.begin(), keys.end());
+      if (bi.from_input) {
+        add_leaf(out, nullptr, all);
+        return true;
+      }
+      return leaf_args_of(bi.base, all, out);
+    }
+    case XK::Count:
+    case XK::Lut:
+      for (auto& a : bi.args) add_leaf(out, a.leaf, a.keys);   // (the keys index the COMPUTED value, not a leaf)
+      return true;
+    default: return false;
+  }
+}
+static bool leafy_arg(const XInfo::Arg& a) {
+  // may this value be (part of) a lookup key?  A whole iterated element, the whole object or its `spec` are not: every
+  // object would be its own key and the host would evaluate the closure once per object again
+  if (!a.leaf) return a.keys.size() >= 4;                       // review.object.<x>.<y>...
+  if (a.leaf->leaf == Closure::Key) return true;
+  return !a.keys.empty();
 }
 
 XInfo closure_xinfo(const Closure& c) {
@@ -196,11 +218,14 @@ XInfo closure_xinfo(const Closure& c) {
     bool lit = true;
     for (auto& a : t.args) lit = lit && a->k == TK::Scalar;
     const CapArg* cap = cap_of(t.head->vid);
-    if (lit && cap && cap->k == CapArg::Col && closure_xinfo(*cap->col).k != XK::Host) {
-      x.k = XK::Path;
-      x.base = cap->col;
-      for (auto& a : t.args) x.keys.push_back(a->val);
-      return x;
+    if (lit && cap && cap->k == CapArg::Col) {
+      const XK bk = closure_xinfo(*cap->col).k;
+      if (bk == XK::Path || bk == XK::Elem || bk == XK::Key) {
+        x.k = XK::Path;
+        x.base = cap->col;
+        for (auto& a : t.args) x.keys.push_back(a->val);
+        return x;
+      }
     }
     if (lit && !cap && t.head->vid == m.vid_input && !t.args.empty() && t.args[0]->val->t == VT::Str && t.args[0]->val->s == "review") {
       x.k = XK::Path;
@@ -216,18 +241,17 @@ XInfo closure_xinfo(const Closure& c) {
       if (bk == XK::Path || bk == XK::Elem) {
         x.k = XK::Count;
         x.base = cap->col;
+        if (!leaf_args_of(cap->col, {}, x.args)) return XInfo();
         return x;
       }
     }
   }
-  if (!lut_args(m, &t, c, x.args)) return XInfo();
-  for (auto& a : x.args) {
-    const XInfo bi = closure_xinfo(*a.base);
-    if (bi.k == XK::Host) return XInfo();
-    // every part of the lookup key must be leaf-like: a whole iterated element / the whole object is not
-    const bool leafy = !a.keys.empty() ? (bi.k != XK::Path || !bi.from_input || bi.keys.size() + a.keys.size() >= 4) : xleafy(bi);
-    if (!leafy) return XInfo();
-  }
+  std::vector<RawArg> raw;
+  if (!lut_args(m, &t, c, raw)) return XInfo();
+  for (auto& r : raw)
+    if (!leaf_args_of(r.base, r.keys, x.args)) return XInfo();
+  for (auto& a : x.args)
+    if (!leafy_arg(a)) return XInfo();
   if (x.args.empty() || x.args.size() > 4) return XInfo();
   x.k = XK::Lut;
   return x;

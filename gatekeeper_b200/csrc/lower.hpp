@@ -53,11 +53,11 @@ struct XInfo {
   bool from_input = false;    // Path: rooted at `input` (keys[0] == "review")
   CP base;                    // Path (not from_input), Count: the closure the value is read from
   std::vector<VP> keys;       // Path: literal keys
-  // Lut: the parts of the hash key -- every maximal `<captured column>["a"]["b"]` path of the term (a bare captured column
-  // has no keys).  The host evaluates the term with each captured variable bound to a skeleton object holding just those paths.
+  // Lut / Count: the LEAF values the closure reads, normalised to `<leaf>["a"]["b"]` with leaf = the element / key of an
+  // enclosing scope, or (leaf == null) the `input` document.  They are the parts of the hash key; the host evaluates the
+  // closure against skeleton documents that hold just these paths.
   struct Arg {
-    int vid = -1;
-    CP base;
+    CP leaf;
     std::vector<VP> keys;
   };
   std::vector<Arg> args;

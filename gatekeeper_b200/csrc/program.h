@@ -53,7 +53,8 @@ typedef struct {
 // header flags (per object)
 enum { GK_F_HAS_OBJ = 1, GK_F_IS_NS = 2, GK_F_HAS_NS = 4 /* metadata.namespace != "" */,
        GK_F_NS_OBJ = 8 /* a Namespace object is known for the review */, GK_F_SRC_SHIFT = 4, GK_F_SRC_MASK = 0x70,
-       GK_F_SKIP = 128 /* review-level error (bad JSON, ...): the kernel skips the object */ };
+       GK_F_SKIP = 128 /* review-level error (bad JSON, ...): the kernel skips the object */,
+       GK_F_NSNAME = 256 /* the row has a namespace NAME for namespaces / excludedNamespaces (nsn_off / nsn_bytes) */ };
 enum { GK_SRC_EMPTY = 0, GK_SRC_ORIGINAL = 1, GK_SRC_GENERATED = 2, GK_SRC_ALL = 3, GK_SRC_INVALID = 4 };
 
 typedef struct {
@@ -62,7 +63,8 @@ typedef struct {
   const uint32_t* flags;         // [n or 2n]
   const uint32_t* kind_sid;      // [..]
   const uint32_t* group_sid;
-  const uint32_t* nsname_sid;    // namespace NAME used by namespaces/excludedNamespaces (match.go:118-179); GK_NONE = none
+  const uint32_t* nsn_off;       // [rows+1] namespace NAME used by namespaces/excludedNamespaces (match.go:118-179); valid with GK_F_NSNAME
+  const uint8_t* nsn_bytes;
   const uint32_t* name_off;      // [rows+1] metadata.name bytes
   const uint8_t* name_bytes;
   const uint32_t* gen_off;       // [rows+1] metadata.generateName bytes

@@ -99,10 +99,9 @@ GK_HD int gk_match_row(const GkBatch& b, const uint32_t* pool, const uint8_t* cb
   }
   // 3/4 namespaces, excludedNamespaces -- match.go:118-179
   if (m.ns_n || m.exns_n) {
-    const uint32_t sid = b.nsname_sid[row];
-    if (sid != GK_NONE) {
-      const uint8_t* s = b.dict_bytes + b.dict_off[sid] + 1;   // skip the intern type char
-      const uint32_t sl = b.dict_off[sid + 1] - b.dict_off[sid] - 1;
+    if (fl & GK_F_NSNAME) {
+      const uint8_t* s = b.nsn_bytes + b.nsn_off[row];
+      const uint32_t sl = b.nsn_off[row + 1] - b.nsn_off[row];
       if (m.ns_n) {
         bool any = false;
         for (uint32_t j = 0; j < m.ns_n && !any; ++j) {

@@ -216,3 +216,24 @@ def config5():
             m.update(pats[i])
         cons.append(_constraint(t["kind"], f"repos-{k}", match=m, params={"repos": regs[:k]}))
     return [(t["kind"], t["rego"])], cons
+
+
+class PyBlob(ObjectBlob):
+    """An ObjectBlob over Python-owned memory: the JSON documents (bytes, or objects to be serialised) back to back."""
+
+    def __init__(self, docs):
+        raw = [d if isinstance(d, (bytes, bytearray)) else json.dumps(d, separators=(",", ":")).encode() for d in docs]
+        self._data = b"".join(raw)
+        self._cbuf = C.create_string_buffer(self._data, len(self._data) + 1)
+        off = (C.c_uint64 * (len(raw) + 1))()
+        pos = 0
+        for i, r in enumerate(raw):
+            off[i] = pos
+            pos += len(r)
+        off[len(raw)] = pos
+        self.buf = C.c_void_p(C.addressof(self._cbuf))
+        self.offsets = off
+        self.count = len(raw)
+
+    def __del__(self):
+        pass

@@ -10,6 +10,7 @@
 
 #include "../../gatekeeper_b200/csrc/backend.hpp"
 #include "../../gatekeeper_b200/csrc/vm_core.h"
+#include "../../gatekeeper_b200/csrc/ingest_core.h"
 
 namespace gk {
 
@@ -49,6 +50,186 @@ class HostEmuBackend : public Backend {
   }
   void release(void* b) override { delete static_cast<EmuBatch*>(b); }
 
+  // The device ingest path, run by CPU loops over the SAME per-object code the CUDA kernels run (ingest_core.h): tokenise,
+  // count, scan, write (+ host-filled lookups), then the arrays are handed to upload() like a host-flattened batch.
+  void* ingest(const IngestReq& rq, IngestStats* st, std::vector<uint32_t>* status) override {
+    std::lock_guard<std::mutex> l(ingest_mu_);
+    const XProgHost& xh = *rq.xprog;
+    const uint32_t n = (uint32_t)rq.n, NS = (uint32_t)xh.scopes.size(), NK = xh.ncounters(), NC = (uint32_t)xh.cols.size();
+    if (sid_.nstrings != rq.strings->size()) build_sid_table(*rq.strings, sid_);
+    if (lut_.mask == 0) lut_.init(1u << 12);
+    // excluder patterns ride in xkeys / xbytes copies
+    std::vector<uint32_t> xkeys = xh.xkeys;
+    std::vector<uint8_t> xbytes = xh.xbytes;
+    GkXProg xp{};
+    xp.excl_off = (uint32_t)xkeys.size();
+    for (auto& pat : rq.excluded) {
+      bool pre = !pat.empty() && pat.front() == '*', suf = pat.size() > (pre ? 1u : 0u) && pat.back() == '*';
+      std::string core = pat.substr(pre ? 1 : 0, pat.size() - (pre ? 1 : 0) - (suf ? 1 : 0));
+      xkeys.push_back(pre && suf ? GK_W_CONTAINS : pre ? GK_W_SUFFIX : suf ? GK_W_PREFIX : GK_W_EXACT);
+      xkeys.push_back((uint32_t)xbytes.size());
+      xkeys.push_back((uint32_t)core.size());
+      xbytes.insert(xbytes.end(), core.begin(), core.end());
+      ++xp.excl_n;
+    }
+    xbytes.push_back(0);
+    NsTableHost ns = *rq.ns;
+    xp.cl = xh.cl.data();
+    xp.cols = xh.cols.data();
+    xp.scopes = xh.scopes.data();
+    xp.col_order = xh.col_order.data();
+    xp.xkeys = xkeys.data();
+    xp.xargs = xh.xargs.data();
+    xp.xbytes = xbytes.data();
+    xp.ncl = (uint32_t)xh.cl.size();
+    xp.ncols = NC;
+    xp.nscopes = NS;
+    xp.nbytecols = xh.nbytecols;
+    xp.sid_tab = sid_.tab.view();
+    xp.sid_true = sid_.sid_true;
+    xp.sid_false = sid_.sid_false;
+    xp.sid_null = sid_.sid_null;
+    xp.ns_tab = ns.tab.view();
+    ns.nsn_bytes.push_back(0);
+    xp.nsn_off = ns.nsn_off.data();
+    xp.nsn_bytes = ns.nsn_bytes.data();
+    // ---- tokenise
+    std::vector<unsigned long long> tape((size_t)(rq.ooff[n] / 2 + 4ull * n + 16));
+    std::vector<uint32_t> ntape(std::max(n, 1u)), stat(std::max(n, 1u)), counts((size_t)NK * std::max(n, 1u)), nmiss(1, 0);
+    std::vector<GkMiss> misses(1u << 16);
+    GkIngestIn in{};
+    in.blob = rq.blob;
+    in.ooff = rq.ooff;
+    in.tape = tape.data();
+    in.ntape = ntape.data();
+    in.status = stat.data();
+    in.n = n;
+    in.source = rq.source;
+    in.counts = counts.data();
+    in.misses = misses.data();
+    in.nmiss = nmiss.data();
+    in.miss_cap = (uint32_t)misses.size();
+    for (uint32_t i = 0; i < n; ++i) gk_tape_obj(in, i);
+    if (status) status->assign(stat.begin(), stat.begin() + n);
+    // ---- count + scan
+    std::vector<uint32_t> cur(NK);
+    GkIngestOut none{};
+    xp.lut_tab = lut_.view();
+    xp.lut_vals = lut_vals_.data();
+    for (uint32_t i = 0; i < n; ++i) gk_ingest_obj<false>(xp, in, none, i, cur.data());
+    std::vector<uint32_t> total(NK, 0);
+    for (uint32_t k = 0; k < NK; ++k) {
+      uint32_t acc = 0;
+      for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t v = counts[(size_t)k * n + i];
+        counts[(size_t)k * n + i] = acc;
+        acc += v;
+      }
+      total[k] = acc;
+    }
+    // ---- destination arrays (a HostBatch) and the write pass
+    HostBatch hb;
+    hb.n = n;
+    hb.schema_version = rq.c->version;
+    const uint32_t K_NAME = NS + xh.nbytecols;
+    hb.flags.assign(n, 0), hb.kind_sid.assign(n, 0), hb.group_sid.assign(n, 0), hb.nsrow.assign(n, GK_NONE);
+    hb.name_off.assign(n + 1, 0), hb.gen_off.assign(n + 1, 0), hb.lbl_off.assign(n + 1, 0), hb.nsn_off.assign(n + 1, 0);
+    hb.name_bytes.assign(total[K_NAME], 0), hb.gen_bytes.assign(total[K_NAME + 1], 0), hb.lbl_kv.assign(2 * (size_t)total[K_NAME + 2], 0);
+    hb.nsn_bytes.assign(total[K_NAME + 3], 0);
+    hb.nsl_off = rq.ns->nsl_off;
+    hb.nsl_kv = rq.ns->nsl_kv;
+    hb.scope_off.resize(NS);
+    hb.scope_rows.assign(NS, 0);
+    std::vector<uint32_t*> p_scope(NS, nullptr);
+    for (uint32_t s2 = 1; s2 < NS; ++s2) {
+      hb.scope_rows[s2] = total[s2];
+      const int par = xh.scopes[s2].parent;
+      hb.scope_off[s2].assign((size_t)(par ? total[par] : n) + 1, 0);
+      p_scope[s2] = hb.scope_off[s2].data();
+    }
+    hb.cols.resize(NC);
+    std::vector<uint8_t*> p_vt(NC, nullptr), p_bytes(NC, nullptr);
+    std::vector<uint32_t*> p_sid(NC, nullptr), p_boff(NC, nullptr), p_head(NC, nullptr);
+    std::vector<long long*> p_num(NC, nullptr);
+    for (uint32_t ci = 0; ci < NC; ++ci) {
+      const GkXCol& xc = xh.cols[ci];
+      const size_t rows = xc.scope ? total[xc.scope] : n;
+      HostColumn& hc = hb.cols[ci];
+      if (xc.enc & GK_ENC_VT) hc.vt.assign(rows, 0), p_vt[ci] = hc.vt.data();
+      if (xc.enc & GK_ENC_SID) hc.sid.assign(rows, 0), p_sid[ci] = hc.sid.data();
+      if (xc.enc & GK_ENC_NUM) hc.num.assign(rows, 0), p_num[ci] = reinterpret_cast<long long*>(hc.num.data());
+      if (xc.enc & GK_ENC_HEAD) hc.head.assign(rows * GK_HEAD_WORDS, 0), p_head[ci] = hc.head.data();
+      if (xc.enc & GK_ENC_BYTES) {
+        hc.boff.assign(rows + 1, 0), p_boff[ci] = hc.boff.data();
+        hc.bytes.assign((size_t)total[NS + xc.bytes_slot] + 1, 0), p_bytes[ci] = hc.bytes.data();
+      }
+    }
+    hb.name_bytes.push_back(0), hb.gen_bytes.push_back(0), hb.nsn_bytes.push_back(0), hb.lbl_kv.push_back(0);
+    GkIngestOut out{};
+    out.flags = hb.flags.data();
+    out.kind_sid = hb.kind_sid.data();
+    out.group_sid = hb.group_sid.data();
+    out.name_off = hb.name_off.data();
+    out.name_bytes = hb.name_bytes.data();
+    out.gen_off = hb.gen_off.data();
+    out.gen_bytes = hb.gen_bytes.data();
+    out.lbl_off = hb.lbl_off.data();
+    out.lbl_kv = hb.lbl_kv.data();
+    out.nsrow = hb.nsrow.data();
+    out.nsn_off = hb.nsn_off.data();
+    out.nsn_bytes = hb.nsn_bytes.data();
+    out.scope_off = p_scope.data();
+    out.vt = p_vt.data();
+    out.sid = p_sid.data();
+    out.num = p_num.data();
+    out.boff = p_boff.data();
+    out.bytes = p_bytes.data();
+    out.head = p_head.data();
+    uint64_t total_miss = 0;
+    for (int round = 0; round < 64; ++round) {
+      nmiss[0] = 0;
+      xp.lut_tab = lut_.view();
+      xp.lut_vals = lut_vals_.data();
+      for (uint32_t i = 0; i < n; ++i) gk_ingest_obj<true>(xp, in, out, i, cur.data());
+      const uint32_t m = std::min<uint32_t>(nmiss[0], in.miss_cap);
+      if (nmiss[0] == 0) break;
+      total_miss += m;
+      std::vector<GkLutVal> vals;
+      rq.lut_fill(misses.data(), m, vals);
+      for (uint32_t j = 0; j < m; ++j) {
+        lut_.vals[misses[j].slot] = (uint32_t)lut_vals_.size();
+        lut_vals_.push_back(vals[j]);
+      }
+      lut_.used += m;
+      if (lut_.used * 2 > lut_.mask) {   // grow: re-insert the filled entries, drop the pending ones
+        HashTabHost big;
+        big.init((lut_.mask + 1) * 4);
+        for (uint32_t i2 = 0; i2 <= lut_.mask; ++i2)
+          if (lut_.keys[i2] && lut_.vals[i2] < GK_HT_LOST) big.put(lut_.keys[i2], lut_.vals[i2]);
+        lut_ = std::move(big);
+      }
+      if (round == 63) throw BackendError{"device ingest: lookups did not converge"};
+    }
+    hb.name_bytes.pop_back(), hb.gen_bytes.pop_back(), hb.nsn_bytes.pop_back(), hb.lbl_kv.pop_back();
+    for (uint32_t ci = 0; ci < NC; ++ci)
+      if (xh.cols[ci].enc & GK_ENC_BYTES) hb.cols[ci].bytes.pop_back();
+    hb.obj_errors.assign(n, std::string());
+    uint64_t b = 0;
+    auto sz = [&](auto& v) { b += (uint64_t)v.size() * sizeof(v[0]); };
+    sz(hb.flags), sz(hb.kind_sid), sz(hb.group_sid), sz(hb.nsn_off), sz(hb.nsn_bytes), sz(hb.name_off), sz(hb.gen_off), sz(hb.lbl_off), sz(hb.lbl_kv);
+    sz(hb.name_bytes), sz(hb.gen_bytes), sz(hb.nsrow), sz(hb.nsl_off), sz(hb.nsl_kv);
+    for (uint32_t s2 = 1; s2 < NS; ++s2) sz(hb.scope_off[s2]);
+    for (auto& col : hb.cols) sz(col.vt), sz(col.sid), sz(col.num), sz(col.boff), sz(col.bytes), sz(col.head);
+    hb.alg_bytes = b;
+    if (st) {
+      st->lut_misses = total_miss;
+      st->alg_bytes = b;
+    }
+    last_ingest_ = hb;   // (tests compare these arrays with the host flattener's)
+    return upload(hb, *rq.c, nullptr, nullptr);
+  }
+  const HostBatch& last_ingest() const { return last_ingest_; }
+
   void eval(void* bb, const std::vector<uint32_t>& active, EvalOut& out, bool) override {
     auto* b = static_cast<EmuBatch*>(bb);
     std::shared_ptr<const Dict> dict;
@@ -61,9 +242,11 @@ class HostEmuBackend : public Backend {
     const Compiled& c = *progp;
     const uint32_t C = (uint32_t)c.cons_match.size(), W = b->words, n = b->n;
     GkBatch h = b->hdr;
-    h.dict_off = dict->off.data();
-    h.dict_bytes = dict->bytes.data();
-    h.dict_n = (uint32_t)dict->off.size() - 1;
+    if (dict) {
+      h.dict_off = dict->off.data();
+      h.dict_bytes = dict->bytes.data();
+      h.dict_n = (uint32_t)dict->off.size() - 1;
+    }
     out.n = n;
     out.nconstraints = C;
     out.words = W;
@@ -202,7 +385,11 @@ class HostEmuBackend : public Backend {
     std::vector<uint32_t> off;
     std::vector<uint8_t> bytes;
   };
-  std::mutex mu_;
+  std::mutex mu_, ingest_mu_;
+  SidTable sid_;
+  HashTabHost lut_;
+  std::vector<GkLutVal> lut_vals_;
+  HostBatch last_ingest_;
   const Compiled* prog_ = nullptr;
   std::shared_ptr<const Dict> dict_;
 };

@@ -973,7 +973,7 @@ def _rf_template(rnd, idx):
     return "package fz%d\nimport future.keywords.in\n" % idx + "".join(bodies) + _RF_HELPERS
 
 
-def case_rego_fuzz(lib, n_templates=40, n_objects=120, seed=1):
+def case_rego_fuzz(lib, n_templates=40, n_objects=120, seed=1, via_blob=False):
     """Random policies: `violation` bodies assembled from a menu of ~50 statement shapes of the in-tree templates (iteration
     over containers / labels / volumes, comprehensions, set difference, helper rules and multi-body functions, negation,
     builtins on object fields against parameters), each with three random parameter sets, against damaged synthetic Pods.
@@ -997,7 +997,8 @@ def case_rego_fuzz(lib, n_templates=40, n_objects=120, seed=1):
                 o["spec"]["containers"] = [c]
                 revs.append(D.Review(object=o))
     # review shapes: UPDATE with an old object, DELETE (the old object is the one reviewed), user info, an explicit namespace object
-    for i in range(len(revs)):
+    # (not through the blob path: a blob holds plain objects, which the ingest kernels flatten on the device)
+    for i in range(0 if via_blob else len(revs)):
         r = rnd.random()
         o = revs[i].object
         if r < 0.12 and i:
@@ -1011,8 +1012,9 @@ def case_rego_fuzz(lib, n_templates=40, n_objects=120, seed=1):
             revs[i] = D.Review(object=o, source="Original", namespace={"apiVersion": "v1", "kind": "Namespace", "metadata": dict(
                 {"name": rnd.choice(["explicit-ns", "ns-0001"])}, **({"labels": {rnd.choice(["team", "label-06", "app"]): rnd.choice(["v9", "team-42"])}} if rnd.random() < 0.7 else {}))})
     n_objects = len(revs)
-    accepted = n_results = 0
+    accepted = n_results = n_device = 0
     rejected = []
+    pyblob = W.PyBlob([r.object for r in revs]) if via_blob else None
     for t in range(n_templates):
         src = _rf_template(rnd, t)
         kind = "Fz%d" % t
@@ -1027,7 +1029,11 @@ def case_rego_fuzz(lib, n_templates=40, n_objects=120, seed=1):
                 continue
         accepted += 1
         try:
-            resp = drv.ReviewBatch(revs, k8s.AUDIT_EP)
+            if via_blob:
+                n_device += "ingest: device" in drv.Dump()
+                resp = drv.ReviewBlob(pyblob, k8s.AUDIT_EP, flags=D.F_MATERIALIZE, source="")
+            else:
+                resp = drv.ReviewBatch(revs, k8s.AUDIT_EP)
         except D.GkError as e:
             m = __import__("re").search(r"object (\d+)\)", str(e))
             raise AssertionError("seed %d template %d: %s\n%s\nparams %s\nobject %s" % (
@@ -1041,6 +1047,8 @@ def case_rego_fuzz(lib, n_templates=40, n_objects=120, seed=1):
             raise AssertionError("seed %d template %d:\n%s\nparams %s\n%s" % (seed, t, src, [c["spec"].get("parameters") for c in cons], str(e)[:1500]))
         n_results += len(want)
     assert accepted >= n_templates * 0.6, rejected
+    if via_blob:
+        return accepted, n_results, rejected, n_device
     return accepted, n_results, rejected
 
 
@@ -1241,3 +1249,131 @@ violation[{"msg": "no owner"}] { not input.review.object.metadata.labels.owner }
     assert_same(want, engine_results(resp))
     assert sum(1 for w in want if w[1] == "K8sNoOwner/owner") == len(vals)
     return resp
+
+
+# ------------------------------------------------------------------------------------------ device ingest (blob path)
+def _blob_parity(orc, drv, docs, ep=k8s.AUDIT_EP, source="Original", expect_errors=()):
+    """Raw JSON documents through gk_review_blob (flattened by the ingest kernels when the snapshot allows it) against the oracle
+    on the parsed documents; `docs` are bytes or objects."""
+    blob = W.PyBlob(docs)
+    resp = drv.ReviewBlob(blob, ep, flags=D.F_MATERIALIZE, source=source)
+    errs = resp.object_errors or [None] * len(docs)
+    bad = {i for i, e in enumerate(errs) if e}
+    assert bad == set(expect_errors), (sorted(bad), [errs[i] for i in sorted(bad)][:5])
+    revs = []
+    for i, d in enumerate(docs):
+        if i in bad:
+            revs.append(None)
+            continue
+        revs.append(D.Review(object=json.loads(d) if isinstance(d, (bytes, bytearray)) else d, source=source))
+    want = set()
+    for i, r in enumerate(revs):
+        if r is None:
+            continue
+        for x in oracle_results(orc, [r], ep):
+            want.add((i,) + x[1:])
+    assert_same(want, {x for x in engine_results(resp) if x[0] not in bad})
+    return resp, want
+
+
+def case_blob_config2(lib, n=1500, start=0):
+    tm, cons = W.config2()
+    orc, drv, _ = make_pair(tm, cons, W.synth_namespaces(), lib_path=lib)
+    assert "ingest: device" in drv.Dump(), drv.Dump().splitlines()[1]
+    blob = W.synth_objects(start, n)
+    docs = [blob.get(i) for i in range(n)]
+    resp, want = _blob_parity(orc, drv, docs)
+    # the same page through the host flattener gives the same bitmap
+    host = drv.ReviewBatch([D.Review(object=json.loads(d), source="Original") for d in docs], k8s.AUDIT_EP, materialize=False)
+    assert (host.viol_bits == resp.viol_bits).all() and host.totals == resp.totals
+    return resp, want
+
+
+def case_blob_fuzz(lib, n=600, seed=4321, start=9000):
+    """config-2 constraints against structurally damaged Pods, raw JSON in, device-flattened."""
+    import random
+    rnd = random.Random(seed)
+    tm, cons = W.config2()
+    orc, drv, _ = make_pair(tm, cons, W.synth_namespaces(), lib_path=lib)
+    blob = W.synth_objects(start, n)
+    docs = [_mutate(rnd, json.loads(blob.get(i)), rnd.choice([0, 1, 1, 2, 3, 5])) for i in range(n)]
+    return _blob_parity(orc, drv, docs)
+
+
+def case_blob_json_oddities(lib):
+    """What a JSON encoder may legally (or illegally) write: whitespace, escapes in keys and values, surrogate pairs, duplicate
+    keys (the last one wins), exponents / fractions / huge numbers, empty containers, and documents the review must refuse."""
+    tm, cons = W.config2()
+    orc, drv, _ = make_pair(tm, cons, W.synth_namespaces(), lib_path=lib)
+    pod = json.loads(W.synth_objects(77, 1).get(0))
+    pod["spec"]["containers"][0]["image"] = "registry.k8s.io/a\"b\\c:la\ttest"
+    pod["metadata"]["labels"] = {"te\u0061m": "x", "team": "pl\u00e4tform", "emoji": "\ud83d\ude00"}
+    good = json.dumps(pod)
+    docs = [
+        good.encode(),
+        json.dumps(pod, indent=2).encode(),                                # whitespace everywhere
+        good.replace('"image"', '"\\u0069mage"').encode(),                 # an escaped key
+        good.replace('"spec":', '"spec": {"containers": "shadowed"}, "spec":').encode(),   # duplicate key: the last wins
+        good.replace('"kind":"Pod"', '"kind":"Job","kind":"Pod"').encode(),
+        json.dumps(dict(pod, spec=dict(pod["spec"], hostNetwork=True, priority=1e3, ratio=1.50, big=123456789012345678901234567890,
+                                       neg=-0.0, tiny=1e-7, exp=12E+2))).encode(),
+        json.dumps(dict(pod, spec={})).encode(), json.dumps(dict(pod, spec=[])).encode(), json.dumps(dict(pod, metadata=None)).encode(),
+        b'{"apiVersion":"v1","kind":"Pod","metadata":{"name":"x","namespace":"default","labels":{}},"spec":{"containers":[]}}',
+        b'  {"apiVersion" : "apps/v1" , "kind" : "Deployment", "metadata" : {"name":"d"} , "spec" : {"replicas" : 3.0e0 } }  ',
+        # ---- refused at the review boundary
+        b'{"apiVersion":"v1","kind":"Pod","metadata":{"name":"x"}',         # truncated
+        b'{"apiVersion":"v1","kind":"Pod",}',                               # trailing comma
+        b'{"apiVersion":"v1","kind":"Pod"} x',                              # trailing characters
+        b'{"apiVersion":"v1","metadata":{"name":"nokind"}}',                # kind missing
+        b'{"apiVersion":"v1","kind":"","metadata":{}}',                     # kind empty
+        b'[1,2,3]', b'"a string"', b'{"kind":"Pod","a":01e}',
+        b'{"kind":"Pod","a":"bad \\q escape"}', b'{"kind":"Pod","a":1.2.3}', b'{"kind":"Pod","a":-}',
+        b'{"kind":"Pod","apiVersion":"v1","metadata":{"name":"ok-after-errors","labels":{"team":"a"}},"spec":{"containers":[{"name":"c","image":"x:latest"}]}}',
+    ]
+    first_bad = next(i for i, d in enumerate(docs) if d.startswith(b'{"apiVersion":"v1","kind":"Pod","metadata":{"name":"x"}') and not d.endswith(b"}}"))
+    bad = set(range(first_bad, len(docs) - 1))
+    resp, want = _blob_parity(orc, drv, docs, expect_errors=bad)
+    # every refusal carries the host parser's wording
+    host = drv.ReviewBatch([D.Review(object=d, source="Original") for d in docs], k8s.AUDIT_EP)
+    assert [bool(e) for e in host.object_errors] == [bool(e) for e in resp.object_errors]
+    assert [e for e in host.object_errors if e] == [e for e in resp.object_errors if e]
+    return resp, want
+
+
+def case_blob_other_templates(lib, n=300, seed=7):
+    """The in-tree templates outside config 2 (regex labels, object.get defaults, custom fields, comprehension allowed repos ...),
+    one engine per template, raw JSON in: device-flattened where the snapshot allows it, host-flattened otherwise."""
+    import random
+    rnd = random.Random(seed)
+    t = golden("templates.json")
+    pick = {"requiredlabels_agilebank": [{"labels": [{"key": "owner", "allowedRegex": "^[a-z]+[.]agilebank[.]demo$"}, {"key": "team"}]},
+                                         {"message": "custom message", "labels": [{"key": "team", "allowedRegex": "^(a|b|team-[0-9]+)$"}]}],
+            "requiredlabels_regov1": [{"labels": ["team", "owner"]}, {"labels": []}],
+            "fooischeck": [{"foo": "bar"}, {"foo": ""}, {}, {"foo": 7}],
+            "namespacelabelcheck": [{"requiredLabel": "team"}],
+            "allowedrepos": [{"repos": ["gcr.io/", "quay.io/"]}, {"repos": []}, {"repos": ["openpolicyagent/opa:", "docker.io/library/nginx"]}],
+            "fixtures_TemplateRestrictCustomField": [{"expectedCustomField": "x"}, {"expectedCustomField": 7}, {"expectedCustomField": {"a": [1, 2]}}]}
+    blob = W.synth_objects(30000, n)
+    docs = []
+    for i in range(n):
+        o = json.loads(blob.get(i))
+        if rnd.random() < 0.3:
+            o.setdefault("metadata", {}).setdefault("labels", {})[rnd.choice(["owner", "team", "app"])] = rnd.choice(
+                ["alice.agilebank.demo", "bob", "team-7", "a", "", "Team-1", "x.agilebank.demo.evil"])
+        if rnd.random() < 0.3:
+            o["foo"] = rnd.choice(["bar", "", "baz", 7, None, ["bar"]])
+        if rnd.random() < 0.3:
+            o.setdefault("spec", {})["customField"] = rnd.choice(["x", "y", 7, 7.0, {"a": [1, 2]}, {"a": [2, 1]}, None, [1]])
+        docs.append(_mutate(rnd, o, rnd.choice([0, 0, 1, 2])))
+    n_dev = n_host = 0
+    for name, plist in pick.items():
+        cons = [W._constraint(t[name]["kind"], "%s-%d" % (name.replace("_", "-").lower(), i), params=params) for i, params in enumerate(plist)]
+        orc, drv, skipped = make_pair([(t[name]["kind"], t[name]["rego"])], cons, W.synth_namespaces(), lib_path=lib, skip_unsupported=True)
+        assert not skipped, skipped
+        if "ingest: device" in drv.Dump():
+            n_dev += 1
+        else:
+            n_host += 1
+        _blob_parity(orc, drv, docs)
+    assert n_dev >= 4, (n_dev, n_host)
+    return n_dev, n_host

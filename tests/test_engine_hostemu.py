@@ -277,3 +277,26 @@ def test_reviews_concurrent_with_constraint_changes():
 
 def test_inexact_numbers_are_compared_not_skipped():
     P.case_inexact_numbers(HOSTEMU)
+
+
+# ---- device ingest: the ingest kernels' per-object code (csrc/ingest_core.h) run by the test backend's CPU loops
+def test_blob_config2_device_ingest():
+    resp, want = P.case_blob_config2(HOSTEMU, 1500)
+    assert len(want) > 10000
+
+
+def test_blob_fuzz_device_ingest():
+    P.case_blob_fuzz(HOSTEMU)
+
+
+def test_blob_json_oddities():
+    P.case_blob_json_oddities(HOSTEMU)
+
+
+def test_blob_other_templates():
+    P.case_blob_other_templates(HOSTEMU)
+
+
+def test_blob_rego_fuzz():
+    accepted, n_results, rejected, n_device = P.case_rego_fuzz(HOSTEMU, n_templates=40, n_objects=100, seed=11, via_blob=True)
+    assert n_device >= accepted // 2, (n_device, accepted)
