@@ -295,7 +295,7 @@ static std::vector<gk_obj> blob_objs(const char* buf, const uint64_t* off, size_
 void upload_blob(gk_engine* e, const std::shared_ptr<const Compiled>& c, const char* buf, const uint64_t* off, size_t n, uint8_t source, uint32_t flags,
                  gk_batch** outb, gk_result* stats) {
   static const bool host_only = getenv("GK_NO_DEVICE_INGEST") != nullptr;
-  if (!c->device_ingest || host_only || n == 0) {
+  if (!c->device_ingest || host_only || n == 0 || getenv("GK_NO_DEVICE_INGEST_RUNTIME")) {   // (the runtime switch is for A/B tests)
     auto v = blob_objs(buf, off, n, source);
     upload_batch(e, c, v.data(), n, flags, outb, stats);
     return;

@@ -1026,6 +1026,13 @@ GK_HD bool gk_wild_val(const GkXCtx& c, uint32_t mode, const uint8_t* pat, uint3
   }
 }
 
+// the per-object working counters: contiguous on the host, strided by the object count on the device (coalesced)
+struct GkCur {
+  uint32_t* p;
+  size_t stride;
+  GK_HD uint32_t& operator[](uint32_t k) const { return p[(size_t)k * stride]; }
+};
+
 struct GkIngestFrame {
   uint32_t scope;
   uint32_t pos, end;        // object iteration: tape index of the next member's key / array: next element; end of the children
@@ -1038,7 +1045,7 @@ struct GkIngestFrame {
 GK_HD const uint8_t* gk_lit(const char* s) { return reinterpret_cast<const uint8_t*>(s); }
 
 template <bool WRITE>
-GK_HD void gk_emit_col(const GkXProg& xp, const GkIngestIn& in, const GkIngestOut& out, GkXCtx& c, uint32_t ci, uint32_t row, uint32_t* bcur) {
+GK_HD void gk_emit_col(const GkXProg& xp, const GkIngestIn& in, const GkIngestOut& out, GkXCtx& c, uint32_t ci, uint32_t row, const GkCur& bcur) {
   const GkXCol& col = xp.cols[ci];
   const GkXClosure& cl = xp.cl[col.closure];
   const uint32_t enc = col.enc;
@@ -1105,11 +1112,11 @@ GK_HD void gk_emit_col(const GkXProg& xp, const GkIngestIn& in, const GkIngestOu
 
 // Count pass (WRITE = false): fills in.counts[k * n + i].  Write pass: in.counts holds the exclusive prefix sums.
 template <bool WRITE>
-GK_HD void gk_ingest_obj(const GkXProg& xp, const GkIngestIn& in, const GkIngestOut& out, uint32_t i, uint32_t* cur /* [nscopes + nbytecols + GK_CNT_EXTRA] scratch */) {
+GK_HD void gk_ingest_obj(const GkXProg& xp, const GkIngestIn& in, const GkIngestOut& out, uint32_t i, const GkCur& cur /* nscopes + nbytecols + GK_CNT_EXTRA working counters */) {
   const uint32_t n = in.n, NS = xp.nscopes, NK = NS + xp.nbytecols + GK_CNT_EXTRA;
   const uint32_t K_NAME = NS + xp.nbytecols, K_GEN = K_NAME + 1, K_LBL = K_NAME + 2, K_NSN = K_NAME + 3;
   for (uint32_t k = 0; k < NK; ++k) cur[k] = WRITE ? in.counts[(size_t)k * n + i] : 0u;
-  uint32_t* bcur = cur + NS;
+  const GkCur bcur{cur.p + (size_t)NS * cur.stride, cur.stride};
   GkXCtx c;
   c.xp = &xp;
   c.in = &in;

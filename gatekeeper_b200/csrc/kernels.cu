@@ -5,11 +5,15 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
+#include <functional>
+#include <memory>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
 
 #include "backend.hpp"
+#include "ingest_kernels.cuh"
 #include "tile_kernel.cuh"
 
 namespace gk {
@@ -54,6 +58,7 @@ class CudaBackend : public Backend {
     max_smem_ = (size_t)prop.sharedMemPerBlockOptin;
     sm_smem_ = (size_t)prop.sharedMemPerMultiprocessor;
     CK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
     CK(cudaEventCreate(&ev0_));
     CK(cudaEventCreate(&ev1_));
     cudaFuncAttributes fa;
@@ -162,22 +167,56 @@ class CudaBackend : public Backend {
       if (t)
         for (uint32_t s = 0; s < NS; ++s) cap[s] = std::max(cap[s], lo[s] - tile_lo[(size_t)(t - 1) * NS + s]);
     }
-    cap[0] = tile;
+    auto* db = new DevBatch();
+    db->bytes = gk_align(plan.total);
+    db->n = hb.n;
+    db->ntiles = ntiles;
+    db->tile = tile;
+    db->prog_version = c.version;
+    CK(cudaMalloc(&db->arena, db->bytes));
+    CK(cudaMalloc(&db->d_tile_lo, tile_lo.size() * 4 + 64));
+    finish_batch(db, c, cap);
+    const size_t tables_bytes = c.ops.size() * sizeof(GkOp) + c.pool.size() * 4 + c.outs.size() * sizeof(GkOutEnt);
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a));
+    CK(cudaEventCreate(&b));
+    {
+      std::lock_guard<std::mutex> l(mu_);
+      // the arena image is assembled by all host threads directly in pinned memory (one copy of every byte), its
+      // in-arena pointer tables are rebased to the device address, and one DMA moves it
+      if (pinned_bytes_ < plan.total) {
+        if (pinned_) cudaFreeHost(pinned_);
+        pinned_bytes_ = plan.total + (plan.total >> 2);
+        CK(cudaMallocHost(&pinned_, pinned_bytes_));
+      }
+      uint8_t* image = static_cast<uint8_t*>(pinned_);
+      pack_copy(plan, image, host_threads_);
+      db->hdr = rebase_batch(pb, image, db->arena);
+      CK(cudaEventRecord(a, stream_));
+      CK(cudaMemcpyAsync(db->arena, image, plan.total, cudaMemcpyHostToDevice, stream_));
+      CK(cudaMemcpyAsync(db->d_tile_lo, tile_lo.data(), tile_lo.size() * 4, cudaMemcpyHostToDevice, stream_));
+      CK(cudaEventRecord(b, stream_));
+      CK(cudaStreamSynchronize(stream_));
+    }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    if (h2d_ms) *h2d_ms = ms;
+    if (h2d_bytes) *h2d_bytes = plan.total + tile_lo.size() * 4 + tables_bytes;
+    return db;
+  }
+
+  // slot area of a tile from the per-scope tile capacities; the netlist with slot ids resolved to word offsets; output planes
+  void finish_batch(DevBatch* db, const Compiled& c, std::vector<uint32_t> cap) {
+    cap[0] = db->tile;
     std::vector<uint32_t> slot_off(c.slot_level.size());
     uint32_t slot_words = 0;
     for (size_t i = 0; i < slot_off.size(); ++i) {
       slot_off[i] = slot_words;
       slot_words += ((cap[c.slot_level[i]] + 31) / 32 + 1 + 3) & ~3u;   // 16-byte aligned, padded: atoms store 4 words at a time
     }
-    auto* db = new DevBatch();
-    db->bytes = gk_align(plan.total);
-    db->n = hb.n;
-    db->ntiles = ntiles;
-    db->tile = tile;
     db->slot_words = slot_words;
-    db->prog_version = c.version;
-    CK(cudaMalloc(&db->arena, db->bytes));
-    CK(cudaMalloc(&db->d_tile_lo, tile_lo.size() * 4 + 64));
     // resolve slot ids -> word offsets once per batch: the kernel then addresses slots without a table lookup
     std::vector<GkOp> ops_r = c.ops;
     std::vector<uint32_t> pool_r = c.pool;
@@ -227,37 +266,9 @@ class CudaBackend : public Backend {
     if (!ops_r.empty()) CK(cudaMemcpy(db->d_ops, ops_r.data(), ops_r.size() * sizeof(GkOp), cudaMemcpyHostToDevice));
     if (!pool_r.empty()) CK(cudaMemcpy(db->d_pool, pool_r.data(), pool_r.size() * 4, cudaMemcpyHostToDevice));
     if (!outs_r.empty()) CK(cudaMemcpy(db->d_outs, outs_r.data(), outs_r.size() * sizeof(GkOutEnt), cudaMemcpyHostToDevice));
-    cudaEvent_t a, b;
-    CK(cudaEventCreate(&a));
-    CK(cudaEventCreate(&b));
-    {
-      std::lock_guard<std::mutex> l(mu_);
-      // the arena image is assembled by all host threads directly in pinned memory (one copy of every byte), its
-      // in-arena pointer tables are rebased to the device address, and one DMA moves it
-      if (pinned_bytes_ < plan.total) {
-        if (pinned_) cudaFreeHost(pinned_);
-        pinned_bytes_ = plan.total + (plan.total >> 2);
-        CK(cudaMallocHost(&pinned_, pinned_bytes_));
-      }
-      uint8_t* image = static_cast<uint8_t*>(pinned_);
-      pack_copy(plan, image, host_threads_);
-      db->hdr = rebase_batch(pb, image, db->arena);
-      CK(cudaEventRecord(a, stream_));
-      CK(cudaMemcpyAsync(db->arena, image, plan.total, cudaMemcpyHostToDevice, stream_));
-      CK(cudaMemcpyAsync(db->d_tile_lo, tile_lo.data(), tile_lo.size() * 4, cudaMemcpyHostToDevice, stream_));
-      CK(cudaEventRecord(b, stream_));
-      CK(cudaStreamSynchronize(stream_));
-    }
-    float ms = 0;
-    cudaEventElapsedTime(&ms, a, b);
-    cudaEventDestroy(a);
-    cudaEventDestroy(b);
-    if (h2d_ms) *h2d_ms = ms;
-    if (h2d_bytes) *h2d_bytes = plan.total + tile_lo.size() * 4 + ops_r.size() * sizeof(GkOp) + pool_r.size() * 4 + outs_r.size() * sizeof(GkOutEnt);
     db->words = std::max<uint32_t>(1, (uint32_t)((c.cons_match.size() + 31) / 32));
     CK(cudaMalloc(&db->viol, (size_t)std::max(db->n, 1u) * db->words * 4));
     CK(cudaMalloc(&db->err, (size_t)std::max(db->n, 1u) * db->words * 4));
-    return db;
   }
 
   void release(void* b) override {
@@ -415,7 +426,423 @@ class CudaBackend : public Backend {
     }
   }
 
-  void* ingest(const IngestReq&, IngestStats*, std::vector<uint32_t>*) override { throw BackendError{"device ingest: not built yet"}; }
+  // ---- device ingest (ingest_core.h / ingest_kernels.cuh): raw JSON blob -> resident columnar batch
+  struct Scratch {   // grow-only device buffer
+    uint8_t* p = nullptr;
+    size_t cap = 0;
+    uint8_t* need(size_t bytes) {
+      if (bytes > cap) {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = bytes + (bytes >> 3) + 4096;
+        cudaError_t e = cudaMalloc(&p, cap);
+        if (e != cudaSuccess) {
+          cap = 0;
+          throw BackendError{std::string("CUDA error: ") + cudaGetErrorString(e) + " allocating ingest scratch"};
+        }
+      }
+      return p;
+    }
+  };
+  struct Carver {   // 256-byte aligned sub-allocations of one buffer
+    size_t off = 0;
+    size_t take(size_t bytes) {
+      size_t o = gk_align(off);
+      off = o + std::max<size_t>(bytes, 16);
+      return o;
+    }
+  };
+
+  void upload_htab(const HashTabHost& h, unsigned long long** dk, uint32_t** dv, size_t* dcap) {
+    const size_t cap = (size_t)h.mask + 1;
+    if (*dcap != cap) {
+      if (*dk) cudaFree(*dk);
+      if (*dv) cudaFree(*dv);
+      CK(cudaMalloc(dk, cap * 8));
+      CK(cudaMalloc(dv, cap * 4));
+      *dcap = cap;
+    }
+    CK(cudaMemcpyAsync(*dk, h.keys.data(), cap * 8, cudaMemcpyHostToDevice, stream_));
+    CK(cudaMemcpyAsync(*dv, h.vals.data(), cap * 4, cudaMemcpyHostToDevice, stream_));
+    CK(cudaStreamSynchronize(stream_));
+  }
+
+  void* ingest(const IngestReq& rq, IngestStats* st, std::vector<uint32_t>* status) override {
+    std::lock_guard<std::mutex> l(ingest_mu_);
+    CK(cudaSetDevice(device_));
+    const auto T0 = std::chrono::steady_clock::now();
+    const XProgHost& xh = *rq.xprog;
+    const Compiled& c = *rq.c;
+    const uint32_t n = (uint32_t)rq.n, NS = (uint32_t)xh.scopes.size(), NK = xh.ncounters(), NC = (uint32_t)xh.cols.size();
+    const unsigned long long B = rq.ooff[n];
+    if (rq.n > 0x7fffff00ull) throw BackendError{"device ingest: more than 2^31 objects in one batch"};
+    // ---- lookup tables
+    if (sid_.nstrings != rq.strings->size()) {
+      build_sid_table(*rq.strings, sid_);
+      upload_htab(sid_.tab, &d_sid_keys_, &d_sid_vals_, &d_sid_cap_);
+    }
+    if (lut_.mask == 0) {
+      lut_.init(1u << 20);
+      upload_htab(lut_, &d_lut_keys_, &d_lut_vals_, &d_lut_cap_);
+    }
+    // ---- extraction program + namespace cache tables: one host image, one copy
+    std::vector<uint32_t> xkeys = xh.xkeys;
+    std::vector<uint8_t> xbytes = xh.xbytes;
+    const uint32_t excl_off = (uint32_t)xkeys.size();
+    uint32_t excl_n = 0;
+    for (auto& pat : rq.excluded) {
+      const bool pre = !pat.empty() && pat.front() == '*', suf = pat.size() > (pre ? 1u : 0u) && pat.back() == '*';
+      const std::string core = pat.substr(pre ? 1 : 0, pat.size() - (pre ? 1 : 0) - (suf ? 1 : 0));
+      xkeys.push_back(pre && suf ? GK_W_CONTAINS : pre ? GK_W_SUFFIX : suf ? GK_W_PREFIX : GK_W_EXACT);
+      xkeys.push_back((uint32_t)xbytes.size());
+      xkeys.push_back((uint32_t)core.size());
+      xbytes.insert(xbytes.end(), core.begin(), core.end());
+      ++excl_n;
+    }
+    const NsTableHost& ns = *rq.ns;
+    Carver tc;
+    const size_t o_cl = tc.take(xh.cl.size() * sizeof(GkXClosure)), o_cols = tc.take(xh.cols.size() * sizeof(GkXCol)),
+                 o_scopes = tc.take(xh.scopes.size() * sizeof(GkXScope)), o_order = tc.take(xh.col_order.size() * 4), o_xkeys = tc.take(xkeys.size() * 4),
+                 o_xargs = tc.take(xh.xargs.size() * 4), o_xbytes = tc.take(xbytes.size()), o_nskeys = tc.take(ns.tab.keys.size() * 8),
+                 o_nsvals = tc.take(ns.tab.vals.size() * 4), o_nsnoff = tc.take(ns.nsn_off.size() * 4), o_nsnbytes = tc.take(ns.nsn_bytes.size());
+    const size_t tab_bytes = gk_align(tc.off);
+    std::vector<uint8_t> timg(tab_bytes, 0);
+    auto putv = [&](size_t off, const void* src, size_t bytes) {
+      if (bytes) memcpy(timg.data() + off, src, bytes);
+    };
+    putv(o_cl, xh.cl.data(), xh.cl.size() * sizeof(GkXClosure));
+    putv(o_cols, xh.cols.data(), xh.cols.size() * sizeof(GkXCol));
+    putv(o_scopes, xh.scopes.data(), xh.scopes.size() * sizeof(GkXScope));
+    putv(o_order, xh.col_order.data(), xh.col_order.size() * 4);
+    putv(o_xkeys, xkeys.data(), xkeys.size() * 4);
+    putv(o_xargs, xh.xargs.data(), xh.xargs.size() * 4);
+    putv(o_xbytes, xbytes.data(), xbytes.size());
+    putv(o_nskeys, ns.tab.keys.data(), ns.tab.keys.size() * 8);
+    putv(o_nsvals, ns.tab.vals.data(), ns.tab.vals.size() * 4);
+    putv(o_nsnoff, ns.nsn_off.data(), ns.nsn_off.size() * 4);
+    putv(o_nsnbytes, ns.nsn_bytes.data(), ns.nsn_bytes.size());
+    uint8_t* d_tab = tabs_.need(tab_bytes);
+    CK(cudaMemcpyAsync(d_tab, timg.data(), tab_bytes, cudaMemcpyHostToDevice, stream_));
+    GkXProg xp;
+    memset(&xp, 0, sizeof xp);
+    xp.cl = reinterpret_cast<const GkXClosure*>(d_tab + o_cl);
+    xp.cols = reinterpret_cast<const GkXCol*>(d_tab + o_cols);
+    xp.scopes = reinterpret_cast<const GkXScope*>(d_tab + o_scopes);
+    xp.col_order = reinterpret_cast<const uint32_t*>(d_tab + o_order);
+    xp.xkeys = reinterpret_cast<const uint32_t*>(d_tab + o_xkeys);
+    xp.xargs = reinterpret_cast<const uint32_t*>(d_tab + o_xargs);
+    xp.xbytes = d_tab + o_xbytes;
+    xp.ncl = (uint32_t)xh.cl.size();
+    xp.ncols = NC;
+    xp.nscopes = NS;
+    xp.nbytecols = xh.nbytecols;
+    xp.sid_tab.keys = d_sid_keys_;
+    xp.sid_tab.vals = d_sid_vals_;
+    xp.sid_tab.mask = sid_.tab.mask;
+    xp.sid_true = sid_.sid_true;
+    xp.sid_false = sid_.sid_false;
+    xp.sid_null = sid_.sid_null;
+    xp.ns_tab.keys = reinterpret_cast<unsigned long long*>(d_tab + o_nskeys);
+    xp.ns_tab.vals = reinterpret_cast<uint32_t*>(d_tab + o_nsvals);
+    xp.ns_tab.mask = ns.tab.mask;
+    xp.nsn_off = reinterpret_cast<const uint32_t*>(d_tab + o_nsnoff);
+    xp.nsn_bytes = d_tab + o_nsnbytes;
+    xp.excl_off = excl_off;
+    xp.excl_n = excl_n;
+    // ---- scratch: blob, offsets, tape, counters, miss list
+    const uint32_t miss_cap = 1u << 17;
+    Carver sc;
+    const size_t o_blob = sc.take((size_t)B + 16), o_ooff = sc.take(((size_t)n + 1) * 8), o_tape = sc.take(((size_t)(B / 2) + 4ull * n + 64) * 8),
+                 o_ntape = sc.take((size_t)n * 4), o_status = sc.take((size_t)n * 4), o_counts = sc.take((size_t)NK * n * 4),
+                 o_work = sc.take((size_t)NK * n * 4), o_totals = sc.take((size_t)(NK + NS + 4) * 4), o_miss = sc.take((size_t)miss_cap * sizeof(GkMiss)),
+                 o_fill = sc.take((size_t)miss_cap * 8);
+    uint8_t* d_s = scratch_.need(gk_align(sc.off));
+    GkIngestIn in;
+    memset(&in, 0, sizeof in);
+    in.blob = d_s + o_blob;
+    in.ooff = reinterpret_cast<const unsigned long long*>(d_s + o_ooff);
+    in.tape = reinterpret_cast<unsigned long long*>(d_s + o_tape);
+    in.ntape = reinterpret_cast<uint32_t*>(d_s + o_ntape);
+    in.status = reinterpret_cast<uint32_t*>(d_s + o_status);
+    in.n = n;
+    in.source = rq.source;
+    in.counts = reinterpret_cast<uint32_t*>(d_s + o_counts);
+    in.misses = reinterpret_cast<GkMiss*>(d_s + o_miss);
+    uint32_t* d_totals = reinterpret_cast<uint32_t*>(d_s + o_totals);
+    uint32_t* d_cap = d_totals + NK;
+    in.nmiss = d_cap + NS;
+    in.miss_cap = miss_cap;
+    uint32_t* d_work = reinterpret_cast<uint32_t*>(d_s + o_work);
+    uint32_t* d_fill = reinterpret_cast<uint32_t*>(d_s + o_fill);
+    cudaEvent_t e0, e1, e2, e3;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    CK(cudaEventCreate(&e2));
+    CK(cudaEventCreate(&e3));
+    // ---- H2D of the raw JSON in chunks on the copy stream; the tokeniser of a chunk starts as soon as its bytes have landed
+    CK(cudaMemcpyAsync(d_s + o_ooff, rq.ooff, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, stream_));
+    CK(cudaEventRecord(e0, stream_));
+    const uint32_t blocks = (n + kIngestThreads - 1) / kIngestThreads;
+    {
+      const size_t kChunk = 32u << 20;
+      uint32_t first = 0;
+      while (first < n) {
+        uint32_t last = first;
+        const unsigned long long lo = rq.ooff[first];
+        while (last < n && rq.ooff[last + 1] - lo <= kChunk) ++last;
+        if (last == first) ++last;   // one object larger than a chunk
+        const unsigned long long hi = rq.ooff[last];
+        CK(cudaMemcpyAsync(d_s + o_blob + lo, rq.blob + lo, (size_t)(hi - lo), cudaMemcpyHostToDevice, copy_stream_));
+        cudaEvent_t ev = chunk_event(first);
+        CK(cudaEventRecord(ev, copy_stream_));
+        CK(cudaStreamWaitEvent(stream_, ev, 0));
+        const uint32_t cnt = last - first;
+        gk_tape_kernel<<<(cnt + kIngestThreads - 1) / kIngestThreads, kIngestThreads, 0, stream_>>>(in, first, cnt);
+        ++launches_;
+        first = last;
+      }
+    }
+    CK(cudaEventRecord(e1, stream_));
+    if (n) {
+      gk_count_kernel<<<blocks, kIngestThreads, 0, stream_>>>(xp, in);
+      gk_scan_kernel<<<NK, 1024, 0, stream_>>>(in.counts, n, d_totals);
+      launches_ += 2;
+    } else {
+      CK(cudaMemsetAsync(d_totals, 0, (size_t)NK * 4, stream_));
+    }
+    std::vector<uint32_t> total(NK + NS + 4, 0);
+    CK(cudaMemcpyAsync(total.data(), d_totals, (size_t)NK * 4, cudaMemcpyDeviceToHost, stream_));
+    CK(cudaStreamSynchronize(stream_));
+    CK(cudaGetLastError());
+    // ---- destination arena (exact sizes) + the pointer tables of the write pass
+    const uint32_t K_NAME = NS + xh.nbytecols;
+    Carver ac;
+    GkBatch h;
+    memset(&h, 0, sizeof h);
+    h.n = n;
+    h.has_old = 0;
+    uint64_t alg = 0;
+    auto arr = [&](size_t bytes) {
+      alg += bytes;
+      return ac.take(bytes);
+    };
+    const size_t a_flags = arr((size_t)n * 4), a_kind = arr((size_t)n * 4), a_group = arr((size_t)n * 4), a_nsnoff = arr(((size_t)n + 1) * 4),
+                 a_nsnb = arr(total[K_NAME + 3]), a_nameoff = arr(((size_t)n + 1) * 4), a_nameb = arr(total[K_NAME]), a_genoff = arr(((size_t)n + 1) * 4),
+                 a_genb = arr(total[K_NAME + 1]), a_lbloff = arr(((size_t)n + 1) * 4), a_lblkv = arr((size_t)total[K_NAME + 2] * 8), a_nsrow = arr((size_t)n * 4),
+                 a_nsloff = arr(ns.nsl_off.size() * 4), a_nslkv = arr(ns.nsl_kv.size() * 4);
+    std::vector<size_t> a_scope(NS, 0);
+    for (uint32_t s2 = 1; s2 < NS; ++s2) a_scope[s2] = arr(((size_t)(xh.scopes[s2].parent ? total[xh.scopes[s2].parent] : n) + 1) * 4);
+    struct ColOff {
+      size_t vt = 0, sid = 0, num = 0, boff = 0, bytes = 0, head = 0;
+    };
+    std::vector<ColOff> a_col(NC);
+    for (uint32_t ci = 0; ci < NC; ++ci) {
+      const GkXCol& xc = xh.cols[ci];
+      const size_t rows = xc.scope ? total[xc.scope] : n;
+      if (xc.enc & GK_ENC_VT) a_col[ci].vt = arr(rows);
+      if (xc.enc & GK_ENC_SID) a_col[ci].sid = arr(rows * 4);
+      if (xc.enc & GK_ENC_NUM) a_col[ci].num = arr(rows * 8);
+      if (xc.enc & GK_ENC_HEAD) a_col[ci].head = arr(rows * 32);
+      if (xc.enc & GK_ENC_BYTES) {
+        a_col[ci].boff = arr((rows + 1) * 4);
+        a_col[ci].bytes = arr(total[NS + xc.bytes_slot]);
+      }
+    }
+    // in-arena tables: GkColumn[], GkScope[], and the pointer arrays of GkIngestOut
+    const size_t a_cols = ac.take((size_t)NC * sizeof(GkColumn)), a_scopes = ac.take((size_t)NS * sizeof(GkScope)), a_pscope = ac.take((size_t)NS * 8),
+                 a_pvt = ac.take((size_t)NC * 8), a_psid = ac.take((size_t)NC * 8), a_pnum = ac.take((size_t)NC * 8), a_pboff = ac.take((size_t)NC * 8),
+                 a_pbytes = ac.take((size_t)NC * 8), a_phead = ac.take((size_t)NC * 8);
+    const size_t tables_lo = gk_align(a_cols) == a_cols ? a_cols : a_cols;
+    auto* db = new DevBatch();
+    std::unique_ptr<DevBatch, std::function<void(DevBatch*)>> guard(db, [this](DevBatch* x) { release(x); });
+    db->bytes = gk_align(ac.off);
+    db->n = n;
+    db->prog_version = c.version;
+    CK(cudaMalloc(&db->arena, db->bytes));
+    uint8_t* A = db->arena;
+    std::vector<uint8_t> aimg(db->bytes - tables_lo, 0);   // host image of the table tail of the arena
+    auto tail = [&](size_t off) { return aimg.data() + (off - tables_lo); };
+    GkColumn* hc = reinterpret_cast<GkColumn*>(tail(a_cols));
+    GkScope* hs = reinterpret_cast<GkScope*>(tail(a_scopes));
+    auto dptr = [&](size_t off) { return reinterpret_cast<uint64_t>(A + off); };
+    for (uint32_t ci = 0; ci < NC; ++ci) {
+      const GkXCol& xc = xh.cols[ci];
+      GkColumn& g = hc[ci];
+      g.scope = (int32_t)xc.scope;
+      g.enc = xc.enc;
+      g.vt = (xc.enc & GK_ENC_VT) ? A + a_col[ci].vt : nullptr;
+      g.sid = (xc.enc & GK_ENC_SID) ? reinterpret_cast<const uint32_t*>(A + a_col[ci].sid) : nullptr;
+      g.num = (xc.enc & GK_ENC_NUM) ? reinterpret_cast<const int64_t*>(A + a_col[ci].num) : nullptr;
+      g.boff = (xc.enc & GK_ENC_BYTES) ? reinterpret_cast<const uint32_t*>(A + a_col[ci].boff) : nullptr;
+      g.bytes = (xc.enc & GK_ENC_BYTES) ? A + a_col[ci].bytes : nullptr;
+      g.head = (xc.enc & GK_ENC_HEAD) ? reinterpret_cast<const uint32_t*>(A + a_col[ci].head) : nullptr;
+      reinterpret_cast<uint64_t*>(tail(a_pvt))[ci] = g.vt ? dptr(a_col[ci].vt) : 0;
+      reinterpret_cast<uint64_t*>(tail(a_psid))[ci] = g.sid ? dptr(a_col[ci].sid) : 0;
+      reinterpret_cast<uint64_t*>(tail(a_pnum))[ci] = g.num ? dptr(a_col[ci].num) : 0;
+      reinterpret_cast<uint64_t*>(tail(a_pboff))[ci] = g.boff ? dptr(a_col[ci].boff) : 0;
+      reinterpret_cast<uint64_t*>(tail(a_pbytes))[ci] = g.bytes ? dptr(a_col[ci].bytes) : 0;
+      reinterpret_cast<uint64_t*>(tail(a_phead))[ci] = g.head ? dptr(a_col[ci].head) : 0;
+    }
+    for (uint32_t s2 = 0; s2 < NS; ++s2) {
+      hs[s2].parent = s2 ? xh.scopes[s2].parent : 0;
+      hs[s2].rows = s2 ? total[s2] : n;
+      hs[s2].off = s2 ? reinterpret_cast<const uint32_t*>(A + a_scope[s2]) : nullptr;
+      reinterpret_cast<uint64_t*>(tail(a_pscope))[s2] = s2 ? dptr(a_scope[s2]) : 0;
+    }
+    CK(cudaMemcpyAsync(A + tables_lo, aimg.data(), aimg.size(), cudaMemcpyHostToDevice, stream_));
+    if (!ns.nsl_off.empty()) CK(cudaMemcpyAsync(A + a_nsloff, ns.nsl_off.data(), ns.nsl_off.size() * 4, cudaMemcpyHostToDevice, stream_));
+    if (!ns.nsl_kv.empty()) CK(cudaMemcpyAsync(A + a_nslkv, ns.nsl_kv.data(), ns.nsl_kv.size() * 4, cudaMemcpyHostToDevice, stream_));
+    h.flags = reinterpret_cast<const uint32_t*>(A + a_flags);
+    h.kind_sid = reinterpret_cast<const uint32_t*>(A + a_kind);
+    h.group_sid = reinterpret_cast<const uint32_t*>(A + a_group);
+    h.nsn_off = reinterpret_cast<const uint32_t*>(A + a_nsnoff);
+    h.nsn_bytes = A + a_nsnb;
+    h.name_off = reinterpret_cast<const uint32_t*>(A + a_nameoff);
+    h.name_bytes = A + a_nameb;
+    h.gen_off = reinterpret_cast<const uint32_t*>(A + a_genoff);
+    h.gen_bytes = A + a_genb;
+    h.lbl_off = reinterpret_cast<const uint32_t*>(A + a_lbloff);
+    h.lbl_kv = reinterpret_cast<const uint32_t*>(A + a_lblkv);
+    h.nsrow = reinterpret_cast<const uint32_t*>(A + a_nsrow);
+    h.nsl_off = reinterpret_cast<const uint32_t*>(A + a_nsloff);
+    h.nsl_kv = reinterpret_cast<const uint32_t*>(A + a_nslkv);
+    h.cols = reinterpret_cast<const GkColumn*>(A + a_cols);
+    h.scopes = reinterpret_cast<const GkScope*>(A + a_scopes);
+    h.ncols = NC;
+    h.nscopes = NS;
+    db->hdr = h;
+    GkIngestOut out;
+    memset(&out, 0, sizeof out);
+    out.flags = reinterpret_cast<uint32_t*>(A + a_flags);
+    out.kind_sid = reinterpret_cast<uint32_t*>(A + a_kind);
+    out.group_sid = reinterpret_cast<uint32_t*>(A + a_group);
+    out.name_off = reinterpret_cast<uint32_t*>(A + a_nameoff);
+    out.name_bytes = A + a_nameb;
+    out.gen_off = reinterpret_cast<uint32_t*>(A + a_genoff);
+    out.gen_bytes = A + a_genb;
+    out.lbl_off = reinterpret_cast<uint32_t*>(A + a_lbloff);
+    out.lbl_kv = reinterpret_cast<uint32_t*>(A + a_lblkv);
+    out.nsrow = reinterpret_cast<uint32_t*>(A + a_nsrow);
+    out.nsn_off = reinterpret_cast<uint32_t*>(A + a_nsnoff);
+    out.nsn_bytes = A + a_nsnb;
+    out.scope_off = reinterpret_cast<uint32_t* const*>(A + a_pscope);
+    out.vt = reinterpret_cast<uint8_t* const*>(A + a_pvt);
+    out.sid = reinterpret_cast<uint32_t* const*>(A + a_psid);
+    out.num = reinterpret_cast<long long* const*>(A + a_pnum);
+    out.boff = reinterpret_cast<uint32_t* const*>(A + a_pboff);
+    out.bytes = reinterpret_cast<uint8_t* const*>(A + a_pbytes);
+    out.head = reinterpret_cast<uint32_t* const*>(A + a_phead);
+    // ---- write pass, repeated while lookups are missing (the host evaluates each distinct argument tuple once)
+    CK(cudaEventRecord(e2, stream_));
+    uint64_t total_miss = 0;
+    double lut_ms = 0;
+    std::vector<GkMiss> hmiss;
+    for (int round = 0; n && round < 4096; ++round) {
+      xp.lut_tab.keys = d_lut_keys_;
+      xp.lut_tab.vals = d_lut_vals_;
+      xp.lut_tab.mask = lut_.mask;
+      xp.lut_vals = d_lutv_;
+      CK(cudaMemcpyAsync(d_work, in.counts, (size_t)NK * n * 4, cudaMemcpyDeviceToDevice, stream_));
+      CK(cudaMemsetAsync(in.nmiss, 0, 4, stream_));
+      gk_write_kernel<<<blocks, kIngestThreads, 0, stream_>>>(xp, in, out, d_work);
+      ++launches_;
+      uint32_t nm = 0;
+      CK(cudaMemcpyAsync(&nm, in.nmiss, 4, cudaMemcpyDeviceToHost, stream_));
+      CK(cudaStreamSynchronize(stream_));
+      CK(cudaGetLastError());
+      if (nm == 0) break;
+      const auto L0 = std::chrono::steady_clock::now();
+      const uint32_t m = std::min(nm, miss_cap);
+      hmiss.resize(m);
+      CK(cudaMemcpy(hmiss.data(), in.misses, (size_t)m * sizeof(GkMiss), cudaMemcpyDeviceToHost));
+      std::vector<GkLutVal> vals;
+      rq.lut_fill(hmiss.data(), m, vals);
+      // append the results, point the claimed slots at them
+      const uint32_t base = (uint32_t)lutv_.size();
+      lutv_.insert(lutv_.end(), vals.begin(), vals.end());
+      if (lutv_.size() > d_lutv_cap_) {
+        GkLutVal* nv = nullptr;
+        const size_t ncap = lutv_.size() * 2 + 1024;
+        CK(cudaMalloc(&nv, ncap * sizeof(GkLutVal)));
+        if (base) CK(cudaMemcpy(nv, d_lutv_, (size_t)base * sizeof(GkLutVal), cudaMemcpyDeviceToDevice));
+        if (d_lutv_) cudaFree(d_lutv_);
+        d_lutv_ = nv;
+        d_lutv_cap_ = ncap;
+      }
+      CK(cudaMemcpy(d_lutv_ + base, vals.data(), (size_t)m * sizeof(GkLutVal), cudaMemcpyHostToDevice));
+      std::vector<uint32_t> pairs((size_t)m * 2);
+      for (uint32_t j = 0; j < m; ++j) {
+        pairs[2 * j] = hmiss[j].slot;
+        pairs[2 * j + 1] = base + j;
+        lut_filled_.emplace_back(hmiss[j].key, base + j);
+      }
+      CK(cudaMemcpy(d_fill, pairs.data(), pairs.size() * 4, cudaMemcpyHostToDevice));
+      gk_fill_kernel<<<(m + 255) / 256, 256, 0, stream_>>>(d_lut_vals_, d_fill, m);
+      ++launches_;
+      total_miss += m;
+      if ((lut_filled_.size() + (nm - m)) * 2 > (size_t)lut_.mask) {   // grow: filled entries re-inserted, pending claims dropped
+        CK(cudaStreamSynchronize(stream_));
+        uint32_t cap = (lut_.mask + 1) * 4;
+        while ((size_t)cap < lut_filled_.size() * 4) cap <<= 1;
+        lut_.init(cap);
+        for (auto& kv : lut_filled_) lut_.put(kv.first, kv.second);
+        upload_htab(lut_, &d_lut_keys_, &d_lut_vals_, &d_lut_cap_);
+      }
+      lut_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - L0).count();
+      if (round == 4095) throw BackendError{"device ingest: lookups did not converge"};
+    }
+    CK(cudaEventRecord(e3, stream_));
+    // ---- status of every object, tiling of the evaluation kernel
+    if (status) {
+      status->assign(n, 0);
+      if (n) CK(cudaMemcpyAsync(status->data(), in.status, (size_t)n * 4, cudaMemcpyDeviceToHost, stream_));
+    }
+    uint32_t tile = kTile;
+    if (const char* ft = getenv("GK_FORCE_TILE")) tile = std::min<uint32_t>(kTile, std::max(32, atoi(ft)) / 32 * 32);
+    const uint32_t ntiles = (n + tile - 1) / tile;
+    db->tile = tile;
+    db->ntiles = ntiles;
+    CK(cudaMalloc(&db->d_tile_lo, ((size_t)(ntiles + 1) * NS) * 4 + 64));
+    CK(cudaMemsetAsync(d_cap, 0, (size_t)NS * 4, stream_));
+    gk_tiles_kernel<<<(ntiles + 1 + 127) / 128, 128, 0, stream_>>>(in.counts, d_totals, n, NS, tile, ntiles, db->d_tile_lo, d_cap);
+    ++launches_;
+    std::vector<uint32_t> cap(NS, 0);
+    CK(cudaMemcpyAsync(cap.data(), d_cap, (size_t)NS * 4, cudaMemcpyDeviceToHost, stream_));
+    CK(cudaStreamSynchronize(stream_));
+    CK(cudaGetLastError());
+    finish_batch(db, c, cap);
+    if (st) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e0, e1);
+      st->h2d_ms = ms;   // copy + tokenise, overlapped chunk by chunk
+      st->tape_ms = ms;
+      cudaEventElapsedTime(&ms, e1, e3);
+      st->extract_ms = ms - lut_ms;
+      st->lut_ms = lut_ms;
+      st->h2d_bytes = B + ((size_t)n + 1) * 8 + tab_bytes + aimg.size();
+      st->lut_misses = total_miss;
+      st->alg_bytes = alg;
+      st->launches = launches_;
+      st->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - T0).count();
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaEventDestroy(e2);
+    cudaEventDestroy(e3);
+    guard.release();
+    return db;
+  }
+  cudaEvent_t chunk_event(uint32_t k) {
+    (void)k;
+    if (chunk_ev_next_ >= chunk_evs_.size()) {
+      cudaEvent_t e;
+      CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      chunk_evs_.push_back(e);
+    }
+    cudaEvent_t e = chunk_evs_[chunk_ev_next_];
+    chunk_ev_next_ = (chunk_ev_next_ + 1) % 64 == 0 ? 0 : chunk_ev_next_ + 1;
+    return e;
+  }
 
   void eval_into(void* b, const std::vector<uint32_t>& active, const DevOutPtrs& dst) override {
     auto* db = static_cast<DevBatch*>(b);
@@ -444,6 +871,23 @@ class CudaBackend : public Backend {
       *pp = nullptr;
     }
   }
+  std::mutex ingest_mu_;
+  Scratch scratch_, tabs_;
+  SidTable sid_;
+  unsigned long long* d_sid_keys_ = nullptr;
+  uint32_t* d_sid_vals_ = nullptr;
+  size_t d_sid_cap_ = 0;
+  HashTabHost lut_;                                               // geometry of the device table (the device copy is authoritative)
+  std::vector<std::pair<unsigned long long, uint32_t>> lut_filled_;   // every answered lookup (key, result index): re-inserted on growth
+  unsigned long long* d_lut_keys_ = nullptr;
+  uint32_t* d_lut_vals_ = nullptr;
+  size_t d_lut_cap_ = 0;
+  std::vector<GkLutVal> lutv_;
+  GkLutVal* d_lutv_ = nullptr;
+  size_t d_lutv_cap_ = 0;
+  cudaStream_t copy_stream_ = nullptr;
+  std::vector<cudaEvent_t> chunk_evs_;
+  size_t chunk_ev_next_ = 0;
   int device_;
   int sms_ = 148;
   size_t max_smem_ = 0, sm_smem_ = 0;

@@ -116,7 +116,7 @@ class HostEmuBackend : public Backend {
     GkIngestOut none{};
     xp.lut_tab = lut_.view();
     xp.lut_vals = lut_vals_.data();
-    for (uint32_t i = 0; i < n; ++i) gk_ingest_obj<false>(xp, in, none, i, cur.data());
+    for (uint32_t i = 0; i < n; ++i) gk_ingest_obj<false>(xp, in, none, i, GkCur{cur.data(), 1});
     std::vector<uint32_t> total(NK, 0);
     for (uint32_t k = 0; k < NK; ++k) {
       uint32_t acc = 0;
@@ -190,7 +190,7 @@ class HostEmuBackend : public Backend {
       nmiss[0] = 0;
       xp.lut_tab = lut_.view();
       xp.lut_vals = lut_vals_.data();
-      for (uint32_t i = 0; i < n; ++i) gk_ingest_obj<true>(xp, in, out, i, cur.data());
+      for (uint32_t i = 0; i < n; ++i) gk_ingest_obj<true>(xp, in, out, i, GkCur{cur.data(), 1});
       const uint32_t m = std::min<uint32_t>(nmiss[0], in.miss_cap);
       if (nmiss[0] == 0) break;
       total_miss += m;

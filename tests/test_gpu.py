@@ -229,3 +229,53 @@ def test_enforcement_point_mask_only_hides_scoped_constraints(big):
     vap = rb.eval("vap.k8s.io")   # scoped constraints list audit + "*": still active ("*")
     assert audit.totals == vap.totals
     rb.free()
+
+
+# ---- device ingest: raw JSON flattened by the ingest kernels (csrc/ingest_kernels.cuh), then the same evaluation kernel
+def test_blob_config2_device_ingest():
+    resp, want = P.case_blob_config2(LIB, 3000)
+    assert len(want) > 20000 and resp.stats["gpu_launches"] >= 4
+
+
+def test_blob_fuzz_device_ingest():
+    P.case_blob_fuzz(LIB)
+
+
+def test_blob_json_oddities():
+    P.case_blob_json_oddities(LIB)
+
+
+def test_blob_other_templates():
+    P.case_blob_other_templates(LIB)
+
+
+def test_blob_rego_fuzz():
+    accepted, n_results, rejected, n_device = P.case_rego_fuzz(LIB, n_templates=30, n_objects=100, seed=12, via_blob=True)
+    assert n_device >= accepted // 2, (n_device, accepted)
+
+
+def test_inexact_numbers_are_compared_not_skipped():
+    P.case_inexact_numbers(LIB)
+
+
+def test_blob_large_batch_properties():
+    """200 k Pods through the device ingest path: same bitmap as the host-flattened batch, totals == popcounts."""
+    tm, cons = W.config2()
+    drv = D.Driver()
+    for k, r in tm:
+        drv.add_template(k, r)
+    for c in cons:
+        drv.AddConstraint(c)
+    for ns in W.synth_namespaces():
+        drv.AddData("t", ["cluster", "v1", "Namespace", ns["metadata"]["name"]], ns)
+    n = 200_000
+    blob = W.synth_objects(0, n)
+    dev = drv.ReviewBlob(blob, k8s.AUDIT_EP, with_results=False)
+    import os
+    os.environ["GK_NO_DEVICE_INGEST_RUNTIME"] = "1"
+    try:
+        host = drv.ReviewBlob(blob, k8s.AUDIT_EP, with_results=False)
+    finally:
+        del os.environ["GK_NO_DEVICE_INGEST_RUNTIME"]
+    assert (dev.viol_bits == host.viol_bits).all() and (dev.err_bits == host.err_bits).all() and dev.totals == host.totals
+    assert sum(dev.totals) > n

@@ -1,0 +1,30 @@
+#!/usr/bin/env python
+"""Stage timing of the device ingest path on the config-2 workload:  python tools/ingest_probe.py [objects] [reps]"""
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from gatekeeper_b200 import driver as D
+from gatekeeper_b200 import workloads as W
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+tm, cons = W.config2()
+drv = D.Driver()
+for k, r in tm:
+    drv.add_template(k, r)
+for c in cons:
+    drv.AddConstraint(c)
+for ns in W.synth_namespaces():
+    drv.AddData("t", ["cluster", "v1", "Namespace", ns["metadata"]["name"]], ns)
+print(drv.Dump().splitlines()[1])
+blob = W.synth_objects(0, n)
+print("blob bytes", blob.total_bytes())
+for r in range(reps):
+    t0 = time.time()
+    resp = drv.ReviewBlob(blob, flags=D.F_NO_COPY_BACK, with_results=False)
+    dt = time.time() - t0
+    print(f"rep {r}: wall {dt*1e3:.1f} ms -> {n*50/dt/1e6:.1f} M evals/s; stats {resp.stats}")
+if os.environ.get("GK_TRACE_INGEST"):
+    pass
