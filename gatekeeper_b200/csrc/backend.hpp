@@ -53,6 +53,8 @@ class Backend {
   // Device ingest (ingest_core.h): raw JSON blob -> resident columnar batch without a host parse.  `status` receives one
   // GK_ING_* code per object (the caller renders the error text of the rare non-OK ones with the host parser).
   virtual void* ingest(const IngestReq& rq, IngestStats* st, std::vector<uint32_t>* status) = 0;
+  // page-lock (or release) a caller-owned host buffer so that the blob copy is a direct DMA at link speed
+  virtual void pin_host(const void* p, size_t bytes, bool pin) { (void)p, (void)bytes, (void)pin; }
 };
 
 Backend* make_backend(int device);   // defined by whichever backend the library links

@@ -161,8 +161,11 @@ void fill_result(gk_result* out, ResultPriv* rp, bool have_bits) {
   out->violations = rp->cvio.data();
   out->n_violations = rp->cvio.size();
   rp->obj_error_ptrs.clear();
-  for (auto& s : rp->obj_errors) rp->obj_error_ptrs.push_back(s.empty() ? nullptr : s.c_str());
-  out->object_errors = rp->obj_error_ptrs.data();
+  bool any_err = false;
+  for (auto& s : rp->obj_errors) any_err = any_err || !s.empty();
+  if (any_err)
+    for (auto& s : rp->obj_errors) rp->obj_error_ptrs.push_back(s.empty() ? nullptr : s.c_str());
+  out->object_errors = any_err ? rp->obj_error_ptrs.data() : nullptr;   // null: no object of the batch has a review-level error
   out->kernel_ms = rp->ev.kernel_ms;
   out->gpu_launches = rp->ev.launches;
   out->priv = rp;
@@ -315,9 +318,9 @@ void upload_blob(gk_engine* e, const std::shared_ptr<const Compiled>& c, const c
   auto slim = std::make_shared<HostBatch>();
   slim->n = (uint32_t)n;
   slim->alg_bytes = ist.alg_bytes;
-  slim->obj_errors.assign(n, std::string());
   for (size_t i = 0; i < n; ++i)
     if (status[i] != GK_ING_OK) {
+      if (slim->obj_errors.empty()) slim->obj_errors.assign(n, std::string());   // (left empty when every object is fine)
       // the rare rejected object: the host parser words the review-level error (bad JSON, not an object, kind missing)
       std::string err;
       VP doc = e->eng->review_doc(b->obj_in(i), nullptr, nullptr, nullptr, &err);
@@ -630,6 +633,11 @@ char* gk_validation_messages(gk_engine_t* e, const gk_result* r, uint32_t object
 }
 
 int gk_host_cpus(void) { return effective_cpus(); }
+
+int gk_pin_host(gk_engine_t* e, const void* p, size_t bytes, int pin, char** err) {
+  if (!e || !p) return GK_ERR_INVALID;
+  return guard(err, [&]() { e->be->pin_host(p, bytes, pin != 0); });
+}
 
 void gk_free_result(gk_result* r) {
   if (!r || !r->priv) return;

@@ -561,7 +561,13 @@ typedef struct {
   uint32_t keys_off, nkeys;   // Path: xkeys[keys_off ..]: (is_index, byte_off | index, len) triples
   uint32_t args_off, nargs;   // Lut: xargs[args_off ..]: closure indices of the leaf arguments
   unsigned long long seed;    // Lut: hash domain
+  // Lut closures made of slicing string builtins only (split / trim / index / last / count over ONE leaf string) also carry a
+  // native program (GK_SX_* postfix ops in xkeys): rows whose leaf has no escape sequence never touch the lookup table --
+  // image names, paths and the like are as many distinct values as there are rows.
+  uint32_t sx_off, sx_n;
 } GkXClosure;
+enum { GK_SX_LEAF = 1 /* a = argument index */, GK_SX_SPLIT = 2 /* a,b = delimiter (byte_off, len) */, GK_SX_TRIM = 3 /* a,b = cutset */,
+       GK_SX_INDEX = 4 /* a = index */, GK_SX_LAST = 5, GK_SX_COUNT = 6, GK_SX_LOWER_UNUSED = 7 };
 typedef struct {
   uint32_t closure;
   uint32_t scope;
@@ -994,6 +1000,126 @@ GK_HD uint32_t gk_x_sid_exotic(const GkXCtx& c, const GkXVal& v) {
   return ix == GK_HT_PENDING ? (uint32_t)GK_SID_OTHER : c.xp->lut_vals[ix].sid;
 }
 
+// ---------------------------------------------------------------------------------------------- native string closures
+struct GkSV {
+  uint32_t kind;          // 0 undefined, 1 string slice, 2 list = split(slice, delim), 3 number
+  const uint8_t* p;
+  uint32_t len;
+  const uint8_t* d;
+  uint32_t dlen;
+  long long num;
+};
+GK_HD bool gk_sv_in_cutset(const uint8_t* cs, uint32_t n, uint32_t b) {
+  for (uint32_t i = 0; i < n; ++i)
+    if (cs[i] == b) return true;
+  return false;
+}
+GK_HD uint32_t gk_sv_find(const uint8_t* p, uint32_t len, const uint8_t* d, uint32_t dlen, uint32_t from) {   // next occurrence or len
+  for (uint32_t i = from; i + dlen <= len; ++i)
+    if (p[i] == d[0] && gk_bytes_eq(p + i, d, dlen)) return i;
+  return len;
+}
+// runs the program; false = not computable natively for this row (escaped leaf, non-ASCII cutset ...): use the lookup table
+GK_HD bool gk_sx_run(const GkXCtx& c, const GkXClosure& cl, GkSV* out) {
+  const GkXProg& xp = *c.xp;
+  GkSV st[4];
+  int sp = 0;
+  for (uint32_t i = 0; i < cl.sx_n; ++i) {
+    const uint32_t* op = xp.xkeys + cl.sx_off + 3u * i;
+    switch (op[0]) {
+      case GK_SX_LEAF: {
+        if (sp >= 4) return false;
+        const GkXVal v = gk_x_eval(c, xp.xargs[cl.args_off + op[1]]);
+        GkSV& x = st[sp++];
+        x.kind = 0;
+        x.p = x.d = nullptr;
+        x.len = x.dlen = 0;
+        x.num = 0;
+        if (v.vt == GK_VT_UNDEF) break;
+        if (v.vt != GK_VT_STR) return false;              // (a non-string operand: the host words the type error / undefined)
+        if (v.node != GK_NONE) {
+          const gk_u64 e = c.doc.tape[v.node];
+          if (gk_te_esc(e)) return false;
+          x.p = c.doc.js + gk_te_off(e);
+          x.len = gk_te_len(e);
+        } else {
+          x.p = v.sp;
+          x.len = v.slen;
+        }
+        for (uint32_t k = 0; k < x.len; ++k)
+          if (x.p[k] >= 0x80u) return false;              // non-ASCII: rune semantics (trim cutsets, split("")) stay with the host
+        x.kind = 1;
+        break;
+      }
+      case GK_SX_SPLIT: {
+        GkSV& x = st[sp - 1];
+        if (x.kind == 0) break;
+        if (x.kind != 1 || op[2] == 0) return false;
+        x.kind = 2;
+        x.d = xp.xbytes + op[1];
+        x.dlen = op[2];
+        break;
+      }
+      case GK_SX_TRIM: {
+        GkSV& x = st[sp - 1];
+        if (x.kind == 0) break;
+        if (x.kind != 1) return false;
+        const uint8_t* cs = xp.xbytes + op[1];
+        while (x.len && gk_sv_in_cutset(cs, op[2], x.p[0])) ++x.p, --x.len;
+        while (x.len && gk_sv_in_cutset(cs, op[2], x.p[x.len - 1])) --x.len;
+        break;
+      }
+      case GK_SX_INDEX:
+      case GK_SX_LAST: {
+        GkSV& x = st[sp - 1];
+        if (x.kind == 0) break;
+        if (x.kind != 2) return false;
+        uint32_t a = 0, seg = 0;
+        bool found = false;
+        for (;;) {
+          const uint32_t b = gk_sv_find(x.p, x.len, x.d, x.dlen, a);
+          const bool last = b == x.len;
+          if (op[0] == GK_SX_LAST ? last : seg == op[1]) {
+            x.p += a;
+            x.len = b - a;
+            found = true;
+            break;
+          }
+          if (last) break;
+          a = b + x.dlen;
+          ++seg;
+        }
+        x.kind = found ? 1u : 0u;
+        break;
+      }
+      case GK_SX_COUNT: {
+        GkSV& x = st[sp - 1];
+        if (x.kind == 0) break;
+        if (x.kind == 1) {
+          x.num = x.len;   // ASCII: bytes == code points
+        } else if (x.kind == 2) {
+          long long nseg = 1;
+          for (uint32_t a = 0;;) {
+            const uint32_t b = gk_sv_find(x.p, x.len, x.d, x.dlen, a);
+            if (b == x.len) break;
+            ++nseg;
+            a = b + x.dlen;
+          }
+          x.num = nseg;
+        } else {
+          return false;
+        }
+        x.kind = 3;
+        break;
+      }
+      default: return false;
+    }
+  }
+  if (sp != 1) return false;
+  *out = st[0];
+  return true;
+}
+
 // ---------------------------------------------------------------------------------------------- one object
 GK_HD uint32_t gk_decoded_len(const GkXCtx& c, const GkXVal& v) {
   if (v.node == GK_NONE) return v.slen;
@@ -1057,7 +1183,20 @@ GK_HD void gk_emit_col(const GkXProg& xp, const GkIngestIn& in, const GkIngestOu
     return;
   }
   GkXVal v = gk_xundef();
-  if (cl.kind == GK_X_LUT) {
+  bool native = false;
+  if (cl.kind == GK_X_LUT && cl.sx_n) {
+    GkSV sv;
+    if (gk_sx_run(c, cl, &sv)) {
+      native = true;
+      if (sv.kind == 1) v = gk_xstr(sv.p, sv.len);
+      else if (sv.kind == 2) v = gk_xsyn(GK_VT_ARR);
+      else if (sv.kind == 3) {
+        v = gk_xsyn(GK_VT_NUM);
+        v.inum = sv.num;
+      }
+    }
+  }
+  if (cl.kind == GK_X_LUT && !native) {
     GkMissArg ma[GK_LUT_MAX_ARGS];
     gk_u64 h = cl.seed;
     for (uint32_t a = 0; a < cl.nargs; ++a) h = gk_x_arg(c, gk_x_eval(c, xp.xargs[cl.args_off + a]), gk_hash_byte(h, 0xEEu), &ma[a]);
@@ -1075,7 +1214,9 @@ GK_HD void gk_emit_col(const GkXProg& xp, const GkIngestIn& in, const GkIngestOu
       for (int w = 0; w < GK_HEAD_WORDS; ++w) out.head[ci][(size_t)row * GK_HEAD_WORDS + w] = lv.head[w];
     return;
   }
-  if (cl.kind == GK_X_COUNT) {
+  if (native) {
+    // (v holds the result)
+  } else if (cl.kind == GK_X_COUNT) {
     const GkXVal b = gk_x_eval(c, (uint32_t)cl.base);
     long long n;
     if (gk_x_count(c, b, &n)) {
@@ -1112,7 +1253,11 @@ GK_HD void gk_emit_col(const GkXProg& xp, const GkIngestIn& in, const GkIngestOu
 
 // Count pass (WRITE = false): fills in.counts[k * n + i].  Write pass: in.counts holds the exclusive prefix sums.
 template <bool WRITE>
-GK_HD void gk_ingest_obj(const GkXProg& xp, const GkIngestIn& in, const GkIngestOut& out, uint32_t i, const GkCur& cur /* nscopes + nbytecols + GK_CNT_EXTRA working counters */) {
+// `lane` / `nlanes`: the GPU runs one WARP per object -- every lane walks the (warp-uniform) scope tree, which costs nothing
+// extra, and the columns of each row are dealt to the lanes; all lanes read the same tape, so its lines stay in L1.  Arrays
+// that are not per column (header, CSR offsets, row counters) are written by lane 0.  The test backend runs it with one lane.
+// `cur`: nscopes + nbytecols + GK_CNT_EXTRA working counters, private to the lane.
+GK_HD void gk_ingest_obj(const GkXProg& xp, const GkIngestIn& in, const GkIngestOut& out, uint32_t i, const GkCur& cur, uint32_t lane, uint32_t nlanes) {
   const uint32_t n = in.n, NS = xp.nscopes, NK = NS + xp.nbytecols + GK_CNT_EXTRA;
   const uint32_t K_NAME = NS + xp.nbytecols, K_GEN = K_NAME + 1, K_LBL = K_NAME + 2, K_NSN = K_NAME + 3;
   for (uint32_t k = 0; k < NK; ++k) cur[k] = WRITE ? in.counts[(size_t)k * n + i] : 0u;
@@ -1210,7 +1355,7 @@ GK_HD void gk_ingest_obj(const GkXProg& xp, const GkIngestIn& in, const GkIngest
   {
     const GkXVal namev = (!skip && c.name_node != GK_NONE) ? gk_xnode(c.doc.tape, c.name_node) : gk_xundef();
     const GkXVal genv = (!skip && gen_node != GK_NONE) ? gk_xnode(c.doc.tape, gen_node) : gk_xundef();
-    if (WRITE) {
+    if (WRITE && lane == 0) {
       out.flags[i] = fl;
       out.kind_sid[i] = kind_sid;
       out.group_sid[i] = group_sid;
@@ -1230,7 +1375,7 @@ GK_HD void gk_ingest_obj(const GkXProg& xp, const GkIngestIn& in, const GkIngest
       const uint32_t end = gk_te_end(c.doc.tape[labels]);
       for (uint32_t k = labels + 1u; k < end; k = gk_tape_skip(c.doc.tape, k + 1u)) {
         if (gk_key_shadowed(c.doc, k, end)) continue;
-        if (WRITE) {
+        if (WRITE && lane == 0) {
           const GkXVal val = gk_xnode(c.doc.tape, k + 1u);
           out.lbl_kv[2u * (size_t)cur[K_LBL]] = gk_x_sid(c, gk_xnode(c.doc.tape, k));
           out.lbl_kv[2u * (size_t)cur[K_LBL] + 1u] = val.vt == GK_VT_STR ? gk_x_sid(c, val) : GK_SID_OTHER;
@@ -1238,7 +1383,7 @@ GK_HD void gk_ingest_obj(const GkXProg& xp, const GkIngestIn& in, const GkIngest
         ++cur[K_LBL];
       }
     }
-    if (WRITE && i + 1u == n) {
+    if (WRITE && lane == 0 && i + 1u == n) {
       out.name_off[n] = cur[K_NAME];
       out.gen_off[n] = cur[K_GEN];
       out.lbl_off[n] = cur[K_LBL];
@@ -1253,7 +1398,7 @@ GK_HD void gk_ingest_obj(const GkXProg& xp, const GkIngestIn& in, const GkIngest
   fr[0].pos = fr[0].end = fr[0].arr_ix = fr[0].is_obj = 0;
   {
     const GkXScope& s0 = xp.scopes[0];
-    for (uint32_t k = 0; k < s0.ncols; ++k) {
+    for (uint32_t k = lane; k < s0.ncols; k += nlanes) {
       const uint32_t ci = xp.col_order[s0.first_col + k];
       if (skip) {
         if (WRITE) {   // placeholder row: every encoding "undefined"
@@ -1277,7 +1422,7 @@ GK_HD void gk_ingest_obj(const GkXProg& xp, const GkIngestIn& in, const GkIngest
       // open the next child scope under the current row of f.scope
       const uint32_t t = f.next_child;
       f.next_child = xp.scopes[t].next_sibling;
-      if (WRITE) out.scope_off[t][f.row] = cur[t];
+      if (WRITE && lane == 0) out.scope_off[t][f.row] = cur[t];
       if (skip || top >= GK_MAX_LOOP_DEPTH) continue;
       c.depth = top;
       const GkXVal coll = gk_x_eval(c, xp.scopes[t].gen);
@@ -1324,16 +1469,33 @@ GK_HD void gk_ingest_obj(const GkXProg& xp, const GkIngestIn& in, const GkIngest
     g.row = cur[g.scope]++;
     c.depth = top;
     const GkXScope& sc = xp.scopes[g.scope];
-    for (uint32_t k = 0; k < sc.ncols; ++k) gk_emit_col<WRITE>(xp, in, out, c, xp.col_order[sc.first_col + k], g.row, bcur);
+    for (uint32_t k = lane; k < sc.ncols; k += nlanes) gk_emit_col<WRITE>(xp, in, out, c, xp.col_order[sc.first_col + k], g.row, bcur);
     g.next_child = sc.first_child;   // (none for a leaf scope: the next turn advances this frame again)
   }
   if (!WRITE) {
-    for (uint32_t k = 0; k < NK; ++k) in.counts[(size_t)k * n + i] = cur[k];
+    // row / header counters by lane 0; a byte column's counter by the lane that owns the column
+    if (lane == 0) {
+      for (uint32_t k = 0; k < NS; ++k) in.counts[(size_t)k * n + i] = cur[k];
+      for (uint32_t k = K_NAME; k < NK; ++k) in.counts[(size_t)k * n + i] = cur[k];
+    }
+    for (uint32_t sc2 = 0; sc2 < NS; ++sc2) {
+      const GkXScope& xs = xp.scopes[sc2];
+      for (uint32_t k = lane; k < xs.ncols; k += nlanes) {
+        const GkXCol& col = xp.cols[xp.col_order[xs.first_col + k]];
+        if (col.enc & GK_ENC_BYTES) in.counts[(size_t)(NS + col.bytes_slot) * n + i] = bcur[col.bytes_slot];
+      }
+    }
   } else if (i + 1u == n) {
     // closing entries of the CSR arrays
-    for (uint32_t s = 1; s < NS; ++s) out.scope_off[s][xp.scopes[s].parent ? cur[xp.scopes[s].parent] : n] = cur[s];
-    for (uint32_t k = 0; k < xp.ncols; ++k)
-      if (xp.cols[k].enc & GK_ENC_BYTES) out.boff[k][xp.cols[k].scope ? cur[xp.cols[k].scope] : n] = bcur[xp.cols[k].bytes_slot];
+    if (lane == 0)
+      for (uint32_t s = 1; s < NS; ++s) out.scope_off[s][xp.scopes[s].parent ? cur[xp.scopes[s].parent] : n] = cur[s];
+    for (uint32_t sc2 = 0; sc2 < NS; ++sc2) {
+      const GkXScope& xs = xp.scopes[sc2];
+      for (uint32_t k = lane; k < xs.ncols; k += nlanes) {
+        const uint32_t ci = xp.col_order[xs.first_col + k];
+        if (xp.cols[ci].enc & GK_ENC_BYTES) out.boff[ci][sc2 ? cur[sc2] : n] = bcur[xp.cols[ci].bytes_slot];
+      }
+    }
   }
 }
 

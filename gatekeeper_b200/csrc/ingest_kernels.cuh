@@ -21,18 +21,23 @@ __global__ void __launch_bounds__(kIngestThreads) gk_tape_kernel(const GkIngestI
   if (i < first + count) gk_tape_obj(in, i);
 }
 
+// count / write: one WARP per object (see gk_ingest_obj): the lanes share the object's tape through L1 and split its columns
+constexpr uint32_t kMaxCounters = GK_MAX_SCOPES + 64 + GK_CNT_EXTRA;
+
 __global__ void __launch_bounds__(kIngestThreads) gk_count_kernel(const GkXProg xp, const GkIngestIn in) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
   if (i >= in.n) return;
   GkIngestOut none;
   memset(&none, 0, sizeof none);
-  gk_ingest_obj<false>(xp, in, none, i, GkCur{in.counts + i, in.n});
+  uint32_t cur[kMaxCounters];
+  gk_ingest_obj<false>(xp, in, none, i, GkCur{cur, 1}, lane, 32u);
 }
 
-__global__ void __launch_bounds__(kIngestThreads) gk_write_kernel(const GkXProg xp, const GkIngestIn in, const GkIngestOut out, uint32_t* work) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(kIngestThreads) gk_write_kernel(const GkXProg xp, const GkIngestIn in, const GkIngestOut out) {
+  const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
   if (i >= in.n) return;
-  gk_ingest_obj<true>(xp, in, out, i, GkCur{work + i, in.n});
+  uint32_t cur[kMaxCounters];
+  gk_ingest_obj<true>(xp, in, out, i, GkCur{cur, 1}, lane, 32u);
 }
 
 // exclusive scan of counts[k * n .. (k + 1) * n) for k = blockIdx.x; totals[k] = the sum

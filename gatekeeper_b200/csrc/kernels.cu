@@ -59,6 +59,14 @@ class CudaBackend : public Backend {
     sm_smem_ = (size_t)prop.sharedMemPerMultiprocessor;
     CK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+    {
+      // per-batch device memory comes from the stream-ordered pool and goes back to it: with the release threshold lifted a
+      // resident-batch-sized arena is reused by the next batch instead of being mapped / unmapped by the driver every time
+      cudaMemPool_t pool;
+      CK(cudaDeviceGetDefaultMemPool(&pool, device_));
+      unsigned long long keep = ~0ull;
+      CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     CK(cudaEventCreate(&ev0_));
     CK(cudaEventCreate(&ev1_));
     cudaFuncAttributes fa;
@@ -173,8 +181,8 @@ class CudaBackend : public Backend {
     db->ntiles = ntiles;
     db->tile = tile;
     db->prog_version = c.version;
-    CK(cudaMalloc(&db->arena, db->bytes));
-    CK(cudaMalloc(&db->d_tile_lo, tile_lo.size() * 4 + 64));
+    dmalloc(&db->arena, db->bytes);
+    dmalloc(&db->d_tile_lo, tile_lo.size() * 4 + 64);
     finish_batch(db, c, cap);
     const size_t tables_bytes = c.ops.size() * sizeof(GkOp) + c.pool.size() * 4 + c.outs.size() * sizeof(GkOutEnt);
     cudaEvent_t a, b;
@@ -257,31 +265,38 @@ class CudaBackend : public Backend {
       }
     }
     auto r64 = [](size_t b) { return (b + 63) / 64 * 64 + 64; };
-    CK(cudaMalloc(&db->d_ops, r64(ops_r.size() * sizeof(GkOp))));
-    CK(cudaMalloc(&db->d_pool, r64(pool_r.size() * 4)));
-    CK(cudaMalloc(&db->d_outs, r64(outs_r.size() * sizeof(GkOutEnt))));
-    CK(cudaMemset(db->d_ops, 0, r64(ops_r.size() * sizeof(GkOp))));
-    CK(cudaMemset(db->d_pool, 0, r64(pool_r.size() * 4)));
-    CK(cudaMemset(db->d_outs, 0, r64(outs_r.size() * sizeof(GkOutEnt))));
-    if (!ops_r.empty()) CK(cudaMemcpy(db->d_ops, ops_r.data(), ops_r.size() * sizeof(GkOp), cudaMemcpyHostToDevice));
-    if (!pool_r.empty()) CK(cudaMemcpy(db->d_pool, pool_r.data(), pool_r.size() * 4, cudaMemcpyHostToDevice));
-    if (!outs_r.empty()) CK(cudaMemcpy(db->d_outs, outs_r.data(), outs_r.size() * sizeof(GkOutEnt), cudaMemcpyHostToDevice));
+    dmalloc(&db->d_ops, r64(ops_r.size() * sizeof(GkOp)));
+    dmalloc(&db->d_pool, r64(pool_r.size() * 4));
+    dmalloc(&db->d_outs, r64(outs_r.size() * sizeof(GkOutEnt)));
+    CK(cudaMemsetAsync(db->d_ops, 0, r64(ops_r.size() * sizeof(GkOp)), stream_));
+    CK(cudaMemsetAsync(db->d_pool, 0, r64(pool_r.size() * 4), stream_));
+    CK(cudaMemsetAsync(db->d_outs, 0, r64(outs_r.size() * sizeof(GkOutEnt)), stream_));
+    if (!ops_r.empty()) CK(cudaMemcpyAsync(db->d_ops, ops_r.data(), ops_r.size() * sizeof(GkOp), cudaMemcpyHostToDevice, stream_));
+    if (!pool_r.empty()) CK(cudaMemcpyAsync(db->d_pool, pool_r.data(), pool_r.size() * 4, cudaMemcpyHostToDevice, stream_));
+    if (!outs_r.empty()) CK(cudaMemcpyAsync(db->d_outs, outs_r.data(), outs_r.size() * sizeof(GkOutEnt), cudaMemcpyHostToDevice, stream_));
+    CK(cudaStreamSynchronize(stream_));   // (the host vectors above are temporaries)
     db->words = std::max<uint32_t>(1, (uint32_t)((c.cons_match.size() + 31) / 32));
-    CK(cudaMalloc(&db->viol, (size_t)std::max(db->n, 1u) * db->words * 4));
-    CK(cudaMalloc(&db->err, (size_t)std::max(db->n, 1u) * db->words * 4));
+    dmalloc(&db->viol, (size_t)std::max(db->n, 1u) * db->words * 4);
+    dmalloc(&db->err, (size_t)std::max(db->n, 1u) * db->words * 4);
+    CK(cudaStreamSynchronize(stream_));
   }
 
+  template <class T>
+  void dmalloc(T** p, size_t bytes) { CK(cudaMallocAsync(reinterpret_cast<void**>(p), std::max<size_t>(bytes, 256), stream_)); }
+  void dfree(void* p) {
+    if (p) cudaFreeAsync(p, stream_);
+  }
   void release(void* b) override {
     auto* db = static_cast<DevBatch*>(b);
     if (!db) return;
     cudaSetDevice(device_);
-    cudaFree(db->arena);
-    cudaFree(db->viol);
-    cudaFree(db->err);
-    cudaFree(db->d_tile_lo);
-    cudaFree(db->d_ops);
-    cudaFree(db->d_pool);
-    cudaFree(db->d_outs);
+    dfree(db->arena);
+    dfree(db->viol);
+    dfree(db->err);
+    dfree(db->d_tile_lo);
+    dfree(db->d_ops);
+    dfree(db->d_pool);
+    dfree(db->d_outs);
     delete db;
   }
 
@@ -554,7 +569,7 @@ class CudaBackend : public Backend {
     Carver sc;
     const size_t o_blob = sc.take((size_t)B + 16), o_ooff = sc.take(((size_t)n + 1) * 8), o_tape = sc.take(((size_t)(B / 2) + 4ull * n + 64) * 8),
                  o_ntape = sc.take((size_t)n * 4), o_status = sc.take((size_t)n * 4), o_counts = sc.take((size_t)NK * n * 4),
-                 o_work = sc.take((size_t)NK * n * 4), o_totals = sc.take((size_t)(NK + NS + 4) * 4), o_miss = sc.take((size_t)miss_cap * sizeof(GkMiss)),
+                 o_totals = sc.take((size_t)(NK + NS + 4) * 4), o_miss = sc.take((size_t)miss_cap * sizeof(GkMiss)),
                  o_fill = sc.take((size_t)miss_cap * 8);
     uint8_t* d_s = scratch_.need(gk_align(sc.off));
     GkIngestIn in;
@@ -572,7 +587,6 @@ class CudaBackend : public Backend {
     uint32_t* d_cap = d_totals + NK;
     in.nmiss = d_cap + NS;
     in.miss_cap = miss_cap;
-    uint32_t* d_work = reinterpret_cast<uint32_t*>(d_s + o_work);
     uint32_t* d_fill = reinterpret_cast<uint32_t*>(d_s + o_fill);
     cudaEvent_t e0, e1, e2, e3;
     CK(cudaEventCreate(&e0));
@@ -582,7 +596,8 @@ class CudaBackend : public Backend {
     // ---- H2D of the raw JSON in chunks on the copy stream; the tokeniser of a chunk starts as soon as its bytes have landed
     CK(cudaMemcpyAsync(d_s + o_ooff, rq.ooff, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, stream_));
     CK(cudaEventRecord(e0, stream_));
-    const uint32_t blocks = (n + kIngestThreads - 1) / kIngestThreads;
+    const uint32_t wblocks = (uint32_t)(((uint64_t)n * 32u + kIngestThreads - 1) / kIngestThreads);   // a warp per object
+    if (NK > kMaxCounters) throw BackendError{"device ingest: too many byte-encoded columns"};
     {
       const size_t kChunk = 32u << 20;
       uint32_t first = 0;
@@ -604,7 +619,7 @@ class CudaBackend : public Backend {
     }
     CK(cudaEventRecord(e1, stream_));
     if (n) {
-      gk_count_kernel<<<blocks, kIngestThreads, 0, stream_>>>(xp, in);
+      gk_count_kernel<<<wblocks, kIngestThreads, 0, stream_>>>(xp, in);
       gk_scan_kernel<<<NK, 1024, 0, stream_>>>(in.counts, n, d_totals);
       launches_ += 2;
     } else {
@@ -658,7 +673,7 @@ class CudaBackend : public Backend {
     db->bytes = gk_align(ac.off);
     db->n = n;
     db->prog_version = c.version;
-    CK(cudaMalloc(&db->arena, db->bytes));
+    dmalloc(&db->arena, db->bytes);
     uint8_t* A = db->arena;
     std::vector<uint8_t> aimg(db->bytes - tables_lo, 0);   // host image of the table tail of the arena
     auto tail = [&](size_t off) { return aimg.data() + (off - tables_lo); };
@@ -742,9 +757,8 @@ class CudaBackend : public Backend {
       xp.lut_tab.vals = d_lut_vals_;
       xp.lut_tab.mask = lut_.mask;
       xp.lut_vals = d_lutv_;
-      CK(cudaMemcpyAsync(d_work, in.counts, (size_t)NK * n * 4, cudaMemcpyDeviceToDevice, stream_));
       CK(cudaMemsetAsync(in.nmiss, 0, 4, stream_));
-      gk_write_kernel<<<blocks, kIngestThreads, 0, stream_>>>(xp, in, out, d_work);
+      gk_write_kernel<<<wblocks, kIngestThreads, 0, stream_>>>(xp, in, out);
       ++launches_;
       uint32_t nm = 0;
       CK(cudaMemcpyAsync(&nm, in.nmiss, 4, cudaMemcpyDeviceToHost, stream_));
@@ -802,7 +816,7 @@ class CudaBackend : public Backend {
     const uint32_t ntiles = (n + tile - 1) / tile;
     db->tile = tile;
     db->ntiles = ntiles;
-    CK(cudaMalloc(&db->d_tile_lo, ((size_t)(ntiles + 1) * NS) * 4 + 64));
+    dmalloc(&db->d_tile_lo, ((size_t)(ntiles + 1) * NS) * 4 + 64);
     CK(cudaMemsetAsync(d_cap, 0, (size_t)NS * 4, stream_));
     gk_tiles_kernel<<<(ntiles + 1 + 127) / 128, 128, 0, stream_>>>(in.counts, d_totals, n, NS, tile, ntiles, db->d_tile_lo, d_cap);
     ++launches_;
@@ -825,12 +839,26 @@ class CudaBackend : public Backend {
       st->launches = launches_;
       st->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - T0).count();
     }
+    if (getenv("GK_TRACE_INGEST")) {
+      float a = 0, b = 0, d = 0;
+      cudaEventElapsedTime(&a, e0, e1);
+      cudaEventElapsedTime(&b, e1, e2);
+      cudaEventElapsedTime(&d, e2, e3);
+      fprintf(stderr, "[ingest] n=%u blob %.1f MB: copy+tokenise %.2f ms, count+scan(+alloc) %.2f ms, write(+lookups: %llu missed, %.1f ms host) %.2f ms, total wall %.2f ms, arena %.1f MB\n",
+              n, B / 1e6, a, b, (unsigned long long)total_miss, lut_ms, d,
+              std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - T0).count(), db->bytes / 1e6);
+    }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     cudaEventDestroy(e2);
     cudaEventDestroy(e3);
     guard.release();
     return db;
+  }
+  void pin_host(const void* p, size_t bytes, bool pin) override {
+    CK(cudaSetDevice(device_));
+    if (pin) CK(cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterDefault));
+    else CK(cudaHostUnregister(const_cast<void*>(p)));
   }
   cudaEvent_t chunk_event(uint32_t k) {
     (void)k;

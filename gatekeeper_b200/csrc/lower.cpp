@@ -196,6 +196,8 @@ static bool leafy_arg(const XInfo::Arg& a) {
   return !a.keys.empty();
 }
 
+bool xinfo_leaf_args(const CP& base, const std::vector<VP>& keys, std::vector<XInfo::Arg>& out) { return leaf_args_of(base, keys, out); }
+
 XInfo closure_xinfo(const Closure& c) {
   XInfo x;
   if (c.leaf == Closure::Elem) {

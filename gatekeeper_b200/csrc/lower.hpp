@@ -63,6 +63,8 @@ struct XInfo {
   std::vector<Arg> args;
 };
 XInfo closure_xinfo(const Closure& c);
+// the leaf values behind <base>[keys...] (false: something on the way needs the host)
+bool xinfo_leaf_args(const CP& base, const std::vector<VP>& keys, std::vector<XInfo::Arg>& out);
 
 struct ScopeDef {
   int parent = 0;

@@ -2,6 +2,7 @@
 // ingest kernels interpret (ingest_core.h GkXProg).
 #include "xprog.hpp"
 
+#include <cstdlib>
 #include <map>
 
 #include "engine.hpp"
@@ -85,6 +86,101 @@ struct Builder {
     return (uint32_t)x.cl.size() - 1;
   }
 
+  // ---- native programs for closures built from slicing string builtins over one leaf (ingest_core.h GK_SX_*)
+  struct SxOp {
+    uint32_t op, a, b;
+  };
+  static const CapArg* cap_of(const Closure& c, int vid) {
+    for (auto& cp : c.caps)
+      if (cp.first == vid) return &cp.second;
+    return nullptr;
+  }
+  static bool ascii(const std::string& s2) {
+    for (unsigned char ch : s2)
+      if (ch >= 0x80) return false;
+    return true;
+  }
+  static int arg_index(const std::vector<XInfo::Arg>& args, const XInfo::Arg& a) {
+    for (size_t i = 0; i < args.size(); ++i) {
+      if ((bool)args[i].leaf != (bool)a.leaf || (a.leaf && args[i].leaf->key != a.leaf->key) || args[i].keys.size() != a.keys.size()) continue;
+      bool same = true;
+      for (size_t k = 0; k < a.keys.size() && same; ++k) same = v_eq(args[i].keys[k], a.keys[k]);
+      if (same) return (int)i;
+    }
+    return -1;
+  }
+  // value of closure `cl` (then indexed by literal `keys`) as ops
+  bool sx_closure(const CP& cl, const std::vector<VP>& keys, const std::vector<XInfo::Arg>& args, std::vector<SxOp>& prog, int depth) {
+    if (depth > 6) return false;
+    const XInfo xi = closure_xinfo(*cl);
+    if (xi.k == XK::Path || xi.k == XK::Elem || xi.k == XK::Key) {
+      std::vector<XInfo::Arg> one;
+      if (!xinfo_leaf_args(cl, keys, one) || one.size() != 1) return false;
+      const int k = arg_index(args, one[0]);
+      if (k < 0) return false;
+      prog.push_back({GK_SX_LEAF, (uint32_t)k, 0});
+      return true;
+    }
+    if (xi.k != XK::Lut || !cl->term) return false;
+    if (!sx_term(*cl, cl->term.get(), args, prog, depth + 1)) return false;
+    for (auto& k : keys) {
+      int64_t v;
+      if (k->t != VT::Num || !num_fits_i64(k->n, &v) || v < 0 || v > 0xffff) return false;
+      prog.push_back({GK_SX_INDEX, (uint32_t)v, 0});
+    }
+    return true;
+  }
+  static bool is_last_index(const Term& a, int head_vid) {   // minus(count(<head>), 1)
+    if (a.k != TK::Call || a.name != "minus" || a.args.size() != 2) return false;
+    const Term& c = *a.args[0];
+    const Term& one = *a.args[1];
+    int64_t v;
+    if (one.k != TK::Scalar || one.val->t != VT::Num || !num_fits_i64(one.val->n, &v) || v != 1) return false;
+    return c.k == TK::Call && c.name == "count" && c.args.size() == 1 && c.args[0]->k == TK::Var && c.args[0]->vid == head_vid;
+  }
+  bool sx_term(const Closure& c, const Term* t, const std::vector<XInfo::Arg>& args, std::vector<SxOp>& prog, int depth) {
+    if (!t || depth > 6) return false;
+    const Module& m = *c.mod;
+    switch (t->k) {
+      case TK::Var: {
+        const CapArg* cap = cap_of(c, t->vid);
+        if (!cap || cap->k != CapArg::Col) return false;
+        return sx_closure(cap->col, {}, args, prog, depth + 1);
+      }
+      case TK::Ref: {
+        if (t->head->k != TK::Var) return false;
+        const CapArg* cap = cap_of(c, t->head->vid);
+        if (!cap || cap->k != CapArg::Col) return false;
+        std::vector<VP> keys;
+        size_t i = 0;
+        for (; i < t->args.size() && t->args[i]->k == TK::Scalar; ++i) keys.push_back(t->args[i]->val);
+        if (!sx_closure(cap->col, keys, args, prog, depth + 1)) return false;
+        for (; i < t->args.size(); ++i) {
+          if (is_last_index(*t->args[i], t->head->vid) && keys.empty() && i == 0) prog.push_back({GK_SX_LAST, 0, 0});
+          else return false;
+        }
+        return true;
+      }
+      case TK::Call: {
+        if (m.is_rule(t->name)) return false;
+        if ((t->name == "split" || t->name == "trim") && t->args.size() == 2 && t->args[1]->k == TK::Scalar && t->args[1]->val->t == VT::Str) {
+          const std::string& lit = t->args[1]->val->s;
+          if (!ascii(lit) || (t->name == "split" && lit.empty())) return false;
+          if (!sx_term(c, t->args[0].get(), args, prog, depth + 1)) return false;
+          prog.push_back({t->name == "split" ? (uint32_t)GK_SX_SPLIT : (uint32_t)GK_SX_TRIM, add_bytes(lit), (uint32_t)lit.size()});
+          return true;
+        }
+        if (t->name == "count" && t->args.size() == 1) {
+          if (!sx_term(c, t->args[0].get(), args, prog, depth + 1)) return false;
+          prog.push_back({GK_SX_COUNT, 0, 0});
+          return true;
+        }
+        return false;
+      }
+      default: return false;
+    }
+  }
+
   uint32_t add(const CP& cp) {
     auto it = ix.find(cp->key);
     if (it != ix.end()) return it->second;
@@ -138,6 +234,19 @@ struct Builder {
         c.nargs = (uint32_t)args.size();
         x.xargs.insert(x.xargs.end(), args.begin(), args.end());
         c.seed = xhash(GK_HASH_INIT, cp->key.data(), cp->key.size());
+        {
+          std::vector<SxOp> prog;
+          static const bool no_sx = getenv("GK_NO_NATIVE_STRINGS") != nullptr;
+          if (!no_sx && cp->term && sx_term(*cp, cp->term.get(), xi.args, prog, 0) && !prog.empty() && prog.size() <= 16) {
+            c.sx_off = (uint32_t)x.xkeys.size();
+            c.sx_n = (uint32_t)prog.size();
+            for (auto& o : prog) {
+              x.xkeys.push_back(o.op);
+              x.xkeys.push_back(o.a);
+              x.xkeys.push_back(o.b);
+            }
+          }
+        }
         x.cl.push_back(c);
         x.cl_src.push_back(cp);
         x.cl_args.push_back(xi.args);

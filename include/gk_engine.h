@@ -88,7 +88,7 @@ typedef struct {
   const uint64_t* err_totals;      /* [n_constraints] */
   const gk_violation* violations;  /* with GK_F_MATERIALIZE */
   size_t n_violations;
-  const char* const* object_errors;/* [n_objects] NULL or review-level error (bad JSON, DELETE without oldObject) */
+  const char* const* object_errors;/* NULL when no object has one; else [n_objects]: NULL or the review-level error (bad JSON, DELETE without oldObject) */
   /* instrumentation (StatsEntry material, pkg/instrumentation/types.go:28-59) */
   double flatten_ms, h2d_ms, kernel_ms, d2h_ms, materialize_ms;
   uint64_t alg_bytes;              /* algorithmic bytes the kernel had to read + bitmap bytes written */
@@ -194,6 +194,11 @@ void gk_coalescer_destroy(gk_coalescer_t* c);
 
 /* CPUs the flattener will use by default (gk_cfg.threads = 0): affinity mask and cgroup CPU quota respected */
 int gk_host_cpus(void);
+
+/* Page-lock (pin != 0) or release (pin == 0) a caller-owned host buffer that blobs are reviewed from (a LIST page buffer the
+ * audit manager reuses, pkg/audit/manager.go:502-561): the blob's host->device copy is then a direct DMA at link speed, chunked
+ * and overlapped with the tokeniser.  Optional: unpinned buffers work, through the driver's staging copies. */
+int gk_pin_host(gk_engine_t* e, const void* p, size_t bytes, int pin, char** err);
 
 void gk_free_result(gk_result* r);
 void gk_free_str(char* s);

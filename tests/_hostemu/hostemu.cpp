@@ -4,6 +4,8 @@
 // It is linked ONLY into tests/_hostemu/libgk_hostemu.so.  The product library
 // (gatekeeper_b200/libgk_engine.so) links kernels.cu instead and has no CPU path at all.
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <chrono>
 #include <memory>
 #include <mutex>
@@ -116,7 +118,7 @@ class HostEmuBackend : public Backend {
     GkIngestOut none{};
     xp.lut_tab = lut_.view();
     xp.lut_vals = lut_vals_.data();
-    for (uint32_t i = 0; i < n; ++i) gk_ingest_obj<false>(xp, in, none, i, GkCur{cur.data(), 1});
+    for (uint32_t i = 0; i < n; ++i) gk_ingest_obj<false>(xp, in, none, i, GkCur{cur.data(), 1}, 0, 1);
     std::vector<uint32_t> total(NK, 0);
     for (uint32_t k = 0; k < NK; ++k) {
       uint32_t acc = 0;
@@ -190,7 +192,7 @@ class HostEmuBackend : public Backend {
       nmiss[0] = 0;
       xp.lut_tab = lut_.view();
       xp.lut_vals = lut_vals_.data();
-      for (uint32_t i = 0; i < n; ++i) gk_ingest_obj<true>(xp, in, out, i, GkCur{cur.data(), 1});
+      for (uint32_t i = 0; i < n; ++i) gk_ingest_obj<true>(xp, in, out, i, GkCur{cur.data(), 1}, 0, 1);
       const uint32_t m = std::min<uint32_t>(nmiss[0], in.miss_cap);
       if (nmiss[0] == 0) break;
       total_miss += m;
@@ -225,6 +227,7 @@ class HostEmuBackend : public Backend {
       st->lut_misses = total_miss;
       st->alg_bytes = b;
     }
+    if (getenv("GK_TRACE_INGEST")) fprintf(stderr, "[ingest hostemu] n=%u lookups missed (host-evaluated) %llu, table entries %u\n", n, (unsigned long long)total_miss, lut_.used);
     last_ingest_ = hb;   // (tests compare these arrays with the host flattener's)
     return upload(hb, *rq.c, nullptr, nullptr);
   }

@@ -21,6 +21,8 @@ for ns in W.synth_namespaces():
 print(drv.Dump().splitlines()[1])
 blob = W.synth_objects(0, n)
 print("blob bytes", blob.total_bytes())
+if os.environ.get("GK_PIN", "1") == "1":
+    drv.pin_blob(blob)
 for r in range(reps):
     t0 = time.time()
     resp = drv.ReviewBlob(blob, flags=D.F_NO_COPY_BACK, with_results=False)
