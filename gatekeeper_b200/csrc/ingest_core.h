@@ -636,7 +636,13 @@ typedef struct {
   uint32_t* const* boff;
   uint8_t* const* bytes;
   uint32_t* const* head;
+  // row handles (scratch, not part of the batch): what the per-row column pass needs to find its element again
+  uint32_t* const* row_elem;     // [nscopes][rows] tape index of the row's element
+  uint32_t* const* row_key;      // [nscopes][rows] tape index of the member's key, or (array index | GK_ROW_INDEX)
+  uint32_t* const* row_parent;   // [nscopes][rows] row of the parent scope (an object index under the root)
+  uint32_t* const* row_obj;      // [nscopes][rows] object index
 } GkIngestOut;
+#define GK_ROW_INDEX 0x80000000u
 
 typedef struct {
   const uint8_t* blob;              // the chunk's JSON bytes
@@ -662,7 +668,8 @@ struct GkXCtx {
   const void* in;                // GkIngestIn of the pass (miss list of the lookup tables)
   unsigned long long blob_off;   // absolute offset of doc.js in the blob
   // review envelope
-  uint32_t api_node, kind_node, name_node, ns_node;   // tape indices or GK_NONE
+  uint32_t env_ready;            // gk_x_envelope has run
+  uint32_t api_node, kind_node, name_node, ns_node, meta_node;   // tape indices or GK_NONE
   const uint8_t* grp;            // group / version slices of apiVersion (raw, apiVersion has no escapes in the supported case)
   uint32_t grp_len;
   const uint8_t* ver;
@@ -673,6 +680,45 @@ struct GkXCtx {
   uint32_t scope_at[GK_MAX_LOOP_DEPTH + 1];   // scope id at each depth
   int depth;
 };
+
+// review envelope fields of the object (apiVersion -> group / version, kind, metadata.name / namespace): computed on first use
+GK_HD void gk_x_envelope(GkXCtx& c) {
+  c.env_ready = 1;
+  c.api_node = gk_obj_find(c.doc, 0, reinterpret_cast<const uint8_t*>("apiVersion"), 10);
+  c.kind_node = gk_obj_find(c.doc, 0, reinterpret_cast<const uint8_t*>("kind"), 4);
+  c.grp = c.ver = nullptr;
+  c.grp_len = c.ver_len = 0;
+  if (c.api_node != GK_NONE && gk_te_type(c.doc.tape[c.api_node]) == GK_T_STR) {
+    const gk_u64 e = c.doc.tape[c.api_node];
+    const uint8_t* p = c.doc.js + gk_te_off(e);
+    const uint32_t len = gk_te_len(e);
+    uint32_t s = 0;
+    while (s < len && p[s] != '/') ++s;
+    if (s == len) {
+      c.ver = p;
+      c.ver_len = len;
+      c.grp = p;
+      c.grp_len = 0;
+    } else {
+      c.grp = p;
+      c.grp_len = s;
+      c.ver = p + s + 1;
+      c.ver_len = len - s - 1;
+    }
+  }
+  c.meta_node = gk_obj_find(c.doc, 0, reinterpret_cast<const uint8_t*>("metadata"), 8);
+  c.name_node = c.ns_node = GK_NONE;
+  if (c.meta_node != GK_NONE && gk_te_type(c.doc.tape[c.meta_node]) == GK_T_OBJ) {
+    uint32_t nm = gk_obj_find(c.doc, c.meta_node, reinterpret_cast<const uint8_t*>("name"), 4);
+    uint32_t ns = gk_obj_find(c.doc, c.meta_node, reinterpret_cast<const uint8_t*>("namespace"), 9);
+    if (nm != GK_NONE && (gk_te_type(c.doc.tape[nm]) != GK_T_STR || gk_te_len(c.doc.tape[nm]) == 0)) nm = GK_NONE;
+    if (ns != GK_NONE && (gk_te_type(c.doc.tape[ns]) != GK_T_STR || gk_te_len(c.doc.tape[ns]) == 0)) ns = GK_NONE;
+    c.name_node = nm;
+    c.ns_node = ns;
+  } else {
+    c.meta_node = GK_NONE;
+  }
+}
 
 GK_HD GkXVal gk_x_follow(const GkXCtx& c, GkXVal v, const uint32_t* keys, uint32_t nkeys) {
   for (uint32_t j = 0; j < nkeys; ++j) {
@@ -703,7 +749,9 @@ GK_HD bool gk_lit_eq(const uint8_t* a, uint32_t n, const char* b) {
 }
 
 // `input.review.<root>` + keys
-GK_HD GkXVal gk_x_root(const GkXCtx& c, uint32_t root, const uint32_t* keys, uint32_t nkeys) {
+GK_HD GkXVal gk_x_root(const GkXCtx& cc, uint32_t root, const uint32_t* keys, uint32_t nkeys) {
+  GkXCtx& c = const_cast<GkXCtx&>(cc);
+  if (!c.env_ready && (root == GK_R_KIND || root == GK_R_NAME || root == GK_R_NAMESPACE)) gk_x_envelope(c);
   switch (root) {
     case GK_R_REVIEW: return nkeys ? gk_xundef() : gk_xsyn(GK_VT_OBJ);
     case GK_R_OBJECT: return gk_x_follow(c, gk_xnode(c.doc.tape, 0), keys, nkeys);
@@ -1170,12 +1218,17 @@ struct GkIngestFrame {
 
 GK_HD const uint8_t* gk_lit(const char* s) { return reinterpret_cast<const uint8_t*>(s); }
 
-template <bool WRITE>
+// MODE 0: count pass (decoded lengths of byte columns).  MODE 1: the per-object pass writes the byte-encoded columns (their
+// offsets run through the object).  MODE 2: the per-row pass writes every other column.
+enum { GK_PASS_COUNT = 0, GK_PASS_ROWS = 1, GK_PASS_COLS = 2 };
+template <int MODE>
 GK_HD void gk_emit_col(const GkXProg& xp, const GkIngestIn& in, const GkIngestOut& out, GkXCtx& c, uint32_t ci, uint32_t row, const GkCur& bcur) {
   const GkXCol& col = xp.cols[ci];
   const GkXClosure& cl = xp.cl[col.closure];
   const uint32_t enc = col.enc;
-  if (!WRITE) {
+  if (MODE == GK_PASS_ROWS && !(enc & GK_ENC_BYTES)) return;
+  if (MODE == GK_PASS_COLS && (enc & GK_ENC_BYTES)) return;
+  if (MODE == GK_PASS_COUNT) {
     // the count pass only needs the decoded length of byte columns
     if (!(enc & GK_ENC_BYTES) || cl.kind == GK_X_LUT || cl.kind == GK_X_COUNT) return;
     const GkXVal v = gk_x_eval(c, col.closure);
@@ -1252,12 +1305,14 @@ GK_HD void gk_emit_col(const GkXProg& xp, const GkIngestIn& in, const GkIngestOu
 }
 
 // Count pass (WRITE = false): fills in.counts[k * n + i].  Write pass: in.counts holds the exclusive prefix sums.
-template <bool WRITE>
-// `lane` / `nlanes`: the GPU runs one WARP per object -- every lane walks the (warp-uniform) scope tree, which costs nothing
-// extra, and the columns of each row are dealt to the lanes; all lanes read the same tape, so its lines stay in L1.  Arrays
-// that are not per column (header, CSR offsets, row counters) are written by lane 0.  The test backend runs it with one lane.
+// The per-object pass.  GK_PASS_COUNT: rows per scope, bytes per byte column, header byte counts.  GK_PASS_ROWS: header arrays,
+// CSR offsets, the row handles of every scope and the byte-encoded columns.
+// `lane` / `nlanes`: several threads may share one object (every lane walks the scope tree, the byte columns of a row are dealt
+// to the lanes; arrays that are not per column are written by lane 0); measured on B200 one thread per object is fastest.
 // `cur`: nscopes + nbytecols + GK_CNT_EXTRA working counters, private to the lane.
+template <int MODE>
 GK_HD void gk_ingest_obj(const GkXProg& xp, const GkIngestIn& in, const GkIngestOut& out, uint32_t i, const GkCur& cur, uint32_t lane, uint32_t nlanes) {
+  constexpr bool WRITE = MODE != GK_PASS_COUNT;
   const uint32_t n = in.n, NS = xp.nscopes, NK = NS + xp.nbytecols + GK_CNT_EXTRA;
   const uint32_t K_NAME = NS + xp.nbytecols, K_GEN = K_NAME + 1, K_LBL = K_NAME + 2, K_NSN = K_NAME + 3;
   for (uint32_t k = 0; k < NK; ++k) cur[k] = WRITE ? in.counts[(size_t)k * n + i] : 0u;
@@ -1271,7 +1326,8 @@ GK_HD void gk_ingest_obj(const GkXProg& xp, const GkIngestIn& in, const GkIngest
   c.doc.ntape = in.ntape[i];
   c.depth = 0;
   c.scope_at[0] = 0;
-  c.api_node = c.kind_node = c.name_node = c.ns_node = GK_NONE;
+  c.env_ready = 0;
+  c.api_node = c.kind_node = c.name_node = c.ns_node = c.meta_node = GK_NONE;
   c.grp = c.ver = nullptr;
   c.grp_len = c.ver_len = 0;
   bool skip = in.status[i] != GK_ING_OK;
@@ -1281,40 +1337,14 @@ GK_HD void gk_ingest_obj(const GkXProg& xp, const GkIngestIn& in, const GkIngest
   GkXVal nsname = gk_xundef();
   if (!skip) {
     // ---- review envelope / header: apiVersion -> (group, version), kind, metadata.{name, generateName, namespace, labels}
-    c.api_node = gk_obj_find(c.doc, 0, gk_lit("apiVersion"), 10);
-    c.kind_node = gk_obj_find(c.doc, 0, gk_lit("kind"), 4);
-    if (c.api_node != GK_NONE && gk_te_type(c.doc.tape[c.api_node]) == GK_T_STR) {
-      const gk_u64 e = c.doc.tape[c.api_node];
-      const uint8_t* p = c.doc.js + gk_te_off(e);
-      const uint32_t len = gk_te_len(e);
-      uint32_t s = 0;
-      while (s < len && p[s] != '/') ++s;
-      if (s == len) {
-        c.ver = p;
-        c.ver_len = len;
-        c.grp = p;
-        c.grp_len = 0;
-      } else {
-        c.grp = p;
-        c.grp_len = s;
-        c.ver = p + s + 1;
-        c.ver_len = len - s - 1;
-      }
-    }
-    const uint32_t meta = gk_obj_find(c.doc, 0, gk_lit("metadata"), 8);
-    uint32_t nm = GK_NONE, ns = GK_NONE;
-    if (meta != GK_NONE && gk_te_type(c.doc.tape[meta]) == GK_T_OBJ) {
-      nm = gk_obj_find(c.doc, meta, gk_lit("name"), 4);
+    gk_x_envelope(c);
+    const uint32_t meta = c.meta_node, nm = c.name_node, ns = c.ns_node;
+    if (meta != GK_NONE) {
       gen_node = gk_obj_find(c.doc, meta, gk_lit("generateName"), 12);
-      ns = gk_obj_find(c.doc, meta, gk_lit("namespace"), 9);
       labels = gk_obj_find(c.doc, meta, gk_lit("labels"), 6);
-      if (nm != GK_NONE && (gk_te_type(c.doc.tape[nm]) != GK_T_STR || gk_te_len(c.doc.tape[nm]) == 0)) nm = GK_NONE;
       if (gen_node != GK_NONE && (gk_te_type(c.doc.tape[gen_node]) != GK_T_STR || gk_te_len(c.doc.tape[gen_node]) == 0)) gen_node = GK_NONE;
-      if (ns != GK_NONE && (gk_te_type(c.doc.tape[ns]) != GK_T_STR || gk_te_len(c.doc.tape[ns]) == 0)) ns = GK_NONE;
       if (labels != GK_NONE && gk_te_type(c.doc.tape[labels]) != GK_T_OBJ) labels = GK_NONE;
     }
-    c.name_node = nm;
-    c.ns_node = ns;
     const GkXVal kindv = gk_xnode(c.doc.tape, c.kind_node);
     const bool is_ns = c.grp_len == 0 && gk_entry_eq(c.doc, c.doc.tape[c.kind_node], gk_lit("Namespace"), 9);
     // ---- stage 0: the process excluder (pkg/controller/config/process/excluder.go:95-127): a Namespace by its own name,
@@ -1401,7 +1431,7 @@ GK_HD void gk_ingest_obj(const GkXProg& xp, const GkIngestIn& in, const GkIngest
     for (uint32_t k = lane; k < s0.ncols; k += nlanes) {
       const uint32_t ci = xp.col_order[s0.first_col + k];
       if (skip) {
-        if (WRITE) {   // placeholder row: every encoding "undefined"
+        if (WRITE && (xp.cols[ci].enc & GK_ENC_BYTES)) {   // placeholder row of a byte column: every encoding "undefined"
           const uint32_t enc = xp.cols[ci].enc;
           if (enc & GK_ENC_VT) out.vt[ci][i] = GK_VT_UNDEF;
           if (enc & GK_ENC_SID) out.sid[ci][i] = GK_SID_UNDEF;
@@ -1411,7 +1441,7 @@ GK_HD void gk_ingest_obj(const GkXProg& xp, const GkIngestIn& in, const GkIngest
           if (enc & GK_ENC_BYTES) out.boff[ci][i] = bcur[xp.cols[ci].bytes_slot];
         }
       } else {
-        gk_emit_col<WRITE>(xp, in, out, c, ci, i, bcur);
+        gk_emit_col<MODE>(xp, in, out, c, ci, i, bcur);
       }
     }
   }
@@ -1468,8 +1498,14 @@ GK_HD void gk_ingest_obj(const GkXProg& xp, const GkIngestIn& in, const GkIngest
     }
     g.row = cur[g.scope]++;
     c.depth = top;
+    if (WRITE && lane == 0) {
+      out.row_elem[g.scope][g.row] = c.elem[top].node;
+      out.row_key[g.scope][g.row] = g.is_obj ? c.key[top].node : ((uint32_t)c.key[top].inum | GK_ROW_INDEX);
+      out.row_parent[g.scope][g.row] = fr[top - 1].row;
+      out.row_obj[g.scope][g.row] = i;
+    }
     const GkXScope& sc = xp.scopes[g.scope];
-    for (uint32_t k = lane; k < sc.ncols; k += nlanes) gk_emit_col<WRITE>(xp, in, out, c, xp.col_order[sc.first_col + k], g.row, bcur);
+    for (uint32_t k = lane; k < sc.ncols; k += nlanes) gk_emit_col<MODE>(xp, in, out, c, xp.col_order[sc.first_col + k], g.row, bcur);
     g.next_child = sc.first_child;   // (none for a leaf scope: the next turn advances this frame again)
   }
   if (!WRITE) {
@@ -1497,6 +1533,60 @@ GK_HD void gk_ingest_obj(const GkXProg& xp, const GkIngestIn& in, const GkIngest
       }
     }
   }
+}
+
+
+// The per-row column pass: every column of scope `sc` that is not byte-encoded, for row `r` (scope 0: r = the object).  Threads
+// of a warp work on different rows of the SAME scope, so they run the same column / the same path at the same time.
+GK_HD void gk_ingest_row(const GkXProg& xp, const GkIngestIn& in, const GkIngestOut& out, uint32_t sc, uint32_t r, uint32_t lane, uint32_t nlanes) {
+  const uint32_t i = sc ? out.row_obj[sc][r] : r;
+  GkXCtx c;
+  c.xp = &xp;
+  c.in = &in;
+  c.blob_off = in.ooff[i];
+  c.doc.js = in.blob + in.ooff[i];
+  c.doc.tape = in.tape + gk_tape_off(in.ooff, i);
+  c.doc.ntape = in.ntape[i];
+  c.env_ready = 0;
+  c.api_node = c.kind_node = c.name_node = c.ns_node = c.meta_node = GK_NONE;
+  c.grp = c.ver = nullptr;
+  c.grp_len = c.ver_len = 0;
+  c.scope_at[0] = 0;
+  const GkXScope& xs = xp.scopes[sc];
+  if (sc == 0 && (out.flags[i] & GK_F_SKIP)) {   // placeholder row: every encoding "undefined"
+    for (uint32_t k = lane; k < xs.ncols; k += nlanes) {
+      const uint32_t ci = xp.col_order[xs.first_col + k];
+      const uint32_t enc = xp.cols[ci].enc;
+      if (enc & GK_ENC_BYTES) continue;
+      if (enc & GK_ENC_VT) out.vt[ci][i] = GK_VT_UNDEF;
+      if (enc & GK_ENC_SID) out.sid[ci][i] = GK_SID_UNDEF;
+      if (enc & GK_ENC_NUM) out.num[ci][i] = 0;
+      if (enc & GK_ENC_HEAD)
+        for (int w = 0; w < GK_HEAD_WORDS; ++w) out.head[ci][(size_t)i * GK_HEAD_WORDS + w] = 0;
+    }
+    return;
+  }
+  int d = 0;
+  for (uint32_t s2 = sc; s2; s2 = (uint32_t)xp.scopes[s2].parent) ++d;
+  c.depth = d;
+  {
+    uint32_t cs = sc, cr = r;
+    for (int dd = d; dd >= 1; --dd) {
+      c.scope_at[dd] = cs;
+      c.elem[dd] = gk_xnode(c.doc.tape, out.row_elem[cs][cr]);
+      const uint32_t k = out.row_key[cs][cr];
+      if (k & GK_ROW_INDEX) {
+        c.key[dd] = gk_xsyn(GK_VT_NUM);
+        c.key[dd].inum = (long long)(k & ~GK_ROW_INDEX);
+      } else {
+        c.key[dd] = gk_xnode(c.doc.tape, k);
+      }
+      cr = out.row_parent[cs][cr];
+      cs = (uint32_t)xp.scopes[cs].parent;
+    }
+  }
+  const GkCur none{nullptr, 0};
+  for (uint32_t k = lane; k < xs.ncols; k += nlanes) gk_emit_col<GK_PASS_COLS>(xp, in, out, c, xp.col_order[xs.first_col + k], r, none);
 }
 
 // tokenise object i of the chunk and run the review-level checks of Engine::review_doc (the object must be a JSON object

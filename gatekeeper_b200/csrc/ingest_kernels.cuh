@@ -2,7 +2,8 @@
 //   gk_tape_kernel   raw JSON -> tape (+ review-level status)
 //   gk_count_kernel  rows per scope / bytes per byte column / header byte counts of every object
 //   gk_scan_kernel   exclusive prefix sums of the counter arrays (one CTA per array), totals
-//   gk_write_kernel  header arrays, CSR scope offsets, every column encoding; lookups through the device hash tables
+//   gk_write_kernel  per object: header arrays, CSR scope offsets, row handles, byte-encoded columns
+//   gk_cols_kernel   per row of one scope: every other column encoding; lookups through the device hash tables
 //   gk_fill_kernel   the host's answers to the miss list -> table slots
 //   gk_tiles_kernel  first row of every scope for every evaluation tile + the largest tile of each scope
 // HBM-bound byte work (no tensor cores): the tape kernel reads the blob once (~1.2 KB per Pod) and writes ~1 tape entry per
@@ -24,20 +25,29 @@ __global__ void __launch_bounds__(kIngestThreads) gk_tape_kernel(const GkIngestI
 // count / write: one WARP per object (see gk_ingest_obj): the lanes share the object's tape through L1 and split its columns
 constexpr uint32_t kMaxCounters = GK_MAX_SCOPES + 64 + GK_CNT_EXTRA;
 
-__global__ void __launch_bounds__(kIngestThreads) gk_count_kernel(const GkXProg xp, const GkIngestIn in) {
-  const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+// `lanes` (a power of two, 1..32) threads share one object
+__global__ void __launch_bounds__(kIngestThreads) gk_count_kernel(const GkXProg xp, const GkIngestIn in, uint32_t lanes) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, i = t / lanes, lane = t % lanes;
   if (i >= in.n) return;
   GkIngestOut none;
   memset(&none, 0, sizeof none);
   uint32_t cur[kMaxCounters];
-  gk_ingest_obj<false>(xp, in, none, i, GkCur{cur, 1}, lane, 32u);
+  gk_ingest_obj<GK_PASS_COUNT>(xp, in, none, i, GkCur{cur, 1}, lane, lanes);
 }
 
-__global__ void __launch_bounds__(kIngestThreads) gk_write_kernel(const GkXProg xp, const GkIngestIn in, const GkIngestOut out) {
-  const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+__global__ void __launch_bounds__(kIngestThreads) gk_write_kernel(const GkXProg xp, const GkIngestIn in, const GkIngestOut out, uint32_t lanes) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, i = t / lanes, lane = t % lanes;
   if (i >= in.n) return;
   uint32_t cur[kMaxCounters];
-  gk_ingest_obj<true>(xp, in, out, i, GkCur{cur, 1}, lane, 32u);
+  gk_ingest_obj<GK_PASS_ROWS>(xp, in, out, i, GkCur{cur, 1}, lane, lanes);
+}
+
+// the per-row column pass of one scope: a thread (or `lanes` threads) per row
+__global__ void __launch_bounds__(kIngestThreads) gk_cols_kernel(const GkXProg xp, const GkIngestIn in, const GkIngestOut out, uint32_t scope, uint32_t rows,
+                                                                 uint32_t lanes) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, r = t / lanes, lane = t % lanes;
+  if (r >= rows) return;
+  gk_ingest_row(xp, in, out, scope, r, lane, lanes);
 }
 
 // exclusive scan of counts[k * n .. (k + 1) * n) for k = blockIdx.x; totals[k] = the sum

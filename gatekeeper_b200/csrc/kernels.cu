@@ -596,7 +596,13 @@ class CudaBackend : public Backend {
     // ---- H2D of the raw JSON in chunks on the copy stream; the tokeniser of a chunk starts as soon as its bytes have landed
     CK(cudaMemcpyAsync(d_s + o_ooff, rq.ooff, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, stream_));
     CK(cudaEventRecord(e0, stream_));
-    const uint32_t wblocks = (uint32_t)(((uint64_t)n * 32u + kIngestThreads - 1) / kIngestThreads);   // a warp per object
+    uint32_t lanes = 1;
+    if (const char* ev = getenv("GK_INGEST_LANES")) lanes = std::max(1, std::min(32, atoi(ev)));
+    while (lanes & (lanes - 1)) --lanes;
+    uint32_t clanes = 1;
+    if (const char* ev = getenv("GK_INGEST_COL_LANES")) clanes = std::max(1, std::min(32, atoi(ev)));
+    while (clanes & (clanes - 1)) --clanes;
+    const uint32_t wblocks = (uint32_t)(((uint64_t)n * lanes + kIngestThreads - 1) / kIngestThreads);
     if (NK > kMaxCounters) throw BackendError{"device ingest: too many byte-encoded columns"};
     {
       const size_t kChunk = 32u << 20;
@@ -619,7 +625,7 @@ class CudaBackend : public Backend {
     }
     CK(cudaEventRecord(e1, stream_));
     if (n) {
-      gk_count_kernel<<<wblocks, kIngestThreads, 0, stream_>>>(xp, in);
+      gk_count_kernel<<<wblocks, kIngestThreads, 0, stream_>>>(xp, in, lanes);
       gk_scan_kernel<<<NK, 1024, 0, stream_>>>(in.counts, n, d_totals);
       launches_ += 2;
     } else {
@@ -747,7 +753,26 @@ class CudaBackend : public Backend {
     out.boff = reinterpret_cast<uint32_t* const*>(A + a_pboff);
     out.bytes = reinterpret_cast<uint8_t* const*>(A + a_pbytes);
     out.head = reinterpret_cast<uint32_t* const*>(A + a_phead);
-    // ---- write pass, repeated while lookups are missing (the host evaluates each distinct argument tuple once)
+    // ---- row handles (scratch): 4 arrays per scope + their pointer tables
+    {
+      Carver rc;
+      const size_t o_ptrs = rc.take((size_t)4 * NS * 8);
+      std::vector<size_t> o_rows(4 * (size_t)NS, 0);
+      for (uint32_t s2 = 1; s2 < NS; ++s2)
+        for (int q = 0; q < 4; ++q) o_rows[(size_t)q * NS + s2] = rc.take(((size_t)total[s2] + 1) * 4);
+      uint8_t* d_r = rows_.need(gk_align(rc.off));
+      std::vector<uint64_t> ptrs(4 * (size_t)NS, 0);
+      for (uint32_t s2 = 1; s2 < NS; ++s2)
+        for (int q = 0; q < 4; ++q) ptrs[(size_t)q * NS + s2] = reinterpret_cast<uint64_t>(d_r + o_rows[(size_t)q * NS + s2]);
+      CK(cudaMemcpyAsync(d_r + o_ptrs, ptrs.data(), ptrs.size() * 8, cudaMemcpyHostToDevice, stream_));
+      CK(cudaStreamSynchronize(stream_));   // (`ptrs` is a temporary)
+      uint32_t* const* base = reinterpret_cast<uint32_t* const*>(d_r + o_ptrs);
+      out.row_elem = base;
+      out.row_key = base + NS;
+      out.row_parent = base + 2 * NS;
+      out.row_obj = base + 3 * NS;
+    }
+    // ---- write passes, repeated while lookups are missing (the host evaluates each distinct argument tuple once)
     CK(cudaEventRecord(e2, stream_));
     uint64_t total_miss = 0;
     double lut_ms = 0;
@@ -758,8 +783,16 @@ class CudaBackend : public Backend {
       xp.lut_tab.mask = lut_.mask;
       xp.lut_vals = d_lutv_;
       CK(cudaMemsetAsync(in.nmiss, 0, 4, stream_));
-      gk_write_kernel<<<wblocks, kIngestThreads, 0, stream_>>>(xp, in, out);
-      ++launches_;
+      if (round == 0 || xh.nbytecols) {   // (row handles and header do not depend on the lookups; a byte column's sid may)
+        gk_write_kernel<<<wblocks, kIngestThreads, 0, stream_>>>(xp, in, out, lanes);
+        ++launches_;
+      }
+      for (uint32_t s2 = 0; s2 < NS; ++s2) {
+        const uint32_t rows = s2 ? total[s2] : n;
+        if (!rows || !xh.scopes[s2].ncols) continue;
+        gk_cols_kernel<<<(uint32_t)(((uint64_t)rows * clanes + kIngestThreads - 1) / kIngestThreads), kIngestThreads, 0, stream_>>>(xp, in, out, s2, rows, clanes);
+        ++launches_;
+      }
       uint32_t nm = 0;
       CK(cudaMemcpyAsync(&nm, in.nmiss, 4, cudaMemcpyDeviceToHost, stream_));
       CK(cudaStreamSynchronize(stream_));
@@ -900,7 +933,7 @@ class CudaBackend : public Backend {
     }
   }
   std::mutex ingest_mu_;
-  Scratch scratch_, tabs_;
+  Scratch scratch_, tabs_, rows_;
   SidTable sid_;
   unsigned long long* d_sid_keys_ = nullptr;
   uint32_t* d_sid_vals_ = nullptr;

@@ -833,9 +833,16 @@ class Lowerer {
     return f_atom(GK_OP_NUM_CMP, schema_.col_for(c, GK_ENC_VT | GK_ENC_NUM), k, cmp);
   }
   FP a_strop(int op, const CP& c, const VP& k) {
-    // prefix tests run on the fixed-width HEAD record (plus the byte pool for prefixes longer than 31 bytes)
-    if (op == GK_OP_PREFIX) return f_atom(GK_OP_ANYPREFIX, schema_.col_for(c, GK_ENC_VT | GK_ENC_BYTES | GK_ENC_HEAD), v_arr({k}));
-    if (op == GK_OP_ANYPREFIX) return f_atom(op, schema_.col_for(c, GK_ENC_VT | GK_ENC_BYTES | GK_ENC_HEAD), k);
+    // prefix tests run on the fixed-width HEAD record; the row's full bytes are only materialised when some prefix is longer
+    // than the 31 bytes the record holds
+    auto prefix_enc = [](const VP& list) {
+      uint32_t enc = GK_ENC_VT | GK_ENC_HEAD;
+      for (auto& x : list->items)
+        if (x->t == VT::Str && x->s.size() > GK_HEAD_BYTES) enc |= GK_ENC_BYTES;
+      return enc;
+    };
+    if (op == GK_OP_PREFIX) return f_atom(GK_OP_ANYPREFIX, schema_.col_for(c, prefix_enc(v_arr({k}))), v_arr({k}));
+    if (op == GK_OP_ANYPREFIX) return f_atom(op, schema_.col_for(c, prefix_enc(k)), k);
     return f_atom(op, schema_.col_for(c, GK_ENC_VT | GK_ENC_BYTES), k);
   }
 

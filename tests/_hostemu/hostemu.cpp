@@ -118,7 +118,7 @@ class HostEmuBackend : public Backend {
     GkIngestOut none{};
     xp.lut_tab = lut_.view();
     xp.lut_vals = lut_vals_.data();
-    for (uint32_t i = 0; i < n; ++i) gk_ingest_obj<false>(xp, in, none, i, GkCur{cur.data(), 1}, 0, 1);
+    for (uint32_t i = 0; i < n; ++i) gk_ingest_obj<GK_PASS_COUNT>(xp, in, none, i, GkCur{cur.data(), 1}, 0, 1);
     std::vector<uint32_t> total(NK, 0);
     for (uint32_t k = 0; k < NK; ++k) {
       uint32_t acc = 0;
@@ -187,12 +187,25 @@ class HostEmuBackend : public Backend {
     out.boff = p_boff.data();
     out.bytes = p_bytes.data();
     out.head = p_head.data();
+    std::vector<std::vector<uint32_t>> rh(4 * NS);
+    std::vector<uint32_t*> p_rh(4 * NS, nullptr);
+    for (uint32_t s2 = 1; s2 < NS; ++s2)
+      for (int q = 0; q < 4; ++q) {
+        rh[q * NS + s2].assign((size_t)total[s2] + 1, 0);
+        p_rh[q * NS + s2] = rh[q * NS + s2].data();
+      }
+    out.row_elem = p_rh.data();
+    out.row_key = p_rh.data() + NS;
+    out.row_parent = p_rh.data() + 2 * NS;
+    out.row_obj = p_rh.data() + 3 * NS;
     uint64_t total_miss = 0;
     for (int round = 0; round < 64; ++round) {
       nmiss[0] = 0;
       xp.lut_tab = lut_.view();
       xp.lut_vals = lut_vals_.data();
-      for (uint32_t i = 0; i < n; ++i) gk_ingest_obj<true>(xp, in, out, i, GkCur{cur.data(), 1}, 0, 1);
+      for (uint32_t i = 0; i < n; ++i) gk_ingest_obj<GK_PASS_ROWS>(xp, in, out, i, GkCur{cur.data(), 1}, 0, 1);
+      for (uint32_t s2 = 0; s2 < NS; ++s2)
+        for (uint32_t r = 0, R = s2 ? total[s2] : n; r < R; ++r) gk_ingest_row(xp, in, out, s2, r, 0, 1);
       const uint32_t m = std::min<uint32_t>(nmiss[0], in.miss_cap);
       if (nmiss[0] == 0) break;
       total_miss += m;
