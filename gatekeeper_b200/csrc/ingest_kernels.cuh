@@ -26,9 +26,9 @@ __global__ void __launch_bounds__(kIngestThreads) gk_tape_kernel(const GkIngestI
 constexpr uint32_t kMaxCounters = GK_MAX_SCOPES + 64 + GK_CNT_EXTRA;
 
 // `lanes` (a power of two, 1..32) threads share one object
-__global__ void __launch_bounds__(kIngestThreads) gk_count_kernel(const GkXProg xp, const GkIngestIn in, uint32_t lanes) {
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, i = t / lanes, lane = t % lanes;
-  if (i >= in.n) return;
+__global__ void __launch_bounds__(kIngestThreads) gk_count_kernel(const GkXProg xp, const GkIngestIn in, uint32_t lanes, uint32_t first, uint32_t count) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, i = first + t / lanes, lane = t % lanes;
+  if (i >= first + count) return;
   GkIngestOut none;
   memset(&none, 0, sizeof none);
   uint32_t cur[kMaxCounters];
