@@ -105,10 +105,7 @@ class CudaBackend : public Backend {
     prog_.ncbytes = (uint32_t)c.cbytes.size();
     prog_.nphases = (uint32_t)c.phase_off.size() - 1;
     prog_.nitems = (uint32_t)c.items.size();
-    if (prog_.nphases > 255) throw BackendError{"netlist has more dependency phases than the kernel supports"};
-    std::vector<uint8_t> op_phase(c.ops.size() + 16, 0);
-    for (uint32_t ph = 0; ph + 1 < c.phase_off.size(); ++ph)
-      for (uint32_t k = c.phase_off[ph]; k < c.phase_off[ph + 1]; ++k) op_phase[c.items[k] & 0xfffffu] = (uint8_t)ph;
+    if (prog_.nphases > kMaxPhases) throw BackendError{"netlist has more dependency phases than the kernel supports"};
     auto up = [&](const void* src, size_t bytes, void** dst) {
       size_t padded = (bytes + 63) / 64 * 64 + 64;
       CK(cudaMalloc(dst, padded));
@@ -122,7 +119,6 @@ class CudaBackend : public Backend {
     up(c.match.data(), c.match.size() * sizeof(GkMatch), (void**)&d_match_);
     up(c.pool.data(), c.pool.size() * 4, (void**)&d_pool_);
     up(c.cbytes.data(), c.cbytes.size(), (void**)&d_cbytes_);
-    up(op_phase.data(), op_phase.size(), (void**)&d_op_phase_);
     prog_.ops = d_ops_;
     prog_.items = d_items_;
     prog_.outs = d_outs_;
@@ -338,7 +334,12 @@ class CudaBackend : public Backend {
       p.peer_viol[q] = nullptr;
       p.peer_tot[q] = nullptr;
     }
-    p.op_phase = d_op_phase_;
+    p.timing = nullptr;
+#ifdef GK_PHASE_TIMING
+    if (!d_timing_) CK(cudaMalloc(&d_timing_, (kMaxPhases + 2 + 16) * 16));
+    CK(cudaMemsetAsync(d_timing_, 0, (kMaxPhases + 2 + 16) * 16, st));
+    p.timing = d_timing_;
+#endif
     if (active.size() != C) throw BackendError{"active mask size mismatch"};
     if (C && active != last_active_) {
       CK(cudaMemcpyAsync(d_active_, active.data(), (size_t)C * 4, cudaMemcpyHostToDevice, st));
@@ -350,10 +351,12 @@ class CudaBackend : public Backend {
     CK(cudaMemsetAsync(d_scalars_, 0, 64, st));
     auto r16 = [](size_t x) { return (x + 15) / 16 * 16; };
     const size_t NS = nscopes_;
-    size_t smem = 3 * r16((size_t)C * 4) + r16((size_t)C * sizeof(GkOutEnt)) + r16((size_t)prog_.nops * sizeof(GkOp)) + r16((size_t)prog_.nops) +
-                  r16((size_t)prog_.nmatch * sizeof(GkMatch)) + r16((size_t)ncols_ * sizeof(GkColumn)) + r16(NS * sizeof(GkScope)) +
-                  r16((size_t)prog_.npool * 4) + r16((size_t)prog_.ncbytes) + 2 * r16((size_t)kWarps * NS * 4) +
-                  r16((size_t)kWarps * db->slot_words * 4) + 64;
+    size_t smem = 3 * r16((size_t)C * 4) + 2 * r16(NS * 4) + r16((size_t)(prog_.nphases + 1) * 4) + r16((size_t)db->slot_words * 4) + 64;
+#if GK_TABLES_IN_SMEM
+    smem += r16((size_t)C * sizeof(GkOutEnt)) + r16((size_t)prog_.nops * sizeof(GkOp)) + r16((size_t)prog_.nitems * 4) +
+            r16((size_t)prog_.nmatch * sizeof(GkMatch)) + r16((size_t)ncols_ * sizeof(GkColumn)) + r16(NS * sizeof(GkScope)) +
+            r16((size_t)prog_.npool * 4) + r16((size_t)prog_.ncbytes);
+#endif
     if (smem > max_smem_)
       throw BackendError{"constraint set needs " + std::to_string(smem) + " bytes of shared memory per CTA (limit " + std::to_string(max_smem_) +
                          "): too many live netlist columns for one launch"};
@@ -368,7 +371,7 @@ class CudaBackend : public Backend {
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gk_eval_kernel, kThreads, smem));
     per_sm = std::max(1, per_sm);
     if (getenv("GK_TRACE_LAUNCH")) fprintf(stderr, "[launch] %d CTAs/SM x %d threads, %zu B smem/CTA, %u tiles of %u objects\n", per_sm, kThreads, smem, p.ntiles, p.tile);
-    uint32_t grid = std::max(1u, std::min<uint32_t>((p.ntiles + kWarps - 1) / kWarps, (uint32_t)(sms_ * per_sm)));
+    uint32_t grid = std::max(1u, std::min<uint32_t>(p.ntiles, (uint32_t)(sms_ * per_sm)));
     gk_eval_kernel<<<grid, kThreads, smem, st>>>(p);
     CK(cudaGetLastError());
     ++launches_;
@@ -393,6 +396,25 @@ class CudaBackend : public Backend {
     CK(cudaEventRecord(ev1_, stream_));
     CK(cudaStreamSynchronize(stream_));
     CK(cudaEventElapsedTime(&out.kernel_ms, ev0_, ev1_));
+#ifdef GK_PHASE_TIMING
+    {
+      std::vector<unsigned long long> t((kMaxPhases + 2 + 16) * 2);
+      CK(cudaMemcpy(t.data(), d_timing_, t.size() * 8, cudaMemcpyDeviceToHost));
+      unsigned long long tot = 0;
+      for (uint32_t ph = 0; ph <= prog_.nphases; ++ph) tot += t[2 * ph];
+      fprintf(stderr, "[phase timing] kernel %.3f ms, %u tiles\n", out.kernel_ms, db->ntiles);
+      for (uint32_t ph = 0; ph <= prog_.nphases; ++ph)
+        fprintf(stderr, "  %s %2u: %5.1f%% of CTA time, %7.0f cycles/tile, warp utilisation %4.1f%%\n", ph == prog_.nphases ? "gather" : "phase ", ph,
+                100.0 * t[2 * ph] / std::max(1ull, tot), (double)t[2 * ph] / std::max(1u, db->ntiles),
+                100.0 * t[2 * ph + 1] / std::max(1.0, (double)t[2 * ph] * kWarps));
+      const char* kn[] = {"", "", "atom", "gate", "const", "bcast", "acc", "match", "atoms", "atoms(head)"};
+      for (uint32_t k = 2; k < 10; ++k) {
+        const unsigned long long cyc = t[2 * (kMaxPhases + 2) + 2 * k], cnt = t[2 * (kMaxPhases + 2) + 2 * k + 1];
+        if (cnt) fprintf(stderr, "  items %-11s: %6.1f per tile, %7.0f cycles each, %8.0f warp-cycles per tile\n", kn[k], (double)cnt / db->ntiles,
+                         (double)cyc / cnt, (double)cyc / db->ntiles);
+      }
+    }
+#endif
     out.launches = launches_;
     out.totals.assign(C, 0);
     out.err_totals.assign(C, 0);
@@ -597,16 +619,15 @@ class CudaBackend : public Backend {
         CK(cudaStreamWaitEvent(stream_, ev, 0));
         const uint32_t cnt = last - first;
         gk_tape_kernel<<<(cnt + kIngestThreads - 1) / kIngestThreads, kIngestThreads, 0, stream_>>>(in, first, cnt);
-        // (the count pass of the chunk rides behind its tokeniser: both overlap the copies of the chunks that follow)
-        gk_count_kernel<<<(uint32_t)(((uint64_t)cnt * lanes + kIngestThreads - 1) / kIngestThreads), kIngestThreads, 0, stream_>>>(xp, in, lanes, first, cnt);
-        launches_ += 2;
+        ++launches_;
         first = last;
       }
     }
     CK(cudaEventRecord(e1, stream_));
     if (n) {
+      gk_count_kernel<<<wblocks, kIngestThreads, 0, stream_>>>(xp, in, lanes, 0, n);
       gk_scan_kernel<<<NK, 1024, 0, stream_>>>(in.counts, n, d_totals);
-      ++launches_;
+      launches_ += 2;
     } else {
       CK(cudaMemsetAsync(d_totals, 0, (size_t)NK * 4, stream_));
     }
@@ -905,7 +926,7 @@ class CudaBackend : public Backend {
  private:
   static constexpr uint32_t kErrCap = 1u << 20;
   void free_tables() {
-    void** ptrs[] = {(void**)&d_outs_, (void**)&d_ops_, (void**)&d_items_, (void**)&d_phase_off_, (void**)&d_match_, (void**)&d_pool_, (void**)&d_cbytes_, (void**)&d_op_phase_};
+    void** ptrs[] = {(void**)&d_outs_, (void**)&d_ops_, (void**)&d_items_, (void**)&d_phase_off_, (void**)&d_match_, (void**)&d_pool_, (void**)&d_cbytes_};
     for (auto pp : ptrs) {
       if (*pp) cudaFree(*pp);
       *pp = nullptr;
@@ -945,7 +966,6 @@ class CudaBackend : public Backend {
   GkMatch* d_match_ = nullptr;
   uint32_t* d_pool_ = nullptr;
   uint8_t* d_cbytes_ = nullptr;
-  uint8_t* d_op_phase_ = nullptr;
   uint32_t* d_dict_off_ = nullptr;
   uint8_t* d_dict_bytes_ = nullptr;
   uint32_t dict_n_ = 0;
@@ -953,6 +973,7 @@ class CudaBackend : public Backend {
   unsigned long long* d_totals_ = nullptr;
   uint32_t* d_errlist_ = nullptr;
   uint32_t* d_active_ = nullptr;
+  unsigned long long* d_timing_ = nullptr;
   int host_threads_ = effective_cpus();
   void* pinned_ = nullptr;
   size_t pinned_bytes_ = 0;

@@ -42,7 +42,7 @@ struct KParams {
   uint32_t npeers;
   uint32_t tot_stride;
   uint32_t* done_ctr;
-  const uint8_t* op_phase;    // [nops] dependency phase of every op (gates of one phase and level are independent)
+  unsigned long long* timing; // GK_PHASE_TIMING builds: [kMaxPhases + 2][2] = (CTA cycles between barriers, summed warp busy cycles)
 };
 
 #ifndef GK_THREADS
@@ -52,7 +52,7 @@ struct KParams {
 #define GK_TABLES_IN_SMEM 1   /* measured: 0.825 ms (tables staged in shared memory) vs 0.858 ms (read through L1) per 1M objects */
 #endif
 #ifndef GK_TILE
-#define GK_TILE 128   /* objects per warp tile: four 32-row groups per atom trip */
+#define GK_TILE 512
 #endif
 constexpr int kThreads = GK_THREADS;
 constexpr int kWarps = kThreads / 32;
@@ -269,7 +269,10 @@ __device__ __forceinline__ void atom_rows(const GkColumn& c, uint32_t aop, uint3
   }
 }
 
-// ---- one atom on values already in registers (the column-fused atom runs of the warp kernel)
+#ifdef GK_FUSED_ATOMS   /* experiment, off: see NetBuilder::build */
+// ---- every atom of one column in one pass (GK_N_ATOMS): the row's encodings are loaded once into registers -- four
+// 32-row groups at a time, all loads in flight together -- and each atom is then a compare + ballot on registers.
+// Columns with a HEAD record (prefix tests) go one group at a time: the 32-byte record is 8 registers per row.
 __device__ __forceinline__ bool atom_on_regs(uint32_t aop, uint32_t a, uint32_t b, uint32_t vt, uint32_t sid, long long num, const uint32_t* pool) {
   switch (aop) {
     case GK_OP_TRUTHY: return vt != GK_VT_UNDEF && vt != GK_VT_FALSE;
@@ -281,28 +284,161 @@ __device__ __forceinline__ bool atom_on_regs(uint32_t aop, uint32_t a, uint32_t 
       for (uint32_t j = 0; j < b; ++j) hit = hit || pool[a + j] == sid;
       return hit;
     }
-    default: {   // GK_OP_NUM_CMP: non-numbers hold INT64_MIN / INT64_MAX by their type rank, so one signed compare is OPA's order
+    default: {   // GK_OP_NUM_CMP (the only other op the register path is used for)
       const long long k = (long long)(((uint64_t)pool[a + 1] << 32) | pool[a]);
-      return vt != GK_VT_UNDEF && gk_cmp_apply(b, num < k ? -1 : (num > k ? 1 : 0));
+      if (vt == GK_VT_UNDEF) return false;
+      if (k == INT64_MIN || k == INT64_MAX) {   // sentinel constants: spell the cross-type order out
+        if (vt == GK_VT_NUM) return gk_cmp_apply(b, num < k ? -1 : (num > k ? 1 : 0));
+        return gk_cmp_apply(b, gk_vt_rank(vt) < 2 ? -1 : 1);
+      }
+      return gk_cmp_apply(b, num < k ? -1 : (num > k ? 1 : 0));
     }
   }
 }
+
 __device__ __forceinline__ bool reg_op(uint32_t aop) { return aop <= GK_OP_NUM_CMP; }
 
-// One WARP = one tile of kTile consecutive objects at a time.  The warp runs the whole netlist for its tile by itself: every
-// intermediate bit column lives in the warp's own slice of shared memory, ops execute in dependency order separated only
-// by __syncwarp(), and there is no CTA-wide barrier inside the tile loop (round 1's phase barriers left 45-80 % of the warps
-// idle in the short later phases).  Work per op:
-//   atoms of one column (adjacent in the op list) : the column slice is loaded ONCE into registers, four 32-row groups per trip,
-//                                                   and every atom of the run is a compare + ballot on registers
-//   gates of one phase and level                  : dealt to the lanes as (gate, word) items -- 32 rows per lane-instruction
-//   EXISTS / broadcast / match / gather           : as before, one lane per parent row / object
+__device__ __noinline__ void atoms_rows(const GkColumn& c, const uint32_t* ent, uint32_t nent, const uint32_t* pool, const uint8_t* cbytes, uint32_t lo,
+                                        uint32_t cnt, uint32_t w0, uint32_t w1, uint32_t lane, uint32_t* slots) {
+  const uint32_t FULL = 0xffffffffu;
+  const uint32_t wcap = (((cnt + 31u) >> 5) + 3u) & ~3u;
+  const bool has_vt = (c.enc & GK_ENC_VT) != 0u, has_sid = (c.enc & GK_ENC_SID) != 0u, has_num = (c.enc & GK_ENC_NUM) != 0u;
+  if (!(c.enc & GK_ENC_HEAD)) {
+    for (uint32_t w = w0; w < w1; w += 4u) {
+      const uint32_t r0 = w * 32u + lane;
+      const size_t row0 = (size_t)lo + r0;
+      uint32_t vt[4], sid[4];
+      long long num[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const bool ok = r0 + 32u * u < cnt;
+        vt[u] = (ok && has_vt) ? c.vt[row0 + 32u * u] : (uint32_t)GK_VT_UNDEF;
+        sid[u] = (ok && has_sid) ? c.sid[row0 + 32u * u] : GK_SID_UNDEF;
+        num[u] = (ok && has_num) ? c.num[row0 + 32u * u] : 0ll;
+      }
+      for (uint32_t j = 0; j < nent; ++j) {
+        const uint4 e = *reinterpret_cast<const uint4*>(ent + j * GK_ATOMS_ENT);
+        const uint32_t aop = e.x & 0xffu;
+        bool v[4];
+        if (reg_op(aop)) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) v[u] = (r0 + 32u * u < cnt) && atom_on_regs(aop, e.y, e.z, vt[u], sid[u], num[u], pool);
+        } else {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) v[u] = (r0 + 32u * u < cnt) && gk_atom(c, (uint32_t)(row0 + 32u * u), aop, e.y, e.z, pool, cbytes);
+        }
+        uint4 wd;
+        wd.x = __ballot_sync(FULL, v[0]);
+        wd.y = __ballot_sync(FULL, v[1]);
+        wd.z = __ballot_sync(FULL, v[2]);
+        wd.w = __ballot_sync(FULL, v[3]);
+        if (lane == 0 && w < wcap) *reinterpret_cast<uint4*>(slots + (e.x >> 16) + w) = wd;
+      }
+    }
+    return;
+  }
+  const uint4* head = reinterpret_cast<const uint4*>(c.head);
+  const uint32_t wend = min(w1, (cnt + 31u) >> 5);
+  for (uint32_t w = w0; w < wend; ++w) {
+    const uint32_t r = w * 32u + lane;
+    const bool ok = r < cnt;
+    const size_t row = (size_t)lo + r;
+    const uint32_t vt = (ok && has_vt) ? c.vt[row] : (uint32_t)GK_VT_UNDEF;
+    const uint32_t sid = (ok && has_sid) ? c.sid[row] : GK_SID_UNDEF;
+    uint4 h0 = make_uint4(0, 0, 0, 0), h1 = make_uint4(0, 0, 0, 0);
+    if (ok) {
+      h0 = head[2 * row];
+      h1 = head[2 * row + 1];
+    }
+    const uint32_t lenb = h1.w >> 24;
+    for (uint32_t j = 0; j < nent; ++j) {
+      const uint4 e = *reinterpret_cast<const uint4*>(ent + j * GK_ATOMS_ENT);
+      const uint32_t aop = e.x & 0xffu;
+      bool v = false;
+      if (aop == GK_OP_ANYPREFIX) {
+        bool all_short = true;
+        for (uint32_t q = 0; q < e.z; ++q) all_short = all_short && pool[e.y + q * GK_PREFIX_ENT] <= GK_HEAD_BYTES;
+        if (all_short) {
+          if (ok && vt == GK_VT_STR)
+            for (uint32_t q = 0; q < e.z && !v; ++q) {
+              const uint32_t* pe = pool + e.y + q * GK_PREFIX_ENT;
+              const uint32_t* m = pe + 2 + GK_HEAD_WORDS;
+              const uint32_t diff = ((h0.x ^ pe[2]) & m[0]) | ((h0.y ^ pe[3]) & m[1]) | ((h0.z ^ pe[4]) & m[2]) | ((h0.w ^ pe[5]) & m[3]) |
+                                    ((h1.x ^ pe[6]) & m[4]) | ((h1.y ^ pe[7]) & m[5]) | ((h1.z ^ pe[8]) & m[6]) | ((h1.w ^ pe[9]) & m[7]);
+              v = diff == 0u && lenb >= pe[0];
+            }
+        } else {
+          v = ok && gk_atom(c, (uint32_t)row, aop, e.y, e.z, pool, cbytes);
+        }
+      } else if (reg_op(aop) && aop != GK_OP_NUM_CMP) {
+        v = ok && atom_on_regs(aop, e.y, e.z, vt, sid, 0ll, pool);
+      } else {
+        v = ok && gk_atom(c, (uint32_t)row, aop, e.y, e.z, pool, cbytes);
+      }
+      const uint32_t wd = __ballot_sync(FULL, v);
+      if (lane == 0) slots[(e.x >> 16) + w] = wd;
+    }
+  }
+}
+
+#endif
+
+#ifdef GK_L2_PREFETCH
+// ---- L2 prefetch of a tile's input slices.
+// The netlist walks ~100 arrays per tile with short dependent loops, so a warp rarely has more than a few loads in flight:
+// without help every one of them pays DRAM latency.  While a CTA is busy with the (load-free) gate / EXISTS phases of tile
+// t, one warp asks the L2 for every array slice tile t + gridDim.x will read -- one bulk-prefetch instruction per array
+// slice, no registers or shared memory tied up.
+__device__ __forceinline__ void l2_prefetch(const void* base, size_t lo_bytes, size_t hi_bytes) {
+  if (!base || hi_bytes <= lo_bytes) return;
+  const uintptr_t a = (reinterpret_cast<uintptr_t>(base) + lo_bytes) & ~(uintptr_t)15;
+  const uintptr_t b = (reinterpret_cast<uintptr_t>(base) + hi_bytes + 15) & ~(uintptr_t)15;
+  const uint32_t n = (uint32_t)(b - a);
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(n) : "memory");
+}
+
+__device__ __noinline__ void prefetch_tile(const KParams& p, const GkColumn* cols, const GkScope* scopes, uint32_t t, uint32_t lane) {
+  const uint32_t NS = p.batch.nscopes;
+  const uint32_t* tl = p.tile_lo + (size_t)t * NS;
+  // header arrays (scope 0 rows) and the CSR offsets of every scope (rows of the parent, +1)
+  if (lane == 0) {
+    const size_t a = tl[0], b = tl[NS];
+    const GkBatch& h = p.batch;
+    l2_prefetch(h.flags, a * 4, b * 4);
+    l2_prefetch(h.kind_sid, a * 4, b * 4);
+    l2_prefetch(h.group_sid, a * 4, b * 4);
+    l2_prefetch(h.nsname_sid, a * 4, b * 4);
+    l2_prefetch(h.nsrow, a * 4, b * 4);
+    l2_prefetch(h.name_off, a * 4, (b + 1) * 4);
+    l2_prefetch(h.gen_off, a * 4, (b + 1) * 4);
+    l2_prefetch(h.lbl_off, a * 4, (b + 1) * 4);
+    if (h.lbl_off && b > a) l2_prefetch(h.lbl_kv, (size_t)h.lbl_off[a] * 8, (size_t)h.lbl_off[b] * 8);
+  }
+  for (uint32_t s = 1 + lane; s < NS; s += 32u) {
+    const uint32_t par = (uint32_t)scopes[s].parent;
+    l2_prefetch(scopes[s].off, (size_t)tl[par] * 4, ((size_t)tl[NS + par] + 1) * 4);
+  }
+  for (uint32_t c = lane; c < p.batch.ncols; c += 32u) {
+    const GkColumn& col = cols[c];
+    const size_t a = tl[col.scope], b = tl[NS + col.scope];
+    if (col.enc & GK_ENC_VT) l2_prefetch(col.vt, a, b);
+    if (col.enc & GK_ENC_SID) l2_prefetch(col.sid, a * 4, b * 4);
+    if (col.enc & GK_ENC_NUM) l2_prefetch(col.num, a * 8, b * 8);
+    if (col.enc & GK_ENC_HEAD) l2_prefetch(col.head, a * 32, b * 32);
+    if (col.enc & GK_ENC_BYTES) l2_prefetch(col.boff, a * 4, (b + 1) * 4);
+  }
+}
+
+#endif
+
+// One CTA = one tile of consecutive objects at a time; all intermediate bit columns live in shared memory.
 #ifndef GK_MIN_CTAS
-#define GK_MIN_CTAS 3
+#define GK_MIN_CTAS 5         /* 5 resident CTAs per SM: the register cap this implies (<= 48) costs no spills */
 #endif
 __global__ void __launch_bounds__(kThreads, GK_MIN_CTAS) gk_eval_kernel(const KParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
-  const uint32_t C = p.prog.nconstraints, W = p.out.words, NS = p.batch.nscopes, NOPS = p.prog.nops;
+  const uint32_t C = p.prog.nconstraints, W = p.out.words, NS = p.batch.nscopes, NP = p.prog.nphases;
+  // ---- shared-memory layout
   size_t off = 0;
   auto take = [&](size_t bytes) {
     void* q = smem + off;
@@ -312,288 +448,309 @@ __global__ void __launch_bounds__(kThreads, GK_MIN_CTAS) gk_eval_kernel(const KP
   uint32_t* s_tot = static_cast<uint32_t*>(take((size_t)C * 4));
   uint32_t* s_err = static_cast<uint32_t*>(take((size_t)C * 4));
   uint32_t* s_act = static_cast<uint32_t*>(take((size_t)C * 4));
+  uint32_t* s_lo = static_cast<uint32_t*>(take((size_t)NS * 4));
+  uint32_t* s_cnt = static_cast<uint32_t*>(take((size_t)NS * 4));
+  uint32_t* s_poff = static_cast<uint32_t*>(take((size_t)(NP + 1) * 4));
+  uint32_t* slots = static_cast<uint32_t*>(take((size_t)p.slot_words * 4));
+#if GK_TABLES_IN_SMEM
   GkOutEnt* outs = static_cast<GkOutEnt*>(take((size_t)C * sizeof(GkOutEnt)));
-  GkOp* ops = static_cast<GkOp*>(take((size_t)NOPS * sizeof(GkOp)));
-  uint8_t* op_phase = static_cast<uint8_t*>(take((size_t)NOPS));
+  GkOp* ops = static_cast<GkOp*>(take((size_t)p.prog.nops * sizeof(GkOp)));
+  uint32_t* items = static_cast<uint32_t*>(take((size_t)p.prog.nitems * 4));
   GkMatch* match = static_cast<GkMatch*>(take((size_t)p.prog.nmatch * sizeof(GkMatch)));
   GkColumn* cols = static_cast<GkColumn*>(take((size_t)p.batch.ncols * sizeof(GkColumn)));
   GkScope* scopes = static_cast<GkScope*>(take((size_t)NS * sizeof(GkScope)));
   uint32_t* pool = static_cast<uint32_t*>(take((size_t)p.prog.npool * 4));
   uint8_t* cbytes = static_cast<uint8_t*>(take((size_t)p.prog.ncbytes));
-  uint32_t* w_lo = static_cast<uint32_t*>(take((size_t)kWarps * NS * 4));
-  uint32_t* w_cnt = static_cast<uint32_t*>(take((size_t)kWarps * NS * 4));
-  uint32_t* w_slots = static_cast<uint32_t*>(take((size_t)kWarps * p.slot_words * 4));
+#else
+  // the program / schema tables stay in global memory: every access is warp-uniform and read-only, so they live in L1
+  // after the first tile, and the shared memory they would occupy buys resident CTAs instead
+  const GkOutEnt* __restrict__ outs = p.prog.outs;
+  const GkOp* __restrict__ ops = p.prog.ops;
+  const uint32_t* __restrict__ items = p.prog.items;
+  const GkMatch* __restrict__ match = p.prog.match;
+  const GkColumn* __restrict__ cols = p.batch.cols;
+  const GkScope* __restrict__ scopes = p.batch.scopes;
+  const uint32_t* __restrict__ pool = p.prog.pool;
+  const uint8_t* __restrict__ cbytes = p.prog.cbytes;
+#endif
 
   for (uint32_t i = threadIdx.x; i < C; i += blockDim.x) {
     s_tot[i] = 0;
     s_err[i] = 0;
     s_act[i] = p.active[i];
   }
+  for (uint32_t i = threadIdx.x; i <= NP; i += blockDim.x) s_poff[i] = p.prog.phase_off[i];
+#if GK_TABLES_IN_SMEM
   stage(outs, p.prog.outs, ((size_t)C * sizeof(GkOutEnt) + 15) / 16 * 16);
-  stage(ops, p.prog.ops, ((size_t)NOPS * sizeof(GkOp) + 15) / 16 * 16);
-  stage(op_phase, p.op_phase, ((size_t)NOPS + 15) / 16 * 16);
+  stage(ops, p.prog.ops, ((size_t)p.prog.nops * sizeof(GkOp) + 15) / 16 * 16);
+  stage(items, p.prog.items, ((size_t)p.prog.nitems * 4 + 15) / 16 * 16);
   stage(match, p.prog.match, ((size_t)p.prog.nmatch * sizeof(GkMatch) + 15) / 16 * 16);
   stage(cols, p.batch.cols, ((size_t)p.batch.ncols * sizeof(GkColumn) + 15) / 16 * 16);
   stage(scopes, p.batch.scopes, ((size_t)NS * sizeof(GkScope) + 15) / 16 * 16);
   stage(pool, p.prog.pool, ((size_t)p.prog.npool * 4 + 15) / 16 * 16);
   stage(cbytes, p.prog.cbytes, ((size_t)p.prog.ncbytes + 15) / 16 * 16);
+#endif
   __syncthreads();
 
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const uint32_t FULL = 0xffffffffu;
-  uint32_t* s_lo = w_lo + warp * NS;
-  uint32_t* s_cnt = w_cnt + warp * NS;
-  uint32_t* slots = w_slots + (size_t)warp * p.slot_words;
+#ifdef GK_L2_PREFETCH   /* measured on B200: 0.78 ms -> 1.04 ms per 1M objects -- the bulk prefetches serialise on the issuing warp; off */
+  if (warp == kWarps - 1 && blockIdx.x < p.ntiles) prefetch_tile(p, cols, scopes, blockIdx.x, lane);
+#endif
 
-  for (uint32_t t = blockIdx.x * kWarps + warp; t < p.ntiles; t += gridDim.x * kWarps) {
-    // ---- tile row ranges (rows of a tile are contiguous at every scope)
-    for (uint32_t s = lane; s < NS; s += 32u) {
+  for (uint32_t t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+    // ---- tile row ranges (precomputed on the host: rows of a tile are contiguous at every scope)
+    for (uint32_t s = threadIdx.x; s < NS; s += blockDim.x) {
       const uint32_t a = p.tile_lo[(size_t)t * NS + s], b = p.tile_lo[(size_t)(t + 1) * NS + s];
       s_lo[s] = a;
       s_cnt[s] = b - a;
     }
-    __syncwarp();
+    __syncthreads();
     const uint32_t nobj = s_cnt[0], obj0 = s_lo[0];
 
-    for (uint32_t i = 0; i < NOPS;) {
-      const GkOp op = ops[i];
-      const uint32_t kind = op.w0 & 0xffu, level = (op.w0 >> 8) & 0xffu;
-      uint32_t* out = slots + (op.w0 >> 16);
-      uint32_t next = i + 1u;
-      switch (kind) {
-        case GK_N_ATOM: {
-          // the run of atoms on this column (NetBuilder emits a column's atoms back to back)
-          const uint32_t col = op.w1 >> 8;
-          while (next < NOPS && (ops[next].w0 & 0xffffu) == (op.w0 & 0xffffu) && (ops[next].w1 >> 8) == col) ++next;
-          const GkColumn& c = cols[col];
-          const uint32_t cnt = s_cnt[level], lo = s_lo[level], words = (cnt + 31u) >> 5;
-          bool any_reg = false;
-          for (uint32_t k = i; k < next; ++k) any_reg = any_reg || reg_op(ops[k].w1 & 0xffu);
-          if (any_reg) {
-            const bool has_vt = (c.enc & GK_ENC_VT) != 0u, has_sid = (c.enc & GK_ENC_SID) != 0u, has_num = (c.enc & GK_ENC_NUM) != 0u;
-            for (uint32_t w = 0; w < words; w += 4u) {
-              const uint32_t r0 = w * 32u + lane;
-              const size_t row0 = (size_t)lo + r0;
-              uint32_t vt[4], sid[4];
-              long long num[4];
-              bool ok[4];
+    for (uint32_t ph = 0; ph < NP; ++ph) {
+      const uint32_t ibase = s_poff[ph], icnt = s_poff[ph + 1] - ibase;
+#ifdef GK_PHASE_TIMING
+      const long long tp0 = clock64();
+#endif
+#ifdef GK_L2_PREFETCH   /* measured on B200: 0.78 ms -> 1.04 ms per 1M objects -- the bulk prefetches serialise on the issuing warp; off */
+      if (ph + 2 == NP && warp == kWarps - 1 && t + gridDim.x < p.ntiles) prefetch_tile(p, cols, scopes, t + gridDim.x, lane);
+#endif
+      // items are sorted heaviest first: dealing them round-robin to the warps is a longest-processing-time schedule
+      for (uint32_t k = warp; k < icnt; k += kWarps) {
+        const uint32_t item = items[ibase + k];
+        const GkOp op = ops[item & 0xfffffu];
+        const uint32_t part = (item >> 20) & 0x3fu, nparts = item >> 26;
+        const uint32_t kind = op.w0 & 0xffu, level = (op.w0 >> 8) & 0xffu;
+        uint32_t* out = slots + (op.w0 >> 16);
+#ifdef GK_PHASE_TIMING
+        const long long ti0 = clock64();
+#endif
+        switch (kind) {
+          case GK_N_ATOM: {
+            const uint32_t cnt = s_cnt[level], words = (cnt + 31u) >> 5;
+            const uint32_t amask = ~(uint32_t)(GK_ATOM_UNROLL - 1);
+            const uint32_t pw0 = (words * part / nparts) & amask, pw1 = part + 1u == nparts ? words : ((words * (part + 1u) / nparts) & amask);
+            atom_rows(cols[op.w1 >> 8], op.w1 & 0xffu, op.w2, op.w3, pool, cbytes, s_lo[level], cnt, pw0, pw1, lane, out);
+            break;
+          }
+#ifdef GK_FUSED_ATOMS
+          case GK_N_ATOMS: {
+            const uint32_t cnt = s_cnt[level], words = (cnt + 31u) >> 5;
+            const uint32_t pw0 = (words * part / nparts) & ~3u, pw1 = part + 1u == nparts ? words : ((words * (part + 1u) / nparts) & ~3u);
+            atoms_rows(cols[op.w1 >> 8], pool + op.w2, op.w3, pool, cbytes, s_lo[level], cnt, pw0, pw1, lane, slots);
+            break;
+          }
+#endif
+          case GK_N_GATE: {
+            const uint32_t f = op.w2, words = (s_cnt[level] + 31u) >> 5, nin = op.w3;
+            const uint32_t* in = pool + op.w1;
+            const uint32_t no = (f & GK_G_NEG_OUT) ? FULL : 0u;
+            const bool is_or = (f & GK_G_OR) != 0u;
+            for (uint32_t i = lane; i < words; i += 32u) {
+              uint32_t acc = is_or ? 0u : FULL;
+              for (uint32_t j = 0; j < nin; ++j) {
+                const uint32_t e = in[j];
+                const uint32_t x = slots[(e & 0xffffu) + i] ^ (uint32_t)((int32_t)e >> 31);
+                acc = is_or ? (acc | x) : (acc & x);
+              }
+              out[i] = acc ^ no;
+            }
+            break;
+          }
+          case GK_N_CONST: {
+            const uint32_t v = (op.w1 & 1u) ? FULL : 0u, words = (s_cnt[level] + 31u) >> 5;
+            for (uint32_t i = lane; i < words; i += 32u) out[i] = v;
+            break;
+          }
+          case GK_N_BCAST: {   // parent-level columns -> rows of the child scope `level`, for every (in, out) pair of the group
+            const uint32_t par = (uint32_t)scopes[level].parent, npair = op.w3;
+            const uint32_t* pairs = pool + op.w1;
+            const uint32_t* coff = scopes[level].off + s_lo[par];
+            const uint32_t clo = s_lo[level], pcnt = s_cnt[par], words = (s_cnt[level] + 31u) >> 5;
+            for (uint32_t j = 0; j < npair; ++j) {
+              uint32_t* dst = slots + (pairs[j] >> 16);
+              for (uint32_t i = lane; i < words; i += 32u) dst[i] = 0u;
+            }
+            __syncwarp();
+            // the CSR offsets are the only global loads here: fetch them for four 32-row groups before touching any, so the
+            // op pays one memory latency per 128 parent rows instead of one per 32
+            for (uint32_t r0 = lane; r0 < pcnt; r0 += 128u) {
+              uint32_t ra[4], rb[4];
 #pragma unroll
               for (int u = 0; u < 4; ++u) {
-                ok[u] = r0 + 32u * u < cnt;
-                vt[u] = (ok[u] && has_vt) ? (uint32_t)c.vt[row0 + 32u * u] : (uint32_t)GK_VT_UNDEF;
-                sid[u] = (ok[u] && has_sid) ? c.sid[row0 + 32u * u] : (uint32_t)GK_SID_UNDEF;
-                num[u] = (ok[u] && has_num) ? c.num[row0 + 32u * u] : 0ll;
+                const uint32_t r = r0 + 32u * u;
+                ra[u] = rb[u] = 0u;
+                if (r < pcnt) {
+                  ra[u] = coff[r] - clo;
+                  rb[u] = coff[r + 1] - clo;
+                }
               }
-              for (uint32_t k = i; k < next; ++k) {
-                const GkOp a = ops[k];
-                const uint32_t aop = a.w1 & 0xffu;
-                if (!reg_op(aop)) continue;
-                uint4 wd;
-                wd.x = __ballot_sync(FULL, ok[0] && atom_on_regs(aop, a.w2, a.w3, vt[0], sid[0], num[0], pool));
-                wd.y = __ballot_sync(FULL, ok[1] && atom_on_regs(aop, a.w2, a.w3, vt[1], sid[1], num[1], pool));
-                wd.z = __ballot_sync(FULL, ok[2] && atom_on_regs(aop, a.w2, a.w3, vt[2], sid[2], num[2], pool));
-                wd.w = __ballot_sync(FULL, ok[3] && atom_on_regs(aop, a.w2, a.w3, vt[3], sid[3], num[3], pool));
-                if (lane == 0) *reinterpret_cast<uint4*>(slots + (a.w0 >> 16) + w) = wd;
-              }
-            }
-          }
-          for (uint32_t k = i; k < next; ++k) {   // prefix / suffix / contains atoms: their own passes over the HEAD / byte columns
-            const GkOp a = ops[k];
-            if (!reg_op(a.w1 & 0xffu)) atom_rows(c, a.w1 & 0xffu, a.w2, a.w3, pool, cbytes, lo, cnt, 0u, words, lane, slots + (a.w0 >> 16));
-          }
-          break;
-        }
-        case GK_N_GATE: {
-          // gates of one phase are independent of each other: the run at this level is dealt to the lanes as (gate, word) items
-          const uint32_t ph = op_phase[i];
-          while (next < NOPS && (ops[next].w0 & 0xffffu) == (op.w0 & 0xffffu) && op_phase[next] == ph) ++next;
-          const uint32_t words = (s_cnt[level] + 31u) >> 5;
-          if (words == 0u) break;
-          uint32_t sh = 0;
-          while ((1u << sh) < words) ++sh;
-          const uint32_t total = (next - i) << sh;
-          for (uint32_t it = lane; it < total; it += 32u) {
-            const uint32_t g = it >> sh, wi = it & ((1u << sh) - 1u);
-            if (wi >= words) continue;
-            const GkOp o = ops[i + g];
-            const uint32_t f = o.w2, nin = o.w3;
-            const uint32_t* in = pool + o.w1;
-            const bool is_or = (f & GK_G_OR) != 0u;
-            uint32_t acc = is_or ? 0u : FULL;
-            for (uint32_t j = 0; j < nin; ++j) {
-              const uint32_t e = in[j];
-              const uint32_t x = slots[(e & 0xffffu) + wi] ^ (uint32_t)((int32_t)e >> 31);
-              acc = is_or ? (acc | x) : (acc & x);
-            }
-            slots[(o.w0 >> 16) + wi] = acc ^ ((f & GK_G_NEG_OUT) ? FULL : 0u);
-          }
-          break;
-        }
-        case GK_N_CONST: {
-          const uint32_t v = (op.w1 & 1u) ? FULL : 0u, words = (s_cnt[level] + 31u) >> 5;
-          for (uint32_t k = lane; k < words; k += 32u) out[k] = v;
-          break;
-        }
-        case GK_N_BCAST: {   // parent-level columns -> rows of the child scope `level`, for every (in, out) pair of the group
-          const uint32_t par = (uint32_t)scopes[level].parent, npair = op.w3;
-          const uint32_t* pairs = pool + op.w1;
-          const uint32_t* coff = scopes[level].off + s_lo[par];
-          const uint32_t clo = s_lo[level], pcnt = s_cnt[par], words = (s_cnt[level] + 31u) >> 5;
-          for (uint32_t j = 0; j < npair; ++j) {
-            uint32_t* dst = slots + (pairs[j] >> 16);
-            for (uint32_t k = lane; k < words; k += 32u) dst[k] = 0u;
-          }
-          __syncwarp();
-          for (uint32_t r = lane; r < pcnt; r += 32u) {
-            const uint32_t a = coff[r] - clo, b = coff[r + 1] - clo;
-            if (b <= a) continue;
-            for (uint32_t j = 0; j < npair; ++j) {
-              const uint32_t e = pairs[j];
-              if ((slots[(e & 0xffffu) + (r >> 5)] >> (r & 31u)) & 1u) {
-                uint32_t* dst = slots + (e >> 16);
-                for (uint32_t w = a >> 5; w <= (b - 1u) >> 5; ++w) atomicOr(&dst[w], range_mask(w, a, b));
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const uint32_t r = r0 + 32u * u, a = ra[u], b = rb[u];
+                if (b <= a) continue;
+                for (uint32_t j = 0; j < npair; ++j) {
+                  const uint32_t e = pairs[j];
+                  if ((slots[(e & 0xffffu) + (r >> 5)] >> (r & 31u)) & 1u) {
+                    uint32_t* dst = slots + (e >> 16);
+                    for (uint32_t w = a >> 5; w <= (b - 1u) >> 5; ++w) atomicOr(&dst[w], range_mask(w, a, b));
+                  }
+                }
               }
             }
+            break;
           }
-          break;
-        }
-        case GK_N_ACC: {     // EXISTS: OR over each parent's child range; the ranges are read once for the whole group of pairs
-          const uint32_t par = (uint32_t)scopes[level].parent, npair = op.w3;
-          const uint32_t* pairs = pool + op.w1;
-          const uint32_t* coff = scopes[level].off + s_lo[par];
-          const uint32_t clo = s_lo[level], pcnt = s_cnt[par];
-          const uint32_t pw = (pcnt + 31u) >> 5, cw = (s_cnt[level] + 31u) >> 5;
-          for (uint32_t g = 0; g < pw; ++g) {
-            const uint32_t r = g * 32u + lane;
-            uint32_t a = 0u, b = 0u;
-            if (r < pcnt) {
-              a = coff[r] - clo;
-              b = coff[r + 1] - clo;
-            }
-            // a range of up to 32 children is a 32-bit window of the child bit column starting at bit a: one funnel shift
-            // over two adjacent words, branch-free for every lane; longer ranges (rare) add a tail loop
-            const uint32_t nb = b - a, shf = a & 31u;
-            const uint32_t m = nb >= 32u ? FULL : ((1u << nb) - 1u);
-            const uint32_t wl = cw ? min(a >> 5, cw - 1u) : 0u, wh = cw ? min((a >> 5) + 1u, cw - 1u) : 0u;
-            const bool wide = nb > 32u;
-            const bool any_wide = __any_sync(FULL, wide);
-            for (uint32_t j = 0; j < npair; ++j) {
-              const uint32_t e = pairs[j];
-              const uint32_t* in = slots + (e & 0xffffu);
-              bool any = cw != 0u && (__funnelshift_r(in[wl], in[wh], shf) & m) != 0u;
-              if (any_wide)
-                if (wide && !any)
-                  for (uint32_t w = (a + 32u) >> 5; w <= (b - 1u) >> 5 && !any; ++w) any = (in[w] & range_mask(w, a + 32u, b)) != 0u;
-              const uint32_t wd = __ballot_sync(FULL, any);
-              if (lane == 0) slots[(e >> 16) + g] = wd;
-            }
-          }
-          break;
-        }
-        case GK_N_MATCH: {
-          uint32_t* err = slots + (op.w1 & 0xffffu);
-          const GkMatch& m = match[op.w2];
-          const uint32_t words = (nobj + 31u) >> 5;
-          for (uint32_t r = lane; r < words * 32u; r += 32u) {
-            int res = 0;
-            if (r < nobj && !(p.batch.flags[obj0 + r] & GK_F_SKIP)) res = gk_match(p.batch, pool, cbytes, m, obj0 + r);
-            if (res < 0) {
-              const uint32_t slot = atomicAdd(p.out.errcount, 1u);
-              if (slot < p.out.errcap) {
-                p.out.errlist[3 * slot] = obj0 + r;
-                p.out.errlist[3 * slot + 1] = op.w2;
-                p.out.errlist[3 * slot + 2] = (uint32_t)(-res);
+          case GK_N_ACC: {     // EXISTS: OR over each parent's child range; ranges + masks computed once for the whole group
+            const uint32_t par = (uint32_t)scopes[level].parent, npair = op.w3;
+            const uint32_t* pairs = pool + op.w1;
+            const uint32_t* coff = scopes[level].off + s_lo[par];
+            const uint32_t clo = s_lo[level], pcnt = s_cnt[par];
+            const uint32_t pw = (pcnt + 31u) >> 5, cw = (s_cnt[level] + 31u) >> 5;
+            const uint32_t g0 = pw * part / nparts, g1 = pw * (part + 1u) / nparts;   // parent-row groups of this part
+            for (uint32_t g = g0; g < g1; g += 4u) {
+              // CSR offsets of four groups first (the only global loads of the op): one memory latency per 128 parent rows
+              uint32_t ra[4], rb[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const uint32_t r = (g + u) * 32u + lane;
+                ra[u] = rb[u] = 0u;
+                if (g + u < g1 && r < pcnt) {
+                  ra[u] = coff[r] - clo;
+                  rb[u] = coff[r + 1] - clo;
+                }
+              }
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                if (g + u >= g1) break;   // warp-uniform
+                const uint32_t a = ra[u], b = rb[u];
+                // A range of up to 32 children is a 32-bit window of the child bit column starting at bit a: one funnel
+                // shift over two adjacent words, branch-free for every lane.  Longer ranges (rare) add a tail loop.
+                const uint32_t nb = b - a, sh = a & 31u;
+                const uint32_t m = nb >= 32u ? FULL : ((1u << nb) - 1u);
+                const uint32_t wl = cw ? min(a >> 5, cw - 1u) : 0u, wh = cw ? min((a >> 5) + 1u, cw - 1u) : 0u;
+                const bool wide = nb > 32u;
+                const bool any_wide = __any_sync(FULL, wide);
+                for (uint32_t j = 0; j < npair; ++j) {
+                  const uint32_t e = pairs[j];
+                  const uint32_t* in = slots + (e & 0xffffu);
+                  bool any = (__funnelshift_r(in[wl], in[wh], sh) & m) != 0u;   // (m == 0 for a parent without children)
+                  if (any_wide)
+                    if (wide && !any)
+                      for (uint32_t w = (a + 32u) >> 5; w <= (b - 1u) >> 5 && !any; ++w) any = (in[w] & range_mask(w, a + 32u, b)) != 0u;
+                  const uint32_t wd = __ballot_sync(FULL, any);
+                  if (lane == 0) slots[(e >> 16) + g + u] = wd;
+                }
               }
             }
-            const uint32_t wm = __ballot_sync(FULL, res > 0), we = __ballot_sync(FULL, res < 0);
-            if (lane == 0) {
-              out[r >> 5] = wm;
-              err[r >> 5] = we;
-            }
+            break;
           }
-          break;
+          case GK_N_MATCH: {
+            uint32_t* err = slots + (op.w1 & 0xffffu);
+            const GkMatch& m = match[op.w2];
+            const uint32_t words = (nobj + 31u) >> 5;
+            for (uint32_t r = (words * part / nparts) * 32u + lane; r < (words * (part + 1u) / nparts) * 32u; r += 32u) {
+              int res = 0;
+              if (r < nobj && !(p.batch.flags[obj0 + r] & GK_F_SKIP)) res = gk_match(p.batch, pool, cbytes, m, obj0 + r);
+              if (res < 0) {
+                const uint32_t slot = atomicAdd(p.out.errcount, 1u);
+                if (slot < p.out.errcap) {
+                  p.out.errlist[3 * slot] = obj0 + r;
+                  p.out.errlist[3 * slot + 1] = op.w2;
+                  p.out.errlist[3 * slot + 2] = (uint32_t)(-res);
+                }
+              }
+              const uint32_t wm = __ballot_sync(FULL, res > 0), we = __ballot_sync(FULL, res < 0);
+              if (lane == 0) {
+                out[r >> 5] = wm;
+                err[r >> 5] = we;
+              }
+            }
+            break;
+          }
+          default: break;
         }
-        default: break;
+#ifdef GK_PHASE_TIMING
+        if (lane == 0) {
+          const uint32_t tk = kind;
+          atomicAdd(p.timing + 2 * (kMaxPhases + 2) + 2 * tk, (unsigned long long)(clock64() - ti0));
+          atomicAdd(p.timing + 2 * (kMaxPhases + 2) + 2 * tk + 1, 1ull);
+        }
+#endif
       }
-      __syncwarp();
-      i = next;
+#ifdef GK_PHASE_TIMING
+      if (lane == 0) atomicAdd(p.timing + 2 * ph + 1, (unsigned long long)(clock64() - tp0));
+      __syncthreads();
+      if (threadIdx.x == 0) atomicAdd(p.timing + 2 * ph, (unsigned long long)(clock64() - tp0));
+#else
+      __syncthreads();
+#endif
     }
-    // ---- gather: lane l holds the result word of constraint (32 wi + l) for one group of 32 objects; 32 ballots transpose
-    // that 32x32 bit block so that lane o ends up with the bitmap word of object o.  The words of one object are stored
-    // together (one 8-byte store per object and destination when W == 2), the 32 objects of a group are consecutive rows.
+#ifdef GK_PHASE_TIMING
+    const long long tg0 = clock64();
+#endif
+    // ---- gather: lane l of a warp holds the result word of constraint (32 w + l) for one group of 32 objects; 32 ballots
+    // transpose that 32x32 bit block so that lane o ends up with the bitmap word of object o.  The 32 objects of a group
+    // are consecutive rows of the object-major output: the stores are contiguous.
     const uint32_t owords = (nobj + 31u) >> 5;
-    for (uint32_t ow = 0; ow < owords; ++ow) {
-      const uint32_t obj = ow * 32u + lane;
-      const uint32_t valid = range_mask(ow, 0u, nobj);
-      uint32_t yv2[2] = {0u, 0u}, ye2[2] = {0u, 0u};
-      for (uint32_t wi = 0; wi < W; ++wi) {
-        const uint32_t c = wi * 32u + lane;
-        uint32_t xv = 0, xe = 0;
-        if (c < C && s_act[c]) {
-          const GkOutEnt oe = outs[c];
-          const uint32_t pv = (oe.flags & 1u) ? FULL : (oe.flags & 2u) ? 0u : slots[(oe.prog_slot) + ow];
-          xv = pv & slots[(oe.match_slot) + ow];
-          xe = slots[(oe.err_slot) + ow];
-        }
-        uint32_t yv = 0, ye = 0;
-        const bool any_e = __any_sync(FULL, xe != 0u);
+    for (uint32_t g = warp; g < owords * W; g += kWarps) {
+      const uint32_t wi = g % W, ow = g / W;          // constraint word, object word
+      const uint32_t c = wi * 32u + lane;
+      uint32_t xv = 0, xe = 0;
+      if (c < C && s_act[c]) {
+        const GkOutEnt oe = outs[c];
+        const uint32_t pv = (oe.flags & 1u) ? FULL : (oe.flags & 2u) ? 0u : slots[(oe.prog_slot) + ow];
+        xv = pv & slots[(oe.match_slot) + ow];
+        xe = slots[(oe.err_slot) + ow];
+      }
+      uint32_t yv = 0, ye = 0;
 #pragma unroll
-        for (uint32_t o = 0; o < 32u; ++o) {
-          const uint32_t bv = __ballot_sync(FULL, (xv >> o) & 1u);
-          if (lane == o) yv = bv;
-        }
-        if (any_e) {
-#pragma unroll
-          for (uint32_t o = 0; o < 32u; ++o) {
-            const uint32_t be = __ballot_sync(FULL, (xe >> o) & 1u);
-            if (lane == o) ye = be;
-          }
-        }
-        if (W == 2u) {
-          yv2[wi] = yv;
-          ye2[wi] = ye;
-        } else if (obj < nobj) {
-          const size_t at = (size_t)(obj0 + obj) * W + wi;
-          if (p.npeers) {
-            for (uint32_t q = 0; q < p.npeers; ++q) p.peer_viol[q][at] = yv;   // this rank is one of the peers
-          } else {
-            p.out.viol[at] = yv;
-          }
-          p.out.err[at] = ye;
-        }
-        // totals: every lane's column word covers 32 objects of ITS constraint
-        const uint32_t nv = __popc(xv & valid), ne = __popc(xe & valid);
-        if (c < C) {
-          if (nv) atomicAdd(&s_tot[c], nv);
-          if (ne) atomicAdd(&s_err[c], ne);
+      for (uint32_t o = 0; o < 32u; ++o) {
+        const uint32_t bv = __ballot_sync(FULL, (xv >> o) & 1u), be = __ballot_sync(FULL, (xe >> o) & 1u);
+        if (lane == o) {
+          yv = bv;
+          ye = be;
         }
       }
-      if (W == 2u && obj < nobj) {
-        const size_t at = (size_t)(obj0 + obj);
-        const uint2 v2 = make_uint2(yv2[0], yv2[1]);
+      const uint32_t obj = ow * 32u + lane;
+      if (obj < nobj) {
+        const size_t at = (size_t)(obj0 + obj) * W + wi;
         if (p.npeers) {
-          for (uint32_t q = 0; q < p.npeers; ++q) reinterpret_cast<uint2*>(p.peer_viol[q])[at] = v2;   // one 8-byte store per peer
+          for (uint32_t q = 0; q < p.npeers; ++q) p.peer_viol[q][at] = yv;   // this rank is one of the peers
         } else {
-          reinterpret_cast<uint2*>(p.out.viol)[at] = v2;
+          p.out.viol[at] = yv;
         }
-        reinterpret_cast<uint2*>(p.out.err)[at] = make_uint2(ye2[0], ye2[1]);
+        p.out.err[at] = ye;
+      }
+      // totals: every lane's column word covers 32 objects of ITS constraint
+      const uint32_t valid = range_mask(ow, 0u, nobj);
+      const uint32_t nv = __popc(xv & valid), ne = __popc(xe & valid);
+      if (c < C) {
+        if (nv) atomicAdd(&s_tot[c], nv);
+        if (ne) atomicAdd(&s_err[c], ne);
       }
     }
-    __syncwarp();
+#ifdef GK_PHASE_TIMING
+    if (lane == 0) atomicAdd(p.timing + 2 * NP + 1, (unsigned long long)(clock64() - tg0));
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAdd(p.timing + 2 * NP, (unsigned long long)(clock64() - tg0));
+#else
+    __syncthreads();
+#endif
   }
-  __syncthreads();
   for (uint32_t c = threadIdx.x; c < C; c += blockDim.x) {
     if (s_tot[c]) atomicAdd(p.out.totals + c, (unsigned long long)s_tot[c]);
     if (s_err[c]) atomicAdd(p.out.err_totals + c, (unsigned long long)s_err[c]);
   }
   if (p.npeers) {
     // the last CTA to arrive sees every CTA's contribution and publishes the totals to all peers
-    __shared__ uint32_t s_last;
+    // (the flag lives in the dynamic shared-memory area -- s_lo is free by now -- so the kernel keeps zero static shared bytes)
+    volatile uint32_t* s_last = s_lo;
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) s_last = atomicAdd(p.done_ctr, 1u) == gridDim.x - 1u ? 1u : 0u;
+    if (threadIdx.x == 0) *s_last = atomicAdd(p.done_ctr, 1u) == gridDim.x - 1u ? 1u : 0u;
     __syncthreads();
-    if (s_last) {
+    if (*s_last) {
       __threadfence();
       for (uint32_t c = threadIdx.x; c < C; c += blockDim.x) {
         const unsigned long long tv = atomicAdd(p.out.totals + c, 0ull), te = atomicAdd(p.out.err_totals + c, 0ull);
