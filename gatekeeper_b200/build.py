@@ -95,6 +95,17 @@ def build(verbose=False, hostemu=True, force=False):
         _run([_nvcc(), "-shared", "-o", LIB, *objs, ko, "-Xcompiler", "-pthread", "-cudart", "static"])
     if hostemu and (force or _stale(EMU, objs + [eo], 0)):
         _run(["g++", "-shared", "-o", EMU, *objs, eo, "-pthread"])
+    # TEST / BENCH ONLY: the C++ CPU restatement of the reference's review loop (oracle/cpu_ref.cpp) over the engine's host objects
+    csrc = os.path.join(ROOT, "oracle", "cpu_ref.cpp")
+    cdir = os.path.join(ROOT, "oracle", "_build")
+    os.makedirs(cdir, exist_ok=True)
+    co = os.path.join(OBJ, "cpu_ref.cpp.o")
+    if force or _stale(co, [csrc], hdr_m):
+        _run(["g++", *CXXFLAGS, "-c", csrc, "-o", co])
+    cobjs = [os.path.join(OBJ, s + ".o") for s in ("val.cpp", "rego_parse.cpp", "rego_eval.cpp", "lower.cpp", "xprog.cpp", "engine.cpp")]
+    CPUREF = os.path.join(cdir, "libgk_cpuref.so")
+    if force or _stale(CPUREF, cobjs + [co], 0):
+        _run(["g++", "-shared", "-o", CPUREF, *cobjs, co, "-pthread"])
     ssrc = os.path.join(CSRC, "synth.cpp")
     if force or _stale(SYNTH, [ssrc], 0):
         _run(["g++", *CXXFLAGS, "-shared", "-o", SYNTH, ssrc])

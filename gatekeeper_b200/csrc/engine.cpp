@@ -1797,6 +1797,13 @@ std::shared_ptr<HostBatch> Engine::flatten(const ObjIn* objs, size_t n, const Co
   return out;
 }
 
+std::map<std::string, VP> Engine::namespaces_snapshot() {
+  std::shared_lock<std::shared_mutex> l(mu_);
+  std::map<std::string, VP> out;
+  for (auto& kv : namespaces_) out.emplace(kv.first, v_deep_copy(kv.second));
+  return out;
+}
+
 // ====================================================================================== device ingest: request + lookups
 IngestReq Engine::ingest_request(const std::shared_ptr<const Compiled>& c, const uint8_t* blob, const unsigned long long* ooff, size_t n, uint32_t source,
                                  const std::string& process) {

@@ -185,6 +185,7 @@ class Engine {
   void autoreject(const Compiled& c, const ObjIn& obj, uint32_t obj_ix, uint32_t cix, uint32_t code, const std::string& ep,
                   std::vector<Violation>& out);
   std::string dump();
+  std::map<std::string, VP> namespaces_snapshot();   // (deep copies: safe to read from another thread without touching shared reference counts)
   // everything a backend needs to flatten a blob of plain objects on the device (xprog.hpp); `blob` must outlive the request
   IngestReq ingest_request(const std::shared_ptr<const Compiled>& c, const uint8_t* blob, const unsigned long long* ooff, size_t n, uint32_t source,
                            const std::string& process);
