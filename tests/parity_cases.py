@@ -1377,3 +1377,57 @@ def case_blob_other_templates(lib, n=300, seed=7):
         _blob_parity(orc, drv, docs)
     assert n_dev >= 4, (n_dev, n_host)
     return n_dev, n_host
+
+
+# ------------------------------------------------------------------------------------------ reference-held pins outside the test tables
+def case_doc_pins(lib):
+    """The exact messages the reference's documentation quotes (website/docs/violations.md, workload-resources.md, audit.md) and
+    the AllowedRepos manifests of the gator suite (tests/golden/make_doc_pins.py): oracle AND engine must print them verbatim --
+    they pin sprintf("%v") of an array, of an object and of strings for K8sAllowedRepos, K8sPSPPrivilegedContainer, K8sContainerLimits."""
+    n = 0
+    for case in golden("doc_pins.json"):
+        tm, cons, nss = _split_docs(case["docs"])
+        orc, drv, skipped = make_pair(tm, cons, nss, lib_path=lib)
+        assert not skipped
+        objs = [d for d in case["docs"] if d.get("kind") not in ("ConstraintTemplate",) and not str(d.get("apiVersion", "")).startswith("constraints.gatekeeper.sh")]
+        revs = [D.Review(object=d, source="Original") for d in objs]
+        ep = case["ep"]
+        want = oracle_results(orc, revs, ep)
+        for via_blob in (False, True):
+            resp = drv.ReviewBlob(W.PyBlob(objs), ep, flags=D.F_MATERIALIZE) if via_blob else drv.ReviewBatch(revs, ep)
+            got = engine_results(resp)
+            assert_same(want, got)
+            have = sorted((r[1], r[2], r[4]) for r in got)
+            exp = sorted((e["constraint"], e["msg"], e["action"]) for e in case["expect"])
+            assert have == exp, (case["name"], have, exp)
+            assert bool(got) == bool(case.get("expect_any", bool(exp)))
+        n += 1
+    return n
+
+
+def case_wildcard_vectors_through_kernel(lib):
+    """pkg/wildcard/wildcard_test.go:7-193 through the DEVICE matcher (vm_core.h gk_wild / gk_wild_gen): `matches` vectors as
+    spec.match.namespaces and as spec.match.name, `generateName` vectors as spec.match.name against metadata.generateName."""
+    t = golden("templates.json")["fixtures_TemplateNeverValidate"]
+    checked = 0
+    for v in golden("wildcard_vectors.json"):
+        pats = []
+        if v["fn"] == "matches":
+            pats.append(({"namespaces": [v["w"]]}, {"apiVersion": "v1", "kind": "Pod", "metadata": {"name": "p", "namespace": v["candidate"]}}))
+            pats.append(({"excludedNamespaces": [v["w"]]}, {"apiVersion": "v1", "kind": "Pod", "metadata": {"name": "p", "namespace": v["candidate"]}}))
+            pats.append(({"name": v["w"]}, {"apiVersion": "v1", "kind": "Pod", "metadata": {"name": v["candidate"], "namespace": "x"}}))
+        else:
+            pats.append(({"name": v["w"]}, {"apiVersion": "v1", "kind": "Pod", "metadata": {"generateName": v["candidate"], "namespace": "x"}}))
+        for match, obj in pats:
+            if not obj["metadata"].get("namespace", "x") or obj["metadata"].get("name") == "":
+                continue                                  # an empty namespace / name is "not set": another branch of match.go
+            drv = D.Driver(lib_path=lib)
+            drv.add_template(t["kind"], t["rego"])
+            drv.AddConstraint({"kind": t["kind"], "metadata": {"name": "c"}, "spec": {"match": match}})
+            want = v["matches"] != ("excludedNamespaces" in match)
+            for via_blob in (False, True):
+                resp = (drv.ReviewBlob(W.PyBlob([obj]), k8s.AUDIT_EP, source="") if via_blob else drv.ReviewBatch([D.Review(object=obj)], k8s.AUDIT_EP))
+                assert bool(resp.viol_bits[0, 0] & 1) == want, (v, match, via_blob)
+            checked += 1
+    assert checked >= 40
+    return checked

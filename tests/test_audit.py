@@ -4,6 +4,8 @@ import json
 
 import parity_cases as P
 from conftest import HOSTEMU
+
+LIB = HOSTEMU   # tests/test_audit_gpu.py re-runs this module against the CUDA library (LIB = None)
 from gatekeeper_b200 import metrics as M
 from oracle import audit as OA
 
@@ -11,15 +13,15 @@ MS = 1_000_000
 
 
 def test_audit_aggregation_matches_oracle():
-    P.case_audit(HOSTEMU, n=1200)
+    P.case_audit(LIB, n=1200)
 
 
 def test_audit_small_limit():
-    P.case_audit(HOSTEMU, n=400, limit=2, excluded=())
+    P.case_audit(LIB, n=400, limit=2, excluded=())
 
 
 def test_validation_messages():
-    P.case_validation_messages(HOSTEMU)
+    P.case_validation_messages(LIB)
 
 
 def test_truncate_string_reference_behaviour():
@@ -64,7 +66,7 @@ def test_excluder_vectors_of_the_reference():
         nsobj = {"apiVersion": "v1", "kind": "Namespace", "metadata": {"name": v["namespace"]}}
         assert k8s.is_namespace_excluded(v["patterns"], pod) == v["excluded"], v["name"]
         assert k8s.is_namespace_excluded(v["patterns"], nsobj) == v["excluded"], v["name"]      # a Namespace is tested by its own name
-        orc, drv, _ = make_pair([(t["kind"], t["rego"])], [{"kind": t["kind"], "metadata": {"name": "c"}}], lib_path=HOSTEMU)
+        orc, drv, _ = make_pair([(t["kind"], t["rego"])], [{"kind": t["kind"], "metadata": {"name": "c"}}], lib_path=LIB)
         drv.SetExcludedNamespaces("audit", v["patterns"])
         for o in (pod, nsobj):
             resp = drv.ReviewBatch([D.Review(object=o, source="Original")], k8s.AUDIT_EP, process="audit")
@@ -91,7 +93,7 @@ def test_audit_from_cache_scenarios_of_the_reference():
     for name, excluded, con, want in (("obj excluded from audit", ["test-namespace-1"], denyall, 0), ("obj not excluded from audit", [], denyall, 1),
                                       ("audit excluded from constraint", [], scoped(k8s.WEBHOOK_EP), 0),
                                       ("audit included in constraints", [], scoped(k8s.AUDIT_EP), 1)):
-        orc, drv, _ = make_pair([("denyall", rego)], [con], lib_path=HOSTEMU)
+        orc, drv, _ = make_pair([("denyall", rego)], [con], lib_path=LIB)
         assert len(OA.audit(orc, [pod], excluded_namespaces=excluded)["results"]) == want, name
         drv.SetExcludedNamespaces("audit", excluded)
         run = D.AuditRun(drv)
@@ -113,7 +115,7 @@ def test_limit_queue_vectors_of_the_reference_through_the_engine():
     objs = [{"apiVersion": "rbac.authorization.k8s.io/v1", "kind": "ClusterRoleBinding", "metadata": {"name": "x"}},
             {"apiVersion": "authorization.k8s.io/v1", "kind": "SubjectAccessReview", "metadata": {"name": "x"}},
             {"apiVersion": "rbac.authorization.k8s.io/v1", "kind": "RoleBinding", "metadata": {"name": "x"}}]
-    orc, drv, _ = make_pair([("P", rego)], [{"kind": "P", "metadata": {"name": "c"}}], lib_path=HOSTEMU)
+    orc, drv, _ = make_pair([("P", rego)], [{"kind": "P", "metadata": {"name": "c"}}], lib_path=LIB)
     for limit, want in ((3, ["RoleBinding", "ClusterRoleBinding", "SubjectAccessReview"]), (2, ["ClusterRoleBinding", "SubjectAccessReview"])):
         run = D.AuditRun(drv, violations_limit=limit)
         run.add_batch(drv.upload([D.Review(object=o, source="Original") for o in objs]), k8s.AUDIT_EP)
@@ -144,7 +146,7 @@ def test_get_validation_messages_vectors_of_the_reference():
         assert (len(d), len(w)) == (n_deny, n_warn), name
         assert all(m == "[ph] test" for m in d + w)
         cons = [{"kind": "Foo", "metadata": {"name": "ph-%d" % i}, "spec": {"enforcementAction": a}} for i, a in enumerate(actions)]
-        orc, drv, _ = make_pair([("Foo", rego)], cons, lib_path=HOSTEMU)
+        orc, drv, _ = make_pair([("Foo", rego)], cons, lib_path=LIB)
         (deny, warn), = drv.ValidationMessages([D.Review(object=ns, namespace_name="")])
         assert (len(deny), len(warn)) == (n_deny, n_warn), (name, deny, warn)
         assert all(m.startswith("[ph-") and m.endswith("] test") for m in deny + warn)
@@ -159,7 +161,7 @@ def test_webhook_excluded_namespaces_vectors_of_the_reference():
     from oracle import k8s
     rego = 'package goodrego\n\nviolation[{"msg": msg}] {\n   msg := "Maybe this will work?"\n}'
     raw = {"apiVersion": "v1", "kind": "Pod", "metadata": {"name": "acbd", "namespace": ""}}
-    orc, drv, _ = make_pair([("K8sGoodRego", rego)], [{"kind": "K8sGoodRego", "metadata": {"name": "constraint"}}], lib_path=HOSTEMU)
+    orc, drv, _ = make_pair([("K8sGoodRego", rego)], [{"kind": "K8sGoodRego", "metadata": {"name": "constraint"}}], lib_path=LIB)
     drv.SetExcludedNamespaces("*", ["kube-*"])
     for name, ns, op, obj, old, allowed in (("ExcludedNamespace invalid create", "notkube-test", "CREATE", raw, None, False),
                                             ("ExcludedNamespace valid create", "kube-test", "CREATE", raw, None, True),
@@ -192,7 +194,7 @@ def test_admission_coalescer_batches_concurrent_reviews():
     psp = golden("psp_suite.json")
     cons = [json.loads(json.dumps(c)) for c in psp["constraints"]]
     cons[0].setdefault("spec", {})["enforcementAction"] = "warn"
-    orc, drv, _ = make_pair([(t["kind"], t["rego"]) for t in psp["templates"]], cons, lib_path=HOSTEMU)
+    orc, drv, _ = make_pair([(t["kind"], t["rego"]) for t in psp["templates"]], cons, lib_path=LIB)
     pods = psp["pods"]
     ok_pod = {"apiVersion": "v1", "kind": "Pod", "metadata": {"name": "fine", "namespace": "default"}, "spec": {"containers": [{"name": "c", "image": "x"}]}}
     reqs = [D.Review(object=(ok_pod if i % 7 == 0 else pods[i % len(pods)]), operation="CREATE", namespace_name="default") for i in range(48)]

@@ -300,3 +300,11 @@ def test_blob_other_templates():
 def test_blob_rego_fuzz():
     accepted, n_results, rejected, n_device = P.case_rego_fuzz(HOSTEMU, n_templates=40, n_objects=100, seed=11, via_blob=True)
     assert n_device >= accepted // 2, (n_device, accepted)
+
+
+def test_doc_pins():
+    assert P.case_doc_pins(HOSTEMU) == 5
+
+
+def test_wildcard_vectors_through_kernel_core():
+    P.case_wildcard_vectors_through_kernel(HOSTEMU)

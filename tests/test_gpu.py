@@ -279,3 +279,11 @@ def test_blob_large_batch_properties():
         del os.environ["GK_NO_DEVICE_INGEST_RUNTIME"]
     assert (dev.viol_bits == host.viol_bits).all() and (dev.err_bits == host.err_bits).all() and dev.totals == host.totals
     assert sum(dev.totals) > n
+
+
+def test_doc_pins():
+    assert P.case_doc_pins(LIB) == 5
+
+
+def test_wildcard_vectors_through_kernel():
+    P.case_wildcard_vectors_through_kernel(LIB)
