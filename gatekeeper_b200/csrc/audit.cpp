@@ -178,8 +178,25 @@ static void sv_json(const StatusViolation& sv, std::string& o) {
   o += "}";
 }
 
+void AuditRun::add_object_errors(const std::vector<std::string>& errs) {
+  for (size_t i = 0; i < errs.size(); ++i)
+    if (!errs[i].empty()) {
+      if (first_object_errors.size() < 20) first_object_errors.emplace_back(seen_objects + i, errs[i]);
+      ++object_errors;
+    }
+  seen_objects += errs.size();
+}
+
 std::string AuditRun::report() {
-  std::string o = "{\"objects\":" + std::to_string(objects) + ",\"results\":" + std::to_string(results) + ",\"totalViolations\":{";
+  std::string o = "{\"objects\":" + std::to_string(objects) + ",\"results\":" + std::to_string(results) + ",\"objectErrors\":{\"count\":" +
+                  std::to_string(object_errors) + ",\"first\":[";
+  for (size_t i = 0; i < first_object_errors.size(); ++i) {
+    if (i) o += ",";
+    o += "{\"object\":" + std::to_string(first_object_errors[i].first) + ",\"error\":";
+    json_quote(first_object_errors[i].second, o);
+    o += "}";
+  }
+  o += "]},\"totalViolations\":{";
   bool first = true;
   for (auto& kv : per_constraint) {
     if (!first) o += ",";

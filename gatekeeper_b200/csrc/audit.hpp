@@ -35,6 +35,11 @@ struct AuditRun {
   std::map<std::string, PerConstraint> per_constraint;   // key: "Kind/name"
   std::map<std::string, uint64_t> by_action;
   uint64_t objects = 0, results = 0;
+  // objects the review refused (undecodable JSON, kind missing ...): counted and the first few kept, so that a sweep never
+  // under-reports silently (the reference logs them per object: pkg/audit/manager.go:722-729)
+  uint64_t object_errors = 0, seen_objects = 0;
+  std::vector<std::pair<uint64_t, std::string>> first_object_errors;   // (object index within the run, text)
+  void add_object_errors(const std::vector<std::string>& errs);
 
   void fold(const std::string& key, StatusViolation sv);
   void merge(AuditRun& other);

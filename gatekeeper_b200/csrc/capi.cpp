@@ -1,6 +1,7 @@
 // C ABI (include/gk_engine.h) over Engine + Backend.  No exceptions cross this file's extern "C" surface.
 #include <chrono>
 #include <condition_variable>
+#include <deque>
 #include <mutex>
 #include <cstdlib>
 #include <cstring>
@@ -20,7 +21,9 @@ struct gk_engine {
   std::unique_ptr<Engine> eng;
   std::unique_ptr<Backend> be;
   std::mutex keys_mu;
-  std::vector<std::string> keys;   // constraint keys of the last compiled program
+  // constraint keys of the last compiled programs: a pointer handed out by gk_constraint_key stays valid until 16 further
+  // constraint-set changes have been observed through gk_constraint_count (results carry their own keys: gk_result_constraint_key)
+  std::deque<std::shared_ptr<std::vector<std::string>>> key_sets;
   uint64_t keys_version = 0;
   // The backend holds ONE program (the tables of one compiled snapshot).  Reviews of the same snapshot run concurrently; a
   // review that needs another snapshot (constraints changed meanwhile) waits until the ones in flight have finished.
@@ -407,12 +410,14 @@ uint32_t gk_constraint_count(gk_engine_t* e) {
   guard(nullptr, [&]() {
     auto c = e->eng->compiled();
     std::lock_guard<std::mutex> l(e->keys_mu);
-    if (e->keys_version != c->version) {
-      e->keys.clear();
-      for (auto* k : c->order) e->keys.push_back(k->kind + "/" + k->name);
+    if (e->keys_version != c->version || e->key_sets.empty()) {
+      auto ks = std::make_shared<std::vector<std::string>>();
+      for (auto* k : c->order) ks->push_back(k->kind + "/" + k->name);
+      e->key_sets.push_back(ks);
+      if (e->key_sets.size() > 16) e->key_sets.pop_front();
       e->keys_version = c->version;
     }
-    n = (uint32_t)e->keys.size();
+    n = (uint32_t)e->key_sets.back()->size();
   });
   return n;
 }
@@ -420,7 +425,7 @@ const char* gk_constraint_key(gk_engine_t* e, uint32_t index) {
   uint32_t n = gk_constraint_count(e);
   if (!e) return nullptr;
   std::lock_guard<std::mutex> l(e->keys_mu);
-  return index < n && index < e->keys.size() ? e->keys[index].c_str() : nullptr;
+  return !e->key_sets.empty() && index < n && index < e->key_sets.back()->size() ? (*e->key_sets.back())[index].c_str() : nullptr;
 }
 const char* gk_result_constraint_key(const gk_result* r, uint32_t index) {
   if (!r || !r->priv) return nullptr;
@@ -596,6 +601,8 @@ int gk_audit_add_batch(gk_audit_t* a, gk_batch_t* b, const char* ep_c, char** er
     std::vector<ObjIn> ins(b->n);
     for (size_t i = 0; i < ins.size(); ++i) ins[i] = b->obj_in(i);
     a->run.add_batch(*e->eng, *c, ins, ev.viol.data(), ev.err.empty() ? nullptr : ev.err.data(), ev.words, ev.errlist, ep);
+    if (b->host->obj_errors.empty()) a->run.add_object_errors(std::vector<std::string>(b->n));
+    else a->run.add_object_errors(b->host->obj_errors);
   });
 }
 

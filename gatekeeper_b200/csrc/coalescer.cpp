@@ -155,7 +155,17 @@ int gk_coalescer_review(gk_coalescer_t* c, const gk_obj* obj, char** out_json, c
     }
   }
   if (leader) {
-    run_batch(c, *mine);   // outside the lock: other batches can form and run meanwhile
+    // outside the lock: other batches can form and run meanwhile.  Whatever happens inside, every follower of this batch is
+    // released: an exception becomes the error of every ticket instead of unwinding past the waiters (and the C boundary).
+    try {
+      run_batch(c, *mine);
+    } catch (std::exception& x) {
+      for (auto* tk : mine->tickets)
+        if (tk->out_json.empty() && tk->error.empty()) tk->error = std::string("admission micro-batch failed: ") + x.what();
+    } catch (...) {
+      for (auto* tk : mine->tickets)
+        if (tk->out_json.empty() && tk->error.empty()) tk->error = "admission micro-batch failed";
+    }
     std::lock_guard<std::mutex> l(c->mu);
     for (auto* x : mine->tickets) x->done = true;
     c->cv_done.notify_all();

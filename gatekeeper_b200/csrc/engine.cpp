@@ -469,8 +469,27 @@ void Engine::add_template(const std::string& kind, const std::string& rego, cons
   t.kind = kind;
   t.src = rego;
   t.mod = mod;
+  // replacing a template re-lowers its existing constraints with THEIR parameters: a replacement that no longer compiles for
+  // them (or pushes the joint set over a limit) is rejected and the old template stays
+  auto old = templates_.find(kind);
+  const bool had = old != templates_.end();
+  TemplateEntry prev;
+  if (had) prev = old->second;
   templates_[kind] = std::move(t);
-  dirty_ = true;
+  bool used = false;
+  for (auto& c : constraints_) used = used || c->kind == kind;
+  if (used) {
+    try {
+      compile_locked();
+    } catch (...) {
+      if (had) templates_[kind] = prev;
+      else templates_.erase(kind);
+      dirty_ = true;
+      throw;
+    }
+  } else {
+    dirty_ = true;
+  }
 }
 
 bool Engine::remove_template(const std::string& kind) {
@@ -538,14 +557,24 @@ void Engine::add_constraint(const std::string& json) {
     Schema tmp;
     check_netlist_shape(lower_violation(tit->second.mod, c->params, tmp), tmp);
   }
+  // The constraint set is compiled JOINTLY (one schema, one netlist): limits that only the whole set can hit -- iteration
+  // scopes, columns, netlist size -- must fail THIS call, not every later review.  Trial-compile the prospective set and roll
+  // the mutation back when it does not compile.
+  auto saved = constraints_;
+  bool replaced = false;
   for (auto& e : constraints_)
     if (e->kind == c->kind && e->name == c->name) {
-      e = std::move(c);
-      dirty_ = true;
-      return;
+      e = c;
+      replaced = true;
     }
-  constraints_.push_back(std::move(c));
-  dirty_ = true;
+  if (!replaced) constraints_.push_back(c);
+  try {
+    compile_locked();
+  } catch (...) {
+    constraints_ = std::move(saved);
+    dirty_ = true;
+    throw;
+  }
 }
 
 bool Engine::remove_constraint(const std::string& kind, const std::string& name) {

@@ -13,6 +13,7 @@ import "C"
 
 import (
 	"encoding/json"
+	"errors"
 	"unsafe"
 )
 
@@ -127,7 +128,8 @@ func (d *Driver) validationMessages(res *C.gk_result, i int) (deny, warn []strin
 // Coalescer gathers the webhook's concurrent Query calls (one goroutine per admission request, policy.go:580-675) into
 // micro-batches: each Review call blocks until the batch it joined has been evaluated on the GPU.
 type Coalescer struct {
-	c *C.gk_coalescer_t
+	c  *C.gk_coalescer_t
+	ep string
 }
 
 // AdmissionOutcome is one request's share of a micro-batch.
@@ -156,24 +158,66 @@ func (d *Driver) NewCoalescer(maxBatch, maxWaitMicros uint32, enforcementPoint s
 	if c == nil {
 		return nil, takeErr(cerr)
 	}
-	return &Coalescer{c: c}, nil
+	return &Coalescer{c: c, ep: enforcementPoint}, nil
 }
 
-// Review blocks until the request's micro-batch is done.  raw / oldRaw are AdmissionRequest.Object.Raw / OldObject.Raw.
-func (c *Coalescer) Review(raw, oldRaw []byte, namespace, operation string) (*AdmissionOutcome, error) {
-	var o C.gk_obj
-	if len(raw) > 0 {
-		o.json, o.len = (*C.char)(unsafe.Pointer(&raw[0])), C.size_t(len(raw))
+// EnableCoalescing routes Query calls at `enforcementPoint` (the webhook's) through a Coalescer.
+func (d *Driver) EnableCoalescing(maxBatch, maxWaitMicros uint32, enforcementPoint string) error {
+	co, err := d.NewCoalescer(maxBatch, maxWaitMicros, enforcementPoint)
+	if err != nil {
+		return err
 	}
-	if len(oldRaw) > 0 {
-		o.old_json, o.old_len = (*C.char)(unsafe.Pointer(&oldRaw[0])), C.size_t(len(oldRaw))
+	d.mux.Lock()
+	d.coalescer = co
+	d.mux.Unlock()
+	return nil
+}
+
+// Review blocks until the request's micro-batch is done.  The gk_obj and every payload it points to live in C memory for the
+// duration of the call (cgo: no Go pointer inside memory passed to C).
+func (c *Coalescer) Review(in reviewIn) ([]BatchResult, error) {
+	o := (*C.gk_obj)(C.calloc(1, C.size_t(unsafe.Sizeof(C.gk_obj{}))))
+	defer C.free(unsafe.Pointer(o))
+	var owned []unsafe.Pointer
+	defer func() {
+		for _, p := range owned {
+			C.free(p)
+		}
+	}()
+	cbytes := func(b []byte) (*C.char, C.size_t) {
+		if len(b) == 0 {
+			return nil, 0
+		}
+		p := C.CBytes(b)
+		owned = append(owned, p)
+		return (*C.char)(p), C.size_t(len(b))
 	}
-	cns, cop := C.CString(namespace), C.CString(operation)
-	defer C.free(unsafe.Pointer(cns))
-	defer C.free(unsafe.Pointer(cop))
-	o.ns_name, o.operation = cns, cop
+	ar := in.ar
+	o.json, o.len = cbytes(ar.Object.Raw)
+	o.old_json, o.old_len = cbytes(ar.OldObject.Raw)
+	if in.ns != nil {
+		b, err := json.Marshal(in.ns)
+		if err != nil {
+			return nil, err
+		}
+		o.ns_json, o.ns_len = cbytes(b)
+	}
+	if ar.Namespace != "" {
+		p := C.CString(ar.Namespace)
+		owned = append(owned, unsafe.Pointer(p))
+		o.ns_name = p
+	}
+	if ar.Operation != "" {
+		p := C.CString(string(ar.Operation))
+		owned = append(owned, unsafe.Pointer(p))
+		o.operation = p
+	}
+	if ub, err := json.Marshal(ar.UserInfo); err == nil && string(ub) != "{}" {
+		o.userinfo_json, o.userinfo_len = cbytes(ub)
+	}
+	o.source = sourceCode(in.source)
 	var out, cerr *C.char
-	if rc := C.gk_coalescer_review(c.c, &o, &out, &cerr); rc != 0 {
+	if rc := C.gk_coalescer_review(c.c, o, &out, &cerr); rc != 0 {
 		return nil, takeErr(cerr)
 	}
 	defer C.gk_free_str(out)
@@ -181,7 +225,15 @@ func (c *Coalescer) Review(raw, oldRaw []byte, namespace, operation string) (*Ad
 	if err := json.Unmarshal([]byte(C.GoString(out)), res); err != nil {
 		return nil, err
 	}
-	return res, nil
+	if res.Error != nil {
+		return nil, errors.New(*res.Error)
+	}
+	br := make([]BatchResult, 0, len(res.Results))
+	for _, r := range res.Results {
+		br = append(br, BatchResult{Constraint: r.Constraint, Msg: r.Msg, Details: r.Details, EnforcementAction: r.EnforcementAction,
+			ScopedActions: r.ScopedEnforcementActions, Autoreject: r.Autoreject})
+	}
+	return br, nil
 }
 
 func (c *Coalescer) Close() {

@@ -5,7 +5,8 @@
 // frameworks/constraint + OPA modules are not vendored.  The file is the binding a Gatekeeper maintainer would add;
 // it follows the only in-tree Driver implementation line by line for locking, review type assertions and stats
 // (pkg/drivers/k8scel/driver.go:60-263).  tests/ exercise the same C ABI through the ctypes mirror
-// gatekeeper_b200/driver.py, method for method.
+// gatekeeper_b200/driver.py, method for method, and tests/c_abi/mirror.c repeats reviewBatch below CALL FOR CALL in C
+// (C-allocated gk_obj array, every field this file populates) against the admission-shape vectors.
 //
 // Registration (replaces rego.New(args...) -- main.go:457-462, pkg/gator/opa.go:32-37, pkg/gator/test/test.go:48-53,
 // pkg/gator/bench/bench.go:313-319):
@@ -39,6 +40,7 @@ import (
 	"github.com/open-policy-agent/opa/v1/storage"
 	admissionv1 "k8s.io/api/admission/v1"
 	"k8s.io/apimachinery/pkg/apis/meta/v1/unstructured"
+	"k8s.io/apimachinery/pkg/runtime"
 )
 
 // Name is "Rego": templates carrying targets[].rego / code[engine: Rego] route to this driver.  It replaces -- and
@@ -51,6 +53,7 @@ type Driver struct {
 	mux sync.RWMutex // mutators exclusive, Query shared: pkg/drivers/k8scel/driver.go:61,130,167
 	e   *C.gk_engine_t
 	gatherStats bool
+	coalescer   *Coalescer // set by EnableCoalescing: Query joins micro-batches at its enforcement point
 }
 
 type Arg func(*Driver, *C.gk_cfg)
@@ -190,8 +193,37 @@ type ARGetter interface {
 	GetAdmissionRequest() *admissionv1.AdmissionRequest
 }
 
-// Query: one review, the constraints Client.Review already matched (pkg/drivers/k8scel/driver.go:161-250).  The
-// webhook path funnels concurrent Query calls through a coalescer (not shown) so that 64 reviews share one launch.
+// SourceGetter: the review's source (pkg/target/review.go:24, `source types.SourceType`).  gkReview needs the one-line accessor
+// `func (g *gkReview) GetSource() types.SourceType { return g.source }` (INTEGRATION.md section 3): the engine runs the spec.match
+// pre-filter itself, and match.source is one of its eight criteria (pkg/mutation/match/match.go:229-253).
+type SourceGetter interface {
+	GetSource() string
+}
+
+// reviewIn is everything of one gkReview the engine consumes (pkg/target/review.go:16-29, target.go:86-172).
+type reviewIn struct {
+	ar     *admissionv1.AdmissionRequest
+	ns     map[string]interface{} // reviews.ReviewCfg.Namespace (the review's Namespace object), may be nil
+	source string                 // "", "Original", "Generated"
+}
+
+func sourceCode(s string) C.uint8_t {
+	switch s {
+	case "":
+		return C.GK_SOURCE_UNSET
+	case "Original":
+		return C.GK_SOURCE_ORIGINAL
+	case "Generated":
+		return C.GK_SOURCE_GENERATED
+	case "All":
+		return C.GK_SOURCE_ALL
+	}
+	return C.GK_SOURCE_INVALID
+}
+
+// Query: one review, the constraints Client.Review already matched (pkg/drivers/k8scel/driver.go:161-250).  With a Coalescer
+// attached (EnableCoalescing) concurrent Query calls of the webhook's handler goroutines join one micro-batch and share one
+// kernel launch; without one the review is a batch of one.
 func (d *Driver) Query(ctx context.Context, target string, constraints []*unstructured.Unstructured, review interface{},
 	opts ...reviews.ReviewOpt) (*drivers.QueryResponse, error) {
 	cfg := &reviews.ReviewCfg{}
@@ -202,9 +234,20 @@ func (d *Driver) Query(ctx context.Context, target string, constraints []*unstru
 	if !ok {
 		return nil, errors.New("cannot convert review to ARGetter")
 	}
-	ar := arGetter.GetAdmissionRequest()
-	results, stats, err := d.reviewBatch(ctx, []*admissionv1.AdmissionRequest{ar}, []map[string]interface{}{cfg.Namespace},
-		cfg.EnforcementPoint, true)
+	in := reviewIn{ar: arGetter.GetAdmissionRequest(), ns: cfg.Namespace}
+	if sg, ok := review.(SourceGetter); ok {
+		in.source = sg.GetSource()
+	} else {
+		in.source = "Original"
+	}
+	var results []BatchResult
+	var stats []*instrumentation.StatsEntry
+	var err error
+	if co := d.coalescer; co != nil && cfg.EnforcementPoint == co.ep {
+		results, err = co.Review(in)
+	} else {
+		results, stats, err = d.reviewBatch(ctx, []reviewIn{in}, cfg.EnforcementPoint, true)
+	}
 	if err != nil {
 		return nil, err
 	}
@@ -214,9 +257,9 @@ func (d *Driver) Query(ctx context.Context, target string, constraints []*unstru
 	}
 	out := &drivers.QueryResponse{}
 	for _, r := range results {
-		if c, ok := want[r.key]; ok {
-			out.Results = append(out.Results, &types.Result{Target: target, Msg: r.msg,
-				Metadata: map[string]interface{}{"details": r.details}, Constraint: c})
+		if c, ok := want[r.Constraint]; ok {
+			out.Results = append(out.Results, &types.Result{Target: target, Msg: r.Msg,
+				Metadata: map[string]interface{}{"details": r.Details}, Constraint: c})
 		}
 	}
 	if d.gatherStats || cfg.StatsEnabled {
@@ -231,6 +274,8 @@ type BatchReviewer interface {
 		enforcementPoint string) ([]BatchResult, error)
 }
 
+var _ BatchReviewer = (*Driver)(nil)
+
 type BatchResult struct {
 	Object            int
 	Constraint        string // "Kind/name"
@@ -241,32 +286,80 @@ type BatchResult struct {
 	Autoreject        bool
 }
 
-type rawResult struct {
-	key, msg string
-	details  interface{}
+// ReviewBatch reviews a page of listed objects (the audit loop's unit of work: pkg/audit/manager.go:579-646,668-777) in one call.
+// A review-level error of one object (undecodable JSON, kind missing) is returned as an error naming that object, like the
+// per-object Review error the audit loop logs at manager.go:722-729.
+func (d *Driver) ReviewBatch(ctx context.Context, _ string, objs []*unstructured.Unstructured, namespaces []map[string]interface{},
+	enforcementPoint string) ([]BatchResult, error) {
+	ins := make([]reviewIn, len(objs))
+	for i, o := range objs {
+		raw, err := o.MarshalJSON()
+		if err != nil {
+			return nil, err
+		}
+		ins[i] = reviewIn{ar: &admissionv1.AdmissionRequest{Object: runtime.RawExtension{Raw: raw}, Name: o.GetName(), Namespace: o.GetNamespace()},
+			source: "Original"}
+		if namespaces != nil {
+			ins[i].ns = namespaces[i]
+		}
+	}
+	res, _, err := d.reviewBatch(ctx, ins, enforcementPoint, true)
+	return res, err
 }
 
-func (d *Driver) reviewBatch(_ context.Context, ars []*admissionv1.AdmissionRequest, nss []map[string]interface{}, ep string,
-	materialize bool) ([]rawResult, []*instrumentation.StatsEntry, error) {
+// cgo rule: no Go pointer may be stored in memory handed to C.  Every payload is therefore copied into C memory (C.CBytes /
+// C.CString) for the duration of the call, and the gk_obj array itself lives in C memory.
+func (d *Driver) reviewBatch(_ context.Context, ins []reviewIn, ep string, materialize bool) ([]BatchResult, []*instrumentation.StatsEntry, error) {
 	d.mux.RLock()
 	defer d.mux.RUnlock()
-	n := len(ars)
-	objs := make([]C.gk_obj, n)
-	keep := make([][]byte, 0, 3*n) // keeps Go memory alive and pinned for the duration of the call
-	for i, ar := range ars {
-		o := &objs[i]
-		if ar.Object.Raw != nil {
-			o.json, o.len = (*C.char)(unsafe.Pointer(&ar.Object.Raw[0])), C.size_t(len(ar.Object.Raw))
+	n := len(ins)
+	if n == 0 {
+		return nil, nil, nil
+	}
+	objs := (*C.gk_obj)(C.calloc(C.size_t(n), C.size_t(unsafe.Sizeof(C.gk_obj{}))))
+	defer C.free(unsafe.Pointer(objs))
+	arr := unsafe.Slice(objs, n)
+	var owned []unsafe.Pointer
+	defer func() {
+		for _, p := range owned {
+			C.free(p)
 		}
-		if ar.OldObject.Raw != nil {
-			o.old_json, o.old_len = (*C.char)(unsafe.Pointer(&ar.OldObject.Raw[0])), C.size_t(len(ar.OldObject.Raw))
+	}()
+	cbytes := func(b []byte) (*C.char, C.size_t) {
+		if len(b) == 0 {
+			return nil, 0
 		}
-		if nss[i] != nil {
-			b, _ := json.Marshal(nss[i])
-			keep = append(keep, b)
-			o.ns_json, o.ns_len = (*C.char)(unsafe.Pointer(&b[0])), C.size_t(len(b))
+		p := C.CBytes(b)
+		owned = append(owned, p)
+		return (*C.char)(p), C.size_t(len(b))
+	}
+	cstr := func(s string) *C.char {
+		p := C.CString(s)
+		owned = append(owned, unsafe.Pointer(p))
+		return p
+	}
+	for i, in := range ins {
+		o := &arr[i]
+		ar := in.ar
+		o.json, o.len = cbytes(ar.Object.Raw)
+		o.old_json, o.old_len = cbytes(ar.OldObject.Raw)
+		if in.ns != nil {
+			b, err := json.Marshal(in.ns)
+			if err != nil {
+				return nil, nil, err
+			}
+			o.ns_json, o.ns_len = cbytes(b)
 		}
-		o.source = C.GK_SOURCE_ORIGINAL
+		if ar.Namespace != "" { // AdmissionRequest.Namespace: review.namespace and the namespace-cache key (target.go:99-105)
+			o.ns_name = cstr(ar.Namespace)
+		}
+		if ar.Operation != "" { // DELETE reviews the old object (target.go:262-280); templates read input.review.operation
+			o.operation = cstr(string(ar.Operation))
+		}
+		if ub, err := json.Marshal(ar.UserInfo); err == nil && string(ub) != "{}" { // input.review.userInfo
+			o.userinfo_json, o.userinfo_len = cbytes(ub)
+		}
+		o.source = sourceCode(in.source)
 	}
 	cep := C.CString(ep)
 	defer C.free(unsafe.Pointer(cep))
@@ -276,19 +369,31 @@ func (d *Driver) reviewBatch(_ context.Context, ars []*admissionv1.AdmissionRequ
 	if materialize {
 		flags = C.GK_F_MATERIALIZE
 	}
-	if rc := C.gk_review_batch(d.e, &objs[0], C.size_t(n), cep, flags, &res, &cerr); rc != 0 {
+	if rc := C.gk_review_batch(d.e, objs, C.size_t(n), cep, flags, &res, &cerr); rc != 0 {
 		return nil, nil, takeErr(cerr)
 	}
 	defer C.gk_free_result(&res)
-	_ = keep
-	out := make([]rawResult, 0, int(res.n_violations))
+	// a review-level error of an object is an error of the call: admission must not fail open, audit must not under-report
+	if res.object_errors != nil {
+		oe := unsafe.Slice(res.object_errors, n)
+		for i, e := range oe {
+			if e != nil {
+				return nil, nil, fmt.Errorf("review of object %d: %s", i, C.GoString(e))
+			}
+		}
+	}
+	out := make([]BatchResult, 0, int(res.n_violations))
 	vs := unsafe.Slice(res.violations, int(res.n_violations))
 	for _, v := range vs {
 		var details interface{}
 		if dj := C.GoString(v.details_json); dj != "" {
 			_ = json.Unmarshal([]byte(dj), &details)
 		}
-		out = append(out, rawResult{key: C.GoString(C.gk_result_constraint_key(&res, v.constraint)), msg: C.GoString(v.msg), details: details})
+		var scoped []string
+		_ = json.Unmarshal([]byte(C.GoString(v.scoped_actions_json)), &scoped)
+		out = append(out, BatchResult{Object: int(v.object), Constraint: C.GoString(C.gk_result_constraint_key(&res, v.constraint)),
+			Msg: C.GoString(v.msg), Details: details, EnforcementAction: C.GoString(v.enforcement_action), ScopedActions: scoped,
+			Autoreject: v.autoreject != 0})
 	}
 	stats := []*instrumentation.StatsEntry{{Scope: "batch", StatsFor: fmt.Sprintf("%d reviews", n),
 		Stats: []*instrumentation.Stat{

@@ -308,3 +308,26 @@ def test_doc_pins():
 
 def test_wildcard_vectors_through_kernel_core():
     P.case_wildcard_vectors_through_kernel(HOSTEMU)
+
+
+def test_aggregate_limits_fail_the_mutation_not_later_reviews():
+    """Round-1 advisor finding: limits only the JOINT constraint set can hit (250 iteration scopes here) used to surface at the next
+    review and break every review from then on.  Now the AddConstraint that crosses the limit fails, and reviews keep working."""
+    rego = """package manyfields
+violation[{"msg": "x"}] { v := input.review.object.spec[input.parameters.field][_]; v == "bad" }
+"""
+    drv = D.Driver(lib_path=HOSTEMU)
+    drv.add_template("ManyFields", rego)
+    ok = 0
+    failed = None
+    for i in range(300):
+        try:
+            drv.AddConstraint({"kind": "ManyFields", "metadata": {"name": "c%d" % i}, "spec": {"parameters": {"field": "f%d" % i}}})
+            ok += 1
+        except D.GkError as e:
+            failed = str(e)
+            break
+    assert failed is not None and "rego_unsupported" in failed and 200 <= ok < 300, (ok, failed)
+    resp = drv.ReviewBatch([D.Review(object={"apiVersion": "v1", "kind": "X", "metadata": {"name": "o"}, "spec": {"f3": ["bad"], "f7": ["ok"]}})], "audit.gatekeeper.sh")
+    assert [r.constraint for r in resp.results] == ["ManyFields/c3"]
+    assert len(drv.constraints()) == ok
