@@ -393,6 +393,16 @@ class Driver:
         finally:
             self._lib.gk_free_result(C.byref(res))
 
+    def review_marshalled(self, arr, n: int, enforcement_point: str, flags: int = 0) -> BatchResponse:
+        """gk_review_batch on requests already marshalled by _marshal(); results stay in the engine's buffers (stats only)."""
+        res = gk_result()
+        err = C.c_char_p()
+        self._check(self._lib.gk_review_batch(self._e, arr, n, enforcement_point.encode(), flags, C.byref(res), C.byref(err)), err)
+        try:
+            return self._unpack(res, None, with_results=False)
+        finally:
+            self._lib.gk_free_result(C.byref(res))
+
     def Query(self, target: str, constraints: Sequence[dict], review, enforcement_point: str = AUDIT_EP) -> list:
         """drivers.Driver.Query shape (pkg/drivers/k8scel/driver.go:161-250): one review, the (already
         matched) constraints; returns the Results for those constraints."""
