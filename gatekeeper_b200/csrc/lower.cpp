@@ -2383,43 +2383,44 @@ void NetBuilder::build(const std::vector<FP>& formulas, const std::vector<uint32
     }
     for (auto& kv : col_atoms) {
       ColAtoms& ca = kv.second;
-      const uint32_t parts = ca.deep ? (ca.heavy ? 6u : 4u) : (ca.heavy ? 2u : 1u);
-      // Fusing every atom of a column into one GK_N_ATOMS op (one load of the row for all of them) is implemented but OFF:
-      // measured on B200 it is slower than one op per atom (1.5 ms vs 0.8 ms per 1M objects) -- the fused loop keeps the
-      // row's encodings live across the whole atom list, and at 48 registers per thread (5 resident CTAs) that spills.
-#ifdef GK_FUSED_ATOMS
-      const bool fuse = true;
-#else
-      const bool fuse = false;
-#endif
-      if (!fuse) {
-        for (auto& a : ca.ops) {
-          const bool heavy1 = (a.w1 & 0xffu) >= GK_OP_PREFIX;
-          const uint32_t cost1 = heavy1 ? (ca.deep ? 1200u : 600u) : (a.w1 & 0xffu) == GK_OP_SID_IN ? (ca.deep ? 300u : 150u) : (ca.deep ? 120u : 60u);
-          add_item(cost1, heavy1 ? (ca.deep ? 4u : 2u) : 1u);
-          ops.push_back(a);
-        }
-        continue;
-      }
-      if (ca.ops.size() == 1) {
-        add_item(ca.cost, ca.heavy ? parts : 1u);
-        ops.push_back(ca.ops[0]);
-        continue;
-      }
-      while (pool.size() % 4) pool.push_back(0);   // entries are read with 128-bit loads
-      GkOp op{};
-      op.w0 = GK_N_ATOMS | ((uint32_t)kv.first.first << 8);
-      op.w1 = (uint32_t)kv.first.second << 8;
-      op.w2 = (uint32_t)pool.size();
-      op.w3 = (uint32_t)ca.ops.size();
+      // Atoms that test a row's type / sid / number (everything but the prefix / suffix / contains tests, which walk the 32-byte
+      // HEAD record or the byte pool) are FUSED per column: one GK_N_ATOMS op loads the column slice once per trip -- four 32-row
+      // groups into registers -- and evaluates every atom of the column on them.  (Round 1 measured this slower at 48 registers
+      // per thread / 5 CTAs per SM because it spilled; the kernel now runs 4 CTAs per SM with 64 registers.)  GK_FUSED_ATOMS=0
+      // keeps one op per atom.
+      static const bool fuse = !(getenv("GK_FUSED_ATOMS") && atoi(getenv("GK_FUSED_ATOMS")) == 0);
+      std::vector<GkOp> fused;
       for (auto& a : ca.ops) {
-        pool.push_back((a.w1 & 0xffu) | (a.w0 & 0xffff0000u));   // atom op | out slot << 16
-        pool.push_back(a.w2);
-        pool.push_back(a.w3);
-        pool.push_back(0);
+        const uint32_t aop = a.w1 & 0xffu;
+        const bool heavy1 = aop >= GK_OP_PREFIX;
+        if (fuse && !heavy1) {
+          fused.push_back(a);
+          continue;
+        }
+        const uint32_t cost1 = heavy1 ? (ca.deep ? 1200u : 600u) : aop == GK_OP_SID_IN ? (ca.deep ? 300u : 150u) : (ca.deep ? 120u : 60u);
+        add_item(cost1, heavy1 ? (ca.deep ? 4u : 2u) : 1u);
+        ops.push_back(a);
       }
-      add_item(ca.cost, parts);
-      ops.push_back(op);
+      if (fused.size() == 1) {
+        add_item(ca.deep ? 120u : 60u, 1u);
+        ops.push_back(fused[0]);
+      } else if (!fused.empty()) {
+        while (pool.size() % 4) pool.push_back(0);   // entries are read with 128-bit loads
+        GkOp op{};
+        op.w0 = GK_N_ATOMS | ((uint32_t)kv.first.first << 8);
+        op.w1 = (uint32_t)kv.first.second << 8;
+        op.w2 = (uint32_t)pool.size();
+        op.w3 = (uint32_t)fused.size();
+        for (auto& a : fused) {
+          pool.push_back((a.w1 & 0xffu) | (a.w0 & 0xffff0000u));   // atom op | out slot << 16
+          pool.push_back(a.w2);
+          pool.push_back(a.w3);
+          pool.push_back(0);
+        }
+        const uint32_t cost = (ca.deep ? 100u : 50u) + (ca.deep ? 50u : 25u) * (uint32_t)fused.size();
+        add_item(cost, ca.deep && fused.size() >= 4 ? 2u : 1u);
+        ops.push_back(op);
+      }
     }
     // every EXISTS (and every hoisted broadcast) over the same scope in this phase is ONE op: the child ranges and
     // their masks are computed once per parent row and applied to all (input, output) column pairs

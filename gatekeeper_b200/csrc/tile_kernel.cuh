@@ -269,171 +269,82 @@ __device__ __forceinline__ void atom_rows(const GkColumn& c, uint32_t aop, uint3
   }
 }
 
-#ifdef GK_FUSED_ATOMS   /* experiment, off: see NetBuilder::build */
-// ---- every atom of one column in one pass (GK_N_ATOMS): the row's encodings are loaded once into registers -- four
-// 32-row groups at a time, all loads in flight together -- and each atom is then a compare + ballot on registers.
-// Columns with a HEAD record (prefix tests) go one group at a time: the 32-byte record is 8 registers per row.
-__device__ __forceinline__ bool atom_on_regs(uint32_t aop, uint32_t a, uint32_t b, uint32_t vt, uint32_t sid, long long num, const uint32_t* pool) {
-  switch (aop) {
-    case GK_OP_TRUTHY: return vt != GK_VT_UNDEF && vt != GK_VT_FALSE;
-    case GK_OP_DEFINED: return vt != GK_VT_UNDEF;
-    case GK_OP_VTMASK: return ((1u << vt) & a) != 0u;
-    case GK_OP_SID_EQ: return sid == a;
-    case GK_OP_SID_IN: {
-      bool hit = false;
-      for (uint32_t j = 0; j < b; ++j) hit = hit || pool[a + j] == sid;
-      return hit;
-    }
-    default: {   // GK_OP_NUM_CMP (the only other op the register path is used for)
-      const long long k = (long long)(((uint64_t)pool[a + 1] << 32) | pool[a]);
-      if (vt == GK_VT_UNDEF) return false;
-      if (k == INT64_MIN || k == INT64_MAX) {   // sentinel constants: spell the cross-type order out
-        if (vt == GK_VT_NUM) return gk_cmp_apply(b, num < k ? -1 : (num > k ? 1 : 0));
-        return gk_cmp_apply(b, gk_vt_rank(vt) < 2 ? -1 : 1);
-      }
-      return gk_cmp_apply(b, num < k ? -1 : (num > k ? 1 : 0));
-    }
+// ---- every register-testable atom of one column in one pass (GK_N_ATOMS): the row's type byte / sid / number are loaded once
+// per trip -- four 32-row groups, all loads in flight together -- and each atom of the column is then a compare + ballot on
+// registers, its four result words stored with one 128-bit shared-memory store.
+#define GK_RUN_ATOM(EXPR)                                                            \
+  {                                                                                  \
+    bool v4[4];                                                                      \
+    _Pragma("unroll") for (int u = 0; u < 4; ++u) v4[u] = ok[u] && (EXPR);           \
+    uint4 wd;                                                                        \
+    wd.x = __ballot_sync(0xffffffffu, v4[0]);                                        \
+    wd.y = __ballot_sync(0xffffffffu, v4[1]);                                        \
+    wd.z = __ballot_sync(0xffffffffu, v4[2]);                                        \
+    wd.w = __ballot_sync(0xffffffffu, v4[3]);                                        \
+    if (lane == 0) *reinterpret_cast<uint4*>(slots + (e.x >> 16) + w) = wd;          \
   }
-}
-
-__device__ __forceinline__ bool reg_op(uint32_t aop) { return aop <= GK_OP_NUM_CMP; }
-
-__device__ __noinline__ void atoms_rows(const GkColumn& c, const uint32_t* ent, uint32_t nent, const uint32_t* pool, const uint8_t* cbytes, uint32_t lo,
-                                        uint32_t cnt, uint32_t w0, uint32_t w1, uint32_t lane, uint32_t* slots) {
-  const uint32_t FULL = 0xffffffffu;
-  const uint32_t wcap = (((cnt + 31u) >> 5) + 3u) & ~3u;
+__device__ __noinline__ void atoms_rows(const GkColumn& c, const uint32_t* ent, uint32_t nent, const uint32_t* pool, uint32_t lo, uint32_t cnt, uint32_t w0,
+                                        uint32_t w1, uint32_t lane, uint32_t* slots) {
   const bool has_vt = (c.enc & GK_ENC_VT) != 0u, has_sid = (c.enc & GK_ENC_SID) != 0u, has_num = (c.enc & GK_ENC_NUM) != 0u;
-  if (!(c.enc & GK_ENC_HEAD)) {
-    for (uint32_t w = w0; w < w1; w += 4u) {
-      const uint32_t r0 = w * 32u + lane;
-      const size_t row0 = (size_t)lo + r0;
-      uint32_t vt[4], sid[4];
-      long long num[4];
+  const uint8_t* __restrict__ pvt = c.vt;
+  const uint32_t* __restrict__ psid = c.sid;
+  const long long* __restrict__ pnum = reinterpret_cast<const long long*>(c.num);
+  for (uint32_t w = w0; w < w1; w += 4u) {
+    const uint32_t r0 = w * 32u + lane;
+    const size_t row0 = (size_t)lo + r0;
+    uint32_t vt[4], sid[4];
+    long long num[4];
+    bool ok[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const bool ok = r0 + 32u * u < cnt;
-        vt[u] = (ok && has_vt) ? c.vt[row0 + 32u * u] : (uint32_t)GK_VT_UNDEF;
-        sid[u] = (ok && has_sid) ? c.sid[row0 + 32u * u] : GK_SID_UNDEF;
-        num[u] = (ok && has_num) ? c.num[row0 + 32u * u] : 0ll;
-      }
-      for (uint32_t j = 0; j < nent; ++j) {
-        const uint4 e = *reinterpret_cast<const uint4*>(ent + j * GK_ATOMS_ENT);
-        const uint32_t aop = e.x & 0xffu;
-        bool v[4];
-        if (reg_op(aop)) {
-#pragma unroll
-          for (int u = 0; u < 4; ++u) v[u] = (r0 + 32u * u < cnt) && atom_on_regs(aop, e.y, e.z, vt[u], sid[u], num[u], pool);
-        } else {
-#pragma unroll
-          for (int u = 0; u < 4; ++u) v[u] = (r0 + 32u * u < cnt) && gk_atom(c, (uint32_t)(row0 + 32u * u), aop, e.y, e.z, pool, cbytes);
-        }
-        uint4 wd;
-        wd.x = __ballot_sync(FULL, v[0]);
-        wd.y = __ballot_sync(FULL, v[1]);
-        wd.z = __ballot_sync(FULL, v[2]);
-        wd.w = __ballot_sync(FULL, v[3]);
-        if (lane == 0 && w < wcap) *reinterpret_cast<uint4*>(slots + (e.x >> 16) + w) = wd;
-      }
+    for (int u = 0; u < 4; ++u) {
+      ok[u] = r0 + 32u * u < cnt;
+      vt[u] = (uint32_t)GK_VT_UNDEF;
+      sid[u] = (uint32_t)GK_SID_UNDEF;
+      num[u] = 0ll;
     }
-    return;
-  }
-  const uint4* head = reinterpret_cast<const uint4*>(c.head);
-  const uint32_t wend = min(w1, (cnt + 31u) >> 5);
-  for (uint32_t w = w0; w < wend; ++w) {
-    const uint32_t r = w * 32u + lane;
-    const bool ok = r < cnt;
-    const size_t row = (size_t)lo + r;
-    const uint32_t vt = (ok && has_vt) ? c.vt[row] : (uint32_t)GK_VT_UNDEF;
-    const uint32_t sid = (ok && has_sid) ? c.sid[row] : GK_SID_UNDEF;
-    uint4 h0 = make_uint4(0, 0, 0, 0), h1 = make_uint4(0, 0, 0, 0);
-    if (ok) {
-      h0 = head[2 * row];
-      h1 = head[2 * row + 1];
+    if (has_vt) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (ok[u]) vt[u] = pvt[row0 + 32u * u];
     }
-    const uint32_t lenb = h1.w >> 24;
+    if (has_sid) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (ok[u]) sid[u] = psid[row0 + 32u * u];
+    }
+    if (has_num) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (ok[u]) num[u] = pnum[row0 + 32u * u];
+    }
     for (uint32_t j = 0; j < nent; ++j) {
       const uint4 e = *reinterpret_cast<const uint4*>(ent + j * GK_ATOMS_ENT);
-      const uint32_t aop = e.x & 0xffu;
-      bool v = false;
-      if (aop == GK_OP_ANYPREFIX) {
-        bool all_short = true;
-        for (uint32_t q = 0; q < e.z; ++q) all_short = all_short && pool[e.y + q * GK_PREFIX_ENT] <= GK_HEAD_BYTES;
-        if (all_short) {
-          if (ok && vt == GK_VT_STR)
-            for (uint32_t q = 0; q < e.z && !v; ++q) {
-              const uint32_t* pe = pool + e.y + q * GK_PREFIX_ENT;
-              const uint32_t* m = pe + 2 + GK_HEAD_WORDS;
-              const uint32_t diff = ((h0.x ^ pe[2]) & m[0]) | ((h0.y ^ pe[3]) & m[1]) | ((h0.z ^ pe[4]) & m[2]) | ((h0.w ^ pe[5]) & m[3]) |
-                                    ((h1.x ^ pe[6]) & m[4]) | ((h1.y ^ pe[7]) & m[5]) | ((h1.z ^ pe[8]) & m[6]) | ((h1.w ^ pe[9]) & m[7]);
-              v = diff == 0u && lenb >= pe[0];
-            }
-        } else {
-          v = ok && gk_atom(c, (uint32_t)row, aop, e.y, e.z, pool, cbytes);
+      switch (e.x & 0xffu) {
+        case GK_OP_TRUTHY: GK_RUN_ATOM(vt[u] != GK_VT_UNDEF && vt[u] != GK_VT_FALSE) break;
+        case GK_OP_DEFINED: GK_RUN_ATOM(vt[u] != GK_VT_UNDEF) break;
+        case GK_OP_VTMASK: GK_RUN_ATOM(((1u << vt[u]) & e.y) != 0u) break;
+        case GK_OP_SID_EQ: GK_RUN_ATOM(sid[u] == e.y) break;
+        case GK_OP_SID_IN: GK_RUN_ATOM(sid_in_small(pool, e.y, e.z, sid[u])) break;
+        default: {   // GK_OP_NUM_CMP: non-numbers hold INT64_MIN / INT64_MAX by their type rank, so one signed compare is OPA's order
+          const long long k = (long long)(((uint64_t)pool[e.y + 1] << 32) | pool[e.y]);
+          switch (e.z) {
+            case GK_CMP_LT: GK_RUN_ATOM(vt[u] != GK_VT_UNDEF && num[u] < k) break;
+            case GK_CMP_LE: GK_RUN_ATOM(vt[u] != GK_VT_UNDEF && num[u] <= k) break;
+            case GK_CMP_GT: GK_RUN_ATOM(vt[u] != GK_VT_UNDEF && num[u] > k) break;
+            case GK_CMP_GE: GK_RUN_ATOM(vt[u] != GK_VT_UNDEF && num[u] >= k) break;
+            case GK_CMP_EQ: GK_RUN_ATOM(vt[u] != GK_VT_UNDEF && num[u] == k) break;
+            default: GK_RUN_ATOM(vt[u] != GK_VT_UNDEF && num[u] != k) break;
+          }
+          break;
         }
-      } else if (reg_op(aop) && aop != GK_OP_NUM_CMP) {
-        v = ok && atom_on_regs(aop, e.y, e.z, vt, sid, 0ll, pool);
-      } else {
-        v = ok && gk_atom(c, (uint32_t)row, aop, e.y, e.z, pool, cbytes);
       }
-      const uint32_t wd = __ballot_sync(FULL, v);
-      if (lane == 0) slots[(e.x >> 16) + w] = wd;
     }
   }
 }
-
-#endif
-
-#ifdef GK_L2_PREFETCH
-// ---- L2 prefetch of a tile's input slices.
-// The netlist walks ~100 arrays per tile with short dependent loops, so a warp rarely has more than a few loads in flight:
-// without help every one of them pays DRAM latency.  While a CTA is busy with the (load-free) gate / EXISTS phases of tile
-// t, one warp asks the L2 for every array slice tile t + gridDim.x will read -- one bulk-prefetch instruction per array
-// slice, no registers or shared memory tied up.
-__device__ __forceinline__ void l2_prefetch(const void* base, size_t lo_bytes, size_t hi_bytes) {
-  if (!base || hi_bytes <= lo_bytes) return;
-  const uintptr_t a = (reinterpret_cast<uintptr_t>(base) + lo_bytes) & ~(uintptr_t)15;
-  const uintptr_t b = (reinterpret_cast<uintptr_t>(base) + hi_bytes + 15) & ~(uintptr_t)15;
-  const uint32_t n = (uint32_t)(b - a);
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(n) : "memory");
-}
-
-__device__ __noinline__ void prefetch_tile(const KParams& p, const GkColumn* cols, const GkScope* scopes, uint32_t t, uint32_t lane) {
-  const uint32_t NS = p.batch.nscopes;
-  const uint32_t* tl = p.tile_lo + (size_t)t * NS;
-  // header arrays (scope 0 rows) and the CSR offsets of every scope (rows of the parent, +1)
-  if (lane == 0) {
-    const size_t a = tl[0], b = tl[NS];
-    const GkBatch& h = p.batch;
-    l2_prefetch(h.flags, a * 4, b * 4);
-    l2_prefetch(h.kind_sid, a * 4, b * 4);
-    l2_prefetch(h.group_sid, a * 4, b * 4);
-    l2_prefetch(h.nsname_sid, a * 4, b * 4);
-    l2_prefetch(h.nsrow, a * 4, b * 4);
-    l2_prefetch(h.name_off, a * 4, (b + 1) * 4);
-    l2_prefetch(h.gen_off, a * 4, (b + 1) * 4);
-    l2_prefetch(h.lbl_off, a * 4, (b + 1) * 4);
-    if (h.lbl_off && b > a) l2_prefetch(h.lbl_kv, (size_t)h.lbl_off[a] * 8, (size_t)h.lbl_off[b] * 8);
-  }
-  for (uint32_t s = 1 + lane; s < NS; s += 32u) {
-    const uint32_t par = (uint32_t)scopes[s].parent;
-    l2_prefetch(scopes[s].off, (size_t)tl[par] * 4, ((size_t)tl[NS + par] + 1) * 4);
-  }
-  for (uint32_t c = lane; c < p.batch.ncols; c += 32u) {
-    const GkColumn& col = cols[c];
-    const size_t a = tl[col.scope], b = tl[NS + col.scope];
-    if (col.enc & GK_ENC_VT) l2_prefetch(col.vt, a, b);
-    if (col.enc & GK_ENC_SID) l2_prefetch(col.sid, a * 4, b * 4);
-    if (col.enc & GK_ENC_NUM) l2_prefetch(col.num, a * 8, b * 8);
-    if (col.enc & GK_ENC_HEAD) l2_prefetch(col.head, a * 32, b * 32);
-    if (col.enc & GK_ENC_BYTES) l2_prefetch(col.boff, a * 4, (b + 1) * 4);
-  }
-}
-
-#endif
 
 // One CTA = one tile of consecutive objects at a time; all intermediate bit columns live in shared memory.
 #ifndef GK_MIN_CTAS
-#define GK_MIN_CTAS 5         /* 5 resident CTAs per SM: the register cap this implies (<= 48) costs no spills */
+#define GK_MIN_CTAS 4         /* 4 resident CTAs per SM = 64 registers per thread: room for the fused atom runs */
 #endif
 __global__ void __launch_bounds__(kThreads, GK_MIN_CTAS) gk_eval_kernel(const KParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -494,9 +405,6 @@ __global__ void __launch_bounds__(kThreads, GK_MIN_CTAS) gk_eval_kernel(const KP
 
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const uint32_t FULL = 0xffffffffu;
-#ifdef GK_L2_PREFETCH   /* measured on B200: 0.78 ms -> 1.04 ms per 1M objects -- the bulk prefetches serialise on the issuing warp; off */
-  if (warp == kWarps - 1 && blockIdx.x < p.ntiles) prefetch_tile(p, cols, scopes, blockIdx.x, lane);
-#endif
 
   for (uint32_t t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
     // ---- tile row ranges (precomputed on the host: rows of a tile are contiguous at every scope)
@@ -512,9 +420,6 @@ __global__ void __launch_bounds__(kThreads, GK_MIN_CTAS) gk_eval_kernel(const KP
       const uint32_t ibase = s_poff[ph], icnt = s_poff[ph + 1] - ibase;
 #ifdef GK_PHASE_TIMING
       const long long tp0 = clock64();
-#endif
-#ifdef GK_L2_PREFETCH   /* measured on B200: 0.78 ms -> 1.04 ms per 1M objects -- the bulk prefetches serialise on the issuing warp; off */
-      if (ph + 2 == NP && warp == kWarps - 1 && t + gridDim.x < p.ntiles) prefetch_tile(p, cols, scopes, t + gridDim.x, lane);
 #endif
       // items are sorted heaviest first: dealing them round-robin to the warps is a longest-processing-time schedule
       for (uint32_t k = warp; k < icnt; k += kWarps) {
@@ -534,14 +439,12 @@ __global__ void __launch_bounds__(kThreads, GK_MIN_CTAS) gk_eval_kernel(const KP
             atom_rows(cols[op.w1 >> 8], op.w1 & 0xffu, op.w2, op.w3, pool, cbytes, s_lo[level], cnt, pw0, pw1, lane, out);
             break;
           }
-#ifdef GK_FUSED_ATOMS
           case GK_N_ATOMS: {
             const uint32_t cnt = s_cnt[level], words = (cnt + 31u) >> 5;
             const uint32_t pw0 = (words * part / nparts) & ~3u, pw1 = part + 1u == nparts ? words : ((words * (part + 1u) / nparts) & ~3u);
-            atoms_rows(cols[op.w1 >> 8], pool + op.w2, op.w3, pool, cbytes, s_lo[level], cnt, pw0, pw1, lane, slots);
+            atoms_rows(cols[op.w1 >> 8], pool + op.w2, op.w3, pool, s_lo[level], cnt, pw0, pw1, lane, slots);
             break;
           }
-#endif
           case GK_N_GATE: {
             const uint32_t f = op.w2, words = (s_cnt[level] + 31u) >> 5, nin = op.w3;
             const uint32_t* in = pool + op.w1;
@@ -706,10 +609,14 @@ __global__ void __launch_bounds__(kThreads, GK_MIN_CTAS) gk_eval_kernel(const KP
       uint32_t yv = 0, ye = 0;
 #pragma unroll
       for (uint32_t o = 0; o < 32u; ++o) {
-        const uint32_t bv = __ballot_sync(FULL, (xv >> o) & 1u), be = __ballot_sync(FULL, (xe >> o) & 1u);
-        if (lane == o) {
-          yv = bv;
-          ye = be;
+        const uint32_t bv = __ballot_sync(FULL, (xv >> o) & 1u);
+        if (lane == o) yv = bv;
+      }
+      if (__any_sync(FULL, xe != 0u)) {   // matcher errors are rare: the second transpose only where one occurred
+#pragma unroll
+        for (uint32_t o = 0; o < 32u; ++o) {
+          const uint32_t be = __ballot_sync(FULL, (xe >> o) & 1u);
+          if (lane == o) ye = be;
         }
       }
       const uint32_t obj = ow * 32u + lane;
