@@ -53,6 +53,10 @@ class Backend {
   // Device ingest (ingest_core.h): raw JSON blob -> resident columnar batch without a host parse.  `status` receives one
   // GK_ING_* code per object (the caller renders the error text of the rare non-OK ones with the host parser).
   virtual void* ingest(const IngestReq& rq, IngestStats* st, std::vector<uint32_t>* status) = 0;
+  // Start moving a blob to the device ahead of its ingest() (copy + tokenise on the copy / front streams, into the idle one of
+  // two front buffers) and return at once: the next page of an audit sweep streams in while the current one is being extracted
+  // and evaluated.  ingest() of the same (blob, n) picks the prefetched copy up; anything else is ingested from scratch.
+  virtual void prefetch(const uint8_t* blob, const unsigned long long* ooff, size_t n) { (void)blob, (void)ooff, (void)n; }
   // page-lock (or release) a caller-owned host buffer so that the blob copy is a direct DMA at link speed
   virtual void pin_host(const void* p, size_t bytes, bool pin) { (void)p, (void)bytes, (void)pin; }
 };

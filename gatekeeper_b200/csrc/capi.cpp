@@ -641,6 +641,15 @@ char* gk_validation_messages(gk_engine_t* e, const gk_result* r, uint32_t object
 
 int gk_host_cpus(void) { return effective_cpus(); }
 
+int gk_blob_prefetch(gk_engine_t* e, const char* buf, const uint64_t* offsets, size_t n, char** err) {
+  if (!e || ((!buf || !offsets) && n)) return GK_ERR_INVALID;
+  return guard(err, [&]() {
+    auto c = e->eng->compiled();
+    if (!c->device_ingest || n == 0) return;   // host-flattened snapshots have nothing to stream ahead
+    e->be->prefetch(reinterpret_cast<const uint8_t*>(buf), reinterpret_cast<const unsigned long long*>(offsets), n);
+  });
+}
+
 int gk_pin_host(gk_engine_t* e, const void* p, size_t bytes, int pin, char** err) {
   if (!e || !p) return GK_ERR_INVALID;
   return guard(err, [&]() { e->be->pin_host(p, bytes, pin != 0); });

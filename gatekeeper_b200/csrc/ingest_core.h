@@ -1220,7 +1220,7 @@ GK_HD const uint8_t* gk_lit(const char* s) { return reinterpret_cast<const uint8
 
 // MODE 0: count pass (decoded lengths of byte columns).  MODE 1: the per-object pass writes the byte-encoded columns (their
 // offsets run through the object).  MODE 2: the per-row pass writes every other column.
-enum { GK_PASS_COUNT = 0, GK_PASS_ROWS = 1, GK_PASS_COLS = 2 };
+enum { GK_PASS_COUNT = 0, GK_PASS_ROWS = 1, GK_PASS_COLS = 2, GK_PASS_HEADER = 3 };
 template <int MODE>
 GK_HD void gk_emit_col(const GkXProg& xp, const GkIngestIn& in, const GkIngestOut& out, GkXCtx& c, uint32_t ci, uint32_t row, const GkCur& bcur) {
   const GkXCol& col = xp.cols[ci];
@@ -1312,7 +1312,11 @@ GK_HD void gk_emit_col(const GkXProg& xp, const GkIngestIn& in, const GkIngestOu
 // `cur`: nscopes + nbytecols + GK_CNT_EXTRA working counters, private to the lane.
 template <int MODE>
 GK_HD void gk_ingest_obj(const GkXProg& xp, const GkIngestIn& in, const GkIngestOut& out, uint32_t i, const GkCur& cur, uint32_t lane, uint32_t nlanes) {
+  // COUNT: header byte / label counts + the scope walk.  HEADER: the header arrays only (every thread runs the same steps in the
+  // same order -- kept out of the scope walk, where threads are at different depths).  ROWS: the scope walk only (skip flag read
+  // back from the header pass, which runs first).
   constexpr bool WRITE = MODE != GK_PASS_COUNT;
+  constexpr bool HDR = MODE != GK_PASS_ROWS;
   const uint32_t n = in.n, NS = xp.nscopes, NK = NS + xp.nbytecols + GK_CNT_EXTRA;
   const uint32_t K_NAME = NS + xp.nbytecols, K_GEN = K_NAME + 1, K_LBL = K_NAME + 2, K_NSN = K_NAME + 3;
   for (uint32_t k = 0; k < NK; ++k) cur[k] = WRITE ? in.counts[(size_t)k * n + i] : 0u;
@@ -1330,12 +1334,12 @@ GK_HD void gk_ingest_obj(const GkXProg& xp, const GkIngestIn& in, const GkIngest
   c.api_node = c.kind_node = c.name_node = c.ns_node = c.meta_node = GK_NONE;
   c.grp = c.ver = nullptr;
   c.grp_len = c.ver_len = 0;
-  bool skip = in.status[i] != GK_ING_OK;
+  bool skip = HDR ? in.status[i] != GK_ING_OK : (out.flags[i] & GK_F_SKIP) != 0u;
   uint32_t fl = (in.source << GK_F_SRC_SHIFT) & GK_F_SRC_MASK;
   uint32_t kind_sid = GK_SID_UNDEF, group_sid = GK_SID_UNDEF, nsrow = GK_NONE;
   uint32_t labels = GK_NONE, gen_node = GK_NONE;
   GkXVal nsname = gk_xundef();
-  if (!skip) {
+  if (HDR && !skip) {
     // ---- review envelope / header: apiVersion -> (group, version), kind, metadata.{name, generateName, namespace, labels}
     gk_x_envelope(c);
     const uint32_t meta = c.meta_node, nm = c.name_node, ns = c.ns_node;
@@ -1360,8 +1364,10 @@ GK_HD void gk_ingest_obj(const GkXProg& xp, const GkIngestIn& in, const GkIngest
       fl |= GK_F_HAS_OBJ;
       if (is_ns) fl |= GK_F_IS_NS;
       if (ns != GK_NONE) fl |= GK_F_HAS_NS;
-      kind_sid = gk_x_sid(c, kindv);
-      group_sid = gk_x_sid(c, gk_xstr(c.grp, c.grp_len));
+      if (MODE == GK_PASS_HEADER) {
+        kind_sid = gk_x_sid(c, kindv);
+        group_sid = gk_x_sid(c, gk_xstr(c.grp, c.grp_len));
+      }
       if (ns != GK_NONE) {   // the Namespace object of the review: the cache entry for the object's namespace (matcher.go:37-39)
         GkStr s = gk_x_str(c, gk_xnode(c.doc.tape, ns));
         gk_u64 h = GK_SEED_NS;
@@ -1382,10 +1388,10 @@ GK_HD void gk_ingest_obj(const GkXProg& xp, const GkIngestIn& in, const GkIngest
   }
   if (skip) fl = (fl & GK_F_SRC_MASK) | GK_F_SKIP;
   // ---- header arrays
-  {
+  if (HDR) {
     const GkXVal namev = (!skip && c.name_node != GK_NONE) ? gk_xnode(c.doc.tape, c.name_node) : gk_xundef();
     const GkXVal genv = (!skip && gen_node != GK_NONE) ? gk_xnode(c.doc.tape, gen_node) : gk_xundef();
-    if (WRITE && lane == 0) {
+    if (MODE == GK_PASS_HEADER && lane == 0) {
       out.flags[i] = fl;
       out.kind_sid[i] = kind_sid;
       out.group_sid[i] = group_sid;
@@ -1405,7 +1411,7 @@ GK_HD void gk_ingest_obj(const GkXProg& xp, const GkIngestIn& in, const GkIngest
       const uint32_t end = gk_te_end(c.doc.tape[labels]);
       for (uint32_t k = labels + 1u; k < end; k = gk_tape_skip(c.doc.tape, k + 1u)) {
         if (gk_key_shadowed(c.doc, k, end)) continue;
-        if (WRITE && lane == 0) {
+        if (MODE == GK_PASS_HEADER && lane == 0) {
           const GkXVal val = gk_xnode(c.doc.tape, k + 1u);
           out.lbl_kv[2u * (size_t)cur[K_LBL]] = gk_x_sid(c, gk_xnode(c.doc.tape, k));
           out.lbl_kv[2u * (size_t)cur[K_LBL] + 1u] = val.vt == GK_VT_STR ? gk_x_sid(c, val) : GK_SID_OTHER;
@@ -1413,13 +1419,14 @@ GK_HD void gk_ingest_obj(const GkXProg& xp, const GkIngestIn& in, const GkIngest
         ++cur[K_LBL];
       }
     }
-    if (WRITE && lane == 0 && i + 1u == n) {
+    if (MODE == GK_PASS_HEADER && lane == 0 && i + 1u == n) {
       out.name_off[n] = cur[K_NAME];
       out.gen_off[n] = cur[K_GEN];
       out.lbl_off[n] = cur[K_LBL];
       out.nsn_off[n] = cur[K_NSN];
     }
   }
+  if (MODE == GK_PASS_HEADER) return;
   // ---- scopes + columns: depth-first over the scope tree, rows of a scope in (parent row, member) order
   GkIngestFrame fr[GK_MAX_LOOP_DEPTH + 1];
   fr[0].scope = 0;

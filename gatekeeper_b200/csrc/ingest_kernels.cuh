@@ -2,7 +2,8 @@
 //   gk_tape_kernel   raw JSON -> tape (+ review-level status)
 //   gk_count_kernel  rows per scope / bytes per byte column / header byte counts of every object
 //   gk_scan_kernel   exclusive prefix sums of the counter arrays (one CTA per array), totals
-//   gk_write_kernel  per object: header arrays, CSR scope offsets, row handles, byte-encoded columns
+//   gk_header_kernel per object: flags, kind / group sids, names, labels, namespace row (the same steps in every thread)
+//   gk_write_kernel  per object: the scope walk -- CSR scope offsets, row handles, byte-encoded columns
 //   gk_cols_kernel   per row of one scope: every other column encoding; lookups through the device hash tables
 //   gk_fill_kernel   the host's answers to the miss list -> table slots
 //   gk_tiles_kernel  first row of every scope for every evaluation tile + the largest tile of each scope
@@ -40,6 +41,13 @@ __global__ void __launch_bounds__(kIngestThreads) gk_write_kernel(const GkXProg 
   if (i >= in.n) return;
   uint32_t cur[kMaxCounters];
   gk_ingest_obj<GK_PASS_ROWS>(xp, in, out, i, GkCur{cur, 1}, lane, lanes);
+}
+
+__global__ void __launch_bounds__(kIngestThreads) gk_header_kernel(const GkXProg xp, const GkIngestIn in, const GkIngestOut out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= in.n) return;
+  uint32_t cur[kMaxCounters];
+  gk_ingest_obj<GK_PASS_HEADER>(xp, in, out, i, GkCur{cur, 1}, 0u, 1u);
 }
 
 // the per-row column pass of one scope: a thread (or `lanes` threads) per row

@@ -59,6 +59,7 @@ class CudaBackend : public Backend {
     sm_smem_ = (size_t)prop.sharedMemPerMultiprocessor;
     CK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&front_stream_, cudaStreamNonBlocking));
     {
       // per-batch device memory comes from the stream-ordered pool and goes back to it: with the release threshold lifted a
       // resident-batch-sized arena is reused by the next batch instead of being mapped / unmapped by the driver every time
@@ -564,38 +565,7 @@ class CudaBackend : public Backend {
     xp.nsn_bytes = d_tab + o_nsnbytes;
     xp.excl_off = excl_off;
     xp.excl_n = excl_n;
-    // ---- scratch: blob, offsets, tape, counters, miss list
-    const uint32_t miss_cap = 1u << 17;
-    Carver sc;
-    const size_t o_blob = sc.take((size_t)B + 16), o_ooff = sc.take(((size_t)n + 1) * 8), o_tape = sc.take(((size_t)(B / 2) + 4ull * n + 64) * 8),
-                 o_ntape = sc.take((size_t)n * 4), o_status = sc.take((size_t)n * 4), o_counts = sc.take((size_t)NK * n * 4),
-                 o_totals = sc.take((size_t)(NK + NS + 4) * 4), o_miss = sc.take((size_t)miss_cap * sizeof(GkMiss)),
-                 o_fill = sc.take((size_t)miss_cap * 8);
-    uint8_t* d_s = scratch_.need(gk_align(sc.off));
-    GkIngestIn in;
-    memset(&in, 0, sizeof in);
-    in.blob = d_s + o_blob;
-    in.ooff = reinterpret_cast<const unsigned long long*>(d_s + o_ooff);
-    in.tape = reinterpret_cast<unsigned long long*>(d_s + o_tape);
-    in.ntape = reinterpret_cast<uint32_t*>(d_s + o_ntape);
-    in.status = reinterpret_cast<uint32_t*>(d_s + o_status);
-    in.n = n;
-    in.source = rq.source;
-    in.counts = reinterpret_cast<uint32_t*>(d_s + o_counts);
-    in.misses = reinterpret_cast<GkMiss*>(d_s + o_miss);
-    uint32_t* d_totals = reinterpret_cast<uint32_t*>(d_s + o_totals);
-    uint32_t* d_cap = d_totals + NK;
-    in.nmiss = d_cap + NS;
-    in.miss_cap = miss_cap;
-    uint32_t* d_fill = reinterpret_cast<uint32_t*>(d_s + o_fill);
-    cudaEvent_t e0, e1, e2, e3;
-    CK(cudaEventCreate(&e0));
-    CK(cudaEventCreate(&e1));
-    CK(cudaEventCreate(&e2));
-    CK(cudaEventCreate(&e3));
-    // ---- H2D of the raw JSON in chunks on the copy stream; the tokeniser of a chunk starts as soon as its bytes have landed
-    CK(cudaMemcpyAsync(d_s + o_ooff, rq.ooff, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, stream_));
-    CK(cudaEventRecord(e0, stream_));
+    // ---- front buffer (blob, offsets, tape): the prefetched copy of this page, or copy + tokenise now
     uint32_t lanes = 1;
     if (const char* ev = getenv("GK_INGEST_LANES")) lanes = std::max(1, std::min(32, atoi(ev)));
     while (lanes & (lanes - 1)) --lanes;
@@ -604,25 +574,37 @@ class CudaBackend : public Backend {
     while (clanes & (clanes - 1)) --clanes;
     const uint32_t wblocks = (uint32_t)(((uint64_t)n * lanes + kIngestThreads - 1) / kIngestThreads);
     if (NK > kMaxCounters) throw BackendError{"device ingest: too many byte-encoded columns"};
+    cudaEvent_t e0, e1, e2, e3;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    CK(cudaEventCreate(&e2));
+    CK(cudaEventCreate(&e3));
+    CK(cudaEventRecord(e0, stream_));
+    Front* fr = nullptr;
+    bool was_prefetched = false;
     {
-      const size_t kChunk = 32u << 20;
-      uint32_t first = 0;
-      while (first < n) {
-        uint32_t last = first;
-        const unsigned long long lo = rq.ooff[first];
-        while (last < n && rq.ooff[last + 1] - lo <= kChunk) ++last;
-        if (last == first) ++last;   // one object larger than a chunk
-        const unsigned long long hi = rq.ooff[last];
-        CK(cudaMemcpyAsync(d_s + o_blob + lo, rq.blob + lo, (size_t)(hi - lo), cudaMemcpyHostToDevice, copy_stream_));
-        cudaEvent_t ev = chunk_event(first);
-        CK(cudaEventRecord(ev, copy_stream_));
-        CK(cudaStreamWaitEvent(stream_, ev, 0));
-        const uint32_t cnt = last - first;
-        gk_tape_kernel<<<(cnt + kIngestThreads - 1) / kIngestThreads, kIngestThreads, 0, stream_>>>(in, first, cnt);
-        ++launches_;
-        first = last;
-      }
+      std::lock_guard<std::mutex> fl(front_mu_);
+      for (auto& f : fronts_)
+        if (f.pending && f.host_blob == rq.blob && f.n == rq.n) fr = &f, was_prefetched = true;
+      if (!fr) fr = &start_front(rq.blob, rq.ooff, rq.n);
+      fr->pending = false;
     }
+    CK(cudaStreamWaitEvent(stream_, fr->done, 0));
+    // ---- back scratch: counters, totals, miss list
+    const uint32_t miss_cap = 1u << 17;
+    Carver sc;
+    const size_t o_counts = sc.take((size_t)NK * n * 4), o_totals = sc.take((size_t)(NK + NS + 4) * 4), o_miss = sc.take((size_t)miss_cap * sizeof(GkMiss)),
+                 o_fill = sc.take((size_t)miss_cap * 8);
+    uint8_t* d_s = scratch_.need(gk_align(sc.off));
+    GkIngestIn in = fr->in;
+    in.source = rq.source;
+    in.counts = reinterpret_cast<uint32_t*>(d_s + o_counts);
+    in.misses = reinterpret_cast<GkMiss*>(d_s + o_miss);
+    uint32_t* d_totals = reinterpret_cast<uint32_t*>(d_s + o_totals);
+    uint32_t* d_cap = d_totals + NK;
+    in.nmiss = d_cap + NS;
+    in.miss_cap = miss_cap;
+    uint32_t* d_fill = reinterpret_cast<uint32_t*>(d_s + o_fill);
     CK(cudaEventRecord(e1, stream_));
     if (n) {
       gk_count_kernel<<<wblocks, kIngestThreads, 0, stream_>>>(xp, in, lanes, 0, n);
@@ -784,8 +766,9 @@ class CudaBackend : public Backend {
       xp.lut_vals = d_lutv_;
       CK(cudaMemsetAsync(in.nmiss, 0, 4, stream_));
       if (round == 0 || xh.nbytecols) {   // (row handles and header do not depend on the lookups; a byte column's sid may)
+        gk_header_kernel<<<(n + kIngestThreads - 1) / kIngestThreads, kIngestThreads, 0, stream_>>>(xp, in, out);
         gk_write_kernel<<<wblocks, kIngestThreads, 0, stream_>>>(xp, in, out, lanes);
-        ++launches_;
+        launches_ += 2;
       }
       for (uint32_t s2 = 0; s2 < NS; ++s2) {
         const uint32_t rows = s2 ? total[s2] : n;
@@ -888,6 +871,72 @@ class CudaBackend : public Backend {
     guard.release();
     return db;
   }
+  // ---- front buffers: a page's JSON, offsets and tape.  Two of them, so that page k+1 streams in (copy stream + front stream)
+  // while page k is extracted and evaluated on the main stream.
+  struct Front {
+    Scratch buf;
+    GkIngestIn in{};            // blob / ooff / tape / ntape / status pointers into buf, n
+    const uint8_t* host_blob = nullptr;
+    size_t n = 0;
+    bool pending = false;       // prefetched, not yet consumed
+    cudaEvent_t done = nullptr; // copy + tokenise finished
+  };
+  Front& start_front(const uint8_t* blob, const unsigned long long* ooff, size_t nn) {   // (front_mu_ held)
+    Front& f = fronts_[next_front_];
+    next_front_ ^= 1;
+    const uint32_t n = (uint32_t)nn;
+    const unsigned long long B = ooff[n];
+    Carver sc;
+    const size_t o_blob = sc.take((size_t)B + 16), o_ooff = sc.take(((size_t)n + 1) * 8), o_tape = sc.take(((size_t)(B / 2) + 4ull * n + 64) * 8),
+                 o_ntape = sc.take((size_t)n * 4), o_status = sc.take((size_t)n * 4);
+    if (!f.done) CK(cudaEventCreateWithFlags(&f.done, cudaEventDisableTiming));
+    // the buffer may still be read by the kernels of the page that used it last: they ran on the main stream
+    CK(cudaStreamSynchronize(stream_));
+    uint8_t* d = f.buf.need(gk_align(sc.off));
+    memset(&f.in, 0, sizeof f.in);
+    f.in.blob = d + o_blob;
+    f.in.ooff = reinterpret_cast<const unsigned long long*>(d + o_ooff);
+    f.in.tape = reinterpret_cast<unsigned long long*>(d + o_tape);
+    f.in.ntape = reinterpret_cast<uint32_t*>(d + o_ntape);
+    f.in.status = reinterpret_cast<uint32_t*>(d + o_status);
+    f.in.n = n;
+    f.host_blob = blob;
+    f.n = nn;
+    // H2D of the raw JSON in chunks on the copy stream; the tokeniser of a chunk starts as soon as its bytes have landed
+    CK(cudaMemcpyAsync(d + o_ooff, ooff, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, copy_stream_));
+    const size_t kChunk = 32u << 20;
+    uint32_t first = 0;
+    while (first < n) {
+      uint32_t last = first;
+      const unsigned long long lo = ooff[first];
+      while (last < n && ooff[last + 1] - lo <= kChunk) ++last;
+      if (last == first) ++last;   // one object larger than a chunk
+      const unsigned long long hi = ooff[last];
+      CK(cudaMemcpyAsync(d + o_blob + lo, blob + lo, (size_t)(hi - lo), cudaMemcpyHostToDevice, copy_stream_));
+      cudaEvent_t ev = chunk_event(first);
+      CK(cudaEventRecord(ev, copy_stream_));
+      CK(cudaStreamWaitEvent(front_stream_, ev, 0));
+      const uint32_t cnt = last - first;
+      gk_tape_kernel<<<(cnt + kIngestThreads - 1) / kIngestThreads, kIngestThreads, 0, front_stream_>>>(f.in, first, cnt);
+      ++launches_;
+      first = last;
+    }
+    if (n == 0) CK(cudaStreamWaitEvent(front_stream_, chunk_event_after_copy(), 0));
+    CK(cudaEventRecord(f.done, front_stream_));
+    f.pending = true;
+    return f;
+  }
+  cudaEvent_t chunk_event_after_copy() {
+    cudaEvent_t ev = chunk_event(0);
+    CK(cudaEventRecord(ev, copy_stream_));
+    return ev;
+  }
+  void prefetch(const uint8_t* blob, const unsigned long long* ooff, size_t n) override {
+    std::lock_guard<std::mutex> fl(front_mu_);
+    CK(cudaSetDevice(device_));
+    start_front(blob, ooff, n);
+  }
+
   void pin_host(const void* p, size_t bytes, bool pin) override {
     CK(cudaSetDevice(device_));
     if (pin) CK(cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterDefault));
@@ -946,7 +995,10 @@ class CudaBackend : public Backend {
   std::vector<GkLutVal> lutv_;
   GkLutVal* d_lutv_ = nullptr;
   size_t d_lutv_cap_ = 0;
-  cudaStream_t copy_stream_ = nullptr;
+  cudaStream_t copy_stream_ = nullptr, front_stream_ = nullptr;
+  std::mutex front_mu_;
+  Front fronts_[2];
+  int next_front_ = 0;
   std::vector<cudaEvent_t> chunk_evs_;
   size_t chunk_ev_next_ = 0;
   int device_;

@@ -68,7 +68,7 @@ EXPORTS = [
     "gk_add_constraint", "gk_validate_constraint", "gk_remove_constraint", "gk_put_namespace", "gk_remove_namespace", "gk_constraint_count",
     "gk_constraint_key", "gk_result_constraint_key", "gk_review_batch", "gk_batch_upload", "gk_batch_eval", "gk_batch_eval_device",
     "gk_batch_eval_device_peers", "gk_batch_upload_blob", "gk_review_blob", "gk_set_excluded_namespaces", "gk_audit_begin", "gk_audit_add_batch", "gk_audit_report",
-    "gk_audit_end", "gk_validation_messages", "gk_host_cpus", "gk_pin_host", "gk_coalescer_create", "gk_coalescer_review", "gk_coalescer_stats",
+    "gk_audit_end", "gk_validation_messages", "gk_host_cpus", "gk_pin_host", "gk_blob_prefetch", "gk_coalescer_create", "gk_coalescer_review", "gk_coalescer_stats",
     "gk_coalescer_destroy", "gk_batch_size", "gk_batch_alg_bytes", "gk_batch_free", "gk_free_result", "gk_free_str", "gk_dump",
     "gk_stat_description",
 ]
@@ -128,6 +128,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.gk_host_cpus.argtypes = []
     lib.gk_host_cpus.restype = C.c_int
     lib.gk_pin_host.argtypes = [P, C.c_void_p, C.c_size_t, C.c_int, PP]
+    lib.gk_blob_prefetch.argtypes = [P, C.c_void_p, C.POINTER(C.c_uint64), C.c_size_t, PP]
     lib.gk_batch_size.argtypes = [P]
     lib.gk_batch_alg_bytes.restype = U64
     lib.gk_batch_alg_bytes.argtypes = [P]
@@ -454,6 +455,11 @@ class Driver:
         """Page-lock the blob's host buffer (gk_pin_host) so its host->device copy runs at link speed."""
         err = C.c_char_p()
         self._check(self._lib.gk_pin_host(self._e, blob.buf, blob.total_bytes(), 1 if pin else 0, C.byref(err)), err)
+
+    def prefetch_blob(self, blob):
+        """Start streaming `blob` to the GPU (gk_blob_prefetch); the following ReviewBlob / upload_blob of it picks the copy up."""
+        err = C.c_char_p()
+        self._check(self._lib.gk_blob_prefetch(self._e, blob.buf, blob.offsets, len(blob), C.byref(err)), err)
 
     def upload_blob(self, blob, source: str = "Original", process: str = ""):
         """Flatten + upload a page of objects held in one contiguous buffer (workloads.ObjectBlob)."""

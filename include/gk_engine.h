@@ -200,6 +200,13 @@ int gk_host_cpus(void);
  * and overlapped with the tokeniser.  Optional: unpinned buffers work, through the driver's staging copies. */
 int gk_pin_host(gk_engine_t* e, const void* p, size_t bytes, int pin, char** err);
 
+/* Start streaming the NEXT page of the sweep to the GPU (host->device copy of the raw JSON, chunked, each chunk tokenised as it
+ * lands) and return at once; the gk_review_blob / gk_batch_upload_blob call for the same (buf, n) then finds it there.  The audit
+ * loop calls it for page k+1 before it reviews page k (pkg/audit/manager.go:579-646 lists and reviews page after page), so the
+ * copy of one page hides behind the extraction and evaluation of the one before.  Optional; the buffer must stay unchanged until
+ * it has been reviewed. */
+int gk_blob_prefetch(gk_engine_t* e, const char* buf, const uint64_t* offsets, size_t n, char** err);
+
 void gk_free_result(gk_result* r);
 void gk_free_str(char* s);
 char* gk_dump(gk_engine_t* e);

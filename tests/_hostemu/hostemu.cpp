@@ -203,6 +203,7 @@ class HostEmuBackend : public Backend {
       nmiss[0] = 0;
       xp.lut_tab = lut_.view();
       xp.lut_vals = lut_vals_.data();
+      for (uint32_t i = 0; i < n; ++i) gk_ingest_obj<GK_PASS_HEADER>(xp, in, out, i, GkCur{cur.data(), 1}, 0, 1);
       for (uint32_t i = 0; i < n; ++i) gk_ingest_obj<GK_PASS_ROWS>(xp, in, out, i, GkCur{cur.data(), 1}, 0, 1);
       for (uint32_t s2 = 0; s2 < NS; ++s2)
         for (uint32_t r = 0, R = s2 ? total[s2] : n; r < R; ++r) gk_ingest_row(xp, in, out, s2, r, 0, 1);

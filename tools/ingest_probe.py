@@ -23,9 +23,18 @@ blob = W.synth_objects(0, n)
 print("blob bytes", blob.total_bytes())
 if os.environ.get("GK_PIN", "1") == "1":
     drv.pin_blob(blob)
+blob2 = W.synth_objects(n, n)
+if os.environ.get("GK_PIN", "1") == "1":
+    drv.pin_blob(blob2)
+pages = [blob, blob2]
+pipelined = os.environ.get("GK_PIPELINE", "1") == "1"
+if pipelined:
+    drv.prefetch_blob(pages[0])
 for r in range(reps):
     t0 = time.time()
-    resp = drv.ReviewBlob(blob, flags=D.F_NO_COPY_BACK, with_results=False)
+    if pipelined and r + 1 < reps:
+        drv.prefetch_blob(pages[(r + 1) % 2])
+    resp = drv.ReviewBlob(pages[r % 2], flags=D.F_NO_COPY_BACK, with_results=False)
     dt = time.time() - t0
     print(f"rep {r}: wall {dt*1e3:.1f} ms -> {n*50/dt/1e6:.1f} M evals/s; stats {resp.stats}")
 if os.environ.get("GK_TRACE_INGEST"):
