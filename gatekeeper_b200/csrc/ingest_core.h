@@ -614,6 +614,13 @@ typedef struct {
 //   then: name bytes, generateName bytes, labels, nsname bytes
 #define GK_CNT_EXTRA 4
 
+typedef struct {
+  uint32_t elem;     // tape index of the row's element
+  uint32_t key;      // tape index of the member's key, or (array index | GK_ROW_INDEX)
+  uint32_t parent;   // row of the parent scope (an object index under the root)
+  uint32_t obj;      // object index
+} GkRowRec;
+
 // per-chunk destination arrays of the WRITE pass (device pointers; offsets are chunk-relative)
 typedef struct {
   uint32_t* flags;
@@ -636,11 +643,9 @@ typedef struct {
   uint32_t* const* boff;
   uint8_t* const* bytes;
   uint32_t* const* head;
-  // row handles (scratch, not part of the batch): what the per-row column pass needs to find its element again
-  uint32_t* const* row_elem;     // [nscopes][rows] tape index of the row's element
-  uint32_t* const* row_key;      // [nscopes][rows] tape index of the member's key, or (array index | GK_ROW_INDEX)
-  uint32_t* const* row_parent;   // [nscopes][rows] row of the parent scope (an object index under the root)
-  uint32_t* const* row_obj;      // [nscopes][rows] object index
+  // row handles (scratch, not part of the batch): what the per-row column pass needs to find its element again -- one
+  // 16-byte record per row, written with one store
+  GkRowRec* const* row_rec;      // [nscopes][rows]
 } GkIngestOut;
 #define GK_ROW_INDEX 0x80000000u
 
@@ -1506,10 +1511,16 @@ GK_HD void gk_ingest_obj(const GkXProg& xp, const GkIngestIn& in, const GkIngest
     g.row = cur[g.scope]++;
     c.depth = top;
     if (WRITE && lane == 0) {
-      out.row_elem[g.scope][g.row] = c.elem[top].node;
-      out.row_key[g.scope][g.row] = g.is_obj ? c.key[top].node : ((uint32_t)c.key[top].inum | GK_ROW_INDEX);
-      out.row_parent[g.scope][g.row] = fr[top - 1].row;
-      out.row_obj[g.scope][g.row] = i;
+      GkRowRec rr;
+      rr.elem = c.elem[top].node;
+      rr.key = g.is_obj ? c.key[top].node : ((uint32_t)c.key[top].inum | GK_ROW_INDEX);
+      rr.parent = fr[top - 1].row;
+      rr.obj = i;
+#ifdef __CUDA_ARCH__
+      *reinterpret_cast<uint4*>(&out.row_rec[g.scope][g.row]) = *reinterpret_cast<const uint4*>(&rr);
+#else
+      out.row_rec[g.scope][g.row] = rr;
+#endif
     }
     const GkXScope& sc = xp.scopes[g.scope];
     for (uint32_t k = lane; k < sc.ncols; k += nlanes) gk_emit_col<MODE>(xp, in, out, c, xp.col_order[sc.first_col + k], g.row, bcur);
@@ -1546,7 +1557,11 @@ GK_HD void gk_ingest_obj(const GkXProg& xp, const GkIngestIn& in, const GkIngest
 // The per-row column pass: every column of scope `sc` that is not byte-encoded, for row `r` (scope 0: r = the object).  Threads
 // of a warp work on different rows of the SAME scope, so they run the same column / the same path at the same time.
 GK_HD void gk_ingest_row(const GkXProg& xp, const GkIngestIn& in, const GkIngestOut& out, uint32_t sc, uint32_t r, uint32_t lane, uint32_t nlanes) {
-  const uint32_t i = sc ? out.row_obj[sc][r] : r;
+  GkRowRec me;
+  me.elem = me.key = me.parent = 0;
+  me.obj = r;
+  if (sc) me = out.row_rec[sc][r];
+  const uint32_t i = me.obj;
   GkXCtx c;
   c.xp = &xp;
   c.in = &in;
@@ -1577,19 +1592,20 @@ GK_HD void gk_ingest_row(const GkXProg& xp, const GkIngestIn& in, const GkIngest
   for (uint32_t s2 = sc; s2; s2 = (uint32_t)xp.scopes[s2].parent) ++d;
   c.depth = d;
   {
-    uint32_t cs = sc, cr = r;
+    uint32_t cs = sc;
+    GkRowRec rr = me;
     for (int dd = d; dd >= 1; --dd) {
       c.scope_at[dd] = cs;
-      c.elem[dd] = gk_xnode(c.doc.tape, out.row_elem[cs][cr]);
-      const uint32_t k = out.row_key[cs][cr];
+      c.elem[dd] = gk_xnode(c.doc.tape, rr.elem);
+      const uint32_t k = rr.key;
       if (k & GK_ROW_INDEX) {
         c.key[dd] = gk_xsyn(GK_VT_NUM);
         c.key[dd].inum = (long long)(k & ~GK_ROW_INDEX);
       } else {
         c.key[dd] = gk_xnode(c.doc.tape, k);
       }
-      cr = out.row_parent[cs][cr];
       cs = (uint32_t)xp.scopes[cs].parent;
+      if (cs) rr = out.row_rec[cs][rr.parent];
     }
   }
   const GkCur none{nullptr, 0};

@@ -735,24 +735,18 @@ class CudaBackend : public Backend {
     out.boff = reinterpret_cast<uint32_t* const*>(A + a_pboff);
     out.bytes = reinterpret_cast<uint8_t* const*>(A + a_pbytes);
     out.head = reinterpret_cast<uint32_t* const*>(A + a_phead);
-    // ---- row handles (scratch): 4 arrays per scope + their pointer tables
+    // ---- row handles (scratch): one 16-byte record per row of every scope + the pointer table
     {
       Carver rc;
-      const size_t o_ptrs = rc.take((size_t)4 * NS * 8);
-      std::vector<size_t> o_rows(4 * (size_t)NS, 0);
-      for (uint32_t s2 = 1; s2 < NS; ++s2)
-        for (int q = 0; q < 4; ++q) o_rows[(size_t)q * NS + s2] = rc.take(((size_t)total[s2] + 1) * 4);
+      const size_t o_ptrs = rc.take((size_t)NS * 8);
+      std::vector<size_t> o_rows(NS, 0);
+      for (uint32_t s2 = 1; s2 < NS; ++s2) o_rows[s2] = rc.take(((size_t)total[s2] + 1) * sizeof(GkRowRec));
       uint8_t* d_r = rows_.need(gk_align(rc.off));
-      std::vector<uint64_t> ptrs(4 * (size_t)NS, 0);
-      for (uint32_t s2 = 1; s2 < NS; ++s2)
-        for (int q = 0; q < 4; ++q) ptrs[(size_t)q * NS + s2] = reinterpret_cast<uint64_t>(d_r + o_rows[(size_t)q * NS + s2]);
+      std::vector<uint64_t> ptrs(NS, 0);
+      for (uint32_t s2 = 1; s2 < NS; ++s2) ptrs[s2] = reinterpret_cast<uint64_t>(d_r + o_rows[s2]);
       CK(cudaMemcpyAsync(d_r + o_ptrs, ptrs.data(), ptrs.size() * 8, cudaMemcpyHostToDevice, stream_));
       CK(cudaStreamSynchronize(stream_));   // (`ptrs` is a temporary)
-      uint32_t* const* base = reinterpret_cast<uint32_t* const*>(d_r + o_ptrs);
-      out.row_elem = base;
-      out.row_key = base + NS;
-      out.row_parent = base + 2 * NS;
-      out.row_obj = base + 3 * NS;
+      out.row_rec = reinterpret_cast<GkRowRec* const*>(d_r + o_ptrs);
     }
     // ---- write passes, repeated while lookups are missing (the host evaluates each distinct argument tuple once)
     CK(cudaEventRecord(e2, stream_));
@@ -904,7 +898,7 @@ class CudaBackend : public Backend {
     f.n = nn;
     // H2D of the raw JSON in chunks on the copy stream; the tokeniser of a chunk starts as soon as its bytes have landed
     CK(cudaMemcpyAsync(d + o_ooff, ooff, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, copy_stream_));
-    const size_t kChunk = 32u << 20;
+    const size_t kChunk = 8u << 20;   // (small enough that the ingest's own little copies never wait long behind one)
     uint32_t first = 0;
     while (first < n) {
       uint32_t last = first;

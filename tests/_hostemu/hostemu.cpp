@@ -187,17 +187,13 @@ class HostEmuBackend : public Backend {
     out.boff = p_boff.data();
     out.bytes = p_bytes.data();
     out.head = p_head.data();
-    std::vector<std::vector<uint32_t>> rh(4 * NS);
-    std::vector<uint32_t*> p_rh(4 * NS, nullptr);
-    for (uint32_t s2 = 1; s2 < NS; ++s2)
-      for (int q = 0; q < 4; ++q) {
-        rh[q * NS + s2].assign((size_t)total[s2] + 1, 0);
-        p_rh[q * NS + s2] = rh[q * NS + s2].data();
-      }
-    out.row_elem = p_rh.data();
-    out.row_key = p_rh.data() + NS;
-    out.row_parent = p_rh.data() + 2 * NS;
-    out.row_obj = p_rh.data() + 3 * NS;
+    std::vector<std::vector<GkRowRec>> rh(NS);
+    std::vector<GkRowRec*> p_rh(NS, nullptr);
+    for (uint32_t s2 = 1; s2 < NS; ++s2) {
+      rh[s2].assign((size_t)total[s2] + 1, GkRowRec{0, 0, 0, 0});
+      p_rh[s2] = rh[s2].data();
+    }
+    out.row_rec = p_rh.data();
     uint64_t total_miss = 0;
     for (int round = 0; round < 64; ++round) {
       nmiss[0] = 0;
