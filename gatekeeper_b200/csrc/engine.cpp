@@ -2052,8 +2052,9 @@ void Engine::autoreject(const Compiled& c, const ObjIn& in, uint32_t obj_ix, uin
   x.object = obj_ix;
   x.constraint = cix;
   x.autoreject = true;
-  if (code == GK_E_NO_OBJECT) x.msg = "invalid request object: neither object nor old object are defined";
-  else x.msg = "error matching the requested object: " + name + " :failed to run Match criteria: " + detail;   // matcher.go:58-60, match.go:52-54
+  // "unable to match constraints: <matcher error>": the frameworks client's wording of an autoreject (test/gator/test/test.bats:276)
+  if (code == GK_E_NO_OBJECT) x.msg = "unable to match constraints: invalid request object: neither object nor old object are defined";
+  else x.msg = "unable to match constraints: error matching the requested object: " + name + " :failed to run Match criteria: " + detail;   // matcher.go:58-60, match.go:52-54
   x.details_json = "{}";
   x.action = con.action;
   x.scoped_json = scoped_json(con.action == "scoped" ? scoped_actions_for(con, ep) : std::vector<std::string>());

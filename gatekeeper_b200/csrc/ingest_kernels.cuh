@@ -17,6 +17,9 @@
 namespace gk {
 
 constexpr int kIngestThreads = 128;
+#ifndef GK_INGEST_MIN_BLOCKS
+#define GK_INGEST_MIN_BLOCKS 8   /* 64 registers per thread: these passes are latency-bound, resident warps are what hides it */
+#endif
 
 __global__ void __launch_bounds__(kIngestThreads) gk_tape_kernel(const GkIngestIn in, uint32_t first, uint32_t count) {
   const uint32_t i = first + blockIdx.x * blockDim.x + threadIdx.x;
@@ -36,7 +39,7 @@ __global__ void __launch_bounds__(kIngestThreads) gk_count_kernel(const GkXProg 
   gk_ingest_obj<GK_PASS_COUNT>(xp, in, none, i, GkCur{cur, 1}, lane, lanes);
 }
 
-__global__ void __launch_bounds__(kIngestThreads) gk_write_kernel(const GkXProg xp, const GkIngestIn in, const GkIngestOut out, uint32_t lanes) {
+__global__ void __launch_bounds__(kIngestThreads, GK_INGEST_MIN_BLOCKS) gk_write_kernel(const GkXProg xp, const GkIngestIn in, const GkIngestOut out, uint32_t lanes) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, i = t / lanes, lane = t % lanes;
   if (i >= in.n) return;
   uint32_t cur[kMaxCounters];
@@ -51,7 +54,7 @@ __global__ void __launch_bounds__(kIngestThreads) gk_header_kernel(const GkXProg
 }
 
 // the per-row column pass of one scope: a thread (or `lanes` threads) per row
-__global__ void __launch_bounds__(kIngestThreads) gk_cols_kernel(const GkXProg xp, const GkIngestIn in, const GkIngestOut out, uint32_t scope, uint32_t rows,
+__global__ void __launch_bounds__(kIngestThreads, GK_INGEST_MIN_BLOCKS) gk_cols_kernel(const GkXProg xp, const GkIngestIn in, const GkIngestOut out, uint32_t scope, uint32_t rows,
                                                                  uint32_t lanes) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, r = t / lanes, lane = t % lanes;
   if (r >= rows) return;

@@ -712,7 +712,9 @@ class Client:
                 if not matcher_match(spec.get("match"), review, self.ns_cache):
                     continue
             except MatchError as e:
-                results.append({"constraint": (kind, name), "msg": str(e), "details": {},
+                # the frameworks client words the autoreject result "unable to match constraints: <matcher error>" -- pinned by
+                # test/gator/test/test.bats:276
+                results.append({"constraint": (kind, name), "msg": "unable to match constraints: " + str(e), "details": {},
                                 "enforcementAction": action, "scopedEnforcementActions": scoped or [],
                                 "autoreject": True})
                 continue

@@ -1147,7 +1147,7 @@ def case_target_matcher(lib):
             assert obj_err or (resp.results and resp.results[0].autoreject and "invalid request object" in resp.results[0].msg), v["name"]
             assert not flagged
         elif v["wantErr"] == "ErrMatching":
-            assert errored and resp.results[0].autoreject and resp.results[0].msg.startswith("error matching the requested object"), v["name"]
+            assert errored and resp.results[0].autoreject and resp.results[0].msg.startswith("unable to match constraints: error matching the requested object"), v["name"]
         else:
             assert not errored and not obj_err, (v["name"], obj_err)
             assert flagged == v["want"], v["name"]
