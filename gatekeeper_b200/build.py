@@ -18,7 +18,7 @@ OBJ = os.path.join(ROOT, "build", "obj")
 LIB = os.path.join(ROOT, "gatekeeper_b200", "libgk_engine.so")
 EMU = os.path.join(ROOT, "tests", "_hostemu", "libgk_hostemu.so")
 
-HOST_SRCS = ["val.cpp", "rego_parse.cpp", "rego_eval.cpp", "lower.cpp", "xprog.cpp", "engine.cpp", "audit.cpp", "capi.cpp", "coalescer.cpp"]
+HOST_SRCS = ["val.cpp", "rego_parse.cpp", "rego_eval.cpp", "lower.cpp", "xprog.cpp", "expansion.cpp", "engine.cpp", "audit.cpp", "capi.cpp", "coalescer.cpp"]
 SYNTH = os.path.join(ROOT, "gatekeeper_b200", "libgk_synth.so")
 CXXFLAGS = ["-std=c++17", "-O2", "-g1", "-fPIC", "-Wall", "-Wextra", "-pthread"]
 NVCCFLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC"]
@@ -102,7 +102,7 @@ def build(verbose=False, hostemu=True, force=False):
     co = os.path.join(OBJ, "cpu_ref.cpp.o")
     if force or _stale(co, [csrc], hdr_m):
         _run(["g++", *CXXFLAGS, "-c", csrc, "-o", co])
-    cobjs = [os.path.join(OBJ, s + ".o") for s in ("val.cpp", "rego_parse.cpp", "rego_eval.cpp", "lower.cpp", "xprog.cpp", "engine.cpp")]
+    cobjs = [os.path.join(OBJ, s + ".o") for s in ("val.cpp", "rego_parse.cpp", "rego_eval.cpp", "lower.cpp", "xprog.cpp", "expansion.cpp", "engine.cpp")]
     CPUREF = os.path.join(cdir, "libgk_cpuref.so")
     if force or _stale(CPUREF, cobjs + [co], 0):
         _run(["g++", "-shared", "-o", CPUREF, *cobjs, co, "-pthread"])

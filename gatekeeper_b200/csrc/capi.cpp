@@ -7,6 +7,7 @@
 #include <cstring>
 #include <functional>
 #include <memory>
+#include <stdexcept>
 #include <thread>
 #include <unordered_map>
 
@@ -433,16 +434,66 @@ const char* gk_result_constraint_key(const gk_result* r, uint32_t index) {
   return index < rp->keys.size() ? rp->keys[index].c_str() : nullptr;
 }
 
+int gk_add_expansion_template(gk_engine_t* e, const char* json, size_t len, char** err) {
+  if (!e || !json) return GK_ERR_INVALID;
+  return guard(err, [&]() { e->eng->add_expansion_template(std::string(json, len)); });
+}
+int gk_remove_expansion_template(gk_engine_t* e, const char* name) {
+  if (!e || !name) return GK_ERR_INVALID;
+  return guard(nullptr, [&]() { e->eng->remove_expansion_template(name); });
+}
+
 int gk_review_batch(gk_engine_t* e, const gk_obj* objs, size_t n, const char* ep, uint32_t flags, gk_result* out, char** err) {
   if (!e || !out || (!objs && n)) return GK_ERR_INVALID;
   memset(out, 0, sizeof *out);
   return guard(err, [&]() {
+    // ---- expansion (pkg/audit/manager.go:733-765, pkg/webhook/policy.go:610-646): the resultants of generator objects are
+    // appended to the batch as generated resources, reviewed with it, and their results folded back onto their parents
+    struct Child {
+      uint32_t parent;
+      std::string json, tmpl, action;
+    };
+    std::vector<Child> children;
+    std::vector<std::string> expand_errors;
+    if (e->eng->has_expansion()) {
+      expand_errors.assign(n, std::string());
+      std::vector<Resultant> res;
+      for (size_t i = 0; i < n; ++i) {
+        res.clear();
+        try {
+          e->eng->expand_object(to_in(objs[i]), res);
+        } catch (std::runtime_error& x) {
+          expand_errors[i] = std::string("unable to expand object: ") + x.what();
+          continue;
+        }
+        for (auto& r : res) children.push_back(Child{(uint32_t)i, json_str(r.obj), r.template_name, r.action});
+      }
+    }
+    std::vector<gk_obj> all;
+    const gk_obj* use = objs;
+    size_t total = n;
+    if (!children.empty()) {
+      all.assign(objs, objs + n);
+      for (auto& c : children) {
+        gk_obj o;
+        memset(&o, 0, sizeof o);
+        o.json = c.json.data();
+        o.len = c.json.size();
+        o.ns_json = objs[c.parent].ns_json;       // createReviewForResultant: the parent's Namespace, source Generated
+        o.ns_len = objs[c.parent].ns_len;
+        o.ns_name = objs[c.parent].ns_name;
+        o.source = GK_SOURCE_GENERATED;
+        all.push_back(o);
+      }
+      use = all.data();
+      total = all.size();
+    }
     gk_batch* b = nullptr;
     gk_result stats;
     memset(&stats, 0, sizeof stats);
     auto c = e->eng->compiled();
     ProgramLease lease(e, *c);   // flatten + upload + kernel + rendering all against this one snapshot
-    upload_batch(e, c, objs, n, flags, &b, &stats);
+    upload_batch(e, c, use, total, flags, &b, &stats);
     std::unique_ptr<gk_batch, std::function<void(gk_batch*)>> hold(b, [&](gk_batch* x) {
       e->be->release(x->dev);
       delete x;
@@ -451,6 +502,45 @@ int gk_review_batch(gk_engine_t* e, const gk_obj* objs, size_t n, const char* ep
     out->flatten_ms = stats.flatten_ms;
     out->h2d_ms = stats.h2d_ms;
     out->h2d_bytes = stats.h2d_bytes;
+    bool any_expand_err = false;
+    for (auto& x : expand_errors) any_expand_err = any_expand_err || !x.empty();
+    if (children.empty() && !any_expand_err) return;
+    // ---- fold the resultants back: bits ORed into the parent's row, results re-indexed with "[Implied by <template>]" and the
+    // template's enforcement-action override (aggregate.go:19-63), their review-level errors reported on the parent
+    auto* rp = static_cast<ResultPriv*>(out->priv);
+    const uint32_t W = rp->ev.words;
+    for (size_t k = 0; k < children.size(); ++k) {
+      const size_t row = n + k, par = children[k].parent;
+      if (!rp->ev.viol.empty())
+        for (uint32_t w = 0; w < W; ++w) rp->ev.viol[par * W + w] |= rp->ev.viol[row * W + w];
+      if (!rp->ev.err.empty())
+        for (uint32_t w = 0; w < W; ++w) rp->ev.err[par * W + w] |= rp->ev.err[row * W + w];
+    }
+    if (!rp->ev.viol.empty()) rp->ev.viol.resize(n * (size_t)W);
+    if (!rp->ev.err.empty()) rp->ev.err.resize(n * (size_t)W);
+    rp->ev.n = (uint32_t)n;
+    for (auto& v : rp->vio)
+      if (v.object >= n) {
+        const Child& ch = children[v.object - n];
+        v.object = ch.parent;
+        v.msg = ExpansionSystem::implied_by(ch.tmpl, v.msg);
+        if (!ch.action.empty()) {   // OverrideEnforcementAction
+          v.action = ch.action;
+          v.scoped_json = "[]";
+        }
+      }
+    std::stable_sort(rp->vio.begin(), rp->vio.end(), [](const Violation& a, const Violation& b2) { return a.object < b2.object; });
+    if (rp->obj_errors.empty() && any_expand_err) rp->obj_errors.assign(total, std::string());
+    if (!rp->obj_errors.empty()) {
+      for (size_t k = 0; k < children.size(); ++k)
+        if (!rp->obj_errors[n + k].empty() && rp->obj_errors[children[k].parent].empty())
+          rp->obj_errors[children[k].parent] = ExpansionSystem::implied_by(children[k].tmpl, rp->obj_errors[n + k]);
+      rp->obj_errors.resize(n);
+      for (size_t i = 0; i < n && i < expand_errors.size(); ++i)
+        if (!expand_errors[i].empty() && rp->obj_errors[i].empty()) rp->obj_errors[i] = expand_errors[i];
+    }
+    const bool give_bits = !(flags & GK_F_NO_COPY_BACK);
+    fill_result(out, rp, give_bits);
   });
 }
 

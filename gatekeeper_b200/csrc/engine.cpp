@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cstring>
 #include <thread>
+#include <stdexcept>
 
 namespace gk {
 
@@ -1824,6 +1825,49 @@ std::shared_ptr<HostBatch> Engine::flatten(const ObjIn* objs, size_t n, const Co
   for (auto& col : hb.cols) sz(col.vt), sz(col.sid), sz(col.num), sz(col.boff), sz(col.bytes), sz(col.head);
   hb.alg_bytes = b;
   return out;
+}
+
+void Engine::add_expansion_template(const std::string& json) {
+  std::unique_lock<std::shared_mutex> l(mu_);
+  try {
+    expansion_.upsert(json);
+  } catch (std::runtime_error& e) {
+    throw RegoError{e.what()};
+  }
+}
+bool Engine::remove_expansion_template(const std::string& name) {
+  std::unique_lock<std::shared_mutex> l(mu_);
+  return expansion_.remove(name);
+}
+bool Engine::has_expansion() {
+  std::shared_lock<std::shared_mutex> l(mu_);
+  return !expansion_.empty();
+}
+void Engine::expand_object(const ObjIn& in, std::vector<Resultant>& out) {
+  if (!in.json || (in.operation && std::string(in.operation) == "DELETE")) return;
+  VP obj;
+  try {
+    obj = json_parse(in.json, in.len);
+  } catch (JsonError&) {
+    return;   // the review itself reports the undecodable object
+  }
+  if (!obj || obj->t != VT::Obj) return;
+  std::shared_lock<std::shared_mutex> l(mu_);
+  // the review's Namespace object: the explicit one, else the cache entry for the request's namespace (policy.go:606-614)
+  std::string nsn;
+  bool have_ns = false;
+  if (in.ns_json) {
+    try {
+      VP ns = json_parse(in.ns_json, in.ns_len);
+      if (ns && ns->t == VT::Obj) nsn = meta_str(ns, "name"), have_ns = true;
+    } catch (JsonError&) {
+    }
+  } else {
+    const std::string key = in.ns_name ? std::string(in.ns_name) : meta_str(obj, "namespace");
+    auto it = key.empty() ? namespaces_.end() : namespaces_.find(key);
+    if (it != namespaces_.end()) nsn = meta_str(it->second, "name"), have_ns = true;
+  }
+  expansion_.expand(obj, have_ns ? &nsn : nullptr, out);
 }
 
 std::map<std::string, VP> Engine::namespaces_snapshot() {

@@ -13,6 +13,7 @@
 #include "lower.hpp"
 #include "program.h"
 #include "rego.hpp"
+#include "expansion.hpp"
 #include "xprog.hpp"
 
 namespace gk {
@@ -185,6 +186,12 @@ class Engine {
   void autoreject(const Compiled& c, const ObjIn& obj, uint32_t obj_ix, uint32_t cix, uint32_t code, const std::string& ep,
                   std::vector<Violation>& out);
   std::string dump();
+  // ExpansionTemplates (pkg/expansion): generator resources imply resultants that are reviewed with them
+  void add_expansion_template(const std::string& json);
+  bool remove_expansion_template(const std::string& name);
+  bool has_expansion();
+  // the resultants of one review's object (empty when no template applies); throws std::runtime_error like System.Expand
+  void expand_object(const ObjIn& in, std::vector<Resultant>& out);
   std::map<std::string, VP> namespaces_snapshot();   // (deep copies: safe to read from another thread without touching shared reference counts)
   // everything a backend needs to flatten a blob of plain objects on the device (xprog.hpp); `blob` must outlive the request
   IngestReq ingest_request(const std::shared_ptr<const Compiled>& c, const uint8_t* blob, const unsigned long long* ooff, size_t n, uint32_t source,
@@ -207,6 +214,7 @@ class Engine {
   uint64_t ns_table_version_ = ~0ull;
   uint32_t ns_table_strings_ = 0;
   std::map<std::string, std::vector<std::string>> excluded_;
+  ExpansionSystem expansion_;
   std::shared_ptr<Compiled> compiled_;
   bool dirty_ = true;
   uint64_t version_ = 0;

@@ -65,7 +65,7 @@ class gk_result(C.Structure):
 
 EXPORTS = [
     "gk_engine_create", "gk_engine_destroy", "gk_backend_name", "gk_add_template", "gk_add_template_libs", "gk_remove_template",
-    "gk_add_constraint", "gk_validate_constraint", "gk_remove_constraint", "gk_put_namespace", "gk_remove_namespace", "gk_constraint_count",
+    "gk_add_constraint", "gk_add_expansion_template", "gk_remove_expansion_template", "gk_validate_constraint", "gk_remove_constraint", "gk_put_namespace", "gk_remove_namespace", "gk_constraint_count",
     "gk_constraint_key", "gk_result_constraint_key", "gk_review_batch", "gk_batch_upload", "gk_batch_eval", "gk_batch_eval_device",
     "gk_batch_eval_device_peers", "gk_batch_upload_blob", "gk_review_blob", "gk_set_excluded_namespaces", "gk_audit_begin", "gk_audit_add_batch", "gk_audit_report",
     "gk_audit_end", "gk_validation_messages", "gk_host_cpus", "gk_pin_host", "gk_blob_prefetch", "gk_coalescer_create", "gk_coalescer_review", "gk_coalescer_stats",
@@ -90,6 +90,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.gk_add_template_libs.argtypes = [P, S, S, C.c_size_t, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), C.c_size_t, PP]
     lib.gk_remove_template.argtypes = [P, S]
     lib.gk_add_constraint.argtypes = [P, S, C.c_size_t, PP]
+    lib.gk_add_expansion_template.argtypes = [P, S, C.c_size_t, PP]
+    lib.gk_remove_expansion_template.argtypes = [P, S]
     lib.gk_validate_constraint.argtypes = [P, S, C.c_size_t, PP]
     lib.gk_remove_constraint.argtypes = [P, S, S]
     lib.gk_put_namespace.argtypes = [P, S, S, C.c_size_t, PP]
@@ -280,6 +282,15 @@ class Driver:
         err = C.c_char_p()
         b = _to_bytes(constraint)
         self._check(self._lib.gk_add_constraint(self._e, b, len(b), C.byref(err)), err)
+
+    def AddExpansionTemplate(self, template: dict) -> None:
+        """expansion.System.UpsertTemplate (pkg/expansion/system.go:60-73)"""
+        b = json.dumps(template).encode()
+        err = C.c_char_p()
+        self._check(self._lib.gk_add_expansion_template(self._e, b, len(b), C.byref(err)), err)
+
+    def RemoveExpansionTemplate(self, name: str) -> None:
+        self._lib.gk_remove_expansion_template(self._e, name.encode())
 
     def ValidateConstraint(self, constraint: dict) -> None:
         """TargetHandler.ValidateConstraint (pkg/target/target.go:178-214); raises GkError for a constraint the reference's

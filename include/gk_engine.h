@@ -113,6 +113,15 @@ int gk_add_constraint(gk_engine_t* e, const char* constraint_json, size_t len, c
  * Driver.AddConstraint; this is the same check for hosts that do not go through that client.  0 = valid, else *err has the text. */
 int gk_validate_constraint(gk_engine_t* e, const char* constraint_json, size_t len, char** err);
 int gk_remove_constraint(gk_engine_t* e, const char* kind, const char* name);
+/* ExpansionTemplates (pkg/expansion/system.go:60-112 UpsertTemplate / RemoveTemplate): `json` is the ExpansionTemplate object.
+ * gk_review_batch then expands every generator object of a batch (System.Expand, system.go:137-247: the resource under
+ * spec.templateSource becomes a resource of spec.generatedGVK named "<parent>-<kind>", owned by the parent, in the parent's
+ * namespace), reviews the resultants with the batch as Generated resources, and reports their results on the parent with the
+ * "[Implied by <template>]" prefix and the template's enforcementAction override (pkg/expansion/aggregate.go:19-63) -- what the
+ * audit loop (pkg/audit/manager.go:733-765) and the webhook (pkg/webhook/policy.go:610-646) do around Client.Review.  Mutators are
+ * not applied (the mutation system is outside this engine). */
+int gk_add_expansion_template(gk_engine_t* e, const char* json, size_t len, char** err);
+int gk_remove_expansion_template(gk_engine_t* e, const char* name);
 int gk_put_namespace(gk_engine_t* e, const char* name, const char* ns_json, size_t len, char** err);
 int gk_remove_namespace(gk_engine_t* e, const char* name);
 

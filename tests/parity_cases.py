@@ -1431,3 +1431,107 @@ def case_wildcard_vectors_through_kernel(lib):
             checked += 1
     assert checked >= 40
     return checked
+
+
+# ------------------------------------------------------------------------------------------ expansion (a-16 / f-3)
+def case_expansion(lib):
+    """ExpansionTemplates through the review batch: (1) the reference's TestExpand vectors (resultant objects) on the oracle,
+    (2) the gator expansion manifests with the messages test.bats asserts, on oracle and engine, (3) a mixed page: Deployments,
+    Pods and a nested generator chain, with and without an action override, engine == oracle result for result."""
+    from oracle import expansion as X
+    vec = golden("expansion_vectors.json")
+    for c in vec["expand"]:
+        s = X.System()
+        for t in c["templates"]:
+            s.upsert(t)
+        try:
+            got, err = s.expand(c["generator"], c["ns"]), False
+        except X.ExpansionError:
+            got, err = [], True
+        assert err == c["expectErr"], c["name"]
+        if not err:
+            assert sorted(json.dumps(list(x), sort_keys=True) for x in got) == sorted(
+                json.dumps([w["obj"], w["templateName"], w["enforcementAction"]], sort_keys=True) for w in c["want"]), c["name"]
+
+    def run(docs, ep, drv_revs=None):
+        tm, cons, nss = _split_docs(docs)
+        orc, drv, skipped = make_pair(tm, cons, nss, lib_path=lib)
+        assert not skipped
+        xs = X.System()
+        for d in docs:
+            if d.get("kind") == "ExpansionTemplate":
+                xs.upsert(d)
+                drv.AddExpansionTemplate(d)
+        objs = [d for d in docs if d.get("kind") not in ("ConstraintTemplate", "ExpansionTemplate") and not str(d.get("apiVersion", "")).startswith("constraints.gatekeeper.sh")]
+        revs = [D.Review(object=d, source="Original") for d in objs]
+        want = set()
+        for i, r in enumerate(revs):
+            rv = k8s.Review(obj=r.object, source="Original")
+            for x in X.review_with_expansion(orc, xs, rv, ep):
+                want.add((i, "%s/%s" % x["constraint"], x["msg"], json.dumps(x["details"], sort_keys=True), x["enforcementAction"],
+                          tuple(x["scopedEnforcementActions"]), bool(x.get("autoreject"))))
+        resp = drv.ReviewBatch(revs, ep)
+        assert_same(want, engine_results(resp))
+        return resp, want
+
+    g = vec["gator"]
+    resp, want = run(g["docs"], k8s.GATOR_EP)
+    assert any(g["without_ns_substring"] in w[2] for w in want), [w[2] for w in want]
+    resp, want = run(g["docs"] + g["ns_docs"], k8s.GATOR_EP)
+    assert any(g["with_ns_substring"] in w[2] for w in want), [w[2] for w in want]
+
+    # (3) a mixed page
+    t = golden("templates.json")
+    tmpl = lambda name, kinds, gen, src="spec.template", action=None, groups=("apps",): {
+        "apiVersion": "expansion.gatekeeper.sh/v1alpha1", "kind": "ExpansionTemplate", "metadata": {"name": name},
+        "spec": dict({"applyTo": [{"groups": list(groups), "versions": ["v1"], "kinds": kinds}], "templateSource": src,
+                      "generatedGVK": {"group": gen[0], "version": gen[1], "kind": gen[2]}}, **({"enforcementAction": action} if action else {}))}
+    podspec = {"metadata": {"labels": {"app": "x"}}, "spec": {"containers": [{"name": "c", "image": "evil.example.com/a:latest",
+                                                                               "securityContext": {"privileged": True}}]}}
+    docs = [
+        {"apiVersion": "templates.gatekeeper.sh/v1", "kind": "ConstraintTemplate", "metadata": {"name": "k8sallowedrepos"},
+         "spec": {"crd": {"spec": {"names": {"kind": t["allowedrepos"]["kind"]}}}, "targets": [{"target": "admission.k8s.gatekeeper.sh", "rego": t["allowedrepos"]["rego"]}]}},
+        {"apiVersion": "templates.gatekeeper.sh/v1", "kind": "ConstraintTemplate", "metadata": {"name": "psp"},
+         "spec": {"crd": {"spec": {"names": {"kind": t["psp_privileged"]["kind"]}}}, "targets": [{"target": "admission.k8s.gatekeeper.sh", "rego": t["psp_privileged"]["rego"]}]}},
+        W._constraint(t["allowedrepos"]["kind"], "repos", match=dict(W.POD), params={"repos": ["gcr.io/"]}, action="warn"),
+        W._constraint(t["psp_privileged"]["kind"], "priv", match={"kinds": [{"apiGroups": [""], "kinds": ["Pod"]}], "source": "Generated"}),
+        tmpl("expand-deployments", ["Deployment", "ReplicaSet"], ("", "v1", "Pod")),
+        tmpl("expand-cronjobs", ["CronJob"], ("batch", "v1", "Job"), src="spec.jobTemplate", groups=("batch",)),
+        tmpl("expand-jobs", ["Job"], ("", "v1", "Pod"), action="dryrun", groups=("batch",)),
+        {"apiVersion": "apps/v1", "kind": "Deployment", "metadata": {"name": "Web", "namespace": "prod"}, "spec": {"replicas": 2, "template": podspec}},
+        {"apiVersion": "apps/v1", "kind": "ReplicaSet", "metadata": {"name": "rs"}, "spec": {"template": podspec}},
+        {"apiVersion": "batch/v1", "kind": "CronJob", "metadata": {"name": "nightly", "namespace": "ops"}, "spec": {"jobTemplate": {"spec": {"template": podspec}}}},
+        dict(podspec, apiVersion="v1", kind="Pod", metadata={"name": "plain", "namespace": "prod"}),
+        {"apiVersion": "apps/v1", "kind": "Deployment", "metadata": {"name": "no-template"}, "spec": {"replicas": 1}},
+        {"apiVersion": "v1", "kind": "ConfigMap", "metadata": {"name": "cm"}, "data": {}},
+    ]
+    for ep in (k8s.AUDIT_EP, k8s.WEBHOOK_EP):
+        tm, cons, nss = _split_docs(docs)
+        orc, drv, _ = make_pair(tm, cons, nss, lib_path=lib)
+        xs = X.System()
+        for d in docs:
+            if d.get("kind") == "ExpansionTemplate":
+                xs.upsert(d)
+                drv.AddExpansionTemplate(d)
+        objs = [d for d in docs if d.get("kind") in ("Deployment", "ReplicaSet", "CronJob", "Pod", "ConfigMap")]
+        revs = [D.Review(object=d, source="Original") for d in objs]
+        resp = drv.ReviewBatch(revs, ep)
+        want = set()
+        expand_errs = {}
+        for i, r in enumerate(revs):
+            try:
+                for x in X.review_with_expansion(orc, xs, k8s.Review(obj=r.object, source="Original"), ep):
+                    want.add((i, "%s/%s" % x["constraint"], x["msg"], json.dumps(x["details"], sort_keys=True), x["enforcementAction"],
+                              tuple(x["scopedEnforcementActions"]), bool(x.get("autoreject"))))
+            except X.ExpansionError as e:
+                expand_errs[i] = str(e)
+        got = {x for x in engine_results(resp) if x[0] not in expand_errs}
+        assert_same(want, got)
+        assert {i for i, e in enumerate(resp.object_errors or []) if e} == set(expand_errs), (resp.object_errors, expand_errs)
+        for i, e in expand_errs.items():
+            assert e in resp.object_errors[i]
+        msgs = [w[2] for w in want]
+        assert any(m.startswith("[Implied by expand-deployments] ") for m in msgs)
+        assert any(m.startswith("[Implied by expand-jobs] ") for m in msgs) and any(w[4] == "dryrun" for w in want)
+        assert resp.viol_bits.shape[0] == len(revs)
+    return len(want)

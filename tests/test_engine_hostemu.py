@@ -331,3 +331,7 @@ violation[{"msg": "x"}] { v := input.review.object.spec[input.parameters.field][
     resp = drv.ReviewBatch([D.Review(object={"apiVersion": "v1", "kind": "X", "metadata": {"name": "o"}, "spec": {"f3": ["bad"], "f7": ["ok"]}})], "audit.gatekeeper.sh")
     assert [r.constraint for r in resp.results] == ["ManyFields/c3"]
     assert len(drv.constraints()) == ok
+
+
+def test_expansion_templates_through_the_batch():
+    assert P.case_expansion(HOSTEMU) >= 6

@@ -287,3 +287,7 @@ def test_doc_pins():
 
 def test_wildcard_vectors_through_kernel():
     P.case_wildcard_vectors_through_kernel(LIB)
+
+
+def test_expansion_templates_through_the_batch():
+    assert P.case_expansion(LIB) >= 6
