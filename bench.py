@@ -486,7 +486,7 @@ def main():
     ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5], help="BASELINE.json workload: 2 = configs[1] (default), 3 = admission replay, 4 = PSP x mixed GVK, 5 = wildcards")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="weak: --objects per GPU; strong: --objects in total")
     ap.add_argument("--objects", type=int, default=0, help="objects per GPU (weak) / in total (strong); 0 = the config's size")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=8, help="pages of the pipelined end-to-end sweep (each is a fresh 1M-object page in pinned host memory)")
     ap.add_argument("--cpu-sample", type=int, default=30_000, help="objects reviewed by the C++ CPU restatement leg (all host threads)")
     ap.add_argument("--msg-sample", type=int, default=50_000, help="objects of the sample whose messages are all rendered (e2e.with_messages)")
     ap.add_argument("--spot-check", type=int, default=300, help="objects of the shard checked against the Python oracle inside the run")

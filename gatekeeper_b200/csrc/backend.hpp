@@ -7,6 +7,8 @@
 #include <thread>
 #include <cstdint>
 #include <cstring>
+#include <new>
+#include <utility>
 #include <string>
 #include <vector>
 
@@ -19,9 +21,38 @@ struct BackendError {
   std::string msg;
 };
 
+// Result bitmaps land in page-locked host memory when the backend has any (the CUDA backend installs the hooks): a device->host
+// copy into pageable memory runs at a fraction of the link rate.  Blocks are recycled through a small size-bucketed pool
+// (page-locking is expensive: ~1 ms per 8 MB).
+struct HostBlockHooks {
+  void* (*alloc)(size_t) = nullptr;   // null: plain malloc / free
+  void (*release)(void*) = nullptr;
+};
+HostBlockHooks& host_block_hooks();
+void* host_block_take(size_t bytes);
+void host_block_give(void* p, size_t bytes);
+template <class T>
+struct HostBlockAlloc {
+  using value_type = T;
+  HostBlockAlloc() = default;
+  template <class U>
+  HostBlockAlloc(const HostBlockAlloc<U>&) {}
+  T* allocate(size_t n) { return static_cast<T*>(host_block_take(n * sizeof(T))); }
+  void deallocate(T* p, size_t n) { host_block_give(p, n * sizeof(T)); }
+  template <class U>
+  void construct(U* p) noexcept { ::new (static_cast<void*>(p)) U; }   // resize() leaves the words unset: the copy-back overwrites all of them
+  template <class U, class... A>
+  void construct(U* p, A&&... a) { ::new (static_cast<void*>(p)) U(std::forward<A>(a)...); }
+  template <class U>
+  bool operator==(const HostBlockAlloc<U>&) const { return true; }
+  template <class U>
+  bool operator!=(const HostBlockAlloc<U>&) const { return false; }
+};
+using BitPlane = std::vector<uint32_t, HostBlockAlloc<uint32_t>>;
+
 struct EvalOut {
   uint32_t n = 0, nconstraints = 0, words = 0;
-  std::vector<uint32_t> viol, err;          // [n * words]  (filled when copy_back)
+  BitPlane viol, err;                       // [n * words]  (filled when copy_back)
   std::vector<uint64_t> totals, err_totals; // [nconstraints]
   std::vector<uint32_t> errlist;            // triples (object, constraint, code)
   float kernel_ms = 0.f;

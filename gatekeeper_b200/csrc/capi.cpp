@@ -13,8 +13,69 @@
 
 #include "../../include/gk_engine.h"
 #include "backend.hpp"
+#include <new>
 #include "audit.hpp"
 #include "engine.hpp"
+
+// ---- page-locked result blocks (backend.hpp HostBlockAlloc): power-of-two buckets, a few spare blocks per bucket
+namespace gk {
+HostBlockHooks& host_block_hooks() {
+  static HostBlockHooks h;
+  return h;
+}
+namespace {
+struct HostBlockPool {
+  std::mutex mu;
+  std::vector<void*> spare[48];
+  static int bucket(size_t bytes) {
+    int b = 12;   // 4 KB and up
+    while (((size_t)1 << b) < bytes) ++b;
+    return b;
+  }
+} g_block_pool;
+}  // namespace
+void* host_block_take(size_t bytes) {
+  if (bytes == 0) bytes = 1;
+  HostBlockHooks& h = host_block_hooks();
+  if (!h.alloc || bytes < (1u << 16)) {   // small planes: not worth page-locking
+    void* p = malloc(bytes);
+    if (!p) throw std::bad_alloc();
+    return p;
+  }
+  const int b = HostBlockPool::bucket(bytes);
+  {
+    std::lock_guard<std::mutex> l(g_block_pool.mu);
+    auto& v = g_block_pool.spare[b];
+    if (!v.empty()) {
+      void* p = v.back();
+      v.pop_back();
+      return p;
+    }
+  }
+  void* p = h.alloc((size_t)1 << b);
+  if (!p) throw std::bad_alloc();
+  return p;
+}
+void host_block_give(void* p, size_t bytes) {
+  if (!p) return;
+  if (bytes == 0) bytes = 1;
+  HostBlockHooks& h = host_block_hooks();
+  if (!h.alloc || bytes < (1u << 16)) {
+    free(p);
+    return;
+  }
+  const int b = HostBlockPool::bucket(bytes);
+  {
+    std::lock_guard<std::mutex> l(g_block_pool.mu);
+    auto& v = g_block_pool.spare[b];
+    if (v.size() < 8) {
+      v.push_back(p);
+      return;
+    }
+  }
+  h.release(p);
+}
+}  // namespace gk
 
 using namespace gk;
 

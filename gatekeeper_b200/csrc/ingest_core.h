@@ -55,160 +55,177 @@ GK_HD int gk_hexval(uint32_t c) {
 
 // Tokeniser: the grammar of the host parser (csrc/val.cpp JP) -- same whitespace, same escapes, same (lenient) number syntax,
 // duplicate keys allowed -- so that the device accepts exactly the documents the host flattener accepts.
+//
+// Shape: ONE loop, one token per turn, one exit (rc), no read-back of the tape (the kinds of the open containers live in a
+// 64-bit mask).  Threads of a warp tokenise different objects of the same list page -- the same serialiser, so mostly the same
+// token kinds in the same order: with a single structured loop body they reconverge at the end of every turn.
 GK_HD int gk_tape_build(const uint8_t* js, uint32_t n, gk_u64* tape, uint32_t cap, uint32_t* ntape) {
   uint32_t stack[GK_TAPE_MAX_DEPTH];   // entry index of the open containers
   uint32_t cnt[GK_TAPE_MAX_DEPTH];
   uint32_t opos[GK_TAPE_MAX_DEPTH];    // byte offset of their opening brackets
+  gk_u64 objmask = 0;                  // bit d: the container open at depth d is an object
   int depth = 0;
   uint32_t p = 0, t = 0;
   // state: 0 expect value, 1 after value (expect , or close), 2 expect key or '}' (just after '{'), 3 expect key (after ,)
   int state = 0;
+  int rc = -1;
   *ntape = 0;
-  for (;;) {
+  while (rc < 0) {
     while (p < n && gk_is_ws(js[p])) ++p;
-    if (state == 1 && depth == 0) {
-      if (p != n) return GK_ING_BAD_JSON;   // trailing characters
-      *ntape = t;
-      return GK_ING_OK;
-    }
-    if (p >= n) return GK_ING_BAD_JSON;
-    const uint32_t c = js[p];
+    const uint32_t c = p < n ? (uint32_t)js[p] : 256u;
+    const bool in_obj = depth > 0 && ((objmask >> (depth - 1)) & 1ull) != 0ull;
     if (state == 1) {
-      const bool in_obj = gk_te_type(tape[stack[depth - 1]]) == GK_T_OBJ;
-      if (c == ',') {
+      if (depth == 0) {
+        rc = (p == n) ? (int)GK_ING_OK : (int)GK_ING_BAD_JSON;   // trailing characters
+      } else if (c == ',') {
         ++p;
         state = in_obj ? 3 : 0;
-        continue;
-      }
-      if (c == (in_obj ? '}' : ']')) {
+      } else if (c == (in_obj ? (uint32_t)'}' : (uint32_t)']')) {
         ++p;
         --depth;
-        const uint32_t open = stack[depth];
-        if (p - opos[depth] > GK_TAPE_LEN_MAX) return GK_ING_TOO_LONG;
-        tape[t++] = gk_te_scalar(GK_T_END, 0, opos[depth], p - opos[depth]);
-        tape[open] = gk_te_container(gk_te_type(tape[open]), cnt[depth], t);
-        state = 1;
-        continue;
+        if (p - opos[depth] > GK_TAPE_LEN_MAX) {
+          rc = GK_ING_TOO_LONG;
+        } else {
+          tape[t++] = gk_te_scalar(GK_T_END, 0, opos[depth], p - opos[depth]);
+          tape[stack[depth]] = gk_te_container(in_obj ? GK_T_OBJ : GK_T_ARR, cnt[depth], t);
+        }
+      } else {
+        rc = GK_ING_BAD_JSON;
       }
-      return GK_ING_BAD_JSON;
-    }
-    if (t + 3 >= cap) return GK_ING_BAD_JSON;   // (cannot happen for cap = gk_tape_capacity(n))
-    if (state == 2 || state == 3) {
-      if (state == 2 && c == '}') {
-        ++p;
-        --depth;
-        const uint32_t open = stack[depth];
-        tape[t++] = gk_te_scalar(GK_T_END, 0, opos[depth], p - opos[depth]);
-        tape[open] = gk_te_container(GK_T_OBJ, 0, t);
-        state = 1;
-        continue;
-      }
-      if (c != '"') return GK_ING_BAD_JSON;   // object key expected
-    }
-    if (c == '"') {
+    } else if (c == 256u || t + 3 >= cap) {   // (the capacity cannot run out for cap = gk_tape_capacity(n))
+      rc = GK_ING_BAD_JSON;
+    } else if (state == 2 && c == '}') {
+      ++p;
+      --depth;
+      tape[t++] = gk_te_scalar(GK_T_END, 0, opos[depth], p - opos[depth]);
+      tape[stack[depth]] = gk_te_container(GK_T_OBJ, 0, t);
+      state = 1;
+    } else if (state >= 2 && c != '"') {
+      rc = GK_ING_BAD_JSON;   // object key expected
+    } else if (c == '"') {
       const uint32_t s = ++p;
       uint32_t esc = 0;
-      while (p < n && js[p] != '"') {
+      bool bad = false;
+      while (p < n && js[p] != '"' && !bad) {
         if (js[p] == '\\') {
           esc = 1;
           ++p;
-          if (p >= n) return GK_ING_BAD_JSON;
-          const uint32_t e = js[p];
-          if (e == 'u') {
-            if (n - p < 5) return GK_ING_BAD_JSON;
-            for (int i = 1; i <= 4; ++i)
-              if (gk_hexval(js[p + i]) < 0) return GK_ING_BAD_JSON;
-            p += 4;
-          } else if (!(e == 'n' || e == 't' || e == 'r' || e == 'b' || e == 'f' || e == '/' || e == '\\' || e == '"')) {
-            return GK_ING_BAD_JSON;
+          if (p >= n) {
+            bad = true;
+          } else {
+            const uint32_t e = js[p];
+            if (e == 'u') {
+              if (n - p < 5) bad = true;
+              else {
+                for (int i = 1; i <= 4; ++i)
+                  if (gk_hexval(js[p + i]) < 0) bad = true;
+                p += 4;
+              }
+            } else if (!(e == 'n' || e == 't' || e == 'r' || e == 'b' || e == 'f' || e == '/' || e == '\\' || e == '"')) {
+              bad = true;
+            }
           }
         }
         ++p;
       }
-      if (p >= n) return GK_ING_BAD_JSON;   // unterminated string
       const uint32_t len = p - s;
-      ++p;
-      if (len > GK_TAPE_LEN_MAX) return GK_ING_TOO_LONG;
-      if (state == 2 || state == 3) {
-        tape[t++] = gk_te_scalar(GK_T_KEY, esc, s, len);
-        while (p < n && gk_is_ws(js[p])) ++p;
-        if (p >= n || js[p] != ':') return GK_ING_BAD_JSON;
-        ++p;
-        ++cnt[depth - 1];
-        state = 0;
-        continue;
-      }
-      tape[t++] = gk_te_scalar(GK_T_STR, esc, s, len);
-      if (depth && gk_te_type(tape[stack[depth - 1]]) == GK_T_ARR) ++cnt[depth - 1];
-      state = 1;
-      continue;
-    }
-    // state 0: a value
-    if (c == '{' || c == '[') {
-      if (depth >= GK_TAPE_MAX_DEPTH) return GK_ING_TOO_DEEP;
-      if (depth && gk_te_type(tape[stack[depth - 1]]) == GK_T_ARR) ++cnt[depth - 1];
-      stack[depth] = t;
-      cnt[depth] = 0;
-      opos[depth] = p;
-      ++depth;
-      tape[t++] = gk_te_container(c == '{' ? GK_T_OBJ : GK_T_ARR, 0, 0);
-      ++p;
-      if (c == '{') {
-        state = 2;
+      if (bad || p >= n) {
+        rc = GK_ING_BAD_JSON;   // bad escape / unterminated string
+      } else if (len > GK_TAPE_LEN_MAX) {
+        rc = GK_ING_TOO_LONG;
       } else {
-        while (p < n && gk_is_ws(js[p])) ++p;
-        if (p < n && js[p] == ']') {
-          ++p;
-          --depth;
-          tape[t++] = gk_te_scalar(GK_T_END, 0, opos[depth], p - opos[depth]);
-          tape[stack[depth]] = gk_te_container(GK_T_ARR, 0, t);
-          state = 1;
+        ++p;
+        if (state >= 2) {
+          tape[t++] = gk_te_scalar(GK_T_KEY, esc, s, len);
+          while (p < n && gk_is_ws(js[p])) ++p;
+          if (p >= n || js[p] != ':') {
+            rc = GK_ING_BAD_JSON;
+          } else {
+            ++p;
+            ++cnt[depth - 1];
+            state = 0;
+          }
         } else {
-          state = 0;
+          tape[t++] = gk_te_scalar(GK_T_STR, esc, s, len);
+          if (depth && !in_obj) ++cnt[depth - 1];
+          state = 1;
         }
       }
-      continue;
-    }
-    uint32_t type = 0, len = 0;
-    if (c == 't' && n - p >= 4 && js[p + 1] == 'r' && js[p + 2] == 'u' && js[p + 3] == 'e') {
-      type = GK_T_TRUE, len = 4;
-    } else if (c == 'f' && n - p >= 5 && js[p + 1] == 'a' && js[p + 2] == 'l' && js[p + 3] == 's' && js[p + 4] == 'e') {
-      type = GK_T_FALSE, len = 5;
-    } else if (c == 'n' && n - p >= 4 && js[p + 1] == 'u' && js[p + 2] == 'l' && js[p + 3] == 'l') {
-      type = GK_T_NULL, len = 4;
-    } else if (c == '-' || gk_is_digit(c)) {
-      // [-] digits* then, if '.', 'e' or 'E' follows, every char of [0-9.eE+-]: the span must be a decimal literal strtod takes whole
-      uint32_t q = p;
-      if (js[q] == '-') ++q;
-      uint32_t nint = 0, nfrac = 0;
-      while (q < n && gk_is_digit(js[q])) ++q, ++nint;
-      if (q < n && (js[q] == '.' || js[q] == 'e' || js[q] == 'E')) {
-        if (js[q] == '.') {
-          ++q;
-          while (q < n && gk_is_digit(js[q])) ++q, ++nfrac;
+    } else if (c == '{' || c == '[') {   // state 0: a value
+      if (depth >= GK_TAPE_MAX_DEPTH) {
+        rc = GK_ING_TOO_DEEP;
+      } else {
+        if (depth && !in_obj) ++cnt[depth - 1];
+        stack[depth] = t;
+        cnt[depth] = 0;
+        opos[depth] = p;
+        if (c == '{') objmask |= 1ull << depth;
+        else objmask &= ~(1ull << depth);
+        ++depth;
+        tape[t++] = gk_te_container(c == '{' ? GK_T_OBJ : GK_T_ARR, 0, 0);
+        ++p;
+        if (c == '{') {
+          state = 2;
+        } else {
+          while (p < n && gk_is_ws(js[p])) ++p;
+          if (p < n && js[p] == ']') {
+            ++p;
+            --depth;
+            tape[t++] = gk_te_scalar(GK_T_END, 0, opos[depth], p - opos[depth]);
+            tape[stack[depth]] = gk_te_container(GK_T_ARR, 0, t);
+            state = 1;
+          } else {
+            state = 0;
+          }
         }
-        if (nint + nfrac == 0) return GK_ING_BAD_JSON;
-        if (q < n && (js[q] == 'e' || js[q] == 'E')) {
-          uint32_t r = q + 1;
-          if (r < n && (js[r] == '+' || js[r] == '-')) ++r;
-          uint32_t nexp = 0;
-          while (r < n && gk_is_digit(js[r])) ++r, ++nexp;
-          if (nexp == 0) return GK_ING_BAD_JSON;
-          q = r;
-        }
-        if (q < n && (gk_is_digit(js[q]) || js[q] == '.' || js[q] == 'e' || js[q] == 'E' || js[q] == '+' || js[q] == '-')) return GK_ING_BAD_JSON;
-      } else if (nint == 0) {
-        return GK_ING_BAD_JSON;
       }
-      type = GK_T_NUM, len = q - p;
     } else {
-      return GK_ING_BAD_JSON;
+      uint32_t type = 0, len = 0;
+      if (c == 't' && n - p >= 4 && js[p + 1] == 'r' && js[p + 2] == 'u' && js[p + 3] == 'e') {
+        type = GK_T_TRUE, len = 4;
+      } else if (c == 'f' && n - p >= 5 && js[p + 1] == 'a' && js[p + 2] == 'l' && js[p + 3] == 's' && js[p + 4] == 'e') {
+        type = GK_T_FALSE, len = 5;
+      } else if (c == 'n' && n - p >= 4 && js[p + 1] == 'u' && js[p + 2] == 'l' && js[p + 3] == 'l') {
+        type = GK_T_NULL, len = 4;
+      } else if (c == '-' || gk_is_digit(c)) {
+        // [-] digits* then, if '.', 'e' or 'E' follows, every char of [0-9.eE+-]: the span must be a decimal literal strtod takes whole
+        uint32_t q = p;
+        if (js[q] == '-') ++q;
+        uint32_t nint = 0, nfrac = 0;
+        bool ok = true;
+        while (q < n && gk_is_digit(js[q])) ++q, ++nint;
+        if (q < n && (js[q] == '.' || js[q] == 'e' || js[q] == 'E')) {
+          if (js[q] == '.') {
+            ++q;
+            while (q < n && gk_is_digit(js[q])) ++q, ++nfrac;
+          }
+          if (nint + nfrac == 0) ok = false;
+          if (ok && q < n && (js[q] == 'e' || js[q] == 'E')) {
+            uint32_t r = q + 1;
+            if (r < n && (js[r] == '+' || js[r] == '-')) ++r;
+            uint32_t nexp = 0;
+            while (r < n && gk_is_digit(js[r])) ++r, ++nexp;
+            if (nexp == 0) ok = false;
+            q = r;
+          }
+          if (ok && q < n && (gk_is_digit(js[q]) || js[q] == '.' || js[q] == 'e' || js[q] == 'E' || js[q] == '+' || js[q] == '-')) ok = false;
+        } else if (nint == 0) {
+          ok = false;
+        }
+        if (ok) type = GK_T_NUM, len = q - p;
+      }
+      if (type == 0) {
+        rc = GK_ING_BAD_JSON;
+      } else {
+        tape[t++] = gk_te_scalar(type, 0, p, len);
+        p += len;
+        if (depth && !in_obj) ++cnt[depth - 1];
+        state = 1;
+      }
     }
-    tape[t++] = gk_te_scalar(type, 0, p, len);
-    p += len;
-    if (depth && gk_te_type(tape[stack[depth - 1]]) == GK_T_ARR) ++cnt[depth - 1];
-    state = 1;
   }
+  if (rc == GK_ING_OK) *ntape = t;
+  return rc;
 }
 
 // ---------------------------------------------------------------------------------------------- strings

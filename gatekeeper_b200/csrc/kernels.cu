@@ -60,6 +60,12 @@ class CudaBackend : public Backend {
     CK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&front_stream_, cudaStreamNonBlocking));
+    // result bitmaps are copied back into page-locked blocks (backend.hpp HostBlockAlloc)
+    host_block_hooks().alloc = [](size_t bytes) -> void* {
+      void* p = nullptr;
+      return cudaHostAlloc(&p, bytes, cudaHostAllocPortable) == cudaSuccess ? p : nullptr;
+    };
+    host_block_hooks().release = [](void* p) { cudaFreeHost(p); };
     {
       // per-batch device memory comes from the stream-ordered pool and goes back to it: with the release threshold lifted a
       // resident-batch-sized arena is reused by the next batch instead of being mapped / unmapped by the driver every time
@@ -436,8 +442,9 @@ class CudaBackend : public Backend {
       out.viol.resize((size_t)db->n * db->words);
       out.err.resize((size_t)db->n * db->words);
       if (db->n) {
-        CK(cudaMemcpy(out.viol.data(), db->viol, out.viol.size() * 4, cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(out.err.data(), db->err, out.err.size() * 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpyAsync(out.viol.data(), db->viol, out.viol.size() * 4, cudaMemcpyDeviceToHost, stream_));
+        CK(cudaMemcpyAsync(out.err.data(), db->err, out.err.size() * 4, cudaMemcpyDeviceToHost, stream_));
+        CK(cudaStreamSynchronize(stream_));
       }
     }
   }
