@@ -125,6 +125,7 @@ struct gk_batch {
   uint8_t blob_source = 0;
   uint32_t n = 0;
   uint64_t alg_bytes = 0;
+  uint64_t data_version = 0;           // data.inventory as of the flatten (referential snapshots only)
   ObjIn obj_in(size_t i) const;
 };
 
@@ -328,6 +329,7 @@ void upload_batch(gk_engine* e, const std::shared_ptr<const Compiled>& c, const 
   uint64_t h2d_bytes = 0;
   b->dev = e->be->upload(*hb, *c, &h2d_ms, &h2d_bytes);
   b->compiled = c;
+  if (c->uses_data) e->eng->data_doc(&b->data_version);
   b->n = hb->n;
   b->alg_bytes = hb->alg_bytes;
   b->objs.assign(objs, objs + n);
@@ -375,6 +377,7 @@ void upload_blob(gk_engine* e, const std::shared_ptr<const Compiled>& c, const c
   auto b = std::make_unique<gk_batch>();
   b->dev = e->be->ingest(rq, &ist, &status);
   b->compiled = c;
+  if (c->uses_data) e->eng->data_doc(&b->data_version);
   b->n = (uint32_t)n;
   b->alg_bytes = ist.alg_bytes;
   b->blob = buf;
@@ -460,6 +463,22 @@ int gk_remove_constraint(gk_engine_t* e, const char* kind, const char* name) {
 int gk_put_namespace(gk_engine_t* e, const char* name, const char* ns_json, size_t len, char** err) {
   if (!e || !name || !ns_json) return GK_ERR_INVALID;
   return guard(err, [&]() { e->eng->put_namespace(name, std::string(ns_json, len)); });
+}
+int gk_add_data(gk_engine_t* e, const char* const* path, size_t npath, const char* json, size_t len, char** err) {
+  if (!e || !json || (!path && npath)) return GK_ERR_INVALID;
+  return guard(err, [&]() {
+    std::vector<std::string> p;
+    for (size_t i = 0; i < npath; ++i) p.push_back(path[i] ? path[i] : "");
+    e->eng->add_data(p, std::string(json, len));
+  });
+}
+int gk_remove_data(gk_engine_t* e, const char* const* path, size_t npath) {
+  if (!e || !path || !npath) return GK_ERR_INVALID;
+  return guard(nullptr, [&]() {
+    std::vector<std::string> p;
+    for (size_t i = 0; i < npath; ++i) p.push_back(path[i] ? path[i] : "");
+    e->eng->remove_data(p);
+  });
 }
 int gk_remove_namespace(gk_engine_t* e, const char* name) {
   if (!e || !name) return GK_ERR_INVALID;
@@ -621,6 +640,11 @@ int gk_batch_eval(gk_engine_t* e, gk_batch_t* b, const char* ep, uint32_t flags,
   return guard(err, [&]() {
     auto c = e->eng->compiled();
     if (c->version != b->compiled->version) throw RegoError{"batch was flattened against an older constraint set; upload it again"};
+    if (c->uses_data) {   // the columns of a referential snapshot hold values computed from data.inventory
+      uint64_t dv = 0;
+      e->eng->data_doc(&dv);
+      if (dv != b->data_version) throw RegoError{"data.inventory changed since the batch was flattened (referential constraints); upload it again"};
+    }
     ProgramLease lease(e, *c);
     eval_batch(e, b, ep, flags, out);
   });
@@ -632,6 +656,11 @@ int gk_batch_eval_device(gk_engine_t* e, gk_batch_t* b, const char* ep, void* d_
   return guard(err, [&]() {
     auto c = e->eng->compiled();
     if (c->version != b->compiled->version) throw RegoError{"batch was flattened against an older constraint set; upload it again"};
+    if (c->uses_data) {   // the columns of a referential snapshot hold values computed from data.inventory
+      uint64_t dv = 0;
+      e->eng->data_doc(&dv);
+      if (dv != b->data_version) throw RegoError{"data.inventory changed since the batch was flattened (referential constraints); upload it again"};
+    }
     ProgramLease lease(e, *c);
     std::vector<uint32_t> active;
     e->eng->active_mask(*c, ep ? ep : "", active);
@@ -652,6 +681,11 @@ int gk_batch_eval_device_peers(gk_engine_t* e, gk_batch_t* b, const char* ep, co
   return guard(err, [&]() {
     auto c = e->eng->compiled();
     if (c->version != b->compiled->version) throw RegoError{"batch was flattened against an older constraint set; upload it again"};
+    if (c->uses_data) {   // the columns of a referential snapshot hold values computed from data.inventory
+      uint64_t dv = 0;
+      e->eng->data_doc(&dv);
+      if (dv != b->data_version) throw RegoError{"data.inventory changed since the batch was flattened (referential constraints); upload it again"};
+    }
     ProgramLease lease(e, *c);
     std::vector<uint32_t> active;
     e->eng->active_mask(*c, ep ? ep : "", active);
@@ -743,6 +777,11 @@ int gk_audit_add_batch(gk_audit_t* a, gk_batch_t* b, const char* ep_c, char** er
     gk_engine* e = a->e;
     auto c = e->eng->compiled();
     if (c->version != b->compiled->version) throw RegoError{"batch was flattened against an older constraint set; upload it again"};
+    if (c->uses_data) {   // the columns of a referential snapshot hold values computed from data.inventory
+      uint64_t dv = 0;
+      e->eng->data_doc(&dv);
+      if (dv != b->data_version) throw RegoError{"data.inventory changed since the batch was flattened (referential constraints); upload it again"};
+    }
     ProgramLease lease(e, *c);
     std::string ep = ep_c ? ep_c : "";
     std::vector<uint32_t> active;

@@ -626,6 +626,81 @@ bool Engine::remove_namespace(const std::string& name) {
   return namespaces_.erase(name) != 0;
 }
 
+// processUnstructured -- pkg/target/target.go:40-57
+static std::vector<std::string> inventory_path(const VP& v) {
+  if (!v || v->t != VT::Obj) throw RegoError{"unrecognized type, got " + std::string(v ? go_type_name(v) : "<nil>")};
+  std::string g, ver, k;
+  split_gv(v, g, ver, k);
+  const std::string name = meta_str(v, "name"), ns = meta_str(v, "namespace");
+  if (ver.empty()) throw RegoError{"invalid request object: resource " + name + " has no version"};
+  if (k.empty()) throw RegoError{"invalid request object: resource " + name + " has no kind"};
+  const std::string gv = g.empty() ? ver : g + "/" + ver;
+  if (ns.empty()) return {"cluster", gv, k, name};
+  return {"namespace", ns, gv, k, name};
+}
+
+std::vector<std::string> Engine::data_path(const std::string& json) {
+  try {
+    return inventory_path(json_parse(json.data(), json.size()));
+  } catch (JsonError& e) {
+    throw RegoError{"invalid data object: " + e.msg};
+  }
+}
+
+void Engine::add_data(const std::vector<std::string>& path, const std::string& json) {
+  VP v;
+  try {
+    v = json_parse(json.data(), json.size());
+  } catch (JsonError& e) {
+    throw RegoError{"invalid data object: " + e.msg};
+  }
+  std::vector<std::string> p = path.empty() ? inventory_path(v) : path;
+  std::unique_lock<std::shared_mutex> l(mu_);
+  inventory_[std::move(p)] = v;
+  ++inventory_version_;
+}
+
+bool Engine::remove_data(const std::vector<std::string>& path) {
+  std::unique_lock<std::shared_mutex> l(mu_);
+  ++inventory_version_;
+  // a path names one object or a whole sub-tree (storage.RemoveData on an inner node)
+  bool any = false;
+  for (auto it = inventory_.begin(); it != inventory_.end();) {
+    const auto& k = it->first;
+    if (k.size() >= path.size() && std::equal(path.begin(), path.end(), k.begin())) {
+      it = inventory_.erase(it);
+      any = true;
+    } else {
+      ++it;
+    }
+  }
+  return any;
+}
+
+VP Engine::data_doc(uint64_t* version) {
+  std::unique_lock<std::shared_mutex> l(mu_);
+  if (!inventory_doc_ || inventory_doc_version_ != inventory_version_) {
+    // the paths are sorted: children of one prefix are adjacent
+    using It = std::map<std::vector<std::string>, VP>::const_iterator;
+    std::function<VP(It, It, size_t)> build = [&](It lo, It hi, size_t depth) -> VP {
+      std::vector<std::pair<VP, VP>> kv;
+      while (lo != hi) {
+        const std::string& key = lo->first[depth];
+        It e = lo;
+        while (e != hi && e->first[depth] == key) ++e;
+        if (lo->first.size() == depth + 1) kv.emplace_back(v_str(key), lo->second);
+        else kv.emplace_back(v_str(key), build(lo, e, depth + 1));
+        lo = e;
+      }
+      return v_obj(std::move(kv));
+    };
+    inventory_doc_ = v_obj({{v_str("inventory"), build(inventory_.begin(), inventory_.end(), 0)}});
+    inventory_doc_version_ = inventory_version_;
+  }
+  if (version) *version = inventory_version_;
+  return inventory_doc_;
+}
+
 std::vector<std::string> scoped_actions_for(const Constraint& c, const std::string& ep) {
   std::vector<std::string> out;
   for (auto& a : c.scoped)
@@ -706,6 +781,7 @@ void Engine::compile_locked() {
   }
   if (!device_ok) lower_all(false);
   out->device_ingest = device_ok;
+  out->uses_data = out->schema.uses_data;
   std::vector<size_t> perm(live.size());
   for (size_t i = 0; i < perm.size(); ++i) perm[i] = i;
   std::stable_sort(perm.begin(), perm.end(), [&](size_t a, size_t b) { return mid_of[a] < mid_of[b]; });
@@ -1062,7 +1138,9 @@ struct Flattener : ChunkOut {
     return const_private.emplace(v.get(), deep_copy(v)).first->second;
   }
 
+  VP data;   // {"inventory": ...}: what closures of referential templates read as `data`
   Flattener(Engine& e, const Compiled& cc, const std::map<std::string, VP>& ns_shared) : eng(e), c(cc) {
+    if (cc.uses_data) data = e.data_doc();
     for (auto& kv : ns_shared) ns_private.emplace(kv.first, deep_copy(kv.second));
     rows.resize(c.schema.scopes.size());
     begin_chunk();
@@ -1117,7 +1195,7 @@ struct Flattener : ChunkOut {
 
   Eval& eval_for(const Closure& cl, const VP& input) {
     auto& slot = evals[cl.mod.get()];
-    if (!slot) slot.reset(new Eval(*cl.mod, input));
+    if (!slot) slot.reset(new Eval(*cl.mod, input, data));
     return *slot;
   }
 
@@ -2037,7 +2115,8 @@ void Engine::materialize_object(const Compiled& c, const ObjIn& in, uint32_t obj
       // parameter-free helper rules (input_containers, ...)
       auto& slot = ctx->evals[&mod];
       uint64_t& seen = ctx->eval_epoch[&mod];
-      if (!slot) slot.reset(new Eval(mod, inp));
+      if (c.uses_data && !ctx->data) ctx->data = data_doc();
+      if (!slot) slot.reset(new Eval(mod, inp, ctx->data));
       else if (seen == ctx->epoch) slot->reset_parameters(inp);
       else slot->reset_input(inp);
       seen = ctx->epoch;

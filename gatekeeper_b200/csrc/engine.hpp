@@ -106,6 +106,7 @@ struct Compiled {
   std::vector<std::shared_ptr<Module>> mods;   // constraint index -> its template's module (pinned by this snapshot)
   size_t n_nodes = 0, n_atoms = 0, n_gates = 0, n_phases = 0;
   std::shared_ptr<const XProgHost> xprog;      // the extraction program of the device ingest path (null: host flattener only)
+  bool uses_data = false;                      // some template reads `data` (data.inventory: referential constraints)
   bool device_ingest = false;                  // every scope / column of `schema` can be computed by the ingest kernels
   std::string host_ingest_reason;              // why not (the first construct that needs the host flattener)
 };
@@ -175,6 +176,7 @@ class Engine {
     std::unordered_map<const Module*, uint64_t> eval_epoch;
     std::unordered_map<const Constraint*, VP> params;
     uint64_t epoch = 0;   // one per object
+    VP data;              // {"inventory": ...} for referential templates (fetched once per context)
   };
   void materialize_object(const Compiled& c, const ObjIn& obj, uint32_t obj_ix, const std::vector<Flagged>& flagged,
                           const std::string& ep, std::vector<Violation>& out, VP* obj_out = nullptr, MaterializeCtx* ctx = nullptr);
@@ -192,6 +194,13 @@ class Engine {
   bool has_expansion();
   // the resultants of one review's object (empty when no template applies); throws std::runtime_error like System.Expand
   void expand_object(const ObjIn& in, std::vector<Resultant>& out);
+  // Client.AddData / RemoveData for any synced object (pkg/target/target.go:40-66 processUnstructured: the path is
+  // cluster/<groupVersion>/<kind>/<name> or namespace/<ns>/<groupVersion>/<kind>/<name>): what referential templates read
+  // as data.inventory.  data_doc() is the immutable {"inventory": {...}} document of the current contents.
+  void add_data(const std::vector<std::string>& path, const std::string& json);   // empty path: derived from the object
+  bool remove_data(const std::vector<std::string>& path);
+  static std::vector<std::string> data_path(const std::string& json);
+  VP data_doc(uint64_t* version = nullptr);
   std::map<std::string, VP> namespaces_snapshot();   // (deep copies: safe to read from another thread without touching shared reference counts)
   // everything a backend needs to flatten a blob of plain objects on the device (xprog.hpp); `blob` must outlive the request
   IngestReq ingest_request(const std::shared_ptr<const Compiled>& c, const uint8_t* blob, const unsigned long long* ooff, size_t n, uint32_t source,
@@ -213,6 +222,10 @@ class Engine {
   std::shared_ptr<const NsTableHost> ns_table_;            // device form of namespaces_ (rebuilt when stale)
   uint64_t ns_table_version_ = ~0ull;
   uint32_t ns_table_strings_ = 0;
+  std::map<std::vector<std::string>, VP> inventory_;       // processUnstructured path -> object
+  uint64_t inventory_version_ = 0;
+  VP inventory_doc_;                                       // built lazily from inventory_
+  uint64_t inventory_doc_version_ = ~0ull;
   std::map<std::string, std::vector<std::string>> excluded_;
   ExpansionSystem expansion_;
   std::shared_ptr<Compiled> compiled_;

@@ -354,7 +354,9 @@ struct LEnv {
 
 struct Deps {
   bool obj = false, param = false, iter = false, mixed = false;
+  bool data = false;   // reads data.inventory, directly or through a captured column
   void operator|=(const Deps& o) {
+    data |= o.data;
     obj |= o.obj;
     param |= o.param;
     iter |= o.iter;
@@ -454,13 +456,15 @@ class Lowerer {
       case TK::Scalar: break;
       case TK::Var: {
         if (const SymVal* s = env.find(t->vid)) {
-          if (s->k == SymVal::Col) d.obj = true;
+          if (s->k == SymVal::Col) d.obj = true, d.data = d.data || s->col->uses_data;
           else if (s->k != SymVal::Conc) d.mixed = d.obj = d.param = true;
           else if (s->tainted) d.param = true;
         } else if (t->vid == m_.vid_input) {
           d.obj = d.param = true;
         } else if (t->vid == m_.vid_data) {
-          unsupported("reference to `data` (referential constraints / data.inventory, SURVEY.md f-4)", t->line);
+          // data.inventory (referential constraints): varies with the synced cache, not with the constraint -- object-side, never folded
+          d.obj = d.data = true;
+          schema_.uses_data = true;
         } else if (m_.is_rule(t->name)) {
           d |= rule_deps(t->name);
         } else if (!local) {
@@ -606,6 +610,60 @@ class Lowerer {
     return buf;
   }
 
+  bool touches_data(const TP& t) const {
+    if (!t) return false;
+    if (t->k == TK::Var && t->vid == m_.vid_data) return true;
+    if (touches_data(t->head) || touches_data(t->key) || touches_data(t->value)) return true;
+    for (auto& a : t->args)
+      if (touches_data(a)) return true;
+    for (auto& kv : t->kvs)
+      if (touches_data(kv.first) || touches_data(kv.second)) return true;
+    for (auto& st : t->body)
+      if (touches_data(st.a) || touches_data(st.b) || touches_data(st.c)) return true;
+    if (t->k == TK::Call && m_.is_rule(t->name)) {   // a helper function that reads data.inventory itself
+      bool doc = false;
+      std::vector<std::string> refs;
+      (void)refs;
+      auto it = m_.rules.find(t->name);
+      if (it != m_.rules.end())
+        for (auto& r : it->second) {
+          for (auto& st : r.body)
+            if (touches_data(st.a) || touches_data(st.b) || touches_data(st.c)) doc = true;
+          if (touches_data(r.value) || touches_data(r.key)) doc = true;
+        }
+      return doc;
+    }
+    return false;
+  }
+  // every variable of the term that the environment binds is a constant or a column: the term can become a closure with the
+  // constants captured (and it names no parameter directly)
+  bool closable(const TP& term, const LEnv& env) {
+    std::vector<int> fv;
+    free_vars(term, fv);
+    for (int v : fv) {
+      const SymVal* sv = env.find(v);
+      if (sv && sv->k != SymVal::Conc && sv->k != SymVal::Col) return false;
+    }
+    return !names_parameters(term);
+  }
+  bool names_parameters(const TP& t) const {
+    if (!t) return false;
+    if (t->k == TK::Var && t->vid == m_.vid_input) return true;   // a bare `input`
+    if (t->k == TK::Ref && t->head && t->head->k == TK::Var && t->head->vid == m_.vid_input) {
+      if (t->args.empty() || t->args[0]->k != TK::Scalar || t->args[0]->val->t != VT::Str || t->args[0]->val->s != "review") return true;
+      for (size_t i = 1; i < t->args.size(); ++i)
+        if (names_parameters(t->args[i])) return true;
+      return false;
+    }
+    if (names_parameters(t->head) || names_parameters(t->key) || names_parameters(t->value)) return true;
+    for (auto& a : t->args)
+      if (names_parameters(a)) return true;
+    for (auto& kv : t->kvs)
+      if (names_parameters(kv.first) || names_parameters(kv.second)) return true;
+    for (auto& st : t->body)
+      if (names_parameters(st.a) || names_parameters(st.b) || names_parameters(st.c)) return true;
+    return false;
+  }
   CP make_closure(const TP& term, const LEnv& env) {
     // <path closure>["a"]["b"] is the same column as the longer path from the root: `spec := input.review.object.spec;
     // spec.containers` and `input.review.object.spec.containers` must not become two scopes / two sets of columns
@@ -667,6 +725,8 @@ class Lowerer {
       c->caps.emplace_back(v, a);
     }
     c->scope = scope;
+    c->uses_data = touches_data(term);
+    for (auto& cp : c->caps) c->uses_data = c->uses_data || (cp.second.k == CapArg::Col && cp.second.col->uses_data);
     std::string body;
     subst_print(*term, sub, body);
     // helper rules are identified by their TEXT (transitively), not by the template they live in: the same
@@ -1118,6 +1178,10 @@ class Lowerer {
       }
       return out;
     }
+    // data.inventory (referential constraints): anything that reads the synced cache is evaluated by the host flattener, with the
+    // constraint's parameters captured as constants -- joins over the inventory have no symbolic form here
+    if (d.data && !d.iter && !schema_.device_only && t->k != TK::Var && !(t->k == TK::Call && t->name == "sprintf") && closable(t, env))
+      return k(SymVal::column(make_closure(t, env)));
     if (pure_obj(d) && !(t->k == TK::Call && t->name == "sprintf") && t->k != TK::Array && t->k != TK::Object && t->k != TK::Set) {
       if (t->k == TK::Var) {
         if (const SymVal* s = env.find(t->vid)) {

@@ -36,6 +36,7 @@ struct Closure {
   TP term;
   std::vector<std::pair<int, CapArg>> caps;             // captured variables (vid -> value)
   int scope = 0;                                         // innermost scope the value depends on (0 = root)
+  bool uses_data = false;                                // reads data.inventory (directly or through a captured column)
   std::string key;                                       // canonical text: dedupes columns across constraints
 };
 
@@ -83,6 +84,7 @@ struct Schema {
   std::vector<ScopeDef> scopes;   // [0] = root
   std::vector<ColDef> cols;
   std::map<std::string, int> scope_ix, col_ix;
+  bool uses_data = false;         // some closure reads `data` (data.inventory)
   bool device_only = false;       // lowering for the device ingest path: a scope / column the ingest kernels cannot compute is an error
   Schema() { scopes.emplace_back(); }
   int scope_for(const CP& gen);

@@ -859,6 +859,212 @@ struct ComprScoper {
   }
 };
 
+// ---- body ordering.  OPA's compiler reorders the expressions of a body so that every variable is bound before it is needed
+// (ast/compile.go reorderBodyForSafety); templates rely on it, e.g. pkg/gator/fixtures/fixtures.go:461
+//   selectors := [s | s = concat(":", [key, val]); val = obj.spec.selector[key]]
+// The evaluator and the lowering walk a body left to right, so bodies are put into a safe order once, at load.  A body that is
+// already safe in its written order is left alone.
+struct BodyOrder {
+  Module& m;
+  using Set = std::set<int>;
+  std::map<int, std::string> names;
+
+  bool plain(const TP& t) {
+    if (!t || t->k != TK::Var || t->vid == m.vid_input || t->vid == m.vid_data || m.is_rule(t->name)) return false;
+    names.emplace(t->vid, t->name);
+    return true;
+  }
+  // `deep` = false: the variables a body itself names (the locals of its comprehensions are not visible outside them)
+  void all_vars(const TP& t, Set& out, bool deep = true) {
+    if (!t) return;
+    if (plain(t)) out.insert(t->vid);
+    if (!deep && (t->k == TK::ArrCompr || t->k == TK::SetCompr || t->k == TK::ObjCompr)) return;
+    all_vars(t->head, out, deep);
+    for (auto& a : t->args) all_vars(a, out, deep);
+    for (auto& kv : t->kvs) all_vars(kv.first, out, deep), all_vars(kv.second, out, deep);
+    all_vars(t->key, out, deep);
+    all_vars(t->value, out, deep);
+    for (auto& st : t->body) all_vars(st, out, deep);
+  }
+  void all_vars(const Stmt& st, Set& out, bool deep = true) { all_vars(st.a, out, deep), all_vars(st.b, out, deep), all_vars(st.c, out, deep); }
+
+  // variables needed to evaluate `t` as a value / variables that doing so binds (reference index positions)
+  void value_use(const TP& t, const Set& scope, Set& need, Set& out) {
+    if (!t) return;
+    switch (t->k) {
+      case TK::Scalar: return;
+      case TK::Var:
+        if (plain(t)) need.insert(t->vid);
+        return;
+      case TK::Ref:
+        if (plain(t->head)) need.insert(t->head->vid);
+        else value_use(t->head, scope, need, out);
+        for (auto& a : t->args) {
+          if (plain(a)) out.insert(a->vid);
+          else value_use(a, scope, need, out);
+        }
+        return;
+      case TK::ArrCompr:
+      case TK::SetCompr:
+      case TK::ObjCompr: {
+        Set inner;
+        all_vars(t->key, inner);
+        all_vars(t->value, inner);
+        for (auto& st : t->body) all_vars(st, inner);
+        for (int v : inner)
+          if (scope.count(v)) need.insert(v);   // its closure: variables of the enclosing bodies
+        return;
+      }
+      default:
+        for (auto& a : t->args) value_use(a, scope, need, out);
+        for (auto& kv : t->kvs) value_use(kv.first, scope, need, out), value_use(kv.second, scope, need, out);
+        return;
+    }
+  }
+  void pattern_use(const TP& t, const Set& scope, Set& need, Set& out) {
+    if (!t) return;
+    if (plain(t)) {
+      out.insert(t->vid);
+    } else if (t->k == TK::Array) {
+      for (auto& a : t->args) pattern_use(a, scope, need, out);
+    } else if (t->k == TK::Object) {
+      for (auto& kv : t->kvs) value_use(kv.first, scope, need, out), pattern_use(kv.second, scope, need, out);
+    } else {
+      value_use(t, scope, need, out);
+    }
+  }
+  struct Opt {
+    Set need, out;
+  };
+  // the statement can run once ONE option's `need` is bound
+  std::vector<Opt> options(const Stmt& st, const Set& scope) {
+    std::vector<Opt> o;
+    switch (st.k) {
+      case Stmt::Some: o.emplace_back(); break;
+      case Stmt::Expr:
+      case Stmt::Not: {
+        Opt x;
+        value_use(st.a, scope, x.need, x.out);
+        if (st.k == Stmt::Not) {
+          for (int v : x.out) {
+            const std::string& n = names[v];
+            if (!(n.size() > 1 && n[0] == '$' && n[1] == 'w')) x.need.insert(v);   // (a wildcard index is local to the negation)
+          }
+          x.out.clear();
+        }
+        o.push_back(std::move(x));
+        break;
+      }
+      case Stmt::Assign:
+      case Stmt::Unify: {
+        for (int side = 0; side < (st.k == Stmt::Unify ? 2 : 1); ++side) {
+          Opt x;
+          value_use(side ? st.a : st.b, scope, x.need, x.out);
+          pattern_use(side ? st.b : st.a, scope, x.need, x.out);
+          o.push_back(std::move(x));
+        }
+        break;
+      }
+      case Stmt::SomeIn: {
+        Opt x;
+        value_use(st.c, scope, x.need, x.out);
+        pattern_use(st.a, scope, x.need, x.out);
+        pattern_use(st.b, scope, x.need, x.out);
+        o.push_back(std::move(x));
+        break;
+      }
+      default: o.emplace_back(); break;
+    }
+    return o;
+  }
+  static bool subset(const Set& a, const Set& b) {
+    for (int v : a)
+      if (!b.count(v)) return false;
+    return true;
+  }
+  std::vector<Stmt> reorder(const std::vector<Stmt>& body0, const Set& bound, Set scope) {
+    for (auto& st : body0) all_vars(st, scope, false);   // closure candidates of nested comprehensions: everything named so far
+    std::vector<Stmt> body;
+    for (auto& st : body0) body.push_back(nested(st, scope));
+    std::vector<std::vector<Opt>> opts;
+    for (auto& st : body) opts.push_back(options(st, scope));
+    auto runnable = [&](size_t i, const Set& b) -> const Opt* {
+      for (auto& o : opts[i])
+        if (subset(o.need, b)) return &o;
+      return nullptr;
+    };
+    {
+      Set b = bound;
+      bool ok = true;
+      for (size_t i = 0; i < body.size() && ok; ++i) {
+        const Opt* o = runnable(i, b);
+        if (!o) ok = false;
+        else b.insert(o->out.begin(), o->out.end());
+      }
+      if (ok) return body;
+    }
+    Set b = bound;
+    std::vector<size_t> left(body.size()), order;
+    for (size_t i = 0; i < left.size(); ++i) left[i] = i;
+    while (!left.empty()) {
+      bool moved = false;
+      for (size_t j = 0; j < left.size(); ++j) {
+        if (const Opt* o = runnable(left[j], b)) {
+          b.insert(o->out.begin(), o->out.end());
+          order.push_back(left[j]);
+          left.erase(left.begin() + (long)j);
+          moved = true;
+          break;
+        }
+      }
+      if (!moved) {   // nothing can run: keep what is left as written (the evaluator reports the unsafe variable)
+        order.insert(order.end(), left.begin(), left.end());
+        break;
+      }
+    }
+    std::vector<Stmt> out;
+    for (size_t i : order) out.push_back(body[i]);
+    return out;
+  }
+  // comprehension bodies inside a term / statement
+  TP nested(const TP& t, const Set& scope) {
+    if (!t || t->k == TK::Scalar || t->k == TK::Var) return t;
+    auto x = std::make_shared<Term>(*t);
+    x->head = nested(t->head, scope);
+    for (auto& a : x->args) a = nested(a, scope);
+    for (auto& kv : x->kvs) kv = {nested(kv.first, scope), nested(kv.second, scope)};
+    if (t->k == TK::ArrCompr || t->k == TK::SetCompr || t->k == TK::ObjCompr) {
+      x->body = reorder(t->body, scope, scope);
+      Set inner = scope;
+      for (auto& st : x->body) all_vars(st, inner, false);
+      x->key = nested(t->key, inner);
+      x->value = nested(t->value, inner);
+    } else {
+      x->key = nested(t->key, scope);
+      x->value = nested(t->value, scope);
+    }
+    return x;
+  }
+  Stmt nested(const Stmt& s, const Set& scope) {
+    Stmt o = s;
+    o.a = nested(s.a, scope), o.b = nested(s.b, scope), o.c = nested(s.c, scope);
+    return o;
+  }
+  void run() {
+    for (auto& kv : m.rules)
+      for (auto& r : kv.second) {
+        Set bound;
+        for (auto& a : r.args) all_vars(a, bound);
+        r.body = reorder(r.body, bound, bound);
+        for (auto& e : r.els) e.second = reorder(e.second, bound, bound);
+        Set inner = bound;
+        for (auto& st : r.body) all_vars(st, inner, false);
+        r.key = nested(r.key, inner);
+        r.value = nested(r.value, inner);
+      }
+  }
+};
+
 // The one compile-time check the reference's tests pin (pkg/gator/fixtures/fixtures.go TemplateCompileError,
 // a body that is just the undeclared identifier `f`): a bare variable statement must be bound earlier.
 void check_unsafe(const Module& m) {
@@ -1012,6 +1218,7 @@ std::shared_ptr<Module> rego_parse(const std::string& src, const std::vector<std
   }
   EveryDesugar{*m}.run();
   ComprScoper{*m}.run();
+  BodyOrder{*m, {}}.run();
   check_unsafe(*m);
   compute_purity(*m);
   return m;

@@ -65,7 +65,7 @@ class gk_result(C.Structure):
 
 EXPORTS = [
     "gk_engine_create", "gk_engine_destroy", "gk_backend_name", "gk_add_template", "gk_add_template_libs", "gk_remove_template",
-    "gk_add_constraint", "gk_add_expansion_template", "gk_remove_expansion_template", "gk_validate_constraint", "gk_remove_constraint", "gk_put_namespace", "gk_remove_namespace", "gk_constraint_count",
+    "gk_add_constraint", "gk_add_expansion_template", "gk_remove_expansion_template", "gk_validate_constraint", "gk_remove_constraint", "gk_put_namespace", "gk_remove_namespace", "gk_add_data", "gk_remove_data", "gk_constraint_count",
     "gk_constraint_key", "gk_result_constraint_key", "gk_review_batch", "gk_batch_upload", "gk_batch_eval", "gk_batch_eval_device",
     "gk_batch_eval_device_peers", "gk_batch_upload_blob", "gk_review_blob", "gk_set_excluded_namespaces", "gk_audit_begin", "gk_audit_add_batch", "gk_audit_report",
     "gk_audit_end", "gk_validation_messages", "gk_host_cpus", "gk_pin_host", "gk_blob_prefetch", "gk_coalescer_create", "gk_coalescer_review", "gk_coalescer_stats",
@@ -95,6 +95,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.gk_validate_constraint.argtypes = [P, S, C.c_size_t, PP]
     lib.gk_remove_constraint.argtypes = [P, S, S]
     lib.gk_put_namespace.argtypes = [P, S, S, C.c_size_t, PP]
+    lib.gk_add_data.argtypes = [P, C.POINTER(C.c_char_p), C.c_size_t, S, C.c_size_t, PP]
+    lib.gk_remove_data.argtypes = [P, C.POINTER(C.c_char_p), C.c_size_t]
     lib.gk_remove_namespace.argtypes = [P, S]
     lib.gk_constraint_count.restype = U32
     lib.gk_constraint_count.argtypes = [P]
@@ -303,16 +305,20 @@ class Driver:
         self._lib.gk_remove_constraint(self._e, constraint["kind"].encode(), constraint["metadata"]["name"].encode())
 
     def AddData(self, target: str, path: Sequence[str], data: Any) -> None:
-        """Only Namespace objects matter to this driver (they feed the namespaceSelector table);
-        path shapes per pkg/target/target.go:60-66."""
+        """Client.AddData (frameworks client): Namespaces feed the namespaceSelector table (nsCache.Add), and every object is
+        stored at its path for referential templates (data.inventory); path shapes per pkg/target/target.go:60-66."""
+        err = C.c_char_p()
+        b = _to_bytes(data)
         if len(path) >= 4 and path[0] == "cluster" and path[2] == "Namespace":
-            err = C.c_char_p()
-            b = _to_bytes(data)
             self._check(self._lib.gk_put_namespace(self._e, path[3].encode(), b, len(b), C.byref(err)), err)
+        arr = (C.c_char_p * len(path))(*[p.encode() for p in path])
+        self._check(self._lib.gk_add_data(self._e, arr, len(path), b, len(b), C.byref(err)), err)
 
     def RemoveData(self, target: str, path: Sequence[str]) -> None:
         if len(path) >= 4 and path[0] == "cluster" and path[2] == "Namespace":
             self._lib.gk_remove_namespace(self._e, path[3].encode())
+        arr = (C.c_char_p * len(path))(*[p.encode() for p in path])
+        self._lib.gk_remove_data(self._e, arr, len(path))
 
     def Dump(self) -> str:
         p = self._lib.gk_dump(self._e)

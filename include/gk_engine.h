@@ -124,6 +124,13 @@ int gk_add_expansion_template(gk_engine_t* e, const char* json, size_t len, char
 int gk_remove_expansion_template(gk_engine_t* e, const char* name);
 int gk_put_namespace(gk_engine_t* e, const char* name, const char* ns_json, size_t len, char** err);
 int gk_remove_namespace(gk_engine_t* e, const char* name);
+/* Driver.AddData / RemoveData for ANY synced object (pkg/drivers/k8scel/driver.go:252-258 are no-ops for CEL; the Rego driver
+ * stores the object under /external/<target>/<path...>, read by referential templates as data.inventory...).  `path` is what
+ * K8sValidationTarget.ProcessData returns (pkg/target/target.go:40-66): {"cluster", groupVersion, kind, name} or
+ * {"namespace", ns, groupVersion, kind, name}; npath == 0 derives it from the object.  gk_remove_data removes one object or a
+ * whole sub-tree.  Namespaces are ALSO given to gk_put_namespace by the caller (Client.AddData feeds both). */
+int gk_add_data(gk_engine_t* e, const char* const* path, size_t npath, const char* obj_json, size_t len, char** err);
+int gk_remove_data(gk_engine_t* e, const char* const* path, size_t npath);
 
 /* constraint index <-> identity ("Kind/name"); the returned string is engine-owned until the next mutation */
 uint32_t gk_constraint_count(gk_engine_t* e);

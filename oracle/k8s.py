@@ -649,6 +649,8 @@ class Client:
         self.templates = {}     # kind -> Template
         self.constraints = {}   # (kind, name) -> constraint dict ; insertion-ordered
         self.ns_cache = {}      # name -> namespace object   (pkg/target/ns_cache.go:15-85)
+        self.inventory = {}     # data.inventory: {"cluster": {gv: {kind: {name: obj}}}, "namespace": {ns: {gv: {kind: {name: obj}}}}}
+        self._inventory_doc = None
 
     def add_template(self, kind, rego_src, libs=()):
         self.templates[kind] = Template(kind, rego_src, libs)
@@ -693,6 +695,44 @@ class Client:
             raise MatchError("cannot cache non-namespace type: cannot cache Namespace: <nil>")
         self.ns_cache[name if name is not None else _meta(ns_obj, "name")] = ns_obj
 
+    @staticmethod
+    def data_path(obj):
+        """processUnstructured (pkg/target/target.go:40-57): where a synced object lives under data.inventory."""
+        api = obj.get("apiVersion") or ""
+        group, _, version = api.rpartition("/")
+        name = _meta(obj, "name") or ""
+        if not version:
+            raise ValueError("invalid request object: resource %s has no version" % name)
+        if not obj.get("kind"):
+            raise ValueError("invalid request object: resource %s has no kind" % name)
+        gv = group + "/" + version if group else version
+        ns = _meta(obj, "namespace") or ""
+        return ["cluster", gv, obj["kind"], name] if not ns else ["namespace", ns, gv, obj["kind"], name]
+
+    def add_data(self, obj, path=None):
+        """Client.AddData: the object is stored at its path for referential templates; Namespaces also enter the nsCache
+        (the caller does that through add_namespace, as the reference's Client does through cache.Add)."""
+        path = list(path) if path else self.data_path(obj)
+        cur = self.inventory
+        for p in path[:-1]:
+            cur = cur.setdefault(p, {})
+        cur[path[-1]] = obj
+        self._inventory_doc = None
+
+    def remove_data(self, path):
+        cur = self.inventory
+        for p in path[:-1]:
+            cur = cur.get(p)
+            if cur is None:
+                return
+        cur.pop(path[-1], None)
+        self._inventory_doc = None
+
+    def data_doc(self):
+        if self._inventory_doc is None:
+            self._inventory_doc = rego.from_json({"inventory": self.inventory})
+        return self._inventory_doc
+
     def review(self, review: Review, enforcement_point: str = AUDIT_EP):
         """Returns a list of result dicts {constraint:(kind,name), msg, details, enforcementAction,
         scopedEnforcementActions}.  Matcher errors become results carrying the error text (pinned by
@@ -719,7 +759,7 @@ class Client:
                                 "autoreject": True})
                 continue
             inp = rego.RObj({"review": doc, "parameters": rego.from_json(spec.get("parameters") or {})})
-            for v in rego.eval_violations(self.templates[kind].module, inp):
+            for v in rego.eval_violations(self.templates[kind].module, inp, self.data_doc()):
                 results.append({"constraint": (kind, name), "msg": v["msg"],
                                 "details": rego.to_json(v["details"]) if "details" in v else None,
                                 "enforcementAction": action, "scopedEnforcementActions": scoped or []})

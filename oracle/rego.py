@@ -1177,6 +1177,185 @@ def _scope_fix(x):
     return x
 
 
+# ---- body ordering.  OPA's compiler reorders the expressions of a body so that every variable is bound before it is needed
+# (ast/compile.go reorderBodyForSafety); templates rely on it, e.g. pkg/gator/fixtures/fixtures.go:461
+#   selectors := [s | s = concat(":", [key, val]); val = obj.spec.selector[key]]
+# The evaluator below runs a body left to right, so bodies are put into a safe order once, at load.  A body that is already safe
+# in its written order is left alone.
+def _vars_of(x, rules):
+    out = set()
+    _all_vars(x, rules, out, False)
+    return out
+
+
+def _is_plain_var(t, rules):
+    return isinstance(t, tuple) and len(t) == 2 and t[0] == "var" and t[1] not in ("input", "data") and t[1] not in rules
+
+
+def _all_vars(x, rules, out, deep=True):
+    """deep=False: the variables a body itself names (the locals of its comprehensions are not visible outside them)."""
+    if isinstance(x, tuple):
+        if _is_plain_var(x, rules):
+            out.add(x[1])
+        elif x and x[0] == "some" and len(x) == 2 and isinstance(x[1], list):
+            out.update(n for n in x[1] if isinstance(n, str))
+        elif not deep and x and x[0] in ("acompr", "scompr", "ocompr"):
+            return
+        else:
+            for y in x:
+                _all_vars(y, rules, out, deep)
+    elif isinstance(x, list):
+        for y in x:
+            _all_vars(y, rules, out, deep)
+
+
+def _value_use(t, rules, scope, need, out):
+    """Variables needed to evaluate term t as a value / variables that doing so binds (reference index positions)."""
+    if not isinstance(t, tuple) or not t:
+        return
+    k = t[0]
+    if k == "scalar":
+        return
+    if k == "var":
+        if _is_plain_var(t, rules):
+            need.add(t[1])
+    elif k == "ref":
+        if _is_plain_var(t[1], rules):
+            need.add(t[1][1])
+        else:
+            _value_use(t[1], rules, scope, need, out)
+        for a in t[2]:
+            if _is_plain_var(a, rules):
+                out.add(a[1])
+            else:
+                _value_use(a, rules, scope, need, out)
+    elif k == "call":
+        for a in t[2]:
+            _value_use(a, rules, scope, need, out)
+    elif k in ("array", "set"):
+        for a in t[1]:
+            _value_use(a, rules, scope, need, out)
+    elif k == "object":
+        for kk, vv in t[1]:
+            _value_use(kk, rules, scope, need, out)
+            _value_use(vv, rules, scope, need, out)
+    elif k in ("acompr", "scompr", "ocompr"):
+        inner = set()
+        _all_vars(t[1:], rules, inner)
+        need.update(v for v in inner if v in scope)      # its closure: variables of the enclosing bodies
+
+
+def _pattern_use(t, rules, scope, need, out):
+    if _is_plain_var(t, rules):
+        out.add(t[1])
+    elif isinstance(t, tuple) and t and t[0] == "array":
+        for a in t[1]:
+            _pattern_use(a, rules, scope, need, out)
+    elif isinstance(t, tuple) and t and t[0] == "object":
+        for kk, vv in t[1]:
+            _value_use(kk, rules, scope, need, out)
+            _pattern_use(vv, rules, scope, need, out)
+    else:
+        _value_use(t, rules, scope, need, out)
+
+
+def _stmt_options(st, rules, scope):
+    """[(need, binds)] -- the statement can run once ONE option's `need` is bound."""
+    k = st[0]
+    if k == "some":
+        return [(set(), set())]
+    if k in ("expr", "not"):
+        need, out = set(), set()
+        _value_use(st[1] if k == "expr" else (st[1][1] if isinstance(st[1], tuple) and st[1] and st[1][0] == "expr" else st[1]), rules, scope, need, out)
+        if k == "not":
+            if isinstance(st[1], tuple) and st[1] and st[1][0] in ("assign", "unify"):
+                need, out = set(), set()
+                _value_use(st[1][1], rules, scope, need, out)
+                _value_use(st[1][2], rules, scope, need, out)
+            need |= {v for v in out if not v.startswith("$")}
+            out = set()
+        return [(need, out)]
+    if k in ("assign", "unify"):
+        opts = []
+        for lhs, rhs in ((st[1], st[2]), (st[2], st[1])):
+            need, out = set(), set()
+            _value_use(rhs, rules, scope, need, out)
+            _pattern_use(lhs, rules, scope, need, out)
+            opts.append((need - (out - need), out))
+            if k == "assign":
+                break
+        return opts
+    if k == "somein":
+        need, out = set(), set()
+        _value_use(st[3], rules, scope, need, out)
+        for t in (st[1], st[2]):
+            if t is not None:
+                _pattern_use(t, rules, scope, need, out)
+        return [(need, out)]
+    if k == "every":
+        need, out = set(), set()
+        _value_use(st[3], rules, scope, need, out)
+        inner = set()
+        _all_vars(st[4], rules, inner)
+        need.update(v for v in inner if v in scope)
+        return [(need, set())]
+    return [(set(), set())]
+
+
+def _reorder_body(body, bound, rules, scope):
+    scope = set(scope)
+    _all_vars([st for st in body], rules, scope, False)      # closure candidates of nested comprehensions: everything named so far
+    body = [_reorder_nested(st, rules, scope) for st in body]
+    opts = [_stmt_options(st, rules, scope) for st in body]
+
+    def runnable(i, b):
+        for need, out in opts[i]:
+            if need <= b:
+                return out
+        return None
+    b = set(bound)
+    ok = True
+    for i in range(len(body)):
+        out = runnable(i, b)
+        if out is None:
+            ok = False
+            break
+        b |= out
+    if ok:
+        return body
+    b = set(bound)
+    left = list(range(len(body)))
+    order = []
+    while left:
+        for i in left:
+            out = runnable(i, b)
+            if out is not None:
+                order.append(i)
+                b |= out
+                left.remove(i)
+                break
+        else:
+            order.extend(left)          # nothing can run: keep what is left as written (the evaluator reports the unsafe variable)
+            break
+    return [body[i] for i in order]
+
+
+def _reorder_nested(x, rules, scope):
+    """Comprehension / every bodies inside a statement or term, innermost last."""
+    if isinstance(x, list):
+        return [_reorder_nested(y, rules, scope) for y in x]
+    if not isinstance(x, tuple) or not x or x[0] in ("scalar", "var", "some"):
+        return x
+    if x[0] in ("acompr", "scompr", "ocompr"):
+        head = tuple(_reorder_nested(y, rules, scope) for y in x[1:-1])
+        return (x[0],) + head + (_reorder_body(x[-1], scope, rules, scope),)
+    if x[0] == "every":
+        inner = set(scope)
+        _all_vars([x[1], x[2]], rules, inner)
+        return ("every", x[1], x[2], _reorder_nested(x[3], rules, scope), _reorder_body(x[4], inner, rules, inner))
+    return tuple(_reorder_nested(y, rules, scope) for y in x)
+
+
 class Module:
     def __init__(self, src, libs=(), _registry=None):
         p = Parser(src)
@@ -1203,6 +1382,15 @@ class Module:
                     if pkg not in self.libs:
                         raise RegoError(f"rego_compile_error: import data.{pkg}: the template has no lib with that package")
         self._check()
+        names = set(self.rules) | set(self.imports)
+        for rs in self.rules.values():
+            for r in rs:
+                bound = set()
+                _all_vars(r.args or [], names, bound)
+                r.body = _reorder_body(r.body, bound, names, bound)
+                r.els = [(ev, _reorder_body(eb, bound, names, bound)) for ev, eb in r.els]
+                for attr in ("key", "value"):
+                    setattr(r, attr, _reorder_nested(getattr(r, attr), names, bound | _vars_of(r.body, names)))
 
     def lib_of_call(self, name):
         """`alias.fn` / `data.lib.<pkg>.fn` -> (lib module, fn) or None."""

@@ -69,6 +69,7 @@ def make_pair(tmpls, constraints, namespaces=(), lib_path=None, skip_unsupported
         orc.add_constraint(c)
     for ns in namespaces:
         orc.add_namespace(ns)
+        orc.add_data(ns)
         drv.AddData("admission.k8s.gatekeeper.sh", ["cluster", "v1", "Namespace", ns["metadata"]["name"]], ns)
     return orc, drv, skipped
 

@@ -2,6 +2,7 @@
 Every case loads the SAME templates / constraints / objects into the oracle and into the engine and
 compares the full result set: (object, constraint, msg, details, enforcement action(s), autoreject)."""
 import json
+import random
 
 from conftest import assert_same, engine_results, golden, make_pair, oracle_results
 from gatekeeper_b200 import driver as D
@@ -199,9 +200,9 @@ def case_unsupported_is_an_error_not_a_fallback(lib):
     drv = D.Driver(lib_path=lib)
     with pytest.raises(D.GkError, match="unsafe"):
         drv.add_template("CompileError", t["fixtures_TemplateCompileError"]["rego"])
-    with pytest.raises(D.GkError, match="data"):
-        drv.add_template("K8sUniqueLabel", 'package u\nviolation[{"msg": msg}] {\n  other := data.inventory.cluster[_][_][_]\n'
-                         '  other.metadata.labels.x == input.review.object.metadata.labels.x\n  msg := "dup"\n}\n')
+    # (referential templates -- data.inventory -- are accepted since round 2: case_referential)
+    drv.add_template("K8sUniqueLabel", 'package u\nviolation[{"msg": msg}] {\n  other := data.inventory.cluster[_][_][_]\n'
+                     '  other.metadata.labels.x == input.review.object.metadata.labels.x\n  msg := "dup"\n}\n')
     # a pattern taken from the OBJECT (not from the parameters) cannot become a feature column: rejected at AddConstraint
     drv.add_template("PatternFromObject", 'package p\nviolation[{"msg": "m"}] {\n  re_match(input.review.object.metadata.annotations.pat, '
                      'input.parameters.v)\n}\n')
@@ -1160,19 +1161,12 @@ def case_target_matcher(lib):
 # ------------------------------------------------------------------------------------------ gator TestTest table
 def case_gator_test_table(lib):
     """pkg/gator/test/test_test.go:85-268: every input document is reviewed at the gator enforcement point; the exact
-    list of (message, constraint, action, scoped actions) is what the reference asserts.  Referential rows
-    (data.inventory) must be REJECTED by the engine at AddTemplate -- they are out of the independent-object model."""
+    list of (message, constraint, action, scoped actions) is what the reference asserts.  gator adds every input object
+    as data before auditing (pkg/gator/test/test.go:91-97), which is what the referential rows (data.inventory) read."""
     import pytest
     n = 0
     for row in golden("gator_test_table.json"):
         tm, cons, nss = _split_docs(row["docs"])
-        referential = any("Referential" in i for i in row["inputs"] if i.startswith("Template"))
-        if referential:
-            drv = D.Driver(lib_path=lib)
-            with pytest.raises(D.GkError):
-                for kind, rego in tm:
-                    drv.add_template(kind, rego)
-            continue
         if row["wantErr"]:
             drv = D.Driver(lib_path=lib)
             with pytest.raises(D.GkError, match="no template|template"):
@@ -1180,6 +1174,10 @@ def case_gator_test_table(lib):
                     drv.AddConstraint(c)
             continue
         orc, drv, _ = make_pair(tm, cons, nss, lib_path=lib)
+        for d in row["docs"]:
+            if d.get("kind") not in ("ConstraintTemplate", "Namespace") and not str(d.get("apiVersion", "")).startswith("constraints.gatekeeper.sh"):
+                orc.add_data(d)
+                drv.AddData("admission.k8s.gatekeeper.sh", orc.data_path(d), d)
         revs = [D.Review(object=d) for d in row["docs"]]
         resp = drv.ReviewBatch(revs, k8s.GATOR_EP)
         assert_same(oracle_results(orc, revs, k8s.GATOR_EP), engine_results(resp))
@@ -1534,4 +1532,78 @@ def case_expansion(lib):
         assert any(m.startswith("[Implied by expand-deployments] ") for m in msgs)
         assert any(m.startswith("[Implied by expand-jobs] ") for m in msgs) and any(w[4] == "dryrun" for w in want)
         assert resp.viol_bits.shape[0] == len(revs)
+    return len(want)
+
+
+# ------------------------------------------------------------------------------------------ referential constraints (f-4)
+def case_referential(lib):
+    """data.inventory: (1) the bats "unique labels test" (test.bats:295-303): with good/no_dupe_cm.yaml synced, bad/no_dupe_cm_2.yaml
+    is denied, the synced objects themselves are not (a review never collides with its own inventory entry); (2) a sweep of
+    Services / ConfigMaps against an inventory of a few hundred objects, engine == oracle result for result, through the host
+    objects path and the raw-JSON blob path; (3) RemoveData takes the violation away again."""
+    v = golden("referential_vectors.json")["uniquelabel"]
+    tmpl = k8s.template_from_yaml_obj(v["template"])
+    orc, drv, skipped = make_pair([tmpl], [v["constraint"]], lib_path=lib)
+    assert not skipped
+    T = "admission.k8s.gatekeeper.sh"
+    for d in v["synced"]:
+        orc.add_data(d)
+        drv.AddData(T, orc.data_path(d), d)
+    revs = [D.Review(object=v["denied"])] + [D.Review(object=d) for d in v["synced"]]
+    resp = drv.ReviewBatch(revs, k8s.WEBHOOK_EP)
+    want = oracle_results(orc, revs, k8s.WEBHOOK_EP)
+    assert_same(want, engine_results(resp))
+    # the denied ConfigMap, and the synced one of the matched namespace (its twin in the other namespace carries the same value)
+    assert {w[0] for w in want} == {0, 1} and {w[2] for w in want} == {"label gatekeeper has duplicate value not_duplicated"}, want
+    twin = v["synced"][1]
+    drv.RemoveData(T, orc.data_path(twin))
+    orc.remove_data(orc.data_path(twin))
+    resp = drv.ReviewBatch(revs, k8s.WEBHOOK_EP)
+    want = oracle_results(orc, revs, k8s.WEBHOOK_EP)
+    assert_same(want, engine_results(resp))
+    assert {w[0] for w in want} == {0}, want          # a review never collides with its own inventory entry
+    # the object admitted and synced: now the first ConfigMap collides with it as well
+    orc.add_data(v["denied"])
+    drv.AddData(T, orc.data_path(v["denied"]), v["denied"])
+    resp = drv.ReviewBatch(revs, k8s.WEBHOOK_EP)
+    want = oracle_results(orc, revs, k8s.WEBHOOK_EP)
+    assert_same(want, engine_results(resp))
+    assert {w[0] for w in want} == {0, 1}, want
+    drv.RemoveData(T, orc.data_path(v["denied"]))
+    orc.remove_data(orc.data_path(v["denied"]))
+    resp = drv.ReviewBatch(revs, k8s.WEBHOOK_EP)
+    assert_same(oracle_results(orc, revs, k8s.WEBHOOK_EP), engine_results(resp))
+    assert {r.object for r in resp.results} == {0}
+
+    # (2) unique service selectors + unique labels over a synthetic inventory
+    svc_t = [d for r in golden("gator_test_table.json") if r["name"] == "referential constraint with violation" for d in r["docs"]]
+    tm, cons, _ = _split_docs(svc_t)
+    rng = random.Random(0xF4)
+    def svc(i, ns, sel):
+        return {"apiVersion": "v1", "kind": "Service", "metadata": {"name": "svc-%d" % i, "namespace": ns}, "spec": {"ports": [{"port": 443}], "selector": sel}}
+    def cm(i, ns, val):
+        return {"apiVersion": "v1", "kind": "ConfigMap", "metadata": {"name": "cm-%d" % i, "namespace": ns, "labels": {"gatekeeper": val, "i": str(i)}}, "data": {}}
+    nss = ["default", "gatekeeper-test-playground", "prod"]
+    inv = []
+    for i in range(150):
+        inv.append(svc(i, rng.choice(nss), {"app": "a%d" % rng.randrange(60), **({"tier": rng.choice(["fe", "be"])} if rng.random() < 0.3 else {})}))
+    for i in range(150):
+        inv.append(cm(i, rng.choice(nss), "v%d" % rng.randrange(90)))
+    inv.append({"apiVersion": "v1", "kind": "Namespace", "metadata": {"name": "prod", "labels": {"gatekeeper": "v3"}}})
+    orc, drv, skipped = make_pair(tm + [tmpl], cons + [v["constraint"]], lib_path=lib)
+    assert not skipped
+    for d in inv:
+        orc.add_data(d)
+        drv.AddData(T, orc.data_path(d), d)
+    objs = rng.sample(inv, 80) + [svc(1000 + i, rng.choice(nss), {"app": "a%d" % rng.randrange(60)}) for i in range(40)] + \
+           [cm(1000 + i, rng.choice(nss), "v%d" % rng.randrange(90)) for i in range(40)] + [cm(2000, "prod", "unique-value"), svc(2000, "prod", {})]
+    revs = [D.Review(object=o) for o in objs]
+    for ep in (k8s.AUDIT_EP, k8s.WEBHOOK_EP):
+        resp = drv.ReviewBatch(revs, ep)
+        want = oracle_results(orc, revs, ep)
+        assert_same(want, engine_results(resp))
+        assert len(want) > 40
+    blob = W.PyBlob([json.dumps(o).encode() for o in objs])
+    got = drv.ReviewBlob(blob, k8s.AUDIT_EP, flags=D.F_MATERIALIZE)
+    assert_same(oracle_results(orc, revs, k8s.AUDIT_EP), engine_results(got))
     return len(want)

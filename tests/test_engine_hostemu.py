@@ -335,3 +335,7 @@ violation[{"msg": "x"}] { v := input.review.object.spec[input.parameters.field][
 
 def test_expansion_templates_through_the_batch():
     assert P.case_expansion(HOSTEMU) >= 6
+
+
+def test_referential_constraints_data_inventory():
+    assert P.case_referential(HOSTEMU) > 40

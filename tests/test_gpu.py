@@ -291,3 +291,7 @@ def test_wildcard_vectors_through_kernel():
 
 def test_expansion_templates_through_the_batch():
     assert P.case_expansion(LIB) >= 6
+
+
+def test_referential_constraints_data_inventory():
+    assert P.case_referential(LIB) > 40
