@@ -625,10 +625,8 @@ typedef struct {
 #define GK_SEED_NUM 0xc3a5c85c97cb3127ull   /* canonical integers -> sid */
 #define GK_SEED_NS 0xb492b66fbe98f273ull    /* namespace names -> namespace table row */
 
-// per-object counters produced by the COUNT pass, one array of n entries each (then scanned): laid out [counter][object]
-//   [0, nscopes)              rows of every scope (index 0 unused)
-//   [nscopes, +nbytecols)     bytes of every byte-column
-//   then: name bytes, generateName bytes, labels, nsname bytes
+// per-object header counters produced by the header COUNT pass, one array of n entries each (then scanned), laid out
+// [counter][object]: name bytes, generateName bytes, labels, nsname bytes
 #define GK_CNT_EXTRA 4
 
 typedef struct {
@@ -674,7 +672,7 @@ typedef struct {
   uint32_t* status;                 // [n] GK_ING_*
   uint32_t n;
   uint32_t source;                  // GK_SRC_* of every object of the chunk
-  uint32_t* counts;                 // [(nscopes + nbytecols + GK_CNT_EXTRA) * n]; after the scan: exclusive prefix sums
+  uint32_t* counts;                 // [GK_CNT_EXTRA * n] header counters; after the scan: exclusive prefix sums
   GkMiss* misses;                   // miss list
   uint32_t* nmiss;
   uint32_t miss_cap;
@@ -1229,34 +1227,18 @@ struct GkCur {
   GK_HD uint32_t& operator[](uint32_t k) const { return p[(size_t)k * stride]; }
 };
 
-struct GkIngestFrame {
-  uint32_t scope;
-  uint32_t pos, end;        // object iteration: tape index of the next member's key / array: next element; end of the children
-  uint32_t arr_ix;          // next array index
-  uint32_t is_obj;
-  uint32_t next_child;      // next child scope to open for the current row
-  uint32_t row;             // chunk-global row index of the current row
-};
-
 GK_HD const uint8_t* gk_lit(const char* s) { return reinterpret_cast<const uint8_t*>(s); }
 
-// MODE 0: count pass (decoded lengths of byte columns).  MODE 1: the per-object pass writes the byte-encoded columns (their
-// offsets run through the object).  MODE 2: the per-row pass writes every other column.
-enum { GK_PASS_COUNT = 0, GK_PASS_ROWS = 1, GK_PASS_COLS = 2, GK_PASS_HEADER = 3 };
+// gk_emit_col<BCOLS>: the byte-encoded columns of a row (offsets = scanned lengths); <COLS>: every other column.
+// gk_ingest_obj<COUNT / HEADER>: the two header passes.
+enum { GK_PASS_COUNT = 0, GK_PASS_BCOLS = 1, GK_PASS_COLS = 2, GK_PASS_HEADER = 3 };
 template <int MODE>
 GK_HD void gk_emit_col(const GkXProg& xp, const GkIngestIn& in, const GkIngestOut& out, GkXCtx& c, uint32_t ci, uint32_t row, const GkCur& bcur) {
   const GkXCol& col = xp.cols[ci];
   const GkXClosure& cl = xp.cl[col.closure];
   const uint32_t enc = col.enc;
-  if (MODE == GK_PASS_ROWS && !(enc & GK_ENC_BYTES)) return;
+  if (MODE == GK_PASS_BCOLS && !(enc & GK_ENC_BYTES)) return;
   if (MODE == GK_PASS_COLS && (enc & GK_ENC_BYTES)) return;
-  if (MODE == GK_PASS_COUNT) {
-    // the count pass only needs the decoded length of byte columns
-    if (!(enc & GK_ENC_BYTES) || cl.kind == GK_X_LUT || cl.kind == GK_X_COUNT) return;
-    const GkXVal v = gk_x_eval(c, col.closure);
-    if (v.vt == GK_VT_STR) bcur[col.bytes_slot] += gk_decoded_len(c, v);
-    return;
-  }
   GkXVal v = gk_xundef();
   bool native = false;
   if (cl.kind == GK_X_LUT && cl.sx_n) {
@@ -1316,33 +1298,24 @@ GK_HD void gk_emit_col(const GkXProg& xp, const GkIngestIn& in, const GkIngestOu
     }
     for (int w = 0; w < GK_HEAD_WORDS; ++w) out.head[ci][(size_t)row * GK_HEAD_WORDS + w] = h[w];
   }
-  if (enc & GK_ENC_BYTES) {
-    uint32_t& cur = bcur[col.bytes_slot];
-    out.boff[ci][row] = cur;
-    if (v.vt == GK_VT_STR) {
-      gk_copy_decoded(c, v, out.bytes[ci] + cur);
-      cur += gk_decoded_len(c, v);
-    }
+  if (enc & GK_ENC_BYTES) {   // (the offsets are there already: the scanned lengths of gk_bcol_len)
+    (void)bcur;
+    if (v.vt == GK_VT_STR) gk_copy_decoded(c, v, out.bytes[ci] + out.boff[ci][row]);
   }
 }
 
-// Count pass (WRITE = false): fills in.counts[k * n + i].  Write pass: in.counts holds the exclusive prefix sums.
-// The per-object pass.  GK_PASS_COUNT: rows per scope, bytes per byte column, header byte counts.  GK_PASS_ROWS: header arrays,
-// CSR offsets, the row handles of every scope and the byte-encoded columns.
-// `lane` / `nlanes`: several threads may share one object (every lane walks the scope tree, the byte columns of a row are dealt
-// to the lanes; arrays that are not per column are written by lane 0); measured on B200 one thread per object is fastest.
-// `cur`: nscopes + nbytecols + GK_CNT_EXTRA working counters, private to the lane.
+// The header pass of one object.  COUNT fills in.counts[k * n + i] (k: name bytes, generateName bytes, labels, nsname bytes);
+// HEADER finds the exclusive prefix sums there.  `cur`: GK_CNT_EXTRA working counters private to the thread.
 template <int MODE>
 GK_HD void gk_ingest_obj(const GkXProg& xp, const GkIngestIn& in, const GkIngestOut& out, uint32_t i, const GkCur& cur, uint32_t lane, uint32_t nlanes) {
-  // COUNT: header byte / label counts + the scope walk.  HEADER: the header arrays only (every thread runs the same steps in the
-  // same order -- kept out of the scope walk, where threads are at different depths).  ROWS: the scope walk only (skip flag read
-  // back from the header pass, which runs first).
+  // The header of object i -- every thread runs the same steps in the same order.  COUNT: byte / label counts of the header
+  // arrays (+ the flags word into out.flags, a scratch array at that point).  HEADER: the header arrays themselves, at the
+  // scanned offsets.  Scopes and columns are level-synchronous passes of their own (gk_scope_count ... gk_bcol_write).
   constexpr bool WRITE = MODE != GK_PASS_COUNT;
-  constexpr bool HDR = MODE != GK_PASS_ROWS;
-  const uint32_t n = in.n, NS = xp.nscopes, NK = NS + xp.nbytecols + GK_CNT_EXTRA;
-  const uint32_t K_NAME = NS + xp.nbytecols, K_GEN = K_NAME + 1, K_LBL = K_NAME + 2, K_NSN = K_NAME + 3;
+  constexpr bool HDR = true;
+  const uint32_t n = in.n, NK = GK_CNT_EXTRA;
+  const uint32_t K_NAME = 0, K_GEN = 1, K_LBL = 2, K_NSN = 3;
   for (uint32_t k = 0; k < NK; ++k) cur[k] = WRITE ? in.counts[(size_t)k * n + i] : 0u;
-  const GkCur bcur{cur.p + (size_t)NS * cur.stride, cur.stride};
   GkXCtx c;
   c.xp = &xp;
   c.in = &in;
@@ -1356,7 +1329,7 @@ GK_HD void gk_ingest_obj(const GkXProg& xp, const GkIngestIn& in, const GkIngest
   c.api_node = c.kind_node = c.name_node = c.ns_node = c.meta_node = GK_NONE;
   c.grp = c.ver = nullptr;
   c.grp_len = c.ver_len = 0;
-  bool skip = HDR ? in.status[i] != GK_ING_OK : (out.flags[i] & GK_F_SKIP) != 0u;
+  bool skip = in.status[i] != GK_ING_OK;
   uint32_t fl = (in.source << GK_F_SRC_SHIFT) & GK_F_SRC_MASK;
   uint32_t kind_sid = GK_SID_UNDEF, group_sid = GK_SID_UNDEF, nsrow = GK_NONE;
   uint32_t labels = GK_NONE, gen_node = GK_NONE;
@@ -1448,138 +1421,27 @@ GK_HD void gk_ingest_obj(const GkXProg& xp, const GkIngestIn& in, const GkIngest
       out.nsn_off[n] = cur[K_NSN];
     }
   }
-  if (MODE == GK_PASS_HEADER) return;
-  // ---- scopes + columns: depth-first over the scope tree, rows of a scope in (parent row, member) order
-  GkIngestFrame fr[GK_MAX_LOOP_DEPTH + 1];
-  fr[0].scope = 0;
-  fr[0].row = i;
-  fr[0].next_child = xp.scopes[0].first_child;
-  fr[0].pos = fr[0].end = fr[0].arr_ix = fr[0].is_obj = 0;
-  {
-    const GkXScope& s0 = xp.scopes[0];
-    for (uint32_t k = lane; k < s0.ncols; k += nlanes) {
-      const uint32_t ci = xp.col_order[s0.first_col + k];
-      if (skip) {
-        if (WRITE && (xp.cols[ci].enc & GK_ENC_BYTES)) {   // placeholder row of a byte column: every encoding "undefined"
-          const uint32_t enc = xp.cols[ci].enc;
-          if (enc & GK_ENC_VT) out.vt[ci][i] = GK_VT_UNDEF;
-          if (enc & GK_ENC_SID) out.sid[ci][i] = GK_SID_UNDEF;
-          if (enc & GK_ENC_NUM) out.num[ci][i] = 0;
-          if (enc & GK_ENC_HEAD)
-            for (int w = 0; w < GK_HEAD_WORDS; ++w) out.head[ci][(size_t)i * GK_HEAD_WORDS + w] = 0;
-          if (enc & GK_ENC_BYTES) out.boff[ci][i] = bcur[xp.cols[ci].bytes_slot];
-        }
-      } else {
-        gk_emit_col<MODE>(xp, in, out, c, ci, i, bcur);
-      }
-    }
-  }
-  int top = 0;
-  while (top >= 0) {
-    GkIngestFrame& f = fr[top];
-    if (f.next_child != GK_NONE) {
-      // open the next child scope under the current row of f.scope
-      const uint32_t t = f.next_child;
-      f.next_child = xp.scopes[t].next_sibling;
-      if (WRITE && lane == 0) out.scope_off[t][f.row] = cur[t];
-      if (skip || top >= GK_MAX_LOOP_DEPTH) continue;
-      c.depth = top;
-      const GkXVal coll = gk_x_eval(c, xp.scopes[t].gen);
-      if (coll.node == GK_NONE || (coll.vt != GK_VT_ARR && coll.vt != GK_VT_OBJ)) continue;
-      GkIngestFrame& g = fr[top + 1];
-      g.scope = t;
-      g.is_obj = coll.vt == GK_VT_OBJ;
-      g.pos = coll.node + 1u;
-      g.end = gk_te_end(c.doc.tape[coll.node]);
-      g.arr_ix = 0;
-      g.next_child = GK_NONE;
-      g.row = 0;
-      ++top;
-      c.scope_at[top] = t;
-      // fall through to "advance" below by marking the frame as between rows
-    } else if (top == 0) {
-      break;
-    }
-    // ---- advance the iterator of the top frame to its next row (or pop)
-    GkIngestFrame& g = fr[top];
-    if (g.next_child != GK_NONE) continue;   // (a freshly opened child of the frame we just advanced)
-    bool have = false;
-    while (g.pos < g.end) {
-      if (g.is_obj) {
-        const uint32_t k = g.pos;
-        g.pos = gk_tape_skip(c.doc.tape, k + 1u);
-        if (gk_key_shadowed(c.doc, k, g.end)) continue;
-        c.key[top] = gk_xnode(c.doc.tape, k);
-        c.elem[top] = gk_xnode(c.doc.tape, k + 1u);
-      } else {
-        const uint32_t e = g.pos;
-        g.pos = gk_tape_skip(c.doc.tape, e);
-        c.key[top] = gk_xsyn(GK_VT_NUM);
-        c.key[top].inum = (long long)g.arr_ix++;
-        c.elem[top] = gk_xnode(c.doc.tape, e);
-      }
-      have = true;
-      break;
-    }
-    if (!have) {
-      --top;
-      continue;
-    }
-    g.row = cur[g.scope]++;
-    c.depth = top;
-    if (WRITE && lane == 0) {
-      GkRowRec rr;
-      rr.elem = c.elem[top].node;
-      rr.key = g.is_obj ? c.key[top].node : ((uint32_t)c.key[top].inum | GK_ROW_INDEX);
-      rr.parent = fr[top - 1].row;
-      rr.obj = i;
-#ifdef __CUDA_ARCH__
-      *reinterpret_cast<uint4*>(&out.row_rec[g.scope][g.row]) = *reinterpret_cast<const uint4*>(&rr);
-#else
-      out.row_rec[g.scope][g.row] = rr;
-#endif
-    }
-    const GkXScope& sc = xp.scopes[g.scope];
-    for (uint32_t k = lane; k < sc.ncols; k += nlanes) gk_emit_col<MODE>(xp, in, out, c, xp.col_order[sc.first_col + k], g.row, bcur);
-    g.next_child = sc.first_child;   // (none for a leaf scope: the next turn advances this frame again)
-  }
-  if (!WRITE) {
-    // row / header counters by lane 0; a byte column's counter by the lane that owns the column
-    if (lane == 0) {
-      for (uint32_t k = 0; k < NS; ++k) in.counts[(size_t)k * n + i] = cur[k];
-      for (uint32_t k = K_NAME; k < NK; ++k) in.counts[(size_t)k * n + i] = cur[k];
-    }
-    for (uint32_t sc2 = 0; sc2 < NS; ++sc2) {
-      const GkXScope& xs = xp.scopes[sc2];
-      for (uint32_t k = lane; k < xs.ncols; k += nlanes) {
-        const GkXCol& col = xp.cols[xp.col_order[xs.first_col + k]];
-        if (col.enc & GK_ENC_BYTES) in.counts[(size_t)(NS + col.bytes_slot) * n + i] = bcur[col.bytes_slot];
-      }
-    }
-  } else if (i + 1u == n) {
-    // closing entries of the CSR arrays
-    if (lane == 0)
-      for (uint32_t s = 1; s < NS; ++s) out.scope_off[s][xp.scopes[s].parent ? cur[xp.scopes[s].parent] : n] = cur[s];
-    for (uint32_t sc2 = 0; sc2 < NS; ++sc2) {
-      const GkXScope& xs = xp.scopes[sc2];
-      for (uint32_t k = lane; k < xs.ncols; k += nlanes) {
-        const uint32_t ci = xp.col_order[xs.first_col + k];
-        if (xp.cols[ci].enc & GK_ENC_BYTES) out.boff[ci][sc2 ? cur[sc2] : n] = bcur[xp.cols[ci].bytes_slot];
-      }
-    }
+  if (MODE == GK_PASS_COUNT && lane == 0) {
+    // header counters (scanned next) + the flags word: the scope passes read the skip bit before the arena exists
+    for (uint32_t k = 0; k < NK; ++k) in.counts[(size_t)k * n + i] = cur[k];
+    out.flags[i] = fl;
   }
 }
 
 
-// The per-row column pass: every column of scope `sc` that is not byte-encoded, for row `r` (scope 0: r = the object).  Threads
-// of a warp work on different rows of the SAME scope, so they run the same column / the same path at the same time.
-GK_HD void gk_ingest_row(const GkXProg& xp, const GkIngestIn& in, const GkIngestOut& out, uint32_t sc, uint32_t r, uint32_t lane, uint32_t nlanes) {
+// ---------------------------------------------------------------------------------------------- level-synchronous passes
+// Scopes are filled level by level: for scope t, one thread per row of its PARENT scope counts the members of the generator
+// collection (gk_scope_count), a device scan of the counts is the CSR offset array, and a second pass writes one 16-byte row
+// handle per member (gk_scope_fill).  Threads of a warp then always work on the same scope, the same generator path and the
+// same columns -- unlike a per-object walk of the whole scope tree, where every thread is somewhere else.
+
+// evaluation context of row r of scope sc (scope 0: r is the object); returns the object index
+GK_HD uint32_t gk_row_ctx(const GkXProg& xp, const GkIngestIn& in, const GkIngestOut& out, uint32_t sc, uint32_t r, GkXCtx& c) {
   GkRowRec me;
   me.elem = me.key = me.parent = 0;
   me.obj = r;
   if (sc) me = out.row_rec[sc][r];
   const uint32_t i = me.obj;
-  GkXCtx c;
   c.xp = &xp;
   c.in = &in;
   c.blob_off = in.ooff[i];
@@ -1591,6 +1453,125 @@ GK_HD void gk_ingest_row(const GkXProg& xp, const GkIngestIn& in, const GkIngest
   c.grp = c.ver = nullptr;
   c.grp_len = c.ver_len = 0;
   c.scope_at[0] = 0;
+  int d = 0;
+  for (uint32_t s2 = sc; s2; s2 = (uint32_t)xp.scopes[s2].parent) ++d;
+  c.depth = d;
+  uint32_t cs = sc;
+  GkRowRec rr = me;
+  for (int dd = d; dd >= 1; --dd) {
+    c.scope_at[dd] = cs;
+    c.elem[dd] = gk_xnode(c.doc.tape, rr.elem);
+    const uint32_t k = rr.key;
+    if (k & GK_ROW_INDEX) {
+      c.key[dd] = gk_xsyn(GK_VT_NUM);
+      c.key[dd].inum = (long long)(k & ~GK_ROW_INDEX);
+    } else {
+      c.key[dd] = gk_xnode(c.doc.tape, k);
+    }
+    cs = (uint32_t)xp.scopes[cs].parent;
+    if (cs) rr = out.row_rec[cs][rr.parent];
+  }
+  return i;
+}
+
+// rows of scope t under row r of its parent scope; *coll = tape index of the generator collection (GK_NONE: no rows)
+GK_HD uint32_t gk_scope_count(const GkXProg& xp, const GkIngestIn& in, const GkIngestOut& out, uint32_t t, uint32_t r, uint32_t* coll_out) {
+  *coll_out = GK_NONE;
+  const uint32_t p = (uint32_t)xp.scopes[t].parent;
+  GkXCtx c;
+  const uint32_t i = gk_row_ctx(xp, in, out, p, r, c);
+  if ((out.flags[i] & GK_F_SKIP) || c.depth >= GK_MAX_LOOP_DEPTH) return 0u;
+  const GkXVal coll = gk_x_eval(c, xp.scopes[t].gen);
+  if (coll.node == GK_NONE || (coll.vt != GK_VT_ARR && coll.vt != GK_VT_OBJ)) return 0u;
+  *coll_out = coll.node;
+  const gk_u64 e = c.doc.tape[coll.node];
+  if (coll.vt == GK_VT_ARR) return gk_te_count(e);
+  // object members: a key repeated later in the same object is shadowed by the later one
+  const uint32_t end = gk_te_end(e);
+  uint32_t cnt = 0;
+  for (uint32_t k = coll.node + 1u; k < end; k = gk_tape_skip(c.doc.tape, k + 1u))
+    if (!gk_key_shadowed(c.doc, k, end)) ++cnt;
+  return cnt;
+}
+
+// the row handles of scope t under parent row r, from row `first` on (rows of a scope are in (parent row, member) order)
+GK_HD void gk_scope_fill(const GkXProg& xp, const GkIngestIn& in, const GkIngestOut& out, uint32_t t, uint32_t r, uint32_t coll, uint32_t first) {
+  if (coll == GK_NONE) return;
+  const uint32_t p = (uint32_t)xp.scopes[t].parent;
+  uint32_t i = r;
+  if (p) i = out.row_rec[p][r].obj;
+  const gk_u64* tape = in.tape + gk_tape_off(in.ooff, i);
+  const gk_u64 e = tape[coll];
+  const uint32_t end = gk_te_end(e);
+  GkRowRec rr;
+  rr.parent = r;
+  rr.obj = i;
+  uint32_t row = first;
+  if (gk_te_type(e) == GK_T_ARR) {
+    uint32_t ix = 0;
+    for (uint32_t k = coll + 1u; k < end; k = gk_tape_skip(tape, k)) {
+      rr.elem = k;
+      rr.key = ix++ | GK_ROW_INDEX;
+#ifdef __CUDA_ARCH__
+      *reinterpret_cast<uint4*>(&out.row_rec[t][row]) = *reinterpret_cast<const uint4*>(&rr);
+#else
+      out.row_rec[t][row] = rr;
+#endif
+      ++row;
+    }
+  } else {
+    GkDoc d;
+    d.js = in.blob + in.ooff[i];
+    d.tape = tape;
+    d.ntape = in.ntape[i];
+    for (uint32_t k = coll + 1u; k < end; k = gk_tape_skip(tape, k + 1u)) {
+      if (gk_key_shadowed(d, k, end)) continue;
+      rr.elem = k + 1u;
+      rr.key = k;
+#ifdef __CUDA_ARCH__
+      *reinterpret_cast<uint4*>(&out.row_rec[t][row]) = *reinterpret_cast<const uint4*>(&rr);
+#else
+      out.row_rec[t][row] = rr;
+#endif
+      ++row;
+    }
+  }
+}
+
+// decoded byte length of byte-encoded column ci at row r of its scope
+GK_HD uint32_t gk_bcol_len(const GkXProg& xp, const GkIngestIn& in, const GkIngestOut& out, uint32_t ci, uint32_t r) {
+  const GkXCol& col = xp.cols[ci];
+  const GkXClosure& cl = xp.cl[col.closure];
+  if (cl.kind == GK_X_LUT || cl.kind == GK_X_COUNT) return 0u;   // (never strings with bytes: values of a lookup / a count)
+  GkXCtx c;
+  const uint32_t i = gk_row_ctx(xp, in, out, (uint32_t)col.scope, r, c);
+  if (out.flags[i] & GK_F_SKIP) return 0u;
+  const GkXVal v = gk_x_eval(c, col.closure);
+  return v.vt == GK_VT_STR ? gk_decoded_len(c, v) : 0u;
+}
+
+// every encoding of byte-encoded column ci at row r (the offsets array is in place: scanned lengths)
+GK_HD void gk_bcol_write(const GkXProg& xp, const GkIngestIn& in, const GkIngestOut& out, uint32_t ci, uint32_t r) {
+  const GkXCol& col = xp.cols[ci];
+  GkXCtx c;
+  const uint32_t i = gk_row_ctx(xp, in, out, (uint32_t)col.scope, r, c);
+  if (out.flags[i] & GK_F_SKIP) {   // placeholder row (scope 0 only: a skipped object has no other rows)
+    const uint32_t enc = col.enc;
+    if (enc & GK_ENC_VT) out.vt[ci][r] = GK_VT_UNDEF;
+    if (enc & GK_ENC_SID) out.sid[ci][r] = GK_SID_UNDEF;
+    if (enc & GK_ENC_NUM) out.num[ci][r] = 0;
+    if (enc & GK_ENC_HEAD)
+      for (int w = 0; w < GK_HEAD_WORDS; ++w) out.head[ci][(size_t)r * GK_HEAD_WORDS + w] = 0;
+    return;
+  }
+  const GkCur none{nullptr, 0};
+  gk_emit_col<GK_PASS_BCOLS>(xp, in, out, c, ci, r, none);
+}
+
+// The per-row column pass: every column of scope `sc` that is not byte-encoded, for row `r` (scope 0: r = the object).
+GK_HD void gk_ingest_row(const GkXProg& xp, const GkIngestIn& in, const GkIngestOut& out, uint32_t sc, uint32_t r, uint32_t lane, uint32_t nlanes) {
+  GkXCtx c;
+  const uint32_t i = gk_row_ctx(xp, in, out, sc, r, c);
   const GkXScope& xs = xp.scopes[sc];
   if (sc == 0 && (out.flags[i] & GK_F_SKIP)) {   // placeholder row: every encoding "undefined"
     for (uint32_t k = lane; k < xs.ncols; k += nlanes) {
@@ -1604,26 +1585,6 @@ GK_HD void gk_ingest_row(const GkXProg& xp, const GkIngestIn& in, const GkIngest
         for (int w = 0; w < GK_HEAD_WORDS; ++w) out.head[ci][(size_t)i * GK_HEAD_WORDS + w] = 0;
     }
     return;
-  }
-  int d = 0;
-  for (uint32_t s2 = sc; s2; s2 = (uint32_t)xp.scopes[s2].parent) ++d;
-  c.depth = d;
-  {
-    uint32_t cs = sc;
-    GkRowRec rr = me;
-    for (int dd = d; dd >= 1; --dd) {
-      c.scope_at[dd] = cs;
-      c.elem[dd] = gk_xnode(c.doc.tape, rr.elem);
-      const uint32_t k = rr.key;
-      if (k & GK_ROW_INDEX) {
-        c.key[dd] = gk_xsyn(GK_VT_NUM);
-        c.key[dd].inum = (long long)(k & ~GK_ROW_INDEX);
-      } else {
-        c.key[dd] = gk_xnode(c.doc.tape, k);
-      }
-      cs = (uint32_t)xp.scopes[cs].parent;
-      if (cs) rr = out.row_rec[cs][rr.parent];
-    }
   }
   const GkCur none{nullptr, 0};
   for (uint32_t k = lane; k < xs.ncols; k += nlanes) gk_emit_col<GK_PASS_COLS>(xp, in, out, c, xp.col_order[xs.first_col + k], r, none);

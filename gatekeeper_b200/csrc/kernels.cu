@@ -573,14 +573,9 @@ class CudaBackend : public Backend {
     xp.excl_off = excl_off;
     xp.excl_n = excl_n;
     // ---- front buffer (blob, offsets, tape): the prefetched copy of this page, or copy + tokenise now
-    uint32_t lanes = 1;
-    if (const char* ev = getenv("GK_INGEST_LANES")) lanes = std::max(1, std::min(32, atoi(ev)));
-    while (lanes & (lanes - 1)) --lanes;
     uint32_t clanes = 1;
     if (const char* ev = getenv("GK_INGEST_COL_LANES")) clanes = std::max(1, std::min(32, atoi(ev)));
     while (clanes & (clanes - 1)) --clanes;
-    const uint32_t wblocks = (uint32_t)(((uint64_t)n * lanes + kIngestThreads - 1) / kIngestThreads);
-    if (NK > kMaxCounters) throw BackendError{"device ingest: too many byte-encoded columns"};
     cudaEvent_t e0, e1, e2, e3;
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
@@ -596,36 +591,123 @@ class CudaBackend : public Backend {
       if (!fr) fr = &start_front(rq.blob, rq.ooff, rq.n);
       fr->pending = false;
     }
+    (void)was_prefetched;
     CK(cudaStreamWaitEvent(stream_, fr->done, 0));
-    // ---- back scratch: counters, totals, miss list
+    // ---- back scratch: header counters + scratch flags, totals, scan block sums, miss list, the pointer tables of the count phase
     const uint32_t miss_cap = 1u << 17;
+    const uint32_t NT = GK_CNT_EXTRA + NS + xh.nbytecols + 4;          // totals: header counters, scopes, byte columns
     Carver sc;
-    const size_t o_counts = sc.take((size_t)NK * n * 4), o_totals = sc.take((size_t)(NK + NS + 4) * 4), o_miss = sc.take((size_t)miss_cap * sizeof(GkMiss)),
-                 o_fill = sc.take((size_t)miss_cap * 8);
+    const size_t o_counts = sc.take((size_t)GK_CNT_EXTRA * n * 4 + 16), o_flags = sc.take((size_t)n * 4 + 16), o_totals = sc.take((size_t)(NT + NS + 4) * 4),
+                 o_sums = sc.take((size_t)NT * 4096 * 4), o_miss = sc.take((size_t)miss_cap * sizeof(GkMiss)), o_fill = sc.take((size_t)miss_cap * 8),
+                 o_prec = sc.take((size_t)NS * 8);
     uint8_t* d_s = scratch_.need(gk_align(sc.off));
     GkIngestIn in = fr->in;
     in.source = rq.source;
     in.counts = reinterpret_cast<uint32_t*>(d_s + o_counts);
     in.misses = reinterpret_cast<GkMiss*>(d_s + o_miss);
-    uint32_t* d_totals = reinterpret_cast<uint32_t*>(d_s + o_totals);
-    uint32_t* d_cap = d_totals + NK;
+    uint32_t* d_totals = reinterpret_cast<uint32_t*>(d_s + o_totals);   // [0,4) header, [4, 4+NS) scopes, then byte columns
+    uint32_t* d_cap = d_totals + NT;
     in.nmiss = d_cap + NS;
     in.miss_cap = miss_cap;
     uint32_t* d_fill = reinterpret_cast<uint32_t*>(d_s + o_fill);
+    uint32_t* d_sums = reinterpret_cast<uint32_t*>(d_s + o_sums);
+    // exclusive scan of a[0..len) in place (+ a[len] = total when `tail`), total also at d_totals[slot]
+    auto scan = [&](uint32_t* a, uint32_t len, uint32_t slot, bool tail) {
+      const uint32_t nb = (len + kScanBlock - 1) / kScanBlock;
+      if (nb > 4096) throw BackendError{"device ingest: more than 16M rows in one scope of one batch"};
+      uint32_t* sums = d_sums + (size_t)slot * 4096;
+      if (nb) gk_scan_sums_kernel<<<nb, kScanThreads, 0, stream_>>>(a, len, sums);
+      gk_scan_top_kernel<<<1, kScanThreads, 0, stream_>>>(sums, nb, d_totals + slot);
+      if (nb) gk_scan_apply_kernel<<<nb, kScanThreads, 0, stream_>>>(a, len, sums, d_totals + slot, tail ? 1u : 0u);
+      else if (tail) CK(cudaMemsetAsync(a, 0, 4, stream_));
+      launches_ += nb ? 3 : 1;
+    };
+    auto blocks = [](uint32_t rows) { return (rows + kIngestThreads - 1) / kIngestThreads; };
+    // the count phase works on scratch: flags, CSR offsets (= scanned member counts), generator nodes, row handles, byte lengths
+    GkIngestOut outc;
+    memset(&outc, 0, sizeof outc);
+    outc.flags = reinterpret_cast<uint32_t*>(d_s + o_flags);
+    outc.row_rec = reinterpret_cast<GkRowRec* const*>(d_s + o_prec);
+    std::vector<uint64_t> h_prec(NS, 0);
+    std::vector<uint32_t*> d_cnt(NS, nullptr), d_coll(NS, nullptr), d_blen(xh.nbytecols, nullptr);
+    std::vector<void*> temps;   // stream-ordered allocations of this call
+    struct TempGuard {
+      CudaBackend* be;
+      std::vector<void*>* v;
+      ~TempGuard() {
+        for (void* p2 : *v) be->dfree(p2);
+      }
+    } temp_guard{this, &temps};
+    auto talloc = [&](size_t bytes) {
+      uint8_t* p2 = nullptr;
+      dmalloc(&p2, bytes);
+      temps.push_back(p2);
+      return p2;
+    };
     CK(cudaEventRecord(e1, stream_));
+    std::vector<uint32_t> total(NS, 0), htot(GK_CNT_EXTRA, 0), btot(xh.nbytecols, 0);
+    total[0] = n;
     if (n) {
-      gk_count_kernel<<<wblocks, kIngestThreads, 0, stream_>>>(xp, in, lanes, 0, n);
-      gk_scan_kernel<<<NK, 1024, 0, stream_>>>(in.counts, n, d_totals);
-      launches_ += 2;
-    } else {
-      CK(cudaMemsetAsync(d_totals, 0, (size_t)NK * 4, stream_));
+      gk_hcount_kernel<<<blocks(n), kIngestThreads, 0, stream_>>>(xp, in, outc);
+      ++launches_;
+      for (uint32_t k = 0; k < GK_CNT_EXTRA; ++k) scan(in.counts + (size_t)k * n, n, k, false);
+      // scopes, one depth level at a time (the rows of a level size the kernels of the next)
+      uint32_t maxd = 0;
+      std::vector<uint32_t> depth(NS, 0);
+      for (uint32_t s2 = 1; s2 < NS; ++s2) depth[s2] = depth[xh.scopes[s2].parent] + 1, maxd = std::max(maxd, depth[s2]);
+      std::vector<uint32_t> hbuf(NT, 0);
+      for (uint32_t d = 1; d <= maxd; ++d) {
+        for (uint32_t t = 1; t < NS; ++t) {
+          if (depth[t] != d) continue;
+          const uint32_t prows = total[xh.scopes[t].parent];
+          d_cnt[t] = reinterpret_cast<uint32_t*>(talloc(((size_t)prows + 1) * 4));
+          d_coll[t] = reinterpret_cast<uint32_t*>(talloc(((size_t)prows + 1) * 4));
+          if (prows) {
+            gk_scope_count_kernel<<<blocks(prows), kIngestThreads, 0, stream_>>>(xp, in, outc, t, prows, d_cnt[t], d_coll[t]);
+            ++launches_;
+          }
+          scan(d_cnt[t], prows, GK_CNT_EXTRA + t, true);
+        }
+        CK(cudaMemcpyAsync(hbuf.data(), d_totals, (size_t)NT * 4, cudaMemcpyDeviceToHost, stream_));
+        CK(cudaStreamSynchronize(stream_));
+        CK(cudaGetLastError());
+        bool any = false;
+        for (uint32_t t = 1; t < NS; ++t) {
+          if (depth[t] != d) continue;
+          total[t] = hbuf[GK_CNT_EXTRA + t];
+          h_prec[t] = reinterpret_cast<uint64_t>(talloc(((size_t)total[t] + 1) * sizeof(GkRowRec)));
+          any = true;
+        }
+        if (!any) continue;
+        CK(cudaMemcpyAsync(d_s + o_prec, h_prec.data(), (size_t)NS * 8, cudaMemcpyHostToDevice, stream_));
+        for (uint32_t t = 1; t < NS; ++t) {
+          if (depth[t] != d) continue;
+          const uint32_t prows = total[xh.scopes[t].parent];
+          if (!prows || !total[t]) continue;
+          gk_scope_fill_kernel<<<blocks(prows), kIngestThreads, 0, stream_>>>(xp, in, outc, t, prows, d_cnt[t], d_coll[t]);
+          ++launches_;
+        }
+        CK(cudaStreamSynchronize(stream_));   // (h_prec is read by the copy above; the next level appends to it)
+      }
+      // byte-encoded columns: decoded length per row -> offsets
+      for (uint32_t ci = 0; ci < NC; ++ci) {
+        const GkXCol& xc = xh.cols[ci];
+        if (!(xc.enc & GK_ENC_BYTES)) continue;
+        const uint32_t rows = total[xc.scope];
+        d_blen[xc.bytes_slot] = reinterpret_cast<uint32_t*>(talloc(((size_t)rows + 1) * 4));
+        if (rows) {
+          gk_bcol_len_kernel<<<blocks(rows), kIngestThreads, 0, stream_>>>(xp, in, outc, ci, rows, d_blen[xc.bytes_slot]);
+          ++launches_;
+        }
+        scan(d_blen[xc.bytes_slot], rows, GK_CNT_EXTRA + NS + xc.bytes_slot, true);
+      }
+      CK(cudaMemcpyAsync(hbuf.data(), d_totals, (size_t)NT * 4, cudaMemcpyDeviceToHost, stream_));
+      CK(cudaStreamSynchronize(stream_));
+      CK(cudaGetLastError());
+      for (uint32_t k = 0; k < GK_CNT_EXTRA; ++k) htot[k] = hbuf[k];
+      for (uint32_t k = 0; k < xh.nbytecols; ++k) btot[k] = hbuf[GK_CNT_EXTRA + NS + k];
     }
-    std::vector<uint32_t> total(NK + NS + 4, 0);
-    CK(cudaMemcpyAsync(total.data(), d_totals, (size_t)NK * 4, cudaMemcpyDeviceToHost, stream_));
-    CK(cudaStreamSynchronize(stream_));
-    CK(cudaGetLastError());
     // ---- destination arena (exact sizes) + the pointer tables of the write pass
-    const uint32_t K_NAME = NS + xh.nbytecols;
     Carver ac;
     GkBatch h;
     memset(&h, 0, sizeof h);
@@ -637,25 +719,25 @@ class CudaBackend : public Backend {
       return ac.take(bytes);
     };
     const size_t a_flags = arr((size_t)n * 4), a_kind = arr((size_t)n * 4), a_group = arr((size_t)n * 4), a_nsnoff = arr(((size_t)n + 1) * 4),
-                 a_nsnb = arr(total[K_NAME + 3]), a_nameoff = arr(((size_t)n + 1) * 4), a_nameb = arr(total[K_NAME]), a_genoff = arr(((size_t)n + 1) * 4),
-                 a_genb = arr(total[K_NAME + 1]), a_lbloff = arr(((size_t)n + 1) * 4), a_lblkv = arr((size_t)total[K_NAME + 2] * 8), a_nsrow = arr((size_t)n * 4),
+                 a_nsnb = arr(htot[3]), a_nameoff = arr(((size_t)n + 1) * 4), a_nameb = arr(htot[0]), a_genoff = arr(((size_t)n + 1) * 4),
+                 a_genb = arr(htot[1]), a_lbloff = arr(((size_t)n + 1) * 4), a_lblkv = arr((size_t)htot[2] * 8), a_nsrow = arr((size_t)n * 4),
                  a_nsloff = arr(ns.nsl_off.size() * 4), a_nslkv = arr(ns.nsl_kv.size() * 4);
     std::vector<size_t> a_scope(NS, 0);
-    for (uint32_t s2 = 1; s2 < NS; ++s2) a_scope[s2] = arr(((size_t)(xh.scopes[s2].parent ? total[xh.scopes[s2].parent] : n) + 1) * 4);
+    for (uint32_t s2 = 1; s2 < NS; ++s2) a_scope[s2] = arr(((size_t)total[xh.scopes[s2].parent] + 1) * 4);
     struct ColOff {
       size_t vt = 0, sid = 0, num = 0, boff = 0, bytes = 0, head = 0;
     };
     std::vector<ColOff> a_col(NC);
     for (uint32_t ci = 0; ci < NC; ++ci) {
       const GkXCol& xc = xh.cols[ci];
-      const size_t rows = xc.scope ? total[xc.scope] : n;
+      const size_t rows = total[xc.scope];
       if (xc.enc & GK_ENC_VT) a_col[ci].vt = arr(rows);
       if (xc.enc & GK_ENC_SID) a_col[ci].sid = arr(rows * 4);
       if (xc.enc & GK_ENC_NUM) a_col[ci].num = arr(rows * 8);
       if (xc.enc & GK_ENC_HEAD) a_col[ci].head = arr(rows * 32);
       if (xc.enc & GK_ENC_BYTES) {
         a_col[ci].boff = arr((rows + 1) * 4);
-        a_col[ci].bytes = arr(total[NS + xc.bytes_slot]);
+        a_col[ci].bytes = arr(btot[xc.bytes_slot]);
       }
     }
     // in-arena tables: GkColumn[], GkScope[], and the pointer arrays of GkIngestOut
@@ -742,18 +824,15 @@ class CudaBackend : public Backend {
     out.boff = reinterpret_cast<uint32_t* const*>(A + a_pboff);
     out.bytes = reinterpret_cast<uint8_t* const*>(A + a_pbytes);
     out.head = reinterpret_cast<uint32_t* const*>(A + a_phead);
-    // ---- row handles (scratch): one 16-byte record per row of every scope + the pointer table
-    {
-      Carver rc;
-      const size_t o_ptrs = rc.take((size_t)NS * 8);
-      std::vector<size_t> o_rows(NS, 0);
-      for (uint32_t s2 = 1; s2 < NS; ++s2) o_rows[s2] = rc.take(((size_t)total[s2] + 1) * sizeof(GkRowRec));
-      uint8_t* d_r = rows_.need(gk_align(rc.off));
-      std::vector<uint64_t> ptrs(NS, 0);
-      for (uint32_t s2 = 1; s2 < NS; ++s2) ptrs[s2] = reinterpret_cast<uint64_t>(d_r + o_rows[s2]);
-      CK(cudaMemcpyAsync(d_r + o_ptrs, ptrs.data(), ptrs.size() * 8, cudaMemcpyHostToDevice, stream_));
-      CK(cudaStreamSynchronize(stream_));   // (`ptrs` is a temporary)
-      out.row_rec = reinterpret_cast<GkRowRec* const*>(d_r + o_ptrs);
+    out.row_rec = outc.row_rec;   // (the row handles of the count phase)
+    if (!n) CK(cudaMemsetAsync(A, 0, db->bytes, stream_));   // (no kernel writes the closing CSR entries of an empty batch)
+    // the CSR offsets of the scopes and of the byte columns are the scanned counts of the count phase
+    for (uint32_t s2 = 1; s2 < NS; ++s2)
+      if (d_cnt[s2]) CK(cudaMemcpyAsync(A + a_scope[s2], d_cnt[s2], ((size_t)total[xh.scopes[s2].parent] + 1) * 4, cudaMemcpyDeviceToDevice, stream_));
+    for (uint32_t ci = 0; ci < NC; ++ci) {
+      const GkXCol& xc = xh.cols[ci];
+      if ((xc.enc & GK_ENC_BYTES) && d_blen[xc.bytes_slot])
+        CK(cudaMemcpyAsync(A + a_col[ci].boff, d_blen[xc.bytes_slot], ((size_t)total[xc.scope] + 1) * 4, cudaMemcpyDeviceToDevice, stream_));
     }
     // ---- write passes, repeated while lookups are missing (the host evaluates each distinct argument tuple once)
     CK(cudaEventRecord(e2, stream_));
@@ -766,13 +845,18 @@ class CudaBackend : public Backend {
       xp.lut_tab.mask = lut_.mask;
       xp.lut_vals = d_lutv_;
       CK(cudaMemsetAsync(in.nmiss, 0, 4, stream_));
-      if (round == 0 || xh.nbytecols) {   // (row handles and header do not depend on the lookups; a byte column's sid may)
-        gk_header_kernel<<<(n + kIngestThreads - 1) / kIngestThreads, kIngestThreads, 0, stream_>>>(xp, in, out);
-        gk_write_kernel<<<wblocks, kIngestThreads, 0, stream_>>>(xp, in, out, lanes);
-        launches_ += 2;
+      if (round == 0 || xh.nbytecols) {   // (the header does not depend on the lookups; a byte column's sid may)
+        gk_header_kernel<<<blocks(n), kIngestThreads, 0, stream_>>>(xp, in, out);
+        ++launches_;
+        for (uint32_t ci = 0; ci < NC; ++ci) {
+          const GkXCol& xc = xh.cols[ci];
+          if (!(xc.enc & GK_ENC_BYTES) || !total[xc.scope]) continue;
+          gk_bcol_write_kernel<<<blocks(total[xc.scope]), kIngestThreads, 0, stream_>>>(xp, in, out, ci, total[xc.scope]);
+          ++launches_;
+        }
       }
       for (uint32_t s2 = 0; s2 < NS; ++s2) {
-        const uint32_t rows = s2 ? total[s2] : n;
+        const uint32_t rows = total[s2];
         if (!rows || !xh.scopes[s2].ncols) continue;
         gk_cols_kernel<<<(uint32_t)(((uint64_t)rows * clanes + kIngestThreads - 1) / kIngestThreads), kIngestThreads, 0, stream_>>>(xp, in, out, s2, rows, clanes);
         ++launches_;
@@ -835,7 +919,7 @@ class CudaBackend : public Backend {
     db->ntiles = ntiles;
     dmalloc(&db->d_tile_lo, ((size_t)(ntiles + 1) * NS) * 4 + 64);
     CK(cudaMemsetAsync(d_cap, 0, (size_t)NS * 4, stream_));
-    gk_tiles_kernel<<<(ntiles + 1 + 127) / 128, 128, 0, stream_>>>(in.counts, d_totals, n, NS, tile, ntiles, db->d_tile_lo, d_cap);
+    gk_tiles_kernel<<<(ntiles + 1 + 127) / 128, 128, 0, stream_>>>(xp, out, n, NS, tile, ntiles, db->d_tile_lo, d_cap);
     ++launches_;
     std::vector<uint32_t> cap(NS, 0);
     CK(cudaMemcpyAsync(cap.data(), d_cap, (size_t)NS * 4, cudaMemcpyDeviceToHost, stream_));

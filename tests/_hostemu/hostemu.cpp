@@ -113,31 +113,64 @@ class HostEmuBackend : public Backend {
     in.miss_cap = (uint32_t)misses.size();
     for (uint32_t i = 0; i < n; ++i) gk_tape_obj(in, i);
     if (status) status->assign(stat.begin(), stat.begin() + n);
-    // ---- count + scan
-    std::vector<uint32_t> cur(NK);
-    GkIngestOut none{};
+    // ---- header counts + scan, then the scopes level by level (the same per-row steps the CUDA kernels run, in plain loops)
+    std::vector<uint32_t> cur(GK_CNT_EXTRA);
+    counts.assign((size_t)GK_CNT_EXTRA * std::max(n, 1u), 0);
+    in.counts = counts.data();
+    std::vector<uint32_t> flags_tmp(std::max(n, 1u), 0);
+    GkIngestOut outc{};
+    outc.flags = flags_tmp.data();
     xp.lut_tab = lut_.view();
     xp.lut_vals = lut_vals_.data();
-    for (uint32_t i = 0; i < n; ++i) gk_ingest_obj<GK_PASS_COUNT>(xp, in, none, i, GkCur{cur.data(), 1}, 0, 1);
-    std::vector<uint32_t> total(NK, 0);
-    for (uint32_t k = 0; k < NK; ++k) {
+    for (uint32_t i = 0; i < n; ++i) gk_ingest_obj<GK_PASS_COUNT>(xp, in, outc, i, GkCur{cur.data(), 1}, 0, 1);
+    auto scan = [](uint32_t* a2, size_t len) {   // exclusive, in place; returns the total
       uint32_t acc = 0;
-      for (uint32_t i = 0; i < n; ++i) {
-        const uint32_t v = counts[(size_t)k * n + i];
-        counts[(size_t)k * n + i] = acc;
+      for (size_t i = 0; i < len; ++i) {
+        const uint32_t v = a2[i];
+        a2[i] = acc;
         acc += v;
       }
-      total[k] = acc;
+      return acc;
+    };
+    std::vector<uint32_t> htot(GK_CNT_EXTRA, 0);
+    for (uint32_t k = 0; k < GK_CNT_EXTRA; ++k) htot[k] = scan(counts.data() + (size_t)k * n, n);
+    std::vector<uint32_t> total(NS, 0);
+    total[0] = n;
+    std::vector<std::vector<uint32_t>> cnt(NS), coll(NS);
+    std::vector<std::vector<GkRowRec>> rh(NS);
+    std::vector<GkRowRec*> p_rh(NS, nullptr);
+    outc.row_rec = p_rh.data();
+    for (uint32_t t = 1; t < NS; ++t) {   // (scopes are numbered parents first)
+      const uint32_t prows = total[xh.scopes[t].parent];
+      cnt[t].assign((size_t)prows + 1, 0);
+      coll[t].assign((size_t)prows + 1, GK_NONE);
+      for (uint32_t r = 0; r < prows; ++r) cnt[t][r] = gk_scope_count(xp, in, outc, t, r, &coll[t][r]);
+      total[t] = scan(cnt[t].data(), prows);
+      cnt[t][prows] = total[t];
+      rh[t].assign((size_t)total[t] + 1, GkRowRec{0, 0, 0, 0});
+      p_rh[t] = rh[t].data();
+      for (uint32_t r = 0; r < prows; ++r) gk_scope_fill(xp, in, outc, t, r, coll[t][r], cnt[t][r]);
+    }
+    std::vector<std::vector<uint32_t>> blen(xh.nbytecols);
+    std::vector<uint32_t> btot(xh.nbytecols, 0);
+    for (uint32_t ci = 0; ci < NC; ++ci) {
+      const GkXCol& xc = xh.cols[ci];
+      if (!(xc.enc & GK_ENC_BYTES)) continue;
+      const uint32_t rows = total[xc.scope];
+      auto& bl = blen[xc.bytes_slot];
+      bl.assign((size_t)rows + 1, 0);
+      for (uint32_t r = 0; r < rows; ++r) bl[r] = gk_bcol_len(xp, in, outc, ci, r);
+      btot[xc.bytes_slot] = scan(bl.data(), rows);
+      bl[rows] = btot[xc.bytes_slot];
     }
     // ---- destination arrays (a HostBatch) and the write pass
     HostBatch hb;
     hb.n = n;
     hb.schema_version = rq.c->version;
-    const uint32_t K_NAME = NS + xh.nbytecols;
     hb.flags.assign(n, 0), hb.kind_sid.assign(n, 0), hb.group_sid.assign(n, 0), hb.nsrow.assign(n, GK_NONE);
     hb.name_off.assign(n + 1, 0), hb.gen_off.assign(n + 1, 0), hb.lbl_off.assign(n + 1, 0), hb.nsn_off.assign(n + 1, 0);
-    hb.name_bytes.assign(total[K_NAME], 0), hb.gen_bytes.assign(total[K_NAME + 1], 0), hb.lbl_kv.assign(2 * (size_t)total[K_NAME + 2], 0);
-    hb.nsn_bytes.assign(total[K_NAME + 3], 0);
+    hb.name_bytes.assign(htot[0], 0), hb.gen_bytes.assign(htot[1], 0), hb.lbl_kv.assign(2 * (size_t)htot[2], 0);
+    hb.nsn_bytes.assign(htot[3], 0);
     hb.nsl_off = rq.ns->nsl_off;
     hb.nsl_kv = rq.ns->nsl_kv;
     hb.scope_off.resize(NS);
@@ -145,8 +178,7 @@ class HostEmuBackend : public Backend {
     std::vector<uint32_t*> p_scope(NS, nullptr);
     for (uint32_t s2 = 1; s2 < NS; ++s2) {
       hb.scope_rows[s2] = total[s2];
-      const int par = xh.scopes[s2].parent;
-      hb.scope_off[s2].assign((size_t)(par ? total[par] : n) + 1, 0);
+      hb.scope_off[s2] = cnt[s2];   // the CSR offsets are the scanned member counts
       p_scope[s2] = hb.scope_off[s2].data();
     }
     hb.cols.resize(NC);
@@ -155,15 +187,15 @@ class HostEmuBackend : public Backend {
     std::vector<long long*> p_num(NC, nullptr);
     for (uint32_t ci = 0; ci < NC; ++ci) {
       const GkXCol& xc = xh.cols[ci];
-      const size_t rows = xc.scope ? total[xc.scope] : n;
+      const size_t rows = total[xc.scope];
       HostColumn& hc = hb.cols[ci];
       if (xc.enc & GK_ENC_VT) hc.vt.assign(rows, 0), p_vt[ci] = hc.vt.data();
       if (xc.enc & GK_ENC_SID) hc.sid.assign(rows, 0), p_sid[ci] = hc.sid.data();
       if (xc.enc & GK_ENC_NUM) hc.num.assign(rows, 0), p_num[ci] = reinterpret_cast<long long*>(hc.num.data());
       if (xc.enc & GK_ENC_HEAD) hc.head.assign(rows * GK_HEAD_WORDS, 0), p_head[ci] = hc.head.data();
       if (xc.enc & GK_ENC_BYTES) {
-        hc.boff.assign(rows + 1, 0), p_boff[ci] = hc.boff.data();
-        hc.bytes.assign((size_t)total[NS + xc.bytes_slot] + 1, 0), p_bytes[ci] = hc.bytes.data();
+        hc.boff = blen[xc.bytes_slot], p_boff[ci] = hc.boff.data();
+        hc.bytes.assign((size_t)btot[xc.bytes_slot] + 1, 0), p_bytes[ci] = hc.bytes.data();
       }
     }
     hb.name_bytes.push_back(0), hb.gen_bytes.push_back(0), hb.nsn_bytes.push_back(0), hb.lbl_kv.push_back(0);
@@ -187,12 +219,6 @@ class HostEmuBackend : public Backend {
     out.boff = p_boff.data();
     out.bytes = p_bytes.data();
     out.head = p_head.data();
-    std::vector<std::vector<GkRowRec>> rh(NS);
-    std::vector<GkRowRec*> p_rh(NS, nullptr);
-    for (uint32_t s2 = 1; s2 < NS; ++s2) {
-      rh[s2].assign((size_t)total[s2] + 1, GkRowRec{0, 0, 0, 0});
-      p_rh[s2] = rh[s2].data();
-    }
     out.row_rec = p_rh.data();
     uint64_t total_miss = 0;
     for (int round = 0; round < 64; ++round) {
@@ -200,9 +226,11 @@ class HostEmuBackend : public Backend {
       xp.lut_tab = lut_.view();
       xp.lut_vals = lut_vals_.data();
       for (uint32_t i = 0; i < n; ++i) gk_ingest_obj<GK_PASS_HEADER>(xp, in, out, i, GkCur{cur.data(), 1}, 0, 1);
-      for (uint32_t i = 0; i < n; ++i) gk_ingest_obj<GK_PASS_ROWS>(xp, in, out, i, GkCur{cur.data(), 1}, 0, 1);
+      for (uint32_t ci = 0; ci < NC; ++ci)
+        if (xh.cols[ci].enc & GK_ENC_BYTES)
+          for (uint32_t r = 0, R = total[xh.cols[ci].scope]; r < R; ++r) gk_bcol_write(xp, in, out, ci, r);
       for (uint32_t s2 = 0; s2 < NS; ++s2)
-        for (uint32_t r = 0, R = s2 ? total[s2] : n; r < R; ++r) gk_ingest_row(xp, in, out, s2, r, 0, 1);
+        for (uint32_t r = 0, R = total[s2]; r < R; ++r) gk_ingest_row(xp, in, out, s2, r, 0, 1);
       const uint32_t m = std::min<uint32_t>(nmiss[0], in.miss_cap);
       if (nmiss[0] == 0) break;
       total_miss += m;
