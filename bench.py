@@ -336,7 +336,7 @@ def run_ours(args):
     for k in range(e2e_steps):
         if k + 1 < e2e_steps:
             drv.prefetch_blob(pages[e2e_warm + k + 1])  # the next page streams in while this one is extracted and evaluated
-        resp = drv.ReviewBlob(pages[e2e_warm + k], ep, with_results=False)
+        resp = drv.ReviewBlob(pages[e2e_warm + k], ep, with_results=False, zero_copy=True)   # (bitmaps read in place, as a C / Go caller does)
         stats.append(resp.stats)
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / e2e_steps

@@ -53,6 +53,35 @@ GK_HD int gk_hexval(uint32_t c) {
   return -1;
 }
 
+// first index >= p holding '"' or '\\' (n if none): byte steps to an 8-byte boundary, then one 64-bit word a step.  The zero-byte
+// test (v - 0x01..) & ~v & 0x80.. can only flag a wrong byte ABOVE a true hit, so the lowest flag is exact.
+GK_HD uint32_t gk_scan_str(const uint8_t* js, uint32_t p, uint32_t n) {
+  while (p < n && (reinterpret_cast<size_t>(js + p) & 7u)) {
+    const uint32_t c = js[p];
+    if (c == '"' || c == '\\') return p;
+    ++p;
+  }
+  while (p + 8u <= n) {
+    const gk_u64 w = *reinterpret_cast<const gk_u64*>(js + p);
+    const gk_u64 q = w ^ 0x2222222222222222ull, b = w ^ 0x5c5c5c5c5c5c5c5cull;
+    const gk_u64 hit = (((q - 0x0101010101010101ull) & ~q) | ((b - 0x0101010101010101ull) & ~b)) & 0x8080808080808080ull;
+    if (hit) {
+#ifdef __CUDA_ARCH__
+      return p + (uint32_t)((__ffsll((long long)hit) - 1) >> 3);
+#else
+      return p + (uint32_t)(__builtin_ctzll(hit) >> 3);
+#endif
+    }
+    p += 8u;
+  }
+  while (p < n) {
+    const uint32_t c = js[p];
+    if (c == '"' || c == '\\') return p;
+    ++p;
+  }
+  return n;
+}
+
 // Tokeniser: the grammar of the host parser (csrc/val.cpp JP) -- same whitespace, same escapes, same (lenient) number syntax,
 // duplicate keys allowed -- so that the device accepts exactly the documents the host flattener accepts.
 //
@@ -106,27 +135,28 @@ GK_HD int gk_tape_build(const uint8_t* js, uint32_t n, gk_u64* tape, uint32_t ca
       const uint32_t s = ++p;
       uint32_t esc = 0;
       bool bad = false;
-      while (p < n && js[p] != '"' && !bad) {
-        if (js[p] == '\\') {
-          esc = 1;
-          ++p;
-          if (p >= n) {
-            bad = true;
-          } else {
-            const uint32_t e = js[p];
-            if (e == 'u') {
-              if (n - p < 5) bad = true;
-              else {
-                for (int i = 1; i <= 4; ++i)
-                  if (gk_hexval(js[p + i]) < 0) bad = true;
-                p += 4;
-              }
-            } else if (!(e == 'n' || e == 't' || e == 'r' || e == 'b' || e == 'f' || e == '/' || e == '\\' || e == '"')) {
-              bad = true;
-            }
+      for (;;) {
+        p = gk_scan_str(js, p, n);   // eight bytes a step: strings are most of the text
+        if (p >= n || js[p] == '"') break;
+        esc = 1;                     // a backslash
+        ++p;
+        if (p >= n) {
+          bad = true;
+          break;
+        }
+        const uint32_t e = js[p];
+        if (e == 'u') {
+          if (n - p < 5) bad = true;
+          else {
+            for (int i = 1; i <= 4; ++i)
+              if (gk_hexval(js[p + i]) < 0) bad = true;
+            p += 4;
           }
+        } else if (!(e == 'n' || e == 't' || e == 'r' || e == 'b' || e == 'f' || e == '/' || e == '\\' || e == '"')) {
+          bad = true;
         }
         ++p;
+        if (bad) break;
       }
       const uint32_t len = p - s;
       if (bad || p >= n) {

@@ -182,6 +182,7 @@ class BatchResponse:
     results: list = field(default_factory=list)
     object_errors: list = field(default_factory=list)
     stats: dict = field(default_factory=dict)
+    _owner: Any = None                 # zero-copy responses: the engine-side result the bitmaps live in
 
     def pairs(self):
         """Set of (object index, constraint key) with the violation bit set."""
@@ -366,9 +367,12 @@ class Driver:
         arr = (gk_obj * max(1, len(arr_t)))(*arr_t)
         return arr, len(arr_t), keep
 
-    def _unpack(self, res: gk_result, keys: list, with_results: bool = True) -> BatchResponse:
+    def _unpack(self, res: gk_result, keys: list, with_results: bool = True, zero_copy: bool = False) -> BatchResponse:
+        """zero_copy: the bitmaps stay in the engine's (page-locked) result buffers; the response owns the result and frees it
+        when it is collected -- what a C / Go caller does by reading gk_result in place."""
         import numpy as np
         n, w, c = res.n_objects, res.words, res.n_constraints
+        take = (lambda a: a) if zero_copy else (lambda a: a.copy())
         if res.priv:
             # the result names its own columns (the engine's constraint set may have changed since the review started)
             own = [self._lib.gk_result_constraint_key(C.byref(res), i) for i in range(c)]
@@ -378,9 +382,9 @@ class Driver:
             keys = self.constraints()
         vb = eb = None
         if res.viol_bits:
-            vb = np.ctypeslib.as_array(res.viol_bits, shape=(n * w,)).copy().reshape(n, w) if n else np.zeros((0, w), np.uint32)
+            vb = take(np.ctypeslib.as_array(res.viol_bits, shape=(n * w,))).reshape(n, w) if n else np.zeros((0, w), np.uint32)
         if res.err_bits:
-            eb = np.ctypeslib.as_array(res.err_bits, shape=(n * w,)).copy().reshape(n, w) if n else np.zeros((0, w), np.uint32)
+            eb = take(np.ctypeslib.as_array(res.err_bits, shape=(n * w,))).reshape(n, w) if n else np.zeros((0, w), np.uint32)
         out = BatchResponse(
             n_objects=n, constraints=keys, viol_bits=vb, err_bits=eb,
             totals=[int(res.totals[i]) for i in range(c)], err_totals=[int(res.err_totals[i]) for i in range(c)],
@@ -394,6 +398,8 @@ class Driver:
                                       v.enforcement_action.decode(), json.loads(v.scoped_actions_json.decode()), bool(v.autoreject)))
         if res.object_errors:
             out.object_errors = [(res.object_errors[i].decode() if res.object_errors[i] else None) for i in range(n)]
+        if zero_copy:
+            out._owner = _ResultOwner(self._lib, res)
         return out
 
     def ReviewBatch(self, reviews: Iterable, enforcement_point: str = AUDIT_EP, materialize: bool = True, process: str = "") -> BatchResponse:
@@ -488,17 +494,33 @@ class Driver:
         return ResidentBatch(self, h, blob, {"flatten_ms": stats.flatten_ms, "h2d_ms": stats.h2d_ms, "h2d_bytes": stats.h2d_bytes,
                                              "alg_bytes": stats.alg_bytes})
 
-    def ReviewBlob(self, blob, enforcement_point: str = AUDIT_EP, flags: int = 0, source: str = "Original", with_results: bool = True) -> BatchResponse:
+    def ReviewBlob(self, blob, enforcement_point: str = AUDIT_EP, flags: int = 0, source: str = "Original", with_results: bool = True,
+                   zero_copy: bool = False) -> BatchResponse:
         """End-to-end audit page: host JSON -> flatten -> H2D -> kernel -> D2H (+ optional message rendering)."""
         res = gk_result()
         err = C.c_char_p()
         keys = None
         self._check(self._lib.gk_review_blob(self._e, blob.buf, blob.offsets, len(blob), SOURCE.get(source, 4), enforcement_point.encode(),
                                              flags, C.byref(res), C.byref(err)), err)
+        if zero_copy:
+            return self._unpack(res, keys, with_results, zero_copy=True)
         try:
             return self._unpack(res, keys, with_results)
         finally:
             self._lib.gk_free_result(C.byref(res))
+
+
+class _ResultOwner:
+    """Keeps a gk_result alive for a zero-copy BatchResponse."""
+
+    def __init__(self, lib, res):
+        self._lib, self._res = lib, res
+
+    def __del__(self):
+        try:
+            self._lib.gk_free_result(C.byref(self._res))
+        except Exception:
+            pass
 
 
 class Coalescer:

@@ -1328,8 +1328,23 @@ def case_blob_json_oddities(lib):
         b'{"kind":"Pod","a":"bad \\q escape"}', b'{"kind":"Pod","a":1.2.3}', b'{"kind":"Pod","a":-}',
         b'{"kind":"Pod","apiVersion":"v1","metadata":{"name":"ok-after-errors","labels":{"team":"a"}},"spec":{"containers":[{"name":"c","image":"x:latest"}]}}',
     ]
+    # the tokeniser scans strings a 64-bit word at a time: closing quotes, escapes and unterminated strings at every byte alignment
+    sweep_ok, sweep_bad = [], []
+    for pad in range(9):
+        for ln in (0, 1, 6, 7, 8, 9, 15, 16, 17, 31):
+            for esc_at in (None, 0, ln // 2, max(ln - 1, 0)):
+                body = "x" * ln
+                if esc_at is not None and ln:
+                    body = body[:esc_at] + (chr(92) * 2 if (pad + ln) % 2 else chr(92) + chr(34)) + body[esc_at + 1:]
+                doc = '{"apiVersion":"v1","kind":"Pod","metadata":{"name":"p%s","namespace":"default","labels":{"team":"%s"}},"spec":{"containers":[{"name":"c","image":"gcr.io/%s:1"}]}}' % (
+                    "y" * pad, body, body)
+                sweep_ok.append(doc.encode())
+        sweep_bad.append(('{"apiVersion":"v1","kind":"Pod","metadata":{"name":"%s","labels":{"team":"ab' % ("y" * pad) + chr(92)).encode())               # ends inside an escape
+        sweep_bad.append(('{"apiVersion":"v1","kind":"Pod","metadata":{"name":"%s","labels":{"team":"ab' % ("y" * pad) + chr(92) + 'u12"}}}').encode())    # short \\u escape
+    docs = docs[:-1] + sweep_bad + [docs[-1]] + sweep_ok
+    n_tail = 1 + len(sweep_ok)
     first_bad = next(i for i, d in enumerate(docs) if d.startswith(b'{"apiVersion":"v1","kind":"Pod","metadata":{"name":"x"}') and not d.endswith(b"}}"))
-    bad = set(range(first_bad, len(docs) - 1))
+    bad = set(range(first_bad, len(docs) - n_tail))
     resp, want = _blob_parity(orc, drv, docs, expect_errors=bad)
     # every refusal carries the host parser's wording
     host = drv.ReviewBatch([D.Review(object=d, source="Original") for d in docs], k8s.AUDIT_EP)
