@@ -74,12 +74,92 @@ void AuditRun::merge(AuditRun& o) {
   for (auto& kv : o.by_action) by_action[kv.first] += kv.second;
   objects += o.objects;
   results += o.results;
+  rendered_pairs += o.rendered_pairs;
+  counted_pairs += o.counted_pairs;
 }
 
+namespace {
+// (namespace, name) of object o as the reference orders results (SVQueue.Less after group / version / kind): a Namespace's own
+// namespace is empty; the header's nsname is the object's metadata.namespace otherwise
+struct IdView {
+  const BatchIdentity& id;
+  void get(uint32_t o, const uint8_t*& ns, uint32_t& nsl, const uint8_t*& nm, uint32_t& nml) const {
+    const uint32_t fl = id.flags[o];
+    if ((fl & GK_F_IS_NS) || !(fl & GK_F_NSNAME)) ns = nullptr, nsl = 0;
+    else ns = id.ns_bytes.data() + id.ns_off[o], nsl = id.ns_off[o + 1] - id.ns_off[o];
+    nm = id.name_bytes.data() + id.name_off[o];
+    nml = id.name_off[o + 1] - id.name_off[o];
+  }
+  static int cmp_bytes(const uint8_t* a, uint32_t al, const uint8_t* b, uint32_t bl) {
+    const int r = memcmp(a, b, std::min(al, bl));
+    return r ? r : (al < bl ? -1 : al > bl ? 1 : 0);
+  }
+  int cmp(uint32_t a, uint32_t b) const {
+    const uint8_t *ans, *anm, *bns, *bnm;
+    uint32_t ansl, anml, bnsl, bnml;
+    get(a, ans, ansl, anm, anml);
+    get(b, bns, bnsl, bnm, bnml);
+    const int r = cmp_bytes(ans, ansl, bns, bnsl);
+    return r ? r : cmp_bytes(anm, anml, bnm, bnml);
+  }
+};
+}  // namespace
+
 void AuditRun::add_batch(Engine& eng, const Compiled& c, const std::vector<ObjIn>& objs, const uint32_t* viol, const uint32_t* err,
-                         uint32_t words, const std::vector<uint32_t>& errlist, const std::string& ep) {
+                         uint32_t words, const std::vector<uint32_t>& errlist, const std::string& ep, const BatchIdentity* id) {
   const size_t n = objs.size();
   const uint32_t C = (uint32_t)c.order.size();
+  // ---- lazy path: which pairs need the host at all
+  // cand[c] = the objects whose results can still enter constraint c's list.  Constraints that may have several results per pair
+  // are evaluated for every pair (their totals count results: pkg/audit/manager.go:886-945).
+  const bool lazy = id && id->uniform_gvk && id->flags.size() == n && std::any_of(c.single_result.begin(), c.single_result.end(), [](uint8_t x) { return x != 0; });
+  std::vector<uint32_t> thr_obj(C, 0);     // per single-result constraint: an object holding the limit-th smallest identity
+  std::vector<uint8_t> thr_all(C, 1);      // fewer than `limit` flagged objects: all are candidates
+  if (lazy && limit) {
+    const IdView iv{*id};
+    const size_t TT = std::min<size_t>((size_t)std::max(1, eng.threads()), std::max<size_t>(1, n / 4096));
+    // per thread, per constraint: max-heap of the `limit` smallest objects seen
+    std::vector<std::vector<std::vector<uint32_t>>> heaps(TT, std::vector<std::vector<uint32_t>>(C));
+    auto less = [&](uint32_t a, uint32_t b) { return iv.cmp(a, b) < 0; };
+    auto scan = [&](size_t t) {
+      auto& hp = heaps[t];
+      const size_t lo = n * t / TT, hi = n * (t + 1) / TT;
+      for (size_t o = lo; o < hi; ++o)
+        for (uint32_t w = 0; w < words; ++w) {
+          uint32_t vb = viol[o * words + w];
+          while (vb) {
+            const uint32_t k = (uint32_t)__builtin_ctz(vb);
+            vb &= vb - 1;
+            const uint32_t cix = w * 32 + k;
+            if (cix >= C || !c.single_result[cix]) continue;
+            auto& h = hp[cix];
+            if (h.size() < limit) {
+              h.push_back((uint32_t)o);
+              std::push_heap(h.begin(), h.end(), less);
+            } else if (less((uint32_t)o, h.front())) {
+              std::pop_heap(h.begin(), h.end(), less);
+              h.back() = (uint32_t)o;
+              std::push_heap(h.begin(), h.end(), less);
+            }
+          }
+        }
+    };
+    if (TT == 1) scan(0);
+    else {
+      std::vector<std::thread> th;
+      for (size_t t = 0; t < TT; ++t) th.emplace_back(scan, t);
+      for (auto& x : th) x.join();
+    }
+    for (uint32_t cix = 0; cix < C; ++cix) {
+      if (!c.single_result[cix]) continue;
+      std::vector<uint32_t> all;
+      for (size_t t = 0; t < TT; ++t) all.insert(all.end(), heaps[t][cix].begin(), heaps[t][cix].end());
+      if (all.size() < limit) continue;
+      std::nth_element(all.begin(), all.begin() + (long)(limit - 1), all.end(), less);
+      thr_obj[cix] = all[limit - 1];
+      thr_all[cix] = 0;
+    }
+  }
   std::unordered_map<uint64_t, uint32_t> err_code;
   for (size_t i = 0; i + 2 < errlist.size(); i += 3) err_code[((uint64_t)errlist[i] << 32) | errlist[i + 1]] = errlist[i + 2];
   size_t T = std::min<size_t>((size_t)std::max(1, eng.threads()), std::max<size_t>(1, n / 64));
@@ -93,6 +173,7 @@ void AuditRun::add_batch(Engine& eng, const Compiled& c, const std::vector<ObjIn
     std::vector<Engine::Flagged> flagged;
     std::vector<Violation> vio;
     Engine::MaterializeCtx mctx;
+    std::vector<uint64_t> counted(C, 0);   // pairs of single-result constraints taken from the bitmap
     try {
       for (;;) {
         size_t lo = next.fetch_add(256), hi = std::min(n, lo + 256);
@@ -108,6 +189,15 @@ void AuditRun::add_batch(Engine& eng, const Compiled& c, const std::vector<ObjIn
               uint32_t cix = w * 32 + k;
               if (cix >= C) continue;
               bool is_err = eb >> k & 1u;
+              if (lazy && !is_err && c.single_result[cix]) {
+                // one result per pair: counted here; evaluated only if the object can still enter the constraint's list
+                const bool cand = limit && (thr_all[cix] || IdView{*id}.cmp((uint32_t)o, thr_obj[cix]) <= 0);
+                if (!cand) {
+                  ++counted[cix];
+                  continue;
+                }
+              }
+              part.rendered_pairs++;
               uint32_t code = 0;
               if (is_err) {
                 auto it = err_code.find(((uint64_t)o << 32) | c.cons_match[cix]);
@@ -143,6 +233,16 @@ void AuditRun::add_batch(Engine& eng, const Compiled& c, const std::vector<ObjIn
     } catch (std::exception& e) {
       errs[t] = e.what();
     }
+    for (uint32_t cix = 0; cix < C; ++cix)
+      if (counted[cix]) {
+        const Constraint& con = *c.order[cix];
+        auto& pc = part.per_constraint[con.kind + "/" + con.name];
+        pc.queue.limit = limit;
+        pc.total += counted[cix];
+        part.by_action[con.action] += counted[cix];
+        part.results += counted[cix];
+        part.counted_pairs += counted[cix];
+      }
   };
   if (T == 1) work(0);
   else {
@@ -188,7 +288,8 @@ void AuditRun::add_object_errors(const std::vector<std::string>& errs) {
 }
 
 std::string AuditRun::report() {
-  std::string o = "{\"objects\":" + std::to_string(objects) + ",\"results\":" + std::to_string(results) + ",\"objectErrors\":{\"count\":" +
+  std::string o = "{\"objects\":" + std::to_string(objects) + ",\"results\":" + std::to_string(results) + ",\"pairsEvaluated\":" + std::to_string(rendered_pairs) +
+                  ",\"pairsCounted\":" + std::to_string(counted_pairs) + ",\"objectErrors\":{\"count\":" +
                   std::to_string(object_errors) + ",\"first\":[";
   for (size_t i = 0; i < first_object_errors.size(); ++i) {
     if (i) o += ",";

@@ -4,6 +4,7 @@
 #include <string>
 #include <vector>
 
+#include "backend.hpp"
 #include "engine.hpp"
 
 namespace gk {
@@ -44,8 +45,12 @@ struct AuditRun {
   void fold(const std::string& key, StatusViolation sv);
   void merge(AuditRun& other);
   // fold every result of a reviewed batch: viol/err are the kernel's bitmaps [n * words]
+  // `id` (the batch's namespace / name arrays, read back from the device): with it, the pairs of constraints that have one
+  // result per pair (Compiled::single_result) are COUNTED from the bitmap, and only the objects that can still enter a
+  // constraint's list -- the `limit` smallest by (namespace, name), ties included -- are evaluated for their messages.
   void add_batch(Engine& eng, const Compiled& c, const std::vector<ObjIn>& objs, const uint32_t* viol, const uint32_t* err,
-                 uint32_t words, const std::vector<uint32_t>& errlist, const std::string& ep);
+                 uint32_t words, const std::vector<uint32_t>& errlist, const std::string& ep, const BatchIdentity* id = nullptr);
+  uint64_t rendered_pairs = 0, counted_pairs = 0;   // pairs evaluated on the host / taken from the bitmap (lazy path)
   std::string report();
 };
 

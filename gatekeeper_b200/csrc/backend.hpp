@@ -71,6 +71,14 @@ struct DevOutPtrs {          // caller-owned device buffers (e.g. torch tensors)
   uint32_t npeers = 0, tot_stride = 0;
 };
 
+// What orders audit results besides the message: group / version / kind, namespace, name (pkg/audit/manager.go:161-202).  Read
+// back from the batch's header arrays; `uniform_gvk`: every object that was not skipped has the same apiVersion and kind.
+struct BatchIdentity {
+  bool uniform_gvk = false;
+  std::vector<uint32_t> flags, ns_off, name_off;
+  std::vector<uint8_t> ns_bytes, name_bytes;
+};
+
 class Backend {
  public:
   virtual ~Backend() {}
@@ -84,6 +92,7 @@ class Backend {
   // Device ingest (ingest_core.h): raw JSON blob -> resident columnar batch without a host parse.  `status` receives one
   // GK_ING_* code per object (the caller renders the error text of the rare non-OK ones with the host parser).
   virtual void* ingest(const IngestReq& rq, IngestStats* st, std::vector<uint32_t>* status) = 0;
+  virtual void identity(void* batch, BatchIdentity& out) = 0;
   // Start moving a blob to the device ahead of its ingest() (copy + tokenise on the copy / front streams, into the idle one of
   // two front buffers) and return at once: the next page of an audit sweep streams in while the current one is being extracted
   // and evaluated.  ingest() of the same (blob, n) picks the prefetched copy up; anything else is ingested from scratch.

@@ -13,6 +13,7 @@
 
 #include "../../include/gk_engine.h"
 #include "backend.hpp"
+#include <algorithm>
 #include <new>
 #include "audit.hpp"
 #include "engine.hpp"
@@ -790,7 +791,12 @@ int gk_audit_add_batch(gk_audit_t* a, gk_batch_t* b, const char* ep_c, char** er
     e->be->eval(b->dev, active, ev, true);
     std::vector<ObjIn> ins(b->n);
     for (size_t i = 0; i < ins.size(); ++i) ins[i] = b->obj_in(i);
-    a->run.add_batch(*e->eng, *c, ins, ev.viol.data(), ev.err.empty() ? nullptr : ev.err.data(), ev.words, ev.errlist, ep);
+    // the namespace / name arrays of the batch let the run count single-result pairs from the bitmap and evaluate only the
+    // objects that can still enter a constraint's list (audit.hpp)
+    BatchIdentity id;
+    const bool lazy = !getenv("GK_AUDIT_EAGER") && std::any_of(c->single_result.begin(), c->single_result.end(), [](uint8_t x) { return x != 0; });
+    if (lazy) e->be->identity(b->dev, id);
+    a->run.add_batch(*e->eng, *c, ins, ev.viol.data(), ev.err.empty() ? nullptr : ev.err.data(), ev.words, ev.errlist, ep, lazy ? &id : nullptr);
     if (b->host->obj_errors.empty()) a->run.add_object_errors(std::vector<std::string>(b->n));
     else a->run.add_object_errors(b->host->obj_errors);
   });

@@ -739,6 +739,7 @@ void Engine::compile_locked() {
   // kernel evaluates each distinct spec.match once per object
   std::vector<Constraint*> live;
   std::vector<FP> live_formula;
+  std::vector<uint8_t> live_single;
   std::map<std::string, uint32_t> match_ix;
   std::vector<uint32_t> mid_of;
   // First choice: every constraint lowered for the DEVICE INGEST path (all scopes / columns computable by the ingest kernels
@@ -749,6 +750,7 @@ void Engine::compile_locked() {
     out->pins.clear();
     live.clear();
     live_formula.clear();
+    live_single.clear();
     match_ix.clear();
     mid_of.clear();
     for (auto& cp : constraints_) {
@@ -756,7 +758,9 @@ void Engine::compile_locked() {
       out->pins.push_back(cp);
       auto tit = templates_.find(c.kind);
       if (tit == templates_.end()) continue;
-      live_formula.push_back(lower_violation(tit->second.mod, c.params, out->schema, device_mode));
+      bool single = false;
+      live_formula.push_back(lower_violation(tit->second.mod, c.params, out->schema, device_mode, &single));
+      live_single.push_back(single ? 1 : 0);
       std::string key = c.match.has ? json_str(c.match.raw) : std::string();
       auto it = match_ix.find(key);
       uint32_t mid = it == match_ix.end() ? (uint32_t)match_ix.size() : it->second;
@@ -791,6 +795,7 @@ void Engine::compile_locked() {
     out->mods.push_back(templates_.at(live[i]->kind).mod);
     all.push_back(live_formula[i]);
     out->formulas.push_back(live_formula[i]);
+    out->single_result.push_back(live_single[i]);
     out->cons_match.push_back(mid_of[i]);
   }
   out->match.resize(match_ix.size());
@@ -965,7 +970,7 @@ std::string Engine::dump() {
     o += "  col " + std::to_string(i) + " scope " + std::to_string(c->schema.cols[i].scope) + " enc " + std::to_string(c->schema.cols[i].enc) + " " +
          std::string(kXK[(int)closure_xinfo(*c->schema.cols[i].expr).k]) + ": " + c->schema.cols[i].expr->key + "\n";
   for (size_t i = 0; i < c->order.size(); ++i)
-    o += "constraint " + std::to_string(i) + " " + c->order[i]->kind + "/" + c->order[i]->name + ": " +
+    o += "constraint " + std::to_string(i) + " " + c->order[i]->kind + "/" + c->order[i]->name + (c->single_result[i] ? " [one result per pair]" : "") + ": " +
          formula_str(c->formulas[i], c->schema) + "\n";
   return o;
 }
@@ -1414,7 +1419,7 @@ struct Flattener : ChunkOut {
   size_t env_depth = 0;
   std::unordered_map<uint64_t, VP> memo;   // per object: (closure, row) -> value
 
-  void header_row(const VP& o, const VP& ns, uint8_t source, bool present) {
+  void header_row(const VP& o, const VP& ns, uint8_t source, bool present, bool second_row = false) {
     uint32_t fl = 0;
     uint32_t kind = GK_SID_UNDEF, group = GK_SID_UNDEF;
     if (present && o) {
@@ -1423,6 +1428,16 @@ struct Flattener : ChunkOut {
       split_gv(o, g, v, k);
       kind = sid_str(k);
       group = sid_str(g);
+      if (!second_row) {   // (apiVersion, kind) of the object: is the batch of one kind?  (audit result order)
+        uint64_t hh = 1469598103934665603ull;
+        for (const std::string* part : {&g, &v, &k}) {
+          for (unsigned char ch : *part) hh = (hh ^ ch) * 1099511628211ull;
+          hh = (hh ^ 0xFFu) * 1099511628211ull;
+        }
+        hh |= 1ull;
+        hb.gvk_lo = std::min(hb.gvk_lo, hh);
+        hb.gvk_hi = std::max(hb.gvk_hi, hh);
+      }
       bool is_ns = k == "Namespace" && g.empty();
       if (is_ns) fl |= GK_F_IS_NS;
       std::string objns = meta_str(o, "namespace");
@@ -1535,7 +1550,7 @@ struct Flattener : ChunkOut {
     std::swap(hb.name_off, o_name_off), std::swap(hb.gen_off, o_gen_off), std::swap(hb.lbl_off, o_lbl_off), std::swap(hb.lbl_kv, o_lbl_kv);
     std::swap(hb.name_bytes, o_name_bytes), std::swap(hb.gen_bytes, o_gen_bytes);
     bool old_distinct = old && old.get() != obj.get();
-    header_row(old, ns, in.source, old_distinct);
+    header_row(old, ns, in.source, old_distinct, true);
     std::swap(hb.flags, o_flags), std::swap(hb.kind_sid, o_kind), std::swap(hb.group_sid, o_group), std::swap(hb.nsn_off, o_nsn_off), std::swap(hb.nsn_bytes, o_nsn_bytes);
     std::swap(hb.name_off, o_name_off), std::swap(hb.gen_off, o_gen_off), std::swap(hb.lbl_off, o_lbl_off), std::swap(hb.lbl_kv, o_lbl_kv);
     std::swap(hb.name_bytes, o_name_bytes), std::swap(hb.gen_bytes, o_gen_bytes);
@@ -1849,6 +1864,7 @@ std::shared_ptr<HostBatch> Engine::flatten(const ObjIn* objs, size_t n, const Co
   tasks.push_back([&]() {
     hb.obj_errors.reserve(hb.n);
     for (auto& p : parts) append(hb.obj_errors, p->hb.obj_errors);
+    for (auto& p : parts) hb.gvk_lo = std::min(hb.gvk_lo, p->hb.gvk_lo), hb.gvk_hi = std::max(hb.gvk_hi, p->hb.gvk_hi);
   });
   for (size_t s2 = 1; s2 < nscopes; ++s2)
     tasks.push_back([&, s2]() {

@@ -56,6 +56,7 @@ struct HostBatch {
   std::vector<std::string> obj_errors;         // per object: "" or a review-level error (bad JSON, missing kind, ...)
   uint64_t alg_bytes = 0;                      // bytes of every array the kernel may read (each counted once)
   uint64_t schema_version = 0;
+  uint64_t gvk_lo = ~0ull, gvk_hi = 0;         // min / max hash of (apiVersion, kind) over the objects that were not skipped
 };
 
 struct MatchSpec {
@@ -99,6 +100,7 @@ struct Compiled {
   std::vector<const Constraint*> order;        // constraint index -> constraint (grouped by match block)
   // per constraint, owned by the snapshot (compiling never writes into a Constraint that an older snapshot may be reading):
   std::vector<FP> formulas;                              // the lowered violation predicate
+  std::vector<uint8_t> single_result;                    // 1: a violating pair has exactly one result (lower.hpp)
   struct MatchErrs { std::string lsel, nssel, src; };
   std::vector<MatchErrs> match_errs;                     // error texts behind the *_INVALID match flags
   std::vector<std::shared_ptr<const Constraint>> pins;   // keeps `order` alive while a review still uses this snapshot

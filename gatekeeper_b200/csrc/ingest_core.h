@@ -53,33 +53,33 @@ GK_HD int gk_hexval(uint32_t c) {
   return -1;
 }
 
-// first index >= p holding '"' or '\\' (n if none): byte steps to an 8-byte boundary, then one 64-bit word a step.  The zero-byte
-// test (v - 0x01..) & ~v & 0x80.. can only flag a wrong byte ABOVE a true hit, so the lowest flag is exact.
+// first index >= p holding '"' or '\\' (n if none), one aligned 64-bit word a step: the bytes of the first word that lie before p
+// are forced to 0xff (neither character).  The zero-byte test (v - 0x01..) & ~v & 0x80.. can only flag a wrong byte ABOVE a true
+// hit, so the lowest flag is exact.  The first and the last word may reach outside [p, n): every word read holds at least one byte of
+// the string, an aligned word never straddles a page, bytes before p are masked and hits at or past n are cut off.
 GK_HD uint32_t gk_scan_str(const uint8_t* js, uint32_t p, uint32_t n) {
-  while (p < n && (reinterpret_cast<size_t>(js + p) & 7u)) {
-    const uint32_t c = js[p];
-    if (c == '"' || c == '\\') return p;
-    ++p;
-  }
-  while (p + 8u <= n) {
-    const gk_u64 w = *reinterpret_cast<const gk_u64*>(js + p);
-    const gk_u64 q = w ^ 0x2222222222222222ull, b = w ^ 0x5c5c5c5c5c5c5c5cull;
-    const gk_u64 hit = (((q - 0x0101010101010101ull) & ~q) | ((b - 0x0101010101010101ull) & ~b)) & 0x8080808080808080ull;
+  if (p >= n) return n;
+  const size_t mis = reinterpret_cast<size_t>(js + p) & 7u;
+  const uint8_t* q8 = js + p - mis;              // aligned address of the first word
+  uint32_t at = p - (uint32_t)mis;               // index of q8[0] (may wrap below zero: only used added to a byte number >= mis)
+  gk_u64 fill = mis ? ((1ull << (8u * mis)) - 1ull) : 0ull;
+  for (;;) {
+    const gk_u64 w = *reinterpret_cast<const gk_u64*>(q8) | fill;
+    const gk_u64 a = w ^ 0x2222222222222222ull, b = w ^ 0x5c5c5c5c5c5c5c5cull;
+    const gk_u64 hit = (((a - 0x0101010101010101ull) & ~a) | ((b - 0x0101010101010101ull) & ~b)) & 0x8080808080808080ull;
     if (hit) {
 #ifdef __CUDA_ARCH__
-      return p + (uint32_t)((__ffsll((long long)hit) - 1) >> 3);
+      const uint32_t at_hit = at + (uint32_t)((__ffsll((long long)hit) - 1) >> 3);
 #else
-      return p + (uint32_t)(__builtin_ctzll(hit) >> 3);
+      const uint32_t at_hit = at + (uint32_t)(__builtin_ctzll(hit) >> 3);
 #endif
+      return at_hit < n ? at_hit : n;
     }
-    p += 8u;
+    at += 8u;
+    q8 += 8;
+    fill = 0;
+    if (at >= n) return n;
   }
-  while (p < n) {
-    const uint32_t c = js[p];
-    if (c == '"' || c == '\\') return p;
-    ++p;
-  }
-  return n;
 }
 
 // Tokeniser: the grammar of the host parser (csrc/val.cpp JP) -- same whitespace, same escapes, same (lenient) number syntax,
@@ -691,6 +691,9 @@ typedef struct {
   // row handles (scratch, not part of the batch): what the per-row column pass needs to find its element again -- one
   // 16-byte record per row, written with one store
   GkRowRec* const* row_rec;      // [nscopes][rows]
+  // scratch: hash of (apiVersion, kind) per object, 0 for a skipped one -- the audit asks whether a batch is of one kind
+  // (results are ordered by group, version, kind first: pkg/audit/manager.go:161-202)
+  gk_u64* gvk;                   // may be null
 } GkIngestOut;
 #define GK_ROW_INDEX 0x80000000u
 
@@ -1417,6 +1420,20 @@ GK_HD void gk_ingest_obj(const GkXProg& xp, const GkIngestIn& in, const GkIngest
     const GkXVal namev = (!skip && c.name_node != GK_NONE) ? gk_xnode(c.doc.tape, c.name_node) : gk_xundef();
     const GkXVal genv = (!skip && gen_node != GK_NONE) ? gk_xnode(c.doc.tape, gen_node) : gk_xundef();
     if (MODE == GK_PASS_HEADER && lane == 0) {
+      if (out.gvk) {
+        gk_u64 hh = 0;
+        if (!skip) {
+          hh = 0x9ae16a3b2f90404full;
+          if (c.api_node != GK_NONE && gk_te_type(c.doc.tape[c.api_node]) == GK_T_STR) {
+            const gk_u64 e = c.doc.tape[c.api_node];
+            hh = gk_hash_bytes(hh, c.doc.js + gk_te_off(e), gk_te_len(e));
+          }
+          hh = gk_hash_byte(hh, 0xFFu);
+          const gk_u64 ek = c.doc.tape[c.kind_node];
+          hh = gk_hash_fin(gk_hash_bytes(hh, c.doc.js + gk_te_off(ek), gk_te_len(ek))) | 1ull;
+        }
+        out.gvk[i] = hh;
+      }
       out.flags[i] = fl;
       out.kind_sid[i] = kind_sid;
       out.group_sid[i] = group_sid;

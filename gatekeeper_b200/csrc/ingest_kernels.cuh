@@ -148,6 +148,24 @@ __global__ void __launch_bounds__(kScanThreads) gk_scan_apply_kernel(uint32_t* a
   if (tail && blockIdx.x == 0 && threadIdx.x == 0) a[n] = *total;
 }
 
+// mm[0] = min, mm[1] = max of the non-zero entries of g (mm preset to ~0 / 0): is the batch of one (apiVersion, kind)?
+__global__ void __launch_bounds__(256) gk_gvk_minmax_kernel(const unsigned long long* g, uint32_t n, unsigned long long* mm) {
+  unsigned long long lo = ~0ull, hi = 0ull;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const unsigned long long v = g[i];
+    if (v) lo = min(lo, v), hi = max(hi, v);
+  }
+#pragma unroll
+  for (int d = 16; d; d >>= 1) {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, d));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, d));
+  }
+  if ((threadIdx.x & 31u) == 0u && hi) {
+    atomicMin(&mm[0], lo);
+    atomicMax(&mm[1], hi);
+  }
+}
+
 __global__ void gk_fill_kernel(uint32_t* vals, const uint32_t* pairs, uint32_t n) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) vals[pairs[2 * i]] = pairs[2 * i + 1];

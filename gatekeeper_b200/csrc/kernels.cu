@@ -41,6 +41,7 @@ struct DevBatch {
   GkOutEnt* d_outs = nullptr;
   uint32_t ntiles = 0, slot_words = 0, tile = 0;
   uint64_t prog_version = 0;
+  bool gvk_uniform = false;   // every object that was not skipped has the same apiVersion and kind
 };
 
 class CudaBackend : public Backend {
@@ -188,6 +189,7 @@ class CudaBackend : public Backend {
     db->ntiles = ntiles;
     db->tile = tile;
     db->prog_version = c.version;
+    db->gvk_uniform = hb.gvk_hi == 0 || hb.gvk_lo == hb.gvk_hi;
     dmalloc(&db->arena, db->bytes);
     dmalloc(&db->d_tile_lo, tile_lo.size() * 4 + 64);
     finish_batch(db, c, cap);
@@ -825,6 +827,12 @@ class CudaBackend : public Backend {
     out.bytes = reinterpret_cast<uint8_t* const*>(A + a_pbytes);
     out.head = reinterpret_cast<uint32_t* const*>(A + a_phead);
     out.row_rec = outc.row_rec;   // (the row handles of the count phase)
+    unsigned long long* d_mm = reinterpret_cast<unsigned long long*>(talloc(64));
+    {
+      const unsigned long long init[2] = {~0ull, 0ull};
+      CK(cudaMemcpyAsync(d_mm, init, 16, cudaMemcpyHostToDevice, stream_));
+      out.gvk = n ? reinterpret_cast<unsigned long long*>(talloc((size_t)n * 8)) : nullptr;
+    }
     if (!n) CK(cudaMemsetAsync(A, 0, db->bytes, stream_));   // (no kernel writes the closing CSR entries of an empty batch)
     // the CSR offsets of the scopes and of the byte columns are the scanned counts of the count phase
     for (uint32_t s2 = 1; s2 < NS; ++s2)
@@ -922,9 +930,16 @@ class CudaBackend : public Backend {
     gk_tiles_kernel<<<(ntiles + 1 + 127) / 128, 128, 0, stream_>>>(xp, out, n, NS, tile, ntiles, db->d_tile_lo, d_cap);
     ++launches_;
     std::vector<uint32_t> cap(NS, 0);
+    unsigned long long mm[2] = {~0ull, 0ull};
+    if (n) {
+      gk_gvk_minmax_kernel<<<std::min<uint32_t>(1024u, (n + 255u) / 256u), 256, 0, stream_>>>(out.gvk, n, d_mm);
+      ++launches_;
+      CK(cudaMemcpyAsync(mm, d_mm, 16, cudaMemcpyDeviceToHost, stream_));
+    }
     CK(cudaMemcpyAsync(cap.data(), d_cap, (size_t)NS * 4, cudaMemcpyDeviceToHost, stream_));
     CK(cudaStreamSynchronize(stream_));
     CK(cudaGetLastError());
+    db->gvk_uniform = mm[1] == 0 || mm[0] == mm[1];
     finish_batch(db, c, cap);
     if (st) {
       float ms = 0;
@@ -956,6 +971,30 @@ class CudaBackend : public Backend {
     guard.release();
     return db;
   }
+  void identity(void* b, BatchIdentity& out) override {
+    auto* db = static_cast<DevBatch*>(b);
+    std::lock_guard<std::mutex> l(mu_);
+    CK(cudaSetDevice(device_));
+    const uint32_t n = db->n;
+    out.uniform_gvk = db->gvk_uniform;
+    out.flags.resize(n);
+    out.ns_off.resize((size_t)n + 1);
+    out.name_off.resize((size_t)n + 1);
+    if (!n) {
+      out.ns_off[0] = out.name_off[0] = 0;
+      return;
+    }
+    CK(cudaMemcpyAsync(out.flags.data(), db->hdr.flags, (size_t)n * 4, cudaMemcpyDeviceToHost, stream_));
+    CK(cudaMemcpyAsync(out.ns_off.data(), db->hdr.nsn_off, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, stream_));
+    CK(cudaMemcpyAsync(out.name_off.data(), db->hdr.name_off, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, stream_));
+    CK(cudaStreamSynchronize(stream_));
+    out.ns_bytes.resize(out.ns_off[n]);
+    out.name_bytes.resize(out.name_off[n]);
+    if (!out.ns_bytes.empty()) CK(cudaMemcpyAsync(out.ns_bytes.data(), db->hdr.nsn_bytes, out.ns_bytes.size(), cudaMemcpyDeviceToHost, stream_));
+    if (!out.name_bytes.empty()) CK(cudaMemcpyAsync(out.name_bytes.data(), db->hdr.name_bytes, out.name_bytes.size(), cudaMemcpyDeviceToHost, stream_));
+    CK(cudaStreamSynchronize(stream_));
+  }
+
   // ---- front buffers: a page's JSON, offsets and tape.  Two of them, so that page k+1 streams in (copy stream + front stream)
   // while page k is extracted and evaluated on the main stream.
   struct Front {

@@ -334,6 +334,7 @@ struct SymVal {
   std::vector<std::pair<FP, SymVal>> items;               // Arr: (guard, element); Count: [0] = counted value
   std::vector<std::pair<VP, SymVal>> fields;              // ObjLit
   bool tainted = false;                                   // Conc: derived from input.parameters
+  bool row_dep = false;                                   // Opaque: built from a value of an iteration that was open at that point
   static SymVal conc(VP v, bool tainted = false) { SymVal s; s.k = Conc; s.v = std::move(v); s.tainted = tainted; return s; }
   static SymVal column(CP c) { SymVal s; s.k = Col; s.col = std::move(c); return s; }
   static SymVal boolean(FP f, FP d = nullptr) { SymVal s; s.k = Bool; s.f = std::move(f); s.d = std::move(d); return s; }
@@ -386,14 +387,56 @@ class Lowerer {
     auto it = m_.rules.find("violation");
     if (it == m_.rules.end()) throw RegoError{"rego_compile_error: template has no `violation` rule"};
     FP out = f_false();
+    head_paths_ = 0;
+    head_object_level_ = true;
     for (auto& r : it->second) {
       if (r.kind != Rule::PSet) throw RegoError{"rego_type_error: `violation` must be a partial set rule"};
       LEnv env;
-      FP f = lower_body(r.body, 0, env, [&](LEnv& e) { return sym_term(r.key, e, [&](const SymVal& kv) { return defined_cond(kv); }); });
+      FP f = lower_body(r.body, 0, env, [&](LEnv& e) {
+        // how many results one (constraint, object) pair can have: the head is reached along `head_paths_` lowering paths; if
+        // that is one and the head names only parameters and object-level values, the set has at most ONE element
+        ++head_paths_;
+        head_object_level_ = head_object_level_ && object_level_term(r.key, e);
+        return sym_term(r.key, e, [&](const SymVal& kv) { return defined_cond(kv); });
+      });
       out = f_or(out, f);
       check_size(out, r.line);
     }
     return out;
+  }
+  // at most one result per (constraint, object): audit totals can take the pair count (pkg/audit/manager.go:886-945 counts results)
+  bool single_result() const { return head_paths_ <= 1 && head_object_level_; }
+
+  // does the value read a column of a scope that is OPEN where the head is evaluated (a per-row value)?  Values aggregated over
+  // a closed iteration (comprehensions, count(), set differences) are one value per object.
+  bool scope_open(int scope) const { return scope != 0 && std::find(iter_stack_.begin(), iter_stack_.end(), scope) != iter_stack_.end(); }
+  bool formula_reads_open(const FP& f) const {
+    if (!f) return false;
+    if (f->k == Formula::Atom) return f->col >= 0 && scope_open(schema_.cols[f->col].scope);
+    for (auto& k : f->kids)
+      if (formula_reads_open(k)) return true;
+    return false;
+  }
+  bool object_level_val(const SymVal& s) const {
+    if (s.row_dep) return false;
+    if (s.k == SymVal::Col && scope_open(s.col->scope)) return false;
+    if (formula_reads_open(s.f) || formula_reads_open(s.d)) return false;
+    if (s.sym && !object_level_val(*s.sym)) return false;
+    for (auto& it : s.items)
+      if (formula_reads_open(it.first) || !object_level_val(it.second)) return false;
+    for (auto& f : s.fields)
+      if (!object_level_val(f.second)) return false;
+    return true;
+  }
+  bool object_level_term(const TP& t, LEnv& env) {
+    Deps d = deps(t, env, false);
+    if (d.iter) return false;   // the head itself iterates
+    std::vector<int> fv;
+    free_vars(t, fv);
+    for (int v : fv)
+      if (const SymVal* sv = env.find(v))
+        if (!object_level_val(*sv)) return false;
+    return true;
   }
 
  private:
@@ -404,6 +447,8 @@ class Lowerer {
   Eval ev_;
   int vid_cur_, vid_key_;
   int depth_ = 0;
+  int head_paths_ = 0;
+  bool head_object_level_ = true;
   std::map<std::string, Deps> rule_deps_;
   std::set<std::string> rule_deps_busy_;
   std::vector<std::shared_ptr<Term>> synth_;   // keeps synthesized terms alive
@@ -860,7 +905,10 @@ class Lowerer {
         return o;
       }
       case Formula::Not: return f_not(fill_tree(f->kids[0], fn));
-      case Formula::Exists: return f_exists(f->scope, fill_tree(f->kids[0], fn));
+      case Formula::Exists: {
+        IterGuard g(iter_stack_, f->scope);   // (the holes are filled inside the iteration: its rows are open there)
+        return f_exists(f->scope, fill_tree(f->kids[0], fn));
+      }
       default: return f;
     }
   }
@@ -1681,7 +1729,9 @@ class Lowerer {
       FP def = f_true();
       for (auto& x : a) def = f_and(def, defined_cond(x));
       if (def->k == Formula::False) return def;
-      return k(SymVal::opaque(def));
+      SymVal o = SymVal::opaque(def);
+      for (auto& x : a) o.row_dep = o.row_dep || !object_level_val(x);   // (the text depends on the rows that are open here)
+      return k(o);
     }
     if (n == "object.get" && a.size() == 3 && a[0].k == SymVal::ObjLit && is_conc(a[1])) {
       for (auto& f : a[0].fields)
@@ -1884,12 +1934,15 @@ void Lowerer::subst_print(const Term& t, const std::map<int, std::string>& sub, 
 
 }  // namespace
 
-FP lower_violation(const std::shared_ptr<const Module>& mod, const VP& parameters, Schema& schema, bool device_mode) {
+FP lower_violation(const std::shared_ptr<const Module>& mod, const VP& parameters, Schema& schema, bool device_mode, bool* single_result) {
   schema.device_only = device_mode;
   const Schema before = schema;   // (a failed attempt must not leave its scopes and columns behind)
+  if (single_result) *single_result = false;
   try {
     Lowerer lw(mod, parameters, schema);
-    return lw.run();
+    FP f = lw.run();
+    if (single_result) *single_result = lw.single_result();
+    return f;
   } catch (RegoError& e) {
     if (e.msg.find("two unrelated iteration scopes") == std::string::npos) {
       schema = before;
@@ -1900,7 +1953,9 @@ FP lower_violation(const std::shared_ptr<const Module>& mod, const VP& parameter
   try {
     Lowerer lw(mod, parameters, schema);
     lw.product_mode = true;
-    return lw.run();
+    FP f = lw.run();
+    if (single_result) *single_result = lw.single_result();
+    return f;
   } catch (RegoError&) {
     schema = before;
     throw;

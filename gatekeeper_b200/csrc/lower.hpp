@@ -123,7 +123,9 @@ struct Interner {
 // Lower one constraint's violation predicate.  Throws RegoError on unsupported constructs.
 // `device_mode`: object-only sub-terms that the ingest kernels cannot compute (helper rules, comprehensions, impure
 // functions) are inlined into the formula instead of becoming host closures; throws when that is not possible.
-FP lower_violation(const std::shared_ptr<const Module>& mod, const VP& parameters, Schema& schema, bool device_mode = false);
+// `single_result`: set when a (constraint, object) pair can have at most one result (one path to the head, a head of parameters
+// and object-level values only) -- the audit then counts the pair without evaluating it.
+FP lower_violation(const std::shared_ptr<const Module>& mod, const VP& parameters, Schema& schema, bool device_mode = false, bool* single_result = nullptr);
 bool schema_device_ingestable(const Schema& s, std::string* why = nullptr);
 
 // Netlist assembly: every constraint's formula is merged into one DAG of bit-column ops (program.h GkOp).

@@ -20,6 +20,7 @@ struct EmuBatch {
   PackedBatch pb;
   GkBatch hdr{};
   uint32_t n = 0, words = 1;
+  bool gvk_uniform = false;
   std::vector<uint32_t> scope_rows;
   std::vector<std::vector<uint32_t>> scope_off;   // host copies for range lookups
 };
@@ -46,11 +47,22 @@ class HostEmuBackend : public Backend {
     b->words = std::max<uint32_t>(1, (uint32_t)((c.cons_match.size() + 31) / 32));
     b->scope_rows = hb.scope_rows;
     b->scope_off = hb.scope_off;
+    b->gvk_uniform = hb.gvk_hi == 0 || hb.gvk_lo == hb.gvk_hi;
     if (ms) *ms = 0;
     if (bytes) *bytes = b->pb.arena.size();
     return b;
   }
   void release(void* b) override { delete static_cast<EmuBatch*>(b); }
+  void identity(void* bb, BatchIdentity& out) override {
+    auto* b = static_cast<EmuBatch*>(bb);
+    const uint32_t n = b->n;
+    out.uniform_gvk = b->gvk_uniform;
+    out.flags.assign(b->hdr.flags, b->hdr.flags + n);
+    out.ns_off.assign(b->hdr.nsn_off, b->hdr.nsn_off + n + 1);
+    out.name_off.assign(b->hdr.name_off, b->hdr.name_off + n + 1);
+    out.ns_bytes.assign(b->hdr.nsn_bytes, b->hdr.nsn_bytes + out.ns_off[n]);
+    out.name_bytes.assign(b->hdr.name_bytes, b->hdr.name_bytes + out.name_off[n]);
+  }
 
   // The device ingest path, run by CPU loops over the SAME per-object code the CUDA kernels run (ingest_core.h): tokenise,
   // count, scan, write (+ host-filled lookups), then the arrays are handed to upload() like a host-flattened batch.
@@ -220,6 +232,8 @@ class HostEmuBackend : public Backend {
     out.bytes = p_bytes.data();
     out.head = p_head.data();
     out.row_rec = p_rh.data();
+    std::vector<unsigned long long> gvk(std::max(n, 1u), 0);
+    out.gvk = gvk.data();
     uint64_t total_miss = 0;
     for (int round = 0; round < 64; ++round) {
       nmiss[0] = 0;
@@ -266,6 +280,8 @@ class HostEmuBackend : public Backend {
       st->alg_bytes = b;
     }
     if (getenv("GK_TRACE_INGEST")) fprintf(stderr, "[ingest hostemu] n=%u lookups missed (host-evaluated) %llu, table entries %u\n", n, (unsigned long long)total_miss, lut_.used);
+    for (uint32_t i = 0; i < n; ++i)
+      if (gvk[i]) hb.gvk_lo = std::min<uint64_t>(hb.gvk_lo, gvk[i]), hb.gvk_hi = std::max<uint64_t>(hb.gvk_hi, gvk[i]);
     last_ingest_ = hb;   // (tests compare these arrays with the host flattener's)
     return upload(hb, *rq.c, nullptr, nullptr);
   }

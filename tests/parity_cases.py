@@ -1622,3 +1622,74 @@ def case_referential(lib):
     got = drv.ReviewBlob(blob, k8s.AUDIT_EP, flags=D.F_MATERIALIZE)
     assert_same(oracle_results(orc, revs, k8s.AUDIT_EP), engine_results(got))
     return len(want)
+
+
+def case_audit_lazy(lib, n=3000, limit=4):
+    """f-1: constraints with one result per violating pair (the lowering proves it: one path to a head of parameters and object-level
+    values) are COUNTED from the bitmap; only the objects that can still enter a constraint's list -- the `limit` smallest by
+    (namespace, name), ties included -- are evaluated for their messages.  The report must be the oracle's byte for byte: totals,
+    per-action totals, the K-smallest lists in emission order.  Ties: objects that share namespace and name; a page of several
+    kinds falls back to evaluating every pair."""
+    from oracle import audit as OA
+    tm, cons = W.config2()
+    nss = W.synth_namespaces()
+    orc, drv, _ = make_pair(tm, cons, nss, lib_path=lib)
+    dump = drv.Dump()
+    single = {l.split()[2] for l in dump.splitlines() if l.startswith("constraint ") and "[one result per pair]" in l}
+    assert len(single) >= 8, single
+    blob = W.synth_objects(7000, n)
+    objs = [json.loads(blob.get(i)) for i in range(n)]
+    # ties on (namespace, name): copies of the smallest objects with other labels (other results, same identity)
+    order = sorted(range(n), key=lambda i: (objs[i]["metadata"].get("namespace", ""), objs[i]["metadata"]["name"]))
+    for j, i in enumerate(order[:6]):
+        twin = json.loads(json.dumps(objs[i]))
+        twin["metadata"]["labels"] = {"copy": str(j)}
+        objs.append(twin)
+    rnd = random.Random(5)
+    rnd.shuffle(objs)
+    nsmap = {x["metadata"]["name"]: x for x in nss}
+
+    def check(run, want):
+        got = run.report()
+        assert got["totalViolations"] == {"%s/%s" % k: v for k, v in want["totals"].items()}
+        assert got["totalViolationsPerEnforcementAction"] == want["by_action"]
+        for key, lst in want["violations"].items():
+            g = got["violations"]["%s/%s" % key]
+            w = [{k: v for k, v in sv.items() if not (k in ("namespace", "enforcementActions") and not v)} for sv in lst]
+            assert g == w, (key, g[:2], w[:2])
+        return got
+
+    want = OA.audit(orc, objs, namespaces=nsmap, limit=limit)
+    # (a) host-flattened pages
+    run = D.AuditRun(drv, violations_limit=limit)
+    keep = []
+    for lo in range(0, len(objs), 1000):
+        rb = drv.upload([D.Review(object=o, source="Original") for o in objs[lo:lo + 1000]])
+        keep.append(rb)
+        run.add_batch(rb, k8s.AUDIT_EP)
+    got = check(run, want)
+    assert got["pairsCounted"] > 0.5 * sum(want["totals"][k] for k in want["totals"] if "%s/%s" % k in single), got["pairsCounted"]
+    # no single-result constraint ever has two results for one pair (what the counting rests on)
+    resp = drv.ReviewBatch([D.Review(object=o, source="Original") for o in objs[:800]], k8s.AUDIT_EP)
+    seen = {}
+    for r in resp.results:
+        seen[(r.object, r.constraint)] = seen.get((r.object, r.constraint), 0) + 1
+    assert all(v == 1 for (o, c), v in seen.items() if c in single)
+    # (b) raw JSON pages through the device ingest
+    run = D.AuditRun(drv, violations_limit=limit)
+    for lo in range(0, len(objs), 1500):
+        pb = W.PyBlob([json.dumps(o).encode() for o in objs[lo:lo + 1500]])
+        rb = drv.upload_blob(pb)
+        keep.append((pb, rb))
+        run.add_batch(rb, k8s.AUDIT_EP)
+    got_b = check(run, want)
+    assert got_b["pairsCounted"] > 0      # (other page sizes: other candidates, the same report)
+    # (c) a page of several kinds: (group, version, kind) orders results first -- every pair is evaluated
+    mixed = objs[:300] + [{"apiVersion": "apps/v1", "kind": "Deployment", "metadata": {"name": "d%d" % i, "namespace": "default"}, "spec": {}} for i in range(5)]
+    want_m = OA.audit(orc, mixed, namespaces=nsmap, limit=limit)
+    run = D.AuditRun(drv, violations_limit=limit)
+    rb = drv.upload([D.Review(object=o, source="Original") for o in mixed])
+    run.add_batch(rb, k8s.AUDIT_EP)
+    got_m = check(run, want_m)
+    assert got_m["pairsCounted"] == 0
+    return got

@@ -339,3 +339,8 @@ def test_expansion_templates_through_the_batch():
 
 def test_referential_constraints_data_inventory():
     assert P.case_referential(HOSTEMU) > 40
+
+
+def test_audit_counts_single_result_pairs_and_evaluates_only_list_candidates():
+    got = P.case_audit_lazy(HOSTEMU)
+    assert got["pairsEvaluated"] < got["results"]

@@ -295,3 +295,8 @@ def test_expansion_templates_through_the_batch():
 
 def test_referential_constraints_data_inventory():
     assert P.case_referential(LIB) > 40
+
+
+def test_audit_counts_single_result_pairs_and_evaluates_only_list_candidates():
+    got = P.case_audit_lazy(LIB)
+    assert got["pairsEvaluated"] < got["results"]
