@@ -106,13 +106,16 @@ struct IdView {
 }  // namespace
 
 void AuditRun::add_batch(Engine& eng, const Compiled& c, const std::vector<ObjIn>& objs, const uint32_t* viol, const uint32_t* err,
-                         uint32_t words, const std::vector<uint32_t>& errlist, const std::string& ep, const BatchIdentity* id) {
+                         uint32_t words, const std::vector<uint32_t>& errlist, const std::string& ep, const BatchIdentity* id, const uint32_t* amb) {
   const size_t n = objs.size();
   const uint32_t C = (uint32_t)c.order.size();
   // ---- lazy path: which pairs need the host at all
   // cand[c] = the objects whose results can still enter constraint c's list.  Constraints that may have several results per pair
   // are evaluated for every pair (their totals count results: pkg/audit/manager.go:886-945).
-  const bool lazy = id && id->uniform_gvk && id->flags.size() == n && std::any_of(c.single_result.begin(), c.single_result.end(), [](uint8_t x) { return x != 0; });
+  const bool lazy = id && id->uniform_gvk && id->flags.size() == n &&
+                    (amb || std::any_of(c.single_result.begin(), c.single_result.end(), [](uint8_t x) { return x != 0; }));
+  // exactly one result for a violating pair: proven for the constraint when it was lowered, or for this pair by the ambiguity bitmap
+  auto one_result = [&](size_t o, uint32_t cix) { return c.single_result[cix] || (amb && !(amb[o * words + (cix >> 5)] >> (cix & 31u) & 1u)); };
   std::vector<uint32_t> thr_obj(C, 0);     // per single-result constraint: an object holding the limit-th smallest identity
   std::vector<uint8_t> thr_all(C, 1);      // fewer than `limit` flagged objects: all are candidates
   if (lazy && limit) {
@@ -131,7 +134,7 @@ void AuditRun::add_batch(Engine& eng, const Compiled& c, const std::vector<ObjIn
             const uint32_t k = (uint32_t)__builtin_ctz(vb);
             vb &= vb - 1;
             const uint32_t cix = w * 32 + k;
-            if (cix >= C || !c.single_result[cix]) continue;
+            if (cix >= C) continue;
             auto& h = hp[cix];
             if (h.size() < limit) {
               h.push_back((uint32_t)o);
@@ -151,7 +154,6 @@ void AuditRun::add_batch(Engine& eng, const Compiled& c, const std::vector<ObjIn
       for (auto& x : th) x.join();
     }
     for (uint32_t cix = 0; cix < C; ++cix) {
-      if (!c.single_result[cix]) continue;
       std::vector<uint32_t> all;
       for (size_t t = 0; t < TT; ++t) all.insert(all.end(), heaps[t][cix].begin(), heaps[t][cix].end());
       if (all.size() < limit) continue;
@@ -189,7 +191,7 @@ void AuditRun::add_batch(Engine& eng, const Compiled& c, const std::vector<ObjIn
               uint32_t cix = w * 32 + k;
               if (cix >= C) continue;
               bool is_err = eb >> k & 1u;
-              if (lazy && !is_err && c.single_result[cix]) {
+              if (lazy && !is_err && one_result(o, cix)) {
                 // one result per pair: counted here; evaluated only if the object can still enter the constraint's list
                 const bool cand = limit && (thr_all[cix] || IdView{*id}.cmp((uint32_t)o, thr_obj[cix]) <= 0);
                 if (!cand) {

@@ -49,7 +49,8 @@ struct AuditRun {
   // result per pair (Compiled::single_result) are COUNTED from the bitmap, and only the objects that can still enter a
   // constraint's list -- the `limit` smallest by (namespace, name), ties included -- are evaluated for their messages.
   void add_batch(Engine& eng, const Compiled& c, const std::vector<ObjIn>& objs, const uint32_t* viol, const uint32_t* err,
-                 uint32_t words, const std::vector<uint32_t>& errlist, const std::string& ep, const BatchIdentity* id = nullptr);
+                 uint32_t words, const std::vector<uint32_t>& errlist, const std::string& ep, const BatchIdentity* id = nullptr,
+                 const uint32_t* amb = nullptr);   // amb: the ambiguity netlist's bitmap (bit clear = at most one result for the pair)
   uint64_t rendered_pairs = 0, counted_pairs = 0;   // pairs evaluated on the host / taken from the bitmap (lazy path)
   std::string report();
 };

@@ -93,6 +93,10 @@ class Backend {
   // GK_ING_* code per object (the caller renders the error text of the rare non-OK ones with the host parser).
   virtual void* ingest(const IngestReq& rq, IngestStats* st, std::vector<uint32_t>* status) = 0;
   virtual void identity(void* batch, BatchIdentity& out) = 0;
+  // A second view of a resident batch for ANOTHER netlist over the same schema (Compiled::amb): shares the columns, owns its
+  // own slot-resolved netlist and output planes.  Evaluate it with eval() while the backend holds `other`; release() it before
+  // the batch it was forked from.
+  virtual void* fork_batch(void* batch, const Compiled& other) = 0;
   // Start moving a blob to the device ahead of its ingest() (copy + tokenise on the copy / front streams, into the idle one of
   // two front buffers) and return at once: the next page of an audit sweep streams in while the current one is being extracted
   // and evaluated.  ingest() of the same (blob, n) picks the prefetched copy up; anything else is ingested from scratch.

@@ -783,20 +783,35 @@ int gk_audit_add_batch(gk_audit_t* a, gk_batch_t* b, const char* ep_c, char** er
       e->eng->data_doc(&dv);
       if (dv != b->data_version) throw RegoError{"data.inventory changed since the batch was flattened (referential constraints); upload it again"};
     }
-    ProgramLease lease(e, *c);
     std::string ep = ep_c ? ep_c : "";
     std::vector<uint32_t> active;
     e->eng->active_mask(*c, ep, active);
-    EvalOut ev;
-    e->be->eval(b->dev, active, ev, true);
+    EvalOut ev, ev_amb;
+    {
+      ProgramLease lease(e, *c);
+      e->be->eval(b->dev, active, ev, true);
+    }
     std::vector<ObjIn> ins(b->n);
     for (size_t i = 0; i < ins.size(); ++i) ins[i] = b->obj_in(i);
-    // the namespace / name arrays of the batch let the run count single-result pairs from the bitmap and evaluate only the
-    // objects that can still enter a constraint's list (audit.hpp)
+    // The lazy path (audit.hpp): the namespace / name arrays of the batch and the bitmap of the ambiguity netlist let the run count
+    // the pairs that have exactly one result and evaluate only what can still enter a constraint's list.
     BatchIdentity id;
-    const bool lazy = !getenv("GK_AUDIT_EAGER") && std::any_of(c->single_result.begin(), c->single_result.end(), [](uint8_t x) { return x != 0; });
+    const bool lazy = !getenv("GK_AUDIT_EAGER") && (c->amb || std::any_of(c->single_result.begin(), c->single_result.end(), [](uint8_t x) { return x != 0; }));
     if (lazy) e->be->identity(b->dev, id);
-    a->run.add_batch(*e->eng, *c, ins, ev.viol.data(), ev.err.empty() ? nullptr : ev.err.data(), ev.words, ev.errlist, ep, lazy ? &id : nullptr);
+    const bool use_amb = lazy && id.uniform_gvk && c->amb && !getenv("GK_AUDIT_NO_AMB");
+    if (use_amb) {
+      ProgramLease lease(e, *c->amb);   // (the backend holds one netlist at a time: waits until no review uses the other)
+      void* fork = e->be->fork_batch(b->dev, *c->amb);
+      try {
+        e->be->eval(fork, active, ev_amb, true);
+      } catch (...) {
+        e->be->release(fork);
+        throw;
+      }
+      e->be->release(fork);
+    }
+    a->run.add_batch(*e->eng, *c, ins, ev.viol.data(), ev.err.empty() ? nullptr : ev.err.data(), ev.words, ev.errlist, ep, lazy ? &id : nullptr,
+                     use_amb ? ev_amb.viol.data() : nullptr);
     if (b->host->obj_errors.empty()) a->run.add_object_errors(std::vector<std::string>(b->n));
     else a->run.add_object_errors(b->host->obj_errors);
   });

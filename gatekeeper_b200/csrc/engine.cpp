@@ -740,6 +740,7 @@ void Engine::compile_locked() {
   std::vector<Constraint*> live;
   std::vector<FP> live_formula;
   std::vector<uint8_t> live_single;
+  std::vector<FP> live_amb;
   std::map<std::string, uint32_t> match_ix;
   std::vector<uint32_t> mid_of;
   // First choice: every constraint lowered for the DEVICE INGEST path (all scopes / columns computable by the ingest kernels
@@ -751,6 +752,7 @@ void Engine::compile_locked() {
     live.clear();
     live_formula.clear();
     live_single.clear();
+    live_amb.clear();
     match_ix.clear();
     mid_of.clear();
     for (auto& cp : constraints_) {
@@ -759,8 +761,10 @@ void Engine::compile_locked() {
       auto tit = templates_.find(c.kind);
       if (tit == templates_.end()) continue;
       bool single = false;
-      live_formula.push_back(lower_violation(tit->second.mod, c.params, out->schema, device_mode, &single));
+      FP amb;
+      live_formula.push_back(lower_violation(tit->second.mod, c.params, out->schema, device_mode, &single, &amb));
       live_single.push_back(single ? 1 : 0);
+      live_amb.push_back(amb);
       std::string key = c.match.has ? json_str(c.match.raw) : std::string();
       auto it = match_ix.find(key);
       uint32_t mid = it == match_ix.end() ? (uint32_t)match_ix.size() : it->second;
@@ -789,8 +793,9 @@ void Engine::compile_locked() {
   std::vector<size_t> perm(live.size());
   for (size_t i = 0; i < perm.size(); ++i) perm[i] = i;
   std::stable_sort(perm.begin(), perm.end(), [&](size_t a, size_t b) { return mid_of[a] < mid_of[b]; });
-  std::vector<FP> all;
+  std::vector<FP> all, all_amb;
   for (size_t i : perm) {
+    all_amb.push_back(live_amb[i]);
     out->order.push_back(live[i]);
     out->mods.push_back(templates_.at(live[i]->kind).mod);
     all.push_back(live_formula[i]);
@@ -907,6 +912,13 @@ void Engine::compile_locked() {
     out->match_errs.push_back(Compiled::MatchErrs{ms.lsel_err, ms.nssel_err, ms.src_err});
   }
   if (out->match.empty()) out->match.push_back(GkMatch{});
+  // the audit's ambiguity netlist (same schema, same match blocks): output c is false only where constraint c has at most one
+  // result for the object -- built from the pool / constant bytes as they stand before the decision netlist is appended
+  NetBuilder pb2;
+  pb2.interner = &strings_;
+  pb2.schema = &out->schema;
+  pb2.pool = pb.pool;
+  pb2.cbytes = pb.cbytes;
   pb.build(all, out->cons_match, (uint32_t)match_ix.size());
   out->ops = std::move(pb.ops);
   out->items = std::move(pb.items);
@@ -922,6 +934,29 @@ void Engine::compile_locked() {
   out->n_atoms = pb.n_atoms;
   out->n_gates = pb.n_gates;
   out->n_phases = pb.n_phases;
+  if (std::any_of(out->single_result.begin(), out->single_result.end(), [](uint8_t x) { return x == 0; })) {
+    try {
+      for (auto& f : all_amb) check_netlist_shape(f, out->schema);
+      pb2.build(all_amb, out->cons_match, (uint32_t)match_ix.size());
+      auto amb = std::make_shared<Compiled>(*out);
+      amb->version = ++version_;
+      amb->formulas = all_amb;
+      amb->ops = std::move(pb2.ops);
+      amb->items = std::move(pb2.items);
+      amb->phase_off = std::move(pb2.phase_off);
+      amb->outs = std::move(pb2.outs);
+      amb->slot_level = std::move(pb2.slot_level);
+      amb->pool = std::move(pb2.pool);
+      amb->cbytes = std::move(pb2.cbytes);
+      if (amb->pool.empty()) amb->pool.push_back(0);
+      if (amb->cbytes.empty()) amb->cbytes.push_back(0);
+      if (amb->slot_level.empty()) amb->slot_level.push_back(0);
+      amb->n_nodes = pb2.n_nodes, amb->n_atoms = pb2.n_atoms, amb->n_gates = pb2.n_gates, amb->n_phases = pb2.n_phases;
+      out->amb = amb;
+    } catch (RegoError&) {
+      out->amb = nullptr;   // (a shape the netlist cannot hold: the audit evaluates every pair of the multi-result constraints)
+    }
+  }
   compiled_ = out;
   dirty_ = false;
 }
@@ -950,11 +985,11 @@ std::string Engine::dump() {
     std::map<uint32_t, int> atoms_per_col;
     for (auto& op : c->ops) {
       uint32_t kind = op.w0 & 0xff, level = (op.w0 >> 8) & 0xff;
-      const char* nm = kind == GK_N_ATOM ? "atom" : kind == GK_N_GATE ? "gate" : kind == GK_N_BCAST ? "bcast" : kind == GK_N_ACC ? "acc"
+      const char* nm = kind == GK_N_ATOM ? "atom" : kind == GK_N_GATE ? "gate" : kind == GK_N_BCAST ? "bcast" : kind == GK_N_ACC ? "acc" : kind == GK_N_ACC2 ? "acc2"
                        : kind == GK_N_MATCH ? "match" : kind == GK_N_CONST ? "const" : kind == GK_N_ATOMS ? "atoms" : kind == GK_N_END ? "end" : "?";
       auto& m = mix[std::string(nm) + "@s" + std::to_string(level)];
       m.first++;
-      m.second += (kind == GK_N_GATE || kind == GK_N_BCAST || kind == GK_N_ACC || kind == GK_N_ATOMS) ? (int)op.w3 : 1;
+      m.second += (kind == GK_N_GATE || kind == GK_N_BCAST || kind == GK_N_ACC || kind == GK_N_ACC2 || kind == GK_N_ATOMS) ? (int)op.w3 : 1;
       if (kind == GK_N_ATOM) atoms_per_col[op.w1 >> 8]++;
       if (kind == GK_N_ATOMS) atoms_per_col[op.w1 >> 8] += (int)op.w3;
     }

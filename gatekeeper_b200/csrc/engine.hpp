@@ -101,6 +101,8 @@ struct Compiled {
   // per constraint, owned by the snapshot (compiling never writes into a Constraint that an older snapshot may be reading):
   std::vector<FP> formulas;                              // the lowered violation predicate
   std::vector<uint8_t> single_result;                    // 1: a violating pair has exactly one result (lower.hpp)
+  std::shared_ptr<const Compiled> amb;                   // the ambiguity netlist of the same constraints over the same schema (audit):
+                                                         // bit c clear = at most one result for that pair (null: not available)
   struct MatchErrs { std::string lsel, nssel, src; };
   std::vector<MatchErrs> match_errs;                     // error texts behind the *_INVALID match flags
   std::vector<std::shared_ptr<const Constraint>> pins;   // keeps `order` alive while a review still uses this snapshot

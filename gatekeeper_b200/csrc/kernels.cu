@@ -42,6 +42,8 @@ struct DevBatch {
   uint32_t ntiles = 0, slot_words = 0, tile = 0;
   uint64_t prog_version = 0;
   bool gvk_uniform = false;   // every object that was not skipped has the same apiVersion and kind
+  std::vector<uint32_t> cap;  // rows of the largest tile per scope (sizes the slot area of any netlist over this batch)
+  bool fork = false;          // a view made by fork_batch: arena and tiling belong to the batch it was forked from
 };
 
 class CudaBackend : public Backend {
@@ -227,6 +229,7 @@ class CudaBackend : public Backend {
   // slot area of a tile from the per-scope tile capacities; the netlist with slot ids resolved to word offsets; output planes
   void finish_batch(DevBatch* db, const Compiled& c, std::vector<uint32_t> cap) {
     cap[0] = db->tile;
+    db->cap = cap;
     std::vector<uint32_t> slot_off(c.slot_level.size());
     uint32_t slot_words = 0;
     for (size_t i = 0; i < slot_off.size(); ++i) {
@@ -251,7 +254,7 @@ class CudaBackend : public Backend {
             if (done[op.w1 + j]++) continue;
             e = (e & 0x80000000u) | so(e & 0xffffu);
           }
-        } else if (kind == GK_N_BCAST || kind == GK_N_ACC) {
+        } else if (kind == GK_N_BCAST || kind == GK_N_ACC || kind == GK_N_ACC2) {
           for (uint32_t j = 0; j < op.w3; ++j) {
             uint32_t& e = pool_r[op.w1 + j];
             if (done[op.w1 + j]++) continue;
@@ -299,10 +302,10 @@ class CudaBackend : public Backend {
     auto* db = static_cast<DevBatch*>(b);
     if (!db) return;
     cudaSetDevice(device_);
-    dfree(db->arena);
+    if (!db->fork) dfree(db->arena);
     dfree(db->viol);
     dfree(db->err);
-    dfree(db->d_tile_lo);
+    if (!db->fork) dfree(db->d_tile_lo);
     dfree(db->d_ops);
     dfree(db->d_pool);
     dfree(db->d_outs);
@@ -971,6 +974,26 @@ class CudaBackend : public Backend {
     guard.release();
     return db;
   }
+  void* fork_batch(void* b, const Compiled& other) override {
+    auto* db = static_cast<DevBatch*>(b);
+    CK(cudaSetDevice(device_));
+    auto* f = new DevBatch();
+    f->arena = db->arena;
+    f->bytes = db->bytes;
+    f->hdr = db->hdr;
+    f->n = db->n;
+    f->d_tile_lo = db->d_tile_lo;
+    f->ntiles = db->ntiles;
+    f->tile = db->tile;
+    f->gvk_uniform = db->gvk_uniform;
+    f->fork = true;
+    f->prog_version = other.version;
+    std::unique_ptr<DevBatch, std::function<void(DevBatch*)>> guard(f, [this](DevBatch* x) { release(x); });
+    finish_batch(f, other, db->cap);
+    guard.release();
+    return f;
+  }
+
   void identity(void* b, BatchIdentity& out) override {
     auto* db = static_cast<DevBatch*>(b);
     std::lock_guard<std::mutex> l(mu_);

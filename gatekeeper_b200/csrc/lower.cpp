@@ -65,6 +65,15 @@ FP f_exists(int scope, FP body) {
   f->kids.push_back(body);
   return f;
 }
+FP f_exists2(int scope, FP body) {
+  if (body->k == Formula::False) return f_false();
+  auto f = std::make_shared<Formula>();
+  f->k = Formula::Exists;
+  f->scope = scope;
+  f->two = true;
+  f->kids.push_back(body);
+  return f;
+}
 static FP f_atom(int op, int col, VP cval = nullptr, uint32_t imm = 0) {
   auto f = std::make_shared<Formula>();
   f->k = Formula::Atom;
@@ -93,7 +102,7 @@ std::string formula_str(const FP& f, const Schema& s) {
       }
       return o + ")";
     }
-    case Formula::Exists: return "E[s" + std::to_string(f->scope) + ":" + s.scopes[f->scope].gen->key + "]{" + formula_str(f->kids[0], s) + "}";
+    case Formula::Exists: return std::string(f->two ? "E2[s" : "E[s") + std::to_string(f->scope) + ":" + s.scopes[f->scope].gen->key + "]{" + formula_str(f->kids[0], s) + "}";
     case Formula::Atom: {
       static const char* names[] = {"?", "truthy", "defined", "vtmask", "sid_eq", "sid_in", "num_cmp", "prefix", "suffix",
                                     "contains", "anyprefix", "anysuffix"};
@@ -397,13 +406,61 @@ class Lowerer {
         // that is one and the head names only parameters and object-level values, the set has at most ONE element
         ++head_paths_;
         head_object_level_ = head_object_level_ && object_level_term(r.key, e);
-        return sym_term(r.key, e, [&](const SymVal& kv) { return defined_cond(kv); });
+        // every arrival at the head is marked with a hole of its own: distinct paths never merge, and the ambiguity formula
+        // below can tell which parts of the predicate a result's bindings come from
+        return sym_term(r.key, e, [&](const SymVal& kv) {
+          auto h = std::make_shared<Formula>();
+          h->k = Formula::Atom;
+          h->op = -1;
+          h->imm = (uint32_t)nholes_++;
+          return f_and(defined_cond(kv), FP(h));
+        });
       });
       out = f_or(out, f);
       check_size(out, r.line);
     }
-    return out;
+    const auto plug = [](uint32_t) { return f_true(); };
+    has_hole_.clear();
+    amb_ = fill_tree(amb_of(out), plug);
+    if (formula_size(amb_) > 40000) amb_ = f_true();
+    return fill_tree(out, plug);
   }
+  FP ambiguity() const { return amb_; }
+
+  // May the pair have more than one result?  Only the parts of the predicate that hold a head (a hole) bind what a result is made
+  // of: two of them true together, or an iteration around a head with two satisfying rows.  Hole-free parts are plain conditions.
+  bool has_hole(const FP& f) {
+    auto it = has_hole_.find(f.get());
+    if (it != has_hole_.end()) return it->second;
+    bool h = f->k == Formula::Atom && f->op == -1;
+    for (auto& k : f->kids) h = has_hole(k) || h;
+    has_hole_.emplace(f.get(), h);
+    return h;
+  }
+  FP amb_of(const FP& f) {
+    if (!has_hole(f)) return f_false();
+    switch (f->k) {
+      case Formula::And: {
+        FP any = f_false();
+        for (auto& k : f->kids) any = f_or(any, amb_of(k));
+        return any->k == Formula::False ? any : f_and(f, any);
+      }
+      case Formula::Or: {
+        FP any = f_false(), two = f_false(), later = f_false();
+        for (size_t i = f->kids.size(); i-- > 0;) {
+          const FP& k = f->kids[i];
+          any = f_or(any, amb_of(k));
+          if (!has_hole(k)) continue;
+          two = f_or(two, f_and(k, later));   // this one and a later one
+          later = f_or(later, k);
+        }
+        return f_or(any, two);
+      }
+      case Formula::Exists: return f_or(f_exists2(f->scope, f->kids[0]), f_exists(f->scope, amb_of(f->kids[0])));
+      default: return f_false();   // a hole itself; (a head never sits under a negation)
+    }
+  }
+
   // at most one result per (constraint, object): audit totals can take the pair count (pkg/audit/manager.go:886-945 counts results)
   bool single_result() const { return head_paths_ <= 1 && head_object_level_; }
 
@@ -449,6 +506,9 @@ class Lowerer {
   int depth_ = 0;
   int head_paths_ = 0;
   bool head_object_level_ = true;
+  int nholes_ = 0;
+  FP amb_;
+  std::unordered_map<const Formula*, bool> has_hole_;
   std::map<std::string, Deps> rule_deps_;
   std::set<std::string> rule_deps_busy_;
   std::vector<std::shared_ptr<Term>> synth_;   // keeps synthesized terms alive
@@ -907,7 +967,7 @@ class Lowerer {
       case Formula::Not: return f_not(fill_tree(f->kids[0], fn));
       case Formula::Exists: {
         IterGuard g(iter_stack_, f->scope);   // (the holes are filled inside the iteration: its rows are open there)
-        return f_exists(f->scope, fill_tree(f->kids[0], fn));
+        return f->two ? f_exists2(f->scope, fill_tree(f->kids[0], fn)) : f_exists(f->scope, fill_tree(f->kids[0], fn));
       }
       default: return f;
     }
@@ -1934,14 +1994,16 @@ void Lowerer::subst_print(const Term& t, const std::map<int, std::string>& sub, 
 
 }  // namespace
 
-FP lower_violation(const std::shared_ptr<const Module>& mod, const VP& parameters, Schema& schema, bool device_mode, bool* single_result) {
+FP lower_violation(const std::shared_ptr<const Module>& mod, const VP& parameters, Schema& schema, bool device_mode, bool* single_result, FP* amb) {
   schema.device_only = device_mode;
   const Schema before = schema;   // (a failed attempt must not leave its scopes and columns behind)
   if (single_result) *single_result = false;
+  if (amb) *amb = f_true();
   try {
     Lowerer lw(mod, parameters, schema);
     FP f = lw.run();
     if (single_result) *single_result = lw.single_result();
+    if (amb) *amb = lw.single_result() ? f_false() : lw.ambiguity();
     return f;
   } catch (RegoError& e) {
     if (e.msg.find("two unrelated iteration scopes") == std::string::npos) {
@@ -1955,6 +2017,7 @@ FP lower_violation(const std::shared_ptr<const Module>& mod, const VP& parameter
     lw.product_mode = true;
     FP f = lw.run();
     if (single_result) *single_result = lw.single_result();
+    if (amb) *amb = lw.single_result() ? f_false() : lw.ambiguity();
     return f;
   } catch (RegoError&) {
     schema = before;
@@ -2147,11 +2210,11 @@ struct Net {
         int body = raise(plain(r), f->scope);
         if (nodes[body].level != f->scope) throw RegoError{"internal: EXISTS body is deeper than its scope"};
         NNode n;
-        n.kind = GK_N_ACC;
+        n.kind = f->two ? GK_N_ACC2 : GK_N_ACC;
         n.level = schema.scopes[f->scope].parent;
         n.scope = f->scope;
         n.a = body;
-        return Ref{intern_node("acc" + std::to_string(body) + "@" + std::to_string(f->scope), n), false};
+        return Ref{intern_node((f->two ? "acc2_" : "acc") + std::to_string(body) + "@" + std::to_string(f->scope), n), false};
       }
     }
     throw RegoError{"internal: unknown formula node"};
@@ -2167,13 +2230,13 @@ static FP merge_exists(const FP& f) {
   std::vector<FP> kids;
   for (auto& k : f->kids) kids.push_back(merge_exists(k));
   if (f->k == Formula::Not) return f_not(kids[0]);
-  if (f->k == Formula::Exists) return f_exists(f->scope, kids[0]);
+  if (f->k == Formula::Exists) return f->two ? f_exists2(f->scope, kids[0]) : f_exists(f->scope, kids[0]);
   const bool is_or = f->k == Formula::Or;
   std::map<int, std::vector<FP>> groups;
   std::vector<FP> rest;
   for (auto& k : kids) {
-    if (is_or && k->k == Formula::Exists) groups[k->scope].push_back(k->kids[0]);
-    else if (!is_or && k->k == Formula::Not && k->kids[0]->k == Formula::Exists) groups[k->kids[0]->scope].push_back(k->kids[0]->kids[0]);
+    if (is_or && k->k == Formula::Exists && !k->two) groups[k->scope].push_back(k->kids[0]);
+    else if (!is_or && k->k == Formula::Not && k->kids[0]->k == Formula::Exists && !k->kids[0]->two) groups[k->kids[0]->scope].push_back(k->kids[0]->kids[0]);
     else rest.push_back(k);
   }
   FP out = is_or ? f_false() : f_true();
@@ -2251,8 +2314,8 @@ static FP hoist_invariants(const FP& f, const Schema& sc) {
           inner = f_and(inner, k);
         }
       }
-      if (!moved) return f_exists(f->scope, body);
-      return f_and(f_exists(f->scope, inner), outer);
+      if (!moved) return f->two ? f_exists2(f->scope, body) : f_exists(f->scope, body);
+      return f_and(f->two ? f_exists2(f->scope, inner) : f_exists(f->scope, inner), outer);
     }
     default: return f;
   }
@@ -2369,7 +2432,7 @@ void NetBuilder::build(const std::vector<FP>& formulas, const std::vector<uint32
       n.slot = alloc(n.level);
       release_at[std::min(n.last_use + 1, out_phase + 1)].push_back(n.slot);
     }
-    std::map<int, std::vector<uint32_t>> acc_groups, bcast_groups;   // scope -> (in slot | out slot << 16)
+    std::map<int, std::vector<uint32_t>> acc_groups, bcast_groups, acc2_groups;   // scope -> (in slot | out slot << 16)
     struct ColAtoms {
       std::vector<GkOp> ops;
       uint32_t cost = 0;
@@ -2379,8 +2442,8 @@ void NetBuilder::build(const std::vector<FP>& formulas, const std::vector<uint32
     for (int id : ids) {
       NNode& n = N[id];
       ++n_nodes;
-      if (n.kind == GK_N_ACC || n.kind == GK_N_BCAST) {
-        (n.kind == GK_N_ACC ? acc_groups : bcast_groups)[n.scope].push_back((uint32_t)N[n.a].slot | ((uint32_t)n.slot << 16));
+      if (n.kind == GK_N_ACC || n.kind == GK_N_BCAST || n.kind == GK_N_ACC2) {
+        (n.kind == GK_N_ACC ? acc_groups : n.kind == GK_N_ACC2 ? acc2_groups : bcast_groups)[n.scope].push_back((uint32_t)N[n.a].slot | ((uint32_t)n.slot << 16));
         continue;
       }
       GkOp op{};
@@ -2485,6 +2548,7 @@ void NetBuilder::build(const std::vector<FP>& formulas, const std::vector<uint32
             break;
           case GK_N_GATE: cost = (uint32_t)(8 + 4 * n.ins.size()) * (deep ? 2 : 1); break;
           case GK_N_BCAST:
+          case GK_N_ACC2:
           case GK_N_ACC: cost = 200; break;
           default: break;
         }
@@ -2543,10 +2607,10 @@ void NetBuilder::build(const std::vector<FP>& formulas, const std::vector<uint32
     }
     // every EXISTS (and every hoisted broadcast) over the same scope in this phase is ONE op: the child ranges and
     // their masks are computed once per parent row and applied to all (input, output) column pairs
-    for (int pass = 0; pass < 2; ++pass)
-      for (auto& g : pass == 0 ? acc_groups : bcast_groups) {
+    for (int pass = 0; pass < 3; ++pass)
+      for (auto& g : pass == 0 ? acc_groups : pass == 1 ? bcast_groups : acc2_groups) {
         GkOp op{};
-        op.w0 = (pass == 0 ? GK_N_ACC : GK_N_BCAST) | ((uint32_t)g.first << 8);
+        op.w0 = (pass == 0 ? GK_N_ACC : pass == 1 ? GK_N_BCAST : GK_N_ACC2) | ((uint32_t)g.first << 8);
         op.w1 = (uint32_t)pool.size();
         op.w3 = (uint32_t)g.second.size();
         pool.insert(pool.end(), g.second.begin(), g.second.end());

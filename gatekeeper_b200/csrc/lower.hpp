@@ -98,6 +98,7 @@ struct Formula {
   enum K : uint8_t { True, False, And, Or, Not, Exists, Atom } k = True;
   std::vector<FP> kids;
   int scope = 0;          // Exists
+  bool two = false;       // Exists: at least TWO rows satisfy the body (ambiguity formulas only)
   // Atom:
   int op = 0;             // GK_OP_*
   int col = -1;           // schema column
@@ -110,6 +111,7 @@ FP f_and(FP a, FP b);
 FP f_or(FP a, FP b);
 FP f_not(FP a);
 FP f_exists(int scope, FP body);
+FP f_exists2(int scope, FP body);
 std::string formula_str(const FP& f, const Schema& s);
 void check_netlist_shape(const FP& formula, const Schema& s);   // throws rego_unsupported for shapes the netlist cannot hold
 size_t formula_size(const FP& f);
@@ -125,7 +127,10 @@ struct Interner {
 // functions) are inlined into the formula instead of becoming host closures; throws when that is not possible.
 // `single_result`: set when a (constraint, object) pair can have at most one result (one path to the head, a head of parameters
 // and object-level values only) -- the audit then counts the pair without evaluating it.
-FP lower_violation(const std::shared_ptr<const Module>& mod, const VP& parameters, Schema& schema, bool device_mode = false, bool* single_result = nullptr);
+// `amb`: a predicate that is FALSE only where the pair has at most one result -- no two rule paths reach a head together and no
+// iteration the head sits in has two satisfying rows (conservative: true means "count it on the host").
+FP lower_violation(const std::shared_ptr<const Module>& mod, const VP& parameters, Schema& schema, bool device_mode = false, bool* single_result = nullptr,
+                   FP* amb = nullptr);
 bool schema_device_ingestable(const Schema& s, std::string* why = nullptr);
 
 // Netlist assembly: every constraint's formula is merged into one DAG of bit-column ops (program.h GkOp).

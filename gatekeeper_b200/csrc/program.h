@@ -135,6 +135,7 @@ enum {
   GK_N_BCAST = 5,   // level = child scope; pool[w1 .. w1+w3) = (input slot at the parent level | output slot << 16)
   GK_N_ACC = 6,     // level = child scope; pool[w1 .. w1+w3) = (input slot at the child level | output slot at the parent level << 16)
   GK_N_MATCH = 7,   // w1 = error-column slot ; w2 = match block id
+  GK_N_ACC2 = 9,    // like ACC, but "at least TWO children have the bit" (the audit's ambiguity netlist: may a pair have > 1 result?)
   GK_N_ATOMS = 8,   // every atom of ONE column (same phase): w1 = col<<8 ; pool[w2 ..]: w3 entries of GK_ATOMS_ENT words
                     //   [atom op | out_slot<<16, operand a, operand b, 0] -- the column is loaded once per row for all of them
 };

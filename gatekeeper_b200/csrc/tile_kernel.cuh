@@ -504,7 +504,9 @@ __global__ void __launch_bounds__(kThreads, GK_MIN_CTAS) gk_eval_kernel(const KP
             }
             break;
           }
+          case GK_N_ACC2:      // "at least two children" (audit ambiguity netlist): the same walk, counting
           case GK_N_ACC: {     // EXISTS: OR over each parent's child range; ranges + masks computed once for the whole group
+            const bool two = (op.w0 & 0xffu) == GK_N_ACC2;
             const uint32_t par = (uint32_t)scopes[level].parent, npair = op.w3;
             const uint32_t* pairs = pool + op.w1;
             const uint32_t* coff = scopes[level].off + s_lo[par];
@@ -537,8 +539,15 @@ __global__ void __launch_bounds__(kThreads, GK_MIN_CTAS) gk_eval_kernel(const KP
                 for (uint32_t j = 0; j < npair; ++j) {
                   const uint32_t e = pairs[j];
                   const uint32_t* in = slots + (e & 0xffffu);
-                  bool any = (__funnelshift_r(in[wl], in[wh], sh) & m) != 0u;   // (m == 0 for a parent without children)
-                  if (any_wide)
+                  const uint32_t win = __funnelshift_r(in[wl], in[wh], sh) & m;   // (m == 0 for a parent without children)
+                  bool any = win != 0u;
+                  if (two) {
+                    uint32_t cnt = (uint32_t)__popc(win);
+                    if (any_wide)
+                      if (wide)
+                        for (uint32_t w = (a + 32u) >> 5; w <= (b - 1u) >> 5 && cnt < 2u; ++w) cnt += (uint32_t)__popc(in[w] & range_mask(w, a + 32u, b));
+                    any = cnt >= 2u;
+                  } else if (any_wide)
                     if (wide && !any)
                       for (uint32_t w = (a + 32u) >> 5; w <= (b - 1u) >> 5 && !any; ++w) any = (in[w] & range_mask(w, a + 32u, b)) != 0u;
                   const uint32_t wd = __ballot_sync(FULL, any);

@@ -53,6 +53,17 @@ class HostEmuBackend : public Backend {
     return b;
   }
   void release(void* b) override { delete static_cast<EmuBatch*>(b); }
+  void* fork_batch(void* bb, const Compiled& other) override {
+    auto* b = static_cast<EmuBatch*>(bb);
+    auto* f = new EmuBatch();
+    f->hdr = b->hdr;   // (points into the parent's arena: the fork is released first)
+    f->n = b->n;
+    f->words = std::max<uint32_t>(1, (uint32_t)((other.cons_match.size() + 31) / 32));
+    f->gvk_uniform = b->gvk_uniform;
+    f->scope_rows = b->scope_rows;
+    f->scope_off = b->scope_off;
+    return f;
+  }
   void identity(void* bb, BatchIdentity& out) override {
     auto* b = static_cast<EmuBatch*>(bb);
     const uint32_t n = b->n;
@@ -364,16 +375,18 @@ class HostEmuBackend : public Backend {
           }
           break;
         }
+        case GK_N_ACC2:
         case GK_N_ACC: {
           const auto& off = b->scope_off[level];
+          const uint32_t need = kind == GK_N_ACC2 ? 2u : 1u;
           for (uint32_t j = 0; j < op.w3; ++j) {
             const uint32_t e = c.pool[op.w1 + j];
             const auto& in = slot[e & 0xffffu];
             auto& dst = slot[e >> 16];
             for (size_t p = 0; p + 1 < off.size(); ++p) {
-              bool any = false;
-              for (uint32_t r = off[p]; r < off[p + 1]; ++r) any = any || in[r];
-              dst[p] = any;
+              uint32_t cnt = 0;
+              for (uint32_t r = off[p]; r < off[p + 1]; ++r) cnt += in[r] ? 1u : 0u;
+              dst[p] = cnt >= need;
             }
           }
           break;

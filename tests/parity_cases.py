@@ -1047,6 +1047,21 @@ def case_rego_fuzz(lib, n_templates=40, n_objects=120, seed=1, via_blob=False):
         except AssertionError as e:
             raise AssertionError("seed %d template %d:\n%s\nparams %s\n%s" % (seed, t, src, [c["spec"].get("parameters") for c in cons], str(e)[:1500]))
         n_results += len(want)
+        # the audit's lazy path (single-result proofs of the lowering + the ambiguity netlist) must count what the renderer renders
+        if not bad:
+            per = {}
+            for r in resp.results:
+                per[r.constraint] = per.get(r.constraint, 0) + 1
+            run = D.AuditRun(drv, violations_limit=3)
+            rb = drv.upload_blob(pyblob, source="") if via_blob else drv.upload(revs)
+            run.add_batch(rb, k8s.AUDIT_EP)
+            rep = run.report()
+            try:
+                assert {k: v for k, v in rep["totalViolations"].items() if v} == per
+            except AssertionError:
+                raise AssertionError("seed %d template %d: audit totals %s != rendered %s (counted %d, evaluated %d)\n%s\nparams %s" % (
+                    seed, t, rep["totalViolations"], per, rep["pairsCounted"], rep["pairsEvaluated"], src, [c["spec"].get("parameters") for c in cons]))
+            n_counted = locals().get("n_counted", 0) + rep["pairsCounted"]
     assert accepted >= n_templates * 0.6, rejected
     if via_blob:
         return accepted, n_results, rejected, n_device
@@ -1684,6 +1699,8 @@ def case_audit_lazy(lib, n=3000, limit=4):
         run.add_batch(rb, k8s.AUDIT_EP)
     got_b = check(run, want)
     assert got_b["pairsCounted"] > 0      # (other page sizes: other candidates, the same report)
+    # most violating pairs have one result; those never reach the host evaluator unless they can enter a list
+    assert got["pairsEvaluated"] < 0.5 * (got["pairsEvaluated"] + got["pairsCounted"]), (got["pairsEvaluated"], got["pairsCounted"])
     # (c) a page of several kinds: (group, version, kind) orders results first -- every pair is evaluated
     mixed = objs[:300] + [{"apiVersion": "apps/v1", "kind": "Deployment", "metadata": {"name": "d%d" % i, "namespace": "default"}, "spec": {}} for i in range(5)]
     want_m = OA.audit(orc, mixed, namespaces=nsmap, limit=limit)
