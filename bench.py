@@ -369,6 +369,20 @@ def run_ours(args):
         e2e_msgs = {"value": msg_n * C / dt, "unit": UNIT, "objects": msg_n, "results_rendered": r2.stats["n_violations"],
                     "materialize_ms": round(r2.stats["materialize_ms"], 1), "flatten_ms": round(r2.stats["flatten_ms"], 1)}
         del r2
+    # the audit sweep proper: one page through gk_batch_upload_blob + gk_audit_add_batch -- totals per constraint and the K smallest
+    # violations with their messages (pkg/audit/manager.go:886-1041).  Pairs with one result are counted from the bitmaps (the
+    # ambiguity netlist runs on the device); the host evaluates what can still enter a list and the pairs that may have several.
+    e2e_audit = None
+    if args.config == 2 and not args.no_audit:
+        ta = time.perf_counter()
+        rb = drv.upload_blob(pages[1])
+        run = D.AuditRun(drv, violations_limit=20)
+        run.add_batch(rb, ep)
+        rep = run.report()
+        dta = time.perf_counter() - ta
+        e2e_audit = {"value": n * C / dta, "unit": UNIT, "objects": n, "ms": round(1e3 * dta, 1), "results": rep["results"],
+                     "pairs_counted_on_device": rep["pairsCounted"], "pairs_evaluated_on_host": rep["pairsEvaluated"], "violations_limit": 20}
+        del rb, run
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -400,7 +414,7 @@ def run_ours(args):
                    "synth_s": round(gen_s, 2), "ingest_ms_once": round(rb.stats["flatten_ms"] + rb.stats["h2d_ms"], 1), "spot_check": spot},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "kernel": "gk_eval_kernel", "kernel_ms": kern_ms, "alg_bytes_per_launch": alg_bytes, "peak_source": peak_src},
-        "e2e": dict(e2e, with_messages=e2e_msgs), "gpu_launches": int(launches), "clocks": clocks,
+        "e2e": dict(e2e, with_messages=e2e_msgs, audit=e2e_audit), "gpu_launches": int(launches), "clocks": clocks,
     }
     if world == 1:
         line["cpu_baseline"] = cpu_baseline(args.config, args.cpu_sample)
@@ -489,6 +503,7 @@ def main():
     ap.add_argument("--objects", type=int, default=0, help="objects per GPU (weak) / in total (strong); 0 = the config's size")
     ap.add_argument("--e2e-steps", type=int, default=8, help="pages of the pipelined end-to-end sweep (each is a fresh 1M-object page in pinned host memory)")
     ap.add_argument("--cpu-sample", type=int, default=30_000, help="objects reviewed by the C++ CPU restatement leg (all host threads)")
+    ap.add_argument("--no-audit", action="store_true", help="skip the audit-aggregation measurement (e2e.audit)")
     ap.add_argument("--msg-sample", type=int, default=50_000, help="objects of the sample whose messages are all rendered (e2e.with_messages)")
     ap.add_argument("--spot-check", type=int, default=300, help="objects of the shard checked against the Python oracle inside the run")
     ap.add_argument("--ref-objects-per-step", type=int, default=40_000)
