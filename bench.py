@@ -375,14 +375,14 @@ def run_ours(args):
     e2e_audit = None
     if args.config == 2 and not args.no_audit:
         ta = time.perf_counter()
-        rb = drv.upload_blob(pages[1])
-        run = D.AuditRun(drv, violations_limit=20)
-        run.add_batch(rb, ep)
-        rep = run.report()
+        audit_rb = drv.upload_blob(pages[1])
+        audit_run = D.AuditRun(drv, violations_limit=20)
+        audit_run.add_batch(audit_rb, ep)
+        rep = audit_run.report()
         dta = time.perf_counter() - ta
         e2e_audit = {"value": n * C / dta, "unit": UNIT, "objects": n, "ms": round(1e3 * dta, 1), "results": rep["results"],
                      "pairs_counted_on_device": rep["pairsCounted"], "pairs_evaluated_on_host": rep["pairsEvaluated"], "violations_limit": 20}
-        del rb, run
+        del audit_rb, audit_run
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
