@@ -20,6 +20,48 @@
 #include "program.h"
 #include "vm_core.h"
 
+// the EXISTS walk shared by GK_N_ACC and GK_N_ACC2 (GK_ACC_TEST decides a parent row from its window of child bits)
+#define GK_ACC_WALK \
+          { \
+            const uint32_t par = (uint32_t)scopes[level].parent, npair = op.w3; \
+            const uint32_t* pairs = pool + op.w1; \
+            const uint32_t* coff = scopes[level].off + s_lo[par]; \
+            const uint32_t clo = s_lo[level], pcnt = s_cnt[par]; \
+            const uint32_t pw = (pcnt + 31u) >> 5, cw = (s_cnt[level] + 31u) >> 5; \
+            const uint32_t g0 = pw * part / nparts, g1 = pw * (part + 1u) / nparts; \
+            for (uint32_t g = g0; g < g1; g += 4u) { \
+              uint32_t ra[4], rb[4]; \
+_Pragma("unroll") \
+              for (int u = 0; u < 4; ++u) { \
+                const uint32_t r = (g + u) * 32u + lane; \
+                ra[u] = rb[u] = 0u; \
+                if (g + u < g1 && r < pcnt) { \
+                  ra[u] = coff[r] - clo; \
+                  rb[u] = coff[r + 1] - clo; \
+                } \
+              } \
+_Pragma("unroll") \
+              for (int u = 0; u < 4; ++u) { \
+                if (g + u >= g1) break; \
+                const uint32_t a = ra[u], b = rb[u]; \
+                const uint32_t nb = b - a, sh = a & 31u; \
+                const uint32_t m = nb >= 32u ? FULL : ((1u << nb) - 1u); \
+                const uint32_t wl = cw ? min(a >> 5, cw - 1u) : 0u, wh = cw ? min((a >> 5) + 1u, cw - 1u) : 0u; \
+                const bool wide = nb > 32u; \
+                const bool any_wide = __any_sync(FULL, wide); \
+                for (uint32_t j = 0; j < npair; ++j) { \
+                  const uint32_t e = pairs[j]; \
+                  const uint32_t* in = slots + (e & 0xffffu); \
+                  const uint32_t win = __funnelshift_r(in[wl], in[wh], sh) & m; \
+                  bool any; \
+                  GK_ACC_TEST \
+                  const uint32_t wd = __ballot_sync(FULL, any); \
+                  if (lane == 0) slots[(e >> 16) + g + u] = wd; \
+                } \
+              } \
+            } \
+          }
+
 namespace gk {
 
 #define GK_MAX_PEERS 8
@@ -504,57 +546,32 @@ __global__ void __launch_bounds__(kThreads, GK_MIN_CTAS) gk_eval_kernel(const KP
             }
             break;
           }
-          case GK_N_ACC2:      // "at least two children" (audit ambiguity netlist): the same walk, counting
-          case GK_N_ACC: {     // EXISTS: OR over each parent's child range; ranges + masks computed once for the whole group
-            const bool two = (op.w0 & 0xffu) == GK_N_ACC2;
-            const uint32_t par = (uint32_t)scopes[level].parent, npair = op.w3;
-            const uint32_t* pairs = pool + op.w1;
-            const uint32_t* coff = scopes[level].off + s_lo[par];
-            const uint32_t clo = s_lo[level], pcnt = s_cnt[par];
-            const uint32_t pw = (pcnt + 31u) >> 5, cw = (s_cnt[level] + 31u) >> 5;
-            const uint32_t g0 = pw * part / nparts, g1 = pw * (part + 1u) / nparts;   // parent-row groups of this part
-            for (uint32_t g = g0; g < g1; g += 4u) {
-              // CSR offsets of four groups first (the only global loads of the op): one memory latency per 128 parent rows
-              uint32_t ra[4], rb[4];
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const uint32_t r = (g + u) * 32u + lane;
-                ra[u] = rb[u] = 0u;
-                if (g + u < g1 && r < pcnt) {
-                  ra[u] = coff[r] - clo;
-                  rb[u] = coff[r + 1] - clo;
-                }
-              }
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                if (g + u >= g1) break;   // warp-uniform
-                const uint32_t a = ra[u], b = rb[u];
-                // A range of up to 32 children is a 32-bit window of the child bit column starting at bit a: one funnel
-                // shift over two adjacent words, branch-free for every lane.  Longer ranges (rare) add a tail loop.
-                const uint32_t nb = b - a, sh = a & 31u;
-                const uint32_t m = nb >= 32u ? FULL : ((1u << nb) - 1u);
-                const uint32_t wl = cw ? min(a >> 5, cw - 1u) : 0u, wh = cw ? min((a >> 5) + 1u, cw - 1u) : 0u;
-                const bool wide = nb > 32u;
-                const bool any_wide = __any_sync(FULL, wide);
-                for (uint32_t j = 0; j < npair; ++j) {
-                  const uint32_t e = pairs[j];
-                  const uint32_t* in = slots + (e & 0xffffu);
-                  const uint32_t win = __funnelshift_r(in[wl], in[wh], sh) & m;   // (m == 0 for a parent without children)
-                  bool any = win != 0u;
-                  if (two) {
-                    uint32_t cnt = (uint32_t)__popc(win);
-                    if (any_wide)
-                      if (wide)
-                        for (uint32_t w = (a + 32u) >> 5; w <= (b - 1u) >> 5 && cnt < 2u; ++w) cnt += (uint32_t)__popc(in[w] & range_mask(w, a + 32u, b));
-                    any = cnt >= 2u;
-                  } else if (any_wide)
-                    if (wide && !any)
-                      for (uint32_t w = (a + 32u) >> 5; w <= (b - 1u) >> 5 && !any; ++w) any = (in[w] & range_mask(w, a + 32u, b)) != 0u;
-                  const uint32_t wd = __ballot_sync(FULL, any);
-                  if (lane == 0) slots[(e >> 16) + g + u] = wd;
-                }
-              }
-            }
+          // EXISTS: OR over each parent's child range; ranges + masks computed once for the whole group.  The CSR offsets of four
+          // parent-row groups are fetched first (the only global loads of the op): one memory latency per 128 parent rows.  A range
+          // of up to 32 children is a 32-bit window of the child bit column starting at bit a: one funnel shift over two adjacent
+          // words, branch-free for every lane; longer ranges (rare) add a tail loop.  (m == 0 for a parent without children.)
+          case GK_N_ACC: {
+#define GK_ACC_TEST                                                                                                                   \
+  any = win != 0u;                                                                                                                    \
+  if (any_wide)                                                                                                                       \
+    if (wide && !any)                                                                                                                 \
+      for (uint32_t w = (a + 32u) >> 5; w <= (b - 1u) >> 5 && !any; ++w) any = (in[w] & range_mask(w, a + 32u, b)) != 0u;
+            GK_ACC_WALK
+#undef GK_ACC_TEST
+            break;
+          }
+          case GK_N_ACC2: {    // "at least two children" (the audit's ambiguity netlist): the same walk, counting -- its own copy so
+                               // that the decision netlist's EXISTS carries no extra branch
+#define GK_ACC_TEST                                                                                                                   \
+  {                                                                                                                                   \
+    uint32_t cnt = (uint32_t)__popc(win);                                                                                             \
+    if (any_wide)                                                                                                                     \
+      if (wide)                                                                                                                       \
+        for (uint32_t w = (a + 32u) >> 5; w <= (b - 1u) >> 5 && cnt < 2u; ++w) cnt += (uint32_t)__popc(in[w] & range_mask(w, a + 32u, b)); \
+    any = cnt >= 2u;                                                                                                                  \
+  }
+            GK_ACC_WALK
+#undef GK_ACC_TEST
             break;
           }
           case GK_N_MATCH: {
