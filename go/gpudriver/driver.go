@@ -158,34 +158,89 @@ func (d *Driver) RemoveConstraint(_ context.Context, c *unstructured.Unstructure
 	return nil
 }
 
-// AddData: only Namespace objects matter (namespaceSelector table); paths per pkg/target/target.go:60-66.
-func (d *Driver) AddData(_ context.Context, _ string, path storage.Path, data interface{}) error {
-	if len(path) >= 4 && path[0] == "cluster" && path[2] == "Namespace" {
-		raw, err := json.Marshal(data)
-		if err != nil {
-			return err
+// cPath copies a storage path into C memory (cgo: no Go pointers to Go pointers); the caller frees with freePath.
+func cPath(path storage.Path) (**C.char, func()) {
+	n := len(path)
+	arr := (**C.char)(C.malloc(C.size_t(n) * C.size_t(unsafe.Sizeof((*C.char)(nil)))))
+	sl := unsafe.Slice(arr, n)
+	for i, p := range path {
+		sl[i] = C.CString(p)
+	}
+	return arr, func() {
+		for i := range sl {
+			C.free(unsafe.Pointer(sl[i]))
 		}
-		d.mux.Lock()
-		defer d.mux.Unlock()
+		C.free(unsafe.Pointer(arr))
+	}
+}
+
+// AddData: every synced object is stored at its path for referential templates (data.inventory); Namespaces also feed the
+// namespaceSelector table (nsCache.Add).  Paths per pkg/target/target.go:40-66.
+func (d *Driver) AddData(_ context.Context, _ string, path storage.Path, data interface{}) error {
+	raw, err := json.Marshal(data)
+	if err != nil {
+		return err
+	}
+	if len(raw) == 0 {
+		return nil
+	}
+	d.mux.Lock()
+	defer d.mux.Unlock()
+	buf := C.CBytes(raw)
+	defer C.free(buf)
+	var cerr *C.char
+	if len(path) >= 4 && path[0] == "cluster" && path[2] == "Namespace" {
 		name := C.CString(path[3])
 		defer C.free(unsafe.Pointer(name))
-		var cerr *C.char
-		if rc := C.gk_put_namespace(d.e, name, (*C.char)(unsafe.Pointer(&raw[0])), C.size_t(len(raw)), &cerr); rc != 0 {
+		if rc := C.gk_put_namespace(d.e, name, (*C.char)(buf), C.size_t(len(raw)), &cerr); rc != 0 {
 			return takeErr(cerr)
 		}
+	}
+	arr, free := cPath(path)
+	defer free()
+	if rc := C.gk_add_data(d.e, arr, C.size_t(len(path)), (*C.char)(buf), C.size_t(len(raw)), &cerr); rc != 0 {
+		return takeErr(cerr)
 	}
 	return nil
 }
 
 func (d *Driver) RemoveData(_ context.Context, _ string, path storage.Path) error {
+	d.mux.Lock()
+	defer d.mux.Unlock()
 	if len(path) >= 4 && path[0] == "cluster" && path[2] == "Namespace" {
-		d.mux.Lock()
-		defer d.mux.Unlock()
 		name := C.CString(path[3])
 		defer C.free(unsafe.Pointer(name))
 		C.gk_remove_namespace(d.e, name)
 	}
+	if len(path) > 0 {
+		arr, free := cPath(path)
+		defer free()
+		C.gk_remove_data(d.e, arr, C.size_t(len(path)))
+	}
 	return nil
+}
+
+// UpsertExpansionTemplate / RemoveExpansionTemplate: the expansion system's templates (pkg/expansion/system.go:60-135).  With them
+// in place ReviewBatch reviews the resultants of every object in the same batch and folds their results onto the parent
+// ([Implied by <template>] prefix, enforcement-action override: pkg/expansion/aggregate.go:19-63).
+func (d *Driver) UpsertExpansionTemplate(templateJSON []byte) error {
+	d.mux.Lock()
+	defer d.mux.Unlock()
+	buf := C.CBytes(templateJSON)
+	defer C.free(buf)
+	var cerr *C.char
+	if rc := C.gk_add_expansion_template(d.e, (*C.char)(buf), C.size_t(len(templateJSON)), &cerr); rc != 0 {
+		return takeErr(cerr)
+	}
+	return nil
+}
+
+func (d *Driver) RemoveExpansionTemplate(name string) {
+	d.mux.Lock()
+	defer d.mux.Unlock()
+	cn := C.CString(name)
+	defer C.free(unsafe.Pointer(cn))
+	C.gk_remove_expansion_template(d.e, cn)
 }
 
 // ARGetter / IsAdmissionGetter: how drivers reach the unexported *gkReview -- pkg/drivers/k8scel/driver.go:265-271.
