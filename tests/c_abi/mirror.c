@@ -29,7 +29,7 @@ int main(int argc, char** argv) {
   if (argc < 3) return 2;
   void* lib = dlopen(argv[1], RTLD_NOW | RTLD_LOCAL);
   if (!lib) { fprintf(stderr, "dlopen: %s\n", dlerror()); return 2; }
-  SYM(gk_engine_create) SYM(gk_engine_destroy) SYM(gk_add_template) SYM(gk_add_constraint) SYM(gk_put_namespace) SYM(gk_review_batch)
+  SYM(gk_engine_create) SYM(gk_engine_destroy) SYM(gk_add_template) SYM(gk_add_constraint) SYM(gk_put_namespace) SYM(gk_add_data) SYM(gk_review_batch)
   SYM(gk_result_constraint_key) SYM(gk_free_result) SYM(gk_free_str)
   FILE* f = fopen(argv[2], "rb");
   if (!f) return 2;
@@ -63,6 +63,10 @@ int main(int argc, char** argv) {
       fgetc(f);
       char* js = read_n(f, len);
       if (p_gk_put_namespace(e, name, js, len, &err)) { fprintf(stderr, "namespace: %s\n", err); return 3; }
+      {   /* (driver.go AddData: the object also goes to data.inventory under its ProcessData path) */
+        const char* path[4] = {"cluster", "v1", "Namespace", name};
+        if (p_gk_add_data(e, path, 4, js, len, &err)) { fprintf(stderr, "data: %s\n", err); return 3; }
+      }
       free(js);
     } else if (tag == 'E') {
       if (fscanf(f, "%127s", ep) != 1) return 2;
