@@ -53,41 +53,38 @@ GK_HD int gk_hexval(uint32_t c) {
   return -1;
 }
 
-// first index >= p holding '"' or '\\' (n if none), one aligned 64-bit word a step: the bytes of the first word that lie before p
-// are forced to 0xff (neither character).  The zero-byte test (v - 0x01..) & ~v & 0x80.. can only flag a wrong byte ABOVE a true
-// hit, so the lowest flag is exact.  The first and the last word may reach outside [p, n): every word read holds at least one byte of
-// the string, an aligned word never straddles a page, bytes before p are masked and hits at or past n are cut off.
-GK_HD uint32_t gk_scan_str(const uint8_t* js, uint32_t p, uint32_t n) {
-  if (p >= n) return n;
-  const size_t mis = reinterpret_cast<size_t>(js + p) & 7u;
-  const uint8_t* q8 = js + p - mis;              // aligned address of the first word
-  uint32_t at = p - (uint32_t)mis;               // index of q8[0] (may wrap below zero: only used added to a byte number >= mis)
-  gk_u64 fill = mis ? ((1ull << (8u * mis)) - 1ull) : 0ull;
-  for (;;) {
-    const gk_u64 w = *reinterpret_cast<const gk_u64*>(q8) | fill;
-    const gk_u64 a = w ^ 0x2222222222222222ull, b = w ^ 0x5c5c5c5c5c5c5c5cull;
-    const gk_u64 hit = (((a - 0x0101010101010101ull) & ~a) | ((b - 0x0101010101010101ull) & ~b)) & 0x8080808080808080ull;
-    if (hit) {
+// String scan, one aligned 64-bit word a step: looks for '"' or '\\' from byte p on.  The bytes of the word that lie before p are
+// forced to 0xff (neither character).  The zero-byte test (v - 0x01..) & ~v & 0x80.. can only flag a wrong byte ABOVE a true hit,
+// so the lowest flag is exact.  The word may reach outside [p, n): it holds at least one byte of the string, an aligned word never
+// straddles a page, and hits at or past n are cut off.
+// *hit: a '"' or '\\' at the returned index (< n); otherwise the returned index is where the next step starts (n: the string ran
+// to the end of the text).
+GK_HD uint32_t gk_scan_step(const uint8_t* js, uint32_t p, uint32_t n, bool* hit) {
+  const uint32_t mis = (uint32_t)(reinterpret_cast<size_t>(js + p) & 7u);
+  const gk_u64 w = *reinterpret_cast<const gk_u64*>(js + p - mis) | (mis ? ((1ull << (8u * mis)) - 1ull) : 0ull);
+  const gk_u64 a = w ^ 0x2222222222222222ull, b = w ^ 0x5c5c5c5c5c5c5c5cull;
+  const gk_u64 m = (((a - 0x0101010101010101ull) & ~a) | ((b - 0x0101010101010101ull) & ~b)) & 0x8080808080808080ull;
+  *hit = false;
+  if (m) {
 #ifdef __CUDA_ARCH__
-      const uint32_t at_hit = at + (uint32_t)((__ffsll((long long)hit) - 1) >> 3);
+    const uint32_t at = p - mis + (uint32_t)((__ffsll((long long)m) - 1) >> 3);
 #else
-      const uint32_t at_hit = at + (uint32_t)(__builtin_ctzll(hit) >> 3);
+    const uint32_t at = p - mis + (uint32_t)(__builtin_ctzll(m) >> 3);
 #endif
-      return at_hit < n ? at_hit : n;
-    }
-    at += 8u;
-    q8 += 8;
-    fill = 0;
-    if (at >= n) return n;
+    if (at < n) *hit = true;
+    return at < n ? at : n;
   }
+  const uint32_t next = p - mis + 8u;
+  return next < n ? next : n;
 }
 
 // Tokeniser: the grammar of the host parser (csrc/val.cpp JP) -- same whitespace, same escapes, same (lenient) number syntax,
 // duplicate keys allowed -- so that the device accepts exactly the documents the host flattener accepts.
 //
-// Shape: ONE loop, one token per turn, one exit (rc), no read-back of the tape (the kinds of the open containers live in a
-// 64-bit mask).  Threads of a warp tokenise different objects of the same list page -- the same serialiser, so mostly the same
-// token kinds in the same order: with a single structured loop body they reconverge at the end of every turn.
+// Shape: ONE loop, one exit (rc), no read-back of the tape (the kinds of the open containers live in a 64-bit mask).  A turn of
+// the loop is either one token step or -- inside a string -- one aligned 64-bit word of the string: strings are most of the
+// text, and with their scan in the loop's common path (not a loop of its own inside a branch) the threads of a warp, which
+// tokenise different objects, reconverge at the end of every turn whatever the lengths of their strings.
 GK_HD int gk_tape_build(const uint8_t* js, uint32_t n, gk_u64* tape, uint32_t cap, uint32_t* ntape) {
   uint32_t stack[GK_TAPE_MAX_DEPTH];   // entry index of the open containers
   uint32_t cnt[GK_TAPE_MAX_DEPTH];
@@ -98,11 +95,61 @@ GK_HD int gk_tape_build(const uint8_t* js, uint32_t n, gk_u64* tape, uint32_t ca
   // state: 0 expect value, 1 after value (expect , or close), 2 expect key or '}' (just after '{'), 3 expect key (after ,)
   int state = 0;
   int rc = -1;
+  bool in_str = false;                 // between the quotes of a string that started at byte s
+  uint32_t s = 0, esc = 0;
   *ntape = 0;
   while (rc < 0) {
+    const bool in_obj = depth > 0 && ((objmask >> (depth - 1)) & 1ull) != 0ull;
+    if (in_str) {
+      bool hit;
+      p = gk_scan_step(js, p, n, &hit);
+      if (!hit) {
+        if (p >= n) rc = GK_ING_BAD_JSON;   // unterminated string
+      } else if (js[p] == '"') {
+        const uint32_t len = p - s;
+        ++p;
+        in_str = false;
+        if (len > GK_TAPE_LEN_MAX) {
+          rc = GK_ING_TOO_LONG;
+        } else if (state >= 2) {
+          tape[t++] = gk_te_scalar(GK_T_KEY, esc, s, len);
+          while (p < n && gk_is_ws(js[p])) ++p;
+          if (p >= n || js[p] != ':') {
+            rc = GK_ING_BAD_JSON;
+          } else {
+            ++p;
+            ++cnt[depth - 1];
+            state = 0;
+          }
+        } else {
+          tape[t++] = gk_te_scalar(GK_T_STR, esc, s, len);
+          if (depth && !in_obj) ++cnt[depth - 1];
+          state = 1;
+        }
+      } else {   // a backslash
+        esc = 1;
+        ++p;
+        if (p >= n) {
+          rc = GK_ING_BAD_JSON;
+        } else {
+          const uint32_t e = js[p];
+          if (e == 'u') {
+            if (n - p < 5) rc = GK_ING_BAD_JSON;
+            else {
+              for (int i = 1; i <= 4; ++i)
+                if (gk_hexval(js[p + i]) < 0) rc = GK_ING_BAD_JSON;
+              p += 4;
+            }
+          } else if (!(e == 'n' || e == 't' || e == 'r' || e == 'b' || e == 'f' || e == '/' || e == '\\' || e == '"')) {
+            rc = GK_ING_BAD_JSON;
+          }
+          ++p;
+        }
+      }
+      continue;
+    }
     while (p < n && gk_is_ws(js[p])) ++p;
     const uint32_t c = p < n ? (uint32_t)js[p] : 256u;
-    const bool in_obj = depth > 0 && ((objmask >> (depth - 1)) & 1ull) != 0ull;
     if (state == 1) {
       if (depth == 0) {
         rc = (p == n) ? (int)GK_ING_OK : (int)GK_ING_BAD_JSON;   // trailing characters
@@ -131,56 +178,10 @@ GK_HD int gk_tape_build(const uint8_t* js, uint32_t n, gk_u64* tape, uint32_t ca
       state = 1;
     } else if (state >= 2 && c != '"') {
       rc = GK_ING_BAD_JSON;   // object key expected
-    } else if (c == '"') {
-      const uint32_t s = ++p;
-      uint32_t esc = 0;
-      bool bad = false;
-      for (;;) {
-        p = gk_scan_str(js, p, n);   // eight bytes a step: strings are most of the text
-        if (p >= n || js[p] == '"') break;
-        esc = 1;                     // a backslash
-        ++p;
-        if (p >= n) {
-          bad = true;
-          break;
-        }
-        const uint32_t e = js[p];
-        if (e == 'u') {
-          if (n - p < 5) bad = true;
-          else {
-            for (int i = 1; i <= 4; ++i)
-              if (gk_hexval(js[p + i]) < 0) bad = true;
-            p += 4;
-          }
-        } else if (!(e == 'n' || e == 't' || e == 'r' || e == 'b' || e == 'f' || e == '/' || e == '\\' || e == '"')) {
-          bad = true;
-        }
-        ++p;
-        if (bad) break;
-      }
-      const uint32_t len = p - s;
-      if (bad || p >= n) {
-        rc = GK_ING_BAD_JSON;   // bad escape / unterminated string
-      } else if (len > GK_TAPE_LEN_MAX) {
-        rc = GK_ING_TOO_LONG;
-      } else {
-        ++p;
-        if (state >= 2) {
-          tape[t++] = gk_te_scalar(GK_T_KEY, esc, s, len);
-          while (p < n && gk_is_ws(js[p])) ++p;
-          if (p >= n || js[p] != ':') {
-            rc = GK_ING_BAD_JSON;
-          } else {
-            ++p;
-            ++cnt[depth - 1];
-            state = 0;
-          }
-        } else {
-          tape[t++] = gk_te_scalar(GK_T_STR, esc, s, len);
-          if (depth && !in_obj) ++cnt[depth - 1];
-          state = 1;
-        }
-      }
+    } else if (c == '"') {   // a string starts (key or value by `state`): scanned by the turns that follow
+      s = ++p;
+      esc = 0;
+      in_str = true;
     } else if (c == '{' || c == '[') {   // state 0: a value
       if (depth >= GK_TAPE_MAX_DEPTH) {
         rc = GK_ING_TOO_DEEP;
