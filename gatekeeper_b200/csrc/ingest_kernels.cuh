@@ -166,6 +166,20 @@ __global__ void __launch_bounds__(256) gk_gvk_minmax_kernel(const unsigned long 
   }
 }
 
+// small host -> device transfers done by the SMs from mapped page-locked memory: they do not queue behind the next page's 32 MB
+// chunks on the copy engine (a 100 KB table upload waited 12 ms there)
+__global__ void __launch_bounds__(256) gk_push_kernel(uint8_t* dst, const uint8_t* src, size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x * 16u;
+  const bool vec = (reinterpret_cast<size_t>(dst) & 15u) == 0u;
+  for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 16u; i < n; i += stride) {
+    if (vec && i + 16u <= n) {
+      *reinterpret_cast<uint4*>(dst + i) = *reinterpret_cast<const uint4*>(src + i);
+    } else {
+      for (size_t k = i; k < n && k < i + 16u; ++k) dst[k] = src[k];
+    }
+  }
+}
+
 __global__ void gk_fill_kernel(uint32_t* vals, const uint32_t* pairs, uint32_t n) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) vals[pairs[2 * i]] = pairs[2 * i + 1];
