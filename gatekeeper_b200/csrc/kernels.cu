@@ -184,14 +184,20 @@ class CudaBackend : public Backend {
     // of 512 objects for 1M -- measured slower: 0.816 vs 0.762 ms; the per-tile fixed cost outweighs the fuller last wave.)
     uint32_t tile = kTile;
     if (const char* ft = getenv("GK_FORCE_TILE")) tile = std::min<uint32_t>(kTile, std::max(32, atoi(ft)) / 32 * 32);
-    const uint32_t ntiles = (hb.n + tile - 1) / tile;
-    std::vector<uint32_t> tile_lo((size_t)(ntiles + 1) * NS), cap(NS, 0);
-    for (uint32_t t = 0; t <= ntiles; ++t) {
-      uint32_t* lo = &tile_lo[(size_t)t * NS];
-      lo[0] = std::min<uint32_t>(t * tile, hb.n);
-      for (uint32_t s = 1; s < NS; ++s) lo[s] = hb.scope_off[s][lo[c.schema.scopes[s].parent]];
-      if (t)
-        for (uint32_t s = 0; s < NS; ++s) cap[s] = std::max(cap[s], lo[s] - tile_lo[(size_t)(t - 1) * NS + s]);
+    uint32_t ntiles = 0;
+    std::vector<uint32_t> tile_lo, cap;
+    for (;; tile = std::max(32u, tile / 2 / 32 * 32)) {
+      ntiles = (hb.n + tile - 1) / tile;
+      tile_lo.assign((size_t)(ntiles + 1) * NS, 0);
+      cap.assign(NS, 0);
+      for (uint32_t t = 0; t <= ntiles; ++t) {
+        uint32_t* lo = &tile_lo[(size_t)t * NS];
+        lo[0] = std::min<uint32_t>(t * tile, hb.n);
+        for (uint32_t s = 1; s < NS; ++s) lo[s] = hb.scope_off[s][lo[c.schema.scopes[s].parent]];
+        if (t)
+          for (uint32_t s = 0; s < NS; ++s) cap[s] = std::max(cap[s], lo[s] - tile_lo[(size_t)(t - 1) * NS + s]);
+      }
+      if (tile <= 32 || tile_fits(c, cap, tile)) break;   // (a 32-object tile that still does not fit is refused at launch)
     }
     auto* db = new DevBatch();
     db->bytes = gk_align(plan.total);
@@ -232,6 +238,30 @@ class CudaBackend : public Backend {
     if (h2d_ms) *h2d_ms = ms;
     if (h2d_bytes) *h2d_bytes = plan.total + tile_lo.size() * 4 + tables_bytes;
     return db;
+  }
+
+  // ---- adaptive tile size: every bit column of a tile lives in the CTA's shared memory, so a page whose objects iterate very
+  // many rows (one Pod with thousands of containers) needs smaller tiles, not a refusal
+  static uint32_t slot_words_of(const Compiled& c, std::vector<uint32_t> cap, uint32_t tile) {
+    cap[0] = tile;
+    uint64_t w = 0;
+    for (size_t i = 0; i < c.slot_level.size(); ++i) w += ((cap[c.slot_level[i]] + 31) / 32 + 1 + 3) & ~3u;
+    return (uint32_t)std::min<uint64_t>(w, 0xffffffffu);
+  }
+  size_t smem_of(const Compiled& c, uint32_t slot_words) const {
+    auto r16 = [](size_t x) { return (x + 15) / 16 * 16; };
+    const size_t C = c.cons_match.size(), NS = c.schema.scopes.size();
+    size_t smem = 3 * r16(C * 4) + 2 * r16(NS * 4) + r16(c.phase_off.size() * 4) + r16((size_t)slot_words * 4) + 64;
+#if GK_TABLES_IN_SMEM
+    smem += r16(C * sizeof(GkOutEnt)) + r16(c.ops.size() * sizeof(GkOp)) + r16(c.items.size() * 4) + r16(c.match.size() * sizeof(GkMatch)) +
+            r16(c.schema.cols.size() * sizeof(GkColumn)) + r16(NS * sizeof(GkScope)) + r16(c.pool.size() * 4) + r16(c.cbytes.size());
+#endif
+    return smem;
+  }
+  bool tile_fits(const Compiled& c, const std::vector<uint32_t>& cap, uint32_t tile) const {
+    const uint32_t sw = slot_words_of(c, cap, tile);
+    if (sw > 0xffffu || smem_of(c, sw) > max_smem_) return false;
+    return !c.amb || (slot_words_of(*c.amb, cap, tile) <= 0xffffu && smem_of(*c.amb, slot_words_of(*c.amb, cap, tile)) <= max_smem_);
   }
 
   // slot area of a tile from the per-scope tile capacities; the netlist with slot ids resolved to word offsets; output planes
@@ -389,6 +419,8 @@ class CudaBackend : public Backend {
     p.timing = d_timing_;
 #endif
     if (active.size() != C) throw BackendError{"active mask size mismatch"};
+    if (db->words == 2 && ((reinterpret_cast<uintptr_t>(viol) | reinterpret_cast<uintptr_t>(err)) & 7u))
+      throw BackendError{"result bitmaps must be 8-byte aligned (two-word rows are stored as one 64-bit word)"};
     if (C && active != last_active_) {
       CK(cudaMemcpyAsync(d_active_, active.data(), (size_t)C * 4, cudaMemcpyHostToDevice, st));
       CK(cudaStreamSynchronize(st));   // `active` is a caller temporary
@@ -960,23 +992,28 @@ class CudaBackend : public Backend {
     }
     uint32_t tile = kTile;
     if (const char* ft = getenv("GK_FORCE_TILE")) tile = std::min<uint32_t>(kTile, std::max(32, atoi(ft)) / 32 * 32);
-    const uint32_t ntiles = (n + tile - 1) / tile;
-    db->tile = tile;
-    db->ntiles = ntiles;
-    dmalloc(&db->d_tile_lo, ((size_t)(ntiles + 1) * NS) * 4 + 64);
-    CK(cudaMemsetAsync(d_cap, 0, (size_t)NS * 4, stream_));
-    gk_tiles_kernel<<<(ntiles + 1 + 127) / 128, 128, 0, stream_>>>(xp, out, n, NS, tile, ntiles, db->d_tile_lo, d_cap);
-    ++launches_;
-    std::vector<uint32_t> cap(NS, 0);
     unsigned long long mm[2] = {~0ull, 0ull};
     if (n) {
       gk_gvk_minmax_kernel<<<std::min<uint32_t>(1024u, (n + 255u) / 256u), 256, 0, stream_>>>(out.gvk, n, d_mm);
       ++launches_;
       CK(cudaMemcpyAsync(mm, d_mm, 16, cudaMemcpyDeviceToHost, stream_));
     }
-    CK(cudaMemcpyAsync(cap.data(), d_cap, (size_t)NS * 4, cudaMemcpyDeviceToHost, stream_));
-    CK(cudaStreamSynchronize(stream_));
-    CK(cudaGetLastError());
+    std::vector<uint32_t> cap(NS, 0);
+    uint32_t ntiles = 0;
+    for (;; tile = std::max(32u, tile / 2 / 32 * 32)) {   // (halved until the tile's bit columns fit the CTA's shared memory)
+      ntiles = (n + tile - 1) / tile;
+      if (db->d_tile_lo) dfree(db->d_tile_lo), db->d_tile_lo = nullptr;
+      dmalloc(&db->d_tile_lo, ((size_t)(ntiles + 1) * NS) * 4 + 64);
+      CK(cudaMemsetAsync(d_cap, 0, (size_t)NS * 4, stream_));
+      gk_tiles_kernel<<<(ntiles + 1 + 127) / 128, 128, 0, stream_>>>(xp, out, n, NS, tile, ntiles, db->d_tile_lo, d_cap);
+      ++launches_;
+      CK(cudaMemcpyAsync(cap.data(), d_cap, (size_t)NS * 4, cudaMemcpyDeviceToHost, stream_));
+      CK(cudaStreamSynchronize(stream_));
+      CK(cudaGetLastError());
+      if (tile <= 32 || tile_fits(c, cap, tile)) break;
+    }
+    db->tile = tile;
+    db->ntiles = ntiles;
     db->gvk_uniform = mm[1] == 0 || mm[0] == mm[1];
     finish_batch(db, c, cap);
     if (st) {

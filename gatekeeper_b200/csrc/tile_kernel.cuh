@@ -622,6 +622,53 @@ __global__ void __launch_bounds__(kThreads, GK_MIN_CTAS) gk_eval_kernel(const KP
     // transpose that 32x32 bit block so that lane o ends up with the bitmap word of object o.  The 32 objects of a group
     // are consecutive rows of the object-major output: the stores are contiguous.
     const uint32_t owords = (nobj + 31u) >> 5;
+    if (W == 2u) {
+      // two constraint words per object (33..64 constraints): one warp produces BOTH words of a group of 32 objects and stores
+      // them as one 8-byte word per object -- whole sectors, and half as many stores per peer over NVLink
+      for (uint32_t ow = warp; ow < owords; ow += kWarps) {
+        uint32_t yv[2] = {0u, 0u}, ye[2] = {0u, 0u};
+#pragma unroll
+        for (uint32_t wi = 0; wi < 2u; ++wi) {
+          const uint32_t c = wi * 32u + lane;
+          uint32_t xv = 0, xe = 0;
+          if (c < C && s_act[c]) {
+            const GkOutEnt oe = outs[c];
+            const uint32_t pv = (oe.flags & 1u) ? FULL : (oe.flags & 2u) ? 0u : slots[(oe.prog_slot) + ow];
+            xv = pv & slots[(oe.match_slot) + ow];
+            xe = slots[(oe.err_slot) + ow];
+          }
+#pragma unroll
+          for (uint32_t o = 0; o < 32u; ++o) {
+            const uint32_t bv = __ballot_sync(FULL, (xv >> o) & 1u);
+            if (lane == o) yv[wi] = bv;
+          }
+          if (__any_sync(FULL, xe != 0u)) {
+#pragma unroll
+            for (uint32_t o = 0; o < 32u; ++o) {
+              const uint32_t be = __ballot_sync(FULL, (xe >> o) & 1u);
+              if (lane == o) ye[wi] = be;
+            }
+          }
+          const uint32_t valid = range_mask(ow, 0u, nobj);
+          const uint32_t nv = __popc(xv & valid), ne = __popc(xe & valid);
+          if (c < C) {
+            if (nv) atomicAdd(&s_tot[c], nv);
+            if (ne) atomicAdd(&s_err[c], ne);
+          }
+        }
+        const uint32_t obj = ow * 32u + lane;
+        if (obj < nobj) {
+          const size_t at = (size_t)(obj0 + obj) * 2u;
+          const uint2 v2 = make_uint2(yv[0], yv[1]);
+          if (p.npeers) {
+            for (uint32_t q = 0; q < p.npeers; ++q) *reinterpret_cast<uint2*>(p.peer_viol[q] + at) = v2;   // this rank is one of the peers
+          } else {
+            *reinterpret_cast<uint2*>(p.out.viol + at) = v2;
+          }
+          *reinterpret_cast<uint2*>(p.out.err + at) = make_uint2(ye[0], ye[1]);
+        }
+      }
+    } else
     for (uint32_t g = warp; g < owords * W; g += kWarps) {
       const uint32_t wi = g % W, ow = g / W;          // constraint word, object word
       const uint32_t c = wi * 32u + lane;

@@ -1710,3 +1710,33 @@ def case_audit_lazy(lib, n=3000, limit=4):
     got_m = check(run, want_m)
     assert got_m["pairsCounted"] == 0
     return got
+
+
+def case_wide_objects(lib, pods=128, containers=400):
+    """Objects that iterate very many rows: every bit column of an evaluation tile lives in the CTA's shared memory, so the
+    backend shrinks the tile (512 -> 32 objects here) instead of refusing the page."""
+    t = golden("templates.json")
+    tm = [(t[k]["kind"], t[k]["rego"]) for k in ("allowedrepos", "containerlimits", "psp_privileged")]
+    cons = [W._constraint(t["allowedrepos"]["kind"], "repos", match=dict(W.POD), params={"repos": ["gcr.io/", "quay.io/team/"]}),
+            W._constraint(t["containerlimits"]["kind"], "limits", match=dict(W.POD), params={"cpu": "2", "memory": "1Gi"}),
+            W._constraint(t["psp_privileged"]["kind"], "priv", match=dict(W.POD))]
+    orc, drv, skipped = make_pair(tm, cons, lib_path=lib)
+    assert not skipped
+    rnd = random.Random(11)
+    objs = []
+    for i in range(pods):
+        cs = []
+        for j in range(containers if i % 3 else 3):
+            c = {"name": "c%d" % j, "image": rnd.choice(["gcr.io/a/b:1", "docker.io/x:latest", "quay.io/team/y:2", "evil.io/z"])}
+            if rnd.random() < 0.7:
+                c["resources"] = {"limits": {"cpu": rnd.choice(["500m", "1", "4", "250m"]), "memory": rnd.choice(["512Mi", "2Gi", "1Gi"])}}
+            if rnd.random() < 0.1:
+                c["securityContext"] = {"privileged": rnd.random() < 0.5}
+            cs.append(c)
+        objs.append({"apiVersion": "v1", "kind": "Pod", "metadata": {"name": "wide-%d" % i, "namespace": "default"}, "spec": {"containers": cs}})
+    revs = [D.Review(object=o, source="Original") for o in objs]
+    want = oracle_results(orc, revs, k8s.AUDIT_EP)
+    assert_same(want, engine_results(drv.ReviewBatch(revs, k8s.AUDIT_EP)))
+    blob = W.PyBlob([json.dumps(o).encode() for o in objs])
+    assert_same(want, engine_results(drv.ReviewBlob(blob, k8s.AUDIT_EP, flags=D.F_MATERIALIZE)))
+    return len(want)

@@ -300,3 +300,7 @@ def test_referential_constraints_data_inventory():
 def test_audit_counts_single_result_pairs_and_evaluates_only_list_candidates():
     got = P.case_audit_lazy(LIB)
     assert got["pairsEvaluated"] < got["results"]
+
+
+def test_pages_of_wide_objects_shrink_the_tile():
+    assert P.case_wide_objects(LIB) > 100
