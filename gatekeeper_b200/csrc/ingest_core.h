@@ -735,7 +735,11 @@ struct GkXCtx {
   GkXVal key[GK_MAX_LOOP_DEPTH + 1];
   uint32_t scope_at[GK_MAX_LOOP_DEPTH + 1];   // scope id at each depth
   int depth;
+  // per-row memo of the path steps: memo[closure] = tape node, GK_NONE (undefined) or GK_MEMO_EMPTY; null: no memo
+  uint32_t* memo;
 };
+#define GK_MEMO_EMPTY 0xfffffffeu
+#define GK_MEMO_MAX 256
 
 // review envelope fields of the object (apiVersion -> group / version, kind, metadata.name / namespace): computed on first use
 GK_HD void gk_x_envelope(GkXCtx& c) {
@@ -852,38 +856,50 @@ GK_HD int gk_depth_of_scope(const GkXCtx& c, uint32_t scope) {
 }
 
 // value of a native closure (Path / Elem / Key) for the current rows; Count and Lut are handled by the encoder
+GK_HD void gk_memo_put(const GkXCtx& c, uint32_t ci, const GkXVal& v) {
+  if (!c.memo || ci >= GK_MEMO_MAX) return;
+  if (v.vt == GK_VT_UNDEF) c.memo[ci] = GK_NONE;
+  else if (v.node != GK_NONE) c.memo[ci] = v.node;   // (a synthetic value -- no tape node -- is recomputed)
+}
 GK_HD GkXVal gk_x_eval(const GkXCtx& c, uint32_t ci) {
-  // collect the chain of Path closures down to its leaf base, then walk forward
-  uint32_t chain[8];
+  // walk down from the requested closure towards its leaf base, collecting the steps still to take; stop at the first step this
+  // row has taken already
+  uint32_t chain[16];
   int nchain = 0;
+  GkXVal v = gk_xundef();
+  bool have = false;
   for (;;) {
     const GkXClosure& cl = c.xp->cl[ci];
-    if (cl.kind == GK_X_PATH) {
-      if (nchain >= 8) return gk_xundef();
-      chain[nchain++] = ci;
-      if (cl.base < 0) break;
-      ci = (uint32_t)cl.base;
-      continue;
+    if (cl.kind != GK_X_PATH) break;
+    if (c.memo && ci < GK_MEMO_MAX && c.memo[ci] != GK_MEMO_EMPTY) {
+      const uint32_t m = c.memo[ci];
+      if (m != GK_NONE) v = gk_xnode(c.doc.tape, m);
+      have = true;
+      break;
     }
-    break;
+    if (cl.base < 0) {   // rooted at the review envelope: gk_x_root walks the closure's own keys
+      v = gk_x_root(c, cl.root, c.xp->xkeys + cl.keys_off, cl.nkeys);
+      gk_memo_put(c, ci, v);
+      have = true;
+      break;
+    }
+    if (nchain >= 16) return gk_xundef();
+    chain[nchain++] = ci;
+    ci = (uint32_t)cl.base;
   }
-  GkXVal v;
-  int from;
-  const GkXClosure& leaf = c.xp->cl[ci];
-  if (leaf.kind == GK_X_PATH) {   // rooted at the review envelope
-    v = gk_x_root(c, leaf.root, c.xp->xkeys + leaf.keys_off, leaf.nkeys);
-    from = nchain - 2;
-  } else if (leaf.kind == GK_X_ELEM || leaf.kind == GK_X_KEY) {
+  if (!have) {
+    const GkXClosure& leaf = c.xp->cl[ci];
+    if (leaf.kind != GK_X_ELEM && leaf.kind != GK_X_KEY) return gk_xundef();
     const int d = gk_depth_of_scope(c, leaf.scope);
     if (d == 0) return gk_xundef();
     v = leaf.kind == GK_X_ELEM ? c.elem[d] : c.key[d];
-    from = nchain - 1;
-  } else {
-    return gk_xundef();
   }
-  for (int j = from; j >= 0 && v.vt != GK_VT_UNDEF; --j) {
-    const GkXClosure& cl = c.xp->cl[chain[j]];
-    v = gk_x_follow(c, v, c.xp->xkeys + cl.keys_off, cl.nkeys);
+  for (int j = nchain - 1; j >= 0; --j) {
+    if (v.vt != GK_VT_UNDEF) {
+      const GkXClosure& cl = c.xp->cl[chain[j]];
+      v = gk_x_follow(c, v, c.xp->xkeys + cl.keys_off, cl.nkeys);
+    }
+    gk_memo_put(c, chain[j], v);
   }
   return v;
 }
@@ -1362,6 +1378,7 @@ GK_HD void gk_ingest_obj(const GkXProg& xp, const GkIngestIn& in, const GkIngest
   c.depth = 0;
   c.scope_at[0] = 0;
   c.env_ready = 0;
+  c.memo = nullptr;
   c.api_node = c.kind_node = c.name_node = c.ns_node = c.meta_node = GK_NONE;
   c.grp = c.ver = nullptr;
   c.grp_len = c.ver_len = 0;
@@ -1499,6 +1516,7 @@ GK_HD uint32_t gk_row_ctx(const GkXProg& xp, const GkIngestIn& in, const GkInges
   c.doc.tape = in.tape + gk_tape_off(in.ooff, i);
   c.doc.ntape = in.ntape[i];
   c.env_ready = 0;
+  c.memo = nullptr;
   c.api_node = c.kind_node = c.name_node = c.ns_node = c.meta_node = GK_NONE;
   c.grp = c.ver = nullptr;
   c.grp_len = c.ver_len = 0;
@@ -1635,6 +1653,12 @@ GK_HD void gk_ingest_row(const GkXProg& xp, const GkIngestIn& in, const GkIngest
         for (int w = 0; w < GK_HEAD_WORDS; ++w) out.head[ci][(size_t)i * GK_HEAD_WORDS + w] = 0;
     }
     return;
+  }
+  // the columns of a row share path prefixes (`resources`, `resources.limits`, `resources.limits.cpu` ...): each step once
+  uint32_t memo[GK_MEMO_MAX];
+  if (xp.ncl <= GK_MEMO_MAX) {
+    for (uint32_t k = 0; k < xp.ncl; ++k) memo[k] = GK_MEMO_EMPTY;
+    c.memo = memo;
   }
   const GkCur none{nullptr, 0};
   for (uint32_t k = lane; k < xs.ncols; k += nlanes) gk_emit_col<GK_PASS_COLS>(xp, in, out, c, xp.col_order[xs.first_col + k], r, none);

@@ -70,8 +70,11 @@ struct Builder {
     x.cl_args.emplace_back();
     return (uint32_t)x.cl.size() - 1;
   }
-  uint32_t add_path(uint32_t base, const std::vector<VP>& keys) {
-    if (keys.empty()) return base;
+  // A path from a base closure is a CHAIN of one-key steps, each step shared by every path that goes through it
+  // (`resources`, `resources.limits`, `resources.limits.cpu`, ... look `resources` up once per row: ingest_core.h memoises
+  // a row's steps).  Beyond 10 keys the rest stays one closure (gk_x_eval walks chains of at most 16).
+  std::map<std::string, uint32_t> step_ix;   // "<base closure>/<key>" -> step closure
+  uint32_t add_step(uint32_t base, const std::vector<VP>& keys) {
     GkXClosure c{};
     c.kind = GK_X_PATH;
     c.base = (int32_t)base;
@@ -84,6 +87,17 @@ struct Builder {
     x.cl_src.push_back(nullptr);
     x.cl_args.emplace_back();
     return (uint32_t)x.cl.size() - 1;
+  }
+  uint32_t add_path(uint32_t base, const std::vector<VP>& keys) {
+    uint32_t cur = base;
+    for (size_t i = 0; i < keys.size(); ++i) {
+      if (i >= 10) return add_step(cur, std::vector<VP>(keys.begin() + (long)i, keys.end()));
+      const std::string k = std::to_string(cur) + "/" + intern_key(keys[i]);
+      auto it = step_ix.find(k);
+      if (it == step_ix.end()) it = step_ix.emplace(k, add_step(cur, {keys[i]})).first;
+      cur = it->second;
+    }
+    return cur;
   }
 
   // ---- native programs for closures built from slicing string builtins over one leaf (ingest_core.h GK_SX_*)
