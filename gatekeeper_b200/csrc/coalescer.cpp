@@ -63,7 +63,14 @@ static void run_batch(gk_coalescer* c, Batch& b) {
     for (auto* t : b.tickets) t->error = msg;
     return;
   }
-  // results are in object order
+  // results are in object order (gk_review_batch sorts them so, also after folding expansion results onto their parents); a
+  // result that is not would be lost below, so check rather than assume
+  for (size_t k = 1; k < res.n_violations; ++k)
+    if (res.violations[k].object < res.violations[k - 1].object) {
+      for (auto* t : b.tickets) t->error = "internal: review results are not in object order";
+      gk_free_result(&res);
+      return;
+    }
   size_t v = 0;
   for (size_t i = 0; i < n; ++i) {
     Ticket& t = *b.tickets[i];

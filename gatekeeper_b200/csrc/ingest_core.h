@@ -731,14 +731,18 @@ struct GkXCtx {
   const uint8_t* ver;
   uint32_t ver_len;
   // current row of every scope on the DFS stack
-  GkXVal elem[GK_MAX_LOOP_DEPTH + 1];
-  GkXVal key[GK_MAX_LOOP_DEPTH + 1];
+  // (kept small: this context lives in per-thread local memory, and ncu showed the column pass bound by local-memory misses --
+  // 4 GB of them per 1.6 M rows -- when each depth held two 32-byte values)
+  uint32_t elem_node[GK_MAX_LOOP_DEPTH + 1];  // tape index of the row's element at each depth
+  uint32_t key_ref[GK_MAX_LOOP_DEPTH + 1];    // tape index of the member's key, or (array index | GK_ROW_INDEX)
   uint32_t scope_at[GK_MAX_LOOP_DEPTH + 1];   // scope id at each depth
   int depth;
-  // per-row memo of the path steps: memo[closure] = tape node, GK_NONE (undefined) or GK_MEMO_EMPTY; null: no memo
-  uint32_t* memo;
+  // per-row memo of the path steps: memo[closure] = tape node (16 bits: a longer tape is not memoised), GK_MEMO_UNDEF or
+  // GK_MEMO_EMPTY; null: no memo
+  unsigned short* memo;
 };
-#define GK_MEMO_EMPTY 0xfffffffeu
+#define GK_MEMO_EMPTY 0xfffeu
+#define GK_MEMO_UNDEF 0xffffu
 #define GK_MEMO_MAX 256
 
 // review envelope fields of the object (apiVersion -> group / version, kind, metadata.name / namespace): computed on first use
@@ -858,8 +862,8 @@ GK_HD int gk_depth_of_scope(const GkXCtx& c, uint32_t scope) {
 // value of a native closure (Path / Elem / Key) for the current rows; Count and Lut are handled by the encoder
 GK_HD void gk_memo_put(const GkXCtx& c, uint32_t ci, const GkXVal& v) {
   if (!c.memo || ci >= GK_MEMO_MAX) return;
-  if (v.vt == GK_VT_UNDEF) c.memo[ci] = GK_NONE;
-  else if (v.node != GK_NONE) c.memo[ci] = v.node;   // (a synthetic value -- no tape node -- is recomputed)
+  if (v.vt == GK_VT_UNDEF) c.memo[ci] = GK_MEMO_UNDEF;
+  else if (v.node < GK_MEMO_EMPTY) c.memo[ci] = (unsigned short)v.node;   // (a synthetic value -- no tape node -- is recomputed)
 }
 GK_HD GkXVal gk_x_eval(const GkXCtx& c, uint32_t ci) {
   // walk down from the requested closure towards its leaf base, collecting the steps still to take; stop at the first step this
@@ -873,7 +877,7 @@ GK_HD GkXVal gk_x_eval(const GkXCtx& c, uint32_t ci) {
     if (cl.kind != GK_X_PATH) break;
     if (c.memo && ci < GK_MEMO_MAX && c.memo[ci] != GK_MEMO_EMPTY) {
       const uint32_t m = c.memo[ci];
-      if (m != GK_NONE) v = gk_xnode(c.doc.tape, m);
+      if (m != GK_MEMO_UNDEF) v = gk_xnode(c.doc.tape, m);
       have = true;
       break;
     }
@@ -892,7 +896,14 @@ GK_HD GkXVal gk_x_eval(const GkXCtx& c, uint32_t ci) {
     if (leaf.kind != GK_X_ELEM && leaf.kind != GK_X_KEY) return gk_xundef();
     const int d = gk_depth_of_scope(c, leaf.scope);
     if (d == 0) return gk_xundef();
-    v = leaf.kind == GK_X_ELEM ? c.elem[d] : c.key[d];
+    if (leaf.kind == GK_X_ELEM) {
+      v = gk_xnode(c.doc.tape, c.elem_node[d]);
+    } else if (c.key_ref[d] & 0x80000000u) {   // GK_ROW_INDEX: an array index
+      v = gk_xsyn(GK_VT_NUM);
+      v.inum = (long long)(c.key_ref[d] & 0x7fffffffu);
+    } else {
+      v = gk_xnode(c.doc.tape, c.key_ref[d]);
+    }
   }
   for (int j = nchain - 1; j >= 0; --j) {
     if (v.vt != GK_VT_UNDEF) {
@@ -1528,14 +1539,8 @@ GK_HD uint32_t gk_row_ctx(const GkXProg& xp, const GkIngestIn& in, const GkInges
   GkRowRec rr = me;
   for (int dd = d; dd >= 1; --dd) {
     c.scope_at[dd] = cs;
-    c.elem[dd] = gk_xnode(c.doc.tape, rr.elem);
-    const uint32_t k = rr.key;
-    if (k & GK_ROW_INDEX) {
-      c.key[dd] = gk_xsyn(GK_VT_NUM);
-      c.key[dd].inum = (long long)(k & ~GK_ROW_INDEX);
-    } else {
-      c.key[dd] = gk_xnode(c.doc.tape, k);
-    }
+    c.elem_node[dd] = rr.elem;
+    c.key_ref[dd] = rr.key;
     cs = (uint32_t)xp.scopes[cs].parent;
     if (cs) rr = out.row_rec[cs][rr.parent];
   }
@@ -1655,7 +1660,7 @@ GK_HD void gk_ingest_row(const GkXProg& xp, const GkIngestIn& in, const GkIngest
     return;
   }
   // the columns of a row share path prefixes (`resources`, `resources.limits`, `resources.limits.cpu` ...): each step once
-  uint32_t memo[GK_MEMO_MAX];
+  unsigned short memo[GK_MEMO_MAX];
   if (xp.ncl <= GK_MEMO_MAX) {
     for (uint32_t k = 0; k < xp.ncl; ++k) memo[k] = GK_MEMO_EMPTY;
     c.memo = memo;
