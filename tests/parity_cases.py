@@ -1740,3 +1740,47 @@ def case_wide_objects(lib, pods=128, containers=400):
     blob = W.PyBlob([json.dumps(o).encode() for o in objs])
     assert_same(want, engine_results(drv.ReviewBlob(blob, k8s.AUDIT_EP, flags=D.F_MATERIALIZE)))
     return len(want)
+
+
+def case_audit_concurrent_with_reviews(lib, rounds=6):
+    """The audit switches the backend between the decision netlist and the ambiguity netlist (one program resident at a time)
+    while other threads review: every review must see its own snapshot's results, and the audit report must not change."""
+    import threading
+    tm, cons = W.config2()
+    nss = W.synth_namespaces()
+    orc, drv, _ = make_pair(tm, cons, nss, lib_path=lib)
+    blob = W.synth_objects(9000, 600)
+    objs = [json.loads(blob.get(i)) for i in range(600)]
+    revs = [D.Review(object=o, source="Original") for o in objs[:200]]
+    base = engine_results(drv.ReviewBatch(revs, k8s.AUDIT_EP))
+    rb = drv.upload([D.Review(object=o, source="Original") for o in objs])
+    run0 = D.AuditRun(drv, violations_limit=5)
+    run0.add_batch(rb, k8s.AUDIT_EP)
+    want = run0.report()
+    errors = []
+
+    def reviewer():
+        try:
+            for _ in range(rounds * 3):
+                assert engine_results(drv.ReviewBatch(revs, k8s.AUDIT_EP)) == base
+        except Exception as e:   # noqa: BLE001
+            errors.append(repr(e))
+
+    def auditor():
+        try:
+            for _ in range(rounds):
+                run = D.AuditRun(drv, violations_limit=5)
+                run.add_batch(rb, k8s.AUDIT_EP)
+                got = run.report()
+                assert got["totalViolations"] == want["totalViolations"] and got["violations"] == want["violations"]
+        except Exception as e:   # noqa: BLE001
+            errors.append(repr(e))
+
+    ts = [threading.Thread(target=reviewer) for _ in range(3)] + [threading.Thread(target=auditor) for _ in range(2)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors[:3]
+    assert want["pairsCounted"] > 0
+    return want

@@ -348,3 +348,7 @@ def test_audit_counts_single_result_pairs_and_evaluates_only_list_candidates():
 
 def test_pages_of_wide_objects_shrink_the_tile():
     assert P.case_wide_objects(HOSTEMU, pods=24, containers=60) > 100
+
+
+def test_audit_concurrent_with_reviews():
+    P.case_audit_concurrent_with_reviews(HOSTEMU)
