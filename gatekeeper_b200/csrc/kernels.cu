@@ -334,6 +334,7 @@ class CudaBackend : public Backend {
   // to go as soon as the call returns.
   void push_small(void* dst, const void* src, size_t bytes) {
     if (!bytes) return;
+    std::lock_guard<std::mutex> sl(stage_mu_);   // (uploads and forks of different batches run concurrently: one ring, one writer)
     if (bytes > (4u << 20) || getenv("GK_NO_PUSH_KERNEL")) {   // (big: the copy engine is the right tool)
       CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream_));
       CK(cudaStreamSynchronize(stream_));
@@ -358,6 +359,7 @@ class CudaBackend : public Backend {
   }
   uint8_t *stage_host_ = nullptr, *stage_dev_ = nullptr;
   size_t stage_cap_ = 0, stage_off_ = 0;
+  std::mutex stage_mu_;
 
   template <class T>
   void dmalloc(T** p, size_t bytes) { CK(cudaMallocAsync(reinterpret_cast<void**>(p), std::max<size_t>(bytes, 256), stream_)); }
