@@ -658,15 +658,13 @@ class CudaBackend : public Backend {
     CK(cudaEventCreate(&e3));
     CK(cudaEventRecord(e0, stream_));
     Front* fr = nullptr;
-    bool was_prefetched = false;
     {
       std::lock_guard<std::mutex> fl(front_mu_);
       for (auto& f : fronts_)
-        if (f.pending && f.host_blob == rq.blob && f.n == rq.n) fr = &f, was_prefetched = true;
+        if (f.pending && f.host_blob == rq.blob && f.n == rq.n) fr = &f;   // (prefetched)
       if (!fr) fr = &start_front(rq.blob, rq.ooff, rq.n);
       fr->pending = false;
     }
-    (void)was_prefetched;
     CK(cudaStreamWaitEvent(stream_, fr->done, 0));
     // ---- back scratch: header counters + scratch flags, totals, scan block sums, miss list, the pointer tables of the count phase
     const uint32_t miss_cap = 1u << 17;

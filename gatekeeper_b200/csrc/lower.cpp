@@ -1090,6 +1090,7 @@ class Lowerer {
     const Stmt& st = body[i];
     auto rest = [&](LEnv& e) { return lower_body(body, i + 1, e, k); };
     switch (st.k) {
+      case Stmt::Every: unsupported("internal: `every` reaches the lowering (the parser rewrites it)", st.line);
       case Stmt::Some: return rest(env);
       case Stmt::Not: {
         size_t mk = env.mark();
@@ -1442,7 +1443,7 @@ class Lowerer {
   }
 
   // complete rule referenced by name whose definition mixes parameters and object fields
-  FP inline_rule_value(const TP& t, LEnv& env, const SymK& k) {
+  FP inline_rule_value(const TP& t, LEnv& /*env*/, const SymK& k) {
     auto& defs = m_.rules.at(t->name);
     if (defs[0].kind != Rule::Complete) unsupported("partial rule `" + t->name + "` used as a value while mixing parameters and object fields", t->line);
     if (++depth_ > 24) unsupported("rule nesting too deep", t->line);

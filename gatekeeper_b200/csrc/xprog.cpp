@@ -279,7 +279,7 @@ struct Builder {
 std::shared_ptr<const XProgHost> build_xprog(const Schema& s) {
   auto out = std::make_shared<XProgHost>();
   XProgHost& x = *out;
-  Builder b{x, {}};
+  Builder b{x, {}, {}};
   x.xbytes.push_back(0);
   const size_t NS = s.scopes.size();
   x.scopes.resize(NS);
