@@ -375,7 +375,7 @@ def run_ours(args):
     # violations with their messages (pkg/audit/manager.go:886-1041).  Pairs with one result are counted from the bitmaps (the
     # ambiguity netlist runs on the device); the host evaluates what can still enter a list and the pairs that may have several.
     e2e_audit = None
-    if args.config == 2 and not args.no_audit:
+    if args.config == 2 and not args.no_audit and rank == 0:   # (host-side aggregation: one rank's page is the measurement)
         ta = time.perf_counter()
         audit_rb = drv.upload_blob(pages[1])
         audit_run = D.AuditRun(drv, violations_limit=20)
