@@ -18,9 +18,9 @@ OBJ = os.path.join(ROOT, "build", "obj")
 LIB = os.path.join(ROOT, "gatekeeper_b200", "libgk_engine.so")
 EMU = os.path.join(ROOT, "tests", "_hostemu", "libgk_hostemu.so")
 
-HOST_SRCS = ["val.cpp", "rego_parse.cpp", "rego_eval.cpp", "lower.cpp", "xprog.cpp", "expansion.cpp", "engine.cpp", "audit.cpp", "capi.cpp", "coalescer.cpp"]
+HOST_SRCS = ["val.cpp", "rego_parse.cpp", "rego_eval.cpp", "lower.cpp", "xprog.cpp", "expansion.cpp", "engine.cpp", "audit.cpp", "capi.cpp", "coalescer.cpp", "spec_codegen.cpp"]
 SYNTH = os.path.join(ROOT, "gatekeeper_b200", "libgk_synth.so")
-CXXFLAGS = ["-std=c++17", "-O2", "-g1", "-fPIC", "-Wall", "-Wextra", "-pthread"]
+CXXFLAGS = ["-std=c++17", "-O2", "-g1", "-fPIC", "-Wall", "-Wextra", "-pthread", "-I", OBJ]
 NVCCFLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC"]
 
 
@@ -62,12 +62,27 @@ def build_variant(suffix, defines):
     _run([_nvcc(), *NVCCFLAGS, *["-D" + d for d in defines], "-c", os.path.join(CSRC, "kernels.cu"), "-o", ko])
     objs = [os.path.join(OBJ, s + ".o") for s in HOST_SRCS]
     out = os.path.join(ROOT, "gatekeeper_b200", "libgk_engine%s.so" % suffix)
-    _run([_nvcc(), "-shared", "-o", out, *objs, ko, "-Xcompiler", "-pthread", "-cudart", "static"])
+    _run([_nvcc(), "-shared", "-o", out, *objs, ko, "-Xcompiler", "-pthread", "-cudart", "static", "-ldl"])
     return out
+
+
+def _spec_headers():
+    """program.h and vm_core.h as string literals: the kernel generated for a constraint set (spec_codegen.cpp) is one
+    self-contained translation unit that NVRTC compiles at run time, with no include path to find them on."""
+    out = os.path.join(OBJ, "spec_headers.inc")
+    txt = ""
+    for name, f in (("kSpecHdrProgram", "program.h"), ("kSpecHdrVmCore", "vm_core.h")):
+        body = open(os.path.join(CSRC, f)).read()
+        assert ')GKHDR"' not in body
+        txt += 'static const char %s[] = R"GKHDR(%s)GKHDR";\n' % (name, body)
+    if not os.path.exists(out) or open(out).read() != txt:
+        with open(out, "w") as fh:
+            fh.write(txt)
 
 
 def build(verbose=False, hostemu=True, force=False):
     os.makedirs(OBJ, exist_ok=True)
+    _spec_headers()
     hdr_m = _deps_mtime()
     jobs = []
     objs = []
@@ -92,9 +107,9 @@ def build(verbose=False, hostemu=True, force=False):
             if verbose and out.strip():
                 print(out)
     if force or _stale(LIB, objs + [ko], 0):
-        _run([_nvcc(), "-shared", "-o", LIB, *objs, ko, "-Xcompiler", "-pthread", "-cudart", "static"])
+        _run([_nvcc(), "-shared", "-o", LIB, *objs, ko, "-Xcompiler", "-pthread", "-cudart", "static", "-ldl"])
     if hostemu and (force or _stale(EMU, objs + [eo], 0)):
-        _run(["g++", "-shared", "-o", EMU, *objs, eo, "-pthread"])
+        _run(["g++", "-shared", "-o", EMU, *objs, eo, "-pthread", "-ldl"])
     # TEST / BENCH ONLY: the C++ CPU restatement of the reference's review loop (oracle/cpu_ref.cpp) over the engine's host objects
     csrc = os.path.join(ROOT, "oracle", "cpu_ref.cpp")
     cdir = os.path.join(ROOT, "oracle", "_build")

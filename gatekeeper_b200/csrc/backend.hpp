@@ -83,6 +83,8 @@ class Backend {
  public:
   virtual ~Backend() {}
   virtual const char* name() const = 0;
+  // which kernel decided the last evaluation: "gk_spec_kernel" (generated for the constraint set, spec_codegen.hpp) or "gk_eval_kernel"
+  virtual const char* last_kernel() const { return "gk_eval_kernel"; }
   virtual void set_program(const Compiled& c) = 0;                       // upload tables when the version changed
   virtual void sync_strings(const StringTable& st) = 0;                  // (re)upload the dictionary if it grew
   virtual void* upload(const HostBatch& hb, const Compiled& c, double* h2d_ms, uint64_t* h2d_bytes) = 0;

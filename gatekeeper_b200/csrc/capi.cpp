@@ -427,6 +427,7 @@ gk_engine_t* gk_engine_create(const gk_cfg* cfg, char** err) {
 
 void gk_engine_destroy(gk_engine_t* e) { delete e; }
 const char* gk_backend_name(gk_engine_t* e) { return e && e->be ? e->be->name() : ""; }
+const char* gk_last_kernel(gk_engine_t* e) { return e && e->be ? e->be->last_kernel() : ""; }
 
 int gk_add_template(gk_engine_t* e, const char* kind, const char* rego_src, size_t len, char** err) {
   if (!e || !kind || !rego_src) return GK_ERR_INVALID;

@@ -12,8 +12,13 @@
 #include <cstring>
 #include <mutex>
 
+#include <dlfcn.h>
+
+#include <list>
+
 #include "backend.hpp"
 #include "ingest_kernels.cuh"
+#include "spec_codegen.hpp"
 #include "tile_kernel.cuh"
 
 namespace gk {
@@ -35,6 +40,7 @@ struct DevBatch {
   uint32_t words = 0;
   // tiling (depends on the batch's row distribution and on the program's slot table)
   uint32_t* d_tile_lo = nullptr;
+  uint32_t* d_tile_list = nullptr;   // [ntiles] tiles the specialised kernel hands to the interpreter (objects too big for its mask registers)
   // the netlist with every slot id replaced by the slot's word offset in this batch's shared-memory slot area
   GkOp* d_ops = nullptr;
   uint32_t* d_pool = nullptr;
@@ -108,6 +114,7 @@ class CudaBackend : public Backend {
     cudaStreamDestroy(stream_);
   }
   const char* name() const override { return "cuda-sm100a"; }
+  const char* last_kernel() const override { return last_kernel_; }
 
   void set_program(const Compiled& c) override {
     std::lock_guard<std::mutex> l(mu_);
@@ -154,6 +161,7 @@ class CudaBackend : public Backend {
     if (!d_errlist_) CK(cudaMalloc(&d_errlist_, (size_t)kErrCap * 3 * 4));
     last_active_.clear();
     version_ = c.version;
+    spec_select(c);
   }
 
   void sync_strings(const StringTable& st) override {
@@ -325,6 +333,7 @@ class CudaBackend : public Backend {
     push_small(db->d_pool, pool_r.data(), pool_r.size() * 4);
     push_small(db->d_outs, outs_r.data(), outs_r.size() * sizeof(GkOutEnt));
     db->words = std::max<uint32_t>(1, (uint32_t)((c.cons_match.size() + 31) / 32));
+    dmalloc(&db->d_tile_list, (size_t)(db->ntiles + 1) * 4);
     dmalloc(&db->viol, (size_t)std::max(db->n, 1u) * db->words * 4);
     dmalloc(&db->err, (size_t)std::max(db->n, 1u) * db->words * 4);
     CK(cudaStreamSynchronize(stream_));
@@ -374,6 +383,7 @@ class CudaBackend : public Backend {
     dfree(db->viol);
     dfree(db->err);
     if (!db->fork) dfree(db->d_tile_lo);
+    dfree(db->d_tile_list);
     dfree(db->d_ops);
     dfree(db->d_pool);
     dfree(db->d_outs);
@@ -415,6 +425,11 @@ class CudaBackend : public Backend {
       p.peer_tot[q] = nullptr;
     }
     p.timing = nullptr;
+    p.tile_list = db->d_tile_list;
+    p.tile_count = reinterpret_cast<uint32_t*>(d_scalars_) + 8;   // zeroed with the error counter before every launch
+    p.list_mode = 0;
+    p.pad_ = 0;
+    spec_next_ = spec_ready(db->n);   // (an NVRTC run the first time: here, outside the timed region)
 #ifdef GK_PHASE_TIMING
     if (!d_timing_) CK(cudaMalloc(&d_timing_, (kMaxPhases + 2 + 16) * 16));
     CK(cudaMemsetAsync(d_timing_, 0, (kMaxPhases + 2 + 16) * 16, st));
@@ -446,7 +461,7 @@ class CudaBackend : public Backend {
     return p;
   }
 
-  void fire(const KParams& p, size_t smem, cudaStream_t st) {
+  void fire(KParams p, size_t smem, cudaStream_t st) {
     if (p.ntiles == 0) return;
     // persistent CTAs: as many as fit per SM (shared-memory bound), each walks tiles with a grid stride
     int per_sm = 1;   // resident CTAs per SM for this launch configuration (registers and shared memory)
@@ -454,9 +469,114 @@ class CudaBackend : public Backend {
     per_sm = std::max(1, per_sm);
     if (getenv("GK_TRACE_LAUNCH")) fprintf(stderr, "[launch] %d CTAs/SM x %d threads, %zu B smem/CTA, %u tiles of %u objects\n", per_sm, kThreads, smem, p.ntiles, p.tile);
     uint32_t grid = std::max(1u, std::min<uint32_t>(p.ntiles, (uint32_t)(sms_ * per_sm)));
+    last_kernel_ = "gk_eval_kernel";
+    if (spec_next_) {
+      // the kernel generated for this constraint set does the tiles whose objects fit its mask registers (all of them, normally);
+      // the interpreter behind it takes the tiles it listed and, in the fused exchange, publishes the totals of both
+      SpecEntry& se = *spec_cur_;
+      void* args[] = {&p};
+      CK(cudaLaunchKernel(reinterpret_cast<const void*>(se.kern), dim3(p.ntiles), dim3((unsigned)se.threads), args, se.src.smem, st));
+      ++launches_;
+      p.list_mode = 1;
+      last_kernel_ = "gk_spec_kernel";
+    }
     gk_eval_kernel<<<grid, kThreads, smem, st>>>(p);
     CK(cudaGetLastError());
     ++launches_;
+  }
+
+  // ---- the specialised kernel: source per constraint-set version (spec_codegen.cpp), compiled by NVRTC when first needed
+  struct SpecEntry {
+    uint64_t version = 0;
+    SpecSource src;
+    int state = 0;            // 0 = not compiled yet, 1 = ready, -1 = failed (the interpreter runs; reported once on stderr)
+    cudaLibrary_t lib = nullptr;
+    cudaKernel_t kern = nullptr;
+    int threads = 128;
+    double compile_ms = 0;
+  };
+  void spec_select(const Compiled& c) {
+    spec_cur_ = nullptr;
+    if (!spec_on_) return;
+    for (auto it = spec_cache_.begin(); it != spec_cache_.end(); ++it)
+      if (it->version == c.version) {
+        spec_cache_.splice(spec_cache_.begin(), spec_cache_, it);
+        spec_cur_ = &spec_cache_.front();
+        return;
+      }
+    spec_cache_.emplace_front();
+    spec_cache_.front().version = c.version;
+    spec_cache_.front().src = spec_codegen(c);
+    spec_cur_ = &spec_cache_.front();
+    while (spec_cache_.size() > 8) {
+      if (spec_cache_.back().lib) cudaLibraryUnload(spec_cache_.back().lib);
+      spec_cache_.pop_back();
+    }
+  }
+  bool spec_ready(uint32_t n) {
+    if (!spec_cur_ || n < spec_min_objects_) return false;
+    if (spec_cur_->state == 0) spec_compile(*spec_cur_);
+    return spec_cur_->state == 1;
+  }
+  void spec_compile(SpecEntry& se) {
+    se.state = -1;
+    const auto t0 = std::chrono::steady_clock::now();
+    try {
+      // NVRTC is loaded at run time: the library itself links only the CUDA runtime (and loads in a container without a driver)
+      typedef void* Prog;
+      typedef int (*CreateFn)(Prog*, const char*, const char*, int, const char* const*, const char* const*);
+      typedef int (*CompileFn)(Prog, int, const char* const*);
+      typedef int (*SizeFn)(Prog, size_t*);
+      typedef int (*GetFn)(Prog, char*);
+      typedef int (*DestroyFn)(Prog*);
+      static void* h = nullptr;
+      if (!h) {
+        for (const char* name : {"libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so"}) {
+          h = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+          if (h) break;
+        }
+      }
+      if (!h) throw BackendError{"libnvrtc.so.12 not found"};
+      auto create = reinterpret_cast<CreateFn>(dlsym(h, "nvrtcCreateProgram"));
+      auto compile = reinterpret_cast<CompileFn>(dlsym(h, "nvrtcCompileProgram"));
+      auto log_size = reinterpret_cast<SizeFn>(dlsym(h, "nvrtcGetProgramLogSize"));
+      auto get_log = reinterpret_cast<GetFn>(dlsym(h, "nvrtcGetProgramLog"));
+      auto bin_size = reinterpret_cast<SizeFn>(dlsym(h, "nvrtcGetCUBINSize"));
+      auto get_bin = reinterpret_cast<GetFn>(dlsym(h, "nvrtcGetCUBIN"));
+      auto destroy = reinterpret_cast<DestroyFn>(dlsym(h, "nvrtcDestroyProgram"));
+      if (!create || !compile || !log_size || !get_log || !bin_size || !get_bin || !destroy) throw BackendError{"NVRTC entry points missing"};
+      Prog prog = nullptr;
+      if (create(&prog, se.src.src.c_str(), "gk_spec_kernel.cu", 0, nullptr, nullptr) != 0) throw BackendError{"nvrtcCreateProgram failed"};
+      const std::string threads = "-DGK_SPEC_THREADS=" + std::to_string(spec_threads_), minb = "-DGK_SPEC_MINB=" + std::to_string(spec_minb_);
+      const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device", threads.c_str(), minb.c_str()};
+      const int rc = compile(prog, (int)(sizeof opts / sizeof opts[0]), opts);
+      if (rc != 0) {
+        size_t ls = 0;
+        log_size(prog, &ls);
+        std::string log(ls + 1, 0);
+        if (ls) get_log(prog, &log[0]);
+        destroy(&prog);
+        throw BackendError{"NVRTC: " + log.substr(0, 2000)};
+      }
+      size_t bs = 0;
+      bin_size(prog, &bs);
+      std::vector<char> cubin(bs);
+      get_bin(prog, cubin.data());
+      destroy(&prog);
+      CK(cudaLibraryLoadData(&se.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+      CK(cudaLibraryGetKernel(&se.kern, se.lib, "gk_spec_kernel"));
+      se.threads = spec_threads_;
+      if (se.src.smem > 48 * 1024)
+        CK(cudaFuncSetAttribute(reinterpret_cast<const void*>(se.kern), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)se.src.smem));
+      se.state = 1;
+    } catch (const BackendError& e) {
+      fprintf(stderr, "[gatekeeper_b200] the kernel generated for constraint set %llu could not be built (%s): the netlist interpreter runs instead\n",
+              (unsigned long long)se.version, e.msg.c_str());
+    }
+    se.compile_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (getenv("GK_TRACE_LAUNCH"))
+      fprintf(stderr, "[spec] constraint set %llu: %zu bytes of source, %zu atoms as immediates / %zu generic, NVRTC %.0f ms, state %d\n", (unsigned long long)se.version,
+              se.src.src.size(), se.src.n_fast, se.src.n_generic, se.compile_ms, se.state);
   }
 
   void eval(void* b, const std::vector<uint32_t>& active, EvalOut& out, bool copy_back) override {
@@ -1253,6 +1373,14 @@ class CudaBackend : public Backend {
   uint32_t* d_active_ = nullptr;
   unsigned long long* d_timing_ = nullptr;
   int host_threads_ = effective_cpus();
+  std::list<SpecEntry> spec_cache_;
+  SpecEntry* spec_cur_ = nullptr;
+  bool spec_on_ = !(getenv("GK_SPEC") && atoi(getenv("GK_SPEC")) == 0);
+  uint32_t spec_min_objects_ = getenv("GK_SPEC_MIN_OBJECTS") ? (uint32_t)atoll(getenv("GK_SPEC_MIN_OBJECTS")) : 8192u;   // below: not worth a ~2 s NVRTC run
+  int spec_threads_ = getenv("GK_SPEC_THREADS") ? std::max(32, atoi(getenv("GK_SPEC_THREADS")) / 32 * 32) : 128;
+  int spec_minb_ = getenv("GK_SPEC_MINB") ? std::max(1, atoi(getenv("GK_SPEC_MINB"))) : 3;
+  const char* last_kernel_ = "gk_eval_kernel";
+  bool spec_next_ = false;
   void* pinned_ = nullptr;
   size_t pinned_bytes_ = 0;
 };

@@ -6,7 +6,19 @@
 //   program: DISTINCT match blocks (the spec.match pre-filter, pkg/mutation/match/match.go:32-65) and one
 //            netlist of bit-column ops shared by all constraints (see GkOp).
 #pragma once
+#ifdef __CUDACC_RTC__   /* NVRTC (the specialised kernel, spec_codegen.cpp) has no system headers */
+typedef unsigned char uint8_t;
+typedef unsigned short uint16_t;
+typedef unsigned int uint32_t;
+typedef int int32_t;
+typedef long long int64_t;
+typedef unsigned long long uint64_t;
+typedef unsigned long size_t;
+typedef unsigned long uintptr_t;
+#else
 #include <stdint.h>
+#include <stddef.h>
+#endif
 
 #ifdef __CUDACC__
 #define GK_HD __host__ __device__ __forceinline__
@@ -195,3 +207,34 @@ typedef struct {
   uint32_t errcap;
   uint32_t words;            // ceil(nconstraints / 32)
 } GkOut;
+
+// ---- launch parameters shared by the netlist interpreter (tile_kernel.cuh: gk_eval_kernel) and the kernel generated for one
+// constraint set (spec_codegen.cpp: gk_spec_kernel, compiled at run time by NVRTC)
+#define GK_MAX_PEERS 8
+typedef struct {
+  GkBatch batch;
+  GkProgram prog;
+  GkOut out;
+  const uint32_t* active;     // [nconstraints] enforcement-point filter
+  const uint32_t* tile_lo;    // [(ntiles + 1) * nscopes] first row of every scope for every tile (row ranges are contiguous)
+  uint32_t ntiles;
+  uint32_t tile;              // objects per tile (multiple of 32)
+  uint32_t slot_words;        // words in the slot area
+  // Fused exchange (multi-GPU sweep): with npeers > 0 the gather epilogue stores every bitmap word straight into each
+  // peer's receive buffer over NVLink (peer_viol[q] already points at THIS rank's shard inside peer q's buffer), and the
+  // last CTA to finish publishes the per-constraint totals the same way.  A device-side barrier on the caller's stream
+  // then replaces the all-gather collective.
+  uint32_t* peer_viol[GK_MAX_PEERS];
+  unsigned long long* peer_tot[GK_MAX_PEERS];   // [2 * tot_stride]: violations, then matcher errors
+  uint32_t npeers;
+  uint32_t tot_stride;
+  uint32_t* done_ctr;
+  unsigned long long* timing; // GK_PHASE_TIMING builds: [kMaxPhases + 2][2] = (CTA cycles between barriers, summed warp busy cycles)
+  // Tile list.  gk_spec_kernel keeps one mask word per netlist node and object, so an object may have at most 32 rows in a
+  // scope: a tile holding a bigger object is appended to tile_list (tile_count = its length) and left alone; gk_eval_kernel,
+  // launched behind it with list_mode = 1, evaluates exactly those tiles (and does the fused exchange's totals publication).
+  uint32_t* tile_list;
+  uint32_t* tile_count;
+  uint32_t list_mode;
+  uint32_t pad_;
+} GkKParams;

@@ -1,0 +1,541 @@
+// Netlist -> CUDA C++ text (see spec_codegen.hpp).  The semantics of every op are those of the interpreter (tile_kernel.cuh) and of
+// the test-only host emulation; tests/_hostemu compiles the SAME text with g++ (-DGK_SPEC_HOST) and compares it object by object
+// with the interpreted netlist (GK_SPEC_CHECK=1), which is how the generator is verified in a container without a GPU.
+#include "spec_codegen.hpp"
+
+#include <algorithm>
+#include <cstdio>
+#include <functional>
+#include <map>
+#include <set>
+#include <sstream>
+
+#include "spec_headers.inc"   // kSpecHdrProgram / kSpecHdrVmCore: the text of program.h and vm_core.h (written by build.py)
+
+namespace gk {
+
+namespace {
+
+std::string strip_includes(const char* text) {
+  std::istringstream in(text);
+  std::string line, out;
+  while (std::getline(in, line)) {
+    if (line.rfind("#pragma once", 0) == 0 || line.rfind("#include \"program.h\"", 0) == 0) continue;
+    out += line;
+    out += '\n';
+  }
+  return out;
+}
+
+std::string hx(uint32_t v) {
+  char b[24];
+  snprintf(b, sizeof b, "0x%xu", v);
+  return b;
+}
+
+// the fixed part: launch wrapper (device) / per-object entry point (host test build)
+const char* kWrapper = R"GKSRC(
+#ifndef GK_SPEC_HOST
+__device__ __forceinline__ uint32_t gk_tr_step(uint32_t x, uint32_t lane, uint32_t j, uint32_t m) {
+  const uint32_t y = __shfl_xor_sync(0xffffffffu, x, j);
+  return (lane & j) ? ((x & ~m) | ((y & ~m) >> j)) : ((x & m) | ((y & m) << j));
+}
+// 32 x 32 bit transpose across the warp: lane i gives row i and receives column i
+__device__ __forceinline__ uint32_t gk_tr32(uint32_t x, uint32_t lane) {
+  x = gk_tr_step(x, lane, 16u, 0x0000ffffu);
+  x = gk_tr_step(x, lane, 8u, 0x00ff00ffu);
+  x = gk_tr_step(x, lane, 4u, 0x0f0f0f0fu);
+  x = gk_tr_step(x, lane, 2u, 0x33333333u);
+  x = gk_tr_step(x, lane, 1u, 0x55555555u);
+  return x;
+}
+
+extern "C" __global__ void __launch_bounds__(GK_SPEC_THREADS, GK_SPEC_MINB) gk_spec_kernel(const __grid_constant__ GkKParams p) {
+  extern __shared__ uint4 gk_smem4[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(gk_smem4);
+  const uint32_t NC = p.batch.ncols, NS = p.batch.nscopes;
+  GkColumn* cols = reinterpret_cast<GkColumn*>(smem);
+  GkScope* scopes = reinterpret_cast<GkScope*>(smem + (size_t)NC * sizeof(GkColumn));
+  uint32_t* act = reinterpret_cast<uint32_t*>(smem + (size_t)NC * sizeof(GkColumn) + (size_t)NS * sizeof(GkScope));
+  uint32_t* s_tot = act + GK_SPEC_W * 32u;
+  uint32_t* s_err = s_tot + GK_SPEC_W * 32u;
+  {
+    const uint4* a = reinterpret_cast<const uint4*>(p.batch.cols);
+    uint4* d = reinterpret_cast<uint4*>(cols);
+    for (uint32_t i = threadIdx.x; i < NC * (uint32_t)(sizeof(GkColumn) / 16); i += blockDim.x) d[i] = a[i];
+    const uint4* b = reinterpret_cast<const uint4*>(p.batch.scopes);
+    uint4* e = reinterpret_cast<uint4*>(scopes);
+    for (uint32_t i = threadIdx.x; i < NS * (uint32_t)(sizeof(GkScope) / 16); i += blockDim.x) e[i] = b[i];
+    for (uint32_t i = threadIdx.x; i < GK_SPEC_W * 32u; i += blockDim.x) {
+      act[i] = i < GK_SPEC_C ? p.active[i] : 0u;
+      s_tot[i] = 0u;
+      s_err[i] = 0u;
+    }
+  }
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31u;
+  uint32_t tv[GK_SPEC_W], te[GK_SPEC_W];
+#pragma unroll
+  for (uint32_t w = 0; w < GK_SPEC_W; ++w) tv[w] = te[w] = 0u;
+  for (uint32_t t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+    const uint32_t obj0 = t * p.tile, nobj = min(p.tile, p.batch.n - obj0);
+    int big = 0;
+    for (uint32_t o = threadIdx.x; o < nobj; o += blockDim.x) big |= gk_spec_overflow(scopes, obj0 + o) ? 1 : 0;
+    if (__syncthreads_or(big)) {   // some object of the tile has more rows in a scope than a mask register holds: the interpreter takes the tile
+      if (threadIdx.x == 0) p.tile_list[atomicAdd(p.tile_count, 1u)] = t;
+      continue;
+    }
+    for (uint32_t base = 0; base < nobj; base += blockDim.x) {
+      const uint32_t o = base + threadIdx.x;
+      uint32_t vw[GK_SPEC_W], ew[GK_SPEC_W];
+#pragma unroll
+      for (uint32_t w = 0; w < GK_SPEC_W; ++w) vw[w] = ew[w] = 0u;
+      if (o < nobj) {
+        gk_spec_object(p.batch, cols, scopes, p.prog.pool, p.prog.cbytes, act, p.out, obj0 + o, vw, ew);
+        const size_t at = (size_t)(obj0 + o) * GK_SPEC_W;
+#if GK_SPEC_W == 2
+        const uint2 v2 = make_uint2(vw[0], vw[1]);
+        if (p.npeers) {
+          for (uint32_t q = 0; q < p.npeers; ++q) *reinterpret_cast<uint2*>(p.peer_viol[q] + at) = v2;   // this rank is one of the peers
+        } else {
+          *reinterpret_cast<uint2*>(p.out.viol + at) = v2;
+        }
+        *reinterpret_cast<uint2*>(p.out.err + at) = make_uint2(ew[0], ew[1]);
+#else
+#pragma unroll
+        for (uint32_t w = 0; w < GK_SPEC_W; ++w) {
+          if (p.npeers) {
+            for (uint32_t q = 0; q < p.npeers; ++q) p.peer_viol[q][at + w] = vw[w];
+          } else {
+            p.out.viol[at + w] = vw[w];
+          }
+          p.out.err[at + w] = ew[w];
+        }
+#endif
+      }
+      // totals: after the transpose lane c holds the bit of constraint (32 w + c) for the warp's 32 objects
+      uint32_t anye = 0u;
+#pragma unroll
+      for (uint32_t w = 0; w < GK_SPEC_W; ++w) {
+        tv[w] += (uint32_t)__popc(gk_tr32(vw[w], lane));
+        anye |= ew[w];
+      }
+      if (__any_sync(0xffffffffu, anye != 0u)) {
+#pragma unroll
+        for (uint32_t w = 0; w < GK_SPEC_W; ++w) te[w] += (uint32_t)__popc(gk_tr32(ew[w], lane));
+      }
+    }
+  }
+#pragma unroll
+  for (uint32_t w = 0; w < GK_SPEC_W; ++w) {
+    if (tv[w]) atomicAdd(&s_tot[w * 32u + lane], tv[w]);
+    if (te[w]) atomicAdd(&s_err[w * 32u + lane], te[w]);
+  }
+  __syncthreads();
+  for (uint32_t c = threadIdx.x; c < GK_SPEC_C; c += blockDim.x) {
+    if (s_tot[c]) atomicAdd(p.out.totals + c, (unsigned long long)s_tot[c]);
+    if (s_err[c]) atomicAdd(p.out.err_totals + c, (unsigned long long)s_err[c]);
+  }
+}
+#else
+// TEST-ONLY host build (tests/_hostemu, GK_SPEC_CHECK=1): one object; returns 1 when the object does not fit the mask registers
+extern "C" int gk_spec_host(const GkKParams* p, uint32_t obj, uint32_t* vw, uint32_t* ew) {
+  if (gk_spec_overflow(p->batch.scopes, obj)) return 1;
+  for (uint32_t w = 0; w < GK_SPEC_W; ++w) vw[w] = ew[w] = 0u;
+  gk_spec_object(p->batch, p->batch.cols, p->batch.scopes, p->prog.pool, p->prog.cbytes, p->active, p->out, obj, vw, ew);
+  return 0;
+}
+#endif
+)GKSRC";
+
+// One netlist op after SSA renaming (slots are reused by liveness; every write gets a fresh variable): its text, what it
+// reads and what it defines.  Nodes are emitted depth-first from the constraint results (see spec_codegen()), not in netlist
+// order, which keeps the live values of one scope subtree together instead of all ~300 at once.
+struct SpecNode {
+  std::string code;
+  std::vector<uint32_t> deps;
+  bool done = false;
+};
+
+struct Gen {
+  const Compiled& c;
+  std::vector<SpecNode> nodes;
+  std::vector<int> producer;               // variable -> node, or -(scope + 1) for an atom of that scope's row loop
+  std::vector<std::string> atom_code;      // per scope: statements inside the row loop
+  std::vector<std::vector<uint32_t>> atom_vars;   // per scope: the mask variables its loop fills
+  std::vector<std::map<uint32_t, uint32_t>> col_need;   // per scope: column -> encodings its specialised atoms read
+  std::vector<uint8_t> scope_used;
+  std::vector<int> cur;                    // slot -> variable holding its current value (-1: never written)
+  uint32_t nvar = 0;
+  size_t n_fast = 0, n_generic = 0;
+  std::set<uint32_t> match_used;
+  std::ostringstream body;                 // the node being built
+  std::vector<uint32_t> deps;
+
+  explicit Gen(const Compiled& cc) : c(cc) {
+    const size_t NS = c.schema.scopes.size();
+    atom_code.resize(NS);
+    atom_vars.resize(NS);
+    col_need.resize(NS);
+    scope_used.assign(NS, 0);
+    cur.assign(c.slot_level.size() + 1, -1);
+  }
+  void use_scope(uint32_t s) {
+    while (!scope_used[s]) {
+      scope_used[s] = 1;
+      if (s == 0) break;
+      s = (uint32_t)c.schema.scopes[s].parent;
+    }
+  }
+  std::string rd(uint32_t slot) {
+    if (slot >= cur.size() || cur[slot] < 0) return "0u";
+    deps.push_back((uint32_t)cur[slot]);
+    return "v" + std::to_string(cur[slot]);
+  }
+  uint32_t fresh(uint32_t slot, int prod) {
+    if (slot >= cur.size()) cur.resize(slot + 1, -1);
+    cur[slot] = (int)nvar;
+    producer.push_back(prod);
+    return nvar++;
+  }
+  uint32_t fresh(uint32_t slot) { return fresh(slot, (int)nodes.size()); }   // defined by the node being built
+  void finish_node() {
+    SpecNode n;
+    n.code = body.str();
+    n.deps = deps;
+    nodes.push_back(std::move(n));
+    body.str("");
+    deps.clear();
+  }
+
+  // a boolean C expression for one atom on `row` of column ci; the loads it needs are recorded in col_need
+  std::string atom_expr(uint32_t level, uint32_t ci, uint32_t aop, uint32_t a, uint32_t b) {
+    const std::string K = std::to_string(ci);
+    auto need = [&](uint32_t enc) { col_need[level][ci] |= enc; };
+    const std::string t = "t" + K, i = "i" + K, n = "n" + K;
+    switch (aop) {
+      case GK_OP_TRUTHY: need(GK_ENC_VT); ++n_fast; return "(" + t + " != 0u && " + t + " != 2u)";
+      case GK_OP_DEFINED: need(GK_ENC_VT); ++n_fast; return "(" + t + " != 0u)";
+      case GK_OP_VTMASK: need(GK_ENC_VT); ++n_fast; return "(((" + hx(a) + " >> " + t + ") & 1u) != 0u)";
+      case GK_OP_SID_EQ: need(GK_ENC_SID); ++n_fast; return "(" + i + " == " + hx(a) + ")";
+      case GK_OP_SID_IN:
+        if (b <= 16u && (size_t)a + b <= c.pool.size()) {
+          need(GK_ENC_SID);
+          ++n_fast;
+          if (b == 0) return "false";
+          std::string e = "(";
+          for (uint32_t j = 0; j < b; ++j) e += (j ? " || " : "") + i + " == " + hx(c.pool[a + j]);
+          return e + ")";
+        }
+        break;
+      case GK_OP_NUM_CMP: {
+        if ((size_t)a + 1 >= c.pool.size()) break;
+        const int64_t k = (int64_t)(((uint64_t)c.pool[a + 1] << 32) | c.pool[a]);
+        if (k == INT64_MIN || k == INT64_MAX) break;   // the sentinels of non-numbers: the generic path orders by type rank
+        // (a defined non-number holds INT64_MIN / INT64_MAX by its type rank, so one signed compare is OPA's order: tile_kernel.cuh)
+        need(GK_ENC_VT | GK_ENC_NUM);
+        ++n_fast;
+        const char* opn = b == GK_CMP_LT ? "<" : b == GK_CMP_LE ? "<=" : b == GK_CMP_GT ? ">" : b == GK_CMP_GE ? ">=" : b == GK_CMP_EQ ? "==" : "!=";
+        return "(" + t + " != 0u && " + n + " " + opn + " " + std::to_string((long long)k) + "LL)";
+      }
+      case GK_OP_ANYPREFIX: {
+        bool all_short = (size_t)a + (size_t)b * GK_PREFIX_ENT <= c.pool.size();
+        for (uint32_t j = 0; all_short && j < b; ++j) all_short = c.pool[a + j * GK_PREFIX_ENT] <= GK_HEAD_BYTES;
+        if (!all_short) break;
+        need(GK_ENC_VT | GK_ENC_HEAD);
+        ++n_fast;
+        if (b == 0) return "false";
+        const std::string h = "h" + K;
+        static const char* comp[8] = {"a.x", "a.y", "a.z", "a.w", "b.x", "b.y", "b.z", "b.w"};
+        std::string e = "(" + t + " == 5u && (";
+        for (uint32_t j = 0; j < b; ++j) {
+          const uint32_t* ent = &c.pool[a + j * GK_PREFIX_ENT];
+          std::string one = "((" + h + "b.w >> 24) >= " + std::to_string(ent[0]) + "u";
+          for (uint32_t w = 0; w < GK_HEAD_WORDS; ++w) {
+            const uint32_t m = ent[2 + GK_HEAD_WORDS + w], v = ent[2 + w] & m;
+            if (!m) continue;
+            if (m == 0xffffffffu) one += " && " + h + comp[w] + " == " + hx(v);
+            else one += " && (" + h + comp[w] + " & " + hx(m) + ") == " + hx(v);
+          }
+          e += (j ? " || " : "") + one + ")";
+        }
+        return e + "))";
+      }
+      default: break;
+    }
+    ++n_generic;
+    return "gk_atom(cols[" + K + "], (uint32_t)row, " + std::to_string(aop) + "u, " + hx(a) + ", " + hx(b) + ", pool, cbytes)";
+  }
+
+  void atom(uint32_t level, uint32_t out_slot, uint32_t ci, uint32_t aop, uint32_t a, uint32_t b) {
+    use_scope(level);
+    const uint32_t v = fresh(out_slot, -(int)(level + 1));
+    atom_vars[level].push_back(v);
+    const std::string e = atom_expr(level, ci, aop, a, b);
+    if (level == 0) atom_code[level] += "    v" + std::to_string(v) + " = " + e + " ? 1u : 0u;\n";
+    else atom_code[level] += "    v" + std::to_string(v) + " |= (uint32_t)" + e + " << j;\n";
+  }
+
+  // `rm` = the mask of the children of parent row pj inside the object's rows of scope L
+  std::string range_loop_head(uint32_t L) {
+    const uint32_t P = (uint32_t)c.schema.scopes[L].parent;
+    const std::string l = std::to_string(L), p = std::to_string(P);
+    return "  for (uint32_t pj = 0; pj < n" + p + "; ++pj) {\n    const uint32_t ra = o" + l + "[lo" + p + " + pj] - lo" + l + ", rb = o" + l + "[lo" + p +
+           " + pj + 1u] - lo" + l + ";\n    const uint32_t rm = rb > ra ? (((rb - ra) >= 32u ? 0xffffffffu : ((1u << (rb - ra)) - 1u)) << ra) : 0u;\n";
+  }
+
+  void op(const GkOp& op) {
+    const uint32_t kind = op.w0 & 0xffu, level = (op.w0 >> 8) & 0xffu, out = op.w0 >> 16;
+    const std::string L = std::to_string(level);
+    switch (kind) {
+      case GK_N_ATOM: atom(level, out, op.w1 >> 8, op.w1 & 0xffu, op.w2, op.w3); break;
+      case GK_N_ATOMS:
+        for (uint32_t j = 0; j < op.w3; ++j) {
+          const uint32_t* e = &c.pool[op.w2 + j * GK_ATOMS_ENT];
+          atom(level, e[0] >> 16, op.w1 >> 8, e[0] & 0xffu, e[1], e[2]);
+        }
+        break;
+      case GK_N_CONST: {
+        use_scope(level);
+        const uint32_t v = fresh(out);
+        body << "  const uint32_t v" << v << " = " << ((op.w1 & 1u) ? "f" + L : std::string("0u")) << ";\n";
+        break;
+      }
+      case GK_N_GATE: {
+        use_scope(level);
+        const bool is_or = (op.w2 & GK_G_OR) != 0u, neg_out = (op.w2 & GK_G_NEG_OUT) != 0u;
+        std::string e;
+        bool any_neg = neg_out;
+        for (uint32_t j = 0; j < op.w3; ++j) {
+          const uint32_t in = c.pool[op.w1 + j];
+          const bool neg = (in >> 31) != 0u;
+          any_neg = any_neg || neg;
+          e += (j ? (is_or ? " | " : " & ") : "") + std::string(neg ? "~" : "") + rd(in & 0xffffu);
+        }
+        if (op.w3 == 0) e = is_or ? "0u" : "0xffffffffu", any_neg = true;
+        if (neg_out) e = "~(" + e + ")";
+        if (any_neg) e = "(" + e + ") & f" + L;
+        const uint32_t v = fresh(out);
+        body << "  const uint32_t v" << v << " = " << e << ";\n";
+        break;
+      }
+      case GK_N_BCAST: {   // parent-level values -> the rows of the child scope `level`
+        use_scope(level);
+        const uint32_t P = (uint32_t)c.schema.scopes[level].parent;
+        std::vector<std::pair<std::string, uint32_t>> pr;
+        for (uint32_t j = 0; j < op.w3; ++j) {
+          const uint32_t e = c.pool[op.w1 + j];
+          const std::string in = rd(e & 0xffffu);
+          pr.emplace_back(in, fresh(e >> 16));
+        }
+        if (P == 0) {
+          for (auto& q : pr) body << "  const uint32_t v" << q.second << " = (0u - (" << q.first << " & 1u)) & f" << L << ";\n";
+        } else {
+          for (auto& q : pr) body << "  uint32_t v" << q.second << " = 0u;\n";
+          body << range_loop_head(level);
+          for (auto& q : pr) body << "    if ((" << q.first << " >> pj) & 1u) v" << q.second << " |= rm;\n";
+          body << "  }\n";
+        }
+        break;
+      }
+      case GK_N_ACC:
+      case GK_N_ACC2: {    // EXISTS (at least one / at least two rows of the child scope `level`) per parent row
+        use_scope(level);
+        const uint32_t P = (uint32_t)c.schema.scopes[level].parent;
+        const bool two = kind == GK_N_ACC2;
+        std::vector<std::pair<std::string, uint32_t>> pr;
+        for (uint32_t j = 0; j < op.w3; ++j) {
+          const uint32_t e = c.pool[op.w1 + j];
+          const std::string in = rd(e & 0xffffu);
+          pr.emplace_back(in, fresh(e >> 16));
+        }
+        auto test = [&](const std::string& x) { return two ? "(GK_SPEC_POPC(" + x + ") >= 2)" : "((" + x + ") != 0u)"; };
+        if (P == 0) {
+          for (auto& q : pr) body << "  const uint32_t v" << q.second << " = " << test(q.first) << " ? 1u : 0u;\n";
+        } else {
+          for (auto& q : pr) body << "  uint32_t v" << q.second << " = 0u;\n";
+          body << range_loop_head(level);
+          for (auto& q : pr) body << "    v" << q.second << " |= (uint32_t)" << test(q.first + " & rm") << " << pj;\n";
+          body << "  }\n";
+        }
+        break;
+      }
+      case GK_N_MATCH: {
+        const uint32_t mid = op.w2;
+        match_used.insert(mid);
+        const uint32_t vm = fresh(out), ve = fresh(op.w1 & 0xffffu);
+        body << "  const int m" << vm << " = skip ? 0 : gk_match(B, pool, cbytes, M" << mid << ", obj);\n";
+        body << "  if (m" << vm << " < 0) GK_SPEC_ERR(obj, " << mid << "u, (uint32_t)(-m" << vm << "));\n";
+        body << "  const uint32_t v" << vm << " = m" << vm << " > 0 ? 1u : 0u, v" << ve << " = m" << vm << " < 0 ? 1u : 0u;\n";
+        break;
+      }
+      default: break;
+    }
+    if (kind != GK_N_ATOM && kind != GK_N_ATOMS) finish_node();
+  }
+};
+
+}  // namespace
+
+SpecSource spec_codegen(const Compiled& c) {
+  SpecSource out;
+  const uint32_t C = (uint32_t)c.cons_match.size(), W = std::max<uint32_t>(1, (C + 31) / 32);
+  const size_t NS = c.schema.scopes.size();
+  Gen g(c);
+  g.use_scope(0);
+  for (const GkOp& op : c.ops) {
+    const uint32_t kind = op.w0 & 0xffu;
+    if (kind == GK_N_END) break;
+    g.op(op);
+  }
+  std::ostringstream o;
+  o << "// generated by spec_codegen.cpp for constraint-set version " << c.version << ": " << C << " constraints, " << c.ops.size() << " netlist ops\n";
+  o << "#define GK_SPEC_C " << C << "u\n#define GK_SPEC_W " << W << "\n";
+  o << "#ifndef GK_SPEC_THREADS\n#define GK_SPEC_THREADS 128\n#endif\n#ifndef GK_SPEC_MINB\n#define GK_SPEC_MINB 3\n#endif\n";
+  o << strip_includes(kSpecHdrProgram) << strip_includes(kSpecHdrVmCore);
+  o << R"GKSRC(
+#ifdef GK_SPEC_HOST
+#define GK_SPEC_FN static inline
+#define GK_SPEC_POPC(x) __builtin_popcount(x)
+#define GK_SPEC_ERR(o, mid, code)                                    \
+  {                                                                  \
+    const uint32_t sl_ = (*out.errcount)++;                          \
+    if (sl_ < out.errcap) {                                          \
+      out.errlist[3 * sl_] = (o);                                    \
+      out.errlist[3 * sl_ + 1] = (mid);                              \
+      out.errlist[3 * sl_ + 2] = (code);                             \
+    }                                                                \
+  }
+struct uint4 { uint32_t x, y, z, w; };
+#else
+#define GK_SPEC_FN __device__ __forceinline__
+#define GK_SPEC_POPC(x) __popc(x)
+#define GK_SPEC_ERR(o, mid, code)                                    \
+  {                                                                  \
+    const uint32_t sl_ = atomicAdd(out.errcount, 1u);                \
+    if (sl_ < out.errcap) {                                          \
+      out.errlist[3 * sl_] = (o);                                    \
+      out.errlist[3 * sl_ + 1] = (mid);                              \
+      out.errlist[3 * sl_ + 2] = (code);                             \
+    }                                                                \
+  }
+#endif
+)GKSRC";
+  // ---- does the object fit the mask registers?
+  o << "GK_SPEC_FN bool gk_spec_overflow(const GkScope* scopes, uint32_t obj) {\n  const uint32_t lo0 = obj, hi0 = obj + 1u;\n  bool big = false;\n  (void)lo0; (void)hi0;\n";
+  auto ranges = [&](bool full) {
+    for (size_t s = 1; s < NS; ++s) {
+      if (!g.scope_used[s]) continue;
+      const int P = c.schema.scopes[s].parent;
+      o << "  const uint32_t* __restrict__ o" << s << " = scopes[" << s << "].off;\n";
+      o << "  const uint32_t lo" << s << " = o" << s << "[lo" << P << "], n" << s << " = o" << s << "[hi" << P << "] - lo" << s << ", hi" << s << " = lo" << s << " + n" << s
+        << ";\n";
+      if (full) o << "  const uint32_t f" << s << " = n" << s << " >= 32u ? 0xffffffffu : ((1u << n" << s << ") - 1u);\n  (void)hi" << s << "; (void)f" << s << ";\n";
+      else o << "  big = big || n" << s << " > 32u;\n  (void)hi" << s << ";\n";
+    }
+  };
+  ranges(false);
+  o << "  return big;\n}\n\n";
+  // ---- match blocks as literals: the compiler folds every branch a block does not use
+  for (uint32_t mid : g.match_used) {
+    const GkMatch& m = c.match[mid];
+    o << "#define M" << mid << " (GkMatch{" << hx(m.flags) << ", " << m.kinds_off << "u, " << m.kinds_n << "u, " << m.ns_off << "u, " << m.ns_n << "u, " << m.exns_off << "u, "
+      << m.exns_n << "u, " << m.lsel_off << "u, " << m.lsel_n << "u, " << m.nssel_off << "u, " << m.nssel_n << "u, " << m.name_mode << "u, " << m.name_boff << "u, "
+      << m.name_len << "u, 0u, 0u})\n";
+  }
+  o << "\nGK_SPEC_FN void gk_spec_object(const GkBatch& B, const GkColumn* cols, const GkScope* scopes, const uint32_t* __restrict__ pool, const uint8_t* __restrict__ cbytes,\n"
+       "                               const uint32_t* act, const GkOut& out, const uint32_t obj, uint32_t* vw, uint32_t* ew) {\n";
+  o << "  const uint32_t lo0 = obj, hi0 = obj + 1u, n0 = 1u, f0 = 1u;\n  (void)lo0; (void)hi0; (void)n0; (void)f0; (void)out; (void)pool; (void)cbytes; (void)cols;\n";
+  o << "  const bool skip = (B.flags[obj] & GK_F_SKIP) != 0u;\n  (void)skip;\n";
+  ranges(true);
+  // ---- atoms: every atom of a scope in ONE loop over the object's rows of that scope; a column is loaded once per row
+  std::vector<uint8_t> scope_done(NS, 0);
+  auto emit_scope_atoms = [&](size_t s) {
+    if (scope_done[s] || g.atom_vars[s].empty()) return;
+    scope_done[s] = 1;
+    o << "  // ---- atoms of scope " << s << "\n";
+    for (auto& kv : g.col_need[s]) {
+      const uint32_t ci = kv.first, enc = kv.second;
+      if (enc & GK_ENC_VT) o << "  const uint8_t* __restrict__ pt" << ci << " = cols[" << ci << "].vt;\n";
+      if (enc & GK_ENC_SID) o << "  const uint32_t* __restrict__ pi" << ci << " = cols[" << ci << "].sid;\n";
+      if (enc & GK_ENC_NUM) o << "  const long long* __restrict__ pn" << ci << " = reinterpret_cast<const long long*>(cols[" << ci << "].num);\n";
+      if (enc & GK_ENC_HEAD) o << "  const uint4* __restrict__ ph" << ci << " = reinterpret_cast<const uint4*>(cols[" << ci << "].head);\n";
+    }
+    o << "  uint32_t";
+    for (size_t k = 0; k < g.atom_vars[s].size(); ++k) o << (k ? ", v" : " v") << g.atom_vars[s][k] << " = 0u";
+    o << ";\n";
+    if (s == 0) o << "  {\n    const size_t row = obj;\n";
+    else o << "  for (uint32_t j = 0; j < n" << s << "; ++j) {\n    const size_t row = (size_t)lo" << s << " + j;\n";
+    for (auto& kv : g.col_need[s]) {
+      const uint32_t ci = kv.first, enc = kv.second;
+      if (enc & GK_ENC_VT) o << "    const uint32_t t" << ci << " = pt" << ci << "[row];\n";
+      if (enc & GK_ENC_SID) o << "    const uint32_t i" << ci << " = pi" << ci << "[row];\n";
+      if (enc & GK_ENC_NUM) o << "    const long long n" << ci << " = pn" << ci << "[row];\n";
+      if (enc & GK_ENC_HEAD) o << "    const uint4 h" << ci << "a = ph" << ci << "[2 * row], h" << ci << "b = ph" << ci << "[2 * row + 1];\n";
+    }
+    o << g.atom_code[s] << "  }\n";
+  };
+  // ---- everything else depth-first from the results: a node right after what it reads.  Constraints whose cones touch the
+  // same scopes are emitted next to each other, so that a scope's atom masks die before the next scope's are born.
+  std::function<void(uint32_t)> emit_var = [&](uint32_t v) {
+    const int pr = g.producer[v];
+    if (pr < 0) {
+      emit_scope_atoms((size_t)(-pr - 1));
+      return;
+    }
+    SpecNode& n = g.nodes[(size_t)pr];
+    if (n.done) return;
+    n.done = true;
+    for (uint32_t d : n.deps) emit_var(d);
+    o << n.code;
+  };
+  std::vector<std::set<int>> memo_scopes(g.nvar);
+  std::vector<uint8_t> memo_done(g.nvar, 0);
+  std::function<const std::set<int>&(uint32_t)> cone_scopes = [&](uint32_t v) -> const std::set<int>& {
+    if (memo_done[v]) return memo_scopes[v];
+    memo_done[v] = 1;
+    const int pr = g.producer[v];
+    if (pr < 0) {
+      memo_scopes[v].insert(-pr - 1);
+    } else {
+      for (uint32_t d : g.nodes[(size_t)pr].deps) {
+        const std::set<int>& sub = cone_scopes(d);
+        memo_scopes[v].insert(sub.begin(), sub.end());
+      }
+    }
+    return memo_scopes[v];
+  };
+  auto var_of = [&](uint32_t slot) -> int { return slot < g.cur.size() ? g.cur[slot] : -1; };
+  std::vector<std::pair<std::vector<int>, uint32_t>> order;
+  for (uint32_t cix = 0; cix < C; ++cix) {
+    const GkOutEnt& oe = c.outs[cix];
+    std::vector<int> sig;
+    if (!(oe.flags & 3u) && var_of(oe.prog_slot) >= 0) {
+      const std::set<int>& sc = cone_scopes((uint32_t)var_of(oe.prog_slot));
+      sig.assign(sc.rbegin(), sc.rend());
+    }
+    order.emplace_back(sig, cix);
+  }
+  std::sort(order.begin(), order.end());
+  for (auto& ent : order) {
+    const uint32_t cix = ent.second;
+    const GkOutEnt& oe = c.outs[cix];
+    g.deps.clear();
+    const std::string pv = (oe.flags & 1u) ? "1u" : (oe.flags & 2u) ? "0u" : "(" + g.rd(oe.prog_slot) + " & 1u)";
+    const std::string mt = g.rd(oe.match_slot), er = g.rd(oe.err_slot);
+    for (uint32_t d : g.deps) emit_var(d);
+    o << "  if (act[" << cix << "]) {   // constraint " << cix << "\n    vw[" << (cix >> 5) << "] |= (" << pv << " & " << mt << ") << " << (cix & 31u) << ";\n    ew["
+      << (cix >> 5) << "] |= (" << er << " & 1u) << " << (cix & 31u) << ";\n  }\n";
+  }
+  o << "}\n";
+  o << kWrapper;
+  out.src = o.str();
+  out.words = W;
+  auto r16 = [](size_t x) { return (x + 15) / 16 * 16; };
+  out.smem = r16(c.schema.cols.size() * sizeof(GkColumn) + NS * sizeof(GkScope) + 3 * (size_t)W * 32 * 4) + 16;
+  out.n_fast = g.n_fast;
+  out.n_generic = g.n_generic;
+  return out;
+}
+
+}  // namespace gk

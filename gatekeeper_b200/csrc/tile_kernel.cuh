@@ -64,28 +64,7 @@ _Pragma("unroll") \
 
 namespace gk {
 
-#define GK_MAX_PEERS 8
-
-struct KParams {
-  GkBatch batch;
-  GkProgram prog;
-  GkOut out;
-  const uint32_t* active;     // [nconstraints] enforcement-point filter
-  const uint32_t* tile_lo;    // [(ntiles + 1) * nscopes] first row of every scope for every tile (row ranges are contiguous)
-  uint32_t ntiles;
-  uint32_t tile;              // objects per tile (multiple of 32)
-  uint32_t slot_words;        // words in the slot area
-  // Fused exchange (multi-GPU sweep): with npeers > 0 the gather epilogue stores every bitmap word straight into each
-  // peer's receive buffer over NVLink (peer_viol[q] already points at THIS rank's shard inside peer q's buffer), and the
-  // last CTA to finish publishes the per-constraint totals the same way.  A device-side barrier on the caller's stream
-  // then replaces the all-gather collective.
-  uint32_t* peer_viol[GK_MAX_PEERS];
-  unsigned long long* peer_tot[GK_MAX_PEERS];   // [2 * tot_stride]: violations, then matcher errors
-  uint32_t npeers;
-  uint32_t tot_stride;
-  uint32_t* done_ctr;
-  unsigned long long* timing; // GK_PHASE_TIMING builds: [kMaxPhases + 2][2] = (CTA cycles between barriers, summed warp busy cycles)
-};
+using KParams = GkKParams;
 
 #ifndef GK_THREADS
 #define GK_THREADS 256
@@ -427,6 +406,8 @@ __global__ void __launch_bounds__(kThreads, GK_MIN_CTAS) gk_eval_kernel(const KP
   const uint8_t* __restrict__ cbytes = p.prog.cbytes;
 #endif
 
+  // list mode (behind gk_spec_kernel): only the tiles that kernel left alone, usually none -- then nothing is staged
+  const uint32_t ntiles = p.list_mode ? *p.tile_count : p.ntiles;
   for (uint32_t i = threadIdx.x; i < C; i += blockDim.x) {
     s_tot[i] = 0;
     s_err[i] = 0;
@@ -434,6 +415,7 @@ __global__ void __launch_bounds__(kThreads, GK_MIN_CTAS) gk_eval_kernel(const KP
   }
   for (uint32_t i = threadIdx.x; i <= NP; i += blockDim.x) s_poff[i] = p.prog.phase_off[i];
 #if GK_TABLES_IN_SMEM
+  if (ntiles) {
   stage(outs, p.prog.outs, ((size_t)C * sizeof(GkOutEnt) + 15) / 16 * 16);
   stage(ops, p.prog.ops, ((size_t)p.prog.nops * sizeof(GkOp) + 15) / 16 * 16);
   stage(items, p.prog.items, ((size_t)p.prog.nitems * 4 + 15) / 16 * 16);
@@ -442,13 +424,15 @@ __global__ void __launch_bounds__(kThreads, GK_MIN_CTAS) gk_eval_kernel(const KP
   stage(scopes, p.batch.scopes, ((size_t)NS * sizeof(GkScope) + 15) / 16 * 16);
   stage(pool, p.prog.pool, ((size_t)p.prog.npool * 4 + 15) / 16 * 16);
   stage(cbytes, p.prog.cbytes, ((size_t)p.prog.ncbytes + 15) / 16 * 16);
+  }
 #endif
   __syncthreads();
 
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const uint32_t FULL = 0xffffffffu;
 
-  for (uint32_t t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+  for (uint32_t ti = blockIdx.x; ti < ntiles; ti += gridDim.x) {
+    const uint32_t t = p.list_mode ? p.tile_list[ti] : ti;
     // ---- tile row ranges (precomputed on the host: rows of a tile are contiguous at every scope)
     for (uint32_t s = threadIdx.x; s < NS; s += blockDim.x) {
       const uint32_t a = p.tile_lo[(size_t)t * NS + s], b = p.tile_lo[(size_t)(t + 1) * NS + s];

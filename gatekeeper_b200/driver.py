@@ -64,7 +64,7 @@ class gk_result(C.Structure):
 
 
 EXPORTS = [
-    "gk_engine_create", "gk_engine_destroy", "gk_backend_name", "gk_add_template", "gk_add_template_libs", "gk_remove_template",
+    "gk_engine_create", "gk_engine_destroy", "gk_backend_name", "gk_last_kernel", "gk_add_template", "gk_add_template_libs", "gk_remove_template",
     "gk_add_constraint", "gk_add_expansion_template", "gk_remove_expansion_template", "gk_validate_constraint", "gk_remove_constraint", "gk_put_namespace", "gk_remove_namespace", "gk_add_data", "gk_remove_data", "gk_constraint_count",
     "gk_constraint_key", "gk_result_constraint_key", "gk_review_batch", "gk_batch_upload", "gk_batch_eval", "gk_batch_eval_device",
     "gk_batch_eval_device_peers", "gk_batch_upload_blob", "gk_review_blob", "gk_set_excluded_namespaces", "gk_audit_begin", "gk_audit_add_batch", "gk_audit_report",
@@ -86,6 +86,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.gk_engine_destroy.argtypes = [P]
     lib.gk_backend_name.restype = S
     lib.gk_backend_name.argtypes = [P]
+    lib.gk_last_kernel.restype = S
+    lib.gk_last_kernel.argtypes = [P]
     lib.gk_add_template.argtypes = [P, S, S, C.c_size_t, PP]
     lib.gk_add_template_libs.argtypes = [P, S, S, C.c_size_t, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), C.c_size_t, PP]
     lib.gk_remove_template.argtypes = [P, S]
@@ -251,6 +253,10 @@ class Driver:
 
     def backend(self) -> str:
         return self._lib.gk_backend_name(self._e).decode()
+
+    def last_kernel(self) -> str:
+        """"gk_spec_kernel" (generated for the constraint set, NVRTC) or "gk_eval_kernel" (the netlist interpreter)."""
+        return self._lib.gk_last_kernel(self._e).decode()
 
     def AddTemplate(self, template: dict) -> None:
         kind = template["spec"]["crd"]["spec"]["names"]["kind"]

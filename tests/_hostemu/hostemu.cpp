@@ -4,6 +4,7 @@
 // It is linked ONLY into tests/_hostemu/libgk_hostemu.so.  The product library
 // (gatekeeper_b200/libgk_engine.so) links kernels.cu instead and has no CPU path at all.
 #include <algorithm>
+#include <array>
 #include <cstdio>
 #include <cstdlib>
 #include <chrono>
@@ -13,6 +14,14 @@
 #include "../../gatekeeper_b200/csrc/backend.hpp"
 #include "../../gatekeeper_b200/csrc/vm_core.h"
 #include "../../gatekeeper_b200/csrc/ingest_core.h"
+#include "../../gatekeeper_b200/csrc/spec_codegen.hpp"
+
+#include <dlfcn.h>
+#include <unistd.h>
+
+#include <fstream>
+#include <functional>
+#include <map>
 
 namespace gk {
 
@@ -426,6 +435,86 @@ class HostEmuBackend : public Backend {
     }
     out.kernel_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
     out.launches = 0;
+    if (getenv("GK_SPEC_CHECK") || getenv("GK_SPEC_DUMP")) spec_check(c, h, active, out);
+  }
+
+  // GK_SPEC_CHECK=1: the text spec_codegen.cpp writes for this constraint set (what NVRTC compiles into gk_spec_kernel on the GPU)
+  // is compiled for the host with g++ and must give, object by object, the words the interpreted netlist gave above.
+  // GK_SPEC_DUMP=<path> writes the text out.
+  typedef int (*SpecHostFn)(const GkKParams*, uint32_t, uint32_t*, uint32_t*);
+  static SpecHostFn spec_host_fn(const std::string& src) {
+    static std::mutex mu;
+    static std::map<size_t, SpecHostFn> cache;
+    std::lock_guard<std::mutex> l(mu);
+    const size_t hv = std::hash<std::string>{}(src);
+    auto it = cache.find(hv);
+    if (it != cache.end()) return it->second;
+    char base[128];
+    snprintf(base, sizeof base, "/tmp/gk_spec_host_%016zx", hv);
+    const std::string so = std::string(base) + ".so";
+    if (access(so.c_str(), R_OK) != 0) {
+      const std::string cpp = std::string(base) + "." + std::to_string((long)getpid()) + ".cpp", tmp = so + "." + std::to_string((long)getpid());
+      {
+        std::ofstream f(cpp);
+        f << src;
+      }
+      const std::string cmd = "g++ -std=c++17 -O1 -w -shared -fPIC -DGK_SPEC_HOST -x c++ " + cpp + " -o " + tmp + " 2> " + cpp + ".log";
+      if (system(cmd.c_str()) != 0) throw BackendError{"GK_SPEC_CHECK: the generated source does not compile for the host: see " + cpp + ".log"};
+      rename(tmp.c_str(), so.c_str());
+      unlink(cpp.c_str());
+      unlink((cpp + ".log").c_str());
+    }
+    void* hnd = dlopen(so.c_str(), RTLD_NOW | RTLD_LOCAL);
+    if (!hnd) throw BackendError{std::string("GK_SPEC_CHECK: dlopen: ") + dlerror()};
+    auto fn = reinterpret_cast<SpecHostFn>(dlsym(hnd, "gk_spec_host"));
+    if (!fn) throw BackendError{"GK_SPEC_CHECK: gk_spec_host missing"};
+    cache[hv] = fn;
+    return fn;
+  }
+  static void spec_check(const Compiled& c, const GkBatch& h, const std::vector<uint32_t>& active, const EvalOut& out) {
+    const SpecSource ss = spec_codegen(c);
+    if (const char* d = getenv("GK_SPEC_DUMP")) {
+      std::ofstream f(d);
+      f << ss.src;
+    }
+    if (!getenv("GK_SPEC_CHECK")) return;
+    SpecHostFn fn = spec_host_fn(ss.src);
+    const uint32_t W = out.words, n = out.n;
+    if (ss.words != W) throw BackendError{"GK_SPEC_CHECK: word count differs"};
+    GkKParams p{};
+    p.batch = h;
+    p.prog.pool = c.pool.data();
+    p.prog.cbytes = c.cbytes.data();
+    p.active = active.data();
+    std::vector<uint32_t> errlist((size_t)3 * (64 + (size_t)n * std::max<size_t>(1, c.match.size())));
+    uint32_t errcount = 0;
+    p.out.errlist = errlist.data();
+    p.out.errcount = &errcount;
+    p.out.errcap = (uint32_t)(errlist.size() / 3);
+    std::vector<uint32_t> vw(W), ew(W);
+    std::vector<uint8_t> big(std::max(n, 1u), 0);
+    size_t nbig = 0;
+    for (uint32_t obj = 0; obj < n; ++obj) {
+      if (fn(&p, obj, vw.data(), ew.data())) {
+        big[obj] = 1;
+        ++nbig;
+        continue;
+      }
+      for (uint32_t w = 0; w < W; ++w)
+        if (vw[w] != out.viol[(size_t)obj * W + w] || ew[w] != out.err[(size_t)obj * W + w])
+          throw BackendError{"GK_SPEC_CHECK: object " + std::to_string(obj) + " word " + std::to_string(w) + ": generated code " + std::to_string(vw[w]) + "/" +
+                             std::to_string(ew[w]) + ", interpreter " + std::to_string(out.viol[(size_t)obj * W + w]) + "/" + std::to_string(out.err[(size_t)obj * W + w])};
+    }
+    // the matcher-error list, as a set
+    std::vector<std::array<uint32_t, 3>> a, b;
+    for (uint32_t i = 0; i < errcount; ++i) a.push_back({errlist[3 * i], errlist[3 * i + 1], errlist[3 * i + 2]});
+    for (size_t i = 0; i + 2 < out.errlist.size(); i += 3)
+      if (!big[out.errlist[i]]) b.push_back({out.errlist[i], out.errlist[i + 1], out.errlist[i + 2]});
+    std::sort(a.begin(), a.end());
+    std::sort(b.begin(), b.end());
+    if (a != b) throw BackendError{"GK_SPEC_CHECK: matcher error lists differ (" + std::to_string(a.size()) + " vs " + std::to_string(b.size()) + ")"};
+    if (getenv("GK_SPEC_TRACE"))
+      fprintf(stderr, "[spec check] %u objects identical (%zu too big for the mask registers), %zu atoms as immediates, %zu generic\n", n, nbig, ss.n_fast, ss.n_generic);
   }
   // "device" buffers are host memory here: the same address arithmetic as the CUDA backend (bitmap shard and totals of this
   // rank stored into every peer's receive buffer), so the C ABI's peer addressing can be tested without GPUs

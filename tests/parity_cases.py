@@ -2,7 +2,10 @@
 Every case loads the SAME templates / constraints / objects into the oracle and into the engine and
 compares the full result set: (object, constraint, msg, details, enforcement action(s), autoreject)."""
 import json
+import os
 import random
+
+import numpy as np
 
 from conftest import assert_same, engine_results, golden, make_pair, oracle_results
 from gatekeeper_b200 import driver as D
@@ -1784,3 +1787,81 @@ def case_audit_concurrent_with_reviews(lib, rounds=6):
     assert not errors, errors[:3]
     assert want["pairsCounted"] > 0
     return want
+
+
+def _spec_env(**kv):
+    for k in ("GK_SPEC", "GK_SPEC_MIN_OBJECTS", "GK_SPEC_CHECK"):
+        os.environ.pop(k, None)
+    os.environ.update(kv)
+
+
+def case_spec_kernel(lib, n=6000, config=2, wide_every=97):
+    """The kernel GENERATED for a constraint set (spec_codegen.cpp -> NVRTC: one thread per object, a mask register per netlist
+    node) against the netlist interpreter on the same resident page, through the decision netlist and the audit's ambiguity
+    netlist.  Every `wide_every`-th object gets 40 containers: more rows than a mask register holds, so its tile goes to the
+    interpreter -- the hand-over is part of the comparison.  On the GPU: two engines (GK_SPEC=0 / forced) must give identical
+    bitmaps, error planes, totals and audit reports.  On the TEST-ONLY host emulation: the generated text is compiled with g++
+    and checked object by object against the interpreted netlist (GK_SPEC_CHECK=1, tests/_hostemu/hostemu.cpp)."""
+    from oracle import audit as OA  # noqa: F401
+    if config == 2:
+        tm, cons = W.config2()
+        mode = 0
+    elif config == 4:
+        tm, cons = W.config4()
+        mode = 1
+    else:
+        tm, cons = W.config5()
+        mode = 0
+    nss = W.synth_namespaces()
+    blob = W.synth_objects(31337, n, mode=mode)
+    docs = [blob.get(i) for i in range(n)]
+    nwide = 0
+    for i in range(0, n, wide_every):
+        d = json.loads(docs[i])
+        spec = d.get("spec")
+        if not isinstance(spec, dict) or not spec.get("containers"):
+            continue
+        cs = spec["containers"]
+        spec["containers"] = [dict(cs[k % len(cs)], name="c%d" % k) for k in range(40)]
+        docs[i] = json.dumps(d).encode()
+        nwide += 1
+    assert nwide > 3
+    page = W.PyBlob(docs)
+    is_emu = lib is not None and "hostemu" in lib
+
+    def run(env):
+        _spec_env(**env)
+        try:
+            drv = D.Driver(lib_path=lib)
+            for k, r in tm:
+                drv.add_template(k, r)
+            for c in cons:
+                drv.AddConstraint(c)
+            for ns in nss:
+                drv.AddData("admission.k8s.gatekeeper.sh", ["cluster", "v1", "Namespace", ns["metadata"]["name"]], ns)
+            rb = drv.upload_blob(page)
+            r = rb.eval(k8s.AUDIT_EP)
+            kern = drv.last_kernel()
+            w = rb.eval(k8s.WEBHOOK_EP)     # another enforcement-point mask over the same compiled kernel
+            au = D.AuditRun(drv, violations_limit=5)
+            au.add_batch(rb)                # (evaluates the ambiguity netlist on a fork of the batch: ACC2 through the generated kernel)
+            rep = au.report()
+            au.close()
+            out = (np.array(r.viol_bits, copy=True), np.array(r.err_bits, copy=True), list(r.totals), list(r.err_totals),
+                   np.array(w.viol_bits, copy=True), list(w.totals), json.dumps(rep, sort_keys=True))
+            rb.free()
+            drv.close()
+            return kern, out
+        finally:
+            _spec_env()
+
+    if is_emu:
+        kern, out = run({"GK_SPEC_CHECK": "1"})
+        return int(sum(out[2]))
+    k0, want = run({"GK_SPEC": "0"})
+    k1, got = run({"GK_SPEC_MIN_OBJECTS": "0"})
+    assert k0 == "gk_eval_kernel" and k1 == "gk_spec_kernel", (k0, k1)
+    assert np.array_equal(want[0], got[0]) and np.array_equal(want[1], got[1]), "bitmaps of the generated kernel differ from the interpreter's"
+    assert want[2] == got[2] and want[3] == got[3] and np.array_equal(want[4], got[4]) and want[5] == got[5]
+    assert want[6] == got[6], "audit reports differ"
+    return int(sum(want[2]))

@@ -352,3 +352,10 @@ def test_pages_of_wide_objects_shrink_the_tile():
 
 def test_audit_concurrent_with_reviews():
     P.case_audit_concurrent_with_reviews(HOSTEMU)
+
+
+@pytest.mark.parametrize("config", [2, 4, 5])
+def test_generated_kernel_text_matches_the_interpreted_netlist(config):
+    """spec_codegen.cpp: the CUDA C++ text generated for the constraint set, compiled for the host, object by object against the
+    interpreter -- decision and ambiguity netlists, pages with objects too wide for the mask registers."""
+    assert P.case_spec_kernel(HOSTEMU, 1500, config=config) > 100
