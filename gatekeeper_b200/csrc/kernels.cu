@@ -15,6 +15,7 @@
 #include <dlfcn.h>
 
 #include <list>
+#include <sstream>
 
 #include "backend.hpp"
 #include "ingest_kernels.cuh"
@@ -548,8 +549,15 @@ class CudaBackend : public Backend {
       Prog prog = nullptr;
       if (create(&prog, se.src.src.c_str(), "gk_spec_kernel.cu", 0, nullptr, nullptr) != 0) throw BackendError{"nvrtcCreateProgram failed"};
       const std::string threads = "-DGK_SPEC_THREADS=" + std::to_string(spec_threads_), minb = "-DGK_SPEC_MINB=" + std::to_string(spec_minb_);
-      const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device", threads.c_str(), minb.c_str()};
-      const int rc = compile(prog, (int)(sizeof opts / sizeof opts[0]), opts);
+      std::vector<std::string> extra;   // GK_SPEC_DEFS="-DX -DY": measurement switches of the generated text
+      if (const char* d = getenv("GK_SPEC_DEFS")) {
+        std::istringstream in(d);
+        std::string tok;
+        while (in >> tok) extra.push_back(tok);
+      }
+      std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device", threads.c_str(), minb.c_str()};
+      for (auto& x : extra) opts.push_back(x.c_str());
+      const int rc = compile(prog, (int)opts.size(), opts.data());
       if (rc != 0) {
         size_t ls = 0;
         log_size(prog, &ls);

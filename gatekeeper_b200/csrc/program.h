@@ -25,6 +25,13 @@ typedef unsigned long uintptr_t;
 #else
 #define GK_HD inline
 #endif
+// loads of batch / program arrays in the shared per-object code (vm_core.h): read-only for the whole evaluation, so on the device
+// they take the non-coherent path and the compiler may keep one load across the stores of the error list
+#ifdef __CUDA_ARCH__
+#define GK_LD(p) __ldg(p)
+#else
+#define GK_LD(p) (*(p))
+#endif
 
 // ---- value-type codes stored in VT columns (== gk::VT)
 enum { GK_VT_UNDEF = 0, GK_VT_NULL = 1, GK_VT_FALSE = 2, GK_VT_TRUE = 3, GK_VT_NUM = 4, GK_VT_STR = 5,

@@ -9,6 +9,7 @@
 #include <map>
 #include <set>
 #include <sstream>
+#include <tuple>
 
 #include "spec_headers.inc"   // kSpecHdrProgram / kSpecHdrVmCore: the text of program.h and vm_core.h (written by build.py)
 
@@ -79,19 +80,19 @@ extern "C" __global__ void __launch_bounds__(GK_SPEC_THREADS, GK_SPEC_MINB) gk_s
   for (uint32_t w = 0; w < GK_SPEC_W; ++w) tv[w] = te[w] = 0u;
   for (uint32_t t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
     const uint32_t obj0 = t * p.tile, nobj = min(p.tile, p.batch.n - obj0);
+    // An object with more rows in a scope than a mask register holds makes gk_spec_object() return true: the tile is then listed
+    // for the interpreter, which evaluates it again and overwrites what this kernel stored for it; its totals are not counted here.
     int big = 0;
-    for (uint32_t o = threadIdx.x; o < nobj; o += blockDim.x) big |= gk_spec_overflow(scopes, obj0 + o) ? 1 : 0;
-    if (__syncthreads_or(big)) {   // some object of the tile has more rows in a scope than a mask register holds: the interpreter takes the tile
-      if (threadIdx.x == 0) p.tile_list[atomicAdd(p.tile_count, 1u)] = t;
-      continue;
-    }
+    uint32_t tvt[GK_SPEC_W], tet[GK_SPEC_W];
+#pragma unroll
+    for (uint32_t w = 0; w < GK_SPEC_W; ++w) tvt[w] = tet[w] = 0u;
     for (uint32_t base = 0; base < nobj; base += blockDim.x) {
       const uint32_t o = base + threadIdx.x;
       uint32_t vw[GK_SPEC_W], ew[GK_SPEC_W];
 #pragma unroll
       for (uint32_t w = 0; w < GK_SPEC_W; ++w) vw[w] = ew[w] = 0u;
       if (o < nobj) {
-        gk_spec_object(p.batch, cols, scopes, p.prog.pool, p.prog.cbytes, act, p.out, obj0 + o, vw, ew);
+        if (gk_spec_object(p.batch, cols, scopes, p.prog.pool, p.prog.cbytes, act, p.out, obj0 + o, vw, ew)) big = 1;
         const size_t at = (size_t)(obj0 + o) * GK_SPEC_W;
 #if GK_SPEC_W == 2
         const uint2 v2 = make_uint2(vw[0], vw[1]);
@@ -117,12 +118,21 @@ extern "C" __global__ void __launch_bounds__(GK_SPEC_THREADS, GK_SPEC_MINB) gk_s
       uint32_t anye = 0u;
 #pragma unroll
       for (uint32_t w = 0; w < GK_SPEC_W; ++w) {
-        tv[w] += (uint32_t)__popc(gk_tr32(vw[w], lane));
+        tvt[w] += (uint32_t)__popc(gk_tr32(vw[w], lane));
         anye |= ew[w];
       }
       if (__any_sync(0xffffffffu, anye != 0u)) {
 #pragma unroll
-        for (uint32_t w = 0; w < GK_SPEC_W; ++w) te[w] += (uint32_t)__popc(gk_tr32(ew[w], lane));
+        for (uint32_t w = 0; w < GK_SPEC_W; ++w) tet[w] += (uint32_t)__popc(gk_tr32(ew[w], lane));
+      }
+    }
+    if (__syncthreads_or(big)) {
+      if (threadIdx.x == 0) p.tile_list[atomicAdd(p.tile_count, 1u)] = t;
+    } else {
+#pragma unroll
+      for (uint32_t w = 0; w < GK_SPEC_W; ++w) {
+        tv[w] += tvt[w];
+        te[w] += tet[w];
       }
     }
   }
@@ -140,10 +150,8 @@ extern "C" __global__ void __launch_bounds__(GK_SPEC_THREADS, GK_SPEC_MINB) gk_s
 #else
 // TEST-ONLY host build (tests/_hostemu, GK_SPEC_CHECK=1): one object; returns 1 when the object does not fit the mask registers
 extern "C" int gk_spec_host(const GkKParams* p, uint32_t obj, uint32_t* vw, uint32_t* ew) {
-  if (gk_spec_overflow(p->batch.scopes, obj)) return 1;
   for (uint32_t w = 0; w < GK_SPEC_W; ++w) vw[w] = ew[w] = 0u;
-  gk_spec_object(p->batch, p->batch.cols, p->batch.scopes, p->prog.pool, p->prog.cbytes, p->active, p->out, obj, vw, ew);
-  return 0;
+  return gk_spec_object(p->batch, p->batch.cols, p->batch.scopes, p->prog.pool, p->prog.cbytes, p->active, p->out, obj, vw, ew) ? 1 : 0;
 }
 #endif
 )GKSRC";
@@ -161,9 +169,15 @@ struct Gen {
   const Compiled& c;
   std::vector<SpecNode> nodes;
   std::vector<int> producer;               // variable -> node, or -(scope + 1) for an atom of that scope's row loop
-  std::vector<std::string> atom_code;      // per scope: statements inside the row loop
-  std::vector<std::vector<uint32_t>> atom_vars;   // per scope: the mask variables its loop fills
-  std::vector<std::map<uint32_t, uint32_t>> col_need;   // per scope: column -> encodings its specialised atoms read
+  struct AtomRec {
+    uint32_t var, scope;
+    std::string expr;                              // boolean expression over the row's loaded values
+    std::map<uint32_t, uint32_t> need;             // column -> encodings the expression reads
+    int group = -1;                                // row loop it is computed in (see spec_codegen())
+  };
+  std::vector<AtomRec> atoms;
+  std::vector<int> atom_of;                        // variable -> atom record, or -1
+  std::map<uint32_t, uint32_t>* need_now = nullptr;
   std::vector<uint8_t> scope_used;
   std::vector<int> cur;                    // slot -> variable holding its current value (-1: never written)
   uint32_t nvar = 0;
@@ -174,9 +188,6 @@ struct Gen {
 
   explicit Gen(const Compiled& cc) : c(cc) {
     const size_t NS = c.schema.scopes.size();
-    atom_code.resize(NS);
-    atom_vars.resize(NS);
-    col_need.resize(NS);
     scope_used.assign(NS, 0);
     cur.assign(c.slot_level.size() + 1, -1);
   }
@@ -196,6 +207,7 @@ struct Gen {
     if (slot >= cur.size()) cur.resize(slot + 1, -1);
     cur[slot] = (int)nvar;
     producer.push_back(prod);
+    atom_of.push_back(-1);
     return nvar++;
   }
   uint32_t fresh(uint32_t slot) { return fresh(slot, (int)nodes.size()); }   // defined by the node being built
@@ -211,7 +223,8 @@ struct Gen {
   // a boolean C expression for one atom on `row` of column ci; the loads it needs are recorded in col_need
   std::string atom_expr(uint32_t level, uint32_t ci, uint32_t aop, uint32_t a, uint32_t b) {
     const std::string K = std::to_string(ci);
-    auto need = [&](uint32_t enc) { col_need[level][ci] |= enc; };
+    (void)level;
+    auto need = [&](uint32_t enc) { (*need_now)[ci] |= enc; };
     const std::string t = "t" + K, i = "i" + K, n = "n" + K;
     switch (aop) {
       case GK_OP_TRUTHY: need(GK_ENC_VT); ++n_fast; return "(" + t + " != 0u && " + t + " != 2u)";
@@ -269,19 +282,22 @@ struct Gen {
 
   void atom(uint32_t level, uint32_t out_slot, uint32_t ci, uint32_t aop, uint32_t a, uint32_t b) {
     use_scope(level);
-    const uint32_t v = fresh(out_slot, -(int)(level + 1));
-    atom_vars[level].push_back(v);
-    const std::string e = atom_expr(level, ci, aop, a, b);
-    if (level == 0) atom_code[level] += "    v" + std::to_string(v) + " = " + e + " ? 1u : 0u;\n";
-    else atom_code[level] += "    v" + std::to_string(v) + " |= (uint32_t)" + e + " << j;\n";
+    AtomRec r;
+    r.var = fresh(out_slot, -1);
+    r.scope = level;
+    need_now = &r.need;
+    r.expr = atom_expr(level, ci, aop, a, b);
+    need_now = nullptr;
+    atom_of[r.var] = (int)atoms.size();
+    atoms.push_back(std::move(r));
   }
 
   // `rm` = the mask of the children of parent row pj inside the object's rows of scope L
   std::string range_loop_head(uint32_t L) {
     const uint32_t P = (uint32_t)c.schema.scopes[L].parent;
     const std::string l = std::to_string(L), p = std::to_string(P);
-    return "  for (uint32_t pj = 0; pj < n" + p + "; ++pj) {\n    const uint32_t ra = o" + l + "[lo" + p + " + pj] - lo" + l + ", rb = o" + l + "[lo" + p +
-           " + pj + 1u] - lo" + l + ";\n    const uint32_t rm = rb > ra ? (((rb - ra) >= 32u ? 0xffffffffu : ((1u << (rb - ra)) - 1u)) << ra) : 0u;\n";
+    return "  for (uint32_t pj = 0; pj < n" + p + "; ++pj) {\n    const uint32_t ra = GK_SPEC_LD(o" + l + " + lo" + p + " + pj) - lo" + l + ", rb = GK_SPEC_LD(o" + l + " + lo" + p +
+           " + pj + 1u) - lo" + l + ";\n    const uint32_t rm = rb > ra ? (((rb - ra) >= 32u ? 0xffffffffu : ((1u << (rb - ra)) - 1u)) << ra) : 0u;\n";
   }
 
   void op(const GkOp& op) {
@@ -364,7 +380,7 @@ struct Gen {
         const uint32_t mid = op.w2;
         match_used.insert(mid);
         const uint32_t vm = fresh(out), ve = fresh(op.w1 & 0xffffu);
-        body << "  const int m" << vm << " = skip ? 0 : gk_match(B, pool, cbytes, M" << mid << ", obj);\n";
+        body << "  const int m" << vm << " = skip ? 0 : GK_SPEC_MATCH(B, pool, cbytes, M" << mid << ", obj);\n";
         body << "  if (m" << vm << " < 0) GK_SPEC_ERR(obj, " << mid << "u, (uint32_t)(-m" << vm << "));\n";
         body << "  const uint32_t v" << vm << " = m" << vm << " > 0 ? 1u : 0u, v" << ve << " = m" << vm << " < 0 ? 1u : 0u;\n";
         break;
@@ -394,8 +410,14 @@ SpecSource spec_codegen(const Compiled& c) {
   o << "#ifndef GK_SPEC_THREADS\n#define GK_SPEC_THREADS 128\n#endif\n#ifndef GK_SPEC_MINB\n#define GK_SPEC_MINB 3\n#endif\n";
   o << strip_includes(kSpecHdrProgram) << strip_includes(kSpecHdrVmCore);
   o << R"GKSRC(
+#ifdef GK_SPEC_X_NOMATCH   /* (measurement only: what the spec.match pre-filter costs) */
+#define GK_SPEC_MATCH(B, pool, cbytes, M, obj) 1
+#else
+#define GK_SPEC_MATCH(B, pool, cbytes, M, obj) gk_match(B, pool, cbytes, M, obj)
+#endif
 #ifdef GK_SPEC_HOST
 #define GK_SPEC_FN static inline
+#define GK_SPEC_LD(p) (*(p))
 #define GK_SPEC_POPC(x) __builtin_popcount(x)
 #define GK_SPEC_ERR(o, mid, code)                                    \
   {                                                                  \
@@ -409,6 +431,7 @@ SpecSource spec_codegen(const Compiled& c) {
 struct uint4 { uint32_t x, y, z, w; };
 #else
 #define GK_SPEC_FN __device__ __forceinline__
+#define GK_SPEC_LD(p) __ldg(p)      /* every array of a resident batch is read-only while it is evaluated */
 #define GK_SPEC_POPC(x) __popc(x)
 #define GK_SPEC_ERR(o, mid, code)                                    \
   {                                                                  \
@@ -421,21 +444,6 @@ struct uint4 { uint32_t x, y, z, w; };
   }
 #endif
 )GKSRC";
-  // ---- does the object fit the mask registers?
-  o << "GK_SPEC_FN bool gk_spec_overflow(const GkScope* scopes, uint32_t obj) {\n  const uint32_t lo0 = obj, hi0 = obj + 1u;\n  bool big = false;\n  (void)lo0; (void)hi0;\n";
-  auto ranges = [&](bool full) {
-    for (size_t s = 1; s < NS; ++s) {
-      if (!g.scope_used[s]) continue;
-      const int P = c.schema.scopes[s].parent;
-      o << "  const uint32_t* __restrict__ o" << s << " = scopes[" << s << "].off;\n";
-      o << "  const uint32_t lo" << s << " = o" << s << "[lo" << P << "], n" << s << " = o" << s << "[hi" << P << "] - lo" << s << ", hi" << s << " = lo" << s << " + n" << s
-        << ";\n";
-      if (full) o << "  const uint32_t f" << s << " = n" << s << " >= 32u ? 0xffffffffu : ((1u << n" << s << ") - 1u);\n  (void)hi" << s << "; (void)f" << s << ";\n";
-      else o << "  big = big || n" << s << " > 32u;\n  (void)hi" << s << ";\n";
-    }
-  };
-  ranges(false);
-  o << "  return big;\n}\n\n";
   // ---- match blocks as literals: the compiler folds every branch a block does not use
   for (uint32_t mid : g.match_used) {
     const GkMatch& m = c.match[mid];
@@ -443,91 +451,148 @@ struct uint4 { uint32_t x, y, z, w; };
       << m.exns_n << "u, " << m.lsel_off << "u, " << m.lsel_n << "u, " << m.nssel_off << "u, " << m.nssel_n << "u, " << m.name_mode << "u, " << m.name_boff << "u, "
       << m.name_len << "u, 0u, 0u})\n";
   }
-  o << "\nGK_SPEC_FN void gk_spec_object(const GkBatch& B, const GkColumn* cols, const GkScope* scopes, const uint32_t* __restrict__ pool, const uint8_t* __restrict__ cbytes,\n"
+  // returns true (and leaves vw / ew alone, reports no matcher error) when the object has more rows in a scope than a mask holds
+  o << "\nGK_SPEC_FN bool gk_spec_object(const GkBatch& B, const GkColumn* cols, const GkScope* scopes, const uint32_t* __restrict__ pool, const uint8_t* __restrict__ cbytes,\n"
        "                               const uint32_t* act, const GkOut& out, const uint32_t obj, uint32_t* vw, uint32_t* ew) {\n";
   o << "  const uint32_t lo0 = obj, hi0 = obj + 1u, n0 = 1u, f0 = 1u;\n  (void)lo0; (void)hi0; (void)n0; (void)f0; (void)out; (void)pool; (void)cbytes; (void)cols;\n";
-  o << "  const bool skip = (B.flags[obj] & GK_F_SKIP) != 0u;\n  (void)skip;\n";
-  ranges(true);
-  // ---- atoms: every atom of a scope in ONE loop over the object's rows of that scope; a column is loaded once per row
-  std::vector<uint8_t> scope_done(NS, 0);
-  auto emit_scope_atoms = [&](size_t s) {
-    if (scope_done[s] || g.atom_vars[s].empty()) return;
-    scope_done[s] = 1;
-    o << "  // ---- atoms of scope " << s << "\n";
-    for (auto& kv : g.col_need[s]) {
+  o << "  const bool skip = (GK_SPEC_LD(B.flags + obj) & GK_F_SKIP) != 0u;\n  (void)skip;\n  bool big = false;\n";
+  for (size_t s = 1; s < NS; ++s) {
+    if (!g.scope_used[s]) continue;
+    const int P = c.schema.scopes[s].parent;
+    o << "  const uint32_t* __restrict__ o" << s << " = scopes[" << s << "].off;\n";
+    o << "  const uint32_t lo" << s << " = GK_SPEC_LD(o" << s << " + lo" << P << "), n" << s << " = GK_SPEC_LD(o" << s << " + hi" << P << ") - lo" << s << ", hi" << s << " = lo" << s
+      << " + n" << s << ";\n";
+    o << "  const uint32_t f" << s << " = n" << s << " >= 32u ? 0xffffffffu : ((1u << n" << s << ") - 1u);\n  (void)hi" << s << "; (void)f" << s << ";\n  big = big || n" << s
+      << " > 32u;\n";
+  }
+  o << "  if (big) return true;\n";
+  // ---- emission order of the constraints: by template kind, then by the scopes their cones touch
+  std::vector<std::vector<uint32_t>> cone_atoms(g.nvar);   // variable -> atoms in its cone (memoised)
+  std::vector<uint8_t> cone_done(g.nvar, 0);
+  std::function<const std::vector<uint32_t>&(uint32_t)> cone = [&](uint32_t v) -> const std::vector<uint32_t>& {
+    if (cone_done[v]) return cone_atoms[v];
+    cone_done[v] = 1;
+    std::set<uint32_t> acc;
+    if (g.atom_of[v] >= 0) {
+      acc.insert((uint32_t)g.atom_of[v]);
+    } else if (g.producer[v] >= 0) {
+      for (uint32_t d : g.nodes[(size_t)g.producer[v]].deps) {
+        const std::vector<uint32_t>& sub = cone(d);
+        acc.insert(sub.begin(), sub.end());
+      }
+    }
+    cone_atoms[v].assign(acc.begin(), acc.end());
+    return cone_atoms[v];
+  };
+  auto var_of = [&](uint32_t slot) -> int { return slot < g.cur.size() ? g.cur[slot] : -1; };
+  struct Ord {
+    std::string kind;
+    std::vector<int> sig;
+    uint32_t cix;
+    bool operator<(const Ord& x) const { return std::tie(kind, sig, cix) < std::tie(x.kind, x.sig, x.cix); }
+  };
+  std::vector<Ord> order;
+  for (uint32_t cix = 0; cix < C; ++cix) {
+    const GkOutEnt& oe = c.outs[cix];
+    Ord e;
+    e.cix = cix;
+    e.kind = cix < c.order.size() && c.order[cix] ? c.order[cix]->kind : std::string();
+    if (!(oe.flags & 3u) && var_of(oe.prog_slot) >= 0) {
+      std::set<int> sc;
+      for (uint32_t ai : cone((uint32_t)var_of(oe.prog_slot))) sc.insert((int)g.atoms[ai].scope);
+      e.sig.assign(sc.rbegin(), sc.rend());
+    }
+    order.push_back(std::move(e));
+  }
+  std::sort(order.begin(), order.end());
+  // ---- atom groups: an atom is computed in the row loop of (its scope, the first template kind that reads it), so that only one
+  // template's masks of a scope are live at a time (one loop per scope keeps ~45 masks of the container scope alive: 246 registers)
+  std::map<std::pair<uint32_t, int>, int> group_ix;
+  std::vector<std::vector<uint32_t>> groups;
+  {
+    int kind_no = -1;
+    std::string last;
+    bool first = true;
+    for (const Ord& e : order) {
+      if (first || e.kind != last) ++kind_no, last = e.kind, first = false;
+      const GkOutEnt& oe = c.outs[e.cix];
+      if ((oe.flags & 3u) || var_of(oe.prog_slot) < 0) continue;
+      for (uint32_t ai : cone((uint32_t)var_of(oe.prog_slot))) {
+        Gen::AtomRec& r = g.atoms[ai];
+        if (r.group >= 0) continue;
+        auto key = std::make_pair(r.scope, kind_no);
+        auto it = group_ix.find(key);
+        if (it == group_ix.end()) {
+          it = group_ix.emplace(key, (int)groups.size()).first;
+          groups.emplace_back();
+        }
+        r.group = it->second;
+        groups[(size_t)r.group].push_back(ai);
+      }
+    }
+  }
+  std::vector<uint8_t> group_done(groups.size(), 0);
+  std::set<std::string> ptr_declared;
+  auto emit_group = [&](int gi) {
+    if (gi < 0 || group_done[(size_t)gi]) return;
+    group_done[(size_t)gi] = 1;
+    const std::vector<uint32_t>& members = groups[(size_t)gi];
+    const uint32_t s = g.atoms[members[0]].scope;
+    std::map<uint32_t, uint32_t> need;
+    for (uint32_t ai : members)
+      for (auto& kv : g.atoms[ai].need) need[kv.first] |= kv.second;
+    o << "  // ---- atoms of scope " << s << " (row loop " << gi << ")\n";
+    auto decl = [&](const std::string& name, const std::string& text) {
+      if (ptr_declared.insert(name).second) o << text;
+    };
+    for (auto& kv : need) {
       const uint32_t ci = kv.first, enc = kv.second;
-      if (enc & GK_ENC_VT) o << "  const uint8_t* __restrict__ pt" << ci << " = cols[" << ci << "].vt;\n";
-      if (enc & GK_ENC_SID) o << "  const uint32_t* __restrict__ pi" << ci << " = cols[" << ci << "].sid;\n";
-      if (enc & GK_ENC_NUM) o << "  const long long* __restrict__ pn" << ci << " = reinterpret_cast<const long long*>(cols[" << ci << "].num);\n";
-      if (enc & GK_ENC_HEAD) o << "  const uint4* __restrict__ ph" << ci << " = reinterpret_cast<const uint4*>(cols[" << ci << "].head);\n";
+      const std::string K = std::to_string(ci);
+      if (enc & GK_ENC_VT) decl("pt" + K, "  const uint8_t* __restrict__ pt" + K + " = cols[" + K + "].vt;\n");
+      if (enc & GK_ENC_SID) decl("pi" + K, "  const uint32_t* __restrict__ pi" + K + " = cols[" + K + "].sid;\n");
+      if (enc & GK_ENC_NUM) decl("pn" + K, "  const long long* __restrict__ pn" + K + " = reinterpret_cast<const long long*>(cols[" + K + "].num);\n");
+      if (enc & GK_ENC_HEAD) decl("ph" + K, "  const uint4* __restrict__ ph" + K + " = reinterpret_cast<const uint4*>(cols[" + K + "].head);\n");
     }
     o << "  uint32_t";
-    for (size_t k = 0; k < g.atom_vars[s].size(); ++k) o << (k ? ", v" : " v") << g.atom_vars[s][k] << " = 0u";
+    for (size_t k = 0; k < members.size(); ++k) o << (k ? ", v" : " v") << g.atoms[members[k]].var << " = 0u";
     o << ";\n";
-    if (s == 0) o << "  {\n    const size_t row = obj;\n";
-    else o << "  for (uint32_t j = 0; j < n" << s << "; ++j) {\n    const size_t row = (size_t)lo" << s << " + j;\n";
-    for (auto& kv : g.col_need[s]) {
+    if (s == 0) o << "  {\n    const size_t row = obj;\n    const uint32_t bit = 1u;\n";
+    else o << "  for (uint32_t j = 0; j < n" << s << "; ++j) {\n    const size_t row = (size_t)lo" << s << " + j;\n    const uint32_t bit = 1u << j;\n";
+    for (auto& kv : need) {
       const uint32_t ci = kv.first, enc = kv.second;
-      if (enc & GK_ENC_VT) o << "    const uint32_t t" << ci << " = pt" << ci << "[row];\n";
-      if (enc & GK_ENC_SID) o << "    const uint32_t i" << ci << " = pi" << ci << "[row];\n";
-      if (enc & GK_ENC_NUM) o << "    const long long n" << ci << " = pn" << ci << "[row];\n";
-      if (enc & GK_ENC_HEAD) o << "    const uint4 h" << ci << "a = ph" << ci << "[2 * row], h" << ci << "b = ph" << ci << "[2 * row + 1];\n";
+      if (enc & GK_ENC_VT) o << "    const uint32_t t" << ci << " = GK_SPEC_LD(pt" << ci << " + row);\n";
+      if (enc & GK_ENC_SID) o << "    const uint32_t i" << ci << " = GK_SPEC_LD(pi" << ci << " + row);\n";
+      if (enc & GK_ENC_NUM) o << "    const long long n" << ci << " = GK_SPEC_LD(pn" << ci << " + row);\n";
+      if (enc & GK_ENC_HEAD) o << "    const uint4 h" << ci << "a = GK_SPEC_LD(ph" << ci << " + 2 * row), h" << ci << "b = GK_SPEC_LD(ph" << ci << " + 2 * row + 1);\n";
     }
-    o << g.atom_code[s] << "  }\n";
+    for (uint32_t ai : members) o << "    if (" << g.atoms[ai].expr << ") v" << g.atoms[ai].var << " |= bit;\n";
+    o << "  }\n";
   };
-  // ---- everything else depth-first from the results: a node right after what it reads.  Constraints whose cones touch the
-  // same scopes are emitted next to each other, so that a scope's atom masks die before the next scope's are born.
+  // ---- everything else depth-first from the results: a node right after what it reads
   std::function<void(uint32_t)> emit_var = [&](uint32_t v) {
-    const int pr = g.producer[v];
-    if (pr < 0) {
-      emit_scope_atoms((size_t)(-pr - 1));
+    if (g.atom_of[v] >= 0) {
+      emit_group(g.atoms[(size_t)g.atom_of[v]].group);
       return;
     }
+    const int pr = g.producer[v];
+    if (pr < 0) return;
     SpecNode& n = g.nodes[(size_t)pr];
     if (n.done) return;
     n.done = true;
     for (uint32_t d : n.deps) emit_var(d);
     o << n.code;
   };
-  std::vector<std::set<int>> memo_scopes(g.nvar);
-  std::vector<uint8_t> memo_done(g.nvar, 0);
-  std::function<const std::set<int>&(uint32_t)> cone_scopes = [&](uint32_t v) -> const std::set<int>& {
-    if (memo_done[v]) return memo_scopes[v];
-    memo_done[v] = 1;
-    const int pr = g.producer[v];
-    if (pr < 0) {
-      memo_scopes[v].insert(-pr - 1);
-    } else {
-      for (uint32_t d : g.nodes[(size_t)pr].deps) {
-        const std::set<int>& sub = cone_scopes(d);
-        memo_scopes[v].insert(sub.begin(), sub.end());
-      }
-    }
-    return memo_scopes[v];
-  };
-  auto var_of = [&](uint32_t slot) -> int { return slot < g.cur.size() ? g.cur[slot] : -1; };
-  std::vector<std::pair<std::vector<int>, uint32_t>> order;
-  for (uint32_t cix = 0; cix < C; ++cix) {
-    const GkOutEnt& oe = c.outs[cix];
-    std::vector<int> sig;
-    if (!(oe.flags & 3u) && var_of(oe.prog_slot) >= 0) {
-      const std::set<int>& sc = cone_scopes((uint32_t)var_of(oe.prog_slot));
-      sig.assign(sc.rbegin(), sc.rend());
-    }
-    order.emplace_back(sig, cix);
-  }
-  std::sort(order.begin(), order.end());
-  for (auto& ent : order) {
-    const uint32_t cix = ent.second;
+  for (const Ord& ent : order) {
+    const uint32_t cix = ent.cix;
     const GkOutEnt& oe = c.outs[cix];
     g.deps.clear();
     const std::string pv = (oe.flags & 1u) ? "1u" : (oe.flags & 2u) ? "0u" : "(" + g.rd(oe.prog_slot) + " & 1u)";
     const std::string mt = g.rd(oe.match_slot), er = g.rd(oe.err_slot);
     for (uint32_t d : g.deps) emit_var(d);
-    o << "  if (act[" << cix << "]) {   // constraint " << cix << "\n    vw[" << (cix >> 5) << "] |= (" << pv << " & " << mt << ") << " << (cix & 31u) << ";\n    ew["
-      << (cix >> 5) << "] |= (" << er << " & 1u) << " << (cix & 31u) << ";\n  }\n";
+    o << "  if (act[" << cix << "]) {   // constraint " << cix << " (" << ent.kind << ")\n    vw[" << (cix >> 5) << "] |= (" << pv << " & " << mt << ") << " << (cix & 31u)
+      << ";\n    ew[" << (cix >> 5) << "] |= (" << er << " & 1u) << " << (cix & 31u) << ";\n  }\n";
   }
-  o << "}\n";
+  o << "  return false;\n}\n";
   o << kWrapper;
   out.src = o.str();
   out.words = W;

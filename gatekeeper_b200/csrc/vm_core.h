@@ -13,7 +13,7 @@
 
 GK_HD bool gk_bytes_eq(const uint8_t* a, const uint8_t* b, uint32_t n) {
   for (uint32_t i = 0; i < n; ++i)
-    if (a[i] != b[i]) return false;
+    if (GK_LD(a + i) != GK_LD(b + i)) return false;
   return true;
 }
 
@@ -27,7 +27,7 @@ GK_HD bool gk_contains(const uint8_t* s, uint32_t sl, const uint8_t* p, uint32_t
   if (pl == 0) return true;
   if (sl < pl) return false;
   for (uint32_t i = 0; i + pl <= sl; ++i)
-    if (s[i] == p[0] && gk_bytes_eq(s + i, p, pl)) return true;
+    if (GK_LD(s + i) == GK_LD(p) && gk_bytes_eq(s + i, p, pl)) return true;
   return false;
 }
 
@@ -51,18 +51,18 @@ GK_HD bool gk_wild_gen(uint32_t mode, const uint8_t* p, uint32_t pl, const uint8
 // label lookup in a (key sid, value sid) run; returns value sid or GK_NONE
 GK_HD uint32_t gk_label(const uint32_t* kv, uint32_t lo, uint32_t hi, uint32_t key) {
   for (uint32_t i = lo; i < hi; ++i)
-    if (kv[2 * i] == key) return kv[2 * i + 1];
+    if (GK_LD(kv + 2 * i) == key) return GK_LD(kv + 2 * i + 1);
   return GK_NONE;
 }
 
 // labels.Selector.Matches over pool-encoded requirements [key, op, nvals, vals...]
 GK_HD bool gk_selector(const uint32_t* pool, uint32_t off, uint32_t nreq, const uint32_t* kv, uint32_t lo, uint32_t hi) {
   for (uint32_t r = 0; r < nreq; ++r) {
-    uint32_t key = pool[off], op = pool[off + 1], nv = pool[off + 2];
+    uint32_t key = GK_LD(pool + off), op = GK_LD(pool + off + 1), nv = GK_LD(pool + off + 2);
     uint32_t val = gk_label(kv, lo, hi, key);
     bool has = val != GK_NONE, in = false;
     if (has)
-      for (uint32_t j = 0; j < nv; ++j) in = in || pool[off + 3 + j] == val;
+      for (uint32_t j = 0; j < nv; ++j) in = in || GK_LD(pool + off + 3 + j) == val;
     bool ok = op == GK_SEL_IN ? in : op == GK_SEL_NOTIN ? !in : op == GK_SEL_EXISTS ? has : !has;
     if (!ok) return false;
     off += 3 + nv;
@@ -73,19 +73,19 @@ GK_HD bool gk_selector(const uint32_t* pool, uint32_t off, uint32_t nreq, const 
 // returns 1 match, 0 no match, <0 = -(GK_E_* code)
 GK_HD int gk_match_row(const GkBatch& b, const uint32_t* pool, const uint8_t* cbytes, const GkMatch& m, uint32_t row,
                        uint32_t obj) {
-  const uint32_t fl = b.flags[row];
+  const uint32_t fl = GK_LD(b.flags + row);
   const bool is_ns = fl & GK_F_IS_NS;
   // 1 kinds -- match.go:181-201 (version ignored)
   if (m.kinds_n) {
-    const uint32_t kind = b.kind_sid[row], group = b.group_sid[row];
+    const uint32_t kind = GK_LD(b.kind_sid + row), group = GK_LD(b.group_sid + row);
     bool any = false;
     uint32_t off = m.kinds_off;
     for (uint32_t e = 0; e < m.kinds_n && !any; ++e) {
-      uint32_t nk = pool[off], ng = pool[off + 1], wild = pool[off + 2];
+      uint32_t nk = GK_LD(pool + off), ng = GK_LD(pool + off + 1), wild = GK_LD(pool + off + 2);
       bool km = nk == 0 || (wild & 1), gm = ng == 0 || (wild & 2);
-      for (uint32_t j = 0; j < nk && !km; ++j) km = pool[off + 3 + j] == kind;
+      for (uint32_t j = 0; j < nk && !km; ++j) km = GK_LD(pool + off + 3 + j) == kind;
       if (km)
-        for (uint32_t j = 0; j < ng && !gm; ++j) gm = pool[off + 3 + nk + j] == group;
+        for (uint32_t j = 0; j < ng && !gm; ++j) gm = GK_LD(pool + off + 3 + nk + j) == group;
       any = km && gm;
       off += 3 + nk + ng;
     }
@@ -100,26 +100,27 @@ GK_HD int gk_match_row(const GkBatch& b, const uint32_t* pool, const uint8_t* cb
   // 3/4 namespaces, excludedNamespaces -- match.go:118-179
   if (m.ns_n || m.exns_n) {
     if (fl & GK_F_NSNAME) {
-      const uint8_t* s = b.nsn_bytes + b.nsn_off[row];
-      const uint32_t sl = b.nsn_off[row + 1] - b.nsn_off[row];
+      const uint32_t s0 = GK_LD(b.nsn_off + row);
+      const uint8_t* s = b.nsn_bytes + s0;
+      const uint32_t sl = GK_LD(b.nsn_off + row + 1) - s0;
       if (m.ns_n) {
         bool any = false;
         for (uint32_t j = 0; j < m.ns_n && !any; ++j) {
           const uint32_t* e = pool + m.ns_off + 3 * j;
-          any = gk_wild(e[0], cbytes + e[1], e[2], s, sl);
+          any = gk_wild(GK_LD(e), cbytes + GK_LD(e + 1), GK_LD(e + 2), s, sl);
         }
         if (!any) return 0;
       }
       for (uint32_t j = 0; j < m.exns_n; ++j) {
         const uint32_t* e = pool + m.exns_off + 3 * j;
-        if (gk_wild(e[0], cbytes + e[1], e[2], s, sl)) return 0;
+        if (gk_wild(GK_LD(e), cbytes + GK_LD(e + 1), GK_LD(e + 2), s, sl)) return 0;
       }
     }
   }
   // 5 labelSelector -- match.go:103-116
   if (m.flags & GK_M_HAS_LSEL) {
     if (m.flags & GK_M_LSEL_INVALID) return -GK_E_LSEL_INVALID;
-    if (!gk_selector(pool, m.lsel_off, m.lsel_n, b.lbl_kv, b.lbl_off[row], b.lbl_off[row + 1])) return 0;
+    if (!gk_selector(pool, m.lsel_off, m.lsel_n, b.lbl_kv, GK_LD(b.lbl_off + row), GK_LD(b.lbl_off + row + 1))) return 0;
   }
   // 6 namespaceSelector -- match.go:73-101
   if (m.flags & GK_M_HAS_NSSEL) {
@@ -127,21 +128,21 @@ GK_HD int gk_match_row(const GkBatch& b, const uint32_t* pool, const uint8_t* cb
     if (is_ns || ns_obj || obj_ns) {
       if (m.flags & GK_M_NSSEL_INVALID) return -GK_E_NSSEL_INVALID;
       if (is_ns) {
-        if (!gk_selector(pool, m.nssel_off, m.nssel_n, b.lbl_kv, b.lbl_off[row], b.lbl_off[row + 1])) return 0;
+        if (!gk_selector(pool, m.nssel_off, m.nssel_n, b.lbl_kv, GK_LD(b.lbl_off + row), GK_LD(b.lbl_off + row + 1))) return 0;
       } else {
         if (!ns_obj) return -GK_E_NS_MISSING;
-        const uint32_t nr = b.nsrow[obj];
-        if (!gk_selector(pool, m.nssel_off, m.nssel_n, b.nsl_kv, b.nsl_off[nr], b.nsl_off[nr + 1])) return 0;
+        const uint32_t nr = GK_LD(b.nsrow + obj);
+        if (!gk_selector(pool, m.nssel_off, m.nssel_n, b.nsl_kv, GK_LD(b.nsl_off + nr), GK_LD(b.nsl_off + nr + 1))) return 0;
       }
     }
   }
   // 7 name -- match.go:203-212
   if (m.flags & GK_M_HAS_NAME) {
     const uint8_t* p = cbytes + m.name_boff;
-    const uint32_t a = b.name_off[row], a1 = b.name_off[row + 1];
+    const uint32_t a = GK_LD(b.name_off + row), a1 = GK_LD(b.name_off + row + 1);
     bool ok = gk_wild(m.name_mode, p, m.name_len, b.name_bytes + a, a1 - a);
     if (!ok) {
-      const uint32_t g = b.gen_off[row], g1 = b.gen_off[row + 1];
+      const uint32_t g = GK_LD(b.gen_off + row), g1 = GK_LD(b.gen_off + row + 1);
       ok = gk_wild_gen(m.name_mode, p, m.name_len, b.gen_bytes + g, g1 - g);
     }
     if (!ok) return 0;
@@ -162,13 +163,13 @@ GK_HD int gk_match_row(const GkBatch& b, const uint32_t* pool, const uint8_t* cb
 GK_HD int gk_match(const GkBatch& b, const uint32_t* pool, const uint8_t* cbytes, const GkMatch& m, uint32_t obj) {
   if (!(m.flags & GK_M_HAS_MATCH)) return 1;   // matcher.go:22-25
   int nil = 0;
-  if (b.flags[obj] & GK_F_HAS_OBJ) {
+  if (GK_LD(b.flags + obj) & GK_F_HAS_OBJ) {
     int r = gk_match_row(b, pool, cbytes, m, obj, obj);
     if (r) return r;
   } else {
     ++nil;
   }
-  if (b.has_old && (b.flags[b.n + obj] & GK_F_HAS_OBJ)) {
+  if (b.has_old && (GK_LD(b.flags + b.n + obj) & GK_F_HAS_OBJ)) {
     int r = gk_match_row(b, pool, cbytes, m, b.n + obj, obj);
     if (r < 0) return r - GK_E_FROM_OLD;   // the error text names the object that failed (matcher.go:58-60): here the old one
     if (r) return r;
