@@ -25,11 +25,10 @@ typedef unsigned long uintptr_t;
 #else
 #define GK_HD inline
 #endif
-// loads of batch / program arrays in the shared per-object code (vm_core.h): read-only for the whole evaluation, so on the device
-// they take the non-coherent path and the compiler may keep one load across the stores of the error list
-#ifdef __CUDA_ARCH__
-#define GK_LD(p) __ldg(p)
-#else
+// loads of batch / program arrays in the shared per-object code (vm_core.h).  The generated kernel (spec_codegen.cpp) defines
+// GK_LD as __ldg: there every such array is in global memory and read-only for the whole evaluation, so the loads take the
+// non-coherent path and survive the stores of the error list.  The interpreter stages pool / cbytes in SHARED memory: plain loads.
+#ifndef GK_LD
 #define GK_LD(p) (*(p))
 #endif
 

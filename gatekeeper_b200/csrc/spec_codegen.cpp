@@ -408,6 +408,7 @@ SpecSource spec_codegen(const Compiled& c) {
   o << "// generated by spec_codegen.cpp for constraint-set version " << c.version << ": " << C << " constraints, " << c.ops.size() << " netlist ops\n";
   o << "#define GK_SPEC_C " << C << "u\n#define GK_SPEC_W " << W << "\n";
   o << "#ifndef GK_SPEC_THREADS\n#define GK_SPEC_THREADS 128\n#endif\n#ifndef GK_SPEC_MINB\n#define GK_SPEC_MINB 3\n#endif\n";
+  o << "#ifndef GK_SPEC_HOST\n#define GK_LD(p) __ldg(p)   /* pool, cbytes and every batch array are global and read-only here */\n#endif\n";
   o << strip_includes(kSpecHdrProgram) << strip_includes(kSpecHdrVmCore);
   o << R"GKSRC(
 #ifdef GK_SPEC_X_NOMATCH   /* (measurement only: what the spec.match pre-filter costs) */
