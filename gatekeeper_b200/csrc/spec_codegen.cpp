@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <functional>
 #include <map>
 #include <set>
@@ -75,6 +76,36 @@ extern "C" __global__ void __launch_bounds__(GK_SPEC_THREADS, GK_SPEC_MINB) gk_s
   }
   __syncthreads();
   const uint32_t lane = threadIdx.x & 31u;
+#ifdef GK_SPEC_X_PREFETCH
+  // Tile-ahead prefetch: the CTA of tile t asks L2 for the rows of tile t + GK_SPEC_PF_DIST (about one wave of resident CTAs
+  // ahead) of every array the generated code reads, so that tile's loads are L2 hits instead of DRAM misses.
+  {
+    const uint32_t tp = blockIdx.x + GK_SPEC_PF_DIST;
+    if (tp < p.ntiles) {
+      const uint32_t* tl = p.tile_lo + (size_t)tp * NS;
+      for (uint32_t k = threadIdx.x >> 5; k < GK_SPEC_NARRS; k += blockDim.x >> 5) {
+        const uint32_t id = gk_spec_arrs[k][0], which = gk_spec_arrs[k][1], es = gk_spec_arrs[k][2];
+        const unsigned char* base;
+        uint32_t sc, extra = 0u;
+        switch (which) {
+          case 0: base = reinterpret_cast<const unsigned char*>(cols[id].vt); sc = (uint32_t)cols[id].scope; break;
+          case 1: base = reinterpret_cast<const unsigned char*>(cols[id].sid); sc = (uint32_t)cols[id].scope; break;
+          case 2: base = reinterpret_cast<const unsigned char*>(cols[id].num); sc = (uint32_t)cols[id].scope; break;
+          case 3: base = reinterpret_cast<const unsigned char*>(cols[id].head); sc = (uint32_t)cols[id].scope; break;
+          case 4: base = reinterpret_cast<const unsigned char*>(scopes[id].off); sc = (uint32_t)scopes[id].parent; extra = 1u; break;
+          case 5: base = reinterpret_cast<const unsigned char*>(p.batch.flags); sc = 0u; break;
+          case 6: base = reinterpret_cast<const unsigned char*>(p.batch.kind_sid); sc = 0u; break;
+          case 7: base = reinterpret_cast<const unsigned char*>(p.batch.group_sid); sc = 0u; break;
+          case 8: base = reinterpret_cast<const unsigned char*>(p.batch.lbl_off); sc = 0u; extra = 1u; break;
+          case 9: base = reinterpret_cast<const unsigned char*>(p.batch.nsn_off); sc = 0u; extra = 1u; break;
+          default: base = reinterpret_cast<const unsigned char*>(p.batch.nsrow); sc = 0u; break;
+        }
+        const size_t a0 = reinterpret_cast<size_t>(base) + (size_t)tl[sc] * es, a1 = reinterpret_cast<size_t>(base) + ((size_t)tl[NS + sc] + extra) * es;
+        for (size_t a = (a0 & ~(size_t)127) + (size_t)lane * 128u; a < a1; a += 32u * 128u) asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+      }
+    }
+  }
+#endif
   uint32_t tv[GK_SPEC_W], te[GK_SPEC_W];
 #pragma unroll
   for (uint32_t w = 0; w < GK_SPEC_W; ++w) tv[w] = te[w] = 0u;
@@ -407,8 +438,8 @@ SpecSource spec_codegen(const Compiled& c) {
   std::ostringstream o;
   o << "// generated by spec_codegen.cpp for constraint-set version " << c.version << ": " << C << " constraints, " << c.ops.size() << " netlist ops\n";
   o << "#define GK_SPEC_C " << C << "u\n#define GK_SPEC_W " << W << "\n";
-  o << "#ifndef GK_SPEC_THREADS\n#define GK_SPEC_THREADS 128\n#endif\n#ifndef GK_SPEC_MINB\n#define GK_SPEC_MINB 3\n#endif\n";
-  o << "#ifndef GK_SPEC_HOST\n#define GK_LD(p) __ldg(p)   /* pool, cbytes and every batch array are global and read-only here */\n#endif\n";
+  o << "#ifndef GK_SPEC_THREADS\n#define GK_SPEC_THREADS 128\n#endif\n#ifndef GK_SPEC_MINB\n#define GK_SPEC_MINB 3\n#endif\n#ifndef GK_SPEC_PF_DIST\n#define GK_SPEC_PF_DIST 296u\n#endif\n";
+  o << "#if !defined(GK_SPEC_HOST) && !defined(GK_SPEC_X_PLAINLD)\n#define GK_LD(p) __ldg(p)   /* pool, cbytes and every batch array are global and read-only here */\n#endif\n";
   o << strip_includes(kSpecHdrProgram) << strip_includes(kSpecHdrVmCore);
   o << R"GKSRC(
 #ifdef GK_SPEC_X_NOMATCH   /* (measurement only: what the spec.match pre-filter costs) */
@@ -432,7 +463,11 @@ SpecSource spec_codegen(const Compiled& c) {
 struct uint4 { uint32_t x, y, z, w; };
 #else
 #define GK_SPEC_FN __device__ __forceinline__
+#ifdef GK_SPEC_X_PLAINLD
+#define GK_SPEC_LD(p) (*(p))
+#else
 #define GK_SPEC_LD(p) __ldg(p)      /* every array of a resident batch is read-only while it is evaluated */
+#endif
 #define GK_SPEC_POPC(x) __popc(x)
 #define GK_SPEC_ERR(o, mid, code)                                    \
   {                                                                  \
@@ -508,6 +543,9 @@ struct uint4 { uint32_t x, y, z, w; };
   std::sort(order.begin(), order.end());
   // ---- atom groups: an atom is computed in the row loop of (its scope, the first template kind that reads it), so that only one
   // template's masks of a scope are live at a time (one loop per scope keeps ~45 masks of the container scope alive: 246 registers)
+  // (GK_SPEC_GROUPING=0: one loop per scope.  Measured on B200, 1 M Pods x 50 constraints: per-kind loops 0.705 ms, per-scope loops
+  // 0.575 ms -- every extra loop is one more exposed memory latency per object, which costs more than the spilled registers.)
+  const bool by_kind = getenv("GK_SPEC_GROUPING") && atoi(getenv("GK_SPEC_GROUPING")) != 0;
   std::map<std::pair<uint32_t, int>, int> group_ix;
   std::vector<std::vector<uint32_t>> groups;
   {
@@ -515,7 +553,7 @@ struct uint4 { uint32_t x, y, z, w; };
     std::string last;
     bool first = true;
     for (const Ord& e : order) {
-      if (first || e.kind != last) ++kind_no, last = e.kind, first = false;
+      if (first || (by_kind && e.kind != last)) ++kind_no, last = e.kind, first = false;
       const GkOutEnt& oe = c.outs[e.cix];
       if ((oe.flags & 3u) || var_of(oe.prog_slot) < 0) continue;
       for (uint32_t ai : cone((uint32_t)var_of(oe.prog_slot))) {
@@ -594,6 +632,24 @@ struct uint4 { uint32_t x, y, z, w; };
       << ";\n    ew[" << (cix >> 5) << "] |= (" << er << " & 1u) << " << (cix & 31u) << ";\n  }\n";
   }
   o << "  return false;\n}\n";
+  // ---- the arrays the generated code reads (for the tile-ahead L2 prefetch of the wrapper): (column | scope, which, element bytes)
+  {
+    std::map<std::pair<uint32_t, uint32_t>, uint32_t> arrs;   // (col, which) -> es
+    for (auto& r : g.atoms)
+      for (auto& kv : r.need) {
+        if (kv.second & GK_ENC_VT) arrs[{kv.first, 0u}] = 1;
+        if (kv.second & GK_ENC_SID) arrs[{kv.first, 1u}] = 4;
+        if (kv.second & GK_ENC_NUM) arrs[{kv.first, 2u}] = 8;
+        if (kv.second & GK_ENC_HEAD) arrs[{kv.first, 3u}] = 32;
+      }
+    o << "#ifndef GK_SPEC_HOST\n__device__ const unsigned short gk_spec_arrs[][3] = {";
+    size_t na = 0;
+    for (auto& kv : arrs) o << (na++ ? ", " : "") << "{" << kv.first.first << ", " << kv.first.second << ", " << kv.second << "}";
+    for (size_t sc = 1; sc < NS; ++sc)
+      if (g.scope_used[sc]) o << (na++ ? ", " : "") << "{" << sc << ", 4, 4}";
+    for (uint32_t hdr = 5; hdr <= 10; ++hdr) o << (na++ ? ", " : "") << "{0, " << hdr << ", 4}";
+    o << "};\n#define GK_SPEC_NARRS " << na << "u\n#endif\n";
+  }
   o << kWrapper;
   out.src = o.str();
   out.words = W;

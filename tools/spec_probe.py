@@ -56,7 +56,7 @@ if a.wide:
 
 
 def run(label, env):
-    for k in ("GK_SPEC", "GK_SPEC_THREADS", "GK_SPEC_MINB", "GK_SPEC_DEFS"):
+    for k in ("GK_SPEC", "GK_SPEC_THREADS", "GK_SPEC_MINB", "GK_SPEC_DEFS", "GK_SPEC_GROUPING"):
         os.environ.pop(k, None)
     os.environ.update(env)
     drv = engine()
@@ -84,8 +84,10 @@ print(json.dumps(base), flush=True)
 for v in a.variants.split(","):     # THREADSxMINB[:SWITCH+SWITCH]  (switches = GK_SPEC_X_* measurement macros: results may differ)
     v, _, sw = v.partition(":")
     th, mb = v.split("x")
-    defs = " ".join("-DGK_SPEC_X_" + x for x in sw.split("+") if x)
-    o, got = run("spec " + v + (" " + sw if sw else ""), {"GK_SPEC_THREADS": th, "GK_SPEC_MINB": mb, "GK_SPEC_MIN_OBJECTS": "0", "GK_SPEC_DEFS": defs})
+    toks = [x for x in sw.split("+") if x]
+    defs = " ".join(("-DGK_SPEC_PF_DIST=%su" % x[2:]) if x.startswith("PF") else "-DGK_SPEC_X_" + x for x in toks if x not in ("G0", "G1"))
+    o, got = run("spec " + v + (" " + sw if sw else ""), {"GK_SPEC_THREADS": th, "GK_SPEC_MINB": mb, "GK_SPEC_MIN_OBJECTS": "0", "GK_SPEC_DEFS": defs,
+                                                         "GK_SPEC_GROUPING": "1" if "G1" in toks else "0"})
     o["identical"] = bool(np.array_equal(want[0], got[0]) and np.array_equal(want[1], got[1]) and want[2] == got[2] and want[3] == got[3])
     print(json.dumps(o), flush=True)
     assert o["identical"] or "NOMATCH" in sw, "generated kernel and interpreter disagree"
