@@ -526,6 +526,7 @@ struct uint4 { uint32_t x, y, z, w; };
     std::vector<int> sig;
     uint32_t cix;
     bool operator<(const Ord& x) const { return std::tie(kind, sig, cix) < std::tie(x.kind, x.sig, x.cix); }
+    static bool by_sig(const Ord& a, const Ord& b) { return std::tie(a.sig, a.cix) < std::tie(b.sig, b.cix); }
   };
   std::vector<Ord> order;
   for (uint32_t cix = 0; cix < C; ++cix) {
@@ -540,12 +541,15 @@ struct uint4 { uint32_t x, y, z, w; };
     }
     order.push_back(std::move(e));
   }
-  std::sort(order.begin(), order.end());
+  if (getenv("GK_SPEC_ORDER") && std::string(getenv("GK_SPEC_ORDER")) == "kind") std::sort(order.begin(), order.end());
+  else std::sort(order.begin(), order.end(), Ord::by_sig);
   // ---- atom groups: an atom is computed in the row loop of (its scope, the first template kind that reads it), so that only one
   // template's masks of a scope are live at a time (one loop per scope keeps ~45 masks of the container scope alive: 246 registers)
   // (GK_SPEC_GROUPING=0: one loop per scope.  Measured on B200, 1 M Pods x 50 constraints: per-kind loops 0.705 ms, per-scope loops
   // 0.575 ms -- every extra loop is one more exposed memory latency per object, which costs more than the spilled registers.)
   const bool by_kind = getenv("GK_SPEC_GROUPING") && atoi(getenv("GK_SPEC_GROUPING")) != 0;
+  const bool shift_form = !(getenv("GK_SPEC_FORM") && std::string(getenv("GK_SPEC_FORM")) == "if");
+  const bool unroll1 = !(getenv("GK_SPEC_UNROLL1") && atoi(getenv("GK_SPEC_UNROLL1")) == 0);
   std::map<std::pair<uint32_t, int>, int> group_ix;
   std::vector<std::vector<uint32_t>> groups;
   {
@@ -596,7 +600,7 @@ struct uint4 { uint32_t x, y, z, w; };
     for (size_t k = 0; k < members.size(); ++k) o << (k ? ", v" : " v") << g.atoms[members[k]].var << " = 0u";
     o << ";\n";
     if (s == 0) o << "  {\n    const size_t row = obj;\n    const uint32_t bit = 1u;\n";
-    else o << "  for (uint32_t j = 0; j < n" << s << "; ++j) {\n    const size_t row = (size_t)lo" << s << " + j;\n    const uint32_t bit = 1u << j;\n";
+    else o << (unroll1 ? "  _Pragma(\"unroll 1\")" : " ") << " for (uint32_t j = 0; j < n" << s << "; ++j) {\n    const size_t row = (size_t)lo" << s << " + j;\n    const uint32_t bit = 1u << j;\n    (void)bit;\n";
     for (auto& kv : need) {
       const uint32_t ci = kv.first, enc = kv.second;
       if (enc & GK_ENC_VT) o << "    const uint32_t t" << ci << " = GK_SPEC_LD(pt" << ci << " + row);\n";
@@ -604,7 +608,10 @@ struct uint4 { uint32_t x, y, z, w; };
       if (enc & GK_ENC_NUM) o << "    const long long n" << ci << " = GK_SPEC_LD(pn" << ci << " + row);\n";
       if (enc & GK_ENC_HEAD) o << "    const uint4 h" << ci << "a = GK_SPEC_LD(ph" << ci << " + 2 * row), h" << ci << "b = GK_SPEC_LD(ph" << ci << " + 2 * row + 1);\n";
     }
-    for (uint32_t ai : members) o << "    if (" << g.atoms[ai].expr << ") v" << g.atoms[ai].var << " |= bit;\n";
+    for (uint32_t ai : members) {
+      if (shift_form) o << "    v" << g.atoms[ai].var << " |= (uint32_t)" << g.atoms[ai].expr << (s == 0 ? ";\n" : " << j;\n");
+      else o << "    if (" << g.atoms[ai].expr << ") v" << g.atoms[ai].var << " |= bit;\n";
+    }
     o << "  }\n";
   };
   // ---- everything else depth-first from the results: a node right after what it reads

@@ -85,7 +85,11 @@ for v in a.variants.split(","):     # THREADSxMINB[:SWITCH+SWITCH]  (switches = 
     v, _, sw = v.partition(":")
     th, mb = v.split("x")
     toks = [x for x in sw.split("+") if x]
-    defs = " ".join(("-DGK_SPEC_PF_DIST=%su" % x[2:]) if x.startswith("PF") else "-DGK_SPEC_X_" + x for x in toks if x not in ("G0", "G1"))
+    gen = ("G0", "G1", "IF", "SHIFT", "U0", "U1", "OKIND", "OSIG")   # generator knobs (environment), the rest are -D switches of the text
+    defs = " ".join(("-DGK_SPEC_PF_DIST=%su" % x[2:]) if x.startswith("PF") else "-DGK_SPEC_X_" + x for x in toks if x not in gen)
+    os.environ["GK_SPEC_FORM"] = "if" if "IF" in toks else "shift"
+    os.environ["GK_SPEC_UNROLL1"] = "0" if "U0" in toks else "1"
+    os.environ["GK_SPEC_ORDER"] = "kind" if "OKIND" in toks else "sig"
     o, got = run("spec " + v + (" " + sw if sw else ""), {"GK_SPEC_THREADS": th, "GK_SPEC_MINB": mb, "GK_SPEC_MIN_OBJECTS": "0", "GK_SPEC_DEFS": defs,
                                                          "GK_SPEC_GROUPING": "1" if "G1" in toks else "0"})
     o["identical"] = bool(np.array_equal(want[0], got[0]) and np.array_equal(want[1], got[1]) and want[2] == got[2] and want[3] == got[3])
