@@ -1385,8 +1385,9 @@ class CudaBackend : public Backend {
   SpecEntry* spec_cur_ = nullptr;
   bool spec_on_ = !(getenv("GK_SPEC") && atoi(getenv("GK_SPEC")) == 0);
   uint32_t spec_min_objects_ = getenv("GK_SPEC_MIN_OBJECTS") ? (uint32_t)atoll(getenv("GK_SPEC_MIN_OBJECTS")) : 8192u;   // below: not worth a ~2 s NVRTC run
-  int spec_threads_ = getenv("GK_SPEC_THREADS") ? std::max(32, atoi(getenv("GK_SPEC_THREADS")) / 32 * 32) : 128;
-  int spec_minb_ = getenv("GK_SPEC_MINB") ? std::max(1, atoi(getenv("GK_SPEC_MINB"))) : 3;
+  // one thread per object of a 512-object tile, 128 registers: the fastest of the shapes measured (profiles/experiments/README.md)
+  int spec_threads_ = getenv("GK_SPEC_THREADS") ? std::min(1024, std::max(32, atoi(getenv("GK_SPEC_THREADS")) / 32 * 32)) : 512;
+  int spec_minb_ = getenv("GK_SPEC_MINB") ? std::max(1, atoi(getenv("GK_SPEC_MINB"))) : 1;
   const char* last_kernel_ = "gk_eval_kernel";
   bool spec_next_ = false;
   void* pinned_ = nullptr;

@@ -507,7 +507,8 @@ class HostEmuBackend : public Backend {
     }
     // the matcher-error list, as a set
     std::vector<std::array<uint32_t, 3>> a, b;
-    for (uint32_t i = 0; i < errcount; ++i) a.push_back({errlist[3 * i], errlist[3 * i + 1], errlist[3 * i + 2]});
+    for (uint32_t i = 0; i < errcount; ++i)
+      if (!big[errlist[3 * i]]) a.push_back({errlist[3 * i], errlist[3 * i + 1], errlist[3 * i + 2]});   // (a too-big object's are listed again by the interpreter)
     for (size_t i = 0; i + 2 < out.errlist.size(); i += 3)
       if (!big[out.errlist[i]]) b.push_back({out.errlist[i], out.errlist[i + 1], out.errlist[i + 2]});
     std::sort(a.begin(), a.end());
