@@ -61,6 +61,7 @@ extern "C" __global__ void __launch_bounds__(GK_SPEC_THREADS, GK_SPEC_MINB) gk_s
   uint32_t* act = reinterpret_cast<uint32_t*>(smem + (size_t)NC * sizeof(GkColumn) + (size_t)NS * sizeof(GkScope));
   uint32_t* s_tot = act + GK_SPEC_W * 32u;
   uint32_t* s_err = s_tot + GK_SPEC_W * 32u;
+  uint32_t* actw = s_err + GK_SPEC_W * 32u;   // the enforcement-point mask packed: bit c of word c / 32
   {
     const uint4* a = reinterpret_cast<const uint4*>(p.batch.cols);
     uint4* d = reinterpret_cast<uint4*>(cols);
@@ -76,6 +77,11 @@ extern "C" __global__ void __launch_bounds__(GK_SPEC_THREADS, GK_SPEC_MINB) gk_s
   }
   __syncthreads();
   const uint32_t lane = threadIdx.x & 31u;
+  for (uint32_t i = threadIdx.x; i < GK_SPEC_W * 32u; i += blockDim.x) {   // (whole warps: both bounds are multiples of 32)
+    const uint32_t bits = __ballot_sync(0xffffffffu, act[i] != 0u);
+    if (lane == 0u) actw[i >> 5] = bits;
+  }
+  __syncthreads();
 #ifdef GK_SPEC_X_PREFETCH
   // Tile-ahead prefetch: the CTA of tile t asks L2 for the rows of tile t + GK_SPEC_PF_DIST (about one wave of resident CTAs
   // ahead) of every array the generated code reads, so that tile's loads are L2 hits instead of DRAM misses.
@@ -123,7 +129,7 @@ extern "C" __global__ void __launch_bounds__(GK_SPEC_THREADS, GK_SPEC_MINB) gk_s
 #pragma unroll
       for (uint32_t w = 0; w < GK_SPEC_W; ++w) vw[w] = ew[w] = 0u;
       if (o < nobj) {
-        if (gk_spec_object(p.batch, cols, scopes, p.prog.pool, p.prog.cbytes, act, p.out, obj0 + o, vw, ew)) big = 1;
+        if (gk_spec_object(p.batch, cols, scopes, p.prog.pool, p.prog.cbytes, actw, p.out, obj0 + o, vw, ew)) big = 1;
         const size_t at = (size_t)(obj0 + o) * GK_SPEC_W;
 #if GK_SPEC_W == 2
         const uint2 v2 = make_uint2(vw[0], vw[1]);
@@ -181,11 +187,196 @@ extern "C" __global__ void __launch_bounds__(GK_SPEC_THREADS, GK_SPEC_MINB) gk_s
 #else
 // TEST-ONLY host build (tests/_hostemu, GK_SPEC_CHECK=1): one object; returns 1 when the object does not fit the mask registers
 extern "C" int gk_spec_host(const GkKParams* p, uint32_t obj, uint32_t* vw, uint32_t* ew) {
-  for (uint32_t w = 0; w < GK_SPEC_W; ++w) vw[w] = ew[w] = 0u;
-  return gk_spec_object(p->batch, p->batch.cols, p->batch.scopes, p->prog.pool, p->prog.cbytes, p->active, p->out, obj, vw, ew) ? 1 : 0;
+  uint32_t actw[GK_SPEC_W];
+  for (uint32_t w = 0; w < GK_SPEC_W; ++w) vw[w] = ew[w] = actw[w] = 0u;
+  for (uint32_t c = 0; c < GK_SPEC_C; ++c)
+    if (p->active[c]) actw[c >> 5] |= 1u << (c & 31u);
+  return gk_spec_object(p->batch, p->batch.cols, p->batch.scopes, p->prog.pool, p->prog.cbytes, actw, p->out, obj, vw, ew) ? 1 : 0;
 }
 #endif
 )GKSRC";
+
+// ---- one spec.match block written out as gk_spec_match_<mid>(): the same eight criteria in the same order as gk_match_row() /
+// gk_match() (vm_core.h; reference pkg/mutation/match/match.go:32-65, pkg/target/matcher.go:21-71), with everything the block fixes
+// folded in.  Returns false (nothing written) when the block's tables do not lie inside the pool: the caller then keeps the generic form.
+// a wildcard pattern (wildcard.go:17-41) against the bytes s[0, sl): the pattern's bytes are immediates
+std::string wild_expr(const Compiled& c, uint32_t mode, uint32_t off, uint32_t len, const std::string& s, const std::string& sl, bool generate_name) {
+  const std::string L = std::to_string(len) + "u";
+  if (generate_name && mode != GK_W_PREFIX && mode != GK_W_CONTAINS) return "false";   // exact and "*x" never match a generateName
+  const std::string generic = std::string(generate_name ? "gk_wild_gen(" : "gk_wild(") + std::to_string(mode) + "u, cbytes + " + std::to_string(off) + "u, " + L + ", " + s + ", " + sl + ")";
+  if ((size_t)off + len > c.cbytes.size() || len > 24u) return generic;
+  if (mode == GK_W_CONTAINS) return len == 0 ? "true" : generic;
+  std::string e = "(" + sl + (mode == GK_W_EXACT ? " == " : " >= ") + L;
+  for (uint32_t i = 0; i < len; ++i) {
+    const std::string at = mode == GK_W_SUFFIX ? s + " + (" + sl + " - " + L + ") + " + std::to_string(i) + "u" : s + " + " + std::to_string(i) + "u";
+    e += " && GK_LD(" + at + ") == " + hx(c.cbytes[off + i]);
+  }
+  return e + ")";
+}
+
+// labels.Selector.Matches over the (key, value) run [lo, hi) of `kv`: one walk of the run fetches the value of every key the
+// selector names (backwards, so that the first entry of a key is the one that stays, as in gk_label()); statements that `return 0`
+bool selector_code(std::ostringstream& o, const Compiled& c, uint32_t off, uint32_t nreq, const std::string& kv, const std::string& lo, const std::string& hi,
+                   const std::string& tag) {
+  struct Req {
+    uint32_t key, op;
+    std::vector<uint32_t> vals;
+  };
+  std::vector<Req> reqs;
+  std::vector<uint32_t> keys;
+  for (uint32_t r = 0; r < nreq; ++r) {
+    if ((size_t)off + 3 > c.pool.size()) return false;
+    Req q{c.pool[off], c.pool[off + 1], {}};
+    const uint32_t nv = c.pool[off + 2];
+    if ((size_t)off + 3 + nv > c.pool.size() || nv > 64u) return false;
+    q.vals.assign(c.pool.begin() + off + 3, c.pool.begin() + off + 3 + nv);
+    off += 3 + nv;
+    if (std::find(keys.begin(), keys.end(), q.key) == keys.end()) keys.push_back(q.key);
+    reqs.push_back(std::move(q));
+  }
+  if (reqs.empty()) return true;
+  o << "  {\n    uint32_t";
+  for (size_t k = 0; k < keys.size(); ++k) o << (k ? ", " : " ") << tag << k << " = GK_NONE";
+  o << ";\n    _Pragma(\"unroll 1\") for (uint32_t i = " << hi << "; i-- > " << lo << ";) {\n      const uint32_t k = GK_LD(" << kv << " + 2u * i), v = GK_LD(" << kv
+    << " + 2u * i + 1u);\n";
+  for (size_t k = 0; k < keys.size(); ++k) o << "      if (k == " << hx(keys[k]) << ") " << tag << k << " = v;\n";
+  o << "    }\n";
+  for (const Req& q : reqs) {
+    const std::string x = tag + std::to_string(std::find(keys.begin(), keys.end(), q.key) - keys.begin());
+    const std::string has = "(" + x + " != GK_NONE)";
+    std::string in = "false";
+    if (!q.vals.empty()) {
+      in = "(" + has + " && (";
+      for (size_t j = 0; j < q.vals.size(); ++j) in += (j ? " || " : "") + x + " == " + hx(q.vals[j]);
+      in += "))";
+    }
+    const std::string ok = q.op == GK_SEL_IN ? in : q.op == GK_SEL_NOTIN ? "!" + in : q.op == GK_SEL_EXISTS ? has : "!" + has;
+    o << "    if (!(" << ok << ")) return 0;\n";
+  }
+  o << "  }\n";
+  return true;
+}
+
+bool emit_match(std::ostringstream& out, const Compiled& c, uint32_t mid) {
+  const GkMatch& m = c.match[mid];
+  const std::string M = std::to_string(mid);
+  const char* sig_tail = "(const GkBatch& B, const uint32_t* __restrict__ pool, const uint8_t* __restrict__ cbytes, ";
+  std::ostringstream o;
+  if (!(m.flags & GK_M_HAS_MATCH)) {   // matcher.go:22-25: no spec.match matches everything
+    out << "GK_SPEC_FN int gk_spec_match_" << M << sig_tail << "const uint32_t obj) {\n  (void)B; (void)pool; (void)cbytes; (void)obj;\n  return 1;\n}\n";
+    return true;
+  }
+  o << "GK_SPEC_FN int gk_spec_mrow_" << M << sig_tail << "const uint32_t row, const uint32_t obj) {\n  (void)pool; (void)cbytes; (void)obj;\n";
+  o << "  const uint32_t fl = GK_LD(B.flags + row);\n  const bool is_ns = (fl & GK_F_IS_NS) != 0u;\n  (void)is_ns;\n";
+  // 1 kinds -- match.go:181-201
+  if (m.kinds_n) {
+    std::string any;
+    uint32_t off = m.kinds_off;
+    bool always = false;
+    for (uint32_t e = 0; e < m.kinds_n; ++e) {
+      if ((size_t)off + 3 > c.pool.size()) return false;
+      const uint32_t nk = c.pool[off], ng = c.pool[off + 1], wild = c.pool[off + 2];
+      if ((size_t)off + 3 + nk + ng > c.pool.size() || nk > 64u || ng > 64u) return false;
+      std::string km, gm;
+      if (!(nk == 0 || (wild & 1u))) {
+        for (uint32_t j = 0; j < nk; ++j) km += (j ? " || kind == " : "kind == ") + hx(c.pool[off + 3 + j]);
+        km = "(" + km + ")";
+      }
+      if (!(ng == 0 || (wild & 2u))) {
+        for (uint32_t j = 0; j < ng; ++j) gm += (j ? " || group == " : "group == ") + hx(c.pool[off + 3 + nk + j]);
+        gm = "(" + gm + ")";
+      }
+      const std::string both = km.empty() && gm.empty() ? "" : km.empty() ? gm : gm.empty() ? km : "(" + km + " && " + gm + ")";
+      if (both.empty()) always = true;
+      else any += (any.empty() ? "" : " || ") + both;
+      off += 3 + nk + ng;
+    }
+    if (!always) o << "  {\n    const uint32_t kind = GK_LD(B.kind_sid + row), group = GK_LD(B.group_sid + row);\n    (void)kind; (void)group;\n    if (!(" << any << ")) return 0;\n  }\n";
+  }
+  // 2 scope -- match.go:214-227
+  if (m.flags & (GK_M_SCOPE_CLUSTER | GK_M_SCOPE_NAMESPACED)) {
+    o << "  {\n    const bool has_ns = (fl & (GK_F_HAS_NS | GK_F_NS_OBJ)) != 0u;\n";
+    if (m.flags & GK_M_SCOPE_CLUSTER) o << "    if (!(is_ns || !has_ns)) return 0;\n";
+    if (m.flags & GK_M_SCOPE_NAMESPACED) o << "    if (!(!is_ns && has_ns)) return 0;\n";
+    o << "  }\n";
+  }
+  // 3/4 namespaces, excludedNamespaces -- match.go:118-179
+  if (m.ns_n || m.exns_n) {
+    if ((size_t)m.ns_off + 3 * (size_t)m.ns_n > c.pool.size() || (size_t)m.exns_off + 3 * (size_t)m.exns_n > c.pool.size() || m.ns_n > 64u || m.exns_n > 64u) return false;
+    o << "  if (fl & GK_F_NSNAME) {\n    const uint32_t s0 = GK_LD(B.nsn_off + row), sl = GK_LD(B.nsn_off + row + 1u) - s0;\n    const uint8_t* s = B.nsn_bytes + s0;\n    (void)s; (void)sl;\n";
+    if (m.ns_n) {
+      o << "    if (!(";
+      for (uint32_t j = 0; j < m.ns_n; ++j) {
+        const uint32_t* e = &c.pool[m.ns_off + 3 * j];
+        o << (j ? "\n          || " : "") << wild_expr(c, e[0], e[1], e[2], "s", "sl", false);
+      }
+      o << ")) return 0;\n";
+    }
+    for (uint32_t j = 0; j < m.exns_n; ++j) {
+      const uint32_t* e = &c.pool[m.exns_off + 3 * j];
+      o << "    if (" << wild_expr(c, e[0], e[1], e[2], "s", "sl", false) << ") return 0;\n";
+    }
+    o << "  }\n";
+  }
+  // 5 labelSelector -- match.go:103-116
+  if (m.flags & GK_M_HAS_LSEL) {
+    if (m.flags & GK_M_LSEL_INVALID) {
+      o << "  return -GK_E_LSEL_INVALID;\n}\n";
+      goto wrapper;
+    }
+    o << "  {\n    const uint32_t l0 = GK_LD(B.lbl_off + row), l1 = GK_LD(B.lbl_off + row + 1u);\n";
+    if (!selector_code(o, c, m.lsel_off, m.lsel_n, "B.lbl_kv", "l0", "l1", "lv")) return false;
+    o << "  }\n";
+  }
+  // 6 namespaceSelector -- match.go:73-101
+  if (m.flags & GK_M_HAS_NSSEL) {
+    o << "  {\n    const bool ns_obj = (fl & GK_F_NS_OBJ) != 0u, obj_ns = (fl & GK_F_HAS_NS) != 0u;\n    if (is_ns || ns_obj || obj_ns) {\n";
+    if (m.flags & GK_M_NSSEL_INVALID) {
+      o << "      return -GK_E_NSSEL_INVALID;\n    }\n  }\n";
+    } else {
+      o << "      if (is_ns) {\n        const uint32_t l0 = GK_LD(B.lbl_off + row), l1 = GK_LD(B.lbl_off + row + 1u);\n";
+      if (!selector_code(o, c, m.nssel_off, m.nssel_n, "B.lbl_kv", "l0", "l1", "sv")) return false;
+      o << "      } else {\n        if (!ns_obj) return -GK_E_NS_MISSING;\n        const uint32_t nr = GK_LD(B.nsrow + obj);\n        const uint32_t l0 = GK_LD(B.nsl_off + nr), l1 = GK_LD(B.nsl_off + nr + 1u);\n";
+      if (!selector_code(o, c, m.nssel_off, m.nssel_n, "B.nsl_kv", "l0", "l1", "nv")) return false;
+      o << "      }\n    }\n  }\n";
+    }
+  }
+  // 7 name -- match.go:203-212
+  if (m.flags & GK_M_HAS_NAME) {
+    o << "  {\n    const uint32_t a = GK_LD(B.name_off + row), al = GK_LD(B.name_off + row + 1u) - a;\n    const uint8_t* nm = B.name_bytes + a;\n    (void)nm; (void)al;\n";
+    o << "    bool ok = " << wild_expr(c, m.name_mode, m.name_boff, m.name_len, "nm", "al", false) << ";\n";
+    const std::string ge = wild_expr(c, m.name_mode, m.name_boff, m.name_len, "gn", "gl", true);
+    if (ge != "false")
+      o << "    if (!ok) {\n      const uint32_t g = GK_LD(B.gen_off + row), gl = GK_LD(B.gen_off + row + 1u) - g;\n      const uint8_t* gn = B.gen_bytes + g;\n      (void)gn; (void)gl;\n      ok = " << ge
+        << ";\n    }\n";
+    o << "    if (!ok) return 0;\n  }\n";
+  }
+  // 8 source -- match.go:229-253
+  {
+    if (m.flags & GK_M_SRC_INVALID) {
+      o << "  return -GK_E_SRC_INVALID_MATCH;\n}\n";
+      goto wrapper;
+    }
+    const uint32_t msrc = (m.flags >> GK_M_SRC_SHIFT) & 7u;
+    if (msrc != GK_SRC_ALL) {
+      o << "  {\n    const uint32_t tsrc = (fl & GK_F_SRC_MASK) >> GK_F_SRC_SHIFT;\n    if (tsrc == GK_SRC_EMPTY) return -GK_E_SRC_UNSPECIFIED;\n    if (tsrc == GK_SRC_INVALID) return -GK_E_SRC_INVALID_OBJ;\n    if (tsrc != "
+        << msrc << "u) return 0;\n  }\n";
+    }
+  }
+  o << "  return 1;\n}\n";
+wrapper:
+  // Matcher.Match: the object, then the old object (matcher.go:21-71); one copy of the row code for both
+  o << "GK_SPEC_FN int gk_spec_match_" << M << sig_tail << "const uint32_t obj) {\n  int nil = 0;\n"
+    << "  _Pragma(\"unroll 1\") for (uint32_t pass = 0u; pass < 2u; ++pass) {\n"
+    << "    if (pass && !B.has_old) {\n      ++nil;\n      break;\n    }\n"
+    << "    const uint32_t row = pass ? B.n + obj : obj;\n"
+    << "    if (!(GK_LD(B.flags + row) & GK_F_HAS_OBJ)) {\n      ++nil;\n      continue;\n    }\n"
+    << "    const int r = gk_spec_mrow_" << M << "(B, pool, cbytes, row, obj);\n"
+    << "    if (r < 0) return pass ? r - GK_E_FROM_OLD : r;   // the error text names the object that failed: here the old one\n"
+    << "    if (r) return r;\n  }\n  return nil == 2 ? -GK_E_NO_OBJECT : 0;\n}\n";
+  out << o.str();
+  return true;
+}
 
 // One netlist op after SSA renaming (slots are reused by liveness; every write gets a fresh variable): its text, what it
 // reads and what it defines.  Nodes are emitted depth-first from the constraint results (see spec_codegen()), not in netlist
@@ -323,12 +514,15 @@ struct Gen {
     atoms.push_back(std::move(r));
   }
 
-  // `rm` = the mask of the children of parent row pj inside the object's rows of scope L
+  // `rm` = the mask of the children of parent row pj inside the object's rows of scope L, `pb` = the parent row's own bit.  The CSR
+  // offsets are monotone, so rm = (rows below the END of pj) & ~(rows below its START), and the start of pj is the end of pj - 1: one
+  // load and one mask per turn, carried.  (lo<L> is by definition the offset at lo<P>: the first parent's children start at bit 0.)
+  // Not unrolled: parents have one to three rows here, the unrolled-by-four body the compiler makes is text that never runs.
   std::string range_loop_head(uint32_t L) {
     const uint32_t P = (uint32_t)c.schema.scopes[L].parent;
     const std::string l = std::to_string(L), p = std::to_string(P);
-    return "  for (uint32_t pj = 0; pj < n" + p + "; ++pj) {\n    const uint32_t ra = GK_SPEC_LD(o" + l + " + lo" + p + " + pj) - lo" + l + ", rb = GK_SPEC_LD(o" + l + " + lo" + p +
-           " + pj + 1u) - lo" + l + ";\n    const uint32_t rm = rb > ra ? (((rb - ra) >= 32u ? 0xffffffffu : ((1u << (rb - ra)) - 1u)) << ra) : 0u;\n";
+    return "  {\n  uint32_t lmp = 0u;\n  _Pragma(\"unroll 1\") for (uint32_t pj = 0; pj < n" + p + "; ++pj) {\n    const uint32_t rb = GK_SPEC_LD(o" + l + " + lo" + p + " + pj + 1u) - lo" + l +
+           ";\n    const uint32_t lm = rb >= 32u ? 0xffffffffu : ((1u << rb) - 1u), rm = lm & ~lmp, pb = 1u << pj;\n    lmp = lm;\n    (void)pb;\n";
   }
 
   void op(const GkOp& op) {
@@ -380,8 +574,8 @@ struct Gen {
         } else {
           for (auto& q : pr) body << "  uint32_t v" << q.second << " = 0u;\n";
           body << range_loop_head(level);
-          for (auto& q : pr) body << "    if ((" << q.first << " >> pj) & 1u) v" << q.second << " |= rm;\n";
-          body << "  }\n";
+          for (auto& q : pr) body << "    if (" << q.first << " & pb) v" << q.second << " |= rm;\n";
+          body << "  }\n  }\n";
         }
         break;
       }
@@ -402,8 +596,8 @@ struct Gen {
         } else {
           for (auto& q : pr) body << "  uint32_t v" << q.second << " = 0u;\n";
           body << range_loop_head(level);
-          for (auto& q : pr) body << "    v" << q.second << " |= (uint32_t)" << test(q.first + " & rm") << " << pj;\n";
-          body << "  }\n";
+          for (auto& q : pr) body << "    if (" << test(q.first + " & rm") << ") v" << q.second << " |= pb;\n";
+          body << "  }\n  }\n";
         }
         break;
       }
@@ -411,7 +605,7 @@ struct Gen {
         const uint32_t mid = op.w2;
         match_used.insert(mid);
         const uint32_t vm = fresh(out), ve = fresh(op.w1 & 0xffffu);
-        body << "  const int m" << vm << " = skip ? 0 : GK_SPEC_MATCH(B, pool, cbytes, M" << mid << ", obj);\n";
+        body << "  const int m" << vm << " = skip ? 0 : GK_SPEC_MATCH(" << mid << ", B, pool, cbytes, obj);\n";
         body << "  if (m" << vm << " < 0) GK_SPEC_ERR(obj, " << mid << "u, (uint32_t)(-m" << vm << "));\n";
         body << "  const uint32_t v" << vm << " = m" << vm << " > 0 ? 1u : 0u, v" << ve << " = m" << vm << " < 0 ? 1u : 0u;\n";
         break;
@@ -443,9 +637,9 @@ SpecSource spec_codegen(const Compiled& c) {
   o << strip_includes(kSpecHdrProgram) << strip_includes(kSpecHdrVmCore);
   o << R"GKSRC(
 #ifdef GK_SPEC_X_NOMATCH   /* (measurement only: what the spec.match pre-filter costs) */
-#define GK_SPEC_MATCH(B, pool, cbytes, M, obj) 1
+#define GK_SPEC_MATCH(MID, B, pool, cbytes, obj) 1
 #else
-#define GK_SPEC_MATCH(B, pool, cbytes, M, obj) gk_match(B, pool, cbytes, M, obj)
+#define GK_SPEC_MATCH(MID, B, pool, cbytes, obj) gk_spec_match_##MID(B, pool, cbytes, obj)
 #endif
 #ifdef GK_SPEC_HOST
 #define GK_SPEC_FN static inline
@@ -480,17 +674,24 @@ struct uint4 { uint32_t x, y, z, w; };
   }
 #endif
 )GKSRC";
-  // ---- match blocks as literals: the compiler folds every branch a block does not use
+  // ---- the spec.match pre-filter of every block the netlist uses, written out (emit_match below): criteria the block does not have are
+  // not emitted, kind / group / label ids and the bytes of the wildcard patterns are immediates, the labels are walked once per selector.
+  // GK_SPEC_MATCHGEN=0: the block as a GkMatch literal through the shared gk_match() (vm_core.h) instead -- the form the first
+  // generated kernels had; the pool / cbytes reads of that form are what the written-out one removes.
+  const bool matchgen = !(getenv("GK_SPEC_MATCHGEN") && atoi(getenv("GK_SPEC_MATCHGEN")) == 0);
   for (uint32_t mid : g.match_used) {
     const GkMatch& m = c.match[mid];
+    if (matchgen && emit_match(o, c, mid)) continue;
     o << "#define M" << mid << " (GkMatch{" << hx(m.flags) << ", " << m.kinds_off << "u, " << m.kinds_n << "u, " << m.ns_off << "u, " << m.ns_n << "u, " << m.exns_off << "u, "
       << m.exns_n << "u, " << m.lsel_off << "u, " << m.lsel_n << "u, " << m.nssel_off << "u, " << m.nssel_n << "u, " << m.name_mode << "u, " << m.name_boff << "u, "
       << m.name_len << "u, 0u, 0u})\n";
+    o << "GK_SPEC_FN int gk_spec_match_" << mid << "(const GkBatch& B, const uint32_t* __restrict__ pool, const uint8_t* __restrict__ cbytes, const uint32_t obj) {\n"
+      << "  return gk_match(B, pool, cbytes, M" << mid << ", obj);\n}\n";
   }
   // returns true when the object has more rows in some scope than a mask holds: its words are then meaningless (the caller
   // hands the tile to the interpreter, which stores them again; a matcher error may be listed twice, with the same code)
   o << "\nGK_SPEC_FN bool gk_spec_object(const GkBatch& B, const GkColumn* cols, const GkScope* scopes, const uint32_t* __restrict__ pool, const uint8_t* __restrict__ cbytes,\n"
-       "                               const uint32_t* act, const GkOut& out, const uint32_t obj, uint32_t* vw, uint32_t* ew) {\n";
+       "                               const uint32_t* actw, const GkOut& out, const uint32_t obj, uint32_t* vw, uint32_t* ew) {\n";
   o << "  const uint32_t lo0 = obj, hi0 = obj + 1u, n0 = 1u, f0 = 1u;\n  (void)lo0; (void)hi0; (void)n0; (void)f0; (void)out; (void)pool; (void)cbytes; (void)cols;\n";
   o << "  const bool skip = (GK_SPEC_LD(B.flags + obj) & GK_F_SKIP) != 0u;\n  (void)skip;\n  bool big = false;\n";
   for (size_t s = 1; s < NS; ++s) {
@@ -637,9 +838,11 @@ struct uint4 { uint32_t x, y, z, w; };
     const std::string pv = (oe.flags & 1u) ? "1u" : (oe.flags & 2u) ? "0u" : "(" + g.rd(oe.prog_slot) + " & 1u)";
     const std::string mt = g.rd(oe.match_slot), er = g.rd(oe.err_slot);
     for (uint32_t d : g.deps) emit_var(d);
-    o << "  if (act[" << cix << "]) {   // constraint " << cix << " (" << ent.kind << ")\n    vw[" << (cix >> 5) << "] |= (" << pv << " & " << mt << ") << " << (cix & 31u)
-      << ";\n    ew[" << (cix >> 5) << "] |= (" << er << " & 1u) << " << (cix & 31u) << ";\n  }\n";
+    o << "  vw[" << (cix >> 5) << "] |= (" << pv << " & " << mt << ") << " << (cix & 31u) << ";   // constraint " << cix << " (" << ent.kind << ")\n  ew[" << (cix >> 5) << "] |= (" << er
+      << " & 1u) << " << (cix & 31u) << ";\n";
   }
+  // the enforcement-point filter: one packed word per 32 constraints (actw), not a test per constraint
+  for (uint32_t w = 0; w < W; ++w) o << "  vw[" << w << "] &= actw[" << w << "];\n  ew[" << w << "] &= actw[" << w << "];\n";
   o << "  return big;\n}\n";
   // ---- the arrays the generated code reads (for the tile-ahead L2 prefetch of the wrapper): (column | scope, which, element bytes)
   {
@@ -663,7 +866,7 @@ struct uint4 { uint32_t x, y, z, w; };
   out.src = o.str();
   out.words = W;
   auto r16 = [](size_t x) { return (x + 15) / 16 * 16; };
-  out.smem = r16(c.schema.cols.size() * sizeof(GkColumn) + NS * sizeof(GkScope) + 3 * (size_t)W * 32 * 4) + 16;
+  out.smem = r16(c.schema.cols.size() * sizeof(GkColumn) + NS * sizeof(GkScope) + 3 * (size_t)W * 32 * 4 + (size_t)W * 4) + 16;
   out.n_fast = g.n_fast;
   out.n_generic = g.n_generic;
   return out;

@@ -359,3 +359,36 @@ def test_generated_kernel_text_matches_the_interpreted_netlist(config):
     """spec_codegen.cpp: the CUDA C++ text generated for the constraint set, compiled for the host, object by object against the
     interpreter -- decision and ambiguity netlists, pages with objects too wide for the mask registers."""
     assert P.case_spec_kernel(HOSTEMU, 1500, config=config) > 100
+
+
+@pytest.mark.parametrize("config", [2, 4, 5])
+def test_generated_kernel_text_compiles_with_nvrtc_for_sm100a(config, tmp_path, monkeypatch):
+    """The text NVRTC gets on the GPU box (kernels.cu: spec_compile, same options) must compile here too -- NVRTC needs no
+    device -- and the spec.match blocks must be the written-out form (no block left on the generic gk_match())."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("spec_nvrtc", os.path.join(ROOT, "tools", "spec_nvrtc.py"))
+    tool = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tool)
+    from gatekeeper_b200 import driver as D, workloads as W
+    out = tmp_path / "spec.cu"
+    monkeypatch.setenv("GK_SPEC_DUMP", str(out))
+    monkeypatch.setenv("GK_SPEC_CHECK", "1")
+    tm, cons = {2: W.config2, 4: W.config4, 5: W.config5}[config]()
+    drv = D.Driver(lib_path=HOSTEMU)
+    for k, r in tm:
+        drv.add_template(k, r)
+    for c in cons:
+        drv.AddConstraint(c)
+    for ns in W.synth_namespaces():
+        drv.AddData("admission.k8s.gatekeeper.sh", ["cluster", "v1", "Namespace", ns["metadata"]["name"]], ns)
+    drv.ReviewBlob(W.synth_objects(7, 300, mode=1 if config == 4 else 0), with_results=False)
+    drv.close()
+    text = out.read_bytes()
+    assert b"GK_SPEC_FN int gk_spec_mrow_" in text and b"return gk_match(B, pool, cbytes, M" not in text
+    try:
+        cubin, log, _ = tool.nvrtc_compile(text)
+    except RuntimeError as e:
+        if "libnvrtc not found" in str(e):
+            pytest.skip("no NVRTC in this container")
+        raise
+    assert len(cubin) > 10000 and b"gk_spec_kernel" in cubin
