@@ -383,14 +383,14 @@ def oracle_results_safe(orc, reviews, ep, skip=()):
 
 
 # ------------------------------------------------------------------------------------------ match fuzz
-def case_match_fuzz(lib, n_constraints=60, n_objects=400, seed=5):
+def case_match_fuzz(lib, n_constraints=60, n_objects=400, seed=5, extra_names=()):
     """Random `spec.match` blocks x random review shapes through the in-kernel pre-filter, against the oracle's
     restatement of match.Matches / Matcher.Match (which the reference's own vectors pin).  The template always
     violates, so the result set is exactly the match relation (plus autoreject results for matcher errors)."""
     import random
     rnd = random.Random(seed)
     t = golden("templates.json")["fixtures_TemplateNeverValidate"]
-    names = ["a", "ab", "abc", "kube-system", "kube-public", "prod-1", "prod-22", "dev", "x-system", ""]
+    names = ["a", "ab", "abc", "kube-system", "kube-public", "prod-1", "prod-22", "dev", "x-system"] + list(extra_names) + [""]
     wild = lambda: rnd.choice(names[:-1] + ["*", "a*", "*a", "*b*", "kube-*", "*-system", "prod-*", "*-1", "**"])
     keys, vals = ["app", "team", "tier", "env", "example.com/role", "bad key!", "", "a/b/c", "-x"], ["a", "b", "c", "", "not ok", "x" * 64]
     def selector():

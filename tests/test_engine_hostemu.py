@@ -392,3 +392,12 @@ def test_generated_kernel_text_compiles_with_nvrtc_for_sm100a(config, tmp_path, 
             pytest.skip("no NVRTC in this container")
         raise
     assert len(cubin) > 10000 and b"gk_spec_kernel" in cubin
+
+
+def test_written_out_match_blocks_on_long_and_non_ascii_patterns(monkeypatch):
+    """emit_match (spec_codegen.cpp) inlines the bytes of a wildcard pattern up to 24 bytes and calls the shared gk_wild() above that:
+    both sides of the limit, bytes >= 0x80, and the generated text checked object by object against the interpreter and the oracle."""
+    monkeypatch.setenv("GK_SPEC_CHECK", "1")
+    extra = ["n\u00e4mespace-\u00fc", "team-\u65e5\u672c", "x" * 24, "y" * 25, "a-namespace-name-of-more-than-twenty-four-bytes"]
+    for seed in (41, 42):
+        assert P.case_match_fuzz(HOSTEMU, n_constraints=40, n_objects=300, seed=seed, extra_names=extra) > 0
