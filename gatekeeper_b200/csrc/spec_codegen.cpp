@@ -82,36 +82,6 @@ extern "C" __global__ void __launch_bounds__(GK_SPEC_THREADS, GK_SPEC_MINB) gk_s
     if (lane == 0u) actw[i >> 5] = bits;
   }
   __syncthreads();
-#ifdef GK_SPEC_X_PREFETCH
-  // Tile-ahead prefetch: the CTA of tile t asks L2 for the rows of tile t + GK_SPEC_PF_DIST (about one wave of resident CTAs
-  // ahead) of every array the generated code reads, so that tile's loads are L2 hits instead of DRAM misses.
-  {
-    const uint32_t tp = blockIdx.x + GK_SPEC_PF_DIST;
-    if (tp < p.ntiles) {
-      const uint32_t* tl = p.tile_lo + (size_t)tp * NS;
-      for (uint32_t k = threadIdx.x >> 5; k < GK_SPEC_NARRS; k += blockDim.x >> 5) {
-        const uint32_t id = gk_spec_arrs[k][0], which = gk_spec_arrs[k][1], es = gk_spec_arrs[k][2];
-        const unsigned char* base;
-        uint32_t sc, extra = 0u;
-        switch (which) {
-          case 0: base = reinterpret_cast<const unsigned char*>(cols[id].vt); sc = (uint32_t)cols[id].scope; break;
-          case 1: base = reinterpret_cast<const unsigned char*>(cols[id].sid); sc = (uint32_t)cols[id].scope; break;
-          case 2: base = reinterpret_cast<const unsigned char*>(cols[id].num); sc = (uint32_t)cols[id].scope; break;
-          case 3: base = reinterpret_cast<const unsigned char*>(cols[id].head); sc = (uint32_t)cols[id].scope; break;
-          case 4: base = reinterpret_cast<const unsigned char*>(scopes[id].off); sc = (uint32_t)scopes[id].parent; extra = 1u; break;
-          case 5: base = reinterpret_cast<const unsigned char*>(p.batch.flags); sc = 0u; break;
-          case 6: base = reinterpret_cast<const unsigned char*>(p.batch.kind_sid); sc = 0u; break;
-          case 7: base = reinterpret_cast<const unsigned char*>(p.batch.group_sid); sc = 0u; break;
-          case 8: base = reinterpret_cast<const unsigned char*>(p.batch.lbl_off); sc = 0u; extra = 1u; break;
-          case 9: base = reinterpret_cast<const unsigned char*>(p.batch.nsn_off); sc = 0u; extra = 1u; break;
-          default: base = reinterpret_cast<const unsigned char*>(p.batch.nsrow); sc = 0u; break;
-        }
-        const size_t a0 = reinterpret_cast<size_t>(base) + (size_t)tl[sc] * es, a1 = reinterpret_cast<size_t>(base) + ((size_t)tl[NS + sc] + extra) * es;
-        for (size_t a = (a0 & ~(size_t)127) + (size_t)lane * 128u; a < a1; a += 32u * 128u) asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
-      }
-    }
-  }
-#endif
   uint32_t tv[GK_SPEC_W], te[GK_SPEC_W];
 #pragma unroll
   for (uint32_t w = 0; w < GK_SPEC_W; ++w) tv[w] = te[w] = 0u;
@@ -632,8 +602,8 @@ SpecSource spec_codegen(const Compiled& c) {
   std::ostringstream o;
   o << "// generated by spec_codegen.cpp for constraint-set version " << c.version << ": " << C << " constraints, " << c.ops.size() << " netlist ops\n";
   o << "#define GK_SPEC_C " << C << "u\n#define GK_SPEC_W " << W << "\n";
-  o << "#ifndef GK_SPEC_THREADS\n#define GK_SPEC_THREADS 512\n#endif\n#ifndef GK_SPEC_MINB\n#define GK_SPEC_MINB 1\n#endif\n#ifndef GK_SPEC_PF_DIST\n#define GK_SPEC_PF_DIST 296u\n#endif\n";
-  o << "#if !defined(GK_SPEC_HOST) && !defined(GK_SPEC_X_PLAINLD)\n#define GK_LD(p) __ldg(p)   /* pool, cbytes and every batch array are global and read-only here */\n#endif\n";
+  o << "#ifndef GK_SPEC_THREADS\n#define GK_SPEC_THREADS 512\n#endif\n#ifndef GK_SPEC_MINB\n#define GK_SPEC_MINB 1\n#endif\n";
+  o << "#ifndef GK_SPEC_HOST\n#define GK_LD(p) __ldg(p)   /* pool, cbytes and every batch array are global and read-only here */\n#endif\n";
   o << strip_includes(kSpecHdrProgram) << strip_includes(kSpecHdrVmCore);
   o << R"GKSRC(
 #ifdef GK_SPEC_X_NOMATCH   /* (measurement only: what the spec.match pre-filter costs) */
@@ -657,11 +627,7 @@ SpecSource spec_codegen(const Compiled& c) {
 struct uint4 { uint32_t x, y, z, w; };
 #else
 #define GK_SPEC_FN __device__ __forceinline__
-#ifdef GK_SPEC_X_PLAINLD
-#define GK_SPEC_LD(p) (*(p))
-#else
 #define GK_SPEC_LD(p) __ldg(p)      /* every array of a resident batch is read-only while it is evaluated */
-#endif
 #define GK_SPEC_POPC(x) __popc(x)
 #define GK_SPEC_ERR(o, mid, code)                                    \
   {                                                                  \
@@ -729,7 +695,6 @@ struct uint4 { uint32_t x, y, z, w; };
     std::vector<int> sig;
     uint32_t cix;
     bool operator<(const Ord& x) const { return std::tie(kind, sig, cix) < std::tie(x.kind, x.sig, x.cix); }
-    static bool by_sig(const Ord& a, const Ord& b) { return std::tie(a.sig, a.cix) < std::tie(b.sig, b.cix); }
   };
   std::vector<Ord> order;
   for (uint32_t cix = 0; cix < C; ++cix) {
@@ -744,37 +709,25 @@ struct uint4 { uint32_t x, y, z, w; };
     }
     order.push_back(std::move(e));
   }
-  if (getenv("GK_SPEC_ORDER") && std::string(getenv("GK_SPEC_ORDER")) == "sig") std::sort(order.begin(), order.end(), Ord::by_sig);
-  else std::sort(order.begin(), order.end());
-  // ---- atom groups: an atom is computed in the row loop of (its scope, the first template kind that reads it), so that only one
-  // template's masks of a scope are live at a time (one loop per scope keeps ~45 masks of the container scope alive: 246 registers)
-  // (GK_SPEC_GROUPING=0: one loop per scope.  Measured on B200, 1 M Pods x 50 constraints: per-kind loops 0.705 ms, per-scope loops
-  // 0.575 ms -- every extra loop is one more exposed memory latency per object, which costs more than the spilled registers.)
-  const bool by_kind = getenv("GK_SPEC_GROUPING") && atoi(getenv("GK_SPEC_GROUPING")) != 0;
-  const bool shift_form = getenv("GK_SPEC_FORM") && std::string(getenv("GK_SPEC_FORM")) == "shift";
-  const bool unroll1 = !(getenv("GK_SPEC_UNROLL1") && atoi(getenv("GK_SPEC_UNROLL1")) == 0);
-  std::map<std::pair<uint32_t, int>, int> group_ix;
+  std::sort(order.begin(), order.end());
+  // ---- atom groups: ONE row loop per scope computes every atom of that scope (~45 mask registers of the container scope alive at
+  // once, some spilled).  A loop per (scope, template kind) keeps fewer masks alive but measured slower on B200 -- 0.705 vs 0.575 ms
+  // at 1 M Pods x 50 constraints: every extra loop is one more exposed memory latency per object (profiles/experiments/README.md).
+  std::map<uint32_t, int> group_ix;   // scope -> row loop
   std::vector<std::vector<uint32_t>> groups;
-  {
-    int kind_no = -1;
-    std::string last;
-    bool first = true;
-    for (const Ord& e : order) {
-      if (first || (by_kind && e.kind != last)) ++kind_no, last = e.kind, first = false;
-      const GkOutEnt& oe = c.outs[e.cix];
-      if ((oe.flags & 3u) || var_of(oe.prog_slot) < 0) continue;
-      for (uint32_t ai : cone((uint32_t)var_of(oe.prog_slot))) {
-        Gen::AtomRec& r = g.atoms[ai];
-        if (r.group >= 0) continue;
-        auto key = std::make_pair(r.scope, kind_no);
-        auto it = group_ix.find(key);
-        if (it == group_ix.end()) {
-          it = group_ix.emplace(key, (int)groups.size()).first;
-          groups.emplace_back();
-        }
-        r.group = it->second;
-        groups[(size_t)r.group].push_back(ai);
+  for (const Ord& e : order) {
+    const GkOutEnt& oe = c.outs[e.cix];
+    if ((oe.flags & 3u) || var_of(oe.prog_slot) < 0) continue;
+    for (uint32_t ai : cone((uint32_t)var_of(oe.prog_slot))) {
+      Gen::AtomRec& r = g.atoms[ai];
+      if (r.group >= 0) continue;
+      auto it = group_ix.find(r.scope);
+      if (it == group_ix.end()) {
+        it = group_ix.emplace(r.scope, (int)groups.size()).first;
+        groups.emplace_back();
       }
+      r.group = it->second;
+      groups[(size_t)r.group].push_back(ai);
     }
   }
   std::vector<uint8_t> group_done(groups.size(), 0);
@@ -803,7 +756,7 @@ struct uint4 { uint32_t x, y, z, w; };
     for (size_t k = 0; k < members.size(); ++k) o << (k ? ", v" : " v") << g.atoms[members[k]].var << " = 0u";
     o << ";\n";
     if (s == 0) o << "  {\n    const size_t row = obj;\n    const uint32_t bit = 1u;\n";
-    else o << (unroll1 ? "  _Pragma(\"unroll 1\")" : " ") << " for (uint32_t j = 0; j < n" << s << "; ++j) {\n    const size_t row = (size_t)lo" << s << " + j;\n    const uint32_t bit = 1u << j;\n    (void)bit;\n";
+    else o << "  _Pragma(\"unroll 1\") for (uint32_t j = 0; j < n" << s << "; ++j) {\n    const size_t row = (size_t)lo" << s << " + j;\n    const uint32_t bit = 1u << j;\n    (void)bit;\n";
     for (auto& kv : need) {
       const uint32_t ci = kv.first, enc = kv.second;
       if (enc & GK_ENC_VT) o << "    const uint32_t t" << ci << " = GK_SPEC_LD(pt" << ci << " + row);\n";
@@ -812,8 +765,7 @@ struct uint4 { uint32_t x, y, z, w; };
       if (enc & GK_ENC_HEAD) o << "    const uint4 h" << ci << "a = GK_SPEC_LD(ph" << ci << " + 2 * row), h" << ci << "b = GK_SPEC_LD(ph" << ci << " + 2 * row + 1);\n";
     }
     for (uint32_t ai : members) {
-      if (shift_form) o << "    v" << g.atoms[ai].var << " |= (uint32_t)" << g.atoms[ai].expr << (s == 0 ? ";\n" : " << j;\n");
-      else o << "    if (" << g.atoms[ai].expr << ") v" << g.atoms[ai].var << " |= bit;\n";
+      o << "    if (" << g.atoms[ai].expr << ") v" << g.atoms[ai].var << " |= bit;\n";
     }
     o << "  }\n";
   };
@@ -844,24 +796,6 @@ struct uint4 { uint32_t x, y, z, w; };
   // the enforcement-point filter: one packed word per 32 constraints (actw), not a test per constraint
   for (uint32_t w = 0; w < W; ++w) o << "  vw[" << w << "] &= actw[" << w << "];\n  ew[" << w << "] &= actw[" << w << "];\n";
   o << "  return big;\n}\n";
-  // ---- the arrays the generated code reads (for the tile-ahead L2 prefetch of the wrapper): (column | scope, which, element bytes)
-  {
-    std::map<std::pair<uint32_t, uint32_t>, uint32_t> arrs;   // (col, which) -> es
-    for (auto& r : g.atoms)
-      for (auto& kv : r.need) {
-        if (kv.second & GK_ENC_VT) arrs[{kv.first, 0u}] = 1;
-        if (kv.second & GK_ENC_SID) arrs[{kv.first, 1u}] = 4;
-        if (kv.second & GK_ENC_NUM) arrs[{kv.first, 2u}] = 8;
-        if (kv.second & GK_ENC_HEAD) arrs[{kv.first, 3u}] = 32;
-      }
-    o << "#ifndef GK_SPEC_HOST\n__device__ const unsigned short gk_spec_arrs[][3] = {";
-    size_t na = 0;
-    for (auto& kv : arrs) o << (na++ ? ", " : "") << "{" << kv.first.first << ", " << kv.first.second << ", " << kv.second << "}";
-    for (size_t sc = 1; sc < NS; ++sc)
-      if (g.scope_used[sc]) o << (na++ ? ", " : "") << "{" << sc << ", 4, 4}";
-    for (uint32_t hdr = 5; hdr <= 10; ++hdr) o << (na++ ? ", " : "") << "{0, " << hdr << ", 4}";
-    o << "};\n#define GK_SPEC_NARRS " << na << "u\n#endif\n";
-  }
   o << kWrapper;
   out.src = o.str();
   out.words = W;

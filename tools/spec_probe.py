@@ -2,7 +2,7 @@
 (gk_eval_kernel) on a resident page of a BASELINE configuration -- identical bitmaps / totals, and the launch time of
 several build variants (threads per CTA x minimum resident CTAs = register cap).
 
-    python tools/spec_probe.py [--config 2] [--objects 1000000] [--variants 128x2,128x3,128x4,64x4,256x2]
+    python tools/spec_probe.py [--config 2] [--objects 1000000] [--variants 512x1,512x1:GENERIC,256x2,384x1,512x1:NOMATCH]
 """
 import argparse
 import json
@@ -18,7 +18,7 @@ sys.path.insert(0, ROOT)
 ap = argparse.ArgumentParser()
 ap.add_argument("--config", type=int, default=2)
 ap.add_argument("--objects", type=int, default=1000000)
-ap.add_argument("--variants", default="128x2,128x3,128x4,64x4,256x2")
+ap.add_argument("--variants", default="512x1,512x1:GENERIC,256x2,384x1,512x1:NOMATCH")
 ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--wide", type=int, default=0, help="every WIDE-th object gets 40 containers (exercises the tile hand-over)")
 a = ap.parse_args()
@@ -56,7 +56,7 @@ if a.wide:
 
 
 def run(label, env):
-    for k in ("GK_SPEC", "GK_SPEC_THREADS", "GK_SPEC_MINB", "GK_SPEC_DEFS", "GK_SPEC_GROUPING"):
+    for k in ("GK_SPEC", "GK_SPEC_THREADS", "GK_SPEC_MINB", "GK_SPEC_DEFS"):
         os.environ.pop(k, None)
     os.environ.update(env)
     drv = engine()
@@ -81,17 +81,13 @@ def run(label, env):
 
 base, want = run("interpreter", {"GK_SPEC": "0"})
 print(json.dumps(base), flush=True)
-for v in a.variants.split(","):     # THREADSxMINB[:SWITCH+SWITCH]  (switches = GK_SPEC_X_* measurement macros: results may differ)
+for v in a.variants.split(","):     # THREADSxMINB[:SWITCH+SWITCH]: GENERIC = spec.match through the shared gk_match(); NOMATCH = -DGK_SPEC_X_NOMATCH (results differ)
     v, _, sw = v.partition(":")
     th, mb = v.split("x")
     toks = [x for x in sw.split("+") if x]
-    gen = ("G0", "G1", "IF", "SHIFT", "U0", "U1", "OKIND", "OSIG")   # generator knobs (environment), the rest are -D switches of the text
-    defs = " ".join(("-DGK_SPEC_PF_DIST=%su" % x[2:]) if x.startswith("PF") else "-DGK_SPEC_X_" + x for x in toks if x not in gen)
-    os.environ["GK_SPEC_FORM"] = "if" if "IF" in toks else "shift"
-    os.environ["GK_SPEC_UNROLL1"] = "0" if "U0" in toks else "1"
-    os.environ["GK_SPEC_ORDER"] = "kind" if "OKIND" in toks else "sig"
-    o, got = run("spec " + v + (" " + sw if sw else ""), {"GK_SPEC_THREADS": th, "GK_SPEC_MINB": mb, "GK_SPEC_MIN_OBJECTS": "0", "GK_SPEC_DEFS": defs,
-                                                         "GK_SPEC_GROUPING": "1" if "G1" in toks else "0"})
+    defs = " ".join("-DGK_SPEC_X_" + x for x in toks if x != "GENERIC")
+    os.environ["GK_SPEC_MATCHGEN"] = "0" if "GENERIC" in toks else "1"
+    o, got = run("spec " + v + (" " + sw if sw else ""), {"GK_SPEC_THREADS": th, "GK_SPEC_MINB": mb, "GK_SPEC_MIN_OBJECTS": "0", "GK_SPEC_DEFS": defs})
     o["identical"] = bool(np.array_equal(want[0], got[0]) and np.array_equal(want[1], got[1]) and want[2] == got[2] and want[3] == got[3])
     print(json.dumps(o), flush=True)
     assert o["identical"] or "NOMATCH" in sw, "generated kernel and interpreter disagree"
