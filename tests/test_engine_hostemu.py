@@ -392,6 +392,14 @@ def test_generated_kernel_text_compiles_with_nvrtc_for_sm100a(config, tmp_path, 
             pytest.skip("no NVRTC in this container")
         raise
     assert len(cubin) > 10000 and b"gk_spec_kernel" in cubin
+    # static size of the kernel (a regression guard, not a timing): the text of config 2 was 8104 SASS instructions with the match
+    # blocks on the shared gk_match() and compiler-unrolled range loops, 4090 written out (tools/spec_nvrtc.py)
+    import shutil
+    if config == 2 and shutil.which("cuobjdump") and shutil.which("nvdisasm"):
+        cb = tmp_path / "spec.cubin"
+        cb.write_bytes(cubin)
+        usage, total, region = tool.static_report(str(cb), str(out))
+        assert total < 5000, (total, dict(region))
 
 
 def test_written_out_match_blocks_on_long_and_non_ascii_patterns(monkeypatch):
