@@ -525,6 +525,21 @@ int gk_remove_expansion_template(gk_engine_t* e, const char* name) {
   return guard(nullptr, [&]() { e->eng->remove_expansion_template(name); });
 }
 
+char* gk_expansion_conflicts(gk_engine_t* e) {
+  if (!e) return nullptr;
+  std::string o = "[";
+  guard(nullptr, [&]() {
+    bool first = true;
+    for (auto& n : e->eng->expansion_conflicts()) {
+      if (!first) o += ",";
+      first = false;
+      json_quote(n, o);
+    }
+  });
+  o += "]";
+  return dup_str(o);
+}
+
 int gk_review_batch(gk_engine_t* e, const gk_obj* objs, size_t n, const char* ep, uint32_t flags, gk_result* out, char** err) {
   if (!e || !out || (!objs && n)) return GK_ERR_INVALID;
   memset(out, 0, sizeof *out);

@@ -1968,6 +1968,10 @@ bool Engine::remove_expansion_template(const std::string& name) {
   std::unique_lock<std::shared_mutex> l(mu_);
   return expansion_.remove(name);
 }
+std::vector<std::string> Engine::expansion_conflicts() {
+  std::shared_lock<std::shared_mutex> l(mu_);
+  return expansion_.conflicts();
+}
 bool Engine::has_expansion() {
   std::shared_lock<std::shared_mutex> l(mu_);
   return !expansion_.empty();

@@ -196,6 +196,7 @@ class Engine {
   void add_expansion_template(const std::string& json);
   bool remove_expansion_template(const std::string& name);
   bool has_expansion();
+  std::vector<std::string> expansion_conflicts();   // System.GetConflicts: templates set aside as part of an expansion cycle, by name
   // the resultants of one review's object (empty when no template applies); throws std::runtime_error like System.Expand
   void expand_object(const ObjIn& in, std::vector<Resultant>& out);
   // Client.AddData / RemoveData for any synced object (pkg/target/target.go:40-66 processUnstructured: the path is

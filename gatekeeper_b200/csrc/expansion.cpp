@@ -61,8 +61,12 @@ void ExpansionSystem::upsert(const std::string& json) {
   if (x.apply.empty()) throw std::runtime_error("ExpansionTemplate " + x.name + " must specify ApplyTo");
   if (x.applies_to(x.group, x.version, x.kind))
     throw std::runtime_error("ExpansionTemplate " + x.name + " generates GVK " + x.group + "/" + x.version + ", Kind=" + x.kind + ", but also applies to that same GVK");
-  templates_[x.name] = std::move(x);
+  const std::string name = x.name;
+  templates_[name] = std::move(x);
   recompute_conflicts();
+  // db.upsert (db.go:222-245): the template is stored even when it closes a cycle -- it and the others on the cycle are set aside -- and the
+  // caller is told (the reference's controller writes the error into the template's status)
+  if (conflicted_[name]) throw std::runtime_error("template forms expansion cycle");
 }
 
 bool ExpansionSystem::remove(const std::string& name) {
@@ -113,7 +117,9 @@ VP expand_resource(const VP& obj, const std::string* ns_name, const ExpansionTem
   while (a <= t.source.size()) {
     size_t b = t.source.find('.', a);
     if (b == std::string::npos) b = t.source.size();
-    VP nx = cur && cur->t == VT::Obj ? obj_get(cur, t.source.substr(a, b - a).c_str()) : nullptr;
+    // unstructured.NestedMap (system.go:225-231): a missing key is "not found", walking into something that is not a map is an accessor error
+    if (!cur || cur->t != VT::Obj) throw std::runtime_error("could not extract source field from unstructured");
+    VP nx = obj_get(cur, t.source.substr(a, b - a).c_str());
     if (!nx) throw std::runtime_error("could not find source field \"" + t.source + "\" in resource " + pname);
     cur = nx;
     a = b + 1;
@@ -126,9 +132,15 @@ VP expand_resource(const VP& obj, const std::string* ns_name, const ExpansionTem
   if (ns_name) {
     md = with(md, "namespace", v_str(*ns_name));
   } else {
+    // unstructured.NestedString(obj, "metadata", "namespace") (system.go:239-246): absent is fine (a cluster-scoped parent), present but
+    // not a string -- or a metadata that is not a map -- is an error
     VP pmd = obj_get(obj, "metadata");
+    if (pmd && pmd->t != VT::Obj) throw std::runtime_error("could not extract namespace field \"" + t.source + "\" in parent resource " + pname);
     VP pns = pmd ? obj_get(pmd, "namespace") : nullptr;
-    if (pns && pns->t == VT::Str) md = with(md, "namespace", pns);
+    if (pns) {
+      if (pns->t != VT::Str) throw std::runtime_error("could not extract namespace field \"" + t.source + "\" in parent resource " + pname);
+      md = with(md, "namespace", pns);
+    }
   }
   std::string mock = pname + (t.kind.empty() ? "" : "-") + t.kind;   // mockNameForResource -- system.go:289-297
   for (auto& ch : mock) ch = (char)std::tolower((unsigned char)ch);

@@ -31,6 +31,12 @@ class ExpansionSystem {
   void upsert(const std::string& json);          // throws JsonError / std::runtime_error with ValidateTemplate's texts
   bool remove(const std::string& name);
   bool empty() const { return templates_.empty(); }
+  std::vector<std::string> conflicts() const {   // System.GetConflicts -- system.go:81-83 (names, sorted)
+    std::vector<std::string> out;
+    for (auto& c : conflicted_)
+      if (c.second) out.push_back(c.first);
+    return out;
+  }
   // System.Expand: every resultant of `obj`, grandchildren before children (system.go:137-167).  `ns_name`: the name of the
   // review's Namespace object, or null.  Throws std::runtime_error ("cannot expand resource ...", "could not find source field ...")
   void expand(const VP& obj, const std::string* ns_name, std::vector<Resultant>& out, int depth = 0) const;

@@ -65,7 +65,7 @@ class gk_result(C.Structure):
 
 EXPORTS = [
     "gk_engine_create", "gk_engine_destroy", "gk_backend_name", "gk_last_kernel", "gk_add_template", "gk_add_template_libs", "gk_remove_template",
-    "gk_add_constraint", "gk_add_expansion_template", "gk_remove_expansion_template", "gk_validate_constraint", "gk_remove_constraint", "gk_put_namespace", "gk_remove_namespace", "gk_add_data", "gk_remove_data", "gk_constraint_count",
+    "gk_add_constraint", "gk_add_expansion_template", "gk_remove_expansion_template", "gk_expansion_conflicts", "gk_validate_constraint", "gk_remove_constraint", "gk_put_namespace", "gk_remove_namespace", "gk_add_data", "gk_remove_data", "gk_constraint_count",
     "gk_constraint_key", "gk_result_constraint_key", "gk_review_batch", "gk_batch_upload", "gk_batch_eval", "gk_batch_eval_device",
     "gk_batch_eval_device_peers", "gk_batch_upload_blob", "gk_review_blob", "gk_set_excluded_namespaces", "gk_audit_begin", "gk_audit_add_batch", "gk_audit_report",
     "gk_audit_end", "gk_validation_messages", "gk_host_cpus", "gk_pin_host", "gk_blob_prefetch", "gk_coalescer_create", "gk_coalescer_review", "gk_coalescer_stats",
@@ -94,6 +94,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.gk_add_constraint.argtypes = [P, S, C.c_size_t, PP]
     lib.gk_add_expansion_template.argtypes = [P, S, C.c_size_t, PP]
     lib.gk_remove_expansion_template.argtypes = [P, S]
+    lib.gk_expansion_conflicts.restype = C.c_void_p
+    lib.gk_expansion_conflicts.argtypes = [P]
     lib.gk_validate_constraint.argtypes = [P, S, C.c_size_t, PP]
     lib.gk_remove_constraint.argtypes = [P, S, S]
     lib.gk_put_namespace.argtypes = [P, S, S, C.c_size_t, PP]
@@ -300,6 +302,14 @@ class Driver:
 
     def RemoveExpansionTemplate(self, name: str) -> None:
         self._lib.gk_remove_expansion_template(self._e, name.encode())
+
+    def ExpansionConflicts(self) -> list:
+        """expansion.System.GetConflicts (pkg/expansion/system.go:81-83): names of the templates set aside as part of an expansion cycle"""
+        p = self._lib.gk_expansion_conflicts(self._e)
+        s = C.string_at(p).decode() if p else "[]"
+        if p:
+            self._lib.gk_free_str(p)
+        return json.loads(s)
 
     def ValidateConstraint(self, constraint: dict) -> None:
         """TargetHandler.ValidateConstraint (pkg/target/target.go:178-214); raises GkError for a constraint the reference's

@@ -243,6 +243,19 @@ func (d *Driver) RemoveExpansionTemplate(name string) {
 	C.gk_remove_expansion_template(d.e, cn)
 }
 
+// ExpansionConflicts mirrors expansion.System.GetConflicts (pkg/expansion/system.go:81-83): the names of the stored templates that are
+// set aside because they lie on an expansion cycle, as a JSON array.
+func (d *Driver) ExpansionConflicts() string {
+	d.mux.RLock()
+	defer d.mux.RUnlock()
+	cs := C.gk_expansion_conflicts(d.e)
+	if cs == nil {
+		return "[]"
+	}
+	defer C.gk_free_str(cs)
+	return C.GoString(cs)
+}
+
 // ARGetter / IsAdmissionGetter: how drivers reach the unexported *gkReview -- pkg/drivers/k8scel/driver.go:265-271.
 type ARGetter interface {
 	GetAdmissionRequest() *admissionv1.AdmissionRequest

@@ -128,6 +128,11 @@ int gk_remove_constraint(gk_engine_t* e, const char* kind, const char* name);
  * not applied (the mutation system is outside this engine). */
 int gk_add_expansion_template(gk_engine_t* e, const char* json, size_t len, char** err);
 int gk_remove_expansion_template(gk_engine_t* e, const char* name);
+/* System.GetConflicts (pkg/expansion/system.go:81-83; db.go:62-70): the names of the stored ExpansionTemplates that are set aside
+ * because they lie on an expansion cycle (a template that closes a cycle is stored all the same, gk_add_expansion_template
+ * reports "template forms expansion cycle" for it -- db.go:222-245 -- and every template on the cycle stops expanding until the
+ * cycle is broken).  A JSON array of names, sorted; free with gk_free_str. */
+char* gk_expansion_conflicts(gk_engine_t* e);
 int gk_put_namespace(gk_engine_t* e, const char* name, const char* ns_json, size_t len, char** err);
 int gk_remove_namespace(gk_engine_t* e, const char* name);
 /* Driver.AddData / RemoveData for ANY synced object (pkg/drivers/k8scel/driver.go:252-258 are no-ops for CEL; the Rego driver

@@ -41,12 +41,19 @@ def validate_template(t):
     g = (gen.get("group") or "", gen.get("version") or "", gen.get("kind") or "")
     for a in spec["applyTo"]:
         if _apply_matches(a, g):
-            raise ExpansionError("ExpansionTemplate %s generates GVK %s, but also applies to that same GVK" % (name, g))
+            raise ExpansionError("ExpansionTemplate %s generates GVK %s/%s, Kind=%s, but also applies to that same GVK" % ((name,) + g))   # %v of a schema.GroupVersionKind
 
 
 def _apply_matches(a, gvk):
     """ApplyTo.Matches -- pkg/mutation/match/apply_to.go:45-57"""
     return gvk[0] in (a.get("groups") or []) and gvk[1] in (a.get("versions") or []) and gvk[2] in (a.get("kinds") or [])
+
+
+def _name(obj):
+    """Unstructured.GetName(): metadata.name when it is a string, else \"\" """
+    md = obj.get("metadata") if isinstance(obj, dict) else None
+    n = md.get("name") if isinstance(md, dict) else None
+    return n if isinstance(n, str) else ""
 
 
 def expand_resource(obj, ns_name, template):
@@ -58,10 +65,14 @@ def expand_resource(obj, ns_name, template):
     gen = spec.get("generatedGVK") or {}
     if not (gen.get("group") or gen.get("version") or gen.get("kind")):
         raise ExpansionError("cannot expand resource using template with empty generatedGVK")
+    # unstructured.NestedMap (system.go:225-231): a missing key is "not found"; walking INTO something that is not a map, or a
+    # value at the end that is not a map, is an accessor error
     cur = obj
     for key in src_path.split("."):
-        if not isinstance(cur, dict) or key not in cur:
-            raise ExpansionError('could not find source field "%s" in resource %s' % (src_path, (obj.get("metadata") or {}).get("name", "")))
+        if not isinstance(cur, dict):
+            raise ExpansionError("could not extract source field from unstructured")
+        if key not in cur:
+            raise ExpansionError('could not find source field "%s" in resource %s' % (src_path, _name(obj)))
         cur = cur[key]
     if not isinstance(cur, dict):
         raise ExpansionError("could not extract source field from unstructured")
@@ -75,9 +86,15 @@ def expand_resource(obj, ns_name, template):
     if ns_name is not None:
         md["namespace"] = ns_name
     else:
-        pns = (obj.get("metadata") or {}).get("namespace")
-        if isinstance(pns, str):
-            md["namespace"] = pns
+        # unstructured.NestedString(obj, "metadata", "namespace") (system.go:239-246): absent is fine (a cluster-scoped parent),
+        # present but not a string -- or a metadata that is not a map -- is an error
+        pmd = obj.get("metadata") if isinstance(obj, dict) else None
+        if pmd is not None and not isinstance(pmd, dict):
+            raise ExpansionError('could not extract namespace field "%s" in parent resource %s' % (src_path, _name(obj)))
+        if isinstance(pmd, dict) and "namespace" in pmd:
+            if not isinstance(pmd["namespace"], str):
+                raise ExpansionError('could not extract namespace field "%s" in parent resource %s' % (src_path, _name(obj)))
+            md["namespace"] = pmd["namespace"]
     pname = (obj.get("metadata") or {}).get("name") or ""
     md["name"] = (pname + ("-" if kind else "") + kind).lower()          # mockNameForResource -- system.go:289-297
     # ensureOwnerReference -- system.go:251-283
@@ -94,8 +111,16 @@ class System:
         self.templates = {}
 
     def upsert(self, t):
+        """System.UpsertTemplate -> db.upsert (system.go:56-66, db.go:222-245): a template that closes a cycle is stored all the same
+        (set aside with the others on the cycle) and reported"""
         validate_template(t)
         self.templates[t["metadata"]["name"]] = t
+        if t["metadata"]["name"] in self._conflicted():
+            raise ExpansionError("template forms expansion cycle")
+
+    def conflicts(self):
+        """System.GetConflicts -- system.go:81-83"""
+        return self._conflicted()
 
     def remove(self, name):
         self.templates.pop(name, None)

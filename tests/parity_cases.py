@@ -1465,6 +1465,20 @@ def case_wildcard_vectors_through_kernel(lib):
 
 
 # ------------------------------------------------------------------------------------------ expansion (a-16 / f-3)
+class pytest_raises_gk:
+    """`with pytest_raises_gk(D, text):` -- the block must raise D.GkError whose message contains `text`"""
+    def __init__(self, D_, text):
+        self.D, self.text = D_, text
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, et, ev, tb):
+        assert et is not None and issubclass(et, self.D.GkError), "expected GkError containing %r" % self.text
+        assert self.text in str(ev), (self.text, str(ev))
+        return True
+
+
 def case_expansion(lib):
     """ExpansionTemplates through the review batch: (1) the reference's TestExpand vectors (resultant objects) on the oracle,
     (2) the gator expansion manifests with the messages test.bats asserts, on oracle and engine, (3) a mixed page: Deployments,
@@ -1483,6 +1497,99 @@ def case_expansion(lib):
         if not err:
             assert sorted(json.dumps(list(x), sort_keys=True) for x in got) == sorted(
                 json.dumps([w["obj"], w["templateName"], w["enforcementAction"]], sort_keys=True) for w in c["want"]), c["name"]
+
+    # (1b) TestValidateTemplate (system_test.go:311-424): the substring each refusal must contain -- oracle and engine
+    drv0 = D.Driver(lib_path=lib)
+    for c in vec["validate"]:
+        errs = []
+        try:
+            X.validate_template(c["template"])
+            errs.append(None)
+        except X.ExpansionError as e:
+            errs.append(str(e))
+        try:
+            drv0.AddExpansionTemplate(c["template"])
+            errs.append(None)
+            drv0.RemoveExpansionTemplate(c["template"]["metadata"]["name"])
+        except D.GkError as e:
+            errs.append(str(e))
+        for e in errs:
+            assert (e is None) if c["errSubstr"] is None else (e is not None and c["errSubstr"] in e), (c["name"], errs)
+        if errs[0] is not None:
+            assert errs[0] in errs[1], (c["name"], errs)     # the same text on both sides
+    drv0.close()
+
+    # (1b') TestDB (db_test.go:27-647): upserts / removals -> which stored templates are set aside as part of an expansion cycle
+    # (GetConflicts), and which upsert reports "template forms expansion cycle" while storing the template all the same
+    for c in vec["db"]:
+        xs, drv2 = X.System(), D.Driver(lib_path=lib)
+        for op in c["ops"]:
+            name = op["template"]["metadata"]["name"]
+            if op["op"] == "remove":
+                xs.remove(name)
+                drv2.RemoveExpansionTemplate(name)
+                continue
+            errs = []
+            try:
+                xs.upsert(op["template"])
+                errs.append(None)
+            except X.ExpansionError as e:
+                errs.append(str(e))
+            try:
+                drv2.AddExpansionTemplate(op["template"])
+                errs.append(None)
+            except D.GkError as e:
+                errs.append(str(e))
+            for e in errs:
+                assert (e is not None and "template forms expansion cycle" in e) if op["wantErr"] else e is None, (c["name"], name, errs)
+        want = sorted(n for n, bad in c["want"].items() if bad)
+        assert sorted(xs.conflicts()) == want, (c["name"], sorted(xs.conflicts()), want)
+        assert drv2.ExpansionConflicts() == want, (c["name"], drv2.ExpansionConflicts(), want)
+        assert sorted(xs.templates) == sorted(c["want"]), (c["name"], sorted(xs.templates))     # the store: cyclic templates are kept
+        drv2.close()
+
+    # (1c) TestExpandResource (system_test.go:426-660): expandResource() itself on the oracle; through a review on the engine, where a
+    # constraint that copies the reviewed object into its details shows the resultant (the vectors' templates carry no applyTo --
+    # expandResource does not look at it -- so the engine path adds the parent's GVK; the two vectors whose template is not a valid
+    # template at all cannot be registered and stay oracle-only, the engine must refuse them)
+    dump_kind = "K8sDumpObject"
+    dump_rego = ('package k8sdumpobject\n\nviolation[{"msg": msg, "details": {"obj": input.review.object}}] {\n'
+                 '  msg := sprintf("%v", [input.review.object.metadata.name])\n}\n')
+    for c in vec["expand_resource"]:
+        try:
+            got, err = X.expand_resource(c["obj"], c["ns"], c["template"]), None
+        except X.ExpansionError as e:
+            got, err = None, str(e)
+        if c["errSubstr"] is not None:
+            assert err is not None and c["errSubstr"] in err, (c["name"], err)
+        else:
+            assert err is None and (c["want"] is None or got == c["want"]), (c["name"], err, got)
+        tdoc = json.loads(json.dumps(c["template"]))
+        g, v, k = X._gvk(c["obj"])
+        tdoc["spec"]["applyTo"] = [{"groups": [g], "versions": [v], "kinds": [k]}]
+        drv1 = D.Driver(lib_path=lib)
+        drv1.add_template(dump_kind, dump_rego)
+        drv1.AddConstraint(W._constraint(dump_kind, "dump", match={"kinds": [{"apiGroups": [""], "kinds": ["Pod"]}]}))
+        try:
+            X.validate_template(tdoc)
+        except X.ExpansionError as e:
+            with pytest_raises_gk(D, str(e)):
+                drv1.AddExpansionTemplate(tdoc)
+            drv1.close()
+            continue
+        drv1.AddExpansionTemplate(tdoc)
+        nsobj = {"apiVersion": "v1", "kind": "Namespace", "metadata": {"name": c["ns"]}} if c["ns"] is not None else None
+        resp = drv1.ReviewBatch([D.Review(object=c["obj"], namespace=nsobj, source="Original")], k8s.AUDIT_EP)
+        if err is not None:
+            assert resp.object_errors and resp.object_errors[0] == "unable to expand object: " + err, (c["name"], resp.object_errors, err)
+            assert c["errSubstr"] in resp.object_errors[0]
+        else:
+            assert not (resp.object_errors and resp.object_errors[0]), (c["name"], resp.object_errors)
+            assert len(resp.results) == 1, (c["name"], [r.msg for r in resp.results])
+            r = resp.results[0]
+            assert r.msg == "[Implied by %s] %s" % (tdoc["metadata"]["name"], got["metadata"]["name"]), r.msg
+            assert r.details == {"obj": got}, (c["name"], r.details, got)
+        drv1.close()
 
     def run(docs, ep, drv_revs=None):
         tm, cons, nss = _split_docs(docs)
