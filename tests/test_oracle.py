@@ -309,3 +309,17 @@ def test_target_matcher_match_vectors():
             assert err is None and got == v["want"], (v["name"], got, err)
         n += 1
     assert n >= 14
+
+
+def test_process_data_paths():
+    """pkg/target/target_test.go:401-495 TestProcessData (the *unstructured.Unstructured rows; makeResource / makeNamespacedResource
+    build {apiVersion, kind, metadata.name[, metadata.namespace]}): where a synced object lives under data.inventory -- the `path` of
+    gk_add_data / Client.add_data (processUnstructured, pkg/target/target.go:40-66)."""
+    res = lambda gv, kind, name, ns=None: {"apiVersion": gv, "kind": kind, "metadata": dict({"name": name}, **({"namespace": ns} if ns else {}))}
+    assert k8s.Client.data_path(res("v1beta1", "Rock", "myrock")) == ["cluster", "v1beta1", "Rock", "myrock"]                      # "Cluster Object"
+    assert k8s.Client.data_path(res("v1beta1", "Rock", "myrock", "foo")) == ["namespace", "foo", "v1beta1", "Rock", "myrock"]      # "Namespaced Object"
+    assert k8s.Client.data_path(res("mygroup/v1beta1", "Rock", "myrock")) == ["cluster", "mygroup/v1beta1", "Rock", "myrock"]      # "Grouped Object"
+    for bad, what in ((res("", "Rock", "myrock"), "has no version"), (res("v1beta1", "", "myrock"), "has no kind")):           # "No Version", "No Kind"
+        with pytest.raises(ValueError) as e:
+            k8s.Client.data_path(bad)
+        assert "invalid request object" in str(e.value) and what in str(e.value)     # ErrRequestObject wrapped: target.go:43-48
