@@ -204,8 +204,25 @@ for m in re.finditer(r"\n\t\t\{\n\t\t\tname: \"([^\"]*)\",\n(.*?)(?=\n\t\t\{\n\t
         assert len(want) == st.count("hasConflicts:"), (m.group(1), want)
     db_cases.append({"name": m.group(1), "source": "pkg/expansion/db_test.go:%d" % (db_line0 + db_tab[:m.start()].count("\n") + 1), "ops": ops, "want": want})
 
+# TestApplyTo (pkg/mutation/match/match_test.go:717-845): ApplyTo.Matches, the relation that selects an expansion template for a GVK
+mt_src = open(os.path.join(REF, "pkg/mutation/match/match_test.go")).read()
+a1 = mt_src.index("func TestApplyTo(t *testing.T)")
+b1 = mt_src.index("\n\tfor _, tc := range table", a1)
+at_tab = mt_src[a1:b1]
+at_line0 = mt_src[:a1].count("\n") + 1
+apply_to = []
+for m in re.finditer(r"\n\t\t\{\n\t\t\tname: \"([^\"]*)\",\n(.*?)\n\t\t\},(?=\n\t\t\{|\n\t\})", at_tab, re.S):
+    body = m.group(2)
+    g = re.search(r'gvk:\s+schema\.GroupVersionKind\{Group: "([^"]*)", Version: "([^"]*)", Kind: "([^"]*)"\}', body)
+    entries = [{"groups": re.findall(r'"([^"]*)"', e.group(1)), "versions": re.findall(r'"([^"]*)"', e.group(2)), "kinds": re.findall(r'"([^"]*)"', e.group(3))}
+               for e in re.finditer(r"Groups:\s+\[\]string\{([^}]*)\},\s*Versions:\s+\[\]string\{([^}]*)\},\s*Kinds:\s+\[\]string\{([^}]*)\}", body)]
+    assert entries and g, m.group(1)
+    apply_to.append({"name": m.group(1), "source": "pkg/mutation/match/match_test.go:%d" % (at_line0 + at_tab[:m.start()].count("\n") + 1),
+                     "gvk": list(g.groups()), "applyTo": entries, "wantApply": re.search(r"wantApply:\s+(true|false)", body).group(1) == "true"})
+
 with open(os.path.join(HERE, "expansion_vectors.json"), "w") as f:
-    json.dump({"expand": cases, "gator": gator, "validate": validate, "expand_resource": expand_resource, "db": db_cases}, f, indent=1, sort_keys=True)
+    json.dump({"expand": cases, "gator": gator, "validate": validate, "expand_resource": expand_resource, "db": db_cases, "apply_to": apply_to}, f, indent=1, sort_keys=True)
+print("TestApplyTo:", [(c["name"], c["wantApply"], len(c["applyTo"])) for c in apply_to])
 print("TestDB:", [(c["name"], len(c["ops"]), sum(o["wantErr"] for o in c["ops"]), c["want"]) for c in db_cases])
 print("TestValidateTemplate:", [(v["name"], v["errSubstr"]) for v in validate])
 print("TestExpandResource:", [(v["name"], v["errSubstr"], v["want"] is not None) for v in expand_resource])

@@ -1591,6 +1591,23 @@ def case_expansion(lib):
             assert r.details == {"obj": got}, (c["name"], r.details, got)
         drv1.close()
 
+    # (1d) TestApplyTo (pkg/mutation/match/match_test.go:717-845): ApplyTo.Matches decides which templates expand a GVK -- on the oracle's
+    # relation, and on the engine as "a generator of that GVK has / has no resultant"
+    drv3 = D.Driver(lib_path=lib)
+    drv3.add_template(dump_kind, dump_rego)
+    drv3.AddConstraint(W._constraint(dump_kind, "dump", match={"kinds": [{"apiGroups": [""], "kinds": ["Pod"]}]}))
+    for c in vec["apply_to"]:
+        g, v, k = c["gvk"]
+        assert any(X._apply_matches(a, (g, v, k)) for a in c["applyTo"]) == c["wantApply"], c["name"]
+        tdoc = {"apiVersion": "expansion.gatekeeper.sh/v1beta1", "kind": "ExpansionTemplate", "metadata": {"name": "apply-to"},
+                "spec": {"applyTo": c["applyTo"], "templateSource": "spec.template", "generatedGVK": {"group": "", "version": "v1", "kind": "Pod"}}}
+        drv3.AddExpansionTemplate(tdoc)
+        gen = {"apiVersion": (g + "/" + v) if g else v, "kind": k, "metadata": {"name": "gen"}, "spec": {"template": {"metadata": {"labels": {"a": "b"}}}}}
+        resp = drv3.ReviewBatch([D.Review(object=gen, source="Original")], k8s.AUDIT_EP)
+        assert [r.msg for r in resp.results] == (["[Implied by apply-to] gen-pod"] if c["wantApply"] else []), (c["name"], [r.msg for r in resp.results])
+        drv3.RemoveExpansionTemplate("apply-to")
+    drv3.close()
+
     def run(docs, ep, drv_revs=None):
         tm, cons, nss = _split_docs(docs)
         orc, drv, skipped = make_pair(tm, cons, nss, lib_path=lib)
