@@ -28,5 +28,5 @@ for _ in range(reps + 3):
     ms.append(rb.eval(flags=D.F_NO_COPY_BACK).stats["kernel_ms"])
 ms = sorted(ms[3:])
 alg = rb.alg_bytes + n * 2 * 4 * 2
-print(f"{os.environ.get('GK_ENGINE_LIB', 'default')}: n={n} upload {up:.1f}s flatten {rb.stats['flatten_ms']:.0f}ms kernel median {ms[len(ms)//2]:.3f} ms "
+print(f"{os.environ.get('GK_ENGINE_LIB', 'default')} [{drv.last_kernel()}]: n={n} upload {up:.1f}s flatten {rb.stats['flatten_ms']:.0f}ms kernel median {ms[len(ms)//2]:.3f} ms "
       f"min {ms[0]:.3f} ms  -> {n * 50 / ms[len(ms)//2] / 1e6:.1f} G evals/s, {alg / ms[len(ms)//2] / 1e6:.0f} GB/s")
