@@ -621,10 +621,7 @@ int gk_review_batch(gk_engine_t* e, const gk_obj* objs, size_t n, const char* ep
         const Child& ch = children[v.object - n];
         v.object = ch.parent;
         v.msg = ExpansionSystem::implied_by(ch.tmpl, v.msg);
-        if (!ch.action.empty()) {   // OverrideEnforcementAction
-          v.action = ch.action;
-          v.scoped_json = "[]";
-        }
+        if (!ch.action.empty()) v.action = ch.action;   // OverrideEnforcementAction (aggregate.go:47-58) sets EnforcementAction only: the scoped list stays
       }
     std::stable_sort(rp->vio.begin(), rp->vio.end(), [](const Violation& a, const Violation& b2) { return a.object < b2.object; });
     if (rp->obj_errors.empty() && any_expand_err) rp->obj_errors.assign(total, std::string());

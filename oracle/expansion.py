@@ -194,7 +194,6 @@ def review_with_expansion(client, system, review, enforcement_point):
             r = dict(r)
             r["msg"] = (CHILD_MSG_PREFIX % tname) + " " + r["msg"]
             if action:
-                r["enforcementAction"] = action
-                r["scopedEnforcementActions"] = []
+                r["enforcementAction"] = action      # OverrideEnforcementAction (aggregate.go:47-58): only this field; the scoped list stays
             results.append(r)
     return results

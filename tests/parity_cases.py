@@ -1650,6 +1650,10 @@ def case_expansion(lib):
          "spec": {"crd": {"spec": {"names": {"kind": t["psp_privileged"]["kind"]}}}, "targets": [{"target": "admission.k8s.gatekeeper.sh", "rego": t["psp_privileged"]["rego"]}]}},
         W._constraint(t["allowedrepos"]["kind"], "repos", match=dict(W.POD), params={"repos": ["gcr.io/"]}, action="warn"),
         W._constraint(t["psp_privileged"]["kind"], "priv", match={"kinds": [{"apiGroups": [""], "kinds": ["Pod"]}], "source": "Generated"}),
+        # a scoped constraint under a template that overrides the action: OverrideEnforcementAction (aggregate.go:47-58) replaces
+        # EnforcementAction only, the result keeps its ScopedEnforcementActions
+        W._constraint(t["psp_privileged"]["kind"], "priv-scoped", match=dict(W.POD), action="scoped",
+                      scoped=[{"action": "warn", "enforcementPoints": [{"name": k8s.AUDIT_EP}]}, {"action": "deny", "enforcementPoints": [{"name": k8s.WEBHOOK_EP}]}]),
         tmpl("expand-deployments", ["Deployment", "ReplicaSet"], ("", "v1", "Pod")),
         tmpl("expand-cronjobs", ["CronJob"], ("batch", "v1", "Job"), src="spec.jobTemplate", groups=("batch",)),
         tmpl("expand-jobs", ["Job"], ("", "v1", "Pod"), action="dryrun", groups=("batch",)),
@@ -1682,6 +1686,7 @@ def case_expansion(lib):
                 expand_errs[i] = str(e)
         got = {x for x in engine_results(resp) if x[0] not in expand_errs}
         assert_same(want, got)
+        assert any(x[1].endswith("/priv-scoped") and x[4] == "dryrun" and x[5] for x in got), "override on a scoped constraint: the scoped list must stay"
         assert {i for i, e in enumerate(resp.object_errors or []) if e} == set(expand_errs), (resp.object_errors, expand_errs)
         for i, e in expand_errs.items():
             assert e in resp.object_errors[i]
