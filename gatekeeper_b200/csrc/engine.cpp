@@ -1977,14 +1977,19 @@ bool Engine::has_expansion() {
   return !expansion_.empty();
 }
 void Engine::expand_object(const ObjIn& in, std::vector<Resultant>& out) {
-  if (!in.json || (in.operation && std::string(in.operation) == "DELETE")) return;
+  // the generator is the request's object -- the OLD object of a DELETE (getReqObject, pkg/webhook/policy.go:435-440,599-603)
+  const bool del = in.operation && std::string(in.operation) == "DELETE";
+  const char* gj = del ? in.old_json : in.json;
+  const size_t gl = del ? in.old_len : in.len;
+  if (!gj) return;
   VP obj;
   try {
-    obj = json_parse(in.json, in.len);
+    obj = json_parse(gj, gl);
   } catch (JsonError&) {
     return;   // the review itself reports the undecodable object
   }
   if (!obj || obj->t != VT::Obj) return;
+  if (in.ns_name) obj = ExpansionSystem::with_namespace(obj, in.ns_name);   // an admission request: obj.SetNamespace(req.Namespace) (policy.go:608)
   std::shared_lock<std::shared_mutex> l(mu_);
   // the review's Namespace object: the explicit one, else the cache entry for the request's namespace (policy.go:606-614)
   std::string nsn;

@@ -35,6 +35,16 @@ VP with(const VP& o, const std::string& key, VP val) {
 }
 }  // namespace
 
+VP ExpansionSystem::with_namespace(const VP& obj, const std::string& ns) {
+  VP md = obj_get(obj, "metadata");
+  std::vector<std::pair<VP, VP>> kv;
+  if (md && md->t == VT::Obj)
+    for (auto& e : md->kv)
+      if (e.first->s != "namespace") kv.push_back(e);
+  if (!ns.empty()) kv.emplace_back(v_str("namespace"), v_str(ns));
+  return with(obj, "metadata", v_obj(std::move(kv)));
+}
+
 bool ExpansionTemplate::applies_to(const std::string& g, const std::string& v, const std::string& k) const {
   for (auto& a : apply)   // ApplyTo.Matches -- pkg/mutation/match/apply_to.go:45-57
     if (has(a.groups, g) && has(a.versions, v) && has(a.kinds, k)) return true;

@@ -41,6 +41,8 @@ class ExpansionSystem {
   // review's Namespace object, or null.  Throws std::runtime_error ("cannot expand resource ...", "could not find source field ...")
   void expand(const VP& obj, const std::string* ns_name, std::vector<Resultant>& out, int depth = 0) const;
   // aggregate.go:11,58-62
+  // Unstructured.SetNamespace on a copy of `obj`: metadata.namespace = ns, or the field removed for ns == ""
+  static VP with_namespace(const VP& obj, const std::string& ns);
   static std::string implied_by(const std::string& template_name, const std::string& msg) { return "[Implied by " + template_name + "] " + msg; }
 
  private:

@@ -178,9 +178,17 @@ def review_with_expansion(client, system, review, enforcement_point):
     enforcement action where the template says so, prefix the child messages, append them to the parent's results."""
     from oracle import k8s
     results = list(client.review(review, enforcement_point))
-    obj = review.obj
-    if obj is None or review.operation == "DELETE":
+    # the generator is the request's object -- the OLD object of a DELETE (getReqObject, pkg/webhook/policy.go:435-440,599-603)
+    obj = review.old if review.operation == "DELETE" else review.obj
+    if not isinstance(obj, dict):
         return results
+    if review.namespace is not None:      # an admission request: obj.SetNamespace(req.Namespace) before expanding (policy.go:608)
+        obj = dict(obj)
+        md = dict(obj.get("metadata") or {}) if isinstance(obj.get("metadata"), dict) or obj.get("metadata") is None else {}
+        md.pop("namespace", None)
+        if review.namespace:
+            md["namespace"] = review.namespace
+        obj["metadata"] = md
     ns_name = None
     if review.ns is not None:
         ns_name = (review.ns.get("metadata") or {}).get("name", "")

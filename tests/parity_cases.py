@@ -1591,6 +1591,22 @@ def case_expansion(lib):
             assert r.details == {"obj": got}, (c["name"], r.details, got)
         drv1.close()
 
+    # (1c') the webhook's generator: obj.SetNamespace(req.Namespace) before expansion (pkg/webhook/policy.go:608) -- with no Namespace
+    # object for the review the resultant takes the request's namespace, not the one written in the object
+    c = vec["expand_resource"][1]     # "successful expansion without namespace": the Deployment carries its own metadata.namespace
+    tdoc = json.loads(json.dumps(c["template"]))
+    g, v, k = X._gvk(c["obj"])
+    tdoc["spec"]["applyTo"] = [{"groups": [g], "versions": [v], "kinds": [k]}]
+    drv4 = D.Driver(lib_path=lib)
+    drv4.add_template(dump_kind, dump_rego)
+    drv4.AddConstraint(W._constraint(dump_kind, "dump", match={"kinds": [{"apiGroups": [""], "kinds": ["Pod"]}]}))
+    drv4.AddExpansionTemplate(tdoc)
+    for req_ns, want_ns in (("elsewhere", "elsewhere"), ("", None), (None, c["want"]["metadata"]["namespace"])):
+        resp = drv4.ReviewBatch([D.Review(object=c["obj"], operation="CREATE", namespace_name=req_ns, source="Original")], k8s.WEBHOOK_EP)
+        assert len(resp.results) == 1, (req_ns, [r.msg for r in resp.results], resp.object_errors)
+        assert resp.results[0].details["obj"]["metadata"].get("namespace") == want_ns, (req_ns, resp.results[0].details["obj"]["metadata"])
+    drv4.close()
+
     # (1d) TestApplyTo (pkg/mutation/match/match_test.go:717-845): ApplyTo.Matches decides which templates expand a GVK -- on the oracle's
     # relation, and on the engine as "a generator of that GVK has / has no resultant"
     drv3 = D.Driver(lib_path=lib)
@@ -1674,12 +1690,19 @@ def case_expansion(lib):
                 drv.AddExpansionTemplate(d)
         objs = [d for d in docs if d.get("kind") in ("Deployment", "ReplicaSet", "CronJob", "Pod", "ConfigMap")]
         revs = [D.Review(object=d, source="Original") for d in objs]
+        # admission shapes: the generator of a DELETE is the OLD object (getReqObject, policy.go:435-440), and the request's namespace is
+        # set on the generator before it is expanded (policy.go:608): the resultant lands in that namespace
+        web = next(d for d in objs if d["metadata"]["name"] == "Web")
+        revs += [D.Review(object=None, old_object=web, operation="DELETE", source="Original"),
+                 D.Review(object=web, operation="CREATE", source="Original", namespace_name="elsewhere"),
+                 D.Review(object=web, old_object=web, operation="UPDATE", source="Original", namespace_name="")]
         resp = drv.ReviewBatch(revs, ep)
         want = set()
         expand_errs = {}
         for i, r in enumerate(revs):
             try:
-                for x in X.review_with_expansion(orc, xs, k8s.Review(obj=r.object, source="Original"), ep):
+                for x in X.review_with_expansion(orc, xs, k8s.Review(obj=r.object, old=r.old_object, operation=r.operation, source="Original",
+                                                                     namespace=r.namespace_name), ep):
                     want.add((i, "%s/%s" % x["constraint"], x["msg"], json.dumps(x["details"], sort_keys=True), x["enforcementAction"],
                               tuple(x["scopedEnforcementActions"]), bool(x.get("autoreject"))))
             except X.ExpansionError as e:
