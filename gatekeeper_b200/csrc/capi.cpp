@@ -125,6 +125,7 @@ struct gk_batch {
   const uint64_t* blob_off = nullptr;
   uint8_t blob_source = 0;
   uint32_t n = 0;
+  uint32_t flags = 0;                  // the upload's flags (the process whose excluder applied): the audit reviews resultants with the same
   uint64_t alg_bytes = 0;
   uint64_t data_version = 0;           // data.inventory as of the flatten (referential snapshots only)
   ObjIn obj_in(size_t i) const;
@@ -332,6 +333,7 @@ void upload_batch(gk_engine* e, const std::shared_ptr<const Compiled>& c, const 
   b->compiled = c;
   if (c->uses_data) e->eng->data_doc(&b->data_version);
   b->n = hb->n;
+  b->flags = flags;
   b->alg_bytes = hb->alg_bytes;
   b->objs.assign(objs, objs + n);
   // drop the host column data; keep the small per-object error list
@@ -380,6 +382,7 @@ void upload_blob(gk_engine* e, const std::shared_ptr<const Compiled>& c, const c
   b->compiled = c;
   if (c->uses_data) e->eng->data_doc(&b->data_version);
   b->n = (uint32_t)n;
+  b->flags = flags;
   b->alg_bytes = ist.alg_bytes;
   b->blob = buf;
   b->blob_off = off;
@@ -823,10 +826,115 @@ int gk_audit_add_batch(gk_audit_t* a, gk_batch_t* b, const char* ep_c, char** er
       }
       e->be->release(fork);
     }
+    // ---- expansion inside the audit loop (pkg/audit/manager.go:733-765): every reviewed object is expanded; its resultants are reviewed
+    // as Generated resources with the parent's Namespace, their results -- "[Implied by <template>]", the template's action override --
+    // are the PARENT's results (addAuditResponsesToUpdateLists names the parent object).  An object whose expansion fails contributes
+    // nothing at all, not even its own violations (the reference logs the error and `continue`s past the bookkeeping of the response).
+    std::vector<std::string> obj_errs = b->host->obj_errors.empty() ? std::vector<std::string>(b->n) : b->host->obj_errors;
+    obj_errs.resize(b->n);
+    struct Child {
+      uint32_t parent;
+      std::string json, tmpl, action;
+    };
+    std::vector<Child> children;
+    if (e->eng->has_expansion() && b->n) {
+      const size_t T = std::min<size_t>((size_t)std::max(1, e->eng->threads()), std::max<size_t>(1, b->n / 256));
+      std::vector<std::vector<Child>> part(T);
+      std::vector<std::vector<std::pair<uint32_t, std::string>>> perr(T);
+      auto work = [&](size_t t) {
+        std::vector<Resultant> res;
+        for (uint32_t i = (uint32_t)((size_t)b->n * t / T); i < (uint32_t)((size_t)b->n * (t + 1) / T); ++i) {
+          if (!obj_errs[i].empty()) continue;   // (the review of the object itself failed: the reference never gets to its expansion)
+          res.clear();
+          try {
+            e->eng->expand_object(ins[i], res);
+          } catch (std::exception& x) {
+            perr[t].emplace_back(i, std::string("unable to expand object: ") + x.what());
+            continue;
+          }
+          for (auto& r : res) part[t].push_back(Child{i, json_str(r.obj), r.template_name, r.action});
+        }
+      };
+      if (T == 1) work(0);
+      else {
+        std::vector<std::thread> th;
+        for (size_t t = 0; t < T; ++t) th.emplace_back(work, t);
+        for (auto& x : th) x.join();
+      }
+      const uint32_t W = ev.words;
+      for (auto& pe : perr)
+        for (auto& x : pe) {
+          obj_errs[x.first] = x.second;
+          for (uint32_t w = 0; w < W; ++w) {
+            if (!ev.viol.empty()) ev.viol[(size_t)x.first * W + w] = 0;
+            if (!ev.err.empty()) ev.err[(size_t)x.first * W + w] = 0;
+          }
+        }
+      for (auto& p : part) children.insert(children.end(), std::make_move_iterator(p.begin()), std::make_move_iterator(p.end()));
+    }
     a->run.add_batch(*e->eng, *c, ins, ev.viol.data(), ev.err.empty() ? nullptr : ev.err.data(), ev.words, ev.errlist, ep, lazy ? &id : nullptr,
                      use_amb ? ev_amb.viol.data() : nullptr);
-    if (b->host->obj_errors.empty()) a->run.add_object_errors(std::vector<std::string>(b->n));
-    else a->run.add_object_errors(b->host->obj_errors);
+    if (!children.empty()) {
+      std::vector<gk_obj> cobjs(children.size());
+      for (size_t k = 0; k < children.size(); ++k) {
+        gk_obj& o = cobjs[k];
+        memset(&o, 0, sizeof o);
+        o.json = children[k].json.data();
+        o.len = children[k].json.size();
+        const ObjIn& par = ins[children[k].parent];
+        o.ns_json = par.ns_json;                // the parent's Namespace object (manager.go:745-749), source Generated
+        o.ns_len = par.ns_len;
+        o.ns_name = par.ns_name;
+        o.source = GK_SOURCE_GENERATED;
+      }
+      gk_batch* cb = nullptr;
+      gk_result cstats, cres;
+      memset(&cstats, 0, sizeof cstats);
+      memset(&cres, 0, sizeof cres);
+      {
+        ProgramLease lease(e, *c);
+        upload_batch(e, c, cobjs.data(), cobjs.size(), b->flags, &cb, &cstats);
+        std::unique_ptr<gk_batch, std::function<void(gk_batch*)>> hold(cb, [&](gk_batch* x) {
+          e->be->release(x->dev);
+          delete x;
+        });
+        eval_batch(e, cb, ep_c, GK_F_MATERIALIZE | GK_F_NO_COPY_BACK, &cres);
+      }
+      std::unique_ptr<ResultPriv> crp(static_cast<ResultPriv*>(cres.priv));
+      cres.priv = nullptr;
+      struct Ident {
+        std::string g, v, k, ns, name;
+      };
+      std::unordered_map<uint32_t, Ident> ident;   // parents that have results from resultants
+      for (auto& v : crp->vio) {
+        const Child& ch = children[v.object];
+        auto it = ident.find(ch.parent);
+        if (it == ident.end()) {
+          Ident id2;
+          try {
+            VP po = json_parse(ins[ch.parent].json, ins[ch.parent].len);
+            split_gv(po, id2.g, id2.v, id2.k);
+            id2.ns = meta_str(po, "namespace");
+            id2.name = meta_str(po, "name");
+          } catch (JsonError&) {
+          }
+          it = ident.emplace(ch.parent, std::move(id2)).first;
+        }
+        const Constraint& con = *c->order[v.constraint];
+        StatusViolation sv;
+        sv.group = it->second.g, sv.version = it->second.v, sv.kind = it->second.k, sv.ns = it->second.ns, sv.name = it->second.name;
+        sv.message = ExpansionSystem::implied_by(ch.tmpl, v.msg);
+        sv.action = ch.action.empty() ? v.action : ch.action;   // OverrideEnforcementAction: the action only
+        sv.scoped_json = v.scoped_json;
+        a->run.fold(con.kind + "/" + con.name, std::move(sv));
+        a->run.results++;
+      }
+      // a resultant the review refused (manager.go:757-760 logs it and goes on): reported on its parent
+      for (size_t k = 0; k < crp->obj_errors.size() && k < children.size(); ++k)
+        if (!crp->obj_errors[k].empty() && obj_errs[children[k].parent].empty())
+          obj_errs[children[k].parent] = ExpansionSystem::implied_by(children[k].tmpl, crp->obj_errors[k]);
+    }
+    a->run.add_object_errors(obj_errs);
   });
 }
 

@@ -62,21 +62,41 @@ class LimitQueue:
 
 
 def audit(client: k8s.Client, objects, namespaces=None, excluded_namespaces=(), limit=DEFAULT_VIOLATIONS_LIMIT,
-          source="Original"):
+          source="Original", expansion=None):
     """reviewObjects + addAuditResponsesToUpdateLists -- pkg/audit/manager.go:668-777,886-945.
 
     objects: iterable of object dicts.  namespaces: {name: namespace object} (the audit's nsCache,
-    :697-706).  Returns {"totals": {(kind,name): n}, "by_action": {action: n},
-    "violations": {(kind,name): [status violation dicts, descending]}, "results": [...]}."""
+    :697-706).  expansion: an oracle.expansion.System -- every object is expanded and its resultants reviewed (:733-765).
+    Returns {"totals": {(kind,name): n}, "by_action": {action: n},
+    "violations": {(kind,name): [status violation dicts, descending]}, "results": [...], "expand_errors": {index: text}}."""
+    from oracle import expansion as X
     namespaces = namespaces or {}
-    totals, by_action, queues, all_results = {}, {}, {}, []
+    totals, by_action, queues, all_results, expand_errors = {}, {}, {}, [], {}
     for idx, obj in enumerate(objects):
         if k8s.is_namespace_excluded(excluded_namespaces, obj):      # :531-538 skipExcludedNamespace
             continue
         ns_name = k8s._meta(obj, "namespace")
         ns = namespaces.get(ns_name) if ns_name else None              # :697-706
         review = k8s.Review(obj=obj, ns=ns, source=source)             # :707-711 AugmentedUnstructured
-        for r in client.review(review, k8s.AUDIT_EP):                  # :720
+        results = list(client.review(review, k8s.AUDIT_EP))            # :720
+        if expansion is not None:
+            # :733-765 -- Expand fails: the error is logged and the loop `continue`s, past the bookkeeping of the object's own results
+            try:
+                resultants = expansion.expand(obj, (ns.get("metadata") or {}).get("name", "") if ns is not None else None)
+            except X.ExpansionError as e:
+                expand_errors[idx] = "unable to expand object: " + str(e)
+                continue
+            for robj, tname, action in resultants:
+                if k8s.is_namespace_excluded(excluded_namespaces, robj):
+                    continue      # (the engine reviews resultants through the same excluder stage as every object of the process)
+                child = k8s.Review(obj=robj, ns=ns, source="Generated")          # :745-749
+                for r in client.review(child, k8s.AUDIT_EP):
+                    r = dict(r)
+                    r["msg"] = (X.CHILD_MSG_PREFIX % tname) + " " + r["msg"]       # AggregateResponses
+                    if action:
+                        r["enforcementAction"] = action                           # OverrideEnforcementAction
+                    results.append(r)
+        for r in results:
             key = r["constraint"]
             totals[key] = totals.get(key, 0) + 1                        # :902
             by_action[r["enforcementAction"]] = by_action.get(r["enforcementAction"], 0) + 1
@@ -88,4 +108,4 @@ def audit(client: k8s.Client, objects, namespaces=None, excluded_namespaces=(), 
             queues.setdefault(key, LimitQueue(limit)).push(sv)           # :925
             all_results.append({"object": idx, **r})
     return {"totals": totals, "by_action": by_action,
-            "violations": {k: q.drain_descending() for k, q in queues.items()}, "results": all_results}
+            "violations": {k: q.drain_descending() for k, q in queues.items()}, "results": all_results, "expand_errors": expand_errors}

@@ -258,6 +258,89 @@ def case_audit(lib, n=1500, limit=20, excluded=("kube-*", "ns-000*")):
     return got
 
 
+def case_audit_expansion(lib, n_pods=300, limit=5):
+    """Expansion inside the audit loop (pkg/audit/manager.go:733-765) through the audit API -- resident batches + gk_audit_add_batch, host-
+    flattened and raw-JSON pages: every object is expanded, the resultants' results are the parent's ("[Implied by ...]", the action
+    override, the parent's identity in the status violation), an object whose expansion fails contributes nothing and is reported,
+    the excluder stage applies to parents and resultants alike.  Report == oracle/audit.py with an expansion system."""
+    from oracle import audit as OA
+    from oracle import expansion as X
+    t = golden("templates.json")
+    tm = [(t[k]["kind"], t[k]["rego"]) for k in ("allowedrepos", "psp_privileged", "requiredlabels_basic")]
+    cons = [W._constraint(t["allowedrepos"]["kind"], "repos", match=dict(W.POD), params={"repos": ["gcr.io/"]}, action="warn"),
+            W._constraint(t["psp_privileged"]["kind"], "priv", match={"kinds": [{"apiGroups": [""], "kinds": ["Pod"]}], "source": "Generated"}),
+            W._constraint(t["psp_privileged"]["kind"], "priv-scoped", match=dict(W.POD), action="scoped",
+                          scoped=[{"action": "warn", "enforcementPoints": [{"name": k8s.AUDIT_EP}]}]),
+            W._constraint(t["requiredlabels_basic"]["kind"], "team", match={"kinds": [{"apiGroups": ["apps"], "kinds": ["Deployment"]}]}, params={"labels": ["team"]})]
+    nss = W.synth_namespaces()
+    orc, drv, _ = make_pair(tm, cons, nss, lib_path=lib)
+    tmpl = lambda name, kinds, gen, src="spec.template", action=None, groups=("apps",): {
+        "apiVersion": "expansion.gatekeeper.sh/v1alpha1", "kind": "ExpansionTemplate", "metadata": {"name": name},
+        "spec": dict({"applyTo": [{"groups": list(groups), "versions": ["v1"], "kinds": kinds}], "templateSource": src,
+                      "generatedGVK": {"group": gen[0], "version": gen[1], "kind": gen[2]}}, **({"enforcementAction": action} if action else {}))}
+    xs = X.System()
+    for d in (tmpl("expand-deployments", ["Deployment", "ReplicaSet"], ("", "v1", "Pod")),
+              tmpl("expand-cronjobs", ["CronJob"], ("batch", "v1", "Job"), src="spec.jobTemplate", groups=("batch",)),
+              tmpl("expand-jobs", ["Job"], ("", "v1", "Pod"), action="dryrun", groups=("batch",))):
+        xs.upsert(d)
+        drv.AddExpansionTemplate(d)
+    nsnames = [x["metadata"]["name"] for x in nss]
+    bad = {"metadata": {"labels": {"app": "x"}}, "spec": {"containers": [{"name": "c", "image": "evil.example.com/a:latest", "securityContext": {"privileged": True}}]}}
+    good = {"metadata": {"labels": {"app": "y"}}, "spec": {"containers": [{"name": "c", "image": "gcr.io/a:1"}]}}
+    blob = W.synth_objects(4242, n_pods)
+    objs = [json.loads(blob.get(i)) for i in range(n_pods)]
+    rnd = random.Random(9)
+    for i in range(60):
+        ns = rnd.choice(nsnames + ["kube-system", "unknown-ns"])
+        spec = rnd.choice([bad, bad, good])
+        kind = rnd.choice(["Deployment", "Deployment", "ReplicaSet", "CronJob"])
+        if kind == "CronJob":
+            o = {"apiVersion": "batch/v1", "kind": "CronJob", "metadata": {"name": "cj-%d" % i, "namespace": ns}, "spec": {"jobTemplate": {"spec": {"template": spec}}}}
+        else:
+            o = {"apiVersion": "apps/v1", "kind": kind, "metadata": {"name": "%s-%d" % (kind.lower(), i), "namespace": ns, **({"labels": {"team": "a"}} if i % 3 else {})},
+                 "spec": {"replicas": 1, "template": spec}}
+        objs.append(o)
+    # generators whose expansion fails: no spec.template at all, a template that is not a map, a namespace that is not a string
+    objs.append({"apiVersion": "apps/v1", "kind": "Deployment", "metadata": {"name": "no-template", "namespace": nsnames[0]}, "spec": {"replicas": 1}})
+    objs.append({"apiVersion": "apps/v1", "kind": "Deployment", "metadata": {"name": "bad-template", "namespace": nsnames[0]}, "spec": {"template": "nope"}})
+    rnd.shuffle(objs)
+    nsmap = {x["metadata"]["name"]: x for x in nss}
+    excluded = ("kube-*",)
+    want = OA.audit(orc, objs, namespaces=nsmap, excluded_namespaces=excluded, limit=limit, expansion=xs)
+    assert len(want["expand_errors"]) == 2, want["expand_errors"]
+    assert any("[Implied by expand-jobs]" in r["msg"] and r["enforcementAction"] == "dryrun" for r in want["results"])
+    assert any("[Implied by expand-deployments]" in r["msg"] and r["constraint"][1] == "priv-scoped" and r["scopedEnforcementActions"] for r in want["results"])
+    drv.SetExcludedNamespaces("audit", list(excluded))
+
+    def check(run):
+        got = run.report()
+        assert got["totalViolations"] == {"%s/%s" % k: v for k, v in want["totals"].items()}, (got["totalViolations"], want["totals"])
+        assert got["totalViolationsPerEnforcementAction"] == want["by_action"]
+        for key, lst in want["violations"].items():
+            g = got["violations"]["%s/%s" % key]
+            w = [{k: v for k, v in sv.items() if not (k in ("namespace", "enforcementActions") and not v)} for sv in lst]
+            assert g == w, (key, g[:2], w[:2])
+        assert got["objectErrors"]["count"] == len(want["expand_errors"])
+        assert sorted(x["error"] for x in got["objectErrors"]["first"]) == sorted(want["expand_errors"].values())
+        return got
+
+    keep = []
+    run = D.AuditRun(drv, violations_limit=limit)
+    half = len(objs) // 2
+    for lo, hi in ((0, half), (half, len(objs))):
+        rb = drv.upload([D.Review(object=o, source="Original") for o in objs[lo:hi]], process="audit")
+        keep.append(rb)
+        run.add_batch(rb, k8s.AUDIT_EP)
+    got = check(run)
+    run = D.AuditRun(drv, violations_limit=limit)
+    pb = W.PyBlob([json.dumps(o).encode() for o in objs])
+    rb = drv.upload_blob(pb, process="audit")
+    keep.append((pb, rb))
+    run.add_batch(rb, k8s.AUDIT_EP)
+    check(run)
+    return got
+
+
 def case_validation_messages(lib):
     """getValidationMessages (a-14): "[<constraint name>] <msg>" lists per admission request, scoped actions resolved for
     the webhook enforcement point, excluder stage of the webhook process."""

@@ -409,3 +409,8 @@ def test_written_out_match_blocks_on_long_and_non_ascii_patterns(monkeypatch):
     extra = ["n\u00e4mespace-\u00fc", "team-\u65e5\u672c", "x" * 24, "y" * 25, "a-namespace-name-of-more-than-twenty-four-bytes"]
     for seed in (41, 42):
         assert P.case_match_fuzz(HOSTEMU, n_constraints=40, n_objects=300, seed=seed, extra_names=extra) > 0
+
+
+def test_audit_expands_generators_like_the_audit_loop():
+    got = P.case_audit_expansion(HOSTEMU)
+    assert got["results"] > 50

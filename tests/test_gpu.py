@@ -313,3 +313,8 @@ def test_audit_concurrent_with_reviews():
 @pytest.mark.parametrize("config", [2, 4, 5])
 def test_generated_kernel_is_identical_to_the_interpreter(config):
     assert P.case_spec_kernel(LIB, 20000 if config == 2 else 6000, config=config) > 500
+
+
+def test_audit_expands_generators_like_the_audit_loop():
+    got = P.case_audit_expansion(LIB)
+    assert got["results"] > 50
