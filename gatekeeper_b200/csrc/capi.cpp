@@ -655,6 +655,9 @@ int gk_batch_eval(gk_engine_t* e, gk_batch_t* b, const char* ep, uint32_t flags,
   if (!e || !b || !out) return GK_ERR_INVALID;
   memset(out, 0, sizeof *out);
   return guard(err, [&]() {
+    if (e->eng->has_expansion())   // (bitmaps of the listed objects only: the resultants of generators would be missing, silently)
+      throw RegoError{"ExpansionTemplates are registered: this entry point does not expand generator objects -- review them through gk_review_batch, or "
+                      "aggregate the batch with gk_audit_add_batch, which do"};
     auto c = e->eng->compiled();
     if (c->version != b->compiled->version) throw RegoError{"batch was flattened against an older constraint set; upload it again"};
     if (c->uses_data) {   // the columns of a referential snapshot hold values computed from data.inventory
@@ -671,6 +674,9 @@ int gk_batch_eval_device(gk_engine_t* e, gk_batch_t* b, const char* ep, void* d_
                          void* stream, char** err) {
   if (!e || !b || !d_viol || !d_err || !d_totals || !d_err_totals) return GK_ERR_INVALID;
   return guard(err, [&]() {
+    if (e->eng->has_expansion())   // (bitmaps of the listed objects only: the resultants of generators would be missing, silently)
+      throw RegoError{"ExpansionTemplates are registered: this entry point does not expand generator objects -- review them through gk_review_batch, or "
+                      "aggregate the batch with gk_audit_add_batch, which do"};
     auto c = e->eng->compiled();
     if (c->version != b->compiled->version) throw RegoError{"batch was flattened against an older constraint set; upload it again"};
     if (c->uses_data) {   // the columns of a referential snapshot hold values computed from data.inventory
@@ -696,6 +702,9 @@ int gk_batch_eval_device_peers(gk_engine_t* e, gk_batch_t* b, const char* ep, co
                                void* stream, char** err) {
   if (!e || !b || !peer_bases || !npeers || npeers > 8 || rank >= npeers || !d_err || !d_totals || !d_err_totals) return GK_ERR_INVALID;
   return guard(err, [&]() {
+    if (e->eng->has_expansion())   // (bitmaps of the listed objects only: the resultants of generators would be missing, silently)
+      throw RegoError{"ExpansionTemplates are registered: this entry point does not expand generator objects -- review them through gk_review_batch, or "
+                      "aggregate the batch with gk_audit_add_batch, which do"};
     auto c = e->eng->compiled();
     if (c->version != b->compiled->version) throw RegoError{"batch was flattened against an older constraint set; upload it again"};
     if (c->uses_data) {   // the columns of a referential snapshot hold values computed from data.inventory
@@ -741,6 +750,9 @@ int gk_review_blob(gk_engine_t* e, const char* buf, const uint64_t* offsets, siz
     gk_batch* b = nullptr;
     gk_result stats;
     memset(&stats, 0, sizeof stats);
+    if (e->eng->has_expansion())   // (bitmaps of the listed objects only: the resultants of generators would be missing, silently)
+      throw RegoError{"ExpansionTemplates are registered: this entry point does not expand generator objects -- review them through gk_review_batch, or "
+                      "aggregate the batch with gk_audit_add_batch, which do"};
     auto c = e->eng->compiled();
     ProgramLease lease(e, *c);
     upload_blob(e, c, buf, offsets, n, source, flags, &b, &stats);

@@ -126,7 +126,9 @@ int gk_remove_constraint(gk_engine_t* e, const char* kind, const char* name);
  * "[Implied by <template>]" prefix and the template's enforcementAction override (pkg/expansion/aggregate.go:19-63) -- what the
  * audit loop (pkg/audit/manager.go:733-765) and the webhook (pkg/webhook/policy.go:610-646) do around Client.Review.  Mutators are
  * not applied (the mutation system is outside this engine).  gk_audit_add_batch does the same for a resident batch: the resultants'
- * results enter the run under the parent's identity, an object whose expansion fails contributes nothing and is an objectErrors entry. */
+ * results enter the run under the parent's identity, an object whose expansion fails contributes nothing and is an objectErrors entry.
+ * The bitmap-only entry points (gk_batch_eval, gk_batch_eval_device(_peers), gk_review_blob) do not expand: while templates are
+ * registered they fail with a text that says so, instead of returning rows in which the resultants' violations are missing. */
 int gk_add_expansion_template(gk_engine_t* e, const char* json, size_t len, char** err);
 int gk_remove_expansion_template(gk_engine_t* e, const char* name);
 /* System.GetConflicts (pkg/expansion/system.go:81-83; db.go:62-70): the names of the stored ExpansionTemplates that are set aside
