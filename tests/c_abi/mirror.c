@@ -7,6 +7,8 @@
  * Input (written by tests/test_c_abi.py), all integers decimal, one item per line, payloads length-prefixed:
  *   T <kind> <len>\n<rego bytes>\n     C <len>\n<constraint json>\n     N <name> <len>\n<namespace json>\n     E <enforcement point>\n
  *   R <source> <operation or -> <ns_name or -> <len obj> <len old> <len ns> <len userinfo>\n<obj><old><ns><userinfo>\n
+ *   X <len>\n<ExpansionTemplate json>\n   (UpsertExpansionTemplate: a refusal is printed as "XERR\t<text>", not fatal -- the shim returns it)
+ * With an X line in the input the run ends with "CONFLICTS\t<json array>" (ExpansionConflicts).
  */
 #include <dlfcn.h>
 #include <stdio.h>
@@ -30,7 +32,8 @@ int main(int argc, char** argv) {
   void* lib = dlopen(argv[1], RTLD_NOW | RTLD_LOCAL);
   if (!lib) { fprintf(stderr, "dlopen: %s\n", dlerror()); return 2; }
   SYM(gk_engine_create) SYM(gk_engine_destroy) SYM(gk_add_template) SYM(gk_add_constraint) SYM(gk_put_namespace) SYM(gk_add_data) SYM(gk_review_batch)
-  SYM(gk_result_constraint_key) SYM(gk_free_result) SYM(gk_free_str)
+  SYM(gk_result_constraint_key) SYM(gk_free_result) SYM(gk_free_str) SYM(gk_add_expansion_template) SYM(gk_expansion_conflicts)
+  int any_x = 0;
   FILE* f = fopen(argv[2], "rb");
   if (!f) return 2;
   char* err = NULL;
@@ -68,6 +71,18 @@ int main(int argc, char** argv) {
         if (p_gk_add_data(e, path, 4, js, len, &err)) { fprintf(stderr, "data: %s\n", err); return 3; }
       }
       free(js);
+    } else if (tag == 'X') {
+      size_t len;
+      if (fscanf(f, "%zu", &len) != 1) return 2;
+      fgetc(f);
+      char* js = read_n(f, len);
+      any_x = 1;
+      if (p_gk_add_expansion_template(e, js, len, &err)) {
+        printf("XERR\t%s\n", err ? err : "?");
+        p_gk_free_str(err);
+        err = NULL;
+      }
+      free(js);
     } else if (tag == 'E') {
       if (fscanf(f, "%127s", ep) != 1) return 2;
     } else if (tag == 'R') {
@@ -97,6 +112,11 @@ int main(int argc, char** argv) {
     printf("%u\t%s\t%s\t%d\t%s\n", v->object, p_gk_result_constraint_key(&res, v->constraint), v->enforcement_action, (int)v->autoreject, v->msg);
   }
   p_gk_free_result(&res);
+  if (any_x) {
+    char* cj = p_gk_expansion_conflicts(e);
+    printf("CONFLICTS\t%s\n", cj ? cj : "[]");
+    p_gk_free_str(cj);
+  }
   p_gk_engine_destroy(e);
   return 0;
 }

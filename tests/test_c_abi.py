@@ -96,9 +96,42 @@ def _run(lib, tmp_path):
     return len(got)
 
 
+def _run_expansion(lib, tmp_path):
+    """UpsertExpansionTemplate / ExpansionConflicts of the shim: a Deployment is reviewed through its resultant Pod ("[Implied by ...]"),
+    a pair of templates that expand into each other is stored, reported ("template forms expansion cycle") and listed as conflicts."""
+    t = golden("templates.json")
+    tmpl = lambda name, group, kind, gen: {"apiVersion": "expansion.gatekeeper.sh/v1beta1", "kind": "ExpansionTemplate", "metadata": {"name": name},
+                                            "spec": {"applyTo": [{"groups": [group], "versions": ["v1"], "kinds": [kind]}], "templateSource": "spec.template",
+                                                     "generatedGVK": {"group": gen[0], "version": "v1", "kind": gen[1]}}}
+    xts = [tmpl("expand-deployments", "apps", "Deployment", ("", "Pod")), tmpl("a-to-b", "ga", "A", ("gb", "B")), tmpl("b-to-a", "gb", "B", ("ga", "A"))]
+    con = {"kind": "NeverValidate", "metadata": {"name": "pods"}, "spec": {"match": {"kinds": [{"apiGroups": [""], "kinds": ["Pod"]}]}}}
+    dep = {"apiVersion": "apps/v1", "kind": "Deployment", "metadata": {"name": "web", "namespace": "a"}, "spec": {"template": {"metadata": {"labels": {"x": "y"}}}}}
+    path = os.path.join(str(tmp_path), "in_x.txt")
+    with open(path, "wb") as f:
+        b = t["fixtures_TemplateNeverValidate"]["rego"].encode()
+        f.write(b"T NeverValidate %d\n" % len(b) + b + b"\n")
+        b = json.dumps(con).encode()
+        f.write(b"C %d\n" % len(b) + b + b"\n")
+        for x in xts:
+            b = json.dumps(x).encode()
+            f.write(b"X %d\n" % len(b) + b + b"\n")
+        f.write(b"E %s\n" % k8s.AUDIT_EP.encode())
+        o = _blob(dep)
+        f.write(b"R 1 - - %d 0 0 0\n" % len(o) + o + b"\n")
+    out = subprocess.run([BIN, lib, path], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    lines = [ln.split("\t") for ln in out.stdout.splitlines()]
+    assert [ln[1] for ln in lines if ln[0] == "XERR"] == ["template forms expansion cycle"], lines
+    assert [json.loads(ln[1]) for ln in lines if ln[0] == "CONFLICTS"] == [["a-to-b", "b-to-a"]], lines
+    res = [ln for ln in lines if ln[0] == "0"]
+    assert len(res) == 1 and res[0][1] == "NeverValidate/pods" and res[0][4].startswith("[Implied by expand-deployments] "), lines
+    return len(res)
+
+
 def test_c_mirror_of_the_go_shim_on_the_test_backend(tmp_path):
     _build()
     assert _run(HOSTEMU, tmp_path) >= 10
+    assert _run_expansion(HOSTEMU, tmp_path) == 1
 
 
 @pytest.mark.gpu
